@@ -1,0 +1,116 @@
+"""ctypes binding of the CPU oracle (oracle/libcgo_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  Never imported by the
+product package cgenie_b200.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(ORACLE_DIR, "libcgo_oracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        P = C.c_void_p
+        L.cgo_create.restype = P
+        L.cgo_create.argtypes = [C.c_char_p] + [P] * 2 + [C.c_int] + [P] * 8
+        L.cgo_destroy.argtypes = [P]
+        for f in ("cgo_surflux", "cgo_embm_step", "cgo_seaice_step", "cgo_goldstein_step", "cgo_tstepo",
+                  "cgo_tstepo_flux", "cgo_co", "cgo_momentum", "cgo_tstipa", "cgo_biogem_step_all"):
+            if hasattr(L, f):
+                getattr(L, f).argtypes = [P]
+                getattr(L, f).restype = None
+        L.cgo_run.argtypes = [P, C.c_long]
+        L.cgo_field.restype = C.POINTER(C.c_double)
+        L.cgo_field.argtypes = [P, C.c_char_p, C.POINTER(C.c_long)]
+        L.cgo_ifield.restype = C.POINTER(C.c_int)
+        L.cgo_ifield.argtypes = [P, C.c_char_p, C.POINTER(C.c_long)]
+        L.cgo_scalar.restype = C.c_double
+        L.cgo_scalar.argtypes = [P, C.c_char_p]
+        L.cgo_set_scalar.argtypes = [P, C.c_char_p, C.c_double]
+        _LIB = L
+    return _LIB
+
+
+def load_inputs(world):
+    z = np.load(os.path.join(ROOT, "configs", "inputs.npz"))
+    d = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(world + "/")}
+    d.update({k.split("/", 1)[1]: z[k] for k in z.files if k.startswith("winds/")})
+    return d
+
+
+class Oracle:
+    """One ensemble member of the CPU restatement."""
+
+    def __init__(self, world="worbe2", **params):
+        self.L = lib()
+        inp = load_inputs(world)
+        kv = "".join("%s=%r\n" % (k, float(v)) for k, v in params.items())
+        keep = []
+
+        def ptr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data_as(C.c_void_p)
+
+        self.h = self.L.cgo_create(kv.encode(), ptr(inp["k1"], np.int32), ptr(inp["psiles"], np.float64),
+                                   len(inp["npi"]), ptr(inp["npi"], np.int32), ptr(inp["paths"], np.int32),
+                                   ptr(inp["taux_u"], np.float64), ptr(inp["tauy_u"], np.float64),
+                                   ptr(inp["taux_v"], np.float64), ptr(inp["tauy_v"], np.float64),
+                                   ptr(inp["uncep"], np.float64), ptr(inp["vncep"], np.float64))
+        if not self.h:
+            raise RuntimeError("cgo_create failed")
+        self.params = params
+
+    def close(self):
+        if self.h:
+            self.L.cgo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def f(self, name):
+        """numpy view (no copy) of a double field, flat Fortran order."""
+        n = C.c_long()
+        p = self.L.cgo_field(self.h, name.encode(), C.byref(n))
+        if not p:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def i(self, name):
+        n = C.c_long()
+        p = self.L.cgo_ifield(self.h, name.encode(), C.byref(n))
+        if not p:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def s(self, name):
+        return self.L.cgo_scalar(self.h, name.encode())
+
+    def set(self, name, v):
+        self.L.cgo_set_scalar(self.h, name.encode(), float(v))
+
+    def run(self, nkoverall):
+        self.L.cgo_run(self.h, int(nkoverall))
+
+    def call(self, fn):
+        getattr(self.L, "cgo_" + fn)(self.h)
