@@ -1,0 +1,91 @@
+"""ctypes loader for libcgenie_b200.so (the C-ABI of include/cgenie_b200.h)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcgenie_b200.so")
+_LIB = None
+
+P = C.c_void_p
+D = C.POINTER(C.c_double)
+
+
+class SurfluxIO(C.Structure):
+    _fields_ = [(n, D) for n in (
+        "albedo_ocn", "latent_ocn", "sensible_ocn", "netsolar_ocn", "netlong_ocn", "evap_ocn", "precip_ocn",
+        "runoff_ocn", "runoff_land", "latent_atm", "sensible_atm", "netsolar_atm", "netlong_atm", "evap_atm",
+        "precip_atm", "dhght_sic", "dfrac_sic", "temp_sic", "albd_sic", "qstar_atm")]
+
+
+class EmbmIO(C.Structure):
+    _fields_ = [(n, D) for n in ("tstar_atm", "qstar_atm")]
+
+
+class SeaiceIO(C.Structure):
+    _fields_ = [(n, D) for n in ("hght_sic", "frac_sic", "waterflux_ocn", "conductflux_ocn")]
+
+
+class GoldsteinIO(C.Structure):
+    _fields_ = [(n, D) for n in (
+        "tstar_ocn", "sstar_ocn", "ustar_ocn", "vstar_ocn", "albedo_ocn", "go_ts", "go_u", "go_rho", "go_cost",
+        "go_psi", "test_energy_ocean", "test_water_ocean")]
+
+
+# every symbol include/cgenie_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "cg_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(P)]),
+    "cg_set_member_param": (C.c_int, [P, C.c_char_p, D]),
+    "cg_initialise": (C.c_int, [P]),
+    "cg_destroy": (C.c_int, [P]),
+    "cg_last_error": (C.c_char_p, []),
+    "cg_surflux_step": (C.c_int, [P, C.c_int, C.POINTER(SurfluxIO)]),
+    "cg_embm_step": (C.c_int, [P, C.c_int, C.POINTER(EmbmIO)]),
+    "cg_seaice_step": (C.c_int, [P, C.c_int, C.POINTER(SeaiceIO)]),
+    "cg_goldstein_step": (C.c_int, [P, C.c_int, C.POINTER(GoldsteinIO)]),
+    "cg_biogem_forcing": (C.c_int, [P, C.c_int64]),
+    "cg_biogem_step": (C.c_int, [P, C.c_double, C.c_int64]),
+    "cg_biogem_tracercoupling": (C.c_int, [P, D, D]),
+    "cg_biogem_climate": (C.c_int, [P]),
+    "cg_atchem_step": (C.c_int, [P, C.c_double]),
+    "cg_run": (C.c_int, [P, C.c_int64]),
+    "cg_field_size": (C.c_int64, [P, C.c_char_p]),
+    "cg_sync_to_host": (C.c_int, [P, C.c_char_p, C.c_int, D, C.c_int64]),
+    "cg_sync_from_host": (C.c_int, [P, C.c_char_p, C.c_int, D, C.c_int64]),
+    "cg_sync_all_to_host": (C.c_int, [P, C.c_char_p, D, C.c_int64]),
+    "cg_sync_all_from_host": (C.c_int, [P, C.c_char_p, D, C.c_int64]),
+    "cg_const_size": (C.c_int64, [P, C.c_char_p]),
+    "cg_get_const": (C.c_int, [P, C.c_char_p, C.c_int, D, C.c_int64]),
+    "cg_get_iconst": (C.c_int, [P, C.c_char_p, C.POINTER(C.c_int32), C.c_int64]),
+    "cg_get_dims": (C.c_int, [P, C.POINTER(C.c_int32)]),
+    "cg_global_means": (C.c_int, [P, D]),
+    "cg_health": (C.c_int, [P, C.POINTER(C.c_int32)]),
+    "cg_synchronize": (C.c_int, [P]),
+    "cg_launch_count": (C.c_int64, [P, C.c_int]),
+    "cg_timer_start": (C.c_int, [P]),
+    "cg_timer_stop_ms": (C.c_int, [P, D]),
+    "cg_profile_enable": (C.c_int, [P, C.c_int]),
+    "cg_profile_get": (C.c_int, [P, C.c_char_p, D, C.POINTER(C.c_int64)]),
+    "cg_set_tracer_variant": (C.c_int, [P, C.c_int]),
+    "cg_set_graphs": (C.c_int, [P, C.c_int]),
+    "cg_tracer_create": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int32), C.c_double, C.c_double, C.c_int, C.POINTER(P)]),
+    "cg_tracer_set": (C.c_int, [P, D, D, D]),
+    "cg_tracer_step": (C.c_int, [P, C.c_int]),
+    "cg_tracer_get": (C.c_int, [P, D, D, D]),
+}
+
+
+def load():
+    """Load the compiled library or raise: the product has no CPU fallback."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libcgenie_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C cgenie_b200`); the B200 path has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library drift apart
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB

@@ -1,0 +1,1122 @@
+// cg_capi.cu -- the C-ABI of include/cgenie_b200.h: handle, device state, step scheduling,
+// state movement.  No torch types, no oracle code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/cgenie_b200.h"
+#include "cg_device.cuh"
+#include "cg_host.hpp"
+
+namespace cg {
+// kernels' launchers (k_physics.cu, k_tracer_*.cu, k_biogem.cu)
+void upload_grid_physics(const GridC &, cudaStream_t);
+void upload_grid_tracer_strict(const GridC &, cudaStream_t);
+void upload_grid_tracer_fast(const GridC &, cudaStream_t);
+int launch_tstepo_flux_strict(const Dev &, cudaStream_t);
+int launch_tstepo_flux_fast(const Dev &, cudaStream_t);
+int launch_co_strict(const Dev &, cudaStream_t);
+int launch_co_fast(const Dev &, cudaStream_t);
+void launch_step_begin(const Dev &, cudaStream_t);
+void launch_hosing(const Dev &, cudaStream_t);
+int launch_surflux(const Dev &, double *meantemp, bool need_mean, cudaStream_t);
+int launch_embm(const Dev &, int nsteps, cudaStream_t);
+int launch_seaice(const Dev &, cudaStream_t);
+int launch_gold_pre(const Dev &, cudaStream_t);
+int launch_momentum(const Dev &, cudaStream_t);
+void launch_global_means(const Dev &, double *out, cudaStream_t);
+void launch_health(const Dev &, int *flags, cudaStream_t);
+
+// member <-> Fortran-shaped staging (gather/scatter one member of a [..][m] field)
+struct FieldDesc {
+  double *d = nullptr;
+  int nd = 0;
+  int dims[4] = {1, 1, 1, 1};
+  long long strides[4] = {0, 0, 0, 0};  // device element stride (before *MS) of each Fortran dim
+  long long count() const { long long n = 1; for (int q = 0; q < nd; q++) n *= dims[q]; return n; }
+};
+__global__ void k_gather_member(const double *__restrict__ src, double *__restrict__ dst, int m, int MS, int nd, int d0, int d1,
+                                int d2, int d3, long long s0, long long s1, long long s2, long long s3, long long n) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  long long r = q;
+  const int i0 = r % d0; r /= d0;
+  const int i1 = r % d1; r /= d1;
+  const int i2 = r % d2; r /= d2;
+  const int i3 = (int)r;
+  (void)nd; (void)d3;
+  dst[q] = src[(i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3) * MS + m];
+}
+__global__ void k_scatter_member(double *__restrict__ dstf, const double *__restrict__ src, int m, int MS, int nd, int d0, int d1,
+                                 int d2, int d3, long long s0, long long s1, long long s2, long long s3, long long n) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  long long r = q;
+  const int i0 = r % d0; r /= d0;
+  const int i1 = r % d1; r /= d1;
+  const int i2 = r % d2; r /= d2;
+  const int i3 = (int)r;
+  (void)nd; (void)d3;
+  dstf[(i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3) * MS + m] = src[q];
+}
+}  // namespace cg
+
+using namespace cg;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_OK(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(CG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct ProfFam { double ms = 0; long long n = 0; };
+
+struct cg_handle {
+  int device = 0, M = 0, MS = 0;
+  bool tracer_only = false, initialised = false;
+  Params base;
+  Grid g;
+  Islands isl;
+  WindFiles w;
+  std::vector<Params> mp;
+  std::vector<MemberConsts> mc;  // one per member (big factor arrays kept on group leaders only)
+  std::vector<int> baro_group;
+  int nbaro = 0;
+  GridC gc;
+  Dev dv;
+  cudaStream_t stream = nullptr;
+  std::vector<void *> allocs;
+  std::map<std::string, FieldDesc> fields;
+  std::map<std::string, std::vector<double>> hconst;   // host constants for cg_get_const (member 0 / shared)
+  std::map<std::string, std::vector<int>> hiconst;
+  double *stage = nullptr;
+  size_t stage_n = 0;
+  double *d_meantemp = nullptr, *d_means = nullptr;
+  int *d_flags = nullptr;
+  bool need_mean = false;
+  long long launches = 0;
+  long long koverall = 0;
+  int istep_ocn = 0, istep_atm = 0, istep_sic = 0;
+  int variant = 0;  // 0 strict, 1 fast
+  bool use_graphs = true;
+  cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [variant][parity]
+  long long graph_launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool profile = false;
+  std::map<std::string, ProfFam> prof;
+  int io_member = 0;
+  ~cg_handle() {
+    cudaSetDevice(device);
+    for (auto &gv : graph) for (auto &ge : gv) if (ge) cudaGraphExecDestroy(ge);
+    for (void *p : allocs) cudaFree(p);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+// ------------------------------------------------------------------ device memory helpers
+template <typename T>
+static int dalloc(cg_handle *h, T **p, size_t n, bool zero = true) {
+  void *q = nullptr;
+  CUDA_OK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  if (zero) CUDA_OK(cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+  h->allocs.push_back(q);
+  *p = (T *)q;
+  return CG_OK;
+}
+template <typename T>
+static int dupload(cg_handle *h, T **p, const std::vector<T> &v) {
+  int rc = dalloc(h, p, v.size(), false);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return CG_OK;
+}
+// per-member scalar -> [MS]
+static int dparam(cg_handle *h, const double **p, const std::vector<double> &v) {
+  std::vector<double> t(h->MS, v.empty() ? 0.0 : v[0]);
+  for (int m = 0; m < h->M; m++) t[m] = v[m];
+  double *q;
+  int rc = dupload(h, &q, t);
+  *p = q;
+  return rc;
+}
+// per-member array of n elements (host [m][n]) -> device [n][MS]
+static int dmember_array(cg_handle *h, double **p, size_t n, const std::vector<const std::vector<double> *> &src) {
+  std::vector<double> t(n * h->MS, 0.0);
+  for (int m = 0; m < h->MS; m++) {
+    const std::vector<double> &s = *src[std::min(m, h->M - 1)];
+    for (size_t q = 0; q < n; q++) t[q * h->MS + m] = s[q];
+  }
+  return dupload(h, p, t);
+}
+
+static void reg_field(cg_handle *h, const std::string &name, double *d, std::initializer_list<int> dims,
+                      std::initializer_list<long long> strides) {
+  FieldDesc f;
+  f.d = d;
+  f.nd = (int)dims.size();
+  int q = 0;
+  for (int x : dims) f.dims[q++] = x;
+  q = 0;
+  for (long long x : strides) f.strides[q++] = x;
+  h->fields[name] = f;
+}
+
+static void fill_gridc(cg_handle *h) {
+  GridC &c = h->gc;
+  const Grid &g = h->g;
+  memset(&c, 0, sizeof(c));
+  c.I = g.I; c.J = g.J; c.K = g.K; c.L = g.L; c.M = h->M; c.MS = h->MS; c.nyear = g.nyear;
+  c.ndta = h->base.ndta; c.isles = h->isl.isles; c.npi1 = h->isl.isles > 0 ? h->isl.npi[1] : 0;
+  c.dphi = g.dphi; c.rdphi = g.rdphi; c.dzz = g.dzz; c.dt = g.dt;
+  for (int j = 0; j <= g.J + 1 && j < kMaxJ; j++) {
+    c.ds[j] = g.ds[j]; c.dsv[j] = g.dsv[j]; c.rds2[j] = g.rds2[j]; c.s[j] = g.s[j]; c.c[j] = g.c[j]; c.sv[j] = g.sv[j];
+    c.cv[j] = g.cv[j]; c.rc[j] = g.rc[j]; c.rc2[j] = g.rc2[j]; c.rcv[j] = g.rcv[j]; c.rdsv[j] = g.rdsv[j];
+    c.cv2[j] = g.cv2[j]; c.rds[j] = g.rds[j];
+  }
+  for (int k = 0; k <= g.K + 1 && k < kMaxK; k++) {
+    c.dz[k] = g.dz[k]; c.dza[k] = g.dza[k]; c.rdz[k] = g.rdz[k]; c.rdza[k] = g.rdza[k]; c.zw[k] = g.zw[k];
+    c.ssmax[k] = h->mc.empty() ? 0.0 : h->mc[0].ssmax[k];
+  }
+}
+static void upload_grid(cg_handle *h) {
+  upload_grid_physics(h->gc, h->stream);
+  upload_grid_tracer_strict(h->gc, h->stream);
+  upload_grid_tracer_fast(h->gc, h->stream);
+}
+// constant memory is per process: re-upload when another handle ran last
+static cg_handle *g_active = nullptr;
+static void activate(cg_handle *h) {
+  cudaSetDevice(h->device);
+  if (g_active != h) {
+    upload_grid(h);
+    g_active = h;
+  }
+}
+
+// host-side constants of member 0, exposed through cg_get_const / cg_get_iconst
+static void register_hconst(cg_handle *h, const MemberConsts &c) {
+  const Grid &g = h->g;
+  auto hc = [&](const char *n, const std::vector<double> &x) { h->hconst[n] = x; };
+  h->hiconst["k1"] = g.k1; h->hiconst["ku"] = g.ku; h->hiconst["mk"] = g.mk; h->hiconst["getj"] = g.getj;
+  h->hiconst["ips"] = g.ips; h->hiconst["ipf"] = g.ipf; h->hiconst["ias"] = g.ias; h->hiconst["iaf"] = g.iaf;
+  h->hiconst["jsf"] = std::vector<int>(1, g.jsf);
+  h->hiconst["ntot"] = std::vector<int>(1, g.ntot);
+  hc("ds", g.ds); hc("dsv", g.dsv); hc("rds2", g.rds2); hc("dz", g.dz); hc("s", g.s); hc("c", g.c); hc("sv", g.sv);
+  hc("cv", g.cv); hc("dza", g.dza); hc("zro", g.zro); hc("zw", g.zw); hc("rc", g.rc); hc("rc2", g.rc2); hc("rcv", g.rcv);
+  hc("rdsv", g.rdsv); hc("cv2", g.cv2); hc("rds", g.rds); hc("rdz", g.rdz); hc("rdza", g.rdza); hc("asurf", g.asurf);
+  hc("rh", g.rh);
+  hc("scalars", {g.dphi, g.rdphi, g.dzz, g.dt, c.diff1, c.diff2, c.adrag, c.ec[1], c.ec[2], c.ec[3], c.ec[4], c.rpmesco,
+                 c.rsictscsf, c.dtatm, c.rdtdim, c.rfluxsca, c.rpmesca, c.dtsic, c.sic_rdtdim, c.diffsic});
+  hc("ssmax", c.ssmax); hc("drag", c.drag); hc("rtv", c.rtv); hc("rtv3", c.rtv3); hc("rhosing", c.rhosing);
+  hc("ts0", c.ts0); hc("rho0", c.rho0);
+  if (!c.gap.empty()) { hc("gap", c.gap); hc("ratm", c.ratm); hc("ubisl", c.ubisl); hc("psisl", c.psisl); hc("erisl", c.erisl); }
+  if (!c.tq0.empty()) {
+    hc("tau", c.tau); hc("dztau", c.dztau); hc("dztav", c.dztav); hc("usurf", c.usurf); hc("diffa", c.diffa);
+    hc("uatm", c.uatm); hc("albcl", c.albcl); hc("ca", c.ca); hc("pmeadj", c.pmeadj); hc("solfor", c.solfor);
+    hc("tq0", c.tq0); hc("us_dztau", c.us_dztau); hc("us_dztav", c.us_dztav);
+    h->hiconst["iroff"] = c.iroff; h->hiconst["jroff"] = c.jroff;
+  }
+}
+
+// ------------------------------------------------------------------ life cycle
+extern "C" const char *cg_last_error(void) { return g_err.c_str(); }
+
+extern "C" int cg_create(const char *jobdir, int n_members, int device, cg_handle **out) {
+  if (!jobdir || !out || n_members < 1) return fail(CG_ERR_ARG, "cg_create: bad argument");
+  std::unique_ptr<cg_handle> h(new cg_handle);
+  h->device = device;
+  h->M = n_members;
+  h->MS = ((n_members + 15) / 16) * 16;
+  std::string err;
+  if (!load_job(jobdir, &h->base, &h->g, &h->isl, &h->w, &err)) {
+    const bool io = err.find("could not open") != std::string::npos || err.find("too short") != std::string::npos;
+    return fail(io ? CG_ERR_IO : CG_ERR_CONFIG, err);
+  }
+  if (h->g.J + 2 > kMaxJ || h->g.K + 2 > kMaxK) return fail(CG_ERR_CONFIG, "grid larger than the compiled metric tables");
+  if (h->isl.isles != 1) return fail(CG_ERR_CONFIG, "only single-island topographies (isles == 1) are on the B200 path");
+  if (h->base.flag_biogem) return fail(CG_ERR_CONFIG, "flag_biogem: BIOGEM kernels are not built yet");
+  h->mp.assign(n_members, h->base);
+  {
+    MemberConsts c0;  // member-0 constants are available without a device (bit-exactness checks)
+    build_member(h->g, h->isl, h->w, h->base, &c0, nullptr);
+    register_hconst(h.get(), c0);
+  }
+  *out = h.release();
+  return CG_OK;
+}
+
+extern "C" int cg_set_member_param(cg_handle *h, const char *name, const double *values) {
+  if (!h || !name || !values) return fail(CG_ERR_ARG, "cg_set_member_param: bad argument");
+  if (h->initialised) return fail(CG_ERR_STATE, "cg_set_member_param after cg_initialise");
+  for (int m = 0; m < h->M; m++)
+    if (!h->mp[m].set(name, values[m])) return fail(CG_ERR_ARG, std::string("unknown member parameter ") + name);
+  return CG_OK;
+}
+
+extern "C" int cg_destroy(cg_handle *h) {
+  if (!h) return CG_OK;
+  if (g_active == h) g_active = nullptr;
+  delete h;
+  return CG_OK;
+}
+
+static int build_device(cg_handle *h);
+
+extern "C" int cg_initialise(cg_handle *h) {
+  if (!h) return fail(CG_ERR_ARG, "null handle");
+  if (h->initialised) return fail(CG_ERR_STATE, "already initialised");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= h->device)
+    return fail(CG_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&h->ev0));
+  CUDA_OK(cudaEventCreate(&h->ev1));
+  // per-member constants; members sharing adrag share one barotropic factorisation
+  h->mc.resize(h->M);
+  h->baro_group.assign(h->MS, 0);
+  std::vector<int> leaders;
+  for (int m = 0; m < h->M; m++) {
+    int grp = -1;
+    for (size_t q = 0; q < leaders.size(); q++)
+      if (h->mp[leaders[q]].adrag == h->mp[m].adrag) { grp = (int)q; break; }
+    const MemberConsts *shared = grp >= 0 ? &h->mc[leaders[grp]] : nullptr;
+    build_member(h->g, h->isl, h->w, h->mp[m], &h->mc[m], shared);
+    if (grp < 0) { grp = (int)leaders.size(); leaders.push_back(m); }
+    else { h->mc[m].gap.clear(); h->mc[m].gap.shrink_to_fit(); h->mc[m].ratm.clear(); h->mc[m].ratm.shrink_to_fit(); }
+    h->baro_group[m] = grp;
+  }
+  for (int m = h->M; m < h->MS; m++) h->baro_group[m] = h->baro_group[h->M - 1];
+  h->nbaro = (int)leaders.size();
+  for (int m = 0; m < h->M; m++)
+    if (h->mp[m].olr_adj != 0.0) h->need_mean = true;
+  fill_gridc(h);
+  register_hconst(h, h->mc[0]);
+  int rc = build_device(h);
+  if (rc) return rc;
+  // keep leaders' factors for cg_get_const, drop the rest of the heavy host arrays
+  h->initialised = true;
+  activate(h);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+
+static int build_device(cg_handle *h) {
+  const Grid &g = h->g;
+  const int I = g.I, J = g.J, K = g.K, L = g.L, M = h->M, MS = h->MS;
+  const size_t ij = (size_t)I * J, ijk = ij * K;
+  Dev &v = h->dv;
+  memset(&v, 0, sizeof(v));
+  v.I = I; v.J = J; v.K = K; v.L = L; v.M = M; v.MS = MS; v.nm = I * (J + 1); v.nbaro = h->nbaro;
+  int rc;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  // ---- masks
+  {
+    std::vector<unsigned char> k1(g.k1.size()), ku(g.ku.size()), mk(g.mk.size()), gj(g.getj.size());
+    for (size_t q = 0; q < k1.size(); q++) k1[q] = (unsigned char)std::min(g.k1[q], 255);
+    for (size_t q = 0; q < ku.size(); q++) ku[q] = (unsigned char)std::min(g.ku[q], 255);
+    for (size_t q = 0; q < mk.size(); q++) mk[q] = (unsigned char)std::min(g.mk[q], 255);
+    for (size_t q = 0; q < gj.size(); q++) gj[q] = (unsigned char)g.getj[q];
+    unsigned char *p;
+    TRY(dupload(h, &p, k1)); v.k1 = p;
+    TRY(dupload(h, &p, ku)); v.ku = p;
+    TRY(dupload(h, &p, mk)); v.mk = p;
+    TRY(dupload(h, &p, gj)); v.getj = p;
+  }
+  // ---- per-member scalars
+  auto col = [&](auto getter) { std::vector<double> t(M); for (int m = 0; m < M; m++) t[m] = getter(h->mc[m]); return t; };
+  MemberP &p = v.p;
+  TRY(dparam(h, &p.diff1, col([](const MemberConsts &c) { return c.diff1; })));
+  TRY(dparam(h, &p.diff2, col([](const MemberConsts &c) { return c.diff2; })));
+  TRY(dparam(h, &p.ec1, col([](const MemberConsts &c) { return c.ec[1]; })));
+  TRY(dparam(h, &p.ec2, col([](const MemberConsts &c) { return c.ec[2]; })));
+  TRY(dparam(h, &p.ec3, col([](const MemberConsts &c) { return c.ec[3]; })));
+  TRY(dparam(h, &p.ec4, col([](const MemberConsts &c) { return c.ec[4]; })));
+  TRY(dparam(h, &p.rel, col([](const MemberConsts &c) { return c.p.rel; })));
+  TRY(dparam(h, &p.scf, col([](const MemberConsts &c) { return c.p.scf; })));
+  TRY(dparam(h, &p.saln0, col([](const MemberConsts &c) { return c.p.saln0; })));
+  TRY(dparam(h, &p.rpmesco, col([](const MemberConsts &c) { return c.rpmesco; })));
+  TRY(dparam(h, &p.rsictscsf, col([](const MemberConsts &c) { return c.rsictscsf; })));
+  TRY(dparam(h, &p.albocn, col([](const MemberConsts &c) { return c.p.albocn; })));
+  TRY(dparam(h, &p.hosing_trend, col([](const MemberConsts &c) { return c.hosing_trend; })));
+  {
+    std::vector<int> t(MS, 0);
+    for (int m = 0; m < M; m++) t[m] = h->mc[m].nsteps_hosing;
+    int *q; TRY(dupload(h, &q, t)); p.nsteps_hosing = q;
+    TRY(dupload(h, &q, h->baro_group)); v.baro_group = q;
+  }
+  {
+    std::vector<double> t(MS, 0.0);
+    for (int m = 0; m < M; m++) t[m] = h->mc[m].hosing;
+    TRY(dupload(h, &v.hosing, t));
+  }
+  // ---- tracer state
+  TRY(dalloc(h, &v.ts_cur, ijk * L * MS));
+  TRY(dalloc(h, &v.ts_new, ijk * L * MS));
+  TRY(dalloc(h, &v.tsflux, 2 * ij * MS));
+  TRY(dalloc(h, &v.rho, ijk * MS));
+  TRY(dalloc(h, &v.u, ijk * 3 * MS));
+  TRY(dalloc(h, &v.u1, ijk * 2 * MS));
+  TRY(dalloc(h, &v.cost, ij * MS));
+  TRY(dalloc(h, &v.istep_ocn, 1));
+  {
+    // initial ts/rho: host (L,I,J,K)/(I,J,K) Fortran order == device cell order with l fastest
+    std::vector<double> t(ijk * L * MS, 0.0), r(ijk * MS, 0.0);
+    for (int m = 0; m < MS; m++) {
+      const MemberConsts &c = h->mc[std::min(m, M - 1)];
+      for (size_t q = 0; q < ijk * L; q++) t[q * MS + m] = c.ts0[q];
+      for (size_t q = 0; q < ijk; q++) r[q * MS + m] = c.rho0[q];
+    }
+    CUDA_OK(cudaMemcpy(v.ts_cur, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(v.ts_new, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(v.rho, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
+  }
+  reg_field(h, "ts", v.ts_cur, {L, I, J, K}, {1, L, (long long)L * I, (long long)L * I * J});
+  reg_field(h, "rho", v.rho, {I, J, K}, {1, I, (long long)I * J});
+  reg_field(h, "u", v.u, {3, I, J, K}, {1, 3, 3LL * I, 3LL * I * J});
+  reg_field(h, "u1", v.u1, {2, I, J, K}, {1, 2, 2LL * I, 2LL * I * J});
+  reg_field(h, "cost", v.cost, {I, J}, {1, I});
+  reg_field(h, "tsflux", v.tsflux, {2, I, J}, {(long long)ij, 1, I});
+  TRY(dalloc(h, &h->d_meantemp, MS));
+  TRY(dalloc(h, &h->d_means, (size_t)MS * L));
+  TRY(dalloc(h, &h->d_flags, MS));
+  if (h->tracer_only) return CG_OK;
+
+  // ---- momentum
+  TRY(dalloc(h, &v.bp, ijk * MS));
+  TRY(dalloc(h, &v.sbp, ij * MS));
+  TRY(dalloc(h, &v.gb, (size_t)v.nm * MS));
+  TRY(dalloc(h, &v.ub, (size_t)2 * (I + 2) * (J + 1) * MS));
+  TRY(dalloc(h, &v.psi, (size_t)(I + 1) * (J + 1) * MS));
+  TRY(dalloc(h, &v.erisl_rhs, MS));
+  TRY(dalloc(h, &v.psibc, MS));
+  { double *q; TRY(dupload(h, &q, g.rh)); v.rh = q; }
+  auto members = [&](auto getter) {
+    std::vector<const std::vector<double> *> s(M);
+    for (int m = 0; m < M; m++) s[m] = &getter(h->mc[m]);
+    return s;
+  };
+  { double *q;
+    TRY(dmember_array(h, &q, (size_t)2 * (I + 1) * J, members([](const MemberConsts &c) -> const std::vector<double> & { return c.drag; }))); v.drag = q;
+    TRY(dmember_array(h, &q, ij, members([](const MemberConsts &c) -> const std::vector<double> & { return c.rtv; }))); v.rtv = q;
+    TRY(dmember_array(h, &q, ij, members([](const MemberConsts &c) -> const std::vector<double> & { return c.rtv3; }))); v.rtv3 = q;
+  }
+  // (2,I,J) host arrays (l fastest) -> device component-major [l][c2][m]
+  auto comp_major = [&](const std::vector<double> &a) {
+    std::vector<double> t(2 * ij);
+    for (size_t c2 = 0; c2 < ij; c2++) { t[c2] = a[0 + 2 * c2]; t[ij + c2] = a[1 + 2 * c2]; }
+    return t;
+  };
+  std::vector<std::vector<double>> tmpA(M), tmpB(M), tmpC(M);
+  for (int m = 0; m < M; m++) { tmpA[m] = comp_major(h->mc[m].tau); tmpB[m] = comp_major(h->mc[m].dztau); tmpC[m] = comp_major(h->mc[m].dztav); }
+  auto vecs = [&](std::vector<std::vector<double>> &x) { std::vector<const std::vector<double> *> s(M); for (int m = 0; m < M; m++) s[m] = &x[m]; return s; };
+  { double *q;
+    TRY(dmember_array(h, &q, 2 * ij, vecs(tmpA))); v.tau = q;
+    TRY(dmember_array(h, &q, 2 * ij, vecs(tmpB))); v.dztau = q;
+    TRY(dmember_array(h, &q, 2 * ij, vecs(tmpC))); v.dztav = q;
+  }
+  // barotropic factors per group, band rows made contiguous: ratm[row][t], gap[row][col]
+  {
+    const int nm = v.nm, bw = I + 1, gw = 2 * I + 3;
+    std::vector<double> R((size_t)h->nbaro * nm * bw), G((size_t)h->nbaro * nm * gw), UBI, PSI, ER;
+    std::vector<int> seen(h->nbaro, 0);
+    UBI.resize((size_t)h->nbaro * 2 * (I + 2) * (J + 1));
+    PSI.resize((size_t)h->nbaro * (I + 1) * (J + 1));
+    ER.resize((size_t)h->nbaro * 2);
+    for (int m = 0; m < M; m++) {
+      const int grp = h->baro_group[m];
+      if (seen[grp]) continue;
+      seen[grp] = 1;
+      const MemberConsts &c = h->mc[m];
+      for (int r = 0; r < nm; r++) {
+        for (int t = 0; t < bw; t++) R[((size_t)grp * nm + r) * bw + t] = c.ratm[(size_t)r + (size_t)nm * t];
+        for (int q = 0; q < gw; q++) G[((size_t)grp * nm + r) * gw + q] = c.gap[(size_t)r + (size_t)nm * q];
+      }
+      std::copy(c.ubisl.begin(), c.ubisl.begin() + (size_t)2 * (I + 2) * (J + 1), UBI.begin() + (size_t)grp * 2 * (I + 2) * (J + 1));
+      std::copy(c.psisl.begin(), c.psisl.begin() + (size_t)(I + 1) * (J + 1), PSI.begin() + (size_t)grp * (I + 1) * (J + 1));
+      ER[2 * grp] = c.erisl[0];
+      ER[2 * grp + 1] = c.erisl.size() > 1 ? c.erisl[1] : 0.0;
+    }
+    double *q;
+    TRY(dupload(h, &q, R)); v.ratm = q;
+    TRY(dupload(h, &q, G)); v.gap = q;
+    TRY(dupload(h, &q, UBI)); v.ubisl = q;
+    TRY(dupload(h, &q, PSI)); v.psisl = q;
+    TRY(dupload(h, &q, ER)); v.erisl = q;
+  }
+  { double *q; TRY(dupload(h, &q, h->mc[0].rhosing)); v.rhosing = q; }
+  {
+    // island 1 path
+    const int n = h->isl.npi[1];
+    std::vector<int> a(n), b(n), c(n);
+    for (int q = 0; q < n; q++) { a[q] = h->isl.lpisl[q]; b[q] = h->isl.ipisl[q]; c[q] = h->isl.jpisl[q]; }
+    int *q;
+    TRY(dupload(h, &q, a)); v.lpisl = q;
+    TRY(dupload(h, &q, b)); v.ipisl = q;
+    TRY(dupload(h, &q, c)); v.jpisl = q;
+  }
+  reg_field(h, "ub", v.ub, {2, I + 2, J + 1}, {1, 2, 2LL * (I + 2)});
+  reg_field(h, "psi", v.psi, {I + 1, J + 1}, {1, I + 1});
+  reg_field(h, "gb", v.gb, {v.nm}, {1});
+  reg_field(h, "bp", v.bp, {I, J, K}, {1, I, (long long)I * J});
+  reg_field(h, "sbp", v.sbp, {I, J}, {1, I});
+
+  // ---- EMBM / surflux / sea ice
+  TRY(dparam(h, &p.dtatm, col([](const MemberConsts &c) { return c.dtatm; })));
+  TRY(dparam(h, &p.rdtdim, col([](const MemberConsts &c) { return c.rdtdim; })));
+  TRY(dparam(h, &p.rfluxsca, col([](const MemberConsts &c) { return c.rfluxsca; })));
+  TRY(dparam(h, &p.rpmesca, col([](const MemberConsts &c) { return c.rpmesca; })));
+  TRY(dparam(h, &p.rmax, col([](const MemberConsts &c) { return c.p.rmax; })));
+  TRY(dparam(h, &p.betaz1, col([](const MemberConsts &c) { return c.p.betaz1; })));
+  TRY(dparam(h, &p.betaz2, col([](const MemberConsts &c) { return c.p.betaz2; })));
+  TRY(dparam(h, &p.betam1, col([](const MemberConsts &c) { return c.p.betam1; })));
+  TRY(dparam(h, &p.betam2, col([](const MemberConsts &c) { return c.p.betam2; })));
+  TRY(dparam(h, &p.ppmin, col([](const MemberConsts &c) { return c.ppmin; })));
+  TRY(dparam(h, &p.ppmax, col([](const MemberConsts &c) { return c.ppmax; })));
+  TRY(dparam(h, &p.delf2x, col([](const MemberConsts &c) { return c.p.delf2x; })));
+  TRY(dparam(h, &p.olr_adj0, col([](const MemberConsts &c) { return c.p.olr_adj0; })));
+  TRY(dparam(h, &p.olr_adj, col([](const MemberConsts &c) { return c.p.olr_adj; })));
+  TRY(dparam(h, &p.t_eqm, col([](const MemberConsts &c) { return c.p.t_eqm; })));
+  TRY(dparam(h, &p.par_sich_max, col([](const MemberConsts &c) { return c.p.par_sich_max; })));
+  TRY(dparam(h, &p.par_albsic_min, col([](const MemberConsts &c) { return c.p.par_albsic_min; })));
+  TRY(dparam(h, &p.par_albsic_max, col([](const MemberConsts &c) { return c.p.par_albsic_max; })));
+  TRY(dparam(h, &p.rate_co2, col([](const MemberConsts &c) { return c.rate_co2; })));
+  TRY(dparam(h, &p.rate_ch4, col([](const MemberConsts &c) { return c.rate_ch4; })));
+  TRY(dparam(h, &p.rate_n2o, col([](const MemberConsts &c) { return c.rate_n2o; })));
+  TRY(dparam(h, &p.hatmbl2, col([](const MemberConsts &c) { return c.hatmbl2; })));
+  TRY(dparam(h, &p.dtsic, col([](const MemberConsts &c) { return c.dtsic; })));
+  TRY(dparam(h, &p.sic_rdtdim, col([](const MemberConsts &c) { return c.sic_rdtdim; })));
+  TRY(dparam(h, &p.diffsic, col([](const MemberConsts &c) { return c.diffsic; })));
+  TRY(dparam(h, &p.par_sica_thresh, col([](const MemberConsts &c) { return c.p.par_sica_thresh; })));
+  TRY(dparam(h, &p.par_sich_thresh, col([](const MemberConsts &c) { return c.p.par_sich_thresh; })));
+  {
+    // diffa host (l, m2, j) l fastest -> device [j][(l-1)+2*(m2-1)][m]: same linear order
+    double *q;
+    TRY(dmember_array(h, &q, (size_t)4 * J, members([](const MemberConsts &c) -> const std::vector<double> & { return c.diffa; })));
+    p.diffa = q;
+  }
+  // effective advective winds: step_embm resets uatm = lowestlu2/usc every call (embm.f90:49-50)
+  std::vector<std::vector<double>> uu(M), vv(M);
+  for (int m = 0; m < M; m++) {
+    uu[m].resize(ij); vv[m].resize(ij);
+    for (size_t c2 = 0; c2 < ij; c2++) { uu[m][c2] = h->mc[m].lowestlu2[c2] / kUsc; vv[m][c2] = h->mc[m].lowestlv3[c2] / kUsc; }
+  }
+  { double *q;
+    TRY(dmember_array(h, &q, ij, vecs(uu))); v.uatm_u = q;
+    TRY(dmember_array(h, &q, ij, vecs(vv))); v.uatm_v = q;
+    TRY(dmember_array(h, &q, ij, members([](const MemberConsts &c) -> const std::vector<double> & { return c.usurf; }))); v.usurf = q;
+    TRY(dmember_array(h, &q, ij, members([](const MemberConsts &c) -> const std::vector<double> & { return c.albcl; }))); v.albcl = q;
+    TRY(dmember_array(h, &q, ij, members([](const MemberConsts &c) -> const std::vector<double> & { return c.ca; }))); v.ca = q;
+    TRY(dmember_array(h, &q, ij, members([](const MemberConsts &c) -> const std::vector<double> & { return c.pmeadj; }))); v.pmeadj = q;
+    TRY(dupload(h, &q, h->mc[0].solfor)); v.solfor = q;
+  }
+  {
+    // runoff gather lists in the reference's accumulation order: i outer, j inner (embm.f90:2955-2956)
+    std::vector<std::vector<int>> src(ij);
+    for (int i = 1; i <= I; i++)
+      for (int j = 1; j <= J; j++)
+        if (g.k1at(i, j) > K) {
+          const int ir = h->mc[0].iroff[(i - 1) + I * (j - 1)], jr = h->mc[0].jroff[(i - 1) + I * (j - 1)];
+          src[(ir - 1) + (size_t)I * (jr - 1)].push_back((i - 1) + I * (j - 1));
+        }
+    std::vector<int> ptr(ij + 1, 0), flat;
+    for (size_t c2 = 0; c2 < ij; c2++) { ptr[c2] = (int)flat.size(); flat.insert(flat.end(), src[c2].begin(), src[c2].end()); }
+    ptr[ij] = (int)flat.size();
+    if (flat.empty()) flat.push_back(0);
+    int *q;
+    TRY(dupload(h, &q, ptr)); v.iroff_ptr = q;
+    TRY(dupload(h, &q, flat)); v.iroff_src = q;
+  }
+  for (double **a : {&v.tq, &v.tq1, &v.tqa, &v.varice, &v.varice1}) TRY(dalloc(h, a, 2 * ij * MS));
+  for (double **a : {&v.co2, &v.ch4, &v.n2o, &v.pptn, &v.evap, &v.evapsic, &v.fx0a, &v.fx0o, &v.fxsen, &v.fxlw, &v.fxsw, &v.fxplw,
+                     &v.tice, &v.albice, &v.albedo, &v.latent_ocn, &v.sensible_ocn, &v.netsolar_ocn, &v.netlong_ocn, &v.evap_ocn,
+                     &v.precip_ocn, &v.runoff_ocn, &v.runoff_land, &v.latent_atm, &v.sensible_atm, &v.netsolar_atm, &v.netlong_atm,
+                     &v.evap_atm, &v.precip_atm, &v.dhght_sic, &v.dfrac_sic, &v.waterflux_ocn, &v.conductflux_ocn, &v.q_pa, &v.rq_pa})
+    TRY(dalloc(h, a, ij * MS));
+  {
+    std::vector<double> t(2 * ij * MS), c1(ij * MS), c2v(ij * MS), c3(ij * MS);
+    for (int m = 0; m < MS; m++) {
+      const MemberConsts &c = h->mc[std::min(m, M - 1)];
+      for (size_t q = 0; q < ij; q++) {
+        t[q * MS + m] = c.tq0[0 + 2 * q];
+        t[(ij + q) * MS + m] = c.tq0[1 + 2 * q];
+        c1[q * MS + m] = c.p.radfor_scl_co2 * kCo20;
+        c2v[q * MS + m] = c.p.radfor_scl_ch4 * kCh40;
+        c3[q * MS + m] = c.p.radfor_scl_n2o * kN2o0;
+      }
+    }
+    CUDA_OK(cudaMemcpy(v.tq, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(v.tq1, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(v.co2, c1.data(), c1.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(v.ch4, c2v.data(), c2v.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(v.n2o, c3.data(), c3.size() * 8, cudaMemcpyHostToDevice));
+  }
+  const long long IJ = (long long)ij;
+  reg_field(h, "tq", v.tq, {2, I, J}, {IJ, 1, I});
+  reg_field(h, "tq1", v.tq1, {2, I, J}, {IJ, 1, I});
+  reg_field(h, "tqa", v.tqa, {2, I, J}, {IJ, 1, I});
+  reg_field(h, "varice", v.varice, {2, I, J}, {IJ, 1, I});
+  reg_field(h, "varice1", v.varice1, {2, I, J}, {IJ, 1, I});
+  struct { const char *n; double *d; } two[] = {
+      {"co2", v.co2}, {"pptn", v.pptn}, {"evap", v.evap}, {"evapsic", v.evapsic}, {"fx0a", v.fx0a}, {"fx0o", v.fx0o},
+      {"fxsen", v.fxsen}, {"fxlw", v.fxlw}, {"fxsw", v.fxsw}, {"fxplw", v.fxplw}, {"tice", v.tice}, {"temp_sic", v.tice},
+      {"albice", v.albice}, {"albd_sic", v.albice}, {"albedo_ocn", v.albedo}, {"latent_ocn", v.latent_ocn},
+      {"sensible_ocn", v.sensible_ocn}, {"netsolar_ocn", v.netsolar_ocn}, {"netlong_ocn", v.netlong_ocn},
+      {"evap_ocn", v.evap_ocn}, {"precip_ocn", v.precip_ocn}, {"runoff_ocn", v.runoff_ocn}, {"runoff_land", v.runoff_land},
+      {"latent_atm", v.latent_atm}, {"sensible_atm", v.sensible_atm}, {"netsolar_atm", v.netsolar_atm},
+      {"netlong_atm", v.netlong_atm}, {"evap_atm", v.evap_atm}, {"precip_atm", v.precip_atm}, {"dhght_sic", v.dhght_sic},
+      {"dfrac_sic", v.dfrac_sic}, {"waterflux_ocn", v.waterflux_ocn}, {"conductflux_ocn", v.conductflux_ocn}};
+  for (auto &e : two) reg_field(h, e.n, e.d, {I, J}, {1, I});
+#undef TRY
+  return CG_OK;
+}
+
+// ------------------------------------------------------------------ one-member staging
+static int ensure_stage(cg_handle *h, size_t n) {
+  if (h->stage_n >= n) return CG_OK;
+  void *q;
+  CUDA_OK(cudaMalloc(&q, n * sizeof(double)));
+  h->allocs.push_back(q);
+  h->stage = (double *)q;
+  h->stage_n = n;
+  return CG_OK;
+}
+static FieldDesc *find_field(cg_handle *h, const char *name) {
+  auto it = h->fields.find(name);
+  if (it == h->fields.end()) return nullptr;
+  // ts / ts1 alias the current ping-pong buffer
+  if (it->first == "ts") it->second.d = h->dv.ts_cur;
+  return &it->second;
+}
+extern "C" int64_t cg_field_size(cg_handle *h, const char *name) {
+  if (!h || !name) return -1;
+  FieldDesc *f = find_field(h, strcmp(name, "ts1") == 0 ? "ts" : name);
+  return f ? f->count() : -1;
+}
+extern "C" int cg_sync_to_host(cg_handle *h, const char *name, int member, double *dst, int64_t n) {
+  if (!h || !name || !dst || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_to_host: bad argument");
+  FieldDesc *f = find_field(h, strcmp(name, "ts1") == 0 ? "ts" : name);
+  if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
+  if (member < 0 || member >= h->M || n != f->count()) return fail(CG_ERR_ARG, "cg_sync_to_host: member/size mismatch");
+  activate(h);
+  int rc = ensure_stage(h, (size_t)n);
+  if (rc) return rc;
+  k_gather_member<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(f->d, h->stage, member, h->MS, f->nd, f->dims[0], f->dims[1],
+                                                                     f->dims[2], f->dims[3], f->strides[0], f->strides[1],
+                                                                     f->strides[2], f->strides[3], n);
+  CUDA_OK(cudaMemcpyAsync(dst, h->stage, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+extern "C" int cg_sync_from_host(cg_handle *h, const char *name, int member, const double *src, int64_t n) {
+  if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_from_host: bad argument");
+  const bool both = strcmp(name, "ts") == 0 || strcmp(name, "ts1") == 0;
+  FieldDesc *f = find_field(h, both ? "ts" : name);
+  if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
+  if (member < 0 || member >= h->M || n != f->count()) return fail(CG_ERR_ARG, "cg_sync_from_host: member/size mismatch");
+  activate(h);
+  int rc = ensure_stage(h, (size_t)n);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(h->stage, src, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  k_scatter_member<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(f->d, h->stage, member, h->MS, f->nd, f->dims[0], f->dims[1],
+                                                                      f->dims[2], f->dims[3], f->strides[0], f->strides[1],
+                                                                      f->strides[2], f->strides[3], n);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+extern "C" int cg_sync_all_to_host(cg_handle *h, const char *name, double *dst, int64_t n) {
+  if (!h || !name || !dst || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_all_to_host: bad argument");
+  FieldDesc *f = find_field(h, name);
+  if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
+  if (n != f->count() * h->MS) return fail(CG_ERR_ARG, "cg_sync_all_to_host: size must be field_size*member_stride");
+  CUDA_OK(cudaMemcpyAsync(dst, f->d, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+extern "C" int cg_sync_all_from_host(cg_handle *h, const char *name, const double *src, int64_t n) {
+  if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_all_from_host: bad argument");
+  FieldDesc *f = find_field(h, name);
+  if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
+  if (n != f->count() * h->MS) return fail(CG_ERR_ARG, "cg_sync_all_from_host: size must be field_size*member_stride");
+  CUDA_OK(cudaMemcpyAsync(f->d, src, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+
+extern "C" int64_t cg_const_size(cg_handle *h, const char *name) {
+  if (!h || !name) return -1;
+  auto it = h->hconst.find(name);
+  if (it != h->hconst.end()) return (int64_t)it->second.size();
+  auto jt = h->hiconst.find(name);
+  if (jt != h->hiconst.end()) return (int64_t)jt->second.size();
+  return -1;
+}
+extern "C" int cg_get_const(cg_handle *h, const char *name, int member, double *dst, int64_t n) {
+  if (!h || !name || !dst) return fail(CG_ERR_ARG, "cg_get_const: bad argument");
+  (void)member;
+  auto it = h->hconst.find(name);
+  if (it == h->hconst.end()) return fail(CG_ERR_ARG, std::string("unknown constant ") + name);
+  if (n != (int64_t)it->second.size()) return fail(CG_ERR_ARG, "cg_get_const: size mismatch");
+  memcpy(dst, it->second.data(), (size_t)n * 8);
+  return CG_OK;
+}
+extern "C" int cg_get_iconst(cg_handle *h, const char *name, int32_t *dst, int64_t n) {
+  if (!h || !name || !dst) return fail(CG_ERR_ARG, "cg_get_iconst: bad argument");
+  auto it = h->hiconst.find(name);
+  if (it == h->hiconst.end()) return fail(CG_ERR_ARG, std::string("unknown constant ") + name);
+  if (n != (int64_t)it->second.size()) return fail(CG_ERR_ARG, "cg_get_iconst: size mismatch");
+  for (int64_t q = 0; q < n; q++) dst[q] = it->second[q];
+  return CG_OK;
+}
+extern "C" int cg_get_dims(cg_handle *h, int32_t dims[8]) {
+  if (!h || !dims) return fail(CG_ERR_ARG, "cg_get_dims: bad argument");
+  dims[0] = h->g.I; dims[1] = h->g.J; dims[2] = h->g.K; dims[3] = h->g.L; dims[4] = h->M; dims[5] = h->MS;
+  dims[6] = h->g.nyear; dims[7] = h->base.ndta;
+  return CG_OK;
+}
+
+// ------------------------------------------------------------------ steps
+struct ProfScope {
+  cg_handle *h; const char *fam; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(cg_handle *h_, const char *f) : h(h_), fam(f) {
+    if (h->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, h->stream); }
+  }
+  void done(int n) {
+    h->launches += n;
+    if (h->profile) {
+      cudaEventRecord(b, h->stream);
+      cudaEventSynchronize(b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      h->prof[fam].ms += ms;
+      h->prof[fam].n += n;
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+    }
+  }
+};
+
+static int do_surflux(cg_handle *h) {
+  { ProfScope ps(h, "surflux"); launch_step_begin(h->dv, h->stream); int n = launch_surflux(h->dv, h->d_meantemp, h->need_mean, h->stream); ps.done(n + 1); }
+  h->istep_ocn++;
+  return CG_OK;
+}
+static int do_embm(cg_handle *h, int nsteps) {
+  ProfScope ps(h, "embm");
+  int n = launch_embm(h->dv, nsteps, h->stream);
+  if (n < 0) return fail(CG_ERR_CONFIG, "EMBM grid too large for the block-resident kernel");
+  ps.done(n);
+  h->istep_atm += nsteps;
+  return CG_OK;
+}
+static int do_seaice(cg_handle *h) {
+  ProfScope ps(h, "seaice");
+  ps.done(launch_seaice(h->dv, h->stream));
+  h->istep_sic++;
+  return CG_OK;
+}
+static void do_tstepo(cg_handle *h) {
+  { ProfScope ps(h, "tstepo_flux"); ps.done(h->variant ? launch_tstepo_flux_fast(h->dv, h->stream) : launch_tstepo_flux_strict(h->dv, h->stream)); }
+  { ProfScope ps(h, "co"); ps.done(h->variant ? launch_co_fast(h->dv, h->stream) : launch_co_strict(h->dv, h->stream)); }
+  std::swap(h->dv.ts_cur, h->dv.ts_new);
+}
+static int do_goldstein(cg_handle *h) {
+  { ProfScope ps(h, "momentum"); launch_hosing(h->dv, h->stream); int n = launch_gold_pre(h->dv, h->stream); n += launch_momentum(h->dv, h->stream); ps.done(n + 1); }
+  do_tstepo(h);
+  return CG_OK;
+}
+static int check_async(cg_handle *h) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  (void)h;
+  return CG_OK;
+}
+#define READY(h) do { if (!(h) || !(h)->initialised) return fail(CG_ERR_STATE, "handle not initialised"); if ((h)->tracer_only) return fail(CG_ERR_STATE, "tracer-only handle"); activate(h); } while (0)
+
+static int put(cg_handle *h, const char *name, const double *src) {
+  return src ? cg_sync_from_host(h, name, h->io_member, src, cg_field_size(h, name)) : CG_OK;
+}
+static int get(cg_handle *h, const char *name, double *dst) {
+  return dst ? cg_sync_to_host(h, name, h->io_member, dst, cg_field_size(h, name)) : CG_OK;
+}
+#define IO(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+extern "C" int cg_surflux_step(cg_handle *h, int istep, const cg_surflux_io *io) {
+  READY(h);
+  if (istep != h->istep_ocn + 1) {  // the host owns the step counter; keep the device copy in line
+    const int v0 = istep - 1;
+    CUDA_OK(cudaMemcpyAsync(h->dv.istep_ocn, &v0, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->istep_ocn = v0;
+  }
+  if (io && io->qstar_atm) {
+    // surf_qstar_atm is INOUT: field 2 of tq
+    std::vector<double> t(cg_field_size(h, "tq"));
+    IO(cg_sync_to_host(h, "tq", h->io_member, t.data(), (int64_t)t.size()));
+    for (size_t q = 0; q < t.size() / 2; q++) t[1 + 2 * q] = io->qstar_atm[q];
+    IO(cg_sync_from_host(h, "tq", h->io_member, t.data(), (int64_t)t.size()));
+  }
+  IO(do_surflux(h));
+  IO(check_async(h));
+  if (io) {
+    IO(get(h, "albedo_ocn", io->albedo_ocn)); IO(get(h, "latent_ocn", io->latent_ocn)); IO(get(h, "sensible_ocn", io->sensible_ocn));
+    IO(get(h, "netsolar_ocn", io->netsolar_ocn)); IO(get(h, "netlong_ocn", io->netlong_ocn)); IO(get(h, "evap_ocn", io->evap_ocn));
+    IO(get(h, "precip_ocn", io->precip_ocn)); IO(get(h, "runoff_ocn", io->runoff_ocn)); IO(get(h, "runoff_land", io->runoff_land));
+    IO(get(h, "latent_atm", io->latent_atm)); IO(get(h, "sensible_atm", io->sensible_atm)); IO(get(h, "netsolar_atm", io->netsolar_atm));
+    IO(get(h, "netlong_atm", io->netlong_atm)); IO(get(h, "evap_atm", io->evap_atm)); IO(get(h, "precip_atm", io->precip_atm));
+    IO(get(h, "dhght_sic", io->dhght_sic)); IO(get(h, "dfrac_sic", io->dfrac_sic)); IO(get(h, "temp_sic", io->temp_sic));
+    IO(get(h, "albd_sic", io->albd_sic));
+    if (io->qstar_atm) {
+      std::vector<double> t(cg_field_size(h, "tq"));
+      IO(cg_sync_to_host(h, "tq", h->io_member, t.data(), (int64_t)t.size()));
+      for (size_t q = 0; q < t.size() / 2; q++) io->qstar_atm[q] = t[1 + 2 * q];
+    }
+  }
+  return CG_OK;
+}
+
+extern "C" int cg_embm_step(cg_handle *h, int istep, const cg_embm_io *io) {
+  READY(h);
+  (void)istep;
+  IO(do_embm(h, 1));
+  IO(check_async(h));
+  if (io && (io->tstar_atm || io->qstar_atm)) {
+    std::vector<double> t(cg_field_size(h, "tq"));
+    IO(cg_sync_to_host(h, "tq", h->io_member, t.data(), (int64_t)t.size()));
+    for (size_t q = 0; q < t.size() / 2; q++) {
+      if (io->tstar_atm) io->tstar_atm[q] = t[2 * q];
+      if (io->qstar_atm) io->qstar_atm[q] = t[1 + 2 * q];
+    }
+  }
+  return CG_OK;
+}
+
+extern "C" int cg_seaice_step(cg_handle *h, int istep, const cg_seaice_io *io) {
+  READY(h);
+  (void)istep;
+  IO(do_seaice(h));
+  IO(check_async(h));
+  if (io) {
+    if (io->hght_sic || io->frac_sic) {
+      std::vector<double> t(cg_field_size(h, "varice"));
+      IO(cg_sync_to_host(h, "varice", h->io_member, t.data(), (int64_t)t.size()));
+      for (size_t q = 0; q < t.size() / 2; q++) {
+        if (io->hght_sic) io->hght_sic[q] = t[2 * q];
+        if (io->frac_sic) io->frac_sic[q] = t[1 + 2 * q];
+      }
+    }
+    IO(get(h, "waterflux_ocn", io->waterflux_ocn));
+    IO(get(h, "conductflux_ocn", io->conductflux_ocn));
+  }
+  return CG_OK;
+}
+
+extern "C" int cg_goldstein_step(cg_handle *h, int istep, const cg_goldstein_io *io) {
+  READY(h);
+  (void)istep;
+  if (io) { IO(put(h, "ts", io->go_ts)); IO(put(h, "cost", io->go_cost)); }
+  IO(do_goldstein(h));
+  IO(check_async(h));
+  if (io) {
+    const int I = h->g.I, J = h->g.J, K = h->g.K, L = h->g.L;
+    IO(get(h, "ts", io->go_ts)); IO(get(h, "u", io->go_u)); IO(get(h, "rho", io->go_rho)); IO(get(h, "cost", io->go_cost));
+    if (io->go_psi) {
+      IO(get(h, "psi", io->go_psi));
+      for (int q = 0; q < (I + 1) * (J + 1); q++) io->go_psi[q] = 1592.5 * io->go_psi[q];  // goldstein.f90:450
+    }
+    if (io->tstar_ocn || io->sstar_ocn || io->ustar_ocn || io->vstar_ocn || io->albedo_ocn || io->test_energy_ocean ||
+        io->test_water_ocean) {
+      std::vector<double> ts((size_t)L * I * J * K), u((size_t)3 * I * J * K);
+      IO(cg_sync_to_host(h, "ts", h->io_member, ts.data(), (int64_t)ts.size()));
+      IO(cg_sync_to_host(h, "u", h->io_member, u.data(), (int64_t)u.size()));
+      for (int j = 1; j <= J; j++)
+        for (int i = 1; i <= I; i++) {
+          const size_t c2 = (size_t)(i - 1) + (size_t)I * (j - 1), c3 = c2 + (size_t)I * J * (K - 1);
+          const bool wet = h->g.k1at(i, j) <= K;
+          if (io->ustar_ocn) io->ustar_ocn[c2] = u[0 + 3 * c3];
+          if (io->vstar_ocn) io->vstar_ocn[c2] = u[1 + 3 * c3];
+          if (io->tstar_ocn) io->tstar_ocn[c2] = wet ? ts[0 + (size_t)L * c3] : 0.0;
+          if (io->sstar_ocn) io->sstar_ocn[c2] = wet ? ts[1 + (size_t)L * c3] : 0.0;
+          if (io->albedo_ocn) io->albedo_ocn[c2] = wet ? h->mp[h->io_member].albocn : 0.0;
+        }
+      if (io->test_energy_ocean || io->test_water_ocean) {
+        // goldstein.f90:458-478 (relative to the initial state, :79-96), host-side at output intervals only
+        const Grid &g = h->g;
+        auto tot = [&](const std::vector<double> &a, int l, double sgn) {
+          double t = 0.0;
+          for (int k = 1; k <= K; k++)
+            for (int j = 1; j <= J; j++) {
+              double s = 0.0;
+              for (int i = 1; i <= I; i++) s = s + a[l + (size_t)L * ((size_t)(i - 1) + (size_t)I * ((j - 1) + (size_t)J * (k - 1)))];
+              t = t + sgn * s * g.dz[k] * g.ds[j];
+            }
+          return t;
+        };
+        auto tot0 = [&](int l, double sgn) {
+          double t = 0.0;
+          const std::vector<double> &a = h->mc[h->io_member].ts0;
+          for (int k = 1; k <= K; k++)
+            for (int j = 1; j <= J; j++)
+              for (int i = 1; i <= I; i++)
+                t = t + sgn * a[l + (size_t)L * ((size_t)(i - 1) + (size_t)I * ((j - 1) + (size_t)J * (k - 1)))] * g.dz[k] * g.ds[j];
+          return t;
+        };
+        const double vsc = g.dphi * kRsc * kRsc, saln0 = h->mp[h->io_member].saln0;
+        if (io->test_energy_ocean)
+          *io->test_energy_ocean = tot(ts, 0, 1.0) * vsc * kDsc * kRh0sc * kCpsc - tot0(0, 1.0) * vsc * kDsc * kRh0sc * kCpsc;
+        if (io->test_water_ocean)
+          *io->test_water_ocean = kM2mm * tot(ts, 1, -1.0) * vsc * kDsc / saln0 - kM2mm * tot0(1, -1.0) * vsc * kDsc / saln0;
+      }
+    }
+  }
+  return CG_OK;
+}
+
+extern "C" int cg_biogem_forcing(cg_handle *h, int64_t) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
+extern "C" int cg_biogem_step(cg_handle *h, double, int64_t) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
+extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *, double *) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
+extern "C" int cg_biogem_climate(cg_handle *h) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
+extern "C" int cg_atchem_step(cg_handle *h, double) { (void)h; return fail(CG_ERR_CONFIG, "ATCHEM kernels are not built yet"); }
+
+// One ocean cycle = kocn_loop iterations of the koverall loop when katm_loop == 1 and
+// ksic_loop == kocn_loop (the only schedule tools/config_utils.py:103-162 generates):
+// surflux, kocn_loop x EMBM, sea ice, ocean.
+static int enqueue_cycle(cg_handle *h) {
+  const Params &p = h->base;
+  IO(do_surflux(h));
+  IO(do_embm(h, p.kocn_loop));
+  IO(do_seaice(h));
+  IO(do_goldstein(h));
+  return CG_OK;
+}
+
+extern "C" int cg_run(cg_handle *h, int64_t n) {
+  READY(h);
+  const Params &p = h->base;
+  const bool regular = p.katm_loop == 1 && p.ksic_loop == p.kocn_loop && p.kocn_loop > 1;
+  while (n > 0) {
+    const long long k = h->koverall + 1;
+    if (regular && (k % p.kocn_loop) == 1 && n >= p.kocn_loop) {
+      if (h->use_graphs && !h->profile) {
+        // two graphs per variant: the tracer ping-pong alternates buffers
+        const int par = (h->dv.ts_cur < h->dv.ts_new) ? 0 : 1;
+        cudaGraphExec_t &ge = h->graph[h->variant][par];
+        if (!ge) {
+          cudaGraph_t gr;
+          const long long l0 = h->launches;
+          const int i0 = h->istep_ocn, a0 = h->istep_atm, s0 = h->istep_sic;
+          CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+          int rc = enqueue_cycle(h);
+          cudaError_t e = cudaStreamEndCapture(h->stream, &gr);
+          if (rc) return rc;
+          if (e != cudaSuccess) return fail(CG_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+          h->graph_launches = h->launches - l0;
+          h->launches = l0; h->istep_ocn = i0; h->istep_atm = a0; h->istep_sic = s0;
+          std::swap(h->dv.ts_cur, h->dv.ts_new);  // undo the swap done while capturing
+          CUDA_OK(cudaGraphInstantiate(&ge, gr, 0));
+          cudaGraphDestroy(gr);
+        }
+        CUDA_OK(cudaGraphLaunch(ge, h->stream));
+        h->launches += h->graph_launches;
+        h->istep_ocn++; h->istep_atm += p.kocn_loop; h->istep_sic++;
+        std::swap(h->dv.ts_cur, h->dv.ts_new);
+      } else {
+        IO(enqueue_cycle(h));
+      }
+      h->koverall += p.kocn_loop;
+      n -= p.kocn_loop;
+      continue;
+    }
+    // general schedule (genie.f90:271-311)
+    if (k % p.kocn_loop == 1) IO(do_surflux(h));
+    if (k % p.katm_loop == 0) IO(do_embm(h, 1));
+    if (k % p.ksic_loop == 0) IO(do_seaice(h));
+    if (k % p.kocn_loop == 0) IO(do_goldstein(h));
+    h->koverall++;
+    n--;
+  }
+  return check_async(h);
+}
+
+// ------------------------------------------------------------------ diagnostics, measurement
+extern "C" int cg_global_means(cg_handle *h, double *out) {
+  if (!h || !h->initialised || !out) return fail(CG_ERR_ARG, "cg_global_means: bad argument");
+  activate(h);
+  launch_global_means(h->dv, h->d_means, h->stream);
+  CUDA_OK(cudaMemcpyAsync(out, h->d_means, (size_t)h->M * h->g.L * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+extern "C" int cg_health(cg_handle *h, int32_t *out) {
+  if (!h || !h->initialised || !out) return fail(CG_ERR_ARG, "cg_health: bad argument");
+  activate(h);
+  launch_health(h->dv, h->d_flags, h->stream);
+  CUDA_OK(cudaMemcpyAsync(out, h->d_flags, (size_t)h->M * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+extern "C" int cg_synchronize(cg_handle *h) {
+  if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+extern "C" int64_t cg_launch_count(cg_handle *h, int reset) {
+  if (!h) return -1;
+  const long long n = h->launches;
+  if (reset) h->launches = 0;
+  return n;
+}
+extern "C" int cg_timer_start(cg_handle *h) {
+  if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  return CG_OK;
+}
+extern "C" int cg_timer_stop_ms(cg_handle *h, double *ms) {
+  if (!h || !h->initialised || !ms) return fail(CG_ERR_STATE, "handle not initialised");
+  CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+  CUDA_OK(cudaEventSynchronize(h->ev1));
+  float f = 0;
+  CUDA_OK(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+  *ms = f;
+  return CG_OK;
+}
+extern "C" int cg_profile_enable(cg_handle *h, int on) {
+  if (!h) return fail(CG_ERR_ARG, "null handle");
+  h->profile = on != 0;
+  if (on) h->prof.clear();
+  return CG_OK;
+}
+extern "C" int cg_profile_get(cg_handle *h, const char *family, double *total_ms, int64_t *launches) {
+  if (!h || !family) return fail(CG_ERR_ARG, "cg_profile_get: bad argument");
+  auto it = h->prof.find(family);
+  if (total_ms) *total_ms = it == h->prof.end() ? 0.0 : it->second.ms;
+  if (launches) *launches = it == h->prof.end() ? 0 : it->second.n;
+  return CG_OK;
+}
+extern "C" int cg_set_tracer_variant(cg_handle *h, int variant) {
+  if (!h || (variant != 0 && variant != 1)) return fail(CG_ERR_ARG, "variant must be 0 (strict) or 1 (fast)");
+  h->variant = variant;
+  return CG_OK;
+}
+extern "C" int cg_set_graphs(cg_handle *h, int on) {
+  if (!h) return fail(CG_ERR_ARG, "null handle");
+  h->use_graphs = on != 0;
+  return CG_OK;
+}
+
+// ------------------------------------------------------------------ stand-alone tracer step
+extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_members, int device, const int32_t *k1, double diff1,
+                                double diff2, int nyear, cg_handle **out) {
+  if (!k1 || !out || maxi < 2 || maxj < 2 || maxk < 2 || maxl < 2 || n_members < 1)
+    return fail(CG_ERR_ARG, "cg_tracer_create: bad argument");
+  if (maxj + 2 > kMaxJ || maxk + 2 > kMaxK) return fail(CG_ERR_CONFIG, "grid larger than the compiled metric tables");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device)
+    return fail(CG_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
+  std::unique_ptr<cg_handle> h(new cg_handle);
+  h->device = device;
+  h->M = n_members;
+  h->MS = ((n_members + 15) / 16) * 16;
+  h->tracer_only = true;
+  Params p;
+  p.maxi = maxi; p.maxj = maxj; p.maxk = maxk; p.maxl = maxl; p.nyear = nyear; p.diff1 = diff1; p.diff2 = diff2;
+  h->base = p;
+  // k1 is given as (0:maxi+1, 0:maxj+1) column-major; Grid::build wants file order (rows j = J+1..0)
+  std::vector<int> k1file((size_t)(maxi + 2) * (maxj + 2));
+  size_t q = 0;
+  for (int j = maxj + 1; j >= 0; j--)
+    for (int i = 0; i <= maxi + 1; i++) k1file[q++] = k1[i + (maxi + 2) * j];
+  h->g.build(maxi, maxj, maxk, maxl, 0, nyear, p.yearlen, k1file);
+  h->isl.isles = 0;
+  h->mp.assign(n_members, p);
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&h->ev0));
+  CUDA_OK(cudaEventCreate(&h->ev1));
+  h->mc.resize(1);
+  build_member(h->g, h->isl, h->w, p, &h->mc[0], nullptr);
+  h->mc.resize(n_members, h->mc[0]);
+  h->baro_group.assign(h->MS, 0);
+  fill_gridc(h.get());
+  int rc = build_device(h.get());
+  if (rc) return rc;
+  h->initialised = true;
+  activate(h.get());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  *out = h.release();
+  return CG_OK;
+}
+
+// ts: [m][(maxl,0:maxi+1,0:maxj+1,0:maxk+1)], u: [m][(3,0:maxi,0:maxj,maxk)], tsflux: [m][(2,maxi,maxj)] or NULL
+extern "C" int cg_tracer_set(cg_handle *h, const double *ts, const double *u, const double *tsflux) {
+  if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  activate(h);
+  const int I = h->g.I, J = h->g.J, K = h->g.K, L = h->g.L, M = h->M, MS = h->MS;
+  const size_t ij = (size_t)I * J, ijk = ij * K;
+  if (ts) {
+    std::vector<double> t(ijk * L * MS, 0.0), r(ijk * MS, 0.0);
+    const size_t nts = (size_t)L * (I + 2) * (J + 2) * (K + 2);
+    for (int m = 0; m < M; m++)
+      for (int k = 1; k <= K; k++)
+        for (int j = 1; j <= J; j++)
+          for (int i = 1; i <= I; i++) {
+            const size_t c = cell3(I, J, i, j, k);
+            const double *src = ts + m * nts + (size_t)L * (i + (size_t)(I + 2) * (j + (size_t)(J + 2) * k));
+            for (int l = 0; l < L; l++) t[(c * L + l) * MS + m] = src[l];
+            r[c * MS + m] = eos(h->mc[0].ec, src[0], src[1]);
+          }
+    CUDA_OK(cudaMemcpy(h->dv.ts_cur, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->dv.ts_new, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->dv.rho, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
+  }
+  if (u) {
+    std::vector<double> t(ijk * 3 * MS, 0.0);
+    const size_t nu = (size_t)3 * (I + 1) * (J + 1) * K;
+    for (int m = 0; m < M; m++)
+      for (int k = 1; k <= K; k++)
+        for (int j = 1; j <= J; j++)
+          for (int i = 1; i <= I; i++) {
+            const size_t c = cell3(I, J, i, j, k);
+            const double *src = u + m * nu + (size_t)3 * (i + (size_t)(I + 1) * (j + (size_t)(J + 1) * (k - 1)));
+            for (int cc = 0; cc < 3; cc++) t[(c * 3 + cc) * MS + m] = src[cc];
+          }
+    CUDA_OK(cudaMemcpy(h->dv.u, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+  }
+  if (tsflux) {
+    std::vector<double> t(2 * ij * MS, 0.0);
+    for (int m = 0; m < M; m++)
+      for (size_t c2 = 0; c2 < ij; c2++)
+        for (int l = 0; l < 2; l++) t[(l * ij + c2) * MS + m] = tsflux[(size_t)m * 2 * ij + l + 2 * c2];
+    CUDA_OK(cudaMemcpy(h->dv.tsflux, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+  }
+  return CG_OK;
+}
+extern "C" int cg_tracer_step(cg_handle *h, int nsteps) {
+  if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  activate(h);
+  for (int s = 0; s < nsteps; s++) do_tstepo(h);
+  return check_async(h);
+}
+// ts: [m][(maxl,maxi,maxj,maxk)], rho: [m][(maxi,maxj,maxk)], cost: [m][(maxi,maxj)]; any may be NULL
+extern "C" int cg_tracer_get(cg_handle *h, double *ts, double *rho, double *cost) {
+  if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  for (int m = 0; m < h->M; m++) {
+    if (ts) IO(cg_sync_to_host(h, "ts", m, ts + (size_t)m * cg_field_size(h, "ts"), cg_field_size(h, "ts")));
+    if (rho) IO(cg_sync_to_host(h, "rho", m, rho + (size_t)m * cg_field_size(h, "rho"), cg_field_size(h, "rho")));
+    if (cost) IO(cg_sync_to_host(h, "cost", m, cost + (size_t)m * cg_field_size(h, "cost"), cg_field_size(h, "cost")));
+  }
+  return CG_OK;
+}

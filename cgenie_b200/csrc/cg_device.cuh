@@ -1,0 +1,94 @@
+// cg_device.cuh -- device-side data layout of the B200 hot path.
+//
+// HBM layout (all fp64): structure-of-arrays with the ENSEMBLE MEMBER as the fastest axis,
+// tracer next:
+//     ts  [k][j][i][l][m]      rho [k][j][i][m]      u [k][j][i][c][m]      2-D [j][i][m]
+// over the interior cells only (i=1..I, j=1..J, k=1..K; the periodic i-halo of the reference is
+// index arithmetic, the j/k boundary rows are never read because every neighbour access is
+// guarded by the bathymetry mask exactly as in the Fortran).  A warp is 32 members of ONE cell
+// and tracer: fully coalesced 256-byte rows, and near-uniform control flow because all members
+// share the bathymetry.  `MS` (member stride) = members rounded up to 16 doubles = 128 bytes.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cg {
+
+constexpr int kMaxJ = 132;  // metric arrays in constant memory (config #5: 128 x 128 x 32)
+constexpr int kMaxK = 36;
+
+// Member-independent grid metrics, uploaded to __constant__ memory of every kernel TU.
+struct GridC {
+  int I, J, K, L, M, MS, nyear, ndta, isles, npi1;
+  double dphi, rdphi, dzz, dt;
+  double ds[kMaxJ], dsv[kMaxJ], rds2[kMaxJ], s[kMaxJ], c[kMaxJ], sv[kMaxJ], cv[kMaxJ], rc[kMaxJ], rc2[kMaxJ],
+      rcv[kMaxJ], rdsv[kMaxJ], cv2[kMaxJ], rds[kMaxJ];
+  double dz[kMaxK], dza[kMaxK], rdz[kMaxK], rdza[kMaxK], zw[kMaxK], ssmax[kMaxK];
+};
+
+// Per-member scalar parameters ([MS] each) and per-member 2-D constants ([j][i][m]).
+struct MemberP {
+  const double *diff1, *diff2, *ec1, *ec2, *ec3, *ec4, *rel, *scf, *saln0, *rpmesco, *rsictscsf, *albocn;
+  const double *hosing_trend;
+  const int *nsteps_hosing;
+  // EMBM / surflux
+  const double *dtatm, *rdtdim, *rfluxsca, *rpmesca, *rmax, *betaz1, *betaz2, *betam1, *betam2, *ppmin, *ppmax,
+      *delf2x, *olr_adj0, *olr_adj, *t_eqm, *par_sich_max, *par_albsic_min, *par_albsic_max, *rate_co2, *rate_ch4,
+      *rate_n2o, *hatmbl2;
+  const double *diffa;   // [j][4][m]  (l,m2) -> (l-1)+2*(m2-1)
+  // sea ice
+  const double *dtsic, *sic_rdtdim, *diffsic, *par_sica_thresh, *par_sich_thresh;
+};
+
+// Everything a kernel needs, passed by value.
+struct Dev {
+  int I, J, K, L, M, MS;
+  int nm;         // psi points I*(J+1)
+  int nbaro;      // number of distinct barotropic factorisations
+  // masks (member independent)
+  const unsigned char *k1;   // (0:I+1, 0:J+1)
+  const unsigned char *ku;   // (2, I, J)
+  const unsigned char *mk;   // (I+1, J)
+  const unsigned char *getj; // (I, J)
+  const int *iroff_src;      // runoff gather lists: CSR over wet cells, sources in reference order
+  const int *iroff_ptr;
+  const int *lpisl, *ipisl, *jpisl;  // island 1 path (npi1 points)
+  // tracer state, ping-pong
+  double *ts_cur, *ts_new;
+  double *tsflux;            // [2][j][i][m] surface flux b.c. for T,S (ts(1:2,:,:,maxk+1))
+  double *rho, *u, *u1, *cost;
+  // momentum
+  double *bp, *sbp, *gb, *ub, *psi, *erisl_rhs, *psibc;
+  const double *rh;          // (3, 0:I+1, 0:J+1) member independent
+  const double *drag, *rtv, *rtv3;   // per member: (2,I+1,J)[m], (I,J)[m]
+  const double *tau, *dztau, *dztav; // per member (2,I,J)[m]
+  const double *gap, *ratm;  // per factor group: [g][nm][2I+3], [g][nm][I+1]  (row-major band rows)
+  const double *ubisl, *psisl, *erisl; // per group
+  const int *baro_group;     // [MS]
+  const double *rhosing;     // (I,J) member independent
+  double *hosing, *fw_anom;  // [MS], unused anomaly kept for completeness
+  // atmosphere / surface fluxes / sea ice ([j][i][m] unless noted)
+  double *tq, *tq1;          // [2][j][i][m]
+  double *tqa;               // [2][j][i][m]
+  const double *uatm_u, *uatm_v, *usurf, *albcl, *ca, *pmeadj;
+  const double *solfor;      // [nyear][J] member independent
+  double *co2, *ch4, *n2o;   // [j][i][m]
+  double *pptn, *evap, *evapsic, *fx0a, *fx0o, *fxsen, *fxlw, *fxsw, *fxplw, *tice, *albice, *albedo;
+  double *latent_ocn, *sensible_ocn, *netsolar_ocn, *netlong_ocn, *evap_ocn, *precip_ocn, *runoff_ocn, *runoff_land;
+  double *latent_atm, *sensible_atm, *netsolar_atm, *netlong_atm, *evap_atm, *precip_atm, *dhght_sic, *dfrac_sic;
+  double *varice, *varice1;  // [2][j][i][m]
+  double *waterflux_ocn, *conductflux_ocn;
+  double *q_pa, *rq_pa;
+  int *istep_ocn;            // device-resident ocean step counter (read by graph-replayed kernels)
+  MemberP p;
+};
+
+// ---- index helpers ----
+__host__ __device__ inline size_t cell3(const int I, const int J, int i, int j, int k) {
+  return (size_t)((k - 1) * J + (j - 1)) * I + (i - 1);
+}
+__host__ __device__ inline size_t cell2(const int I, int i, int j) { return (size_t)(j - 1) * I + (i - 1); }
+
+#define CG_K1(v, i, j) ((int)(v).k1[(i) + ((v).I + 2) * (j)])
+
+}  // namespace cg

@@ -1,0 +1,839 @@
+// k_physics.cu -- momentum (wind, jbar, barotropic solve, island, velc), EMBM (tstipa),
+// surflux and sea-ice kernels, sm_100a.  Compiled with -fmad=false: every expression keeps the
+// reference's operation order, so all non-transcendental results are bit-identical to the CPU
+// oracle; exp/log/pow differ from glibc by <= 2 ulp.
+//
+// Reference: src/goldstein/goldstein.f90 (step_goldstein :98-233, jbar :3217-3315,
+// ubarsolv :3500-3565, velc :3568-3679, wind :3685-3714, get_hosing :3086-3129),
+// src/goldstein/goldstein_lib.f90 (island :186-241), src/embm/embm.f90 (step_embm :22-195,
+// tstipa :2039-2138, surflux :2548-3738), src/goldsteinseaice/gold_seaice.f90
+// (step_seaice :511-733, tstepsic :844-929).
+#include "cg_device.cuh"
+#include "cg_host.hpp"
+
+namespace cg {
+
+static __constant__ GridC c_g;
+
+void upload_grid_physics(const GridC &g, cudaStream_t s) { cudaMemcpyToSymbolAsync(c_g, &g, sizeof(GridC), 0, cudaMemcpyHostToDevice, s); }
+
+#define A2I(i, j) (cell2(I, (i), (j)) * MS + m)
+#define A3I(l, i, j) (((size_t)((l)-1) * I * J + cell2(I, (i), (j))) * MS + m)
+#define RHX(l, i, j) v.rh[((l)-1) + 3 * ((i) + (I + 2) * (j))]
+#define DRAGX(l, i, j) v.drag[((size_t)((l)-1) + 2 * (((i)-1) + (I + 1) * ((j)-1))) * MS + m]
+#define UBX(l, i, j) v.ub[((size_t)((l)-1) + 2 * ((i) + (I + 2) * (j))) * MS + m]
+#define PSIX(i, j) v.psi[((size_t)(i) + (I + 1) * (j)) * MS + m]
+#define UX(c, i, j, k) v.u[(cell3(I, J, (i), (j), (k)) * 3 + ((c)-1)) * MS + m]
+#define U1X(c, i, j, k) v.u1[(cell3(I, J, (i), (j), (k)) * 2 + ((c)-1)) * MS + m]
+#define RHOX(i, j, k) v.rho[cell3(I, J, (i), (j), (k)) * MS + m]
+#define BPX(i, j, k) v.bp[cell3(I, J, (i), (j), (k)) * MS + m]
+#define SBPX(i, j) v.sbp[A2I(i, j)]
+#define KUX(l, i, j) ((int)v.ku[((l)-1) + 2 * (((i)-1) + I * ((j)-1))])
+#define MKX(i, j) ((int)v.mk[((i)-1) + (I + 1) * ((j)-1)])
+#define DIMS const int I = v.I, J = v.J, K = v.K, MS = v.MS; (void)K;
+
+// ---------------------------------------------------------------- step bookkeeping
+// istep_ocn = istep_ocn + 1 (genie.f90:271-277) and the hosing increment (goldstein.f90:3101)
+__global__ void k_step_begin(const Dev v) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m == 0) *v.istep_ocn = *v.istep_ocn + 1;
+}
+__global__ void k_hosing(const Dev v) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < v.M) v.hosing[m] = v.hosing[m] + v.p.hosing_trend[m] * kTsc * c_g.dt;
+}
+
+// ---------------------------------------------------------------- surflux, part 1 (per cell)
+__device__ inline double ch4_func(double ch4, double n2o) {
+  return 0.47 * log(1.0 + 2.01e-5 * pow(ch4 * n2o, 0.75) + 5.31e-15 * ch4 * pow(ch4 * n2o, 1.52));
+}
+
+// global-mean air temperature, SUM(atemp)/REAL(maxj*maxi) in array order (embm.f90:2950)
+__global__ void k_meantemp(const Dev v, double *meantemp) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= v.M) return;
+  double s = 0.0;
+  for (int q = 0; q < I * J; q++) s = s + v.tq[(size_t)q * MS + m];
+  meantemp[m] = s / (double)(J * I);
+}
+
+__global__ void __launch_bounds__(128) k_surflux1(const Dev v, const double *meantemp_arr) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const size_t q = (size_t)c2 * MS + m, q2 = ((size_t)I * J + c2) * MS + m;  // field 1 / field 2 of (2,i,j)
+  const int istot = *v.istep_ocn;
+  const int nsol = (istot - 1) % c_g.nyear + 1;
+  const double solf = v.solfor[(j - 1) + (size_t)J * (nsol - 1)];
+  const double zeroc = 273.15, tol = 1.0e-10;
+  const double rmax = v.p.rmax[m], rdtdim = v.p.rdtdim[m], hat2 = v.p.hatmbl2[m];
+  // greenhouse gases, compound increase (embm.f90:2913-2919)
+  const double co2 = (1.0 + v.p.rate_co2[m]) * v.co2[q], ch4 = (1.0 + v.p.rate_ch4[m]) * v.ch4[q],
+               n2o = (1.0 + v.p.rate_n2o[m]) * v.n2o[q];
+  v.co2[q] = co2; v.ch4[q] = ch4; v.n2o[q] = n2o;
+  const double at = v.tq[q];
+  double ashum = v.tq[q2];
+  const double qsata = kConst1 * exp(kConst4 * at / (at + kConst5));
+  const double pptn = fmax(0.0, (ashum - rmax * qsata) * kRhoao * hat2 * rdtdim);
+  ashum = fmin(ashum, rmax * qsata);
+  v.tq1[q2] = ashum;
+  v.tq[q2] = ashum;
+  v.pptn[q] = pptn;
+  const double rq = ashum / qsata;
+  const double albcl = v.albcl[q];
+  const double fxsw = solf * (1.0 - albcl);
+  const double tv0 = 2.43414e2 + rq * (-3.47968e1 + 1.02790e1 * rq);
+  const double tv1 = 2.60065 + rq * (-1.62064 + 6.34856e-1 * rq);
+  const double tv2 = 4.40272e-3 + rq * (-2.26092e-2 + 1.12265e-2 * rq);
+  const double tv3 = -2.05237e-5 + rq * (-9.67000e-5 + 5.62925e-5 * rq);
+  const double ch4_term = kAlphaCh4 * (sqrt(1.0e9 * ch4) - sqrt(1.0e9 * kCh40)) - ch4_func(1.0e9 * ch4, 1.0e9 * kN2o0) +
+                          ch4_func(1.0e9 * kCh40, 1.0e9 * kN2o0);
+  const double n2o_term = kAlphaN2o * (sqrt(1.0e9 * n2o) - sqrt(1.0e9 * kN2o0)) - ch4_func(1.0e9 * kCh40, 1.0e9 * n2o) +
+                          ch4_func(1.0e9 * kCh40, 1.0e9 * kN2o0);
+  const double meantemp = meantemp_arr ? meantemp_arr[m] : 0.0;
+  const double fxplw = tv0 + at * (tv1 + at * (tv2 + at * tv3)) - v.p.delf2x[m] * log(co2 / kCo20) - ch4_term - n2o_term +
+                       v.p.olr_adj[m] * (meantemp - v.p.t_eqm[m]) - v.p.olr_adj0[m];
+  const double fxlata = kRho0 * pptn * kHlv;
+  v.fxsw[q] = fxsw;
+  v.fxplw[q] = fxplw;
+  v.albedo[q] = albcl;
+  const int k1c = CG_K1(v, i, j);
+  if (k1c <= K) {
+    const size_t sC = (size_t)v.L * MS;
+    const size_t ot = cell3(I, J, i, j, K) * sC + m;
+    const double otemp = v.ts_cur[ot], osaln = v.ts_cur[ot + MS];
+    const double us = v.usurf[q], cca = v.ca[q], sa = v.varice1[q2], sich = v.varice1[q];
+    double alw = at + zeroc;
+    alw = alw * alw;
+    alw = alw * alw;
+    alw = kEma * alw;
+    const double salt = v.p.saln0[m] + osaln;
+    const double tsfreez = salt * (-0.0575 + 0.0017 * sqrt(salt) - 0.0002 * salt);
+    const double qb = v.p.rsictscsf[m] * (tsfreez - otemp);
+    double qbsic = qb;
+    double albsic, fx0sica, dhsic, evapsic, tice, atm_latenti, atm_sensiblei, atm_netsoli, atm_netlongi;
+    if (sa > 0.0) {
+      albsic = fmax(v.p.par_albsic_min[m], fmin(v.p.par_albsic_max[m], 0.40 - 0.04 * at));
+      const double fxswsic = solf * (1.0 - albsic);
+      tice = v.tice[q];
+      double ticold, cesic, chsic, cfxsensic, qsatsic, tieqn, dtieq;
+      for (int iter = 1; iter <= 21; iter++) {
+        ticold = tice;
+        cesic = 1.0e-3 * (1.0022 - 0.0822 * (at - ticold) + 0.0266 * us);
+        cesic = fmax(6.0e-5, fmin(2.19e-3, cesic));
+        chsic = 0.94 * cesic;
+        cfxsensic = kRhoair * chsic * kCpa * us;
+        qsatsic = kConst1 * exp(kConst2 * ticold / (ticold + kConst3));
+        evapsic = fmax(0.0, (qsatsic - ashum) * kRhoao * cesic * us);
+        const double tz = ticold + zeroc, tc3 = ticold + kConst3;
+        tieqn = sich * ((1 - cca) * fxswsic + alw - kEmo * ((tz * tz) * (tz * tz)) - cfxsensic * (ticold - at) -
+                        kRho0 * kHls * evapsic) +
+                kConsic * (tsfreez - ticold);
+        dtieq = sich * (-4.0 * kEmo * (tz * tz * tz) - cfxsensic -
+                        kHls * kRhoair * cesic * us * qsatsic * kConst2 * kConst3 / (tc3 * tc3) * 0.5 *
+                            (1.0 + copysign(1.0, qsatsic - ashum))) -
+                kConsic;
+        tice = ticold - tieqn / dtieq;
+        if (fabs(tice - ticold) < tol || (ticold > kTfreez && tieqn > 0.0)) break;
+      }
+      tice = fmin(kTfreez, tice);
+      const double tz = tice + zeroc;
+      const double fxlwsic = kEmo * ((tz * tz) * (tz * tz)) - alw;
+      cesic = 1.0e-3 * (1.0022 - 0.0822 * (at - tice) + 0.0266 * us);
+      cesic = fmax(6.0e-5, fmin(2.19e-3, cesic));
+      chsic = 0.94 * cesic;
+      cfxsensic = kRhoair * chsic * kCpa * us;
+      const double fxsensic = cfxsensic * (tice - at);
+      qsatsic = kConst1 * exp(kConst2 * tice / (tice + kConst3));
+      evapsic = fmax(0.0, (qsatsic - ashum) * kRhoao * cesic * us);
+      const double fx0sic = (1 - cca) * fxswsic - fxsensic - fxlwsic - kRho0 * kHls * evapsic;
+      fx0sica = cca * fxswsic + fxlata + fxsensic + fxlwsic - fxplw;
+      atm_latenti = +fxlata;
+      atm_sensiblei = +fxsensic;
+      atm_netsoli = +cca * fxswsic;
+      atm_netlongi = +fxlwsic - fxplw;
+      dhsic = kRrholf * (qb - fx0sic) - kRhooi * evapsic;
+      if (sich >= v.p.par_sich_max[m]) {
+        if (dhsic > 0.0) {
+          qbsic = (0.0 + kRhooi * evapsic) / kRrholf + fx0sic;
+          dhsic = kRrholf * (qbsic - fx0sic) - kRhooi * evapsic;
+        }
+      }
+    } else {
+      albsic = 0.0; fx0sica = 0.0; dhsic = 0.0; evapsic = 0.0; tice = 0.0;
+      atm_latenti = 0.0; atm_sensiblei = 0.0; atm_netsoli = 0.0; atm_netlongi = 0.0;
+    }
+    const double tzo = otemp + zeroc;
+    const double fxlw = kEmo * ((tzo * tzo) * (tzo * tzo)) - alw;
+    double ce = 1.0e-3 * (1.0022 - 0.0822 * (at - otemp) + 0.0266 * us);
+    ce = fmax(6.0e-5, fmin(2.19e-3, ce));
+    const double ch = 0.94 * ce;
+    const double fxsen = kRhoair * ch * kCpa * us * (otemp - at);
+    const double qsato = kConst1 * exp(kConst4 * otemp / (otemp + kConst5));
+    const double evap = fmax(0.0, (qsato - ashum) * kRhoao * ce * us);
+    const double fx0oa = cca * fxsw + fxlata + fxsen + fxlw - fxplw;
+    const double atm_latent = +fxlata, atm_sensible = +fxsen, atm_netsol = +cca * fxsw, atm_netlong = +fxlw - fxplw;
+    v.fx0a[q] = (1 - sa) * fx0oa + sa * fx0sica;
+    v.latent_atm[q] = (sa * atm_latenti) + ((1 - sa) * atm_latent);
+    v.sensible_atm[q] = (sa * atm_sensiblei) + ((1 - sa) * atm_sensible);
+    v.netsolar_atm[q] = (sa * atm_netsoli) + ((1 - sa) * atm_netsol);
+    v.netlong_atm[q] = (sa * atm_netlongi) + ((1 - sa) * atm_netlong);
+    const double fx0o = (1 - cca) * fxsw - fxsen - fxlw - kRho0 * kHlv * evap;
+    v.fx0o[q] = fx0o;
+    v.latent_ocn[q] = (1 - sa) * (-kRho0 * kHlv * evap + fmax(0.0, qb - fx0o)) + sa * qbsic;
+    v.sensible_ocn[q] = -((1 - sa) * fxsen);
+    v.netsolar_ocn[q] = (1 - sa) * (1 - cca) * fxsw;
+    v.netlong_ocn[q] = -((1 - sa) * fxlw);
+    const double dho = fmax(0.0, kRrholf * (qb - fx0o));
+    v.dhght_sic[q] = sa * dhsic + (1 - sa) * dho;
+    double dta = fmax(0.0, kRhmin * dho * (1 - sa));
+    if (sich > 1.0e-12) dta = dta + fmin(0.0, 0.5 * sa * sa * dhsic / sich);
+    v.dfrac_sic[q] = dta;
+    v.albedo[q] = sa * albsic + (1 - sa) * albcl;
+    v.albice[q] = albsic;
+    v.tice[q] = tice;
+    v.evap[q] = evap;
+    v.evapsic[q] = evapsic;
+    v.fxsen[q] = fxsen;
+    v.fxlw[q] = fxlw;
+    v.runoff_land[q] = 0.0;
+  } else {
+    v.fx0a[q] = fxsw + fxlata - fxplw;
+    v.latent_atm[q] = +fxlata;
+    v.sensible_atm[q] = +0.0;
+    v.netsolar_atm[q] = +fxsw;
+    v.netlong_atm[q] = -fxplw;
+    v.evap[q] = 0.0;
+    v.latent_ocn[q] = 0.0; v.sensible_ocn[q] = 0.0; v.netsolar_ocn[q] = 0.0; v.netlong_ocn[q] = 0.0;
+    v.dhght_sic[q] = 0.0; v.dfrac_sic[q] = 0.0; v.albice[q] = 0.0;
+    v.runoff_land[q] = pptn * kM2mm;
+  }
+}
+
+// surflux part 2: runoff routing as an order-preserving gather + final flux scaling (embm.f90:3351-3357, 3657-3695)
+__global__ void __launch_bounds__(128) k_surflux2(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const size_t q = (size_t)c2 * MS + m, q2 = ((size_t)I * J + c2) * MS + m;
+  const double pptn = v.pptn[q];
+  double pptn_ocn, runoff_ocn, evap_atm;
+  if (CG_K1(v, i, j) <= K) {
+    double runoff = 0.0;
+    for (int p = v.iroff_ptr[c2]; p < v.iroff_ptr[c2 + 1]; p++) runoff = runoff + v.pptn[(size_t)v.iroff_src[p] * MS + m];
+    const double sa = v.varice1[q2];
+    pptn_ocn = pptn;
+    runoff_ocn = runoff + 0.0;
+    evap_atm = v.evap[q] * (1 - sa) + v.evapsic[q] * sa;
+    pptn_ocn = pptn_ocn + v.pmeadj[q];
+  } else {
+    pptn_ocn = 0.0; runoff_ocn = 0.0; evap_atm = 0.0;
+  }
+  const double evap_ocn = -evap_atm;
+  v.precip_atm[q] = pptn * kM2mm;
+  v.precip_ocn[q] = pptn_ocn * kM2mm;
+  v.evap_ocn[q] = evap_ocn * kM2mm;
+  v.runoff_ocn[q] = runoff_ocn * kM2mm;
+  v.evap_atm[q] = evap_atm * kM2mm;
+}
+
+// ---------------------------------------------------------------- EMBM: tstipa, nsteps fused
+// One block = one member; thread owns CPT cells; tq2 lives in shared memory (halo rows 0 and J+1
+// are zero, the i-halo is index arithmetic).  embm.f90:2039-2138 + step_embm :48-70.
+template <int CPT>
+__global__ void __launch_bounds__(704) k_embm(const Dev v, const int nsteps) {
+  DIMS
+  extern __shared__ double tq2[];  // (I, 0:J+1)
+  const int m = blockIdx.x;
+  const int nc = I * J, tc = blockDim.x;
+  const double cimp = 0.5;
+  const double dtloc = v.p.dtatm[m], rfluxsca = v.p.rfluxsca[m], rpmesca = v.p.rpmesca[m];
+  double tq[2][CPT], tq1[2][CPT], tqa[2][CPT];
+  double cie[2][CPT], ciwm[2][CPT], cin[2][CPT], cism[2][CPT], cdiv[2][CPT];
+#define T2(i, j) tq2[((i)-1) + I * (j)]
+  for (int q = threadIdx.x; q < I; q += tc) { T2(q + 1, 0) = 0.0; T2(q + 1, J + 1) = 0.0; }
+#pragma unroll
+  for (int n = 0; n < CPT; n++) {
+    const int c2 = threadIdx.x + n * tc;
+    if (c2 < nc) {
+      const int i = c2 % I + 1, j = c2 / I + 1, im = (i > 1) ? i - 1 : I;
+      const size_t q = (size_t)c2 * MS + m, q2 = ((size_t)nc + c2) * MS + m;
+      tq[0][n] = v.tq[q]; tq[1][n] = v.tq[q2];
+      tq1[0][n] = v.tq1[q]; tq1[1][n] = v.tq1[q2];
+      tqa[0][n] = (v.netsolar_atm[q] + v.latent_atm[q] + v.sensible_atm[q] + v.netlong_atm[q]) * rfluxsca;
+      tqa[1][n] = v.evap_atm[q] * kMm2m * rpmesca;
+      const double ua = v.uatm_u[q], uaw = v.uatm_u[A2I(im, j)], va = v.uatm_v[q], vas = (j > 1) ? v.uatm_v[A2I(i, j - 1)] : 0.0;
+#pragma unroll
+      for (int l = 0; l < 2; l++) {
+        const double bz = l ? v.p.betaz2[m] : v.p.betaz1[m], bm = l ? v.p.betam2[m] : v.p.betam1[m];
+        const double da1 = v.p.diffa[((size_t)(j - 1) * 4 + l) * MS + m], da2 = v.p.diffa[((size_t)(j - 1) * 4 + l + 2) * MS + m];
+        // east face of (i,j) and of (i-1,j)
+        double e = bz * ua * c_g.rc[j] * 0.5 * c_g.rdphi;
+        double tv = c_g.rc[j] * c_g.rc[j] * c_g.rdphi * da1 * c_g.rdphi;
+        double pec = bz * ua * c_g.dphi / da1;
+        double ups = pec / (2.0 + fabs(pec));
+        const double ciw_c = e * (1 + ups) + tv;
+        const double cie_c = e * (1 - ups) - tv;
+        e = bz * uaw * c_g.rc[j] * 0.5 * c_g.rdphi;
+        pec = bz * uaw * c_g.dphi / da1;
+        ups = pec / (2.0 + fabs(pec));
+        const double ciw_w = e * (1 + ups) + tv;
+        const double cie_w = e * (1 - ups) - tv;
+        // north face of (i,j) and of (i,j-1)
+        double nn = c_g.cv[j] * bm * va * 0.5;
+        if (j < J) {
+          tv = c_g.cv[j] * c_g.cv[j] * c_g.rdsv[j] * da2;
+          pec = bm * va * c_g.dsv[j] / da2;
+          ups = pec / (2.0 + fabs(pec));
+        } else {
+          tv = 0.0;
+          ups = 0.0;
+        }
+        const double cis_c = nn * (1 + ups) + tv;
+        const double cin_c = nn * (1 - ups) - tv;
+        double cis_s = 0.0, cin_s = 0.0;
+        if (j > 1) {
+          const double das = v.p.diffa[((size_t)(j - 2) * 4 + l + 2) * MS + m];
+          nn = c_g.cv[j - 1] * bm * vas * 0.5;
+          tv = c_g.cv[j - 1] * c_g.cv[j - 1] * c_g.rdsv[j - 1] * das;
+          pec = bm * vas * c_g.dsv[j - 1] / das;
+          ups = pec / (2.0 + fabs(pec));
+          cis_s = nn * (1 + ups) + tv;
+          cin_s = nn * (1 - ups) - tv;
+        }
+        cie[l][n] = cie_c; ciwm[l][n] = ciw_w; cin[l][n] = cin_c; cism[l][n] = cis_s;
+        cdiv[l][n] = ciw_c - cie_w + (cis_c - cin_s) * c_g.rds[j];
+      }
+    }
+  }
+  for (int step = 0; step < nsteps; step++) {
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+      for (int iits = 0; iits < 5; iits++) {
+        __syncthreads();
+#pragma unroll
+        for (int n = 0; n < CPT; n++) {
+          const int c2 = threadIdx.x + n * tc;
+          if (c2 < nc) {
+            const int i = c2 % I + 1, j = c2 / I + 1;
+            if (iits < 4)
+              T2(i, j) = cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n];
+            else
+              T2(i, j) = 0.5 * (T2(i, j) + cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n]);
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int n = 0; n < CPT; n++) {
+          const int c2 = threadIdx.x + n * tc;
+          if (c2 < nc) {
+            const int i = c2 % I + 1, j = c2 / I + 1, ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
+            const double flx = -tqa[l][n] + cie[l][n] * T2(ip, j) - ciwm[l][n] * T2(im, j) +
+                               (cin[l][n] * T2(i, j + 1) - cism[l][n] * T2(i, j - 1)) * c_g.rds[j];
+            if (iits < 4) {
+              const double centre = dtloc * cdiv[l][n];
+              tq[l][n] = (tq1[l][n] * (1.0 - (1.0 - cimp) * centre) - dtloc * flx) / (1 + cimp * centre);
+            } else {
+              tq[l][n] = tq1[l][n] - dtloc * flx - dtloc * T2(i, j) * cdiv[l][n];
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < CPT; n++) { tq1[0][n] = tq[0][n]; tq1[1][n] = tq[1][n]; }
+  }
+#pragma unroll
+  for (int n = 0; n < CPT; n++) {
+    const int c2 = threadIdx.x + n * tc;
+    if (c2 < nc) {
+      const size_t q = (size_t)c2 * MS + m, q2 = ((size_t)nc + c2) * MS + m;
+      v.tq[q] = tq[0][n]; v.tq[q2] = tq[1][n];
+      v.tq1[q] = tq1[0][n]; v.tq1[q2] = tq1[1][n];
+      v.tqa[q] = tqa[0][n]; v.tqa[q2] = tqa[1][n];
+    }
+  }
+#undef T2
+}
+
+// ---------------------------------------------------------------- sea ice
+// tstepsic (gold_seaice.f90:844-929): varice1 -> varice
+__global__ void __launch_bounds__(128) k_seaice1(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const int k1c = CG_K1(v, i, j);
+  if (K < k1c) return;
+  const int ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
+  const int k1e = CG_K1(v, ip, j), k1w = CG_K1(v, im, j), k1n = CG_K1(v, i, j + 1), k1s = CG_K1(v, i, j - 1);
+  const double sath = v.p.par_sica_thresh[m], shth = v.p.par_sich_thresh[m], diffsic = v.p.diffsic[m], dtsic = v.p.dtsic[m];
+  const double rc = c_g.rc[j], rdphi = c_g.rdphi;
+  // surface ocean velocities (ustar_ocn = u(1,:,:,maxk), goldstein.f90:428-429)
+  const double uE = UX(1, i, j, K), uW = UX(1, im, j, K), vN = UX(2, i, j, K), vS = (j > 1) ? UX(2, i, j - 1, K) : 0.0;
+  const size_t nf = (size_t)I * J * MS;
+  const size_t qc = A2I(i, j), qe = A2I(ip, j), qw = A2I(im, j), qn = (j < J) ? A2I(i, j + 1) : qc, qs = (j > 1) ? A2I(i, j - 1) : qc;
+  const double hc = v.varice1[qc], ac = v.varice1[qc + nf];
+#pragma unroll
+  for (int l = 0; l < 2; l++) {
+    const size_t lo = l * nf;
+    const double c0 = v.varice1[qc + lo];
+    double fe = 0.0, fw = 0.0, fn = 0.0, fs = 0.0;
+    if (K >= max(k1c, k1e)) {
+      const double e0 = v.varice1[qe + lo], he = v.varice1[qe], ae = v.varice1[qe + nf];
+      fe = uE * rc * (e0 + c0) * 0.5;
+      if (uE >= 0.0) { if (ae > sath) fe = 0; if (he > shth) fe = 0; }
+      else { if (ac > sath) fe = 0; if (hc > shth) fe = 0; }
+      fe = fe - (e0 - c0) * rc * rc * rdphi * diffsic;
+    }
+    if (K >= max(k1c, k1w)) {
+      const double w0 = v.varice1[qw + lo], hw = v.varice1[qw], aw = v.varice1[qw + nf];
+      fw = uW * rc * (c0 + w0) * 0.5;
+      if (uW >= 0.0) { if (ac > sath) fw = 0; if (hc > shth) fw = 0; }
+      else { if (aw > sath) fw = 0; if (hw > shth) fw = 0; }
+      fw = fw - (c0 - w0) * rc * rc * rdphi * diffsic;
+    }
+    if (K >= max(k1c, k1n)) {
+      const double n0 = v.varice1[qn + lo], hn = v.varice1[qn], an = v.varice1[qn + nf];
+      fn = c_g.cv[j] * vN * (n0 + c0) * 0.5;
+      if (vN >= 0.0) { if (an > sath) fn = 0; if (hn > shth) fn = 0; }
+      else { if (ac > sath) fn = 0; if (hc > shth) fn = 0; }
+      fn = fn - c_g.cv[j] * c_g.cv[j] * (n0 - c0) * c_g.rdsv[j] * diffsic;
+    }
+    if (j > 1 && K >= max(k1c, k1s)) {
+      const double s0 = v.varice1[qs + lo], hs = v.varice1[qs], as = v.varice1[qs + nf];
+      fs = c_g.cv[j - 1] * vS * (c0 + s0) * 0.5;
+      if (vS >= 0.0) { if (ac > sath) fs = 0; if (hc > shth) fs = 0; }
+      else { if (as > sath) fs = 0; if (hs > shth) fs = 0; }
+      fs = fs - c_g.cv[j - 1] * c_g.cv[j - 1] * (c0 - s0) * c_g.rdsv[j - 1] * diffsic;
+    }
+    const double dtha = l ? v.dfrac_sic[qc] : v.dhght_sic[qc];
+    v.varice[qc + lo] = c0 - dtsic * ((fe - fw) * rdphi + (fn - fs) * c_g.rds[j]) + kTsc * dtsic * dtha;
+  }
+}
+// step_seaice post-processing (gold_seaice.f90:605-622, 691-702)
+__global__ void __launch_bounds__(128) k_seaice2(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const size_t q = (size_t)c2 * MS + m, q2 = ((size_t)I * J + c2) * MS + m;
+  double fw_delta = 0.0, fx_delta = 0.0;
+  if (K >= CG_K1(v, i, j)) {
+    const double rdt = v.p.sic_rdtdim[m];
+    double h = v.varice[q], a = v.varice[q2];
+    fw_delta = -kRhoio * v.dhght_sic[q];
+    a = fmax(0.0, fmin(1.0, a));
+    if (h < kHmin) {
+      fx_delta = -h * kRhoice * kHlf * rdt;
+      fw_delta = fw_delta + h * kRhoio * rdt;
+      h = 0.0;
+      a = 0.0;
+    }
+    v.varice[q] = h; v.varice[q2] = a;
+    v.varice1[q] = h; v.varice1[q2] = a;
+    fw_delta = fw_delta * kM2mm;
+  }
+  v.waterflux_ocn[q] = fw_delta;
+  v.conductflux_ocn[q] = fx_delta;
+}
+
+// ---------------------------------------------------------------- ocean: surface b.c.
+// net heat / freshwater flux into ts(1:2,:,:,maxk+1) (goldstein.f90:143-170, get_hosing :3114-3127)
+__global__ void __launch_bounds__(128) k_gold_pre(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || c2 >= I * J) return;
+  const size_t q = (size_t)c2 * MS + m;
+  const int istep = *v.istep_ocn;
+  const double fw_hosing = (istep <= v.p.nsteps_hosing[m]) ? kM2mm * v.hosing[m] * v.rhosing[c2] : 0.0;
+  const double fw_anom = 0.0;
+  const double fx0neto = v.netsolar_ocn[q] + v.sensible_ocn[q] + v.netlong_ocn[q] + v.latent_ocn[q] + v.conductflux_ocn[q];
+  double fwfxneto = v.precip_ocn[q] + v.evap_ocn[q] + v.runoff_ocn[q] + v.waterflux_ocn[q] + fw_hosing + fw_anom;
+  fwfxneto = fwfxneto * kMm2m;
+  v.tsflux[q] = -fx0neto * kRfluxsc;
+  v.tsflux[(size_t)I * J * MS + q] = fwfxneto * v.p.rpmesco[m];
+}
+
+// ---------------------------------------------------------------- ocean: momentum
+// bottom pressure integrals (jbar, goldstein.f90:3226-3247)
+__global__ void __launch_bounds__(128) k_bp(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const int k1c = CG_K1(v, i, j);
+  if (k1c > K) return;
+  const int mk = MKX(i, j);
+  double bp = BPX(i, j, k1c), rl = RHOX(i, j, k1c), sbp = 0.0;
+  for (int k = k1c + 1; k <= K; k++) {
+    const double r = RHOX(i, j, k);
+    bp = bp - (r + rl) * c_g.dza[k - 1] * 0.5;
+    BPX(i, j, k) = bp;
+    rl = r;
+    if (mk > 0 && k >= mk + 1) sbp = sbp + bp * c_g.dz[k];
+  }
+  if (mk > 0) SBPX(i, j) = sbp;
+}
+
+// wind stress curl + JEBAR source of the barotropic streamfunction (wind :3695-3713, jbar :3265-3314)
+__global__ void __launch_bounds__(128) k_gb(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y * blockDim.y + threadIdx.y;  // 0-based psi point
+  if (m >= v.M || p >= v.nm) return;
+  const int i = p % I + 1, j = p / I;  // j = 0..J
+  const int ip1 = i % I + 1;
+  double gb = 0.0;
+  if (max(max(CG_K1(v, i, j), CG_K1(v, i + 1, j)), max(CG_K1(v, i, j + 1), CG_K1(v, i + 1, j + 1))) <= K) {
+    const size_t nf = (size_t)I * J * MS;
+    gb = (v.tau[A2I(ip1, j) + nf] * RHX(2, i + 1, j) - v.tau[A2I(i, j) + nf] * RHX(2, i, j)) * c_g.rdphi * c_g.rcv[j] -
+         (v.tau[A2I(i, j + 1)] * c_g.c[j + 1] * RHX(1, i, j + 1) - v.tau[A2I(i, j)] * c_g.c[j] * RHX(1, i, j)) * c_g.rdsv[j];
+  }
+  if (j >= 1 && j <= J - 1 && v.getj[(i - 1) + I * (j - 1)]) {
+    const double gbold = gb;
+    double tv1 = 0, tv2 = 0, tv3 = 0, tv4 = 0;
+    for (int k = KUX(2, ip1, j); k <= MKX(ip1, j + 1); k++) tv1 = tv1 + BPX(ip1, j + 1, k) * c_g.dz[k];
+    for (int k = KUX(2, ip1, j); k <= MKX(ip1, j); k++) tv2 = tv2 + BPX(ip1, j, k) * c_g.dz[k];
+    for (int k = KUX(2, i, j); k <= MKX(i, j + 1); k++) tv3 = tv3 + BPX(i, j + 1, k) * c_g.dz[k];
+    for (int k = KUX(2, i, j); k <= MKX(i, j); k++) tv4 = tv4 + BPX(i, j, k) * c_g.dz[k];
+    gb = gbold + ((tv3 + SBPX(i, j + 1) - tv4 - SBPX(i, j)) * RHX(2, i, j) -
+                  (tv1 + SBPX(ip1, j + 1) - tv2 - SBPX(ip1, j)) * RHX(2, ip1, j)) *
+                     c_g.rdphi * c_g.rdsv[j];
+    tv1 = 0; tv2 = 0; tv3 = 0; tv4 = 0;
+    for (int k = KUX(1, i, j + 1); k <= MKX(ip1, j + 1); k++) tv1 = tv1 + BPX(ip1, j + 1, k) * c_g.dz[k];
+    for (int k = KUX(1, i, j); k <= MKX(ip1, j); k++) tv2 = tv2 + BPX(ip1, j, k) * c_g.dz[k];
+    for (int k = KUX(1, i, j + 1); k <= MKX(i, j + 1); k++) tv3 = tv3 + BPX(i, j + 1, k) * c_g.dz[k];
+    for (int k = KUX(1, i, j); k <= MKX(i, j); k++) tv4 = tv4 + BPX(i, j, k) * c_g.dz[k];
+    gb = gb + ((tv1 + SBPX(ip1, j + 1) - tv3 - SBPX(i, j + 1)) * RHX(1, i, j + 1) -
+               (tv2 + SBPX(ip1, j) - tv4 - SBPX(i, j)) * RHX(1, i, j)) *
+                  c_g.rdphi * c_g.rdsv[j];
+  }
+  v.gb[(size_t)p * MS + m] = gb;
+}
+
+// banded LU solve of the streamfunction equation, reference operation order (ubarsolv :3511-3524).
+// thread = member; gb is [point][m] so every access is coalesced across the warp, the factors of a
+// shared factorisation are warp-uniform (broadcast) loads.
+__global__ void __launch_bounds__(32) k_baro_strict(const Dev v) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= v.M) return;
+  const int n = v.I, nm = v.nm, MS = v.MS;
+  const int bw = n + 1, gw = 2 * n + 3;
+  const double *__restrict__ ratm = v.ratm + (size_t)v.baro_group[m] * nm * bw;   // [row][t], t = j-i in 1..n+1
+  const double *__restrict__ gap = v.gap + (size_t)v.baro_group[m] * nm * gw;     // [row][col]
+  double *__restrict__ gb = v.gb + m;
+#define GB(r) gb[(size_t)((r)-1) * MS]
+  for (int i = 1; i <= nm - 1; i++) {
+    const int im = min(i + n + 1, nm);
+    const double gi = GB(i);
+    for (int j = i + 1; j <= im; j++) GB(j) = GB(j) - ratm[(size_t)(j - 1) * bw + (j - i - 1)] * gi;
+  }
+  GB(nm) = GB(nm) / gap[(size_t)(nm - 1) * gw + (n + 1)];
+  for (int i = nm - 1; i >= 1; i--) {
+    const int km = min(n + 1, nm - i);
+    double acc = GB(i);
+    const double *g = gap + (size_t)(i - 1) * gw;
+    for (int k = 1; k <= km; k++) acc = acc - g[n + 1 + k] * GB(i + k);
+    GB(i) = acc / g[n + 1];
+  }
+#undef GB
+}
+
+// psi and barotropic velocity from the solved gb (ubarsolv :3527-3564)
+__global__ void __launch_bounds__(128) k_psi2ub(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y * blockDim.y + threadIdx.y;  // over (0:I+1, 0:J)
+  if (m >= v.M || p >= (I + 2) * (J + 1)) return;
+  const int i = p % (I + 2), j = p / (I + 2);
+  const int iw = (i == 0) ? I : ((i == I + 1) ? 1 : i);  // periodic image
+#define GBP(ii, jj) v.gb[(size_t)(((ii)-1) + (jj)*I) * MS + m]
+  if (i <= I) PSIX(i, j) = GBP(iw, j);
+  double u1 = 0.0, u2 = 0.0;
+  if (j >= 1) u1 = -RHX(1, iw, j) * c_g.c[j] * (GBP(iw, j) - GBP(iw, j - 1)) * c_g.rds[j];
+  if (j >= 1 && j <= J - 1) {
+    const int iww = (iw > 1) ? iw - 1 : I;
+    u2 = RHX(2, iw, j) * (GBP(iw, j) - GBP(iww, j)) * c_g.rcv[j] * c_g.rdphi;
+  }
+  if (j >= 1) UBX(1, i, j) = u1;
+  UBX(2, i, j) = u2;
+#undef GBP
+}
+
+// island path integral (island, goldstein_lib.f90:186-241, indj = 1) and psibc (goldstein.f90:203-216)
+__global__ void __launch_bounds__(32) k_island(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= v.M) return;
+  const size_t nf = (size_t)I * J * MS;
+  double e = 0.0;
+  for (int p = 0; p < c_g.npi1; p++) {
+    const int lpi = v.lpisl[p], ipi = v.ipisl[p], jpi = v.jpisl[p];
+    const int al = abs(lpi), sg = (lpi >= 0) ? 1 : -1;
+    double cor;
+    if (al == 1)
+      cor = -c_g.s[jpi] * 0.25 * (UBX(2, ipi, jpi) + UBX(2, ipi + 1, jpi) + UBX(2, ipi, jpi - 1) + UBX(2, ipi + 1, jpi - 1));
+    else
+      cor = c_g.sv[jpi] * 0.25 * (UBX(1, ipi - 1, jpi) + UBX(1, ipi, jpi) + UBX(1, ipi - 1, jpi + 1) + UBX(1, ipi, jpi + 1));
+    const double tau = v.tau[A2I(ipi, jpi) + (al - 1) * nf];
+    e = e + sg * (DRAGX(al, ipi, jpi) * UBX(al, ipi, jpi) + cor - 1 * tau * RHX(al, ipi, jpi)) *
+                (c_g.c[jpi] * c_g.dphi * (2.0 - al) + c_g.rcv[jpi] * c_g.dsv[jpi] * (al - 1.0));
+    const int ipw = (ipi < I) ? ipi + 1 : 1;
+    if (al == 1) {
+      double tv1 = 0.0;
+      for (int k = KUX(1, ipi, jpi); k <= MKX(ipi + 1, jpi); k++) tv1 = tv1 + BPX(ipw, jpi, k) * c_g.dz[k];
+      for (int k = KUX(1, ipi, jpi); k <= MKX(ipi, jpi); k++) tv1 = tv1 - BPX(ipi, jpi, k) * c_g.dz[k];
+      e = e + (SBPX(ipw, jpi) - SBPX(ipi, jpi) + tv1) * sg * RHX(1, ipi, jpi);
+    } else {
+      double tv2 = 0.0;
+      for (int k = KUX(2, ipi, jpi); k <= MKX(ipi, jpi + 1); k++) tv2 = tv2 + BPX(ipi, jpi + 1, k) * c_g.dz[k];
+      for (int k = KUX(2, ipi, jpi); k <= MKX(ipi, jpi); k++) tv2 = tv2 - BPX(ipi, jpi, k) * c_g.dz[k];
+      e = e + (SBPX(ipi, jpi + 1) - SBPX(ipi, jpi) + tv2) * sg * RHX(2, ipi, jpi);
+    }
+  }
+  v.erisl_rhs[m] = e;
+  v.psibc[m] = -e / v.erisl[2 * v.baro_group[m]];  // isles == 1: psibc(1) = -erisl(1,2)/erisl(1,1)
+}
+
+// add the island contribution to ub and psi (goldstein.f90:218-230)
+__global__ void __launch_bounds__(128) k_ubadd(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || p >= (I + 2) * (J + 1)) return;
+  const int i = p % (I + 2), j = p / (I + 2);
+  const double psibc = v.psibc[m];
+  const size_t g = v.baro_group[m];
+  if (j >= 1) {
+    const double *ubisl = v.ubisl + g * 2 * (I + 2) * (J + 1);
+    UBX(1, i, j) = UBX(1, i, j) + ubisl[0 + 2 * (i + (I + 2) * j)] * psibc;
+    UBX(2, i, j) = UBX(2, i, j) + ubisl[1 + 2 * (i + (I + 2) * j)] * psibc;
+  }
+  if (i <= I) {
+    const double *psisl = v.psisl + g * (I + 1) * (J + 1);
+    PSIX(i, j) = PSIX(i, j) + psisl[i + (I + 1) * j] * psibc;
+  }
+}
+
+// baroclinic velocities, barotropic correction and relaxation (velc :3574-3658)
+__global__ void __launch_bounds__(128) k_velc(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const int k1c = CG_K1(v, i, j);
+  if (k1c > K) return;
+  const int ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
+  const int k_e = CG_K1(v, ip, j), k_w = CG_K1(v, im, j), k_n = CG_K1(v, i, j + 1), k_s = CG_K1(v, i, j - 1);
+  const int k_ne = CG_K1(v, ip, j + 1), k_se = CG_K1(v, ip, j - 1), k_nw = CG_K1(v, im, j + 1);
+  const double sj = c_g.s[j], svj = c_g.sv[j], cj = c_g.c[j], cvj = c_g.cv[j], rdphi = c_g.rdphi, rcj = c_g.rc[j];
+  const double rcvj = (j < J) ? c_g.rcv[j] : 0.0, rdsvj = (j < J) ? c_g.rdsv[j] : 0.0, rdsvjm = (j > 1) ? c_g.rdsv[j - 1] : 0.0,
+               rds2j = (j > 1 && j < J) ? c_g.rds2[j] : 0.0;
+  const double drag1 = DRAGX(1, i, j), drag2 = DRAGX(2, i, j), rtv = v.rtv[A2I(i, j)], rtv3 = v.rtv3[A2I(i, j)];
+  const size_t nf = (size_t)I * J * MS;
+  const double rel = v.p.rel[m];
+  double sum1 = 0, sum2 = 0, dzu1p = 0, dzu2p = 0, u1p = 0, u2p = 0;
+  for (int k = k1c; k <= K; k++) {
+    double tv1, tv2, tv4, tv5;
+    const double rc0 = RHOX(i, j, k);
+    if (k_e > k) {
+      tv1 = 0;
+      tv2 = 0;
+    } else {
+      const double re = RHOX(ip, j, k);
+      tv2 = -(re - rc0) * rdphi * rcj;
+      if (max(max(k_s, k_n), max(k_se, k_ne)) <= k)
+        tv1 = -cj * (RHOX(ip, j + 1, k) - RHOX(ip, j - 1, k) + RHOX(i, j + 1, k) - RHOX(i, j - 1, k)) * rds2j * 0.25;
+      else if (max(k_s, k_se) <= k)
+        tv1 = -cj * (re - RHOX(ip, j - 1, k) + rc0 - RHOX(i, j - 1, k)) * rdsvjm * 0.5;
+      else if (max(k_n, k_ne) <= k)
+        tv1 = -cj * (RHOX(ip, j + 1, k) - re + RHOX(i, j + 1, k) - rc0) * rdsvj * 0.5;
+      else
+        tv1 = 0;
+    }
+    if (k_n > k) {
+      tv4 = 0;
+      tv5 = 0;
+    } else {
+      const double rn = RHOX(i, j + 1, k);
+      tv4 = -cvj * (rn - rc0) * rdsvj;
+      if (max(max(k_w, k_nw), max(k_e, k_ne)) <= k)
+        tv5 = -(RHOX(ip, j + 1, k) - RHOX(im, j + 1, k) + RHOX(ip, j, k) - RHOX(im, j, k)) * rdphi * 0.25 * rcvj;
+      else if (max(k_w, k_nw) <= k)
+        tv5 = -(rn - RHOX(im, j + 1, k) + rc0 - RHOX(im, j, k)) * rdphi * 0.5 * rcvj;
+      else if (max(k_e, k_ne) <= k)
+        tv5 = -(RHOX(ip, j + 1, k) - rn + RHOX(ip, j, k) - rc0) * rdphi * 0.5 * rcvj;
+      else
+        tv5 = 0;
+    }
+    if (k == K) {
+      if (k_e <= k) {
+        tv1 = tv1 - v.dztau[A2I(i, j) + nf];
+        tv2 = tv2 - v.dztau[A2I(i, j)];
+      }
+      if (k_n <= k) {
+        tv4 = tv4 - v.dztav[A2I(i, j) + nf];
+        tv5 = tv5 - v.dztav[A2I(i, j)];
+      }
+    }
+    const double dzu1 = -(sj * tv1 + drag1 * tv2) * rtv;
+    const double dzu2 = -(drag2 * tv4 - svj * tv5) * rtv3;
+    double ua, ub_;
+    if (k == k1c) {
+      ua = 0;
+      ub_ = 0;
+    } else {
+      ua = u1p + c_g.dza[k - 1] * (dzu1 + dzu1p) * 0.5;
+      ub_ = u2p + c_g.dza[k - 1] * (dzu2 + dzu2p) * 0.5;
+      sum1 = sum1 + c_g.dz[k] * ua;
+      sum2 = sum2 + c_g.dz[k] * ub_;
+    }
+    UX(1, i, j, k) = ua;
+    UX(2, i, j, k) = ub_;
+    u1p = ua; u2p = ub_; dzu1p = dzu1; dzu2p = dzu2;
+  }
+  const double rh1 = RHX(1, i, j), rh2 = RHX(2, i, j), ub1 = UBX(1, i, j), ub2 = UBX(2, i, j);
+  for (int k = k1c; k <= K; k++) {
+    if (k_e <= k) {
+      double x = UX(1, i, j, k) - sum1 * rh1 + ub1;
+      x = rel * U1X(1, i, j, k) + (1.0 - rel) * x;
+      UX(1, i, j, k) = x;
+      U1X(1, i, j, k) = x;
+    }
+    if (k_n <= k) {
+      double x = UX(2, i, j, k) - sum2 * rh2 + ub2;
+      x = rel * U1X(2, i, j, k) + (1.0 - rel) * x;
+      UX(2, i, j, k) = x;
+      U1X(2, i, j, k) = x;
+    }
+  }
+}
+
+// vertical velocity from continuity (velc :3668-3678)
+__global__ void __launch_bounds__(128) k_w(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const int k1c = CG_K1(v, i, j);
+  if (k1c > K) return;
+  const int im = (i > 1) ? i - 1 : I;
+  double tv = 0;
+  for (int k = k1c; k <= K - 1; k++) {
+    const double uw = UX(1, im, j, k), vs = (j > 1) ? UX(2, i, j - 1, k) : 0.0;
+    const double tv1 = (UX(1, i, j, k) - uw) * c_g.rdphi * c_g.rc[j];
+    const double tv2 = (UX(2, i, j, k) * c_g.cv[j] - vs * c_g.cv[j - 1]) * c_g.rds[j];
+    const double w = tv - c_g.dz[k] * (tv1 + tv2);
+    UX(3, i, j, k) = w;
+    tv = w;
+  }
+}
+
+// ---------------------------------------------------------------- diagnostics
+// volume-weighted global tracer means per member: one warp per (member-chunk of 32? no:) block per
+// tracer, warp-shuffle reduction over cells; the sum order is fixed (deterministic).
+__global__ void __launch_bounds__(256) k_global_means(const Dev v, double *out) {
+  DIMS
+  const int m = blockIdx.x, l = blockIdx.y, L = v.L;
+  double num = 0.0, den = 0.0;
+  const int ncell = I * J * K;
+  for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+    const int i = c % I + 1, j = (c / I) % J + 1, k = c / (I * J) + 1;
+    if (k >= CG_K1(v, i, j)) {
+      const double w = c_g.ds[j] * c_g.dz[k];
+      num += v.ts_cur[((size_t)c * L + l) * MS + m] * w;
+      den += w;
+    }
+  }
+  __shared__ double sn[8], sd[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    num += __shfl_down_sync(0xffffffffu, num, o);
+    den += __shfl_down_sync(0xffffffffu, den, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sn[threadIdx.x >> 5] = num; sd[threadIdx.x >> 5] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += sn[w]; b += sd[w]; }
+    out[(size_t)m * L + l] = a / b;
+  }
+}
+
+// non-finite guard (mirrors the avs blow-up check, goldstein_diag.f90:52-58)
+__global__ void __launch_bounds__(256) k_health(const Dev v, int *flags) {
+  DIMS
+  const int m = blockIdx.x;
+  const size_t n = (size_t)I * J * K * v.L;
+  int bad = 0;
+  for (size_t c = threadIdx.x; c < n; c += blockDim.x) {
+    const double x = v.ts_cur[c * MS + m];
+    if (!(fabs(x) < 1.0e20)) bad = 1;
+  }
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) flags[m] = bad;
+}
+
+// ---------------------------------------------------------------- launchers
+struct LaunchCtx { cudaStream_t s; long long *count; };
+
+static inline dim3 grid2(const Dev &v, int ncells, dim3 b) { return dim3((v.M + b.x - 1) / b.x, (ncells + b.y - 1) / b.y); }
+
+void launch_step_begin(const Dev &v, cudaStream_t s) { k_step_begin<<<1, 32, 0, s>>>(v); }
+void launch_hosing(const Dev &v, cudaStream_t s) { k_hosing<<<(v.M + 127) / 128, 128, 0, s>>>(v); }
+int launch_surflux(const Dev &v, double *meantemp, bool need_mean, cudaStream_t s) {
+  int n = 0;
+  if (need_mean) { k_meantemp<<<(v.M + 31) / 32, 32, 0, s>>>(v, meantemp); n++; }
+  const dim3 b(32, 4);
+  k_surflux1<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v, need_mean ? meantemp : nullptr);
+  k_surflux2<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  return n + 2;
+}
+int launch_embm(const Dev &v, int nsteps, cudaStream_t s) {
+  const int nc = v.I * v.J;
+  const size_t sm = sizeof(double) * v.I * (v.J + 2);
+  auto thr = [&](int cpt) { return (((nc + cpt - 1) / cpt + 31) / 32) * 32; };
+  if (nc <= 704) k_embm<1><<<v.M, thr(1), sm, s>>>(v, nsteps);
+  else if (nc <= 1408) k_embm<2><<<v.M, thr(2), sm, s>>>(v, nsteps);
+  else if (nc <= 2816) k_embm<4><<<v.M, thr(4), sm, s>>>(v, nsteps);
+  else return -1;
+  return 1;
+}
+int launch_seaice(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_seaice1<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  k_seaice2<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  return 2;
+}
+int launch_gold_pre(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_gold_pre<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  return 1;
+}
+int launch_momentum(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_bp<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  k_gb<<<grid2(v, v.nm, b), b, 0, s>>>(v);
+  k_baro_strict<<<(v.M + 31) / 32, 32, 0, s>>>(v);
+  k_psi2ub<<<grid2(v, (v.I + 2) * (v.J + 1), b), b, 0, s>>>(v);
+  k_island<<<(v.M + 31) / 32, 32, 0, s>>>(v);
+  k_ubadd<<<grid2(v, (v.I + 2) * (v.J + 1), b), b, 0, s>>>(v);
+  k_velc<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  k_w<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  return 8;
+}
+void launch_global_means(const Dev &v, double *out, cudaStream_t s) { k_global_means<<<dim3(v.M, v.L), 256, 0, s>>>(v, out); }
+void launch_health(const Dev &v, int *flags, cudaStream_t s) { k_health<<<v.M, 256, 0, s>>>(v, flags); }
+
+}  // namespace cg

@@ -1,0 +1,365 @@
+// k_tracer_body.cuh -- GOLDSTEIN tracer timestep kernels (tstepo_flux + co), sm_100a.
+//
+// Reference: src/goldstein/goldstein.f90:2436-2642 (tstepo_flux), :2657-2777 (co),
+//            :3048-3082 (eos, eosd).
+//
+// Included by two translation units:
+//   k_tracer_strict.cu  (CG_TRACER_FAST=0, nvcc -fmad=false): every expression in the reference's
+//                       operation order -> bit-identical to the CPU oracle;
+//   k_tracer_fast.cu    (CG_TRACER_FAST=1, FMA on): face fluxes as 2-term stencils with per-cell
+//                       coefficients hoisted out of the tracer loop and the isoneutral sum factored,
+//                       ~4x fewer fp64 instructions per tracer-cell (<=1e-10 relative per step).
+//
+// Parallelisation: thread = (member m, column i,j, tracer chunk); the thread marches k upward
+// carrying the bottom-face flux fb(l) in registers exactly as the Fortran carries fb(l,i,j);
+// the west/south face fluxes are recomputed from the neighbour side with the same expression
+// the Fortran stored (fw = fe(i-1), fs = fn(j-1)), so the result is the sequential one.
+#pragma once
+#include "cg_device.cuh"
+
+namespace cg {
+
+// `static __constant__ GridC c_g;` is defined by the including translation unit
+
+#if CG_TRACER_FAST
+#define CG_KNAME(x) x##_fast
+#else
+#define CG_KNAME(x) x##_strict
+#endif
+
+// thread-block shape: x = members (MX lanes), y = cells along i, z = cells along j
+template <int LC>
+__global__ void __launch_bounds__(256) CG_KNAME(k_tstepo_flux)(const Dev v, const int mx, const int ci) {
+  const int I = v.I, J = v.J, K = v.K, L = v.L, MS = v.MS;
+  const int nmg = (v.M + mx - 1) / mx;
+  const int mg = blockIdx.x % nmg, it = blockIdx.x / nmg;
+  const int m = mg * mx + threadIdx.x;
+  const int i = it * ci + threadIdx.y + 1;
+  const int j = blockIdx.y * blockDim.z + threadIdx.z + 1;
+  const int l0 = blockIdx.z * LC;
+  if (m >= v.M || i > I || j > J) return;
+  const int k1c = CG_K1(v, i, j);
+  if (k1c > K) return;
+  const int ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
+  const int k1e = CG_K1(v, ip, j), k1w = CG_K1(v, im, j), k1n = CG_K1(v, i, j + 1), k1s = CG_K1(v, i, j - 1);
+
+  const double diff1 = v.p.diff1[m], diffv = v.p.diff2[m];
+  const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
+  const double scc = ec2;
+  const double dt = c_g.dt, dphi = c_g.dphi, rdphi = c_g.rdphi;
+  const double rc = c_g.rc[j], rc2 = c_g.rc2[j], cvj = c_g.cv[j], cvjm = c_g.cv[j - 1], cv2j = c_g.cv2[j],
+               cv2jm = (j > 1) ? c_g.cv2[j - 1] : 0.0, rdsj = c_g.rds[j];
+  const double dsvN = c_g.dsv[(j < J - 1) ? j : J - 1], dsvS = c_g.dsv[(j - 1 < J - 1) ? ((j > 1) ? j - 1 : 1) : J - 1];
+  const double rdsvN = c_g.rdsv[j], rdsvS = (j > 1) ? c_g.rdsv[j - 1] : 0.0;
+
+  const double *__restrict__ ts1 = v.ts_cur;
+  double *__restrict__ tsn = v.ts_new;
+  const double *__restrict__ uu = v.u;
+
+  const size_t sL = (size_t)MS;             // tracer stride
+  const size_t sC = (size_t)L * MS;         // cell stride
+  const size_t sK = (size_t)I * J * sC;     // level stride
+  // column base offsets (level k=1) of the five stencil columns, at tracer 0, member m
+  const size_t oC = cell3(I, J, i, j, 1) * sC + m;
+  const size_t oE = cell3(I, J, ip, j, 1) * sC + m;
+  const size_t oW = cell3(I, J, im, j, 1) * sC + m;
+  const size_t oN = (j < J) ? cell3(I, J, i, j + 1, 1) * sC + m : oC;
+  const size_t oS = (j > 1) ? cell3(I, J, i, j - 1, 1) * sC + m : oC;
+  const size_t uC = cell3(I, J, i, j, 1) * 3 * MS + m, uWo = cell3(I, J, im, j, 1) * 3 * MS + m,
+               uSo = (j > 1) ? cell3(I, J, i, j - 1, 1) * 3 * MS + m : uC;
+  const size_t uK = (size_t)I * J * 3 * MS;
+
+  double fb[LC];
+#pragma unroll
+  for (int q = 0; q < LC; q++) fb[q] = 0.0;
+
+  for (int k = k1c; k <= K; k++) {
+    const size_t ko = (size_t)(k - 1) * sK, kuo = (size_t)(k - 1) * uK;
+    const bool topl = (k == K);
+    // face openness at this level (k >= k1c holds)
+    const bool opE = k >= k1e, opW = k >= k1w, opN = k >= k1n, opS = (j > 1) && (k >= k1s);
+    // isoneutral masks one level up
+    const bool upE = !topl && (k + 1 >= k1e), upW = !topl && (k + 1 >= k1w), upN = !topl && (k + 1 >= k1n),
+               upS = !topl && (k + 1 >= k1s);
+    // velocities and upstream weights (goldstein.f90:2517-2523)
+    const double uE = uu[uC + kuo], vN = uu[uC + kuo + MS], ww = topl ? 0.0 : uu[uC + kuo + 2 * MS];
+    const double uW = uu[uWo + kuo], vS = (j > 1) ? uu[uSo + kuo + MS] : 0.0;
+    double pec = uE * dphi / diff1;
+    const double upsE = pec / (2.0 + fabs(pec));
+    pec = uW * dphi / diff1;
+    const double upsW = pec / (2.0 + fabs(pec));
+    pec = vN * dsvN / diff1;
+    const double upsN = pec / (2.0 + fabs(pec));
+    pec = vS * dsvS / diff1;
+    const double upsS = pec / (2.0 + fabs(pec));
+    pec = ww * c_g.dza[k] / diffv;
+    const double upsA = pec / (2.0 + fabs(pec));
+    const double rdza = topl ? 0.0 : c_g.rdza[k], rdzk = c_g.rdz[k];
+
+    // ---- density slopes from T,S (goldstein.f90:2490-2500, 2561-2603)
+    bool iso = false;
+    double dzrho = 0.0, slim = 1.0;
+    double dxr[4], dyr[4];
+    if (!topl) {
+      const double t0 = ts1[oC + ko], t1 = ts1[oC + ko + sK], s0 = ts1[oC + ko + sL], s1 = ts1[oC + ko + sK + sL];
+      const double tatw = 0.5 * (t0 + t1);
+      const double tec = -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3;
+      dzrho = (ec2 * (s1 - s0) - tec * (t1 - t0)) * rdza;
+      if (dzrho < -1.0e-12) {
+        iso = true;
+        const double rdzrho = 1.0 / dzrho;
+        double tv1 = 0.0;
+#pragma unroll
+        for (int knp = 0; knp <= 1; knp++) {
+          const size_t kk = ko + (size_t)knp * sK;
+          const double tc = knp ? t1 : t0, sc = knp ? s1 : s0;
+#pragma unroll
+          for (int nnp = 0; nnp <= 1; nnp++) {
+            const int a = nnp + 2 * knp;
+            const bool mx_ = nnp ? (knp ? upE : opE) : (knp ? upW : opW);
+            const bool my_ = nnp ? (knp ? upN : opN) : (knp ? upS : (k >= k1s));
+            double dxt = 0.0, dxs = 0.0, dyt = 0.0, dys = 0.0;
+            if (mx_) {
+              const size_t on = (nnp ? oE : oW) + kk;
+              const double tn = ts1[on], sn = ts1[on + sL];
+              dxt = (nnp ? (tn - tc) : (tc - tn)) * rc * rdphi;
+              dxs = (nnp ? (sn - sc) : (sc - sn)) * rc * rdphi;
+            }
+            if (my_) {
+              const size_t on = (nnp ? oN : oS) + kk;
+              const double tn = ts1[on], sn = ts1[on + sL];
+              dyt = (nnp ? (tn - tc) : (tc - tn)) * (nnp ? cvj : cvjm) * (nnp ? rdsvN : rdsvS);
+              dys = (nnp ? (sn - sc) : (sc - sn)) * (nnp ? cvj : cvjm) * (nnp ? rdsvN : rdsvS);
+            }
+            dxr[a] = scc * dxs - tec * dxt;
+            dyr[a] = scc * dys - tec * dyt;
+            tv1 = tv1 + dxr[a] * dxr[a] + dyr[a] * dyr[a];
+          }
+        }
+        tv1 = 0.25 * tv1 * rdzrho * rdzrho;
+        const double ssm = c_g.ssmax[k];
+        if (tv1 > ssm) slim = ssm * ssm / (tv1 * tv1);
+      }
+    }
+
+#if CG_TRACER_FAST
+    // ---- per-cell stencil coefficients (hoisted out of the tracer loop)
+    // east/west/north/south/above faces: flux = A * ts(neighbour) + B * ts(centre)
+    const double hE = uE * rc * 0.5, dE = rc2 * diff1;
+    const double aE = opE ? (hE * (1.0 - upsE) - dE) : 0.0, bE = opE ? (hE * (1.0 + upsE) + dE) : 0.0;
+    const double hW = uW * rc * 0.5;
+    // west face seen from the west cell: fw = hW*((1-ups)*c + (1+ups)*W) - (c - W)*dE
+    const double aW = opW ? (hW * (1.0 + upsW) + dE) : 0.0, bW = opW ? (hW * (1.0 - upsW) - dE) : 0.0;
+    const double hN = cvj * vN * 0.5, dN = cv2j * diff1;
+    const double aN = opN ? (hN * (1.0 - upsN) - dN) : 0.0, bN = opN ? (hN * (1.0 + upsN) + dN) : 0.0;
+    const double hS = cvjm * vS * 0.5, dS = cv2jm * diff1;
+    const double aS = opS ? (hS * (1.0 + upsS) + dS) : 0.0, bS = opS ? (hS * (1.0 - upsS) - dS) : 0.0;
+    const double hA = ww * 0.5, dA = rdza * diffv;
+    double aA = hA * (1.0 - upsA) - dA, bA = hA * (1.0 + upsA) + dA;   // fa = aA*c1 + bA*c0 (k<K)
+    // isoneutral: tv = 2 dzrho Sum(dx_a wx_a + dy_a wy_a) - dzts * S2 ; fa += cf * tv
+    double wx[4], wy[4], cf = 0.0, s2 = 0.0;
+    if (iso) {
+      cf = 0.25 * slim * diff1 / (dzrho * dzrho);
+      const double gx = rc * rdphi * 2.0 * dzrho * cf;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const bool nn = a & 1;
+        wx[a] = dxr[a] * gx;
+        wy[a] = dyr[a] * (nn ? cvj * rdsvN : cvjm * rdsvS) * 2.0 * dzrho * cf;
+        s2 += dxr[a] * dxr[a] + dyr[a] * dyr[a];
+      }
+      s2 = s2 * cf * rdza;
+      // fold the centre-column part of dzts*S2 into the vertical coefficients
+      aA -= s2;
+      bA += s2;
+    }
+    const double cX = dt * rdphi, cY = dt * rdsj, cZ = dt * rdzk;
+#endif
+
+    // ---- tracer loop
+    double tnew = 0.0, snew = 0.0;
+#pragma unroll
+    for (int q = 0; q < LC; q++) {
+      const int l = l0 + q;
+      if (l < L) {
+        const size_t lo = ko + (size_t)l * sL;
+        const double c0 = ts1[oC + lo];
+        const double E0 = opE ? ts1[oE + lo] : 0.0, W0 = opW ? ts1[oW + lo] : 0.0;
+        const double N0 = opN ? ts1[oN + lo] : 0.0, S0 = (opS || (iso && k >= k1s)) ? ts1[oS + lo] : 0.0;
+        double c1 = 0.0, E1 = 0.0, W1 = 0.0, N1 = 0.0, S1 = 0.0;
+        if (!topl) {
+          c1 = ts1[oC + lo + sK];
+          if (iso) {
+            if (upE) E1 = ts1[oE + lo + sK];
+            if (upW) W1 = ts1[oW + lo + sK];
+            if (upN) N1 = ts1[oN + lo + sK];
+            if (upS) S1 = ts1[oS + lo + sK];
+          }
+        }
+#if CG_TRACER_FAST
+        const double fe = aE * E0 + bE * c0;
+        const double fw = aW * W0 + bW * c0;
+        const double fn = aN * N0 + bN * c0;
+        const double fs = aS * S0 + bS * c0;
+        double fa;
+        if (topl) {
+          fa = (l < 2) ? v.tsflux[((size_t)l * I * J + cell2(I, i, j)) * MS + m] : 0.0;
+        } else {
+          fa = aA * c1 + bA * c0;
+          if (iso) {
+            double acc = 0.0;
+            acc += (opW ? (c0 - W0) : 0.0) * wx[0];
+            acc += (opE ? (E0 - c0) : 0.0) * wx[1];
+            acc += (upW ? (c1 - W1) : 0.0) * wx[2];
+            acc += (upE ? (E1 - c1) : 0.0) * wx[3];
+            acc += ((k >= k1s) ? (c0 - S0) : 0.0) * wy[0];
+            acc += (opN ? (N0 - c0) : 0.0) * wy[1];
+            acc += (upS ? (c1 - S1) : 0.0) * wy[2];
+            acc += (upN ? (N1 - c1) : 0.0) * wy[3];
+            fa += acc;
+          }
+        }
+        const double tn = c0 - ((fe - fw) * cX + (fn - fs) * cY + (fa - fb[q]) * cZ);
+#else
+        // east / west (goldstein.f90:2526-2537, 2476-2486, 2633)
+        double fe = 0.0, fw = 0.0, fn = 0.0, fs = 0.0, fa;
+        if (opE) {
+          fe = uE * rc * ((1.0 - upsE) * E0 + (1.0 + upsE) * c0) * 0.5;
+          fe = fe - (E0 - c0) * rc2 * diff1;
+        }
+        if (opW) {
+          fw = uW * rc * ((1.0 - upsW) * c0 + (1.0 + upsW) * W0) * 0.5;
+          fw = fw - (c0 - W0) * rc2 * diff1;
+        }
+        // north / south (goldstein.f90:2539-2547, 2634)
+        if (opN) {
+          fn = cvj * vN * ((1.0 - upsN) * N0 + (1.0 + upsN) * c0) * 0.5;
+          fn = fn - cv2j * (N0 - c0) * diff1;
+        }
+        if (opS) {
+          fs = cvjm * vS * ((1.0 - upsS) * c0 + (1.0 + upsS) * S0) * 0.5;
+          fs = fs - cv2jm * (c0 - S0) * diff1;
+        }
+        // above (goldstein.f90:2549-2559)
+        if (topl) {
+          fa = (l < 2) ? v.tsflux[((size_t)l * I * J + cell2(I, i, j)) * MS + m] : 0.0;
+        } else {
+          fa = ww * ((1.0 - upsA) * c1 + (1.0 + upsA) * c0) * 0.5;
+          fa = fa - (c1 - c0) * rdza * diffv;
+          if (iso) {  // goldstein.f90:2609-2621
+            const double dzts = (c1 - c0) * rdza;
+            double dxt[4], dyt[4];
+            dxt[0] = opW ? (c0 - W0) * rc * rdphi : 0.0;
+            dxt[1] = opE ? (E0 - c0) * rc * rdphi : 0.0;
+            dxt[2] = upW ? (c1 - W1) * rc * rdphi : 0.0;
+            dxt[3] = upE ? (E1 - c1) * rc * rdphi : 0.0;
+            dyt[0] = (k >= k1s) ? (c0 - S0) * cvjm * rdsvS : 0.0;
+            dyt[1] = opN ? (N0 - c0) * cvj * rdsvN : 0.0;
+            dyt[2] = upS ? (c1 - S1) * cvjm * rdsvS : 0.0;
+            dyt[3] = upN ? (N1 - c1) * cvj * rdsvN : 0.0;
+            double tv = 0.0;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+              tv = tv + (2 * dzrho * dxt[a] - dxr[a] * dzts) * dxr[a] + (2 * dzrho * dyt[a] - dyr[a] * dzts) * dyr[a];
+            tv = 0.25 * slim * diff1 * tv / (dzrho * dzrho);
+            fa = fa + tv;
+          }
+        }
+        // update (goldstein.f90:2627-2632)
+        const double tn = c0 - dt * ((fe - fw) * rdphi + (fn - fs) * rdsj + (fa - fb[q]) * rdzk);
+#endif
+        tsn[oC + lo] = tn;
+        fb[q] = fa;
+        if (l == 0) tnew = tn;
+        if (l == 1) snew = tn;
+      }
+    }
+    // density of the new state (goldstein.f90:2638)
+    if (l0 == 0) v.rho[cell3(I, J, i, j, k) * MS + m] = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
+  }
+}
+
+// Convective adjustment, goldstein.f90:2657-2777 (iconv == 0, ieos == 0).
+// thread = (member, column); the index array k(0:maxk) and dzm live in local memory.
+__global__ void __launch_bounds__(128) CG_KNAME(k_co)(const Dev v) {
+  const int I = v.I, J = v.J, K = v.K, L = v.L, MS = v.MS;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;  // 0-based column index
+  if (m >= v.M || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const int k1c = CG_K1(v, i, j);
+  if (k1c > K) return;
+  const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
+  double *__restrict__ ts = v.ts_new;
+  double *__restrict__ rho = v.rho;
+  const size_t sL = (size_t)MS, sC = (size_t)L * MS, sK = (size_t)I * J * sC;
+  const size_t oC = cell3(I, J, i, j, 1) * sC + m;
+  const size_t rK = (size_t)I * J * MS, rC = cell3(I, J, i, j, 1) * MS + m;
+#define RHOK(k) rho[rC + (size_t)((k)-1) * rK]
+#define TSK(l, k) ts[oC + (size_t)((k)-1) * sK + (size_t)(l) * sL]
+  int kk[kMaxK + 2];
+  double dzm[kMaxK + 2];
+  kk[k1c - 1] = 0;
+  for (int q = k1c; q <= K; q++) {
+    kk[q] = q;
+    dzm[q] = c_g.dz[q];
+  }
+  int mm = K, lastmix = 0;
+  bool any = false;
+  while (kk[mm - 1] > 0 || (lastmix != 0 && kk[mm] != K)) {
+    if (kk[mm - 1] == 0 || RHOK(kk[mm]) < RHOK(kk[mm - 1])) {
+      if (lastmix == 0 || kk[mm] == K) mm = mm - 1; else mm = mm + 1;
+      lastmix = 0;
+    } else {
+      lastmix = 1;
+      any = true;
+      int n = mm - 1;
+      while (kk[n - 1] > 0 && RHOK(kk[n]) >= RHOK(kk[n - 1])) n = n - 1;
+      // thickness-weighted mix of all tracers over index entries n..mm (:2732-2737)
+      double dznew = dzm[kk[mm]];
+      for (int ni = 1; ni <= mm - n; ni++) dznew = dznew + dzm[kk[mm - ni]];
+      double tmix = 0.0, smix = 0.0;
+      for (int l = 0; l < L; l++) {
+        double sum = TSK(l, kk[mm]) * dzm[kk[mm]];
+        for (int ni = 1; ni <= mm - n; ni++) sum = sum + TSK(l, kk[mm - ni]) * dzm[kk[mm - ni]];
+        const double val = sum / dznew;
+        TSK(l, kk[mm]) = val;
+        if (l == 0) tmix = val;
+        if (l == 1) smix = val;
+      }
+      dzm[kk[mm]] = dznew;
+      RHOK(kk[mm]) = ec1 * tmix + ec2 * smix + ec3 * (tmix * tmix) + ec4 * (tmix * tmix * tmix);
+      int ni = mm - 1;
+      while (kk[ni + 1] > 0) {
+        kk[ni] = kk[ni - mm + n];
+        ni = ni - 1;
+      }
+    }
+  }
+  if (any) {
+    // fill in T,S values in mixed regions (:2749-2764)
+    int mq = K - 1;
+    double cnt = 0.0;
+    for (int n = K - 1; n >= k1c; n--) {
+      if (n > kk[mq]) {
+        double tmix = 0.0, smix = 0.0;
+        for (int l = 0; l < L; l++) {
+          const double val = TSK(l, kk[mq + 1]);
+          TSK(l, n) = val;
+          if (l == 0) tmix = val;
+          if (l == 1) smix = val;
+        }
+        RHOK(n) = ec1 * tmix + ec2 * smix + ec3 * (tmix * tmix) + ec4 * (tmix * tmix * tmix);
+        cnt = cnt + 1.0;
+      } else {
+        mq = mq - 1;
+      }
+    }
+    // cost(i,j) is incremented by 1.0 per filled level; a sum of small integers is exact
+    v.cost[cell2(I, i, j) * MS + m] += cnt;
+  }
+#undef RHOK
+#undef TSK
+}
+
+}  // namespace cg

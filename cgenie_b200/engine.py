@@ -1,0 +1,218 @@
+"""Python host mirror of the reference's module entry points for the hot path.
+
+Method names, argument meaning and error behaviour follow the Fortran module procedures the coupler
+calls through src/wrappers/genie_loop_wrappers.f90 (surflux, step_embm, step_seaice, step_goldstein,
+...).  Everything forwards to the C-ABI of include/cgenie_b200.h; there is no Python or CPU compute
+path.  A non-zero status raises CgenieError, the analogue of die()/write_status('ERRORED')
+(src/wrappers/genie_util.f90:15-33).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class CgenieError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cgenie_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _dp(a):
+    return a.ctypes.data_as(_lib.D) if a is not None else None
+
+
+class _Base:
+    h = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CgenieError(rc, self.L.cg_last_error().decode())
+
+    def close(self):
+        if self.h is not None:
+            self.L.cg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- state movement
+    def field_size(self, name):
+        n = self.L.cg_field_size(self.h, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        return n
+
+    def get(self, name, member=0):
+        """One member of a named field, flat in the reference's Fortran order."""
+        out = np.empty(self.field_size(name), dtype=np.float64)
+        self._ck(self.L.cg_sync_to_host(self.h, name.encode(), member, _dp(out), out.size))
+        return out
+
+    def put(self, name, values, member=0):
+        a = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        self._ck(self.L.cg_sync_from_host(self.h, name.encode(), member, _dp(a), a.size))
+
+    def get_all(self, name, out=None):
+        """All members in the device-native layout [...][member_stride]."""
+        n = self.field_size(name) * self.member_stride
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        self._ck(self.L.cg_sync_all_to_host(self.h, name.encode(), _dp(out), n))
+        return out
+
+    def put_all(self, name, values):
+        a = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        self._ck(self.L.cg_sync_all_from_host(self.h, name.encode(), _dp(a), a.size))
+
+    def const(self, name):
+        n = self.L.cg_const_size(self.h, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype=np.float64)
+        self._ck(self.L.cg_get_const(self.h, name.encode(), 0, _dp(out), n))
+        return out
+
+    def iconst(self, name):
+        n = self.L.cg_const_size(self.h, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype=np.int32)
+        self._ck(self.L.cg_get_iconst(self.h, name.encode(), out.ctypes.data_as(C.POINTER(C.c_int32)), n))
+        return out
+
+    def _dims(self):
+        d = (C.c_int32 * 8)()
+        self._ck(self.L.cg_get_dims(self.h, d))
+        (self.maxi, self.maxj, self.maxk, self.maxl, self.n_members, self.member_stride, self.nyear, self.ndta) = list(d)
+
+    # ---- measurement
+    def synchronize(self):
+        self._ck(self.L.cg_synchronize(self.h))
+
+    def launch_count(self, reset=False):
+        return int(self.L.cg_launch_count(self.h, 1 if reset else 0))
+
+    def timer_start(self):
+        self._ck(self.L.cg_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_double()
+        self._ck(self.L.cg_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile(self, on=True):
+        self._ck(self.L.cg_profile_enable(self.h, 1 if on else 0))
+
+    def profile_get(self, family):
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(self.L.cg_profile_get(self.h, family.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def set_tracer_variant(self, variant):
+        """'strict' = reference operation order (bit-exact vs the oracle); 'fast' = FMA + hoisted coefficients."""
+        self._ck(self.L.cg_set_tracer_variant(self.h, {"strict": 0, "fast": 1}.get(variant, variant)))
+
+    def set_graphs(self, on):
+        self._ck(self.L.cg_set_graphs(self.h, 1 if on else 0))
+
+    def global_means(self):
+        out = np.empty(self.n_members * self.maxl, dtype=np.float64)
+        self._ck(self.L.cg_global_means(self.h, _dp(out)))
+        return out.reshape(self.n_members, self.maxl)
+
+    def health(self):
+        out = np.empty(self.n_members, dtype=np.int32)
+        self._ck(self.L.cg_health(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+
+class Ensemble(_Base):
+    """A batch of independent, parameter-perturbed cGENIE members resident on one GPU.
+
+    jobdir     : job directory as written by the reference's new-job (namelists + input/<module>/ data)
+    n_members  : ensemble size on this GPU
+    perturb    : {param_name: array(n_members)} per-member overrides (cg_set_member_param)
+    """
+
+    def __init__(self, jobdir, n_members=1, device=0, perturb=None):
+        self.L = _lib.load()
+        h = _lib.P()
+        self._ck(self.L.cg_create(str(jobdir).encode(), int(n_members), int(device), C.byref(h)))
+        self.h = h
+        for name, vals in (perturb or {}).items():
+            a = np.ascontiguousarray(vals, dtype=np.float64)
+            if a.size != n_members:
+                raise ValueError("perturbation %s needs %d values" % (name, n_members))
+            self._ck(self.L.cg_set_member_param(self.h, name.encode(), _dp(a)))
+        self._ck(self.L.cg_initialise(self.h))
+        self._dims()
+        self.istep_ocn = self.istep_atm = self.istep_sic = 0
+
+    # ---- module entry points (argument-less wrappers of genie_loop_wrappers.f90) ----
+    def surflux(self, io=None):
+        """surflux_wrapper (genie_loop_wrappers.f90:7-59): istep_ocn is incremented first (genie.f90:275)."""
+        self.istep_ocn += 1
+        self._ck(self.L.cg_surflux_step(self.h, self.istep_ocn, io))
+
+    def step_embm(self, io=None):
+        """embm_wrapper (:61-86)."""
+        self.istep_atm += 1
+        self._ck(self.L.cg_embm_step(self.h, self.istep_atm, io))
+
+    def step_seaice(self, io=None):
+        """gold_seaice_wrapper (:94-113)."""
+        self.istep_sic += 1
+        self._ck(self.L.cg_seaice_step(self.h, self.istep_sic, io))
+
+    def step_goldstein(self, io=None):
+        """goldstein_wrapper (:122-151)."""
+        self._ck(self.L.cg_goldstein_step(self.h, self.istep_ocn, io))
+
+    def run(self, n_koverall):
+        """n iterations of the genie.f90 main loop entirely on the device."""
+        self._ck(self.L.cg_run(self.h, int(n_koverall)))
+
+    def run_years(self, years):
+        self.run(int(round(years * self.nyear * self.ndta)))
+
+
+class TracerStep(_Base):
+    """Stand-alone tstepo (flux + convection) on caller-provided fields (BASELINE config #5, kernel tests)."""
+
+    def __init__(self, maxi, maxj, maxk, maxl, k1, n_members=1, device=0, diff1=2000.0, diff2=1.0e-5, nyear=96):
+        self.L = _lib.load()
+        k1 = np.ascontiguousarray(k1, dtype=np.int32).ravel()
+        if k1.size != (maxi + 2) * (maxj + 2):
+            raise ValueError("k1 must be (0:maxi+1, 0:maxj+1)")
+        h = _lib.P()
+        self._ck(self.L.cg_tracer_create(maxi, maxj, maxk, maxl, n_members, device, k1.ctypes.data_as(C.POINTER(C.c_int32)),
+                                         diff1, diff2, nyear, C.byref(h)))
+        self.h = h
+        self._dims()
+
+    def set(self, ts=None, u=None, tsflux=None):
+        a = [None if x is None else np.ascontiguousarray(x, dtype=np.float64).ravel() for x in (ts, u, tsflux)]
+        self._ck(self.L.cg_tracer_set(self.h, _dp(a[0]), _dp(a[1]), _dp(a[2])))
+
+    def step(self, n=1):
+        self._ck(self.L.cg_tracer_step(self.h, int(n)))
+
+    def fetch(self):
+        M, I, J, K, Lt = self.n_members, self.maxi, self.maxj, self.maxk, self.maxl
+        ts = np.empty(M * Lt * I * J * K)
+        rho = np.empty(M * I * J * K)
+        cost = np.empty(M * I * J)
+        self._ck(self.L.cg_tracer_get(self.h, _dp(ts), _dp(rho), _dp(cost)))
+        return ts.reshape(M, K, J, I, Lt), rho.reshape(M, K, J, I), cost.reshape(M, J, I)

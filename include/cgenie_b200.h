@@ -1,0 +1,172 @@
+/*
+ * cgenie_b200.h -- C-ABI of the B200-native cGENIE hot path (libcgenie_b200.so).
+ *
+ * This is the drop-in boundary: one entry point per module procedure that the
+ * reference's coupler calls each coupling step through the argument-less
+ * wrappers of src/wrappers/genie_loop_wrappers.f90.  A Fortran shim module
+ * with the reference's own public names (fortran/*.f90) binds these through
+ * ISO_C_BINDING; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - all reals are fp64, INTEGER is int32, the GENIE clock is int64 (ms);
+ *  - host arrays are caller-owned, column-major, exactly the shapes the
+ *    reference passes (citations per struct below);
+ *  - a NULL array pointer (or a NULL io struct) means "leave the field
+ *    resident on the GPU": between output/coupling intervals the host passes
+ *    only scalars;
+ *  - host arrays always carry ensemble member `io_member` (default 0, the
+ *    control member the Fortran host drives); the other members advance in
+ *    lock-step on the device and never cross the boundary per step;
+ *  - every function returns 0 on success; non-zero maps to the reference's
+ *    die()/write_status('ERRORED') (src/wrappers/genie_util.f90:15-33).
+ *    cg_last_error() returns the message.
+ */
+#ifndef CGENIE_B200_H
+#define CGENIE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cg_handle cg_handle;
+
+enum {
+  CG_OK = 0,
+  CG_ERR_ARG = 1,          /* bad argument / unknown name            */
+  CG_ERR_IO = 2,           /* namelist or data file unreadable       */
+  CG_ERR_CONFIG = 3,       /* option outside the B200 hot path       */
+  CG_ERR_CUDA = 4,         /* CUDA runtime error                     */
+  CG_ERR_STATE = 5,        /* call order violated                    */
+  CG_ERR_BLOWUP = 6        /* non-finite state (avs guard, goldstein_diag.f90:52-58) */
+};
+
+/* ---- life cycle ------------------------------------------------------- */
+
+/* Parse <jobdir>/data_genie, data_GOLD, data_EMBM, data_goldSIC (and
+ * data_BIOGEM/data_ATCHEM/data_GEM when flag_biogem) plus the data files they
+ * name (<world>.k1/.psiles/.paths, wind stress *.interp, wind speed *.silo),
+ * exactly as initialise_goldstein/initialise_embm/initialise_seaice do
+ * (goldstein.f90:514-2084, embm.f90:198-2018, gold_seaice.f90:17-508).
+ * Nothing is uploaded yet.                                                  */
+int cg_create(const char *jobdir, int n_members, int device, cg_handle **out);
+
+/* Per-member override of a whitelisted scalar parameter BEFORE cg_initialise:
+ * "diff1","diff2","adrag","scf","diffamp1","diffamp2","betaz2","betam2",
+ * "rmax","temp0","temp1","diffsic", ... ; values[n_members].               */
+int cg_set_member_param(cg_handle *, const char *name, const double *values);
+
+/* Build constants (grid, masks, drag, barotropic factorisation, island
+ * solves, insolation table ...) bit-exactly as the reference's initialise_*
+ * routines, set the initial state and upload everything.                    */
+int cg_initialise(cg_handle *);
+int cg_destroy(cg_handle *);
+const char *cg_last_error(void);
+
+/* ---- module steps (genie_loop_wrappers.f90) --------------------------- */
+
+/* surflux(...)  embm.f90:2548-2588 via surflux_wrapper :7-59.  All members. */
+typedef struct {
+  /* OUT (ocean side) */ double *albedo_ocn, *latent_ocn, *sensible_ocn, *netsolar_ocn, *netlong_ocn,
+      *evap_ocn, *precip_ocn, *runoff_ocn, *runoff_land;
+  /* OUT (atm side)   */ double *latent_atm, *sensible_atm, *netsolar_atm, *netlong_atm, *evap_atm, *precip_atm;
+  /* OUT (sea ice)    */ double *dhght_sic, *dfrac_sic, *temp_sic, *albd_sic;
+  /* INOUT            */ double *qstar_atm;
+} cg_surflux_io; /* every array (maxi,maxj) */
+int cg_surflux_step(cg_handle *, int istep, const cg_surflux_io *io);
+
+/* step_embm(...)  embm.f90:22-38 via embm_wrapper :61-86 */
+typedef struct {
+  double *tstar_atm, *qstar_atm; /* OUT (maxi,maxj) */
+} cg_embm_io;
+int cg_embm_step(cg_handle *, int istep, const cg_embm_io *io);
+
+/* step_seaice(...)  gold_seaice.f90:511-520 via gold_seaice_wrapper :94-113 */
+typedef struct {
+  double *hght_sic, *frac_sic, *waterflux_ocn, *conductflux_ocn; /* OUT (maxi,maxj) */
+} cg_seaice_io;
+int cg_seaice_step(cg_handle *, int istep, const cg_seaice_io *io);
+
+/* step_goldstein(...)  goldstein.f90:17-38 via goldstein_wrapper :122-151 */
+typedef struct {
+  double *tstar_ocn, *sstar_ocn, *ustar_ocn, *vstar_ocn, *albedo_ocn; /* OUT (maxi,maxj)          */
+  double *go_ts;   /* INOUT (maxl,maxi,maxj,maxk): uploaded before, downloaded after the step   */
+  double *go_u;    /* OUT   (3,maxi,maxj,maxk)                                                  */
+  double *go_rho;  /* OUT   (maxi,maxj,maxk)                                                    */
+  double *go_cost; /* INOUT (maxi,maxj)                                                         */
+  double *go_psi;  /* OUT   (0:maxi,0:maxj)                                                     */
+  double *test_energy_ocean, *test_water_ocean; /* OUT scalars (goldstein.f90:458-478)          */
+} cg_goldstein_io;
+int cg_goldstein_step(cg_handle *, int istep, const cg_goldstein_io *io);
+
+/* BIOGEM / ATCHEM (biogem.f90:528-547, 1885-1890, 2083-2087, 2132-2150; atchem.f90:63-67) */
+int cg_biogem_forcing(cg_handle *, int64_t genie_clock_ms);
+int cg_biogem_step(cg_handle *, double dts, int64_t genie_clock_ms);
+int cg_biogem_tracercoupling(cg_handle *, double *go_ts, double *go_ts1);
+int cg_biogem_climate(cg_handle *);
+int cg_atchem_step(cg_handle *, double dts);
+
+/* ---- whole coupling loop on the device -------------------------------- */
+/* n iterations of genie.f90's koverall loop (:117-534, "normal" branch) with
+ * no host involvement: surflux / EMBM / sea ice / ocean (/ BIOGEM / ATCHEM)
+ * on the reference's MOD(koverall, k*_loop) schedule.                       */
+int cg_run(cg_handle *, int64_t n_koverall);
+
+/* ---- state movement (restart / output / coupling intervals) ----------- */
+/* Named field of ONE member, in the reference's Fortran shape:
+ *  "ts" (maxl,maxi,maxj,maxk)  "u" (3,maxi,maxj,maxk)  "rho" (maxi,maxj,maxk)
+ *  "tq" (2,maxi,maxj)  "varice" (2,maxi,maxj)  "psi" (0:maxi,0:maxj)
+ *  "cost","tice","usurf","pptn","evap","fx0a","fxlw"... (maxi,maxj), BIOGEM: "ocn","bio_part","atm",...
+ * cg_field_size returns the number of doubles.                              */
+int64_t cg_field_size(cg_handle *, const char *name);
+int cg_sync_to_host(cg_handle *, const char *name, int member, double *dst, int64_t n);
+int cg_sync_from_host(cg_handle *, const char *name, int member, const double *src, int64_t n);
+/* All members at once, device-native layout [..][member]; pinned-host friendly. */
+int cg_sync_all_to_host(cg_handle *, const char *name, double *dst, int64_t n);
+int cg_sync_all_from_host(cg_handle *, const char *name, const double *src, int64_t n);
+
+/* Host-side constants as built by cg_initialise (bit-exactness checks):
+ * "dz","dza","s","c","sv","cv","ds","dsv","rc","rc2","cv2","rds","rdsv","zro","zw","ssmax",
+ * "drag","rh","gap","ratm","ubisl","psisl","erisl","solfor","diffa","albcl","pmeadj","uatm","ca",...
+ * integer: "k1","ku","mk","getj","ips","ipf","ias","iaf","iroff","jroff".   */
+int64_t cg_const_size(cg_handle *, const char *name);
+int cg_get_const(cg_handle *, const char *name, int member, double *dst, int64_t n);
+int cg_get_iconst(cg_handle *, const char *name, int32_t *dst, int64_t n);
+int cg_get_dims(cg_handle *, int32_t dims[8]); /* maxi,maxj,maxk,maxl,n_members,member_stride,nyear,ndta */
+
+/* ---- diagnostics (warp-shuffle reductions on the device) -------------- */
+/* Per-member volume-weighted global means of every ts tracer: out[n_members*maxl] */
+int cg_global_means(cg_handle *, double *out);
+/* per-member blow-up flag (non-finite ts); out[n_members] */
+int cg_health(cg_handle *, int32_t *out);
+
+/* ---- measurement helpers ---------------------------------------------- */
+int cg_synchronize(cg_handle *);
+/* kernels the library launched since the last reset (the bench's gpu_launches) */
+int64_t cg_launch_count(cg_handle *, int reset);
+/* CUDA-event timing on the library's own stream */
+int cg_timer_start(cg_handle *);
+int cg_timer_stop_ms(cg_handle *, double *ms);
+/* per-kernel-family event timing: name in {"tstepo_flux","co","momentum","embm","surflux","seaice","biogem"} */
+int cg_profile_enable(cg_handle *, int on);
+int cg_profile_get(cg_handle *, const char *family, double *total_ms, int64_t *launches);
+/* tracer kernel variant: 0 = strict reference operation order (bit-exact vs the oracle),
+ *                        1 = fast (FMA + factored isoneutral sums; <=1e-10 relative per step) */
+int cg_set_tracer_variant(cg_handle *, int variant);
+/* use CUDA-graph replay of one ocean step inside cg_run (default on) */
+int cg_set_graphs(cg_handle *, int on);
+
+/* ---- stand-alone tracer step on caller-provided fields (kernel tests, stress config #5) ---- */
+/* One tstepo (flux + convection) on a synthetic grid without the rest of the model:
+ * k1 (0:maxi+1,0:maxj+1) int32; u (3,0:maxi,0:maxj,maxk); ts (maxl,0:maxi+1,0:maxj+1,0:maxk+1) per member
+ * laid out member-slowest on the host.  Used for BASELINE config #5 and parity tests.       */
+int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_members, int device, const int32_t *k1,
+                     double diff1, double diff2, int nyear, cg_handle **out);
+int cg_tracer_set(cg_handle *, const double *ts, const double *u, const double *tsflux);
+int cg_tracer_step(cg_handle *, int nsteps);
+int cg_tracer_get(cg_handle *, double *ts, double *rho, double *cost);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGENIE_B200_H */
