@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- ensemble model-years per wall-hour of the cGENIE hot path on B200.
+
+One "step" = one model year of every ensemble member resident on this rank's GPU: nyear ocean
+steps (tstepo_flux + co + momentum), 5*nyear EMBM steps, nyear surflux and sea-ice steps (and the
+BIOGEM/ATCHEM steps once those kernels exist).  Members are sharded across ranks with no collective
+on the timestep path (weak scaling: members per GPU fixed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--members M] [--impl reference]
+
+Prints ONE JSON line (see the task contract): value = whole-job model-years/hour with state
+resident in HBM; e2e = the same through the per-module C-ABI entry points the Fortran host calls,
+with the year's state uploaded from / downloaded to pinned host memory inside the timed region;
+roofline = tracer-step kernel (tstepo_flux) algorithmic bytes / CUDA-event time vs the measured
+HBM peak; cpu_baseline = the CPU oracle on the host cores (bounded sample).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIG = "eb_go_gs_36x36x16_L16"
+WORKLOAD = ("eb_go_gs 36x36x16 worjh2, 16 tracers on ts (T,S + 14 passive; BIOGEM sources not on device yet), "
+            "parameter-perturbed ensemble sharded by member (BASELINE config #4 shape: 128 members/GPU)")
+PERTURBED = ["diff1", "diff2", "adrag", "scf", "diffamp1", "diffamp2", "betaz2", "betam2"]
+SEED = 20261017
+
+
+def perturbation_table(n_total):
+    """Member m perturbs each parameter by x U(0.8,1.25); member 0 is the unperturbed control.
+    adrag is perturbed per group of 16 members so that barotropic factorisations are shared."""
+    base = dict(diff1=2000.0, diff2=1.0e-5, adrag=2.5, scf=2.0, diffamp1=5.0e6, diffamp2=1.0e6, betaz2=0.4, betam2=0.4)
+    rng = np.random.default_rng(SEED)
+    tab = {}
+    for k in PERTURBED:
+        f = rng.uniform(0.8, 1.25, size=n_total)
+        if k == "adrag":
+            f = np.repeat(f[::16], 16)[:n_total]
+        f[0] = 1.0
+        if k == "adrag":
+            f[:16] = 1.0
+        tab[k] = base[k] * f
+    return tab
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.rows, self.stop_flag = dev, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for q, n in enumerate(names) if any(len(r) > 2 + q and r[2 + q].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- CPU (oracle) arms
+def _oracle_worker(args):
+    years, params = args
+    from oracle_lib import Oracle
+    o = Oracle("worjh2", maxk=16, maxl=16, nyear=96, **params)
+    t0 = time.perf_counter()
+    o.run(int(round(years * 96 * 5)))
+    dt = time.perf_counter() - t0
+    o.close()
+    return dt
+
+
+def cpu_oracle_rate(years_per_core, cores):
+    """Aggregate model-years/hour of `cores` single-threaded oracle processes, one member each."""
+    import oracle_lib
+    oracle_lib.lib()  # build once before forking
+    tab = perturbation_table(max(cores, 16))
+    jobs = [(years_per_core, {k: float(v[c]) for k, v in tab.items()}) for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_oracle_worker, jobs)
+    wall = time.perf_counter() - t0
+    return cores * years_per_core / (wall / 3600.0), wall
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ypc = 0.25  # bounded sample: each step = 0.25 model year of one member on every host core
+    for _ in range(args.warmup):
+        cpu_oracle_rate(0.05, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_rate(ypc, cores)
+    wall = time.perf_counter() - t0
+    value = cores * ypc * args.steps / (wall / 3600.0)
+    sample = "%d oracle processes (one per host core) x %.2f model-year per step" % (cores, ypc)
+    print(json.dumps({
+        "impl": "reference", "metric": "ensemble model-years/wall-hour", "value": value, "unit": "model-years/hour",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "C restatement of the reference (oracle/), not a gfortran build"},
+        "cpu_baseline": {"value": value, "unit": "model-years/hour", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "model-years/hour", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--members", type=int, default=128, help="ensemble members per GPU")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--variant", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from cgenie_b200 import Ensemble, materialise
+    M = args.members
+    tab = perturbation_table(M * world)
+    pert = {k: v[rank * M:(rank + 1) * M] for k, v in tab.items()}
+    tmp = tempfile.mkdtemp(prefix="cgenie_job_")
+    materialise(tmp, CONFIG)
+    e = Ensemble(tmp, n_members=M, device=local, perturb=pert)
+    e.set_tracer_variant(args.variant)
+    kyear = e.nyear * e.ndta
+    # passive tracers 3..L get a smooth non-trivial field (identical recipe on every member)
+    L, I, J, K = e.maxl, e.maxi, e.maxj, e.maxk
+    ts = e.get_all("ts").reshape(K, J, I, L, e.member_stride)
+    kk, jj, ii = np.meshgrid(np.arange(1, K + 1), np.arange(1, J + 1), np.arange(1, I + 1), indexing="ij")
+    for l in range(2, L):
+        ts[:, :, :, l, :] = (1.0 + 0.1 * np.sin(2 * np.pi * ii / I) * np.cos(np.pi * jj / J) * (kk / K) * (1 + l / L))[..., None]
+    e.put_all("ts", ts)
+    del ts
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        e.run(kyear)
+    e.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e.launch_count(reset=True)
+    barrier()
+    e.timer_start()
+    for _ in range(args.steps):
+        e.run(kyear)
+    ms = e.timer_stop_ms()
+    barrier()
+    launches = e.launch_count()
+    clocks = sampler.summary()
+    ms = max_over_ranks(ms)
+    value = world * M * args.steps / (ms / 3.6e6)
+    bad = int(e.health().sum())
+
+    # ---- roofline of the dominant kernel: instrumented pass over the same step (CUDA events per launch family)
+    e.profile(True)
+    e.run(kyear)
+    e.profile(False)
+    fam = {f: e.profile_get(f) for f in ("tstepo_flux", "co", "momentum", "embm", "surflux", "seaice")}
+    n_wet = int((e.iconst("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1] <= K).sum() * 0)  # placeholder, recomputed below
+    k1 = e.iconst("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    n_wet = int(np.sum(np.clip(K - k1 + 1, 0, None)[k1 <= K]))
+    bytes_per_launch = n_wet * (16 * L + 32) * M          # B_tr x members of one launch
+    t_ms, t_n = fam["tstepo_flux"]
+    c_ms, c_n = fam["co"]
+    avg_ms = (t_ms + c_ms) / max(t_n, 1)                   # tstepo = flux + convection (B_tr covers both)
+    peak, peak_src = peaks()
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_tstepo_flux_%s<8> + k_co" % args.variant, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                "family_ms_per_year": {k: v[0] for k, v in fam.items()}}
+
+    # ---- end to end through the per-module C-ABI entry points with host buffers
+    try:
+        pin = {n: torch.empty(e.field_size(n) * e.member_stride, dtype=torch.float64).pin_memory().numpy()
+               for n in ("ts", "tq", "varice")}
+    except Exception:
+        pin = {n: np.empty(e.field_size(n) * e.member_stride) for n in ("ts", "tq", "varice")}
+    for n in pin:
+        e.get_all(n, out=pin[n])
+    h2d = sum(a.nbytes for a in pin.values())
+    d2h = h2d
+
+    def e2e_year():
+        for n in pin:
+            e.put_all(n, pin[n])
+        e.put_all("varice1", pin["varice"])
+        e.put_all("tq1", pin["tq"])
+        for k in range(1, kyear + 1):
+            if k % 5 == 1:
+                e.surflux()
+            e.step_embm()
+            if k % 5 == 0:
+                e.step_seaice()
+                e.step_goldstein()
+        for n in pin:
+            e.get_all(n, out=pin[n])
+
+    e2e_year()
+    barrier()
+    t0 = time.perf_counter()
+    nrep = max(1, min(args.steps, 2))
+    for _ in range(nrep):
+        e2e_year()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_val = world * M * nrep / (e2e_s / 3600.0)
+
+    out = {
+        "metric": "ensemble model-years/wall-hour", "value": value, "unit": "model-years/hour", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "members_per_gpu": M, "grid": [I, J, K], "tracers": L, "nyear": e.nyear,
+                   "tracer_variant": args.variant, "perturbed": PERTURBED, "seed": SEED,
+                   "l2": "working set %.0f MB per GPU (two ts buffers + u + rho) exceeds the 126 MB L2" %
+                         ((2 * L + 6) * I * J * K * 8 * e.member_stride / 1e6),
+                   "step": "one model year of every member: %d koverall iterations" % kyear},
+        "clocks": clocks, "gpu_launches": launches, "blown_up_members": bad, "roofline": roofline,
+        "e2e": {"value": e2e_val, "unit": "model-years/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "path": "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein), state in/out of pinned host per year"},
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, wall = cpu_oracle_rate(0.25, cores)
+        out["cpu_baseline"] = {"value": rate, "unit": "model-years/hour", "cores": cores, "kind": "port",
+                               "sample": "%d oracle processes (one member per host core) x 0.25 model-year, %.1f s wall" % (cores, wall)}
+    e.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -634,6 +634,10 @@ extern "C" int cg_sync_from_host(cg_handle *h, const char *name, int member, con
   k_scatter_member<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(f->d, h->stage, member, h->MS, f->nd, f->dims[0], f->dims[1],
                                                                       f->dims[2], f->dims[3], f->strides[0], f->strides[1],
                                                                       f->strides[2], f->strides[3], n);
+  if (both)  // ts and ts1 are one field on the device; keep the ping-pong partner's dry cells in line
+    k_scatter_member<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->dv.ts_new, h->stage, member, h->MS, f->nd, f->dims[0],
+                                                                        f->dims[1], f->dims[2], f->dims[3], f->strides[0],
+                                                                        f->strides[1], f->strides[2], f->strides[3], n);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return CG_OK;
 }
@@ -652,6 +656,7 @@ extern "C" int cg_sync_all_from_host(cg_handle *h, const char *name, const doubl
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
   if (n != f->count() * h->MS) return fail(CG_ERR_ARG, "cg_sync_all_from_host: size must be field_size*member_stride");
   CUDA_OK(cudaMemcpyAsync(f->d, src, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  if (strcmp(name, "ts") == 0) CUDA_OK(cudaMemcpyAsync(h->dv.ts_new, src, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return CG_OK;
 }

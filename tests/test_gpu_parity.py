@@ -1,0 +1,257 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C-ABI against the CPU
+oracle on identical inputs.
+
+Bars: integer/index work and every kernel without transcendental functions (tracer step in the
+'strict' variant, momentum, EMBM tstipa, sea ice) must be BIT-EXACT; surflux (exp/log/pow) and the
+'fast' tracer variant must agree to <= 1e-10 relative per step (BASELINE.json north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from cgenie_b200 import Ensemble, TracerStep, materialise, _lib
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"A": ("eb_go_gs_36x36x8", dict(world="worbe2", maxk=8, maxl=2, nyear=100)),
+       "B": ("eb_go_gs_36x36x16_L16", dict(world="worjh2", maxk=16, maxl=16, nyear=96))}
+FLUX2D = ["latent_ocn", "sensible_ocn", "netsolar_ocn", "netlong_ocn", "evap_ocn", "precip_ocn", "runoff_ocn",
+          "latent_atm", "sensible_atm", "netsolar_atm", "netlong_atm", "evap_atm", "dhght_sic", "dfrac_sic",
+          "waterflux_ocn", "conductflux_ocn"]
+
+
+def interior(o, name):
+    I = J = 36
+    K, L = int(o.params["maxk"]), int(o.params["maxl"])
+    if name in ("ts", "ts1"):
+        return o.f(name).reshape(K + 2, J + 2, I + 2, L)[1:K + 1, 1:J + 1, 1:I + 1, :].ravel()
+    if name in ("u", "u1"):
+        return o.f(name).reshape(K, J + 1, I + 1, 3)[:, 1:, 1:, :].ravel()
+    if name == "rho":
+        return o.f(name).reshape(K + 1, J + 2, I + 2)[1:, 1:J + 1, 1:I + 1].ravel()
+    return o.f(name).copy()
+
+
+def u1_2comp(o):
+    I = J = 36
+    K = int(o.params["maxk"])
+    return o.f("u1").reshape(K, J + 1, I + 1, 3)[:, 1:, 1:, :2].ravel()
+
+
+def tsflux_of(o):
+    I = J = 36
+    K, L = int(o.params["maxk"]), int(o.params["maxl"])
+    return o.f("ts").reshape(K + 2, J + 2, I + 2, L)[K + 1, 1:J + 1, 1:I + 1, :2].ravel()
+
+
+def add_passive_tracers(o, seed=1):
+    """Fill tracers 3..L of the oracle with smooth synthetic fields (wet and dry cells alike)."""
+    I = J = 36
+    K, L = int(o.params["maxk"]), int(o.params["maxl"])
+    ts = o.f("ts").reshape(K + 2, J + 2, I + 2, L)
+    ts1 = o.f("ts1").reshape(K + 2, J + 2, I + 2, L)
+    kk, jj, ii = np.meshgrid(np.arange(K + 2), np.arange(J + 2), np.arange(I + 2), indexing="ij")
+    for l in range(2, L):
+        f = 1.0 + 0.1 * np.sin(2 * np.pi * ii / I * (1 + l % 3)) * np.cos(np.pi * jj / J) * (kk / K) * (1 + l / L) \
+            + 0.01 * l
+        f[K + 1] = 0.0
+        ts[..., l] = f
+        ts1[..., l] = f
+    # periodic halo as step_goldstein leaves it
+    ts[:, :, 0, :] = ts[:, :, I, :]
+    ts[:, :, I + 1, :] = ts[:, :, 1, :]
+    ts1[:, :, 0, :] = ts[:, :, I, :]
+    ts1[:, :, I + 1, :] = ts[:, :, 1, :]
+
+
+def inject(e, o, member=0):
+    """Copy the oracle's complete prognostic + coupling state into one ensemble member."""
+    e.put("ts", interior(o, "ts"), member)
+    e.put("rho", interior(o, "rho"), member)
+    e.put("u", interior(o, "u"), member)
+    e.put("u1", u1_2comp(o), member)
+    e.put("cost", o.f("cost"), member)
+    e.put("tsflux", tsflux_of(o), member)
+    for n in ("tq", "tq1", "varice", "varice1"):
+        e.put(n, o.f(n), member)
+    e.put("tice", o.f("temp_sic"), member)
+    e.put("co2", o.f("co2"), member)
+    for n in FLUX2D:
+        e.put(n, o.f(n), member)
+
+
+def bits_equal(a, b):
+    return np.array_equal(np.asarray(a).view(np.uint64), np.asarray(b).view(np.uint64))
+
+
+def relerr(a, b, floor):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+@pytest.fixture(scope="module")
+def spun():
+    """Oracles advanced 40 ocean steps so velocities, ice and convection are active."""
+    out = {}
+    for key, (cfg, okw) in CFG.items():
+        o = Oracle(**okw)
+        o.run(200)
+        if okw["maxl"] > 2:
+            add_passive_tracers(o)
+        out[key] = o
+    return out
+
+
+@pytest.mark.parametrize("key", ["A", "B"])
+def test_tracer_step_strict_bit_exact(built, tmp_path, spun, key):
+    cfg, okw = CFG[key]
+    o = spun[key]
+    materialise(str(tmp_path), cfg)
+    with Ensemble(str(tmp_path), n_members=3) as e:
+        for m in range(3):
+            inject(e, o, m)
+        e.set_tracer_variant("strict")
+        e._ck(e.L.cg_tracer_step(e.h, 1))
+        got = [(e.get("ts", m), e.get("rho", m), e.get("cost", m)) for m in range(3)]
+    cost0 = o.f("cost").copy()
+    o.call("tstepo")
+    for ts, rho, cost in got:
+        wet = np.isfinite(ts)
+        assert bits_equal(ts, interior(o, "ts")), "ts max diff %.3e" % np.max(np.abs(ts - interior(o, "ts")))
+        assert bits_equal(rho, interior(o, "rho"))
+        assert bits_equal(cost, o.f("cost"))
+    assert o.f("cost").sum() > cost0.sum()  # convection was exercised
+    assert o.s("limps") > 0                # and the isoneutral slope limiter
+
+
+@pytest.mark.parametrize("key", ["A", "B"])
+def test_tracer_step_fast_within_tolerance(built, tmp_path, spun, key):
+    cfg, okw = CFG[key]
+    o = spun[key]
+    before = interior(o, "ts").copy()
+    materialise(str(tmp_path), cfg)
+    with Ensemble(str(tmp_path), n_members=2) as e:
+        for m in range(2):
+            inject(e, o, m)
+        e.set_tracer_variant("strict")
+        e._ck(e.L.cg_tracer_step(e.h, 1))
+        strict = e.get("ts", 1)
+        for m in range(2):
+            inject(e, o, m)
+        e.set_tracer_variant("fast")
+        e._ck(e.L.cg_tracer_step(e.h, 1))
+        fast = e.get("ts", 1)
+    L = okw["maxl"]
+    scale = np.maximum(np.abs(strict), 1e-3)
+    err = float(np.max(np.abs(fast - strict) / scale))
+    # the increment itself must also agree to high relative accuracy
+    inc = np.abs(strict - before).max()
+    print("fast vs strict: max rel err %.3e (largest increment %.3e)" % (err, inc))
+    assert err <= 1e-10
+
+
+def test_momentum_embm_seaice_bit_exact(built, tmp_path, spun):
+    """One full coupling cycle from an injected state: every kernel without transcendentals is bit-exact."""
+    cfg, okw = CFG["A"]
+    o = Oracle(**okw)
+    o.run(200)
+    materialise(str(tmp_path), cfg)
+    with Ensemble(str(tmp_path), n_members=2) as e:
+        for m in range(2):
+            inject(e, o, m)
+        # EMBM step (tstipa)
+        e.step_embm()
+        o.call("embm_step")
+        assert bits_equal(e.get("tq", 1), o.f("tq"))
+        # sea ice
+        e.step_seaice()
+        o.call("seaice_step")
+        assert bits_equal(e.get("varice", 1), o.f("varice"))
+        assert bits_equal(e.get("waterflux_ocn", 1), o.f("waterflux_ocn"))
+        assert bits_equal(e.get("conductflux_ocn", 1), o.f("conductflux_ocn"))
+        # ocean: momentum + tracers
+        e.istep_ocn = int(o.s("istep_ocn"))
+        e.step_goldstein()
+        o.call("goldstein_step")
+        assert bits_equal(e.get("psi", 1), o.f("psi")), np.max(np.abs(e.get("psi", 1) - o.f("psi")))
+        assert bits_equal(e.get("u", 1), interior(o, "u"))
+        assert bits_equal(e.get("ts", 1), interior(o, "ts"))
+        assert bits_equal(e.get("rho", 1), interior(o, "rho"))
+        assert bits_equal(e.get("cost", 1), o.f("cost"))
+
+
+def test_surflux_within_tolerance(built, tmp_path):
+    cfg, okw = CFG["A"]
+    o = Oracle(**okw)
+    o.run(200)  # ends after an ocean step: the next call in the schedule is surflux
+    materialise(str(tmp_path), cfg)
+    with Ensemble(str(tmp_path), n_members=2) as e:
+        for m in range(2):
+            inject(e, o, m)
+        e.istep_ocn = int(o.s("istep_ocn"))
+        e.surflux()
+        o.set("istep_ocn", o.s("istep_ocn") + 1)
+        o.call("surflux")
+        worst = 0.0
+        for n in FLUX2D[:14] + ["tq", "pptn", "evap", "fx0a", "fxlw"]:
+            a, b = e.get(n, 1), o.f(n)
+            err = relerr(a, b, 1e-30 + 1e-9 * np.abs(b).max())
+            worst = max(worst, err)
+            assert err <= 1e-10, (n, err)
+        assert bits_equal(e.get("tice", 1) != 0, o.f("temp_sic") != 0)
+        print("surflux worst relative error %.3e" % worst)
+
+
+@pytest.mark.parametrize("key,nk", [("A", 100), ("B", 50)])
+def test_full_model_from_init(built, tmp_path, key, nk):
+    """Whole coupling loop on the device (cg_run, CUDA graphs) vs the oracle from the initial state,
+    with per-member perturbed parameters."""
+    cfg, okw = CFG[key]
+    okw = dict(okw, maxl=2) if key == "B" else okw
+    cfgname = "eb_go_gs_36x36x16" if key == "B" else cfg
+    materialise(str(tmp_path), cfgname)
+    pert = {"diff1": np.array([2000.0, 1700.0, 2300.0]), "diff2": np.array([1e-5, 1.2e-5, 0.9e-5]),
+            "scf": np.array([2.0, 1.8, 2.2]), "adrag": np.array([2.5, 2.5, 3.0]), "diffamp1": np.array([5e6, 4.5e6, 5.5e6]),
+            "betaz2": np.array([0.4, 0.35, 0.45]), "betam2": np.array([0.4, 0.35, 0.45])}
+    with Ensemble(str(tmp_path), n_members=3, perturb=pert) as e:
+        e.run(nk)
+        res = [{n: e.get(n, m) for n in ("ts", "u", "rho", "tq", "varice", "psi", "cost")} for m in range(3)]
+        assert e.health().sum() == 0
+    for m in range(3):
+        o = Oracle(**okw, **{k: v[m] for k, v in pert.items()})
+        o.run(nk)
+        ref = {"ts": interior(o, "ts"), "u": interior(o, "u"), "rho": interior(o, "rho"), "tq": o.f("tq"),
+               "varice": o.f("varice"), "psi": o.f("psi"), "cost": o.f("cost")}
+        floors = {"ts": 1e-3, "u": 1e-6, "rho": 1e-6, "tq": 1e-6, "varice": 1e-6, "psi": 1e-6, "cost": 1.0}
+        for n, b in ref.items():
+            err = relerr(res[m][n], b, floors[n])
+            print("member %d %-7s max rel err %.3e" % (m, n, err))
+            assert err <= 1e-10 * (nk / 5), (m, n, err)
+
+
+def test_tracer_step_conserves_inventory_full_size(built, tmp_path, spun):
+    """Size-independent property at the bench size: with zero surface flux, tstepo (flux form +
+    convective mixing) conserves every tracer's volume integral; 128 members x 16 tracers."""
+    cfg, okw = CFG["B"]
+    o = spun["B"]
+    materialise(str(tmp_path), cfg)
+    M = 128
+    with Ensemble(str(tmp_path), n_members=M) as e:
+        inject(e, o, 0)
+        base = e.get_all("ts").reshape(-1, e.member_stride)
+        base[:] = base[:, :1]
+        e.put_all("ts", base)
+        for n in ("u", "rho"):
+            a = e.get_all(n).reshape(-1, e.member_stride)
+            a[:] = a[:, :1]
+            e.put_all(n, a)
+        e.put_all("tsflux", np.zeros(e.field_size("tsflux") * e.member_stride))
+        before = e.global_means()
+        for variant in ("strict", "fast"):
+            e.set_tracer_variant(variant)
+            e._ck(e.L.cg_tracer_step(e.h, 2))
+            after = e.global_means()
+            drift = np.max(np.abs(after - before) / np.maximum(np.abs(before), 1e-3))
+            print(variant, "inventory drift", drift)
+            assert drift < 1e-12
+        assert np.allclose(after, after[:1], rtol=0, atol=0)  # identical members stay identical
