@@ -29,7 +29,7 @@ int launch_surflux(const Dev &, double *meantemp, bool need_mean, cudaStream_t);
 int launch_embm(const Dev &, int nsteps, cudaStream_t);
 int launch_seaice(const Dev &, cudaStream_t);
 int launch_gold_pre(const Dev &, cudaStream_t);
-int launch_momentum(const Dev &, cudaStream_t);
+int launch_momentum(const Dev &, int fast, const double *bf, const double *bb, const double *rd, cudaStream_t);
 void launch_global_means(const Dev &, double *out, cudaStream_t);
 void launch_health(const Dev &, int *flags, cudaStream_t);
 
@@ -103,6 +103,7 @@ struct cg_handle {
   double *stage = nullptr;
   size_t stage_n = 0;
   double *d_meantemp = nullptr, *d_means = nullptr;
+  double *d_bf = nullptr, *d_bb = nullptr, *d_rd = nullptr;  // pivot-major barotropic factors (fast solve)
   int *d_flags = nullptr;
   bool need_mean = false;
   long long launches = 0;
@@ -239,7 +240,7 @@ extern "C" int cg_create(const char *jobdir, int n_members, int device, cg_handl
   std::unique_ptr<cg_handle> h(new cg_handle);
   h->device = device;
   h->M = n_members;
-  h->MS = ((n_members + 15) / 16) * 16;
+  h->MS = ((n_members + 31) / 32) * 32;
   std::string err;
   if (!load_job(jobdir, &h->base, &h->g, &h->isl, &h->w, &err)) {
     const bool io = err.find("could not open") != std::string::npos || err.find("too short") != std::string::npos;
@@ -337,6 +338,19 @@ static int build_device(cg_handle *h) {
     TRY(dupload(h, &p, gj)); v.getj = p;
   }
   // ---- per-member scalars
+  {
+    // wet columns, deepest first (load balance: long columns start early)
+    std::vector<int> wc;
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++)
+        if (g.k1at(i, j) <= K) wc.push_back((i - 1) + I * (j - 1));
+    std::stable_sort(wc.begin(), wc.end(), [&](int a, int b) { return g.k1at(a % I + 1, a / I + 1) < g.k1at(b % I + 1, b / I + 1); });
+    v.nwet = (int)wc.size();
+    if (wc.empty()) wc.push_back(0);
+    int *q;
+    TRY(dupload(h, &q, wc));
+    v.wetcols = q;
+  }
   auto col = [&](auto getter) { std::vector<double> t(M); for (int m = 0; m < M; m++) t[m] = getter(h->mc[m]); return t; };
   MemberP &p = v.p;
   TRY(dparam(h, &p.diff1, col([](const MemberConsts &c) { return c.diff1; })));
@@ -449,6 +463,23 @@ static int build_device(cg_handle *h) {
       std::copy(c.psisl.begin(), c.psisl.begin() + (size_t)(I + 1) * (J + 1), PSI.begin() + (size_t)grp * (I + 1) * (J + 1));
       ER[2 * grp] = c.erisl[0];
       ER[2 * grp + 1] = c.erisl.size() > 1 ? c.erisl[1] : 0.0;
+    }
+    {
+      // pivot-major copies for the warp-cooperative solve
+      std::vector<double> BF((size_t)h->nbaro * nm * bw, 0.0), BB((size_t)h->nbaro * nm * bw, 0.0), RD((size_t)h->nbaro * nm, 0.0);
+      for (int grp = 0; grp < h->nbaro; grp++) {
+        const double *Rg = &R[(size_t)grp * nm * bw], *Gg = &G[(size_t)grp * nm * gw];
+        for (int i = 1; i <= nm; i++) {
+          RD[(size_t)grp * nm + i - 1] = 1.0 / Gg[(size_t)(i - 1) * gw + (I + 1)];
+          for (int t = 1; t <= bw; t++) {
+            if (i + t <= nm) BF[((size_t)grp * nm + i - 1) * bw + t - 1] = Rg[(size_t)(i + t - 1) * bw + (t - 1)];
+            if (i - t >= 1) BB[((size_t)grp * nm + i - 1) * bw + t - 1] = Gg[(size_t)(i - t - 1) * gw + (I + 1 + t)];
+          }
+        }
+      }
+      TRY(dupload(h, &h->d_bf, BF));
+      TRY(dupload(h, &h->d_bb, BB));
+      TRY(dupload(h, &h->d_rd, RD));
     }
     double *q;
     TRY(dupload(h, &q, R)); v.ratm = q;
@@ -739,7 +770,7 @@ static void do_tstepo(cg_handle *h) {
   std::swap(h->dv.ts_cur, h->dv.ts_new);
 }
 static int do_goldstein(cg_handle *h) {
-  { ProfScope ps(h, "momentum"); launch_hosing(h->dv, h->stream); int n = launch_gold_pre(h->dv, h->stream); n += launch_momentum(h->dv, h->stream); ps.done(n + 1); }
+  { ProfScope ps(h, "momentum"); launch_hosing(h->dv, h->stream); int n = launch_gold_pre(h->dv, h->stream); n += launch_momentum(h->dv, h->variant, h->d_bf, h->d_bb, h->d_rd, h->stream); ps.done(n + 1); }
   do_tstepo(h);
   return CG_OK;
 }
@@ -1034,7 +1065,7 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
   std::unique_ptr<cg_handle> h(new cg_handle);
   h->device = device;
   h->M = n_members;
-  h->MS = ((n_members + 15) / 16) * 16;
+  h->MS = ((n_members + 31) / 32) * 32;
   h->tracer_only = true;
   Params p;
   p.maxi = maxi; p.maxj = maxj; p.maxk = maxk; p.maxl = maxl; p.nyear = nyear; p.diff1 = diff1; p.diff2 = diff2;

@@ -7,7 +7,8 @@
 // index arithmetic, the j/k boundary rows are never read because every neighbour access is
 // guarded by the bathymetry mask exactly as in the Fortran).  A warp is 32 members of ONE cell
 // and tracer: fully coalesced 256-byte rows, and near-uniform control flow because all members
-// share the bathymetry.  `MS` (member stride) = members rounded up to 16 doubles = 128 bytes.
+// share the bathymetry.  `MS` (member stride) = members rounded up to a whole number of 32-member warps (256-byte rows);
+// padding lanes carry copies of the last member, so kernels need no member guard for safety.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -53,6 +54,8 @@ struct Dev {
   const int *iroff_src;      // runoff gather lists: CSR over wet cells, sources in reference order
   const int *iroff_ptr;
   const int *lpisl, *ipisl, *jpisl;  // island 1 path (npi1 points)
+  const int *wetcols;        // 0-based (i-1)+I*(j-1) of the wet columns, deepest first
+  int nwet;
   // tracer state, ping-pong
   double *ts_cur, *ts_new;
   double *tsflux;            // [2][j][i][m] surface flux b.c. for T,S (ts(1:2,:,:,maxk+1))

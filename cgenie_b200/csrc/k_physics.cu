@@ -549,6 +549,89 @@ __global__ void __launch_bounds__(32) k_baro_strict(const Dev v) {
 #undef GB
 }
 
+
+// Fast barotropic solve: one warp per member, the right-hand side lives in shared memory and both
+// sweeps are column-oriented (pivot value broadcast, 37 band updates in parallel across lanes).
+// The forward sweep performs exactly the reference's operations (ubarsolv :3511-3516); the back
+// substitution applies the same eliminations in column order with reciprocal pivots, so it differs
+// from the reference's row-order subtraction by rounding only.  Factors are stored pivot-major:
+//   bf[(i-1)*bw + t-1] = ratm(i+t, t)          bb[(i-1)*bw + t-1] = gap(i-t, n+2+t)     rd[i-1] = 1/gap(i, n+2)
+constexpr int kBaroPF = 8;
+__global__ void __launch_bounds__(128) k_baro_fast(const Dev v, const double *__restrict__ bf_all, const double *__restrict__ bb_all,
+                                                   const double *__restrict__ rd_all) {
+  extern __shared__ double xs[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (m >= v.M) return;
+  const int n = v.I, nm = v.nm, MS = v.MS, bw = n + 1;
+  double *x = xs + (size_t)wib * nm;
+  const size_t g = v.baro_group[m];
+  const double *__restrict__ bf = bf_all + g * nm * bw, *__restrict__ bb = bb_all + g * nm * bw, *__restrict__ rd = rd_all + g * nm;
+  for (int r = lane; r < nm; r += 32) x[r] = v.gb[(size_t)r * MS + m];
+  __syncwarp();
+  const bool two = lane + 33 <= bw;
+  double fa[kBaroPF], fb[kBaroPF], na[kBaroPF], nb[kBaroPF];
+  // ---- forward elimination
+#pragma unroll
+  for (int u = 0; u < kBaroPF; u++) {
+    const int i = 1 + u;
+    fa[u] = (i <= nm - 1) ? bf[(size_t)(i - 1) * bw + lane] : 0.0;
+    fb[u] = (two && i <= nm - 1) ? bf[(size_t)(i - 1) * bw + lane + 32] : 0.0;
+  }
+  for (int ib = 1; ib <= nm - 1; ib += kBaroPF) {
+#pragma unroll
+    for (int u = 0; u < kBaroPF; u++) {
+      const int i = ib + kBaroPF + u;
+      na[u] = (i <= nm - 1) ? bf[(size_t)(i - 1) * bw + lane] : 0.0;
+      nb[u] = (two && i <= nm - 1) ? bf[(size_t)(i - 1) * bw + lane + 32] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kBaroPF; u++) {
+      const int i = ib + u;
+      if (i <= nm - 1) {
+        const double gi = x[i - 1];
+        const int r1 = i + lane + 1, r2 = i + lane + 33;
+        if (r1 <= nm) x[r1 - 1] = x[r1 - 1] - fa[u] * gi;
+        if (two && r2 <= nm) x[r2 - 1] = x[r2 - 1] - fb[u] * gi;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int u = 0; u < kBaroPF; u++) { fa[u] = na[u]; fb[u] = nb[u]; }
+  }
+  // ---- back substitution, column oriented
+#pragma unroll
+  for (int u = 0; u < kBaroPF; u++) {
+    const int i = nm - u;
+    fa[u] = (i >= 1) ? bb[(size_t)(i - 1) * bw + lane] : 0.0;
+    fb[u] = (two && i >= 1) ? bb[(size_t)(i - 1) * bw + lane + 32] : 0.0;
+  }
+  for (int ib = nm; ib >= 1; ib -= kBaroPF) {
+#pragma unroll
+    for (int u = 0; u < kBaroPF; u++) {
+      const int i = ib - kBaroPF - u;
+      na[u] = (i >= 1) ? bb[(size_t)(i - 1) * bw + lane] : 0.0;
+      nb[u] = (two && i >= 1) ? bb[(size_t)(i - 1) * bw + lane + 32] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kBaroPF; u++) {
+      const int i = ib - u;
+      if (i >= 1) {
+        const double xi = x[i - 1] * rd[i - 1];
+        __syncwarp();  // every lane has read the pivot before lane 0 overwrites it
+        const int r1 = i - lane - 1, r2 = i - lane - 33;
+        if (r1 >= 1) x[r1 - 1] = x[r1 - 1] - fa[u] * xi;
+        if (two && r2 >= 1) x[r2 - 1] = x[r2 - 1] - fb[u] * xi;
+        if (lane == 0) x[i - 1] = xi;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int u = 0; u < kBaroPF; u++) { fa[u] = na[u]; fb[u] = nb[u]; }
+  }
+  for (int r = lane; r < nm; r += 32) v.gb[(size_t)r * MS + m] = x[r];
+}
+
 // psi and barotropic velocity from the solved gb (ubarsolv :3527-3564)
 __global__ void __launch_bounds__(128) k_psi2ub(const Dev v) {
   DIMS
@@ -570,14 +653,18 @@ __global__ void __launch_bounds__(128) k_psi2ub(const Dev v) {
 #undef GBP
 }
 
-// island path integral (island, goldstein_lib.f90:186-241, indj = 1) and psibc (goldstein.f90:203-216)
-__global__ void __launch_bounds__(32) k_island(const Dev v) {
+// island path integral (island, goldstein_lib.f90:186-241, indj = 1) and psibc (goldstein.f90:203-216).
+// One warp per member: lanes evaluate the path points in parallel, lane 0 adds the terms in the
+// reference's order (t1(1), t2(1), t1(2), ...), so the sum is the sequential one bit for bit.
+__global__ void __launch_bounds__(128) k_island(const Dev v) {
   DIMS
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double terms[4][2 * 160];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + wib;
   if (m >= v.M) return;
   const size_t nf = (size_t)I * J * MS;
-  double e = 0.0;
-  for (int p = 0; p < c_g.npi1; p++) {
+  const int np = c_g.npi1;
+  for (int p = lane; p < np; p += 32) {
     const int lpi = v.lpisl[p], ipi = v.ipisl[p], jpi = v.jpisl[p];
     const int al = abs(lpi), sg = (lpi >= 0) ? 1 : -1;
     double cor;
@@ -586,23 +673,31 @@ __global__ void __launch_bounds__(32) k_island(const Dev v) {
     else
       cor = c_g.sv[jpi] * 0.25 * (UBX(1, ipi - 1, jpi) + UBX(1, ipi, jpi) + UBX(1, ipi - 1, jpi + 1) + UBX(1, ipi, jpi + 1));
     const double tau = v.tau[A2I(ipi, jpi) + (al - 1) * nf];
-    e = e + sg * (DRAGX(al, ipi, jpi) * UBX(al, ipi, jpi) + cor - 1 * tau * RHX(al, ipi, jpi)) *
-                (c_g.c[jpi] * c_g.dphi * (2.0 - al) + c_g.rcv[jpi] * c_g.dsv[jpi] * (al - 1.0));
+    const double t1 = sg * (DRAGX(al, ipi, jpi) * UBX(al, ipi, jpi) + cor - 1 * tau * RHX(al, ipi, jpi)) *
+                      (c_g.c[jpi] * c_g.dphi * (2.0 - al) + c_g.rcv[jpi] * c_g.dsv[jpi] * (al - 1.0));
+    double t2;
     const int ipw = (ipi < I) ? ipi + 1 : 1;
     if (al == 1) {
       double tv1 = 0.0;
       for (int k = KUX(1, ipi, jpi); k <= MKX(ipi + 1, jpi); k++) tv1 = tv1 + BPX(ipw, jpi, k) * c_g.dz[k];
       for (int k = KUX(1, ipi, jpi); k <= MKX(ipi, jpi); k++) tv1 = tv1 - BPX(ipi, jpi, k) * c_g.dz[k];
-      e = e + (SBPX(ipw, jpi) - SBPX(ipi, jpi) + tv1) * sg * RHX(1, ipi, jpi);
+      t2 = (SBPX(ipw, jpi) - SBPX(ipi, jpi) + tv1) * sg * RHX(1, ipi, jpi);
     } else {
       double tv2 = 0.0;
       for (int k = KUX(2, ipi, jpi); k <= MKX(ipi, jpi + 1); k++) tv2 = tv2 + BPX(ipi, jpi + 1, k) * c_g.dz[k];
       for (int k = KUX(2, ipi, jpi); k <= MKX(ipi, jpi); k++) tv2 = tv2 - BPX(ipi, jpi, k) * c_g.dz[k];
-      e = e + (SBPX(ipi, jpi + 1) - SBPX(ipi, jpi) + tv2) * sg * RHX(2, ipi, jpi);
+      t2 = (SBPX(ipi, jpi + 1) - SBPX(ipi, jpi) + tv2) * sg * RHX(2, ipi, jpi);
     }
+    terms[wib][2 * p] = t1;
+    terms[wib][2 * p + 1] = t2;
   }
-  v.erisl_rhs[m] = e;
-  v.psibc[m] = -e / v.erisl[2 * v.baro_group[m]];  // isles == 1: psibc(1) = -erisl(1,2)/erisl(1,1)
+  __syncwarp();
+  if (lane == 0) {
+    double e = 0.0;
+    for (int p = 0; p < 2 * np; p++) e = e + terms[wib][p];
+    v.erisl_rhs[m] = e;
+    v.psibc[m] = -e / v.erisl[2 * v.baro_group[m]];  // isles == 1: psibc(1) = -erisl(1,2)/erisl(1,1)
+  }
 }
 
 // add the island contribution to ub and psi (goldstein.f90:218-230)
@@ -821,13 +916,18 @@ int launch_gold_pre(const Dev &v, cudaStream_t s) {
   k_gold_pre<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
   return 1;
 }
-int launch_momentum(const Dev &v, cudaStream_t s) {
+int launch_momentum(const Dev &v, int fast, const double *bf, const double *bb, const double *rd, cudaStream_t s) {
   const dim3 b(32, 4);
   k_bp<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
   k_gb<<<grid2(v, v.nm, b), b, 0, s>>>(v);
-  k_baro_strict<<<(v.M + 31) / 32, 32, 0, s>>>(v);
+  if (fast) {
+    const int wpb = 2;  // members (warps) per block
+    k_baro_fast<<<(v.M + wpb - 1) / wpb, 32 * wpb, sizeof(double) * v.nm * wpb, s>>>(v, bf, bb, rd);
+  } else {
+    k_baro_strict<<<(v.M + 31) / 32, 32, 0, s>>>(v);
+  }
   k_psi2ub<<<grid2(v, (v.I + 2) * (v.J + 1), b), b, 0, s>>>(v);
-  k_island<<<(v.M + 31) / 32, 32, 0, s>>>(v);
+  k_island<<<(v.M + 3) / 4, 128, 0, s>>>(v);
   k_ubadd<<<grid2(v, (v.I + 2) * (v.J + 1), b), b, 0, s>>>(v);
   k_velc<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
   k_w<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);

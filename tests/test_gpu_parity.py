@@ -202,8 +202,8 @@ def test_surflux_within_tolerance(built, tmp_path):
         print("surflux worst relative error %.3e" % worst)
 
 
-@pytest.mark.parametrize("key,nk", [("A", 100), ("B", 50)])
-def test_full_model_from_init(built, tmp_path, key, nk):
+@pytest.mark.parametrize("key,nk,variant", [("A", 100, "strict"), ("B", 50, "strict"), ("B", 50, "fast")])
+def test_full_model_from_init(built, tmp_path, key, nk, variant):
     """Whole coupling loop on the device (cg_run, CUDA graphs) vs the oracle from the initial state,
     with per-member perturbed parameters."""
     cfg, okw = CFG[key]
@@ -214,6 +214,7 @@ def test_full_model_from_init(built, tmp_path, key, nk):
             "scf": np.array([2.0, 1.8, 2.2]), "adrag": np.array([2.5, 2.5, 3.0]), "diffamp1": np.array([5e6, 4.5e6, 5.5e6]),
             "betaz2": np.array([0.4, 0.35, 0.45]), "betam2": np.array([0.4, 0.35, 0.45])}
     with Ensemble(str(tmp_path), n_members=3, perturb=pert) as e:
+        e.set_tracer_variant(variant)
         e.run(nk)
         res = [{n: e.get(n, m) for n in ("ts", "u", "rho", "tq", "varice", "psi", "cost")} for m in range(3)]
         assert e.health().sum() == 0
@@ -226,6 +227,15 @@ def test_full_model_from_init(built, tmp_path, key, nk):
         for n, b in ref.items():
             err = relerr(res[m][n], b, floors[n])
             print("member %d %-7s max rel err %.3e" % (m, n, err))
+            if n == "cost" and variant == "fast":
+                # convection counter: a 1-ulp difference in T,S can flip a near-neutral stability test
+                # (goldstein.f90:2700); report the flip rate instead of demanding identical counts
+                wet = b > 0
+                flips = np.abs(res[m][n] - b)
+                rate = float((flips > 0).sum()) / max(int(wet.sum()), 1)
+                print("member %d convection-count flip rate %.4f (max |diff| %g)" % (m, rate, flips.max()))
+                assert rate <= 0.05 and flips.max() <= 4
+                continue
             assert err <= 1e-10 * (nk / 5), (m, n, err)
 
 
