@@ -386,7 +386,7 @@ static int build_device(cg_handle *h) {
   TRY(dalloc(h, &v.u1, ijk * 2 * MS));
   TRY(dalloc(h, &v.cost, ij * MS));
   TRY(dalloc(h, &v.istep_ocn, 1));
-  {
+  if (!h->tracer_only) {
     // initial ts/rho: host (L,I,J,K)/(I,J,K) Fortran order == device cell order with l fastest
     std::vector<double> t(ijk * L * MS, 0.0), r(ijk * MS, 0.0);
     for (int m = 0; m < MS; m++) {
@@ -652,12 +652,21 @@ extern "C" int cg_sync_to_host(cg_handle *h, const char *name, int member, doubl
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return CG_OK;
 }
+static int sync_from_host_lane(cg_handle *h, const char *name, int member, const double *src, int64_t n);
 extern "C" int cg_sync_from_host(cg_handle *h, const char *name, int member, const double *src, int64_t n) {
+  if (!h || member < 0 || member >= h->M) return fail(CG_ERR_ARG, "cg_sync_from_host: member out of range");
+  int rc = sync_from_host_lane(h, name, member, src, n);
+  // padding lanes mirror the last member (kernels run them unguarded)
+  if (!rc && member == h->M - 1)
+    for (int q = h->M; q < h->MS && !rc; q++) rc = sync_from_host_lane(h, name, q, src, n);
+  return rc;
+}
+static int sync_from_host_lane(cg_handle *h, const char *name, int member, const double *src, int64_t n) {
   if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_from_host: bad argument");
   const bool both = strcmp(name, "ts") == 0 || strcmp(name, "ts1") == 0;
   FieldDesc *f = find_field(h, both ? "ts" : name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
-  if (member < 0 || member >= h->M || n != f->count()) return fail(CG_ERR_ARG, "cg_sync_from_host: member/size mismatch");
+  if (member < 0 || member >= h->MS || n != f->count()) return fail(CG_ERR_ARG, "cg_sync_from_host: member/size mismatch");
   activate(h);
   int rc = ensure_stage(h, (size_t)n);
   if (rc) return rc;
@@ -1087,6 +1096,7 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
   h->mc.resize(n_members, h->mc[0]);
   h->baro_group.assign(h->MS, 0);
   fill_gridc(h.get());
+  register_hconst(h.get(), h->mc[0]);
   int rc = build_device(h.get());
   if (rc) return rc;
   h->initialised = true;
@@ -1100,44 +1110,40 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
 extern "C" int cg_tracer_set(cg_handle *h, const double *ts, const double *u, const double *tsflux) {
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
   activate(h);
-  const int I = h->g.I, J = h->g.J, K = h->g.K, L = h->g.L, M = h->M, MS = h->MS;
+  const int I = h->g.I, J = h->g.J, K = h->g.K, L = h->g.L, M = h->M;
   const size_t ij = (size_t)I * J, ijk = ij * K;
   if (ts) {
-    std::vector<double> t(ijk * L * MS, 0.0), r(ijk * MS, 0.0);
+    std::vector<double> t(ijk * L), r(ijk);
     const size_t nts = (size_t)L * (I + 2) * (J + 2) * (K + 2);
-    for (int m = 0; m < M; m++)
+    for (int m = 0; m < M; m++) {
       for (int k = 1; k <= K; k++)
         for (int j = 1; j <= J; j++)
           for (int i = 1; i <= I; i++) {
             const size_t c = cell3(I, J, i, j, k);
             const double *src = ts + m * nts + (size_t)L * (i + (size_t)(I + 2) * (j + (size_t)(J + 2) * k));
-            for (int l = 0; l < L; l++) t[(c * L + l) * MS + m] = src[l];
-            r[c * MS + m] = eos(h->mc[0].ec, src[0], src[1]);
+            for (int l = 0; l < L; l++) t[c * L + l] = src[l];
+            r[c] = eos(h->mc[0].ec, src[0], src[1]);
           }
-    CUDA_OK(cudaMemcpy(h->dv.ts_cur, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(h->dv.ts_new, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(h->dv.rho, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
+      IO(cg_sync_from_host(h, "ts", m, t.data(), (int64_t)t.size()));
+      IO(cg_sync_from_host(h, "rho", m, r.data(), (int64_t)r.size()));
+    }
   }
   if (u) {
-    std::vector<double> t(ijk * 3 * MS, 0.0);
+    std::vector<double> t(ijk * 3);
     const size_t nu = (size_t)3 * (I + 1) * (J + 1) * K;
-    for (int m = 0; m < M; m++)
+    for (int m = 0; m < M; m++) {
       for (int k = 1; k <= K; k++)
         for (int j = 1; j <= J; j++)
           for (int i = 1; i <= I; i++) {
             const size_t c = cell3(I, J, i, j, k);
             const double *src = u + m * nu + (size_t)3 * (i + (size_t)(I + 1) * (j + (size_t)(J + 1) * (k - 1)));
-            for (int cc = 0; cc < 3; cc++) t[(c * 3 + cc) * MS + m] = src[cc];
+            for (int cc = 0; cc < 3; cc++) t[c * 3 + cc] = src[cc];
           }
-    CUDA_OK(cudaMemcpy(h->dv.u, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+      IO(cg_sync_from_host(h, "u", m, t.data(), (int64_t)t.size()));
+    }
   }
-  if (tsflux) {
-    std::vector<double> t(2 * ij * MS, 0.0);
-    for (int m = 0; m < M; m++)
-      for (size_t c2 = 0; c2 < ij; c2++)
-        for (int l = 0; l < 2; l++) t[(l * ij + c2) * MS + m] = tsflux[(size_t)m * 2 * ij + l + 2 * c2];
-    CUDA_OK(cudaMemcpy(h->dv.tsflux, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
-  }
+  if (tsflux)
+    for (int m = 0; m < M; m++) IO(cg_sync_from_host(h, "tsflux", m, tsflux + (size_t)m * 2 * ij, (int64_t)(2 * ij)));
   return CG_OK;
 }
 extern "C" int cg_tracer_step(cg_handle *h, int nsteps) {

@@ -150,7 +150,7 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
     AL1(evap, ij); AL1(fxsw, ij); AL1(fxplw, ij); AL1(fx0a, ij); AL1(fx0o, ij); AL1(fxsen, ij); AL1(fxlata, ij);
     AL1(fxlw, ij); AL1(qb, ij); AL1(qbsic, ij); AL1(fx0sic, ij); AL1(fx0neto_eb, ij); AL1(evapsic, ij);
     AL1(tsfreez, ij); AL1(qsata, ij); AL1(qsato, ij); AL1(q_pa, ij); AL1(rq_pa, ij);
-    AL1(solfor, (long)J * o->nyear); AL1(us_dztau, 2 * ij); AL1(us_dztav, 2 * ij);
+    AL1(solfor, (long)J * o->nyear + 1); AL1(us_dztau, 2 * ij); AL1(us_dztav, 2 * ij);
     AL1(eb_tau, 2 * ij); AL1(eb_dztau, 2 * ij); AL1(eb_dztav, 2 * ij);
     /* sea ice */
     AL1(varice, 2 * ij); AL1(varice1, 2 * ij); AL1(dtha, 2 * ij); AL1(sic_u, 2L * (I + 1) * (J + 1));
@@ -186,7 +186,12 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
     for (p = 0; p < I * (J + 1); p++)
       if (psiles[p] > (double)o->isles) o->isles = (int)psiles[p];
     o->isles = o->isles - 1;
-    if (o->isles < 1 || npaths < o->isles) { fprintf(stderr, "cgo: need >=1 island + paths\n"); return NULL; }
+    {
+      double tro = 0.0;
+      parse_kv(params, "tracer_only", &tro);
+      if (tro != 0.0) o->isles = 0;  /* stand-alone tracer step on a synthetic grid: no barotropic/island set-up */
+      else if (o->isles < 1 || npaths < o->isles) { fprintf(stderr, "cgo: need >=1 island + paths\n"); return NULL; }
+    }
     isl = o->isles;
     o->npi = cgo_ialloc(o, "npi", isl + 2);
     o->lpisl = cgo_ialloc(o, "lpisl", (long)o->mpi * isl);
@@ -208,8 +213,10 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
   }
   /* genie.f90:79-82 order: ocean, atmosphere, sea ice */
   cgo_goldstein_init(o);
-  cgo_embm_init(o, taux_u, tauy_u, taux_v, tauy_v, uncep, vncep);
-  cgo_seaice_init(o);
+  if (taux_u) {
+    cgo_embm_init(o, taux_u, tauy_u, taux_v, tauy_v, uncep, vncep);
+    cgo_seaice_init(o);
+  }
   o->istep_ocn = 0; o->istep_atm = 0; o->istep_sic = 0; o->koverall = 0;
   return o;
 }

@@ -965,7 +965,7 @@ void cgo_goldstein_init(cgo_t *o) {
         TS1(l, NI + 1, j, k) = TS(l, 1, j, k);
       }
     }
-  invert(o);
+  if (o->isles > 0) invert(o);
   for (isol = 1; isol <= o->isles; isol++) {
     for (j = 0; j <= NJ; j++)
       for (i = 1; i <= NI; i++) {

@@ -55,13 +55,29 @@ def load_inputs(world):
 
 
 class Oracle:
-    """One ensemble member of the CPU restatement."""
+    """One ensemble member of the CPU restatement.  world=None + k1=(maxj+2, maxi+2) file-order array gives a
+    stand-alone tracer-step oracle on a synthetic grid (no atmosphere, no barotropic set-up)."""
 
-    def __init__(self, world="worbe2", **params):
+    def __init__(self, world="worbe2", k1=None, **params):
         self.L = lib()
+        keep = []
+        if world is None:
+            params = dict(params, tracer_only=1)
+            kv = "".join("%s=%r\n" % (k, float(v)) for k, v in params.items())
+            k1 = np.ascontiguousarray(k1, dtype=np.int32)
+            I, J = int(params["maxi"]), int(params["maxj"])
+            ps = np.zeros((J + 1) * I)
+            npi = np.zeros(1, dtype=np.int32)
+            keep += [k1, ps, npi]
+            self.h = self.L.cgo_create(kv.encode(), k1.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p), 0,
+                                       npi.ctypes.data_as(C.c_void_p), None, None, None, None, None, None, None)
+            if not self.h:
+                raise RuntimeError("cgo_create failed")
+            self.params = params
+            self._keep = keep
+            return
         inp = load_inputs(world)
         kv = "".join("%s=%r\n" % (k, float(v)) for k, v in params.items())
-        keep = []
 
         def ptr(a, dt):
             a = np.ascontiguousarray(a, dtype=dt)

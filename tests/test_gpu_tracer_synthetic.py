@@ -1,0 +1,136 @@
+"""BASELINE config #5 (synthetic grid, many tracers) through the stand-alone tracer-step entry points
+cg_tracer_create/set/step/get: parity against the oracle at a size the oracle finishes in seconds, and
+size-independent properties at the full 128x128x32, 40-tracer size."""
+import numpy as np
+import pytest
+
+from cgenie_b200 import TracerStep
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def make_k1(I, J, K, rough):
+    """k1(j, i) over (0:J+1, 0:I+1): land rows at both ends, a 2-cell polar land cap; optionally a seamount + island."""
+    k1 = np.ones((J + 2, I + 2), dtype=np.int32)
+    k1[0, :] = 94
+    k1[J + 1, :] = 92
+    k1[J - 1:J + 1, :] = 92
+    if rough:
+        jj, ii = np.meshgrid(np.arange(J + 2), np.arange(I + 2), indexing="ij")
+        bump = (K // 2) * np.exp(-((ii - I // 3) ** 2 + (jj - J // 2) ** 2) / 9.0)
+        k1[1:J - 1, 1:I + 1] = np.clip(1 + bump[1:J - 1, 1:I + 1].astype(int), 1, K)
+        k1[J // 3:J // 3 + 2, 2 * I // 3:2 * I // 3 + 3] = 93          # an island
+        k1[2:4, 3:6] = K                                              # a one-level shelf
+    k1[:, 0] = k1[:, I]
+    k1[:, I + 1] = k1[:, 1]
+    return k1
+
+
+def make_fields(ts_obj, k1, I, J, K, L, M, seed=0, rigid_lid=False):
+    """Smooth tracers, stratified T/S, velocities from a stream function plus a divergent part whose w
+    follows from continuity exactly as velc computes it (goldstein.f90:3668-3678)."""
+    c, cv, ds, dz = ts_obj.const("c"), ts_obj.const("cv"), ts_obj.const("ds"), ts_obj.const("dz")
+    sc = ts_obj.const("scalars")
+    dphi, rdphi = sc[0], sc[1]
+    rng = np.random.default_rng(seed)
+    kk, jj, ii = np.meshgrid(np.arange(K + 2), np.arange(J + 2), np.arange(I + 2), indexing="ij")
+    ts = np.zeros((M, K + 2, J + 2, I + 2, L))
+    for m in range(M):
+        ts[m, ..., 0] = 2.0 + 18.0 * (kk / (K + 1.0)) ** 2 + 1.5 * np.cos(2 * np.pi * ii / I) * np.sin(np.pi * jj / J) + 0.1 * m
+        ts[m, ..., 1] = 0.3 * np.sin(2 * np.pi * ii / I + 0.3 * m) * (kk / (K + 1.0)) - 0.1 * np.cos(np.pi * jj / J)
+        for l in range(2, L):
+            ts[m, ..., l] = 1.0 + 0.1 * np.sin(2 * np.pi * ii / I) * np.cos(np.pi * jj / J) * (kk / K) * (1 + l / L) + 0.01 * m
+        # a statically unstable patch so that convection runs
+        ts[m, K - 1:K + 1, J // 4:J // 4 + 3, I // 2:I // 2 + 4, 0] = 1.0
+    ts[:, K + 1] = 0.0
+    ts[:, K + 1, 1:J + 1, 1:I + 1, 0] = 1.0e-3 * rng.standard_normal((J, I))   # surface flux slab for T
+    ts[:, :, :, 0, :] = ts[:, :, :, I, :]
+    ts[:, :, :, I + 1, :] = ts[:, :, :, 1, :]
+    u = np.zeros((M, K, J + 1, I + 1, 3))
+    psi = np.zeros((K + 1, J + 1, I + 1))
+    for k in range(1, K + 1):
+        psi[k] = 0.02 * (k / K) * np.sin(np.pi * np.minimum(np.arange(J + 1), J - 2) / (J - 2))[:, None] ** 2 * (1 + 0.5 * np.sin(2 * np.pi * np.arange(I + 1) / I))[None, :]
+    # divergent part: with rigid_lid its thickness-weighted column integral vanishes (flat bottom), so w = 0 at the
+    # surface and a uniform tracer must stay uniform
+    prof = np.arange(K + 1) / K
+    if rigid_lid:
+        prof = prof - (prof[1:] * dz[1:K + 1]).sum() / dz[1:K + 1].sum()
+    for k in range(1, K + 1):
+        for j in range(1, J + 1):
+            for i in range(1, I + 1):
+                if k >= max(k1[j, i], k1[j, i + 1]):
+                    u[:, k - 1, j, i, 0] = -c[j] * (psi[k, j, i] - psi[k, j - 1, i]) / ds[j] + 0.003 * np.sin(2 * np.pi * i / I) * prof[k]
+                if j < J and k >= max(k1[j, i], k1[j + 1, i]):
+                    u[:, k - 1, j, i, 1] = (psi[k, j, i] - psi[k, j, i - 1]) * rdphi / cv[j]
+    u[:, :, :, 0, 0] = u[:, :, :, I, 0]
+    for j in range(1, J + 1):
+        for i in range(1, I + 1):
+            if k1[j, i] <= K:
+                w = 0.0
+                for k in range(k1[j, i], K):
+                    tv1 = (u[0, k - 1, j, i, 0] - u[0, k - 1, j, i - 1, 0]) * rdphi / c[j]
+                    tv2 = (u[0, k - 1, j, i, 1] * cv[j] - u[0, k - 1, j - 1, i, 1] * cv[j - 1]) / ds[j]
+                    w = w - dz[k] * (tv1 + tv2)
+                    u[:, k - 1, j, i, 2] = w
+    return ts, u
+
+
+@pytest.mark.parametrize("variant", ["strict", "fast"])
+def test_synthetic_grid_parity(built, variant):
+    I, J, K, L, M = 24, 20, 10, 5, 3
+    k1 = make_k1(I, J, K, rough=True)
+    t = TracerStep(I, J, K, L, k1, n_members=M, diff1=2000.0, diff2=1e-5, nyear=96)
+    ts, u = make_fields(t, k1, I, J, K, L, M)
+    t.set(ts=ts, u=u, tsflux=ts[:, K + 1, 1:J + 1, 1:I + 1, :2])
+    t.set_tracer_variant(variant)
+    t.step(2)
+    got_ts, got_rho, got_cost = t.fetch()
+    for m in range(M):
+        o = Oracle(world=None, k1=k1[::-1], maxi=I, maxj=J, maxk=K, maxl=L, nyear=96, diff1=2000.0, diff2=1e-5)
+        o.f("ts")[:] = ts[m].ravel()
+        o.f("ts1")[:] = ts[m].ravel()
+        o.f("u")[:] = u[m].ravel()
+        rho = o.f("rho").reshape(K + 1, J + 2, I + 2)
+        tt, ss = ts[m, :K + 1, :, :, 0], ts[m, :K + 1, :, :, 1]
+        rho[:] = o.s("ec1") * tt + o.s("ec2") * ss + o.s("ec3") * (tt * tt) + o.s("ec4") * (tt * tt * tt)
+        o.call("tstepo")
+        o.call("tstepo")
+        ref = o.f("ts").reshape(K + 2, J + 2, I + 2, L)[1:K + 1, 1:J + 1, 1:I + 1, :]
+        wet = (k1[None, 1:J + 1, 1:I + 1] <= np.arange(1, K + 1)[:, None, None])
+        if variant == "strict":
+            assert np.array_equal(got_ts[m][wet], ref[wet]), np.abs(got_ts[m][wet] - ref[wet]).max()
+            assert np.array_equal(got_cost[m], o.f("cost").reshape(J, I))
+        else:
+            err = np.max(np.abs(got_ts[m][wet] - ref[wet]) / np.maximum(np.abs(ref[wet]), 1e-3))
+            print("member %d fast-vs-oracle max rel err %.3e" % (m, err))
+            assert err <= 2e-10
+        assert o.f("cost").sum() > 0
+    t.close()
+
+
+def test_config5_full_size_properties(built):
+    """128 x 128 x 32, 40 tracers (BASELINE config #5): uniform tracer stays uniform, inventories are
+    conserved without surface flux, and identical members stay bit-identical."""
+    I, J, K, L, M = 128, 128, 32, 40, 2
+    k1 = make_k1(I, J, K, rough=False)
+    t = TracerStep(I, J, K, L, k1, n_members=M, diff1=2000.0, diff2=1e-5, nyear=96)
+    ts, u = make_fields(t, k1, I, J, K, L, 1, rigid_lid=True)
+    ts = np.repeat(ts, M, axis=0)
+    u = np.repeat(u, M, axis=0)
+    ts[..., 5] = 1.0                      # a uniform passive tracer
+    ts[:, K + 1] = 0.0                    # no surface flux
+    t.set(ts=ts, u=u, tsflux=np.zeros((M, J, I, 2)))
+    ds, dz = t.const("ds"), t.const("dz")
+    wgt = ds[1:J + 1][None, :, None] * dz[1:K + 1][:, None, None] * (k1[None, 1:J + 1, 1:I + 1] <= np.arange(1, K + 1)[:, None, None])
+    before = (ts[0, 1:K + 1, 1:J + 1, 1:I + 1, :] * wgt[..., None]).sum((0, 1, 2))
+    t.set_tracer_variant("fast")
+    t.step(3)
+    got, rho, cost = t.fetch()
+    after = (got[0] * wgt[..., None]).sum((0, 1, 2))
+    wet = wgt > 0
+    assert np.abs(got[0][..., 5][wet] - 1.0).max() < 1e-11
+    assert np.all(np.abs(after - before) <= 1e-11 * np.maximum(np.abs(before), 1e-3))
+    assert np.array_equal(got[0], got[1])
+    assert np.isfinite(got).all()
+    t.close()
