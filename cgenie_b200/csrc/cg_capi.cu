@@ -31,6 +31,8 @@ int launch_seaice(const Dev &, cudaStream_t);
 int launch_gold_pre(const Dev &, cudaStream_t);
 int launch_momentum(const Dev &, int fast, const double *bf, const double *bb, const double *rd, cudaStream_t);
 void launch_global_means(const Dev &, double *out, cudaStream_t);
+int launch_tracercoupling(const Dev &, cudaStream_t);
+int launch_bg_reset_cost(const Dev &, cudaStream_t);
 void launch_health(const Dev &, int *flags, cudaStream_t);
 
 // member <-> Fortran-shaped staging (gather/scatter one member of a [..][m] field)
@@ -404,6 +406,48 @@ static int build_device(cg_handle *h) {
   reg_field(h, "u1", v.u1, {2, I, J, K}, {1, 2, 2LL * I, 2LL * I * J});
   reg_field(h, "cost", v.cost, {I, J}, {1, I});
   reg_field(h, "tsflux", v.tsflux, {2, I, J}, {(long long)ij, 1, I});
+  if (L > 2) {
+    // BIOGEM tracer coupling state (sub_init_phys_ocn, biogem_data.f90:1098-1137; ts->ocn offsets biogem.f90:283-285)
+    const double pi_bg = 3.141592653589793, rEarth = 6.37e6, m3_kg = 1027.649;
+    std::vector<double> V(ijk, 0.0), Mm(ijk * MS, 0.0), rMm(ijk * MS, 0.0);
+    std::vector<int> cols;
+    for (int i = 1; i <= I; i++)
+      for (int j = 1; j <= J; j++)
+        if (g.k1at(i, j) <= K) {
+          cols.push_back((i - 1) + I * (j - 1));
+          for (int k = g.k1at(i, j); k <= K; k++) {
+            const double dD = kDsc * g.dz[k];
+            const double A = 2.0 * pi_bg * (rEarth * rEarth) * (1.0 / I) * (g.sv[j] - g.sv[j - 1]);
+            const size_t c = cell3(I, J, i, j, k);
+            V[c] = dD * A;
+            const double M0 = m3_kg * V[c], rM0 = 1.0 / M0;
+            for (int m = 0; m < MS; m++) { Mm[c * MS + m] = M0; rMm[c * MS + m] = rM0; }
+          }
+        }
+    // total volume in the reference's order: per-column sums over k, then over columns (biogem.f90:1934-1941)
+    double totV = 0.0;
+    for (int c2 : cols) {
+      const int i = c2 % I + 1, j = c2 / I + 1;
+      double sV = 0.0;
+      for (int k = g.k1at(i, j); k <= K; k++) sV = sV + V[cell3(I, J, i, j, k)];
+      totV = totV + sV;
+    }
+    v.bg_rtot_V = 1.0 / totV;
+    if (cols.empty()) cols.push_back(0);
+    { double *q; TRY(dupload(h, &q, V)); v.bg_V = q; }
+    TRY(dupload(h, &v.bg_M, Mm));
+    TRY(dupload(h, &v.bg_rM, rMm));
+    { int *q; TRY(dupload(h, &q, cols)); v.bgcols = q; }
+    TRY(dalloc(h, &v.bg_ocn, ijk * L * MS));
+    TRY(dalloc(h, &v.bg_vdocn, ijk * L * MS));
+    TRY(dalloc(h, &v.bg_part, (size_t)2 * L * std::max(v.nwet, 1) * MS));
+    TRY(dalloc(h, &v.bg_tot, (size_t)2 * L * MS));
+    reg_field(h, "ocn", v.bg_ocn, {L, I, J, K}, {1, L, (long long)L * I, (long long)L * I * J});
+    reg_field(h, "vdocn", v.bg_vdocn, {L, I, J, K}, {1, L, (long long)L * I, (long long)L * I * J});
+    reg_field(h, "bg_M", v.bg_M, {I, J, K}, {1, I, (long long)I * J});
+    reg_field(h, "bg_rM", v.bg_rM, {I, J, K}, {1, I, (long long)I * J});
+    h->hconst["bg_V"] = V;
+  }
   TRY(dalloc(h, &h->d_meantemp, MS));
   TRY(dalloc(h, &h->d_means, (size_t)MS * L));
   TRY(dalloc(h, &h->d_flags, MS));
@@ -932,8 +976,42 @@ extern "C" int cg_goldstein_step(cg_handle *h, int istep, const cg_goldstein_io 
 
 extern "C" int cg_biogem_forcing(cg_handle *h, int64_t) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
 extern "C" int cg_biogem_step(cg_handle *h, double, int64_t) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
-extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *, double *) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
-extern "C" int cg_biogem_climate(cg_handle *h) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
+// biogem_tracercoupling(go_ts, go_ts1), biogem.f90:1885-1890.  Host arrays are optional (NULL = resident).
+extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_ts1) {
+  if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  if (h->g.L <= 2 || !h->dv.bg_ocn) return fail(CG_ERR_CONFIG, "tracer coupling needs biogeochemical tracers (maxl > 2)");
+  activate(h);
+  if (go_ts) IO(cg_sync_from_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
+  { ProfScope ps(h, "biogem"); ps.done(launch_tracercoupling(h->dv, h->stream)); }
+  IO(check_async(h));
+  if (go_ts) IO(cg_sync_to_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
+  if (go_ts1) IO(cg_sync_to_host(h, "ts", h->io_member, go_ts1, cg_field_size(h, "ts")));
+  return CG_OK;
+}
+// biogem_climate, biogem.f90:2132-2239: the physics it copies (u, rho, sea ice, winds, cost, MLD) is aliased
+// in place on the device; the only state change on this path is the reset of the convection counter (:2238).
+extern "C" int cg_biogem_climate(cg_handle *h) {
+  if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  activate(h);
+  { ProfScope ps(h, "biogem"); ps.done(launch_bg_reset_cost(h->dv, h->stream)); }
+  return check_async(h);
+}
+// (re)build BIOGEM's ocn from the current ts: T in K, S absolute, tracers as they are (initialise_biogem)
+extern "C" int cg_biogem_init_ocn(cg_handle *h) {
+  if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  if (h->g.L <= 2 || !h->dv.bg_ocn) return fail(CG_ERR_CONFIG, "needs biogeochemical tracers (maxl > 2)");
+  const int I = h->g.I, J = h->g.J, K = h->g.K, L = h->g.L;
+  std::vector<double> t((size_t)L * I * J * K);
+  for (int m = 0; m < h->M; m++) {
+    IO(cg_sync_to_host(h, "ts", m, t.data(), (int64_t)t.size()));
+    for (size_t c = 0; c < (size_t)I * J * K; c++) {
+      t[c * L] = t[c * L] + 273.15;
+      t[c * L + 1] = t[c * L + 1] + h->mp[m].saln0;
+    }
+    IO(cg_sync_from_host(h, "ocn", m, t.data(), (int64_t)t.size()));
+  }
+  return CG_OK;
+}
 extern "C" int cg_atchem_step(cg_handle *h, double) { (void)h; return fail(CG_ERR_CONFIG, "ATCHEM kernels are not built yet"); }
 
 // One ocean cycle = kocn_loop iterations of the koverall loop when katm_loop == 1 and

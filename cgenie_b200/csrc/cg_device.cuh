@@ -82,6 +82,13 @@ struct Dev {
   double *varice, *varice1;  // [2][j][i][m]
   double *waterflux_ocn, *conductflux_ocn;
   double *q_pa, *rq_pa;
+  // BIOGEM tracer coupling (biogem.f90:1885-2077)
+  double *bg_ocn, *bg_vdocn;   // [k][j][i][l][m] BIOGEM-unit tracers and the step anomaly
+  double *bg_M, *bg_rM;        // [k][j][i][m] cell mass and reciprocal (rescaled by the salinity ratio per member)
+  const double *bg_V;          // [k][j][i] cell volume (member independent)
+  const int *bgcols;           // wet columns in BIOGEM order (i outer, j inner), 0-based (i-1)+I*(j-1)
+  double *bg_part, *bg_tot;    // reduction scratch: [q][n][m] partial sums, [q][m] totals
+  double bg_rtot_V;
   int *istep_ocn;            // device-resident ocean step counter (read by graph-replayed kernels)
   MemberP p;
 };

@@ -180,6 +180,19 @@ class Ensemble(_Base):
         """goldstein_wrapper (:122-151)."""
         self._ck(self.L.cg_goldstein_step(self.h, self.istep_ocn, io))
 
+    def biogem_init_ocn(self):
+        """Build BIOGEM's ocn from the current ts (initialise_biogem, biogem.f90:283-285)."""
+        self._ck(self.L.cg_biogem_init_ocn(self.h))
+
+    def biogem_tracercoupling(self, go_ts=None, go_ts1=None):
+        """biogem_tracercoupling_wrapper (genie_loop_wrappers.f90:318-322)."""
+        self._ck(self.L.cg_biogem_tracercoupling(self.h, _dp(go_ts) if go_ts is not None else None,
+                                                  _dp(go_ts1) if go_ts1 is not None else None))
+
+    def biogem_climate(self):
+        """biogem_climate_wrapper (genie_loop_wrappers.f90:324-345); resets the convection counter."""
+        self._ck(self.L.cg_biogem_climate(self.h))
+
     def run(self, n_koverall):
         """n iterations of the genie.f90 main loop entirely on the device."""
         self._ck(self.L.cg_run(self.h, int(n_koverall)))

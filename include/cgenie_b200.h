@@ -104,6 +104,8 @@ int cg_biogem_forcing(cg_handle *, int64_t genie_clock_ms);
 int cg_biogem_step(cg_handle *, double dts, int64_t genie_clock_ms);
 int cg_biogem_tracercoupling(cg_handle *, double *go_ts, double *go_ts1);
 int cg_biogem_climate(cg_handle *);
+/* (re)build BIOGEM's ocn array from the current ts (initialise_biogem, biogem.f90:283-285: T in K, S absolute) */
+int cg_biogem_init_ocn(cg_handle *);
 int cg_atchem_step(cg_handle *, double dts);
 
 /* ---- whole coupling loop on the device -------------------------------- */

@@ -66,6 +66,9 @@ void cgo_tstepo_flux(cgo_t *);
 void cgo_co(cgo_t *);
 void cgo_momentum(cgo_t *);       /* wind..velc of step_goldstein :198-233 */
 void cgo_tstipa(cgo_t *);
+/* BIOGEM: biogem_tracercoupling_wrapper (genie_loop_wrappers.f90:318-322); cgo_biogem_init builds ocn from ts */
+void cgo_biogem_init(cgo_t *);
+void cgo_biogem_tracercoupling(cgo_t *);
 
 /* run n iterations of the genie.f90 koverall loop (one EMBM step each) */
 void cgo_run(cgo_t *, long nkoverall);

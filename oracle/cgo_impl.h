@@ -113,6 +113,9 @@ struct cgo {
   double dtsic, sic_rdtdim, diffsic;
   double *varice, *varice1, *dtha, *sic_u;
 
+  /* ---------------- BIOGEM (tracer coupling) ---------------- */
+  double *bg_ocn, *bg_vdocn, *bg_M, *bg_rM, *bg_V;
+
   /* ---------------- coupling arrays (genie_global) ---------------- */
   double *tstar_ocn, *sstar_ocn, *ustar_ocn, *vstar_ocn, *albedo_ocn;
   double *tstar_atm, *qstar_atm, *hght_sic, *frac_sic, *temp_sic, *albd_sic;
@@ -180,6 +183,7 @@ void cgo_embm_init(cgo_t *o, const double *taux_u, const double *tauy_u,
                    const double *taux_v, const double *tauy_v,
                    const double *uncep, const double *vncep);
 void cgo_seaice_init(cgo_t *o);
+void cgo_biogem_init(cgo_t *o);
 void cgo_eos(const cgo_t *o, double t, double s, double z, double *rho);
 void cgo_reg(cgo_t *o, const char *name, double *p, long n);
 void cgo_ireg(cgo_t *o, const char *name, int *p, long n);

@@ -31,7 +31,8 @@ def lib():
         L.cgo_create.argtypes = [C.c_char_p] + [P] * 2 + [C.c_int] + [P] * 8
         L.cgo_destroy.argtypes = [P]
         for f in ("cgo_surflux", "cgo_embm_step", "cgo_seaice_step", "cgo_goldstein_step", "cgo_tstepo",
-                  "cgo_tstepo_flux", "cgo_co", "cgo_momentum", "cgo_tstipa", "cgo_biogem_step_all"):
+                  "cgo_tstepo_flux", "cgo_co", "cgo_momentum", "cgo_tstipa", "cgo_biogem_init",
+                  "cgo_biogem_tracercoupling"):
             if hasattr(L, f):
                 getattr(L, f).argtypes = [P]
                 getattr(L, f).restype = None

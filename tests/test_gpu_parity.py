@@ -265,3 +265,50 @@ def test_tracer_step_conserves_inventory_full_size(built, tmp_path, spun):
             print(variant, "inventory drift", drift)
             assert drift < 1e-12
         assert np.allclose(after, after[:1], rtol=0, atol=0)  # identical members stay identical
+
+
+def test_biogem_tracercoupling_bit_exact(built, tmp_path):
+    """biogem_tracercoupling (biogem.f90:1885-2077): salinity normalisation + per-tracer global inventories.
+    The device sums in the reference's order (k ascending per column, columns i-outer/j-inner) -> bit-exact.
+    Members carry different saln0-independent states (different step counts) to catch lane mix-ups."""
+    cfg, okw = CFG["B"]
+    I = J = 36
+    K, L = okw["maxk"], okw["maxl"]
+    materialise(str(tmp_path), cfg)
+    oracles = []
+    for m, nk in enumerate((100, 150)):
+        o = Oracle(**okw)
+        o.run(nk)
+        add_passive_tracers(o, seed=m)
+        o.call("biogem_init")
+        o.run(25)                      # 5 ocean steps move ts away from ocn
+        rng = np.random.default_rng(10 + m)
+        o.f("vdocn")[:] = 1e-3 * rng.standard_normal(o.f("vdocn").size)
+        oracles.append(o)
+    with Ensemble(str(tmp_path), n_members=2) as e:
+        for m, o in enumerate(oracles):
+            inject(e, o, m)
+            e.put("ocn", o.f("ocn"), m)
+            e.put("vdocn", o.f("vdocn"), m)
+        e.biogem_tracercoupling()
+        got = [(e.get("ts", m), e.get("ocn", m), e.get("bg_M", m), e.get("bg_rM", m)) for m in range(2)]
+        # a second call (M, rM now rescaled) and the host-array form of the call
+        ts_host = got[0][0].copy()
+        e.biogem_tracercoupling(go_ts=ts_host)
+        second = e.get("ocn", 0)
+        e.biogem_climate()
+        assert np.all(e.get("cost", 0) == 0.0)
+    for (ts, ocn, M, rM), o in zip(got, oracles):
+        before = interior(o, "ts").copy()
+        o.call("biogem_tracercoupling")
+        k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+        wet = (np.arange(1, K + 1)[:, None, None] >= k1[None]).ravel()
+        wl = np.repeat(wet, L)
+        assert bits_equal(ts[wl], interior(o, "ts")[wl]), np.abs(ts - interior(o, "ts"))[wl].max()
+        assert bits_equal(ocn[wl], o.f("ocn")[wl])
+        assert bits_equal(M[wet], o.f("bg_M")[wet]) and bits_equal(rM[wet], o.f("bg_rM")[wet])
+        assert bits_equal(interior(o, "ts1")[wl], interior(o, "ts")[wl])
+        assert np.abs(ts[wl] - before[wl]).max() > 1e-6        # the coupling did something
+    oracles[0].call("biogem_tracercoupling")
+    assert bits_equal(second[wl], oracles[0].f("ocn")[wl])
+    assert bits_equal(ts_host[wl], interior(oracles[0], "ts")[wl])
