@@ -150,7 +150,7 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
     AL1(evap, ij); AL1(fxsw, ij); AL1(fxplw, ij); AL1(fx0a, ij); AL1(fx0o, ij); AL1(fxsen, ij); AL1(fxlata, ij);
     AL1(fxlw, ij); AL1(qb, ij); AL1(qbsic, ij); AL1(fx0sic, ij); AL1(fx0neto_eb, ij); AL1(evapsic, ij);
     AL1(tsfreez, ij); AL1(qsata, ij); AL1(qsato, ij); AL1(q_pa, ij); AL1(rq_pa, ij);
-    AL1(solfor, (long)J * o->nyear + 1); AL1(us_dztau, 2 * ij); AL1(us_dztav, 2 * ij);
+    AL1(solfor, (long)J * o->nyear); AL1(us_dztau, 2 * ij); AL1(us_dztav, 2 * ij);
     AL1(eb_tau, 2 * ij); AL1(eb_dztau, 2 * ij); AL1(eb_dztav, 2 * ij);
     /* sea ice */
     AL1(varice, 2 * ij); AL1(varice1, 2 * ij); AL1(dtha, 2 * ij); AL1(sic_u, 2L * (I + 1) * (J + 1));
