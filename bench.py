@@ -33,25 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CONFIG = "eb_go_gs_36x36x16_L16"
 WORKLOAD = ("eb_go_gs 36x36x16 worjh2, 16 tracers on ts (T,S + 14 passive; BIOGEM sources not on device yet), "
             "parameter-perturbed ensemble sharded by member (BASELINE config #4 shape: 128 members/GPU)")
-PERTURBED = ["diff1", "diff2", "adrag", "scf", "diffamp1", "diffamp2", "betaz2", "betam2"]
-SEED = 20261017
-
-
-def perturbation_table(n_total):
-    """Member m perturbs each parameter by x U(0.8,1.25); member 0 is the unperturbed control.
-    adrag is perturbed per group of 16 members so that barotropic factorisations are shared."""
-    base = dict(diff1=2000.0, diff2=1.0e-5, adrag=2.5, scf=2.0, diffamp1=5.0e6, diffamp2=1.0e6, betaz2=0.4, betam2=0.4)
-    rng = np.random.default_rng(SEED)
-    tab = {}
-    for k in PERTURBED:
-        f = rng.uniform(0.8, 1.25, size=n_total)
-        if k == "adrag":
-            f = np.repeat(f[::16], 16)[:n_total]
-        f[0] = 1.0
-        if k == "adrag":
-            f[:16] = 1.0
-        tab[k] = base[k] * f
-    return tab
+from cgenie_b200.sharding import PERTURBED, SEED, perturbation_table, shard  # noqa: E402  (pure numpy)
 
 
 def peaks():
@@ -62,6 +44,19 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(members, variant):
+    """dram__bytes_read.sum + dram__bytes_write.sum per tstepo launch (flux + convection kernels) from the committed
+    `ncu --set full` capture of this configuration (profiles/ncu_traffic.json), or None when none was taken."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        for row in json.load(open(p))["captures"]:
+            if row["members"] == members and row["variant"] == variant and row["config"] == CONFIG:
+                return row["dram_bytes_per_tstepo_launch"]
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -80,7 +75,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         self.stop_flag = True
@@ -123,9 +118,9 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    ypc = 0.25  # bounded sample: each step = 0.25 model year of one member on every host core
+    ypc = 4.0  # bounded sample: each step = 4 model years of one member on every host core (~5 s)
     for _ in range(args.warmup):
-        cpu_oracle_rate(0.05, cores)
+        cpu_oracle_rate(0.5, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_oracle_rate(ypc, cores)
@@ -146,7 +141,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--members", type=int, default=128, help="ensemble members per GPU")
     ap.add_argument("--impl", default="b200")
@@ -182,8 +177,7 @@ def main():
 
     from cgenie_b200 import Ensemble, materialise
     M = args.members
-    tab = perturbation_table(M * world)
-    pert = {k: v[rank * M:(rank + 1) * M] for k, v in tab.items()}
+    pert = shard(perturbation_table(M * world), rank, world, M)
     tmp = tempfile.mkdtemp(prefix="cgenie_job_")
     materialise(tmp, CONFIG)
     e = Ensemble(tmp, n_members=M, device=local, perturb=pert)
@@ -222,7 +216,6 @@ def main():
     e.run(kyear)
     e.profile(False)
     fam = {f: e.profile_get(f) for f in ("tstepo_flux", "co", "momentum", "embm", "surflux", "seaice")}
-    n_wet = int((e.iconst("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1] <= K).sum() * 0)  # placeholder, recomputed below
     k1 = e.iconst("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
     n_wet = int(np.sum(np.clip(K - k1 + 1, 0, None)[k1 <= K]))
     bytes_per_launch = n_wet * (16 * L + 32) * M          # B_tr x members of one launch
@@ -231,8 +224,9 @@ def main():
     avg_ms = (t_ms + c_ms) / max(t_n, 1)                   # tstepo = flux + convection (B_tr covers both)
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_tstepo_flux_%s<8> + k_co" % args.variant, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "tstepo = k_tstepo_flux_* + k_co_* (%s variant), SURVEY 8d B_tr" % args.variant,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(M, args.variant), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "family_ms_per_year": {k: v[0] for k, v in fam.items()}}
 
@@ -287,9 +281,9 @@ def main():
     }
     if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rate, wall = cpu_oracle_rate(0.25, cores)
+        rate, wall = cpu_oracle_rate(10.0, cores)
         out["cpu_baseline"] = {"value": rate, "unit": "model-years/hour", "cores": cores, "kind": "port",
-                               "sample": "%d oracle processes (one member per host core) x 0.25 model-year, %.1f s wall" % (cores, wall)}
+                               "sample": "%d oracle processes (one member per host core) x 10 model-years, %.1f s wall" % (cores, wall)}
     e.close()
     if world > 1:
         dist.barrier()

@@ -1,0 +1,21 @@
+#!/bin/bash
+# One GPU-box session: GPU parity tests, the default bench line, the ncu launch list of the same bench command and
+# one `ncu --set full` capture of the two tstepo kernels.  Run as:  gpurun --timeout 1500 -- 'bash tools/gpu_session.sh r1c'
+TAG=${1:-r1}
+OUT=gpurun_out
+mkdir -p $OUT
+nproc > $OUT/nproc_$TAG.txt
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $OUT/smi_$TAG.txt
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1
+tail -3 $OUT/pytest_gpu_$TAG.log
+timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+cat $OUT/bench_$TAG.json
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err
+cat $OUT/bench_ref_$TAG.json
+# launch list of the same command (first launches: build + spin-up year; kernel SHARES are what is compared)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_$TAG.csv \
+  python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu_$TAG.log 2>&1
+# full capture of the tracer kernels at the bench's member count
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_tstepo_flux|k_co_' -s 20 -c 2 \
+  -o $OUT/prof_tstepo_$TAG -f python tools/prof_run.py --members 128 --spin 3 --steps 12 --variant fast > $OUT/prof_full_$TAG.log 2>&1
+ls -la $OUT | tail -12
