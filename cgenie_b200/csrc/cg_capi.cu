@@ -13,6 +13,7 @@
 #include "../../include/cgenie_b200.h"
 #include "cg_device.cuh"
 #include "cg_host.hpp"
+#include "cg_biogem.hpp"
 
 namespace cg {
 // kernels' launchers (k_physics.cu, k_tracer_*.cu, k_biogem.cu)
@@ -33,6 +34,9 @@ int launch_momentum(const Dev &, int fast, const double *bf, const double *bb, c
 void launch_global_means(const Dev &, double *out, cudaStream_t);
 int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
+int launch_bg_step(const Dev &, const BgDev &, int init_only, cudaStream_t);
+int launch_bg_climate(const Dev &, const BgDev &, cudaStream_t);
+int launch_bg_atchem(const Dev &, const BgDev &, double atm_totV, cudaStream_t);
 void launch_health(const Dev &, int *flags, cudaStream_t);
 
 // member <-> Fortran-shaped staging (gather/scatter one member of a [..][m] field)
@@ -119,6 +123,12 @@ struct cg_handle {
   bool profile = false;
   std::map<std::string, ProfFam> prof;
   int io_member = 0;
+  // BIOGEM / ATCHEM
+  BgConfig bg;
+  BgDev bgd;
+  std::vector<double> bg_ocn0;   // initial ocn (device layout), dropped after upload
+  double atm_totV = 0.0;
+  bool bg_go = true;
   ~cg_handle() {
     cudaSetDevice(device);
     for (auto &gv : graph) for (auto &ge : gv) if (ge) cudaGraphExecDestroy(ge);
@@ -250,7 +260,19 @@ extern "C" int cg_create(const char *jobdir, int n_members, int device, cg_handl
   }
   if (h->g.J + 2 > kMaxJ || h->g.K + 2 > kMaxK) return fail(CG_ERR_CONFIG, "grid larger than the compiled metric tables");
   if (h->isl.isles != 1) return fail(CG_ERR_CONFIG, "only single-island topographies (isles == 1) are on the B200 path");
-  if (h->base.flag_biogem) return fail(CG_ERR_CONFIG, "flag_biogem: BIOGEM kernels are not built yet");
+  if (!load_biogem(jobdir, h->base, h->g, &h->bg, &err)) {
+    const bool io = err.find("could not open") != std::string::npos;
+    return fail(io ? CG_ERR_IO : CG_ERR_CONFIG, err);
+  }
+  if (h->bg.on) {  // the perturbable BIOGEM parameters travel with the member parameter sets
+    Namelist nb;
+    std::string e2;
+    if (nb.load(std::string(jobdir) + "/data_BIOGEM", &e2)) {
+      h->base.par_bio_k0_PO4 = nb.num("par_bio_k0_PO4", h->base.par_bio_k0_PO4);
+      h->base.par_bio_remin_POC_eL1 = nb.num("par_bio_remin_POC_eL1", h->base.par_bio_remin_POC_eL1);
+      h->base.par_bio_red_POC_CaCO3 = nb.num("par_bio_red_POC_CaCO3", h->base.par_bio_red_POC_CaCO3);
+    }
+  }
   h->mp.assign(n_members, h->base);
   {
     MemberConsts c0;  // member-0 constants are available without a device (bit-exactness checks)
@@ -313,6 +335,12 @@ extern "C" int cg_initialise(cg_handle *h) {
   // keep leaders' factors for cg_get_const, drop the rest of the heavy host arrays
   h->initialised = true;
   activate(h);
+  if (h->bg.on) {
+    // sub_init_carb (biogem_data.f90:2336-2430) and the biogem_climate call before the main loop (genie.f90:109-112)
+    h->launches += launch_bg_step(h->dv, h->bgd, 1, h->stream);
+    h->bgd.nsol = 0;
+    h->launches += launch_bg_climate(h->dv, h->bgd, h->stream);
+  }
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return CG_OK;
 }
@@ -396,6 +424,43 @@ static int build_device(cg_handle *h) {
       for (size_t q = 0; q < ijk * L; q++) t[q * MS + m] = c.ts0[q];
       for (size_t q = 0; q < ijk; q++) r[q * MS + m] = c.rho0[q];
     }
+    if (h->bg.on) {
+      // initialise_biogem: sub_init_tracer_ocn_comp (biogem_data.f90:1281-1309), sub_biogem_copy_tstoocn (:3745-3763) and
+      // the salinity-normalised copy back to ts, sub_biogem_copy_ocntots (biogem_box.f90:3691-3739)
+      const BgConfig &bc = h->bg;
+      h->bg_ocn0.assign(ijk * L * MS, 0.0);
+      std::vector<double> V(ijk, 0.0);
+      for (int i = 1; i <= I; i++)
+        for (int j = 1; j <= J; j++)
+          for (int k = g.k1at(i, j); k <= K; k++)
+            V[cell3(I, J, i, j, k)] = (kDsc * g.dz[k]) * (2.0 * kBgPi * (kBgREarth * kBgREarth) * (1.0 / I) * (g.sv[j] - g.sv[j - 1]));
+      double totV = 0.0;
+      for (size_t q = 0; q < ijk; q++) totV = totV + V[q];   // SUM(phys_ocn(ipo_V,:,:,:)), array element order
+      for (int m = 0; m < MS; m++) {
+        const double saln0 = h->mp[std::min(m, M - 1)].saln0;
+        double sumSV = 0.0;
+        for (size_t q = 0; q < ijk; q++) {
+          const int k = (int)(q / ij) + 1, jj = (int)((q % ij) / I) + 1, ii = (int)(q % I) + 1;
+          if (k < g.k1at(ii, jj)) continue;
+          double *o = &h->bg_ocn0[(q * L) * MS + m];
+          for (int l = 1; l <= L; l++) {
+            if (bc.otype[l] == 1) o[(size_t)(l - 1) * MS] = bc.ocn_init[l];
+            else if (bc.otype[l] >= 11)
+              o[(size_t)(l - 1) * MS] = bg_iso_fraction(bc.ocn_init[l], bc.otype[l] == 11 ? kBgStd13C : kBgStd14C) * bc.ocn_init[bc.odep[l]];
+          }
+          o[0] = t[(q * L) * MS + m] + kBgZeroC;
+          o[(size_t)MS] = t[(q * L + 1) * MS + m] + saln0;
+        }
+        for (size_t q = 0; q < ijk; q++) sumSV = sumSV + h->bg_ocn0[(q * L + 1) * MS + m] * V[q];
+        const double meanS = sumSV / totV;
+        for (size_t q = 0; q < ijk; q++) {
+          const int k = (int)(q / ij) + 1, jj = (int)((q % ij) / I) + 1, ii = (int)(q % I) + 1;
+          if (k < g.k1at(ii, jj)) continue;
+          const double Sc = h->bg_ocn0[(q * L + 1) * MS + m];
+          for (int l = 3; l <= L; l++) t[(q * L + (l - 1)) * MS + m] = h->bg_ocn0[(q * L + (l - 1)) * MS + m] * (meanS / Sc);
+        }
+      }
+    }
     CUDA_OK(cudaMemcpy(v.ts_cur, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(v.ts_new, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(v.rho, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
@@ -447,6 +512,85 @@ static int build_device(cg_handle *h) {
     reg_field(h, "bg_M", v.bg_M, {I, J, K}, {1, I, (long long)I * J});
     reg_field(h, "bg_rM", v.bg_rM, {I, J, K}, {1, I, (long long)I * J});
     h->hconst["bg_V"] = V;
+  }
+  if (h->bg.on) {
+    const BgConfig &bc = h->bg;
+    BgDev &b = h->bgd;
+    const int LS = bc.LS, LA = bc.LA;
+    bg_fill_tables(bc, h->base, g, &b);
+    if (b.n_lrem >= 8) return fail(CG_ERR_CONFIG, "BIOGEM: too many remineralisation targets for the compiled kernel");
+    CUDA_OK(cudaMemcpy(v.bg_ocn, h->bg_ocn0.data(), h->bg_ocn0.size() * 8, cudaMemcpyHostToDevice));
+    h->bg_ocn0.clear(); h->bg_ocn0.shrink_to_fit();
+    TRY(dalloc(h, &b.bio_part, ijk * LS * MS));
+    TRY(dalloc(h, &b.settle_k1, ij * LS * MS));
+    TRY(dalloc(h, &b.carbH, ij * MS));
+    TRY(dalloc(h, &b.seaice, ij * MS));
+    TRY(dalloc(h, &b.sfxsumatm, ij * LA * MS));
+    TRY(dalloc(h, &b.sfcocn1, ij * L * MS));
+    TRY(dalloc(h, &b.sfxsed1, ij * LS * MS));
+    TRY(dalloc(h, &b.focnatm, ij * LA * MS));
+    TRY(dalloc(h, &b.err, MS));
+    v.bg_biopart = b.bio_part; v.bg_LS = LS;
+    { double *q; TRY(dupload(h, &q, bc.windspeed)); b.wspeed = q; }
+    {
+      std::vector<double> A(ij), rA(ij), aA(ij), aV(ij);
+      // sub_init_phys_ocnatm (biogem_data.f90:1143-1161) and sub_init_phys_atm (atchem_data.f90:195-229)
+      const double th0 = -kBgPi / 2, th1 = kBgPi / 2;
+      const double s0 = std::sin(th0), s1 = std::sin(th1);
+      const double ds = (s1 - s0) / (double)J;
+      for (int j = 1; j <= J; j++)
+        for (int i = 1; i <= I; i++) {
+          const size_t c = cell2(I, i, j);
+          A[c] = 2.0 * kBgPi * (kBgREarth * kBgREarth) * (1.0 / I) * (g.sv[j] - g.sv[j - 1]);
+          rA[c] = 1.0 / A[c];
+          const double svj = s0 + (double)j * ds, svjm = s0 + (double)(j - 1) * ds;
+          aA[c] = 2.0 * kBgPi * (kBgREarth * kBgREarth) * (1.0 / (double)I) * (svj - svjm);
+          aV[c] = 7777.0 * aA[c];   // par_atm_th, atchem_lib.f90:86
+        }
+      h->atm_totV = 0.0;
+      for (size_t c = 0; c < ij; c++) h->atm_totV = h->atm_totV + aV[c];
+      double *q;
+      TRY(dupload(h, &q, A)); b.A = q;
+      TRY(dupload(h, &q, rA)); b.rA = q;
+      TRY(dupload(h, &q, aA)); b.atm_A = q;
+      TRY(dupload(h, &q, aV)); b.atm_V = q;
+    }
+    {
+      // sub_init_tracer_atm_comp (atchem_data.f90:234-261) and the initial cpl_comp_atmocn (genie.f90:87-90)
+      std::vector<double> atm(ij * LA * MS, 0.0), sfc(ij * LA * MS, 0.0);
+      for (int la = 1; la <= LA; la++) {
+        double val = 0.0;
+        if (bc.atype[la] == 0) { if (bc.ia[la] == 1) val = kBgZeroC; }
+        else if (bc.atype[la] == 1) val = bc.atm_init[la];
+        else val = bg_iso_fraction(bc.atm_init[la], bc.atype[la] == 11 ? kBgStd13C : kBgStd14C) * bc.atm_init[bc.adep[la]];
+        for (size_t c = 0; c < ij * MS; c++) {
+          atm[(size_t)(la - 1) * ij * MS + c] = val;
+          if (la >= 3) sfc[(size_t)(la - 1) * ij * MS + c] = val;
+        }
+      }
+      TRY(dupload(h, &b.atm, atm));
+      TRY(dupload(h, &b.sfcatm1, sfc));
+    }
+    {
+      // perturbable parameters and the e-folding table of POC fraction 1 (1 - exp(-dD(k)/eL1)), [k][m]
+      std::vector<double> k0(M), rr(M), f1((size_t)(K + 1) * MS, 0.0);
+      for (int m = 0; m < M; m++) { k0[m] = h->mp[m].par_bio_k0_PO4; rr[m] = h->mp[m].par_bio_red_POC_CaCO3; }
+      for (int m = 0; m < MS; m++)
+        for (int k = 1; k <= K; k++) f1[(size_t)k * MS + m] = (1.0 - std::exp(-b.dD[k] / h->mp[std::min(m, M - 1)].par_bio_remin_POC_eL1));
+      TRY(dparam(h, &b.k0_PO4, k0));
+      TRY(dparam(h, &b.red_POC_CaCO3, rr));
+      { double *q; TRY(dupload(h, &q, f1)); b.POC_f1 = q; }
+    }
+    reg_field(h, "bio_part", b.bio_part, {LS, I, J, K}, {1, LS, (long long)LS * I, (long long)LS * I * J});
+    reg_field(h, "settle_k1", b.settle_k1, {LS, I, J}, {1, LS, (long long)LS * I});
+    reg_field(h, "carbH", b.carbH, {I, J}, {1, I});
+    reg_field(h, "bg_seaice", b.seaice, {I, J}, {1, I});
+    reg_field(h, "atm", b.atm, {LA, I, J}, {(long long)ij, 1, I});
+    reg_field(h, "sfcatm1", b.sfcatm1, {LA, I, J}, {(long long)ij, 1, I});
+    reg_field(h, "sfxsumatm", b.sfxsumatm, {LA, I, J}, {(long long)ij, 1, I});
+    reg_field(h, "focnatm", b.focnatm, {LA, I, J}, {(long long)ij, 1, I});
+    reg_field(h, "sfcocn1", b.sfcocn1, {L, I, J}, {(long long)ij, 1, I});
+    reg_field(h, "sfxsed1", b.sfxsed1, {LS, I, J}, {(long long)ij, 1, I});
   }
   TRY(dalloc(h, &h->d_meantemp, MS));
   TRY(dalloc(h, &h->d_means, (size_t)MS * L));
@@ -974,14 +1118,36 @@ extern "C" int cg_goldstein_step(cg_handle *h, int istep, const cg_goldstein_io 
   return CG_OK;
 }
 
-extern "C" int cg_biogem_forcing(cg_handle *h, int64_t) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
-extern "C" int cg_biogem_step(cg_handle *h, double, int64_t) { (void)h; return fail(CG_ERR_CONFIG, "BIOGEM kernels are not built yet"); }
+// ---- BIOGEM / ATCHEM -------------------------------------------------------------------------------------------
+#define BGREADY(h) do { READY(h); if (!(h)->bg.on) return fail(CG_ERR_CONFIG, "flag_biogem is off in this job"); } while (0)
+static long long nint_ll(double x) { return (long long)(x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5)); }
+
+// biogem_forcing(genie_clock), biogem.f90:2083-2127: time-interpolated restoring targets (host scalars, bit-exact)
+extern "C" int cg_biogem_forcing(cg_handle *h, int64_t genie_clock_ms) {
+  BGREADY(h);
+  bg_forcing(&h->bg, (long long)genie_clock_ms, &h->bgd);
+  return CG_OK;
+}
+// step_biogem(dts, genie_clock, ...), biogem.f90:528-547.  The interface arrays stay on the device
+// ("sfcocn1", "sfxsed1", "sfxsumatm", "focnatm" fields); cpl_flux_ocnatm (atchem.f90:306-320) is fused into the kernel.
+extern "C" int cg_biogem_step(cg_handle *h, double dts, int64_t genie_clock_ms) {
+  BGREADY(h);
+  if (dts != h->bgd.dts) return fail(CG_ERR_ARG, "cg_biogem_step: dts differs from conv_kocn_kbiogem*kocn_loop*genie_timestep");
+  const double t = h->bg.t_runtime - (double)genie_clock_ms / (1000.0 * kBgYrS);
+  if (!h->bg_go) return CG_OK;   // par_misc_t_go (biogem.f90:1851-1853)
+  { ProfScope ps(h, "biogem"); ps.done(launch_bg_step(h->dv, h->bgd, 0, h->stream)); }
+  if (t < kBgNullSmall) h->bg_go = false;
+  return check_async(h);
+}
+// cpl_flux_ocnatm_wrapper (genie_loop_wrappers.f90:178-183): already applied by cg_biogem_step
+extern "C" int cg_cpl_flux_ocnatm(cg_handle *h) { BGREADY(h); return CG_OK; }
 // biogem_tracercoupling(go_ts, go_ts1), biogem.f90:1885-1890.  Host arrays are optional (NULL = resident).
 extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_ts1) {
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
   if (h->g.L <= 2 || !h->dv.bg_ocn) return fail(CG_ERR_CONFIG, "tracer coupling needs biogeochemical tracers (maxl > 2)");
   activate(h);
   if (go_ts) IO(cg_sync_from_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
+  if (h->bg.on && !h->bg_go) return CG_OK;
   { ProfScope ps(h, "biogem"); ps.done(launch_tracercoupling(h->dv, h->stream)); }
   IO(check_async(h));
   if (go_ts) IO(cg_sync_to_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
@@ -993,8 +1159,22 @@ extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_
 extern "C" int cg_biogem_climate(cg_handle *h) {
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
   activate(h);
-  { ProfScope ps(h, "biogem"); ps.done(launch_bg_reset_cost(h->dv, h->stream)); }
+  if (h->bg.on) {
+    // go_solfor of the last surflux call (embm.f90:3727-3729): row MOD(istot-1,nyear)+1 of solfor
+    h->bgd.nsol = h->istep_ocn > 0 ? (h->istep_ocn - 1) % h->g.nyear + 1 : 0;
+    ProfScope ps(h, "biogem");
+    ps.done(launch_bg_climate(h->dv, h->bgd, h->stream));
+  } else {
+    ProfScope ps(h, "biogem");
+    ps.done(launch_bg_reset_cost(h->dv, h->stream));
+  }
   return check_async(h);
+}
+// biogem_climate_sol_wrapper (genie_loop_wrappers.f90:338-342): insolation only
+extern "C" int cg_biogem_climate_sol(cg_handle *h) {
+  BGREADY(h);
+  h->bgd.nsol = h->istep_ocn > 0 ? (h->istep_ocn - 1) % h->g.nyear + 1 : 0;
+  return CG_OK;
 }
 // (re)build BIOGEM's ocn from the current ts: T in K, S absolute, tracers as they are (initialise_biogem)
 extern "C" int cg_biogem_init_ocn(cg_handle *h) {
@@ -1012,7 +1192,28 @@ extern "C" int cg_biogem_init_ocn(cg_handle *h) {
   }
   return CG_OK;
 }
-extern "C" int cg_atchem_step(cg_handle *h, double) { (void)h; return fail(CG_ERR_CONFIG, "ATCHEM kernels are not built yet"); }
+// step_atchem(dts, sfxsumatm, sfcatm), atchem.f90:63-67, with cpl_comp_atmocn (:252-264) fused
+extern "C" int cg_atchem_step(cg_handle *h, double dts) {
+  BGREADY(h);
+  if (dts != h->bgd.dts_atchem) return fail(CG_ERR_ARG, "cg_atchem_step: dts differs from conv_kocn_katchem*kocn_loop*genie_timestep");
+  { ProfScope ps(h, "biogem"); ps.done(launch_bg_atchem(h->dv, h->bgd, h->atm_totV, h->stream)); }
+  return check_async(h);
+}
+// the BIOGEM / ATCHEM block of one koverall iteration (genie.f90:352-447)
+static int do_biogem_block(cg_handle *h, long long k) {
+  const Params &p = h->base;
+  if (!h->bg.on) return CG_OK;
+  const long long clock = k * nint_ll(1000.0 * p.genie_timestep);   // increment_genie_clock, genie_global.f90:401-410
+  if (k % ((long long)p.conv_kocn_kbiogem * p.kocn_loop) == 0) {
+    if (k == (long long)p.conv_kocn_kbiogem * p.kocn_loop) IO(cg_biogem_climate_sol(h));
+    IO(cg_biogem_forcing(h, clock));
+    IO(cg_biogem_step(h, h->bgd.dts, clock));
+    IO(cg_biogem_tracercoupling(h, nullptr, nullptr));
+    IO(cg_biogem_climate(h));
+  }
+  if (k % ((long long)p.conv_kocn_katchem * p.kocn_loop) == 0) IO(cg_atchem_step(h, h->bgd.dts_atchem));
+  return CG_OK;
+}
 
 // One ocean cycle = kocn_loop iterations of the koverall loop when katm_loop == 1 and
 // ksic_loop == kocn_loop (the only schedule tools/config_utils.py:103-162 generates):
@@ -1061,6 +1262,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
       }
       h->koverall += p.kocn_loop;
       n -= p.kocn_loop;
+      IO(do_biogem_block(h, h->koverall));
       continue;
     }
     // general schedule (genie.f90:271-311)
@@ -1070,6 +1272,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
     if (k % p.kocn_loop == 0) IO(do_goldstein(h));
     h->koverall++;
     n--;
+    IO(do_biogem_block(h, h->koverall));
   }
   return check_async(h);
 }

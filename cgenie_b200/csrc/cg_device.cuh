@@ -89,6 +89,8 @@ struct Dev {
   const int *bgcols;           // wet columns in BIOGEM order (i outer, j inner), 0-based (i-1)+I*(j-1)
   double *bg_part, *bg_tot;    // reduction scratch: [q][n][m] partial sums, [q][m] totals
   double bg_rtot_V;
+  double *bg_biopart;          // BIOGEM particulates [k][j][i][ls][m] (rescaled by tracer coupling), NULL without BIOGEM
+  int bg_LS;
   int *istep_ocn;            // device-resident ocean step counter (read by graph-replayed kernels)
   MemberP p;
 };
@@ -101,4 +103,49 @@ __host__ __device__ inline size_t cell2(const int I, int i, int j) { return (siz
 
 #define CG_K1(v, i, j) ((int)(v).k1[(i) + ((v).I + 2) * (j)])
 
+}  // namespace cg
+
+// ---------------------------------------------------------------------------------------------------------------
+// BIOGEM / ATCHEM device view (passed by value next to Dev).  Compact tracer indices as in the reference's
+// conv_iselected_io/is/ia maps (gem_cmn.f90:366-381): l = 1..L ocean, ls = 1..LS particulate, la = 1..LA atmosphere.
+namespace cg {
+constexpr int kBgMaxL = 16, kBgMaxLS = 9, kBgMaxLA = 8, kBgMaxK = 16, kBgMaxRel = 3;
+struct BgDev {
+  int LS, LA;
+  // tracer relationships: conv_ls_lo_i / conv_ls_lo (sed -> ocean, io ascending), DOM <-> POM, atm -> ocean
+  int n_ls_lo[kBgMaxLS + 1], ls_lo[kBgMaxLS + 1][kBgMaxRel];
+  double conv_ls_lo[kBgMaxLS + 1][kBgMaxRel];
+  int dom2pom[kBgMaxL + 1], pom2dom[kBgMaxLS + 1], atm2ocn[kBgMaxLA + 1];
+  int stype[kBgMaxLS + 1], sdep_ls[kBgMaxLS + 1], sdep_id[kBgMaxLS + 1];
+  int atype[kBgMaxLA + 1], aid[kBgMaxLA + 1], adep[kBgMaxLA + 1];
+  int lrem_slot[kBgMaxL + 1], n_lrem;     // ocean tracers that receive remineralisation products -> slot in the local accumulator
+  int l_DIC, l_DIC13, l_DIC14, l_PO4, l_O2, l_ALK, l_DOMC, l_Ca, l_Mg;
+  int s_POC, s_POC13, s_POC14, s_POP, s_CaCO3, s_CaCO313, s_CaCO314, s_POCf2, s_CaCO3f2;
+  int a_CO2, a_CO213, a_CO214;
+  // decay / relaxation factors of this step (host: exp(-dtyr*lambda), 1-exp(-dtyr/tau))
+  double fd_ocn[kBgMaxL + 1], fd_sed[kBgMaxLS + 1], fd_atm[kBgMaxLA + 1], lam_ocn[kBgMaxL + 1], lam_sed[kBgMaxLS + 1],
+      lam_atm[kBgMaxLA + 1], tmod[kBgMaxLA + 1];
+  int rst_active[kBgMaxLA + 1];           // restoring selected and inside the signal interval
+  double rst_target[kBgMaxLA + 1];        // force_restore_atm at wet points (uniform: I = 0, II = 1)
+  double Sc[kBgMaxLA + 1][4], bunsen[kBgMaxLA + 1][6];
+  // parameters
+  double c0_PO4, red_POP_POC, red_DOMfrac, red_RDOMfrac, red_POC_CaCO3_pP, DOMlifetime, POC_frac2, POC_dfrac2, POC_c0frac2,
+      CaCO3_frac2, sinkingrate, remin_k_O2, remin_c0_O2, gastransfer_a, d13C_DIC_Corg_ef, Fgeothermal, solar_constant, dsc;
+  double dts, dtyr, dts_atchem, dtyr_atchem;
+  double Dbot[kBgMaxK + 1], dD[kBgMaxK + 2], Dmid_surf;
+  double CaCO3_f1[kBgMaxK + 1], CaCO3_f2[kBgMaxK + 1], POC_f2[kBgMaxK + 1];   // 1-exp(-dD(k)/eL), host computed
+  const double *POC_f1;                   // [k][m] (par_bio_remin_POC_eL1 is a perturbed parameter)
+  const double *k0_PO4, *red_POC_CaCO3;   // [m]
+  int nsol;                               // solfor row (1-based) of the last biogem_climate call, 0 = none yet
+  // state
+  double *bio_part;                       // [k][j][i][ls][m]
+  double *settle_k1;                      // [j][i][ls][m]   bio_settle at the deepest wet level
+  double *carbH;                          // [j][i][m]       surface [H+], seed of the next pH solve
+  double *seaice;                         // [j][i][m]       snapshot taken by biogem_climate
+  const double *wspeed, *A, *rA;          // [j][i] member independent
+  double *atm, *sfcatm1, *sfxsumatm;      // [la][j][i][m]
+  const double *atm_A, *atm_V;            // [j][i]
+  double *sfcocn1, *sfxsed1, *focnatm;    // interface / diagnostics: [l|ls|la][j][i][m]
+  int *err;                               // [m] carbonate chemistry failure flag (error_stop)
+};
 }  // namespace cg

@@ -109,7 +109,7 @@ bool Params::set(const std::string &n, double v) {
   S(tatm) S(relh0_ocean) S(relh0_land) S(extra1a) S(extra1b) S(extra1c) S(scl_fwf) S(diffa_scl) S(delf2x)
   S(olr_adj0) S(olr_adj) S(t_eqm) S(albedop_offs) S(albedop_amp) S(par_sich_max) S(par_albsic_min)
   S(par_albsic_max) S(radfor_scl_co2) S(radfor_pc_co2_rise) S(diffsic) S(par_sica_thresh) S(par_sich_thresh)
-  S(solconst)
+  S(solconst) S(par_bio_k0_PO4) S(par_bio_remin_POC_eL1) S(par_bio_red_POC_CaCO3)
 #undef S
   return false;
 }

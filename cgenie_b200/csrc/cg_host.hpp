@@ -70,6 +70,8 @@ struct Params {
               v_wspeed = "vncep.silo";
   // data_goldSIC
   double diffsic = 2000.0, par_sica_thresh = 1.0, par_sich_thresh = 1000.0;
+  // data_BIOGEM: the perturbable subset; everything else lives in BgConfig
+  double par_bio_k0_PO4 = 2.0E-06, par_bio_remin_POC_eL1 = 500.0, par_bio_red_POC_CaCO3 = 0.2;
   bool set(const std::string &name, double v);  // per-member override by name
 };
 

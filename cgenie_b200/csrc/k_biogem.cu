@@ -107,6 +107,10 @@ __global__ void __launch_bounds__(128) k_tc_apply(const Dev v) {
       v.bg_ocn[o + (size_t)l * MS] = x;
       v.ts_cur[o + (size_t)l * MS] = (mean_S_NEW / Sn) * x;
     }
+    if (v.bg_biopart) {  // biogem.f90:2042-2043 (vdbio_part = 0: no particulate flux forcing)
+      const size_t q = (cell3(I, J, i, j, k) * v.bg_LS) * MS + m;
+      for (int ls = 0; ls < v.bg_LS; ls++) v.bg_biopart[q + (size_t)ls * MS] = Sratio * (v.bg_biopart[q + (size_t)ls * MS] + 0.0);
+    }
     v.bg_M[p0 + (size_t)(k - 1) * pK] = rSratio * v.bg_M[p0 + (size_t)(k - 1) * pK];
     v.bg_rM[p0 + (size_t)(k - 1) * pK] = Sratio * v.bg_rM[p0 + (size_t)(k - 1) * pK];
   }
@@ -116,6 +120,563 @@ __global__ void __launch_bounds__(128) k_tc_apply(const Dev v) {
 __global__ void k_bg_reset_cost(const Dev v) {
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < (size_t)v.I * v.J * v.MS) v.cost[q] = 0.0;
+}
+
+
+// =============================================================================================================
+// step_biogem (biogem.f90:528-1877) for the frozen configuration: one thread = (member, wet column).  The thread
+// runs the column's decay, closed-system sediment return, DOM and particulate remineralisation
+// (sub_box_remin_DOM/part, biogem_box.f90:2287-2875), then the surface cell's carbonate chemistry
+// (gem_carbchem.f90:59-780), gas exchange (biogem_box.f90:27-299), restoring forcing, biological uptake
+// (sub_calc_bio_uptake :346-1514) and writes the tracer anomaly vdocn (:1811-1844).  No cross-column terms exist
+// inside step_biogem, so the reference's three sweeps over columns collapse into one pass per column; every
+// accumulation keeps the reference's order (see oracle/cgo_biogem.c for the plain restatement).
+// =============================================================================================================
+namespace bgk {
+enum { CC_K1, CC_K2, CC_K, CC_KB, CC_KW, CC_KSI, CC_KHF, CC_KHSO4, CC_KP1, CC_KP2, CC_KP3, CC_KCAL, CC_KARG, CC_QCO2, N_CC };
+struct Carb { double H, co2, co3, hco3, ohm_cal, RF0; };
+constexpr double kZeroC = 273.15, kNull = -0.999999e19, kNS = 0.999999e-19, kYrS = 3600.0 * (24.0 * 365.25);
+constexpr double kAtmMol = 1.7692e+020, kR = 83.145, kRSI = 8.3145, kVmol = 0.022414, kCp = 4.1855, kConcMg = 0.05282,
+                 kConcMgtoCa = 5.155, kStd13C = 0.011202, kStd14C = 1.176e-12, kPaAtm = 1.0 / 1.01325e+05;
+
+__device__ __forceinline__ double iso_delta(double tot, double iso, double standard) {  // gem_util.f90:568-598, allow_negative = F
+  if (tot > kNS) {
+    const double fr = iso / tot;
+    if ((1.0 - fr) > kNS) {
+      const double R = fr / (1.0 - fr);
+      return 1000.0 * (R / standard - 1.0);
+    }
+    return kNull;
+  }
+  return kNull;
+}
+__device__ __forceinline__ double iso_fraction(double delta, double standard) {  // gem_util.f90:604-617
+  const double R = standard * (1.0 + delta / 1000.0);
+  return R / (1.0 + R);
+}
+__device__ __forceinline__ double calc_rho(double T, double S) {  // gem_util.f90:670-682
+  const double TC = T - kZeroC;
+  return 1000.0 + (0.7968 * S - 0.0559 * TC - 0.0063 * (TC * TC) + 3.7315E-05 * ((TC * TC) * TC));
+}
+__device__ __forceinline__ double corr_p(double TC, double P, double rRT, double d1, double d2, double d3, double d4, double d5) {
+  return (-(d1 + d2 * TC + d3 * TC * TC) + (5.0E-4 * (d4 + d5 * TC)) * P) * P * rRT;  // gem_carbchem.f90:1175-1186
+}
+__device__ __forceinline__ double fS(double c, double S) { double x = c * S / 35.0; if (x < kNS) x = kNS; return x; }
+
+// sub_calc_carbconst (Mehrbach) + sub_adj_carbconst, gem_carbchem.f90:59-297; only the constants the surface solve reads
+__device__ void carbconst(double D, double T_in, double S_in, double Ca, double Mg, double *cc) {
+  double T = T_in, S = S_in;
+  if (T < (kZeroC + 2.0)) T = kZeroC + 2.0;
+  if (T > (kZeroC + 35.0)) T = kZeroC + 35.0;
+  if (S < 26.0) S = 26.0;
+  if (S > 43.0) S = 43.0;
+  const double P = D / 10.0;
+  const double S_p05 = pow(S, 0.5), S_p15 = pow(S, 1.5), S_p20 = S * S;
+  const double T_ln = log(T), T_log = log10(T), rT = 1.0 / T, Tr100 = T / 100.0, TC = T - kZeroC;
+  const double rRT = 1.0 / (kR * T);
+  const double Ii = (S > kNS) ? 19.924 * S / (1000.0 - 1.005 * S) : kNS;
+  const double I_p05 = pow(Ii, 0.5), I_p15 = pow(Ii, 1.5), I_p20 = Ii * Ii;
+  double Cl = S_in / 1.80655;
+  if (Cl < kNS) Cl = kNS;
+  const double ION = (Cl > kNS) ? 0.00147 + 0.03592 * Cl + 0.000068 * Cl * Cl : kNS;
+  const double ION_p05 = pow(ION, 0.5);
+  const double m2c = log(1 - 0.001005 * S);
+  const double SO4tot = fS(0.02824, S), Ftot = fS(0.00007, S);
+  const double lnkHSO4 = 141.328 - 4276.1 * rT - 23.093 * T_ln + (324.57 - 13856.0 * rT - 47.986 * T_ln) * I_p05 +
+                         (-771.54 + 35474.0 * rT + 114.723 * T_ln) * Ii - 2698.0 * rT * I_p15 + 1776.0 * rT * I_p20;
+  const double lnkHF = 1590.2 / T - 12.641 + 1.525 * ION_p05;
+  cc[CC_KHSO4] = exp(lnkHSO4 + m2c);
+  const double f2t = log(1.0 + SO4tot / cc[CC_KHSO4]);
+  cc[CC_KHF] = exp(lnkHF + m2c + f2t);
+  const double f2s = log(1.0 + SO4tot / cc[CC_KHSO4] + Ftot / cc[CC_KHF]);
+  const double t2s = -f2t + f2s;
+  cc[CC_K1] = exp(log(pow(10.0, -(3670.7 * rT - 62.008 + 9.7944 * T_ln - 0.0118 * S + 0.000116 * S_p20))) +
+                  corr_p(TC, P, rRT, -2.550E+1, +1.271E-1, +0.000E+0, -3.080E+0, +8.770E-2));
+  cc[CC_K2] = exp(log(pow(10.0, -(1394.7 * rT + 4.777 - 0.0184 * S + 0.000118 * S_p20))) +
+                  corr_p(TC, P, rRT, -1.582E+1, -2.190E-2, +0.000E+0, +1.130E+0, -1.475E-1));
+  cc[CC_K] = cc[CC_K1] / cc[CC_K2];
+  cc[CC_KB] = exp((148.0248 + 137.194 * S_p05 + 1.62247 * S +
+                   (-8966.90 - 2890.51 * S_p05 - 77.942 * S + 1.726 * S_p15 - 0.0993 * S_p20) * rT +
+                   (-24.4344 - 25.085 * S_p05 - 0.2474 * S) * T_ln + 0.053105 * S_p05 * T) +
+                  m2c + t2s + corr_p(TC, P, rRT, -2.948E+1, +1.622E-1, +2.608E-3, -2.840E+0, +0.000E+0));
+  cc[CC_KW] = exp((148.9802 - 13847.26 * rT - 23.6521 * T_ln + (-5.977 + 118.67 * rT + 1.0495 * T_ln) * S_p05 - 0.01615 * S) +
+                  corr_p(TC, P, rRT, -2.002E+1, +1.119E-1, -1.409E-3, -5.130E+0, +7.940E-2));
+  cc[CC_KSI] = exp((117.40 - 8904.2 * rT - 19.334 * T_ln + (3.5913 - 458.79 * rT) * I_p05 + (-1.5998 + 188.74 * rT) * Ii +
+                    (0.07871 - 12.1652 * rT) * Ii * Ii) +
+                   m2c + corr_p(TC, P, rRT, -2.948E+1, +1.622E-1, +2.608E-3, -2.840E+0, +0.000E+0));
+  cc[CC_KHF] = exp(lnkHF + m2c + f2s + corr_p(TC, P, rRT, -9.780E+0, -9.000E-3, -9.420E-4, -3.910E+0, +5.400E-2));
+  cc[CC_KHSO4] = exp(lnkHSO4 + m2c + f2s + corr_p(TC, P, rRT, -1.803E+1, +4.660E-2, +3.160E-4, -4.530E+0, +9.000E-2));
+  cc[CC_KP1] = exp((115.54 - 4576.752 / T - 18.453 * T_ln + (0.69171 - 106.736 / T) * S_p05 + (-0.01844 - 0.65643 / T) * S) +
+                   corr_p(TC, P, rRT, -1.451E+1, +1.211E-1, -3.210E-4, -2.670E+0, +4.270E-2));
+  cc[CC_KP2] = exp((172.1033 - 8814.715 / T - 27.927 * T_ln + (1.3566 - 160.340 / T) * S_p05 + (-0.05778 + 0.37335 / T) * S) +
+                   corr_p(TC, P, rRT, -2.312E+1, +1.758E-1, -2.647E-3, -5.150E+0, +9.000E-2));
+  cc[CC_KP3] = exp((-18.126 - 3070.75 / T + (2.81197 + 17.27039 / T) * S_p05 + (-0.09984 - 44.99486 / T) * S) +
+                   corr_p(TC, P, rRT, -2.657E+1, +2.020E-1, -3.042E-3, -4.080E+0, +7.140E-2));
+  cc[CC_KCAL] = exp(corr_p(TC, P, rRT, -4.876E+1, +5.304E-1, +0.000E+0, -1.176E+1, +3.692E-1)) *
+                pow(10.0, (-171.9065 - 0.077993 * T + 2839.319 * rT + 71.595 * T_log +
+                           (-0.77712 + 0.0028426 * T + 178.34 * rT) * S_p05 - 0.07711 * S + 0.0041249 * S_p15));
+  cc[CC_KARG] = 0.0;  // aragonite saturation is diagnostic only
+  cc[CC_QCO2] = exp(-60.2409 + 93.4517 * (100 * rT) + 23.3585 * log(Tr100) +
+                    S * (0.023517 - 0.023656 * (Tr100) + 0.0047036 * (Tr100 * Tr100)));
+  // sub_adj_carbconst
+  double ratio = 1.0;
+  if (Ca > kNS) ratio = Mg / Ca;
+  cc[CC_KCAL] = cc[CC_KCAL] - 3.655E-8 * (kConcMgtoCa - ratio);
+  cc[CC_K1] = (1.0 + 0.155 * (Mg - kConcMg) / kConcMg) * cc[CC_K1];
+  cc[CC_K2] = (1.0 + 0.422 * (Mg - kConcMg) / kConcMg) * cc[CC_K2];
+}
+// one pass of the implicit [H] loop (gem_carbchem.f90:352-424 / 578-640); H2S, NH4, SiO2 totals are zero here
+__device__ __forceinline__ void carb_iter(double DIC, double ALK, double PO4tot, double Btot, double SO4tot, double Ftot,
+                                          const double *cc, double H, double &co2, double &co3, double &hco3, double &H1, double &H2) {
+  const double H_p2 = H * H, H_p3 = H * H_p2;
+  const double OH = cc[CC_KW] / H;
+  const double H4BO4 = Btot / (1.0 + H / cc[CC_KB]);
+  const double H3SiO4 = 0.0 / (1.0 + H / cc[CC_KSI]);
+  const double HSO4 = SO4tot / (1.0 + cc[CC_KHSO4] / H);
+  const double HF = Ftot / (1.0 + cc[CC_KHF] / H);
+  const double H3PO4 = PO4tot / (1.0 + cc[CC_KP1] / H + (cc[CC_KP1] * cc[CC_KP2]) / H_p2 + (cc[CC_KP1] * cc[CC_KP2] * cc[CC_KP3]) / H_p3);
+  const double HPO4 = PO4tot / (1.0 + H / cc[CC_KP2] + H_p2 / (cc[CC_KP1] * cc[CC_KP2]) + cc[CC_KP3] / H);
+  const double PO4 = PO4tot / (1.0 + H / cc[CC_KP3] + H_p2 / (cc[CC_KP2] * cc[CC_KP3]) + H_p3 / (cc[CC_KP1] * cc[CC_KP2] * cc[CC_KP3]));
+  const double ALK_DIC = ALK - H4BO4 - OH - HPO4 - 2.0 * PO4 - H3SiO4 - 0.0 - 0.0 + H + HSO4 + HF + H3PO4;
+  const double k = cc[CC_K];
+  const double a = 4.0 * ALK_DIC + DIC * k - ALK_DIC * k;
+  const double zed = pow(a * a + 4.0 * (k - 4.0) * (ALK_DIC * ALK_DIC), 0.5);
+  hco3 = (DIC * k - zed) / (k - 4.0);
+  co3 = (ALK_DIC * k - DIC * k - 4.0 * ALK_DIC + zed) / (2.0 * (k - 4.0));
+  co2 = DIC - ALK_DIC + (ALK_DIC * k - DIC * k - 4.0 * ALK_DIC + zed) / (2.0 * (k - 4.0));
+  H1 = cc[CC_K1] * co2 / hco3;
+  H2 = cc[CC_K2] * hco3 / co3;
+}
+// sub_calc_carb + sub_calc_carb_RF0; returns false when the reference sets error_stop
+__device__ bool solve_carb(double DIC, double ALK, double Ca, double PO4tot, double S, const double *cc, Carb &c, bool with_RF0) {
+  const double Btot = fS(0.000416, S), SO4tot = fS(0.02824, S), Ftot = fS(0.00007, S);
+  double H = c.H, H_old, co2, co3, hco3, H1, H2;
+  int n = 1;
+  for (;;) {
+    H_old = H;
+    carb_iter(DIC, ALK, PO4tot, Btot, SO4tot, Ftot, cc, H, co2, co3, hco3, H1, H2);
+    if ((H1 < kNS) || (H2 < kNS)) return false;
+    H = sqrt(H1 * H2);
+    if (fabs(1.0 - H / H_old) < (1.0E-8 / H) * 0.001) {
+      c.co2 = co2; c.co3 = co3; c.hco3 = hco3; c.ohm_cal = Ca * co3 / cc[CC_KCAL]; c.H = H;
+      break;
+    }
+    n = n + 1;
+    if (n > 100) return false;
+  }
+  if (!with_RF0) return true;
+  {
+    const double DIC_RF0 = DIC + 1.0e-6;
+    n = 1;
+    for (;;) {
+      H_old = H;
+      carb_iter(DIC_RF0, ALK, PO4tot, Btot, SO4tot, Ftot, cc, H, co2, co3, hco3, H1, H2);
+      H = sqrt(H1 * H2);
+      if (fabs(1.0 - H / H_old) < 0.001) { c.RF0 = (co2 / c.co2 - 1.0) / (DIC_RF0 / DIC - 1.0); break; }
+      n = n + 1;
+      if ((H1 < kNS) || (H2 < kNS) || (n > 100)) { c.RF0 = 0.0; break; }
+    }
+  }
+  return true;
+}
+// sub_calc_carb_r13C (mult = 1) / r14C (mult = 2): r of CO2(aq) and HCO3-
+__device__ void carb_riso(double T, double DIC, double DICiso, const Carb &c, double mult, double standard, double &rCO2, double &rHCO3) {
+  const double TC = T - kZeroC;
+  const double d = iso_delta(DIC, DICiso, standard);
+  double e_bg, e_dg, e_cg;
+  if (mult == 1.0) { e_bg = -0.1141 * TC + 10.78; e_dg = +0.0049 * TC - 1.31; e_cg = -0.052 * TC + 7.22; }
+  else { e_bg = 2.0 * (-0.1141 * TC + 10.78); e_dg = 2.0 * (+0.0049 * TC - 1.31); e_cg = 2.0 * (-0.052 * TC + 7.22); }
+  const double e_cb = e_cg - e_bg / (1.0 + e_bg * 1.0E-3);
+  const double e_db = e_dg - e_bg / (1.0 + e_bg * 1.0E-3);
+  const double dHCO3 = (d * DIC - (e_db * c.co2 + e_cb * c.co3)) /
+                       ((1.0 + e_db * 1.0E-3) * c.co2 + c.hco3 + (1.0 + e_cb * 1.0E-3) * c.co3);
+  const double dCO2 = e_db + dHCO3 * (1.0 + e_db * 1.0E-3);
+  rCO2 = iso_fraction(dCO2, standard);
+  rHCO3 = iso_fraction(dHCO3, standard);
+}
+__device__ __forceinline__ double redfield_factor(const BgDev &b, double o2) {  // sub_box_remin_redfield, O2 only
+  double loc_k = 0.0;
+  const double O2 = fmax(0.0, o2);
+  double kO2 = O2 / (O2 + b.remin_c0_O2);
+  loc_k = loc_k + b.remin_k_O2 * kO2;
+  if (loc_k < kNS) loc_k = 1.0;
+  if (O2 < kNS) kO2 = 1.0;
+  return b.remin_k_O2 * kO2 / loc_k;
+}
+}  // namespace bgk
+
+constexpr int kBgSlots = 8;  // ocean tracers receiving remineralisation products (DIC, 13C, 14C, PO4, O2, ALK, Ca)
+
+__global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, const int init_only) {
+  using namespace bgk;
+  const int I = v.I, J = v.J, K = v.K, L = v.L, MS = v.MS, LS = b.LS, LA = b.LA;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= MS || n >= v.nwet) return;
+  const int c2 = v.bgcols[n];
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const int k1 = CG_K1(v, i, j);
+  const size_t c2d = cell2(I, i, j);
+  const size_t sK = (size_t)I * J * L * MS, o0 = cell3(I, J, i, j, 1) * L * MS + m;
+  const size_t qK = (size_t)I * J * LS * MS, q0 = cell3(I, J, i, j, 1) * LS * MS + m;
+  const size_t pK = (size_t)I * J * MS, p0 = cell3(I, J, i, j, 1) * MS + m;
+#define OCN_(l, k) v.bg_ocn[o0 + (size_t)((k)-1) * sK + (size_t)((l)-1) * MS]
+#define DOCN_(l, k) v.bg_vdocn[o0 + (size_t)((k)-1) * sK + (size_t)((l)-1) * MS]
+#define PART_(ls, k) b.bio_part[q0 + (size_t)((k)-1) * qK + (size_t)((ls)-1) * MS]
+#define M_(k) v.bg_M[p0 + (size_t)((k)-1) * pK]
+#define RM_(k) v.bg_rM[p0 + (size_t)((k)-1) * pK]
+#define SET1_(ls) b.settle_k1[(c2d * LS + ((ls)-1)) * MS + m]
+  const double dtyr = b.dtyr;
+  const double T = OCN_(1, K), S = OCN_(2, K);
+  double cc[N_CC];
+  Carb cb;
+  if (init_only) {  // sub_init_carb, biogem_data.f90:2336-2430 (surface cell)
+    carbconst(b.Dmid_surf, T, S, OCN_(b.l_Ca, K), OCN_(b.l_Mg, K), cc);
+    cb.H = pow(10.0, -7.8);
+    if (!solve_carb(OCN_(b.l_DIC, K), OCN_(b.l_ALK, K), OCN_(b.l_Ca, K), OCN_(b.l_PO4, K), S, cc, cb, false)) b.err[m] = 1;
+    b.carbH[c2d * MS + m] = cb.H;
+    return;
+  }
+  double lrem[kBgSlots][kBgMaxK + 1];   // loc_bio_remin of sub_box_remin_part
+  double pnew[kBgMaxLS + 1][kBgMaxK + 1];
+  double fsed[kBgSlots];
+  double tprev[kBgMaxLS + 1], tcur[kBgMaxLS + 1], set1[kBgMaxLS + 1];
+  // ---- decay of radioactive particulates (:862-871) and closed-system sediment return (:887-940)
+  for (int ls = 1; ls <= LS; ls++)
+    if (fabs(b.lam_sed[ls]) > kNS)
+      for (int k = k1; k <= K; k++) PART_(ls, k) = b.fd_sed[ls] * PART_(ls, k);
+  for (int q = 0; q < kBgSlots; q++) fsed[q] = 0.0;
+  {
+    const double f = redfield_factor(b, OCN_(b.l_O2, k1));
+    for (int ls = 1; ls <= LS; ls++)
+      for (int r = 0; r < b.n_ls_lo[ls]; r++) {
+        const int q = b.lrem_slot[b.ls_lo[ls][r]];
+        fsed[q] = fsed[q] + (f * b.conv_ls_lo[ls][r]) * SET1_(ls);
+      }
+  }
+  // ---- sub_box_remin_DOM: result straight into vdocn(l,k)
+  for (int k = K; k >= k1; k--) {
+    double ratio;
+    for (int l = 1; l <= L; l++) DOCN_(l, k) = 0.0;
+    for (int ls = 1; ls <= LS; ls++) tcur[ls] = 0.0;
+    if (b.DOMlifetime > dtyr) ratio = dtyr / b.DOMlifetime; else ratio = 1.0;
+    if (OCN_(b.l_DOMC, k) > kNS) {
+      for (int l = 3; l <= L; l++)
+        if (b.dom2pom[l]) {
+          const double x = OCN_(l, k);
+          tcur[b.dom2pom[l]] = tcur[b.dom2pom[l]] + 1.0 * ratio * x;
+          DOCN_(l, k) = DOCN_(l, k) - ratio * x;
+        }
+    }
+    const double f = redfield_factor(b, OCN_(b.l_O2, k));
+    for (int ls = 1; ls <= LS; ls++)
+      for (int r = 0; r < b.n_ls_lo[ls]; r++) {
+        const int lo = b.ls_lo[ls][r];
+        DOCN_(lo, k) = DOCN_(lo, k) + (f * b.conv_ls_lo[ls][r]) * tcur[ls];
+      }
+  }
+  // ---- sub_box_remin_part
+  for (int q = 0; q < kBgSlots; q++)
+    for (int k = 1; k <= K; k++) lrem[q][k] = 0.0;
+  for (int ls = 1; ls <= LS; ls++) {
+    set1[ls] = 0.0;
+    for (int k = 1; k <= K; k++) pnew[ls][k] = 0.0;
+  }
+  {
+    const int klim = (dtyr * b.sinkingrate <= b.dsc) ? k1 : K;
+    for (int k = K; k >= klim; k--) {
+      double part_tot = 0.0;
+      part_tot = part_tot + PART_(b.s_POC, k);
+      part_tot = part_tot + PART_(b.s_CaCO3, k);
+      if (part_tot > kNS) {
+        int min_k;
+        if (k == k1) min_k = k1 - 1;
+        else {
+          const double max_D = b.Dbot[k] + dtyr * b.sinkingrate;
+          min_k = k1 - 1;
+          for (int kk = k - 1; kk >= k1; kk--)
+            if (b.Dbot[kk] > max_D) { min_k = kk; break; }
+        }
+        for (int ls = 1; ls <= LS; ls++) tprev[ls] = PART_(ls, k);
+        // settling flux at the base of the source layer (kk = k)
+        if (k == k1)
+          for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((b.stype[ls] == 9) ? tprev[ls] : M_(k) * tprev[ls]);
+        for (int kk = k - 1; kk >= min_k; kk--) {
+          if (kk >= k1) {
+            const double layerratio = b.dD[kk + 1] / b.dD[kk];
+            const double Ca_f1 = b.CaCO3_f1[kk], Ca_f2 = b.CaCO3_f2[kk];
+            const double Ca_ratio = 1.0 - ((1.0 - tprev[b.s_CaCO3f2]) * Ca_f1 + tprev[b.s_CaCO3f2] * Ca_f2);
+            const double PO_f1 = b.POC_f1[(size_t)kk * MS + m], PO_f2 = b.POC_f2[kk];
+            const double PO_ratio = 1.0 - ((1.0 - tprev[b.s_POCf2]) * PO_f1 + tprev[b.s_POCf2] * PO_f2);
+            for (int ls = 1; ls <= LS; ls++) tcur[ls] = 0.0;
+            if (tprev[b.s_CaCO3f2] > kNS) tcur[b.s_CaCO3f2] = (1.0 - Ca_f2) * tprev[b.s_CaCO3f2] / Ca_ratio;
+            if (tprev[b.s_POCf2] > kNS) tcur[b.s_POCf2] = (1.0 - PO_f2) * tprev[b.s_POCf2] / PO_ratio;
+            for (int ls = 1; ls <= LS; ls++) {
+              const int dep_type = b.stype[b.sdep_ls[ls]];
+              if ((b.sdep_id[ls] == 3) || (b.stype[ls] == 3) || (dep_type == 3)) tcur[ls] = tprev[ls] * layerratio * PO_ratio;
+              else if ((b.sdep_id[ls] == 14) || (b.stype[ls] == 4) || (dep_type == 4)) tcur[ls] = tprev[ls] * layerratio * Ca_ratio;
+            }
+            const double f = redfield_factor(b, OCN_(b.l_O2, kk));
+            for (int ls = 1; ls <= LS; ls++) {
+              const double part_remin = (layerratio * tprev[ls] - tcur[ls]);
+              for (int r = 0; r < b.n_ls_lo[ls]; r++) {
+                const int q = b.lrem_slot[b.ls_lo[ls][r]];
+                lrem[q][kk] = lrem[q][kk] + (f * b.conv_ls_lo[ls][r]) * part_remin;
+              }
+            }
+            if (kk == min_k)
+              for (int ls = 1; ls <= LS; ls++) pnew[ls][kk] = pnew[ls][kk] + tcur[ls];
+            else if (kk == k1)   // kk > min_k = k1-1: flux through the base of the deepest layer
+              for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((b.stype[ls] == 9) ? tcur[ls] : M_(kk) * tcur[ls]);
+            for (int ls = 1; ls <= LS; ls++) tprev[ls] = tcur[ls];
+          }
+        }
+      }
+    }
+  }
+  for (int ls = 1; ls <= LS; ls++) {
+    for (int k = k1; k <= K; k++) PART_(ls, k) = pnew[ls][k];
+    SET1_(ls) = set1[ls];
+  }
+  // ---- surface cell: carbonate chemistry, solubility, piston velocity (:1026-1104)
+  carbconst(b.Dmid_surf, T, S, OCN_(b.l_Ca, K), OCN_(b.l_Mg, K), cc);
+  cb.H = b.carbH[c2d * MS + m];
+  cb.RF0 = 0.0;
+  const double DIC = OCN_(b.l_DIC, K), PO4 = OCN_(b.l_PO4, K);
+  if (!solve_carb(DIC, OCN_(b.l_ALK, K), OCN_(b.l_Ca, K), PO4, S, cc, cb, true)) { b.err[m] = 1; return; }
+  b.carbH[c2d * MS + m] = cb.H;
+  double r13_CO2, r13_HCO3, r14_CO2, r14_HCO3;
+  carb_riso(T, DIC, OCN_(b.l_DIC13, K), cb, 1.0, kStd13C, r13_CO2, r13_HCO3);
+  carb_riso(T, DIC, OCN_(b.l_DIC14, K), cb, 2.0, kStd14C, r14_CO2, r14_HCO3);
+  const double rho = calc_rho(T, S);   // phys_ocn(ipo_rho) as left by biogem_climate (:2171)
+  const double seaice = b.seaice[c2d * MS + m];
+  const double A = b.A[c2d], rA = b.rA[c2d];
+  double focn_surf[kBgMaxL + 1];        // locijk_focn(:,i,j,n_k) contributions of the (i,j) loop
+  for (int l = 1; l <= L; l++) focn_surf[l] = 0.0;
+  {
+    double fatm[kBgMaxLA + 1], focnatm[kBgMaxLA + 1], f_oa[kBgMaxLA + 1], f_ao[kBgMaxLA + 1];
+    double TC = T - kZeroC, TC2, TC3;
+    const double TCf = T - kZeroC;
+    if (TC < 0.0) TC = 0.0;
+    if (TC > 30.0) TC = 30.0;
+    TC2 = TC * TC; TC3 = TC2 * TC;
+    const double ws = b.wspeed[c2d];
+    const double u2 = ws * ws;
+    const double area = (1.0 - seaice) * A;
+    double alpha_as = 0.0, alpha_sa = 0.0;
+    for (int la = 1; la <= LA; la++) { fatm[la] = 0.0; focnatm[la] = 0.0; f_oa[la] = 0.0; f_ao[la] = 0.0; }
+    // restoring of the atmosphere (:1119-1146)
+    for (int la = 3; la <= LA; la++)
+      if (b.rst_active[la]) {
+        const double sfc = b.sfcatm1[((size_t)(la - 1) * I * J + c2d) * MS + m];
+        double tgt = b.rst_target[la];
+        if (b.atype[la] == 1) { if (tgt < 0.0) tgt = sfc; } else { if (tgt <= kNull) tgt = sfc; }
+        const double d = (tgt - sfc) * b.tmod[la];
+        fatm[la] = (1.0 / (double)(I * J)) * kAtmMol * d * (1.0 / dtyr);
+      }
+    // air-sea gas exchange (fun_calc_ocnatm_flux :123-299)
+    for (int la = 3; la <= LA; la++) {
+      const int lo = b.atm2ocn[la];
+      const double sfc = b.sfcatm1[((size_t)(la - 1) * I * J + c2d) * MS + m];
+      if (b.atype[la] == 1) {
+        // fun_calc_solconst (gem_carbchem.f90:1390-1429) and sub_calc_pv (:81-117)
+        double Ts, Ss;
+        if (T < kZeroC + 2.0) Ts = kZeroC + 2.0; else if (T > (kZeroC + 35.0)) Ts = kZeroC + 35.0; else Ts = T;
+        if (S < 26.0) Ss = 26.0; else if (S > 43.0) Ss = 43.0; else Ss = S;
+        const double rT = 1.0 / Ts, Tr100 = Ts / 100.0;
+        const double *bc = b.bunsen[la];
+        double sol = exp(bc[0] + bc[1] * (100 * rT) + bc[2] * log(Tr100) + Ss * (bc[3] + bc[4] * (Tr100) + bc[5] * (Tr100 * Tr100)));
+        if (!(b.aid[la] == 3 || b.aid[la] == 18 || b.aid[la] == 19)) sol = sol / (rho * kVmol);
+        const double Sc = b.Sc[la][0] - b.Sc[la][1] * TC + b.Sc[la][2] * TC2 - b.Sc[la][3] * TC3;
+        const double pv = (1.0 / 1.0E+02) * (24.0 * 365.25) * b.gastransfer_a * u2 * pow(Sc * 1.515E-3, -0.5);
+        double loc_atm = sol * sfc, loc_ocn, buff;
+        if (lo == b.l_DIC) {
+          loc_ocn = cb.co2;
+          if (cb.RF0 > kNS) buff = 1.0 / (cb.RF0 * cb.co2 / DIC);
+          else { loc_ocn = 0.0; loc_atm = 0.0; buff = 1.0; }
+        } else { loc_ocn = OCN_(lo, K); buff = 1.0; }
+        if (loc_ocn < kNS) loc_ocn = 0.0;
+        if (loc_atm < kNS) loc_atm = 0.0;
+        f_oa[la] = pv * area * rho * loc_ocn;
+        f_ao[la] = pv * area * rho * loc_atm;
+        const double deqm = b.dD[K] * A * rho * buff * fabs(loc_atm - loc_ocn);
+        const double dflux = dtyr * fabs(f_oa[la] - f_ao[la]);
+        if (deqm > kNS) {
+          const double r = dflux / deqm;
+          if (r > 1.00) { f_oa[la] = (1.00 / r) * f_oa[la]; f_ao[la] = (1.00 / r) * f_ao[la]; }
+        }
+      } else if (b.aid[la] == 4) {
+        const double r_atm = sfc / b.sfcatm1[((size_t)(b.a_CO2 - 1) * I * J + c2d) * MS + m];
+        const double R_atm = r_atm / (1.0 - r_atm), R_ocn = r13_CO2 / (1.0 - r13_CO2);
+        const double alpha_k = 0.99912, alpha_alpha = 0.99869 + 4.9E-6 * TCf;
+        alpha_as = alpha_alpha * alpha_k; alpha_sa = alpha_k;
+        f_ao[la] = (alpha_as * R_atm / (1.0 + alpha_as * R_atm)) * f_ao[b.a_CO2];
+        f_oa[la] = (alpha_sa * R_ocn / (1.0 + alpha_sa * R_ocn)) * f_oa[b.a_CO2];
+      } else if (b.aid[la] == 5) {
+        const double r_atm = sfc / b.sfcatm1[((size_t)(b.a_CO2 - 1) * I * J + c2d) * MS + m];
+        const double R_atm = r_atm / (1.0 - r_atm), R_ocn = r14_CO2 / (1.0 - r14_CO2);
+        f_ao[la] = ((alpha_as * alpha_as) * R_atm / (1.0 + (alpha_as * alpha_as) * R_atm)) * f_ao[b.a_CO2];
+        f_oa[la] = ((alpha_sa * alpha_sa) * R_ocn / (1.0 + (alpha_sa * alpha_sa) * R_ocn)) * f_oa[b.a_CO2];
+      }
+      focnatm[la] = f_oa[la] - f_ao[la];
+    }
+    for (int la = 3; la <= LA; la++) {
+      const int lo = b.atm2ocn[la];
+      fatm[la] = fatm[la] + focnatm[la];
+      if (lo) focn_surf[lo] = focn_surf[lo] - 1.0 * focnatm[la];
+      const size_t qa = ((size_t)(la - 1) * I * J + c2d) * MS + m;
+      b.focnatm[qa] = focnatm[la];
+      // interface (:1731-1734) and cpl_flux_ocnatm (atchem.f90:306-320): sfxsumatm += dts*sfxatm1
+      const double sfx = rA * (1.0 / kYrS) * fatm[la];
+      b.sfxsumatm[qa] = b.sfxsumatm[qa] + b.dts * sfx;
+    }
+  }
+  // ---- biological uptake at the surface (k_mld = K because mld = 0), sub_calc_bio_uptake 1N1T_PO4MM
+  double pDOM[kBgMaxLS + 1], psurf[kBgMaxLS + 1], uptake[kBgSlots], dom_add[kBgMaxLS + 1];
+  {
+    const double kPO4 = PO4 / (PO4 + b.c0_PO4);
+    const double ficefree = (1.0 - seaice);
+    const double solfor = b.nsol > 0 ? v.solfor[(size_t)(b.nsol - 1) * J + (j - 1)] : 0.0;
+    const double kI = solfor / b.solar_constant;
+    double dPO4;
+    if (PO4 > kNS) dPO4 = dtyr * ficefree * kI * kPO4 * b.k0_PO4[m]; else dPO4 = 0.0;
+    double DOMfrac = b.red_DOMfrac, RDOMfrac = b.red_RDOMfrac, DOMtotal = DOMfrac + RDOMfrac;
+    if (DOMtotal > 1.0) { DOMfrac = DOMfrac / DOMtotal; RDOMfrac = 1.0 - DOMfrac; DOMtotal = 1.0; }
+    double red_POC_CaCO3;
+    if (cb.ohm_cal > 1.0) red_POC_CaCO3 = (1.0 - DOMtotal) * b.red_POC_CaCO3[m] * pow(cb.ohm_cal - 1.0, b.red_POC_CaCO3_pP);
+    else red_POC_CaCO3 = 0.0;
+    const double Kq = 3.170E-05 + (-1.788E-07) * T + 2.829E-10 * (T * T);
+    const double delta_Corg = -b.d13C_DIC_Corg_ef + (b.d13C_DIC_Corg_ef - 0.7) * Kq / cb.co2;
+    double alpha = 1.0 + delta_Corg / 1000.0, R = r13_CO2 / (1.0 - r13_CO2);
+    const double red_POC13 = alpha * R / (1.0 + alpha * R);
+    alpha = 1.0 + 2.0 * delta_Corg / 1000.0; R = r14_CO2 / (1.0 - r14_CO2);
+    const double red_POC14 = alpha * R / (1.0 + alpha * R);
+    const double delta_CaCO3 = 15.10 - 4232.0 / T;
+    alpha = 1.0 + delta_CaCO3 / 1000.0; R = r13_HCO3 / (1.0 - r13_HCO3);
+    const double red_Ca13 = alpha * R / (1.0 + alpha * R);
+    alpha = 1.0 + 2.0 * delta_CaCO3 / 1000.0; R = r14_HCO3 / (1.0 - r14_HCO3);
+    const double red_Ca14 = alpha * R / (1.0 + alpha * R);
+    for (int ls = 1; ls <= LS; ls++) psurf[ls] = PART_(ls, K);   // what remin left in the surface layer (0)
+    // bulk export (:1186-1230): POC currency, CaCO3, POP, isotopes
+    psurf[b.s_POC] = b.red_POP_POC * dPO4;
+    psurf[b.s_POC] = 1.0 * psurf[b.s_POC];
+    psurf[b.s_CaCO3] = red_POC_CaCO3 * psurf[b.s_POC];
+    psurf[b.s_POP] = (1.0 / b.red_POP_POC) * psurf[b.s_POC];
+    psurf[b.s_POC13] = red_POC13 * psurf[b.s_POC];
+    psurf[b.s_POC14] = red_POC14 * psurf[b.s_POC];
+    psurf[b.s_CaCO313] = red_Ca13 * psurf[b.s_CaCO3];
+    psurf[b.s_CaCO314] = red_Ca14 * psurf[b.s_CaCO3];
+    for (int q = 0; q < kBgSlots; q++) uptake[q] = 0.0;
+    for (int ls = 1; ls <= LS; ls++)
+      for (int r = 0; r < b.n_ls_lo[ls]; r++) {
+        const int q = b.lrem_slot[b.ls_lo[ls][r]];
+        uptake[q] = uptake[q] + b.conv_ls_lo[ls][r] * psurf[ls];
+      }
+    for (int ls = 1; ls <= LS; ls++) {
+      pDOM[ls] = 0.0; dom_add[ls] = 0.0;
+      if (b.pom2dom[ls]) { pDOM[ls] = 1.0 * DOMfrac * psurf[ls]; dom_add[ls] = pDOM[ls]; }
+    }
+    for (int ls = 1; ls <= LS; ls++) psurf[ls] = psurf[ls] - (pDOM[ls] + 0.0);
+    {
+      const double kP = PO4 / (PO4 + b.POC_c0frac2);
+      psurf[b.s_POCf2] = (1.0 - kP) * b.POC_dfrac2 + b.POC_frac2;
+      psurf[b.s_CaCO3f2] = b.CaCO3_frac2;
+    }
+    for (int ls = 1; ls <= LS; ls++) PART_(ls, K) = psurf[ls];
+  }
+  // ---- tracer anomaly (:1811-1844) and bottom-water interface (:1736-1744)
+  for (int k = k1; k <= K; k++) {
+    const double rM = RM_(k), Mk = M_(k);
+    for (int l = 1; l <= L; l++) {
+      const int q = b.lrem_slot[l];
+      double rem = 0.0;
+      if (k == k1 && l >= 3 && q) rem = rem + rM * fsed[q];
+      else if (k == k1 && l >= 3) rem = rem + rM * 0.0;
+      rem = rem + (DOCN_(l, k) + (q ? lrem[q][k] : 0.0));
+      double focn = 0.0;
+      if (l >= 3 && fabs(b.lam_ocn[l]) > kNS) focn = focn - Mk * (1.0 - b.fd_ocn[l]) * OCN_(l, k) / dtyr;
+      if (l == 1 && k == k1) focn = focn + kYrS * b.Fgeothermal * A / (1.0E+03 * kCp);
+      if (k == K) {
+        focn = focn + focn_surf[l];
+        if (l >= 3) {
+          const int ls = b.dom2pom[l];
+          if (ls) rem = rem + dom_add[ls];
+          rem = rem - (q ? uptake[q] : 0.0);
+        }
+      }
+      const double d = rem + dtyr * rM * focn;
+      DOCN_(l, k) = d;
+      if (k == k1) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = OCN_(l, k) + rem + dtyr * rM * focn;
+    }
+  }
+  for (int ls = 1; ls <= LS; ls++) {
+    const double fs = set1[ls];
+    const double rdts = 1.0 / b.dts;
+    b.sfxsed1[((size_t)(ls - 1) * I * J + c2d) * MS + m] = (b.stype[ls] == 9) ? fs * rdts * dtyr : rA * fs * rdts;
+  }
+#undef OCN_
+#undef DOCN_
+#undef PART_
+#undef M_
+#undef RM_
+#undef SET1_
+}
+
+// biogem_climate (:2132-2239): snapshot the sea-ice fraction, reset the convection counter
+__global__ void k_bg_climate(const Dev v, const BgDev b) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)v.I * v.J * v.MS;
+  if (q >= n) return;
+  b.seaice[q] = v.varice[n + q];   // varice(2,:,:) = fractional cover
+  v.cost[q] = 0.0;
+}
+
+// step_atchem (atchem.f90:63-158) + cpl_comp_atmocn (:252-264): thread = (member, tracer la >= 3)
+__global__ void __launch_bounds__(128) k_bg_atchem(const Dev v, const BgDev b, const double atm_totV) {
+  using namespace bgk;
+  const int I = v.I, J = v.J, MS = v.MS;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int la = 3 + blockIdx.y;
+  if (m >= MS || la > b.LA) return;
+  const size_t ij = (size_t)I * J;
+  double *atm = b.atm + (size_t)(la - 1) * ij * MS + m;
+  const double *atmT = b.atm + m;
+  double *sfx = b.sfxsumatm + (size_t)(la - 1) * ij * MS + m;
+  double *sfc = b.sfcatm1 + (size_t)(la - 1) * ij * MS + m;
+  const bool decays = fabs(b.lam_atm[la]) > kNS;
+  const double F14C = 0.0;   // par_atm_F14C (atchem-defaults.nml)
+  double tot = 0.0;
+  for (size_t c = 0; c < ij; c++) {   // array element order: i fastest
+    const double c_am = b.atm_V[c] / (kPaAtm * kRSI * atmT[c * MS]);
+    const double c_ma = 1.0 / c_am;
+    double a = atm[c * MS];
+    if (decays) a = b.fd_atm[la] * a;
+    double fl = 0.0;
+    if (la == b.a_CO214) fl = fl + b.dtyr_atchem * (1.0 / (double)(I * J)) * F14C;
+    a = a + c_ma * b.atm_A[c] * sfx[c * MS] + c_ma * fl;
+    atm[c * MS] = a;
+    tot = tot + c_am * a;
+  }
+  for (size_t c = 0; c < ij; c++) {
+    const double a = (tot / atm_totV) * kPaAtm * kRSI * atmT[c * MS];
+    atm[c * MS] = a;
+    sfc[c * MS] = a;
+    sfx[c * MS] = 0.0;
+  }
+}
+
+int launch_bg_step(const Dev &v, const BgDev &b, int init_only, cudaStream_t s) {
+  k_bg_step<<<dim3(v.MS / 32, (v.nwet + 3) / 4), dim3(32, 4), 0, s>>>(v, b, init_only);
+  return 1;
+}
+int launch_bg_climate(const Dev &v, const BgDev &b, cudaStream_t s) {
+  const size_t n = (size_t)v.I * v.J * v.MS;
+  k_bg_climate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v, b);
+  return 1;
+}
+int launch_bg_atchem(const Dev &v, const BgDev &b, double atm_totV, cudaStream_t s) {
+  k_bg_atchem<<<dim3(v.MS / 32, b.LA - 2), 32, 0, s>>>(v, b, atm_totV);
+  return 1;
 }
 
 int launch_tracercoupling(const Dev &v, cudaStream_t s) {

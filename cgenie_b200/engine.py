@@ -193,6 +193,18 @@ class Ensemble(_Base):
         """biogem_climate_wrapper (genie_loop_wrappers.f90:324-345); resets the convection counter."""
         self._ck(self.L.cg_biogem_climate(self.h))
 
+    def biogem_forcing(self, genie_clock_ms):
+        """biogem_forcing_wrapper (genie_loop_wrappers.f90:324-328)."""
+        self._ck(self.L.cg_biogem_forcing(self.h, int(genie_clock_ms)))
+
+    def biogem_step(self, dts, genie_clock_ms):
+        """biogem_wrapper (genie_loop_wrappers.f90:310-316); interface arrays stay on the device."""
+        self._ck(self.L.cg_biogem_step(self.h, float(dts), int(genie_clock_ms)))
+
+    def atchem_step(self, dts):
+        """atchem_wrapper + cpl_comp_atmocn_wrapper (genie_loop_wrappers.f90:452-462)."""
+        self._ck(self.L.cg_atchem_step(self.h, float(dts)))
+
     def run(self, n_koverall):
         """n iterations of the genie.f90 main loop entirely on the device."""
         self._ck(self.L.cg_run(self.h, int(n_koverall)))

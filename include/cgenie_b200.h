@@ -104,6 +104,9 @@ int cg_biogem_forcing(cg_handle *, int64_t genie_clock_ms);
 int cg_biogem_step(cg_handle *, double dts, int64_t genie_clock_ms);
 int cg_biogem_tracercoupling(cg_handle *, double *go_ts, double *go_ts1);
 int cg_biogem_climate(cg_handle *);
+int cg_biogem_climate_sol(cg_handle *);   /* biogem_climate_sol, biogem.f90:2243-2263 (first BIOGEM step only) */
+/* cpl_flux_ocnatm (atchem.f90:306-320) is fused into cg_biogem_step; kept so that the wrapper has a target */
+int cg_cpl_flux_ocnatm(cg_handle *);
 /* (re)build BIOGEM's ocn array from the current ts (initialise_biogem, biogem.f90:283-285: T in K, S absolute) */
 int cg_biogem_init_ocn(cg_handle *);
 int cg_atchem_step(cg_handle *, double dts);

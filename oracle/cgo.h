@@ -69,6 +69,14 @@ void cgo_tstipa(cgo_t *);
 /* BIOGEM: biogem_tracercoupling_wrapper (genie_loop_wrappers.f90:318-322); cgo_biogem_init builds ocn from ts */
 void cgo_biogem_init(cgo_t *);
 void cgo_biogem_tracercoupling(cgo_t *);
+/* full BIOGEM + ATCHEM (frozen eb_go_gs_ac_bg configuration): fill field "bg_windspeed" first, then set up; afterwards
+ * cgo_run also executes the BIOGEM/ATCHEM block of genie.f90:352-447.  params: extra "key=value\n" overrides or NULL. */
+void cgo_biogem_setup(cgo_t *, const char *params);
+void cgo_biogem_forcing(cgo_t *);
+int cgo_biogem_step(cgo_t *);
+void cgo_biogem_climate(cgo_t *);
+void cgo_cpl_flux_ocnatm(cgo_t *);
+void cgo_atchem_step(cgo_t *);
 
 /* run n iterations of the genie.f90 koverall loop (one EMBM step each) */
 void cgo_run(cgo_t *, long nkoverall);

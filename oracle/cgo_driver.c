@@ -3,7 +3,7 @@
 #include "cgo_impl.h"
 
 void cgo_reg(cgo_t *o, const char *name, double *p, long n) {
-  if (o->nfields >= 160) { fprintf(stderr, "cgo: field registry full\n"); abort(); }
+  if (o->nfields >= 256) { fprintf(stderr, "cgo: field registry full\n"); abort(); }
   o->fields[o->nfields].name = name; o->fields[o->nfields].p = p; o->fields[o->nfields].n = n; o->nfields++;
 }
 void cgo_ireg(cgo_t *o, const char *name, int *p, long n) {
@@ -47,7 +47,7 @@ double cgo_scalar(cgo_t *o, const char *name) {
   if (!strcmp(name, "ntot")) return o->ntot;
   if (!strcmp(name, "limps")) return o->limps;
   if (!strcmp(name, "istep_ocn")) return o->istep_ocn;
-  return NAN;
+  return cgo_biogem_scalar(o, name);
 }
 void cgo_set_scalar(cgo_t *o, const char *name, double v) {
   for (int i = 0; i < o->nscalars; i++)
@@ -77,6 +77,7 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
   int i, j, p, isl;
   double v;
   if (!params) params = "";
+  o->params = strdup(params);
   /* dims: main-defaults.nml */
   PI_(maxi, 36); PI_(maxj, 36); PI_(maxk, 8); PI_(maxl, 2);
   /* goldstein-defaults.nml */
@@ -163,6 +164,8 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
     AL1(netsolar_atm, ij); AL1(netlong_atm, ij); AL1(evap_atm, ij); AL1(precip_atm, ij); AL1(dhght_sic, ij);
     AL1(dfrac_sic, ij); AL1(waterflux_ocn, ij); AL1(conductflux_ocn, ij); AL1(lowestlu2, ij); AL1(lowestlv3, ij);
     AL1(psiles, (long)I * (J + 1));
+    AL1(go_solfor, J + 2);
+    cgo_alloc(o, "bg_windspeed", ij);
 #undef AL1
     cgo_sreg(o, "dphi", &o->dphi); cgo_sreg(o, "rdphi", &o->rdphi); cgo_sreg(o, "dzz", &o->dzz);
     cgo_sreg(o, "diff1", &o->diff[1]); cgo_sreg(o, "diff2", &o->diff[2]); cgo_sreg(o, "adrag", &o->adrag);
@@ -225,6 +228,8 @@ void cgo_destroy(cgo_t *o) {
   if (!o) return;
   for (int i = 0; i < o->nfields; i++) free(o->fields[i].p - 64);
   for (int i = 0; i < o->nifields; i++) free(o->ifields[i].p - 64);
+  free(o->params);
+  free(o->bg);
   free(o);
 }
 
@@ -232,9 +237,11 @@ void cgo_destroy(cgo_t *o) {
 void cgo_run(cgo_t *o, long n) {
   for (long it = 0; it < n; it++) {
     long k = ++o->koverall;
+    cgo_biogem_tick(o);
     if (k % o->kocn_loop == 1) { o->istep_ocn++; cgo_surflux(o); }
     if (k % o->katm_loop == 0) { o->istep_atm++; cgo_embm_step(o); }
     if (k % o->ksic_loop == 0) { o->istep_sic++; cgo_seaice_step(o); }
     if (k % o->kocn_loop == 0) { cgo_goldstein_step(o); }
+    if (o->bg && cgo_biogem_koverall(o, k)) { fprintf(stderr, "cgo: BIOGEM carbonate chemistry failed at koverall %ld\n", k); }
   }
 }

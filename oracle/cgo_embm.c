@@ -386,6 +386,7 @@ void cgo_surflux(cgo_t *o) {
   for (i = 0; i < NI * NJ; i++) meantemp = meantemp + atemp[i];
   meantemp = meantemp / (double)(NJ * NI);
   nsol = (istot - 1) % o->nyear + 1;
+  for (j = 1; j <= NJ; j++) o->go_solfor[j] = SOLFOR(j, nsol);   /* embm.f90:3727-3729 */
   for (i = 1; i <= NI; i++)
     for (j = 1; j <= NJ; j++) {
       const double at = A2(atemp, i, j);

@@ -60,6 +60,7 @@
 struct cgo_field_ent { const char *name; double *p; long n; };
 struct cgo_ifield_ent { const char *name; int *p; long n; };
 struct cgo_scalar_ent { const char *name; double *p; };
+struct cgo_bg;
 
 struct cgo {
   int maxi, maxj, maxk, maxl;
@@ -115,6 +116,9 @@ struct cgo {
 
   /* ---------------- BIOGEM (tracer coupling) ---------------- */
   double *bg_ocn, *bg_vdocn, *bg_M, *bg_rM, *bg_V;
+  struct cgo_bg *bg;      /* full BIOGEM/ATCHEM state (cgo_biogem.c), NULL unless cgo_biogem_setup was called */
+  double *go_solfor;      /* (maxj) solfor of the last surflux call (embm.f90:3728) */
+  char *params;           /* copy of the construction parameters */
 
   /* ---------------- coupling arrays (genie_global) ---------------- */
   double *tstar_ocn, *sstar_ocn, *ustar_ocn, *vstar_ocn, *albedo_ocn;
@@ -126,7 +130,7 @@ struct cgo {
       *dfrac_sic, *waterflux_ocn, *conductflux_ocn, *lowestlu2, *lowestlv3;
 
   /* registry */
-  struct cgo_field_ent fields[160]; int nfields;
+  struct cgo_field_ent fields[256]; int nfields;
   struct cgo_ifield_ent ifields[32]; int nifields;
   struct cgo_scalar_ent scalars[64]; int nscalars;
 };
@@ -184,6 +188,10 @@ void cgo_embm_init(cgo_t *o, const double *taux_u, const double *tauy_u,
                    const double *uncep, const double *vncep);
 void cgo_seaice_init(cgo_t *o);
 void cgo_biogem_init(cgo_t *o);
+void cgo_biogem_setup(cgo_t *o, const char *params);
+int cgo_biogem_koverall(cgo_t *o, long k);
+void cgo_biogem_tick(cgo_t *o);
+double cgo_biogem_scalar(cgo_t *o, const char *name);
 void cgo_eos(const cgo_t *o, double t, double s, double z, double *rho);
 void cgo_reg(cgo_t *o, const char *name, double *p, long n);
 void cgo_ireg(cgo_t *o, const char *name, int *p, long n);

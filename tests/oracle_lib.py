@@ -36,6 +36,13 @@ def lib():
             if hasattr(L, f):
                 getattr(L, f).argtypes = [P]
                 getattr(L, f).restype = None
+        for f in ("cgo_biogem_forcing", "cgo_biogem_climate", "cgo_cpl_flux_ocnatm", "cgo_atchem_step"):
+            getattr(L, f).argtypes = [P]
+            getattr(L, f).restype = None
+        L.cgo_biogem_step.argtypes = [P]
+        L.cgo_biogem_step.restype = C.c_int
+        L.cgo_biogem_setup.argtypes = [P, C.c_char_p]
+        L.cgo_biogem_setup.restype = None
         L.cgo_run.argtypes = [P, C.c_long]
         L.cgo_field.restype = C.POINTER(C.c_double)
         L.cgo_field.argtypes = [P, C.c_char_p, C.POINTER(C.c_long)]
@@ -93,6 +100,14 @@ class Oracle:
         if not self.h:
             raise RuntimeError("cgo_create failed")
         self.params = params
+
+    def biogem_setup(self, **bg_params):
+        """initialise_biogem + initialise_atchem for the frozen eb_go_gs_ac_bg configuration (oracle/cgo_biogem.c);
+        afterwards run() also executes the BIOGEM/ATCHEM block of genie.f90.  bg_params override data_BIOGEM keys."""
+        z = np.load(os.path.join(ROOT, "configs", "inputs.npz"))
+        self.f("bg_windspeed")[:] = z["biogem/worjh2_windspeed"][::-1, :].ravel()   # file rows j = maxj..1
+        kv = "".join("%s=%r\n" % (k, float(v)) for k, v in dict(self.params, **bg_params).items())
+        self.L.cgo_biogem_setup(self.h, kv.encode())
 
     def close(self):
         if self.h:

@@ -1,0 +1,117 @@
+"""GPU parity of the BIOGEM + ATCHEM path (run with -m gpu on a B200): the frozen eb_go_gs_ac_bg configuration
+through cg_run (device) against oracle/cgo_biogem.c on identical inputs, from the initial state.
+
+Bars (BASELINE.json north_star): <= 1e-10 relative per step on ts and the BIOGEM tracers.  The physics runs in the
+'strict' variant (bit-exact), so every difference comes from the transcendental functions of the carbonate
+chemistry / gas exchange (CUDA libm vs glibc, ~1 ulp)."""
+import numpy as np
+import pytest
+
+from cgenie_b200 import Ensemble, materialise
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+CFG = "eb_go_gs_ac_bg_36x36x16"
+OKW = dict(world="worjh2", maxk=16, maxl=16, nyear=96)
+I = J = 36
+K = L = 16
+LS, LA = 9, 8
+PERT = {"par_bio_k0_PO4": 2.3e-6, "par_bio_remin_POC_eL1": 430.0, "par_bio_red_POC_CaCO3": 0.17, "diff1": 2200.0,
+        "scf": 1.9}
+
+
+def rel(a, b, floor):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def wet_masks(o):
+    k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    wet3 = (np.arange(1, K + 1)[:, None, None] >= k1[None])
+    return k1, wet3
+
+
+@pytest.fixture(scope="module")
+def pair(built, tmp_path_factory):
+    d = tmp_path_factory.mktemp("bgjob")
+    materialise(str(d), CFG)
+    base = {k: {"par_bio_k0_PO4": 2.0e-6, "par_bio_remin_POC_eL1": 500.0, "par_bio_red_POC_CaCO3": 0.2, "diff1": 2000.0,
+                "scf": 2.0}[k] for k in PERT}
+    pert = {k: np.array([base[k], PERT[k]]) for k in PERT}
+    oracles = []
+    for m in range(2):
+        kw = dict(OKW)
+        kw.update({k: float(pert[k][m]) for k in ("diff1", "scf")})
+        o = Oracle(**kw)
+        o.biogem_setup(**{k: float(pert[k][m]) for k in PERT if k.startswith("par_bio")})
+        oracles.append(o)
+    e = Ensemble(str(d), n_members=2, perturb=pert)
+    e.set_tracer_variant("strict")
+    yield e, oracles
+    e.close()
+
+
+def compare(e, oracles, tol, what):
+    worst = {}
+    for m, o in enumerate(oracles):
+        k1, wet3 = wet_masks(o)
+        wl = np.repeat(wet3.ravel(), L)
+        ws = np.repeat(wet3.ravel(), LS)
+        ocn_o = o.f("ocn")
+        ocn_d = e.get("ocn", m)
+        ts_o = o.f("ts").reshape(K + 2, J + 2, I + 2, L)[1:K + 1, 1:J + 1, 1:I + 1, :].ravel()
+        ts_d = e.get("ts", m)
+        # per-tracer floors: a tracer's own typical magnitude (relative error of the field, not of near-zero cells)
+        scale = np.abs(ocn_o.reshape(-1, L)[wet3.ravel()]).max(axis=0)
+        floor = np.tile(np.maximum(scale, 1e-300), wet3.size)
+        worst["ocn"] = max(worst.get("ocn", 0), rel(ocn_d[wl], ocn_o[wl], floor[wl]))
+        worst["ts"] = max(worst.get("ts", 0), rel(ts_d[wl], ts_o[wl], floor[wl]))
+        po, pd = o.f("bio_part"), e.get("bio_part", m)
+        pscale = np.tile(np.maximum(np.abs(po.reshape(-1, LS)).max(axis=0), 1e-300), wet3.size)
+        worst["bio_part"] = max(worst.get("bio_part", 0), rel(pd[ws], po[ws], pscale[ws]))
+        wet2 = (k1 <= K).ravel()
+        Ho = o.f("carb").reshape(J * I, -1)[:, 0]
+        worst["carbH"] = max(worst.get("carbH", 0), rel(e.get("carbH", m)[wet2], Ho[wet2], 1e-300))
+        ao, ad = o.f("atm").reshape(J * I, LA), e.get("atm", m).reshape(J * I, LA)
+        for la in (2, 3, 4, 5):
+            worst["atm"] = max(worst.get("atm", 0), rel(ad[:, la], ao[:, la], 1e-300))
+        so = o.f("bio_settle").reshape(K, J, I, LS)
+        sd = e.get("settle_k1", m).reshape(J, I, LS)
+        kk = np.clip(k1 - 1, 0, K - 1)
+        so1 = np.take_along_axis(so, kk[None, :, :, None], axis=0)[0]
+        sscale = np.maximum(np.abs(so1).reshape(-1, LS).max(axis=0), 1e-300)
+        worst["settle"] = max(worst.get("settle", 0), float(np.max(np.abs(sd - so1)[k1 <= K] / sscale)))
+    print(what, {k: "%.2e" % v for k, v in worst.items()})
+    for k, v in worst.items():
+        assert v <= tol, (what, k, v)
+    return worst
+
+
+def test_biogem_initial_state(pair):
+    """initialise_biogem / initialise_atchem: ocn, salinity-normalised ts, pH seed, atmosphere."""
+    e, oracles = pair
+    compare(e, oracles, 1e-13, "init")
+    for m, o in enumerate(oracles):
+        _, wet3 = wet_masks(o)
+        wl = np.repeat(wet3.ravel(), L)
+        # everything but the pH solve is transcendental-free: bit-exact
+        assert np.array_equal(e.get("ocn", m)[wl], o.f("ocn")[wl])
+        assert np.array_equal(e.get("atm", m), o.f("atm"))
+
+
+def test_biogem_model_steps(pair):
+    """100 koverall iterations = 20 ocean steps, 10 BIOGEM steps, 10 ATCHEM steps, member 1 with perturbed
+    biological parameters; checked after the first BIOGEM step and at the end."""
+    e, oracles = pair
+    e.run(10)
+    for o in oracles:
+        o.run(10)
+    compare(e, oracles, 1e-10, "after 1 BIOGEM step")
+    e.run(90)
+    for o in oracles:
+        o.run(90)
+    w = compare(e, oracles, 1e-10 * 10, "after 10 BIOGEM steps")
+    assert int(e.health().sum()) == 0
+    # the biology did something: particulates and a pCO2 drift exist
+    assert np.abs(oracles[0].f("bio_part")).max() > 1e-8
+    assert w["ts"] < 1e-9

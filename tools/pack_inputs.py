@@ -11,6 +11,7 @@ Sources (all under /root/reference/data):
   goldstein/<world>.k1 .psiles .paths   (goldstein.f90:1109-1123, 1502-1577)
   embm/taux_u.interp ... tauy_v.interp  (embm.f90:845-860)
   embm/uncep.silo vncep.silo            (embm.f90:989-995)
+  biogem/worjh2_preindustrial/windspeed.dat (biogem_data.f90:1171-1175)
 """
 import os
 import sys
@@ -53,6 +54,9 @@ def main():
         out["winds/" + nm] = np.array(read_numbers(os.path.join(e, nm + ".interp")))
     for nm in ("uncep", "vncep"):
         out["winds/" + nm] = np.array(read_numbers(os.path.join(e, nm + ".silo")))
+    # BIOGEM prescribed wind speed, file rows j = maxj..1, i = 1..maxi per row (gem_util.f90:511-536)
+    b = os.path.join(REF, "data", "biogem", "worjh2_preindustrial", "windspeed.dat")
+    out["biogem/worjh2_windspeed"] = np.array(read_numbers(b)).reshape(36, 36)   # [row = maxj - j][i - 1]
     for k, v in out.items():
         print(k, v.shape, v.dtype)
     np.savez_compressed(OUT, **out)
