@@ -30,6 +30,7 @@ int launch_surflux(const Dev &, double *meantemp, bool need_mean, cudaStream_t);
 int launch_embm(const Dev &, int nsteps, cudaStream_t);
 int launch_seaice(const Dev &, cudaStream_t);
 int launch_gold_pre(const Dev &, cudaStream_t);
+int launch_sst(const Dev &, cudaStream_t);
 int launch_momentum(const Dev &, int fast, const double *bf, const double *bb, const double *rd, cudaStream_t);
 void launch_global_means(const Dev &, double *out, cudaStream_t);
 int launch_tracercoupling(const Dev &, cudaStream_t);
@@ -531,6 +532,22 @@ static int build_device(cg_handle *h) {
     TRY(dalloc(h, &b.focnatm, ij * LA * MS));
     TRY(dalloc(h, &b.err, MS));
     v.bg_biopart = b.bio_part; v.bg_LS = LS;
+    {
+      // SST/SSS as exported by the last step_goldstein (initially the initial state, goldstein.f90:2061-2068)
+      std::vector<double> sst(2 * ij * MS, 0.0);
+      for (int m = 0; m < MS; m++) {
+        const MemberConsts &c = h->mc[std::min(m, M - 1)];
+        for (int j = 1; j <= J; j++)
+          for (int i = 1; i <= I; i++)
+            if (g.k1at(i, j) <= K) {
+              const size_t q = cell3(I, J, i, j, K) * L;
+              sst[cell2(I, i, j) * MS + m] = c.ts0[q];
+              sst[(ij + cell2(I, i, j)) * MS + m] = c.ts0[q + 1];
+            }
+      }
+      TRY(dupload(h, &v.sst, sst));
+      reg_field(h, "sst", v.sst, {2, I, J}, {(long long)ij, 1, I});
+    }
     { double *q; TRY(dupload(h, &q, bc.windspeed)); b.wspeed = q; }
     {
       std::vector<double> A(ij), rA(ij), aA(ij), aV(ij);
@@ -965,6 +982,7 @@ static void do_tstepo(cg_handle *h) {
   { ProfScope ps(h, "tstepo_flux"); ps.done(h->variant ? launch_tstepo_flux_fast(h->dv, h->stream) : launch_tstepo_flux_strict(h->dv, h->stream)); }
   { ProfScope ps(h, "co"); ps.done(h->variant ? launch_co_fast(h->dv, h->stream) : launch_co_strict(h->dv, h->stream)); }
   std::swap(h->dv.ts_cur, h->dv.ts_new);
+  if (h->dv.sst) { ProfScope ps(h, "co"); ps.done(launch_sst(h->dv, h->stream)); }
 }
 static int do_goldstein(cg_handle *h) {
   { ProfScope ps(h, "momentum"); launch_hosing(h->dv, h->stream); int n = launch_gold_pre(h->dv, h->stream); n += launch_momentum(h->dv, h->variant, h->d_bf, h->d_bb, h->d_rd, h->stream); ps.done(n + 1); }
@@ -1277,6 +1295,29 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
   return check_async(h);
 }
 
+// Restart support: place the coupling loop at iteration `koverall` (a multiple of kocn_loop).  The prognostic fields are
+// restored with cg_sync_from_host; this restores the counters the reference keeps in genie_global (koverall, istep_*,
+// genie_clock) and everything BIOGEM derives from them.
+extern "C" int cg_set_koverall(cg_handle *h, int64_t koverall) {
+  READY(h);
+  const Params &p = h->base;
+  if (koverall < 0 || koverall % p.kocn_loop != 0) return fail(CG_ERR_ARG, "cg_set_koverall: koverall must be a non-negative multiple of kocn_loop");
+  h->koverall = koverall;
+  h->istep_ocn = (int)(koverall / p.kocn_loop);
+  h->istep_atm = (int)(koverall / p.katm_loop);
+  h->istep_sic = (int)(koverall / p.ksic_loop);
+  CUDA_OK(cudaMemcpyAsync(h->dv.istep_ocn, &h->istep_ocn, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (h->bg.on) {
+    h->bgd.nsol = h->istep_ocn > 0 ? (h->istep_ocn - 1) % h->g.nyear + 1 : 0;
+    const long long clock = koverall * nint_ll(1000.0 * p.genie_timestep);
+    h->bg_go = !((h->bg.t_runtime - (double)clock / (1000.0 * kBgYrS)) < kBgNullSmall) || koverall == 0;
+    for (int la = 3; la <= h->bg.LA; la++)
+      if (h->bg.rst_sel[la]) { h->bg.rst_sig_i1[la] = (int)h->bg.rst_sig_t[la].size(); h->bg.rst_sig_i2[la] = h->bg.rst_sig_i1[la]; }
+  }
+  return CG_OK;
+}
+
 // ------------------------------------------------------------------ diagnostics, measurement
 extern "C" int cg_global_means(cg_handle *h, double *out) {
   if (!h || !h->initialised || !out) return fail(CG_ERR_ARG, "cg_global_means: bad argument");
@@ -1292,6 +1333,11 @@ extern "C" int cg_health(cg_handle *h, int32_t *out) {
   launch_health(h->dv, h->d_flags, h->stream);
   CUDA_OK(cudaMemcpyAsync(out, h->d_flags, (size_t)h->M * 4, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (h->bg.on) {  // carbonate-chemistry failure = the reference's error_stop (gem_carbchem.f90:452-456)
+    std::vector<int> e(h->M);
+    CUDA_OK(cudaMemcpy(e.data(), h->bgd.err, (size_t)h->M * 4, cudaMemcpyDeviceToHost));
+    for (int m = 0; m < h->M; m++) if (e[m]) out[m] |= 2;
+  }
   return CG_OK;
 }
 extern "C" int cg_synchronize(cg_handle *h) {

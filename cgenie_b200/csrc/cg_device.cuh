@@ -59,6 +59,8 @@ struct Dev {
   // tracer state, ping-pong
   double *ts_cur, *ts_new;
   double *tsflux;            // [2][j][i][m] surface flux b.c. for T,S (ts(1:2,:,:,maxk+1))
+  double *sst;               // [2][j][i][m] tstar_ocn/sstar_ocn as exported by step_goldstein (goldstein.f90:428-431);
+                             // NULL = read ts directly (identical unless BIOGEM rewrites ts in between)
   double *rho, *u, *u1, *cost;
   // momentum
   double *bp, *sbp, *gb, *ub, *psi, *erisl_rhs, *psibc;

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) k_surflux1(const Dev v, const double *mea
   if (k1c <= K) {
     const size_t sC = (size_t)v.L * MS;
     const size_t ot = cell3(I, J, i, j, K) * sC + m;
-    const double otemp = v.ts_cur[ot], osaln = v.ts_cur[ot + MS];
+    const double otemp = v.sst ? v.sst[q] : v.ts_cur[ot], osaln = v.sst ? v.sst[(size_t)I * J * MS + q] : v.ts_cur[ot + MS];
     const double us = v.usurf[q], cca = v.ca[q], sa = v.varice1[q2], sich = v.varice1[q];
     double alw = at + zeroc;
     alw = alw * alw;
@@ -910,6 +910,24 @@ int launch_seaice(const Dev &v, cudaStream_t s) {
   k_seaice1<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
   k_seaice2<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
   return 2;
+}
+// tstar_ocn / sstar_ocn export at the end of step_goldstein (goldstein.f90:428-431)
+__global__ void k_sst(const Dev v) {
+  const int I = v.I, J = v.J, K = v.K, MS = v.MS;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= MS || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const size_t q = (size_t)c2 * MS + m;
+  if (CG_K1(v, i, j) > K) return;
+  const size_t ot = cell3(I, J, i, j, K) * (size_t)v.L * MS + m;
+  v.sst[q] = v.ts_cur[ot];
+  v.sst[(size_t)I * J * MS + q] = v.ts_cur[ot + MS];
+}
+int launch_sst(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_sst<<<dim3(v.MS / 32, (v.I * v.J + 3) / 4), b, 0, s>>>(v);
+  return 1;
 }
 int launch_gold_pre(const Dev &v, cudaStream_t s) {
   const dim3 b(32, 4);

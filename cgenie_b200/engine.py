@@ -209,6 +209,14 @@ class Ensemble(_Base):
         """n iterations of the genie.f90 main loop entirely on the device."""
         self._ck(self.L.cg_run(self.h, int(n_koverall)))
 
+    def set_koverall(self, koverall):
+        """Restart support: continue the coupling loop from iteration `koverall` (multiple of kocn_loop)."""
+        self._ck(self.L.cg_set_koverall(self.h, int(koverall)))
+        kocn = 5
+        self.istep_ocn = int(koverall) // kocn
+        self.istep_sic = int(koverall) // kocn
+        self.istep_atm = int(koverall)
+
     def run_years(self, years):
         self.run(int(round(years * self.nyear * self.ndta)))
 

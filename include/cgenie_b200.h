@@ -117,6 +117,10 @@ int cg_atchem_step(cg_handle *, double dts);
  * on the reference's MOD(koverall, k*_loop) schedule.                       */
 int cg_run(cg_handle *, int64_t n_koverall);
 
+/* Restart: continue the coupling loop from iteration `koverall` (multiple of kocn_loop) after the prognostic fields were
+ * restored with cg_sync_from_host; sets koverall, istep_ocn/atm/sic, the GENIE clock and BIOGEM's derived counters.   */
+int cg_set_koverall(cg_handle *, int64_t koverall);
+
 /* ---- state movement (restart / output / coupling intervals) ----------- */
 /* Named field of ONE member, in the reference's Fortran shape:
  *  "ts" (maxl,maxi,maxj,maxk)  "u" (3,maxi,maxj,maxk)  "rho" (maxi,maxj,maxk)
@@ -142,7 +146,7 @@ int cg_get_dims(cg_handle *, int32_t dims[8]); /* maxi,maxj,maxk,maxl,n_members,
 /* ---- diagnostics (warp-shuffle reductions on the device) -------------- */
 /* Per-member volume-weighted global means of every ts tracer: out[n_members*maxl] */
 int cg_global_means(cg_handle *, double *out);
-/* per-member blow-up flag (non-finite ts); out[n_members] */
+/* per-member flags: bit 0 = non-finite ts (blow-up), bit 1 = BIOGEM carbonate chemistry failed (error_stop); out[n_members] */
 int cg_health(cg_handle *, int32_t *out);
 
 /* ---- measurement helpers ---------------------------------------------- */

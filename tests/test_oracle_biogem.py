@@ -1,0 +1,107 @@
+"""CPU tests of the BIOGEM/ATCHEM oracle (oracle/cgo_biogem.c; test infrastructure, parity unpinned): element mass
+balances that the reference's own audit checks (biogem.f90:1766-1785), hand-derivable known answers, and a
+self-generated regression vector (tests/golden/, tools/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+I = J = 36
+K = L = 16
+LS, LA = 9, 8
+# compact indices (0-based) of the frozen configuration
+DIC, DIC13, DIC14, PO4, O2, ALK, DOMC, DOMC13, DOMC14, DOMP, CA = 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
+POC, POC13, POC14, POP, CACO3 = 0, 1, 2, 3, 4
+
+
+@pytest.fixture(scope="module")
+def bg():
+    o = Oracle("worjh2", maxk=K, maxl=L, nyear=96)
+    o.biogem_setup()
+    return o
+
+
+def budgets(o):
+    """Ocean inventories (mol) including particulates in the water column and the settled material that the closed
+    system returns to the bottom cell at the next step (biogem.f90:887-925)."""
+    ocn = o.f("ocn").reshape(K, J, I, L)
+    part = o.f("bio_part").reshape(K, J, I, LS)
+    M = o.f("bg_M").reshape(K, J, I)
+    k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    so = o.f("bio_settle").reshape(K, J, I, LS)
+    s1 = np.take_along_axis(so, np.clip(k1 - 1, 0, K - 1)[None, :, :, None], axis=0)[0] * (k1 <= K)[..., None]
+    inv = lambda a: float((a * M).sum())
+    P = inv(ocn[..., PO4]) + inv(ocn[..., DOMP]) + inv(part[..., POP]) + float(s1[..., POP].sum())
+    Ca = inv(ocn[..., CA]) + inv(part[..., CACO3]) + float(s1[..., CACO3].sum())
+    A = (inv(ocn[..., ALK]) - 16.0 * (inv(ocn[..., DOMP]) + inv(part[..., POP]) + float(s1[..., POP].sum()))
+         + 2.0 * (inv(part[..., CACO3]) + float(s1[..., CACO3].sum())))
+    return dict(P=P, Ca=Ca, ALKstar=A)
+
+
+def test_initial_state(bg):
+    o = bg
+    ocn = o.f("ocn").reshape(K, J, I, L)
+    k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    wet = np.arange(1, K + 1)[:, None, None] >= k1[None]
+    assert np.all(ocn[..., DIC][wet] == 2.244e-3) and np.all(ocn[..., PO4][wet] == 2.159e-6)
+    # isotopes: abundance = R/(1+R)*total with R = standard*(1+delta/1000) (gem_util.f90:604-617)
+    R = 0.011202 * (1.0 + 0.4 / 1000.0)
+    assert np.allclose(ocn[..., DIC13][wet], R / (1 + R) * 2.244e-3, rtol=1e-15)
+    # salinity-normalised copy on ts: uniform S -> ts == ocn to rounding
+    ts = o.f("ts").reshape(K + 2, J + 2, I + 2, L)[1:K + 1, 1:J + 1, 1:I + 1]
+    assert np.allclose(ts[..., DIC][wet], 2.244e-3, rtol=1e-14)
+    # initial surface carbonate system for DIC 2244 / ALK 2363 umol/kg at 5 C, S 34.9: seeded at pH 7.8, solves to
+    # pH(SWS) 7.94, [CO3] ~ ALK-DIC-borate ~ 95 umol/kg, calcite saturation ~2.3, Revelle factor ~16 (cold water)
+    carb = o.f("carb").reshape(J, I, -1)[k1 <= K]
+    assert np.all(np.abs(-np.log10(carb[:, 0]) - 7.944) < 0.01)
+    assert np.all(np.abs(carb[:, 2] - 95e-6) < 5e-6) and np.all(np.abs(carb[:, 5] - 2.26) < 0.05)
+    assert np.all(np.abs(carb[:, 9] - 16.0) < 0.5)
+    assert np.allclose(carb[:, 1] + carb[:, 2] + carb[:, 3], 2.244e-3, rtol=1e-12)   # CO2 + CO3 + HCO3 = DIC
+    atm = o.f("atm").reshape(J, I, LA)
+    assert np.all(atm[..., 2] == 278.0e-6) and np.all(atm[..., 0] == 273.15)
+
+
+def test_mass_balances_over_a_year(bg):
+    """P, Ca and the alkalinity combination ALK - 16 (POP + DOP) + 2 CaCO3 are conserved by uptake, DOM cycling,
+    sinking, remineralisation, the closed-system sediment return and the salinity-normalised tracer coupling."""
+    o = bg
+    b0 = budgets(o)
+    o.run(480)
+    b1 = budgets(o)
+    for k in b0:
+        assert abs(b1[k] - b0[k]) <= 2e-11 * abs(b0[k]), (k, b0[k], b1[k])
+    part = o.f("bio_part").reshape(K, J, I, LS)
+    assert part[..., POC].max() > 1e-8                      # export production happened
+    assert np.abs(o.f("ocn").reshape(K, J, I, L)[..., DOMC]).max() > 1e-6   # DOM pool built up
+    atm = o.f("atm").reshape(J, I, LA)
+    assert abs(atm[0, 0, 2] - 278e-6) < 5e-6                # pCO2 restored towards 278 ppm (tau = 0.1 yr)
+    assert np.ptp(atm[..., 2]) == 0.0                       # homogenised atmosphere (atchem.f90:140-150)
+    assert o.s("bg_go") == 1.0 and o.s("bg_clock_ms") == 480 * round(1000.0 * 3600.0 * 24.0 * 365.25 / 5.0 / 96)
+
+
+def test_particle_flux_profile(bg):
+    """After a year the POC reaching depth follows the two-fraction e-folding profile: below ~1 km the labile
+    fraction (eL1 = 500 m) is gone and the recalcitrant share frac2 approaches 1."""
+    o = bg
+    part = o.f("bio_part").reshape(K, J, I, LS)
+    f2 = part[..., 7]
+    poc = part[..., POC]
+    deep = (poc > 1e-12) & (np.arange(K)[:, None, None] < 6)
+    assert deep.any() and f2[deep].min() > 0.3
+    assert np.all((f2 >= 0) & (f2 <= 1.0 + 1e-12))
+
+
+def test_regression_vector(bg):
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_eb_go_gs_ac_bg_36x36x16_1yr.json")))["values"]
+    o = bg                                                   # state after exactly one model year (test above)
+    ocn = o.f("ocn").reshape(K, J, I, L)
+    M = o.f("bg_M").reshape(K, J, I)
+    got = dict(DIC=float((ocn[..., DIC] * M).sum()), O2=float((ocn[..., O2] * M).sum()),
+               PO4=float((ocn[..., PO4] * M).sum()), pCO2=float(o.f("atm").reshape(J, I, LA)[0, 0, 2]),
+               POC_max=float(o.f("bio_part").reshape(K, J, I, LS)[..., POC].max()))
+    for k, v in want.items():
+        assert np.isclose(got[k], v, rtol=1e-9, atol=0.0), (k, got[k], v)
