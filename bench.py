@@ -2,8 +2,8 @@
 """bench.py -- ensemble model-years per wall-hour of the cGENIE hot path on B200.
 
 One "step" = one model year of every ensemble member resident on this rank's GPU: nyear ocean
-steps (tstepo_flux + co + momentum), 5*nyear EMBM steps, nyear surflux and sea-ice steps (and the
-BIOGEM/ATCHEM steps once those kernels exist).  Members are sharded across ranks with no collective
+steps (tstepo_flux + co + momentum), 5*nyear EMBM steps, nyear surflux and sea-ice steps, nyear/2
+BIOGEM steps (step_biogem + tracer coupling + climate) and nyear/2 ATCHEM steps.  Members are sharded across ranks with no collective
 on the timestep path (weak scaling: members per GPU fixed).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--members M] [--impl reference]
@@ -30,10 +30,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CONFIG = "eb_go_gs_36x36x16_L16"
-WORKLOAD = ("eb_go_gs 36x36x16 worjh2, 16 tracers on ts (T,S + 14 passive; BIOGEM sources not on device yet), "
-            "parameter-perturbed ensemble sharded by member (BASELINE config #4 shape: 128 members/GPU)")
-from cgenie_b200.sharding import PERTURBED, SEED, perturbation_table, shard  # noqa: E402  (pure numpy)
+CONFIG = "eb_go_gs_ac_bg_36x36x16"
+WORKLOAD = ("eb_go_gs_ac_bg 36x36x16 worjh2: EMBM + GOLDSTEIN + sea ice + BIOGEM (16 ocean tracers, 1N1T_PO4MM, "
+            "13C/14C, CFCs) + ATCHEM, parameter-perturbed ensemble sharded by member "
+            "(BASELINE config #4 shape: 128 members/GPU = 1024 at 8 GPUs)")
+from cgenie_b200.sharding import PERTURBED, PERTURBED_BIOGEM, SEED, perturbation_table, shard  # noqa: E402  (pure numpy)
 
 
 def peaks():
@@ -93,7 +94,8 @@ class ClockSampler(threading.Thread):
 def _oracle_worker(args):
     years, params = args
     from oracle_lib import Oracle
-    o = Oracle("worjh2", maxk=16, maxl=16, nyear=96, **params)
+    o = Oracle("worjh2", maxk=16, maxl=16, nyear=96, **{k: v for k, v in params.items() if not k.startswith("par_bio")})
+    o.biogem_setup(**{k: v for k, v in params.items() if k.startswith("par_bio")})
     t0 = time.perf_counter()
     o.run(int(round(years * 96 * 5)))
     dt = time.perf_counter() - t0
@@ -105,7 +107,7 @@ def cpu_oracle_rate(years_per_core, cores):
     """Aggregate model-years/hour of `cores` single-threaded oracle processes, one member each."""
     import oracle_lib
     oracle_lib.lib()  # build once before forking
-    tab = perturbation_table(max(cores, 16))
+    tab = perturbation_table(max(cores, 16), biogem=True)
     jobs = [(years_per_core, {k: float(v[c]) for k, v in tab.items()}) for c in range(cores)]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
@@ -177,20 +179,13 @@ def main():
 
     from cgenie_b200 import Ensemble, materialise
     M = args.members
-    pert = shard(perturbation_table(M * world), rank, world, M)
+    pert = shard(perturbation_table(M * world, biogem=True), rank, world, M)
     tmp = tempfile.mkdtemp(prefix="cgenie_job_")
     materialise(tmp, CONFIG)
     e = Ensemble(tmp, n_members=M, device=local, perturb=pert)
     e.set_tracer_variant(args.variant)
     kyear = e.nyear * e.ndta
-    # passive tracers 3..L get a smooth non-trivial field (identical recipe on every member)
     L, I, J, K = e.maxl, e.maxi, e.maxj, e.maxk
-    ts = e.get_all("ts").reshape(K, J, I, L, e.member_stride)
-    kk, jj, ii = np.meshgrid(np.arange(1, K + 1), np.arange(1, J + 1), np.arange(1, I + 1), indexing="ij")
-    for l in range(2, L):
-        ts[:, :, :, l, :] = (1.0 + 0.1 * np.sin(2 * np.pi * ii / I) * np.cos(np.pi * jj / J) * (kk / K) * (1 + l / L))[..., None]
-    e.put_all("ts", ts)
-    del ts
 
     # ---- device-resident throughput
     for _ in range(args.warmup):
@@ -215,7 +210,7 @@ def main():
     e.profile(True)
     e.run(kyear)
     e.profile(False)
-    fam = {f: e.profile_get(f) for f in ("tstepo_flux", "co", "momentum", "embm", "surflux", "seaice")}
+    fam = {f: e.profile_get(f) for f in ("tstepo_flux", "co", "momentum", "embm", "surflux", "seaice", "biogem")}
     k1 = e.iconst("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
     n_wet = int(np.sum(np.clip(K - k1 + 1, 0, None)[k1 <= K]))
     bytes_per_launch = n_wet * (16 * L + 32) * M          # B_tr x members of one launch
@@ -241,6 +236,11 @@ def main():
     h2d = sum(a.nbytes for a in pin.values())
     d2h = h2d
 
+    genie_timestep = 3600.0 * 24.0 * 365.25 / 5.0 / e.nyear
+    clock_tick = int(round(1000.0 * genie_timestep))
+    dts_bg = float(2 * 5) * genie_timestep
+    e2e_k0 = [(args.warmup + args.steps + 1) * kyear]
+
     def e2e_year():
         for n in pin:
             e.put_all(n, pin[n])
@@ -253,6 +253,14 @@ def main():
             if k % 5 == 0:
                 e.step_seaice()
                 e.step_goldstein()
+            if k % 10 == 0:   # conv_kocn_kbiogem = conv_kocn_katchem = 2 (genie.f90:352-447)
+                clock = (e2e_k0[0] + k) * clock_tick
+                e.biogem_forcing(clock)
+                e.biogem_step(dts_bg, clock)
+                e.biogem_tracercoupling()
+                e.biogem_climate()
+                e.atchem_step(dts_bg)
+        e2e_k0[0] += kyear
         for n in pin:
             e.get_all(n, out=pin[n])
 
@@ -271,13 +279,13 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "members_per_gpu": M, "grid": [I, J, K], "tracers": L, "nyear": e.nyear,
-                   "tracer_variant": args.variant, "perturbed": PERTURBED, "seed": SEED,
+                   "tracer_variant": args.variant, "perturbed": PERTURBED + PERTURBED_BIOGEM, "seed": SEED,
                    "l2": "working set %.0f MB per GPU (two ts buffers + u + rho) exceeds the 126 MB L2" %
                          ((2 * L + 6) * I * J * K * 8 * e.member_stride / 1e6),
                    "step": "one model year of every member: %d koverall iterations" % kyear},
         "clocks": clocks, "gpu_launches": launches, "blown_up_members": bad, "roofline": roofline,
         "e2e": {"value": e2e_val, "unit": "model-years/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "path": "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein), state in/out of pinned host per year"},
+                "path": "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein/biogem_*/atchem), state in/out of pinned host per year"},
     }
     if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -5,22 +5,26 @@ import numpy as np
 
 SEED = 20261017
 BASE = dict(diff1=2000.0, diff2=1.0e-5, adrag=2.5, scf=2.0, diffamp1=5.0e6, diffamp2=1.0e6, betaz2=0.4, betam2=0.4)
+# BIOGEM parameters of SURVEY.md 8d; appended so that the physics columns of the table keep their values
+BASE_BIOGEM = dict(par_bio_k0_PO4=2.0e-6, par_bio_remin_POC_eL1=500.0, par_bio_red_POC_CaCO3=0.2)
 PERTURBED = list(BASE)
+PERTURBED_BIOGEM = list(BASE_BIOGEM)
 ADRAG_GROUP = 16  # members per barotropic factorisation (adrag is perturbed per group)
 
 
-def perturbation_table(n_total, seed=SEED):
+def perturbation_table(n_total, seed=SEED, biogem=False):
     """Member m scales each whitelisted parameter by U(0.8, 1.25); member 0 is the unperturbed control
     (SURVEY.md 8d).  Deterministic in (n_total, seed); the first n rows do not depend on n_total."""
     tab = {}
-    for q, k in enumerate(PERTURBED):
+    base = dict(BASE, **BASE_BIOGEM) if biogem else BASE
+    for q, k in enumerate(PERTURBED + (PERTURBED_BIOGEM if biogem else [])):
         rng = np.random.default_rng([seed, q])
         f = rng.uniform(0.8, 1.25, size=n_total)
         if k == "adrag":
             f = np.repeat(f[::ADRAG_GROUP], ADRAG_GROUP)[:n_total]
             f[:ADRAG_GROUP] = 1.0
         f[0] = 1.0
-        tab[k] = BASE[k] * f
+        tab[k] = base[k] * f
     return tab
 
 

@@ -17,7 +17,7 @@ ap.add_argument("--members", type=int, default=128)
 ap.add_argument("--spin", type=int, default=10, help="ocean steps before the measured ones")
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--variant", default="fast")
-ap.add_argument("--config", default="eb_go_gs_36x36x16_L16")
+ap.add_argument("--config", default="eb_go_gs_ac_bg_36x36x16")
 ap.add_argument("--profile", action="store_true", help="print CUDA-event time per kernel family")
 a = ap.parse_args()
 d = tempfile.mkdtemp()
@@ -26,11 +26,12 @@ e = Ensemble(d, n_members=a.members)
 e.set_tracer_variant(a.variant)
 e.set_graphs(False)
 L, I, J, K = e.maxl, e.maxi, e.maxj, e.maxk
-ts = e.get_all("ts").reshape(K, J, I, L, e.member_stride)
-kk, jj, ii = np.meshgrid(np.arange(1, K + 1), np.arange(1, J + 1), np.arange(1, I + 1), indexing="ij")
-for l in range(2, L):
-    ts[:, :, :, l, :] = (1.0 + 0.1 * np.sin(2 * np.pi * ii / I) * np.cos(np.pi * jj / J) * (kk / K) * (1 + l / L))[..., None]
-e.put_all("ts", ts)
+if "ac_bg" not in a.config and L > 2:   # passive tracers of the physics-only configurations
+    ts = e.get_all("ts").reshape(K, J, I, L, e.member_stride)
+    kk, jj, ii = np.meshgrid(np.arange(1, K + 1), np.arange(1, J + 1), np.arange(1, I + 1), indexing="ij")
+    for l in range(2, L):
+        ts[:, :, :, l, :] = (1.0 + 0.1 * np.sin(2 * np.pi * ii / I) * np.cos(np.pi * jj / J) * (kk / K) * (1 + l / L))[..., None]
+    e.put_all("ts", ts)
 e.run(5 * a.spin)
 e.synchronize()
 if a.profile:
@@ -38,7 +39,7 @@ if a.profile:
 e.run(5 * a.steps)
 e.synchronize()
 if a.profile:
-    fam = {f: e.profile_get(f) for f in ("tstepo_flux", "co", "momentum", "embm", "surflux", "seaice")}
+    fam = {f: e.profile_get(f) for f in ("tstepo_flux", "co", "momentum", "embm", "surflux", "seaice", "biogem")}
     print("cfg=%s variant=%s M=%d us/step: " % (os.environ.get("CG_TRACER_CFG", "0"), a.variant, a.members) +
           " ".join("%s=%.1f" % (k, 1e3 * v[0] / a.steps) for k, v in fam.items()))
 print("done", e.launch_count())
