@@ -61,58 +61,102 @@ __global__ void __launch_bounds__(128) k_tc_partial(const Dev v, const int phase
   }
 }
 
-// ordered sum over the wet columns: thread = (member, quantity)
-__global__ void __launch_bounds__(128) k_tc_sum(const Dev v, const int q0, const int q1) {
-  const int MS = v.MS;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  const int q = q0 + blockIdx.y * blockDim.y + threadIdx.y;
-  if (m >= MS || q >= q1) return;
-  const double *part = v.bg_part + (size_t)q * v.nwet * MS + m;
+// Sum of n terms per member IN ORDER (term t of lane's member at p[t*stride]), done by one warp: the terms are staged
+// through shared memory in tiles of kSumTile x 32 by all warps of the block (coalesced, many loads in flight), then
+// warp 0 adds its lane's column of the tile sequentially.  Bit-identical to the reference's scalar loop, but the memory
+// latency is paid once per tile instead of once per term.
+constexpr int kSumTile = 128, kSumWarps = 8;   // blocks using ordered_sum_block have 32*kSumWarps threads
+__device__ double ordered_sum_block(const double *__restrict__ p, const size_t stride, const int n, double *tile /* [kSumTile][32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kPer = kSumTile / kSumWarps;
   double s = 0.0;
-  for (int n = 0; n < v.nwet; n++) s = s + part[(size_t)n * MS];
-  v.bg_tot[(size_t)q * MS + m] = s;
+  for (int t0 = 0; t0 < n; t0 += kSumTile) {
+    const int nt = min(kSumTile, n - t0);
+    double r[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; u++) {   // all loads of the tile in flight before the first use
+      const int t = warp + u * kSumWarps;
+      r[u] = (t < nt) ? p[(size_t)(t0 + t) * stride + lane] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kPer; u++) tile[(warp + u * kSumWarps) * 32 + lane] = r[u];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll 16
+      for (int t = 0; t < nt; t++) s = s + tile[t * 32 + lane];
+    }
+    __syncthreads();
+  }
+  return s;  // valid in warp 0
 }
 
-// (2)+(3) of biogem_tracercoupling: new T,S, rescaled tracers, cell masses, ts <- normalised ocn
-__global__ void __launch_bounds__(128) k_tc_apply(const Dev v) {
+// ordered sum over the wet columns: block = (32-member tile, quantity)
+__global__ void __launch_bounds__(32 * kSumWarps) k_tc_sum(const Dev v, const int q0, const int q1) {
+  __shared__ double tile[kSumTile * 32];
+  const int MS = v.MS;
+  const int m0 = blockIdx.x * 32;
+  const int q = q0 + blockIdx.y;
+  if (q >= q1) return;
+  const double s = ordered_sum_block(v.bg_part + (size_t)q * v.nwet * MS + m0, (size_t)MS, v.nwet, tile);
+  if (threadIdx.x < 32) v.bg_tot[(size_t)q * MS + m0 + threadIdx.x] = s;
+}
+
+// (2)+(3) of biogem_tracercoupling: new T,S, rescaled tracers, cell masses, ts <- normalised ocn.  Cells are independent
+// here, so the grid runs over (member tile, cell) with one warp per cell; the per-member totals are staged once per
+// block in shared memory.
+constexpr int kApplyCellsPerWarp = 4, kApplyWarps = 8;
+__global__ void __launch_bounds__(32 * kApplyWarps) k_tc_apply(const Dev v) {
+  __shared__ double s_f[kBgMaxL][32], s_rmean[32], s_sr[32], s_rsr[32], s_mnew[32];
   const int I = v.I, J = v.J, K = v.K, L = v.L, MS = v.MS;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = blockIdx.y * blockDim.y + threadIdx.y;
-  if (m >= MS || n >= v.nwet) return;
-  const int c2 = v.bgcols[n];
-  const int i = c2 % I + 1, j = c2 / I + 1;
-  const int k1c = CG_K1(v, i, j);
-  const size_t sC = (size_t)L * MS, sK = (size_t)I * J * sC;
-  const size_t o0 = cell3(I, J, i, j, 1) * sC + m;
-  const size_t p0 = cell3(I, J, i, j, 1) * MS + m, pK = (size_t)I * J * MS;
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int m = blockIdx.x * 32 + lane;
+  if (warp == 0) {
+    const double mean_S_OLD = v.bg_tot[m], mean_S_NEW = v.bg_tot[MS + m];
+    s_rmean[lane] = 1.0 / mean_S_OLD;
+    const double Sratio = mean_S_NEW / mean_S_OLD;
+    s_sr[lane] = Sratio;
+    s_rsr[lane] = 1.0 / Sratio;
+    s_mnew[lane] = mean_S_NEW;
+  }
+  for (int l = 2 + warp; l < L; l += kApplyWarps) {
+    const double told = v.bg_tot[(size_t)l * MS + m], tnew = v.bg_tot[(size_t)(L - 2 + l) * MS + m];
+    const double rtnew = (fabs(tnew) < kBgNullSmall) ? 0.0 : 1.0 / tnew;
+    s_f[l][lane] = told * rtnew;
+  }
+  __syncthreads();
+  const double rmean_S_OLD = s_rmean[lane], Sratio = s_sr[lane], rSratio = s_rsr[lane], mean_S_NEW = s_mnew[lane];
   const double saln0 = v.p.saln0[m];
-  const double mean_S_OLD = v.bg_tot[m], mean_S_NEW = v.bg_tot[MS + m];
-  const double rmean_S_OLD = 1.0 / mean_S_OLD;
-  const double Sratio = mean_S_NEW / mean_S_OLD, rSratio = 1.0 / Sratio;
-  for (int k = K; k >= k1c; k--) {
-    const size_t o = o0 + (size_t)(k - 1) * sK;
-    const double Sold = v.bg_ocn[o + MS];
-    const double Tn = v.ts_cur[o] + kBgZeroC + v.bg_vdocn[o];
-    const double Sn = v.ts_cur[o + MS] + saln0 + v.bg_vdocn[o + MS];
-    v.bg_ocn[o] = Tn;
-    v.bg_ocn[o + MS] = Sn;
-    v.ts_cur[o] = Tn - kBgZeroC;
-    v.ts_cur[o + MS] = Sn - saln0;
+  const int ncell = I * J * K;
+  const int c0 = (blockIdx.y * kApplyWarps + warp) * kApplyCellsPerWarp;
+  for (int c = c0; c < min(c0 + kApplyCellsPerWarp, ncell); c++) {
+    const int k = c / (I * J) + 1, r = c % (I * J), j = r / I + 1, i = r % I + 1;
+    if (k < CG_K1(v, i, j)) continue;
+    const size_t o = (size_t)c * L * MS + m;
+    double *__restrict__ ocn = v.bg_ocn + o;
+    double *__restrict__ ts = v.ts_cur + o;
+    const double *__restrict__ dv = v.bg_vdocn + o;
+    const double Sold = ocn[MS];
+    const double Tn = ts[0] + kBgZeroC + dv[0];
+    const double Sn = ts[MS] + saln0 + dv[MS];
+    const double rn = mean_S_NEW / Sn;
+    ocn[0] = Tn;
+    ocn[MS] = Sn;
+    ts[0] = Tn - kBgZeroC;
+    ts[MS] = Sn - saln0;
+#pragma unroll 7
     for (int l = 2; l < L; l++) {
-      const double told = v.bg_tot[(size_t)l * MS + m], tnew = v.bg_tot[(size_t)(L - 2 + l) * MS + m];
-      const double rtnew = (fabs(tnew) < kBgNullSmall) ? 0.0 : 1.0 / tnew;
-      const double lv = v.ts_cur[o + (size_t)l * MS] * Sold * rmean_S_OLD;
-      double x = (told * rtnew) * lv + v.bg_vdocn[o + (size_t)l * MS];
+      const double lv = ts[(size_t)l * MS] * Sold * rmean_S_OLD;
+      double x = s_f[l][lane] * lv + dv[(size_t)l * MS];
       x = Sratio * x;
-      v.bg_ocn[o + (size_t)l * MS] = x;
-      v.ts_cur[o + (size_t)l * MS] = (mean_S_NEW / Sn) * x;
+      ocn[(size_t)l * MS] = x;
+      ts[(size_t)l * MS] = rn * x;
     }
     if (v.bg_biopart) {  // biogem.f90:2042-2043 (vdbio_part = 0: no particulate flux forcing)
-      const size_t q = (cell3(I, J, i, j, k) * v.bg_LS) * MS + m;
-      for (int ls = 0; ls < v.bg_LS; ls++) v.bg_biopart[q + (size_t)ls * MS] = Sratio * (v.bg_biopart[q + (size_t)ls * MS] + 0.0);
+      double *__restrict__ bp = v.bg_biopart + (size_t)c * v.bg_LS * MS + m;
+      for (int ls = 0; ls < v.bg_LS; ls++) bp[(size_t)ls * MS] = Sratio * (bp[(size_t)ls * MS] + 0.0);
     }
-    v.bg_M[p0 + (size_t)(k - 1) * pK] = rSratio * v.bg_M[p0 + (size_t)(k - 1) * pK];
-    v.bg_rM[p0 + (size_t)(k - 1) * pK] = Sratio * v.bg_rM[p0 + (size_t)(k - 1) * pK];
+    v.bg_M[(size_t)c * MS + m] = rSratio * v.bg_M[(size_t)c * MS + m];
+    v.bg_rM[(size_t)c * MS + m] = Sratio * v.bg_rM[(size_t)c * MS + m];
   }
 }
 
@@ -337,14 +381,9 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
     b.carbH[c2d * MS + m] = cb.H;
     return;
   }
-  double lrem[kBgSlots][kBgMaxK + 1];   // loc_bio_remin of sub_box_remin_part
-  double pnew[kBgMaxLS + 1][kBgMaxK + 1];
   double fsed[kBgSlots];
-  double tprev[kBgMaxLS + 1], tcur[kBgMaxLS + 1], set1[kBgMaxLS + 1];
-  // ---- decay of radioactive particulates (:862-871) and closed-system sediment return (:887-940)
-  for (int ls = 1; ls <= LS; ls++)
-    if (fabs(b.lam_sed[ls]) > kNS)
-      for (int k = k1; k <= K; k++) PART_(ls, k) = b.fd_sed[ls] * PART_(ls, k);
+  double set1[kBgMaxLS + 1];
+  // ---- closed-system sediment return (:887-940) from the settling flux of the previous step
   for (int q = 0; q < kBgSlots; q++) fsed[q] = 0.0;
   {
     const double f = redfield_factor(b, OCN_(b.l_O2, k1));
@@ -353,90 +392,6 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
         const int q = b.lrem_slot[b.ls_lo[ls][r]];
         fsed[q] = fsed[q] + (f * b.conv_ls_lo[ls][r]) * SET1_(ls);
       }
-  }
-  // ---- sub_box_remin_DOM: result straight into vdocn(l,k)
-  for (int k = K; k >= k1; k--) {
-    double ratio;
-    for (int l = 1; l <= L; l++) DOCN_(l, k) = 0.0;
-    for (int ls = 1; ls <= LS; ls++) tcur[ls] = 0.0;
-    if (b.DOMlifetime > dtyr) ratio = dtyr / b.DOMlifetime; else ratio = 1.0;
-    if (OCN_(b.l_DOMC, k) > kNS) {
-      for (int l = 3; l <= L; l++)
-        if (b.dom2pom[l]) {
-          const double x = OCN_(l, k);
-          tcur[b.dom2pom[l]] = tcur[b.dom2pom[l]] + 1.0 * ratio * x;
-          DOCN_(l, k) = DOCN_(l, k) - ratio * x;
-        }
-    }
-    const double f = redfield_factor(b, OCN_(b.l_O2, k));
-    for (int ls = 1; ls <= LS; ls++)
-      for (int r = 0; r < b.n_ls_lo[ls]; r++) {
-        const int lo = b.ls_lo[ls][r];
-        DOCN_(lo, k) = DOCN_(lo, k) + (f * b.conv_ls_lo[ls][r]) * tcur[ls];
-      }
-  }
-  // ---- sub_box_remin_part
-  for (int q = 0; q < kBgSlots; q++)
-    for (int k = 1; k <= K; k++) lrem[q][k] = 0.0;
-  for (int ls = 1; ls <= LS; ls++) {
-    set1[ls] = 0.0;
-    for (int k = 1; k <= K; k++) pnew[ls][k] = 0.0;
-  }
-  {
-    const int klim = (dtyr * b.sinkingrate <= b.dsc) ? k1 : K;
-    for (int k = K; k >= klim; k--) {
-      double part_tot = 0.0;
-      part_tot = part_tot + PART_(b.s_POC, k);
-      part_tot = part_tot + PART_(b.s_CaCO3, k);
-      if (part_tot > kNS) {
-        int min_k;
-        if (k == k1) min_k = k1 - 1;
-        else {
-          const double max_D = b.Dbot[k] + dtyr * b.sinkingrate;
-          min_k = k1 - 1;
-          for (int kk = k - 1; kk >= k1; kk--)
-            if (b.Dbot[kk] > max_D) { min_k = kk; break; }
-        }
-        for (int ls = 1; ls <= LS; ls++) tprev[ls] = PART_(ls, k);
-        // settling flux at the base of the source layer (kk = k)
-        if (k == k1)
-          for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((b.stype[ls] == 9) ? tprev[ls] : M_(k) * tprev[ls]);
-        for (int kk = k - 1; kk >= min_k; kk--) {
-          if (kk >= k1) {
-            const double layerratio = b.dD[kk + 1] / b.dD[kk];
-            const double Ca_f1 = b.CaCO3_f1[kk], Ca_f2 = b.CaCO3_f2[kk];
-            const double Ca_ratio = 1.0 - ((1.0 - tprev[b.s_CaCO3f2]) * Ca_f1 + tprev[b.s_CaCO3f2] * Ca_f2);
-            const double PO_f1 = b.POC_f1[(size_t)kk * MS + m], PO_f2 = b.POC_f2[kk];
-            const double PO_ratio = 1.0 - ((1.0 - tprev[b.s_POCf2]) * PO_f1 + tprev[b.s_POCf2] * PO_f2);
-            for (int ls = 1; ls <= LS; ls++) tcur[ls] = 0.0;
-            if (tprev[b.s_CaCO3f2] > kNS) tcur[b.s_CaCO3f2] = (1.0 - Ca_f2) * tprev[b.s_CaCO3f2] / Ca_ratio;
-            if (tprev[b.s_POCf2] > kNS) tcur[b.s_POCf2] = (1.0 - PO_f2) * tprev[b.s_POCf2] / PO_ratio;
-            for (int ls = 1; ls <= LS; ls++) {
-              const int dep_type = b.stype[b.sdep_ls[ls]];
-              if ((b.sdep_id[ls] == 3) || (b.stype[ls] == 3) || (dep_type == 3)) tcur[ls] = tprev[ls] * layerratio * PO_ratio;
-              else if ((b.sdep_id[ls] == 14) || (b.stype[ls] == 4) || (dep_type == 4)) tcur[ls] = tprev[ls] * layerratio * Ca_ratio;
-            }
-            const double f = redfield_factor(b, OCN_(b.l_O2, kk));
-            for (int ls = 1; ls <= LS; ls++) {
-              const double part_remin = (layerratio * tprev[ls] - tcur[ls]);
-              for (int r = 0; r < b.n_ls_lo[ls]; r++) {
-                const int q = b.lrem_slot[b.ls_lo[ls][r]];
-                lrem[q][kk] = lrem[q][kk] + (f * b.conv_ls_lo[ls][r]) * part_remin;
-              }
-            }
-            if (kk == min_k)
-              for (int ls = 1; ls <= LS; ls++) pnew[ls][kk] = pnew[ls][kk] + tcur[ls];
-            else if (kk == k1)   // kk > min_k = k1-1: flux through the base of the deepest layer
-              for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((b.stype[ls] == 9) ? tcur[ls] : M_(kk) * tcur[ls]);
-            for (int ls = 1; ls <= LS; ls++) tprev[ls] = tcur[ls];
-          }
-        }
-      }
-    }
-  }
-  for (int ls = 1; ls <= LS; ls++) {
-    for (int k = k1; k <= K; k++) PART_(ls, k) = pnew[ls][k];
-    SET1_(ls) = set1[ls];
   }
   // ---- surface cell: carbonate chemistry, solubility, piston velocity (:1026-1104)
   carbconst(b.Dmid_surf, T, S, OCN_(b.l_Ca, K), OCN_(b.l_Mg, K), cc);
@@ -556,7 +511,7 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
     const double red_Ca13 = alpha * R / (1.0 + alpha * R);
     alpha = 1.0 + 2.0 * delta_CaCO3 / 1000.0; R = r14_HCO3 / (1.0 - r14_HCO3);
     const double red_Ca14 = alpha * R / (1.0 + alpha * R);
-    for (int ls = 1; ls <= LS; ls++) psurf[ls] = PART_(ls, K);   // what remin left in the surface layer (0)
+    for (int ls = 1; ls <= LS; ls++) psurf[ls] = 0.0;   // nothing settles into the surface layer
     // bulk export (:1186-1230): POC currency, CaCO3, POP, isotopes
     psurf[b.s_POC] = b.red_POP_POC * dPO4;
     psurf[b.s_POC] = 1.0 * psurf[b.s_POC];
@@ -582,21 +537,117 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
       psurf[b.s_POCf2] = (1.0 - kP) * b.POC_dfrac2 + b.POC_frac2;
       psurf[b.s_CaCO3f2] = b.CaCO3_frac2;
     }
-    for (int ls = 1; ls <= LS; ls++) PART_(ls, K) = psurf[ls];
   }
-  // ---- tracer anomaly (:1811-1844) and bottom-water interface (:1736-1744)
-  for (int k = k1; k <= K; k++) {
-    const double rM = RM_(k), Mk = M_(k);
+  // ---- water column, one downward sweep (K -> k1).  sub_box_remin_part (:2412-2875) follows each source layer's
+  // particles down to the deepest layer they reach in dt; here all packets in flight are advanced level by level, kept in
+  // source order (shallowest source first = the reference's k loop), so every sum over sources at a given layer
+  // (remineralisation products, parked particles, settling flux) is accumulated in the reference's order.  Per level the
+  // sweep also does sub_box_remin_DOM (:2287-2406), the decay terms (:838-871) and the tracer anomaly (:1811-1844).
+  double pk[kBgMaxK][kBgMaxLS + 1];   // TMP(:, current level) of each packet
+  int pk_min[kBgMaxK];                // loc_bio_remin_min_k of each packet
+  int npk = 0;
+  const int klim = (dtyr * b.sinkingrate <= b.dsc) ? k1 : K;
+  for (int ls = 1; ls <= LS; ls++) set1[ls] = 0.0;
+  for (int kk = K; kk >= k1; kk--) {
+    double lrem[kBgSlots], pnew[kBgMaxLS + 1], dom[kBgMaxLS + 1];
+    for (int q = 0; q < kBgSlots; q++) lrem[q] = 0.0;
+    for (int ls = 1; ls <= LS; ls++) pnew[ls] = 0.0;
+    const double Mk = M_(kk), rM = RM_(kk);
+    const double f = redfield_factor(b, OCN_(b.l_O2, kk));
+    // (1) packets from the layers above pass through / stop in layer kk
+    if (npk > 0) {
+      const double layerratio = b.dD[kk + 1] / b.dD[kk];
+      const double Ca_f1 = b.CaCO3_f1[kk], Ca_f2 = b.CaCO3_f2[kk];
+      const double PO_f1 = b.POC_f1[(size_t)kk * MS + m], PO_f2 = b.POC_f2[kk];
+      int keep = 0;
+      for (int p = 0; p < npk; p++) {
+        double *tp = pk[p];
+        double tcur[kBgMaxLS + 1];
+        const double Ca_ratio = 1.0 - ((1.0 - tp[b.s_CaCO3f2]) * Ca_f1 + tp[b.s_CaCO3f2] * Ca_f2);
+        const double PO_ratio = 1.0 - ((1.0 - tp[b.s_POCf2]) * PO_f1 + tp[b.s_POCf2] * PO_f2);
+        for (int ls = 1; ls <= LS; ls++) tcur[ls] = 0.0;
+        if (tp[b.s_CaCO3f2] > kNS) tcur[b.s_CaCO3f2] = (1.0 - Ca_f2) * tp[b.s_CaCO3f2] / Ca_ratio;
+        if (tp[b.s_POCf2] > kNS) tcur[b.s_POCf2] = (1.0 - PO_f2) * tp[b.s_POCf2] / PO_ratio;
+        for (int ls = 1; ls <= LS; ls++) {
+          const int dep_type = b.stype[b.sdep_ls[ls]];
+          if ((b.sdep_id[ls] == 3) || (b.stype[ls] == 3) || (dep_type == 3)) tcur[ls] = tp[ls] * layerratio * PO_ratio;
+          else if ((b.sdep_id[ls] == 14) || (b.stype[ls] == 4) || (dep_type == 4)) tcur[ls] = tp[ls] * layerratio * Ca_ratio;
+        }
+        for (int ls = 1; ls <= LS; ls++) {
+          const double part_remin = (layerratio * tp[ls] - tcur[ls]);
+          for (int r = 0; r < b.n_ls_lo[ls]; r++) {
+            const int q = b.lrem_slot[b.ls_lo[ls][r]];
+            lrem[q] = lrem[q] + (f * b.conv_ls_lo[ls][r]) * part_remin;
+          }
+        }
+        if (kk == pk_min[p]) {            // deepest layer reached within dt: park the remainder here
+          for (int ls = 1; ls <= LS; ls++) pnew[ls] = pnew[ls] + tcur[ls];
+        } else if (kk == k1) {            // through the base of the deepest layer: settling flux
+          for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((b.stype[ls] == 9) ? tcur[ls] : Mk * tcur[ls]);
+        } else {                          // keeps sinking
+          for (int ls = 1; ls <= LS; ls++) pk[keep][ls] = tcur[ls];
+          pk_min[keep] = pk_min[p];
+          keep++;
+        }
+      }
+      npk = keep;
+    }
+    // (2) layer kk as a source (decayed particulates of the previous step, :862-871)
+    if (kk >= klim) {
+      double old[kBgMaxLS + 1];
+      for (int ls = 1; ls <= LS; ls++) {
+        old[ls] = PART_(ls, kk);
+        if (fabs(b.lam_sed[ls]) > kNS) old[ls] = b.fd_sed[ls] * old[ls];
+      }
+      double part_tot = 0.0;
+      part_tot = part_tot + old[b.s_POC];
+      part_tot = part_tot + old[b.s_CaCO3];
+      if (part_tot > kNS) {
+        if (kk == k1) {
+          for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((b.stype[ls] == 9) ? old[ls] : Mk * old[ls]);
+        } else {
+          const double max_D = b.Dbot[kk] + dtyr * b.sinkingrate;
+          int min_k = k1 - 1;
+          for (int k2 = kk - 1; k2 >= k1; k2--)
+            if (b.Dbot[k2] > max_D) { min_k = k2; break; }
+          for (int ls = 1; ls <= LS; ls++) pk[npk][ls] = old[ls];
+          pk_min[npk] = min_k;
+          npk++;
+        }
+      }
+    }
+    // (3) new particulate field of this layer
+    if (kk == K) { for (int ls = 1; ls <= LS; ls++) PART_(ls, kk) = psurf[ls]; }
+    else { for (int ls = 1; ls <= LS; ls++) PART_(ls, kk) = pnew[ls]; }
+    // (4) sub_box_remin_DOM for this layer
+    double ratio;
+    for (int ls = 1; ls <= LS; ls++) dom[ls] = 0.0;
+    if (b.DOMlifetime > dtyr) ratio = dtyr / b.DOMlifetime; else ratio = 1.0;
+    const bool has_dom = OCN_(b.l_DOMC, kk) > kNS;
+    // (5) tracer anomaly vdocn(l, kk) = bio_remin + dtyr*rM*focn
+    if (has_dom)
+      for (int l = 3; l <= L; l++)
+        if (b.dom2pom[l]) dom[b.dom2pom[l]] = dom[b.dom2pom[l]] + 1.0 * ratio * OCN_(l, kk);
+    double domrem[kBgSlots];   // DOM -> POM -> inorganic products (conv_ls_lo order)
+    for (int q = 0; q < kBgSlots; q++) domrem[q] = 0.0;
+    for (int ls = 1; ls <= LS; ls++)
+      for (int r = 0; r < b.n_ls_lo[ls]; r++) {
+        const int q = b.lrem_slot[b.ls_lo[ls][r]];
+        domrem[q] = domrem[q] + (f * b.conv_ls_lo[ls][r]) * dom[ls];
+      }
     for (int l = 1; l <= L; l++) {
       const int q = b.lrem_slot[l];
+      const double x = OCN_(l, kk);
+      double vrem = 0.0;                                   // loc_vbio_remin(l,k) of sub_box_remin_DOM
+      if (has_dom && l >= 3 && b.dom2pom[l]) vrem = vrem - ratio * x;
+      if (q) vrem = vrem + domrem[q];
       double rem = 0.0;
-      if (k == k1 && l >= 3 && q) rem = rem + rM * fsed[q];
-      else if (k == k1 && l >= 3) rem = rem + rM * 0.0;
-      rem = rem + (DOCN_(l, k) + (q ? lrem[q][k] : 0.0));
+      if (kk == k1 && l >= 3) rem = rem + rM * (q ? fsed[q] : 0.0);
+      rem = rem + (vrem + (q ? lrem[q] : 0.0));
       double focn = 0.0;
-      if (l >= 3 && fabs(b.lam_ocn[l]) > kNS) focn = focn - Mk * (1.0 - b.fd_ocn[l]) * OCN_(l, k) / dtyr;
-      if (l == 1 && k == k1) focn = focn + kYrS * b.Fgeothermal * A / (1.0E+03 * kCp);
-      if (k == K) {
+      if (l >= 3 && fabs(b.lam_ocn[l]) > kNS) focn = focn - Mk * (1.0 - b.fd_ocn[l]) * x / dtyr;
+      if (l == 1 && kk == k1) focn = focn + kYrS * b.Fgeothermal * A / (1.0E+03 * kCp);
+      if (kk == K) {
         focn = focn + focn_surf[l];
         if (l >= 3) {
           const int ls = b.dom2pom[l];
@@ -604,11 +655,11 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
           rem = rem - (q ? uptake[q] : 0.0);
         }
       }
-      const double d = rem + dtyr * rM * focn;
-      DOCN_(l, k) = d;
-      if (k == k1) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = OCN_(l, k) + rem + dtyr * rM * focn;
+      DOCN_(l, kk) = rem + dtyr * rM * focn;
+      if (kk == k1) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = x + rem + dtyr * rM * focn;
     }
   }
+  for (int ls = 1; ls <= LS; ls++) SET1_(ls) = set1[ls];
   for (int ls = 1; ls <= LS; ls++) {
     const double fs = set1[ls];
     const double rdts = 1.0 / b.dts;
@@ -631,37 +682,52 @@ __global__ void k_bg_climate(const Dev v, const BgDev b) {
   v.cost[q] = 0.0;
 }
 
-// step_atchem (atchem.f90:63-158) + cpl_comp_atmocn (:252-264): thread = (member, tracer la >= 3)
-__global__ void __launch_bounds__(128) k_bg_atchem(const Dev v, const BgDev b, const double atm_totV) {
+// step_atchem (atchem.f90:63-158) + cpl_comp_atmocn (:252-264).  k_bg_atchem1: thread = (member, cell, tracer), the
+// per-cell decay + flux update and the mole product loc_conv_atm_mol*atm.  k_bg_atchem2: block = (32-member tile, tracer),
+// the mole-weighted global sum (:146) taken in array-element order (ordered_sum_block: bit-identical to the sequential
+// code), then the homogenised partial pressure is written back to atm and the interface array.
+__global__ void __launch_bounds__(256) k_bg_atchem1(const Dev v, const BgDev b, double *__restrict__ scratch) {
   using namespace bgk;
   const int I = v.I, J = v.J, MS = v.MS;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  const int la = 3 + blockIdx.y;
-  if (m >= MS || la > b.LA) return;
-  const size_t ij = (size_t)I * J;
-  double *atm = b.atm + (size_t)(la - 1) * ij * MS + m;
-  const double *atmT = b.atm + m;
-  double *sfx = b.sfxsumatm + (size_t)(la - 1) * ij * MS + m;
-  double *sfc = b.sfcatm1 + (size_t)(la - 1) * ij * MS + m;
-  const bool decays = fabs(b.lam_atm[la]) > kNS;
+  const int m = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.y * blockDim.y + threadIdx.y;
+  const int la = 3 + blockIdx.z;
+  const int ij = I * J;
+  if (c >= ij) return;
+  const size_t q = ((size_t)(la - 1) * ij + c) * MS + m;
+  const double c_am = b.atm_V[c] / (kPaAtm * kRSI * b.atm[(size_t)c * MS + m]);
+  const double c_ma = 1.0 / c_am;
+  double a = b.atm[q];
+  if (fabs(b.lam_atm[la]) > kNS) a = b.fd_atm[la] * a;
   const double F14C = 0.0;   // par_atm_F14C (atchem-defaults.nml)
-  double tot = 0.0;
-  for (size_t c = 0; c < ij; c++) {   // array element order: i fastest
-    const double c_am = b.atm_V[c] / (kPaAtm * kRSI * atmT[c * MS]);
-    const double c_ma = 1.0 / c_am;
-    double a = atm[c * MS];
-    if (decays) a = b.fd_atm[la] * a;
-    double fl = 0.0;
-    if (la == b.a_CO214) fl = fl + b.dtyr_atchem * (1.0 / (double)(I * J)) * F14C;
-    a = a + c_ma * b.atm_A[c] * sfx[c * MS] + c_ma * fl;
-    atm[c * MS] = a;
-    tot = tot + c_am * a;
-  }
-  for (size_t c = 0; c < ij; c++) {
-    const double a = (tot / atm_totV) * kPaAtm * kRSI * atmT[c * MS];
-    atm[c * MS] = a;
-    sfc[c * MS] = a;
-    sfx[c * MS] = 0.0;
+  double fl = 0.0;
+  if (la == b.a_CO214) fl = fl + b.dtyr_atchem * (1.0 / (double)(I * J)) * F14C;
+  a = a + c_ma * b.atm_A[c] * b.sfxsumatm[q] + c_ma * fl;
+  scratch[((size_t)(la - 3) * ij + c) * MS + m] = c_am * a;
+}
+__global__ void __launch_bounds__(32 * kSumWarps) k_bg_atchem2(const Dev v, const BgDev b, const double atm_totV, const double *__restrict__ scratch) {
+  using namespace bgk;
+  __shared__ double tile[kSumTile * 32];
+  __shared__ double tot_s[32];
+  const int I = v.I, J = v.J, MS = v.MS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * 32;
+  const int la = 3 + blockIdx.y;
+  const int ij = I * J;
+  const double tot = ordered_sum_block(scratch + (size_t)(la - 3) * ij * MS + m0, (size_t)MS, ij, tile);
+  if (warp == 0) tot_s[lane] = tot;
+  __syncthreads();
+  const double t = tot_s[lane];
+  double *__restrict__ atm = b.atm + (size_t)(la - 1) * ij * MS + m0 + lane;
+  const double *__restrict__ atmT = b.atm + m0 + lane;
+  double *__restrict__ sfx = b.sfxsumatm + (size_t)(la - 1) * ij * MS + m0 + lane;
+  double *__restrict__ sfc = b.sfcatm1 + (size_t)(la - 1) * ij * MS + m0 + lane;
+#pragma unroll 6
+  for (int c = warp; c < ij; c += kSumWarps) {
+    const double a = (t / atm_totV) * kPaAtm * kRSI * atmT[(size_t)c * MS];
+    atm[(size_t)c * MS] = a;
+    sfc[(size_t)c * MS] = a;
+    sfx[(size_t)c * MS] = 0.0;
   }
 }
 
@@ -675,8 +741,11 @@ int launch_bg_climate(const Dev &v, const BgDev &b, cudaStream_t s) {
   return 1;
 }
 int launch_bg_atchem(const Dev &v, const BgDev &b, double atm_totV, cudaStream_t s) {
-  k_bg_atchem<<<dim3(v.MS / 32, b.LA - 2), 32, 0, s>>>(v, b, atm_totV);
-  return 1;
+  // scratch: the reduction buffer of the tracer coupling (idle here), (LA-2)*I*J*MS doubles
+  const int ij = v.I * v.J;
+  k_bg_atchem1<<<dim3(v.MS / 32, (ij + 7) / 8, b.LA - 2), dim3(32, 8), 0, s>>>(v, b, v.bg_part);
+  k_bg_atchem2<<<dim3(v.MS / 32, b.LA - 2), 32 * kSumWarps, 0, s>>>(v, b, atm_totV, v.bg_part);
+  return 2;
 }
 
 int launch_tracercoupling(const Dev &v, cudaStream_t s) {
@@ -684,12 +753,15 @@ int launch_tracercoupling(const Dev &v, cudaStream_t s) {
   const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
   const int L = v.L;
   k_tc_partial<<<gc, b, 0, s>>>(v, 0);
-  k_tc_sum<<<dim3(v.MS / 32, (L + 3) / 4), b, 0, s>>>(v, 0, L);
+  k_tc_sum<<<dim3(v.MS / 32, L), 32 * kSumWarps, 0, s>>>(v, 0, L);
   if (L > 2) {
     k_tc_partial<<<gc, b, 0, s>>>(v, 1);
-    k_tc_sum<<<dim3(v.MS / 32, (L - 2 + 3) / 4), b, 0, s>>>(v, L, 2 * L - 2);
+    k_tc_sum<<<dim3(v.MS / 32, L - 2), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2);
   }
-  k_tc_apply<<<gc, b, 0, s>>>(v);
+  {
+    const int ncell = v.I * v.J * v.K, per_block = kApplyWarps * kApplyCellsPerWarp;
+    k_tc_apply<<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
+  }
   return L > 2 ? 5 : 3;
 }
 int launch_bg_reset_cost(const Dev &v, cudaStream_t s) {
