@@ -36,6 +36,7 @@ void launch_global_means(const Dev &, double *out, cudaStream_t);
 int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
 int launch_bg_step(const Dev &, const BgDev &, int init_only, cudaStream_t);
+bool bg_layout_ok(const BgDev &, int L);
 int launch_bg_climate(const Dev &, const BgDev &, cudaStream_t);
 int launch_bg_atchem(const Dev &, const BgDev &, double atm_totV, cudaStream_t);
 void launch_health(const Dev &, int *flags, cudaStream_t);
@@ -519,7 +520,7 @@ static int build_device(cg_handle *h) {
     BgDev &b = h->bgd;
     const int LS = bc.LS, LA = bc.LA;
     bg_fill_tables(bc, h->base, g, &b);
-    if (b.n_lrem >= 8) return fail(CG_ERR_CONFIG, "BIOGEM: too many remineralisation targets for the compiled kernel");
+    if (!bg_layout_ok(b, L)) return fail(CG_ERR_CONFIG, "BIOGEM: tracer tables differ from the layout k_bg_step is compiled for");
     CUDA_OK(cudaMemcpy(v.bg_ocn, h->bg_ocn0.data(), h->bg_ocn0.size() * 8, cudaMemcpyHostToDevice));
     h->bg_ocn0.clear(); h->bg_ocn0.shrink_to_fit();
     TRY(dalloc(h, &b.bio_part, ijk * LS * MS));

@@ -349,11 +349,67 @@ __device__ __forceinline__ double redfield_factor(const BgDev &b, double o2) {  
 }
 }  // namespace bgk
 
-constexpr int kBgSlots = 8;  // ocean tracers receiving remineralisation products (DIC, 13C, 14C, PO4, O2, ALK, Ca)
+// Compact tracer layout of the frozen configuration (cg_biogem.cu builds the tables; bg_layout_ok() on the host refuses
+// anything else).  k_bg_step is written against this layout so that the tracer relationships of
+// sub_data_update_tracerrelationships (biogem_data.f90:731-920) become straight-line code in the reference's loop order.
+namespace lay {
+enum { T = 1, S, DIC, DIC13, DIC14, PO4, O2, ALK, DOMC, DOMC13, DOMC14, DOMP, CA, CFC11, CFC12, MG, NL = 16 };
+enum { POC = 1, POC13, POC14, POP, CACO3, CACO313, CACO314, POCF2, CACO3F2, NLS = 9 };
+enum { A_T = 1, A_Q, A_CO2, A_CO213, A_CO214, A_O2, A_CFC11, A_CFC12, NLA = 8 };
+}  // namespace lay
+bool bg_layout_ok(const BgDev &b, int L) {
+  using namespace lay;
+  if (L != NL || b.LS != NLS || b.LA != NLA) return false;
+  if (b.l_DIC != DIC || b.l_DIC13 != DIC13 || b.l_DIC14 != DIC14 || b.l_PO4 != PO4 || b.l_O2 != O2 || b.l_ALK != ALK ||
+      b.l_DOMC != DOMC || b.l_Ca != CA || b.l_Mg != MG) return false;
+  if (b.s_POC != POC || b.s_POC13 != POC13 || b.s_POC14 != POC14 || b.s_POP != POP || b.s_CaCO3 != CACO3 ||
+      b.s_CaCO313 != CACO313 || b.s_CaCO314 != CACO314 || b.s_POCf2 != POCF2 || b.s_CaCO3f2 != CACO3F2) return false;
+  if (b.a_CO2 != A_CO2 || b.a_CO213 != A_CO213 || b.a_CO214 != A_CO214) return false;
+  const int want_n[NLS + 1] = {0, 2, 1, 1, 3, 3, 1, 1, 0, 0};
+  const int want_lo[NLS + 1][3] = {{0, 0, 0}, {DIC, O2, 0}, {DIC13, 0, 0}, {DIC14, 0, 0}, {PO4, O2, ALK}, {DIC, ALK, CA},
+                                   {DIC13, 0, 0}, {DIC14, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int ls = 1; ls <= NLS; ls++) {
+    if (b.n_ls_lo[ls] != want_n[ls]) return false;
+    for (int r = 0; r < want_n[ls]; r++) if (b.ls_lo[ls][r] != want_lo[ls][r]) return false;
+  }
+  // unit coefficients that the kernel folds away
+  if (b.conv_ls_lo[POC][0] != 1.0 || b.conv_ls_lo[POC13][0] != 1.0 || b.conv_ls_lo[POC14][0] != 1.0 || b.conv_ls_lo[POP][0] != 1.0 ||
+      b.conv_ls_lo[CACO3][0] != 1.0 || b.conv_ls_lo[CACO3][2] != 1.0 || b.conv_ls_lo[CACO313][0] != 1.0 || b.conv_ls_lo[CACO314][0] != 1.0)
+    return false;
+  if (b.dom2pom[DOMC] != POC || b.dom2pom[DOMC13] != POC13 || b.dom2pom[DOMC14] != POC14 || b.dom2pom[DOMP] != POP) return false;
+  if (b.atm2ocn[A_CO2] != DIC || b.atm2ocn[A_CO213] != DIC13 || b.atm2ocn[A_CO214] != DIC14 || b.atm2ocn[A_O2] != O2 ||
+      b.atm2ocn[A_CFC11] != CFC11 || b.atm2ocn[A_CFC12] != CFC12) return false;
+  const int want_st[NLS + 1] = {0, 1, 11, 12, 3, 1, 11, 12, 9, 9};
+  for (int ls = 1; ls <= NLS; ls++) if (b.stype[ls] != want_st[ls]) return false;
+  return true;
+}
+
+// dissolved products of remineralising particulates, accumulated in the order of the reference's (ls, io) loops
+struct Rem7 { double dic, d13, d14, po4, o2, alk, ca; };
+__device__ __forceinline__ void rem_zero(Rem7 &r) { r.dic = r.d13 = r.d14 = r.po4 = r.o2 = r.alk = r.ca = 0.0; }
+// r += (f*conv_ls_lo(lo,ls)) * p(ls) for ls = POC .. CaCO3_14C (conv = 1 folds to f)
+__device__ __forceinline__ void rem_add(Rem7 &r, const double f, const double *p, const double fO2POC, const double fO2POP,
+                                        const double fALKPOP, const double fALKCa) {
+  using namespace lay;
+  r.dic = r.dic + f * p[POC];
+  r.o2 = r.o2 + fO2POC * p[POC];
+  r.d13 = r.d13 + f * p[POC13];
+  r.d14 = r.d14 + f * p[POC14];
+  r.po4 = r.po4 + f * p[POP];
+  r.o2 = r.o2 + fO2POP * p[POP];
+  r.alk = r.alk + fALKPOP * p[POP];
+  r.dic = r.dic + f * p[CACO3];
+  r.alk = r.alk + fALKCa * p[CACO3];
+  r.ca = r.ca + f * p[CACO3];
+  r.d13 = r.d13 + f * p[CACO313];
+  r.d14 = r.d14 + f * p[CACO314];
+}
 
 __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, const int init_only) {
   using namespace bgk;
-  const int I = v.I, J = v.J, K = v.K, L = v.L, MS = v.MS, LS = b.LS, LA = b.LA;
+  using namespace lay;
+  const int I = v.I, J = v.J, K = v.K, MS = v.MS;
+  constexpr int L = NL, LS = NLS, LA = NLA;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y * blockDim.y + threadIdx.y;
   if (m >= MS || n >= v.nwet) return;
@@ -371,47 +427,47 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
 #define RM_(k) v.bg_rM[p0 + (size_t)((k)-1) * pK]
 #define SET1_(ls) b.settle_k1[(c2d * LS + ((ls)-1)) * MS + m]
   const double dtyr = b.dtyr;
-  const double T = OCN_(1, K), S = OCN_(2, K);
+  const double Tsf = OCN_(T, K), Ssf = OCN_(S, K);
   double cc[N_CC];
   Carb cb;
   if (init_only) {  // sub_init_carb, biogem_data.f90:2336-2430 (surface cell)
-    carbconst(b.Dmid_surf, T, S, OCN_(b.l_Ca, K), OCN_(b.l_Mg, K), cc);
+    carbconst(b.Dmid_surf, Tsf, Ssf, OCN_(CA, K), OCN_(MG, K), cc);
     cb.H = pow(10.0, -7.8);
-    if (!solve_carb(OCN_(b.l_DIC, K), OCN_(b.l_ALK, K), OCN_(b.l_Ca, K), OCN_(b.l_PO4, K), S, cc, cb, false)) b.err[m] = 1;
+    if (!solve_carb(OCN_(DIC, K), OCN_(ALK, K), OCN_(CA, K), OCN_(PO4, K), Ssf, cc, cb, false)) b.err[m] = 1;
     b.carbH[c2d * MS + m] = cb.H;
     return;
   }
-  double fsed[kBgSlots];
-  double set1[kBgMaxLS + 1];
+  // conv_ls_lo coefficients that are not 1
+  const double cO2POC = b.conv_ls_lo[POC][1], cO2POP = b.conv_ls_lo[POP][1], cALKPOP = b.conv_ls_lo[POP][2],
+               cALKCa = b.conv_ls_lo[CACO3][1];
   // ---- closed-system sediment return (:887-940) from the settling flux of the previous step
-  for (int q = 0; q < kBgSlots; q++) fsed[q] = 0.0;
+  Rem7 fsed;
+  rem_zero(fsed);
   {
-    const double f = redfield_factor(b, OCN_(b.l_O2, k1));
-    for (int ls = 1; ls <= LS; ls++)
-      for (int r = 0; r < b.n_ls_lo[ls]; r++) {
-        const int q = b.lrem_slot[b.ls_lo[ls][r]];
-        fsed[q] = fsed[q] + (f * b.conv_ls_lo[ls][r]) * SET1_(ls);
-      }
+    const double f = redfield_factor(b, OCN_(O2, k1));
+    double st[LS + 1];
+#pragma unroll
+    for (int ls = 1; ls <= LS; ls++) st[ls] = SET1_(ls);
+    rem_add(fsed, f, st, f * cO2POC, f * cO2POP, f * cALKPOP, f * cALKCa);
   }
   // ---- surface cell: carbonate chemistry, solubility, piston velocity (:1026-1104)
-  carbconst(b.Dmid_surf, T, S, OCN_(b.l_Ca, K), OCN_(b.l_Mg, K), cc);
+  carbconst(b.Dmid_surf, Tsf, Ssf, OCN_(CA, K), OCN_(MG, K), cc);
   cb.H = b.carbH[c2d * MS + m];
   cb.RF0 = 0.0;
-  const double DIC = OCN_(b.l_DIC, K), PO4 = OCN_(b.l_PO4, K);
-  if (!solve_carb(DIC, OCN_(b.l_ALK, K), OCN_(b.l_Ca, K), PO4, S, cc, cb, true)) { b.err[m] = 1; return; }
+  const double DICs = OCN_(DIC, K), PO4s = OCN_(PO4, K);
+  if (!solve_carb(DICs, OCN_(ALK, K), OCN_(CA, K), PO4s, Ssf, cc, cb, true)) { b.err[m] = 1; return; }
   b.carbH[c2d * MS + m] = cb.H;
   double r13_CO2, r13_HCO3, r14_CO2, r14_HCO3;
-  carb_riso(T, DIC, OCN_(b.l_DIC13, K), cb, 1.0, kStd13C, r13_CO2, r13_HCO3);
-  carb_riso(T, DIC, OCN_(b.l_DIC14, K), cb, 2.0, kStd14C, r14_CO2, r14_HCO3);
-  const double rho = calc_rho(T, S);   // phys_ocn(ipo_rho) as left by biogem_climate (:2171)
+  carb_riso(Tsf, DICs, OCN_(DIC13, K), cb, 1.0, kStd13C, r13_CO2, r13_HCO3);
+  carb_riso(Tsf, DICs, OCN_(DIC14, K), cb, 2.0, kStd14C, r14_CO2, r14_HCO3);
+  const double rho = calc_rho(Tsf, Ssf);   // phys_ocn(ipo_rho) as left by biogem_climate (:2171)
   const double seaice = b.seaice[c2d * MS + m];
   const double A = b.A[c2d], rA = b.rA[c2d];
-  double focn_surf[kBgMaxL + 1];        // locijk_focn(:,i,j,n_k) contributions of the (i,j) loop
-  for (int l = 1; l <= L; l++) focn_surf[l] = 0.0;
+  double focn_surf[LA + 1];   // -conv_atm_ocn*focnatm of each gas, applied to its ocean tracer at the surface (:1612-1616)
   {
-    double fatm[kBgMaxLA + 1], focnatm[kBgMaxLA + 1], f_oa[kBgMaxLA + 1], f_ao[kBgMaxLA + 1];
-    double TC = T - kZeroC, TC2, TC3;
-    const double TCf = T - kZeroC;
+    double fatm[LA + 1], focnatm[LA + 1], f_oa[LA + 1], f_ao[LA + 1];
+    double TC = Tsf - kZeroC, TC2, TC3;
+    const double TCf = Tsf - kZeroC;
     if (TC < 0.0) TC = 0.0;
     if (TC > 30.0) TC = 30.0;
     TC2 = TC * TC; TC3 = TC2 * TC;
@@ -419,37 +475,42 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
     const double u2 = ws * ws;
     const double area = (1.0 - seaice) * A;
     double alpha_as = 0.0, alpha_sa = 0.0;
+#pragma unroll
     for (int la = 1; la <= LA; la++) { fatm[la] = 0.0; focnatm[la] = 0.0; f_oa[la] = 0.0; f_ao[la] = 0.0; }
+    double sfc[LA + 1];
+#pragma unroll
+    for (int la = 3; la <= LA; la++) sfc[la] = b.sfcatm1[((size_t)(la - 1) * I * J + c2d) * MS + m];
     // restoring of the atmosphere (:1119-1146)
+#pragma unroll
     for (int la = 3; la <= LA; la++)
       if (b.rst_active[la]) {
-        const double sfc = b.sfcatm1[((size_t)(la - 1) * I * J + c2d) * MS + m];
         double tgt = b.rst_target[la];
-        if (b.atype[la] == 1) { if (tgt < 0.0) tgt = sfc; } else { if (tgt <= kNull) tgt = sfc; }
-        const double d = (tgt - sfc) * b.tmod[la];
+        if (b.atype[la] == 1) { if (tgt < 0.0) tgt = sfc[la]; } else { if (tgt <= kNull) tgt = sfc[la]; }
+        const double d = (tgt - sfc[la]) * b.tmod[la];
         fatm[la] = (1.0 / (double)(I * J)) * kAtmMol * d * (1.0 / dtyr);
       }
     // air-sea gas exchange (fun_calc_ocnatm_flux :123-299)
+    double Ts, Ss;   // fun_calc_solconst clamps (gem_carbchem.f90:1396-1409)
+    if (Tsf < kZeroC + 2.0) Ts = kZeroC + 2.0; else if (Tsf > (kZeroC + 35.0)) Ts = kZeroC + 35.0; else Ts = Tsf;
+    if (Ssf < 26.0) Ss = 26.0; else if (Ssf > 43.0) Ss = 43.0; else Ss = Ssf;
+    const double rT = 1.0 / Ts, Tr100 = Ts / 100.0, lnTr100 = log(Tr100);
+#pragma unroll
     for (int la = 3; la <= LA; la++) {
-      const int lo = b.atm2ocn[la];
-      const double sfc = b.sfcatm1[((size_t)(la - 1) * I * J + c2d) * MS + m];
-      if (b.atype[la] == 1) {
-        // fun_calc_solconst (gem_carbchem.f90:1390-1429) and sub_calc_pv (:81-117)
-        double Ts, Ss;
-        if (T < kZeroC + 2.0) Ts = kZeroC + 2.0; else if (T > (kZeroC + 35.0)) Ts = kZeroC + 35.0; else Ts = T;
-        if (S < 26.0) Ss = 26.0; else if (S > 43.0) Ss = 43.0; else Ss = S;
-        const double rT = 1.0 / Ts, Tr100 = Ts / 100.0;
+      if (la == A_CO2 || la == A_O2 || la == A_CFC11 || la == A_CFC12) {
         const double *bc = b.bunsen[la];
-        double sol = exp(bc[0] + bc[1] * (100 * rT) + bc[2] * log(Tr100) + Ss * (bc[3] + bc[4] * (Tr100) + bc[5] * (Tr100 * Tr100)));
-        if (!(b.aid[la] == 3 || b.aid[la] == 18 || b.aid[la] == 19)) sol = sol / (rho * kVmol);
+        double sol = exp(bc[0] + bc[1] * (100 * rT) + bc[2] * lnTr100 + Ss * (bc[3] + bc[4] * (Tr100) + bc[5] * (Tr100 * Tr100)));
+        if (la == A_O2) sol = sol / (rho * kVmol);
         const double Sc = b.Sc[la][0] - b.Sc[la][1] * TC + b.Sc[la][2] * TC2 - b.Sc[la][3] * TC3;
         const double pv = (1.0 / 1.0E+02) * (24.0 * 365.25) * b.gastransfer_a * u2 * pow(Sc * 1.515E-3, -0.5);
-        double loc_atm = sol * sfc, loc_ocn, buff;
-        if (lo == b.l_DIC) {
+        double loc_atm = sol * sfc[la], loc_ocn, buff;
+        if (la == A_CO2) {
           loc_ocn = cb.co2;
-          if (cb.RF0 > kNS) buff = 1.0 / (cb.RF0 * cb.co2 / DIC);
+          if (cb.RF0 > kNS) buff = 1.0 / (cb.RF0 * cb.co2 / DICs);
           else { loc_ocn = 0.0; loc_atm = 0.0; buff = 1.0; }
-        } else { loc_ocn = OCN_(lo, K); buff = 1.0; }
+        } else {
+          loc_ocn = OCN_((la == A_O2 ? O2 : (la == A_CFC11 ? CFC11 : CFC12)), K);
+          buff = 1.0;
+        }
         if (loc_ocn < kNS) loc_ocn = 0.0;
         if (loc_atm < kNS) loc_atm = 0.0;
         f_oa[la] = pv * area * rho * loc_ocn;
@@ -460,25 +521,25 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
           const double r = dflux / deqm;
           if (r > 1.00) { f_oa[la] = (1.00 / r) * f_oa[la]; f_ao[la] = (1.00 / r) * f_ao[la]; }
         }
-      } else if (b.aid[la] == 4) {
-        const double r_atm = sfc / b.sfcatm1[((size_t)(b.a_CO2 - 1) * I * J + c2d) * MS + m];
+      } else if (la == A_CO213) {
+        const double r_atm = sfc[la] / sfc[A_CO2];
         const double R_atm = r_atm / (1.0 - r_atm), R_ocn = r13_CO2 / (1.0 - r13_CO2);
         const double alpha_k = 0.99912, alpha_alpha = 0.99869 + 4.9E-6 * TCf;
         alpha_as = alpha_alpha * alpha_k; alpha_sa = alpha_k;
-        f_ao[la] = (alpha_as * R_atm / (1.0 + alpha_as * R_atm)) * f_ao[b.a_CO2];
-        f_oa[la] = (alpha_sa * R_ocn / (1.0 + alpha_sa * R_ocn)) * f_oa[b.a_CO2];
-      } else if (b.aid[la] == 5) {
-        const double r_atm = sfc / b.sfcatm1[((size_t)(b.a_CO2 - 1) * I * J + c2d) * MS + m];
+        f_ao[la] = (alpha_as * R_atm / (1.0 + alpha_as * R_atm)) * f_ao[A_CO2];
+        f_oa[la] = (alpha_sa * R_ocn / (1.0 + alpha_sa * R_ocn)) * f_oa[A_CO2];
+      } else if (la == A_CO214) {
+        const double r_atm = sfc[la] / sfc[A_CO2];
         const double R_atm = r_atm / (1.0 - r_atm), R_ocn = r14_CO2 / (1.0 - r14_CO2);
-        f_ao[la] = ((alpha_as * alpha_as) * R_atm / (1.0 + (alpha_as * alpha_as) * R_atm)) * f_ao[b.a_CO2];
-        f_oa[la] = ((alpha_sa * alpha_sa) * R_ocn / (1.0 + (alpha_sa * alpha_sa) * R_ocn)) * f_oa[b.a_CO2];
+        f_ao[la] = ((alpha_as * alpha_as) * R_atm / (1.0 + (alpha_as * alpha_as) * R_atm)) * f_ao[A_CO2];
+        f_oa[la] = ((alpha_sa * alpha_sa) * R_ocn / (1.0 + (alpha_sa * alpha_sa) * R_ocn)) * f_oa[A_CO2];
       }
       focnatm[la] = f_oa[la] - f_ao[la];
     }
+#pragma unroll
     for (int la = 3; la <= LA; la++) {
-      const int lo = b.atm2ocn[la];
       fatm[la] = fatm[la] + focnatm[la];
-      if (lo) focn_surf[lo] = focn_surf[lo] - 1.0 * focnatm[la];
+      focn_surf[la] = 0.0 - 1.0 * focnatm[la];
       const size_t qa = ((size_t)(la - 1) * I * J + c2d) * MS + m;
       b.focnatm[qa] = focnatm[la];
       // interface (:1731-1734) and cpl_flux_ocnatm (atchem.f90:306-320): sfxsumatm += dts*sfxatm1
@@ -487,73 +548,85 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
     }
   }
   // ---- biological uptake at the surface (k_mld = K because mld = 0), sub_calc_bio_uptake 1N1T_PO4MM
-  double pDOM[kBgMaxLS + 1], psurf[kBgMaxLS + 1], uptake[kBgSlots], dom_add[kBgMaxLS + 1];
+  double psurf[LS + 1], dom_add[LS + 1];
+  Rem7 uptake;
   {
-    const double kPO4 = PO4 / (PO4 + b.c0_PO4);
+    const double kPO4 = PO4s / (PO4s + b.c0_PO4);
     const double ficefree = (1.0 - seaice);
     const double solfor = b.nsol > 0 ? v.solfor[(size_t)(b.nsol - 1) * J + (j - 1)] : 0.0;
     const double kI = solfor / b.solar_constant;
     double dPO4;
-    if (PO4 > kNS) dPO4 = dtyr * ficefree * kI * kPO4 * b.k0_PO4[m]; else dPO4 = 0.0;
+    if (PO4s > kNS) dPO4 = dtyr * ficefree * kI * kPO4 * b.k0_PO4[m]; else dPO4 = 0.0;
     double DOMfrac = b.red_DOMfrac, RDOMfrac = b.red_RDOMfrac, DOMtotal = DOMfrac + RDOMfrac;
     if (DOMtotal > 1.0) { DOMfrac = DOMfrac / DOMtotal; RDOMfrac = 1.0 - DOMfrac; DOMtotal = 1.0; }
     double red_POC_CaCO3;
     if (cb.ohm_cal > 1.0) red_POC_CaCO3 = (1.0 - DOMtotal) * b.red_POC_CaCO3[m] * pow(cb.ohm_cal - 1.0, b.red_POC_CaCO3_pP);
     else red_POC_CaCO3 = 0.0;
-    const double Kq = 3.170E-05 + (-1.788E-07) * T + 2.829E-10 * (T * T);
+    const double Kq = 3.170E-05 + (-1.788E-07) * Tsf + 2.829E-10 * (Tsf * Tsf);
     const double delta_Corg = -b.d13C_DIC_Corg_ef + (b.d13C_DIC_Corg_ef - 0.7) * Kq / cb.co2;
     double alpha = 1.0 + delta_Corg / 1000.0, R = r13_CO2 / (1.0 - r13_CO2);
     const double red_POC13 = alpha * R / (1.0 + alpha * R);
     alpha = 1.0 + 2.0 * delta_Corg / 1000.0; R = r14_CO2 / (1.0 - r14_CO2);
     const double red_POC14 = alpha * R / (1.0 + alpha * R);
-    const double delta_CaCO3 = 15.10 - 4232.0 / T;
+    const double delta_CaCO3 = 15.10 - 4232.0 / Tsf;
     alpha = 1.0 + delta_CaCO3 / 1000.0; R = r13_HCO3 / (1.0 - r13_HCO3);
     const double red_Ca13 = alpha * R / (1.0 + alpha * R);
     alpha = 1.0 + 2.0 * delta_CaCO3 / 1000.0; R = r14_HCO3 / (1.0 - r14_HCO3);
     const double red_Ca14 = alpha * R / (1.0 + alpha * R);
-    for (int ls = 1; ls <= LS; ls++) psurf[ls] = 0.0;   // nothing settles into the surface layer
     // bulk export (:1186-1230): POC currency, CaCO3, POP, isotopes
-    psurf[b.s_POC] = b.red_POP_POC * dPO4;
-    psurf[b.s_POC] = 1.0 * psurf[b.s_POC];
-    psurf[b.s_CaCO3] = red_POC_CaCO3 * psurf[b.s_POC];
-    psurf[b.s_POP] = (1.0 / b.red_POP_POC) * psurf[b.s_POC];
-    psurf[b.s_POC13] = red_POC13 * psurf[b.s_POC];
-    psurf[b.s_POC14] = red_POC14 * psurf[b.s_POC];
-    psurf[b.s_CaCO313] = red_Ca13 * psurf[b.s_CaCO3];
-    psurf[b.s_CaCO314] = red_Ca14 * psurf[b.s_CaCO3];
-    for (int q = 0; q < kBgSlots; q++) uptake[q] = 0.0;
-    for (int ls = 1; ls <= LS; ls++)
-      for (int r = 0; r < b.n_ls_lo[ls]; r++) {
-        const int q = b.lrem_slot[b.ls_lo[ls][r]];
-        uptake[q] = uptake[q] + b.conv_ls_lo[ls][r] * psurf[ls];
-      }
-    for (int ls = 1; ls <= LS; ls++) {
-      pDOM[ls] = 0.0; dom_add[ls] = 0.0;
-      if (b.pom2dom[ls]) { pDOM[ls] = 1.0 * DOMfrac * psurf[ls]; dom_add[ls] = pDOM[ls]; }
-    }
-    for (int ls = 1; ls <= LS; ls++) psurf[ls] = psurf[ls] - (pDOM[ls] + 0.0);
-    {
-      const double kP = PO4 / (PO4 + b.POC_c0frac2);
-      psurf[b.s_POCf2] = (1.0 - kP) * b.POC_dfrac2 + b.POC_frac2;
-      psurf[b.s_CaCO3f2] = b.CaCO3_frac2;
-    }
+    psurf[POC] = b.red_POP_POC * dPO4;
+    psurf[POC] = 1.0 * psurf[POC];
+    psurf[CACO3] = red_POC_CaCO3 * psurf[POC];
+    psurf[POP] = (1.0 / b.red_POP_POC) * psurf[POC];
+    psurf[POC13] = red_POC13 * psurf[POC];
+    psurf[POC14] = red_POC14 * psurf[POC];
+    psurf[CACO313] = red_Ca13 * psurf[CACO3];
+    psurf[CACO314] = red_Ca14 * psurf[CACO3];
+    psurf[POCF2] = 0.0; psurf[CACO3F2] = 0.0;
+    rem_zero(uptake);   // inorganic uptake (:1254-1262): conv_sed_ocn*bio_part
+    rem_add(uptake, 1.0, psurf, cO2POC, cO2POP, cALKPOP, cALKCa);
+#pragma unroll
+    for (int ls = 1; ls <= LS; ls++) dom_add[ls] = 0.0;
+    dom_add[POC] = 1.0 * DOMfrac * psurf[POC];       // DOM production (:1316-1352), r_POM_DOM = 1
+    dom_add[POC13] = 1.0 * DOMfrac * psurf[POC13];
+    dom_add[POC14] = 1.0 * DOMfrac * psurf[POC14];
+    dom_add[POP] = 1.0 * DOMfrac * psurf[POP];
+#pragma unroll
+    for (int ls = 1; ls <= LS; ls++) psurf[ls] = psurf[ls] - (dom_add[ls] + 0.0);
+    const double kP = PO4s / (PO4s + b.POC_c0frac2);   // initial particulate fraction partitioning (:1354-1378)
+    psurf[POCF2] = (1.0 - kP) * b.POC_dfrac2 + b.POC_frac2;
+    psurf[CACO3F2] = b.CaCO3_frac2;
   }
   // ---- water column, one downward sweep (K -> k1).  sub_box_remin_part (:2412-2875) follows each source layer's
   // particles down to the deepest layer they reach in dt; here all packets in flight are advanced level by level, kept in
   // source order (shallowest source first = the reference's k loop), so every sum over sources at a given layer
   // (remineralisation products, parked particles, settling flux) is accumulated in the reference's order.  Per level the
   // sweep also does sub_box_remin_DOM (:2287-2406), the decay terms (:838-871) and the tracer anomaly (:1811-1844).
-  double pk[kBgMaxK][kBgMaxLS + 1];   // TMP(:, current level) of each packet
-  int pk_min[kBgMaxK];                // loc_bio_remin_min_k of each packet
+  double pk[kBgMaxK][LS + 1];   // TMP(:, current level) of each packet
+  int pk_min[kBgMaxK];          // loc_bio_remin_min_k of each packet
   int npk = 0;
+  double set1[LS + 1];
   const int klim = (dtyr * b.sinkingrate <= b.dsc) ? k1 : K;
+  const double fd13 = b.fd_sed[POC14];   // decay factor of the 14C particulates (POC_14C and CaCO3_14C share lambda)
+  const bool sed_decays = fabs(b.lam_sed[POC14]) > kNS;
+  const bool ocn_decays = fabs(b.lam_ocn[DIC14]) > kNS;
+  const double decay14 = 1.0 - b.fd_ocn[DIC14];
+  double ratio;
+  if (b.DOMlifetime > dtyr) ratio = dtyr / b.DOMlifetime; else ratio = 1.0;
+#pragma unroll
   for (int ls = 1; ls <= LS; ls++) set1[ls] = 0.0;
   for (int kk = K; kk >= k1; kk--) {
-    double lrem[kBgSlots], pnew[kBgMaxLS + 1], dom[kBgMaxLS + 1];
-    for (int q = 0; q < kBgSlots; q++) lrem[q] = 0.0;
+    Rem7 lrem;
+    double pnew[LS + 1];
+    rem_zero(lrem);
+#pragma unroll
     for (int ls = 1; ls <= LS; ls++) pnew[ls] = 0.0;
     const double Mk = M_(kk), rM = RM_(kk);
-    const double f = redfield_factor(b, OCN_(b.l_O2, kk));
+    double x[L + 1];
+#pragma unroll
+    for (int l = 1; l <= L; l++) x[l] = OCN_(l, kk);
+    const double f = redfield_factor(b, x[O2]);
+    const double fO2POC = f * cO2POC, fO2POP = f * cO2POP, fALKPOP = f * cALKPOP, fALKCa = f * cALKCa;
     // (1) packets from the layers above pass through / stop in layer kk
     if (npk > 0) {
       const double layerratio = b.dD[kk + 1] / b.dD[kk];
@@ -561,32 +634,34 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
       const double PO_f1 = b.POC_f1[(size_t)kk * MS + m], PO_f2 = b.POC_f2[kk];
       int keep = 0;
       for (int p = 0; p < npk; p++) {
-        double *tp = pk[p];
-        double tcur[kBgMaxLS + 1];
-        const double Ca_ratio = 1.0 - ((1.0 - tp[b.s_CaCO3f2]) * Ca_f1 + tp[b.s_CaCO3f2] * Ca_f2);
-        const double PO_ratio = 1.0 - ((1.0 - tp[b.s_POCf2]) * PO_f1 + tp[b.s_POCf2] * PO_f2);
-        for (int ls = 1; ls <= LS; ls++) tcur[ls] = 0.0;
-        if (tp[b.s_CaCO3f2] > kNS) tcur[b.s_CaCO3f2] = (1.0 - Ca_f2) * tp[b.s_CaCO3f2] / Ca_ratio;
-        if (tp[b.s_POCf2] > kNS) tcur[b.s_POCf2] = (1.0 - PO_f2) * tp[b.s_POCf2] / PO_ratio;
-        for (int ls = 1; ls <= LS; ls++) {
-          const int dep_type = b.stype[b.sdep_ls[ls]];
-          if ((b.sdep_id[ls] == 3) || (b.stype[ls] == 3) || (dep_type == 3)) tcur[ls] = tp[ls] * layerratio * PO_ratio;
-          else if ((b.sdep_id[ls] == 14) || (b.stype[ls] == 4) || (dep_type == 4)) tcur[ls] = tp[ls] * layerratio * Ca_ratio;
-        }
-        for (int ls = 1; ls <= LS; ls++) {
-          const double part_remin = (layerratio * tp[ls] - tcur[ls]);
-          for (int r = 0; r < b.n_ls_lo[ls]; r++) {
-            const int q = b.lrem_slot[b.ls_lo[ls][r]];
-            lrem[q] = lrem[q] + (f * b.conv_ls_lo[ls][r]) * part_remin;
-          }
-        }
-        if (kk == pk_min[p]) {            // deepest layer reached within dt: park the remainder here
+        double tp[LS + 1], tcur[LS + 1], pr[LS + 1];
+#pragma unroll
+        for (int ls = 1; ls <= LS; ls++) tp[ls] = pk[p][ls];
+        const double Ca_ratio = 1.0 - ((1.0 - tp[CACO3F2]) * Ca_f1 + tp[CACO3F2] * Ca_f2);
+        const double PO_ratio = 1.0 - ((1.0 - tp[POCF2]) * PO_f1 + tp[POCF2] * PO_f2);
+        tcur[CACO3F2] = (tp[CACO3F2] > kNS) ? (1.0 - Ca_f2) * tp[CACO3F2] / Ca_ratio : 0.0;
+        tcur[POCF2] = (tp[POCF2] > kNS) ? (1.0 - PO_f2) * tp[POCF2] / PO_ratio : 0.0;
+        tcur[POC] = tp[POC] * layerratio * PO_ratio;
+        tcur[POC13] = tp[POC13] * layerratio * PO_ratio;
+        tcur[POC14] = tp[POC14] * layerratio * PO_ratio;
+        tcur[POP] = tp[POP] * layerratio * PO_ratio;
+        tcur[CACO3] = tp[CACO3] * layerratio * Ca_ratio;
+        tcur[CACO313] = tp[CACO313] * layerratio * Ca_ratio;
+        tcur[CACO314] = tp[CACO314] * layerratio * Ca_ratio;
+#pragma unroll
+        for (int ls = 1; ls <= LS; ls++) pr[ls] = (layerratio * tp[ls] - tcur[ls]);
+        rem_add(lrem, f, pr, fO2POC, fO2POP, fALKPOP, fALKCa);
+        const int mk = pk_min[p];
+        if (kk == mk) {                   // deepest layer reached within dt: park the remainder here
+#pragma unroll
           for (int ls = 1; ls <= LS; ls++) pnew[ls] = pnew[ls] + tcur[ls];
         } else if (kk == k1) {            // through the base of the deepest layer: settling flux
-          for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((b.stype[ls] == 9) ? tcur[ls] : Mk * tcur[ls]);
+#pragma unroll
+          for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((ls >= POCF2) ? tcur[ls] : Mk * tcur[ls]);
         } else {                          // keeps sinking
+#pragma unroll
           for (int ls = 1; ls <= LS; ls++) pk[keep][ls] = tcur[ls];
-          pk_min[keep] = pk_min[p];
+          pk_min[keep] = mk;
           keep++;
         }
       }
@@ -594,22 +669,23 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
     }
     // (2) layer kk as a source (decayed particulates of the previous step, :862-871)
     if (kk >= klim) {
-      double old[kBgMaxLS + 1];
-      for (int ls = 1; ls <= LS; ls++) {
-        old[ls] = PART_(ls, kk);
-        if (fabs(b.lam_sed[ls]) > kNS) old[ls] = b.fd_sed[ls] * old[ls];
-      }
+      double old[LS + 1];
+#pragma unroll
+      for (int ls = 1; ls <= LS; ls++) old[ls] = PART_(ls, kk);
+      if (sed_decays) { old[POC14] = fd13 * old[POC14]; old[CACO314] = fd13 * old[CACO314]; }
       double part_tot = 0.0;
-      part_tot = part_tot + old[b.s_POC];
-      part_tot = part_tot + old[b.s_CaCO3];
+      part_tot = part_tot + old[POC];
+      part_tot = part_tot + old[CACO3];
       if (part_tot > kNS) {
         if (kk == k1) {
-          for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((b.stype[ls] == 9) ? old[ls] : Mk * old[ls]);
+#pragma unroll
+          for (int ls = 1; ls <= LS; ls++) set1[ls] = set1[ls] + ((ls >= POCF2) ? old[ls] : Mk * old[ls]);
         } else {
           const double max_D = b.Dbot[kk] + dtyr * b.sinkingrate;
           int min_k = k1 - 1;
           for (int k2 = kk - 1; k2 >= k1; k2--)
             if (b.Dbot[k2] > max_D) { min_k = k2; break; }
+#pragma unroll
           for (int ls = 1; ls <= LS; ls++) pk[npk][ls] = old[ls];
           pk_min[npk] = min_k;
           npk++;
@@ -617,53 +693,66 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
       }
     }
     // (3) new particulate field of this layer
-    if (kk == K) { for (int ls = 1; ls <= LS; ls++) PART_(ls, kk) = psurf[ls]; }
-    else { for (int ls = 1; ls <= LS; ls++) PART_(ls, kk) = pnew[ls]; }
-    // (4) sub_box_remin_DOM for this layer
-    double ratio;
+#pragma unroll
+    for (int ls = 1; ls <= LS; ls++) PART_(ls, kk) = (kk == K) ? psurf[ls] : pnew[ls];
+    // (4) sub_box_remin_DOM for this layer: DOM -> POM -> inorganic products
+    const bool has_dom = x[DOMC] > kNS;
+    double dom[LS + 1];
+#pragma unroll
     for (int ls = 1; ls <= LS; ls++) dom[ls] = 0.0;
-    if (b.DOMlifetime > dtyr) ratio = dtyr / b.DOMlifetime; else ratio = 1.0;
-    const bool has_dom = OCN_(b.l_DOMC, kk) > kNS;
-    // (5) tracer anomaly vdocn(l, kk) = bio_remin + dtyr*rM*focn
-    if (has_dom)
-      for (int l = 3; l <= L; l++)
-        if (b.dom2pom[l]) dom[b.dom2pom[l]] = dom[b.dom2pom[l]] + 1.0 * ratio * OCN_(l, kk);
-    double domrem[kBgSlots];   // DOM -> POM -> inorganic products (conv_ls_lo order)
-    for (int q = 0; q < kBgSlots; q++) domrem[q] = 0.0;
-    for (int ls = 1; ls <= LS; ls++)
-      for (int r = 0; r < b.n_ls_lo[ls]; r++) {
-        const int q = b.lrem_slot[b.ls_lo[ls][r]];
-        domrem[q] = domrem[q] + (f * b.conv_ls_lo[ls][r]) * dom[ls];
-      }
+    if (has_dom) {
+      dom[POC] = dom[POC] + 1.0 * ratio * x[DOMC];
+      dom[POC13] = dom[POC13] + 1.0 * ratio * x[DOMC13];
+      dom[POC14] = dom[POC14] + 1.0 * ratio * x[DOMC14];
+      dom[POP] = dom[POP] + 1.0 * ratio * x[DOMP];
+    }
+    Rem7 domrem;
+    rem_zero(domrem);
+    rem_add(domrem, f, dom, fO2POC, fO2POP, fALKPOP, fALKCa);
+    // (5) tracer anomaly vdocn(l, kk) = bio_remin + dtyr*rM*focn and the bottom-water interface (:1736-1744)
+    const bool bot = (kk == k1), top = (kk == K);
+#pragma unroll
     for (int l = 1; l <= L; l++) {
-      const int q = b.lrem_slot[l];
-      const double x = OCN_(l, kk);
-      double vrem = 0.0;                                   // loc_vbio_remin(l,k) of sub_box_remin_DOM
-      if (has_dom && l >= 3 && b.dom2pom[l]) vrem = vrem - ratio * x;
-      if (q) vrem = vrem + domrem[q];
+      double vrem = 0.0, lr = 0.0, fs = 0.0, up = 0.0, da = 0.0, gas = 0.0;
+      bool slot = false;
+      switch (l) {
+        case DIC: vrem = vrem + domrem.dic; lr = lrem.dic; fs = fsed.dic; up = uptake.dic; slot = true; gas = focn_surf[A_CO2]; break;
+        case DIC13: vrem = vrem + domrem.d13; lr = lrem.d13; fs = fsed.d13; up = uptake.d13; slot = true; gas = focn_surf[A_CO213]; break;
+        case DIC14: vrem = vrem + domrem.d14; lr = lrem.d14; fs = fsed.d14; up = uptake.d14; slot = true; gas = focn_surf[A_CO214]; break;
+        case PO4: vrem = vrem + domrem.po4; lr = lrem.po4; fs = fsed.po4; up = uptake.po4; slot = true; break;
+        case O2: vrem = vrem + domrem.o2; lr = lrem.o2; fs = fsed.o2; up = uptake.o2; slot = true; gas = focn_surf[A_O2]; break;
+        case ALK: vrem = vrem + domrem.alk; lr = lrem.alk; fs = fsed.alk; up = uptake.alk; slot = true; break;
+        case CA: vrem = vrem + domrem.ca; lr = lrem.ca; fs = fsed.ca; up = uptake.ca; slot = true; break;
+        case DOMC: if (has_dom) vrem = vrem - ratio * x[l]; da = dom_add[POC]; break;
+        case DOMC13: if (has_dom) vrem = vrem - ratio * x[l]; da = dom_add[POC13]; break;
+        case DOMC14: if (has_dom) vrem = vrem - ratio * x[l]; da = dom_add[POC14]; break;
+        case DOMP: if (has_dom) vrem = vrem - ratio * x[l]; da = dom_add[POP]; break;
+        case CFC11: gas = focn_surf[A_CFC11]; break;
+        case CFC12: gas = focn_surf[A_CFC12]; break;
+        default: break;
+      }
       double rem = 0.0;
-      if (kk == k1 && l >= 3) rem = rem + rM * (q ? fsed[q] : 0.0);
-      rem = rem + (vrem + (q ? lrem[q] : 0.0));
+      if (bot && l >= 3) rem = rem + rM * fs;
+      rem = rem + (vrem + lr);
       double focn = 0.0;
-      if (l >= 3 && fabs(b.lam_ocn[l]) > kNS) focn = focn - Mk * (1.0 - b.fd_ocn[l]) * x / dtyr;
-      if (l == 1 && kk == k1) focn = focn + kYrS * b.Fgeothermal * A / (1.0E+03 * kCp);
-      if (kk == K) {
-        focn = focn + focn_surf[l];
+      if ((l == DIC14 || l == DOMC14) && ocn_decays) focn = focn - Mk * decay14 * x[l] / dtyr;
+      if (l == 1 && bot) focn = focn + kYrS * b.Fgeothermal * A / (1.0E+03 * kCp);
+      if (top) {
+        focn = focn + gas;
         if (l >= 3) {
-          const int ls = b.dom2pom[l];
-          if (ls) rem = rem + dom_add[ls];
-          rem = rem - (q ? uptake[q] : 0.0);
+          if (l == DOMC || l == DOMC13 || l == DOMC14 || l == DOMP) rem = rem + da;
+          rem = rem - (slot ? up : 0.0);
         }
       }
       DOCN_(l, kk) = rem + dtyr * rM * focn;
-      if (kk == k1) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = x + rem + dtyr * rM * focn;
+      if (bot) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = x[l] + rem + dtyr * rM * focn;
     }
   }
-  for (int ls = 1; ls <= LS; ls++) SET1_(ls) = set1[ls];
+#pragma unroll
   for (int ls = 1; ls <= LS; ls++) {
-    const double fs = set1[ls];
+    SET1_(ls) = set1[ls];
     const double rdts = 1.0 / b.dts;
-    b.sfxsed1[((size_t)(ls - 1) * I * J + c2d) * MS + m] = (b.stype[ls] == 9) ? fs * rdts * dtyr : rA * fs * rdts;
+    b.sfxsed1[((size_t)(ls - 1) * I * J + c2d) * MS + m] = (ls >= POCF2) ? set1[ls] * rdts * dtyr : rA * set1[ls] * rdts;
   }
 #undef OCN_
 #undef DOCN_

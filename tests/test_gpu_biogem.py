@@ -157,3 +157,29 @@ def test_biogem_model_steps(pair):
             inv_d = float((e.get("ocn", m).reshape(-1, L)[:, l] * e.get("bg_M", m)).sum())
             assert abs(inv_d - inv_o) <= 1e-9 * abs(inv_o), (m, l, inv_d, inv_o)
     assert np.abs(oracles[0].f("bio_part")).max() > 1e-8
+
+
+def test_biogem_multi_year_drift(built, tmp_path):
+    """North-star drift criterion, shortened to what the CPU oracle finishes in seconds: after 3 model years from the
+    initial state (fast tracer variant, the production path) the global means of T, S, DIC and O2 and the atmospheric
+    pCO2 agree with the oracle to 1e-6 relative."""
+    materialise(str(tmp_path), CFG)
+    years = 3
+    o = Oracle(**OKW)
+    o.biogem_setup()
+    o.run(480 * years)
+    with Ensemble(str(tmp_path), n_members=1) as e:
+        e.set_tracer_variant("fast")
+        e.run(480 * years)
+        assert int(e.health().sum()) == 0
+        ocn_d = e.get("ocn", 0).reshape(-1, L)
+        M_d = e.get("bg_M", 0)
+        atm_d = e.get("atm", 0).reshape(-1, LA)
+    ocn_o = o.f("ocn").reshape(-1, L)
+    M_o = o.f("bg_M")
+    for l, name in ((0, "T"), (1, "S"), (2, "DIC"), (6, "O2")):
+        mo = float((ocn_o[:, l] * M_o).sum() / M_o.sum())
+        md = float((ocn_d[:, l] * M_d).sum() / M_d.sum())
+        print("global mean %s: oracle %.12e device %.12e rel %.2e" % (name, mo, md, abs(md - mo) / abs(mo)))
+        assert abs(md - mo) <= 1e-6 * abs(mo), (name, mo, md)
+    assert abs(atm_d[0, 2] - o.f("atm").reshape(-1, LA)[0, 2]) <= 1e-6 * 278e-6
