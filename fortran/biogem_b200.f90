@@ -1,0 +1,107 @@
+! biogem_b200.f90 -- drop-in replacement for the loop entry points of MODULE biogem and MODULE atchem
+! (reference: src/biogem/biogem.f90:528-547, 1885-1890, 2083-2087, 2132-2150, 2243-2247;
+!  src/atchem/atchem.f90:63-67, 252-264, 306-320).  Same module and procedure names and argument lists, so
+! src/wrappers/genie_loop_wrappers.f90:178-183, 310-345, 452-462 compile unchanged.  The biogeochemistry runs
+! on the GPU; the padded interface arrays (dum_sfcatm1, dum_sfxatm1, dum_sfcocn1, dum_sfxsed1 ...) are only
+! filled from the device fields "sfcatm1", "sfcocn1", "sfxsed1" on BIOGEM save intervals
+! (par_data_save_sig / timeslice), through cg_sync_to_host.
+! Syntax-reviewed only: no Fortran compiler exists in the build image (DESIGN.md 1).
+MODULE biogem
+  USE, INTRINSIC :: ISO_C_BINDING
+  USE cgenie_b200_c
+  IMPLICIT NONE
+  PRIVATE
+  PUBLIC :: step_biogem, biogem_tracercoupling, biogem_forcing, biogem_climate, biogem_climate_sol
+
+CONTAINS
+
+  SUBROUTINE biogem_forcing(dum_genie_clock)
+    INTEGER(KIND=8), INTENT(IN) :: dum_genie_clock
+    CALL cg_ensure_handle()
+    CALL cg_check(cg_biogem_forcing(cg_h, INT(dum_genie_clock, C_INT64_T)), 'cg_biogem_forcing')
+  END SUBROUTINE biogem_forcing
+
+  SUBROUTINE step_biogem(dum_dts, dum_genie_clock, dum_sfcatm1, dum_sfxatm1, &
+       & dum_sfcocn1, dum_sfxocn1, dum_sfcsed1, dum_sfxsed1, dum_sfxsumrok1)
+    REAL, INTENT(IN) :: dum_dts
+    INTEGER(KIND=8), INTENT(IN) :: dum_genie_clock
+    REAL, INTENT(IN),    DIMENSION(:,:,:) :: dum_sfcatm1
+    REAL, INTENT(INOUT), DIMENSION(:,:,:) :: dum_sfxatm1
+    REAL, INTENT(OUT),   DIMENSION(:,:,:) :: dum_sfcocn1
+    REAL, INTENT(INOUT), DIMENSION(:,:,:) :: dum_sfxocn1
+    REAL, INTENT(IN),    DIMENSION(:,:,:) :: dum_sfcsed1
+    REAL, INTENT(INOUT), DIMENSION(:,:,:) :: dum_sfxsed1
+    REAL, INTENT(INOUT), DIMENSION(:,:,:) :: dum_sfxsumrok1
+    CALL cg_ensure_handle()
+    ! the air-sea flux is accumulated on the device (cpl_flux_ocnatm is fused into the kernel), so the
+    ! host copy handed to the unchanged cpl_flux_ocnatm_wrapper stays zero
+    dum_sfxatm1 = 0.0
+    CALL cg_check(cg_biogem_step(cg_h, REAL(dum_dts, C_DOUBLE), INT(dum_genie_clock, C_INT64_T)), 'cg_biogem_step')
+  END SUBROUTINE step_biogem
+
+  SUBROUTINE biogem_tracercoupling(dum_ts, dum_ts1)
+    REAL, DIMENSION(:,:,:,:), INTENT(INOUT) :: dum_ts, dum_ts1
+    CALL cg_ensure_handle()
+    CALL cg_check(cg_biogem_tracercoupling(cg_h, C_NULL_PTR, C_NULL_PTR), 'cg_biogem_tracercoupling')
+  END SUBROUTINE biogem_tracercoupling
+
+  SUBROUTINE biogem_climate(dum_hght_sic, dum_frac_sic, dum_cost, dum_solfor, dum_fxsw, dum_uvw, dum_tau, dum_psi, &
+       & dum_uv, dum_usurf, dum_mld, dum_evap, dum_pptn, dum_solconst)
+    REAL, DIMENSION(:,:), INTENT(IN) :: dum_hght_sic, dum_frac_sic
+    REAL, DIMENSION(:,:), INTENT(INOUT) :: dum_cost
+    REAL, DIMENSION(:), INTENT(IN) :: dum_solfor
+    REAL, DIMENSION(:,:), INTENT(IN) :: dum_fxsw
+    REAL, DIMENSION(:,:,:,:), INTENT(IN) :: dum_uvw
+    REAL, DIMENSION(:,:,:), INTENT(IN) :: dum_tau
+    REAL, DIMENSION(:,:), INTENT(IN) :: dum_psi
+    REAL, DIMENSION(:,:,:), INTENT(IN) :: dum_uv
+    REAL, DIMENSION(:,:), INTENT(IN) :: dum_usurf, dum_mld, dum_evap, dum_pptn
+    REAL, INTENT(INOUT) :: dum_solconst
+    CALL cg_ensure_handle()
+    CALL cg_check(cg_biogem_climate(cg_h), 'cg_biogem_climate')   ! physics is aliased on the device; resets go_cost there
+    dum_cost = 0.0
+  END SUBROUTINE biogem_climate
+
+  SUBROUTINE biogem_climate_sol(dum_solfor, dum_fxsw, dum_solconst)
+    REAL, DIMENSION(:), INTENT(IN) :: dum_solfor
+    REAL, DIMENSION(:,:), INTENT(IN) :: dum_fxsw
+    REAL, INTENT(INOUT) :: dum_solconst
+    CALL cg_ensure_handle()
+    CALL cg_check(cg_biogem_climate_sol(cg_h), 'cg_biogem_climate_sol')
+  END SUBROUTINE biogem_climate_sol
+
+END MODULE biogem
+
+MODULE atchem
+  USE, INTRINSIC :: ISO_C_BINDING
+  USE cgenie_b200_c
+  IMPLICIT NONE
+  PRIVATE
+  PUBLIC :: step_atchem, cpl_flux_ocnatm, cpl_comp_atmocn
+
+CONTAINS
+
+  SUBROUTINE step_atchem(dum_dts, dum_sfxsumatm, dum_sfcatm)
+    REAL, INTENT(IN) :: dum_dts
+    REAL, DIMENSION(:,:,:), INTENT(INOUT) :: dum_sfxsumatm
+    REAL, DIMENSION(:,:,:), INTENT(OUT), TARGET, CONTIGUOUS :: dum_sfcatm
+    CALL cg_ensure_handle()
+    CALL cg_check(cg_atchem_step(cg_h, REAL(dum_dts, C_DOUBLE)), 'cg_atchem_step')   ! includes cpl_comp_atmocn
+    dum_sfxsumatm = 0.0
+  END SUBROUTINE step_atchem
+
+  SUBROUTINE cpl_flux_ocnatm(dum_dts, dum_sfxatm1, dum_sfxsumatm)
+    REAL, INTENT(IN) :: dum_dts
+    REAL, DIMENSION(:,:,:), INTENT(INOUT) :: dum_sfxatm1, dum_sfxsumatm
+    CALL cg_check(cg_cpl_flux_ocnatm(cg_h), 'cg_cpl_flux_ocnatm')   ! already applied by cg_biogem_step
+    dum_sfxatm1 = 0.0
+  END SUBROUTINE cpl_flux_ocnatm
+
+  SUBROUTINE cpl_comp_atmocn(dum_n_atm, dum_sfcatm, dum_sfcatm1)
+    INTEGER, INTENT(IN) :: dum_n_atm
+    REAL, DIMENSION(:,:,:), INTENT(IN) :: dum_sfcatm
+    REAL, DIMENSION(:,:,:), INTENT(INOUT) :: dum_sfcatm1
+    ! fused into cg_atchem_step: the ocean-grid copy "sfcatm1" is device resident
+  END SUBROUTINE cpl_comp_atmocn
+
+END MODULE atchem

@@ -80,6 +80,39 @@ MODULE cgenie_b200_c
        INTEGER(C_INT), VALUE :: member
        INTEGER(C_INT64_T), VALUE :: n
      END FUNCTION cg_sync_from_host
+     ! ---- BIOGEM / ATCHEM (include/cgenie_b200.h) ----
+     INTEGER(C_INT) FUNCTION cg_biogem_forcing(h, genie_clock_ms) BIND(C, NAME='cg_biogem_forcing')
+       IMPORT :: C_INT, C_INT64_T, C_PTR
+       TYPE(C_PTR), VALUE :: h
+       INTEGER(C_INT64_T), VALUE :: genie_clock_ms
+     END FUNCTION cg_biogem_forcing
+     INTEGER(C_INT) FUNCTION cg_biogem_step(h, dts, genie_clock_ms) BIND(C, NAME='cg_biogem_step')
+       IMPORT :: C_INT, C_INT64_T, C_DOUBLE, C_PTR
+       TYPE(C_PTR), VALUE :: h
+       REAL(C_DOUBLE), VALUE :: dts
+       INTEGER(C_INT64_T), VALUE :: genie_clock_ms
+     END FUNCTION cg_biogem_step
+     INTEGER(C_INT) FUNCTION cg_biogem_tracercoupling(h, go_ts, go_ts1) BIND(C, NAME='cg_biogem_tracercoupling')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h, go_ts, go_ts1      ! C_NULL_PTR = ts stays resident
+     END FUNCTION cg_biogem_tracercoupling
+     INTEGER(C_INT) FUNCTION cg_biogem_climate(h) BIND(C, NAME='cg_biogem_climate')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h
+     END FUNCTION cg_biogem_climate
+     INTEGER(C_INT) FUNCTION cg_biogem_climate_sol(h) BIND(C, NAME='cg_biogem_climate_sol')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h
+     END FUNCTION cg_biogem_climate_sol
+     INTEGER(C_INT) FUNCTION cg_atchem_step(h, dts) BIND(C, NAME='cg_atchem_step')
+       IMPORT :: C_INT, C_DOUBLE, C_PTR
+       TYPE(C_PTR), VALUE :: h
+       REAL(C_DOUBLE), VALUE :: dts
+     END FUNCTION cg_atchem_step
+     INTEGER(C_INT) FUNCTION cg_cpl_flux_ocnatm(h) BIND(C, NAME='cg_cpl_flux_ocnatm')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h
+     END FUNCTION cg_cpl_flux_ocnatm
   END INTERFACE
 
 CONTAINS
