@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--members", type=int, default=128, help="ensemble members per GPU")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--variant", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--variant", default="col", choices=["col", "fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

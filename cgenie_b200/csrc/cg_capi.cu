@@ -24,6 +24,9 @@ int launch_tstepo_flux_strict(const Dev &, cudaStream_t);
 int launch_tstepo_flux_fast(const Dev &, cudaStream_t);
 int launch_co_strict(const Dev &, cudaStream_t);
 int launch_co_fast(const Dev &, cudaStream_t);
+void upload_grid_tracer_col(const GridC &, cudaStream_t);
+int launch_tstep_col(const Dev &, cudaStream_t);
+bool tstep_col_supported(const Dev &);
 void launch_step_begin(const Dev &, cudaStream_t);
 void launch_hosing(const Dev &, cudaStream_t);
 int launch_surflux(const Dev &, double *meantemp, bool need_mean, cudaStream_t);
@@ -117,10 +120,10 @@ struct cg_handle {
   long long launches = 0;
   long long koverall = 0;
   int istep_ocn = 0, istep_atm = 0, istep_sic = 0;
-  int variant = 0;  // 0 strict, 1 fast
+  int variant = 0;  // 0 strict, 1 fast (cooperative flux kernel + separate convection), 2 fused column kernel (falls back to 1)
   bool use_graphs = true;
-  cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [variant][parity]
-  long long graph_launches = 0;
+  cudaGraphExec_t graph[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [variant][parity]
+  long long graph_launches[3] = {0, 0, 0};   // launches inside one replayed cycle, per variant
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool profile = false;
   std::map<std::string, ProfFam> prof;
@@ -210,6 +213,7 @@ static void upload_grid(cg_handle *h) {
   upload_grid_physics(h->gc, h->stream);
   upload_grid_tracer_strict(h->gc, h->stream);
   upload_grid_tracer_fast(h->gc, h->stream);
+  upload_grid_tracer_col(h->gc, h->stream);
 }
 // constant memory is per process: re-upload when another handle ran last
 static cg_handle *g_active = nullptr;
@@ -382,6 +386,10 @@ static int build_device(cg_handle *h) {
     int *q;
     TRY(dupload(h, &q, wc));
     v.wetcols = q;
+    // the same columns row by row (fused column kernel: the CPB columns of a block are neighbours in i)
+    std::sort(wc.begin(), wc.end());
+    TRY(dupload(h, &q, wc));
+    v.rowcols = q;
   }
   auto col = [&](auto getter) { std::vector<double> t(M); for (int m = 0; m < M; m++) t[m] = getter(h->mc[m]); return t; };
   MemberP &p = v.p;
@@ -413,6 +421,7 @@ static int build_device(cg_handle *h) {
   TRY(dalloc(h, &v.ts_cur, ijk * L * MS));
   TRY(dalloc(h, &v.ts_new, ijk * L * MS));
   TRY(dalloc(h, &v.tsflux, 2 * ij * MS));
+  TRY(dalloc(h, &v.comap, ij * K * MS));
   TRY(dalloc(h, &v.rho, ijk * MS));
   TRY(dalloc(h, &v.u, ijk * 3 * MS));
   TRY(dalloc(h, &v.u1, ijk * 2 * MS));
@@ -980,6 +989,16 @@ static int do_seaice(cg_handle *h) {
   return CG_OK;
 }
 static void do_tstepo(cg_handle *h) {
+  if (h->variant == 2) {  // fused column kernel: flux + convection + SST export in one pass (compiled shapes only)
+    ProfScope ps(h, "tstepo_flux");
+    const int n = launch_tstep_col(h->dv, h->stream);
+    if (n > 0) {
+      ps.done(n);
+      std::swap(h->dv.ts_cur, h->dv.ts_new);
+      return;
+    }
+    ps.done(0);
+  }
   { ProfScope ps(h, "tstepo_flux"); ps.done(h->variant ? launch_tstepo_flux_fast(h->dv, h->stream) : launch_tstepo_flux_strict(h->dv, h->stream)); }
   { ProfScope ps(h, "co"); ps.done(h->variant ? launch_co_fast(h->dv, h->stream) : launch_co_strict(h->dv, h->stream)); }
   std::swap(h->dv.ts_cur, h->dv.ts_new);
@@ -1266,14 +1285,14 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
           cudaError_t e = cudaStreamEndCapture(h->stream, &gr);
           if (rc) return rc;
           if (e != cudaSuccess) return fail(CG_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-          h->graph_launches = h->launches - l0;
+          h->graph_launches[h->variant] = h->launches - l0;
           h->launches = l0; h->istep_ocn = i0; h->istep_atm = a0; h->istep_sic = s0;
           std::swap(h->dv.ts_cur, h->dv.ts_new);  // undo the swap done while capturing
           CUDA_OK(cudaGraphInstantiate(&ge, gr, 0));
           cudaGraphDestroy(gr);
         }
         CUDA_OK(cudaGraphLaunch(ge, h->stream));
-        h->launches += h->graph_launches;
+        h->launches += h->graph_launches[h->variant];
         h->istep_ocn++; h->istep_atm += p.kocn_loop; h->istep_sic++;
         std::swap(h->dv.ts_cur, h->dv.ts_new);
       } else {
@@ -1379,8 +1398,12 @@ extern "C" int cg_profile_get(cg_handle *h, const char *family, double *total_ms
   if (launches) *launches = it == h->prof.end() ? 0 : it->second.n;
   return CG_OK;
 }
+extern "C" int cg_tracer_variant_active(cg_handle *h) {
+  if (!h) return -1;
+  return (h->variant == 2 && !tstep_col_supported(h->dv)) ? 1 : h->variant;
+}
 extern "C" int cg_set_tracer_variant(cg_handle *h, int variant) {
-  if (!h || (variant != 0 && variant != 1)) return fail(CG_ERR_ARG, "variant must be 0 (strict) or 1 (fast)");
+  if (!h || variant < 0 || variant > 2) return fail(CG_ERR_ARG, "variant must be 0 (strict), 1 (fast) or 2 (fused column kernel)");
   h->variant = variant;
   return CG_OK;
 }

@@ -55,6 +55,7 @@ struct Dev {
   const int *iroff_ptr;
   const int *lpisl, *ipisl, *jpisl;  // island 1 path (npi1 points)
   const int *wetcols;        // 0-based (i-1)+I*(j-1) of the wet columns, deepest first
+  const int *rowcols;        // the same columns in row-major (j, then i) order: neighbours in the list are neighbours in i
   int nwet;
   // tracer state, ping-pong
   double *ts_cur, *ts_new;
@@ -62,6 +63,7 @@ struct Dev {
   double *sst;               // [2][j][i][m] tstar_ocn/sstar_ocn as exported by step_goldstein (goldstein.f90:428-431);
                              // NULL = read ts directly (identical unless BIOGEM rewrites ts in between)
   double *rho, *u, *u1, *cost;
+  unsigned char *comap;      // [k][j][i][m] top level of the mixed region each level belongs to (fused column kernel -> k_co_passive)
   // momentum
   double *bp, *sbp, *gb, *ub, *psi, *erisl_rhs, *psibc;
   const double *rh;          // (3, 0:I+1, 0:J+1) member independent

@@ -1,0 +1,70 @@
+// k_tracer_col.cu -- fused tracer step (tstepo_flux + co decisions + SST export) with cp.async.bulk staging, plus the
+// passive-tracer half of the convective adjustment.  See k_tracer_col.cuh for the formulation.  Compiled with FMA
+// contraction (fast variant family, <= 1e-10 per step against the strict kernels / the oracle).
+#include <cstdlib>
+#include "k_tracer_col.cuh"
+
+namespace cg {
+
+static __constant__ GridC c_g;
+
+void upload_grid_tracer_col(const GridC &g, cudaStream_t s) {
+  cudaMemcpyToSymbolAsync(c_g, &g, sizeof(GridC), 0, cudaMemcpyHostToDevice, s);
+}
+
+// one block = the MS members of ONE wet column (row-major column order: neighbouring blocks share stencil rows in L2)
+template <int I, int J, int K, int L, int MS, int MINB>
+__global__ void __launch_bounds__(MS, MINB) k_tstep_col(const Dev v) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ColStage st;
+  st.sm = reinterpret_cast<double *>(smem_raw);
+  st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows<L>::rows * MS * 8);
+  st.tid = threadIdx.x;
+  const int c2 = v.rowcols[blockIdx.x];
+  tstep_column<I, J, K, L, MS, MS>(v, c_g, c2, threadIdx.x, st, v.comap);
+}
+
+template <int I, int J, int K, int L, int MS>
+__global__ void __launch_bounds__(128) k_co_passive(const Dev v) {
+  const unsigned m = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ci = blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (ci >= v.nwet) return;
+  co_passive_column<I, J, K, L, MS>(v, c_g, v.rowcols[ci], m, v.comap);
+}
+
+template <int I, int J, int K, int L, int MS>
+static int go(const Dev &v, cudaStream_t s, int cfg) {
+  constexpr size_t smem = (size_t)ColRows<L>::rows * MS * 8 + 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  if (cfg == 1) k_tstep_col<I, J, K, L, MS, 1><<<v.nwet, MS, smem, s>>>(v);
+  else k_tstep_col<I, J, K, L, MS, 2><<<v.nwet, MS, smem, s>>>(v);
+  if (L > 2) {
+    k_co_passive<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v);
+    return 2;
+  }
+  return 1;
+}
+
+bool tstep_col_supported(const Dev &v) {
+  return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && (v.MS == 32 || v.MS == 64 || v.MS == 128);
+}
+
+// 0 = this grid shape / member stride has no compiled instance (the caller falls back to the generic kernels)
+int launch_tstep_col(const Dev &v, cudaStream_t s) {
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char *e = getenv("CG_COL_CFG");
+    cfg = e ? atoi(e) : 0;
+  }
+  if (!tstep_col_supported(v)) return 0;
+  if (v.MS == 32) return go<36, 36, 16, 16, 32>(v, s, cfg);
+  if (v.MS == 64) return go<36, 36, 16, 16, 64>(v, s, cfg);
+  return go<36, 36, 16, 16, 128>(v, s, cfg);
+}
+
+}  // namespace cg

@@ -121,8 +121,13 @@ class _Base:
         return ms.value, n.value
 
     def set_tracer_variant(self, variant):
-        """'strict' = reference operation order (bit-exact vs the oracle); 'fast' = FMA + hoisted coefficients."""
-        self._ck(self.L.cg_set_tracer_variant(self.h, {"strict": 0, "fast": 1}.get(variant, variant)))
+        """'strict' = reference operation order (bit-exact vs the oracle); 'fast' = FMA + hoisted coefficients;
+        'col' = fused flux + convection column kernel (same tolerance as 'fast')."""
+        self._ck(self.L.cg_set_tracer_variant(self.h, {"strict": 0, "fast": 1, "col": 2}.get(variant, variant)))
+
+    def tracer_variant_active(self):
+        """'strict' / 'fast' / 'col': what the tracer step really runs ('col' exists for compiled grid shapes only)."""
+        return ("strict", "fast", "col")[self.L.cg_tracer_variant_active(self.h)]
 
     def set_graphs(self, on):
         self._ck(self.L.cg_set_graphs(self.h, 1 if on else 0))

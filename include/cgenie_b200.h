@@ -160,8 +160,12 @@ int cg_timer_stop_ms(cg_handle *, double *ms);
 int cg_profile_enable(cg_handle *, int on);
 int cg_profile_get(cg_handle *, const char *family, double *total_ms, int64_t *launches);
 /* tracer kernel variant: 0 = strict reference operation order (bit-exact vs the oracle),
- *                        1 = fast (FMA + factored isoneutral sums; <=1e-10 relative per step) */
+ *                        1 = fast (FMA + factored isoneutral sums; <=1e-10 relative per step),
+ *                        2 = fused column kernel (tstepo_flux + co + SST export in one pass over ts; same tolerance;
+ *                            compiled for the 36x36x16, 16-tracer shape, any other shape runs variant 1) */
 int cg_set_tracer_variant(cg_handle *, int variant);
+/* the variant that actually runs (2 is reported as 1 when the grid shape has no compiled column kernel); -1 = bad handle */
+int cg_tracer_variant_active(cg_handle *);
 /* use CUDA-graph replay of one ocean step inside cg_run (default on) */
 int cg_set_graphs(cg_handle *, int on);
 

@@ -1,0 +1,85 @@
+"""GPU parity of the fused tracer column kernel (variant 'col': tstepo_flux + co + SST export in one pass,
+cgenie_b200/csrc/k_tracer_col.cuh) -- run with -m gpu on a B200.
+
+Bars (BASELINE.json north_star): <= 1e-10 relative per step on ts and the BIOGEM tracers against the oracle on
+identical inputs; global means within 1e-6 after a multi-year run.  The same per-thread body is checked on the host
+against the oracle in tests/test_col_body_host.py."""
+import numpy as np
+import pytest
+
+from cgenie_b200 import Ensemble, materialise
+from oracle_lib import Oracle
+from test_gpu_biogem import CFG, OKW, I, J, K, L, LA, compare, inject_all
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("members,check", [(1, (0,)), (33, (0, 32)), (100, (0, 99))])
+def test_col_step_parity_from_spun_state(built, tmp_path, members, check):
+    """Restart chosen members (first / last warp of the 32-, 64- and 128-lane instances) from the oracle's state after
+    2 model years (convection active, particles in transit; not the first months, where the uniform initial state is
+    neutrally stable and mixing decisions flip on the last bit) and advance 2 BIOGEM steps = 4 ocean steps."""
+    materialise(str(tmp_path), CFG)
+    o = Oracle(**OKW)
+    o.biogem_setup()
+    o.run(960)
+    with Ensemble(str(tmp_path), n_members=members) as e:
+        e.set_tracer_variant("col")
+        assert e.tracer_variant_active() == "col"
+        for m in check:
+            inject_all(e, o, m)
+        e.set_koverall(960)
+        for step in (1, 2):
+            e.run(10)
+            o.run(10)
+            for m in check:
+                compare(_Member(e, m), [o], 1e-10, "col, M=%d, member %d, BIOGEM step %d" % (members, m, step))
+        assert int(e.health()[list(check)].sum()) == 0
+
+
+class _Member:
+    """view of one ensemble member as member 0 (compare() walks oracles by index)"""
+
+    def __init__(self, e, m):
+        self.e, self.m = e, m
+
+    def get(self, name, _m):
+        return self.e.get(name, self.m)
+
+
+def test_col_launch_count(built, tmp_path):
+    materialise(str(tmp_path), CFG)
+    counts = {}
+    for variant in ("fast", "col"):
+        with Ensemble(str(tmp_path), n_members=2) as e:
+            e.set_tracer_variant(variant)
+            e.set_graphs(False)
+            n0 = e.launch_count()
+            e.run(5)
+            counts[variant] = e.launch_count() - n0
+    assert counts["fast"] - counts["col"] == 1       # flux + co + sst -> column kernel + passive-tracer mixing
+
+
+def test_col_multi_year_drift(built, tmp_path):
+    """North-star drift criterion (shortened to what the CPU oracle finishes in seconds): 3 model years from the
+    initial state, global means of T, S, DIC, O2 and atmospheric pCO2 within 1e-6 relative of the oracle."""
+    materialise(str(tmp_path), CFG)
+    years = 3
+    o = Oracle(**OKW)
+    o.biogem_setup()
+    o.run(480 * years)
+    with Ensemble(str(tmp_path), n_members=1) as e:
+        e.set_tracer_variant("col")
+        e.run(480 * years)
+        assert int(e.health().sum()) == 0
+        ocn_d = e.get("ocn", 0).reshape(-1, L)
+        M_d = e.get("bg_M", 0)
+        atm_d = e.get("atm", 0).reshape(-1, LA)
+    ocn_o = o.f("ocn").reshape(-1, L)
+    M_o = o.f("bg_M")
+    for l, name in ((0, "T"), (1, "S"), (2, "DIC"), (6, "O2")):
+        mo = float((ocn_o[:, l] * M_o).sum() / M_o.sum())
+        md = float((ocn_d[:, l] * M_d).sum() / M_d.sum())
+        print("global mean %s: oracle %.12e device %.12e rel %.2e" % (name, mo, md, abs(md - mo) / abs(mo)))
+        assert abs(md - mo) <= 1e-6 * abs(mo), (name, mo, md)
+    assert abs(atm_d[0, 2] - o.f("atm").reshape(-1, LA)[0, 2]) <= 1e-6 * 278e-6
