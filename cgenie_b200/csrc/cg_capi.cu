@@ -421,7 +421,6 @@ static int build_device(cg_handle *h) {
   TRY(dalloc(h, &v.ts_cur, ijk * L * MS));
   TRY(dalloc(h, &v.ts_new, ijk * L * MS));
   TRY(dalloc(h, &v.tsflux, 2 * ij * MS));
-  TRY(dalloc(h, &v.comap, ij * K * MS));
   TRY(dalloc(h, &v.rho, ijk * MS));
   TRY(dalloc(h, &v.u, ijk * 3 * MS));
   TRY(dalloc(h, &v.u1, ijk * 2 * MS));

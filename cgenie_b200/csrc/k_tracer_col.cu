@@ -1,5 +1,5 @@
-// k_tracer_col.cu -- fused tracer step (tstepo_flux + co decisions + SST export) with cp.async.bulk staging, plus the
-// passive-tracer half of the convective adjustment.  See k_tracer_col.cuh for the formulation.  Compiled with FMA
+// k_tracer_col.cu -- tracer step as two kernels: tstepo_flux with cp.async.bulk staging (one block per wet column), then
+// the convective adjustment + SST export (one thread per member-column).  See k_tracer_col.cuh for the formulation.  Compiled with FMA
 // contraction (fast variant family, <= 1e-10 per step against the strict kernels / the oracle).
 #include <cstdlib>
 #include "k_tracer_col.cuh"
@@ -21,20 +21,20 @@ __global__ void __launch_bounds__(MS, MINB) k_tstep_col(const Dev v) {
   st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows<L>::rows * MS * 8);
   st.tid = threadIdx.x;
   const int c2 = v.rowcols[blockIdx.x];
-  tstep_column<I, J, K, L, MS, MS>(v, c_g, c2, threadIdx.x, st, v.comap);
+  tstep_column<I, J, K, L, MS, MS>(v, c_g, c2, threadIdx.x, st);
 }
 
 template <int I, int J, int K, int L, int MS>
-__global__ void __launch_bounds__(128) k_co_passive(const Dev v) {
+__global__ void __launch_bounds__(128) k_co_col(const Dev v) {
   const unsigned m = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ci = blockIdx.y * 4 + (threadIdx.x >> 5);
   if (ci >= v.nwet) return;
-  co_passive_column<I, J, K, L, MS>(v, c_g, v.rowcols[ci], m, v.comap);
+  co_column<I, J, K, L, MS>(v, c_g, v.rowcols[ci], m);
 }
 
 template <int I, int J, int K, int L, int MS>
 static int go(const Dev &v, cudaStream_t s, int cfg) {
-  constexpr size_t smem = (size_t)ColRows<L>::rows * MS * 8 + 16;
+  constexpr size_t smem = (size_t)ColRows<L>::rows * MS * 8 + 32;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -43,11 +43,8 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   }
   if (cfg == 1) k_tstep_col<I, J, K, L, MS, 1><<<v.nwet, MS, smem, s>>>(v);
   else k_tstep_col<I, J, K, L, MS, 2><<<v.nwet, MS, smem, s>>>(v);
-  if (L > 2) {
-    k_co_passive<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v);
-    return 2;
-  }
-  return 1;
+  k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v);
+  return 2;
 }
 
 bool tstep_col_supported(const Dev &v) {

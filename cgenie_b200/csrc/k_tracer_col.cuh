@@ -38,7 +38,7 @@ namespace cg {
 // ---- staging primitives (device: mbarrier + cp.async.bulk; host emulation: element copies, no barriers)
 struct ColStage {
   double *sm;              // staging area of the block
-  unsigned long long *bar; // two mbarriers (A, B)
+  unsigned long long *bar; // four mbarriers: C0, C1 (T,S + velocities, double buffered), A, B (tracer halves)
   int tid;
 };
 
@@ -46,8 +46,7 @@ CG_HD void stage_init(const ColStage &s) {
 #ifdef __CUDA_ARCH__
   if (s.tid == 0) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(s.bar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(1) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a + 8), "r"(1) : "memory");
+    for (unsigned q = 0; q < 4; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a + 8 * q), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -103,25 +102,25 @@ CG_HD bool stage_leader(const ColStage &s) {
 #endif
 }
 
-// rows of the two staging buffers
+// rows of the staging buffers.  Unit C (double buffered, issued 1.5 levels ahead): T,S of the five columns one level
+// up + the five velocities; unit A: tracers 2..LH-1 of the five columns; unit B: tracers LH..L-1.
 template <int L>
 struct ColRows {
-  static constexpr int LH = L / 2;                 // tracers 2..LH-1 travel with unit A, LH..L-1 with unit B
-  static constexpr int nA = (LH > 2) ? LH - 2 : 0, nB = L - (LH > 2 ? LH : 2);
-  static constexpr int rTS = 0;                    // 5 cells x (T,S)
-  static constexpr int rU = 10;                    // uE, vN, ww (centre), uW (west cell), vS (south cell)
-  static constexpr int rTA = 15;                   // + cell * nA + (l - 2)
-  static constexpr int rowsA = 15 + 5 * nA;
-  static constexpr int rB = rowsA;                 // unit B: rB + cell * nB + (l - lB0)
+  static constexpr int LH = L / 2;
   static constexpr int lB0 = (LH > 2) ? LH : 2;
+  static constexpr int nA = lB0 - 2, nB = L - lB0;
+  static constexpr int rowsC = 15;                 // rTS: 5 cells x (T,S); rU: uE, vN, ww (centre), uW (west), vS (south)
+  static constexpr int rTS = 0, rU = 10;
+  static constexpr int rA = 2 * rowsC;             // + cell * nA + (l - 2)
+  static constexpr int rowsA = 5 * nA;
+  static constexpr int rB = rA + rowsA;            // + cell * nB + (l - lB0)
   static constexpr int rowsB = 5 * nB;
-  static constexpr int rows = rowsA + rowsB;
+  static constexpr int rows = rB + rowsB;
 };
 
 // One (member, column).  All NT threads of a block call this with the same c2.
 template <int I, int J, int K, int L, int MS, int NT>
-CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st,
-                        unsigned char *__restrict__ comap) {
+CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st) {
   static_assert(NT == MS, "a block covers all members of one column");
   using R = ColRows<L>;
   constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
@@ -153,42 +152,51 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   const double *const u0 = v.u + (long)c2 * uC3;
   const double *const sm = st.sm + st.tid;
 
-  // issue the two half-level units of level `lev` (lev <= K).  Unit A: T,S one level up (or the level itself at the
-  // top, where every upper coefficient is zero), the five velocities, tracers 2..LH-1; unit B: tracers LH..L-1.
-  auto issueA = [&](const int lev) {
-    stage_expect(st, 0, (unsigned)(R::rowsA * NT * 8));
+  // issue the staging units of level `lev` (lev <= K).  Unit C: T,S one level up (or the level itself at the top,
+  // where every upper coefficient is zero) and the five velocities; units A / B: the passive tracers.
+  auto issueC = [&](const int lev) {
+    const int b = (lev - k1c) & 1;
+    stage_expect(st, b, (unsigned)(R::rowsC * NT * 8));
     const int lu = (lev < K) ? lev + 1 : K;
     const double *c1 = ts0 + (long)(lu - 1) * sK;
-    stage_copy<NT>(st, 0, R::rTS + 0, c1, 2);
-    stage_copy<NT>(st, 0, R::rTS + 2, c1 + ((lu >= k1e) ? dE : 0), 2);
-    stage_copy<NT>(st, 0, R::rTS + 4, c1 + ((lu >= k1w) ? dW : 0), 2);
-    stage_copy<NT>(st, 0, R::rTS + 6, c1 + ((lu >= k1n) ? dN : 0), 2);
-    stage_copy<NT>(st, 0, R::rTS + 8, c1 + ((lu >= k1s) ? dS : 0), 2);
+    const int r0 = b * R::rowsC;
+    stage_copy<NT>(st, b, r0 + R::rTS + 0, c1, 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 2, c1 + ((lu >= k1e) ? dE : 0), 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 4, c1 + ((lu >= k1w) ? dW : 0), 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 6, c1 + ((lu >= k1n) ? dN : 0), 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 8, c1 + ((lu >= k1s) ? dS : 0), 2);
     const double *pu = u0 + (long)(lev - 1) * uK;
-    stage_copy<NT>(st, 0, R::rU + 0, pu, 3);
-    stage_copy<NT>(st, 0, R::rU + 3, pu + dUW, 1);
-    stage_copy<NT>(st, 0, R::rU + 4, pu + dUS + sL, 1);
-    if (R::nA > 0) {
-      const double *c0 = ts0 + (long)(lev - 1) * sK + 2 * sL;
-      stage_copy<NT>(st, 0, R::rTA + 0 * R::nA, c0, R::nA);
-      stage_copy<NT>(st, 0, R::rTA + 1 * R::nA, c0 + ((lev >= k1e) ? dE : 0), R::nA);
-      stage_copy<NT>(st, 0, R::rTA + 2 * R::nA, c0 + ((lev >= k1w) ? dW : 0), R::nA);
-      stage_copy<NT>(st, 0, R::rTA + 3 * R::nA, c0 + ((lev >= k1n) ? dN : 0), R::nA);
-      stage_copy<NT>(st, 0, R::rTA + 4 * R::nA, c0 + ((lev >= k1s) ? dS : 0), R::nA);
-    }
+    stage_copy<NT>(st, b, r0 + R::rU + 0, pu, 3);
+    stage_copy<NT>(st, b, r0 + R::rU + 3, pu + dUW, 1);
+    stage_copy<NT>(st, b, r0 + R::rU + 4, pu + dUS + sL, 1);
+  };
+  auto issueA = [&](const int lev) {
+    if (R::nA == 0) return;
+    stage_expect(st, 2, (unsigned)(R::rowsA * NT * 8));
+    const double *c0 = ts0 + (long)(lev - 1) * sK + 2 * sL;
+    stage_copy<NT>(st, 2, R::rA + 0 * R::nA, c0, R::nA);
+    stage_copy<NT>(st, 2, R::rA + 1 * R::nA, c0 + ((lev >= k1e) ? dE : 0), R::nA);
+    stage_copy<NT>(st, 2, R::rA + 2 * R::nA, c0 + ((lev >= k1w) ? dW : 0), R::nA);
+    stage_copy<NT>(st, 2, R::rA + 3 * R::nA, c0 + ((lev >= k1n) ? dN : 0), R::nA);
+    stage_copy<NT>(st, 2, R::rA + 4 * R::nA, c0 + ((lev >= k1s) ? dS : 0), R::nA);
   };
   auto issueB = [&](const int lev) {
-    stage_expect(st, 1, (unsigned)(R::rowsB * NT * 8));
+    stage_expect(st, 3, (unsigned)(R::rowsB * NT * 8));
     const double *c0 = ts0 + (long)(lev - 1) * sK + R::lB0 * sL;
-    stage_copy<NT>(st, 1, R::rB + 0 * R::nB, c0, R::nB);
-    stage_copy<NT>(st, 1, R::rB + 1 * R::nB, c0 + ((lev >= k1e) ? dE : 0), R::nB);
-    stage_copy<NT>(st, 1, R::rB + 2 * R::nB, c0 + ((lev >= k1w) ? dW : 0), R::nB);
-    stage_copy<NT>(st, 1, R::rB + 3 * R::nB, c0 + ((lev >= k1n) ? dN : 0), R::nB);
-    stage_copy<NT>(st, 1, R::rB + 4 * R::nB, c0 + ((lev >= k1s) ? dS : 0), R::nB);
+    stage_copy<NT>(st, 3, R::rB + 0 * R::nB, c0, R::nB);
+    stage_copy<NT>(st, 3, R::rB + 1 * R::nB, c0 + ((lev >= k1e) ? dE : 0), R::nB);
+    stage_copy<NT>(st, 3, R::rB + 2 * R::nB, c0 + ((lev >= k1w) ? dW : 0), R::nB);
+    stage_copy<NT>(st, 3, R::rB + 3 * R::nB, c0 + ((lev >= k1n) ? dN : 0), R::nB);
+    stage_copy<NT>(st, 3, R::rB + 4 * R::nB, c0 + ((lev >= k1s) ? dS : 0), R::nB);
   };
 
   stage_init(st);
-  if (stage_leader(st)) { issueA(k1c); issueB(k1c); }
+  if (stage_leader(st)) {
+    issueC(k1c);
+    if (k1c < K) issueC(k1c + 1);
+    issueA(k1c);
+    issueB(k1c);
+  }
 
   // T,S of the five columns at the bottom level (direct loads, once per column)
   double tC0, sC0, tE0, sE0, tW0, sW0, tN0, sN0, tS0, sS0;
@@ -206,19 +214,19 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   double P[L], Q[L];
 #pragma unroll
   for (int l = 0; l < L; l++) { P[l] = 0.0; Q[l] = 0.0; }
-  // new T, S, rho column for the convective adjustment
-  double tt[K + 2], ss[K + 2], rl[K + 2];
   unsigned par = 0;
 
   for (int kk = k1c; kk <= K; kk++) {
     const bool top = (kk == K);
     const bool opE = kk >= k1e, opW = kk >= k1w, opN = kk >= k1n, opS = kk >= k1s;
-    stage_wait(st, 0, par);
-    const double tC1 = sm[(R::rTS + 0) * NT], sC1 = sm[(R::rTS + 1) * NT], tE1 = sm[(R::rTS + 2) * NT], sE1 = sm[(R::rTS + 3) * NT];
-    const double tW1 = sm[(R::rTS + 4) * NT], sW1 = sm[(R::rTS + 5) * NT], tN1 = sm[(R::rTS + 6) * NT], sN1 = sm[(R::rTS + 7) * NT];
-    const double tS1 = sm[(R::rTS + 8) * NT], sS1 = sm[(R::rTS + 9) * NT];
-    const double vuE = sm[(R::rU + 0) * NT], vvN = sm[(R::rU + 1) * NT], vww = sm[(R::rU + 2) * NT], vuW = sm[(R::rU + 3) * NT],
-                 vvS = sm[(R::rU + 4) * NT];
+    const int cb = (kk - k1c) & 1;
+    stage_wait(st, cb, ((unsigned)(kk - k1c) >> 1) & 1u);
+    const double *const smc = sm + cb * R::rowsC * NT;
+    const double tC1 = smc[(R::rTS + 0) * NT], sC1 = smc[(R::rTS + 1) * NT], tE1 = smc[(R::rTS + 2) * NT], sE1 = smc[(R::rTS + 3) * NT];
+    const double tW1 = smc[(R::rTS + 4) * NT], sW1 = smc[(R::rTS + 5) * NT], tN1 = smc[(R::rTS + 6) * NT], sN1 = smc[(R::rTS + 7) * NT];
+    const double tS1 = smc[(R::rTS + 8) * NT], sS1 = smc[(R::rTS + 9) * NT];
+    const double vuE = smc[(R::rU + 0) * NT], vvN = smc[(R::rU + 1) * NT], vww = smc[(R::rU + 2) * NT], vuW = smc[(R::rU + 3) * NT],
+                 vvS = smc[(R::rU + 4) * NT];
 
     // ---- horizontal faces of level kk: flux = a * ts(neighbour) + b * ts(centre)   (goldstein.f90:2517-2547)
     double hE = 0.0, hW = 0.0, hN = 0.0, hS = 0.0, hC = 0.0;
@@ -301,15 +309,19 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   }
     CG_TRACER(0, tC0, tE0, tW0, tN0, tS0)
     CG_TRACER(1, sC0, sE0, sW0, sN0, sS0)
+    if (R::nA > 0) stage_wait(st, 2, par);
 #pragma unroll
     for (int l = 2; l < R::lB0; l++) {
-      const int r = R::rTA + (l - 2);
+      const int r = R::rA + (l - 2);
       CG_TRACER(l, sm[(r + 0 * R::nA) * NT], sm[(r + 1 * R::nA) * NT], sm[(r + 2 * R::nA) * NT], sm[(r + 3 * R::nA) * NT],
                 sm[(r + 4 * R::nA) * NT])
     }
-    stage_sync();                                           // every thread is done with buffer A
-    if (!top && stage_leader(st)) issueA(kk + 1);
-    stage_wait(st, 1, par);
+    stage_sync();                                           // every thread is done with buffers C[cb] and A
+    if (stage_leader(st)) {
+      if (kk + 2 <= K) issueC(kk + 2);
+      if (!top) issueA(kk + 1);
+    }
+    stage_wait(st, 3, par);
 #pragma unroll
     for (int l = R::lB0; l < L; l++) {
       const int r = R::rB + (l - R::lB0);
@@ -323,7 +335,6 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     if (stv) {
       const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);   // :2638
       rP[0] = r;
-      tt[kk - 1] = tnew; ss[kk - 1] = snew; rl[kk - 1] = r;
     }
     // ---- shift one level up
     tC0 = tC1; sC0 = sC1; tE0 = tE1; sE0 = sE1; tW0 = tW1; sW0 = sW1; tN0 = tN1; sN0 = sN1; tS0 = tS1; sS0 = sS1;
@@ -343,127 +354,117 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     }
     const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
     rP[0] = r;
-    tt[K] = tnew; ss[K] = snew; rl[K] = r;
   }
 
-  // ---- convective adjustment (goldstein.f90:2657-2777, iconv == 0): the decisions and the T,S,rho values follow the
-  // reference operation for operation on the local column
-  {
-    double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);         // level-1 cell of this column
-    double *__restrict__ rho = v.rho + ((long)c2 * MS + m);
-    int kx[K + 2], head[K + 2];
-    double dzm[K + 2];
-    kx[k1c - 1] = 0;
-    rl[0] = 0.0;
-    for (int q = k1c; q <= K; q++) { kx[q] = q; head[q] = q; dzm[q] = g.dz[q]; }
-    int mm = K, lastmix = 0;
-    bool any = false;
-    while (kx[mm - 1] > 0 || (lastmix != 0 && kx[mm] != K)) {
-      if (kx[mm - 1] == 0 || rl[kx[mm]] < rl[kx[mm - 1]]) {
-        if (lastmix == 0 || kx[mm] == K) mm = mm - 1; else mm = mm + 1;
-        lastmix = 0;
-      } else {
-        lastmix = 1;
-        any = true;
-        int n = mm - 1;
-        while (kx[n - 1] > 0 && rl[kx[n]] >= rl[kx[n - 1]]) n = n - 1;
-        const int h = kx[mm];
-        double sumT = tt[h] * dzm[h], sumS = ss[h] * dzm[h], dznew = dzm[h];
-        for (int ni = 1; ni <= mm - n; ni++) {
-          const int q = kx[mm - ni];
-          sumT = sumT + tt[q] * dzm[q];
-          sumS = sumS + ss[q] * dzm[q];
-          dznew = dznew + dzm[q];
-        }
-        dzm[h] = dznew;
-        tt[h] = sumT / dznew;
-        ss[h] = sumS / dznew;
-        rl[h] = ec1 * tt[h] + ec2 * ss[h] + ec3 * (tt[h] * tt[h]) + ec4 * (tt[h] * tt[h] * tt[h]);
-        int ni = mm - 1;
-        while (kx[ni + 1] > 0) {
-          kx[ni] = kx[ni - mm + n];
-          ni = ni - 1;
-        }
-      }
-    }
-    if (any) {
-      // fill in (:2749-2764): head[n] = top level of the mixed region level n ended up in
-      int mq = K - 1;
-      double cnt = 0.0;
-      for (int n = K - 1; n >= k1c; n--) {
-        if (n > kx[mq]) {
-          head[n] = kx[mq + 1];
-          cnt = cnt + 1.0;
-        } else {
-          mq = mq - 1;
-        }
-      }
-      v.cost[(long)c2 * MS + m] += cnt;
-      for (int n = k1c; n < K; n++) {
-        const int hd = head[n];
-        if (hd != n) {
-          ts[(long)(n - 1) * sK] = tt[hd];
-          ts[(long)(n - 1) * sK + sL] = ss[hd];
-          rho[(long)(n - 1) * rK] = rl[hd];
-          // the head level itself
-          ts[(long)(hd - 1) * sK] = tt[hd];
-          ts[(long)(hd - 1) * sK + sL] = ss[hd];
-          rho[(long)(hd - 1) * rK] = rl[hd];
-        }
-      }
-    }
-    // region map for k_co_passive: [k][column][member] = top level of the region (== k: not mixed)
-    for (int n = k1c; n <= K; n++) comap[((long)(n - 1) * (I * J) + c2) * MS + m] = (unsigned char)head[n];
-    // SST / SSS as exported by step_goldstein (:428-431)
-    if (v.sst) {
-      v.sst[(long)c2 * MS + m] = tt[K];
-      v.sst[((long)(I * J) + c2) * MS + m] = ss[K];
-    }
-  }
 }
 
-// Passive tracers (l >= 2) of the mixed regions recorded in comap: thickness-weighted mean over each region, summed
-// top-down (goldstein.f90:2732-2737 applied once per final region; equal to the reference's incremental merges up to
-// rounding).  One thread per (member, wet column); every load of a tracer pair is independent of the others.
+// Convective adjustment (goldstein.f90:2657-2777, iconv == 0) + SST export (:428-431), one thread per (member, wet
+// column), run at high occupancy right after the flux kernel.  The mixing DECISIONS and the T, S, rho values follow
+// the reference operation for operation on a local copy of the column; the passive tracers (l >= 2), which never feed
+// back into a decision, are averaged once per final mixed region (thickness weighted, summed top-down) instead of
+// being re-mixed at every incremental merge -- equal up to rounding.  Every load of a tracer pair is independent of
+// the others, so the pass is bandwidth bound.
 template <int I, int J, int K, int L, int MS>
-CG_HD void co_passive_column(const Dev &v, const GridC &g, const int c2, const unsigned m,
-                             const unsigned char *__restrict__ comap) {
-  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
+CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m) {
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC, rK = (long)I * J * MS;
   const int k1c = (int)v.k1[(c2 % I + 1) + (I + 2) * (c2 / I + 1)];
+  const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
+  double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);         // level-1 cell of this column
+  double *__restrict__ rho = v.rho + ((long)c2 * MS + m);
+  int kx[K + 2], head[K + 2];
+  double dzm[K + 2], tt[K + 2], ss[K + 2], rl[K + 2];
+#pragma unroll
+  for (int q = 1; q <= K; q++) {
+    kx[q] = q; head[q] = q; dzm[q] = g.dz[q];
+    tt[q] = 0.0; ss[q] = 0.0; rl[q] = 0.0;
+    if (q >= k1c) {
+      tt[q] = ts[(long)(q - 1) * sK];
+      ss[q] = ts[(long)(q - 1) * sK + sL];
+      rl[q] = rho[(long)(q - 1) * rK];
+    }
+  }
+  kx[k1c - 1] = 0;
+  rl[0] = 0.0;
+  int mm = K, lastmix = 0;
+  bool any = false;
+  while (kx[mm - 1] > 0 || (lastmix != 0 && kx[mm] != K)) {
+    if (kx[mm - 1] == 0 || rl[kx[mm]] < rl[kx[mm - 1]]) {
+      if (lastmix == 0 || kx[mm] == K) mm = mm - 1; else mm = mm + 1;
+      lastmix = 0;
+    } else {
+      lastmix = 1;
+      any = true;
+      int n = mm - 1;
+      while (kx[n - 1] > 0 && rl[kx[n]] >= rl[kx[n - 1]]) n = n - 1;
+      const int h = kx[mm];
+      double sumT = tt[h] * dzm[h], sumS = ss[h] * dzm[h], dznew = dzm[h];
+      for (int ni = 1; ni <= mm - n; ni++) {
+        const int q = kx[mm - ni];
+        sumT = sumT + tt[q] * dzm[q];
+        sumS = sumS + ss[q] * dzm[q];
+        dznew = dznew + dzm[q];
+      }
+      dzm[h] = dznew;
+      tt[h] = sumT / dznew;
+      ss[h] = sumS / dznew;
+      rl[h] = ec1 * tt[h] + ec2 * ss[h] + ec3 * (tt[h] * tt[h]) + ec4 * (tt[h] * tt[h] * tt[h]);
+      int ni = mm - 1;
+      while (kx[ni + 1] > 0) {
+        kx[ni] = kx[ni - mm + n];
+        ni = ni - 1;
+      }
+    }
+  }
+  // SST / SSS as exported by step_goldstein (:428-431)
+  if (v.sst) {
+    v.sst[(long)c2 * MS + m] = tt[K];
+    v.sst[((long)(I * J) + c2) * MS + m] = ss[K];
+  }
+  if (!any) return;
+  // fill in (:2749-2764): head[n] = top level of the mixed region level n ended up in
+  {
+    int mq = K - 1;
+    double cnt = 0.0;
+    for (int n = K - 1; n >= k1c; n--) {
+      if (n > kx[mq]) {
+        head[n] = kx[mq + 1];
+        cnt = cnt + 1.0;
+      } else {
+        mq = mq - 1;
+      }
+    }
+    v.cost[(long)c2 * MS + m] += cnt;
+  }
   // region structure: bit k-1 of `in` = level k belongs to a mixed region; `topb` / `botb` = it is its top / bottom
   unsigned in = 0, topb = 0, botb = 0;
   double rdzt[K];
   {
-    int prev = 0;   // head of the level below
-    double dzt = 0.0;
-    int hd[K + 2];
-#pragma unroll
-    for (int k = 1; k <= K; k++) hd[k] = (k >= k1c) ? (int)comap[((long)(k - 1) * (I * J) + c2) * MS + m] : 0;
-    hd[K + 1] = 0;
-    hd[0] = 0;
-    // top-down thickness sums, stored at the bottom level of each region
+    head[0] = 0;
+    for (int k = 1; k < k1c; k++) head[k] = 0;
 #pragma unroll
     for (int k = K; k >= 1; k--) {
       rdzt[k - 1] = 0.0;
-      if (k >= k1c && hd[k] != k) {            // inside a region, below its top
+      if (k >= k1c && head[k] != k) {            // inside a region, below its top
         in |= 1u << (k - 1);
-        in |= 1u << (hd[k] - 1);
+        in |= 1u << (head[k] - 1);
       }
     }
-    (void)prev;
+    double dzt = 0.0;
 #pragma unroll
     for (int k = K; k >= 1; k--) {
       if ((in >> (k - 1)) & 1u) {
-        const bool istop = (hd[k] == k);
-        const bool isbot = (k == k1c) || (hd[k - 1] != hd[k]);
+        const int hd = head[k];
+        const bool istop = (hd == k), isbot = (head[k - 1] != hd);
         dzt = istop ? g.dz[k] : dzt + g.dz[k];
         if (istop) topb |= 1u << (k - 1);
         if (isbot) { botb |= 1u << (k - 1); rdzt[k - 1] = 1.0 / dzt; }
+        // T, S, rho of the region (the reference's own values, kept at the region top)
+        ts[(long)(k - 1) * sK] = tt[hd];
+        ts[(long)(k - 1) * sK + sL] = ss[hd];
+        rho[(long)(k - 1) * rK] = rl[hd];
       }
     }
   }
-  if (in == 0) return;
-  double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);
 #pragma unroll 1
   for (int l = 2; l < L; l += 2) {
     const bool two = (l + 1 < L);

@@ -39,15 +39,13 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
   v.p.ec1 = ec; v.p.ec2 = ec + MS; v.p.ec3 = ec + 2 * MS; v.p.ec4 = ec + 3 * MS;
   // the whole "block" (32 members of one column) shares one staging area; bulk copies are emulated element-wise
   std::vector<double> sm((size_t)ColRows<L>::rows * 32);
-  unsigned long long bar[2] = {0, 0};
-  std::vector<unsigned char> comap((size_t)I * J * K * MS, 0);
-  v.comap = comap.data();
+  unsigned long long bar[4] = {0, 0, 0, 0};
   for (int n = 0; n < ncol; n++)
     for (int m = 0; m < MS; m++) {
       ColStage st{sm.data(), bar, m};
-      tstep_column<I, J, K, L, 32, 32>(v, g, cols[n], (unsigned)m, st, comap.data());
+      tstep_column<I, J, K, L, 32, 32>(v, g, cols[n], (unsigned)m, st);
     }
   for (int n = 0; n < ncol; n++)
-    for (int m = 0; m < MS; m++) co_passive_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m, comap.data());
+    for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m);
   return 0;
 }
