@@ -632,6 +632,159 @@ __global__ void __launch_bounds__(128) k_baro_fast(const Dev v, const double *__
   for (int r = lane; r < nm; r += 32) v.gb[(size_t)r * MS + m] = x[r];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Barotropic solve, register-resident variant (same arithmetic, operation for operation, as k_baro_fast: the results
+// are bit-identical; only the data movement differs).  One warp = one member.  The banded substitutions are a chain of
+// 2 x nm dependent pivots; k_baro_fast pays a shared-memory round trip (STS -> LDS) per pivot, here the active window
+// of the vector lives in registers -- lane l holds the elements e with e mod 32 == l, two live blocks of 32 (the band
+// is 32 < bw = I+1 <= 64 wide) -- and the pivot travels by one warp shuffle: the chain per pivot is
+// SHFL -> DMUL -> DADD.  At pivot u of a chunk of 32, lane l updates its "current block" register with factor
+// f[(l-u-1) mod 64] and its "next block" register with f[l-u+31] (zero outside the band).  To make both factor reads
+// `lane base + immediate`, each pivot's factor row is expanded in shared memory to 96 entries,
+//     row'[32+j] = f[j] (j < bw),   row'[j] = f[32+j] (j < bw-32),   zero elsewhere,
+// so that the two reads are row'[l+31-u] and row'[l+63-u].  The packed pivot-major rows (bw doubles per pivot) stream
+// from HBM through a 4-deep ring of 32-pivot chunks filled by cp.async.bulk (one elected lane, completion on an
+// mbarrier, three chunks in flight); the expansion of chunk g+1 is interleaved with the pivots of chunk g.
+// The backward sweep runs on the reversed index e' = nm-1-e so that both sweeps share one body.
+constexpr int kBaroRing = 4, kBaroRow = 96;
+__device__ __forceinline__ unsigned baro_sa(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+struct BaroChunk { int sw, c, row0, rows; };
+__device__ __forceinline__ BaroChunk baro_chunk(const int g, const int nch, const int nm) {
+  // global chunk g: sweep g / nch (0 forward, 1 backward), chunk c = g % nch covers pivots [32c, 32c+32) of that sweep
+  BaroChunk k;
+  k.sw = (g >= nch) ? 1 : 0;
+  k.c = g - k.sw * nch;
+  if (k.sw == 0) { k.row0 = 32 * k.c; k.rows = min(32, nm - k.row0); }
+  else { const int hi = nm - 32 * k.c; k.row0 = max(hi - 32, 0); k.rows = hi - k.row0; }
+  return k;
+}
+__device__ __forceinline__ void baro_issue(const int g, const int nch, const int nm, const int bw, const double *bf, const double *bb,
+                                           double *stage, unsigned long long *bar) {
+  const BaroChunk k = baro_chunk(g, nch, nm);
+  const unsigned bytes = (unsigned)(k.rows * bw * 8);
+  const unsigned b = baro_sa(bar + (g & (kBaroRing - 1)));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   baro_sa(stage + (size_t)(g & (kBaroRing - 1)) * 32 * bw)),
+               "l"((k.sw ? bb : bf) + (size_t)k.row0 * bw), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void baro_wait(const int g, unsigned long long *bar) {
+  const unsigned b = baro_sa(bar + (g & (kBaroRing - 1))), par = (unsigned)(g / kBaroRing) & 1u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tBRW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra BRD_%=;\n\tbra BRW_%=;\n\tBRD_%=:\n\t}" ::"r"(b),
+      "r"(par)
+      : "memory");
+}
+// the 32 pivots of one chunk.  FULL: this chunk and the chunk being expanded both hold 32 pivots (no per-pivot bounds
+// checks); otherwise every pivot / row is guarded.  xe = &x[phys(32c)], xs = +-1 (x is padded by 64 zeros on both
+// sides, so the register recycling load needs no guard).
+template <bool SW, bool FULL>
+__device__ __forceinline__ void baro_steps(double &P, double &N, const double rdv, const double *__restrict__ fb, double *xe,
+                                           const int rows, const bool more, const double *src0, const int sstep, const int nrows,
+                                           double *dst, const int lane, const bool dup) {
+  constexpr int xs = SW ? -1 : 1;
+#pragma unroll
+  for (int u = 0; u < 32; u++) {
+    if (FULL || u < rows) {
+      const double fP = fb[u * kBaroRow + 31 - u], fN = fb[u * kBaroRow + 63 - u];
+      if (SW) { if (lane == u) P = P * rdv; }                         // xi = x(i) / gap(i, n+2)
+      const double gi = __shfl_sync(0xffffffffu, P, u);
+      if (lane == u) {
+        xe[xs * u] = P;                                               // final value of this sweep
+        P = xe[xs * (u + 64)];                                        // the freed register takes element e+64
+      }
+      P = P - fP * gi;
+      N = N - fN * gi;
+    }
+    // expansion of row u of the next chunk (already landed in the staging ring)
+    if (FULL || (more && u < nrows)) {
+      const double *src = src0 + u * sstep;
+      dst[u * kBaroRow + 32] = src[0];
+      if (dup) {
+        const double f = src[32];
+        dst[u * kBaroRow + 64] = f;
+        dst[u * kBaroRow] = f;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(32) k_baro_reg(const Dev v, const double *__restrict__ bf_all, const double *__restrict__ bb_all,
+                                                 const double *__restrict__ rd_all) {
+  extern __shared__ __align__(128) double bsm[];
+  const int lane = threadIdx.x, m = blockIdx.x;
+  const int nm = v.nm, MS = v.MS, bw = v.I + 1, nd = bw - 32;
+  const bool dup = lane < nd;
+  double *stage = bsm;                                           // kBaroRing packed chunks of 32 x bw factors
+  double *ex = stage + (size_t)kBaroRing * 32 * bw;              // two expanded chunks of 32 x 96
+  double *xpad = ex + 2 * 32 * kBaroRow;                         // 64 zeros | the vector (rhs -> forward result -> solution) | 64 zeros
+  double *x = xpad + 64;
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(xpad + 128 + ((nm + 1) & ~1));
+  const size_t grp = v.baro_group[m];
+  const double *__restrict__ bf = bf_all + grp * nm * bw, *__restrict__ bb = bb_all + grp * nm * bw, *__restrict__ rd = rd_all + grp * nm;
+  const int nch = (nm + 31) / 32, ntot = 2 * nch;
+  if (lane == 0) {
+    for (int q = 0; q < kBaroRing; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(baro_sa(bar + q)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int g = 0; g < kBaroRing && g < ntot; g++) baro_issue(g, nch, nm, bw, bf, bb, stage, bar);
+  }
+  for (int r = lane; r < 2 * 32 * kBaroRow; r += 32) ex[r] = 0.0;
+  for (int r = lane; r < 64; r += 32) { xpad[r] = 0.0; x[nm + r] = 0.0; }
+  for (int r = lane; r < nm; r += 32) x[r] = v.gb[(size_t)r * MS + m];
+  __syncwarp();
+  {
+    // chunk 0 is expanded on its own, every later chunk while the pivots of its predecessor run
+    baro_wait(0, bar);
+    const BaroChunk k0 = baro_chunk(0, nch, nm);
+    for (int u = 0; u < k0.rows; u++) {
+      const double *src = stage + u * bw + lane;
+      double *dst = ex + u * kBaroRow + lane;
+      dst[32] = src[0];
+      if (dup) { const double f = src[32]; dst[64] = f; dst[0] = f; }
+    }
+    __syncwarp();
+    if (lane == 0 && kBaroRing < ntot) baro_issue(kBaroRing, nch, nm, bw, bf, bb, stage, bar);
+  }
+  double P = 0.0, N = 0.0, rdv = 0.0;   // P: block of the current chunk, N: the next block (roles swap every chunk)
+  for (int g = 0; g < ntot; g++) {
+    const BaroChunk k = baro_chunk(g, nch, nm);
+    const int sw = k.sw, c = k.c;
+    if (c == 0) {
+      __syncwarp();
+      const int e0 = lane, e1 = 32 + lane;                            // element e' of this sweep lives at x[sw ? nm-1-e' : e']
+      P = x[sw ? nm - 1 - e0 : e0];
+      N = x[sw ? nm - 1 - e1 : e1];
+      rdv = (sw && lane < nm) ? rd[nm - 1 - lane] : 0.0;
+    }
+    // reciprocal pivots of the next chunk (backward sweep), one chunk ahead of their use
+    double rdn = 0.0;
+    if (sw && 32 * (c + 1) + lane < nm) rdn = rd[nm - 1 - 32 * (c + 1) - lane];
+    const bool more = g + 1 < ntot;
+    BaroChunk kn = k;
+    if (more) { kn = baro_chunk(g + 1, nch, nm); baro_wait(g + 1, bar); }
+    const double *fb = ex + (g & 1) * 32 * kBaroRow + lane;
+    double *xe = x + (sw ? nm - 1 - 32 * c : 32 * c);                // &x[phys(32c)]
+    const double *src0 = stage + (size_t)((g + 1) & (kBaroRing - 1)) * 32 * bw + (kn.sw ? (kn.rows - 1) * bw : 0) + lane;
+    const int sstep = kn.sw ? -bw : bw;
+    double *dst = ex + ((g + 1) & 1) * 32 * kBaroRow + lane;
+    const bool full = more && k.rows == 32 && kn.rows == 32;
+    if (sw) {
+      if (full) baro_steps<true, true>(P, N, rdv, fb, xe, k.rows, more, src0, sstep, kn.rows, dst, lane, dup);
+      else baro_steps<true, false>(P, N, rdv, fb, xe, k.rows, more, src0, sstep, kn.rows, dst, lane, dup);
+    } else {
+      if (full) baro_steps<false, true>(P, N, rdv, fb, xe, k.rows, more, src0, sstep, kn.rows, dst, lane, dup);
+      else baro_steps<false, false>(P, N, rdv, fb, xe, k.rows, more, src0, sstep, kn.rows, dst, lane, dup);
+    }
+    { const double t = P; P = N; N = t; }
+    rdv = rdn;
+    __syncwarp();                                                     // staging slot of chunk g+1 and ex[g&1] are free
+    if (lane == 0 && g + 1 + kBaroRing < ntot) baro_issue(g + 1 + kBaroRing, nch, nm, bw, bf, bb, stage, bar);
+  }
+  __syncwarp();
+  for (int r = lane; r < nm; r += 32) v.gb[(size_t)r * MS + m] = x[r];
+}
+bool baro_reg_ok(const Dev &v) { return v.I + 1 > 32 && v.I + 1 <= 64 && (v.nm % 2) == 0 && v.nm >= 64; }
+
 // psi and barotropic velocity from the solved gb (ubarsolv :3527-3564)
 __global__ void __launch_bounds__(128) k_psi2ub(const Dev v) {
   DIMS
@@ -938,7 +1091,12 @@ int launch_momentum(const Dev &v, int fast, const double *bf, const double *bb, 
   const dim3 b(32, 4);
   k_bp<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
   k_gb<<<grid2(v, v.nm, b), b, 0, s>>>(v);
-  if (fast) {
+  if (fast == 2 && baro_reg_ok(v)) {
+    const size_t smem = sizeof(double) * ((size_t)kBaroRing * 32 * (v.I + 1) + 2 * 32 * kBaroRow + 128 + ((v.nm + 1) & ~1)) + 8 * kBaroRing;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_baro_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    k_baro_reg<<<v.M, 32, smem, s>>>(v, bf, bb, rd);
+  } else if (fast) {
     const int wpb = 2;  // members (warps) per block
     k_baro_fast<<<(v.M + wpb - 1) / wpb, 32 * wpb, sizeof(double) * v.nm * wpb, s>>>(v, bf, bb, rd);
   } else {

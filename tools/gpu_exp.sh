@@ -16,6 +16,6 @@ tail -15 $OUT/pytest_col_$TAG.log
   CG_COL_CFG=0 timeout 300 python tools/prof_run.py --members 32 --spin 400 --steps 48 --variant col --profile
 } > $OUT/prof_variants_$TAG.log 2>&1
 cat $OUT/prof_variants_$TAG.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_tstep_col|k_co_passive" -s 20 -c 4 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_tstep_col|k_co_col|k_baro_reg" -s 30 -c 6 \
     -o $OUT/prof_col_$TAG -f python tools/prof_run.py --members 128 --spin 400 --steps 6 --variant col > $OUT/prof_col_$TAG.log 2>&1
 ls -la $OUT | tail -5
