@@ -216,12 +216,16 @@ def main():
     bytes_per_launch = n_wet * (16 * L + 32) * M          # B_tr x members of one launch
     t_ms, t_n = fam["tstepo_flux"]
     c_ms, c_n = fam["co"]
-    avg_ms = (t_ms + c_ms) / max(t_n, 1)                   # tstepo = flux + convection (B_tr covers both)
+    nstep = e.nyear                                         # tracer steps in the instrumented year
+    avg_ms = (t_ms + c_ms) / max(nstep, 1)                  # tstepo = flux + convection kernels of one step (B_tr covers both)
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tstepo = k_tstepo_flux_* + k_co_* (%s variant), SURVEY 8d B_tr" % args.variant,
+    kern = {"col": "tstepo = k_tstep_col + k_co_col", "fast": "tstepo = k_tstepo_flux_coop + k_co_fast2 (+ k_sst)",
+            "strict": "tstepo = k_tstepo_flux_strict + k_co_strict (+ k_sst)"}[e.tracer_variant_active()]
+    roofline = {"bound": "hbm", "kernel": kern + " (%s variant), SURVEY 8d B_tr" % e.tracer_variant_active(),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(M, args.variant), "peak_source": peak_src,
+                "traffic": ncu_traffic(M, e.tracer_variant_active()), "peak_source": peak_src,
+                "launches_per_step": (t_n + c_n) / max(nstep, 1),
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "family_ms_per_year": {k: v[0] for k, v in fam.items()}}
 

@@ -28,6 +28,7 @@ void upload_grid_tracer_col(const GridC &, cudaStream_t);
 int launch_tstep_col(const Dev &, cudaStream_t);
 bool tstep_col_supported(const Dev &);
 void launch_step_begin(const Dev &, cudaStream_t);
+void launch_usnap(const Dev &, cudaStream_t);
 void launch_hosing(const Dev &, cudaStream_t);
 int launch_surflux(const Dev &, double *meantemp, bool need_mean, cudaStream_t);
 int launch_embm(const Dev &, int nsteps, cudaStream_t);
@@ -107,6 +108,10 @@ struct cg_handle {
   GridC gc;
   Dev dv;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;                 // momentum branch of the graph-captured ocean cycle
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  bool fork_momentum = true;                      // CG_FORK=0 keeps the captured cycle on one stream
+  bool forked = false;                            // inside enqueue_cycle with the momentum branch on stream2
   std::vector<void *> allocs;
   std::map<std::string, FieldDesc> fields;
   std::map<std::string, std::vector<double>> hconst;   // host constants for cg_get_const (member 0 / shared)
@@ -140,6 +145,9 @@ struct cg_handle {
     for (void *p : allocs) cudaFree(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (evFork) cudaEventDestroy(evFork);
+    if (evJoin) cudaEventDestroy(evJoin);
+    if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -314,6 +322,9 @@ extern "C" int cg_initialise(cg_handle *h) {
     return fail(CG_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
   CUDA_OK(cudaSetDevice(h->device));
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
   // per-member constants; members sharing adrag share one barotropic factorisation
@@ -421,6 +432,7 @@ static int build_device(cg_handle *h) {
   TRY(dalloc(h, &v.ts_cur, ijk * L * MS));
   TRY(dalloc(h, &v.ts_new, ijk * L * MS));
   TRY(dalloc(h, &v.tsflux, 2 * ij * MS));
+  TRY(dalloc(h, &v.usnap, 2 * ij * MS));
   TRY(dalloc(h, &v.rho, ijk * MS));
   TRY(dalloc(h, &v.u, ijk * 3 * MS));
   TRY(dalloc(h, &v.u1, ijk * 2 * MS));
@@ -983,7 +995,11 @@ static int do_embm(cg_handle *h, int nsteps) {
 }
 static int do_seaice(cg_handle *h) {
   ProfScope ps(h, "seaice");
-  ps.done(launch_seaice(h->dv, h->stream));
+  // the sea-ice step advects with the surface velocities exported by the last step_goldstein: a snapshot, taken here
+  // unless the forked cycle already took it before the momentum branch started
+  int n = 0;
+  if (!h->forked) { launch_usnap(h->dv, h->stream); n++; }
+  ps.done(n + launch_seaice(h->dv, h->stream));
   h->istep_sic++;
   return CG_OK;
 }
@@ -1003,8 +1019,18 @@ static void do_tstepo(cg_handle *h) {
   std::swap(h->dv.ts_cur, h->dv.ts_new);
   if (h->dv.sst) { ProfScope ps(h, "co"); ps.done(launch_sst(h->dv, h->stream)); }
 }
+static void do_gold_pre(cg_handle *h) {
+  ProfScope ps(h, "momentum");
+  launch_hosing(h->dv, h->stream);
+  ps.done(1 + launch_gold_pre(h->dv, h->stream));
+}
+static void do_momentum(cg_handle *h, cudaStream_t s) {
+  ProfScope ps(h, "momentum");
+  ps.done(launch_momentum(h->dv, h->variant, h->d_bf, h->d_bb, h->d_rd, s));
+}
 static int do_goldstein(cg_handle *h) {
-  { ProfScope ps(h, "momentum"); launch_hosing(h->dv, h->stream); int n = launch_gold_pre(h->dv, h->stream); n += launch_momentum(h->dv, h->variant, h->d_bf, h->d_bb, h->d_rd, h->stream); ps.done(n + 1); }
+  do_gold_pre(h);
+  do_momentum(h, h->stream);
   do_tstepo(h);
   return CG_OK;
 }
@@ -1255,13 +1281,33 @@ static int do_biogem_block(cg_handle *h, long long k) {
 // One ocean cycle = kocn_loop iterations of the koverall loop when katm_loop == 1 and
 // ksic_loop == kocn_loop (the only schedule tools/config_utils.py:103-162 generates):
 // surflux, kocn_loop x EMBM, sea ice, ocean.
-static int enqueue_cycle(cg_handle *h) {
+// One ocean cycle (kocn_loop iterations of the koverall loop, regular schedule).  fork = true (graph capture only): the
+// momentum step -- which needs nothing but rho of the previous tracer step and constants, and is dominated by the
+// latency-bound barotropic solve -- runs on a second stream next to surflux / EMBM / sea ice and joins before tstepo.
+static int enqueue_cycle(cg_handle *h, bool fork) {
   const Params &p = h->base;
-  IO(do_surflux(h));
-  IO(do_embm(h, p.kocn_loop));
-  IO(do_seaice(h));
-  IO(do_goldstein(h));
-  return CG_OK;
+  if (fork) {
+    launch_usnap(h->dv, h->stream);
+    h->launches++;
+    CUDA_OK(cudaEventRecord(h->evFork, h->stream));
+    CUDA_OK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
+    do_momentum(h, h->stream2);
+    CUDA_OK(cudaEventRecord(h->evJoin, h->stream2));
+    h->forked = true;
+  }
+  int rc = do_surflux(h);
+  if (!rc) rc = do_embm(h, p.kocn_loop);
+  if (!rc) rc = do_seaice(h);
+  h->forked = false;
+  if (fork) {
+    do_gold_pre(h);
+    CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin, 0));
+    if (rc) return rc;
+    do_tstepo(h);
+    return CG_OK;
+  }
+  if (rc) return rc;
+  return do_goldstein(h);
 }
 
 extern "C" int cg_run(cg_handle *h, int64_t n) {
@@ -1280,7 +1326,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
           const long long l0 = h->launches;
           const int i0 = h->istep_ocn, a0 = h->istep_atm, s0 = h->istep_sic;
           CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-          int rc = enqueue_cycle(h);
+          int rc = enqueue_cycle(h, h->fork_momentum && !getenv("CG_NOFORK"));
           cudaError_t e = cudaStreamEndCapture(h->stream, &gr);
           if (rc) return rc;
           if (e != cudaSuccess) return fail(CG_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
@@ -1295,7 +1341,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
         h->istep_ocn++; h->istep_atm += p.kocn_loop; h->istep_sic++;
         std::swap(h->dv.ts_cur, h->dv.ts_new);
       } else {
-        IO(enqueue_cycle(h));
+        IO(enqueue_cycle(h, false));
       }
       h->koverall += p.kocn_loop;
       n -= p.kocn_loop;
@@ -1439,6 +1485,9 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
   h->mp.assign(n_members, p);
   CUDA_OK(cudaSetDevice(device));
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
   h->mc.resize(1);

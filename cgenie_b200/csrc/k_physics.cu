@@ -38,6 +38,17 @@ __global__ void k_step_begin(const Dev v) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m == 0) *v.istep_ocn = *v.istep_ocn + 1;
 }
+// surface ocean velocities as the sea-ice step sees them (ustar_ocn/vstar_ocn, goldstein.f90:428-429): a snapshot, so
+// that the momentum step of the same cycle may overwrite u while surflux / EMBM / sea ice are still running
+__global__ void __launch_bounds__(128) k_usnap(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= MS || c2 >= I * J) return;
+  const size_t o = ((size_t)(K - 1) * I * J + c2) * 3 * MS + m;
+  v.usnap[(size_t)c2 * MS + m] = v.u[o];
+  v.usnap[((size_t)I * J + c2) * MS + m] = v.u[o + MS];
+}
 __global__ void k_hosing(const Dev v) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m < v.M) v.hosing[m] = v.hosing[m] + v.p.hosing_trend[m] * kTsc * c_g.dt;
@@ -376,7 +387,9 @@ __global__ void __launch_bounds__(128) k_seaice1(const Dev v) {
   const double sath = v.p.par_sica_thresh[m], shth = v.p.par_sich_thresh[m], diffsic = v.p.diffsic[m], dtsic = v.p.dtsic[m];
   const double rc = c_g.rc[j], rdphi = c_g.rdphi;
   // surface ocean velocities (ustar_ocn = u(1,:,:,maxk), goldstein.f90:428-429)
-  const double uE = UX(1, i, j, K), uW = UX(1, im, j, K), vN = UX(2, i, j, K), vS = (j > 1) ? UX(2, i, j - 1, K) : 0.0;
+#define USN(c, ii, jj) v.usnap[((size_t)((c)-1) * I * J + cell2(I, (ii), (jj))) * MS + m]
+  const double uE = USN(1, i, j), uW = USN(1, im, j), vN = USN(2, i, j), vS = (j > 1) ? USN(2, i, j - 1) : 0.0;
+#undef USN
   const size_t nf = (size_t)I * J * MS;
   const size_t qc = A2I(i, j), qe = A2I(ip, j), qw = A2I(im, j), qn = (j < J) ? A2I(i, j + 1) : qc, qs = (j > 1) ? A2I(i, j - 1) : qc;
   const double hc = v.varice1[qc], ac = v.varice1[qc + nf];
@@ -1039,6 +1052,10 @@ struct LaunchCtx { cudaStream_t s; long long *count; };
 static inline dim3 grid2(const Dev &v, int ncells, dim3 b) { return dim3((v.M + b.x - 1) / b.x, (ncells + b.y - 1) / b.y); }
 
 void launch_step_begin(const Dev &v, cudaStream_t s) { k_step_begin<<<1, 32, 0, s>>>(v); }
+void launch_usnap(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_usnap<<<dim3(v.MS / 32, (v.I * v.J + 3) / 4), b, 0, s>>>(v);
+}
 void launch_hosing(const Dev &v, cudaStream_t s) { k_hosing<<<(v.M + 127) / 128, 128, 0, s>>>(v); }
 int launch_surflux(const Dev &v, double *meantemp, bool need_mean, cudaStream_t s) {
   int n = 0;
