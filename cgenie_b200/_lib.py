@@ -71,6 +71,7 @@ SYMBOLS = {
     "cg_profile_get": (C.c_int, [P, C.c_char_p, D, C.POINTER(C.c_int64)]),
     "cg_set_tracer_variant": (C.c_int, [P, C.c_int]),
     "cg_tracer_variant_active": (C.c_int, [P]),
+    "cg_set_biogem_fusion": (C.c_int, [P, C.c_int]),
     "cg_set_graphs": (C.c_int, [P, C.c_int]),
     "cg_tracer_create": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int32), C.c_double, C.c_double, C.c_int, C.POINTER(P)]),
     "cg_tracer_set": (C.c_int, [P, D, D, D]),

@@ -39,7 +39,8 @@ int launch_momentum(const Dev &, int fast, const double *bf, const double *bb, c
 void launch_global_means(const Dev &, double *out, cudaStream_t);
 int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
-int launch_bg_step(const Dev &, const BgDev &, int init_only, cudaStream_t);
+int launch_bg_step(const Dev &, const BgDev &, int init_only, int fuse, cudaStream_t);
+int launch_tc_sums_first(const Dev &, cudaStream_t);
 bool bg_layout_ok(const BgDev &, int L);
 int launch_bg_climate(const Dev &, const BgDev &, cudaStream_t);
 int launch_bg_atchem(const Dev &, const BgDev &, double atm_totV, cudaStream_t);
@@ -110,6 +111,7 @@ struct cg_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;                 // momentum branch of the graph-captured ocean cycle
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  bool bg_fuse = true;                            // cg_run: tracer coupling fused into the BIOGEM step kernel
   bool fork_momentum = true;                      // CG_FORK=0 keeps the captured cycle on one stream
   bool forked = false;                            // inside enqueue_cycle with the momentum branch on stream2
   std::vector<void *> allocs;
@@ -354,7 +356,7 @@ extern "C" int cg_initialise(cg_handle *h) {
   activate(h);
   if (h->bg.on) {
     // sub_init_carb (biogem_data.f90:2336-2430) and the biogem_climate call before the main loop (genie.f90:109-112)
-    h->launches += launch_bg_step(h->dv, h->bgd, 1, h->stream);
+    h->launches += launch_bg_step(h->dv, h->bgd, 1, 0, h->stream);
     h->bgd.nsol = 0;
     h->launches += launch_bg_climate(h->dv, h->bgd, h->stream);
   }
@@ -1198,7 +1200,7 @@ extern "C" int cg_biogem_step(cg_handle *h, double dts, int64_t genie_clock_ms) 
   if (dts != h->bgd.dts) return fail(CG_ERR_ARG, "cg_biogem_step: dts differs from conv_kocn_kbiogem*kocn_loop*genie_timestep");
   const double t = h->bg.t_runtime - (double)genie_clock_ms / (1000.0 * kBgYrS);
   if (!h->bg_go) return CG_OK;   // par_misc_t_go (biogem.f90:1851-1853)
-  { ProfScope ps(h, "biogem"); ps.done(launch_bg_step(h->dv, h->bgd, 0, h->stream)); }
+  { ProfScope ps(h, "biogem"); ps.done(launch_bg_step(h->dv, h->bgd, 0, 0, h->stream)); }
   if (t < kBgNullSmall) h->bg_go = false;
   return check_async(h);
 }
@@ -1270,8 +1272,21 @@ static int do_biogem_block(cg_handle *h, long long k) {
   if (k % ((long long)p.conv_kocn_kbiogem * p.kocn_loop) == 0) {
     if (k == (long long)p.conv_kocn_kbiogem * p.kocn_loop) IO(cg_biogem_climate_sol(h));
     IO(cg_biogem_forcing(h, clock));
-    IO(cg_biogem_step(h, h->bgd.dts, clock));
-    IO(cg_biogem_tracercoupling(h, nullptr, nullptr));
+    static const bool nofuse = getenv("CG_BG_NOFUSE") != nullptr;
+    if (nofuse || !h->bg_fuse) {
+      IO(cg_biogem_step(h, h->bgd.dts, clock));
+      IO(cg_biogem_tracercoupling(h, nullptr, nullptr));
+    } else if (h->bg_go) {
+      // step_biogem with biogem_tracercoupling's per-cell update fused in: the coupling's global sums do not depend on
+      // this step's anomaly, so they are taken first; bit-identical to the two separate calls (tests/test_gpu_col.py)
+      const double t = h->bg.t_runtime - (double)clock / (1000.0 * kBgYrS);
+      ProfScope ps(h, "biogem");
+      int n = launch_tc_sums_first(h->dv, h->stream);
+      n += launch_bg_step(h->dv, h->bgd, 0, 1, h->stream);
+      ps.done(n);
+      if (t < kBgNullSmall) h->bg_go = false;
+      IO(check_async(h));
+    }
     IO(cg_biogem_climate(h));
   }
   if (k % ((long long)p.conv_kocn_katchem * p.kocn_loop) == 0) IO(cg_atchem_step(h, h->bgd.dts_atchem));
@@ -1441,6 +1456,11 @@ extern "C" int cg_profile_get(cg_handle *h, const char *family, double *total_ms
   auto it = h->prof.find(family);
   if (total_ms) *total_ms = it == h->prof.end() ? 0.0 : it->second.ms;
   if (launches) *launches = it == h->prof.end() ? 0 : it->second.n;
+  return CG_OK;
+}
+extern "C" int cg_set_biogem_fusion(cg_handle *h, int on) {
+  if (!h) return fail(CG_ERR_ARG, "cg_set_biogem_fusion: bad handle");
+  h->bg_fuse = on != 0;
   return CG_OK;
 }
 extern "C" int cg_tracer_variant_active(cg_handle *h) {

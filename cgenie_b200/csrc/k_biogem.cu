@@ -33,13 +33,16 @@ __global__ void __launch_bounds__(128) k_tc_partial(const Dev v, const int phase
   const size_t v0 = cell3(I, J, i, j, 1), vK = (size_t)I * J;
   const size_t nq = (size_t)v.nwet * MS;
   double *part = v.bg_part + (size_t)n * MS + m;
-  if (phase == 0) {
+  if (phase == 0 || phase == 2) {
+    // phase 2 = phase 0 taken BEFORE step_biogem (fused coupling): the salinity anomaly of the frozen configuration is
+    // exactly +0.0 (no BIOGEM source or sink of salt), so the sum does not need vdocn
     const double saln0 = v.p.saln0[m];
     double a = 0.0, b = 0.0;
     for (int k = k1c; k <= K; k++) {
       const double V = v.bg_V[v0 + (size_t)(k - 1) * vK];
       a = a + v.bg_ocn[o0 + (size_t)(k - 1) * sK + MS] * V;
-      b = b + (v.ts_cur[o0 + (size_t)(k - 1) * sK + MS] + saln0 + v.bg_vdocn[o0 + (size_t)(k - 1) * sK + MS]) * V;
+      const double dS = (phase == 0) ? v.bg_vdocn[o0 + (size_t)(k - 1) * sK + MS] : 0.0;
+      b = b + (v.ts_cur[o0 + (size_t)(k - 1) * sK + MS] + saln0 + dS) * V;
     }
     part[0] = a * v.bg_rtot_V;
     part[nq] = b * v.bg_rtot_V;
@@ -405,13 +408,35 @@ __device__ __forceinline__ void rem_add(Rem7 &r, const double f, const double *p
   r.d14 = r.d14 + f * p[CACO314];
 }
 
-__global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, const int init_only) {
+// fuse != 0: biogem_tracercoupling's steps (2)+(3) (biogem.f90:2033-2061, k_tc_apply) are applied to each cell as soon
+// as its anomaly is known -- same expressions, same order, bit-identical -- instead of writing vdocn and re-reading ocn,
+// ts, vdocn and bio_part in a separate pass.  The global sums of step (1) do not depend on step_biogem's output (the
+// salinity anomaly is +0.0), so the caller takes them first (k_tc_partial phases 2 and 1).
+__global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, const int init_only, const int fuse) {
   using namespace bgk;
   using namespace lay;
   const int I = v.I, J = v.J, K = v.K, MS = v.MS;
   constexpr int L = NL, LS = NLS, LA = NLA;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y * blockDim.y + threadIdx.y;
+  __shared__ double s_f[L][32], s_rmean[32], s_sr[32], s_rsr[32], s_mnew[32];
+  if (fuse) {   // per-member totals of the coupling, staged once per block (blockDim = (32, 4), m < MS always)
+    const int lane = threadIdx.x;
+    if (threadIdx.y == 0) {
+      const double mean_S_OLD = v.bg_tot[m], mean_S_NEW = v.bg_tot[MS + m];
+      s_rmean[lane] = 1.0 / mean_S_OLD;
+      const double Sratio = mean_S_NEW / mean_S_OLD;
+      s_sr[lane] = Sratio;
+      s_rsr[lane] = 1.0 / Sratio;
+      s_mnew[lane] = mean_S_NEW;
+    }
+    for (int l = 2 + threadIdx.y; l < L; l += blockDim.y) {
+      const double told = v.bg_tot[(size_t)l * MS + m], tnew = v.bg_tot[(size_t)(L - 2 + l) * MS + m];
+      const double rtnew = (fabs(tnew) < kBgNullSmall) ? 0.0 : 1.0 / tnew;
+      s_f[l][lane] = told * rtnew;
+    }
+    __syncthreads();
+  }
   if (m >= MS || n >= v.nwet) return;
   const int c2 = v.bgcols[n];
   const int i = c2 % I + 1, j = c2 / I + 1;
@@ -616,6 +641,21 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
 #pragma unroll
   for (int ls = 1; ls <= LS; ls++) set1[ls] = 0.0;
   for (int kk = K; kk >= k1; kk--) {
+    // pull the next level's rows towards the SM while this level is being worked on (no registers tied up)
+    if (kk > k1) {
+#pragma unroll
+      for (int l = 1; l <= L; l++) asm volatile("prefetch.global.L1 [%0];" ::"l"(&OCN_(l, kk - 1)));
+      if (fuse) {
+#pragma unroll
+        for (int l = 1; l <= L; l++) asm volatile("prefetch.global.L1 [%0];" ::"l"(v.ts_cur + (o0 + (size_t)(kk - 2) * sK + (size_t)(l - 1) * MS)));
+      }
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(&M_(kk - 1)));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(&RM_(kk - 1)));
+      if (kk - 1 >= klim) {
+#pragma unroll
+        for (int ls = 1; ls <= LS; ls++) asm volatile("prefetch.global.L1 [%0];" ::"l"(&PART_(ls, kk - 1)));
+      }
+    }
     Rem7 lrem;
     double pnew[LS + 1];
     rem_zero(lrem);
@@ -694,7 +734,10 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
     }
     // (3) new particulate field of this layer
 #pragma unroll
-    for (int ls = 1; ls <= LS; ls++) PART_(ls, kk) = (kk == K) ? psurf[ls] : pnew[ls];
+    for (int ls = 1; ls <= LS; ls++) {
+      const double pv = (kk == K) ? psurf[ls] : pnew[ls];
+      PART_(ls, kk) = fuse ? s_sr[threadIdx.x] * (pv + 0.0) : pv;   // biogem.f90:2042-2043 (vdbio_part = 0)
+    }
     // (4) sub_box_remin_DOM for this layer: DOM -> POM -> inorganic products
     const bool has_dom = x[DOMC] > kNS;
     double dom[LS + 1];
@@ -711,6 +754,7 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
     rem_add(domrem, f, dom, fO2POC, fO2POP, fALKPOP, fALKCa);
     // (5) tracer anomaly vdocn(l, kk) = bio_remin + dtyr*rM*focn and the bottom-water interface (:1736-1744)
     const bool bot = (kk == k1), top = (kk == K);
+    double rn_cpl = 0.0;   // mean_S_NEW / Snew of this cell (fused coupling)
 #pragma unroll
     for (int l = 1; l <= L; l++) {
       double vrem = 0.0, lr = 0.0, fs = 0.0, up = 0.0, da = 0.0, gas = 0.0;
@@ -744,8 +788,33 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
           rem = rem - (slot ? up : 0.0);
         }
       }
-      DOCN_(l, kk) = rem + dtyr * rM * focn;
+      const double dval = rem + dtyr * rM * focn;
       if (bot) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = x[l] + rem + dtyr * rM * focn;
+      if (!fuse) {
+        DOCN_(l, kk) = dval;
+      } else {
+        double *tsp = v.ts_cur + (o0 + (size_t)(kk - 1) * sK + (size_t)(l - 1) * MS);
+        if (l == 1) {
+          const double Tn = *tsp + kBgZeroC + dval;
+          OCN_(l, kk) = Tn;
+          *tsp = Tn - kBgZeroC;
+        } else if (l == 2) {
+          const double Sn = *tsp + v.p.saln0[m] + dval;
+          rn_cpl = s_mnew[threadIdx.x] / Sn;
+          OCN_(l, kk) = Sn;
+          *tsp = Sn - v.p.saln0[m];
+        } else {
+          const double lv = *tsp * x[S] * s_rmean[threadIdx.x];
+          double xx = s_f[l - 1][threadIdx.x] * lv + dval;
+          xx = s_sr[threadIdx.x] * xx;
+          OCN_(l, kk) = xx;
+          *tsp = rn_cpl * xx;
+        }
+      }
+    }
+    if (fuse) {
+      M_(kk) = s_rsr[threadIdx.x] * Mk;
+      RM_(kk) = s_sr[threadIdx.x] * rM;
     }
   }
 #pragma unroll
@@ -820,9 +889,20 @@ __global__ void __launch_bounds__(32 * kSumWarps) k_bg_atchem2(const Dev v, cons
   }
 }
 
-int launch_bg_step(const Dev &v, const BgDev &b, int init_only, cudaStream_t s) {
-  k_bg_step<<<dim3(v.MS / 32, (v.nwet + 3) / 4), dim3(32, 4), 0, s>>>(v, b, init_only);
+int launch_bg_step(const Dev &v, const BgDev &b, int init_only, int fuse, cudaStream_t s) {
+  k_bg_step<<<dim3(v.MS / 32, (v.nwet + 3) / 4), dim3(32, 4), 0, s>>>(v, b, init_only, fuse);
   return 1;
+}
+// step (1) of biogem_tracercoupling taken BEFORE step_biogem (fused coupling, see k_bg_step)
+int launch_tc_sums_first(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
+  const int L = v.L;
+  k_tc_partial<<<gc, b, 0, s>>>(v, 2);
+  k_tc_sum<<<dim3(v.MS / 32, L), 32 * kSumWarps, 0, s>>>(v, 0, L);
+  k_tc_partial<<<gc, b, 0, s>>>(v, 1);
+  k_tc_sum<<<dim3(v.MS / 32, L - 2), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2);
+  return 4;
 }
 int launch_bg_climate(const Dev &v, const BgDev &b, cudaStream_t s) {
   const size_t n = (size_t)v.I * v.J * v.MS;

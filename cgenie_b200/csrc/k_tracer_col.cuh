@@ -468,6 +468,16 @@ CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned 
 #pragma unroll 1
   for (int l = 2; l < L; l += 2) {
     const bool two = (l + 1 < L);
+#ifdef __CUDA_ARCH__
+    if (l + 2 < L) {   // next tracer pair: towards L1 while this pair is summed
+#pragma unroll
+      for (int k = 0; k < K; k++)
+        if ((in >> k) & 1u) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(ts + (long)k * sK + (l + 2) * sL));
+          if (l + 3 < L) asm volatile("prefetch.global.L1 [%0];" ::"l"(ts + (long)k * sK + (l + 3) * sL));
+        }
+    }
+#endif
     double a[K], b[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {

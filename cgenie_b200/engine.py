@@ -129,6 +129,10 @@ class _Base:
         """'strict' / 'fast' / 'col': what the tracer step really runs ('col' exists for compiled grid shapes only)."""
         return ("strict", "fast", "col")[self.L.cg_tracer_variant_active(self.h)]
 
+    def set_biogem_fusion(self, on):
+        """run(): fuse biogem_tracercoupling's per-cell update into the step_biogem kernel (default on)."""
+        self._ck(self.L.cg_set_biogem_fusion(self.h, 1 if on else 0))
+
     def set_graphs(self, on):
         self._ck(self.L.cg_set_graphs(self.h, 1 if on else 0))
 
