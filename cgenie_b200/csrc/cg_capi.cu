@@ -111,7 +111,7 @@ struct cg_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;                 // momentum branch of the graph-captured ocean cycle
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
-  bool bg_fuse = true;                            // cg_run: tracer coupling fused into the BIOGEM step kernel
+  bool bg_fuse = false;                           // cg_run: tracer coupling fused into the BIOGEM step kernel (slower on B200)
   bool fork_momentum = true;                      // CG_FORK=0 keeps the captured cycle on one stream
   bool forked = false;                            // inside enqueue_cycle with the momentum branch on stream2
   std::vector<void *> allocs;

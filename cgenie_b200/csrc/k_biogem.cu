@@ -6,6 +6,7 @@
 // over k (ascending) and then the column partials in its vocn order (i outer, j inner); the kernels
 // keep exactly that order -- thread (member, column) for the partials, thread (member, quantity) for
 // the ordered sum over columns -- so every total is bit-identical to the sequential code.
+#include <cstdlib>
 #include "cg_device.cuh"
 #include "cg_host.hpp"
 
@@ -412,7 +413,9 @@ __device__ __forceinline__ void rem_add(Rem7 &r, const double f, const double *p
 // as its anomaly is known -- same expressions, same order, bit-identical -- instead of writing vdocn and re-reading ocn,
 // ts, vdocn and bio_part in a separate pass.  The global sums of step (1) do not depend on step_biogem's output (the
 // salinity anomaly is +0.0), so the caller takes them first (k_tc_partial phases 2 and 1).
-__global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, const int init_only, const int fuse) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev b, const int init_only, const int mode) {
+  const bool fuse = (mode & 1) != 0, pf = (mode & 2) == 0;
   using namespace bgk;
   using namespace lay;
   const int I = v.I, J = v.J, K = v.K, MS = v.MS;
@@ -642,7 +645,7 @@ __global__ void __launch_bounds__(128) k_bg_step(const Dev v, const BgDev b, con
   for (int ls = 1; ls <= LS; ls++) set1[ls] = 0.0;
   for (int kk = K; kk >= k1; kk--) {
     // pull the next level's rows towards the SM while this level is being worked on (no registers tied up)
-    if (kk > k1) {
+    if (pf && kk > k1) {
 #pragma unroll
       for (int l = 1; l <= L; l++) asm volatile("prefetch.global.L1 [%0];" ::"l"(&OCN_(l, kk - 1)));
       if (fuse) {
@@ -890,7 +893,16 @@ __global__ void __launch_bounds__(32 * kSumWarps) k_bg_atchem2(const Dev v, cons
 }
 
 int launch_bg_step(const Dev &v, const BgDev &b, int init_only, int fuse, cudaStream_t s) {
-  k_bg_step<<<dim3(v.MS / 32, (v.nwet + 3) / 4), dim3(32, 4), 0, s>>>(v, b, init_only, fuse);
+  // registers per thread 255 / 168 / 128 for MINB = 2 / 3 / 4 (CG_BG_MINB overrides; tuning knob)
+  static int minb = -1;
+  if (minb < 0) { const char *e = getenv("CG_BG_MINB"); minb = e ? atoi(e) : 2; }
+  static int nopf = -1;
+  if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
+  fuse |= nopf;
+  const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
+  if (minb == 4) k_bg_step<4><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  else if (minb == 3) k_bg_step<3><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  else k_bg_step<2><<<g, bl, 0, s>>>(v, b, init_only, fuse);
   return 1;
 }
 // step (1) of biogem_tracercoupling taken BEFORE step_biogem (fused coupling, see k_bg_step)

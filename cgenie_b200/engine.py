@@ -130,7 +130,7 @@ class _Base:
         return ("strict", "fast", "col")[self.L.cg_tracer_variant_active(self.h)]
 
     def set_biogem_fusion(self, on):
-        """run(): fuse biogem_tracercoupling's per-cell update into the step_biogem kernel (default on)."""
+        """run(): fuse biogem_tracercoupling's per-cell update into the step_biogem kernel (default off: slower)."""
         self._ck(self.L.cg_set_biogem_fusion(self.h, 1 if on else 0))
 
     def set_graphs(self, on):

@@ -166,8 +166,9 @@ int cg_profile_get(cg_handle *, const char *family, double *total_ms, int64_t *l
 int cg_set_tracer_variant(cg_handle *, int variant);
 /* the variant that actually runs (2 is reported as 1 when the grid shape has no compiled column kernel); -1 = bad handle */
 int cg_tracer_variant_active(cg_handle *);
-/* cg_run only: apply biogem_tracercoupling's per-cell update inside the step_biogem kernel (default on; bit-identical
- * to the two separate calls, which the per-module entry points cg_biogem_step / cg_biogem_tracercoupling always use) */
+/* cg_run only: apply biogem_tracercoupling's per-cell update inside the step_biogem kernel (bit-identical to the two
+ * separate calls, which the per-module entry points always use).  Default OFF: measured slower on B200 -- the step
+ * kernel is latency bound at 255 registers and the separate update streams at 3.4 TB/s. */
 int cg_set_biogem_fusion(cg_handle *, int on);
 /* use CUDA-graph replay of one ocean step inside cg_run (default on) */
 int cg_set_graphs(cg_handle *, int on);

@@ -1,7 +1,12 @@
 #!/bin/bash
-# quick A/B: col-variant tests + per-family timings (no ncu)
+# quick A/B on the bench state: BIOGEM fusion / prefetch knobs
 TAG=${1:-q}
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 600 python -m pytest tests/test_gpu_col.py tests/test_gpu_biogem.py -x -q 2>&1 | tail -3
-timeout 300 python tools/prof_run.py --members 128 --spin 400 --steps 48 --variant col --profile 2>&1 | tee $OUT/prof_quick_$TAG.log
+run() { echo "== $1"; env $1 timeout 600 python bench.py --steps 6 --warmup 12 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('ms/yr %.2f' % d['ms_per_step'], {k: round(v,1) for k,v in d['roofline']['family_ms_per_year'].items()})"; }
+run "CG_X=0" | tee -a $OUT/quick_$TAG.log
+run "CG_BG_NOFUSE=1" | tee -a $OUT/quick_$TAG.log
+run "CG_BG_NOPF=1" | tee -a $OUT/quick_$TAG.log
+run "CG_BG_NOFUSE=1 CG_BG_NOPF=1" | tee -a $OUT/quick_$TAG.log
