@@ -47,20 +47,55 @@ __global__ void __launch_bounds__(128) k_tc_partial(const Dev v, const int phase
     }
     part[0] = a * v.bg_rtot_V;
     part[nq] = b * v.bg_rtot_V;
-    for (int l = 2; l < L; l++) {
-      double s = 0.0;
-      for (int k = k1c; k <= K; k++) s = s + v.bg_ocn[o0 + (size_t)(k - 1) * sK + (size_t)l * MS] * v.bg_M[p0 + (size_t)(k - 1) * pK];
-      part[(size_t)l * nq] = s;
+    // old inventories: level outer / tracer inner, so that the loads of a level are all in flight at once and the
+    // per-tracer sums (each still accumulated over k ascending, as the reference does) are independent chains
+    if (L <= kBgMaxL) {
+      double s[kBgMaxL];
+#pragma unroll
+      for (int l = 2; l < kBgMaxL; l++) s[l] = 0.0;
+      for (int k = k1c; k <= K; k++) {
+        const double Mk = v.bg_M[p0 + (size_t)(k - 1) * pK];
+        const double *__restrict__ oc = v.bg_ocn + o0 + (size_t)(k - 1) * sK;
+#pragma unroll
+        for (int l = 2; l < kBgMaxL; l++)
+          if (l < L) s[l] = s[l] + oc[(size_t)l * MS] * Mk;
+      }
+#pragma unroll
+      for (int l = 2; l < kBgMaxL; l++)
+        if (l < L) part[(size_t)l * nq] = s[l];
+    } else {
+      for (int l = 2; l < L; l++) {
+        double s = 0.0;
+        for (int k = k1c; k <= K; k++) s = s + v.bg_ocn[o0 + (size_t)(k - 1) * sK + (size_t)l * MS] * v.bg_M[p0 + (size_t)(k - 1) * pK];
+        part[(size_t)l * nq] = s;
+      }
     }
   } else {
     const double rmean = 1.0 / v.bg_tot[m];  // loc_ocn_rmean_S_OLD
-    for (int l = 2; l < L; l++) {
-      double s = 0.0;
+    if (L <= kBgMaxL) {
+      double s[kBgMaxL];
+#pragma unroll
+      for (int l = 2; l < kBgMaxL; l++) s[l] = 0.0;
       for (int k = k1c; k <= K; k++) {
         const size_t o = o0 + (size_t)(k - 1) * sK;
-        s = s + (v.ts_cur[o + (size_t)l * MS] * v.bg_ocn[o + MS] * rmean) * v.bg_M[p0 + (size_t)(k - 1) * pK];
+        const double Mk = v.bg_M[p0 + (size_t)(k - 1) * pK], Sk = v.bg_ocn[o + MS];
+        const double *__restrict__ tc = v.ts_cur + o;
+#pragma unroll
+        for (int l = 2; l < kBgMaxL; l++)
+          if (l < L) s[l] = s[l] + (tc[(size_t)l * MS] * Sk * rmean) * Mk;
       }
-      part[(size_t)(L - 2 + l) * nq] = s;
+#pragma unroll
+      for (int l = 2; l < kBgMaxL; l++)
+        if (l < L) part[(size_t)(L - 2 + l) * nq] = s[l];
+    } else {
+      for (int l = 2; l < L; l++) {
+        double s = 0.0;
+        for (int k = k1c; k <= K; k++) {
+          const size_t o = o0 + (size_t)(k - 1) * sK;
+          s = s + (v.ts_cur[o + (size_t)l * MS] * v.bg_ocn[o + MS] * rmean) * v.bg_M[p0 + (size_t)(k - 1) * pK];
+        }
+        part[(size_t)(L - 2 + l) * nq] = s;
+      }
     }
   }
 }
