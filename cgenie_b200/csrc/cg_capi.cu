@@ -530,7 +530,7 @@ static int build_device(cg_handle *h) {
     TRY(dalloc(h, &v.bg_ocn, ijk * L * MS));
     TRY(dalloc(h, &v.bg_vdocn, ijk * L * MS));
     TRY(dalloc(h, &v.bg_part, (size_t)2 * L * std::max(v.nwet, 1) * MS));
-    TRY(dalloc(h, &v.bg_tot, (size_t)2 * L * MS));
+    TRY(dalloc(h, &v.bg_tot, (size_t)(3 * L + 4) * MS));   // 2L-2 totals, then the per-member factors of k_tc_factors
     reg_field(h, "ocn", v.bg_ocn, {L, I, J, K}, {1, L, (long long)L * I, (long long)L * I * J});
     reg_field(h, "vdocn", v.bg_vdocn, {L, I, J, K}, {1, L, (long long)L * I, (long long)L * I * J});
     reg_field(h, "bg_M", v.bg_M, {I, J, K}, {1, I, (long long)I * J});

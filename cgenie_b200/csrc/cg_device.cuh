@@ -95,6 +95,7 @@ struct Dev {
   double bg_rtot_V;
   double *bg_biopart;          // BIOGEM particulates [k][j][i][ls][m] (rescaled by tracer coupling), NULL without BIOGEM
   int bg_LS;
+  int co_prefetch;           // k_co_col: prefetch the column's passive tracers during the decisions (tuning knob)
   int *istep_ocn;            // device-resident ocean step counter (read by graph-replayed kernels)
   MemberP p;
 };

@@ -143,24 +143,40 @@ __global__ void __launch_bounds__(32 * kSumWarps) k_tc_sum(const Dev v, const in
 // (2)+(3) of biogem_tracercoupling: new T,S, rescaled tracers, cell masses, ts <- normalised ocn.  Cells are independent
 // here, so the grid runs over (member tile, cell) with one warp per cell; the per-member totals are staged once per
 // block in shared memory.
-constexpr int kApplyCellsPerWarp = 4, kApplyWarps = 8;
-__global__ void __launch_bounds__(32 * kApplyWarps) k_tc_apply(const Dev v) {
+// per-member factors of steps (2)+(3), computed once: slots 2L .. 2L+3 = 1/mean_S_OLD, Sratio, 1/Sratio, mean_S_NEW,
+// slots 2L+4+l = tot_OLD(l) / tot_NEW(l)
+__global__ void k_tc_factors(const Dev v) {
+  const int L = v.L, MS = v.MS;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= MS) return;
+  double *fac = v.bg_tot + (size_t)2 * L * MS + m;
+  const double mean_S_OLD = v.bg_tot[m], mean_S_NEW = v.bg_tot[MS + m];
+  const double Sratio = mean_S_NEW / mean_S_OLD;
+  fac[0] = 1.0 / mean_S_OLD;
+  fac[(size_t)MS] = Sratio;
+  fac[(size_t)2 * MS] = 1.0 / Sratio;
+  fac[(size_t)3 * MS] = mean_S_NEW;
+  for (int l = 2; l < L; l++) {
+    const double told = v.bg_tot[(size_t)l * MS + m], tnew = v.bg_tot[(size_t)(L - 2 + l) * MS + m];
+    const double rtnew = (fabs(tnew) < kBgNullSmall) ? 0.0 : 1.0 / tnew;
+    fac[(size_t)(4 + l) * MS] = told * rtnew;
+  }
+}
+constexpr int kApplyCellsPerWarp = 1, kApplyWarps = 4;
+__global__ void __launch_bounds__(32 * kApplyWarps, 4) k_tc_apply(const Dev v) {
   __shared__ double s_f[kBgMaxL][32], s_rmean[32], s_sr[32], s_rsr[32], s_mnew[32];
   const int I = v.I, J = v.J, K = v.K, L = v.L, MS = v.MS;
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int m = blockIdx.x * 32 + lane;
-  if (warp == 0) {
-    const double mean_S_OLD = v.bg_tot[m], mean_S_NEW = v.bg_tot[MS + m];
-    s_rmean[lane] = 1.0 / mean_S_OLD;
-    const double Sratio = mean_S_NEW / mean_S_OLD;
-    s_sr[lane] = Sratio;
-    s_rsr[lane] = 1.0 / Sratio;
-    s_mnew[lane] = mean_S_NEW;
-  }
-  for (int l = 2 + warp; l < L; l += kApplyWarps) {
-    const double told = v.bg_tot[(size_t)l * MS + m], tnew = v.bg_tot[(size_t)(L - 2 + l) * MS + m];
-    const double rtnew = (fabs(tnew) < kBgNullSmall) ? 0.0 : 1.0 / tnew;
-    s_f[l][lane] = told * rtnew;
+  {
+    const double *fac = v.bg_tot + (size_t)2 * L * MS + m;
+    if (warp == 0) {
+      s_rmean[lane] = fac[0];
+      s_sr[lane] = fac[(size_t)MS];
+      s_rsr[lane] = fac[(size_t)2 * MS];
+      s_mnew[lane] = fac[(size_t)3 * MS];
+    }
+    for (int l = 2 + warp; l < L; l += kApplyWarps) s_f[l][lane] = fac[(size_t)(4 + l) * MS];
   }
   __syncthreads();
   const double rmean_S_OLD = s_rmean[lane], Sratio = s_sr[lane], rSratio = s_rsr[lane], mean_S_NEW = s_mnew[lane];
@@ -174,6 +190,46 @@ __global__ void __launch_bounds__(32 * kApplyWarps) k_tc_apply(const Dev v) {
     double *__restrict__ ocn = v.bg_ocn + o;
     double *__restrict__ ts = v.ts_cur + o;
     const double *__restrict__ dv = v.bg_vdocn + o;
+    if (L <= kBgMaxL) {
+      // every load of the cell first (ts and ocn are rewritten in place: the compiler cannot hoist a load of ts above a
+      // store to ts by itself), then the arithmetic in the reference's order, then the stores
+      double tv[kBgMaxL], dd[kBgMaxL], bpv[kBgMaxLS];
+      const double Sold = ocn[MS];
+#pragma unroll
+      for (int l = 0; l < kBgMaxL; l++)
+        if (l < L) { tv[l] = ts[(size_t)l * MS]; dd[l] = dv[(size_t)l * MS]; }
+      const double Mc = v.bg_M[(size_t)c * MS + m], rMc = v.bg_rM[(size_t)c * MS + m];
+      double *__restrict__ bp = v.bg_biopart ? v.bg_biopart + (size_t)c * v.bg_LS * MS + m : nullptr;
+      if (bp) {
+#pragma unroll
+        for (int ls = 0; ls < kBgMaxLS; ls++)
+          if (ls < v.bg_LS) bpv[ls] = bp[(size_t)ls * MS];
+      }
+      const double Tn = tv[0] + kBgZeroC + dd[0];
+      const double Sn = tv[1] + saln0 + dd[1];
+      const double rn = mean_S_NEW / Sn;
+      ocn[0] = Tn;
+      ocn[MS] = Sn;
+      ts[0] = Tn - kBgZeroC;
+      ts[MS] = Sn - saln0;
+#pragma unroll
+      for (int l = 2; l < kBgMaxL; l++)
+        if (l < L) {
+          const double lv = tv[l] * Sold * rmean_S_OLD;
+          double x = s_f[l][lane] * lv + dd[l];
+          x = Sratio * x;
+          ocn[(size_t)l * MS] = x;
+          ts[(size_t)l * MS] = rn * x;
+        }
+      if (bp) {  // biogem.f90:2042-2043 (vdbio_part = 0: no particulate flux forcing)
+#pragma unroll
+        for (int ls = 0; ls < kBgMaxLS; ls++)
+          if (ls < v.bg_LS) bp[(size_t)ls * MS] = Sratio * (bpv[ls] + 0.0);
+      }
+      v.bg_M[(size_t)c * MS + m] = rSratio * Mc;
+      v.bg_rM[(size_t)c * MS + m] = Sratio * rMc;
+      continue;
+    }
     const double Sold = ocn[MS];
     const double Tn = ts[0] + kBgZeroC + dv[0];
     const double Sn = ts[MS] + saln0 + dv[MS];
@@ -182,7 +238,6 @@ __global__ void __launch_bounds__(32 * kApplyWarps) k_tc_apply(const Dev v) {
     ocn[MS] = Sn;
     ts[0] = Tn - kBgZeroC;
     ts[MS] = Sn - saln0;
-#pragma unroll 7
     for (int l = 2; l < L; l++) {
       const double lv = ts[(size_t)l * MS] * Sold * rmean_S_OLD;
       double x = s_f[l][lane] * lv + dv[(size_t)l * MS];
@@ -976,9 +1031,10 @@ int launch_tracercoupling(const Dev &v, cudaStream_t s) {
   }
   {
     const int ncell = v.I * v.J * v.K, per_block = kApplyWarps * kApplyCellsPerWarp;
+    k_tc_factors<<<(v.MS + 127) / 128, 128, 0, s>>>(v);
     k_tc_apply<<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
   }
-  return L > 2 ? 5 : 3;
+  return L > 2 ? 6 : 4;
 }
 int launch_bg_reset_cost(const Dev &v, cudaStream_t s) {
   const size_t n = (size_t)v.I * v.J * v.MS;

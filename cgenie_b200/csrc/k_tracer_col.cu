@@ -43,7 +43,11 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   }
   if (cfg == 1) k_tstep_col<I, J, K, L, MS, 1><<<v.nwet, MS, smem, s>>>(v);
   else k_tstep_col<I, J, K, L, MS, 2><<<v.nwet, MS, smem, s>>>(v);
-  k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v);
+  static int copf = -1;
+  if (copf < 0) { const char *e = getenv("CG_CO_PF"); copf = e ? atoi(e) : 0; }   // measured: the L2 prefetch costs more than it hides (profiles/README_r1.md)
+  Dev v2 = v;
+  v2.co_prefetch = copf;
+  k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
   return 2;
 }
 

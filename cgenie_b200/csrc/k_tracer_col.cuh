@@ -385,6 +385,16 @@ CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned 
   }
   kx[k1c - 1] = 0;
   rl[0] = 0.0;
+#ifdef __CUDA_ARCH__
+  // the decisions below are a serial, memory-idle stretch: start pulling the column's passive tracers (written by the
+  // flux kernel a moment ago, partly evicted since) towards L2 so that the averaging pass finds them there
+  if (v.co_prefetch) {
+    for (int k = k1c; k <= K; k++) {
+#pragma unroll
+      for (int l = 2; l < L; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ts + (long)(k - 1) * sK + l * sL));
+    }
+  }
+#endif
   int mm = K, lastmix = 0;
   bool any = false;
   while (kx[mm - 1] > 0 || (lastmix != 0 && kx[mm] != K)) {
