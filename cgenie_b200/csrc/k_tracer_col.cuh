@@ -364,9 +364,14 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 // back into a decision, are averaged once per final mixed region (thickness weighted, summed top-down) instead of
 // being re-mixed at every incremental merge -- equal up to rounding.  Every load of a tracer pair is independent of
 // the others, so the pass is bandwidth bound.
+// Part 1: decisions, T/S/rho of the mixed regions, cost, SST.  Returns the region structure: bit k-1 of `in` = level k
+// belongs to a mixed region, `topb` / `botb` = it is the region's top / bottom, rdzt[k-1] = 1 / thickness of the region
+// (at its bottom level).  in == 0: nothing mixed.
 template <int I, int J, int K, int L, int MS>
-CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m) {
+CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned m, unsigned &in, unsigned &topb, unsigned &botb,
+                     double *rdzt) {
   constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC, rK = (long)I * J * MS;
+  in = 0; topb = 0; botb = 0;
   const int k1c = (int)v.k1[(c2 % I + 1) + (I + 2) * (c2 / I + 1)];
   const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
   double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);         // level-1 cell of this column
@@ -445,9 +450,6 @@ CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned 
     }
     v.cost[(long)c2 * MS + m] += cnt;
   }
-  // region structure: bit k-1 of `in` = level k belongs to a mixed region; `topb` / `botb` = it is its top / bottom
-  unsigned in = 0, topb = 0, botb = 0;
-  double rdzt[K];
   {
     head[0] = 0;
     for (int k = 1; k < k1c; k++) head[k] = 0;
@@ -475,49 +477,55 @@ CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned 
       }
     }
   }
-#pragma unroll 1
-  for (int l = 2; l < L; l += 2) {
-    const bool two = (l + 1 < L);
-#ifdef __CUDA_ARCH__
-    if (l + 2 < L) {   // next tracer pair: towards L1 while this pair is summed
+}
+
+// Part 2: one pair (l, l+1) of passive tracers of one (member, column): thickness-weighted mean over every mixed region,
+// summed top-down; all loads of the pair are independent.
+template <int I, int J, int K, int L, int MS>
+CG_HD void co_passive_pair(const Dev &v, const GridC &g, const int c2, const unsigned m, const unsigned in, const unsigned topb,
+                           const unsigned botb, const double *rdzt, const int l) {
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
+  double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);
+  const bool two = (l + 1 < L);
+  double a[K], b[K];
 #pragma unroll
-      for (int k = 0; k < K; k++)
-        if ((in >> k) & 1u) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(ts + (long)k * sK + (l + 2) * sL));
-          if (l + 3 < L) asm volatile("prefetch.global.L1 [%0];" ::"l"(ts + (long)k * sK + (l + 3) * sL));
-        }
-    }
-#endif
-    double a[K], b[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      a[k] = 0.0; b[k] = 0.0;
-      if ((in >> k) & 1u) {
-        a[k] = ts[(long)k * sK + l * sL];
-        if (two) b[k] = ts[(long)k * sK + (l + 1) * sL];
-      }
-    }
-    double accA = 0.0, accB = 0.0;
-#pragma unroll
-    for (int k = K - 1; k >= 0; k--) {
-      if ((in >> k) & 1u) {
-        const double dz = g.dz[k + 1];
-        if ((topb >> k) & 1u) { accA = 0.0; accB = 0.0; }
-        accA += a[k] * dz;
-        accB += b[k] * dz;
-        if ((botb >> k) & 1u) { a[k] = accA * rdzt[k]; b[k] = accB * rdzt[k]; }
-      }
-    }
-    double curA = 0.0, curB = 0.0;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      if ((in >> k) & 1u) {
-        if ((botb >> k) & 1u) { curA = a[k]; curB = b[k]; }
-        ts[(long)k * sK + l * sL] = curA;
-        if (two) ts[(long)k * sK + (l + 1) * sL] = curB;
-      }
+  for (int k = 0; k < K; k++) {
+    a[k] = 0.0; b[k] = 0.0;
+    if ((in >> k) & 1u) {
+      a[k] = ts[(long)k * sK + l * sL];
+      if (two) b[k] = ts[(long)k * sK + (l + 1) * sL];
     }
   }
+  double accA = 0.0, accB = 0.0;
+#pragma unroll
+  for (int k = K - 1; k >= 0; k--) {
+    if ((in >> k) & 1u) {
+      const double dz = g.dz[k + 1];
+      if ((topb >> k) & 1u) { accA = 0.0; accB = 0.0; }
+      accA += a[k] * dz;
+      accB += b[k] * dz;
+      if ((botb >> k) & 1u) { a[k] = accA * rdzt[k]; b[k] = accB * rdzt[k]; }
+    }
+  }
+  double curA = 0.0, curB = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if ((in >> k) & 1u) {
+      if ((botb >> k) & 1u) { curA = a[k]; curB = b[k]; }
+      ts[(long)k * sK + l * sL] = curA;
+      if (two) ts[(long)k * sK + (l + 1) * sL] = curB;
+    }
+  }
+}
+
+// both parts by one thread (host test harness; single-kernel fallback)
+template <int I, int J, int K, int L, int MS>
+CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m) {
+  unsigned in, topb, botb;
+  double rdzt[K];
+  co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt);
+  if (in == 0) return;
+  for (int l = 2; l < L; l += 2) co_passive_pair<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, l);
 }
 
 }  // namespace cg
