@@ -36,6 +36,8 @@ int launch_seaice(const Dev &, cudaStream_t);
 int launch_gold_pre(const Dev &, cudaStream_t);
 int launch_sst(const Dev &, cudaStream_t);
 int launch_momentum(const Dev &, int fast, const double *bf, const double *bb, const double *rd, cudaStream_t);
+int launch_velc1(const Dev &, cudaStream_t);
+int launch_velc2(const Dev &, cudaStream_t);
 void launch_global_means(const Dev &, double *out, cudaStream_t);
 int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
@@ -110,7 +112,8 @@ struct cg_handle {
   Dev dv;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;                 // momentum branch of the graph-captured ocean cycle
-  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  cudaStream_t stream3 = nullptr;                 // baroclinic shear next to the barotropic solve
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork3 = nullptr, evJoin3 = nullptr;
   bool bg_fuse = false;                           // cg_run: tracer coupling fused into the BIOGEM step kernel (slower on B200)
   bool fork_momentum = true;                      // CG_FORK=0 keeps the captured cycle on one stream
   bool forked = false;                            // inside enqueue_cycle with the momentum branch on stream2
@@ -149,6 +152,9 @@ struct cg_handle {
     if (ev1) cudaEventDestroy(ev1);
     if (evFork) cudaEventDestroy(evFork);
     if (evJoin) cudaEventDestroy(evJoin);
+    if (evFork3) cudaEventDestroy(evFork3);
+    if (evJoin3) cudaEventDestroy(evJoin3);
+    if (stream3) cudaStreamDestroy(stream3);
     if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -327,6 +333,9 @@ extern "C" int cg_initialise(cg_handle *h) {
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evJoin3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
   // per-member constants; members sharing adrag share one barotropic factorisation
@@ -435,6 +444,7 @@ static int build_device(cg_handle *h) {
   TRY(dalloc(h, &v.ts_new, ijk * L * MS));
   TRY(dalloc(h, &v.tsflux, 2 * ij * MS));
   TRY(dalloc(h, &v.usnap, 2 * ij * MS));
+  TRY(dalloc(h, &v.velsum, 2 * ij * MS));
   TRY(dalloc(h, &v.rho, ijk * MS));
   TRY(dalloc(h, &v.u, ijk * 3 * MS));
   TRY(dalloc(h, &v.u1, ijk * 2 * MS));
@@ -1026,13 +1036,26 @@ static void do_gold_pre(cg_handle *h) {
   launch_hosing(h->dv, h->stream);
   ps.done(1 + launch_gold_pre(h->dv, h->stream));
 }
-static void do_momentum(cg_handle *h, cudaStream_t s) {
+// s3 != nullptr (graph capture only): the baroclinic shear integral runs on s3 next to the barotropic solve on s
+static int do_momentum(cg_handle *h, cudaStream_t s, cudaStream_t s3 = nullptr) {
   ProfScope ps(h, "momentum");
-  ps.done(launch_momentum(h->dv, h->variant, h->d_bf, h->d_bb, h->d_rd, s));
+  int n = 0;
+  if (s3) {
+    CUDA_OK(cudaEventRecord(h->evFork3, s));
+    CUDA_OK(cudaStreamWaitEvent(s3, h->evFork3, 0));
+    n += launch_velc1(h->dv, s3);
+    CUDA_OK(cudaEventRecord(h->evJoin3, s3));
+  }
+  n += launch_momentum(h->dv, h->variant, h->d_bf, h->d_bb, h->d_rd, s);
+  if (s3) CUDA_OK(cudaStreamWaitEvent(s, h->evJoin3, 0));
+  else n += launch_velc1(h->dv, s);
+  n += launch_velc2(h->dv, s);
+  ps.done(n);
+  return CG_OK;
 }
 static int do_goldstein(cg_handle *h) {
   do_gold_pre(h);
-  do_momentum(h, h->stream);
+  { int rc = do_momentum(h, h->stream); if (rc) return rc; }
   do_tstepo(h);
   return CG_OK;
 }
@@ -1306,7 +1329,7 @@ static int enqueue_cycle(cg_handle *h, bool fork) {
     h->launches++;
     CUDA_OK(cudaEventRecord(h->evFork, h->stream));
     CUDA_OK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
-    do_momentum(h, h->stream2);
+    IO(do_momentum(h, h->stream2, h->stream3));
     CUDA_OK(cudaEventRecord(h->evJoin, h->stream2));
     h->forked = true;
   }
@@ -1508,6 +1531,9 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evJoin3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
   h->mc.resize(1);

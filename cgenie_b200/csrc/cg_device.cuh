@@ -63,6 +63,7 @@ struct Dev {
   double *sst;               // [2][j][i][m] tstar_ocn/sstar_ocn as exported by step_goldstein (goldstein.f90:428-431);
                              // NULL = read ts directly (identical unless BIOGEM rewrites ts in between)
   double *rho, *u, *u1, *cost;
+  double *velsum;            // [2][j][i][m] depth means of the baroclinic velocities (k_velc1 -> k_velc2)
   double *usnap;             // [2][j][i][m] surface u, v as exported to the sea-ice step (snapshot taken by k_usnap)
   // momentum
   double *bp, *sbp, *gb, *ub, *psi, *erisl_rhs, *psibc;

@@ -887,7 +887,9 @@ __global__ void __launch_bounds__(128) k_ubadd(const Dev v) {
 }
 
 // baroclinic velocities, barotropic correction and relaxation (velc :3574-3658)
-__global__ void __launch_bounds__(128) k_velc(const Dev v) {
+// Two kernels: k_velc1 needs only rho and constants (the baroclinic shear integral and its depth mean), so it can run
+// next to the barotropic solve; k_velc2 adds the barotropic velocity and the time relaxation.
+__global__ void __launch_bounds__(128) k_velc1(const Dev v) {
   DIMS
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
@@ -964,6 +966,22 @@ __global__ void __launch_bounds__(128) k_velc(const Dev v) {
     UX(2, i, j, k) = ub_;
     u1p = ua; u2p = ub_; dzu1p = dzu1; dzu2p = dzu2;
   }
+  v.velsum[A2I(i, j)] = sum1;
+  v.velsum[A2I(i, j) + nf] = sum2;
+}
+__global__ void __launch_bounds__(128) k_velc2(const Dev v) {
+  DIMS
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= v.M || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const int k1c = CG_K1(v, i, j);
+  if (k1c > K) return;
+  const int ip = (i < I) ? i + 1 : 1;
+  const int k_e = CG_K1(v, ip, j), k_n = CG_K1(v, i, j + 1);
+  const size_t nf = (size_t)I * J * MS;
+  const double rel = v.p.rel[m];
+  const double sum1 = v.velsum[A2I(i, j)], sum2 = v.velsum[A2I(i, j) + nf];
   const double rh1 = RHX(1, i, j), rh2 = RHX(2, i, j), ub1 = UBX(1, i, j), ub2 = UBX(2, i, j);
   for (int k = k1c; k <= K; k++) {
     if (k_e <= k) {
@@ -1122,9 +1140,20 @@ int launch_momentum(const Dev &v, int fast, const double *bf, const double *bb, 
   k_psi2ub<<<grid2(v, (v.I + 2) * (v.J + 1), b), b, 0, s>>>(v);
   k_island<<<(v.M + 3) / 4, 128, 0, s>>>(v);
   k_ubadd<<<grid2(v, (v.I + 2) * (v.J + 1), b), b, 0, s>>>(v);
-  k_velc<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  return 6;
+}
+// baroclinic shear (independent of the barotropic solve: may run on another stream, next to launch_momentum)
+int launch_velc1(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_velc1<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  return 1;
+}
+// after both: total velocity, relaxation, vertical velocity
+int launch_velc2(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_velc2<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
   k_w<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
-  return 8;
+  return 2;
 }
 void launch_global_means(const Dev &v, double *out, cudaStream_t s) { k_global_means<<<dim3(v.M, v.L), 256, 0, s>>>(v, out); }
 void launch_health(const Dev &v, int *flags, cudaStream_t s) { k_health<<<v.M, 256, 0, s>>>(v, flags); }
