@@ -45,6 +45,7 @@ int launch_bg_step(const Dev &, const BgDev &, int init_only, int fuse, cudaStre
 int launch_tc_sums_first(const Dev &, cudaStream_t);
 bool bg_layout_ok(const BgDev &, int L);
 int launch_bg_climate(const Dev &, const BgDev &, cudaStream_t);
+int launch_bg_stage_seaice(const Dev &, const BgDev &, cudaStream_t);
 int launch_bg_atchem(const Dev &, const BgDev &, double atm_totV, cudaStream_t);
 void launch_health(const Dev &, int *flags, cudaStream_t);
 
@@ -112,6 +113,9 @@ struct cg_handle {
   Dev dv;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;                 // momentum branch of the graph-captured ocean cycle
+  cudaStream_t stream4 = nullptr;                 // BIOGEM / ATCHEM block next to the head of the following cycle (low priority)
+  cudaEvent_t evT = nullptr, evBG = nullptr;
+  bool bg_overlap = true, bg_pending = false, bg_staged = false;
   cudaStream_t stream3 = nullptr;                 // baroclinic shear next to the barotropic solve
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork3 = nullptr, evJoin3 = nullptr;
   bool bg_fuse = false;                           // cg_run: tracer coupling fused into the BIOGEM step kernel (slower on B200)
@@ -132,7 +136,8 @@ struct cg_handle {
   int istep_ocn = 0, istep_atm = 0, istep_sic = 0;
   int variant = 0;  // 0 strict, 1 fast (cooperative flux kernel + separate convection), 2 fused column kernel (falls back to 1)
   bool use_graphs = true;
-  cudaGraphExec_t graph[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [variant][parity]
+  cudaGraphExec_t graph[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  cudaGraphExec_t graph2[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [variant][parity]
   long long graph_launches[3] = {0, 0, 0};   // launches inside one replayed cycle, per variant
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool profile = false;
@@ -147,11 +152,15 @@ struct cg_handle {
   ~cg_handle() {
     cudaSetDevice(device);
     for (auto &gv : graph) for (auto &ge : gv) if (ge) cudaGraphExecDestroy(ge);
+    for (auto &gv : graph2) for (auto &ge : gv) if (ge) cudaGraphExecDestroy(ge);
     for (void *p : allocs) cudaFree(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (evFork) cudaEventDestroy(evFork);
     if (evJoin) cudaEventDestroy(evJoin);
+    if (evT) cudaEventDestroy(evT);
+    if (evBG) cudaEventDestroy(evBG);
+    if (stream4) cudaStreamDestroy(stream4);
     if (evFork3) cudaEventDestroy(evFork3);
     if (evJoin3) cudaEventDestroy(evJoin3);
     if (stream3) cudaStreamDestroy(stream3);
@@ -334,6 +343,13 @@ extern "C" int cg_initialise(cg_handle *h) {
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least urgent
+    CUDA_OK(cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, lo));
+  }
+  CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));
@@ -559,6 +575,7 @@ static int build_device(cg_handle *h) {
     TRY(dalloc(h, &b.settle_k1, ij * LS * MS));
     TRY(dalloc(h, &b.carbH, ij * MS));
     TRY(dalloc(h, &b.seaice, ij * MS));
+    TRY(dalloc(h, &b.seaice_stage, ij * MS));
     TRY(dalloc(h, &b.sfxsumatm, ij * LA * MS));
     TRY(dalloc(h, &b.sfcocn1, ij * L * MS));
     TRY(dalloc(h, &b.sfxsed1, ij * LS * MS));
@@ -1251,7 +1268,9 @@ extern "C" int cg_biogem_climate(cg_handle *h) {
     // go_solfor of the last surflux call (embm.f90:3727-3729): row MOD(istot-1,nyear)+1 of solfor
     h->bgd.nsol = h->istep_ocn > 0 ? (h->istep_ocn - 1) % h->g.nyear + 1 : 0;
     ProfScope ps(h, "biogem");
-    ps.done(launch_bg_climate(h->dv, h->bgd, h->stream));
+    int n = 0;
+    if (!h->bg_staged) n += launch_bg_stage_seaice(h->dv, h->bgd, h->stream);
+    ps.done(n + launch_bg_climate(h->dv, h->bgd, h->stream));
   } else {
     ProfScope ps(h, "biogem");
     ps.done(launch_bg_reset_cost(h->dv, h->stream));
@@ -1322,7 +1341,7 @@ static int do_biogem_block(cg_handle *h, long long k) {
 // One ocean cycle (kocn_loop iterations of the koverall loop, regular schedule).  fork = true (graph capture only): the
 // momentum step -- which needs nothing but rho of the previous tracer step and constants, and is dominated by the
 // latency-bound barotropic solve -- runs on a second stream next to surflux / EMBM / sea ice and joins before tstepo.
-static int enqueue_cycle(cg_handle *h, bool fork) {
+static int enqueue_cycle_head(cg_handle *h, bool fork) {   // everything of the cycle that precedes tstepo
   const Params &p = h->base;
   if (fork) {
     launch_usnap(h->dv, h->stream);
@@ -1337,15 +1356,58 @@ static int enqueue_cycle(cg_handle *h, bool fork) {
   if (!rc) rc = do_embm(h, p.kocn_loop);
   if (!rc) rc = do_seaice(h);
   h->forked = false;
-  if (fork) {
-    do_gold_pre(h);
-    CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin, 0));
-    if (rc) return rc;
-    do_tstepo(h);
-    return CG_OK;
-  }
+  do_gold_pre(h);
+  if (fork) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin, 0));
+  else if (!rc) rc = do_momentum(h, h->stream);
+  return rc;
+}
+static int enqueue_cycle(cg_handle *h, bool fork) {
+  IO(enqueue_cycle_head(h, fork));
+  do_tstepo(h);
+  return CG_OK;
+}
+// capture `body` (launches on h->stream) into an executable graph
+template <class F>
+static int capture_graph(cg_handle *h, cudaGraphExec_t *ge, F body) {
+  cudaGraph_t gr;
+  CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = body();
+  cudaError_t e = cudaStreamEndCapture(h->stream, &gr);
   if (rc) return rc;
-  return do_goldstein(h);
+  if (e != cudaSuccess) return fail(CG_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+  CUDA_OK(cudaGraphInstantiate(ge, gr, 0));
+  cudaGraphDestroy(gr);
+  return CG_OK;
+}
+// The BIOGEM / ATCHEM block of step n touches nothing the head of cycle n+1 (momentum, surflux, EMBM, sea ice) reads or
+// writes -- ts_cur, ocn, bio_part, atm ... on one side; rho, u, tq, varice, sst ... on the other -- except the sea-ice
+// cover biogem_climate snapshots, which is staged before the streams part.  So inside cg_run the block goes to its own
+// low-priority stream and only tstepo(n+1) waits for it.
+static int do_biogem_block_async(cg_handle *h, long long k) {
+  const Params &p = h->base;
+  if (!h->bg.on) return CG_OK;
+  const bool due = k % ((long long)p.conv_kocn_kbiogem * p.kocn_loop) == 0 || k % ((long long)p.conv_kocn_katchem * p.kocn_loop) == 0;
+  if (!due) return CG_OK;
+  const bool climate_due = k % ((long long)p.conv_kocn_kbiogem * p.kocn_loop) == 0;
+  if (climate_due) { h->launches += launch_bg_stage_seaice(h->dv, h->bgd, h->stream); h->bg_staged = true; }
+  CUDA_OK(cudaEventRecord(h->evT, h->stream));
+  CUDA_OK(cudaStreamWaitEvent(h->stream4, h->evT, 0));
+  cudaStream_t save = h->stream;
+  h->stream = h->stream4;
+  int rc = do_biogem_block(h, k);
+  h->stream = save;
+  h->bg_staged = false;
+  if (rc) return rc;
+  CUDA_OK(cudaEventRecord(h->evBG, h->stream4));
+  h->bg_pending = true;
+  return CG_OK;
+}
+static int bg_join(cg_handle *h) {   // order the main stream after an outstanding BIOGEM block
+  if (h->bg_pending) {
+    CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBG, 0));
+    h->bg_pending = false;
+  }
+  return CG_OK;
 }
 
 extern "C" int cg_run(cg_handle *h, int64_t n) {
@@ -1356,31 +1418,34 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
     const long long k = h->koverall + 1;
     if (regular && (k % p.kocn_loop) == 1 && n >= p.kocn_loop) {
       if (h->use_graphs && !h->profile) {
-        // two graphs per variant: the tracer ping-pong alternates buffers
+        // two graphs per variant and ping-pong parity: the head of the cycle and the tracer step
         const int par = (h->dv.ts_cur < h->dv.ts_new) ? 0 : 1;
-        cudaGraphExec_t &ge = h->graph[h->variant][par];
-        if (!ge) {
-          cudaGraph_t gr;
+        cudaGraphExec_t &g1 = h->graph[h->variant][par], &g2 = h->graph2[h->variant][par];
+        if (!g1 || !g2) {
           const long long l0 = h->launches;
           const int i0 = h->istep_ocn, a0 = h->istep_atm, s0 = h->istep_sic;
-          CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-          int rc = enqueue_cycle(h, h->fork_momentum && !getenv("CG_NOFORK"));
-          cudaError_t e = cudaStreamEndCapture(h->stream, &gr);
-          if (rc) return rc;
-          if (e != cudaSuccess) return fail(CG_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+          const bool fork = h->fork_momentum && !getenv("CG_NOFORK");
+          if (g1) { cudaGraphExecDestroy(g1); g1 = nullptr; }
+          if (g2) { cudaGraphExecDestroy(g2); g2 = nullptr; }
+          IO(capture_graph(h, &g1, [&]() { return enqueue_cycle_head(h, fork); }));
+          IO(capture_graph(h, &g2, [&]() { do_tstepo(h); return (int)CG_OK; }));
           h->graph_launches[h->variant] = h->launches - l0;
           h->launches = l0; h->istep_ocn = i0; h->istep_atm = a0; h->istep_sic = s0;
           std::swap(h->dv.ts_cur, h->dv.ts_new);  // undo the swap done while capturing
-          CUDA_OK(cudaGraphInstantiate(&ge, gr, 0));
-          cudaGraphDestroy(gr);
         }
-        CUDA_OK(cudaGraphLaunch(ge, h->stream));
+        CUDA_OK(cudaGraphLaunch(g1, h->stream));
+        IO(bg_join(h));                            // tstepo reads the ts the tracer coupling rewrote
+        CUDA_OK(cudaGraphLaunch(g2, h->stream));
         h->launches += h->graph_launches[h->variant];
         h->istep_ocn++; h->istep_atm += p.kocn_loop; h->istep_sic++;
         std::swap(h->dv.ts_cur, h->dv.ts_new);
-      } else {
-        IO(enqueue_cycle(h, false));
+        h->koverall += p.kocn_loop;
+        n -= p.kocn_loop;
+        if (h->bg_overlap && !getenv("CG_BG_SERIAL")) IO(do_biogem_block_async(h, h->koverall));
+        else IO(do_biogem_block(h, h->koverall));
+        continue;
       }
+      IO(enqueue_cycle(h, false));
       h->koverall += p.kocn_loop;
       n -= p.kocn_loop;
       IO(do_biogem_block(h, h->koverall));
@@ -1395,6 +1460,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
     n--;
     IO(do_biogem_block(h, h->koverall));
   }
+  IO(bg_join(h));
   return check_async(h);
 }
 
@@ -1532,6 +1598,13 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least urgent
+    CUDA_OK(cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, lo));
+  }
+  CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));

@@ -148,6 +148,7 @@ struct BgDev {
   double *settle_k1;                      // [j][i][ls][m]   bio_settle at the deepest wet level
   double *carbH;                          // [j][i][m]       surface [H+], seed of the next pH solve
   double *seaice;                         // [j][i][m]       snapshot taken by biogem_climate
+  double *seaice_stage;                   // [j][i][m]       sea-ice cover at biogem_climate's call time (k_bg_stage_seaice)
   const double *wspeed, *A, *rA;          // [j][i] member independent
   double *atm, *sfcatm1, *sfxsumatm;      // [la][j][i][m]
   const double *atm_A, *atm_V;            // [j][i]

@@ -925,11 +925,18 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
 }
 
 // biogem_climate (:2132-2239): snapshot the sea-ice fraction, reset the convection counter
+// (the cover is read through a staging copy taken by k_bg_stage_seaice at the reference's call time, so that the block
+// may run while the next cycle's sea-ice step is already rewriting varice)
+__global__ void k_bg_stage_seaice(const Dev v, const BgDev b) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)v.I * v.J * v.MS;
+  if (q < n) b.seaice_stage[q] = v.varice[n + q];   // varice(2,:,:) = fractional cover
+}
 __global__ void k_bg_climate(const Dev v, const BgDev b) {
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n = (size_t)v.I * v.J * v.MS;
   if (q >= n) return;
-  b.seaice[q] = v.varice[n + q];   // varice(2,:,:) = fractional cover
+  b.seaice[q] = b.seaice_stage[q];
   v.cost[q] = 0.0;
 }
 
@@ -1005,6 +1012,11 @@ int launch_tc_sums_first(const Dev &v, cudaStream_t s) {
   k_tc_partial<<<gc, b, 0, s>>>(v, 1);
   k_tc_sum<<<dim3(v.MS / 32, L - 2), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2);
   return 4;
+}
+int launch_bg_stage_seaice(const Dev &v, const BgDev &b, cudaStream_t s) {
+  const size_t n = (size_t)v.I * v.J * v.MS;
+  k_bg_stage_seaice<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v, b);
+  return 1;
 }
 int launch_bg_climate(const Dev &v, const BgDev &b, cudaStream_t s) {
   const size_t n = (size_t)v.I * v.J * v.MS;
