@@ -43,6 +43,7 @@ int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
 int launch_bg_step(const Dev &, const BgDev &, int init_only, int fuse, cudaStream_t);
 int launch_tc_sums_first(const Dev &, cudaStream_t);
+int launch_tc_apply_only(const Dev &, cudaStream_t);
 bool bg_layout_ok(const BgDev &, int L);
 int launch_bg_climate(const Dev &, const BgDev &, cudaStream_t);
 int launch_bg_stage_seaice(const Dev &, const BgDev &, cudaStream_t);
@@ -115,6 +116,8 @@ struct cg_handle {
   cudaStream_t stream2 = nullptr;                 // momentum branch of the graph-captured ocean cycle
   cudaStream_t stream4 = nullptr;                 // BIOGEM / ATCHEM block next to the head of the following cycle (low priority)
   cudaEvent_t evT = nullptr, evBG = nullptr;
+  cudaStream_t stream5 = nullptr;                 // tracer-coupling sums next to the BIOGEM step kernel
+  cudaEvent_t evFork5 = nullptr, evJoin5 = nullptr;
   bool bg_overlap = true, bg_pending = false, bg_staged = false;
   cudaStream_t stream3 = nullptr;                 // baroclinic shear next to the barotropic solve
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork3 = nullptr, evJoin3 = nullptr;
@@ -158,6 +161,9 @@ struct cg_handle {
     if (ev1) cudaEventDestroy(ev1);
     if (evFork) cudaEventDestroy(evFork);
     if (evJoin) cudaEventDestroy(evJoin);
+    if (evFork5) cudaEventDestroy(evFork5);
+    if (evJoin5) cudaEventDestroy(evJoin5);
+    if (stream5) cudaStreamDestroy(stream5);
     if (evT) cudaEventDestroy(evT);
     if (evBG) cudaEventDestroy(evBG);
     if (stream4) cudaStreamDestroy(stream4);
@@ -348,6 +354,9 @@ extern "C" int cg_initialise(cg_handle *h) {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least urgent
     CUDA_OK(cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, lo));
   }
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream5, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evFork5, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evJoin5, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));
@@ -1315,7 +1324,20 @@ static int do_biogem_block(cg_handle *h, long long k) {
     if (k == (long long)p.conv_kocn_kbiogem * p.kocn_loop) IO(cg_biogem_climate_sol(h));
     IO(cg_biogem_forcing(h, clock));
     static const bool nofuse = getenv("CG_BG_NOFUSE") != nullptr;
-    if (nofuse || !h->bg_fuse) {
+    if (h->bg_staged && h->bg_go && !h->bg_fuse && !getenv("CG_BG_NOSPLIT")) {
+      // asynchronous block (cg_run): the coupling's global sums do not depend on this step's anomaly (the salinity
+      // anomaly is +0.0), so they run on a side stream next to the latency-bound step kernel; bit-identical
+      const double t = h->bg.t_runtime - (double)clock / (1000.0 * kBgYrS);
+      CUDA_OK(cudaEventRecord(h->evFork5, h->stream));
+      CUDA_OK(cudaStreamWaitEvent(h->stream5, h->evFork5, 0));
+      h->launches += launch_tc_sums_first(h->dv, h->stream5);
+      CUDA_OK(cudaEventRecord(h->evJoin5, h->stream5));
+      h->launches += launch_bg_step(h->dv, h->bgd, 0, 0, h->stream);
+      CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin5, 0));
+      h->launches += launch_tc_apply_only(h->dv, h->stream);
+      if (t < kBgNullSmall) h->bg_go = false;
+      IO(check_async(h));
+    } else if (nofuse || !h->bg_fuse) {
       IO(cg_biogem_step(h, h->bgd.dts, clock));
       IO(cg_biogem_tracercoupling(h, nullptr, nullptr));
     } else if (h->bg_go) {
@@ -1603,6 +1625,9 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least urgent
     CUDA_OK(cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, lo));
   }
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream5, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evFork5, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evJoin5, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));

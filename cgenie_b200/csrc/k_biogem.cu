@@ -1011,7 +1011,14 @@ int launch_tc_sums_first(const Dev &v, cudaStream_t s) {
   k_tc_sum<<<dim3(v.MS / 32, L), 32 * kSumWarps, 0, s>>>(v, 0, L);
   k_tc_partial<<<gc, b, 0, s>>>(v, 1);
   k_tc_sum<<<dim3(v.MS / 32, L - 2), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2);
-  return 4;
+  k_tc_factors<<<(v.MS + 127) / 128, 128, 0, s>>>(v);
+  return 5;
+}
+// steps (2)+(3) alone, after launch_tc_sums_first
+int launch_tc_apply_only(const Dev &v, cudaStream_t s) {
+  const int ncell = v.I * v.J * v.K, per_block = kApplyWarps * kApplyCellsPerWarp;
+  k_tc_apply<<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
+  return 1;
 }
 int launch_bg_stage_seaice(const Dev &v, const BgDev &b, cudaStream_t s) {
   const size_t n = (size_t)v.I * v.J * v.MS;
