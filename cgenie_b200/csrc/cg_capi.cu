@@ -119,6 +119,8 @@ struct cg_handle {
   cudaStream_t stream5 = nullptr;                 // tracer-coupling sums next to the BIOGEM step kernel
   cudaEvent_t evFork5 = nullptr, evJoin5 = nullptr;
   bool bg_overlap = true, bg_pending = false, bg_staged = false;
+  bool eager = true;                              // per-module entry points: momentum at surflux time, BIOGEM calls on stream4
+  bool mom_pending = false, mom_ready = false;    // eager momentum: still running on stream2 / result valid and unconsumed
   cudaStream_t stream3 = nullptr;                 // baroclinic shear next to the barotropic solve
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork3 = nullptr, evJoin3 = nullptr;
   bool bg_fuse = false;                           // cg_run: tracer coupling fused into the BIOGEM step kernel (slower on B200)
@@ -254,6 +256,21 @@ static void activate(cg_handle *h) {
     upload_grid(h);
     g_active = h;
   }
+}
+
+// Order the main stream after everything the per-module entry points or cg_run left running on the side streams.
+// Called by every entry point that reads or writes state from the host side.
+#define IO0(x) do { int rc0_ = (x); if (rc0_) return rc0_; } while (0)
+static int join_side(cg_handle *h) {
+  if (h->mom_pending) {
+    CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin, 0));
+    h->mom_pending = false;
+  }
+  if (h->bg_pending) {
+    CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBG, 0));
+    h->bg_pending = false;
+  }
+  return CG_OK;
 }
 
 // host-side constants of member 0, exposed through cg_get_const / cg_get_iconst
@@ -902,6 +919,7 @@ extern "C" int64_t cg_field_size(cg_handle *h, const char *name) {
   return f ? f->count() : -1;
 }
 extern "C" int cg_sync_to_host(cg_handle *h, const char *name, int member, double *dst, int64_t n) {
+  IO0(join_side(h));
   if (!h || !name || !dst || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_to_host: bad argument");
   FieldDesc *f = find_field(h, strcmp(name, "ts1") == 0 ? "ts" : name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
@@ -926,6 +944,8 @@ extern "C" int cg_sync_from_host(cg_handle *h, const char *name, int member, con
   return rc;
 }
 static int sync_from_host_lane(cg_handle *h, const char *name, int member, const double *src, int64_t n) {
+  IO0(join_side(h));
+  h->mom_ready = false;   // a momentum step computed ahead of time is stale once the host has written state
   if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_from_host: bad argument");
   const bool both = strcmp(name, "ts") == 0 || strcmp(name, "ts1") == 0;
   FieldDesc *f = find_field(h, both ? "ts" : name);
@@ -946,6 +966,7 @@ static int sync_from_host_lane(cg_handle *h, const char *name, int member, const
   return CG_OK;
 }
 extern "C" int cg_sync_all_to_host(cg_handle *h, const char *name, double *dst, int64_t n) {
+  IO0(join_side(h));
   if (!h || !name || !dst || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_all_to_host: bad argument");
   FieldDesc *f = find_field(h, name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
@@ -955,6 +976,8 @@ extern "C" int cg_sync_all_to_host(cg_handle *h, const char *name, double *dst, 
   return CG_OK;
 }
 extern "C" int cg_sync_all_from_host(cg_handle *h, const char *name, const double *src, int64_t n) {
+  IO0(join_side(h));
+  h->mom_ready = false;
   if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_all_from_host: bad argument");
   FieldDesc *f = find_field(h, name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
@@ -1036,7 +1059,7 @@ static int do_seaice(cg_handle *h) {
   // the sea-ice step advects with the surface velocities exported by the last step_goldstein: a snapshot, taken here
   // unless the forked cycle already took it before the momentum branch started
   int n = 0;
-  if (!h->forked) { launch_usnap(h->dv, h->stream); n++; }
+  if (!h->forked && !h->mom_ready) { launch_usnap(h->dv, h->stream); n++; }
   ps.done(n + launch_seaice(h->dv, h->stream));
   h->istep_sic++;
   return CG_OK;
@@ -1079,12 +1102,52 @@ static int do_momentum(cg_handle *h, cudaStream_t s, cudaStream_t s3 = nullptr) 
   ps.done(n);
   return CG_OK;
 }
+static int bg_join(cg_handle *h);
 static int do_goldstein(cg_handle *h) {
   do_gold_pre(h);
-  { int rc = do_momentum(h, h->stream); if (rc) return rc; }
+  if (h->mom_ready) {   // computed on stream2 since the surflux call of this cycle
+    if (h->mom_pending) { CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin, 0)); h->mom_pending = false; }
+    h->mom_ready = false;
+  } else {
+    int rc = do_momentum(h, h->stream);
+    if (rc) return rc;
+  }
+  { int rc = bg_join(h); if (rc) return rc; }   // tstepo reads the ts an asynchronous tracer coupling rewrote
   do_tstepo(h);
   return CG_OK;
 }
+// per-module path: start the momentum step of this cycle now (it needs rho of the previous tracer step only)
+static int eager_momentum(cg_handle *h) {
+  if (!h->eager || h->profile || h->mom_ready || getenv("CG_NOEAGER")) return CG_OK;
+  launch_usnap(h->dv, h->stream);
+  h->launches++;
+  CUDA_OK(cudaEventRecord(h->evFork, h->stream));
+  CUDA_OK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
+  int rc = do_momentum(h, h->stream2, h->stream3);
+  if (rc) return rc;
+  CUDA_OK(cudaEventRecord(h->evJoin, h->stream2));
+  h->mom_pending = true;
+  h->mom_ready = true;
+  return CG_OK;
+}
+// per-module path: run one BIOGEM / ATCHEM entry point on stream4, ordered after everything issued so far on the main
+// stream; the next tracer step (or any host access) joins.  RAII: restores h->stream and records the completion event.
+struct BgAsyncScope {
+  cg_handle *h; cudaStream_t save = nullptr; bool on = false;
+  explicit BgAsyncScope(cg_handle *h_, bool allow) : h(h_) {
+    if (!allow || !h->eager || h->profile || !h->bg.on || h->stream == h->stream4 || getenv("CG_NOEAGER")) return;
+    if (cudaEventRecord(h->evT, h->stream) != cudaSuccess || cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) return;
+    save = h->stream;
+    h->stream = h->stream4;
+    on = true;
+  }
+  ~BgAsyncScope() {
+    if (!on) return;
+    cudaEventRecord(h->evBG, h->stream4);
+    h->stream = save;
+    h->bg_pending = true;
+  }
+};
 static int check_async(cg_handle *h) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -1116,6 +1179,7 @@ extern "C" int cg_surflux_step(cg_handle *h, int istep, const cg_surflux_io *io)
     for (size_t q = 0; q < t.size() / 2; q++) t[1 + 2 * q] = io->qstar_atm[q];
     IO(cg_sync_from_host(h, "tq", h->io_member, t.data(), (int64_t)t.size()));
   }
+  IO(eager_momentum(h));
   IO(do_surflux(h));
   IO(check_async(h));
   if (io) {
@@ -1249,6 +1313,7 @@ extern "C" int cg_biogem_step(cg_handle *h, double dts, int64_t genie_clock_ms) 
   if (dts != h->bgd.dts) return fail(CG_ERR_ARG, "cg_biogem_step: dts differs from conv_kocn_kbiogem*kocn_loop*genie_timestep");
   const double t = h->bg.t_runtime - (double)genie_clock_ms / (1000.0 * kBgYrS);
   if (!h->bg_go) return CG_OK;   // par_misc_t_go (biogem.f90:1851-1853)
+  BgAsyncScope as(h, true);
   { ProfScope ps(h, "biogem"); ps.done(launch_bg_step(h->dv, h->bgd, 0, 0, h->stream)); }
   if (t < kBgNullSmall) h->bg_go = false;
   return check_async(h);
@@ -1262,6 +1327,7 @@ extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_
   activate(h);
   if (go_ts) IO(cg_sync_from_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
   if (h->bg.on && !h->bg_go) return CG_OK;
+  BgAsyncScope as(h, !go_ts && !go_ts1);
   { ProfScope ps(h, "biogem"); ps.done(launch_tracercoupling(h->dv, h->stream)); }
   IO(check_async(h));
   if (go_ts) IO(cg_sync_to_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
@@ -1276,9 +1342,10 @@ extern "C" int cg_biogem_climate(cg_handle *h) {
   if (h->bg.on) {
     // go_solfor of the last surflux call (embm.f90:3727-3729): row MOD(istot-1,nyear)+1 of solfor
     h->bgd.nsol = h->istep_ocn > 0 ? (h->istep_ocn - 1) % h->g.nyear + 1 : 0;
-    ProfScope ps(h, "biogem");
     int n = 0;
-    if (!h->bg_staged) n += launch_bg_stage_seaice(h->dv, h->bgd, h->stream);
+    if (!h->bg_staged) n += launch_bg_stage_seaice(h->dv, h->bgd, h->stream);   // on the caller's stream: at call time
+    BgAsyncScope as(h, true);
+    ProfScope ps(h, "biogem");
     ps.done(n + launch_bg_climate(h->dv, h->bgd, h->stream));
   } else {
     ProfScope ps(h, "biogem");
@@ -1312,6 +1379,7 @@ extern "C" int cg_biogem_init_ocn(cg_handle *h) {
 extern "C" int cg_atchem_step(cg_handle *h, double dts) {
   BGREADY(h);
   if (dts != h->bgd.dts_atchem) return fail(CG_ERR_ARG, "cg_atchem_step: dts differs from conv_kocn_katchem*kocn_loop*genie_timestep");
+  BgAsyncScope as(h, true);
   { ProfScope ps(h, "biogem"); ps.done(launch_bg_atchem(h->dv, h->bgd, h->atm_totV, h->stream)); }
   return check_async(h);
 }
@@ -1433,6 +1501,8 @@ static int bg_join(cg_handle *h) {   // order the main stream after an outstandi
 }
 
 extern "C" int cg_run(cg_handle *h, int64_t n) {
+  IO0(join_side(h));
+  if (h->mom_ready) { h->mom_ready = false; }   // cg_run recomputes the momentum step inside its own schedule
   READY(h);
   const Params &p = h->base;
   const bool regular = p.katm_loop == 1 && p.ksic_loop == p.kocn_loop && p.kocn_loop > 1;
@@ -1490,6 +1560,8 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
 // restored with cg_sync_from_host; this restores the counters the reference keeps in genie_global (koverall, istep_*,
 // genie_clock) and everything BIOGEM derives from them.
 extern "C" int cg_set_koverall(cg_handle *h, int64_t koverall) {
+  IO0(join_side(h));
+  h->mom_ready = false;
   READY(h);
   const Params &p = h->base;
   if (koverall < 0 || koverall % p.kocn_loop != 0) return fail(CG_ERR_ARG, "cg_set_koverall: koverall must be a non-negative multiple of kocn_loop");
@@ -1511,6 +1583,7 @@ extern "C" int cg_set_koverall(cg_handle *h, int64_t koverall) {
 
 // ------------------------------------------------------------------ diagnostics, measurement
 extern "C" int cg_global_means(cg_handle *h, double *out) {
+  IO0(join_side(h));
   if (!h || !h->initialised || !out) return fail(CG_ERR_ARG, "cg_global_means: bad argument");
   activate(h);
   launch_global_means(h->dv, h->d_means, h->stream);
@@ -1519,6 +1592,7 @@ extern "C" int cg_global_means(cg_handle *h, double *out) {
   return CG_OK;
 }
 extern "C" int cg_health(cg_handle *h, int32_t *out) {
+  IO0(join_side(h));
   if (!h || !h->initialised || !out) return fail(CG_ERR_ARG, "cg_health: bad argument");
   activate(h);
   launch_health(h->dv, h->d_flags, h->stream);
@@ -1532,6 +1606,7 @@ extern "C" int cg_health(cg_handle *h, int32_t *out) {
   return CG_OK;
 }
 extern "C" int cg_synchronize(cg_handle *h) {
+  IO0(join_side(h));
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return CG_OK;
@@ -1543,11 +1618,13 @@ extern "C" int64_t cg_launch_count(cg_handle *h, int reset) {
   return n;
 }
 extern "C" int cg_timer_start(cg_handle *h) {
+  IO0(join_side(h));
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
   CUDA_OK(cudaEventRecord(h->ev0, h->stream));
   return CG_OK;
 }
 extern "C" int cg_timer_stop_ms(cg_handle *h, double *ms) {
+  IO0(join_side(h));
   if (!h || !h->initialised || !ms) return fail(CG_ERR_STATE, "handle not initialised");
   CUDA_OK(cudaEventRecord(h->ev1, h->stream));
   CUDA_OK(cudaEventSynchronize(h->ev1));

@@ -216,7 +216,15 @@ class Ensemble(_Base):
 
     def run(self, n_koverall):
         """n iterations of the genie.f90 main loop entirely on the device."""
-        self._ck(self.L.cg_run(self.h, int(n_koverall)))
+        n = int(n_koverall)
+        self._ck(self.L.cg_run(self.h, n))
+        # keep the host-side step counters of the module-by-module interface in line (genie.f90:271-311)
+        k0 = getattr(self, "koverall", 0)
+        kocn = 5
+        self.istep_atm += n
+        self.istep_ocn += (k0 + n + kocn - 1) // kocn - (k0 + kocn - 1) // kocn     # iterations with MOD(k, kocn) == 1
+        self.istep_sic += (k0 + n) // kocn - k0 // kocn                              # iterations with MOD(k, ksic) == 0
+        self.koverall = k0 + n
 
     def set_koverall(self, koverall):
         """Restart support: continue the coupling loop from iteration `koverall` (multiple of kocn_loop)."""
@@ -225,6 +233,7 @@ class Ensemble(_Base):
         self.istep_ocn = int(koverall) // kocn
         self.istep_sic = int(koverall) // kocn
         self.istep_atm = int(koverall)
+        self.koverall = int(koverall)
 
     def run_years(self, years):
         self.run(int(round(years * self.nyear * self.ndta)))
