@@ -919,8 +919,8 @@ extern "C" int64_t cg_field_size(cg_handle *h, const char *name) {
   return f ? f->count() : -1;
 }
 extern "C" int cg_sync_to_host(cg_handle *h, const char *name, int member, double *dst, int64_t n) {
-  IO0(join_side(h));
   if (!h || !name || !dst || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_to_host: bad argument");
+  IO0(join_side(h));
   FieldDesc *f = find_field(h, strcmp(name, "ts1") == 0 ? "ts" : name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
   if (member < 0 || member >= h->M || n != f->count()) return fail(CG_ERR_ARG, "cg_sync_to_host: member/size mismatch");
@@ -944,9 +944,9 @@ extern "C" int cg_sync_from_host(cg_handle *h, const char *name, int member, con
   return rc;
 }
 static int sync_from_host_lane(cg_handle *h, const char *name, int member, const double *src, int64_t n) {
+  if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_from_host: bad argument");
   IO0(join_side(h));
   h->mom_ready = false;   // a momentum step computed ahead of time is stale once the host has written state
-  if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_from_host: bad argument");
   const bool both = strcmp(name, "ts") == 0 || strcmp(name, "ts1") == 0;
   FieldDesc *f = find_field(h, both ? "ts" : name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
@@ -966,8 +966,8 @@ static int sync_from_host_lane(cg_handle *h, const char *name, int member, const
   return CG_OK;
 }
 extern "C" int cg_sync_all_to_host(cg_handle *h, const char *name, double *dst, int64_t n) {
-  IO0(join_side(h));
   if (!h || !name || !dst || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_all_to_host: bad argument");
+  IO0(join_side(h));
   FieldDesc *f = find_field(h, name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
   if (n != f->count() * h->MS) return fail(CG_ERR_ARG, "cg_sync_all_to_host: size must be field_size*member_stride");
@@ -976,14 +976,15 @@ extern "C" int cg_sync_all_to_host(cg_handle *h, const char *name, double *dst, 
   return CG_OK;
 }
 extern "C" int cg_sync_all_from_host(cg_handle *h, const char *name, const double *src, int64_t n) {
+  if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_all_from_host: bad argument");
   IO0(join_side(h));
   h->mom_ready = false;
-  if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_all_from_host: bad argument");
   FieldDesc *f = find_field(h, name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
   if (n != f->count() * h->MS) return fail(CG_ERR_ARG, "cg_sync_all_from_host: size must be field_size*member_stride");
   CUDA_OK(cudaMemcpyAsync(f->d, src, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-  if (strcmp(name, "ts") == 0) CUDA_OK(cudaMemcpyAsync(h->dv.ts_new, src, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  if (strcmp(name, "ts") == 0)   // the ping-pong partner's dry cells stay in line: device copy, the host data crosses PCIe once
+    CUDA_OK(cudaMemcpyAsync(h->dv.ts_new, f->d, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return CG_OK;
 }
@@ -1501,9 +1502,9 @@ static int bg_join(cg_handle *h) {   // order the main stream after an outstandi
 }
 
 extern "C" int cg_run(cg_handle *h, int64_t n) {
-  IO0(join_side(h));
-  if (h->mom_ready) { h->mom_ready = false; }   // cg_run recomputes the momentum step inside its own schedule
   READY(h);
+  IO0(join_side(h));
+  h->mom_ready = false;   // cg_run computes the momentum step inside its own schedule
   const Params &p = h->base;
   const bool regular = p.katm_loop == 1 && p.ksic_loop == p.kocn_loop && p.kocn_loop > 1;
   while (n > 0) {
@@ -1560,9 +1561,9 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
 // restored with cg_sync_from_host; this restores the counters the reference keeps in genie_global (koverall, istep_*,
 // genie_clock) and everything BIOGEM derives from them.
 extern "C" int cg_set_koverall(cg_handle *h, int64_t koverall) {
+  READY(h);
   IO0(join_side(h));
   h->mom_ready = false;
-  READY(h);
   const Params &p = h->base;
   if (koverall < 0 || koverall % p.kocn_loop != 0) return fail(CG_ERR_ARG, "cg_set_koverall: koverall must be a non-negative multiple of kocn_loop");
   h->koverall = koverall;
@@ -1583,8 +1584,8 @@ extern "C" int cg_set_koverall(cg_handle *h, int64_t koverall) {
 
 // ------------------------------------------------------------------ diagnostics, measurement
 extern "C" int cg_global_means(cg_handle *h, double *out) {
-  IO0(join_side(h));
   if (!h || !h->initialised || !out) return fail(CG_ERR_ARG, "cg_global_means: bad argument");
+  IO0(join_side(h));
   activate(h);
   launch_global_means(h->dv, h->d_means, h->stream);
   CUDA_OK(cudaMemcpyAsync(out, h->d_means, (size_t)h->M * h->g.L * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1592,8 +1593,8 @@ extern "C" int cg_global_means(cg_handle *h, double *out) {
   return CG_OK;
 }
 extern "C" int cg_health(cg_handle *h, int32_t *out) {
-  IO0(join_side(h));
   if (!h || !h->initialised || !out) return fail(CG_ERR_ARG, "cg_health: bad argument");
+  IO0(join_side(h));
   activate(h);
   launch_health(h->dv, h->d_flags, h->stream);
   CUDA_OK(cudaMemcpyAsync(out, h->d_flags, (size_t)h->M * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1606,8 +1607,8 @@ extern "C" int cg_health(cg_handle *h, int32_t *out) {
   return CG_OK;
 }
 extern "C" int cg_synchronize(cg_handle *h) {
-  IO0(join_side(h));
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  IO0(join_side(h));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return CG_OK;
 }
@@ -1618,14 +1619,14 @@ extern "C" int64_t cg_launch_count(cg_handle *h, int reset) {
   return n;
 }
 extern "C" int cg_timer_start(cg_handle *h) {
-  IO0(join_side(h));
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
+  IO0(join_side(h));
   CUDA_OK(cudaEventRecord(h->ev0, h->stream));
   return CG_OK;
 }
 extern "C" int cg_timer_stop_ms(cg_handle *h, double *ms) {
-  IO0(join_side(h));
   if (!h || !h->initialised || !ms) return fail(CG_ERR_STATE, "handle not initialised");
+  IO0(join_side(h));
   CUDA_OK(cudaEventRecord(h->ev1, h->stream));
   CUDA_OK(cudaEventSynchronize(h->ev1));
   float f = 0;
