@@ -115,7 +115,8 @@ struct cg_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;                 // momentum branch of the graph-captured ocean cycle
   cudaStream_t stream4 = nullptr;                 // BIOGEM / ATCHEM block next to the head of the following cycle (low priority)
-  cudaEvent_t evT = nullptr, evBG = nullptr;
+  cudaEvent_t evT = nullptr, evBG = nullptr, evBGtail = nullptr;   // evBG: ts is ready for tstepo; evBGtail: the whole block (ATCHEM) is done
+  bool bg_tail_pending = false;
   cudaStream_t stream5 = nullptr;                 // tracer-coupling sums next to the BIOGEM step kernel
   cudaEvent_t evFork5 = nullptr, evJoin5 = nullptr;
   bool bg_overlap = true, bg_pending = false, bg_staged = false;
@@ -166,6 +167,7 @@ struct cg_handle {
     if (evFork5) cudaEventDestroy(evFork5);
     if (evJoin5) cudaEventDestroy(evJoin5);
     if (stream5) cudaStreamDestroy(stream5);
+    if (evBGtail) cudaEventDestroy(evBGtail);
     if (evT) cudaEventDestroy(evT);
     if (evBG) cudaEventDestroy(evBG);
     if (stream4) cudaStreamDestroy(stream4);
@@ -269,6 +271,10 @@ static int join_side(cg_handle *h) {
   if (h->bg_pending) {
     CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBG, 0));
     h->bg_pending = false;
+  }
+  if (h->bg_tail_pending) {
+    CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBGtail, 0));
+    h->bg_tail_pending = false;
   }
   return CG_OK;
 }
@@ -376,6 +382,7 @@ extern "C" int cg_initialise(cg_handle *h) {
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin5, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evBGtail, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));
@@ -1134,8 +1141,8 @@ static int eager_momentum(cg_handle *h) {
 // per-module path: run one BIOGEM / ATCHEM entry point on stream4, ordered after everything issued so far on the main
 // stream; the next tracer step (or any host access) joins.  RAII: restores h->stream and records the completion event.
 struct BgAsyncScope {
-  cg_handle *h; cudaStream_t save = nullptr; bool on = false;
-  explicit BgAsyncScope(cg_handle *h_, bool allow) : h(h_) {
+  cg_handle *h; cudaStream_t save = nullptr; bool on = false, tail = false;
+  explicit BgAsyncScope(cg_handle *h_, bool allow, bool tail_ = false) : h(h_), tail(tail_) {
     if (!allow || !h->eager || h->profile || !h->bg.on || h->stream == h->stream4 || getenv("CG_NOEAGER")) return;
     if (cudaEventRecord(h->evT, h->stream) != cudaSuccess || cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) return;
     save = h->stream;
@@ -1144,9 +1151,10 @@ struct BgAsyncScope {
   }
   ~BgAsyncScope() {
     if (!on) return;
-    cudaEventRecord(h->evBG, h->stream4);
+    // tail = ATCHEM: nothing on the physics side reads the atmosphere tracers, only a host access has to wait for it
+    cudaEventRecord(tail ? h->evBGtail : h->evBG, h->stream4);
     h->stream = save;
-    h->bg_pending = true;
+    if (tail) h->bg_tail_pending = true; else h->bg_pending = true;
   }
 };
 static int check_async(cg_handle *h) {
@@ -1380,7 +1388,7 @@ extern "C" int cg_biogem_init_ocn(cg_handle *h) {
 extern "C" int cg_atchem_step(cg_handle *h, double dts) {
   BGREADY(h);
   if (dts != h->bgd.dts_atchem) return fail(CG_ERR_ARG, "cg_atchem_step: dts differs from conv_kocn_katchem*kocn_loop*genie_timestep");
-  BgAsyncScope as(h, true);
+  BgAsyncScope as(h, true, true);
   { ProfScope ps(h, "biogem"); ps.done(launch_bg_atchem(h->dv, h->bgd, h->atm_totV, h->stream)); }
   return check_async(h);
 }
@@ -1422,6 +1430,8 @@ static int do_biogem_block(cg_handle *h, long long k) {
     }
     IO(cg_biogem_climate(h));
   }
+  // asynchronous block: the next tracer step needs ts (tracer coupling) and cost (climate), not the atmosphere
+  if (h->stream == h->stream4) { CUDA_OK(cudaEventRecord(h->evBG, h->stream4)); h->bg_pending = true; }
   if (k % ((long long)p.conv_kocn_katchem * p.kocn_loop) == 0) IO(cg_atchem_step(h, h->bgd.dts_atchem));
   return CG_OK;
 }
@@ -1489,8 +1499,8 @@ static int do_biogem_block_async(cg_handle *h, long long k) {
   h->stream = save;
   h->bg_staged = false;
   if (rc) return rc;
-  CUDA_OK(cudaEventRecord(h->evBG, h->stream4));
-  h->bg_pending = true;
+  CUDA_OK(cudaEventRecord(h->evBGtail, h->stream4));
+  h->bg_tail_pending = true;
   return CG_OK;
 }
 static int bg_join(cg_handle *h) {   // order the main stream after an outstanding BIOGEM block
@@ -1553,7 +1563,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
     n--;
     IO(do_biogem_block(h, h->koverall));
   }
-  IO(bg_join(h));
+  IO(join_side(h));
   return check_async(h);
 }
 
@@ -1708,6 +1718,7 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin5, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evBGtail, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));
