@@ -117,6 +117,7 @@ struct cg_handle {
   cudaStream_t stream4 = nullptr;                 // BIOGEM / ATCHEM block next to the head of the following cycle (low priority)
   cudaEvent_t evT = nullptr, evBG = nullptr, evBGtail = nullptr;   // evBG: ts is ready for tstepo; evBGtail: the whole block (ATCHEM) is done
   bool bg_tail_pending = false;
+  bool bg_ahead = false;                          // the step kernel of the next BIOGEM block is already in stream4
   cudaStream_t stream5 = nullptr;                 // tracer-coupling sums next to the BIOGEM step kernel
   cudaEvent_t evFork5 = nullptr, evJoin5 = nullptr;
   bool bg_overlap = true, bg_pending = false, bg_staged = false;
@@ -1503,6 +1504,62 @@ static int do_biogem_block_async(cg_handle *h, long long k) {
   h->bg_tail_pending = true;
   return CG_OK;
 }
+// Pipelined form of the asynchronous block (kbiogem == katchem, no fusion): step_biogem reads BIOGEM's own state only
+// (ocn, bio_part, the atmosphere, the sea-ice snapshot -- all last written by the previous block) and the forcing of its
+// clock, never ts, so the step kernel of block n+1 is enqueued on stream4 as soon as block n has been, and runs next to
+// the two ocean cycles in between.  At its nominal time only the coupling (sums, update), the climate snapshot and
+// ATCHEM remain.  The order of every read and write of every field is the serial one: bit-identical.
+// `remaining` = koverall iterations this cg_run call will still execute (the step kernel is only issued ahead if its own
+// block is certain to follow inside the same call, so the host never observes state from the future).
+static int bg_issue_step(cg_handle *h, long long clock) {
+  IO(cg_biogem_forcing(h, clock));
+  const double t = h->bg.t_runtime - (double)clock / (1000.0 * kBgYrS);
+  if (!h->bg_go) return CG_OK;   // par_misc_t_go (biogem.f90:1851-1853)
+  h->launches += launch_bg_step(h->dv, h->bgd, 0, 0, h->stream);
+  if (t < kBgNullSmall) h->bg_go = false;
+  return CG_OK;
+}
+static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remaining) {
+  const Params &p = h->base;
+  const long long period = (long long)p.conv_kocn_kbiogem * p.kocn_loop;
+  if (!h->bg.on || k % period != 0) return CG_OK;
+  const long long tick = nint_ll(1000.0 * p.genie_timestep);
+  if (k == period) IO(cg_biogem_climate_sol(h));
+  h->launches += launch_bg_stage_seaice(h->dv, h->bgd, h->stream);
+  CUDA_OK(cudaEventRecord(h->evT, h->stream));
+  CUDA_OK(cudaStreamWaitEvent(h->stream5, h->evT, 0));
+  cudaStream_t save = h->stream;
+  h->stream = h->stream4;
+  h->bg_staged = true;
+  int rc = CG_OK;
+  do {
+    if (!h->bg_ahead) {   // first block of this call: the step kernel at its nominal place
+      if (cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
+      if ((rc = bg_issue_step(h, k * tick))) break;
+    }
+    h->bg_ahead = false;
+    if (h->bg_go) {       // biogem_tracercoupling: sums on stream5 (they need ts of this cycle, not the step's anomaly)
+      h->launches += launch_tc_sums_first(h->dv, h->stream5);
+      if (cudaEventRecord(h->evJoin5, h->stream5) != cudaSuccess || cudaStreamWaitEvent(h->stream4, h->evJoin5, 0) != cudaSuccess ||
+          cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
+      h->launches += launch_tc_apply_only(h->dv, h->stream4);
+    } else if (cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
+    if ((rc = cg_biogem_climate(h))) break;
+    if (cudaEventRecord(h->evBG, h->stream4) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "event record"); break; }
+    h->bg_pending = true;
+    if ((rc = cg_atchem_step(h, h->bgd.dts_atchem))) break;
+    if (remaining >= period) {   // the step kernel of the next block, one block ahead
+      if ((rc = bg_issue_step(h, (k + period) * tick))) break;
+      h->bg_ahead = true;
+    }
+    if (cudaEventRecord(h->evBGtail, h->stream4) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "event record"); break; }
+    h->bg_tail_pending = true;
+  } while (0);
+  h->stream = save;
+  h->bg_staged = false;
+  if (rc) return rc;
+  return check_async(h);
+}
 static int bg_join(cg_handle *h) {   // order the main stream after an outstanding BIOGEM block
   if (h->bg_pending) {
     CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBG, 0));
@@ -1544,8 +1601,14 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
         std::swap(h->dv.ts_cur, h->dv.ts_new);
         h->koverall += p.kocn_loop;
         n -= p.kocn_loop;
-        if (h->bg_overlap && !getenv("CG_BG_SERIAL")) IO(do_biogem_block_async(h, h->koverall));
-        else IO(do_biogem_block(h, h->koverall));
+        if (h->bg_overlap && !getenv("CG_BG_SERIAL")) {
+          // opt-in (CG_BG_PIPE=1): measured 4 % slower on B200 -- the step kernel then shares the SMs with the tracer step
+          const bool pipe = !h->bg_fuse && p.conv_kocn_kbiogem == p.conv_kocn_katchem && getenv("CG_BG_PIPE");
+          if (pipe || h->bg_ahead) IO(do_biogem_block_pipelined(h, h->koverall, n));
+          else IO(do_biogem_block_async(h, h->koverall));
+        } else {
+          IO(do_biogem_block(h, h->koverall));
+        }
         continue;
       }
       IO(enqueue_cycle(h, false));
