@@ -32,6 +32,13 @@
 #else
 #define CG_HD inline
 #endif
+#ifdef __CUDA_ARCH__
+#define CG_CLZ(x) __clz((int)(x))
+#define CG_FFS(x) __ffs((int)(x))
+#else
+#define CG_CLZ(x) __builtin_clz(x)
+#define CG_FFS(x) __builtin_ffs((int)(x))
+#endif
 
 namespace cg {
 
@@ -376,11 +383,14 @@ CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned 
   const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
   double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);         // level-1 cell of this column
   double *__restrict__ rho = v.rho + ((long)c2 * MS + m);
-  int kx[K + 2], head[K + 2];
+  // The reference keeps a compacted index array k(0:maxk) of the levels that still exist as separate boxes and shifts
+  // it down after every merge; here the same set is a bit mask (bit l-1 = level l is a separate box), the neighbours of
+  // a level come from clz / ffs, and a merge clears bits -- the sequence of comparisons and merges is the reference's.
+  int head[K + 2];
   double dzm[K + 2], tt[K + 2], ss[K + 2], rl[K + 2];
 #pragma unroll
   for (int q = 1; q <= K; q++) {
-    kx[q] = q; head[q] = q; dzm[q] = g.dz[q];
+    head[q] = q; dzm[q] = g.dz[q];
     tt[q] = 0.0; ss[q] = 0.0; rl[q] = 0.0;
     if (q >= k1c) {
       tt[q] = ts[(long)(q - 1) * sK];
@@ -388,7 +398,6 @@ CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned 
       rl[q] = rho[(long)(q - 1) * rK];
     }
   }
-  kx[k1c - 1] = 0;
   rl[0] = 0.0;
 #ifdef __CUDA_ARCH__
   // the decisions below are a serial, memory-idle stretch: start pulling the column's passive tracers (written by the
@@ -400,34 +409,40 @@ CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned 
     }
   }
 #endif
-  int mm = K, lastmix = 0;
+  unsigned act = (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)) & ~((1u << (k1c - 1)) - 1u);   // levels k1c..K
+#define CG_BELOW(x) ({ const unsigned mb_ = act & ((1u << ((x) - 1)) - 1u); mb_ ? 32 - CG_CLZ(mb_) : 0; })
+#define CG_ABOVE(x) ({ const unsigned ma_ = act >> (x); (x) + CG_FFS(ma_); })
+  int cur = K, lastmix = 0;
   bool any = false;
-  while (kx[mm - 1] > 0 || (lastmix != 0 && kx[mm] != K)) {
-    if (kx[mm - 1] == 0 || rl[kx[mm]] < rl[kx[mm - 1]]) {
-      if (lastmix == 0 || kx[mm] == K) mm = mm - 1; else mm = mm + 1;
+  for (;;) {
+    const int bl = CG_BELOW(cur);
+    if (!(bl > 0 || (lastmix != 0 && cur != K))) break;
+    if (bl == 0 || rl[cur] < rl[bl]) {
+      if (lastmix == 0 || cur == K) cur = bl; else cur = CG_ABOVE(cur);
       lastmix = 0;
     } else {
       lastmix = 1;
       any = true;
-      int n = mm - 1;
-      while (kx[n - 1] > 0 && rl[kx[n]] >= rl[kx[n - 1]]) n = n - 1;
-      const int h = kx[mm];
+      // extend the unstable run downward (goldstein.f90:2722-2731), then mix it into the top box in the order m-1 .. n
+      int lo = bl;
+      for (;;) {
+        const int b2 = CG_BELOW(lo);
+        if (!(b2 > 0 && rl[lo] >= rl[b2])) break;
+        lo = b2;
+      }
+      const int h = cur;
       double sumT = tt[h] * dzm[h], sumS = ss[h] * dzm[h], dznew = dzm[h];
-      for (int ni = 1; ni <= mm - n; ni++) {
-        const int q = kx[mm - ni];
+      for (int q = bl;; q = CG_BELOW(q)) {
         sumT = sumT + tt[q] * dzm[q];
         sumS = sumS + ss[q] * dzm[q];
         dznew = dznew + dzm[q];
+        if (q == lo) break;
       }
       dzm[h] = dznew;
       tt[h] = sumT / dznew;
       ss[h] = sumS / dznew;
       rl[h] = ec1 * tt[h] + ec2 * ss[h] + ec3 * (tt[h] * tt[h]) + ec4 * (tt[h] * tt[h] * tt[h]);
-      int ni = mm - 1;
-      while (kx[ni + 1] > 0) {
-        kx[ni] = kx[ni - mm + n];
-        ni = ni - 1;
-      }
+      act &= ~(((1u << bl) - 1u) & ~((1u << (lo - 1)) - 1u));   // levels lo..bl are now part of box h
     }
   }
   // SST / SSS as exported by step_goldstein (:428-431)
@@ -436,20 +451,19 @@ CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned 
     v.sst[((long)(I * J) + c2) * MS + m] = ss[K];
   }
   if (!any) return;
-  // fill in (:2749-2764): head[n] = top level of the mixed region level n ended up in
+  // fill in (:2749-2764): head[n] = the box level n ended up in (the next separate level above it)
   {
-    int mq = K - 1;
     double cnt = 0.0;
     for (int n = K - 1; n >= k1c; n--) {
-      if (n > kx[mq]) {
-        head[n] = kx[mq + 1];
+      if (!((act >> (n - 1)) & 1u)) {
+        head[n] = CG_ABOVE(n);
         cnt = cnt + 1.0;
-      } else {
-        mq = mq - 1;
       }
     }
     v.cost[(long)c2 * MS + m] += cnt;
   }
+#undef CG_BELOW
+#undef CG_ABOVE
   {
     head[0] = 0;
     for (int k = 1; k < k1c; k++) head[k] = 0;

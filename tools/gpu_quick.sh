@@ -7,4 +7,3 @@ run() { echo "== $1"; env $1 timeout 600 python bench.py --steps 6 --warmup 12 -
 import json,sys
 d=json.loads(sys.stdin.read()); print('ms/yr %.2f e2e %.0f' % (d['ms_per_step'], d['e2e']['value']), {k: round(v,1) for k,v in d['roofline']['family_ms_per_year'].items()})"; }
 run "CG_X=1" | tee -a $OUT/quick_$TAG.log
-run "CG_BG_NOPIPE=1" | tee -a $OUT/quick_$TAG.log
