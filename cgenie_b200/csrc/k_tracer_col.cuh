@@ -252,65 +252,59 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     const double vuE = smc[(R::rU + 0) * NT], vvN = smc[(R::rU + 1) * NT], vww = smc[(R::rU + 2) * NT], vuW = smc[(R::rU + 3) * NT],
                  vvS = smc[(R::rU + 4) * NT];
 
-    // ---- horizontal faces of level kk: flux = a * ts(neighbour) + b * ts(centre)   (goldstein.f90:2517-2547)
-    double hE = 0.0, hW = 0.0, hN = 0.0, hS = 0.0, hC = 0.0;
-    if (opE) {
-      const double pec = vuE * dphi * rdiff1, ups = pec * col_rcp(2.0 + fabs(pec)), h = vuE * rc * 0.5;
-      hE = (h * (1.0 - ups) - dEh) * cX;
-      hC += (h * (1.0 + ups) + dEh) * cX;
-    }
-    if (opW) {
-      const double pec = vuW * dphi * rdiff1, ups = pec * col_rcp(2.0 + fabs(pec)), h = vuW * rc * 0.5;
-      hW = -(h * (1.0 + ups) + dEh) * cX;
-      hC -= (h * (1.0 - ups) - dEh) * cX;
-    }
-    if (opN) {
-      const double pec = vvN * dsvN * rdiff1, ups = pec * col_rcp(2.0 + fabs(pec)), h = cvj * vvN * 0.5;
-      hN = (h * (1.0 - ups) - dNh) * cY;
-      hC += (h * (1.0 + ups) + dNh) * cY;
-    }
-    if (opS) {
-      const double pec = vvS * dsvS * rdiff1, ups = pec * col_rcp(2.0 + fabs(pec)), h = cvjm * vvS * 0.5;
-      hS = -(h * (1.0 + ups) + dSh) * cY;
-      hC -= (h * (1.0 - ups) - dSh) * cY;
+    // ---- horizontal faces of level kk: flux = a * ts(neighbour) + b * ts(centre)   (goldstein.f90:2517-2547).
+    // Branch free (closed faces and the top level through 0/1 masks): the whole level is one basic block, so the
+    // scheduler can run the tracers' independent FMA chains under the long dependent chain of the slope terms.
+    const double mE = opE ? 1.0 : 0.0, mW = opW ? 1.0 : 0.0, mN = opN ? 1.0 : 0.0, mS = opS ? 1.0 : 0.0, mT = top ? 0.0 : 1.0;
+    double hE, hW, hN, hS, hC;
+    {
+      const double pE = vuE * dphi * rdiff1, pW = vuW * dphi * rdiff1, pN = vvN * dsvN * rdiff1, pS = vvS * dsvS * rdiff1;
+      const double uE_ = pE * col_rcp(2.0 + fabs(pE)), uW_ = pW * col_rcp(2.0 + fabs(pW));
+      const double uN_ = pN * col_rcp(2.0 + fabs(pN)), uS_ = pS * col_rcp(2.0 + fabs(pS));
+      const double gE = vuE * rc * 0.5, gW = vuW * rc * 0.5, gN = cvj * vvN * 0.5, gS = cvjm * vvS * 0.5;
+      const double cXE = cX * mE, cXW = cX * mW, cYN = cY * mN, cYS = cY * mS;
+      hE = (gE * (1.0 - uE_) - dEh) * cXE;
+      hW = -(gW * (1.0 + uW_) + dEh) * cXW;
+      hN = (gN * (1.0 - uN_) - dNh) * cYN;
+      hS = -(gS * (1.0 + uS_) + dSh) * cYS;
+      hC = ((gE * (1.0 + uE_) + dEh) * cXE - (gW * (1.0 - uW_) - dEh) * cXW) +
+           ((gN * (1.0 + uN_) + dNh) * cYN - (gS * (1.0 - uS_) - dSh) * cYS);
     }
     // ---- face kk+1/2: vertical advection/diffusion + isoneutral terms (goldstein.f90:2549-2621)
-    double lc = 0.0, lE = 0.0, lW = 0.0, lN = 0.0, lS = 0.0;        // coefficients of the level-kk values
-    double nuc = 0.0, nuE = 0.0, nuW = 0.0, nuN = 0.0, nuS = 0.0;   // coefficients of the level-kk+1 values
-    if (!top) {
-      const double rdza = g.rdza[kk];
-      {
-        const double pec = vww * g.dza[kk] * rdiffv, ups = pec * col_rcp(2.0 + fabs(pec)), h = vww * 0.5, d = rdza * diffv;
-        nuc = h * (1.0 - ups) - d;
-        lc = h * (1.0 + ups) + d;
-      }
+    double lc, lE, lW, lN, lS;        // coefficients of the level-kk values
+    double nuc, nuE, nuW, nuN, nuS;   // coefficients of the level-kk+1 values
+    {
+      const double rdza = top ? 0.0 : g.rdza[kk];
+      const double pA = vww * g.dza[kk] * rdiffv, uA_ = pA * col_rcp(2.0 + fabs(pA)), gA = vww * 0.5 * mT, dA = rdza * diffv;
+      nuc = gA * (1.0 - uA_) - dA;
+      lc = gA * (1.0 + uA_) + dA;
       const double tatw = 0.5 * (tC0 + tC1);
       const double tec = -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3;
       const double dzrho = (ec2 * (sC1 - sC0) - tec * (tC1 - tC0)) * rdza;
-      if (dzrho < -1.0e-12) {
-        // density slopes on the four stencils; a closed face has neighbour == centre, i.e. a zero difference
-        const double x0 = ec2 * ((sC0 - sW0) * gxx) - tec * ((tC0 - tW0) * gxx);
-        const double x1 = ec2 * ((sE0 - sC0) * gxx) - tec * ((tE0 - tC0) * gxx);
-        const double x2 = ec2 * ((sC1 - sW1) * gxx) - tec * ((tC1 - tW1) * gxx);
-        const double x3 = ec2 * ((sE1 - sC1) * gxx) - tec * ((tE1 - tC1) * gxx);
-        const double y0 = ec2 * ((sC0 - sS0) * gyS) - tec * ((tC0 - tS0) * gyS);
-        const double y1 = ec2 * ((sN0 - sC0) * gyN) - tec * ((tN0 - tC0) * gyN);
-        const double y2 = ec2 * ((sC1 - sS1) * gyS) - tec * ((tC1 - tS1) * gyS);
-        const double y3 = ec2 * ((sN1 - sC1) * gyN) - tec * ((tN1 - tC1) * gyN);
-        const double tv1 = (((x0 * x0 + y0 * y0) + (x1 * x1 + y1 * y1)) + (x2 * x2 + y2 * y2)) + (x3 * x3 + y3 * y3);
-        const double rdz = col_rcp(dzrho), rdz2 = rdz * rdz;
-        const double sl = 0.25 * tv1 * rdz2, ssm = g.ssmax[kk];
-        const double slim = (sl > ssm) ? ssm * ssm * col_rcp(sl * sl) : 1.0;
-        const double cf = 0.25 * slim * diff1 * rdz2;
-        const double g2 = 2.0 * dzrho * cf, gX = g2 * gxx, gS = g2 * gyS, gN = g2 * gyN;
-        const double s2 = tv1 * cf * rdza;
-        const double wx0 = x0 * gX, wx1 = x1 * gX, wx2 = x2 * gX, wx3 = x3 * gX;
-        const double wy0 = y0 * gS, wy1 = y1 * gN, wy2 = y2 * gS, wy3 = y3 * gN;
-        lc += (wx0 - wx1) + (wy0 - wy1) + s2;
-        nuc += (wx2 - wx3) + (wy2 - wy3) - s2;
-        lW = -wx0; lE = wx1; lS = -wy0; lN = wy1;
-        nuW = -wx2; nuE = wx3; nuS = -wy2; nuN = wy3;
-      }
+      const bool iso = dzrho < -1.0e-12;                     // false at the top level (rdza = 0)
+      const double dzs = iso ? dzrho : -1.0, mI = iso ? 1.0 : 0.0;
+      // density slopes on the four stencils; a closed face has neighbour == centre, i.e. a zero difference
+      const double x0 = ec2 * ((sC0 - sW0) * gxx) - tec * ((tC0 - tW0) * gxx);
+      const double x1 = ec2 * ((sE0 - sC0) * gxx) - tec * ((tE0 - tC0) * gxx);
+      const double x2 = ec2 * ((sC1 - sW1) * gxx) - tec * ((tC1 - tW1) * gxx);
+      const double x3 = ec2 * ((sE1 - sC1) * gxx) - tec * ((tE1 - tC1) * gxx);
+      const double y0 = ec2 * ((sC0 - sS0) * gyS) - tec * ((tC0 - tS0) * gyS);
+      const double y1 = ec2 * ((sN0 - sC0) * gyN) - tec * ((tN0 - tC0) * gyN);
+      const double y2 = ec2 * ((sC1 - sS1) * gyS) - tec * ((tC1 - tS1) * gyS);
+      const double y3 = ec2 * ((sN1 - sC1) * gyN) - tec * ((tN1 - tC1) * gyN);
+      const double tv1 = (((x0 * x0 + y0 * y0) + (x1 * x1 + y1 * y1)) + (x2 * x2 + y2 * y2)) + (x3 * x3 + y3 * y3);
+      const double rdz = col_rcp(dzs), rdz2 = rdz * rdz;
+      const double sl = 0.25 * tv1 * rdz2, ssm = g.ssmax[kk];
+      const double slim = (sl > ssm) ? ssm * ssm * col_rcp(sl * sl) : 1.0;
+      const double cf = 0.25 * slim * diff1 * rdz2 * mI;
+      const double g2 = 2.0 * dzs * cf, gX = g2 * gxx, gS = g2 * gyS, gN = g2 * gyN;
+      const double s2 = tv1 * cf * rdza;
+      const double wx0 = x0 * gX, wx1 = x1 * gX, wx2 = x2 * gX, wx3 = x3 * gX;
+      const double wy0 = y0 * gS, wy1 = y1 * gN, wy2 = y2 * gS, wy3 = y3 * gN;
+      lc += (wx0 - wx1) + (wy0 - wy1) + s2;
+      nuc += (wx2 - wx3) + (wy2 - wy3) - s2;
+      lW = -wx0; lE = wx1; lS = -wy0; lN = wy1;
+      nuW = -wx2; nuE = wx3; nuS = -wy2; nuN = wy3;
     }
     const double cZ = dt * g.rdz[kk];
     const bool stv = kk > k1c;
