@@ -495,6 +495,7 @@ static int build_device(cg_handle *h) {
   TRY(dalloc(h, &v.tsflux, 2 * ij * MS));
   TRY(dalloc(h, &v.usnap, 2 * ij * MS));
   TRY(dalloc(h, &v.velsum, 2 * ij * MS));
+  TRY(dalloc(h, &v.comask, ij * MS));
   TRY(dalloc(h, &v.rho, ijk * MS));
   TRY(dalloc(h, &v.u, ijk * 3 * MS));
   TRY(dalloc(h, &v.u1, ijk * 2 * MS));

@@ -96,6 +96,8 @@ struct Dev {
   double bg_rtot_V;
   double *bg_biopart;          // BIOGEM particulates [k][j][i][ls][m] (rescaled by tracer coupling), NULL without BIOGEM
   int bg_LS;
+  unsigned *comask;          // [j][i][m] region map of the convective adjustment (k_ts_pre -> k_tstep_col passive pass):
+                             // bit k-1 = level k lies in a mixed region, bit 16+k-1 = it is the region's top
   int co_prefetch;           // k_co_col: prefetch the column's passive tracers during the decisions (tuning knob)
   int *istep_ocn;            // device-resident ocean step counter (read by graph-replayed kernels)
   MemberP p;

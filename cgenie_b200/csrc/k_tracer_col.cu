@@ -13,7 +13,7 @@ void upload_grid_tracer_col(const GridC &g, cudaStream_t s) {
 }
 
 // one block = the MS members of ONE wet column (row-major column order: neighbouring blocks share stencil rows in L2)
-template <int I, int J, int K, int L, int MS, int MINB>
+template <int I, int J, int K, int L, int MS, int MINB, bool PV>
 __global__ void __launch_bounds__(MS, MINB) k_tstep_col(const Dev v) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ColStage st;
@@ -21,7 +21,16 @@ __global__ void __launch_bounds__(MS, MINB) k_tstep_col(const Dev v) {
   st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows<L>::rows * MS * 8);
   st.tid = threadIdx.x;
   const int c2 = v.rowcols[blockIdx.x];
-  tstep_column<I, J, K, L, MS, MS>(v, c_g, c2, threadIdx.x, st);
+  tstep_column<I, J, K, L, MS, MS, PV>(v, c_g, c2, threadIdx.x, st);
+}
+
+// T, S pre-pass + convective-adjustment decisions of the mix-on-write form: one thread per (member, wet column)
+template <int I, int J, int K, int L, int MS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_ts_pre(const Dev v) {
+  const unsigned m = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ci = blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (ci >= v.nwet) return;
+  ts_pre_column<I, J, K, L, MS>(v, c_g, v.rowcols[ci], m);
 }
 
 // convective adjustment + SST export: one thread per (member, wet column).  (A split into a decisions kernel and a
@@ -39,12 +48,29 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   constexpr size_t smem = (size_t)ColRows<L>::rows * MS * 8 + 32;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  if (cfg == 1) k_tstep_col<I, J, K, L, MS, 1><<<v.nwet, MS, smem, s>>>(v);
-  else k_tstep_col<I, J, K, L, MS, 2><<<v.nwet, MS, smem, s>>>(v);
+  // mix-on-write form (CG_COL_MIX=1, opt-in): T, S pre-pass with the convection decisions, then the passive tracers with
+  // the mixing applied as they are written -- the second pass over ts of k_co_col disappears (528 MB of DRAM traffic per
+  // step instead of 844 MB) but the per-cell coefficients are computed twice; measured slower on B200 (241 us against
+  // 217 us at 128 members: both forms are bound by fp64 latency, not by bandwidth; profiles/README_r1.md).
+  static int mix = -1;
+  if (mix < 0) { const char *e = getenv("CG_COL_MIX"); mix = e ? atoi(e) : 0; }
+  if (mix && v.comask && K <= 16) {
+    static int minb = -1;   // registers / occupancy of the pre-pass: 2 -> 202 regs, 3 -> 168, 4 -> 128 (spills)
+    if (minb < 0) { const char *e = getenv("CG_PRE_MINB"); minb = e ? atoi(e) : 3; }
+    const dim3 gp(MS / 32, (v.nwet + 3) / 4);
+    if (minb == 2) k_ts_pre<I, J, K, L, MS, 2><<<gp, 128, 0, s>>>(v);
+    else if (minb == 4) k_ts_pre<I, J, K, L, MS, 4><<<gp, 128, 0, s>>>(v);
+    else k_ts_pre<I, J, K, L, MS, 3><<<gp, 128, 0, s>>>(v);
+    k_tstep_col<I, J, K, L, MS, 2, true><<<v.nwet, MS, smem, s>>>(v);
+    return 2;
+  }
+  if (cfg == 1) k_tstep_col<I, J, K, L, MS, 1, false><<<v.nwet, MS, smem, s>>>(v);
+  else k_tstep_col<I, J, K, L, MS, 2, false><<<v.nwet, MS, smem, s>>>(v);
   static int copf = -1;
   if (copf < 0) { const char *e = getenv("CG_CO_PF"); copf = e ? atoi(e) : 0; }   // measured: the L2 prefetch costs more than it hides (profiles/README_r1.md)
   Dev v2 = v;

@@ -142,10 +142,106 @@ struct ColRows {
   static constexpr int rows = rB + rowsB;
 };
 
+// Per-(member, column) constants of the flux formulation.
+struct ColK {
+  double diff1, diffv, rdiff1, rdiffv, ec1, ec2, ec3, ec4, dt, dphi;
+  double rc, cvj, cvjm, dsvN, dsvS, gyN, gyS, gxx, cX, cY, dEh, dNh, dSh;
+};
+template <int I, int J>
+CG_HD ColK col_consts(const Dev &v, const GridC &g, const unsigned m, const int j) {
+  ColK q;
+  q.diff1 = v.p.diff1[m]; q.diffv = v.p.diff2[m]; q.rdiff1 = 1.0 / q.diff1; q.rdiffv = 1.0 / q.diffv;
+  q.ec1 = v.p.ec1[m]; q.ec2 = v.p.ec2[m]; q.ec3 = v.p.ec3[m]; q.ec4 = v.p.ec4[m];
+  q.dt = g.dt; q.dphi = g.dphi;
+  const double rdphi = g.rdphi, rc2 = g.rc2[j], cv2j = g.cv2[j], cv2jm = (j > 1) ? g.cv2[j - 1] : 0.0;
+  q.rc = g.rc[j]; q.cvj = g.cv[j]; q.cvjm = g.cv[j - 1];
+  q.dsvN = g.dsv[(j < J - 1) ? j : J - 1]; q.dsvS = (j > 1) ? g.dsv[j - 1] : 0.0;
+  q.gyN = (j < J) ? q.cvj * g.rdsv[j] : 0.0; q.gyS = (j > 1) ? q.cvjm * g.rdsv[j - 1] : 0.0; q.gxx = q.rc * rdphi;
+  q.cX = q.dt * rdphi; q.cY = q.dt * g.rds[j];
+  q.dEh = rc2 * q.diff1; q.dNh = cv2j * q.diff1; q.dSh = cv2jm * q.diff1;
+  return q;
+}
+// T, S of the centre column and its four neighbours at one level (a closed face carries the centre values)
+struct TS5 { double tC, sC, tE, sE, tW, sW, tN, sN, tS, sS; };
+// The 15 linear coefficients of one cell: horizontal faces of level kk (h*), lower half (l*) and upper half (nu*) of the
+// vertical face kk+1/2, and dt/dz of the level.
+struct ColCoef { double hE, hW, hN, hS, hC, lc, lE, lW, lN, lS, nuc, nuE, nuW, nuN, nuS, cZ; };
+
+// goldstein.f90:2517-2621 for one (member, cell): `a` = T,S at level kk, `b` = one level up, velocities of the five faces.
+template <int K>
+CG_HD void col_coefs(const ColK &q, const GridC &g, const int kk, const bool opE, const bool opW, const bool opN, const bool opS,
+                     const TS5 &a, const TS5 &b, const double vuE, const double vvN, const double vww, const double vuW,
+                     const double vvS, ColCoef &o) {
+  const bool top = (kk == K);
+  // ---- horizontal faces of level kk: flux = a * ts(neighbour) + b * ts(centre)   (goldstein.f90:2517-2547).
+  // Branch free (closed faces and the top level through 0/1 masks): the whole level is one basic block, so the
+  // scheduler can run the tracers' independent FMA chains under the long dependent chain of the slope terms.
+  const double mE = opE ? 1.0 : 0.0, mW = opW ? 1.0 : 0.0, mN = opN ? 1.0 : 0.0, mS = opS ? 1.0 : 0.0, mT = top ? 0.0 : 1.0;
+  {
+    const double pE = vuE * q.dphi * q.rdiff1, pW = vuW * q.dphi * q.rdiff1, pN = vvN * q.dsvN * q.rdiff1, pS = vvS * q.dsvS * q.rdiff1;
+    const double uE_ = pE * col_rcp(2.0 + fabs(pE)), uW_ = pW * col_rcp(2.0 + fabs(pW));
+    const double uN_ = pN * col_rcp(2.0 + fabs(pN)), uS_ = pS * col_rcp(2.0 + fabs(pS));
+    const double gE = vuE * q.rc * 0.5, gW = vuW * q.rc * 0.5, gN = q.cvj * vvN * 0.5, gS = q.cvjm * vvS * 0.5;
+    const double cXE = q.cX * mE, cXW = q.cX * mW, cYN = q.cY * mN, cYS = q.cY * mS;
+    o.hE = (gE * (1.0 - uE_) - q.dEh) * cXE;
+    o.hW = -(gW * (1.0 + uW_) + q.dEh) * cXW;
+    o.hN = (gN * (1.0 - uN_) - q.dNh) * cYN;
+    o.hS = -(gS * (1.0 + uS_) + q.dSh) * cYS;
+    o.hC = ((gE * (1.0 + uE_) + q.dEh) * cXE - (gW * (1.0 - uW_) - q.dEh) * cXW) +
+           ((gN * (1.0 + uN_) + q.dNh) * cYN - (gS * (1.0 - uS_) - q.dSh) * cYS);
+  }
+  // ---- face kk+1/2: vertical advection/diffusion + isoneutral terms (goldstein.f90:2549-2621)
+  {
+    const double tC0 = a.tC, sC0 = a.sC, tE0 = a.tE, sE0 = a.sE, tW0 = a.tW, sW0 = a.sW, tN0 = a.tN, sN0 = a.sN, tS0 = a.tS, sS0 = a.sS;
+    const double tC1 = b.tC, sC1 = b.sC, tE1 = b.tE, sE1 = b.sE, tW1 = b.tW, sW1 = b.sW, tN1 = b.tN, sN1 = b.sN, tS1 = b.tS, sS1 = b.sS;
+    const double ec1 = q.ec1, ec2 = q.ec2, ec3 = q.ec3, ec4 = q.ec4, gxx = q.gxx, gyS = q.gyS, gyN = q.gyN;
+    const double rdza = top ? 0.0 : g.rdza[kk];
+    const double pA = vww * g.dza[kk] * q.rdiffv, uA_ = pA * col_rcp(2.0 + fabs(pA)), gA = vww * 0.5 * mT, dA = rdza * q.diffv;
+    double nuc = gA * (1.0 - uA_) - dA;
+    double lc = gA * (1.0 + uA_) + dA;
+    const double tatw = 0.5 * (tC0 + tC1);
+    const double tec = -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3;
+    const double dzrho = (ec2 * (sC1 - sC0) - tec * (tC1 - tC0)) * rdza;
+    const bool iso = dzrho < -1.0e-12;                     // false at the top level (rdza = 0)
+    const double dzs = iso ? dzrho : -1.0, mI = iso ? 1.0 : 0.0;
+    // density slopes on the four stencils; a closed face has neighbour == centre, i.e. a zero difference
+    const double x0 = ec2 * ((sC0 - sW0) * gxx) - tec * ((tC0 - tW0) * gxx);
+    const double x1 = ec2 * ((sE0 - sC0) * gxx) - tec * ((tE0 - tC0) * gxx);
+    const double x2 = ec2 * ((sC1 - sW1) * gxx) - tec * ((tC1 - tW1) * gxx);
+    const double x3 = ec2 * ((sE1 - sC1) * gxx) - tec * ((tE1 - tC1) * gxx);
+    const double y0 = ec2 * ((sC0 - sS0) * gyS) - tec * ((tC0 - tS0) * gyS);
+    const double y1 = ec2 * ((sN0 - sC0) * gyN) - tec * ((tN0 - tC0) * gyN);
+    const double y2 = ec2 * ((sC1 - sS1) * gyS) - tec * ((tC1 - tS1) * gyS);
+    const double y3 = ec2 * ((sN1 - sC1) * gyN) - tec * ((tN1 - tC1) * gyN);
+    const double tv1 = (((x0 * x0 + y0 * y0) + (x1 * x1 + y1 * y1)) + (x2 * x2 + y2 * y2)) + (x3 * x3 + y3 * y3);
+    const double rdz = col_rcp(dzs), rdz2 = rdz * rdz;
+    const double sl = 0.25 * tv1 * rdz2, ssm = g.ssmax[kk];
+    const double slim = (sl > ssm) ? ssm * ssm * col_rcp(sl * sl) : 1.0;
+    const double cf = 0.25 * slim * q.diff1 * rdz2 * mI;
+    const double g2 = 2.0 * dzs * cf, gX = g2 * gxx, gS = g2 * gyS, gN = g2 * gyN;
+    const double s2 = tv1 * cf * rdza;
+    const double wx0 = x0 * gX, wx1 = x1 * gX, wx2 = x2 * gX, wx3 = x3 * gX;
+    const double wy0 = y0 * gS, wy1 = y1 * gN, wy2 = y2 * gS, wy3 = y3 * gN;
+    lc += (wx0 - wx1) + (wy0 - wy1) + s2;
+    nuc += (wx2 - wx3) + (wy2 - wy3) - s2;
+    o.lc = lc; o.nuc = nuc;
+    o.lW = -wx0; o.lE = wx1; o.lS = -wy0; o.lN = wy1;
+    o.nuW = -wx2; o.nuE = wx3; o.nuS = -wy2; o.nuN = wy3;
+  }
+  o.cZ = q.dt * g.rdz[kk];
+}
+
 // One (member, column).  All NT threads of a block call this with the same c2.
-template <int I, int J, int K, int L, int MS, int NT>
+// PV = false: all L tracers, new T, S, rho written unmixed (the convective adjustment follows in k_co_col).
+// PV = true : the passive tracers (l >= 2) only, convective mixing applied ON WRITE.  T, S, rho and the region map of the
+//   column (v.comask: bit k-1 = level k lies in a mixed region, bit 16+k-1 = it is the region's top) come from
+//   ts_pre_column.  While the march is inside a region the running thickness-weighted sum rides in Q (Q = sum + dz * the
+//   level's partial update), so no extra accumulator is needed; at the region's top the mean is stored to all of its
+//   levels.  A level outside any region has weight 1 and carry 0: its value is exactly the unmixed one.
+template <int I, int J, int K, int L, int MS, int NT, bool PV>
 CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st) {
   static_assert(NT == MS, "a block covers all members of one column");
+  static_assert(!PV || K <= 16, "region map is 16 + 16 bits");
   using R = ColRows<L>;
   constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
   constexpr long uC3 = 3L * MS, uK = (long)I * J * uC3, rK = (long)I * J * MS;
@@ -155,16 +251,8 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   const int ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
   const int k1e = CGC_K1(ip, j), k1w = CGC_K1(im, j), k1n = CGC_K1(i, j + 1), k1s = CGC_K1(i, j - 1);
 #undef CGC_K1
-
-  const double diff1 = v.p.diff1[m], diffv = v.p.diff2[m], rdiff1 = 1.0 / diff1, rdiffv = 1.0 / diffv;
-  const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
-  const double dt = g.dt, dphi = g.dphi, rdphi = g.rdphi;
-  const double rc = g.rc[j], rc2 = g.rc2[j], cvj = g.cv[j], cvjm = g.cv[j - 1], cv2j = g.cv2[j],
-               cv2jm = (j > 1) ? g.cv2[j - 1] : 0.0;
-  const double dsvN = g.dsv[(j < J - 1) ? j : J - 1], dsvS = (j > 1) ? g.dsv[j - 1] : 0.0;
-  const double gyN = (j < J) ? cvj * g.rdsv[j] : 0.0, gyS = (j > 1) ? cvjm * g.rdsv[j - 1] : 0.0, gxx = rc * rdphi;
-  const double cX = dt * rdphi, cY = dt * g.rds[j];
-  const double dEh = rc2 * diff1, dNh = cv2j * diff1, dSh = cv2jm * diff1;
+  const ColK q = col_consts<I, J>(v, g, m, j);
+  const double ec1 = q.ec1, ec2 = q.ec2, ec3 = q.ec3, ec4 = q.ec4;
 
   // element offsets of the neighbour columns relative to the centre column (periodic in i)
   const long dE = (i < I) ? sC : -(long)(I - 1) * sC, dW = (i > 1) ? -sC : (long)(I - 1) * sC;
@@ -223,13 +311,13 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   }
 
   // T,S of the five columns at the bottom level (direct loads, once per column)
-  double tC0, sC0, tE0, sE0, tW0, sW0, tN0, sN0, tS0, sS0;
+  TS5 a;
   {
     const double *qC = ts0 + (long)(k1c - 1) * sK + m;
     const double *qE = qC + ((k1c >= k1e) ? dE : 0), *qW = qC + ((k1c >= k1w) ? dW : 0);
     const double *qN = qC + ((k1c >= k1n) ? dN : 0), *qS = qC + ((k1c >= k1s) ? dS : 0);
-    tC0 = qC[0]; sC0 = qC[sL]; tE0 = qE[0]; sE0 = qE[sL]; tW0 = qW[0]; sW0 = qW[sL];
-    tN0 = qN[0]; sN0 = qN[sL]; tS0 = qS[0]; sS0 = qS[sL];
+    a.tC = qC[0]; a.sC = qC[sL]; a.tE = qE[0]; a.sE = qE[sL]; a.tW = qW[0]; a.sW = qW[sL];
+    a.tN = qN[0]; a.sN = qN[sL]; a.tS = qS[0]; a.sS = qS[sL];
   }
   double *wP = v.ts_new + ((long)(k1c - 2) * (I * J) + c2) * sC + m;   // level kk-1 of the new array
   double *rP = v.rho + ((long)(k1c - 2) * (I * J) + c2) * MS + m;
@@ -239,6 +327,10 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 #pragma unroll
   for (int l = 0; l < L; l++) { P[l] = 0.0; Q[l] = 0.0; }
   unsigned par = 0;
+  // PV: region map of this (member, column); thickness and depth (levels) of the region the march is inside
+  const unsigned cmask = PV ? v.comask[(long)c2 * MS + m] : 0u;
+  double dzt = 0.0;
+  int nreg = 0;
 
   for (int kk = k1c; kk <= K; kk++) {
     const bool top = (kk == K);
@@ -246,68 +338,32 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     const int cb = (kk - k1c) & 1;
     stage_wait(st, cb, ((unsigned)(kk - k1c) >> 1) & 1u);
     const double *const smc = sm + cb * R::rowsC * NT;
-    const double tC1 = smc[(R::rTS + 0) * NT], sC1 = smc[(R::rTS + 1) * NT], tE1 = smc[(R::rTS + 2) * NT], sE1 = smc[(R::rTS + 3) * NT];
-    const double tW1 = smc[(R::rTS + 4) * NT], sW1 = smc[(R::rTS + 5) * NT], tN1 = smc[(R::rTS + 6) * NT], sN1 = smc[(R::rTS + 7) * NT];
-    const double tS1 = smc[(R::rTS + 8) * NT], sS1 = smc[(R::rTS + 9) * NT];
+    TS5 b;
+    b.tC = smc[(R::rTS + 0) * NT]; b.sC = smc[(R::rTS + 1) * NT]; b.tE = smc[(R::rTS + 2) * NT]; b.sE = smc[(R::rTS + 3) * NT];
+    b.tW = smc[(R::rTS + 4) * NT]; b.sW = smc[(R::rTS + 5) * NT]; b.tN = smc[(R::rTS + 6) * NT]; b.sN = smc[(R::rTS + 7) * NT];
+    b.tS = smc[(R::rTS + 8) * NT]; b.sS = smc[(R::rTS + 9) * NT];
     const double vuE = smc[(R::rU + 0) * NT], vvN = smc[(R::rU + 1) * NT], vww = smc[(R::rU + 2) * NT], vuW = smc[(R::rU + 3) * NT],
                  vvS = smc[(R::rU + 4) * NT];
-
-    // ---- horizontal faces of level kk: flux = a * ts(neighbour) + b * ts(centre)   (goldstein.f90:2517-2547).
-    // Branch free (closed faces and the top level through 0/1 masks): the whole level is one basic block, so the
-    // scheduler can run the tracers' independent FMA chains under the long dependent chain of the slope terms.
-    const double mE = opE ? 1.0 : 0.0, mW = opW ? 1.0 : 0.0, mN = opN ? 1.0 : 0.0, mS = opS ? 1.0 : 0.0, mT = top ? 0.0 : 1.0;
-    double hE, hW, hN, hS, hC;
-    {
-      const double pE = vuE * dphi * rdiff1, pW = vuW * dphi * rdiff1, pN = vvN * dsvN * rdiff1, pS = vvS * dsvS * rdiff1;
-      const double uE_ = pE * col_rcp(2.0 + fabs(pE)), uW_ = pW * col_rcp(2.0 + fabs(pW));
-      const double uN_ = pN * col_rcp(2.0 + fabs(pN)), uS_ = pS * col_rcp(2.0 + fabs(pS));
-      const double gE = vuE * rc * 0.5, gW = vuW * rc * 0.5, gN = cvj * vvN * 0.5, gS = cvjm * vvS * 0.5;
-      const double cXE = cX * mE, cXW = cX * mW, cYN = cY * mN, cYS = cY * mS;
-      hE = (gE * (1.0 - uE_) - dEh) * cXE;
-      hW = -(gW * (1.0 + uW_) + dEh) * cXW;
-      hN = (gN * (1.0 - uN_) - dNh) * cYN;
-      hS = -(gS * (1.0 + uS_) + dSh) * cYS;
-      hC = ((gE * (1.0 + uE_) + dEh) * cXE - (gW * (1.0 - uW_) - dEh) * cXW) +
-           ((gN * (1.0 + uN_) + dNh) * cYN - (gS * (1.0 - uS_) - dSh) * cYS);
-    }
-    // ---- face kk+1/2: vertical advection/diffusion + isoneutral terms (goldstein.f90:2549-2621)
-    double lc, lE, lW, lN, lS;        // coefficients of the level-kk values
-    double nuc, nuE, nuW, nuN, nuS;   // coefficients of the level-kk+1 values
-    {
-      const double rdza = top ? 0.0 : g.rdza[kk];
-      const double pA = vww * g.dza[kk] * rdiffv, uA_ = pA * col_rcp(2.0 + fabs(pA)), gA = vww * 0.5 * mT, dA = rdza * diffv;
-      nuc = gA * (1.0 - uA_) - dA;
-      lc = gA * (1.0 + uA_) + dA;
-      const double tatw = 0.5 * (tC0 + tC1);
-      const double tec = -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3;
-      const double dzrho = (ec2 * (sC1 - sC0) - tec * (tC1 - tC0)) * rdza;
-      const bool iso = dzrho < -1.0e-12;                     // false at the top level (rdza = 0)
-      const double dzs = iso ? dzrho : -1.0, mI = iso ? 1.0 : 0.0;
-      // density slopes on the four stencils; a closed face has neighbour == centre, i.e. a zero difference
-      const double x0 = ec2 * ((sC0 - sW0) * gxx) - tec * ((tC0 - tW0) * gxx);
-      const double x1 = ec2 * ((sE0 - sC0) * gxx) - tec * ((tE0 - tC0) * gxx);
-      const double x2 = ec2 * ((sC1 - sW1) * gxx) - tec * ((tC1 - tW1) * gxx);
-      const double x3 = ec2 * ((sE1 - sC1) * gxx) - tec * ((tE1 - tC1) * gxx);
-      const double y0 = ec2 * ((sC0 - sS0) * gyS) - tec * ((tC0 - tS0) * gyS);
-      const double y1 = ec2 * ((sN0 - sC0) * gyN) - tec * ((tN0 - tC0) * gyN);
-      const double y2 = ec2 * ((sC1 - sS1) * gyS) - tec * ((tC1 - tS1) * gyS);
-      const double y3 = ec2 * ((sN1 - sC1) * gyN) - tec * ((tN1 - tC1) * gyN);
-      const double tv1 = (((x0 * x0 + y0 * y0) + (x1 * x1 + y1 * y1)) + (x2 * x2 + y2 * y2)) + (x3 * x3 + y3 * y3);
-      const double rdz = col_rcp(dzs), rdz2 = rdz * rdz;
-      const double sl = 0.25 * tv1 * rdz2, ssm = g.ssmax[kk];
-      const double slim = (sl > ssm) ? ssm * ssm * col_rcp(sl * sl) : 1.0;
-      const double cf = 0.25 * slim * diff1 * rdz2 * mI;
-      const double g2 = 2.0 * dzs * cf, gX = g2 * gxx, gS = g2 * gyS, gN = g2 * gyN;
-      const double s2 = tv1 * cf * rdza;
-      const double wx0 = x0 * gX, wx1 = x1 * gX, wx2 = x2 * gX, wx3 = x3 * gX;
-      const double wy0 = y0 * gS, wy1 = y1 * gN, wy2 = y2 * gS, wy3 = y3 * gN;
-      lc += (wx0 - wx1) + (wy0 - wy1) + s2;
-      nuc += (wx2 - wx3) + (wy2 - wy3) - s2;
-      lW = -wx0; lE = wx1; lS = -wy0; lN = wy1;
-      nuW = -wx2; nuE = wx3; nuS = -wy2; nuN = wy3;
-    }
-    const double cZ = dt * g.rdz[kk];
+    ColCoef cf;
+    col_coefs<K>(q, g, kk, opE, opW, opN, opS, a, b, vuE, vvN, vww, vuW, vvS, cf);
+    const double hE = cf.hE, hW = cf.hW, hN = cf.hN, hS = cf.hS, hC = cf.hC;
+    const double lc = cf.lc, lE = cf.lE, lW = cf.lW, lN = cf.lN, lS = cf.lS, cZ = cf.cZ;
     const bool stv = kk > k1c;
+
+    // PV: the level being finalised (f = kk-1) closes a region (store the mean to nst levels), continues one (nothing is
+    // stored, the sum is carried) or lies outside (nst = 1, scale = 1); the level being formed enters with weight wcur
+    double cZw = cZp, scale = 1.0, wcur = 1.0;
+    int nst = 1;
+    if (PV) {
+      if (stv && ((cmask >> (kk - 2)) & 1u)) {
+        const double dzf = g.dz[kk - 1];
+        dzt += dzf; nreg++;
+        cZw = cZp * dzf;
+        if ((cmask >> (kk + 14)) & 1u) { scale = 1.0 / dzt; nst = nreg; nreg = 0; dzt = 0.0; }
+        else nst = 0;
+      }
+      if ((cmask >> (kk - 1)) & 1u) wcur = g.dz[kk];
+    }
 
     // ---- tracers: one tracer-cell = 15 FMA + 5
     double tnew = 0.0, snew = 0.0;
@@ -315,18 +371,32 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   {                                                                                           \
     const double c = (cc), E = (EE), W = (WW), N = (NN), S = (SS);                            \
     const double fab = P[l] + (uc * c + uE * E + uW * W + uN * N + uS * S);                   \
+    double cr = 0.0;                                                                          \
     if (stv) {                                                                                \
-      const double tn = Q[l] - fab * cZp;                                                     \
-      wP[(l) * sL] = tn;                                                                      \
-      if ((l) == 0) tnew = tn;                                                                \
-      if ((l) == 1) snew = tn;                                                                \
+      if (!PV) {                                                                              \
+        const double tn = Q[l] - fab * cZp;                                                   \
+        wP[(l) * sL] = tn;                                                                    \
+        if ((l) == 0) tnew = tn;                                                              \
+        if ((l) == 1) snew = tn;                                                              \
+      } else {                                                                                \
+        const double rs = Q[l] - fab * cZw;                                                   \
+        if (nst > 0) {                                                                        \
+          const double val = rs * scale;                                                      \
+          double *w = wP + (l) * sL;                                                          \
+          w[0] = val;                                                                         \
+          for (int q_ = 1; q_ < nst; q_++) w[-(long)q_ * sK] = val;                           \
+        } else cr = rs;                                                                       \
+      }                                                                                       \
     }                                                                                         \
     const double Hh = hC * c + hE * E + hW * W + hN * N + hS * S;                             \
-    Q[l] = (c - Hh) + fab * cZ;                                                               \
+    if (!PV) Q[l] = (c - Hh) + fab * cZ;                                                      \
+    else Q[l] = wcur * ((c - Hh) + fab * cZ) + cr;                                            \
     P[l] = lc * c + lE * E + lW * W + lN * N + lS * S;                                        \
   }
-    CG_TRACER(0, tC0, tE0, tW0, tN0, tS0)
-    CG_TRACER(1, sC0, sE0, sW0, sN0, sS0)
+    if (!PV) {
+      CG_TRACER(0, a.tC, a.tE, a.tW, a.tN, a.tS)
+      CG_TRACER(1, a.sC, a.sE, a.sW, a.sN, a.sS)
+    }
     if (R::nA > 0) stage_wait(st, 2, par);
 #pragma unroll
     for (int l = 2; l < R::lB0; l++) {
@@ -350,17 +420,17 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     stage_sync();                                           // ... and with buffer B
     if (!top && stage_leader(st)) issueB(kk + 1);
     par ^= 1u;
-    if (stv) {
+    if (!PV && stv) {
       const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);   // :2638
       rP[0] = r;
     }
     // ---- shift one level up
-    tC0 = tC1; sC0 = sC1; tE0 = tE1; sE0 = sE1; tW0 = tW1; sW0 = sW1; tN0 = tN1; sN0 = sN1; tS0 = tS1; sS0 = sS1;
-    uc = nuc; uE = nuE; uW = nuW; uN = nuN; uS = nuS; cZp = cZ;
+    a = b;
+    uc = cf.nuc; uE = cf.nuE; uW = cf.nuW; uN = cf.nuN; uS = cf.nuS; cZp = cZ;
     wP += sK; rP += rK;
   }
   // ---- top level: the flux through the surface is the boundary condition ts(1:2,:,:,maxk+1)   (:2550-2552)
-  {
+  if (!PV) {
     double tnew = 0.0, snew = 0.0;
 #pragma unroll
     for (int l = 0; l < L; l++) {
@@ -372,8 +442,99 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     }
     const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
     rP[0] = r;
+  } else {
+    // passive tracers have no surface flux; level K is either outside any region or the top of one
+    double scale = 1.0;
+    int nst = 1;
+    if ((cmask >> (K - 1)) & 1u) { dzt += g.dz[K]; nreg++; scale = 1.0 / dzt; nst = nreg; }
+#pragma unroll
+    for (int l = 2; l < L; l++) {
+      const double val = Q[l] * scale;
+      double *w = wP + l * sL;
+      w[0] = val;
+      for (int q_ = 1; q_ < nst; q_++) w[-(long)q_ * sK] = val;
+    }
   }
+}
 
+// T, S pre-pass of the mix-on-write form of the tracer step: one thread = (member, wet column).  The thread marches up
+// the column with the same per-cell coefficients as tstep_column (col_coefs), applies them to T and S only, evaluates
+// rho (goldstein.f90:2638), runs the convective-adjustment decisions on its column while it is still thread-private
+// (co_decide_core), and writes the final T, S, rho of every wet level, SST/SSS, cost and the region map v.comask that the
+// passive pass (tstep_column<PV = true>) applies on write.
+template <int I, int J, int K, int L, int MS, bool ALL>
+CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsigned m, const int k1c, double *tt, double *ss,
+                          double *rl, unsigned &in, unsigned &topb, unsigned &botb, double *rdzt);
+
+template <int I, int J, int K, int L, int MS>
+CG_HD void ts_pre_column(const Dev &v, const GridC &g, const int c2, const unsigned m) {
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
+  constexpr long uC3 = 3L * MS, uK = (long)I * J * uC3;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+#define CGC_K1(ii, jj) ((int)v.k1[(ii) + (I + 2) * (jj)])
+  const int k1c = CGC_K1(i, j);
+  const int ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
+  const int k1e = CGC_K1(ip, j), k1w = CGC_K1(im, j), k1n = CGC_K1(i, j + 1), k1s = CGC_K1(i, j - 1);
+#undef CGC_K1
+  const ColK q = col_consts<I, J>(v, g, m, j);
+  const long dE = (i < I) ? sC : -(long)(I - 1) * sC, dW = (i > 1) ? -sC : (long)(I - 1) * sC;
+  constexpr long dN = (long)I * sC, dS = -(long)I * sC;
+  const long dUW = (i > 1) ? -uC3 : (long)(I - 1) * uC3, dUS = (j > 1) ? -(long)I * uC3 : 0;
+  const double *const ts0 = v.ts_cur + (long)c2 * sC + m;
+  const double *const u0 = v.u + (long)c2 * uC3 + m;
+  auto loadTS = [&](const int lev, TS5 &o) {
+    const double *qC = ts0 + (long)(lev - 1) * sK;
+    const double *qE = qC + ((lev >= k1e) ? dE : 0), *qW = qC + ((lev >= k1w) ? dW : 0);
+    const double *qN = qC + ((lev >= k1n) ? dN : 0), *qS = qC + ((lev >= k1s) ? dS : 0);
+    o.tC = qC[0]; o.sC = qC[sL]; o.tE = qE[0]; o.sE = qE[sL]; o.tW = qW[0]; o.sW = qW[sL];
+    o.tN = qN[0]; o.sN = qN[sL]; o.tS = qS[0]; o.sS = qS[sL];
+  };
+  struct Vel { double uE, vN, ww, uW, vS; };
+  auto loadU = [&](const int lev, Vel &o) {
+    const double *pu = u0 + (long)(lev - 1) * uK;
+    o.uE = pu[0]; o.vN = pu[sL]; o.ww = pu[2 * sL]; o.uW = pu[dUW]; o.vS = pu[dUS + sL];
+  };
+  double tt[K + 2], ss[K + 2], rl[K + 2];
+#pragma unroll
+  for (int k = 0; k < K + 2; k++) { tt[k] = 0.0; ss[k] = 0.0; rl[k] = 0.0; }
+  TS5 a, b;
+  Vel w;
+  loadTS(k1c, a);
+  loadTS((k1c < K) ? k1c + 1 : K, b);
+  loadU(k1c, w);
+  double uc = 0.0, uE = 0.0, uW = 0.0, uN = 0.0, uS = 0.0, cZp = 0.0, PT = 0.0, QT = 0.0, PS = 0.0, QS = 0.0;
+  for (int kk = k1c; kk <= K; kk++) {
+    // the rows of the next level are requested before this level's dependent chain starts
+    TS5 nb = b;
+    Vel nw = w;
+    if (kk < K) { loadTS((kk + 2 <= K) ? kk + 2 : K, nb); loadU(kk + 1, nw); }
+    ColCoef cf;
+    col_coefs<K>(q, g, kk, kk >= k1e, kk >= k1w, kk >= k1n, kk >= k1s, a, b, w.uE, w.vN, w.ww, w.uW, w.vS, cf);
+    const double fabT = PT + (uc * a.tC + uE * a.tE + uW * a.tW + uN * a.tN + uS * a.tS);
+    const double fabS = PS + (uc * a.sC + uE * a.sE + uW * a.sW + uN * a.sN + uS * a.sS);
+    if (kk > k1c) {
+      const double tn = QT - fabT * cZp, sn = QS - fabS * cZp;
+      tt[kk - 1] = tn; ss[kk - 1] = sn;
+      rl[kk - 1] = q.ec1 * tn + q.ec2 * sn + q.ec3 * (tn * tn) + q.ec4 * (tn * tn * tn);   // :2638
+    }
+    const double HT = cf.hC * a.tC + cf.hE * a.tE + cf.hW * a.tW + cf.hN * a.tN + cf.hS * a.tS;
+    const double HS = cf.hC * a.sC + cf.hE * a.sE + cf.hW * a.sW + cf.hN * a.sN + cf.hS * a.sS;
+    QT = (a.tC - HT) + fabT * cf.cZ;
+    QS = (a.sC - HS) + fabS * cf.cZ;
+    PT = cf.lc * a.tC + cf.lE * a.tE + cf.lW * a.tW + cf.lN * a.tN + cf.lS * a.tS;
+    PS = cf.lc * a.sC + cf.lE * a.sE + cf.lW * a.sW + cf.lN * a.sN + cf.lS * a.sS;
+    a = b; b = nb; w = nw;
+    uc = cf.nuc; uE = cf.nuE; uW = cf.nuW; uN = cf.nuN; uS = cf.nuS; cZp = cf.cZ;
+  }
+  {   // top level: surface boundary condition ts(1:2,:,:,maxk+1)   (:2550-2552)
+    const double tn = QT - v.tsflux[(long)c2 * MS + m] * cZp, sn = QS - v.tsflux[((long)(I * J) + c2) * MS + m] * cZp;
+    tt[K] = tn; ss[K] = sn;
+    rl[K] = q.ec1 * tn + q.ec2 * sn + q.ec3 * (tn * tn) + q.ec4 * (tn * tn * tn);
+  }
+  unsigned in, topb, botb;
+  double rdzt[K];
+  co_decide_core<I, J, K, L, MS, true>(v, g, c2, m, k1c, tt, ss, rl, in, topb, botb, rdzt);
+  v.comask[(long)c2 * MS + m] = in | (topb << 16);
 }
 
 // Convective adjustment (goldstein.f90:2657-2777, iconv == 0) + SST export (:428-431), one thread per (member, wet
@@ -385,23 +546,20 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 // Part 1: decisions, T/S/rho of the mixed regions, cost, SST.  Returns the region structure: bit k-1 of `in` = level k
 // belongs to a mixed region, `topb` / `botb` = it is the region's top / bottom, rdzt[k-1] = 1 / thickness of the region
 // (at its bottom level).  in == 0: nothing mixed.
+template <int I, int J, int K, int L, int MS, bool ALL>
+CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsigned m, const int k1c, double *tt, double *ss,
+                          double *rl, unsigned &in, unsigned &topb, unsigned &botb, double *rdzt);
+
 template <int I, int J, int K, int L, int MS>
 CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned m, unsigned &in, unsigned &topb, unsigned &botb,
                      double *rdzt) {
   constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC, rK = (long)I * J * MS;
-  in = 0; topb = 0; botb = 0;
   const int k1c = (int)v.k1[(c2 % I + 1) + (I + 2) * (c2 / I + 1)];
-  const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
-  double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);         // level-1 cell of this column
-  double *__restrict__ rho = v.rho + ((long)c2 * MS + m);
-  // The reference keeps a compacted index array k(0:maxk) of the levels that still exist as separate boxes and shifts
-  // it down after every merge; here the same set is a bit mask (bit l-1 = level l is a separate box), the neighbours of
-  // a level come from clz / ffs, and a merge clears bits -- the sequence of comparisons and merges is the reference's.
-  int head[K + 2];
-  double dzm[K + 2], tt[K + 2], ss[K + 2], rl[K + 2];
+  const double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);         // level-1 cell of this column
+  const double *__restrict__ rho = v.rho + ((long)c2 * MS + m);
+  double tt[K + 2], ss[K + 2], rl[K + 2];
 #pragma unroll
   for (int q = 1; q <= K; q++) {
-    head[q] = q; dzm[q] = g.dz[q];
     tt[q] = 0.0; ss[q] = 0.0; rl[q] = 0.0;
     if (q >= k1c) {
       tt[q] = ts[(long)(q - 1) * sK];
@@ -409,7 +567,6 @@ CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned 
       rl[q] = rho[(long)(q - 1) * rK];
     }
   }
-  rl[0] = 0.0;
 #ifdef __CUDA_ARCH__
   // the decisions below are a serial, memory-idle stretch: start pulling the column's passive tracers (written by the
   // flux kernel a moment ago, partly evicted since) towards L2 so that the averaging pass finds them there
@@ -420,6 +577,27 @@ CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned 
     }
   }
 #endif
+  co_decide_core<I, J, K, L, MS, false>(v, g, c2, m, k1c, tt, ss, rl, in, topb, botb, rdzt);
+}
+
+// The decisions proper, on the column's new T, S, rho held in tt, ss, rl[1..K] (thread-private).  ALL = false: T, S, rho
+// of the mixed levels are rewritten in place (they are in memory already); ALL = true: every wet level is written.
+template <int I, int J, int K, int L, int MS, bool ALL>
+CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsigned m, const int k1c, double *tt, double *ss,
+                          double *rl, unsigned &in, unsigned &topb, unsigned &botb, double *rdzt) {
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC, rK = (long)I * J * MS;
+  in = 0; topb = 0; botb = 0;
+  const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
+  double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);         // level-1 cell of this column
+  double *__restrict__ rho = v.rho + ((long)c2 * MS + m);
+  // The reference keeps a compacted index array k(0:maxk) of the levels that still exist as separate boxes and shifts
+  // it down after every merge; here the same set is a bit mask (bit l-1 = level l is a separate box), the neighbours of
+  // a level come from clz / ffs, and a merge clears bits -- the sequence of comparisons and merges is the reference's.
+  int head[K + 2];
+  double dzm[K + 2];
+#pragma unroll
+  for (int q = 1; q <= K; q++) { head[q] = q; dzm[q] = g.dz[q]; }
+  rl[0] = 0.0;
   unsigned act = (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)) & ~((1u << (k1c - 1)) - 1u);   // levels k1c..K
 #define CG_BELOW(x) ({ const unsigned mb_ = act & ((1u << ((x) - 1)) - 1u); mb_ ? 32 - CG_CLZ(mb_) : 0; })
 #define CG_ABOVE(x) ({ const unsigned ma_ = act >> (x); (x) + CG_FFS(ma_); })
@@ -461,7 +639,18 @@ CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned 
     v.sst[(long)c2 * MS + m] = tt[K];
     v.sst[((long)(I * J) + c2) * MS + m] = ss[K];
   }
-  if (!any) return;
+  if (!any) {
+    if (ALL) {
+#pragma unroll
+      for (int k = 1; k <= K; k++)
+        if (k >= k1c) {
+          ts[(long)(k - 1) * sK] = tt[k];
+          ts[(long)(k - 1) * sK + sL] = ss[k];
+          rho[(long)(k - 1) * rK] = rl[k];
+        }
+    }
+    return;
+  }
   // fill in (:2749-2764): head[n] = the box level n ended up in (the next separate level above it)
   {
     double cnt = 0.0;
@@ -499,6 +688,10 @@ CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned 
         ts[(long)(k - 1) * sK] = tt[hd];
         ts[(long)(k - 1) * sK + sL] = ss[hd];
         rho[(long)(k - 1) * rK] = rl[hd];
+      } else if (ALL && k >= k1c) {
+        ts[(long)(k - 1) * sK] = tt[k];
+        ts[(long)(k - 1) * sK + sL] = ss[k];
+        rho[(long)(k - 1) * rK] = rl[k];
       }
     }
   }

@@ -13,7 +13,7 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
                              const double *diff1, const double *diff2, const double *ec /* [4][MS] */,
                              const double *jm /* rc, rc2, cv, cv2, dsv, rdsv, rds: 7 x (J+2) */,
                              const double *km /* dz, dza, rdz, rdza, ssmax: 5 x (K+2) */, double dphi, double rdphi,
-                             double dt) {
+                             double dt, int mix) {
   constexpr int I = 36, J = 36, K = 16, L = 16;
   if (MS != 32) return 1;
   static GridC g;
@@ -40,10 +40,22 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
   // the whole "block" (32 members of one column) shares one staging area; bulk copies are emulated element-wise
   std::vector<double> sm((size_t)ColRows<L>::rows * 32);
   unsigned long long bar[4] = {0, 0, 0, 0};
+  if (mix) {   // T,S pre-pass + decisions, then the passive tracers mixed on write (k_ts_pre + k_tstep_col<PV>)
+    std::vector<unsigned> comask((size_t)I * J * MS, 0u);
+    v.comask = comask.data();
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) ts_pre_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m);
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) {
+        ColStage st{sm.data(), bar, m};
+        tstep_column<I, J, K, L, 32, 32, true>(v, g, cols[n], (unsigned)m, st);
+      }
+    return 0;
+  }
   for (int n = 0; n < ncol; n++)
     for (int m = 0; m < MS; m++) {
       ColStage st{sm.data(), bar, m};
-      tstep_column<I, J, K, L, 32, 32>(v, g, cols[n], (unsigned)m, st);
+      tstep_column<I, J, K, L, 32, 32, false>(v, g, cols[n], (unsigned)m, st);
     }
   for (int n = 0; n < ncol; n++)
     for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m);

@@ -39,9 +39,10 @@ def _after(o):
     return ts[1:K + 1, 1:J + 1, 1:I + 1, :].copy(), rho[1:, 1:J + 1, 1:I + 1].copy(), o.f("cost").reshape(J, I).copy()
 
 
+@pytest.mark.parametrize("mix", [1, 0])               # 1: T,S pre-pass + mix-on-write passive pass; 0: flux kernel + co
 @pytest.mark.parametrize("nsteps", [5 * 40, 5 * 150])   # not the first steps: a uniform start is neutrally stable and
 # the convection decisions there flip on the last bit (true of every non-strict variant)
-def test_col_body_matches_oracle(nsteps):
+def test_col_body_matches_oracle(nsteps, mix):
     lib = _lib()
     oras = [Oracle("worjh2", maxk=K, maxl=L, nyear=96), Oracle("worjh2", maxk=K, maxl=L, nyear=96, diff1=2600.0, diff2=1.3e-5)]
     for o in oras:
@@ -73,7 +74,7 @@ def test_col_body_matches_oracle(nsteps):
     dp = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib.col_host_step(MS, dp(k1), dp(cols), len(cols), dp(ts_cur), dp(ts_new), dp(tsflux), dp(sst), dp(rho), dp(u),
                            dp(cost), dp(diff1), dp(diff2), dp(ec), dp(jm), dp(km), C.c_double(o0.s("dphi")),
-                           C.c_double(o0.s("rdphi")), C.c_double(float(o0.f("dt")[K])))
+                           C.c_double(o0.s("rdphi")), C.c_double(float(o0.f("dt")[K])), mix)
     assert rc == 0
     wet = (k1i[1:J + 1, 1:I + 1][None, :, :] <= np.arange(1, K + 1)[:, None, None])
     nmixed = 0
