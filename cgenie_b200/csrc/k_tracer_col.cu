@@ -13,7 +13,7 @@ void upload_grid_tracer_col(const GridC &g, cudaStream_t s) {
 }
 
 // one block = the MS members of ONE wet column (row-major column order: neighbouring blocks share stencil rows in L2)
-template <int I, int J, int K, int L, int MS, int MINB, bool PV>
+template <int I, int J, int K, int L, int MS, int MINB, bool PV, bool AR = false>
 __global__ void __launch_bounds__(MS, MINB) k_tstep_col(const Dev v) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ColStage st;
@@ -21,7 +21,19 @@ __global__ void __launch_bounds__(MS, MINB) k_tstep_col(const Dev v) {
   st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows<L>::rows * MS * 8);
   st.tid = threadIdx.x;
   const int c2 = v.rowcols[blockIdx.x];
-  tstep_column<I, J, K, L, MS, MS, PV>(v, c_g, c2, threadIdx.x, st);
+  tstep_column<I, J, K, L, MS, MS, PV, AR>(v, c_g, c2, threadIdx.x, st);
+}
+
+// split form: two threads per (member, column), 2 * MS threads per block (see tstep_column_split)
+template <int I, int J, int K, int L, int MS, int MINB>
+__global__ void __launch_bounds__(2 * MS, MINB) k_tstep_split(const Dev v) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ColStage st;
+  st.sm = reinterpret_cast<double *>(smem_raw);
+  st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)SplitRows<L>::rows * MS * 8);
+  st.tid = threadIdx.x;
+  const int c2 = v.rowcols[blockIdx.x];
+  tstep_column_split<I, J, K, L, MS, MS, false>(v, c_g, c2, threadIdx.x, st);
 }
 
 // T, S pre-pass + convective-adjustment decisions of the mix-on-write form: one thread per (member, wet column)
@@ -45,12 +57,13 @@ __global__ void __launch_bounds__(128) k_co_col(const Dev v) {
 
 template <int I, int J, int K, int L, int MS>
 static int go(const Dev &v, cudaStream_t s, int cfg) {
-  constexpr size_t smem = (size_t)ColRows<L>::rows * MS * 8 + 32;
+  constexpr size_t smem = (size_t)ColRows<L>::rows * MS * 8 + 64;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tstep_col<I, J, K, L, MS, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
   // mix-on-write form (CG_COL_MIX=1, opt-in): T, S pre-pass with the convection decisions, then the passive tracers with
@@ -69,7 +82,22 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
     k_tstep_col<I, J, K, L, MS, 2, true><<<v.nwet, MS, smem, s>>>(v);
     return 2;
   }
+  // split form (CG_COL_SPLIT=1): two threads per member-column, <= 128 registers, 16 warps per SM
+  static int split = -1;
+  if (split < 0) { const char *e = getenv("CG_COL_SPLIT"); split = e ? atoi(e) : 0; }
+  if (split && MS == 128) {
+    constexpr size_t smem2 = (size_t)SplitRows<L>::rows * MS * 8 + 64;
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(k_tstep_split<I, J, K, L, MS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      cudaFuncSetAttribute(k_tstep_split<I, J, K, L, MS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      attr2 = true;
+    }
+    if (split == 2) k_tstep_split<I, J, K, L, MS, 1><<<v.nwet, 2 * MS, smem2, s>>>(v);
+    else k_tstep_split<I, J, K, L, MS, 2><<<v.nwet, 2 * MS, smem2, s>>>(v);
+  } else
   if (cfg == 1) k_tstep_col<I, J, K, L, MS, 1, false><<<v.nwet, MS, smem, s>>>(v);
+  else if (cfg == 2) k_tstep_col<I, J, K, L, MS, 2, false, true><<<v.nwet, MS, smem, s>>>(v);   // mbarrier buffer release
   else k_tstep_col<I, J, K, L, MS, 2, false><<<v.nwet, MS, smem, s>>>(v);
   static int copf = -1;
   if (copf < 0) { const char *e = getenv("CG_CO_PF"); copf = e ? atoi(e) : 0; }   // measured: the L2 prefetch costs more than it hides (profiles/README_r1.md)

@@ -66,11 +66,11 @@ struct ColStage {
   int tid;
 };
 
-CG_HD void stage_init(const ColStage &s) {
+CG_HD void stage_init(const ColStage &s, const unsigned nbar = 4) {
 #ifdef __CUDA_ARCH__
   if (s.tid == 0) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(s.bar);
-    for (unsigned q = 0; q < 4; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a + 8 * q), "r"(1) : "memory");
+    for (unsigned q = 0; q < nbar; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a + 8 * q), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -115,6 +115,47 @@ CG_HD void stage_wait(const ColStage &s, const int which, const unsigned parity)
 CG_HD void stage_sync() {
 #ifdef __CUDA_ARCH__
   __syncthreads();
+#endif
+}
+// Consumer release / producer acquire of a staging buffer without a block barrier: every warp arrives once on an "empty"
+// mbarrier (initialised with the number of warps) when it has read the buffer for the last time; only the thread that
+// issues the refill waits for the phase to complete, the other warps run on to their next data wait.
+CG_HD void stage_init_empty(const ColStage &s, const unsigned first, const unsigned n, const unsigned nwarps) {
+#ifdef __CUDA_ARCH__
+  if (s.tid == 0) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(s.bar);
+    for (unsigned q = first; q < first + n; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a + 8 * q), "r"(nwarps) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+#else
+  (void)s; (void)first; (void)n; (void)nwarps;
+#endif
+}
+CG_HD void stage_release(const ColStage &s, const int which) {
+#ifdef __CUDA_ARCH__
+  __syncwarp();
+  if ((s.tid & 31) == 0) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(s.bar) + 8u * which;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+  }
+#else
+  (void)s; (void)which;
+#endif
+}
+// barrier over one half of a split block (named barrier 1 + half, nthreads threads)
+CG_HD void stage_sync_half(const int half, const int nthreads) {
+#ifdef __CUDA_ARCH__
+  if (half == 0) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+  else asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory");
+#else
+  (void)half; (void)nthreads;
+#endif
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before the bulk copies it issues next
+CG_HD void stage_fence() {
+#ifdef __CUDA_ARCH__
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
 }
 CG_HD bool stage_leader(const ColStage &s) {
@@ -167,67 +208,77 @@ struct TS5 { double tC, sC, tE, sE, tW, sW, tN, sN, tS, sS; };
 // vertical face kk+1/2, and dt/dz of the level.
 struct ColCoef { double hE, hW, hN, hS, hC, lc, lE, lW, lN, lS, nuc, nuE, nuW, nuN, nuS, cZ; };
 
-// goldstein.f90:2517-2621 for one (member, cell): `a` = T,S at level kk, `b` = one level up, velocities of the five faces.
+// goldstein.f90:2517-2547 for one (member, cell): the horizontal faces of a level, flux = a * ts(neighbour) + b * ts(centre).
+// Branch free (closed faces through 0/1 masks): the whole level is one basic block, so the scheduler can run the tracers'
+// independent FMA chains under the long dependent chain of the slope terms.
+CG_HD void col_coefs_h(const ColK &q, const bool opE, const bool opW, const bool opN, const bool opS, const double vuE,
+                       const double vvN, const double vuW, const double vvS, double &hE, double &hW, double &hN, double &hS,
+                       double &hC) {
+  const double mE = opE ? 1.0 : 0.0, mW = opW ? 1.0 : 0.0, mN = opN ? 1.0 : 0.0, mS = opS ? 1.0 : 0.0;
+  const double pE = vuE * q.dphi * q.rdiff1, pW = vuW * q.dphi * q.rdiff1, pN = vvN * q.dsvN * q.rdiff1, pS = vvS * q.dsvS * q.rdiff1;
+  const double uE_ = pE * col_rcp(2.0 + fabs(pE)), uW_ = pW * col_rcp(2.0 + fabs(pW));
+  const double uN_ = pN * col_rcp(2.0 + fabs(pN)), uS_ = pS * col_rcp(2.0 + fabs(pS));
+  const double gE = vuE * q.rc * 0.5, gW = vuW * q.rc * 0.5, gN = q.cvj * vvN * 0.5, gS = q.cvjm * vvS * 0.5;
+  const double cXE = q.cX * mE, cXW = q.cX * mW, cYN = q.cY * mN, cYS = q.cY * mS;
+  hE = (gE * (1.0 - uE_) - q.dEh) * cXE;
+  hW = -(gW * (1.0 + uW_) + q.dEh) * cXW;
+  hN = (gN * (1.0 - uN_) - q.dNh) * cYN;
+  hS = -(gS * (1.0 + uS_) + q.dSh) * cYS;
+  hC = ((gE * (1.0 + uE_) + q.dEh) * cXE - (gW * (1.0 - uW_) - q.dEh) * cXW) +
+       ((gN * (1.0 + uN_) + q.dNh) * cYN - (gS * (1.0 - uS_) - q.dSh) * cYS);
+}
+// goldstein.f90:2549-2621: face kk+1/2, vertical advection / diffusion + isoneutral terms.  `a` = T,S at level kk, `b` = one
+// level up (a closed face carries the centre values, i.e. a zero difference); l* multiply the level-kk values, nu* the
+// level-kk+1 values.
+template <int K>
+CG_HD void col_coefs_v(const ColK &q, const GridC &g, const int kk, const TS5 &a, const TS5 &b, const double vww, double &lc_,
+                       double &lE, double &lW, double &lN, double &lS, double &nuc_, double &nuE, double &nuW, double &nuN,
+                       double &nuS) {
+  const bool top = (kk == K);
+  const double mT = top ? 0.0 : 1.0;
+  const double tC0 = a.tC, sC0 = a.sC, tE0 = a.tE, sE0 = a.sE, tW0 = a.tW, sW0 = a.sW, tN0 = a.tN, sN0 = a.sN, tS0 = a.tS, sS0 = a.sS;
+  const double tC1 = b.tC, sC1 = b.sC, tE1 = b.tE, sE1 = b.sE, tW1 = b.tW, sW1 = b.sW, tN1 = b.tN, sN1 = b.sN, tS1 = b.tS, sS1 = b.sS;
+  const double ec1 = q.ec1, ec2 = q.ec2, ec3 = q.ec3, ec4 = q.ec4, gxx = q.gxx, gyS = q.gyS, gyN = q.gyN;
+  const double rdza = top ? 0.0 : g.rdza[kk];
+  const double pA = vww * g.dza[kk] * q.rdiffv, uA_ = pA * col_rcp(2.0 + fabs(pA)), gA = vww * 0.5 * mT, dA = rdza * q.diffv;
+  double nuc = gA * (1.0 - uA_) - dA;
+  double lc = gA * (1.0 + uA_) + dA;
+  const double tatw = 0.5 * (tC0 + tC1);
+  const double tec = -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3;
+  const double dzrho = (ec2 * (sC1 - sC0) - tec * (tC1 - tC0)) * rdza;
+  const bool iso = dzrho < -1.0e-12;                     // false at the top level (rdza = 0)
+  const double dzs = iso ? dzrho : -1.0, mI = iso ? 1.0 : 0.0;
+  // density slopes on the four stencils
+  const double x0 = ec2 * ((sC0 - sW0) * gxx) - tec * ((tC0 - tW0) * gxx);
+  const double x1 = ec2 * ((sE0 - sC0) * gxx) - tec * ((tE0 - tC0) * gxx);
+  const double x2 = ec2 * ((sC1 - sW1) * gxx) - tec * ((tC1 - tW1) * gxx);
+  const double x3 = ec2 * ((sE1 - sC1) * gxx) - tec * ((tE1 - tC1) * gxx);
+  const double y0 = ec2 * ((sC0 - sS0) * gyS) - tec * ((tC0 - tS0) * gyS);
+  const double y1 = ec2 * ((sN0 - sC0) * gyN) - tec * ((tN0 - tC0) * gyN);
+  const double y2 = ec2 * ((sC1 - sS1) * gyS) - tec * ((tC1 - tS1) * gyS);
+  const double y3 = ec2 * ((sN1 - sC1) * gyN) - tec * ((tN1 - tC1) * gyN);
+  const double tv1 = (((x0 * x0 + y0 * y0) + (x1 * x1 + y1 * y1)) + (x2 * x2 + y2 * y2)) + (x3 * x3 + y3 * y3);
+  const double rdz = col_rcp(dzs), rdz2 = rdz * rdz;
+  const double sl = 0.25 * tv1 * rdz2, ssm = g.ssmax[kk];
+  const double slim = (sl > ssm) ? ssm * ssm * col_rcp(sl * sl) : 1.0;
+  const double cf = 0.25 * slim * q.diff1 * rdz2 * mI;
+  const double g2 = 2.0 * dzs * cf, gX = g2 * gxx, gS = g2 * gyS, gN = g2 * gyN;
+  const double s2 = tv1 * cf * rdza;
+  const double wx0 = x0 * gX, wx1 = x1 * gX, wx2 = x2 * gX, wx3 = x3 * gX;
+  const double wy0 = y0 * gS, wy1 = y1 * gN, wy2 = y2 * gS, wy3 = y3 * gN;
+  lc += (wx0 - wx1) + (wy0 - wy1) + s2;
+  nuc += (wx2 - wx3) + (wy2 - wy3) - s2;
+  lc_ = lc; nuc_ = nuc;
+  lW = -wx0; lE = wx1; lS = -wy0; lN = wy1;
+  nuW = -wx2; nuE = wx3; nuS = -wy2; nuN = wy3;
+}
+// all 15 coefficients + dt/dz of one (member, cell)
 template <int K>
 CG_HD void col_coefs(const ColK &q, const GridC &g, const int kk, const bool opE, const bool opW, const bool opN, const bool opS,
                      const TS5 &a, const TS5 &b, const double vuE, const double vvN, const double vww, const double vuW,
                      const double vvS, ColCoef &o) {
-  const bool top = (kk == K);
-  // ---- horizontal faces of level kk: flux = a * ts(neighbour) + b * ts(centre)   (goldstein.f90:2517-2547).
-  // Branch free (closed faces and the top level through 0/1 masks): the whole level is one basic block, so the
-  // scheduler can run the tracers' independent FMA chains under the long dependent chain of the slope terms.
-  const double mE = opE ? 1.0 : 0.0, mW = opW ? 1.0 : 0.0, mN = opN ? 1.0 : 0.0, mS = opS ? 1.0 : 0.0, mT = top ? 0.0 : 1.0;
-  {
-    const double pE = vuE * q.dphi * q.rdiff1, pW = vuW * q.dphi * q.rdiff1, pN = vvN * q.dsvN * q.rdiff1, pS = vvS * q.dsvS * q.rdiff1;
-    const double uE_ = pE * col_rcp(2.0 + fabs(pE)), uW_ = pW * col_rcp(2.0 + fabs(pW));
-    const double uN_ = pN * col_rcp(2.0 + fabs(pN)), uS_ = pS * col_rcp(2.0 + fabs(pS));
-    const double gE = vuE * q.rc * 0.5, gW = vuW * q.rc * 0.5, gN = q.cvj * vvN * 0.5, gS = q.cvjm * vvS * 0.5;
-    const double cXE = q.cX * mE, cXW = q.cX * mW, cYN = q.cY * mN, cYS = q.cY * mS;
-    o.hE = (gE * (1.0 - uE_) - q.dEh) * cXE;
-    o.hW = -(gW * (1.0 + uW_) + q.dEh) * cXW;
-    o.hN = (gN * (1.0 - uN_) - q.dNh) * cYN;
-    o.hS = -(gS * (1.0 + uS_) + q.dSh) * cYS;
-    o.hC = ((gE * (1.0 + uE_) + q.dEh) * cXE - (gW * (1.0 - uW_) - q.dEh) * cXW) +
-           ((gN * (1.0 + uN_) + q.dNh) * cYN - (gS * (1.0 - uS_) - q.dSh) * cYS);
-  }
-  // ---- face kk+1/2: vertical advection/diffusion + isoneutral terms (goldstein.f90:2549-2621)
-  {
-    const double tC0 = a.tC, sC0 = a.sC, tE0 = a.tE, sE0 = a.sE, tW0 = a.tW, sW0 = a.sW, tN0 = a.tN, sN0 = a.sN, tS0 = a.tS, sS0 = a.sS;
-    const double tC1 = b.tC, sC1 = b.sC, tE1 = b.tE, sE1 = b.sE, tW1 = b.tW, sW1 = b.sW, tN1 = b.tN, sN1 = b.sN, tS1 = b.tS, sS1 = b.sS;
-    const double ec1 = q.ec1, ec2 = q.ec2, ec3 = q.ec3, ec4 = q.ec4, gxx = q.gxx, gyS = q.gyS, gyN = q.gyN;
-    const double rdza = top ? 0.0 : g.rdza[kk];
-    const double pA = vww * g.dza[kk] * q.rdiffv, uA_ = pA * col_rcp(2.0 + fabs(pA)), gA = vww * 0.5 * mT, dA = rdza * q.diffv;
-    double nuc = gA * (1.0 - uA_) - dA;
-    double lc = gA * (1.0 + uA_) + dA;
-    const double tatw = 0.5 * (tC0 + tC1);
-    const double tec = -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3;
-    const double dzrho = (ec2 * (sC1 - sC0) - tec * (tC1 - tC0)) * rdza;
-    const bool iso = dzrho < -1.0e-12;                     // false at the top level (rdza = 0)
-    const double dzs = iso ? dzrho : -1.0, mI = iso ? 1.0 : 0.0;
-    // density slopes on the four stencils; a closed face has neighbour == centre, i.e. a zero difference
-    const double x0 = ec2 * ((sC0 - sW0) * gxx) - tec * ((tC0 - tW0) * gxx);
-    const double x1 = ec2 * ((sE0 - sC0) * gxx) - tec * ((tE0 - tC0) * gxx);
-    const double x2 = ec2 * ((sC1 - sW1) * gxx) - tec * ((tC1 - tW1) * gxx);
-    const double x3 = ec2 * ((sE1 - sC1) * gxx) - tec * ((tE1 - tC1) * gxx);
-    const double y0 = ec2 * ((sC0 - sS0) * gyS) - tec * ((tC0 - tS0) * gyS);
-    const double y1 = ec2 * ((sN0 - sC0) * gyN) - tec * ((tN0 - tC0) * gyN);
-    const double y2 = ec2 * ((sC1 - sS1) * gyS) - tec * ((tC1 - tS1) * gyS);
-    const double y3 = ec2 * ((sN1 - sC1) * gyN) - tec * ((tN1 - tC1) * gyN);
-    const double tv1 = (((x0 * x0 + y0 * y0) + (x1 * x1 + y1 * y1)) + (x2 * x2 + y2 * y2)) + (x3 * x3 + y3 * y3);
-    const double rdz = col_rcp(dzs), rdz2 = rdz * rdz;
-    const double sl = 0.25 * tv1 * rdz2, ssm = g.ssmax[kk];
-    const double slim = (sl > ssm) ? ssm * ssm * col_rcp(sl * sl) : 1.0;
-    const double cf = 0.25 * slim * q.diff1 * rdz2 * mI;
-    const double g2 = 2.0 * dzs * cf, gX = g2 * gxx, gS = g2 * gyS, gN = g2 * gyN;
-    const double s2 = tv1 * cf * rdza;
-    const double wx0 = x0 * gX, wx1 = x1 * gX, wx2 = x2 * gX, wx3 = x3 * gX;
-    const double wy0 = y0 * gS, wy1 = y1 * gN, wy2 = y2 * gS, wy3 = y3 * gN;
-    lc += (wx0 - wx1) + (wy0 - wy1) + s2;
-    nuc += (wx2 - wx3) + (wy2 - wy3) - s2;
-    o.lc = lc; o.nuc = nuc;
-    o.lW = -wx0; o.lE = wx1; o.lS = -wy0; o.lN = wy1;
-    o.nuW = -wx2; o.nuE = wx3; o.nuS = -wy2; o.nuN = wy3;
-  }
+  col_coefs_h(q, opE, opW, opN, opS, vuE, vvN, vuW, vvS, o.hE, o.hW, o.hN, o.hS, o.hC);
+  col_coefs_v<K>(q, g, kk, a, b, vww, o.lc, o.lE, o.lW, o.lN, o.lS, o.nuc, o.nuE, o.nuW, o.nuN, o.nuS);
   o.cZ = q.dt * g.rdz[kk];
 }
 
@@ -238,7 +289,7 @@ CG_HD void col_coefs(const ColK &q, const GridC &g, const int kk, const bool opE
 //   ts_pre_column.  While the march is inside a region the running thickness-weighted sum rides in Q (Q = sum + dz * the
 //   level's partial update), so no extra accumulator is needed; at the region's top the mean is stored to all of its
 //   levels.  A level outside any region has weight 1 and carry 0: its value is exactly the unmixed one.
-template <int I, int J, int K, int L, int MS, int NT, bool PV>
+template <int I, int J, int K, int L, int MS, int NT, bool PV, bool ASYNC_REL = false>
 CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st) {
   static_assert(NT == MS, "a block covers all members of one column");
   static_assert(!PV || K <= 16, "region map is 16 + 16 bits");
@@ -303,6 +354,7 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   };
 
   stage_init(st);
+  if (ASYNC_REL) stage_init_empty(st, 4, 2, NT / 32);
   if (stage_leader(st)) {
     issueC(k1c);
     if (k1c < K) issueC(k1c + 1);
@@ -404,10 +456,20 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
       CG_TRACER(l, sm[(r + 0 * R::nA) * NT], sm[(r + 1 * R::nA) * NT], sm[(r + 2 * R::nA) * NT], sm[(r + 3 * R::nA) * NT],
                 sm[(r + 4 * R::nA) * NT])
     }
-    stage_sync();                                           // every thread is done with buffers C[cb] and A
-    if (stage_leader(st)) {
-      if (kk + 2 <= K) issueC(kk + 2);
-      if (!top) issueA(kk + 1);
+    // every warp announces that it is done with buffers C[cb] and A; the leader alone waits for all of them
+    if (ASYNC_REL) {
+      stage_release(st, 4);
+      if (stage_leader(st)) {
+        stage_wait(st, 4, par);
+        if (kk + 2 <= K) issueC(kk + 2);
+        if (!top) issueA(kk + 1);
+      }
+    } else {
+      stage_sync();
+      if (stage_leader(st)) {
+        if (kk + 2 <= K) issueC(kk + 2);
+        if (!top) issueA(kk + 1);
+      }
     }
     stage_wait(st, 3, par);
 #pragma unroll
@@ -417,8 +479,16 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
                 sm[(r + 4 * R::nB) * NT])
     }
 #undef CG_TRACER
-    stage_sync();                                           // ... and with buffer B
-    if (!top && stage_leader(st)) issueB(kk + 1);
+    if (ASYNC_REL) {                                        // ... and with buffer B
+      stage_release(st, 5);
+      if (stage_leader(st)) {
+        stage_wait(st, 5, par);
+        if (!top) issueB(kk + 1);
+      }
+    } else {
+      stage_sync();
+      if (!top && stage_leader(st)) issueB(kk + 1);
+    }
     par ^= 1u;
     if (!PV && stv) {
       const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);   // :2638
@@ -453,6 +523,211 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
       double *w = wP + l * sL;
       w[0] = val;
       for (int q_ = 1; q_ < nst; q_++) w[-(long)q_ * sK] = val;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split form of the column kernel: TWO threads per (member, column), 2 * NT threads per block.  Half 0 computes the
+// horizontal coefficients of the cell and carries tracers 0 .. L/2-1 (T and S among them), half 1 computes the vertical /
+// isoneutral coefficients and carries tracers L/2 .. L-1.  The halves exchange their coefficients through the rows of
+// the T,S / velocity staging buffer they have just consumed (each half overwrites only the rows it alone reads, in its own
+// member column), so per thread the state is half the tracers' (P, Q) plus half of the coefficient work: <= 128
+// registers, 16 warps per SM instead of 8, and the dependent chain of a level is split in two.  Every tracer (T, S too)
+// comes from shared memory; each half refills its own two sub-units (named barrier over the half), the block barrier in
+// the middle of a level publishes the coefficients, the one at its end frees the buffers.
+// BOTH = true (host test harness): one caller plays both halves of a member in turn.
+template <int L>
+struct SplitRows {
+  static constexpr int LH = L / 2, LQ = L / 4;       // tracers per half / per staging sub-unit
+  static constexpr int rowsC = 16;                   // T,S one level up of 5 cells (10) | uE vN ww uW vS (5) | spare (1)
+  static constexpr int rTS = 0, rU = 10, rX = 15;
+  static constexpr int rowsX = 5 * LQ;               // sub-unit (half hh, u): rows rUnit + (2 hh + u) rowsX + cell LQ + s
+  static constexpr int rUnit = 2 * rowsC;
+  static constexpr int rows = rUnit + 4 * rowsX;
+  static constexpr int nbar = 6;                     // mbarriers: C0, C1, then 2 + 2 hh + u
+};
+
+template <int I, int J, int K, int L, int MS, int NT, bool BOTH>
+CG_HD void tstep_column_split(const Dev &v, const GridC &g, const int c2, const int tid, const ColStage &st) {
+  static_assert(NT == MS, "a block covers all members of one column");
+  static_assert(L % 4 == 0 && L >= 8, "tracers are split in four staging sub-units");
+  using R = SplitRows<L>;
+  constexpr int LH = R::LH, LQ = R::LQ, NH = BOTH ? 2 : 1;
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
+  constexpr long uC3 = 3L * MS, uK = (long)I * J * uC3, rK = (long)I * J * MS;
+  const int h = BOTH ? 0 : tid / NT;
+  const unsigned m = BOTH ? (unsigned)tid : (unsigned)(tid - h * NT);
+  const int hlo = BOTH ? 0 : h, hhi = BOTH ? 2 : h + 1;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+#define CGC_K1(ii, jj) ((int)v.k1[(ii) + (I + 2) * (jj)])
+  const int k1c = CGC_K1(i, j);
+  const int ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
+  const int k1e = CGC_K1(ip, j), k1w = CGC_K1(im, j), k1n = CGC_K1(i, j + 1), k1s = CGC_K1(i, j - 1);
+#undef CGC_K1
+  const ColK q = col_consts<I, J>(v, g, m, j);
+  const long dE = (i < I) ? sC : -(long)(I - 1) * sC, dW = (i > 1) ? -sC : (long)(I - 1) * sC;
+  constexpr long dN = (long)I * sC, dS = -(long)I * sC;
+  const long dUW = (i > 1) ? -uC3 : (long)(I - 1) * uC3, dUS = (j > 1) ? -(long)I * uC3 : 0;
+  const double *const ts0 = v.ts_cur + (long)c2 * sC;
+  const double *const u0 = v.u + (long)c2 * uC3;
+  double *const sm = st.sm + m;
+#ifdef __CUDA_ARCH__
+  const bool lead0 = (tid == 0), lead1 = (tid == NT);
+#else
+  const bool lead0 = true, lead1 = true;   // host emulation: every caller copies its own elements
+#endif
+
+  auto issueC = [&](const int lev) {
+    const int b = (lev - k1c) & 1;
+    stage_expect(st, b, (unsigned)(15 * NT * 8));
+    const int lu = (lev < K) ? lev + 1 : K;
+    const double *c1 = ts0 + (long)(lu - 1) * sK;
+    const int r0 = b * R::rowsC;
+    stage_copy<NT>(st, b, r0 + R::rTS + 0, c1, 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 2, c1 + ((lu >= k1e) ? dE : 0), 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 4, c1 + ((lu >= k1w) ? dW : 0), 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 6, c1 + ((lu >= k1n) ? dN : 0), 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 8, c1 + ((lu >= k1s) ? dS : 0), 2);
+    const double *pu = u0 + (long)(lev - 1) * uK;
+    stage_copy<NT>(st, b, r0 + R::rU + 0, pu, 3);
+    stage_copy<NT>(st, b, r0 + R::rU + 3, pu + dUW, 1);
+    stage_copy<NT>(st, b, r0 + R::rU + 4, pu + dUS + sL, 1);
+  };
+  auto issueX = [&](const int hh, const int u, const int lev) {
+    const int bar = 2 + 2 * hh + u;
+    stage_expect(st, bar, (unsigned)(R::rowsX * NT * 8));
+    const double *c0 = ts0 + (long)(lev - 1) * sK + (long)(hh * LH + u * LQ) * sL;
+    const int r0 = R::rUnit + (2 * hh + u) * R::rowsX;
+    stage_copy<NT>(st, bar, r0 + 0 * LQ, c0, LQ);
+    stage_copy<NT>(st, bar, r0 + 1 * LQ, c0 + ((lev >= k1e) ? dE : 0), LQ);
+    stage_copy<NT>(st, bar, r0 + 2 * LQ, c0 + ((lev >= k1w) ? dW : 0), LQ);
+    stage_copy<NT>(st, bar, r0 + 3 * LQ, c0 + ((lev >= k1n) ? dN : 0), LQ);
+    stage_copy<NT>(st, bar, r0 + 4 * LQ, c0 + ((lev >= k1s) ? dS : 0), LQ);
+  };
+
+  stage_init(st, R::nbar);
+  if (lead0) {
+    issueC(k1c);
+    if (k1c < K) issueC(k1c + 1);
+    issueX(0, 0, k1c);
+    issueX(0, 1, k1c);
+  }
+  if (lead1) {
+    issueX(1, 0, k1c);
+    issueX(1, 1, k1c);
+  }
+
+  double *wP = v.ts_new + ((long)(k1c - 2) * (I * J) + c2) * sC + m;   // level kk-1 of the new array
+  double *rP = v.rho + ((long)(k1c - 2) * (I * J) + c2) * MS + m;
+  double uc = 0.0, uE = 0.0, uW = 0.0, uN = 0.0, uS = 0.0, cZp = 0.0;
+  double P[NH][LH], Q[NH][LH];
+#pragma unroll
+  for (int a_ = 0; a_ < NH; a_++)
+#pragma unroll
+    for (int s_ = 0; s_ < LH; s_++) { P[a_][s_] = 0.0; Q[a_][s_] = 0.0; }
+  unsigned par = 0;
+
+  for (int kk = k1c; kk <= K; kk++) {
+    const bool top = (kk == K), stv = kk > k1c;
+    const int cb = (kk - k1c) & 1;
+    stage_wait(st, cb, ((unsigned)(kk - k1c) >> 1) & 1u);
+    double *const smc = sm + cb * R::rowsC * NT;
+    // ---- coefficients: each half its share, written over the rows it has just read
+    for (int hh = hlo; hh < hhi; hh++) {
+      if (hh == 0) {
+        const double vuE = smc[(R::rU + 0) * NT], vvN = smc[(R::rU + 1) * NT], vuW = smc[(R::rU + 3) * NT], vvS = smc[(R::rU + 4) * NT];
+        double hE, hW, hN, hS, hC;
+        col_coefs_h(q, kk >= k1e, kk >= k1w, kk >= k1n, kk >= k1s, vuE, vvN, vuW, vvS, hE, hW, hN, hS, hC);
+        smc[(R::rU + 0) * NT] = hE; smc[(R::rU + 1) * NT] = hN; smc[(R::rU + 3) * NT] = hW; smc[(R::rU + 4) * NT] = hS;
+        smc[R::rX * NT] = hC;
+      } else {
+        stage_wait(st, 2, par);   // T,S of level kk: tracers 0, 1 of sub-unit (0, 0), shared read-only with half 0
+        const double *const sa = sm + R::rUnit * NT;
+        TS5 a, b;
+        a.tC = sa[(0 * LQ + 0) * NT]; a.sC = sa[(0 * LQ + 1) * NT]; a.tE = sa[(1 * LQ + 0) * NT]; a.sE = sa[(1 * LQ + 1) * NT];
+        a.tW = sa[(2 * LQ + 0) * NT]; a.sW = sa[(2 * LQ + 1) * NT]; a.tN = sa[(3 * LQ + 0) * NT]; a.sN = sa[(3 * LQ + 1) * NT];
+        a.tS = sa[(4 * LQ + 0) * NT]; a.sS = sa[(4 * LQ + 1) * NT];
+        b.tC = smc[(R::rTS + 0) * NT]; b.sC = smc[(R::rTS + 1) * NT]; b.tE = smc[(R::rTS + 2) * NT]; b.sE = smc[(R::rTS + 3) * NT];
+        b.tW = smc[(R::rTS + 4) * NT]; b.sW = smc[(R::rTS + 5) * NT]; b.tN = smc[(R::rTS + 6) * NT]; b.sN = smc[(R::rTS + 7) * NT];
+        b.tS = smc[(R::rTS + 8) * NT]; b.sS = smc[(R::rTS + 9) * NT];
+        const double vww = smc[(R::rU + 2) * NT];
+        double lc, lE, lW, lN, lS, nuc, nuE, nuW, nuN, nuS;
+        col_coefs_v<K>(q, g, kk, a, b, vww, lc, lE, lW, lN, lS, nuc, nuE, nuW, nuN, nuS);
+        smc[(R::rTS + 0) * NT] = lc; smc[(R::rTS + 1) * NT] = lE; smc[(R::rTS + 2) * NT] = lW; smc[(R::rTS + 3) * NT] = lN;
+        smc[(R::rTS + 4) * NT] = lS; smc[(R::rTS + 5) * NT] = nuc; smc[(R::rTS + 6) * NT] = nuE; smc[(R::rTS + 7) * NT] = nuW;
+        smc[(R::rTS + 8) * NT] = nuN; smc[(R::rTS + 9) * NT] = nuS;
+      }
+    }
+    stage_sync();                                           // the coefficients of this level are published
+    const double lc = smc[(R::rTS + 0) * NT], lE = smc[(R::rTS + 1) * NT], lW = smc[(R::rTS + 2) * NT], lN = smc[(R::rTS + 3) * NT],
+                 lS = smc[(R::rTS + 4) * NT];
+    const double hE = smc[(R::rU + 0) * NT], hN = smc[(R::rU + 1) * NT], hW = smc[(R::rU + 3) * NT], hS = smc[(R::rU + 4) * NT],
+                 hC = smc[R::rX * NT];
+    const double cZ = q.dt * g.rdz[kk];
+    // ---- tracers: one tracer-cell = 15 FMA + 5
+    for (int hh = hlo; hh < hhi; hh++) {
+      const int hs = BOTH ? hh : 0;
+      double tnew = 0.0, snew = 0.0;
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        stage_wait(st, 2 + 2 * hh + u, par);
+        const double *const su = sm + (R::rUnit + (2 * hh + u) * R::rowsX) * NT;
+        double *const w = wP + (long)(hh * LH + u * LQ) * sL;
+#pragma unroll
+        for (int s_ = 0; s_ < LQ; s_++) {
+          const int sl = u * LQ + s_;
+          const double c = su[(0 * LQ + s_) * NT], E = su[(1 * LQ + s_) * NT], W = su[(2 * LQ + s_) * NT], N = su[(3 * LQ + s_) * NT],
+                       S = su[(4 * LQ + s_) * NT];
+          const double fab = P[hs][sl] + (uc * c + uE * E + uW * W + uN * N + uS * S);
+          if (stv) {
+            const double tn = Q[hs][sl] - fab * cZp;
+            w[s_ * sL] = tn;
+            if (sl == 0) tnew = tn;
+            if (sl == 1) snew = tn;
+          }
+          const double Hh = hC * c + hE * E + hW * W + hN * N + hS * S;
+          Q[hs][sl] = (c - Hh) + fab * cZ;
+          P[hs][sl] = lc * c + lE * E + lW * W + lN * N + lS * S;
+        }
+        if (u == 0) {
+          stage_sync_half(hh, NT);                          // this half is done with its first sub-unit
+          if ((hh == 0 ? lead0 : lead1) && !top) { stage_fence(); issueX(hh, 0, kk + 1); }
+        }
+      }
+      if (hh == 0 && stv) {
+        const double r = q.ec1 * tnew + q.ec2 * snew + q.ec3 * (tnew * tnew) + q.ec4 * (tnew * tnew * tnew);   // :2638
+        rP[0] = r;
+      }
+    }
+    const double nuc = smc[(R::rTS + 5) * NT], nuE = smc[(R::rTS + 6) * NT], nuW = smc[(R::rTS + 7) * NT], nuN = smc[(R::rTS + 8) * NT],
+                 nuS = smc[(R::rTS + 9) * NT];
+    stage_sync();                                           // every thread is done with buffer C[cb] and the second sub-units
+    if (lead0) {
+      stage_fence();
+      if (kk + 2 <= K) issueC(kk + 2);
+      if (!top) issueX(0, 1, kk + 1);
+    }
+    if (lead1 && !top) { stage_fence(); issueX(1, 1, kk + 1); }
+    par ^= 1u;
+    uc = nuc; uE = nuE; uW = nuW; uN = nuN; uS = nuS; cZp = cZ;
+    wP += sK; rP += rK;
+  }
+  // ---- top level: the flux through the surface is the boundary condition ts(1:2,:,:,maxk+1)   (:2550-2552)
+  for (int hh = hlo; hh < hhi; hh++) {
+    const int hs = BOTH ? hh : 0;
+    double tnew = 0.0, snew = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < LH; sl++) {
+      double tn = Q[hs][sl];
+      if (hh == 0 && sl < 2) tn -= v.tsflux[((long)sl * (I * J) + c2) * MS + m] * cZp;
+      wP[(long)(hh * LH + sl) * sL] = tn;
+      if (sl == 0) tnew = tn;
+      if (sl == 1) snew = tn;
+    }
+    if (hh == 0) {
+      const double r = q.ec1 * tnew + q.ec2 * snew + q.ec3 * (tnew * tnew) + q.ec4 * (tnew * tnew * tnew);
+      rP[0] = r;
     }
   }
 }

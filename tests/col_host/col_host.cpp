@@ -38,8 +38,18 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
   v.p.diff1 = diff1; v.p.diff2 = diff2;
   v.p.ec1 = ec; v.p.ec2 = ec + MS; v.p.ec3 = ec + 2 * MS; v.p.ec4 = ec + 3 * MS;
   // the whole "block" (32 members of one column) shares one staging area; bulk copies are emulated element-wise
-  std::vector<double> sm((size_t)ColRows<L>::rows * 32);
-  unsigned long long bar[4] = {0, 0, 0, 0};
+  std::vector<double> sm((size_t)(ColRows<L>::rows > SplitRows<L>::rows ? ColRows<L>::rows : SplitRows<L>::rows) * 32);
+  unsigned long long bar[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (mix == 2) {   // split form (two threads per member-column; here one caller plays both halves), then co
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) {
+        ColStage st{sm.data(), bar, m};
+        tstep_column_split<I, J, K, L, 32, 32, true>(v, g, cols[n], m, st);
+      }
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m);
+    return 0;
+  }
   if (mix) {   // T,S pre-pass + decisions, then the passive tracers mixed on write (k_ts_pre + k_tstep_col<PV>)
     std::vector<unsigned> comask((size_t)I * J * MS, 0u);
     v.comask = comask.data();
