@@ -43,6 +43,8 @@ int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
 int launch_bg_step(const Dev &, const BgDev &, int init_only, int fuse, cudaStream_t);
 int launch_tc_sums_first(const Dev &, cudaStream_t);
+int launch_bg_surf(const Dev &, const BgDev &, cudaStream_t);
+int launch_bg_sweep(const Dev &, const BgDev &, cudaStream_t);
 int launch_tc_apply_only(const Dev &, cudaStream_t);
 bool bg_layout_ok(const BgDev &, int L);
 int launch_bg_climate(const Dev &, const BgDev &, cudaStream_t);
@@ -141,6 +143,13 @@ struct cg_handle {
   long long launches = 0;
   long long koverall = 0;
   int istep_ocn = 0, istep_atm = 0, istep_sic = 0;
+  bool bg_split = false, bg_surf_issued = false;   // pipelined BIOGEM block, split form (see bg_issue_surf)
+  // per-module entry points: the surface part of the NEXT step_biogem is issued speculatively at the end of cg_atchem_step
+  // (it has no side effect outside bgd.surf); cg_biogem_step uses it if it is called with the predicted clock and nothing
+  // touched the state in between, and drops it otherwise
+  bool spec_valid = false;
+  long long spec_clock = 0, bg_last_clock = -1;
+  int bg_stage = 0;                               // 1 step, 2 tracercoupling, 3 climate seen in the canonical order
   int variant = 0;  // 0 strict, 1 fast (cooperative flux kernel + separate convection), 2 fused column kernel (falls back to 1)
   bool use_graphs = true;
   cudaGraphExec_t graph[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -609,6 +618,7 @@ static int build_device(cg_handle *h) {
     TRY(dalloc(h, &b.bio_part, ijk * LS * MS));
     TRY(dalloc(h, &b.settle_k1, ij * LS * MS));
     TRY(dalloc(h, &b.carbH, ij * MS));
+    TRY(dalloc(h, &b.surf, (size_t)kBgSurfSlots * ij * MS));
     TRY(dalloc(h, &b.seaice, ij * MS));
     TRY(dalloc(h, &b.seaice_stage, ij * MS));
     TRY(dalloc(h, &b.sfxsumatm, ij * LA * MS));
@@ -955,6 +965,7 @@ extern "C" int cg_sync_from_host(cg_handle *h, const char *name, int member, con
 static int sync_from_host_lane(cg_handle *h, const char *name, int member, const double *src, int64_t n) {
   if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_from_host: bad argument");
   IO0(join_side(h));
+  h->spec_valid = false;
   h->mom_ready = false;   // a momentum step computed ahead of time is stale once the host has written state
   const bool both = strcmp(name, "ts") == 0 || strcmp(name, "ts1") == 0;
   FieldDesc *f = find_field(h, both ? "ts" : name);
@@ -988,6 +999,7 @@ extern "C" int cg_sync_all_from_host(cg_handle *h, const char *name, const doubl
   if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_all_from_host: bad argument");
   IO0(join_side(h));
   h->mom_ready = false;
+  h->spec_valid = false;
   FieldDesc *f = find_field(h, name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
   if (n != f->count() * h->MS) return fail(CG_ERR_ARG, "cg_sync_all_from_host: size must be field_size*member_stride");
@@ -1325,7 +1337,14 @@ extern "C" int cg_biogem_step(cg_handle *h, double dts, int64_t genie_clock_ms) 
   const double t = h->bg.t_runtime - (double)genie_clock_ms / (1000.0 * kBgYrS);
   if (!h->bg_go) return CG_OK;   // par_misc_t_go (biogem.f90:1851-1853)
   BgAsyncScope as(h, true);
-  { ProfScope ps(h, "biogem"); ps.done(launch_bg_step(h->dv, h->bgd, 0, 0, h->stream)); }
+  {
+    ProfScope ps(h, "biogem");
+    if (as.on && h->spec_valid && h->spec_clock == (long long)genie_clock_ms) ps.done(launch_bg_sweep(h->dv, h->bgd, h->stream));
+    else ps.done(launch_bg_step(h->dv, h->bgd, 0, 0, h->stream));
+  }
+  h->spec_valid = false;
+  h->bg_last_clock = (long long)genie_clock_ms;
+  h->bg_stage = 1;
   if (t < kBgNullSmall) h->bg_go = false;
   return check_async(h);
 }
@@ -1339,6 +1358,7 @@ extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_
   if (go_ts) IO(cg_sync_from_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
   if (h->bg.on && !h->bg_go) return CG_OK;
   BgAsyncScope as(h, !go_ts && !go_ts1);
+  h->bg_stage = (h->bg_stage == 1 && !go_ts && !go_ts1) ? 2 : 0;
   { ProfScope ps(h, "biogem"); ps.done(launch_tracercoupling(h->dv, h->stream)); }
   IO(check_async(h));
   if (go_ts) IO(cg_sync_to_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
@@ -1356,6 +1376,7 @@ extern "C" int cg_biogem_climate(cg_handle *h) {
     int n = 0;
     if (!h->bg_staged) n += launch_bg_stage_seaice(h->dv, h->bgd, h->stream);   // on the caller's stream: at call time
     BgAsyncScope as(h, true);
+    h->bg_stage = (h->bg_stage == 2) ? 3 : 0;
     ProfScope ps(h, "biogem");
     ps.done(n + launch_bg_climate(h->dv, h->bgd, h->stream));
   } else {
@@ -1392,6 +1413,18 @@ extern "C" int cg_atchem_step(cg_handle *h, double dts) {
   if (dts != h->bgd.dts_atchem) return fail(CG_ERR_ARG, "cg_atchem_step: dts differs from conv_kocn_katchem*kocn_loop*genie_timestep");
   BgAsyncScope as(h, true, true);
   { ProfScope ps(h, "biogem"); ps.done(launch_bg_atchem(h->dv, h->bgd, h->atm_totV, h->stream)); }
+  // the block came in the canonical order (step, coupling, climate, ATCHEM) on the asynchronous stream: issue the surface
+  // part of the next step behind it, for the clock one BIOGEM period later
+  const Params &p = h->base;
+  static const bool nospec = getenv("CG_BG_SPLIT") && atoi(getenv("CG_BG_SPLIT")) == 0;
+  if (as.on && h->bg_stage == 3 && h->bg_go && !h->bg_fuse && !nospec && p.conv_kocn_kbiogem == p.conv_kocn_katchem) {
+    const long long next = h->bg_last_clock + (long long)p.conv_kocn_kbiogem * p.kocn_loop * nint_ll(1000.0 * p.genie_timestep);
+    bg_forcing(&h->bg, next, &h->bgd);
+    h->launches += launch_bg_surf(h->dv, h->bgd, h->stream);
+    h->spec_valid = true;
+    h->spec_clock = next;
+  }
+  h->bg_stage = 0;
   return check_async(h);
 }
 // the BIOGEM / ATCHEM block of one koverall iteration (genie.f90:352-447)
@@ -1520,6 +1553,19 @@ static int bg_issue_step(cg_handle *h, long long clock) {
   if (t < kBgNullSmall) h->bg_go = false;
   return CG_OK;
 }
+// Split form of the pipelined block: only the SURFACE part of step_biogem (carbonate chemistry, gas exchange, export
+// production: transcendental-bound, no HBM traffic to speak of) is issued one block ahead, where it runs next to the
+// latency-bound momentum kernels; the water-column sweep stays at its nominal place.
+static int bg_issue_surf(cg_handle *h, long long clock) {
+  IO(cg_biogem_forcing(h, clock));
+  const double t = h->bg.t_runtime - (double)clock / (1000.0 * kBgYrS);
+  h->bg_surf_issued = false;
+  if (!h->bg_go) return CG_OK;   // par_misc_t_go (biogem.f90:1851-1853)
+  h->launches += launch_bg_surf(h->dv, h->bgd, h->stream);
+  h->bg_surf_issued = true;
+  if (t < kBgNullSmall) h->bg_go = false;
+  return CG_OK;
+}
 static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remaining) {
   const Params &p = h->base;
   const long long period = (long long)p.conv_kocn_kbiogem * p.kocn_loop;
@@ -1536,7 +1582,12 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
   do {
     if (!h->bg_ahead) {   // first block of this call: the step kernel at its nominal place
       if (cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
-      if ((rc = bg_issue_step(h, k * tick))) break;
+      if ((rc = h->bg_split ? bg_issue_surf(h, k * tick) : bg_issue_step(h, k * tick))) break;
+    }
+    if (h->bg_split && h->bg_surf_issued) {   // sediment return + water-column sweep, after this cycle's tracer step
+      if (cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
+      h->launches += launch_bg_sweep(h->dv, h->bgd, h->stream4);
+      h->bg_surf_issued = false;
     }
     h->bg_ahead = false;
     if (h->bg_go) {       // biogem_tracercoupling: sums on stream5 (they need ts of this cycle, not the step's anomaly)
@@ -1549,8 +1600,8 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
     if (cudaEventRecord(h->evBG, h->stream4) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "event record"); break; }
     h->bg_pending = true;
     if ((rc = cg_atchem_step(h, h->bgd.dts_atchem))) break;
-    if (remaining >= period) {   // the step kernel of the next block, one block ahead
-      if ((rc = bg_issue_step(h, (k + period) * tick))) break;
+    if (remaining >= period) {   // the step kernel (split form: its surface part) of the next block, one block ahead
+      if ((rc = h->bg_split ? bg_issue_surf(h, (k + period) * tick) : bg_issue_step(h, (k + period) * tick))) break;
       h->bg_ahead = true;
     }
     if (cudaEventRecord(h->evBGtail, h->stream4) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "event record"); break; }
@@ -1572,6 +1623,7 @@ static int bg_join(cg_handle *h) {   // order the main stream after an outstandi
 extern "C" int cg_run(cg_handle *h, int64_t n) {
   READY(h);
   IO0(join_side(h));
+  h->spec_valid = false;
   h->mom_ready = false;   // cg_run computes the momentum step inside its own schedule
   const Params &p = h->base;
   const bool regular = p.katm_loop == 1 && p.ksic_loop == p.kocn_loop && p.kocn_loop > 1;
@@ -1603,8 +1655,11 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
         h->koverall += p.kocn_loop;
         n -= p.kocn_loop;
         if (h->bg_overlap && !getenv("CG_BG_SERIAL")) {
-          // opt-in (CG_BG_PIPE=1): measured 4 % slower on B200 -- the step kernel then shares the SMs with the tracer step
-          const bool pipe = !h->bg_fuse && p.conv_kocn_kbiogem == p.conv_kocn_katchem && getenv("CG_BG_PIPE");
+          // CG_BG_PIPE=1 (whole step kernel ahead): no gain on B200 -- the 255-register kernel then shares the SMs with the tracer step
+          // default: pipelined block with only the surface part of the step issued ahead (CG_BG_SPLIT=0: off;
+          // 99.5 -> 81.4 ms per model year at 128 members, bit-identical)
+          if (!h->bg_ahead) { const char *e = getenv("CG_BG_SPLIT"); h->bg_split = e ? atoi(e) != 0 : true; }
+          const bool pipe = !h->bg_fuse && p.conv_kocn_kbiogem == p.conv_kocn_katchem && (getenv("CG_BG_PIPE") || h->bg_split);
           if (pipe || h->bg_ahead) IO(do_biogem_block_pipelined(h, h->koverall, n));
           else IO(do_biogem_block_async(h, h->koverall));
         } else {
@@ -1638,6 +1693,7 @@ extern "C" int cg_set_koverall(cg_handle *h, int64_t koverall) {
   READY(h);
   IO0(join_side(h));
   h->mom_ready = false;
+  h->spec_valid = false;
   const Params &p = h->base;
   if (koverall < 0 || koverall % p.kocn_loop != 0) return fail(CG_ERR_ARG, "cg_set_koverall: koverall must be a non-negative multiple of kocn_loop");
   h->koverall = koverall;

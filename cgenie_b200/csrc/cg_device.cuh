@@ -118,6 +118,10 @@ __host__ __device__ inline size_t cell2(const int I, int i, int j) { return (siz
 // conv_iselected_io/is/ia maps (gem_cmn.f90:366-381): l = 1..L ocean, ls = 1..LS particulate, la = 1..LA atmosphere.
 namespace cg {
 constexpr int kBgMaxL = 16, kBgMaxLS = 9, kBgMaxLA = 8, kBgMaxK = 16, kBgMaxRel = 3;
+// surface-cell results handed from k_bg_step PART 1 to PART 2: gas fluxes into the ocean, export, DOM production, uptake;
+// then the deferred side effects ([H+] seed, focnatm and sfxatm1 of each gas) and the error flag (last slot)
+constexpr int kBgSurfH = (kBgMaxLA - 2) + kBgMaxLS + 4 + 7;
+constexpr int kBgSurfSlots = kBgSurfH + 1 + 2 * (kBgMaxLA - 2) + 1;
 struct BgDev {
   int LS, LA;
   // tracer relationships: conv_ls_lo_i / conv_ls_lo (sed -> ocean, io ascending), DOM <-> POM, atm -> ocean
@@ -156,5 +160,6 @@ struct BgDev {
   const double *atm_A, *atm_V;            // [j][i]
   double *sfcocn1, *sfxsed1, *focnatm;    // interface / diagnostics: [l|ls|la][j][i][m]
   int *err;                               // [m] carbonate chemistry failure flag (error_stop)
+  double *surf;                           // [kBgSurfSlots][wet column][m] surface-cell results (k_bg_step PART 1 -> PART 2)
 };
 }  // namespace cg

@@ -503,7 +503,12 @@ __device__ __forceinline__ void rem_add(Rem7 &r, const double f, const double *p
 // as its anomaly is known -- same expressions, same order, bit-identical -- instead of writing vdocn and re-reading ocn,
 // ts, vdocn and bio_part in a separate pass.  The global sums of step (1) do not depend on step_biogem's output (the
 // salinity anomaly is +0.0), so the caller takes them first (k_tc_partial phases 2 and 1).
-template <int MINB>
+// PART = 0: the whole step.  PART = 1: the surface cell only (carbonate chemistry, gas exchange, restoring, export
+// production) -- it reads nothing but BIOGEM's own state of the previous block, so cg_run issues it one block ahead, next to
+// the latency-bound momentum kernels of the two ocean cycles in between; its results cross to PART = 2 (sediment return +
+// water-column sweep, at the nominal time) through b.surf (kBgSurfSlots doubles per member-column).  Same operations in
+// the same order: bit-identical to PART = 0.
+template <int MINB, int PART>
 __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev b, const int init_only, const int mode) {
   const bool fuse = (mode & 1) != 0, pf = (mode & 2) == 0;
   using namespace bgk;
@@ -558,30 +563,37 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
   // conv_ls_lo coefficients that are not 1
   const double cO2POC = b.conv_ls_lo[POC][1], cO2POP = b.conv_ls_lo[POP][1], cALKPOP = b.conv_ls_lo[POP][2],
                cALKCa = b.conv_ls_lo[CACO3][1];
+#define SC_(slot) b.surf[((size_t)(slot) * v.nwet + n) * MS + m]
   // ---- closed-system sediment return (:887-940) from the settling flux of the previous step
   Rem7 fsed;
   rem_zero(fsed);
-  {
+  if (PART != 1) {
     const double f = redfield_factor(b, OCN_(O2, k1));
     double st[LS + 1];
 #pragma unroll
     for (int ls = 1; ls <= LS; ls++) st[ls] = SET1_(ls);
     rem_add(fsed, f, st, f * cO2POC, f * cO2POP, f * cALKPOP, f * cALKCa);
   }
+  const double A = b.A[c2d], rA = b.rA[c2d];
+  double focn_surf[LA + 1];   // -conv_atm_ocn*focnatm of each gas, applied to its ocean tracer at the surface (:1612-1616)
+  double psurf[LS + 1], dom_add[LS + 1];
+  Rem7 uptake;
+  if (PART != 2) {
   // ---- surface cell: carbonate chemistry, solubility, piston velocity (:1026-1104)
   carbconst(b.Dmid_surf, Tsf, Ssf, OCN_(CA, K), OCN_(MG, K), cc);
   cb.H = b.carbH[c2d * MS + m];
   cb.RF0 = 0.0;
   const double DICs = OCN_(DIC, K), PO4s = OCN_(PO4, K);
-  if (!solve_carb(DICs, OCN_(ALK, K), OCN_(CA, K), PO4s, Ssf, cc, cb, true)) { b.err[m] = 1; return; }
-  b.carbH[c2d * MS + m] = cb.H;
+  if (!solve_carb(DICs, OCN_(ALK, K), OCN_(CA, K), PO4s, Ssf, cc, cb, true)) {
+    if (PART == 1) SC_(kBgSurfSlots - 1) = 1.0; else b.err[m] = 1;
+    return;
+  }
+  if (PART == 1) SC_(kBgSurfH) = cb.H; else b.carbH[c2d * MS + m] = cb.H;
   double r13_CO2, r13_HCO3, r14_CO2, r14_HCO3;
   carb_riso(Tsf, DICs, OCN_(DIC13, K), cb, 1.0, kStd13C, r13_CO2, r13_HCO3);
   carb_riso(Tsf, DICs, OCN_(DIC14, K), cb, 2.0, kStd14C, r14_CO2, r14_HCO3);
   const double rho = calc_rho(Tsf, Ssf);   // phys_ocn(ipo_rho) as left by biogem_climate (:2171)
   const double seaice = b.seaice[c2d * MS + m];
-  const double A = b.A[c2d], rA = b.rA[c2d];
-  double focn_surf[LA + 1];   // -conv_atm_ocn*focnatm of each gas, applied to its ocean tracer at the surface (:1612-1616)
   {
     double fatm[LA + 1], focnatm[LA + 1], f_oa[LA + 1], f_ao[LA + 1];
     double TC = Tsf - kZeroC, TC2, TC3;
@@ -659,15 +671,18 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
       fatm[la] = fatm[la] + focnatm[la];
       focn_surf[la] = 0.0 - 1.0 * focnatm[la];
       const size_t qa = ((size_t)(la - 1) * I * J + c2d) * MS + m;
-      b.focnatm[qa] = focnatm[la];
       // interface (:1731-1734) and cpl_flux_ocnatm (atchem.f90:306-320): sfxsumatm += dts*sfxatm1
       const double sfx = rA * (1.0 / kYrS) * fatm[la];
-      b.sfxsumatm[qa] = b.sfxsumatm[qa] + b.dts * sfx;
+      if (PART == 1) {   // no side effect outside b.surf: a part issued ahead can be dropped (PART 2 commits)
+        SC_(kBgSurfH + 1 + (la - 3)) = focnatm[la];
+        SC_(kBgSurfH + 1 + (LA - 2) + (la - 3)) = sfx;
+      } else {
+        b.focnatm[qa] = focnatm[la];
+        b.sfxsumatm[qa] = b.sfxsumatm[qa] + b.dts * sfx;
+      }
     }
   }
   // ---- biological uptake at the surface (k_mld = K because mld = 0), sub_calc_bio_uptake 1N1T_PO4MM
-  double psurf[LS + 1], dom_add[LS + 1];
-  Rem7 uptake;
   {
     const double kPO4 = PO4s / (PO4s + b.c0_PO4);
     const double ficefree = (1.0 - seaice);
@@ -714,6 +729,40 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
     const double kP = PO4s / (PO4s + b.POC_c0frac2);   // initial particulate fraction partitioning (:1354-1378)
     psurf[POCF2] = (1.0 - kP) * b.POC_dfrac2 + b.POC_frac2;
     psurf[CACO3F2] = b.CaCO3_frac2;
+  }
+  }   // PART != 2
+  if (PART == 1) {   // hand the surface cell's results to the sweep kernel
+#pragma unroll
+    for (int la = 3; la <= LA; la++) SC_(la - 3) = focn_surf[la];
+#pragma unroll
+    for (int ls = 1; ls <= LS; ls++) SC_(LA - 2 + ls - 1) = psurf[ls];
+    SC_(LA - 2 + LS + 0) = dom_add[POC]; SC_(LA - 2 + LS + 1) = dom_add[POC13]; SC_(LA - 2 + LS + 2) = dom_add[POC14];
+    SC_(LA - 2 + LS + 3) = dom_add[POP];
+    SC_(LA - 2 + LS + 4) = uptake.dic; SC_(LA - 2 + LS + 5) = uptake.d13; SC_(LA - 2 + LS + 6) = uptake.d14;
+    SC_(LA - 2 + LS + 7) = uptake.po4; SC_(LA - 2 + LS + 8) = uptake.o2; SC_(LA - 2 + LS + 9) = uptake.alk;
+    SC_(LA - 2 + LS + 10) = uptake.ca;
+    SC_(kBgSurfSlots - 1) = 0.0;
+    return;
+  }
+  if (PART == 2) {
+    if (SC_(kBgSurfSlots - 1) != 0.0) { b.err[m] = 1; return; }   // the carbonate solve of this column failed (error_stop)
+    b.carbH[c2d * MS + m] = SC_(kBgSurfH);
+#pragma unroll
+    for (int la = 3; la <= LA; la++) {
+      const size_t qa = ((size_t)(la - 1) * I * J + c2d) * MS + m;
+      b.focnatm[qa] = SC_(kBgSurfH + 1 + (la - 3));
+      const double sfx = SC_(kBgSurfH + 1 + (LA - 2) + (la - 3));
+      b.sfxsumatm[qa] = b.sfxsumatm[qa] + b.dts * sfx;
+    }
+#pragma unroll
+    for (int la = 1; la <= LA; la++) focn_surf[la] = (la >= 3) ? SC_(la - 3) : 0.0;
+#pragma unroll
+    for (int ls = 1; ls <= LS; ls++) { psurf[ls] = SC_(LA - 2 + ls - 1); dom_add[ls] = 0.0; }
+    dom_add[POC] = SC_(LA - 2 + LS + 0); dom_add[POC13] = SC_(LA - 2 + LS + 1); dom_add[POC14] = SC_(LA - 2 + LS + 2);
+    dom_add[POP] = SC_(LA - 2 + LS + 3);
+    uptake.dic = SC_(LA - 2 + LS + 4); uptake.d13 = SC_(LA - 2 + LS + 5); uptake.d14 = SC_(LA - 2 + LS + 6);
+    uptake.po4 = SC_(LA - 2 + LS + 7); uptake.o2 = SC_(LA - 2 + LS + 8); uptake.alk = SC_(LA - 2 + LS + 9);
+    uptake.ca = SC_(LA - 2 + LS + 10);
   }
   // ---- water column, one downward sweep (K -> k1).  sub_box_remin_part (:2412-2875) follows each source layer's
   // particles down to the deepest layer they reach in dt; here all packets in flight are advanced level by level, kept in
@@ -922,6 +971,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
 #undef M_
 #undef RM_
 #undef SET1_
+#undef SC_
 }
 
 // biogem_climate (:2132-2239): snapshot the sea-ice fraction, reset the convection counter
@@ -997,9 +1047,29 @@ int launch_bg_step(const Dev &v, const BgDev &b, int init_only, int fuse, cudaSt
   if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
   fuse |= nopf;
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
-  if (minb == 4) k_bg_step<4><<<g, bl, 0, s>>>(v, b, init_only, fuse);
-  else if (minb == 3) k_bg_step<3><<<g, bl, 0, s>>>(v, b, init_only, fuse);
-  else k_bg_step<2><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  if (minb == 4) k_bg_step<4, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  else if (minb == 3) k_bg_step<3, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  else k_bg_step<2, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  return 1;
+}
+// the two parts of the step (see k_bg_step): surface cell, then sediment return + water-column sweep
+int launch_bg_surf(const Dev &v, const BgDev &b, cudaStream_t s) {
+  static int minb = -1;   // registers per thread 255 / 168 / 128 for 2 / 3 / 4 (CG_BG_SURF_MINB; tuning knob)
+  if (minb < 0) { const char *e = getenv("CG_BG_SURF_MINB"); minb = e ? atoi(e) : 4; }
+  const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
+  if (minb == 4) k_bg_step<4, 1><<<g, bl, 0, s>>>(v, b, 0, 0);
+  else if (minb == 2) k_bg_step<2, 1><<<g, bl, 0, s>>>(v, b, 0, 0);
+  else k_bg_step<3, 1><<<g, bl, 0, s>>>(v, b, 0, 0);
+  return 1;
+}
+int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s) {
+  static int minb = -1;
+  if (minb < 0) { const char *e = getenv("CG_BG_SWEEP_MINB"); minb = e ? atoi(e) : 2; }
+  static int nopf = -1;
+  if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
+  const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
+  if (minb == 3) k_bg_step<3, 2><<<g, bl, 0, s>>>(v, b, 0, nopf);
+  else k_bg_step<2, 2><<<g, bl, 0, s>>>(v, b, 0, nopf);
   return 1;
 }
 // step (1) of biogem_tracercoupling taken BEFORE step_biogem (fused coupling, see k_bg_step)
