@@ -1068,8 +1068,19 @@ int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s) {
   static int nopf = -1;
   if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
-  if (minb == 3) k_bg_step<3, 2><<<g, bl, 0, s>>>(v, b, 0, nopf);
-  else k_bg_step<2, 2><<<g, bl, 0, s>>>(v, b, 0, nopf);
+  // CG_BG_SWEEP_SMEM=<KB>: unused dynamic shared memory that caps the kernel's residency (116 -> one block per SM), so that
+  // a sweep issued ahead leaves registers for the kernels it runs next to
+  static int pad = -1;
+  if (pad < 0) {
+    const char *e = getenv("CG_BG_SWEEP_SMEM");
+    pad = e ? atoi(e) * 1024 : 0;
+    if (pad > 0) {
+      cudaFuncSetAttribute(k_bg_step<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+      cudaFuncSetAttribute(k_bg_step<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    }
+  }
+  if (minb == 3) k_bg_step<3, 2><<<g, bl, pad, s>>>(v, b, 0, nopf);
+  else k_bg_step<2, 2><<<g, bl, pad, s>>>(v, b, 0, nopf);
   return 1;
 }
 // step (1) of biogem_tracercoupling taken BEFORE step_biogem (fused coupling, see k_bg_step)
