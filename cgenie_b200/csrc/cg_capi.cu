@@ -35,7 +35,7 @@ int launch_embm(const Dev &, int nsteps, cudaStream_t);
 int launch_seaice(const Dev &, cudaStream_t);
 int launch_gold_pre(const Dev &, cudaStream_t);
 int launch_sst(const Dev &, cudaStream_t);
-int launch_momentum(const Dev &, int fast, const double *bf, const double *bb, const double *rd, cudaStream_t);
+int launch_momentum(const Dev &, int fast, const double *bf, const double *bb, const double *rd, const double *bk, cudaStream_t);
 int launch_velc1(const Dev &, cudaStream_t);
 int launch_velc2(const Dev &, cudaStream_t);
 void launch_global_means(const Dev &, double *out, cudaStream_t);
@@ -138,6 +138,7 @@ struct cg_handle {
   size_t stage_n = 0;
   double *d_meantemp = nullptr, *d_means = nullptr;
   double *d_bf = nullptr, *d_bb = nullptr, *d_rd = nullptr;  // pivot-major barotropic factors (fast solve)
+  double *d_bk = nullptr;                                    // block slabs of the blocked solve (k_baro_blk)
   int *d_flags = nullptr;
   bool need_mean = false;
   long long launches = 0;
@@ -781,6 +782,46 @@ static int build_device(cg_handle *h) {
       TRY(dupload(h, &h->d_bb, BB));
       TRY(dupload(h, &h->d_rd, RD));
     }
+    if (bw <= 64) {
+      // Blocked form of the two banded substitutions (k_baro_blk): the rows are taken in blocks of 32, in sweep order
+      // (forward: e' = e; backward: e' = npad-1-e, so that both are lower triangular).  Per block the slab holds, lane =
+      // row within the block: bw rows of off-block coefficients T(e', e'-d), d = 1..bw (zero where e'-d lies inside the
+      // block or outside the vector), then the 32 x 32 inverse of the block's own triangle, column by column.  The inverse
+      // is formed in extended precision; padding rows are identity rows.
+      const int nb = (nm + 31) / 32, npad = nb * 32, T = bw + 32;
+      std::vector<double> BK((size_t)h->nbaro * 2 * nb * T * 32, 0.0);
+      for (int grp = 0; grp < h->nbaro; grp++) {
+        const double *Rg = &R[(size_t)grp * nm * bw], *Gg = &G[(size_t)grp * nm * gw];
+        for (int sw = 0; sw < 2; sw++) {
+          auto offd = [&](const int ep, const int d) -> double {   // T(e', e'-d), d >= 1
+            if (sw == 0) return (ep < nm && ep - d >= 0 && d <= bw) ? Rg[(size_t)ep * bw + (d - 1)] : 0.0;
+            const int e = npad - 1 - ep;
+            return (e < nm && e + d < nm && d <= bw) ? Gg[(size_t)e * gw + (I + 1 + d)] : 0.0;
+          };
+          auto diag = [&](const int ep) -> double {
+            if (sw == 0) return 1.0;
+            const int e = npad - 1 - ep;
+            return e < nm ? Gg[(size_t)e * gw + (I + 1)] : 1.0;
+          };
+          for (int B = 0; B < nb; B++) {
+            double *slab = &BK[(((size_t)grp * 2 + sw) * nb + B) * T * 32];
+            for (int l = 0; l < 32; l++)
+              for (int d = 1; d <= bw; d++)
+                if (l - d < 0 && 32 * B + l - d >= 0) slab[(size_t)(d - 1) * 32 + l] = offd(32 * B + l, d);
+            long double Ai[32][32];
+            for (int c = 0; c < 32; c++)
+              for (int l = 0; l < 32; l++) {
+                long double acc = (l == c) ? 1.0L : 0.0L;
+                for (int k2 = (l - bw > c ? l - bw : c); k2 < l; k2++) acc -= (long double)offd(32 * B + l, l - k2) * Ai[k2][c];
+                Ai[l][c] = (l < c) ? 0.0L : acc / (long double)diag(32 * B + l);
+              }
+            for (int c = 0; c < 32; c++)
+              for (int l = 0; l < 32; l++) slab[(size_t)(bw + c) * 32 + l] = (double)Ai[l][c];
+          }
+        }
+      }
+      TRY(dupload(h, &h->d_bk, BK));
+    }
     double *q;
     TRY(dupload(h, &q, R)); v.ratm = q;
     TRY(dupload(h, &q, G)); v.gap = q;
@@ -1117,7 +1158,7 @@ static int do_momentum(cg_handle *h, cudaStream_t s, cudaStream_t s3 = nullptr) 
     n += launch_velc1(h->dv, s3);
     CUDA_OK(cudaEventRecord(h->evJoin3, s3));
   }
-  n += launch_momentum(h->dv, h->variant, h->d_bf, h->d_bb, h->d_rd, s);
+  n += launch_momentum(h->dv, h->variant, h->d_bf, h->d_bb, h->d_rd, h->d_bk, s);
   if (s3) CUDA_OK(cudaStreamWaitEvent(s, h->evJoin3, 0));
   else n += launch_velc1(h->dv, s);
   n += launch_velc2(h->dv, s);

@@ -796,6 +796,86 @@ __global__ void __launch_bounds__(32) k_baro_reg(const Dev v, const double *__re
   __syncwarp();
   for (int r = lane; r < nm; r += 32) v.gb[(size_t)r * MS + m] = x[r];
 }
+// Barotropic solve, blocked form.  One warp = one member, lane = row within a block of 32 rows.  The pivot-by-pivot
+// substitution is a chain of 2 x nm dependent (shuffle, multiply, subtract) steps; here a block's 32 unknowns come out
+// together:   y_blk = Tbb^-1 (b_blk - sum_d T(e', e'-d) y(e'-d))   with the inverse of the block's own 32 x 32 triangle
+// precomputed on the host (extended precision) -- per block bw + 32 independent shuffle + FMA pairs on four accumulators
+// instead of 32 dependent pivots.  The backward sweep runs on the reversed index so that both share one body.  The
+// coefficient slabs ((bw + 32) x 32 doubles per block, contiguous over the 2 nb blocks) stream through a ring of
+// cp.async.bulk buffers.  Same equations, different summation order: agrees with k_baro_reg to rounding (<= 1e-13
+// relative on psi, tests/test_gpu_col.py), not bit for bit.
+constexpr int kBlkRing = 4;
+template <int BW>
+__global__ void __launch_bounds__(32) k_baro_blk(const Dev v, const double *__restrict__ bk_all, const int nb) {
+  extern __shared__ __align__(128) double bsm[];
+  constexpr int T = BW + 32;
+  const int lane = threadIdx.x, m = blockIdx.x;
+  const int nm = v.nm, MS = v.MS, npad = nb * 32, ntot = 2 * nb;
+  double *ring = bsm;                                   // kBlkRing slabs of T x 32
+  double *x = ring + (size_t)kBlkRing * T * 32;         // the vector, padded to npad
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(x + npad);
+  const double *__restrict__ bk = bk_all + (size_t)v.baro_group[m] * ntot * T * 32;
+  auto issue = [&](const int g) {
+    const unsigned b = baro_sa(bar + (g & (kBlkRing - 1)));
+    constexpr unsigned bytes = T * 32 * 8;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     baro_sa(ring + (size_t)(g & (kBlkRing - 1)) * T * 32)),
+                 "l"(bk + (size_t)g * T * 32), "r"(bytes), "r"(b)
+                 : "memory");
+  };
+  if (lane == 0) {
+    for (int q = 0; q < kBlkRing; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(baro_sa(bar + q)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int g = 0; g < kBlkRing && g < ntot; g++) issue(g);
+  }
+  for (int r = lane; r < npad; r += 32) x[r] = (r < nm) ? v.gb[(size_t)r * MS + m] : 0.0;
+  __syncwarp();
+  double Y1 = 0.0, Y2 = 0.0;
+  for (int g = 0; g < ntot; g++) {
+    const int sw = (g >= nb) ? 1 : 0, B = g - sw * nb;
+    if (B == 0) { Y1 = 0.0; Y2 = 0.0; }
+    baro_wait(g, bar);   // ring slot g % kBlkRing, parity (g / kBlkRing) & 1 (kBlkRing == kBaroRing)
+    const double *cf = ring + (size_t)(g & (kBlkRing - 1)) * T * 32 + lane;
+    const int ep = 32 * B + lane, phys = sw ? npad - 1 - ep : ep;
+    double r = x[phys];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int d = 1; d <= BW; d++) {
+      const int src = (lane - d) & 31;
+      double val = __shfl_sync(0xffffffffu, Y1, src);
+      if (d > 32) {                                       // rows more than one block back
+        const double v2 = __shfl_sync(0xffffffffu, Y2, src);
+        val = (lane - d >= -32) ? val : v2;
+      }
+      const double c = cf[(d - 1) * 32];
+      if ((d & 3) == 0) a0 = __fma_rn(c, val, a0);
+      else if ((d & 3) == 1) a1 = __fma_rn(c, val, a1);
+      else if ((d & 3) == 2) a2 = __fma_rn(c, val, a2);
+      else a3 = __fma_rn(c, val, a3);
+    }
+    r = r - ((a0 + a1) + (a2 + a3));
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      const double rc = __shfl_sync(0xffffffffu, r, c);
+      const double w = cf[(BW + c) * 32];
+      if ((c & 3) == 0) b0 = __fma_rn(w, rc, b0);
+      else if ((c & 3) == 1) b1 = __fma_rn(w, rc, b1);
+      else if ((c & 3) == 2) b2 = __fma_rn(w, rc, b2);
+      else b3 = __fma_rn(w, rc, b3);
+    }
+    const double y = (b0 + b1) + (b2 + b3);
+    x[phys] = y;
+    Y2 = Y1; Y1 = y;
+    __syncwarp();                                         // the slab of block g is free
+    if (lane == 0 && g + kBlkRing < ntot) issue(g + kBlkRing);
+  }
+  __syncwarp();
+  for (int r = lane; r < nm; r += 32) v.gb[(size_t)r * MS + m] = x[r];
+}
+static_assert(kBlkRing == kBaroRing, "k_baro_blk reuses baro_wait");
+
 bool baro_reg_ok(const Dev &v) { return v.I + 1 > 32 && v.I + 1 <= 64 && (v.nm % 2) == 0 && v.nm >= 64; }
 
 // psi and barotropic velocity from the solved gb (ubarsolv :3527-3564)
@@ -1122,11 +1202,20 @@ int launch_gold_pre(const Dev &v, cudaStream_t s) {
   k_gold_pre<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
   return 1;
 }
-int launch_momentum(const Dev &v, int fast, const double *bf, const double *bb, const double *rd, cudaStream_t s) {
+int launch_momentum(const Dev &v, int fast, const double *bf, const double *bb, const double *rd, const double *bk, cudaStream_t s) {
   const dim3 b(32, 4);
   k_bp<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
   k_gb<<<grid2(v, v.nm, b), b, 0, s>>>(v);
-  if (fast == 2 && baro_reg_ok(v)) {
+  int blk = 1;           // CG_BARO_BLK=0: pivot-by-pivot k_baro_reg instead of the blocked solve
+  { const char *e = getenv("CG_BARO_BLK"); if (e) blk = atoi(e); }
+  if (fast == 2 && blk && bk && v.I + 1 == 37) {
+    constexpr int BW = 37;
+    const int nb = (v.nm + 31) / 32;
+    const size_t smem = sizeof(double) * ((size_t)kBlkRing * (BW + 32) * 32 + (size_t)nb * 32) + 8 * kBlkRing;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_baro_blk<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    k_baro_blk<BW><<<v.M, 32, smem, s>>>(v, bk, nb);
+  } else if (fast == 2 && baro_reg_ok(v)) {
     const size_t smem = sizeof(double) * ((size_t)kBaroRing * 32 * (v.I + 1) + 2 * 32 * kBaroRow + 128 + ((v.nm + 1) & ~1)) + 8 * kBaroRing;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_baro_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }

@@ -85,24 +85,37 @@ def test_col_multi_year_drift(built, tmp_path):
     assert abs(atm_d[0, 2] - o.f("atm").reshape(-1, LA)[0, 2]) <= 1e-6 * 278e-6
 
 
-def test_baro_reg_bit_identical_to_baro_fast(built, tmp_path):
-    """The register-resident barotropic solve (k_baro_reg, variant 'col') performs the same operations in the same
-    order as the shared-memory one (k_baro_fast, variant 'fast'): after the momentum part of the first ocean steps the
-    stream function, the barotropic and the 3-D velocities of perturbed members are bit-identical.  (The tracer step
-    runs after the momentum step, so from step 2 on the variants' own rounding enters through rho.)"""
+def test_baro_solves_agree(built, tmp_path):
+    """Barotropic solve of variant 'col'.  (i) The register-resident pivot-by-pivot solve (k_baro_reg, CG_BARO_BLK=0)
+    performs the same operations in the same order as the shared-memory one (k_baro_fast, variant 'fast'): after the
+    momentum part of the first ocean step the stream function, the barotropic and the 3-D velocities of perturbed members
+    are bit-identical.  (ii) The blocked solve (k_baro_blk, the default: 32 unknowns at a time through the precomputed
+    inverse of the block's triangle) solves the same equations in another summation order: equal to rounding.
+    (The tracer step runs after the momentum step, so from step 2 on the variants' own rounding enters through rho.)"""
+    import os
     materialise(str(tmp_path), CFG)
     M = 5
     pert = {"adrag": np.linspace(2.0, 3.0, M), "scf": np.linspace(1.5, 2.5, M), "diff1": np.linspace(1500.0, 2500.0, M)}
     out = {}
-    for variant in ("fast", "col"):
-        with Ensemble(str(tmp_path), n_members=M, perturb=pert) as e:
-            e.set_tracer_variant(variant)
-            e.run(5)
-            out[variant] = {n: np.stack([e.get(n, m) for m in range(M)]) for n in ("gb", "psi", "ub", "u")}
-            assert int(e.health().sum()) == 0
+    for variant, blk in (("fast", None), ("col", "0"), ("col", "1")):
+        os.environ.pop("CG_BARO_BLK", None)
+        if blk is not None:
+            os.environ["CG_BARO_BLK"] = blk
+        try:
+            with Ensemble(str(tmp_path), n_members=M, perturb=pert) as e:
+                e.set_tracer_variant(variant)
+                e.run(5)
+                out[(variant, blk)] = {n: np.stack([e.get(n, m) for m in range(M)]) for n in ("gb", "psi", "ub", "u")}
+                assert int(e.health().sum()) == 0
+        finally:
+            os.environ.pop("CG_BARO_BLK", None)
     for n in ("gb", "psi", "ub", "u"):
-        assert np.array_equal(out["fast"][n], out["col"][n]), n
-    assert np.abs(out["col"]["psi"]).max() > 0.0
+        assert np.array_equal(out[("fast", None)][n], out[("col", "0")][n]), n
+    for n in ("psi", "ub", "u"):
+        ref, got = out[("col", "0")][n], out[("col", "1")][n]
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        assert err < 1e-13, (n, err)
+    assert np.abs(out[("col", "1")]["psi"]).max() > 0.0
 
 
 def test_biogem_fused_coupling_bit_identical(built, tmp_path):
