@@ -785,9 +785,9 @@ static int build_device(cg_handle *h) {
     if (bw <= 64) {
       // Blocked form of the two banded substitutions (k_baro_blk): the rows are taken in blocks of 32, in sweep order
       // (forward: e' = e; backward: e' = npad-1-e, so that both are lower triangular).  Per block the slab holds, lane =
-      // row within the block: bw rows of off-block coefficients T(e', e'-d), d = 1..bw (zero where e'-d lies inside the
-      // block or outside the vector), then the 32 x 32 inverse of the block's own triangle, column by column.  The inverse
-      // is formed in extended precision; padding rows are identity rows.
+      // row within the block: bw rows W(:, d) = Tbb^-1 x (coefficients of the value d rows before the block), d = 1..bw,
+      // then the 32 x 32 inverse Tbb^-1 of the block's own triangle, column by column.  Both are formed in extended
+      // precision; padding rows are identity rows.
       const int nb = (nm + 31) / 32, npad = nb * 32, T = bw + 32;
       std::vector<double> BK((size_t)h->nbaro * 2 * nb * T * 32, 0.0);
       for (int grp = 0; grp < h->nbaro; grp++) {
@@ -805,9 +805,6 @@ static int build_device(cg_handle *h) {
           };
           for (int B = 0; B < nb; B++) {
             double *slab = &BK[(((size_t)grp * 2 + sw) * nb + B) * T * 32];
-            for (int l = 0; l < 32; l++)
-              for (int d = 1; d <= bw; d++)
-                if (l - d < 0 && 32 * B + l - d >= 0) slab[(size_t)(d - 1) * 32 + l] = offd(32 * B + l, d);
             long double Ai[32][32];
             for (int c = 0; c < 32; c++)
               for (int l = 0; l < 32; l++) {
@@ -817,6 +814,16 @@ static int build_device(cg_handle *h) {
               }
             for (int c = 0; c < 32; c++)
               for (int l = 0; l < 32; l++) slab[(size_t)(bw + c) * 32 + l] = (double)Ai[l][c];
+            // W = Tbb^-1 x (off-block coefficients): row e' of the block against the value d rows before the block's
+            // first row, d = 1..bw, so that the block's unknowns are z - W y_prev with z = Tbb^-1 b_blk
+            for (int d = 1; d <= bw; d++) {
+              if (32 * B - d < 0) continue;
+              for (int l = 0; l < 32; l++) {
+                long double acc = 0.0L;
+                for (int c = 0; c <= l; c++) acc += Ai[l][c] * (long double)offd(32 * B + c, c + d);   // row c reaches back c + d
+                slab[(size_t)(d - 1) * 32 + l] = (double)acc;
+              }
+            }
           }
         }
       }

@@ -831,30 +831,13 @@ __global__ void __launch_bounds__(32) k_baro_blk(const Dev v, const double *__re
   }
   for (int r = lane; r < npad; r += 32) x[r] = (r < nm) ? v.gb[(size_t)r * MS + m] : 0.0;
   __syncwarp();
-  double Y1 = 0.0, Y2 = 0.0;
-  for (int g = 0; g < ntot; g++) {
+  // z = Tbb^-1 b_blk of block g (independent of the unknowns of earlier blocks: computed one block ahead, under the
+  // dependent chain of the block before)
+  auto zblock = [&](const int g) -> double {
     const int sw = (g >= nb) ? 1 : 0, B = g - sw * nb;
-    if (B == 0) { Y1 = 0.0; Y2 = 0.0; }
-    baro_wait(g, bar);   // ring slot g % kBlkRing, parity (g / kBlkRing) & 1 (kBlkRing == kBaroRing)
     const double *cf = ring + (size_t)(g & (kBlkRing - 1)) * T * 32 + lane;
-    const int ep = 32 * B + lane, phys = sw ? npad - 1 - ep : ep;
-    double r = x[phys];
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-    for (int d = 1; d <= BW; d++) {
-      const int src = (lane - d) & 31;
-      double val = __shfl_sync(0xffffffffu, Y1, src);
-      if (d > 32) {                                       // rows more than one block back
-        const double v2 = __shfl_sync(0xffffffffu, Y2, src);
-        val = (lane - d >= -32) ? val : v2;
-      }
-      const double c = cf[(d - 1) * 32];
-      if ((d & 3) == 0) a0 = __fma_rn(c, val, a0);
-      else if ((d & 3) == 1) a1 = __fma_rn(c, val, a1);
-      else if ((d & 3) == 2) a2 = __fma_rn(c, val, a2);
-      else a3 = __fma_rn(c, val, a3);
-    }
-    r = r - ((a0 + a1) + (a2 + a3));
+    const int ep = 32 * B + lane;
+    const double r = x[sw ? npad - 1 - ep : ep];
     double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
 #pragma unroll
     for (int c = 0; c < 32; c++) {
@@ -865,11 +848,39 @@ __global__ void __launch_bounds__(32) k_baro_blk(const Dev v, const double *__re
       else if ((c & 3) == 2) b2 = __fma_rn(w, rc, b2);
       else b3 = __fma_rn(w, rc, b3);
     }
-    const double y = (b0 + b1) + (b2 + b3);
+    return (b0 + b1) + (b2 + b3);
+  };
+  double Y1 = 0.0, Y2 = 0.0;
+  baro_wait(0, bar);
+  double z = zblock(0);
+  for (int g = 0; g < ntot; g++) {
+    const int sw = (g >= nb) ? 1 : 0, B = g - sw * nb;
+    if (B == 0) { Y1 = 0.0; Y2 = 0.0; }
+    const double *cf = ring + (size_t)(g & (kBlkRing - 1)) * T * 32 + lane;
+    const int ep = 32 * B + lane, phys = sw ? npad - 1 - ep : ep;
+    // the next block's z; at the turn of the sweeps it needs this block's result and is taken afterwards
+    const bool ahead = (g + 1 < ntot) && (g + 1 != nb);
+    double zn = 0.0;
+    if (g + 1 < ntot) baro_wait(g + 1, bar);
+    if (ahead) zn = zblock(g + 1);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int d = 1; d <= BW; d++) {
+      // the value d rows before this block's first row: lane 32-d of the previous block, lane 64-d of the one before
+      const double val = (d <= 32) ? __shfl_sync(0xffffffffu, Y1, 32 - d) : __shfl_sync(0xffffffffu, Y2, 64 - d);
+      const double c = cf[(d - 1) * 32];
+      if ((d & 3) == 0) a0 = __fma_rn(c, val, a0);
+      else if ((d & 3) == 1) a1 = __fma_rn(c, val, a1);
+      else if ((d & 3) == 2) a2 = __fma_rn(c, val, a2);
+      else a3 = __fma_rn(c, val, a3);
+    }
+    const double y = z - ((a0 + a1) + (a2 + a3));
     x[phys] = y;
     Y2 = Y1; Y1 = y;
-    __syncwarp();                                         // the slab of block g is free
+    __syncwarp();                                         // the slab of block g is free, x holds this block's result
     if (lane == 0 && g + kBlkRing < ntot) issue(g + kBlkRing);
+    if (!ahead && g + 1 < ntot) zn = zblock(g + 1);
+    z = zn;
   }
   __syncwarp();
   for (int r = lane; r < nm; r += 32) v.gb[(size_t)r * MS + m] = x[r];

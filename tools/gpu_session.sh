@@ -16,6 +16,6 @@ cat $OUT/bench_ref_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_$TAG.csv \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu_$TAG.log 2>&1
 # full capture of the tracer / barotropic / BIOGEM kernels at the bench's member count, ~4-year-old state
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_tstep_col|k_co_col|k_baro_reg|k_bg_step|k_tc_partial" -s 40 -c 10 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_tstep_col|k_co_col|k_baro_blk|k_bg_step|k_tc_partial|k_tc_apply" -s 40 -c 14 \
   -o $OUT/prof_tstepo_$TAG -f python tools/prof_run.py --members 128 --spin 400 --steps 8 --variant col > $OUT/prof_full_$TAG.log 2>&1
 ls -la $OUT | tail -12
