@@ -1681,6 +1681,28 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
   h->mom_ready = false;   // cg_run computes the momentum step inside its own schedule
   const Params &p = h->base;
   const bool regular = p.katm_loop == 1 && p.ksic_loop == p.kocn_loop && p.kocn_loop > 1;
+  const int trace_n = getenv("CG_TRACE") ? atoi(getenv("CG_TRACE")) : 0;
+  std::vector<cudaEvent_t> trace_ev;
+  std::vector<int> trace_blk;
+  struct TraceDump {
+    std::vector<cudaEvent_t> &ev; std::vector<int> &blk; cg_handle *h;
+    ~TraceDump() {
+      if (ev.empty()) return;
+      cudaDeviceSynchronize();
+      float t0 = 0.f;
+      for (size_t c = 0; c + 3 < ev.size(); c += 4) {
+        float head, wait, ts, gap = 0.f;
+        cudaEventElapsedTime(&head, ev[c], ev[c + 1]);
+        cudaEventElapsedTime(&wait, ev[c + 1], ev[c + 2]);
+        cudaEventElapsedTime(&ts, ev[c + 2], ev[c + 3]);
+        if (c) cudaEventElapsedTime(&gap, ev[c - 1], ev[c]);
+        cudaEventElapsedTime(&t0, ev[0], ev[c + 3]);
+        fprintf(stderr, "trace cycle %2zu%s: gap %6.1f head %6.1f wait %6.1f tstep %6.1f us  (t = %8.1f)\n", c / 4, blk[c / 4] ? " B" : "  ",
+                1e3 * gap, 1e3 * head, 1e3 * wait, 1e3 * ts, 1e3 * t0);
+      }
+      for (auto e : ev) cudaEventDestroy(e);
+    }
+  } trace_dump{trace_ev, trace_blk, h};
   while (n > 0) {
     const long long k = h->koverall + 1;
     if (regular && (k % p.kocn_loop) == 1 && n >= p.kocn_loop) {
@@ -1700,9 +1722,21 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
           h->launches = l0; h->istep_ocn = i0; h->istep_atm = a0; h->istep_sic = s0;
           std::swap(h->dv.ts_cur, h->dv.ts_new);  // undo the swap done while capturing
         }
+        // CG_TRACE=<cycles>: main-stream time stamps of the first cycles of this call (head / wait for the BIOGEM block /
+        // tracer step), printed to stderr at the end of the call -- a diagnostic of the schedule, not used by the bench
+        cudaEvent_t *tev = nullptr;
+        if (trace_n > 0 && (int)trace_ev.size() < 4 * trace_n) {
+          for (int q = 0; q < 4; q++) { cudaEvent_t e; cudaEventCreate(&e); trace_ev.push_back(e); }
+          tev = &trace_ev[trace_ev.size() - 4];
+          trace_blk.push_back((h->koverall + p.kocn_loop) % ((long long)p.conv_kocn_kbiogem * p.kocn_loop) == 0);
+        }
+        if (tev) cudaEventRecord(tev[0], h->stream);
         CUDA_OK(cudaGraphLaunch(g1, h->stream));
+        if (tev) cudaEventRecord(tev[1], h->stream);
         IO(bg_join(h));                            // tstepo reads the ts the tracer coupling rewrote
+        if (tev) cudaEventRecord(tev[2], h->stream);
         CUDA_OK(cudaGraphLaunch(g2, h->stream));
+        if (tev) cudaEventRecord(tev[3], h->stream);
         h->launches += h->graph_launches[h->variant];
         h->istep_ocn++; h->istep_atm += p.kocn_loop; h->istep_sic++;
         std::swap(h->dv.ts_cur, h->dv.ts_new);

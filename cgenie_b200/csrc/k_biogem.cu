@@ -11,6 +11,7 @@
 #include "cg_host.hpp"
 
 namespace cg {
+static inline bool tc_fix_shape(const Dev &v) { return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && v.MS == 128 && !getenv("CG_BG_NOFIX"); }
 
 constexpr double kBgZeroC = 273.15;          // gem_cmn.f90:690
 constexpr double kBgNullSmall = 0.999999e-19; // gem_cmn.f90:719
@@ -20,8 +21,10 @@ constexpr double kBgNullSmall = 0.999999e-19; // gem_cmn.f90:719
 //   1            : sum_k (ts(S)+saln0+docn(S))*V*rtot_V (new mean salinity)        [phase A]
 //   2 .. L-1     : sum_k ocn(l)*M, l = 3..L             (old inventories)          [phase A]
 //   L .. 2L-3    : sum_k loc_vocn(l)*M, l = 3..L        (salinity-adjusted new)    [phase B]
+// FIX: grid shape, tracer count and member stride of the bench configuration as compile-time constants (see k_bg_step)
+template <bool FIX>
 __global__ void __launch_bounds__(128) k_tc_partial(const Dev v, const int phase) {
-  const int I = v.I, J = v.J, K = v.K, L = v.L, MS = v.MS;
+  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, L = FIX ? 16 : v.L, MS = FIX ? 128 : v.MS;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y * blockDim.y + threadIdx.y;
   if (m >= MS || n >= v.nwet) return;
@@ -163,9 +166,10 @@ __global__ void k_tc_factors(const Dev v) {
   }
 }
 constexpr int kApplyCellsPerWarp = 1, kApplyWarps = 4;
+template <bool FIX>
 __global__ void __launch_bounds__(32 * kApplyWarps, 4) k_tc_apply(const Dev v) {
   __shared__ double s_f[kBgMaxL][32], s_rmean[32], s_sr[32], s_rsr[32], s_mnew[32];
-  const int I = v.I, J = v.J, K = v.K, L = v.L, MS = v.MS;
+  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, L = FIX ? 16 : v.L, MS = FIX ? 128 : v.MS;
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int m = blockIdx.x * 32 + lane;
   {
@@ -508,12 +512,15 @@ __device__ __forceinline__ void rem_add(Rem7 &r, const double f, const double *p
 // the latency-bound momentum kernels of the two ocean cycles in between; its results cross to PART = 2 (sediment return +
 // water-column sweep, at the nominal time) through b.surf (kBgSurfSlots doubles per member-column).  Same operations in
 // the same order: bit-identical to PART = 0.
-template <int MINB, int PART>
+// FIX: the grid shape and the member stride of the bench configuration (36 x 36 x 16, 128 members) as compile-time
+// constants -- every address becomes base + immediate (40 % of the generic kernel's instructions are 64-bit address
+// arithmetic).
+template <int MINB, int PART, bool FIX>
 __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev b, const int init_only, const int mode) {
   const bool fuse = (mode & 1) != 0, pf = (mode & 2) == 0;
   using namespace bgk;
   using namespace lay;
-  const int I = v.I, J = v.J, K = v.K, MS = v.MS;
+  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, MS = FIX ? 128 : v.MS;
   constexpr int L = NL, LS = NLS, LA = NLA;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y * blockDim.y + threadIdx.y;
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
   if (m >= MS || n >= v.nwet) return;
   const int c2 = v.bgcols[n];
   const int i = c2 % I + 1, j = c2 / I + 1;
-  const int k1 = CG_K1(v, i, j);
+  const int k1 = (int)v.k1[i + (I + 2) * j];
   const size_t c2d = cell2(I, i, j);
   const size_t sK = (size_t)I * J * L * MS, o0 = cell3(I, J, i, j, 1) * L * MS + m;
   const size_t qK = (size_t)I * J * LS * MS, q0 = cell3(I, J, i, j, 1) * LS * MS + m;
@@ -563,7 +570,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
   // conv_ls_lo coefficients that are not 1
   const double cO2POC = b.conv_ls_lo[POC][1], cO2POP = b.conv_ls_lo[POP][1], cALKPOP = b.conv_ls_lo[POP][2],
                cALKCa = b.conv_ls_lo[CACO3][1];
-#define SC_(slot) b.surf[((size_t)(slot) * v.nwet + n) * MS + m]
+#define SC_(slot) b.surf[((size_t)(slot) * (I * J) + n) * MS + m]
   // ---- closed-system sediment return (:887-940) from the settling flux of the previous step
   Rem7 fsed;
   rem_zero(fsed);
@@ -1039,6 +1046,7 @@ __global__ void __launch_bounds__(32 * kSumWarps) k_bg_atchem2(const Dev v, cons
   }
 }
 
+static bool bg_fix_shape(const Dev &v) { return v.I == 36 && v.J == 36 && v.K == 16 && v.MS == 128 && !getenv("CG_BG_NOFIX"); }
 int launch_bg_step(const Dev &v, const BgDev &b, int init_only, int fuse, cudaStream_t s) {
   // registers per thread 255 / 168 / 128 for MINB = 2 / 3 / 4 (CG_BG_MINB overrides; tuning knob)
   static int minb = -1;
@@ -1047,19 +1055,20 @@ int launch_bg_step(const Dev &v, const BgDev &b, int init_only, int fuse, cudaSt
   if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
   fuse |= nopf;
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
-  if (minb == 4) k_bg_step<4, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
-  else if (minb == 3) k_bg_step<3, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
-  else k_bg_step<2, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  if (minb == 4) k_bg_step<4, 0, false><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  else if (minb == 3) k_bg_step<3, 0, false><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  else if (bg_fix_shape(v)) k_bg_step<2, 0, true><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  else k_bg_step<2, 0, false><<<g, bl, 0, s>>>(v, b, init_only, fuse);
   return 1;
 }
 // the two parts of the step (see k_bg_step): surface cell, then sediment return + water-column sweep
 int launch_bg_surf(const Dev &v, const BgDev &b, cudaStream_t s) {
-  static int minb = -1;   // registers per thread 255 / 168 / 128 for 2 / 3 / 4 (CG_BG_SURF_MINB; tuning knob)
+  static int minb = -1;   // registers per thread 134 / 128 for 3 / 4 (CG_BG_SURF_MINB; tuning knob)
   if (minb < 0) { const char *e = getenv("CG_BG_SURF_MINB"); minb = e ? atoi(e) : 4; }
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
-  if (minb == 4) k_bg_step<4, 1><<<g, bl, 0, s>>>(v, b, 0, 0);
-  else if (minb == 2) k_bg_step<2, 1><<<g, bl, 0, s>>>(v, b, 0, 0);
-  else k_bg_step<3, 1><<<g, bl, 0, s>>>(v, b, 0, 0);
+  if (minb == 3) k_bg_step<3, 1, false><<<g, bl, 0, s>>>(v, b, 0, 0);
+  else if (bg_fix_shape(v)) k_bg_step<4, 1, true><<<g, bl, 0, s>>>(v, b, 0, 0);
+  else k_bg_step<4, 1, false><<<g, bl, 0, s>>>(v, b, 0, 0);
   return 1;
 }
 int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s) {
@@ -1068,19 +1077,11 @@ int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s) {
   static int nopf = -1;
   if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
-  // CG_BG_SWEEP_SMEM=<KB>: unused dynamic shared memory that caps the kernel's residency (116 -> one block per SM), so that
-  // a sweep issued ahead leaves registers for the kernels it runs next to
-  static int pad = -1;
-  if (pad < 0) {
-    const char *e = getenv("CG_BG_SWEEP_SMEM");
-    pad = e ? atoi(e) * 1024 : 0;
-    if (pad > 0) {
-      cudaFuncSetAttribute(k_bg_step<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-      cudaFuncSetAttribute(k_bg_step<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-    }
-  }
-  if (minb == 3) k_bg_step<3, 2><<<g, bl, pad, s>>>(v, b, 0, nopf);
-  else k_bg_step<2, 2><<<g, bl, pad, s>>>(v, b, 0, nopf);
+  if (minb == 3) {
+    if (bg_fix_shape(v)) k_bg_step<3, 2, true><<<g, bl, 0, s>>>(v, b, 0, nopf);
+    else k_bg_step<3, 2, false><<<g, bl, 0, s>>>(v, b, 0, nopf);
+  } else if (bg_fix_shape(v)) k_bg_step<2, 2, true><<<g, bl, 0, s>>>(v, b, 0, nopf);
+  else k_bg_step<2, 2, false><<<g, bl, 0, s>>>(v, b, 0, nopf);
   return 1;
 }
 // step (1) of biogem_tracercoupling taken BEFORE step_biogem (fused coupling, see k_bg_step)
@@ -1088,9 +1089,9 @@ int launch_tc_sums_first(const Dev &v, cudaStream_t s) {
   const dim3 b(32, 4);
   const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
   const int L = v.L;
-  k_tc_partial<<<gc, b, 0, s>>>(v, 2);
+  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 2); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 2);
   k_tc_sum<<<dim3(v.MS / 32, L), 32 * kSumWarps, 0, s>>>(v, 0, L);
-  k_tc_partial<<<gc, b, 0, s>>>(v, 1);
+  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 1); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 1);
   k_tc_sum<<<dim3(v.MS / 32, L - 2), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2);
   k_tc_factors<<<(v.MS + 127) / 128, 128, 0, s>>>(v);
   return 5;
@@ -1098,7 +1099,8 @@ int launch_tc_sums_first(const Dev &v, cudaStream_t s) {
 // steps (2)+(3) alone, after launch_tc_sums_first
 int launch_tc_apply_only(const Dev &v, cudaStream_t s) {
   const int ncell = v.I * v.J * v.K, per_block = kApplyWarps * kApplyCellsPerWarp;
-  k_tc_apply<<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
+  if (tc_fix_shape(v)) k_tc_apply<true><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
+  else k_tc_apply<false><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
   return 1;
 }
 int launch_bg_stage_seaice(const Dev &v, const BgDev &b, cudaStream_t s) {
@@ -1123,16 +1125,17 @@ int launch_tracercoupling(const Dev &v, cudaStream_t s) {
   const dim3 b(32, 4);
   const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
   const int L = v.L;
-  k_tc_partial<<<gc, b, 0, s>>>(v, 0);
+  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 0); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 0);
   k_tc_sum<<<dim3(v.MS / 32, L), 32 * kSumWarps, 0, s>>>(v, 0, L);
   if (L > 2) {
-    k_tc_partial<<<gc, b, 0, s>>>(v, 1);
+    if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 1); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 1);
     k_tc_sum<<<dim3(v.MS / 32, L - 2), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2);
   }
   {
     const int ncell = v.I * v.J * v.K, per_block = kApplyWarps * kApplyCellsPerWarp;
     k_tc_factors<<<(v.MS + 127) / 128, 128, 0, s>>>(v);
-    k_tc_apply<<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
+    if (tc_fix_shape(v)) k_tc_apply<true><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
+  else k_tc_apply<false><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
   }
   return L > 2 ? 6 : 4;
 }
