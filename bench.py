@@ -52,7 +52,7 @@ def ncu_traffic(members, variant):
     `ncu --set full` capture of this configuration (profiles/ncu_traffic.json), or None when none was taken."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        for row in json.load(open(p))["captures"]:
+        for row in reversed(json.load(open(p))["captures"]):   # latest capture of this configuration
             if row["members"] == members and row["variant"] == variant and row["config"] == CONFIG:
                 return row["dram_bytes_per_tstepo_launch"]
     except Exception:
