@@ -7,7 +7,7 @@ behaviour) for tests, benchmarks and Python users.  There is no CPU fallback:
 importing works anywhere, but every compute call fails loudly without the
 compiled library and a CUDA device.
 """
-from .engine import CgenieError, Ensemble, TracerStep  # noqa: F401
+from .engine import CgenieError, Ensemble, EnsembleGroups, TracerStep  # noqa: F401
 from .jobdir import materialise  # noqa: F401
 
-__all__ = ["Ensemble", "TracerStep", "CgenieError", "materialise"]
+__all__ = ["Ensemble", "EnsembleGroups", "TracerStep", "CgenieError", "materialise"]

@@ -219,3 +219,75 @@ def test_module_by_module_matches_run(built, tmp_path):
             assert int(e.health().sum()) == 0
     for n in names:
         assert np.array_equal(out["run"][n], out["modules"][n]), n
+
+
+def test_ensemble_groups_match_single_handle(built, tmp_path):
+    """A shard run as independent groups (EnsembleGroups: one library handle per group of <= 128 members, driven from host
+    threads) gives every member the state it has in a single handle: members never interact, so the grouping is invisible."""
+    from cgenie_b200 import EnsembleGroups
+    materialise(str(tmp_path), CFG)
+    M = 64
+    rng = np.random.default_rng(5)
+    pert = {"diff1": rng.uniform(1500.0, 2500.0, M), "adrag": np.repeat(rng.uniform(2.0, 3.0, 2), 32),
+            "par_bio_k0_PO4": rng.uniform(1.7e-6, 2.4e-6, M)}
+    names = ("ts", "rho", "u", "tq", "varice", "ocn", "bio_part", "atm")
+    check = (0, 31, 32, 63)
+    with Ensemble(str(tmp_path), n_members=M, perturb=pert) as e:
+        e.set_tracer_variant("col")
+        e.run(200)
+        one = {(n, m): e.get(n, m).copy() for n in names for m in check}
+        means_one = e.global_means()
+    with EnsembleGroups(str(tmp_path), n_members=M, perturb=pert, group=32) as g:
+        assert len(g.parts) == 2
+        g.set_tracer_variant("col")
+        assert g.tracer_variant_active() == "col"
+        g.run(200)
+        g.synchronize()
+        assert int(g.health().sum()) == 0 and g.health().shape == (M,)
+        assert g.launch_count() > 0
+        for n in names:
+            for m in check:
+                a, b = one[(n, m)], g.get(n, m)
+                assert np.allclose(a, b, rtol=1e-12, atol=1e-12 * max(np.abs(a).max(), 1e-300)), (n, m, np.abs(a - b).max())
+        assert np.allclose(means_one, g.global_means(), rtol=1e-12)
+
+
+def test_col_century_drift(built, tmp_path):
+    """North-star drift criterion at its full length: 100 model years from the initial state, the unperturbed control and
+    one perturbed member (physics + biology), global means of T, S, DIC, O2 and atmospheric pCO2 within 1e-6 relative of
+    the oracle (measured on B200: <= 2.1e-10).  The device needs ~4 s, the two oracle threads ~80 s."""
+    import threading
+    from cgenie_b200.sharding import perturbation_table
+    materialise(str(tmp_path), CFG)
+    years = 100
+    tab = perturbation_table(4, biogem=True)
+    members = (0, 3)
+    ref = {}
+
+    def oracle_run(m):
+        kw = {k: float(v[m]) for k, v in tab.items()}
+        o = Oracle(**dict(OKW, **{k: v for k, v in kw.items() if not k.startswith("par_bio")}))
+        o.biogem_setup(**{k: v for k, v in kw.items() if k.startswith("par_bio")})
+        o.run(480 * years)
+        ref[m] = (o.f("ocn").reshape(-1, L).copy(), o.f("bg_M").copy(), o.f("atm").reshape(-1, LA).copy())
+        o.close()
+    th = [threading.Thread(target=oracle_run, args=(m,)) for m in members]
+    for t in th:
+        t.start()
+    with Ensemble(str(tmp_path), n_members=4, perturb=tab) as e:
+        e.set_tracer_variant("col")
+        e.run(480 * years)
+        assert int(e.health().sum()) == 0
+        dev = {m: (e.get("ocn", m).reshape(-1, L), e.get("bg_M", m), e.get("atm", m).reshape(-1, LA)) for m in members}
+    for t in th:
+        t.join()
+    for m in members:
+        assert m in ref, "oracle thread failed"
+        ocn_o, M_o, atm_o = ref[m]
+        ocn_d, M_d, atm_d = dev[m]
+        for l, name in ((0, "T"), (1, "S"), (2, "DIC"), (6, "O2")):
+            mo = float((ocn_o[:, l] * M_o).sum() / M_o.sum())
+            md = float((ocn_d[:, l] * M_d).sum() / M_d.sum())
+            print("member %d global mean %s: oracle %.12e device %.12e rel %.2e" % (m, name, mo, md, abs(md - mo) / abs(mo)))
+            assert abs(md - mo) <= 1e-6 * abs(mo), (m, name, mo, md)
+        assert abs(atm_d[0, 2] - atm_o[0, 2]) <= 1e-6 * atm_o[0, 2]

@@ -66,3 +66,12 @@ def test_table_properties():
     assert len(np.unique(t1024["adrag"])) <= 1024 // sharding.ADRAG_GROUP
     lo, hi = sharding.shard_bounds(3, 8, 128)
     assert (lo, hi) == (384, 512)
+
+
+def test_ensemble_groups_argument_check():
+    """group size outside 1..128 is refused before anything touches the device"""
+    import pytest
+    from cgenie_b200 import EnsembleGroups
+    for bad in (0, 129):
+        with pytest.raises(ValueError):
+            EnsembleGroups("/nonexistent", n_members=4, group=bad)

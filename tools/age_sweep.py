@@ -26,7 +26,7 @@ args = ap.parse_args()
 CFG = "eb_go_gs_ac_bg_36x36x16"
 d = tempfile.mkdtemp()
 materialise(d, CFG)
-L, LA = 16, 6
+L, LA = 16, 8
 
 # ---------------------------------------------------------------- (2) started first: the oracle threads need ~100 s
 res = {}
