@@ -43,6 +43,8 @@ int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
 int launch_bg_step(const Dev &, const BgDev &, int init_only, int fuse, cudaStream_t);
 int launch_tc_sums_first(const Dev &, cudaStream_t);
+int launch_tc_sums_old(const Dev &, cudaStream_t);
+int launch_tc_sums_new(const Dev &, cudaStream_t);
 int launch_bg_surf(const Dev &, const BgDev &, cudaStream_t);
 int launch_bg_sweep(const Dev &, const BgDev &, cudaStream_t);
 int launch_tc_apply_only(const Dev &, cudaStream_t);
@@ -120,6 +122,7 @@ struct cg_handle {
   cudaEvent_t evT = nullptr, evBG = nullptr, evBGtail = nullptr;   // evBG: ts is ready for tstepo; evBGtail: the whole block (ATCHEM) is done
   bool bg_tail_pending = false;
   bool bg_ahead = false;                          // the step kernel of the next BIOGEM block is already in stream4
+  bool tc_old_ready = false;                      // ... and the "old" half of its tracer-coupling sums in stream5 (same validity as bg_ahead)
   cudaStream_t stream5 = nullptr;                 // tracer-coupling sums next to the BIOGEM step kernel
   cudaEvent_t evFork5 = nullptr, evJoin5 = nullptr;
   bool bg_overlap = true, bg_pending = false, bg_staged = false;
@@ -1637,9 +1640,12 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
       h->launches += launch_bg_sweep(h->dv, h->bgd, h->stream4);
       h->bg_surf_issued = false;
     }
+    const bool old_ready = h->bg_ahead && h->tc_old_ready;
     h->bg_ahead = false;
+    h->tc_old_ready = false;
     if (h->bg_go) {       // biogem_tracercoupling: sums on stream5 (they need ts of this cycle, not the step's anomaly)
-      h->launches += launch_tc_sums_first(h->dv, h->stream5);
+      // the sums over BIOGEM's own state (old mean salinity, old inventories) were taken one block ahead if old_ready
+      h->launches += old_ready ? launch_tc_sums_new(h->dv, h->stream5) : launch_tc_sums_first(h->dv, h->stream5);
       if (cudaEventRecord(h->evJoin5, h->stream5) != cudaSuccess || cudaStreamWaitEvent(h->stream4, h->evJoin5, 0) != cudaSuccess ||
           cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
       h->launches += launch_tc_apply_only(h->dv, h->stream4);
@@ -1649,6 +1655,17 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
     h->bg_pending = true;
     if ((rc = cg_atchem_step(h, h->bgd.dts_atchem))) break;
     if (remaining >= period) {   // the step kernel (split form: its surface part) of the next block, one block ahead
+      // the half of the next block's coupling sums that reads ocn, V, M only (all final once this block's update has run):
+      // on stream5 behind ATCHEM (which borrows the same scratch), next to the transcendental-bound surface part.
+      // 144 -> 77 us of kernels between the tracer step and k_tc_apply.  CG_TC_AHEAD=0: off.
+      const bool tc_ahead = !(getenv("CG_TC_AHEAD") && atoi(getenv("CG_TC_AHEAD")) == 0);
+      if (tc_ahead && h->bg_go && h->dv.L > 2) {
+        if (cudaEventRecord(h->evFork5, h->stream4) != cudaSuccess || cudaStreamWaitEvent(h->stream5, h->evFork5, 0) != cudaSuccess) {
+          rc = fail(CG_ERR_CUDA, "stream wait"); break;
+        }
+        h->launches += launch_tc_sums_old(h->dv, h->stream5);
+        h->tc_old_ready = true;
+      }
       if ((rc = h->bg_split ? bg_issue_surf(h, (k + period) * tick) : bg_issue_step(h, (k + period) * tick))) break;
       // ... and the sweep right behind it (default; CG_BG_SWEEP_EARLY=1: behind the tracer step of the cycle before the
       // block's, 0: at the block's nominal place.  Measured 79.5 / 81.2 / 82.4 ms per model year.)

@@ -37,19 +37,26 @@ __global__ void __launch_bounds__(128) k_tc_partial(const Dev v, const int phase
   const size_t v0 = cell3(I, J, i, j, 1), vK = (size_t)I * J;
   const size_t nq = (size_t)v.nwet * MS;
   double *part = v.bg_part + (size_t)n * MS + m;
-  if (phase == 0 || phase == 2) {
+  // phase 3 / 4 = phase 2 + phase 1 regrouped by what they read (cg_run's pipelined block): 3 = everything that depends on
+  // BIOGEM's own state only (old mean salinity, old inventories: ocn, V, M as the PREVIOUS coupling left them), taken
+  // one block ahead; 4 = what needs this cycle's ts (new mean salinity, salinity-adjusted new inventories -- the latter
+  // need the old mean salinity only, which phase 3 + its ordered sum have produced by then).  Same expressions per slot.
+  const bool do_old = phase == 0 || phase == 2 || phase == 3, do_newS = phase == 0 || phase == 2 || phase == 4;
+  if (do_old || do_newS) {
     // phase 2 = phase 0 taken BEFORE step_biogem (fused coupling): the salinity anomaly of the frozen configuration is
     // exactly +0.0 (no BIOGEM source or sink of salt), so the sum does not need vdocn
     const double saln0 = v.p.saln0[m];
     double a = 0.0, b = 0.0;
     for (int k = k1c; k <= K; k++) {
       const double V = v.bg_V[v0 + (size_t)(k - 1) * vK];
-      a = a + v.bg_ocn[o0 + (size_t)(k - 1) * sK + MS] * V;
+      if (do_old) a = a + v.bg_ocn[o0 + (size_t)(k - 1) * sK + MS] * V;
       const double dS = (phase == 0) ? v.bg_vdocn[o0 + (size_t)(k - 1) * sK + MS] : 0.0;
-      b = b + (v.ts_cur[o0 + (size_t)(k - 1) * sK + MS] + saln0 + dS) * V;
+      if (do_newS) b = b + (v.ts_cur[o0 + (size_t)(k - 1) * sK + MS] + saln0 + dS) * V;
     }
-    part[0] = a * v.bg_rtot_V;
-    part[nq] = b * v.bg_rtot_V;
+    if (do_old) part[0] = a * v.bg_rtot_V;
+    if (do_newS) part[nq] = b * v.bg_rtot_V;
+  }
+  if (do_old) {
     // old inventories: level outer / tracer inner, so that the loads of a level are all in flight at once and the
     // per-tracer sums (each still accumulated over k ascending, as the reference does) are independent chains
     if (L <= kBgMaxL) {
@@ -73,7 +80,8 @@ __global__ void __launch_bounds__(128) k_tc_partial(const Dev v, const int phase
         part[(size_t)l * nq] = s;
       }
     }
-  } else {
+  }
+  if (phase == 1 || phase == 4) {
     const double rmean = 1.0 / v.bg_tot[m];  // loc_ocn_rmean_S_OLD
     if (L <= kBgMaxL) {
       double s[kBgMaxL];
@@ -133,12 +141,14 @@ __device__ double ordered_sum_block(const double *__restrict__ p, const size_t s
 }
 
 // ordered sum over the wet columns: block = (32-member tile, quantity)
-__global__ void __launch_bounds__(32 * kSumWarps) k_tc_sum(const Dev v, const int q0, const int q1) {
+// skip >= 0: blockIdx.y = 0 sums quantity `skip`, blockIdx.y >= 1 quantities q0 .. q1-1 (the "new" set: slot 1 and L .. 2L-3);
+// skip = -2: quantities q0 .. q1-1 without slot 1 (the "old" set)
+__global__ void __launch_bounds__(32 * kSumWarps) k_tc_sum(const Dev v, const int q0, const int q1, const int skip = -1) {
   __shared__ double tile[kSumTile * 32];
   const int MS = v.MS;
   const int m0 = blockIdx.x * 32;
-  const int q = q0 + blockIdx.y;
-  if (q >= q1) return;
+  const int q = skip >= 0 ? (blockIdx.y == 0 ? skip : q0 + (int)blockIdx.y - 1) : q0 + (int)blockIdx.y;
+  if (q >= q1 || (skip == -2 && q == 1)) return;
   const double s = ordered_sum_block(v.bg_part + (size_t)q * v.nwet * MS + m0, (size_t)MS, v.nwet, tile);
   if (threadIdx.x < 32) v.bg_tot[(size_t)q * MS + m0 + threadIdx.x] = s;
 }
@@ -1095,6 +1105,24 @@ int launch_tc_sums_first(const Dev &v, cudaStream_t s) {
   k_tc_sum<<<dim3(v.MS / 32, L - 2), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2);
   k_tc_factors<<<(v.MS + 127) / 128, 128, 0, s>>>(v);
   return 5;
+}
+// launch_tc_sums_first in two halves (see k_tc_partial phases 3 / 4): the half that reads BIOGEM's own state only ...
+int launch_tc_sums_old(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
+  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 3); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 3);
+  k_tc_sum<<<dim3(v.MS / 32, v.L), 32 * kSumWarps, 0, s>>>(v, 0, v.L, -2);
+  return 2;
+}
+// ... and the half that needs this cycle's ts, + the per-member factors
+int launch_tc_sums_new(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
+  const int L = v.L;
+  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 4); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 4);
+  k_tc_sum<<<dim3(v.MS / 32, L - 1), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2, 1);
+  k_tc_factors<<<(v.MS + 127) / 128, 128, 0, s>>>(v);
+  return 3;
 }
 // steps (2)+(3) alone, after launch_tc_sums_first
 int launch_tc_apply_only(const Dev &v, cudaStream_t s) {

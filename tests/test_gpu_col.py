@@ -153,12 +153,14 @@ def test_concurrent_schedule_bit_identical(built, tmp_path):
             "par_bio_k0_PO4": rng.uniform(1.7e-6, 2.4e-6, M)}
     names = ("ts", "rho", "u", "psi", "tq", "varice", "ocn", "bio_part", "atm", "cost", "bg_seaice", "sst", "carbH")
     out = {}
-    knobs = ("CG_NOFORK", "CG_BG_SERIAL", "CG_NOEAGER", "CG_BG_PIPE", "CG_BG_SPLIT", "CG_BG_SWEEP_EARLY")
+    knobs = ("CG_NOFORK", "CG_BG_SERIAL", "CG_NOEAGER", "CG_BG_PIPE", "CG_BG_SPLIT", "CG_BG_SWEEP_EARLY", "CG_TC_AHEAD")
     # "default" = what cg_run does out of the box; "async" = the block next to the following cycle's head, step kernel at
     # its nominal place; "pipelined" = whole step kernel one block ahead; "split" = only its surface part one block ahead
     env = {"serial": {"CG_NOFORK": "1", "CG_BG_SERIAL": "1", "CG_NOEAGER": "1"}, "default": {}, "async": {"CG_BG_SPLIT": "0"},
            "pipelined": {"CG_BG_PIPE": "1", "CG_BG_SPLIT": "0"}, "split": {"CG_BG_SPLIT": "1", "CG_BG_SWEEP_EARLY": "0"},
-           "split, sweep one cycle ahead": {"CG_BG_SWEEP_EARLY": "1"}}
+           "split, sweep one cycle ahead": {"CG_BG_SWEEP_EARLY": "1"},
+           # default takes the coupling sums over BIOGEM's own state one block ahead; this mode takes all sums in place
+           "split, all coupling sums in place": {"CG_TC_AHEAD": "0"}}
     for mode in env:
         for k in knobs:
             os.environ.pop(k, None)
