@@ -123,6 +123,10 @@ struct cg_handle {
   bool bg_tail_pending = false;
   bool bg_ahead = false;                          // the step kernel of the next BIOGEM block is already in stream4
   bool tc_old_ready = false;                      // ... and the "old" half of its tracer-coupling sums in stream5 (same validity as bg_ahead)
+  // per-module path: the same half issued by cg_atchem_step for the next cg_biogem_tracercoupling call (valid until the host
+  // writes state); tc_old_pending = its kernels may still be running on stream5 (they own the reduction scratch)
+  bool tc_spec_valid = false, tc_old_pending = false;
+  cudaEvent_t evTcOld = nullptr;
   cudaStream_t stream5 = nullptr;                 // tracer-coupling sums next to the BIOGEM step kernel
   cudaEvent_t evFork5 = nullptr, evJoin5 = nullptr;
   bool bg_overlap = true, bg_pending = false, bg_staged = false;
@@ -180,6 +184,7 @@ struct cg_handle {
     if (evJoin) cudaEventDestroy(evJoin);
     if (evFork5) cudaEventDestroy(evFork5);
     if (evJoin5) cudaEventDestroy(evJoin5);
+    if (evTcOld) cudaEventDestroy(evTcOld);
     if (stream5) cudaStreamDestroy(stream5);
     if (evBGtail) cudaEventDestroy(evBGtail);
     if (evT) cudaEventDestroy(evT);
@@ -290,6 +295,10 @@ static int join_side(cg_handle *h) {
     CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBGtail, 0));
     h->bg_tail_pending = false;
   }
+  if (h->tc_old_pending) {
+    CUDA_OK(cudaStreamWaitEvent(h->stream, h->evTcOld, 0));
+    h->tc_old_pending = false;
+  }
   return CG_OK;
 }
 
@@ -394,6 +403,7 @@ extern "C" int cg_initialise(cg_handle *h) {
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream5, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork5, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin5, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evTcOld, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBGtail, cudaEventDisableTiming));
@@ -1017,6 +1027,7 @@ static int sync_from_host_lane(cg_handle *h, const char *name, int member, const
   if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_from_host: bad argument");
   IO0(join_side(h));
   h->spec_valid = false;
+  h->tc_spec_valid = false;
   h->mom_ready = false;   // a momentum step computed ahead of time is stale once the host has written state
   const bool both = strcmp(name, "ts") == 0 || strcmp(name, "ts1") == 0;
   FieldDesc *f = find_field(h, both ? "ts" : name);
@@ -1051,6 +1062,7 @@ extern "C" int cg_sync_all_from_host(cg_handle *h, const char *name, const doubl
   IO0(join_side(h));
   h->mom_ready = false;
   h->spec_valid = false;
+  h->tc_spec_valid = false;
   FieldDesc *f = find_field(h, name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
   if (n != f->count() * h->MS) return fail(CG_ERR_ARG, "cg_sync_all_from_host: size must be field_size*member_stride");
@@ -1410,7 +1422,15 @@ extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_
   if (h->bg.on && !h->bg_go) return CG_OK;
   BgAsyncScope as(h, !go_ts && !go_ts1);
   h->bg_stage = (h->bg_stage == 1 && !go_ts && !go_ts1) ? 2 : 0;
-  { ProfScope ps(h, "biogem"); ps.done(launch_tracercoupling(h->dv, h->stream)); }
+  // the sums cg_atchem_step took ahead of time own the reduction scratch until their event has passed
+  const bool ahead = as.on && h->tc_spec_valid && h->tc_old_pending;
+  if (h->tc_old_pending) { CUDA_OK(cudaStreamWaitEvent(h->stream, h->evTcOld, 0)); h->tc_old_pending = false; }
+  h->tc_spec_valid = false;
+  {
+    ProfScope ps(h, "biogem");
+    if (ahead) { const int n = launch_tc_sums_new(h->dv, h->stream); ps.done(n + launch_tc_apply_only(h->dv, h->stream)); }
+    else ps.done(launch_tracercoupling(h->dv, h->stream));
+  }
   IO(check_async(h));
   if (go_ts) IO(cg_sync_to_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
   if (go_ts1) IO(cg_sync_to_host(h, "ts", h->io_member, go_ts1, cg_field_size(h, "ts")));
@@ -1469,6 +1489,15 @@ extern "C" int cg_atchem_step(cg_handle *h, double dts) {
   const Params &p = h->base;
   static const bool nospec = getenv("CG_BG_SPLIT") && atoi(getenv("CG_BG_SPLIT")) == 0;
   if (as.on && h->bg_stage == 3 && h->bg_go && !h->bg_fuse && !nospec && p.conv_kocn_kbiogem == p.conv_kocn_katchem) {
+    // ... and, next to it on stream5, the half of the next coupling's sums that reads BIOGEM's own state only (see
+    // do_biogem_block_pipelined); ATCHEM borrowed the same scratch, hence the event
+    if (!(getenv("CG_TC_AHEAD") && atoi(getenv("CG_TC_AHEAD")) == 0) && h->dv.L > 2 &&
+        cudaEventRecord(h->evFork5, h->stream) == cudaSuccess && cudaStreamWaitEvent(h->stream5, h->evFork5, 0) == cudaSuccess) {
+      h->launches += launch_tc_sums_old(h->dv, h->stream5);
+      CUDA_OK(cudaEventRecord(h->evTcOld, h->stream5));
+      h->tc_spec_valid = true;
+      h->tc_old_pending = true;
+    }
     const long long next = h->bg_last_clock + (long long)p.conv_kocn_kbiogem * p.kocn_loop * nint_ll(1000.0 * p.genie_timestep);
     bg_forcing(&h->bg, next, &h->bgd);
     h->launches += launch_bg_surf(h->dv, h->bgd, h->stream);
@@ -1695,6 +1724,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
   READY(h);
   IO0(join_side(h));
   h->spec_valid = false;
+  h->tc_spec_valid = false;
   h->mom_ready = false;   // cg_run computes the momentum step inside its own schedule
   const Params &p = h->base;
   const bool regular = p.katm_loop == 1 && p.ksic_loop == p.kocn_loop && p.kocn_loop > 1;
@@ -1812,6 +1842,7 @@ extern "C" int cg_set_koverall(cg_handle *h, int64_t koverall) {
   IO0(join_side(h));
   h->mom_ready = false;
   h->spec_valid = false;
+  h->tc_spec_valid = false;
   const Params &p = h->base;
   if (koverall < 0 || koverall % p.kocn_loop != 0) return fail(CG_ERR_ARG, "cg_set_koverall: koverall must be a non-negative multiple of kocn_loop");
   h->koverall = koverall;
@@ -1954,6 +1985,7 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream5, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork5, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin5, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evTcOld, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBGtail, cudaEventDisableTiming));
