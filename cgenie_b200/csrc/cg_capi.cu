@@ -126,6 +126,10 @@ struct cg_handle {
   // per-module path: the same half issued by cg_atchem_step for the next cg_biogem_tracercoupling call (valid until the host
   // writes state); tc_old_pending = its kernels may still be running on stream5 (they own the reduction scratch)
   bool tc_spec_valid = false, tc_old_pending = false;
+  // per-module path, lazy cycle: module calls without host arrays are only noted (1 = surflux, 1 + n = n EMBM steps,
+  // kocn_loop + 2 = sea ice); if step_goldstein completes the canonical cycle, the cycle is issued as cg_run issues it
+  // (two graph replays); anything else replays the noted calls one by one first (flush_lazy)
+  int lazy_stage = 0;
   cudaEvent_t evTcOld = nullptr;
   cudaStream_t stream5 = nullptr;                 // tracer-coupling sums next to the BIOGEM step kernel
   cudaEvent_t evFork5 = nullptr, evJoin5 = nullptr;
@@ -282,7 +286,9 @@ static void activate(cg_handle *h) {
 // Order the main stream after everything the per-module entry points or cg_run left running on the side streams.
 // Called by every entry point that reads or writes state from the host side.
 #define IO0(x) do { int rc0_ = (x); if (rc0_) return rc0_; } while (0)
+static int flush_lazy(cg_handle *h);
 static int join_side(cg_handle *h) {
+  if (h->lazy_stage) IO0(flush_lazy(h));
   if (h->mom_pending) {
     CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin, 0));
     h->mom_pending = false;
@@ -1250,8 +1256,11 @@ static int get(cg_handle *h, const char *name, double *dst) {
 }
 #define IO(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
+static bool lazy_ok(const cg_handle *h);
+static int lazy_cycle(cg_handle *h);
 extern "C" int cg_surflux_step(cg_handle *h, int istep, const cg_surflux_io *io) {
   READY(h);
+  if (h->lazy_stage) IO(flush_lazy(h));   // out of pattern: replay what was noted
   if (istep != h->istep_ocn + 1) {  // the host owns the step counter; keep the device copy in line
     const int v0 = istep - 1;
     CUDA_OK(cudaMemcpyAsync(h->dv.istep_ocn, &v0, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1265,6 +1274,7 @@ extern "C" int cg_surflux_step(cg_handle *h, int istep, const cg_surflux_io *io)
     for (size_t q = 0; q < t.size() / 2; q++) t[1 + 2 * q] = io->qstar_atm[q];
     IO(cg_sync_from_host(h, "tq", h->io_member, t.data(), (int64_t)t.size()));
   }
+  if (!io && lazy_ok(h)) { h->lazy_stage = 1; return CG_OK; }
   IO(eager_momentum(h));
   IO(do_surflux(h));
   IO(check_async(h));
@@ -1288,6 +1298,8 @@ extern "C" int cg_surflux_step(cg_handle *h, int istep, const cg_surflux_io *io)
 extern "C" int cg_embm_step(cg_handle *h, int istep, const cg_embm_io *io) {
   READY(h);
   (void)istep;
+  if (!io && h->lazy_stage >= 1 && h->lazy_stage <= h->base.kocn_loop) { h->lazy_stage++; return CG_OK; }
+  if (h->lazy_stage) IO(flush_lazy(h));
   IO(do_embm(h, 1));
   IO(check_async(h));
   if (io && (io->tstar_atm || io->qstar_atm)) {
@@ -1304,6 +1316,8 @@ extern "C" int cg_embm_step(cg_handle *h, int istep, const cg_embm_io *io) {
 extern "C" int cg_seaice_step(cg_handle *h, int istep, const cg_seaice_io *io) {
   READY(h);
   (void)istep;
+  if (!io && h->lazy_stage == h->base.kocn_loop + 1) { h->lazy_stage++; return CG_OK; }
+  if (h->lazy_stage) IO(flush_lazy(h));
   IO(do_seaice(h));
   IO(check_async(h));
   if (io) {
@@ -1324,6 +1338,8 @@ extern "C" int cg_seaice_step(cg_handle *h, int istep, const cg_seaice_io *io) {
 extern "C" int cg_goldstein_step(cg_handle *h, int istep, const cg_goldstein_io *io) {
   READY(h);
   (void)istep;
+  if (!io && h->lazy_stage == h->base.kocn_loop + 2 && lazy_ok(h)) return lazy_cycle(h);
+  if (h->lazy_stage) IO(flush_lazy(h));
   if (io) { IO(put(h, "ts", io->go_ts)); IO(put(h, "cost", io->go_cost)); }
   IO(do_goldstein(h));
   IO(check_async(h));
@@ -1383,7 +1399,7 @@ extern "C" int cg_goldstein_step(cg_handle *h, int istep, const cg_goldstein_io 
 }
 
 // ---- BIOGEM / ATCHEM -------------------------------------------------------------------------------------------
-#define BGREADY(h) do { READY(h); if (!(h)->bg.on) return fail(CG_ERR_CONFIG, "flag_biogem is off in this job"); } while (0)
+#define BGREADY(h) do { READY(h); if (!(h)->bg.on) return fail(CG_ERR_CONFIG, "flag_biogem is off in this job"); if ((h)->lazy_stage) IO(flush_lazy(h)); } while (0)
 static long long nint_ll(double x) { return (long long)(x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5)); }
 
 // biogem_forcing(genie_clock), biogem.f90:2083-2127: time-interpolated restoring targets (host scalars, bit-exact)
@@ -1418,6 +1434,7 @@ extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
   if (h->g.L <= 2 || !h->dv.bg_ocn) return fail(CG_ERR_CONFIG, "tracer coupling needs biogeochemical tracers (maxl > 2)");
   activate(h);
+  if (h->lazy_stage) IO(flush_lazy(h));
   if (go_ts) IO(cg_sync_from_host(h, "ts", h->io_member, go_ts, cg_field_size(h, "ts")));
   if (h->bg.on && !h->bg_go) return CG_OK;
   BgAsyncScope as(h, !go_ts && !go_ts1);
@@ -1441,6 +1458,7 @@ extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_
 extern "C" int cg_biogem_climate(cg_handle *h) {
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
   activate(h);
+  if (h->lazy_stage) IO(flush_lazy(h));
   if (h->bg.on) {
     // go_solfor of the last surflux call (embm.f90:3727-3729): row MOD(istot-1,nyear)+1 of solfor
     h->bgd.nsol = h->istep_ocn > 0 ? (h->istep_ocn - 1) % h->g.nyear + 1 : 0;
@@ -1720,6 +1738,59 @@ static int bg_join(cg_handle *h) {   // order the main stream after an outstandi
   return CG_OK;
 }
 
+// the two executable graphs of an ocean cycle for the current variant and ping-pong parity, captured on first use
+static int cycle_graphs(cg_handle *h) {
+  const int par = (h->dv.ts_cur < h->dv.ts_new) ? 0 : 1;
+  cudaGraphExec_t &g1 = h->graph[h->variant][par], &g2 = h->graph2[h->variant][par];
+  if (g1 && g2) return CG_OK;
+  const long long l0 = h->launches;
+  const int i0 = h->istep_ocn, a0 = h->istep_atm, s0 = h->istep_sic;
+  const bool fork = h->fork_momentum && !getenv("CG_NOFORK");
+  if (g1) { cudaGraphExecDestroy(g1); g1 = nullptr; }
+  if (g2) { cudaGraphExecDestroy(g2); g2 = nullptr; }
+  IO(capture_graph(h, &g1, [&]() { return enqueue_cycle_head(h, fork); }));
+  IO(capture_graph(h, &g2, [&]() { do_tstepo(h); return (int)CG_OK; }));
+  h->graph_launches[h->variant] = h->launches - l0;
+  h->launches = l0; h->istep_ocn = i0; h->istep_atm = a0; h->istep_sic = s0;
+  std::swap(h->dv.ts_cur, h->dv.ts_new);  // undo the swap done while capturing
+  return CG_OK;
+}
+// Per-module path, lazy cycle.  The Fortran host calls surflux, kocn_loop x step_embm, step_seaice, step_goldstein once per
+// ocean cycle, mostly with no array to exchange (NULL = stay resident).  Such calls are only noted; when step_goldstein
+// completes the canonical sequence the cycle is issued exactly as cg_run issues it -- the captured head graph (momentum
+// next to surflux / EMBM / sea ice, 5 EMBM steps in one launch), the join with the BIOGEM block, the tracer-step graph --
+// instead of ~30 separate launches.  State is observable from the host only through calls that pass arrays or through the
+// sync / get entry points, and all of those replay the noted calls first (flush_lazy).  Bit-identical to both other paths
+// (tests/test_gpu_col.py::test_module_by_module_matches_run).  CG_NOLAZY=1: off.
+static bool lazy_ok(const cg_handle *h) {
+  const Params &p = h->base;
+  return h->eager && !h->profile && h->use_graphs && p.katm_loop == 1 && p.ksic_loop == p.kocn_loop && p.kocn_loop > 1 &&
+         !getenv("CG_NOEAGER") && !(getenv("CG_NOLAZY") && atoi(getenv("CG_NOLAZY")) != 0);
+}
+static int flush_lazy(cg_handle *h) {
+  const int st = h->lazy_stage, nl = h->base.kocn_loop;
+  if (!st) return CG_OK;
+  h->lazy_stage = 0;
+  IO(eager_momentum(h));
+  IO(do_surflux(h));
+  for (int q = 0; q < std::min(st - 1, nl); q++) IO(do_embm(h, 1));
+  if (st == nl + 2) IO(do_seaice(h));
+  return check_async(h);
+}
+static int lazy_cycle(cg_handle *h) {   // step_goldstein closing a fully noted cycle
+  const Params &p = h->base;
+  h->lazy_stage = 0;
+  const int par = (h->dv.ts_cur < h->dv.ts_new) ? 0 : 1;
+  IO(cycle_graphs(h));
+  CUDA_OK(cudaGraphLaunch(h->graph[h->variant][par], h->stream));
+  IO(bg_join(h));                            // tstepo reads the ts the tracer coupling rewrote
+  CUDA_OK(cudaGraphLaunch(h->graph2[h->variant][par], h->stream));
+  h->launches += h->graph_launches[h->variant];
+  h->istep_ocn++; h->istep_atm += p.kocn_loop; h->istep_sic++;
+  std::swap(h->dv.ts_cur, h->dv.ts_new);
+  return check_async(h);
+}
+
 extern "C" int cg_run(cg_handle *h, int64_t n) {
   READY(h);
   IO0(join_side(h));
@@ -1756,19 +1827,8 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
       if (h->use_graphs && !h->profile) {
         // two graphs per variant and ping-pong parity: the head of the cycle and the tracer step
         const int par = (h->dv.ts_cur < h->dv.ts_new) ? 0 : 1;
+        IO(cycle_graphs(h));
         cudaGraphExec_t &g1 = h->graph[h->variant][par], &g2 = h->graph2[h->variant][par];
-        if (!g1 || !g2) {
-          const long long l0 = h->launches;
-          const int i0 = h->istep_ocn, a0 = h->istep_atm, s0 = h->istep_sic;
-          const bool fork = h->fork_momentum && !getenv("CG_NOFORK");
-          if (g1) { cudaGraphExecDestroy(g1); g1 = nullptr; }
-          if (g2) { cudaGraphExecDestroy(g2); g2 = nullptr; }
-          IO(capture_graph(h, &g1, [&]() { return enqueue_cycle_head(h, fork); }));
-          IO(capture_graph(h, &g2, [&]() { do_tstepo(h); return (int)CG_OK; }));
-          h->graph_launches[h->variant] = h->launches - l0;
-          h->launches = l0; h->istep_ocn = i0; h->istep_atm = a0; h->istep_sic = s0;
-          std::swap(h->dv.ts_cur, h->dv.ts_new);  // undo the swap done while capturing
-        }
         // CG_TRACE=<cycles>: main-stream time stamps of the first cycles of this call (head / wait for the BIOGEM block /
         // tracer step), printed to stderr at the end of the call -- a diagnostic of the schedule, not used by the bench
         cudaEvent_t *tev = nullptr;

@@ -98,6 +98,11 @@ typedef struct {
   double *test_energy_ocean, *test_water_ocean; /* OUT scalars (goldstein.f90:458-478)          */
 } cg_goldstein_io;
 int cg_goldstein_step(cg_handle *, int istep, const cg_goldstein_io *io);
+/* io == NULL ("stay resident") calls of the four steps above are deferred: they are executed, in order, at the latest when
+ * the next call passes arrays or touches state from the host (cg_sync_*, cg_get_*, cg_synchronize, cg_run, BIOGEM / ATCHEM);
+ * a complete cycle surflux, kocn_loop x step_embm, step_seaice, step_goldstein is executed at the step_goldstein call as
+ * two CUDA-graph replays.  Results are bit-identical either way; an error of a deferred call is returned by the call that
+ * triggers its execution. */
 
 /* BIOGEM / ATCHEM (biogem.f90:528-547, 1885-1890, 2083-2087, 2132-2150; atchem.f90:63-67) */
 int cg_biogem_forcing(cg_handle *, int64_t genie_clock_ms);

@@ -183,8 +183,9 @@ def test_concurrent_schedule_bit_identical(built, tmp_path):
 
 
 def test_module_by_module_matches_run(built, tmp_path):
-    """The per-module entry points (what the Fortran shims call once per koverall iteration; momentum started at
-    surflux time, BIOGEM calls on their own stream) give bit-identical state to cg_run's graph-replayed schedule."""
+    """The per-module entry points (what the Fortran shims call once per koverall iteration: a cycle of calls without host
+    arrays is issued as cg_run issues it, two graph replays, when step_goldstein completes it; otherwise momentum is started
+    at surflux time; BIOGEM calls run on their own stream) give bit-identical state to cg_run's schedule."""
     materialise(str(tmp_path), CFG)
     M = 6
     rng = np.random.default_rng(11)
@@ -208,8 +209,12 @@ def test_module_by_module_matches_run(built, tmp_path):
                     if k % 5 == 1:
                         e.surflux()
                     e.step_embm()
+                    if k == 153:      # a host read in the middle of a cycle: the calls noted so far are replayed one by one
+                        e.get("tq", 0)
                     if k % 5 == 0:
                         e.step_seaice()
+                        if k == 175:  # ... and between the sea-ice and the ocean step
+                            e.get("varice", 0)
                         e.step_goldstein()
                     if k % 10 == 0:
                         e.biogem_forcing(k * tick)
