@@ -8,6 +8,7 @@ _LIB = None
 
 P = C.c_void_p
 D = C.POINTER(C.c_double)
+I32 = C.POINTER(C.c_int32)
 
 
 class SurfluxIO(C.Structure):
@@ -77,6 +78,13 @@ SYMBOLS = {
     "cg_tracer_set": (C.c_int, [P, D, D, D]),
     "cg_tracer_step": (C.c_int, [P, C.c_int]),
     "cg_tracer_get": (C.c_int, [P, D, D, D]),
+    "cg_restart_last_error": (C.c_char_p, []),
+    "cg_restart_goldstein_write": (C.c_int, [C.c_char_p] + [C.c_int] * 4 + [I32] + [D] * 8 + [I32]),
+    "cg_restart_goldstein_read": (C.c_int, [C.c_char_p] + [C.c_int] * 4 + [D] * 5 + [I32]),
+    "cg_restart_embm_write": (C.c_int, [C.c_char_p, C.c_int, C.c_int, D, D, D, I32]),
+    "cg_restart_embm_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, D, I32]),
+    "cg_restart_seaice_write": (C.c_int, [C.c_char_p, C.c_int, C.c_int, I32, D, D, D, D, D, I32]),
+    "cg_restart_seaice_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, D, D, D, I32]),
 }
 
 

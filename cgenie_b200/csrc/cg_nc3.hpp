@@ -1,0 +1,45 @@
+// cg_nc3.hpp -- minimal NetCDF-3 "classic" (CDF-1) codec for the restart files of the physics modules.
+//
+// The reference writes its restarts through netCDF-Fortran (goldstein_data.f90:153-300, embm_data.f90:83-200,
+// gold_seaice_data.f90:100-230); neither that library nor its C core exists in this image, and the files it produces for
+// these layouts are plain CDF-1: a header (dimensions, global attributes, variables with their attributes and data
+// offsets) followed by the fixed-size variables in definition order, big-endian, each padded to 4 bytes.  This codec
+// writes and reads exactly that subset: fixed dimensions (no record dimension), NC_INT / NC_FLOAT / NC_DOUBLE variables,
+// NC_CHAR attributes.  Files written here open with any netCDF library (checked against scipy.io.netcdf_file in
+// tests/test_restart_nc.py) and files written by netCDF-3 for these layouts read back here.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace cg {
+
+enum Nc3Type { NC3_CHAR = 2, NC3_INT = 4, NC3_FLOAT = 5, NC3_DOUBLE = 6 };
+
+struct Nc3Var {
+  std::string name;
+  int type = NC3_DOUBLE;
+  std::vector<int> dimids;                                     // file order: slowest first (reverse of the Fortran order)
+  std::vector<std::pair<std::string, std::string>> atts;       // text attributes
+  std::vector<double> data;                                    // values, file order (converted on write / read)
+  long long count = 0;                                         // product of the dimension lengths
+};
+
+class Nc3File {
+ public:
+  int add_dim(const std::string &name, int len);
+  int add_var(const std::string &name, int type, const std::vector<int> &dimids);   // dimids in FILE order
+  void put_att(int varid, const std::string &name, const std::string &value);
+  void put(int varid, const double *v, long long n);
+  void put(int varid, const int *v, long long n);
+  bool write(const std::string &path, std::string *err) const;
+  bool read(const std::string &path, std::string *err);
+  const Nc3Var *var(const std::string &name) const;
+  int dim_len(const std::string &name) const;                   // -1 if absent
+  std::vector<std::pair<std::string, int>> dims;
+  std::vector<std::pair<std::string, std::string>> gatts;
+  std::vector<Nc3Var> vars;
+};
+
+}  // namespace cg

@@ -1,0 +1,396 @@
+// cg_restart.cpp -- netCDF restart files of GOLDSTEIN, the EMBM and the sea-ice model in the reference's layout
+// ("restart/output wire formats"), host code only.
+//
+// What the reference does (variable names, types, order of definition, masks) is followed routine by routine:
+//   outm_netcdf / inm_netcdf   src/goldstein/goldstein_data.f90:153-300 / 11-150
+//   outm_netcdf_embm / inm_netcdf_embm   src/embm/embm_data.f90:83-200 / 11-80
+//   outm_netcdf_sic / inm_netcdf_sic     src/goldsteinseaice/gold_seaice_data.f90:100-230 / 11-98
+// The container format is written by cg_nc3 (no netCDF library in this image).  netCDF-Fortran reverses the order of the
+// dimension list, so a Fortran (maxi,maxj,maxk) array is a file variable (depth, latitude, longitude) with the same bytes.
+#include "cg_nc3.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/cgenie_b200.h"
+
+namespace cg {
+
+// ------------------------------------------------------------------ CDF-1 codec
+namespace {
+constexpr uint32_t kDimTag = 0x0A, kVarTag = 0x0B, kAttTag = 0x0C;
+int type_size(int t) { return t == NC3_DOUBLE ? 8 : (t == NC3_CHAR ? 1 : 4); }
+struct Out {
+  std::vector<unsigned char> b;
+  void u32(uint32_t v) { for (int s = 24; s >= 0; s -= 8) b.push_back((unsigned char)(v >> s)); }
+  void u64(uint64_t v) { for (int s = 56; s >= 0; s -= 8) b.push_back((unsigned char)(v >> s)); }
+  void pad() { while (b.size() % 4) b.push_back(0); }
+  void name(const std::string &s) { u32((uint32_t)s.size()); b.insert(b.end(), s.begin(), s.end()); pad(); }
+  void atts(const std::vector<std::pair<std::string, std::string>> &a) {
+    if (a.empty()) { u32(0); u32(0); return; }
+    u32(kAttTag); u32((uint32_t)a.size());
+    for (auto &kv : a) { name(kv.first); u32(NC3_CHAR); u32((uint32_t)kv.second.size()); b.insert(b.end(), kv.second.begin(), kv.second.end()); pad(); }
+  }
+};
+struct In {
+  const std::vector<unsigned char> &b; size_t p = 0; bool ok = true;
+  explicit In(const std::vector<unsigned char> &b_) : b(b_) {}
+  uint32_t u32() { if (p + 4 > b.size()) { ok = false; return 0; } uint32_t v = 0; for (int q = 0; q < 4; q++) v = (v << 8) | b[p++]; return v; }
+  uint64_t u64() { uint64_t hi = u32(); return (hi << 32) | u32(); }
+  std::string name() {
+    const uint32_t n = u32();
+    if (!ok || p + n > b.size()) { ok = false; return ""; }
+    std::string s((const char *)&b[p], n);
+    p += (n + 3) / 4 * 4;
+    return s;
+  }
+  void atts(std::vector<std::pair<std::string, std::string>> *out) {
+    const uint32_t tag = u32(), n = u32();
+    if (tag == 0 && n == 0) return;
+    if (tag != kAttTag) { ok = false; return; }
+    for (uint32_t q = 0; q < n && ok; q++) {
+      const std::string nm = name();
+      const uint32_t ty = u32(), ne = u32();
+      const size_t bytes = (size_t)ne * (ty == NC3_CHAR || ty == 1 ? 1 : ty == 3 ? 2 : ty == NC3_DOUBLE ? 8 : 4);
+      if (p + bytes > b.size()) { ok = false; return; }
+      if (ty == NC3_CHAR && out) out->push_back({nm, std::string((const char *)&b[p], ne)});
+      p += (bytes + 3) / 4 * 4;
+    }
+  }
+};
+}  // namespace
+
+int Nc3File::add_dim(const std::string &name, int len) { dims.push_back({name, len}); return (int)dims.size() - 1; }
+int Nc3File::add_var(const std::string &name, int type, const std::vector<int> &dimids) {
+  Nc3Var v;
+  v.name = name; v.type = type; v.dimids = dimids; v.count = 1;
+  for (int d : dimids) v.count *= dims[d].second;
+  v.data.assign((size_t)v.count, 0.0);
+  vars.push_back(v);
+  return (int)vars.size() - 1;
+}
+void Nc3File::put_att(int varid, const std::string &name, const std::string &value) { vars[varid].atts.push_back({name, value}); }
+void Nc3File::put(int varid, const double *v, long long n) { for (long long q = 0; q < n && q < vars[varid].count; q++) vars[varid].data[q] = v[q]; }
+void Nc3File::put(int varid, const int *v, long long n) { for (long long q = 0; q < n && q < vars[varid].count; q++) vars[varid].data[q] = v[q]; }
+const Nc3Var *Nc3File::var(const std::string &name) const {
+  for (auto &v : vars) if (v.name == name) return &v;
+  return nullptr;
+}
+int Nc3File::dim_len(const std::string &name) const {
+  for (auto &d : dims) if (d.first == name) return d.second;
+  return -1;
+}
+
+bool Nc3File::write(const std::string &path, std::string *err) const {
+  auto header = [&](const std::vector<uint32_t> &begin) {
+    Out o;
+    o.b = {'C', 'D', 'F', 1};
+    o.u32(0);   // numrecs: no record variables
+    if (dims.empty()) { o.u32(0); o.u32(0); }
+    else { o.u32(kDimTag); o.u32((uint32_t)dims.size()); for (auto &d : dims) { o.name(d.first); o.u32((uint32_t)d.second); } }
+    o.atts(gatts);
+    if (vars.empty()) { o.u32(0); o.u32(0); }
+    else {
+      o.u32(kVarTag); o.u32((uint32_t)vars.size());
+      for (size_t q = 0; q < vars.size(); q++) {
+        const Nc3Var &v = vars[q];
+        o.name(v.name);
+        o.u32((uint32_t)v.dimids.size());
+        for (int d : v.dimids) o.u32((uint32_t)d);
+        o.atts(v.atts);
+        o.u32((uint32_t)v.type);
+        o.u32((uint32_t)(((size_t)v.count * type_size(v.type) + 3) / 4 * 4));
+        o.u32(begin[q]);
+      }
+    }
+    return o;
+  };
+  std::vector<uint32_t> begin(vars.size(), 0);
+  size_t off = header(begin).b.size();
+  for (size_t q = 0; q < vars.size(); q++) {
+    begin[q] = (uint32_t)off;
+    off += ((size_t)vars[q].count * type_size(vars[q].type) + 3) / 4 * 4;
+    if (off > 0x7fffffffULL) { if (err) *err = "file too large for the classic format"; return false; }
+  }
+  Out o = header(begin);
+  for (auto &v : vars) {
+    for (long long q = 0; q < v.count; q++) {
+      if (v.type == NC3_DOUBLE) { uint64_t u; std::memcpy(&u, &v.data[q], 8); o.u64(u); }
+      else if (v.type == NC3_FLOAT) { const float f = (float)v.data[q]; uint32_t u; std::memcpy(&u, &f, 4); o.u32(u); }
+      else if (v.type == NC3_INT) o.u32((uint32_t)(int32_t)std::llround(v.data[q]));
+      else o.b.push_back((unsigned char)v.data[q]);
+    }
+    o.pad();
+  }
+  FILE *f = std::fopen(path.c_str(), "wb");
+  if (!f) { if (err) *err = "cannot open " + path + " for writing"; return false; }
+  const bool ok = std::fwrite(o.b.data(), 1, o.b.size(), f) == o.b.size();
+  std::fclose(f);
+  if (!ok && err) *err = "short write to " + path;
+  return ok;
+}
+
+bool Nc3File::read(const std::string &path, std::string *err) {
+  dims.clear(); gatts.clear(); vars.clear();
+  FILE *f = std::fopen(path.c_str(), "rb");
+  if (!f) { if (err) *err = "Missing file " + path; return false; }
+  std::vector<unsigned char> b;
+  unsigned char buf[1 << 16];
+  size_t n;
+  while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) b.insert(b.end(), buf, buf + n);
+  std::fclose(f);
+  if (b.size() < 8 || b[0] != 'C' || b[1] != 'D' || b[2] != 'F' || (b[3] != 1 && b[3] != 2)) {
+    if (err) *err = path + ": not a netCDF classic (CDF-1/2) file";
+    return false;
+  }
+  const bool wide = b[3] == 2;
+  In in(b);
+  in.p = 4;
+  in.u32();   // numrecs
+  int recdim = -1;
+  {
+    const uint32_t tag = in.u32(), nd = in.u32();
+    if (!(tag == 0 && nd == 0)) {
+      if (tag != kDimTag) in.ok = false;
+      for (uint32_t q = 0; q < nd && in.ok; q++) {
+        const std::string nm = in.name();
+        const int len = (int)in.u32();
+        if (len == 0) recdim = (int)q;
+        dims.push_back({nm, len});
+      }
+    }
+  }
+  in.atts(&gatts);
+  std::vector<uint64_t> begin;
+  {
+    const uint32_t tag = in.u32(), nv = in.u32();
+    if (!(tag == 0 && nv == 0)) {
+      if (tag != kVarTag) in.ok = false;
+      for (uint32_t q = 0; q < nv && in.ok; q++) {
+        Nc3Var v;
+        v.name = in.name();
+        const uint32_t nd = in.u32();
+        v.count = 1;
+        for (uint32_t d = 0; d < nd && in.ok; d++) {
+          const int id = (int)in.u32();
+          if (id < 0 || id >= (int)dims.size()) { in.ok = false; break; }
+          if (id == recdim) { if (err) *err = path + ": record variables are not supported (" + v.name + ")"; return false; }
+          v.dimids.push_back(id);
+          v.count *= dims[id].second;
+        }
+        in.atts(&v.atts);
+        v.type = (int)in.u32();
+        in.u32();   // vsize
+        begin.push_back(wide ? in.u64() : in.u32());
+        vars.push_back(v);
+      }
+    }
+  }
+  if (!in.ok) { if (err) *err = path + ": damaged netCDF header"; return false; }
+  for (size_t q = 0; q < vars.size(); q++) {
+    Nc3Var &v = vars[q];
+    if (v.type != NC3_DOUBLE && v.type != NC3_FLOAT && v.type != NC3_INT && v.type != NC3_CHAR) {
+      if (err) *err = path + ": unsupported type of variable " + v.name;
+      return false;
+    }
+    const size_t ts = (size_t)type_size(v.type);
+    if (begin[q] + (uint64_t)v.count * ts > b.size()) { if (err) *err = path + ": truncated data of variable " + v.name; return false; }
+    v.data.resize((size_t)v.count);
+    const unsigned char *p = &b[begin[q]];
+    for (long long e = 0; e < v.count; e++, p += ts) {
+      if (v.type == NC3_DOUBLE) { uint64_t u = 0; for (int s = 0; s < 8; s++) u = (u << 8) | p[s]; double d; std::memcpy(&d, &u, 8); v.data[e] = d; }
+      else if (v.type == NC3_CHAR) v.data[e] = p[0];
+      else {
+        uint32_t u = 0; for (int s = 0; s < 4; s++) u = (u << 8) | p[s];
+        if (v.type == NC3_FLOAT) { float x; std::memcpy(&x, &u, 4); v.data[e] = x; } else v.data[e] = (int32_t)u;
+      }
+    }
+  }
+  return true;
+}
+
+}  // namespace cg
+
+// ------------------------------------------------------------------ restart layouts (C ABI, plain host arrays)
+namespace {
+thread_local std::string g_restart_err;
+int rfail(const std::string &m) { g_restart_err = m; return CG_ERR_IO; }
+
+// dimensions and the scalar date variables every module's restart starts with
+struct Common { int nrecs, lon, lat, dep = -1, v_lon, v_lat, v_dep = -1; };
+Common define_axes(cg::Nc3File &f, int maxi, int maxj, int maxk, bool axis_atts) {
+  Common c;
+  c.nrecs = f.add_dim("nrecs", 1);
+  c.lon = f.add_dim("longitude", maxi);
+  c.lat = f.add_dim("latitude", maxj);
+  if (maxk > 0) c.dep = f.add_dim("depth", maxk);
+  c.v_lon = f.add_var("longitude", cg::NC3_FLOAT, {c.lon});
+  c.v_lat = f.add_var("latitude", cg::NC3_FLOAT, {c.lat});
+  if (maxk > 0) c.v_dep = f.add_var("depth", cg::NC3_FLOAT, {c.dep});
+  if (axis_atts) {   // goldstein_data.f90:271-274
+    f.put_att(c.v_lon, "units", "degrees_east"); f.put_att(c.v_lon, "long_name", "longitude");
+    f.put_att(c.v_lat, "units", "degrees_north"); f.put_att(c.v_lat, "long_name", "latitude");
+  }
+  return c;
+}
+void define_date(cg::Nc3File &f, const Common &c, const int32_t date[4]) {
+  // definition order ioffset, iyear, imonth, iday (goldstein_data.f90:247-251); date = {iyear, imonth, iday, ioffset}
+  const int order[4] = {3, 0, 1, 2};
+  const char *names[4] = {"ioffset", "iyear", "imonth", "iday"};
+  for (int q = 0; q < 4; q++) { const int id = f.add_var(names[q], cg::NC3_INT, {c.nrecs}); const int v = date[order[q]]; f.put(id, &v, 1); }
+}
+bool get_date(const cg::Nc3File &f, int32_t date[4]) {
+  const char *names[4] = {"iyear", "imonth", "iday", "ioffset"};
+  for (int q = 0; q < 4; q++) {
+    const cg::Nc3Var *v = f.var(names[q]);
+    if (!v || v->count < 1) return false;
+    if (date) date[q] = (int32_t)v->data[0];
+  }
+  return true;
+}
+const cg::Nc3Var *need(const cg::Nc3File &f, const char *name, long long count, std::string *err) {
+  const cg::Nc3Var *v = f.var(name);
+  if (!v) { *err = std::string("variable ") + name + " missing"; return nullptr; }
+  if (v->count != count) { *err = std::string("variable ") + name + " has the wrong size"; return nullptr; }
+  return v;
+}
+}  // namespace
+
+extern "C" const char *cg_restart_last_error(void) { return g_restart_err.c_str(); }
+
+// outm_netcdf, goldstein_data.f90:153-300.  ts (maxl,maxi,maxj,maxk), u (3,maxi,maxj,maxk), k1 (0:maxi+1,0:maxj+1), all Fortran order.
+extern "C" int cg_restart_goldstein_write(const char *path, int maxi, int maxj, int maxk, int maxl, const int32_t *k1,
+                                          const double *lon, const double *lat, const double *depth, const double *ts,
+                                          const double *u, const double *evap, const double *late, const double *sens,
+                                          const int32_t date[4]) {
+  if (!path || !k1 || !lon || !lat || !depth || !ts || !u || !date || maxl < 2) return rfail("cg_restart_goldstein_write: bad argument");
+  cg::Nc3File f;
+  const Common c = define_axes(f, maxi, maxj, maxk, true);
+  define_date(f, c, date);
+  const size_t n3 = (size_t)maxi * maxj * maxk, n2 = (size_t)maxi * maxj;
+  std::vector<double> a(n3);
+  const char *n3d[4] = {"temp", "salinity", "uvel", "vvel"};
+  int id3[4], id2[3];
+  for (int q = 0; q < 4; q++) id3[q] = f.add_var(n3d[q], cg::NC3_DOUBLE, {c.dep, c.lat, c.lon});
+  const char *n2d[3] = {"evap", "late", "sens"};
+  for (int q = 0; q < 3; q++) id2[q] = f.add_var(n2d[q], cg::NC3_DOUBLE, {c.lat, c.lon});
+  f.put(c.v_lon, lon, maxi); f.put(c.v_lat, lat, maxj); f.put(c.v_dep, depth, maxk);
+  for (int q = 0; q < 4; q++) {
+    for (int k = 0; k < maxk; k++)
+      for (int j = 0; j < maxj; j++)
+        for (int i = 0; i < maxi; i++) {
+          const size_t cell = (size_t)i + (size_t)maxi * (j + (size_t)maxj * k);
+          // landmask(i,j,:) = 1 wherever ANY level of the column is wet (goldstein_data.f90:200-207): ocean columns are
+          // written whole, land columns as zeros; velocities are not masked (:212-213)
+          const bool ocean = k1[(i + 1) + (size_t)(maxi + 2) * (j + 1)] <= maxk;
+          a[cell] = q < 2 ? (ocean ? ts[q + (size_t)maxl * cell] : 0.0) : u[(q - 2) + 3 * cell];
+        }
+    f.put(id3[q], a.data(), (long long)n3);
+  }
+  const double *two[3] = {evap, late, sens};
+  for (int q = 0; q < 3; q++) if (two[q]) f.put(id2[q], two[q], (long long)n2);
+  std::string err;
+  if (!f.write(path, &err)) return rfail(err);
+  return CG_OK;
+}
+// inm_netcdf, goldstein_data.f90:11-150: T and S replace ts(1:2), uvel/vvel replace u(1:2) (the caller copies u to u1,
+// :94-96); evap/late/sens only if wanted (lrestart_genie).  date = the file's {iyear, imonth, iday, ioffset}.
+extern "C" int cg_restart_goldstein_read(const char *path, int maxi, int maxj, int maxk, int maxl, double *ts, double *u,
+                                         double *evap, double *late, double *sens, int32_t date[4]) {
+  if (!path || !ts || !u || maxl < 2) return rfail("cg_restart_goldstein_read: bad argument");
+  cg::Nc3File f;
+  std::string err;
+  if (!f.read(path, &err)) return rfail(err);
+  if (!get_date(f, date)) return rfail(std::string(path) + ": date variables missing");
+  const long long n3 = (long long)maxi * maxj * maxk, n2 = (long long)maxi * maxj;
+  const char *n3d[4] = {"temp", "salinity", "uvel", "vvel"};
+  for (int q = 0; q < 4; q++) {
+    const cg::Nc3Var *v = need(f, n3d[q], n3, &err);
+    if (!v) return rfail(std::string(path) + ": " + err);
+    for (long long cell = 0; cell < n3; cell++) {
+      if (q < 2) ts[q + (size_t)maxl * cell] = v->data[cell]; else u[(q - 2) + 3 * cell] = v->data[cell];
+    }
+  }
+  const char *n2d[3] = {"evap", "late", "sens"};
+  double *two[3] = {evap, late, sens};
+  for (int q = 0; q < 3; q++) {
+    if (!two[q]) continue;
+    const cg::Nc3Var *v = need(f, n2d[q], n2, &err);
+    if (!v) return rfail(std::string(path) + ": " + err);
+    std::memcpy(two[q], v->data.data(), (size_t)n2 * 8);
+  }
+  return CG_OK;
+}
+
+// outm_netcdf_embm, embm_data.f90:83-200: tq (2,maxi,maxj) -> air_temp, humidity
+extern "C" int cg_restart_embm_write(const char *path, int maxi, int maxj, const double *lon, const double *lat, const double *tq,
+                                     const int32_t date[4]) {
+  if (!path || !lon || !lat || !tq || !date) return rfail("cg_restart_embm_write: bad argument");
+  cg::Nc3File f;
+  const Common c = define_axes(f, maxi, maxj, 0, false);
+  define_date(f, c, date);
+  const size_t n2 = (size_t)maxi * maxj;
+  const int idt = f.add_var("air_temp", cg::NC3_DOUBLE, {c.lat, c.lon}), idq = f.add_var("humidity", cg::NC3_DOUBLE, {c.lat, c.lon});
+  f.put(c.v_lon, lon, maxi); f.put(c.v_lat, lat, maxj);
+  std::vector<double> a(n2), b(n2);
+  for (size_t q = 0; q < n2; q++) { a[q] = tq[2 * q]; b[q] = tq[2 * q + 1]; }
+  f.put(idt, a.data(), (long long)n2); f.put(idq, b.data(), (long long)n2);
+  std::string err;
+  if (!f.write(path, &err)) return rfail(err);
+  return CG_OK;
+}
+// inm_netcdf_embm, embm_data.f90:11-80
+extern "C" int cg_restart_embm_read(const char *path, int maxi, int maxj, double *tq, int32_t date[4]) {
+  if (!path || !tq) return rfail("cg_restart_embm_read: bad argument");
+  cg::Nc3File f;
+  std::string err;
+  if (!f.read(path, &err)) return rfail(err);
+  if (!get_date(f, date)) return rfail(std::string(path) + ": date variables missing");
+  const long long n2 = (long long)maxi * maxj;
+  const cg::Nc3Var *t = need(f, "air_temp", n2, &err), *q = t ? need(f, "humidity", n2, &err) : nullptr;
+  if (!t || !q) return rfail(std::string(path) + ": " + err);
+  for (long long c = 0; c < n2; c++) { tq[2 * c] = t->data[c]; tq[2 * c + 1] = q->data[c]; }
+  return CG_OK;
+}
+
+// outm_netcdf_sic, gold_seaice_data.f90:100-230: varice (2,maxi,maxj) masked by k1 < 90 (:141-148), tice, albice unmasked
+extern "C" int cg_restart_seaice_write(const char *path, int maxi, int maxj, const int32_t *k1, const double *lon, const double *lat,
+                                       const double *varice, const double *tice, const double *albice, const int32_t date[4]) {
+  if (!path || !k1 || !lon || !lat || !varice || !tice || !albice || !date) return rfail("cg_restart_seaice_write: bad argument");
+  cg::Nc3File f;
+  const Common c = define_axes(f, maxi, maxj, 0, false);
+  define_date(f, c, date);
+  const size_t n2 = (size_t)maxi * maxj;
+  const char *names[4] = {"sic_height", "sic_cover", "sic_temp", "sic_albedo"};
+  int id[4];
+  for (int q = 0; q < 4; q++) id[q] = f.add_var(names[q], cg::NC3_DOUBLE, {c.lat, c.lon});
+  f.put(c.v_lon, lon, maxi); f.put(c.v_lat, lat, maxj);
+  std::vector<double> a(n2), b(n2);
+  for (int j = 0; j < maxj; j++)
+    for (int i = 0; i < maxi; i++) {
+      const size_t q = (size_t)i + (size_t)maxi * j;
+      const bool ocean = k1[(i + 1) + (size_t)(maxi + 2) * (j + 1)] < 90;
+      a[q] = ocean ? varice[2 * q] : 0.0;
+      b[q] = ocean ? varice[2 * q + 1] : 0.0;
+    }
+  f.put(id[0], a.data(), (long long)n2); f.put(id[1], b.data(), (long long)n2);
+  f.put(id[2], tice, (long long)n2); f.put(id[3], albice, (long long)n2);
+  std::string err;
+  if (!f.write(path, &err)) return rfail(err);
+  return CG_OK;
+}
+// inm_netcdf_sic, gold_seaice_data.f90:11-98
+extern "C" int cg_restart_seaice_read(const char *path, int maxi, int maxj, double *varice, double *tice, double *albice, int32_t date[4]) {
+  if (!path || !varice || !tice || !albice) return rfail("cg_restart_seaice_read: bad argument");
+  cg::Nc3File f;
+  std::string err;
+  if (!f.read(path, &err)) return rfail(err);
+  if (!get_date(f, date)) return rfail(std::string(path) + ": date variables missing");
+  const long long n2 = (long long)maxi * maxj;
+  const char *names[4] = {"sic_height", "sic_cover", "sic_temp", "sic_albedo"};
+  const cg::Nc3Var *v[4];
+  for (int q = 0; q < 4; q++) { v[q] = need(f, names[q], n2, &err); if (!v[q]) return rfail(std::string(path) + ": " + err); }
+  for (long long c = 0; c < n2; c++) { varice[2 * c] = v[0]->data[c]; varice[2 * c + 1] = v[1]->data[c]; tice[c] = v[2]->data[c]; albice[c] = v[3]->data[c]; }
+  return CG_OK;
+}

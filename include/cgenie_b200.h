@@ -4,7 +4,7 @@
  * This is the drop-in boundary: one entry point per module procedure that the
  * reference's coupler calls each coupling step through the argument-less
  * wrappers of src/wrappers/genie_loop_wrappers.f90.  A Fortran shim module
- * with the reference's own public names (fortran/*.f90) binds these through
+ * with the reference's own public names (the files under fortran/) binds these through
  * ISO_C_BINDING; INTEGRATION.md shows the binding.
  *
  * Conventions
@@ -187,6 +187,29 @@ int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_members, int 
 int cg_tracer_set(cg_handle *, const double *ts, const double *u, const double *tsflux);
 int cg_tracer_step(cg_handle *, int nsteps);
 int cg_tracer_get(cg_handle *, double *ts, double *rho, double *cost);
+
+/* ---- netCDF restart files in the reference's layout (host only: plain arrays, no handle, no device) ----
+ * Replace outm_netcdf / inm_netcdf (src/goldstein/goldstein_data.f90:153-300 / :11-150), outm_netcdf_embm / inm_netcdf_embm
+ * (src/embm/embm_data.f90:83-200 / :11-80), outm_netcdf_sic / inm_netcdf_sic (src/goldsteinseaice/gold_seaice_data.f90:100-230 /
+ * :11-98) for hosts without netCDF-Fortran (the Python engine; the Fortran model keeps writing its own restarts from the
+ * arrays cg_sync_to_host fills).  Files are netCDF-3 classic with the reference's dimension / variable names, types and
+ * definition order.  Arrays are column-major as in Fortran: ts (maxl,maxi,maxj,maxk), u (3,maxi,maxj,maxk), tq and varice
+ * (2,maxi,maxj), k1 (0:maxi+1,0:maxj+1) int32; lon / lat / depth are the nclon1 / nclat1 / depths1 axes.
+ * date = {iyear_rest, imonth_rest, iday, ioffset_rest}.  evap / late / sens may be NULL (written as zeros, not read).
+ * Non-zero return: CG_ERR_ARG / CG_ERR_IO with the text in cg_restart_last_error(). */
+const char *cg_restart_last_error(void);
+int cg_restart_goldstein_write(const char *path, int maxi, int maxj, int maxk, int maxl, const int32_t *k1, const double *lon,
+                               const double *lat, const double *depth, const double *ts, const double *u, const double *evap,
+                               const double *late, const double *sens, const int32_t date[4]);
+/* ts(1:2) and u(1:2) are replaced, everything else in ts / u is left as it is (goldstein_data.f90:88-96) */
+int cg_restart_goldstein_read(const char *path, int maxi, int maxj, int maxk, int maxl, double *ts, double *u, double *evap,
+                              double *late, double *sens, int32_t date[4]);
+int cg_restart_embm_write(const char *path, int maxi, int maxj, const double *lon, const double *lat, const double *tq,
+                          const int32_t date[4]);
+int cg_restart_embm_read(const char *path, int maxi, int maxj, double *tq, int32_t date[4]);
+int cg_restart_seaice_write(const char *path, int maxi, int maxj, const int32_t *k1, const double *lon, const double *lat,
+                            const double *varice, const double *tice, const double *albice, const int32_t date[4]);
+int cg_restart_seaice_read(const char *path, int maxi, int maxj, double *varice, double *tice, double *albice, int32_t date[4]);
 
 #ifdef __cplusplus
 }

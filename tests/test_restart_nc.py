@@ -1,0 +1,130 @@
+"""netCDF restart files in the reference's layout (csrc/cg_restart.cpp, cgenie_b200/restart.py): the C-ABI writers are
+checked against an independent netCDF-3 reader (scipy.io.netcdf_file), the readers against files scipy writes, and the
+layout against what outm_netcdf defines (goldstein_data.f90:153-300, embm_data.f90:83-200, gold_seaice_data.f90:100-230)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+from cgenie_b200 import _lib
+from cgenie_b200.restart import axes
+
+I, J, K, Lt = 36, 36, 16, 16
+
+
+def dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+@pytest.fixture(scope="module")
+def state(built):
+    rng = np.random.default_rng(3)
+    k1 = np.full((J + 2, I + 2), 91, dtype=np.int32)          # (0:maxi+1, 0:maxj+1) column-major = [j][i]
+    k1[1:J + 1, 1:I + 1] = rng.integers(1, K + 1, size=(J, I))
+    k1[5:9, 7:12] = 91                                        # some land
+    k1[20, 3] = 94
+    ts = rng.normal(size=(K, J, I, Lt))                       # Fortran (maxl,maxi,maxj,maxk)
+    u = rng.normal(size=(K, J, I, 3))
+    tq = rng.normal(size=(J, I, 2))
+    va = rng.uniform(size=(J, I, 2))
+    tice, alb = rng.normal(size=(J, I)), rng.uniform(size=(J, I))
+    s = np.concatenate([[0.0], np.linspace(-0.97, 0.97, J)])
+    zro = -np.concatenate([[0.0], np.linspace(0.9, 0.01, K)])
+    lon, lat, depth = axes(I, J, K, s, zro)
+    date = np.array([2010, 7, 4, 123], dtype=np.int32)
+    return dict(k1=k1, ts=ts, u=u, tq=tq, va=va, tice=tice, alb=alb, lon=lon, lat=lat, depth=depth, date=date)
+
+
+def test_goldstein_restart_matches_reference_layout(state, tmp_path):
+    L = _lib.load()
+    p = str(tmp_path / "goldstein_restart_2010_07_04.nc")
+    s = state
+    assert L.cg_restart_goldstein_write(p.encode(), I, J, K, Lt, ip(s["k1"]), dp(s["lon"]), dp(s["lat"]), dp(s["depth"]),
+                                        dp(s["ts"]), dp(s["u"]), None, None, None, ip(s["date"])) == 0
+    with netcdf_file(p, "r", mmap=False) as f:
+        assert f.version_byte == 1
+        assert list(f.dimensions.items()) == [("nrecs", 1), ("longitude", I), ("latitude", J), ("depth", K)]
+        assert list(f.variables) == ["longitude", "latitude", "depth", "ioffset", "iyear", "imonth", "iday", "temp",
+                                     "salinity", "uvel", "vvel", "evap", "late", "sens"]
+        assert f.variables["longitude"].units == b"degrees_east" and f.variables["latitude"].long_name == b"latitude"
+        assert f.variables["longitude"].data.dtype == np.dtype(">f4") and f.variables["temp"].data.dtype == np.dtype(">f8")
+        assert f.variables["iyear"].data.dtype == np.dtype(">i4") and f.variables["temp"].dimensions == ("depth", "latitude", "longitude")
+        assert [int(f.variables[n].data[0]) for n in ("iyear", "imonth", "iday", "ioffset")] == [2010, 7, 4, 123]
+        assert np.array_equal(f.variables["longitude"].data, s["lon"].astype(np.float32))
+        assert np.array_equal(f.variables["depth"].data, s["depth"].astype(np.float32))
+        ocean = (s["k1"][1:J + 1, 1:I + 1] <= K)[None, :, :]            # whole column written if any level is wet
+        assert np.array_equal(f.variables["temp"].data, s["ts"][..., 0] * ocean)
+        assert np.array_equal(f.variables["salinity"].data, s["ts"][..., 1] * ocean)
+        assert np.array_equal(f.variables["uvel"].data, s["u"][..., 0]) and np.array_equal(f.variables["vvel"].data, s["u"][..., 1])
+        assert not f.variables["evap"].data.any() and f.variables["sens"].data.shape == (J, I)
+    # read back: T, S and u, v replaced, the other tracers and w untouched
+    ts2, u2 = np.full_like(s["ts"], 7.0), np.full_like(s["u"], 7.0)
+    date = np.zeros(4, dtype=np.int32)
+    assert L.cg_restart_goldstein_read(p.encode(), I, J, K, Lt, dp(ts2), dp(u2), None, None, None, ip(date)) == 0
+    assert np.array_equal(date, s["date"])
+    assert np.array_equal(ts2[..., 0], s["ts"][..., 0] * ocean) and np.array_equal(u2[..., :2], s["u"][..., :2])
+    assert (ts2[..., 2:] == 7.0).all() and (u2[..., 2] == 7.0).all()
+
+
+def test_embm_and_seaice_restart_round_trip(state, tmp_path):
+    L = _lib.load()
+    s = state
+    pe, ps = str(tmp_path / "embm.nc"), str(tmp_path / "sic.nc")
+    assert L.cg_restart_embm_write(pe.encode(), I, J, dp(s["lon"]), dp(s["lat"]), dp(s["tq"]), ip(s["date"])) == 0
+    assert L.cg_restart_seaice_write(ps.encode(), I, J, ip(s["k1"]), dp(s["lon"]), dp(s["lat"]), dp(s["va"]), dp(s["tice"]),
+                                     dp(s["alb"]), ip(s["date"])) == 0
+    with netcdf_file(pe, "r", mmap=False) as f:
+        assert list(f.variables) == ["longitude", "latitude", "ioffset", "iyear", "imonth", "iday", "air_temp", "humidity"]
+        assert np.array_equal(f.variables["air_temp"].data, s["tq"][..., 0]) and np.array_equal(f.variables["humidity"].data, s["tq"][..., 1])
+        assert not hasattr(f.variables["longitude"], "units")            # only GOLDSTEIN's file carries axis attributes
+    sea = s["k1"][1:J + 1, 1:I + 1] < 90
+    with netcdf_file(ps, "r", mmap=False) as f:
+        assert list(f.variables)[-4:] == ["sic_height", "sic_cover", "sic_temp", "sic_albedo"]
+        assert np.array_equal(f.variables["sic_height"].data, s["va"][..., 0] * sea)
+        assert np.array_equal(f.variables["sic_temp"].data, s["tice"])   # temperature and albedo are not masked
+    tq, va, ti, al, date = np.empty(2 * I * J), np.empty(2 * I * J), np.empty(I * J), np.empty(I * J), np.zeros(4, dtype=np.int32)
+    assert L.cg_restart_embm_read(pe.encode(), I, J, dp(tq), ip(date)) == 0 and np.array_equal(tq.reshape(J, I, 2), s["tq"])
+    assert L.cg_restart_seaice_read(ps.encode(), I, J, dp(va), dp(ti), dp(al), ip(date)) == 0
+    assert np.array_equal(va.reshape(J, I, 2), s["va"] * sea[..., None]) and np.array_equal(al.reshape(J, I), s["alb"])
+
+
+def test_reads_files_written_by_another_netcdf3_writer(state, tmp_path):
+    """A restart as netCDF-3 itself lays it out (scipy's writer: different variable order, an extra variable, a global
+    attribute, 64-bit offsets) is read back bit for bit."""
+    L = _lib.load()
+    s = state
+    for version in (1, 2):
+        p = str(tmp_path / ("other%d.nc" % version))
+        with netcdf_file(p, "w", version=version) as f:
+            f.history = "written by scipy"
+            for n, l in (("longitude", I), ("latitude", J), ("nrecs", 1)):
+                f.createDimension(n, l)
+            f.createVariable("humidity", "d", ("latitude", "longitude"))[:] = s["tq"][..., 1]
+            f.createVariable("extra", "f", ("longitude",))[:] = 1.5
+            f.createVariable("air_temp", "d", ("latitude", "longitude"))[:] = s["tq"][..., 0]
+            for n, v in (("iday", 30), ("imonth", 12), ("iyear", 1999), ("ioffset", 0)):
+                f.createVariable(n, "i", ("nrecs",))[:] = v
+        tq, date = np.empty(2 * I * J), np.zeros(4, dtype=np.int32)
+        assert L.cg_restart_embm_read(p.encode(), I, J, dp(tq), ip(date)) == 0
+        assert np.array_equal(tq.reshape(J, I, 2), s["tq"]) and list(date) == [1999, 12, 30, 0]
+
+
+def test_restart_errors_are_loud(state, tmp_path):
+    L = _lib.load()
+    tq, date = np.empty(2 * I * J), np.zeros(4, dtype=np.int32)
+    assert L.cg_restart_embm_read(str(tmp_path / "nope.nc").encode(), I, J, dp(tq), ip(date)) == 2
+    assert b"Missing file" in L.cg_restart_last_error()                  # the reference's message (embm_data.f90:30-33)
+    bad = tmp_path / "bad.nc"
+    bad.write_bytes(b"HDF5 is not what this reads")
+    assert L.cg_restart_embm_read(str(bad).encode(), I, J, dp(tq), ip(date)) == 2 and b"not a netCDF classic" in L.cg_restart_last_error()
+    s = state
+    p = str(tmp_path / "small.nc")
+    assert L.cg_restart_embm_write(p.encode(), I, J, dp(s["lon"]), dp(s["lat"]), dp(s["tq"]), ip(s["date"])) == 0
+    assert L.cg_restart_embm_read(p.encode(), I + 1, J, dp(np.empty(2 * (I + 1) * J)), ip(date)) == 2
+    assert b"wrong size" in L.cg_restart_last_error()
+    assert L.cg_restart_seaice_read(p.encode(), I, J, dp(tq), dp(tq), dp(tq), ip(date)) == 2 and b"sic_height missing" in L.cg_restart_last_error()
