@@ -128,3 +128,19 @@ def test_restart_errors_are_loud(state, tmp_path):
     assert L.cg_restart_embm_read(p.encode(), I + 1, J, dp(np.empty(2 * (I + 1) * J)), ip(date)) == 2
     assert b"wrong size" in L.cg_restart_last_error()
     assert L.cg_restart_seaice_read(p.encode(), I, J, dp(tq), dp(tq), dp(tq), ip(date)) == 2 and b"sic_height missing" in L.cg_restart_last_error()
+
+
+def test_axes_from_host_constants(built, tmp_path):
+    """The restart's coordinate variables from the library's own grid constants (cg_create only, no device): cGENIE's
+    36x36x8 grid -- longitudes -255 .. 95 in steps of 10, sin(latitude) uniform, layer mid-depths 4234.5 .. 80.8 m."""
+    from cgenie_b200 import materialise
+    from test_host_init import HostOnly
+    materialise(str(tmp_path), "eb_go_gs_36x36x8")
+    h = HostOnly(str(tmp_path))
+    try:
+        lon, lat, depth = axes(36, 36, 8, h.const("s"), h.const("zro"))
+    finally:
+        h.close()
+    assert np.allclose(lon, np.arange(-255.0, 100.0, 10.0), rtol=0, atol=1e-12)
+    assert np.allclose(np.sin(np.radians(lat)), (np.arange(36) + 0.5) / 18.0 - 1.0, atol=1e-14)
+    assert np.allclose(depth, [4234.5166, 3008.3391, 2099.7254, 1426.4307, 927.5105, 557.8040, 283.8467, 80.8407], atol=1e-3)
