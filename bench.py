@@ -301,7 +301,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": "model-years/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "path": "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein/biogem_*/atchem), state in/out of pinned host per year"},
     }
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # the CPU arm is timed next to the N=1 line only
         cores = os.cpu_count() or 1
         rate, wall = cpu_oracle_rate(10.0, cores)
         out["cpu_baseline"] = {"value": rate, "unit": "model-years/hour", "cores": cores, "kind": "port",
