@@ -9,6 +9,7 @@ _LIB = None
 P = C.c_void_p
 D = C.POINTER(C.c_double)
 I32 = C.POINTER(C.c_int32)
+STRS = C.POINTER(C.c_char_p)
 
 
 class SurfluxIO(C.Structure):
@@ -85,6 +86,9 @@ SYMBOLS = {
     "cg_restart_embm_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, D, I32]),
     "cg_restart_seaice_write": (C.c_int, [C.c_char_p, C.c_int, C.c_int, I32, D, D, D, D, D, I32]),
     "cg_restart_seaice_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, D, D, D, I32]),
+    "cg_restart_biogem_write": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [I32] + [D] * 6 + [C.c_int, STRS, STRS, D] * 2 +
+                                [C.c_double, C.c_char_p]),
+    "cg_restart_biogem_read": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [I32] + [C.c_int, STRS, D, I32] * 2),
 }
 
 

@@ -27,10 +27,22 @@ struct Out {
   void u64(uint64_t v) { for (int s = 56; s >= 0; s -= 8) b.push_back((unsigned char)(v >> s)); }
   void pad() { while (b.size() % 4) b.push_back(0); }
   void name(const std::string &s) { u32((uint32_t)s.size()); b.insert(b.end(), s.begin(), s.end()); pad(); }
-  void atts(const std::vector<std::pair<std::string, std::string>> &a) {
+  void atts(const std::vector<cg::Nc3Att> &a) {
     if (a.empty()) { u32(0); u32(0); return; }
     u32(kAttTag); u32((uint32_t)a.size());
-    for (auto &kv : a) { name(kv.first); u32(NC3_CHAR); u32((uint32_t)kv.second.size()); b.insert(b.end(), kv.second.begin(), kv.second.end()); pad(); }
+    for (auto &t : a) {
+      name(t.name); u32((uint32_t)t.type);
+      if (t.type == NC3_CHAR) { u32((uint32_t)t.text.size()); b.insert(b.end(), t.text.begin(), t.text.end()); }
+      else {
+        u32((uint32_t)t.num.size());
+        for (double x : t.num) {
+          if (t.type == NC3_DOUBLE) { uint64_t u; std::memcpy(&u, &x, 8); u64(u); }
+          else if (t.type == NC3_FLOAT) { const float f = (float)x; uint32_t u; std::memcpy(&u, &f, 4); u32(u); }
+          else u32((uint32_t)(int32_t)std::llround(x));
+        }
+      }
+      pad();
+    }
   }
 };
 struct In {
@@ -45,16 +57,29 @@ struct In {
     p += (n + 3) / 4 * 4;
     return s;
   }
-  void atts(std::vector<std::pair<std::string, std::string>> *out) {
+  void atts(std::vector<cg::Nc3Att> *out) {
     const uint32_t tag = u32(), n = u32();
     if (tag == 0 && n == 0) return;
     if (tag != kAttTag) { ok = false; return; }
     for (uint32_t q = 0; q < n && ok; q++) {
-      const std::string nm = name();
-      const uint32_t ty = u32(), ne = u32();
-      const size_t bytes = (size_t)ne * (ty == NC3_CHAR || ty == 1 ? 1 : ty == 3 ? 2 : ty == NC3_DOUBLE ? 8 : 4);
+      cg::Nc3Att t;
+      t.name = name();
+      t.type = (int)u32();
+      const uint32_t ne = u32();
+      const size_t es = (t.type == NC3_CHAR || t.type == 1) ? 1 : t.type == 3 ? 2 : t.type == NC3_DOUBLE ? 8 : 4;
+      const size_t bytes = (size_t)ne * es;
       if (p + bytes > b.size()) { ok = false; return; }
-      if (ty == NC3_CHAR && out) out->push_back({nm, std::string((const char *)&b[p], ne)});
+      if (t.type == NC3_CHAR) t.text.assign((const char *)&b[p], ne);
+      else if (t.type == NC3_DOUBLE || t.type == NC3_FLOAT || t.type == NC3_INT)
+        for (uint32_t e = 0; e < ne; e++) {
+          const unsigned char *c = &b[p + e * es];
+          uint64_t u = 0;
+          for (size_t s2 = 0; s2 < es; s2++) u = (u << 8) | c[s2];
+          if (t.type == NC3_DOUBLE) { double d; std::memcpy(&d, &u, 8); t.num.push_back(d); }
+          else if (t.type == NC3_FLOAT) { const uint32_t u4 = (uint32_t)u; float f; std::memcpy(&f, &u4, 4); t.num.push_back(f); }
+          else t.num.push_back((int32_t)(uint32_t)u);
+        }
+      if (out) out->push_back(t);
       p += (bytes + 3) / 4 * 4;
     }
   }
@@ -70,7 +95,14 @@ int Nc3File::add_var(const std::string &name, int type, const std::vector<int> &
   vars.push_back(v);
   return (int)vars.size() - 1;
 }
-void Nc3File::put_att(int varid, const std::string &name, const std::string &value) { vars[varid].atts.push_back({name, value}); }
+void Nc3File::put_att(int varid, const std::string &name, const std::string &value) {
+  Nc3Att t; t.name = name; t.type = NC3_CHAR; t.text = value;
+  (varid < 0 ? gatts : vars[varid].atts).push_back(t);
+}
+void Nc3File::put_att_num(int varid, const std::string &name, int type, const std::vector<double> &v) {
+  Nc3Att t; t.name = name; t.type = type; t.num = v;
+  (varid < 0 ? gatts : vars[varid].atts).push_back(t);
+}
 void Nc3File::put(int varid, const double *v, long long n) { for (long long q = 0; q < n && q < vars[varid].count; q++) vars[varid].data[q] = v[q]; }
 void Nc3File::put(int varid, const int *v, long long n) { for (long long q = 0; q < n && q < vars[varid].count; q++) vars[varid].data[q] = v[q]; }
 const Nc3Var *Nc3File::var(const std::string &name) const {
@@ -392,5 +424,123 @@ extern "C" int cg_restart_seaice_read(const char *path, int maxi, int maxj, doub
   const cg::Nc3Var *v[4];
   for (int q = 0; q < 4; q++) { v[q] = need(f, names[q], n2, &err); if (!v[q]) return rfail(std::string(path) + ": " + err); }
   for (long long c = 0; c < n2; c++) { varice[2 * c] = v[0]->data[c]; varice[2 * c + 1] = v[1]->data[c]; tice[c] = v[2]->data[c]; albice[c] = v[3]->data[c]; }
+  return CG_OK;
+}
+
+// ------------------------------------------------------------------ BIOGEM restart (ctrl_ncrst = .TRUE., the default)
+// sub_data_netCDF_ncrstsave, src/biogem/biogem_data_netCDF.f90:24-142, through the helpers of src/common/gem_netcdf.f90
+// (sub_putglobal :176-217, sub_defvar :250-359, sub_putvar1d :569-602, sub_putvar3d :746-786, edge_maker :877-913).
+namespace {
+constexpr double kNcFillDouble = 9.9692099683868690e+36;   // nf90_fill_double
+// sub_defvar: [valid_range only if rmin != rmax -- never here], missing_value (always a DOUBLE attribute, also on float
+// variables), axis, edges (axis variables that are not themselves *_edges), long_name, standard_name, units
+int defvar(cg::Nc3File &f, const std::string &name, int type, const std::vector<int> &dimids, const std::string &axis,
+           const std::string &lname, const std::string &sname, const std::string &units) {
+  const int id = f.add_var(name, type, dimids);
+  f.put_att_num(id, "missing_value", cg::NC3_DOUBLE, {kNcFillDouble});
+  if (axis != " ") {
+    f.put_att(id, "axis", axis);
+    const bool is_edges = name.size() >= 6 && name.compare(name.size() - 6, 6, "_edges") == 0;
+    if (axis != "T" && !is_edges) f.put_att(id, "edges", name + "_edges");
+  }
+  if (lname != " ") f.put_att(id, "long_name", lname);
+  if (sname != " ") f.put_att(id, "standard_name", sname);
+  if (units != " ") f.put_att(id, "units", units);
+  return id;
+}
+}  // namespace
+
+// ocn (n_ocn,n_i,n_j,n_k) and bio_part (n_sed,n_i,n_j,n_k) in Fortran order, k = 1 the deepest level; the file holds every
+// tracer as a FLOAT variable (zt, lat, lon) with the surface first and the fill value on dry cells (mask = k >= k1(i,j)).
+// lon / lat (t grid), lon_e (0:n_i), lat_e (0:n_j), zt (n_k, surface first) and zt_e (0:n_k) are the axes the reference
+// takes from phys_ocn (biogem_data.f90:1115-1123) through edge_maker.
+extern "C" int cg_restart_biogem_write(const char *path, int n_i, int n_j, int n_k, const int32_t *k1, const double *lon,
+                                       const double *lat, const double *lon_e, const double *lat_e, const double *zt,
+                                       const double *zt_e, int n_ocn, const char *const *ocn_names,
+                                       const char *const *ocn_longnames, const double *ocn, int n_sed,
+                                       const char *const *sed_names, const char *const *sed_longnames, const double *bio_part,
+                                       double year, const char *run_id) {
+  if (!path || !k1 || !lon || !lat || !lon_e || !lat_e || !zt || !zt_e || n_ocn < 0 || n_sed < 0 || (n_ocn && (!ocn_names || !ocn_longnames || !ocn)) ||
+      (n_sed && (!sed_names || !sed_longnames || !bio_part)))
+    return rfail("cg_restart_biogem_write: bad argument");
+  cg::Nc3File f;
+  // sub_putglobal; loc_string_year is CHARACTER(7) and receives the 8-digit fun_conv_num_char_n(8, int(yr)): the last
+  // digit is cut off (biogem_data_netCDF.f90:41,62).  loc_timunit is never set there; it is left out.
+  char y8[16];
+  std::snprintf(y8, sizeof y8, "%08d", (int)year);
+  f.put_att(-1, "Conventions", "CF-1.0");
+  f.put_att(-1, "file_name", path);
+  f.put_att(-1, "title", std::string("BIOGEM restart @ year ") + std::string(y8).substr(0, 7));
+  if (run_id && *run_id) f.put_att(-1, "experiment_name", run_id);
+  const int d_lon = f.add_dim("lon", n_i), d_lat = f.add_dim("lat", n_j), d_lone = f.add_dim("lon_edges", n_i + 1),
+            d_late = f.add_dim("lat_edges", n_j + 1), d_zt = f.add_dim("zt", n_k), d_zte = f.add_dim("zt_edges", n_k + 1);
+  const int v_lon = defvar(f, "lon", cg::NC3_DOUBLE, {d_lon}, "X", "longitude of the t grid", "longitude", "degrees_east");
+  const int v_lat = defvar(f, "lat", cg::NC3_DOUBLE, {d_lat}, "Y", "latitude of the t grid", "latitude", "degrees_north");
+  const int v_lone = defvar(f, "lon_edges", cg::NC3_DOUBLE, {d_lone}, " ", "longitude of t grid edges", " ", "degrees");
+  const int v_late = defvar(f, "lat_edges", cg::NC3_DOUBLE, {d_late}, " ", "latitude of t grid edges", " ", "degrees");
+  const int v_zt = defvar(f, "zt", cg::NC3_DOUBLE, {d_zt}, "Z", "depth of z grid", " ", "cm");
+  const int v_zte = defvar(f, "zt_edges", cg::NC3_DOUBLE, {d_zte}, " ", "depth of z grid edges", " ", "m");
+  std::vector<int> ido(n_ocn), ids(n_sed);
+  for (int l = 0; l < n_ocn; l++)
+    ido[l] = defvar(f, std::string("ocn_") + ocn_names[l], cg::NC3_FLOAT, {d_zt, d_lat, d_lon}, " ", ocn_longnames[l],
+                    std::string("Ocean tracer - ") + ocn_names[l], " ");
+  for (int l = 0; l < n_sed; l++)
+    ids[l] = defvar(f, std::string("bio_part_") + sed_names[l], cg::NC3_FLOAT, {d_zt, d_lat, d_lon}, " ", sed_longnames[l],
+                    std::string("Particulate tracer - ") + sed_names[l], " ");
+  f.put(v_lon, lon, n_i); f.put(v_lat, lat, n_j); f.put(v_lone, lon_e, n_i + 1); f.put(v_late, lat_e, n_j + 1);
+  f.put(v_zt, zt, n_k); f.put(v_zte, zt_e, n_k + 1);
+  const size_t n3 = (size_t)n_i * n_j * n_k;
+  std::vector<double> a(n3);
+  for (int pass = 0; pass < 2; pass++) {
+    const int nt = pass ? n_sed : n_ocn;
+    const double *src = pass ? bio_part : ocn;
+    for (int l = 0; l < nt; l++) {
+      for (int k = 0; k < n_k; k++)       // file level k (0 = surface) = model level n_k - k (loc_ijk(:,:,n_k:1:-1))
+        for (int j = 0; j < n_j; j++)
+          for (int i = 0; i < n_i; i++) {
+            const int km = n_k - k;       // 1-based model level
+            const bool wet = km >= k1[(i + 1) + (size_t)(n_i + 2) * (j + 1)];
+            const size_t cell = (size_t)i + (size_t)n_i * (j + (size_t)n_j * (km - 1));
+            a[(size_t)i + (size_t)n_i * (j + (size_t)n_j * k)] = wet ? src[l + (size_t)nt * cell] : kNcFillDouble;
+          }
+      f.put(pass ? ids[l] : ido[l], a.data(), (long long)n3);
+    }
+  }
+  std::string err;
+  if (!f.write(path, &err)) return rfail(err);
+  return CG_OK;
+}
+// sub_data_load_rst, biogem_data.f90:438-568 (netCDF branch) with sub_getvarijk (gem_netcdf.f90:1120-1151): every selected
+// tracer whose variable is in the file is replaced (levels flipped back); tracers without a variable keep their values.
+// The reference also stores the file's fill value on dry cells; here dry cells are left alone (nothing reads them).
+// found_ocn / found_sed (may be NULL): 1 for tracers that were in the file.
+extern "C" int cg_restart_biogem_read(const char *path, int n_i, int n_j, int n_k, const int32_t *k1, int n_ocn,
+                                      const char *const *ocn_names, double *ocn, int32_t *found_ocn, int n_sed,
+                                      const char *const *sed_names, double *bio_part, int32_t *found_sed) {
+  if (!path || !k1 || (n_ocn && (!ocn_names || !ocn)) || (n_sed && (!sed_names || !bio_part))) return rfail("cg_restart_biogem_read: bad argument");
+  cg::Nc3File f;
+  std::string err;
+  if (!f.read(path, &err)) return rfail(err);
+  const long long n3 = (long long)n_i * n_j * n_k;
+  for (int pass = 0; pass < 2; pass++) {
+    const int nt = pass ? n_sed : n_ocn;
+    double *dst = pass ? bio_part : ocn;
+    for (int l = 0; l < nt; l++) {
+      const std::string name = std::string(pass ? "bio_part_" : "ocn_") + (pass ? sed_names : ocn_names)[l];
+      const cg::Nc3Var *v = f.var(name);
+      int32_t *found = pass ? found_sed : found_ocn;
+      if (found) found[l] = v ? 1 : 0;
+      if (!v) continue;
+      if (v->count != n3) return rfail(std::string(path) + ": variable " + name + " has the wrong size");
+      for (int k = 0; k < n_k; k++)
+        for (int j = 0; j < n_j; j++)
+          for (int i = 0; i < n_i; i++) {
+            const int km = n_k - k;
+            if (km < k1[(i + 1) + (size_t)(n_i + 2) * (j + 1)]) continue;
+            const size_t cell = (size_t)i + (size_t)n_i * (j + (size_t)n_j * (km - 1));
+            dst[l + (size_t)nt * cell] = v->data[(size_t)i + (size_t)n_i * (j + (size_t)n_j * k)];
+          }
+    }
+  }
   return CG_OK;
 }

@@ -95,3 +95,91 @@ def read_restart(e, paths, member=0):
     e.put("tice", tice, member)
     e.put("albice", alb, member)
     return date
+
+
+# ------------------------------------------------------------------ BIOGEM (frozen tracer selection)
+# string_ocn / string_longname_ocn and string_sed / string_longname_sed of the selected tracers, in conv_iselected order
+# (data/main/tracer_define.ocn, tracer_define.sed: columns 1 and 5)
+OCN_TRACERS = [("temp", "temperature"), ("sal", "salinity"), ("DIC", "dissolved inorganic carbon (DIC)"),
+               ("DIC_13C", "d13C of DIC"), ("DIC_14C", "d14C of DIC"), ("PO4", "dissolved phosphate (PO4)"),
+               ("O2", "dissolved oxygen (O2)"), ("ALK", "alkalinity (ALK)"),
+               ("DOM_C", "dissolved organic matter (DOM); carbon"), ("DOM_C_13C", "d13C of DOM-C"),
+               ("DOM_C_14C", "d14C of DOM-C"), ("DOM_P", "dissolved organic matter; phosphorous"),
+               ("Ca", "dissolved calcium (Ca)"), ("CFC11", "dissolved CFC-11"), ("CFC12", "dissolved CFC-12"),
+               ("Mg", "dissolved Magnesium (Mg)")]
+SED_TRACERS = [("POC", "particulate organic carbon (POC)"), ("POC_13C", "d13C of POC"), ("POC_14C", "d14C of POC"),
+               ("POP", "particulate organic phosphate (POP)"), ("CaCO3", "calcium carbonate (CaCO3)"),
+               ("CaCO3_13C", "d13C of CaCO3"), ("CaCO3_14C", "d14C of CaCO3"), ("POC_frac2", "n/a"), ("CaCO3_frac2", "n/a")]
+
+
+def _strs(items):
+    arr = (C.c_char_p * len(items))(*[x.encode() for x in items])
+    return C.cast(arr, C.POINTER(C.c_char_p)), arr
+
+
+def biogem_axes(n_i, n_j, n_k, s, sv, dz, dza):
+    """The coordinate variables of BIOGEM's files: phys_ocn lon / lat / Dmid, their edges through edge_maker
+    (biogem_data.f90:1115-1123, gem_netcdf.f90:877-913, biogem_data_netCDF.f90:107-119).  s, sv (0:n_j), dz, dza (0:n_k)
+    are GOLDSTEIN's grid arrays; par_grid_lon_offset = -260."""
+    off = -260.0
+    lon = np.array([(360.0 / n_i) * (float(i) - 0.5) + off for i in range(1, n_i + 1)])
+    lone = np.array([(360.0 / n_i) * float(i) + off for i in range(1, n_i + 1)])
+    lon_e = np.concatenate([[lone[0] - 360.0 / n_i], lone])
+    rad = 180.0 / np.pi
+    lat = np.array([rad * np.arcsin(s[j]) for j in range(1, n_j + 1)])
+    latn = np.array([rad * np.arcsin(sv[j]) for j in range(1, n_j + 1)])
+    dlat1 = rad * (np.arcsin(sv[1]) - np.arcsin(sv[0]))
+    lat_e = np.concatenate([[latn[0] - dlat1], latn])
+
+    dza = np.array(dza, dtype=np.float64)
+    dza[n_k] = dz[n_k] / 2.0     # loc_grid_dza(n_k) = loc_grid_dz(n_k)/2.0, biogem_data.f90:1105
+
+    def tail_sum(a, k):          # SUM(dsc * a(k:n_k)), added in index order
+        t = 0.0
+        for q in range(k, n_k + 1):
+            t = t + DSC * a[q]
+        return t
+    dmid = [tail_sum(dza, k) for k in range(1, n_k + 1)]
+    dbot = [tail_sum(dz, k) for k in range(1, n_k + 1)]
+    zt = np.array(dmid[::-1])
+    zt_e = np.concatenate([[0.0], dbot[::-1]])       # loc_zt_e(0) = 0.0 overrides edge_maker's first edge
+    return lon, lat, lon_e, lat_e, zt, zt_e
+
+
+def write_biogem_restart(e, path, member=0, year=0.0, run_id=""):
+    """BIOGEM's netCDF restart of one member (ocean tracers and particulates as FLOAT variables, as the reference stores them)."""
+    L = _lib.load()
+    I, J, K = e.maxi, e.maxj, e.maxk
+    if e.maxl != len(OCN_TRACERS):
+        raise RestartError("BIOGEM restart: the job's tracer selection is not the frozen one")
+    k1 = np.ascontiguousarray(e.iconst("k1"), dtype=np.int32)
+    ax = [np.ascontiguousarray(a, dtype=np.float64) for a in
+          biogem_axes(I, J, K, e.const("s"), e.const("sv"), e.const("dz"), e.const("dza"))]
+    ocn = np.ascontiguousarray(e.get("ocn", member), dtype=np.float64)
+    part = np.ascontiguousarray(e.get("bio_part", member), dtype=np.float64)
+    on, keep1 = _strs([n for n, _ in OCN_TRACERS])
+    ol, keep2 = _strs([l for _, l in OCN_TRACERS])
+    sn, keep3 = _strs([n for n, _ in SED_TRACERS])
+    sl, keep4 = _strs([l for _, l in SED_TRACERS])
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    _ck(L.cg_restart_biogem_write(path.encode(), I, J, K, _ip(k1), *[_dp(a) for a in ax], len(OCN_TRACERS), on, ol, _dp(ocn),
+                                  len(SED_TRACERS), sn, sl, _dp(part), float(year), run_id.encode()))
+    return path
+
+
+def read_biogem_restart(e, path, member=0):
+    """sub_data_load_rst: ocn and bio_part of one member from a BIOGEM netCDF restart (any cGENIE run with the same grid; tracers
+    the file does not hold keep their values), then ts is rebuilt from ocn as initialise_biogem does.  Returns the names found."""
+    L = _lib.load()
+    I, J, K = e.maxi, e.maxj, e.maxk
+    k1 = np.ascontiguousarray(e.iconst("k1"), dtype=np.int32)
+    ocn = np.ascontiguousarray(e.get("ocn", member), dtype=np.float64)
+    part = np.ascontiguousarray(e.get("bio_part", member), dtype=np.float64)
+    on, keep1 = _strs([n for n, _ in OCN_TRACERS])
+    sn, keep3 = _strs([n for n, _ in SED_TRACERS])
+    fo, fs = np.zeros(len(OCN_TRACERS), dtype=np.int32), np.zeros(len(SED_TRACERS), dtype=np.int32)
+    _ck(L.cg_restart_biogem_read(path.encode(), I, J, K, _ip(k1), len(OCN_TRACERS), on, _dp(ocn), _ip(fo),
+                                 len(SED_TRACERS), sn, _dp(part), _ip(fs)))
+    e.put("ocn", ocn, member)
+    e.put("bio_part", part, member)
+    return [n for (n, _), f in zip(OCN_TRACERS, fo) if f] + [n for (n, _), f in zip(SED_TRACERS, fs) if f]

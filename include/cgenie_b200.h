@@ -210,6 +210,19 @@ int cg_restart_embm_read(const char *path, int maxi, int maxj, double *tq, int32
 int cg_restart_seaice_write(const char *path, int maxi, int maxj, const int32_t *k1, const double *lon, const double *lat,
                             const double *varice, const double *tice, const double *albice, const int32_t date[4]);
 int cg_restart_seaice_read(const char *path, int maxi, int maxj, double *varice, double *tice, double *albice, int32_t date[4]);
+/* BIOGEM's restart (ctrl_ncrst = .TRUE.): sub_data_netCDF_ncrstsave (src/biogem/biogem_data_netCDF.f90:24-142) and the netCDF
+ * branch of sub_data_load_rst (src/biogem/biogem_data.f90:438-568).  ocn (n_ocn,n_i,n_j,n_k), bio_part (n_sed,n_i,n_j,n_k);
+ * names = string_ocn / string_sed of the selected tracers (tracer_define.ocn / .sed column 1), long names column 5.  The
+ * file stores FLOAT variables "ocn_<name>", "bio_part_<name>" (zt, lat, lon), surface first, fill value on dry cells --
+ * the reference's restart is single precision.  read: tracers without a variable keep their values (found_* = 0). */
+int cg_restart_biogem_write(const char *path, int n_i, int n_j, int n_k, const int32_t *k1, const double *lon, const double *lat,
+                            const double *lon_e, const double *lat_e, const double *zt, const double *zt_e, int n_ocn,
+                            const char *const *ocn_names, const char *const *ocn_longnames, const double *ocn, int n_sed,
+                            const char *const *sed_names, const char *const *sed_longnames, const double *bio_part,
+                            double year, const char *run_id);
+int cg_restart_biogem_read(const char *path, int n_i, int n_j, int n_k, const int32_t *k1, int n_ocn, const char *const *ocn_names,
+                           double *ocn, int32_t *found_ocn, int n_sed, const char *const *sed_names, double *bio_part,
+                           int32_t *found_sed);
 
 #ifdef __cplusplus
 }

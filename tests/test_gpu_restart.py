@@ -45,3 +45,36 @@ def test_restart_round_trip_through_device(built, tmp_path):
             assert np.array_equal(e.get(n, 0), before0[n]), n
         e.run(5 * 4)                      # the restarted member keeps running
         assert int(e.health().sum()) == 0
+
+
+def test_biogem_restart_through_device(built, tmp_path):
+    """BIOGEM's netCDF restart (single precision, as the reference stores it) of one member written from the device and
+    read into another member: wet cells carry the float-rounded values, the second member keeps running."""
+    from cgenie_b200.restart import OCN_TRACERS, SED_TRACERS, read_biogem_restart, write_biogem_restart
+    job = tmp_path / "job"
+    materialise(str(job), "eb_go_gs_ac_bg_36x36x16")
+    k0 = np.array([2.0e-6, 1.7e-6])
+    with Ensemble(str(job), n_members=2, perturb={"par_bio_k0_PO4": k0}) as e:
+        e.run(5 * 40)
+        I, J, K, L = e.maxi, e.maxj, e.maxk, e.maxl
+        LS = len(SED_TRACERS)
+        p = write_biogem_restart(e, str(tmp_path / "rst" / "biogem_restart.nc"), member=1, year=0.4, run_id="test")
+        with netcdf_file(p, "r", mmap=False) as f:
+            assert len(f.variables) == 6 + L + LS and f.variables["ocn_temp"].data.dtype == np.dtype(">f4")
+            sst = f.variables["ocn_temp"].data[0]
+            assert 270.0 < sst[sst < 1e30].min() and sst[sst < 1e30].max() < 310.0      # BIOGEM keeps temperature in K
+        src_ocn = e.get("ocn", 1).reshape(K, J, I, L).copy()
+        src_part = e.get("bio_part", 1).reshape(K, J, I, LS).copy()
+        found = read_biogem_restart(e, p, member=0)
+        assert found == [n for n, _ in OCN_TRACERS] + [n for n, _ in SED_TRACERS]
+        k1 = e.iconst("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+        wet = np.arange(1, K + 1)[:, None, None] >= k1[None]
+        got_ocn = e.get("ocn", 0).reshape(K, J, I, L)
+        got_part = e.get("bio_part", 0).reshape(K, J, I, LS)
+        for l in range(L):
+            assert np.array_equal(got_ocn[..., l][wet], src_ocn[..., l].astype(np.float32).astype(np.float64)[wet]), OCN_TRACERS[l]
+        for l in range(LS):
+            assert np.array_equal(got_part[..., l][wet], src_part[..., l].astype(np.float32).astype(np.float64)[wet]), SED_TRACERS[l]
+        assert np.array_equal(e.get("ocn", 1).reshape(K, J, I, L), src_ocn)              # the source member is untouched
+        e.run(5 * 4)
+        assert int(e.health().sum()) == 0

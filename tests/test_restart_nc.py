@@ -144,3 +144,67 @@ def test_axes_from_host_constants(built, tmp_path):
     assert np.allclose(lon, np.arange(-255.0, 100.0, 10.0), rtol=0, atol=1e-12)
     assert np.allclose(np.sin(np.radians(lat)), (np.arange(36) + 0.5) / 18.0 - 1.0, atol=1e-14)
     assert np.allclose(depth, [4234.5166, 3008.3391, 2099.7254, 1426.4307, 927.5105, 557.8040, 283.8467, 80.8407], atol=1e-3)
+
+
+def test_biogem_restart_layout_and_round_trip(state, tmp_path):
+    """BIOGEM's restart (biogem_data_netCDF.f90:24-142): FLOAT tracer variables, surface first, fill value on dry cells, the
+    attributes sub_defvar writes; read back with the levels flipped and dry cells left alone."""
+    from cgenie_b200.restart import OCN_TRACERS, SED_TRACERS, _strs, biogem_axes
+    from cgenie_b200 import materialise
+    from test_host_init import HostOnly
+    L = _lib.load()
+    job = tmp_path / "job"
+    materialise(str(job), "eb_go_gs_ac_bg_36x36x16")
+    h = HostOnly(str(job))
+    try:
+        k1 = h.iconst("k1")
+        ax = [np.ascontiguousarray(a) for a in biogem_axes(I, J, K, h.const("s"), h.const("sv"), h.const("dz"), h.const("dza"))]
+    finally:
+        h.close()
+    rng = np.random.default_rng(9)
+    no, ns = len(OCN_TRACERS), len(SED_TRACERS)
+    ocn = rng.uniform(1e-6, 3e-3, size=(K, J, I, no))
+    part = rng.uniform(0, 1e-9, size=(K, J, I, ns))
+    on, k_1 = _strs([n for n, _ in OCN_TRACERS]); ol, k_2 = _strs([l for _, l in OCN_TRACERS])
+    sn, k_3 = _strs([n for n, _ in SED_TRACERS]); sl, k_4 = _strs([l for _, l in SED_TRACERS])
+    p = str(tmp_path / "biogem_restart.nc")
+    assert L.cg_restart_biogem_write(p.encode(), I, J, K, ip(k1), *[dp(a) for a in ax], no, on, ol, dp(ocn), ns, sn, sl, dp(part),
+                                     123.0, b"run_x") == 0, L.cg_restart_last_error()
+    k1ij = k1.reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    wet = (np.arange(1, K + 1)[:, None, None] >= k1ij[None])             # [k][j][i], k = 1 deepest
+    with netcdf_file(p, "r", mmap=False) as f:
+        assert f.title == b"BIOGEM restart @ year 0000012" and f.Conventions == b"CF-1.0" and f.experiment_name == b"run_x"
+        assert list(f.dimensions.items()) == [("lon", I), ("lat", J), ("lon_edges", I + 1), ("lat_edges", J + 1), ("zt", K), ("zt_edges", K + 1)]
+        names = list(f.variables)
+        assert names[:6] == ["lon", "lat", "lon_edges", "lat_edges", "zt", "zt_edges"]
+        assert names[6:6 + no] == ["ocn_" + n for n, _ in OCN_TRACERS] and names[6 + no:] == ["bio_part_" + n for n, _ in SED_TRACERS]
+        lon = f.variables["lon"]
+        assert lon.axis == b"X" and lon.edges == b"lon_edges" and lon.units == b"degrees_east" and lon.standard_name == b"longitude"
+        assert lon.missing_value == 9.9692099683868690e+36 and not hasattr(f.variables["lon_edges"], "axis")
+        assert f.variables["zt"].units == b"cm" and f.variables["zt_edges"].units == b"m"
+        assert np.allclose(f.variables["lon_edges"].data, np.arange(-260.0, 101.0, 10.0)) and f.variables["zt_edges"].data[0] == 0.0
+        zt, zte = f.variables["zt"].data, f.variables["zt_edges"].data
+        assert np.all(np.diff(zt) > 0) and np.all(zte[:-1] < zt) and np.all(zt < zte[1:]) and abs(zte[-1] - 5000.0) < 1e-9
+        assert abs(zt[0] - 0.5 * zte[1]) < 1e-9            # the top level's mid-depth is half its thickness (biogem_data.f90:1105)
+        v = f.variables["ocn_DIC"]
+        assert v.data.dtype == np.dtype(">f4") and v.dimensions == ("zt", "lat", "lon")
+        assert v.long_name == b"dissolved inorganic carbon (DIC)" and v.standard_name == b"Ocean tracer - DIC"
+        assert v.missing_value == 9.9692099683868690e+36 and not hasattr(v, "units")
+        want = np.where(wet, ocn[..., 2], 9.9692099683868690e+36)[::-1].astype(np.float32)
+        assert np.array_equal(v.data, want)
+        assert np.array_equal(f.variables["bio_part_CaCO3_frac2"].data, np.where(wet, part[..., 8], 9.9692099683868690e+36)[::-1].astype(np.float32))
+    ocn2, part2 = np.full_like(ocn, -1.0), np.full_like(part, -1.0)
+    fo, fs = np.zeros(no, dtype=np.int32), np.zeros(ns, dtype=np.int32)
+    assert L.cg_restart_biogem_read(p.encode(), I, J, K, ip(k1), no, on, dp(ocn2), ip(fo), ns, sn, dp(part2), ip(fs)) == 0
+    assert fo.all() and fs.all()
+    w4 = np.broadcast_to(wet[..., None], ocn.shape)
+    assert np.array_equal(ocn2[w4], ocn.astype(np.float32).astype(np.float64)[w4]) and (ocn2[~w4] == -1.0).all()
+    assert np.array_equal(part2[..., 3][wet], part[..., 3].astype(np.float32).astype(np.float64)[wet])
+    # a file with fewer tracers (another tracer selection): what it holds is taken, the rest is kept
+    q = str(tmp_path / "partial.nc")
+    with netcdf_file(q, "w") as f:
+        f.createDimension("lon", I); f.createDimension("lat", J); f.createDimension("zt", K)
+        f.createVariable("ocn_PO4", "f", ("zt", "lat", "lon"))[:] = 2.5e-6
+    assert L.cg_restart_biogem_read(q.encode(), I, J, K, ip(k1), no, on, dp(ocn2), ip(fo), ns, sn, dp(part2), ip(fs)) == 0
+    assert list(np.nonzero(fo)[0]) == [5] and not fs.any()
+    assert np.all(ocn2[..., 5][wet] == np.float32(2.5e-6)) and np.array_equal(ocn2[..., 2][wet], ocn.astype(np.float32).astype(np.float64)[..., 2][wet])
