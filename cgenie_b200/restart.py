@@ -167,9 +167,10 @@ def write_biogem_restart(e, path, member=0, year=0.0, run_id=""):
     return path
 
 
-def read_biogem_restart(e, path, member=0):
+def read_biogem_restart(e, path, member=0, force_goldstein_ts=True, saln0=34.9):
     """sub_data_load_rst: ocn and bio_part of one member from a BIOGEM netCDF restart (any cGENIE run with the same grid; tracers
-    the file does not hold keep their values), then ts is rebuilt from ocn as initialise_biogem does.  Returns the names found."""
+    the file does not hold keep their values), then the biogeochemical tracers of ts are rebuilt from ocn as initialise_biogem
+    does (biogem.f90:495-508).  Returns the names found."""
     L = _lib.load()
     I, J, K = e.maxi, e.maxj, e.maxk
     k1 = np.ascontiguousarray(e.iconst("k1"), dtype=np.int32)
@@ -182,4 +183,21 @@ def read_biogem_restart(e, path, member=0):
                                  len(SED_TRACERS), sn, _dp(part), _ip(fs)))
     e.put("ocn", ocn, member)
     e.put("bio_part", part, member)
+    # sub_biogem_copy_ocntots (biogem_box.f90:3691-3739, ctrl_misc_Snorm): the biogeochemical tracers of GOLDSTEIN's ts
+    # (and ts1) are the salinity-normalised ocn
+    Lt = e.maxl
+    o4 = ocn.reshape(K, J, I, Lt)
+    k1ij = k1.reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    wet = np.arange(1, K + 1)[:, None, None] >= k1ij[None]
+    V = np.asarray(e.const("bg_V"), dtype=np.float64).reshape(K, J, I)
+    tot_V = np.cumsum(np.where(wet, V, 0.0).ravel())[-1]                      # sequential, in array order
+    mean_S = np.cumsum(np.where(wet, o4[..., 1] * V, 0.0).ravel())[-1] / tot_V
+    ts = np.ascontiguousarray(e.get("ts", member), dtype=np.float64).reshape(K, J, I, Lt)
+    S = np.where(wet, o4[..., 1], 1.0)
+    for l in range(2, Lt):
+        ts[..., l] = np.where(wet, o4[..., l] * (mean_S / S), ts[..., l])
+    if force_goldstein_ts:   # ctrl_force_GOLDSTEInTS (default .TRUE.): sub_biogem_copy_ocntotsTS, biogem_box.f90:3769-3790
+        ts[..., 0] = np.where(wet, o4[..., 0] - 273.15, ts[..., 0])
+        ts[..., 1] = np.where(wet, o4[..., 1] - saln0, ts[..., 1])
+    e.put("ts", ts.ravel(), member)
     return [n for (n, _), f in zip(OCN_TRACERS, fo) if f] + [n for (n, _), f in zip(SED_TRACERS, fs) if f]

@@ -76,5 +76,13 @@ def test_biogem_restart_through_device(built, tmp_path):
         for l in range(LS):
             assert np.array_equal(got_part[..., l][wet], src_part[..., l].astype(np.float32).astype(np.float64)[wet]), SED_TRACERS[l]
         assert np.array_equal(e.get("ocn", 1).reshape(K, J, I, L), src_ocn)              # the source member is untouched
+        # GOLDSTEIN's ts of the restarted member: T, S from ocn (ctrl_force_GOLDSTEInTS), the other tracers salinity-normalised
+        ts0 = e.get("ts", 0).reshape(K, J, I, L)
+        V = e.const("bg_V").reshape(K, J, I)
+        mean_S = (got_ocn[..., 1] * V)[wet].sum() / V[wet].sum()
+        assert np.array_equal(ts0[..., 0][wet], (got_ocn[..., 0] - 273.15)[wet])
+        assert np.allclose(ts0[..., 1][wet], got_ocn[..., 1][wet] - 34.9, rtol=0, atol=1e-12)
+        for l in (2, 5, 15):
+            assert np.allclose(ts0[..., l][wet], (got_ocn[..., l] * mean_S / got_ocn[..., 1])[wet], rtol=1e-12, atol=0)
         e.run(5 * 4)
         assert int(e.health().sum()) == 0
