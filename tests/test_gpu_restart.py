@@ -83,6 +83,6 @@ def test_biogem_restart_through_device(built, tmp_path):
         assert np.array_equal(ts0[..., 0][wet], (got_ocn[..., 0] - 273.15)[wet])
         assert np.allclose(ts0[..., 1][wet], got_ocn[..., 1][wet] - 34.9, rtol=0, atol=1e-12)
         for l in (2, 5, 15):
-            assert np.allclose(ts0[..., l][wet], (got_ocn[..., l] * mean_S / got_ocn[..., 1])[wet], rtol=1e-12, atol=0)
+            assert np.allclose(ts0[..., l][wet], got_ocn[..., l][wet] * mean_S / got_ocn[..., 1][wet], rtol=1e-12, atol=0)
         e.run(5 * 4)
         assert int(e.health().sum()) == 0
