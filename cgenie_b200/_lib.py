@@ -89,6 +89,12 @@ SYMBOLS = {
     "cg_restart_biogem_write": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [I32] + [D] * 6 + [C.c_int, STRS, STRS, D] * 2 +
                                 [C.c_double, C.c_char_p]),
     "cg_restart_biogem_read": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [I32] + [C.c_int, STRS, D, I32] * 2),
+    "cg_restart_atchem_write": (C.c_int, [C.c_char_p, C.c_int, C.c_int] + [D] * 4 + [C.c_int, STRS, STRS, D, C.c_double, C.c_char_p]),
+    "cg_restart_atchem_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, STRS, D, I32]),
+    "cg_restart_atchem_write_bin": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, I32, D]),
+    "cg_restart_atchem_read_bin": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, I32, D, I32]),
+    "cg_restart_biogem_write_bin": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [C.c_int, I32, D] * 2),
+    "cg_restart_biogem_read_bin": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [C.c_int, I32, D, I32] * 2),
 }
 
 

@@ -544,3 +544,176 @@ extern "C" int cg_restart_biogem_read(const char *path, int n_i, int n_j, int n_
   }
   return CG_OK;
 }
+
+// ------------------------------------------------------------------ ATCHEM restart (ctrl_ncrst = .TRUE., the default)
+// sub_data_netCDF_ncrstsave, src/atchem/atchem_data_netCDF.f90:22-109 (title, dimensions lon / lat / lon_edges / lat_edges, one
+// FLOAT variable atm_<name>(lat, lon) per selected atmosphere tracer, mask = 1 everywhere: sub_putvar2d, gem_netcdf.f90:664-699).
+// atm (n_atm, n_i, n_j) in Fortran order.  lon / lat / lon_e / lat_e: phys_atm's axes through edge_maker
+// (atchem_data.f90:195-229); they equal BIOGEM's (biogem_axes in restart.py) on the same grid.
+extern "C" int cg_restart_atchem_write(const char *path, int n_i, int n_j, const double *lon, const double *lat, const double *lon_e,
+                                       const double *lat_e, int n_atm, const char *const *atm_names,
+                                       const char *const *atm_longnames, const double *atm, double year, const char *run_id) {
+  if (!path || !lon || !lat || !lon_e || !lat_e || n_i <= 0 || n_j <= 0 || n_atm < 0 || (n_atm && (!atm_names || !atm_longnames || !atm)))
+    return rfail("cg_restart_atchem_write: bad argument");
+  cg::Nc3File f;
+  char y8[16];                                       // CHARACTER(7) receives 8 digits, as in BIOGEM's writer (:34,59)
+  std::snprintf(y8, sizeof y8, "%08d", (int)year);
+  f.put_att(-1, "Conventions", "CF-1.0");
+  f.put_att(-1, "file_name", path);
+  f.put_att(-1, "title", std::string("ATCHEM restart @ year ") + std::string(y8).substr(0, 7));
+  if (run_id && *run_id) f.put_att(-1, "experiment_name", run_id);
+  const int d_lon = f.add_dim("lon", n_i), d_lat = f.add_dim("lat", n_j), d_lone = f.add_dim("lon_edges", n_i + 1),
+            d_late = f.add_dim("lat_edges", n_j + 1);
+  const int v_lon = defvar(f, "lon", cg::NC3_DOUBLE, {d_lon}, "X", "longitude of the t grid", "longitude", "degrees_east");
+  const int v_lat = defvar(f, "lat", cg::NC3_DOUBLE, {d_lat}, "Y", "latitude of the t grid", "latitude", "degrees_north");
+  const int v_lone = defvar(f, "lon_edges", cg::NC3_DOUBLE, {d_lone}, " ", "longitude of t grid edges", " ", "degrees");
+  const int v_late = defvar(f, "lat_edges", cg::NC3_DOUBLE, {d_late}, " ", "latitude of t grid edges", " ", "degrees");
+  std::vector<int> ida(n_atm);
+  for (int l = 0; l < n_atm; l++)
+    ida[l] = defvar(f, std::string("atm_") + atm_names[l], cg::NC3_FLOAT, {d_lat, d_lon}, " ", atm_longnames[l],
+                    std::string("Atmosphere tracer - ") + atm_names[l], " ");
+  f.put(v_lon, lon, n_i); f.put(v_lat, lat, n_j); f.put(v_lone, lon_e, n_i + 1); f.put(v_late, lat_e, n_j + 1);
+  const size_t n2 = (size_t)n_i * n_j;
+  std::vector<double> a(n2);
+  for (int l = 0; l < n_atm; l++) {
+    for (size_t c = 0; c < n2; c++) a[c] = atm[l + (size_t)n_atm * c];
+    f.put(ida[l], a.data(), (long long)n2);
+  }
+  std::string err;
+  if (!f.write(path, &err)) return rfail(err);
+  return CG_OK;
+}
+// sub_data_load_rst, atchem_data.f90:89-189 (netCDF branch) with sub_getvarij (gem_netcdf.f90:1048-1079): every selected tracer
+// whose variable atm_<name> is in the file is replaced; the others keep their values.  found (may be NULL): 1 if in the file.
+extern "C" int cg_restart_atchem_read(const char *path, int n_i, int n_j, int n_atm, const char *const *atm_names, double *atm,
+                                      int32_t *found) {
+  if (!path || n_i <= 0 || n_j <= 0 || n_atm < 0 || (n_atm && (!atm_names || !atm))) return rfail("cg_restart_atchem_read: bad argument");
+  cg::Nc3File f;
+  std::string err;
+  if (!f.read(path, &err)) return rfail(err);
+  const long long n2 = (long long)n_i * n_j;
+  for (int l = 0; l < n_atm; l++) {
+    const std::string name = std::string("atm_") + atm_names[l];
+    const cg::Nc3Var *v = f.var(name);
+    if (found) found[l] = v ? 1 : 0;
+    if (!v) continue;
+    if (v->count != n2) return rfail(std::string(path) + ": variable " + name + " has the wrong size");
+    for (long long c = 0; c < n2; c++) atm[l + (size_t)n_atm * c] = v->data[c];
+  }
+  return CG_OK;
+}
+
+// ------------------------------------------------------------------ binary restarts (ctrl_ncrst = .FALSE.)
+// One Fortran unformatted sequential record (gfortran: 4-byte little-endian length before and after the payload; INTEGER is
+// 4 bytes, REAL is 8 under -fdefault-real-8, platforms/LINUX:9):
+//   ATCHEM  atchem.f90:192-197      n_l_atm, conv_iselected_ia(1:n_l_atm), (atm(ia,:,:), l = 1,n_l_atm)
+//   BIOGEM  biogem.f90:2347-2355    n_l_ocn, conv_iselected_io, (ocn(io,:,:,:)), n_l_sed, conv_iselected_is, (bio_part(is,:,:,:))
+// ids: the tracers' global indices (ia / io / is of tracer_define.*), which is what the reader matches on
+// (atchem_data.f90:176-180, biogem_data.f90:540-547).  Arrays (n_sel, cells) in Fortran order as above, written in full
+// (dry cells included, as the reference does).
+namespace {
+struct FRecord {
+  std::vector<unsigned char> b;
+  void i32(int32_t v) { unsigned char *p = (unsigned char *)&v; b.insert(b.end(), p, p + 4); }
+  void f64(double v) { unsigned char *p = (unsigned char *)&v; b.insert(b.end(), p, p + 8); }
+  // tracer l of an (n, cells) array, as the array section a(id,:,:[,:])
+  void section(const double *a, int n, int l, size_t cells) { for (size_t c = 0; c < cells; c++) f64(a[l + (size_t)n * c]); }
+  bool write(const char *path, std::string *err) const {
+    if (b.size() > 0x7fffffffu) { *err = std::string(path) + ": record longer than 2 GiB (gfortran would split it)"; return false; }
+    FILE *fp = std::fopen(path, "wb");
+    if (!fp) { *err = std::string("cannot open ") + path + " for writing"; return false; }
+    const int32_t n = (int32_t)b.size();
+    bool ok = std::fwrite(&n, 4, 1, fp) == 1 && (b.empty() || std::fwrite(b.data(), 1, b.size(), fp) == b.size()) && std::fwrite(&n, 4, 1, fp) == 1;
+    ok = (std::fclose(fp) == 0) && ok;
+    if (!ok) *err = std::string("short write to ") + path;
+    return ok;
+  }
+};
+struct FReader {
+  std::vector<unsigned char> b;
+  size_t pos = 0;
+  bool open(const char *path, std::string *err) {
+    FILE *fp = std::fopen(path, "rb");
+    if (!fp) { *err = std::string("cannot open ") + path; return false; }
+    int32_t n = 0, n2 = -1;
+    bool ok = std::fread(&n, 4, 1, fp) == 1 && n >= 0;
+    if (ok) { b.resize((size_t)n); ok = (n == 0 || std::fread(b.data(), 1, b.size(), fp) == b.size()) && std::fread(&n2, 4, 1, fp) == 1 && n2 == n; }
+    std::fclose(fp);
+    if (!ok) *err = std::string(path) + ": not a single-record Fortran unformatted file";
+    return ok;
+  }
+  bool i32(int32_t *v) { if (pos + 4 > b.size()) return false; std::memcpy(v, &b[pos], 4); pos += 4; return true; }
+  // reads the section of tracer id into column l of an (n, cells) array; l < 0: skipped (a tracer the caller did not select)
+  bool section(double *a, int n, int l, size_t cells) {
+    if (pos + 8 * cells > b.size()) return false;
+    if (l >= 0) for (size_t c = 0; c < cells; c++) std::memcpy(&a[l + (size_t)n * c], &b[pos + 8 * c], 8);
+    pos += 8 * cells;
+    return true;
+  }
+};
+int find_id(const int32_t *ids, int n, int32_t id) { for (int l = 0; l < n; l++) if (ids[l] == id) return l; return -1; }
+// one (count, ids, sections) group of a record into an (n, cells) array
+bool read_group(FReader &r, int n, const int32_t *ids, double *a, int32_t *found, size_t cells) {
+  int32_t nf = 0;
+  if (!r.i32(&nf) || nf < 0 || nf > 4096) return false;
+  std::vector<int32_t> fid(nf);
+  for (int l = 0; l < nf; l++) if (!r.i32(&fid[l])) return false;
+  if (found) for (int l = 0; l < n; l++) found[l] = 0;
+  for (int l = 0; l < nf; l++) {
+    const int mine = find_id(ids, n, fid[l]);
+    if (mine >= 0 && found) found[mine] = 1;
+    if (!r.section(a, n, mine, cells)) return false;
+  }
+  return true;
+}
+}  // namespace
+
+extern "C" int cg_restart_atchem_write_bin(const char *path, int n_i, int n_j, int n_atm, const int32_t *atm_ids, const double *atm) {
+  if (!path || n_i <= 0 || n_j <= 0 || n_atm < 0 || (n_atm && (!atm_ids || !atm))) return rfail("cg_restart_atchem_write_bin: bad argument");
+  FRecord r;
+  r.i32(n_atm);
+  for (int l = 0; l < n_atm; l++) r.i32(atm_ids[l]);
+  for (int l = 0; l < n_atm; l++) r.section(atm, n_atm, l, (size_t)n_i * n_j);
+  std::string err;
+  return r.write(path, &err) ? CG_OK : rfail(err);
+}
+// The reference reads atm(loc_conv_iselected_ia(l),:,:) for every tracer of the FILE (atchem_data.f90:176-180): tracers of the
+// file the caller has not selected are skipped here (the reference stores them in its full-size array, where nothing uses them).
+extern "C" int cg_restart_atchem_read_bin(const char *path, int n_i, int n_j, int n_atm, const int32_t *atm_ids, double *atm,
+                                          int32_t *found) {
+  if (!path || n_i <= 0 || n_j <= 0 || n_atm < 0 || (n_atm && (!atm_ids || !atm))) return rfail("cg_restart_atchem_read_bin: bad argument");
+  FReader r;
+  std::string err;
+  if (!r.open(path, &err)) return rfail(err);
+  if (!read_group(r, n_atm, atm_ids, atm, found, (size_t)n_i * n_j) || r.pos != r.b.size())
+    return rfail(std::string(path) + ": record does not hold an ATCHEM restart of this grid");
+  return CG_OK;
+}
+extern "C" int cg_restart_biogem_write_bin(const char *path, int n_i, int n_j, int n_k, int n_ocn, const int32_t *ocn_ids,
+                                           const double *ocn, int n_sed, const int32_t *sed_ids, const double *bio_part) {
+  if (!path || n_i <= 0 || n_j <= 0 || n_k <= 0 || n_ocn < 0 || n_sed < 0 || (n_ocn && (!ocn_ids || !ocn)) || (n_sed && (!sed_ids || !bio_part)))
+    return rfail("cg_restart_biogem_write_bin: bad argument");
+  const size_t n3 = (size_t)n_i * n_j * n_k;
+  FRecord r;
+  r.b.reserve(8 + 4 * (size_t)(n_ocn + n_sed) + 8 * n3 * (size_t)(n_ocn + n_sed));
+  r.i32(n_ocn);
+  for (int l = 0; l < n_ocn; l++) r.i32(ocn_ids[l]);
+  for (int l = 0; l < n_ocn; l++) r.section(ocn, n_ocn, l, n3);
+  r.i32(n_sed);
+  for (int l = 0; l < n_sed; l++) r.i32(sed_ids[l]);
+  for (int l = 0; l < n_sed; l++) r.section(bio_part, n_sed, l, n3);
+  std::string err;
+  return r.write(path, &err) ? CG_OK : rfail(err);
+}
+extern "C" int cg_restart_biogem_read_bin(const char *path, int n_i, int n_j, int n_k, int n_ocn, const int32_t *ocn_ids, double *ocn,
+                                          int32_t *found_ocn, int n_sed, const int32_t *sed_ids, double *bio_part, int32_t *found_sed) {
+  if (!path || n_i <= 0 || n_j <= 0 || n_k <= 0 || n_ocn < 0 || n_sed < 0 || (n_ocn && (!ocn_ids || !ocn)) || (n_sed && (!sed_ids || !bio_part)))
+    return rfail("cg_restart_biogem_read_bin: bad argument");
+  FReader r;
+  std::string err;
+  if (!r.open(path, &err)) return rfail(err);
+  const size_t n3 = (size_t)n_i * n_j * n_k;
+  if (!read_group(r, n_ocn, ocn_ids, ocn, found_ocn, n3) || !read_group(r, n_sed, sed_ids, bio_part, found_sed, n3) || r.pos != r.b.size())
+    return rfail(std::string(path) + ": record does not hold a BIOGEM restart of this grid");
+  return CG_OK;
+}

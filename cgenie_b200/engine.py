@@ -363,6 +363,9 @@ class EnsembleGroups:
     def put(self, name, values, member=0):
         self.parts[member // self.group].put(name, values, member % self.group)
 
+    def field_size(self, name):
+        return self.parts[0].field_size(name)
+
     def iconst(self, name):
         return self.parts[0].iconst(name)
 

@@ -167,20 +167,9 @@ def write_biogem_restart(e, path, member=0, year=0.0, run_id=""):
     return path
 
 
-def read_biogem_restart(e, path, member=0, force_goldstein_ts=True, saln0=34.9):
-    """sub_data_load_rst: ocn and bio_part of one member from a BIOGEM netCDF restart (any cGENIE run with the same grid; tracers
-    the file does not hold keep their values), then the biogeochemical tracers of ts are rebuilt from ocn as initialise_biogem
-    does (biogem.f90:495-508).  Returns the names found."""
-    L = _lib.load()
+def _apply_biogem_restart(e, member, ocn, part, k1, force_goldstein_ts, saln0):
+    """Stores a loaded ocn / bio_part and rebuilds GOLDSTEIN's ts from ocn as initialise_biogem does (biogem.f90:495-508)."""
     I, J, K = e.maxi, e.maxj, e.maxk
-    k1 = np.ascontiguousarray(e.iconst("k1"), dtype=np.int32)
-    ocn = np.ascontiguousarray(e.get("ocn", member), dtype=np.float64)
-    part = np.ascontiguousarray(e.get("bio_part", member), dtype=np.float64)
-    on, keep1 = _strs([n for n, _ in OCN_TRACERS])
-    sn, keep3 = _strs([n for n, _ in SED_TRACERS])
-    fo, fs = np.zeros(len(OCN_TRACERS), dtype=np.int32), np.zeros(len(SED_TRACERS), dtype=np.int32)
-    _ck(L.cg_restart_biogem_read(path.encode(), I, J, K, _ip(k1), len(OCN_TRACERS), on, _dp(ocn), _ip(fo),
-                                 len(SED_TRACERS), sn, _dp(part), _ip(fs)))
     e.put("ocn", ocn, member)
     e.put("bio_part", part, member)
     # sub_biogem_copy_ocntots (biogem_box.f90:3691-3739, ctrl_misc_Snorm): the biogeochemical tracers of GOLDSTEIN's ts
@@ -200,4 +189,123 @@ def read_biogem_restart(e, path, member=0, force_goldstein_ts=True, saln0=34.9):
         ts[..., 0] = np.where(wet, o4[..., 0] - 273.15, ts[..., 0])
         ts[..., 1] = np.where(wet, o4[..., 1] - saln0, ts[..., 1])
     e.put("ts", ts.ravel(), member)
+
+
+def read_biogem_restart(e, path, member=0, force_goldstein_ts=True, saln0=34.9):
+    """sub_data_load_rst: ocn and bio_part of one member from a BIOGEM netCDF restart (any cGENIE run with the same grid; tracers
+    the file does not hold keep their values), then the biogeochemical tracers of ts are rebuilt from ocn as initialise_biogem
+    does (biogem.f90:495-508).  Returns the names found."""
+    L = _lib.load()
+    I, J, K = e.maxi, e.maxj, e.maxk
+    k1 = np.ascontiguousarray(e.iconst("k1"), dtype=np.int32)
+    ocn = np.ascontiguousarray(e.get("ocn", member), dtype=np.float64)
+    part = np.ascontiguousarray(e.get("bio_part", member), dtype=np.float64)
+    on, keep1 = _strs([n for n, _ in OCN_TRACERS])
+    sn, keep3 = _strs([n for n, _ in SED_TRACERS])
+    fo, fs = np.zeros(len(OCN_TRACERS), dtype=np.int32), np.zeros(len(SED_TRACERS), dtype=np.int32)
+    _ck(L.cg_restart_biogem_read(path.encode(), I, J, K, _ip(k1), len(OCN_TRACERS), on, _dp(ocn), _ip(fo),
+                                 len(SED_TRACERS), sn, _dp(part), _ip(fs)))
+    _apply_biogem_restart(e, member, ocn, part, k1, force_goldstein_ts, saln0)
+    return [n for (n, _), f in zip(OCN_TRACERS, fo) if f] + [n for (n, _), f in zip(SED_TRACERS, fs) if f]
+
+
+# ------------------------------------------------------------------ ATCHEM (frozen selection: ia = 1,2,3,4,5,6,18,19)
+# (ia, string_atm, string_longname_atm) from data/main/tracer_define.atm columns 2, 1 and 5
+ATM_TRACERS = [(1, "temp", "surface air temperature"), (2, "humidity", "specific humidity"), (3, "pCO2", "carbon dioxide (CO2)"),
+               (4, "pCO2_13C", "d13C CO2"), (5, "pCO2_14C", "d14C CO2"), (6, "pO2", "oxygen (O2)"), (18, "pCFC11", "CFC-11"),
+               (19, "pCFC12", "CFC-12")]
+# io / is of the frozen ocean and particulate selections (tracer_define.ocn / .sed column 2), in OCN_TRACERS / SED_TRACERS order
+OCN_IDS = [1, 2, 3, 4, 5, 8, 10, 12, 15, 16, 17, 20, 35, 45, 46, 50]
+SED_IDS = [3, 4, 5, 8, 14, 15, 16, 33, 34]
+
+
+def atchem_axes(n_i, n_j):
+    """phys_atm's lon / lat and their edges through edge_maker (atchem_data.f90:195-229, atchem_data_netCDF.f90:87-92): the
+    sine-latitude grid is rebuilt from -pi/2 .. pi/2 there, not taken from GOLDSTEIN."""
+    off = -260.0
+    lon = np.array([(360.0 / n_i) * (float(i) - 0.5) + off for i in range(1, n_i + 1)])
+    lone = np.array([(360.0 / n_i) * float(i) + off for i in range(1, n_i + 1)])
+    lon_e = np.concatenate([[lone[0] - 360.0 / n_i], lone])
+    s0, s1 = np.sin(-np.pi / 2), np.sin(np.pi / 2)
+    ds = (s1 - s0) / float(n_j)
+    sv = np.array([s0 + float(j) * ds for j in range(0, n_j + 1)])
+    s = sv - 0.5 * ds
+    rad = 180.0 / np.pi
+    lat = rad * np.arcsin(s[1:])
+    latn = rad * np.arcsin(sv[1:])
+    lat_e = np.concatenate([[latn[0] - rad * (np.arcsin(sv[1]) - np.arcsin(sv[0]))], latn])
+    return lon, lat, lon_e, lat_e
+
+
+def _atm_check(e):
+    if e.field_size("atm") != len(ATM_TRACERS) * e.maxi * e.maxj:
+        raise RestartError("ATCHEM restart: the job's atmosphere tracer selection is not the frozen one")
+
+
+def write_atchem_restart(e, path, member=0, year=0.0, run_id="", binary=False):
+    """atchem_save_rst (atchem.f90:160-199): the netCDF restart of one member's atm array, or the unformatted dump."""
+    L = _lib.load()
+    _atm_check(e)
+    I, J = e.maxi, e.maxj
+    atm = np.ascontiguousarray(e.get("atm", member), dtype=np.float64)
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    if binary:
+        ids = np.array([ia for ia, _, _ in ATM_TRACERS], dtype=np.int32)
+        _ck(L.cg_restart_atchem_write_bin(path.encode(), I, J, len(ATM_TRACERS), _ip(ids), _dp(atm)))
+        return path
+    ax = [np.ascontiguousarray(a, dtype=np.float64) for a in atchem_axes(I, J)]
+    an, keep1 = _strs([n for _, n, _ in ATM_TRACERS])
+    al, keep2 = _strs([l for _, _, l in ATM_TRACERS])
+    _ck(L.cg_restart_atchem_write(path.encode(), I, J, *[_dp(a) for a in ax], len(ATM_TRACERS), an, al, _dp(atm), float(year),
+                                  run_id.encode()))
+    return path
+
+
+def read_atchem_restart(e, path, member=0, binary=False):
+    """sub_data_load_rst (atchem_data.f90:89-189): the member's atm array from an ATCHEM restart; initialise_atchem hands the
+    same values to the coupler as sfcatm (atchem.f90:54), and cpl_comp_atmocn copies tracers 3..n_atm of it to the ocean-grid
+    sfcatm1 (atchem.f90:252-264), so those rows of sfcatm1 are rewritten too.  Returns the names found."""
+    L = _lib.load()
+    _atm_check(e)
+    I, J = e.maxi, e.maxj
+    atm = np.ascontiguousarray(e.get("atm", member), dtype=np.float64)
+    fa = np.zeros(len(ATM_TRACERS), dtype=np.int32)
+    if binary:
+        ids = np.array([ia for ia, _, _ in ATM_TRACERS], dtype=np.int32)
+        _ck(L.cg_restart_atchem_read_bin(path.encode(), I, J, len(ATM_TRACERS), _ip(ids), _dp(atm), _ip(fa)))
+    else:
+        an, keep1 = _strs([n for _, n, _ in ATM_TRACERS])
+        _ck(L.cg_restart_atchem_read(path.encode(), I, J, len(ATM_TRACERS), an, _dp(atm), _ip(fa)))
+    e.put("atm", atm, member)
+    n = len(ATM_TRACERS)
+    sfc = np.ascontiguousarray(e.get("sfcatm1", member), dtype=np.float64).reshape(J * I, n)
+    sfc[:, 2:] = atm.reshape(J * I, n)[:, 2:]
+    e.put("sfcatm1", sfc.ravel(), member)
+    return [n for (_, n, _), f in zip(ATM_TRACERS, fa) if f]
+
+
+def write_biogem_restart_bin(e, path, member=0):
+    """biogem_save_restart, binary branch (biogem.f90:2340-2358): ocn and bio_part in full double precision."""
+    L = _lib.load()
+    if e.maxl != len(OCN_TRACERS):
+        raise RestartError("BIOGEM restart: the job's tracer selection is not the frozen one")
+    ocn = np.ascontiguousarray(e.get("ocn", member), dtype=np.float64)
+    part = np.ascontiguousarray(e.get("bio_part", member), dtype=np.float64)
+    io, isd = np.array(OCN_IDS, dtype=np.int32), np.array(SED_IDS, dtype=np.int32)
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    _ck(L.cg_restart_biogem_write_bin(path.encode(), e.maxi, e.maxj, e.maxk, len(io), _ip(io), _dp(ocn), len(isd), _ip(isd), _dp(part)))
+    return path
+
+
+def read_biogem_restart_bin(e, path, member=0, force_goldstein_ts=True, saln0=34.9):
+    """sub_data_load_rst, binary branch (biogem_data.f90:540-550), then the same ts rebuild as read_biogem_restart."""
+    L = _lib.load()
+    k1 = np.ascontiguousarray(e.iconst("k1"), dtype=np.int32)
+    ocn = np.ascontiguousarray(e.get("ocn", member), dtype=np.float64)
+    part = np.ascontiguousarray(e.get("bio_part", member), dtype=np.float64)
+    io, isd = np.array(OCN_IDS, dtype=np.int32), np.array(SED_IDS, dtype=np.int32)
+    fo, fs = np.zeros(len(io), dtype=np.int32), np.zeros(len(isd), dtype=np.int32)
+    _ck(L.cg_restart_biogem_read_bin(path.encode(), e.maxi, e.maxj, e.maxk, len(io), _ip(io), _dp(ocn), _ip(fo), len(isd), _ip(isd),
+                                     _dp(part), _ip(fs)))
+    _apply_biogem_restart(e, member, ocn, part, k1, force_goldstein_ts, saln0)
     return [n for (n, _), f in zip(OCN_TRACERS, fo) if f] + [n for (n, _), f in zip(SED_TRACERS, fs) if f]

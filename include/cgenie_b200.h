@@ -224,6 +224,26 @@ int cg_restart_biogem_read(const char *path, int n_i, int n_j, int n_k, const in
                            double *ocn, int32_t *found_ocn, int n_sed, const char *const *sed_names, double *bio_part,
                            int32_t *found_sed);
 
+/* ATCHEM's restart (ctrl_ncrst = .TRUE.): sub_data_netCDF_ncrstsave (src/atchem/atchem_data_netCDF.f90:22-109) and the netCDF
+ * branch of sub_data_load_rst (src/atchem/atchem_data.f90:89-189).  atm (n_atm,n_i,n_j); names / long names = string_atm /
+ * string_longname_atm of the selected tracers (tracer_define.atm columns 1 and 5).  FLOAT variables "atm_<name>" (lat, lon),
+ * no mask.  lon / lat / lon_e (0:n_i) / lat_e (0:n_j): phys_atm's axes (atchem_data.f90:195-229) through edge_maker. */
+int cg_restart_atchem_write(const char *path, int n_i, int n_j, const double *lon, const double *lat, const double *lon_e,
+                            const double *lat_e, int n_atm, const char *const *atm_names, const char *const *atm_longnames,
+                            const double *atm, double year, const char *run_id);
+int cg_restart_atchem_read(const char *path, int n_i, int n_j, int n_atm, const char *const *atm_names, double *atm, int32_t *found);
+/* Binary restarts (ctrl_ncrst = .FALSE.): one gfortran unformatted sequential record, INTEGER*4 and REAL*8
+ * (-fdefault-real-8, platforms/LINUX:9), full double precision.  ATCHEM: atchem_save_rst (src/atchem/atchem.f90:186-198) /
+ * sub_data_load_rst (atchem_data.f90:175-181); BIOGEM: biogem_save_restart (src/biogem/biogem.f90:2340-2358) /
+ * sub_data_load_rst (biogem_data.f90:540-550).  *_ids: the tracers' global indices (conv_iselected_ia / _io / _is), which
+ * the record carries and the reader matches on; tracers of the file the caller did not select are skipped. */
+int cg_restart_atchem_write_bin(const char *path, int n_i, int n_j, int n_atm, const int32_t *atm_ids, const double *atm);
+int cg_restart_atchem_read_bin(const char *path, int n_i, int n_j, int n_atm, const int32_t *atm_ids, double *atm, int32_t *found);
+int cg_restart_biogem_write_bin(const char *path, int n_i, int n_j, int n_k, int n_ocn, const int32_t *ocn_ids, const double *ocn,
+                                int n_sed, const int32_t *sed_ids, const double *bio_part);
+int cg_restart_biogem_read_bin(const char *path, int n_i, int n_j, int n_k, int n_ocn, const int32_t *ocn_ids, double *ocn,
+                               int32_t *found_ocn, int n_sed, const int32_t *sed_ids, double *bio_part, int32_t *found_sed);
+
 #ifdef __cplusplus
 }
 #endif

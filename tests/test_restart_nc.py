@@ -208,3 +208,101 @@ def test_biogem_restart_layout_and_round_trip(state, tmp_path):
     assert L.cg_restart_biogem_read(q.encode(), I, J, K, ip(k1), no, on, dp(ocn2), ip(fo), ns, sn, dp(part2), ip(fs)) == 0
     assert list(np.nonzero(fo)[0]) == [5] and not fs.any()
     assert np.all(ocn2[..., 5][wet] == np.float32(2.5e-6)) and np.array_equal(ocn2[..., 2][wet], ocn.astype(np.float32).astype(np.float64)[..., 2][wet])
+
+
+def test_atchem_restart_layout_and_round_trip(built, tmp_path):
+    """ATCHEM's netCDF restart (atchem_data_netCDF.f90:22-109): four dimensions, the axes sub_defvar describes, one FLOAT
+    variable (lat, lon) per selected tracer with no mask; the reader replaces what the file holds (atchem_data.f90:152-163)."""
+    from cgenie_b200.restart import ATM_TRACERS, _strs, atchem_axes
+    L = _lib.load()
+    na = len(ATM_TRACERS)
+    rng = np.random.default_rng(21)
+    atm = rng.uniform(1e-9, 3e-4, size=(J, I, na))                       # Fortran (n_atm, n_i, n_j)
+    ax = [np.ascontiguousarray(a) for a in atchem_axes(I, J)]
+    an, k_1 = _strs([n for _, n, _ in ATM_TRACERS]); al, k_2 = _strs([l for _, _, l in ATM_TRACERS])
+    p = str(tmp_path / "atchem_restart.nc")
+    assert L.cg_restart_atchem_write(p.encode(), I, J, *[dp(a) for a in ax], na, an, al, dp(atm), 10000.0, b"run_y") == 0, L.cg_restart_last_error()
+    with netcdf_file(p, "r", mmap=False) as f:
+        assert f.version_byte == 1
+        assert f.title == b"ATCHEM restart @ year 0001000" and f.Conventions == b"CF-1.0" and f.experiment_name == b"run_y"
+        assert list(f.dimensions.items()) == [("lon", I), ("lat", J), ("lon_edges", I + 1), ("lat_edges", J + 1)]
+        assert list(f.variables) == ["lon", "lat", "lon_edges", "lat_edges"] + ["atm_" + n for _, n, _ in ATM_TRACERS]
+        lat = f.variables["lat"]
+        assert lat.axis == b"Y" and lat.edges == b"lat_edges" and lat.units == b"degrees_north" and lat.data.dtype == np.dtype(">f8")
+        assert np.allclose(f.variables["lon"].data, np.arange(-255.0, 100.0, 10.0), rtol=0, atol=1e-12)
+        assert np.allclose(f.variables["lon_edges"].data, np.arange(-260.0, 101.0, 10.0), rtol=0, atol=1e-12)
+        assert np.allclose(np.sin(np.radians(lat.data)), (np.arange(J) + 0.5) / 18.0 - 1.0, atol=1e-14)
+        late = f.variables["lat_edges"].data
+        assert abs(late[0] + 90.0) < 1e-9 and abs(late[-1] - 90.0) < 1e-9 and np.all(late[:-1] < lat.data) and np.all(lat.data < late[1:])
+        v = f.variables["atm_pCO2_13C"]
+        assert v.data.dtype == np.dtype(">f4") and v.dimensions == ("lat", "lon")
+        assert v.long_name == b"d13C CO2" and v.standard_name == b"Atmosphere tracer - pCO2_13C" and not hasattr(v, "units")
+        assert v.missing_value == 9.9692099683868690e+36
+        for l, (_, n, _) in enumerate(ATM_TRACERS):
+            assert np.array_equal(f.variables["atm_" + n].data, atm[..., l].astype(np.float32)), n
+    atm2 = np.full_like(atm, -1.0)
+    fa = np.zeros(na, dtype=np.int32)
+    assert L.cg_restart_atchem_read(p.encode(), I, J, na, an, dp(atm2), ip(fa)) == 0
+    assert fa.all() and np.array_equal(atm2, atm.astype(np.float32).astype(np.float64))
+    # a restart of a run with another selection: what it holds is taken, the rest kept
+    q = str(tmp_path / "partial.nc")
+    with netcdf_file(q, "w") as f:
+        f.createDimension("lon", I); f.createDimension("lat", J)
+        f.createVariable("atm_pCO2", "f", ("lat", "lon"))[:] = 278.0e-6
+        f.createVariable("atm_pCH4", "f", ("lat", "lon"))[:] = 7.0e-7
+    assert L.cg_restart_atchem_read(q.encode(), I, J, na, an, dp(atm2), ip(fa)) == 0
+    assert list(np.nonzero(fa)[0]) == [2] and np.all(atm2[..., 2] == np.float32(278.0e-6))
+    assert np.array_equal(atm2[..., 5], atm[..., 5].astype(np.float32).astype(np.float64))
+    # wrong grid and missing file are errors with a message
+    assert L.cg_restart_atchem_read(p.encode(), I, J + 1, na, an, dp(atm2), ip(fa)) != 0 and b"wrong size" in L.cg_restart_last_error()
+    assert L.cg_restart_atchem_read(str(tmp_path / "none.nc").encode(), I, J, na, an, dp(atm2), ip(fa)) != 0
+
+
+def _fortran_record(path):
+    """Independent reader of a single-record gfortran unformatted sequential file."""
+    raw = open(path, "rb").read()
+    n = int(np.frombuffer(raw[:4], "<i4")[0])
+    assert len(raw) == n + 8 and int(np.frombuffer(raw[-4:], "<i4")[0]) == n
+    return raw[4:-4]
+
+
+def test_binary_restarts_are_fortran_records(built, tmp_path):
+    """ctrl_ncrst = .FALSE.: atchem.f90:192-197 and biogem.f90:2347-2355 write ONE unformatted record (count, global tracer
+    indices, the array sections in selection order; INTEGER*4 / REAL*8); checked byte for byte against numpy, read back exactly,
+    and read by a caller with another selection (biogem_data.f90:540-547 matches on the indices the record carries)."""
+    from cgenie_b200.restart import ATM_TRACERS, OCN_IDS, SED_IDS
+    L = _lib.load()
+    rng = np.random.default_rng(22)
+    na, no, ns = len(ATM_TRACERS), len(OCN_IDS), len(SED_IDS)
+    ia = np.array([a for a, _, _ in ATM_TRACERS], dtype=np.int32)
+    io, isd = np.array(OCN_IDS, dtype=np.int32), np.array(SED_IDS, dtype=np.int32)
+    atm = rng.normal(size=(J, I, na))
+    ocn, part = rng.normal(size=(K, J, I, no)), rng.normal(size=(K, J, I, ns))
+    pa, pb = str(tmp_path / "atchem"), str(tmp_path / "biogem")
+    assert L.cg_restart_atchem_write_bin(pa.encode(), I, J, na, ip(ia), dp(atm)) == 0
+    assert L.cg_restart_biogem_write_bin(pb.encode(), I, J, K, no, ip(io), dp(ocn), ns, ip(isd), dp(part)) == 0
+    want = np.int32(na).tobytes() + ia.tobytes() + b"".join(np.ascontiguousarray(atm[..., l]).tobytes() for l in range(na))
+    assert _fortran_record(pa) == want
+    want = (np.int32(no).tobytes() + io.tobytes() + b"".join(np.ascontiguousarray(ocn[..., l]).tobytes() for l in range(no)) +
+            np.int32(ns).tobytes() + isd.tobytes() + b"".join(np.ascontiguousarray(part[..., l]).tobytes() for l in range(ns)))
+    assert _fortran_record(pb) == want
+    atm2, ocn2, part2 = np.zeros_like(atm), np.zeros_like(ocn), np.zeros_like(part)
+    fa, fo, fs = np.zeros(na, dtype=np.int32), np.zeros(no, dtype=np.int32), np.zeros(ns, dtype=np.int32)
+    assert L.cg_restart_atchem_read_bin(pa.encode(), I, J, na, ip(ia), dp(atm2), ip(fa)) == 0
+    assert L.cg_restart_biogem_read_bin(pb.encode(), I, J, K, no, ip(io), dp(ocn2), ip(fo), ns, ip(isd), dp(part2), ip(fs)) == 0
+    assert fa.all() and fo.all() and fs.all()
+    assert np.array_equal(atm2, atm) and np.array_equal(ocn2, ocn) and np.array_equal(part2, part)      # bit-exact, unlike netCDF
+    # a caller that selected fewer tracers, in another order, plus one the file does not hold
+    sel = np.array([12, 3, 99, 1], dtype=np.int32)                     # ALK, DIC, (absent), temp
+    o3 = np.full((K, J, I, 4), -7.0)
+    f3 = np.zeros(4, dtype=np.int32)
+    assert L.cg_restart_biogem_read_bin(pb.encode(), I, J, K, 4, ip(sel), dp(o3), ip(f3), 0, None, None, None) == 0
+    assert list(f3) == [1, 1, 0, 1]
+    assert np.array_equal(o3[..., 0], ocn[..., 7]) and np.array_equal(o3[..., 1], ocn[..., 2]) and np.array_equal(o3[..., 3], ocn[..., 0])
+    assert (o3[..., 2] == -7.0).all()
+    # wrong grid: the record's length does not fit
+    assert L.cg_restart_biogem_read_bin(pb.encode(), I, J, K - 1, no, ip(io), dp(ocn2), ip(fo), ns, ip(isd), dp(part2), ip(fs)) != 0
+    assert b"BIOGEM restart" in L.cg_restart_last_error()
+    assert L.cg_restart_atchem_read_bin(pb.encode(), I, J, na, ip(ia), dp(atm2), ip(fa)) != 0
+    open(str(tmp_path / "trunc"), "wb").write(open(pa, "rb").read()[:-9])
+    assert L.cg_restart_atchem_read_bin(str(tmp_path / "trunc").encode(), I, J, na, ip(ia), dp(atm2), ip(fa)) != 0
