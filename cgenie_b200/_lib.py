@@ -51,6 +51,9 @@ SYMBOLS = {
     "cg_biogem_init_ocn": (C.c_int, [P]),
     "cg_biogem_climate_sol": (C.c_int, [P]),
     "cg_cpl_flux_ocnatm": (C.c_int, [P]),
+    "cg_cpl_flux_ocnsed": (C.c_int, [P, C.c_double]),
+    "cg_cpl_comp_ocnsed": (C.c_int, [P, C.c_int, C.c_int, C.c_int]),
+    "cg_reinit_flux_rokocn": (C.c_int, [P]),
     "cg_set_koverall": (C.c_int, [P, C.c_int64]),
     "cg_atchem_step": (C.c_int, [P, C.c_double]),
     "cg_run": (C.c_int, [P, C.c_int64]),

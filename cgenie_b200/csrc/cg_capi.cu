@@ -41,6 +41,7 @@ int launch_velc2(const Dev &, cudaStream_t);
 void launch_global_means(const Dev &, double *out, cudaStream_t);
 int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
+int launch_cpl_ocnsed(double *sum, const double *src, size_t n, double a, double b, int mode, cudaStream_t);
 int launch_bg_step(const Dev &, const BgDev &, int init_only, int fuse, cudaStream_t);
 int launch_tc_sums_first(const Dev &, cudaStream_t);
 int launch_tc_sums_old(const Dev &, cudaStream_t);
@@ -177,6 +178,7 @@ struct cg_handle {
   std::vector<double> bg_ocn0;   // initial ocn (device layout), dropped after upload
   double atm_totV = 0.0;
   bool bg_go = true;
+  double *sfxsumsed = nullptr, *sfcsumocn = nullptr, *sfxsumrok1 = nullptr;   // SEDGEM / ROKGEM interface sums, [ls|l][j][i][m]
   ~cg_handle() {
     cudaSetDevice(device);
     for (auto &gv : graph) for (auto &ge : gv) if (ge) cudaGraphExecDestroy(ge);
@@ -723,6 +725,13 @@ static int build_device(cg_handle *h) {
     reg_field(h, "focnatm", b.focnatm, {LA, I, J}, {(long long)ij, 1, I});
     reg_field(h, "sfcocn1", b.sfcocn1, {L, I, J}, {(long long)ij, 1, I});
     reg_field(h, "sfxsed1", b.sfxsed1, {LS, I, J}, {(long long)ij, 1, I});
+    // genie_sfxsumsed, genie_sfcsumocn, genie_sfxsumrok1 (genie_global.f90) of a job whose sediment grid is the ocean grid
+    TRY(dalloc(h, &h->sfxsumsed, ij * LS * MS));
+    TRY(dalloc(h, &h->sfcsumocn, ij * L * MS));
+    TRY(dalloc(h, &h->sfxsumrok1, ij * L * MS));
+    reg_field(h, "sfxsumsed", h->sfxsumsed, {LS, I, J}, {(long long)ij, 1, I});
+    reg_field(h, "sfcsumocn", h->sfcsumocn, {L, I, J}, {(long long)ij, 1, I});
+    reg_field(h, "sfxsumrok1", h->sfxsumrok1, {L, I, J}, {(long long)ij, 1, I});
   }
   TRY(dalloc(h, &h->d_meantemp, MS));
   TRY(dalloc(h, &h->d_means, (size_t)MS * L));
@@ -1429,6 +1438,47 @@ extern "C" int cg_biogem_step(cg_handle *h, double dts, int64_t genie_clock_ms) 
 }
 // cpl_flux_ocnatm_wrapper (genie_loop_wrappers.f90:178-183): already applied by cg_biogem_step
 extern "C" int cg_cpl_flux_ocnatm(cg_handle *h) { BGREADY(h); return CG_OK; }
+// The SEDGEM / ROKGEM coupler calls genie.f90 makes after every BIOGEM step whether or not those modules run
+// (genie.f90:413-427).  The interface arrays stay on the device ("sfxsumsed", "sfcsumocn", "sfxsumrok1"
+// fields); they follow cg_biogem_step on its stream.  cg_run does not issue them: without SEDGEM nothing reads the sums.
+// The stream these calls run on waits for every piece of work still in flight on a side stream (the flags stay set: the
+// main stream joins later as it would have), so that sfxsed1 / sfcocn1 are complete whichever schedule produced them.
+static int side_wait(cg_handle *h) {
+  if (h->mom_pending) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin, 0));
+  if (h->bg_pending) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBG, 0));
+  if (h->bg_tail_pending) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBGtail, 0));
+  if (h->tc_old_pending) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evTcOld, 0));
+  return CG_OK;
+}
+// cpl_flux_ocnsed(dts, ...), sedgem.f90:1029-1068: sfxsumsed = sfxsumsed + dts * sfxsed1 (sediment grid = ocean grid)
+extern "C" int cg_cpl_flux_ocnsed(cg_handle *h, double dts) {
+  BGREADY(h);
+  BgAsyncScope as(h, true);
+  IO(side_wait(h));
+  ProfScope ps(h, "biogem");
+  ps.done(launch_cpl_ocnsed(h->sfxsumsed, h->bgd.sfxsed1, (size_t)h->g.I * h->g.J * h->bg.LS * h->dv.MS, dts, 0.0, 0, h->stream));
+  return check_async(h);
+}
+// cpl_comp_ocnsed(ocnstep, mbiogem, msedgem, ...), sedgem.f90:894-937: running mean of the bottom-water composition over
+// the BIOGEM steps of one SEDGEM step; ocnstep = koverall / kocn_loop (genie_loop_wrappers.f90:219-226)
+extern "C" int cg_cpl_comp_ocnsed(cg_handle *h, int ocnstep, int mbiogem, int msedgem) {
+  BGREADY(h);
+  if (mbiogem <= 0 || msedgem <= 0) return fail(CG_ERR_ARG, "cg_cpl_comp_ocnsed: conv_kocn_kbiogem and conv_kocn_ksedgem must be positive");
+  const int w = ((ocnstep - mbiogem) % msedgem) / mbiogem;     // Fortran MOD and C % both truncate towards zero
+  BgAsyncScope as(h, true);
+  IO(side_wait(h));
+  ProfScope ps(h, "biogem");
+  ps.done(launch_cpl_ocnsed(h->sfcsumocn, h->bgd.sfcocn1, (size_t)h->g.I * h->g.J * h->g.L * h->dv.MS, (double)w, (double)(w + 1), 1, h->stream));
+  return check_async(h);
+}
+// reinit_flux_rokocn(sfxsumrok1), rokgem.f90:472-480
+extern "C" int cg_reinit_flux_rokocn(cg_handle *h) {
+  BGREADY(h);
+  BgAsyncScope as(h, true);
+  IO(side_wait(h));
+  CUDA_OK(cudaMemsetAsync(h->sfxsumrok1, 0, (size_t)h->g.I * h->g.J * h->g.L * h->dv.MS * sizeof(double), h->stream));
+  return CG_OK;
+}
 // biogem_tracercoupling(go_ts, go_ts1), biogem.f90:1885-1890.  Host arrays are optional (NULL = resident).
 extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_ts1) {
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");

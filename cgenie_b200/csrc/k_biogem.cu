@@ -6,6 +6,7 @@
 // over k (ascending) and then the column partials in its vocn order (i outer, j inner); the kernels
 // keep exactly that order -- thread (member, column) for the partials, thread (member, quantity) for
 // the ordered sum over columns -- so every total is bit-identical to the sequential code.
+#include <algorithm>
 #include <cstdlib>
 #include "cg_device.cuh"
 #include "cg_host.hpp"
@@ -1170,6 +1171,21 @@ int launch_tracercoupling(const Dev &v, cudaStream_t s) {
 int launch_bg_reset_cost(const Dev &v, cudaStream_t s) {
   const size_t n = (size_t)v.I * v.J * v.MS;
   k_bg_reset_cost<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v);
+  return 1;
+}
+
+// ---- SEDGEM coupler accumulations on the interface arrays (sediment grid = ocean grid) -------------------------------
+// mode 0: cpl_flux_ocnsed, sedgem.f90:1029-1068        sum = sum + dts * src               (a = dts)
+// mode 1: cpl_comp_ocnsed, sedgem.f90:894-937          sum = (w * sum + src) / (w + 1)     (a = w, b = w + 1)
+// Elementwise over [tracer][j][i][member]: 3 x 8 bytes of HBM traffic per element, nothing else.
+__global__ void __launch_bounds__(256) k_cpl_ocnsed(double *__restrict__ sum, const double *__restrict__ src, size_t n, double a,
+                                                    double b, int mode) {
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x)
+    sum[q] = mode ? (a * sum[q] + src[q]) / b : sum[q] + a * src[q];
+}
+int launch_cpl_ocnsed(double *sum, const double *src, size_t n, double a, double b, int mode, cudaStream_t s) {
+  const size_t blocks = (n + 255) / 256;
+  k_cpl_ocnsed<<<(unsigned)std::min<size_t>(blocks, 148 * 8), 256, 0, s>>>(sum, src, n, a, b, mode);
   return 1;
 }
 

@@ -214,6 +214,18 @@ class Ensemble(_Base):
         """atchem_wrapper + cpl_comp_atmocn_wrapper (genie_loop_wrappers.f90:452-462)."""
         self._ck(self.L.cg_atchem_step(self.h, float(dts)))
 
+    def cpl_flux_ocnsed(self, dts):
+        """cpl_flux_ocnsed_wrapper (genie_loop_wrappers.f90:197-203): sfxsumsed += dts * sfxsed1 on the device."""
+        self._ck(self.L.cg_cpl_flux_ocnsed(self.h, float(dts)))
+
+    def cpl_comp_ocnsed(self, ocnstep, mbiogem, msedgem):
+        """cpl_comp_ocnsed_wrapper (genie_loop_wrappers.f90:219-226): running mean of sfcocn1 into sfcsumocn."""
+        self._ck(self.L.cg_cpl_comp_ocnsed(self.h, int(ocnstep), int(mbiogem), int(msedgem)))
+
+    def reinit_flux_rokocn(self):
+        """reinit_flux_rokocn_wrapper (genie_loop_wrappers.f90:289-293): sfxsumrok1 = 0."""
+        self._ck(self.L.cg_reinit_flux_rokocn(self.h))
+
     def run(self, n_koverall):
         """n iterations of the genie.f90 main loop entirely on the device."""
         n = int(n_koverall)

@@ -105,3 +105,53 @@ CONTAINS
   END SUBROUTINE cpl_comp_atmocn
 
 END MODULE atchem
+
+! SEDGEM / ROKGEM coupler routines genie.f90 calls after every BIOGEM step whether or not the modules run
+! (genie.f90:413-427 through genie_loop_wrappers.f90:197-226, 289-293).  The interface arrays are device resident
+! (fields "sfxsumsed", "sfcsumocn", "sfxsumrok1"); the host arrays are left alone.  Jobs that really run SEDGEM or ROKGEM
+! keep the reference's modules and exchange the arrays through cg_sync_to_host / cg_sync_from_host.
+MODULE sedgem
+  USE, INTRINSIC :: ISO_C_BINDING
+  USE cgenie_b200_c
+  IMPLICIT NONE
+  PRIVATE
+  PUBLIC :: cpl_flux_ocnsed, cpl_comp_ocnsed
+
+CONTAINS
+
+  SUBROUTINE cpl_flux_ocnsed(dum_dts, dum_n_maxsed, dum_n_maxi, dum_n_maxj, dum_ns_maxi, dum_ns_maxj, dum_sfxsed1, dum_sfxsumsed)
+    REAL, INTENT(IN) :: dum_dts
+    INTEGER, INTENT(IN) :: dum_n_maxsed, dum_n_maxi, dum_n_maxj, dum_ns_maxi, dum_ns_maxj
+    REAL, DIMENSION(dum_n_maxsed,dum_n_maxi,dum_n_maxj), INTENT(INOUT) :: dum_sfxsed1
+    REAL, DIMENSION(dum_n_maxsed,dum_ns_maxi,dum_ns_maxj), INTENT(INOUT) :: dum_sfxsumsed
+    IF (dum_ns_maxi /= dum_n_maxi .OR. dum_ns_maxj /= dum_n_maxj) CALL cg_check(2_C_INT, 'cpl_flux_ocnsed: sediment grid /= ocean grid')
+    CALL cg_check(cg_cpl_flux_ocnsed(cg_h, REAL(dum_dts, C_DOUBLE)), 'cg_cpl_flux_ocnsed')
+  END SUBROUTINE cpl_flux_ocnsed
+
+  SUBROUTINE cpl_comp_ocnsed(dum_ocnstep, dum_mbiogem, dum_msedgem, dum_n_i_ocn, dum_n_j_ocn, dum_n_i_sed, dum_n_j_sed, &
+       & dum_sfcocn1, dum_sfcsumocn)
+    INTEGER, INTENT(IN) :: dum_ocnstep, dum_mbiogem, dum_msedgem, dum_n_i_ocn, dum_n_j_ocn, dum_n_i_sed, dum_n_j_sed
+    REAL, DIMENSION(:,:,:), INTENT(IN) :: dum_sfcocn1
+    REAL, DIMENSION(:,:,:), INTENT(INOUT) :: dum_sfcsumocn
+    IF (dum_n_i_sed /= dum_n_i_ocn .OR. dum_n_j_sed /= dum_n_j_ocn) CALL cg_check(2_C_INT, 'cpl_comp_ocnsed: sediment grid /= ocean grid')
+    CALL cg_check(cg_cpl_comp_ocnsed(cg_h, INT(dum_ocnstep, C_INT), INT(dum_mbiogem, C_INT), INT(dum_msedgem, C_INT)), 'cg_cpl_comp_ocnsed')
+  END SUBROUTINE cpl_comp_ocnsed
+
+END MODULE sedgem
+
+MODULE rokgem
+  USE, INTRINSIC :: ISO_C_BINDING
+  USE cgenie_b200_c
+  IMPLICIT NONE
+  PRIVATE
+  PUBLIC :: reinit_flux_rokocn
+
+CONTAINS
+
+  SUBROUTINE reinit_flux_rokocn(dum_sfxsumrok1)
+    REAL, DIMENSION(:,:,:), INTENT(INOUT) :: dum_sfxsumrok1
+    dum_sfxsumrok1 = 0.0
+    CALL cg_check(cg_reinit_flux_rokocn(cg_h), 'cg_reinit_flux_rokocn')
+  END SUBROUTINE reinit_flux_rokocn
+
+END MODULE rokgem

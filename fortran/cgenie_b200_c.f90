@@ -113,6 +113,20 @@ MODULE cgenie_b200_c
        IMPORT :: C_INT, C_PTR
        TYPE(C_PTR), VALUE :: h
      END FUNCTION cg_cpl_flux_ocnatm
+     INTEGER(C_INT) FUNCTION cg_cpl_flux_ocnsed(h, dts) BIND(C, NAME='cg_cpl_flux_ocnsed')
+       IMPORT :: C_INT, C_PTR, C_DOUBLE
+       TYPE(C_PTR), VALUE :: h
+       REAL(C_DOUBLE), VALUE :: dts
+     END FUNCTION cg_cpl_flux_ocnsed
+     INTEGER(C_INT) FUNCTION cg_cpl_comp_ocnsed(h, ocnstep, mbiogem, msedgem) BIND(C, NAME='cg_cpl_comp_ocnsed')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h
+       INTEGER(C_INT), VALUE :: ocnstep, mbiogem, msedgem
+     END FUNCTION cg_cpl_comp_ocnsed
+     INTEGER(C_INT) FUNCTION cg_reinit_flux_rokocn(h) BIND(C, NAME='cg_reinit_flux_rokocn')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h
+     END FUNCTION cg_reinit_flux_rokocn
   END INTERFACE
 
 CONTAINS

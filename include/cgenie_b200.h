@@ -112,6 +112,15 @@ int cg_biogem_climate(cg_handle *);
 int cg_biogem_climate_sol(cg_handle *);   /* biogem_climate_sol, biogem.f90:2243-2263 (first BIOGEM step only) */
 /* cpl_flux_ocnatm (atchem.f90:306-320) is fused into cg_biogem_step; kept so that the wrapper has a target */
 int cg_cpl_flux_ocnatm(cg_handle *);
+/* The SEDGEM / ROKGEM coupler calls genie.f90:413-427 makes after every BIOGEM step even when those modules are off
+ * (SURVEY 8f row 2), on device-resident interface arrays (fields "sfxsumsed", "sfcsumocn", "sfxsumrok1"; sediment grid =
+ * ocean grid):  cpl_flux_ocnsed (src/sedgem/sedgem.f90:1029-1068)  sfxsumsed += dts * sfxsed1;
+ * cpl_comp_ocnsed (sedgem.f90:894-937) running mean of sfcocn1 into sfcsumocn, ocnstep = koverall / kocn_loop, mbiogem /
+ * msedgem = conv_kocn_kbiogem / conv_kocn_ksedgem (genie_loop_wrappers.f90:197-226);  reinit_flux_rokocn
+ * (src/rokgem/rokgem.f90:472-480) sfxsumrok1 = 0.  cg_run does not issue them (no consumer without SEDGEM). */
+int cg_cpl_flux_ocnsed(cg_handle *, double dts);
+int cg_cpl_comp_ocnsed(cg_handle *, int ocnstep, int mbiogem, int msedgem);
+int cg_reinit_flux_rokocn(cg_handle *);
 /* (re)build BIOGEM's ocn array from the current ts (initialise_biogem, biogem.f90:283-285: T in K, S absolute) */
 int cg_biogem_init_ocn(cg_handle *);
 int cg_atchem_step(cg_handle *, double dts);

@@ -76,6 +76,9 @@ void cgo_biogem_forcing(cgo_t *);
 int cgo_biogem_step(cgo_t *);
 void cgo_biogem_climate(cgo_t *);
 void cgo_cpl_flux_ocnatm(cgo_t *);
+void cgo_cpl_flux_ocnsed(cgo_t *, double dts);
+void cgo_cpl_comp_ocnsed(cgo_t *, int ocnstep, int mbiogem, int msedgem);
+void cgo_reinit_flux_rokocn(cgo_t *);
 void cgo_atchem_step(cgo_t *);
 
 /* run n iterations of the genie.f90 koverall loop (one EMBM step each) */

@@ -100,6 +100,7 @@ struct cgo_bg {
   double solar_constant;
   double *atm, *sfcatm1, *sfxatm1, *sfxsumatm, *atm_A, *atm_V;   /* [la][i][j] */
   double *sfcocn1, *sfxsed1, *focnatm;                 /* interface / diagnostics [l|ls|la][i][j] */
+  double *sfxsumsed, *sfcsumocn, *sfxsumrok1;          /* SEDGEM / ROKGEM interface sums (sediment grid = ocean grid) */
   double Dbot[64], dD[64], Dmid_surf;
   int go;
 };
@@ -491,6 +492,7 @@ void cgo_biogem_setup(cgo_t *o, const char *params) {
   b->sfxatm1 = bg_alloc(o, "sfxatm1", ij * b->LA); b->sfxsumatm = bg_alloc(o, "sfxsumatm", ij * b->LA);
   b->atm_A = bg_alloc(o, "atm_A", ij); b->atm_V = bg_alloc(o, "atm_V", ij);
   b->sfcocn1 = bg_alloc(o, "sfcocn1", ij * NL); b->sfxsed1 = bg_alloc(o, "sfxsed1", ij * b->LS); b->focnatm = bg_alloc(o, "focnatm", ij * b->LA);
+  b->sfxsumsed = bg_alloc(o, "sfxsumsed", ij * b->LS); b->sfcsumocn = bg_alloc(o, "sfcsumocn", ij * NL); b->sfxsumrok1 = bg_alloc(o, "sfxsumrok1", ij * NL);
   b->rst_I = bg_alloc(o, "rst_atm_I", ij * b->LA); b->rst_II = bg_alloc(o, "rst_atm_II", ij * b->LA);
   b->rst_atm = bg_alloc(o, "force_restore_atm", ij * b->LA);
   b->solar_constant = o->solconst;
@@ -1176,6 +1178,26 @@ void cgo_cpl_flux_ocnatm(cgo_t *o) {
   const double dts = (double)(b->kbiogem * o->kocn_loop) * b->genie_timestep;
   long n;
   for (n = 0; n < (long)NI * NJ * b->LA; n++) { b->sfxsumatm[n] = b->sfxsumatm[n] + dts * b->sfxatm1[n]; b->sfxatm1[n] = 0.0; }
+}
+
+/* cpl_flux_ocnsed, sedgem.f90:1029-1068 (loc_scalei = loc_scalej = 1: i1 = i, j1 = j) */
+void cgo_cpl_flux_ocnsed(cgo_t *o, double dts) {
+  struct cgo_bg *b = BG;
+  long n;
+  for (n = 0; n < (long)NI * NJ * b->LS; n++) b->sfxsumsed[n] = b->sfxsumsed[n] + dts * b->sfxsed1[n];
+}
+/* cpl_comp_ocnsed, sedgem.f90:894-937 */
+void cgo_cpl_comp_ocnsed(cgo_t *o, int ocnstep, int mbiogem, int msedgem) {
+  struct cgo_bg *b = BG;
+  const int w = ((ocnstep - mbiogem) % msedgem) / mbiogem;   /* int(MOD(ocnstep - mbiogem, msedgem)/mbiogem) */
+  long n;
+  for (n = 0; n < (long)NI * NJ * NL; n++) b->sfcsumocn[n] = ((double)w * b->sfcsumocn[n] + b->sfcocn1[n]) / (double)(w + 1);
+}
+/* reinit_flux_rokocn, rokgem.f90:472-480 */
+void cgo_reinit_flux_rokocn(cgo_t *o) {
+  struct cgo_bg *b = BG;
+  long n;
+  for (n = 0; n < (long)NI * NJ * NL; n++) b->sfxsumrok1[n] = 0.0;
 }
 
 /* step_atchem :63-158 + cpl_comp_atmocn :252-264 + cpl_comp_EMBM :270-282 */

@@ -39,6 +39,9 @@ def lib():
         for f in ("cgo_biogem_forcing", "cgo_biogem_climate", "cgo_cpl_flux_ocnatm", "cgo_atchem_step"):
             getattr(L, f).argtypes = [P]
             getattr(L, f).restype = None
+        L.cgo_cpl_flux_ocnsed.argtypes, L.cgo_cpl_flux_ocnsed.restype = [P, C.c_double], None
+        L.cgo_cpl_comp_ocnsed.argtypes, L.cgo_cpl_comp_ocnsed.restype = [P, C.c_int, C.c_int, C.c_int], None
+        L.cgo_reinit_flux_rokocn.argtypes, L.cgo_reinit_flux_rokocn.restype = [P], None
         L.cgo_biogem_step.argtypes = [P]
         L.cgo_biogem_step.restype = C.c_int
         L.cgo_biogem_setup.argtypes = [P, C.c_char_p]

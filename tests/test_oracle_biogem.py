@@ -105,3 +105,33 @@ def test_regression_vector(bg):
                POC_max=float(o.f("bio_part").reshape(K, J, I, LS)[..., POC].max()))
     for k, v in want.items():
         assert np.isclose(got[k], v, rtol=1e-9, atol=0.0), (k, got[k], v)
+
+
+def test_sedgem_coupler_sums():
+    """cpl_flux_ocnsed / cpl_comp_ocnsed / reinit_flux_rokocn (sedgem.f90:1029-1068, :894-937, rokgem.f90:472-480; called
+    after every BIOGEM step whether or not SEDGEM runs, genie.f90:413-427): time integral of the ocean->sediment flux and the
+    running mean of the bottom-water composition over the BIOGEM steps of one SEDGEM step (conv_kocn_ksedgem = 8 here)."""
+    o = Oracle("worjh2", maxk=K, maxl=L, nyear=96)
+    o.biogem_setup()
+    dts = float(2 * 5) * (3600.0 * 24.0 * 365.25 / 5.0 / 96)
+    flux, comp, want_w = np.zeros(J * I * LS), np.zeros(J * I * L), [0, 1, 2, 3, 0, 1]
+    seen = []
+    for blk in range(1, 7):
+        o.run(10)
+        ocnstep = 10 * blk // 5
+        o.L.cgo_cpl_flux_ocnsed(o.h, dts)
+        o.L.cgo_cpl_comp_ocnsed(o.h, ocnstep, 2, 8)
+        w = want_w[blk - 1]
+        flux = flux + dts * o.f("sfxsed1")
+        comp = (float(w) * comp + o.f("sfcocn1")) / float(w + 1)
+        assert np.array_equal(o.f("sfxsumsed"), flux) and np.array_equal(o.f("sfcsumocn"), comp), blk
+        seen.append(o.f("sfcocn1").copy())
+    # the mean restarts with each SEDGEM step: after 6 BIOGEM steps it is the mean of the last two
+    assert np.allclose(comp, 0.5 * (seen[4] + seen[5]), rtol=1e-15, atol=0)
+    # what left the ocean for the sediments is what the closed system hands back: CaCO3 rain integrated over the run is positive
+    k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    rain = o.f("sfxsumsed").reshape(J, I, LS)
+    assert rain[..., POC][k1 <= K].min() >= 0.0 and rain[..., CACO3][k1 <= K].max() > 0.0 and np.all(rain[k1 > K] == 0.0)
+    o.f("sfxsumrok1")[:] = 3.0
+    o.L.cgo_reinit_flux_rokocn(o.h)
+    assert np.all(o.f("sfxsumrok1") == 0.0)
