@@ -41,6 +41,7 @@ int launch_velc2(const Dev &, cudaStream_t);
 void launch_global_means(const Dev &, double *out, cudaStream_t);
 int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
+int launch_bg_sig(const Dev &, const BgDev &, const SigDev &, double dtyr, cudaStream_t);
 int launch_cpl_ocnsed(double *sum, const double *src, size_t n, double a, double b, int mode, cudaStream_t);
 int launch_bg_step(const Dev &, const BgDev &, int init_only, int fuse, cudaStream_t);
 int launch_tc_sums_first(const Dev &, cudaStream_t);
@@ -178,6 +179,9 @@ struct cg_handle {
   std::vector<double> bg_ocn0;   // initial ocn (device layout), dropped after upload
   double atm_totV = 0.0;
   bool bg_go = true;
+  SigDev sig{};                       // BIOGEM time-series integrals
+  double sig_ben_Dmin = -1.0;
+  double *sig_w_ben = nullptr;
   double *sfxsumsed = nullptr, *sfcsumocn = nullptr, *sfxsumrok1 = nullptr;   // SEDGEM / ROKGEM interface sums, [ls|l][j][i][m]
   ~cg_handle() {
     cudaSetDevice(device);
@@ -725,6 +729,30 @@ static int build_device(cg_handle *h) {
     reg_field(h, "focnatm", b.focnatm, {LA, I, J}, {(long long)ij, 1, I});
     reg_field(h, "sfcocn1", b.sfcocn1, {L, I, J}, {(long long)ij, 1, I});
     reg_field(h, "sfxsed1", b.sfxsed1, {LS, I, J}, {(long long)ij, 1, I});
+    {
+      // time-series integrals (cg_biogem_sig_update): bottom level and area per column, sums and integrals [q][m]
+      std::vector<int> kb(ij);
+      std::vector<double> Aall(ij);
+      double totA = 0.0;
+      for (int j = 1; j <= J; j++)
+        for (int i = 1; i <= I; i++) {
+          const size_t c = cell2(I, i, j);
+          kb[c] = g.k1at(i, j) <= K ? g.k1at(i, j) - 1 : K;
+          Aall[c] = 2.0 * kBgPi * (kBgREarth * kBgREarth) * (1.0 / I) * (g.sv[j] - g.sv[j - 1]);   // phys_ocnatm(ipoa_A), biogem_data.f90:1156
+        }
+      for (int j = 1; j <= J; j++)          // SUM(phys_ocnatm(ipoa_A,:,:)) in array element order
+        for (int i = 1; i <= I; i++) totA = totA + Aall[cell2(I, i, j)];
+      const int nq = kSigHead + 3 * L + LA;
+      int *qi; double *qd;
+      TRY(dupload(h, &qi, kb)); h->sig.kbot = qi;
+      TRY(dupload(h, &qd, Aall)); h->sig.A = qd;
+      TRY(dalloc(h, &h->sig_w_ben, ij)); h->sig.w_ben = h->sig_w_ben;
+      TRY(dalloc(h, &h->sig.raw, (size_t)nq * MS));
+      TRY(dalloc(h, &h->sig.acc, (size_t)nq * MS));
+      h->sig.rtot_A_atm = totA > kBgNullSmall ? 1.0 / totA : 0.0;
+      h->sig.LA = LA;
+      reg_field(h, "bg_sig", h->sig.acc, {nq}, {1});
+    }
     // genie_sfxsumsed, genie_sfcsumocn, genie_sfxsumrok1 (genie_global.f90) of a job whose sediment grid is the ocean grid
     TRY(dalloc(h, &h->sfxsumsed, ij * LS * MS));
     TRY(dalloc(h, &h->sfcsumocn, ij * L * MS));
@@ -1448,6 +1476,46 @@ static int side_wait(cg_handle *h) {
   if (h->bg_pending) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBG, 0));
   if (h->bg_tail_pending) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evBGtail, 0));
   if (h->tc_old_pending) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evTcOld, 0));
+  return CG_OK;
+}
+// The ocean / atmosphere part of diag_biogem_timeseries (biogem.f90:2703-3159): one BIOGEM step's contribution to the window
+// integrals int_t_sig, int_ocn_tot_M(_sur)_sig, int_ocn_sig, int_ocn_sur_sig, int_ocn_ben_sig, int_ocnatm_sig (:2851-2917,
+// :3082), taken on the device behind the BIOGEM step.  The caller keeps the reference's save-window logic (:2760-2769, the
+// list of biogem_save_sig.dat) and reads the integrals as field "bg_sig" = [int_t_sig, tot_M, tot_M_sur, ocn(L), ocn_sur(L),
+// ocn_ben(L), ocnatm(LA)] when a window closes; cg_biogem_sig_reset = sub_init_int_timeseries (biogem_data.f90:964-1007).
+// ben_Dmin = par_data_save_ben_Dmin (benthic mask: bottom cells whose floor lies deeper).
+extern "C" int cg_biogem_sig_update(cg_handle *h, double dts, double ben_Dmin) {
+  BGREADY(h);
+  const Grid &g = h->g;
+  const int I = g.I, J = g.J, K = g.K;
+  if (ben_Dmin != h->sig_ben_Dmin) {
+    std::vector<double> w((size_t)I * J, 0.0);
+    double tot = 0.0;
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++) {
+        const int k1 = g.k1at(i, j);
+        if (k1 > K) continue;
+        double Dbot = 0.0;                                  // phys_ocn(ipo_Dbot,i,j,k1) = SUM(dsc*dz(k1:n_k)), biogem_data.f90:1123
+        for (int k = k1; k <= K; k++) Dbot = Dbot + kDsc * g.dz[k];
+        if (Dbot > ben_Dmin) w[cell2(I, i, j)] = 2.0 * kBgPi * (kBgREarth * kBgREarth) * (1.0 / I) * (g.sv[j] - g.sv[j - 1]);
+      }
+    for (size_t c = 0; c < w.size(); c++) tot = tot + w[c];
+    IO(join_side(h));
+    CUDA_OK(cudaMemcpy(h->sig_w_ben, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->sig.rtot_A_ben = tot > kBgNullSmall ? 1.0 / tot : 0.0;
+    h->sig_ben_Dmin = ben_Dmin;
+  }
+  BgAsyncScope as(h, true);
+  IO(side_wait(h));
+  ProfScope ps(h, "biogem");
+  ps.done(launch_bg_sig(h->dv, h->bgd, h->sig, dts / kBgYrS, h->stream));
+  return check_async(h);
+}
+extern "C" int cg_biogem_sig_reset(cg_handle *h) {
+  BGREADY(h);
+  BgAsyncScope as(h, true);
+  IO(side_wait(h));
+  CUDA_OK(cudaMemsetAsync(h->sig.acc, 0, (size_t)(kSigHead + 3 * h->g.L + h->bg.LA) * h->dv.MS * sizeof(double), h->stream));
   return CG_OK;
 }
 // cpl_flux_ocnsed(dts, ...), sedgem.f90:1029-1068: sfxsumsed = sfxsumsed + dts * sfxsed1 (sediment grid = ocean grid)

@@ -162,4 +162,13 @@ struct BgDev {
   int *err;                               // [m] carbonate chemistry failure flag (error_stop)
   double *surf;                           // [kBgSurfSlots][wet column][m] surface-cell results (k_bg_step PART 1 -> PART 2)
 };
+// window integrals of BIOGEM's time series (k_bg_sig_*): per-quantity rows of MS members
+constexpr int kSigHead = 3;
+struct SigDev {
+  const int *kbot;                        // [j][i] 0-based level of the bottom cell, K on land
+  const double *A, *w_ben;                // [j][i] cell area (all cells); benthic mask * area
+  double *raw, *acc;                      // [q][m] sums of this step; integrals of the window
+  double rtot_A_ben, rtot_A_atm;          // 1 / SUM(mask_ben * A), 1 / SUM(phys_ocnatm(ipoa_A))
+  int LA;
+};
 }  // namespace cg

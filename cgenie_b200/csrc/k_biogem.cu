@@ -1189,4 +1189,89 @@ int launch_cpl_ocnsed(double *sum, const double *src, size_t n, double a, double
   return 1;
 }
 
+// ---- BIOGEM time-series integrals (diag_biogem_timeseries, biogem.f90:2836-2917: sig_ocn, sig_ocn_sur / _ben, sig_ocnatm) ------
+// Quantities q (kSigHead = 3 ahead of the tracer blocks):
+//   0 SUM(M)   1 SUM(M(:,:,n_k))   2 SUM((1-seaice)*A(n_k))
+//   3+l        SUM(M*ocn(l))                                      over the wet cells
+//   3+L+l      SUM((1-seaice)*A*ocn(l,:,:,n_k))                   ice-free surface
+//   3+2L+l     SUM(mask_ben*A*ocn(l,i,j,k1))                      bottom cells deeper than par_data_save_ben_Dmin
+//   3+3L+la    SUM(A*sfcatm1(la))                                 whole atmosphere grid
+// Pass 1: block = (32-member tile, quantity), lanes = members, 8 warps stride over the cells; the 8 partial sums are added
+// in warp order (deterministic; not the reference's element order -- relative difference ~1e-16, bar 1e-10).  Each block
+// streams its operands once: M and one tracer of ocn for the 3-D sums (16 B per wet cell and member).
+// Pass 2: one thread per member folds the sums into the window integrals in the reference's expression order.
+__global__ void __launch_bounds__(256) k_bg_sig_sums(const Dev v, const BgDev b, const SigDev g) {
+  __shared__ double part[8][32];
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int I = v.I, J = v.J, K = v.K, L = v.L, MS = v.MS, ij = I * J;
+  const int m = blockIdx.x * 32 + lane, q = blockIdx.y;
+  double s = 0.0;
+  if (q == 0 || (q >= kSigHead && q < kSigHead + L)) {
+    const int l = q - kSigHead;
+    for (int c2 = warp; c2 < ij; c2 += 8) {
+      for (int k = g.kbot[c2]; k < K; k++) {
+        const size_t c = (size_t)k * ij + c2;
+        const double M = v.bg_M[c * MS + m];
+        s = s + (q == 0 ? M : M * v.bg_ocn[(c * L + l) * MS + m]);
+      }
+    }
+  } else if (q == 1) {
+    for (int c2 = warp; c2 < ij; c2 += 8)
+      if (g.kbot[c2] < K) s = s + v.bg_M[((size_t)(K - 1) * ij + c2) * MS + m];
+  } else if (q == 2 || (q >= kSigHead + L && q < kSigHead + 2 * L)) {
+    const int l = q - kSigHead - L;
+    for (int c2 = warp; c2 < ij; c2 += 8) {
+      if (g.kbot[c2] >= K) continue;
+      const double w = (1.0 - b.seaice[(size_t)c2 * MS + m]) * g.A[c2];
+      s = s + (q == 2 ? w : w * v.bg_ocn[(((size_t)(K - 1) * ij + c2) * L + l) * MS + m]);
+    }
+  } else if (q < kSigHead + 3 * L) {
+    const int l = q - kSigHead - 2 * L;
+    for (int c2 = warp; c2 < ij; c2 += 8) {
+      const double w = g.w_ben[c2];
+      if (w == 0.0) continue;
+      s = s + w * v.bg_ocn[(((size_t)g.kbot[c2] * ij + c2) * L + l) * MS + m];
+    }
+  } else {
+    const int la = q - kSigHead - 3 * L;
+    for (int c2 = warp; c2 < ij; c2 += 8) s = s + g.A[c2] * b.sfcatm1[((size_t)la * ij + c2) * MS + m];
+  }
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double t = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; w++) t = t + part[w][lane];
+    g.raw[(size_t)q * MS + m] = t;
+  }
+}
+__global__ void k_bg_sig_acc(const Dev v, const SigDev g, const double dtyr) {
+  const int MS = v.MS, L = v.L;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= MS) return;
+  const double *r = g.raw + m;
+  double *a = g.acc + m;
+  const double tot_M = r[0], tot_A = r[(size_t)2 * MS];
+  const double rtot_M = tot_M > kBgNullSmall ? 1.0 / tot_M : 0.0, rtot_A = tot_A > kBgNullSmall ? 1.0 / tot_A : 0.0;
+  a[0] = a[0] + dtyr;                                            // int_t_sig, :3082
+  a[(size_t)MS] = a[(size_t)MS] + dtyr * tot_M;                  // int_ocn_tot_M_sig
+  a[(size_t)2 * MS] = a[(size_t)2 * MS] + dtyr * r[(size_t)MS];  // int_ocn_tot_M_sur_sig
+  for (int l = 0; l < L; l++) {
+    const size_t q0 = (size_t)(kSigHead + l) * MS, q1 = (size_t)(kSigHead + L + l) * MS, q2 = (size_t)(kSigHead + 2 * L + l) * MS;
+    a[q0] = a[q0] + dtyr * r[q0] * rtot_M;
+    a[q1] = a[q1] + dtyr * r[q1] * rtot_A;
+    a[q2] = a[q2] + dtyr * r[q2] * g.rtot_A_ben;
+  }
+  for (int la = 0; la < g.LA; la++) {
+    const size_t q = (size_t)(kSigHead + 3 * L + la) * MS;
+    a[q] = a[q] + dtyr * r[q] * g.rtot_A_atm;
+  }
+}
+int launch_bg_sig(const Dev &v, const BgDev &b, const SigDev &g, double dtyr, cudaStream_t s) {
+  const int nq = kSigHead + 3 * v.L + g.LA;
+  k_bg_sig_sums<<<dim3(v.MS / 32, nq), dim3(32, 8), 0, s>>>(v, b, g);
+  k_bg_sig_acc<<<(v.MS + 127) / 128, 128, 0, s>>>(v, g, dtyr);
+  return 2;
+}
+
 }  // namespace cg

@@ -214,6 +214,15 @@ class Ensemble(_Base):
         """atchem_wrapper + cpl_comp_atmocn_wrapper (genie_loop_wrappers.f90:452-462)."""
         self._ck(self.L.cg_atchem_step(self.h, float(dts)))
 
+    def biogem_sig_update(self, dts, ben_Dmin=0.0):
+        """The ocean / atmosphere integrals of diag_biogem_timeseries (biogem.f90:2836-2917) for one BIOGEM step, on the device;
+        call it on the steps of a save window, read the window with get("bg_sig", member)."""
+        self._ck(self.L.cg_biogem_sig_update(self.h, float(dts), float(ben_Dmin)))
+
+    def biogem_sig_reset(self):
+        """sub_init_int_timeseries (biogem_data.f90:964-1007)."""
+        self._ck(self.L.cg_biogem_sig_reset(self.h))
+
     def cpl_flux_ocnsed(self, dts):
         """cpl_flux_ocnsed_wrapper (genie_loop_wrappers.f90:197-203): sfxsumsed += dts * sfxsed1 on the device."""
         self._ck(self.L.cg_cpl_flux_ocnsed(self.h, float(dts)))

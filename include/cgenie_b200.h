@@ -121,6 +121,27 @@ int cg_cpl_flux_ocnatm(cg_handle *);
 int cg_cpl_flux_ocnsed(cg_handle *, double dts);
 int cg_cpl_comp_ocnsed(cg_handle *, int ocnstep, int mbiogem, int msedgem);
 int cg_reinit_flux_rokocn(cg_handle *);
+/* The 3-D / 2-D sums of diag_biogem_timeseries (src/biogem/biogem.f90:2703-3159; SURVEY 8f row 1, time-series part): one BIOGEM
+ * step's contribution to the window integrals int_t_sig, int_ocn_tot_M_sig, int_ocn_tot_M_sur_sig, int_ocn_sig(:),
+ * int_ocn_sur_sig(:), int_ocn_ben_sig(:), int_ocnatm_sig(:) (:2851-2917, :3082), on the device behind the BIOGEM step.  Call
+ * it where genie.f90:395-405 calls diag_biogem_timeseries_wrapper, on the steps that fall in a save window (the window logic
+ * of :2760-2769 and biogem_save_sig.dat stay with the caller).  Field "bg_sig" (cg_sync_to_host) = the integrals of one
+ * member in that order, 3 + 3*maxl + n_l_atm values, tracers in the compact selection order; cg_biogem_sig_reset =
+ * sub_init_int_timeseries (biogem_data.f90:964-1007).  ben_Dmin = par_data_save_ben_Dmin (m). */
+int cg_biogem_sig_update(cg_handle *, double dts, double ben_Dmin);
+int cg_biogem_sig_reset(cg_handle *);
+/* sub_init_data_save_runtime / sub_data_save_runtime (src/biogem/biogem_data_ascii.f90:23-110, 669-935), the ocn_* and atm_*
+ * series: <outdir>/<outfile_name>_series_ocn_<name>.res and ..._atm_<name>.res in the reference's formats
+ * (header through list-directed output; f12.3 / f12.6 / e15.7 / f14.3 columns; T in degrees C; isotopes as delta values
+ * through fun_calc_isotope_delta, gem_util.f90:568-598).  create != 0: (re)create the files with their header lines;
+ * create == 0: append one line per file from the integrals `sig` of one member (the "bg_sig" layout).  *_type: 0 (T, S /
+ * temp, humidity), 1 (bulk), 11 (13C), 12 (14C); *_dep: 0-based compact index of an isotope's bulk tracer; with_sur =
+ * ctrl_data_save_sig_ocn_sur.  Host only. */
+const char *cg_series_last_error(void);
+int cg_biogem_series_write(const char *outdir, const char *outfile_name, int create, double t_yr, int n_ocn,
+                           const char *const *ocn_names, const int32_t *ocn_type, const int32_t *ocn_dep, int n_atm,
+                           const char *const *atm_names, const int32_t *atm_type, const int32_t *atm_dep, const double *sig,
+                           int with_sur);
 /* (re)build BIOGEM's ocn array from the current ts (initialise_biogem, biogem.f90:283-285: T in K, S absolute) */
 int cg_biogem_init_ocn(cg_handle *);
 int cg_atchem_step(cg_handle *, double dts);

@@ -101,6 +101,7 @@ struct cgo_bg {
   double *atm, *sfcatm1, *sfxatm1, *sfxsumatm, *atm_A, *atm_V;   /* [la][i][j] */
   double *sfcocn1, *sfxsed1, *focnatm;                 /* interface / diagnostics [l|ls|la][i][j] */
   double *sfxsumsed, *sfcsumocn, *sfxsumrok1;          /* SEDGEM / ROKGEM interface sums (sediment grid = ocean grid) */
+  double *sig;                                         /* time-series integrals: t, tot_M, tot_M_sur, ocn(L), sur(L), ben(L), atm(LA) */
   double Dbot[64], dD[64], Dmid_surf;
   int go;
 };
@@ -492,6 +493,7 @@ void cgo_biogem_setup(cgo_t *o, const char *params) {
   b->sfxatm1 = bg_alloc(o, "sfxatm1", ij * b->LA); b->sfxsumatm = bg_alloc(o, "sfxsumatm", ij * b->LA);
   b->atm_A = bg_alloc(o, "atm_A", ij); b->atm_V = bg_alloc(o, "atm_V", ij);
   b->sfcocn1 = bg_alloc(o, "sfcocn1", ij * NL); b->sfxsed1 = bg_alloc(o, "sfxsed1", ij * b->LS); b->focnatm = bg_alloc(o, "focnatm", ij * b->LA);
+  b->sig = bg_alloc(o, "bg_sig", 3 + 3 * NL + b->LA);
   b->sfxsumsed = bg_alloc(o, "sfxsumsed", ij * b->LS); b->sfcsumocn = bg_alloc(o, "sfcsumocn", ij * NL); b->sfxsumrok1 = bg_alloc(o, "sfxsumrok1", ij * NL);
   b->rst_I = bg_alloc(o, "rst_atm_I", ij * b->LA); b->rst_II = bg_alloc(o, "rst_atm_II", ij * b->LA);
   b->rst_atm = bg_alloc(o, "force_restore_atm", ij * b->LA);
@@ -1178,6 +1180,57 @@ void cgo_cpl_flux_ocnatm(cgo_t *o) {
   const double dts = (double)(b->kbiogem * o->kocn_loop) * b->genie_timestep;
   long n;
   for (n = 0; n < (long)NI * NJ * b->LA; n++) { b->sfxsumatm[n] = b->sfxsumatm[n] + dts * b->sfxatm1[n]; b->sfxatm1[n] = 0.0; }
+}
+
+/* diag_biogem_timeseries, biogem.f90:2703-3159: the sig_ocn / sig_ocn_sur (+ benthic) / sig_ocnatm integrals of one BIOGEM
+ * step (:2771-2917) and int_t_sig (:3082); sums in array element order (i fastest) */
+void cgo_biogem_sig_update(cgo_t *o, double ben_Dmin) {
+  struct cgo_bg *b = BG;
+  const int I = NI, J = NJ, K = NK;
+  const double dts = (double)(b->kbiogem * o->kocn_loop) * b->genie_timestep, dtyr = dts / BG_YR_S;
+  double *S = b->sig;
+  double tot_M = 0.0, tot_M_sur = 0.0, tot_A = 0.0, tot_A_ben = 0.0, tot_A_atm = 0.0, rtot_M, rtot_A, rtot_A_ben, rtot_A_atm;
+  double *mask = (double *)calloc((size_t)I * J, 8);
+  int i, j, k, l, la;
+  for (k = 1; k <= K; k++) for (j = 1; j <= J; j++) for (i = 1; i <= I; i++) if (k >= K1(i, j)) tot_M = tot_M + o->bg_M[(i - 1) + I * ((j - 1) + J * (k - 1))];
+  for (j = 1; j <= J; j++) for (i = 1; i <= I; i++) {
+    const double A = 2.0 * BG_PI * (BG_REARTH * BG_REARTH) * (1.0 / I) * (o->sv[j] - o->sv[j - 1]);
+    tot_A_atm = tot_A_atm + A;
+    if (K1(i, j) > K) continue;
+    tot_M_sur = tot_M_sur + o->bg_M[(i - 1) + I * ((j - 1) + J * (K - 1))];
+    tot_A = tot_A + (1.0 - A2(b->seaice, i, j)) * A;
+    {
+      double Dbot = 0.0;
+      for (k = K1(i, j); k <= K; k++) Dbot = Dbot + CG_DSC * o->dz[k];
+      if (Dbot > ben_Dmin) { mask[(i - 1) + I * (j - 1)] = 1.0; tot_A_ben = tot_A_ben + 1.0 * A; }
+    }
+  }
+  rtot_M = tot_M > BG_NULLSMALL ? 1.0 / tot_M : 0.0; rtot_A = tot_A > BG_NULLSMALL ? 1.0 / tot_A : 0.0;
+  rtot_A_ben = tot_A_ben > BG_NULLSMALL ? 1.0 / tot_A_ben : 0.0; rtot_A_atm = tot_A_atm > BG_NULLSMALL ? 1.0 / tot_A_atm : 0.0;
+  S[1] = S[1] + dtyr * tot_M;
+  S[2] = S[2] + dtyr * tot_M_sur;
+  for (l = 1; l <= NL; l++) {
+    double s3 = 0.0, ss = 0.0, sb = 0.0;
+    for (k = 1; k <= K; k++) for (j = 1; j <= J; j++) for (i = 1; i <= I; i++)
+      if (k >= K1(i, j)) s3 = s3 + o->bg_M[(i - 1) + I * ((j - 1) + J * (k - 1))] * OCN(l, i, j, k);
+    for (j = 1; j <= J; j++) for (i = 1; i <= I; i++) {
+      const double A = 2.0 * BG_PI * (BG_REARTH * BG_REARTH) * (1.0 / I) * (o->sv[j] - o->sv[j - 1]);
+      if (K1(i, j) > K) continue;
+      ss = ss + (1.0 - A2(b->seaice, i, j)) * A * OCN(l, i, j, K);
+      if (mask[(i - 1) + I * (j - 1)] != 0.0) sb = sb + 1.0 * A * OCN(l, i, j, K1(i, j));
+    }
+    S[3 + (l - 1)] = S[3 + (l - 1)] + dtyr * s3 * rtot_M;
+    S[3 + NL + (l - 1)] = S[3 + NL + (l - 1)] + dtyr * ss * rtot_A;
+    S[3 + 2 * NL + (l - 1)] = S[3 + 2 * NL + (l - 1)] + dtyr * sb * rtot_A_ben;
+  }
+  for (la = 1; la <= b->LA; la++) {
+    double sa = 0.0;
+    for (j = 1; j <= J; j++) for (i = 1; i <= I; i++)
+      sa = sa + 2.0 * BG_PI * (BG_REARTH * BG_REARTH) * (1.0 / I) * (o->sv[j] - o->sv[j - 1]) * b->sfcatm1[(la - 1) + b->LA * ((i - 1) + I * (j - 1))];
+    S[3 + 3 * NL + (la - 1)] = S[3 + 3 * NL + (la - 1)] + dtyr * sa * rtot_A_atm;
+  }
+  S[0] = S[0] + dtyr;
+  free(mask);
 }
 
 /* cpl_flux_ocnsed, sedgem.f90:1029-1068 (loc_scalei = loc_scalej = 1: i1 = i, j1 = j) */

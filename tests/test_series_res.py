@@ -1,0 +1,92 @@
+"""BIOGEM's .res time series: the Fortran edit descriptors of cg_biogem_series_write (csrc/cg_series.cpp) against hand-worked
+known answers of sub_data_save_runtime's formats (biogem_data_ascii.f90:669-935), and the oracle's window integrals
+(cgo_biogem_sig_update, biogem.f90:2836-2917) against numpy on the oracle's own state."""
+import numpy as np
+
+from cgenie_b200.series import write_series
+from oracle_lib import Oracle
+
+I = J = 36
+K = L = 16
+LA = 8
+
+
+def test_res_files_formats(built, tmp_path):
+    out = tmp_path / "biogem"
+    write_series(str(out))
+    head = open(out / "biogem_series_ocn_DIC.res").read()
+    assert head == " % time (yr) / global DIC (mol) / global DIC (mol kg-1) / surface DIC (mol kg-1) / benthic DIC (mol kg-1)\n"
+    assert open(out / "biogem_series_ocn_temp.res").read() == " % time (yr) / temperature (C) / _surT (C) / _benT (degrees C)\n"
+    assert open(out / "biogem_series_ocn_DIC_13C.res").read().startswith(" % time (yr) / global DIC_13C (mol) / global DIC_13C (o/oo) / surface")
+    assert open(out / "biogem_series_atm_pCO2.res").read() == " % time (yr) / global pCO2 (mol) / global pCO2 (atm)\n"
+    assert open(out / "biogem_series_atm_humidity.res").read() == " % time (yr) / surface humidity (???)\n"
+    # a window of 2 years: integrals = 2 x the means
+    sig = np.zeros(3 + 3 * L + LA)
+    sig[0], sig[1], sig[2] = 2.0, 2.0 * 1.35e21, 2.0 * 3.0e19
+    ocn, sur, ben, atm = sig[3:3 + L], sig[3 + L:3 + 2 * L], sig[3 + 2 * L:3 + 3 * L], sig[3 + 3 * L:]
+    ocn[0], sur[0], ben[0] = 2.0 * 276.65, 2.0 * 291.4, 2.0 * 272.9          # K
+    ocn[1], sur[1], ben[1] = 2.0 * 34.9, 2.0 * 34.61234567, 2.0 * 34.95
+    ocn[2], sur[2], ben[2] = 2.0 * 2.244e-3, 2.0 * 2.0123456e-3, 2.0 * 2.3e-3
+    R = 0.011202 * (1.0 + 0.4 / 1000.0)
+    ocn[3] = 2.0 * 2.244e-3 * R / (1.0 + R)                                   # d13C = +0.4
+    sur[3] = 2.0 * 2.0123456e-3 * (0.011202 * 1.002) / (1.0 + 0.011202 * 1.002)  # +2.0
+    ben[3] = 0.0                                                               # R = 0 -> -1000
+    ocn[5] = 2.0 * 2.159e-6
+    ocn[6] = -2.0 * 1.0e-101                                                   # three-digit exponent, negative
+    atm[0], atm[1], atm[2] = 2.0 * 12.5, 2.0 * 0.0085, 2.0 * 278.0e-6
+    Ra = 0.011202 * (1.0 - 6.5 / 1000.0)
+    atm[3] = 2.0 * 278.0e-6 * Ra / (1.0 + Ra)
+    write_series(str(out), sig, t_yr=0.5)
+    write_series(str(out), sig, t_yr=12345.678)
+    lines = open(out / "biogem_series_ocn_temp.res").read().split("\n")
+    assert lines[1] == "       0.500    3.500000   18.250000   -0.250000"
+    assert lines[2].startswith("   12345.678") and lines[3] == ""
+    assert open(out / "biogem_series_ocn_sal.res").read().split("\n")[1] == "       0.500   34.900000   34.612346   34.950000"
+    assert open(out / "biogem_series_ocn_DIC.res").read().split("\n")[1] == \
+        "       0.500  0.3029400E+19  0.2244000E-02  0.2012346E-02  0.2300000E-02"
+    l13 = open(out / "biogem_series_ocn_DIC_13C.res").read().split("\n")[1]
+    assert l13[:12] == "       0.500" and l13[27:] == "       0.400       2.000   -1000.000" and l13[12:27].endswith("E+17")
+    assert open(out / "biogem_series_ocn_PO4.res").read().split("\n")[1] == \
+        "       0.500  0.2914650E+16  0.2159000E-05  0.0000000E+00  0.0000000E+00"
+    assert open(out / "biogem_series_ocn_O2.res").read().split("\n")[1][12:42] == " -0.1350000E-79 -0.1000000-100"
+    # an isotope whose bulk tracer is zero: const_nulliso
+    assert open(out / "biogem_series_ocn_DOM_C_13C.res").read().split("\n")[1] == \
+        "       0.500  0.0000000E+00    -999.999    -999.999    -999.999"
+    assert open(out / "biogem_series_atm_temp.res").read().split("\n")[1] == "       0.500   12.500000"
+    assert open(out / "biogem_series_atm_pCO2.res").read().split("\n")[1] == "       0.500  0.4918376E+17  0.2780000E-03"
+    la = open(out / "biogem_series_atm_pCO2_13C.res").read().split("\n")[1]
+    assert la[27:] == "        -6.500" and len(la) == 12 + 15 + 14
+    # nothing integrated: nothing written (biogem.f90:3119)
+    write_series(str(out), np.zeros_like(sig), t_yr=3.0)
+    assert len(open(out / "biogem_series_ocn_temp.res").read().split("\n")) == 4
+
+
+def test_oracle_sig_integrals():
+    o = Oracle("worjh2", maxk=K, maxl=L, nyear=96)
+    o.biogem_setup()
+    dtyr = float(2 * 5) * (3600.0 * 24.0 * 365.25 / 5.0 / 96) / (3600.0 * 24.0 * 365.25)
+    want = np.zeros(3 + 3 * L + LA)
+    k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    wet = np.arange(1, K + 1)[:, None, None] >= k1[None]
+    for blk in range(1, 4):
+        o.run(10)
+        o.L.cgo_biogem_sig_update(o.h, 1000.0)
+        M = np.where(wet, o.f("bg_M").reshape(K, J, I), 0.0)
+        ocn = o.f("ocn").reshape(K, J, I, L)
+        want[0] += dtyr
+        want[1] += dtyr * M.sum()
+        want[2] += dtyr * M[K - 1].sum()
+        want[3:3 + L] += dtyr * (M[..., None] * ocn).reshape(-1, L).sum(axis=0) / M.sum()
+    got = o.f("bg_sig")
+    assert abs(got[0] - 3 * dtyr) < 1e-15
+    assert np.allclose(got[1:3 + L], want[1:3 + L], rtol=1e-13, atol=0)
+    t = got[0]
+    # initial uniform concentrations barely move in 30 steps: the means are the initial values to a few per mil
+    assert abs(got[3 + 2] / t - 2.244e-3) < 2e-5 and abs(got[3 + 5] / t - 2.159e-6) < 1e-7
+    # surface (ice-free) and benthic means: bounded by the extremes of the levels they are taken from
+    sur, ben, atm = got[3 + L:3 + 2 * L] / t, got[3 + 2 * L:3 + 3 * L] / t, got[3 + 3 * L:] / t
+    ocn = o.f("ocn").reshape(K, J, I, L)
+    top = ocn[K - 1][k1 <= K]
+    assert top[:, 0].min() - 1.0 < sur[0] < top[:, 0].max() + 1.0 and sur[0] > ben[0]          # warm surface, cold abyss
+    assert ocn[..., 5][wet].min() <= ben[5] <= ocn[..., 5][wet].max() * 1.01 and ben[5] > sur[5]   # PO4 depleted at the surface
+    assert abs(atm[2] - 278.0e-6) < 3e-6 and abs(atm[0] - o.f("sfcatm1").reshape(J, I, LA)[..., 0].mean()) < 5.0
