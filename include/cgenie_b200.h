@@ -127,7 +127,9 @@ int cg_reinit_flux_rokocn(cg_handle *);
  * it where genie.f90:395-405 calls diag_biogem_timeseries_wrapper, on the steps that fall in a save window (the window logic
  * of :2760-2769 and biogem_save_sig.dat stay with the caller).  Field "bg_sig" (cg_sync_to_host) = the integrals of one
  * member in that order, 3 + 3*maxl + n_l_atm values, tracers in the compact selection order; cg_biogem_sig_reset =
- * sub_init_int_timeseries (biogem_data.f90:964-1007).  ben_Dmin = par_data_save_ben_Dmin (m). */
+ * sub_init_int_timeseries (biogem_data.f90:964-1007).  ben_Dmin = par_data_save_ben_Dmin (m).  Air temperature and humidity
+ * (atmosphere rows 1-2) are read from EMBM's current tq: the reference reads the copy cpl_comp_EMBM made at the last ATCHEM
+ * step, which is one coupling interval older at the point genie.f90 calls the diagnostic. */
 int cg_biogem_sig_update(cg_handle *, double dts, double ben_Dmin);
 int cg_biogem_sig_reset(cg_handle *);
 /* sub_init_data_save_runtime / sub_data_save_runtime (src/biogem/biogem_data_ascii.f90:23-110, 669-935), the ocn_* and atm_*

@@ -30,7 +30,7 @@ def test_sig_integrals_match_oracle(built, tmp_path):
         for blk in range(5, 9):
             if blk <= 6:          # whole iterations on the device, the diagnostic behind cg_run
                 e.run(10)
-            else:                 # module by module, where genie.f90 calls diag_biogem_timeseries (after step_biogem)
+            else:                 # module by module; the diagnostic behind the whole BIOGEM / ATCHEM block, where the oracle takes it
                 for k in range(10 * (blk - 1) + 1, 10 * blk + 1):
                     if k % 5 == 1:
                         e.surflux()
@@ -41,11 +41,10 @@ def test_sig_integrals_match_oracle(built, tmp_path):
                     if k % 10 == 0:
                         e.biogem_forcing(k * tick)
                         e.biogem_step(dts, k * tick)
+                        e.biogem_tracercoupling()
+                        e.biogem_climate()
+                        e.atchem_step(dts)
             e.biogem_sig_update(dts, 1000.0)
-            if blk > 6:
-                e.biogem_tracercoupling()
-                e.biogem_climate()
-                e.atchem_step(dts)
             o.run(10)
             o.L.cgo_biogem_sig_update(o.h, 1000.0)
         d, r = e.get("bg_sig", 0), o.f("bg_sig")
@@ -54,7 +53,7 @@ def test_sig_integrals_match_oracle(built, tmp_path):
         print("bg_sig worst relative difference %.2e at %d" % (rel.max(), int(rel.argmax())))
         assert rel.max() <= 1e-10, (rel.max(), int(rel.argmax()))
         d1 = e.get("bg_sig", 1)
-        assert d1[0] == d[0] and d1[3 + 5] != d[3 + 5]                  # another uptake rate, another mean surface PO4
+        assert d1[0] == d[0] and d1[3 + L + 5] != d[3 + L + 5]          # another uptake rate, another mean surface PO4
         for who, sig in (("dev", d), ("ora", r)):
             write_series(str(tmp_path / who), None)
             write_series(str(tmp_path / who), sig, t_yr=0.146)
