@@ -181,7 +181,7 @@ struct cg_handle {
   bool bg_go = true;
   SigDev sig{};                       // BIOGEM time-series integrals
   double sig_ben_Dmin = -1.0;
-  double *sig_w_ben = nullptr;
+  double *sig_w_ben = nullptr, *sig_tq = nullptr;
   double *sfxsumsed = nullptr, *sfcsumocn = nullptr, *sfxsumrok1 = nullptr;   // SEDGEM / ROKGEM interface sums, [ls|l][j][i][m]
   ~cg_handle() {
     cudaSetDevice(device);
@@ -747,6 +747,7 @@ static int build_device(cg_handle *h) {
       TRY(dupload(h, &qi, kb)); h->sig.kbot = qi;
       TRY(dupload(h, &qd, Aall)); h->sig.A = qd;
       TRY(dalloc(h, &h->sig_w_ben, ij)); h->sig.w_ben = h->sig_w_ben;
+      TRY(dalloc(h, &h->sig_tq, 2 * ij * MS)); h->sig.tq = h->sig_tq;
       TRY(dalloc(h, &h->sig.raw, (size_t)nq * MS));
       TRY(dalloc(h, &h->sig.acc, (size_t)nq * MS));
       h->sig.rtot_A_atm = totA > kBgNullSmall ? 1.0 / totA : 0.0;
@@ -1505,6 +1506,9 @@ extern "C" int cg_biogem_sig_update(cg_handle *h, double dts, double ben_Dmin) {
     h->sig.rtot_A_ben = tot > kBgNullSmall ? 1.0 / tot : 0.0;
     h->sig_ben_Dmin = ben_Dmin;
   }
+  // the atmosphere's T, q as they are now, on the caller's stream (as k_bg_stage_seaice does for the sea-ice cover): the
+  // sums themselves run on the BIOGEM stream while the caller's stream goes on with the next cycle's surflux / EMBM steps
+  CUDA_OK(cudaMemcpyAsync(h->sig_tq, h->dv.tq, (size_t)2 * I * J * h->dv.MS * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   BgAsyncScope as(h, true);
   IO(side_wait(h));
   ProfScope ps(h, "biogem");

@@ -167,6 +167,7 @@ constexpr int kSigHead = 3;
 struct SigDev {
   const int *kbot;                        // [j][i] 0-based level of the bottom cell, K on land
   const double *A, *w_ben;                // [j][i] cell area (all cells); benthic mask * area
+  const double *tq;                       // [2][j][i][m] EMBM's tq as it was when the diagnostic was called
   double *raw, *acc;                      // [q][m] sums of this step; integrals of the window
   double rtot_A_ben, rtot_A_atm;          // 1 / SUM(mask_ben * A), 1 / SUM(phys_ocnatm(ipoa_A))
   int LA;

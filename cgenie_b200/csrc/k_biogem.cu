@@ -1235,9 +1235,10 @@ __global__ void __launch_bounds__(256) k_bg_sig_sums(const Dev v, const BgDev b,
   } else {
     const int la = q - kSigHead - 3 * L;
     // rows 1-2 of sfcatm1 (air temperature, humidity: cpl_comp_EMBM, atchem.f90:270-282) are not kept on the device; EMBM's
-    // current tq stands in for them (same values when the diagnostic follows the ATCHEM step, one coupling interval newer
-    // when it is taken before it as genie.f90 does)
-    const double *src = la < 2 ? v.tq : b.sfcatm1;
+    // tq stands in for them (same values when the diagnostic follows the ATCHEM step, one coupling interval newer when it
+    // is taken before it as genie.f90 does).  g.tq is the copy made on the caller's stream at call time: this kernel runs
+    // on the BIOGEM stream, next to the physics of the following cycle, whose surflux already rewrites the humidity.
+    const double *src = la < 2 ? g.tq : b.sfcatm1;
     for (int c2 = warp; c2 < ij; c2 += 8) s = s + g.A[c2] * src[((size_t)la * ij + c2) * MS + m];
   }
   part[warp][lane] = s;
