@@ -127,6 +127,15 @@ MODULE cgenie_b200_c
        IMPORT :: C_INT, C_PTR
        TYPE(C_PTR), VALUE :: h
      END FUNCTION cg_reinit_flux_rokocn
+     INTEGER(C_INT) FUNCTION cg_biogem_sig_update(h, dts, ben_dmin) BIND(C, NAME='cg_biogem_sig_update')
+       IMPORT :: C_INT, C_PTR, C_DOUBLE
+       TYPE(C_PTR), VALUE :: h
+       REAL(C_DOUBLE), VALUE :: dts, ben_dmin
+     END FUNCTION cg_biogem_sig_update
+     INTEGER(C_INT) FUNCTION cg_biogem_sig_reset(h) BIND(C, NAME='cg_biogem_sig_reset')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h
+     END FUNCTION cg_biogem_sig_reset
   END INTERFACE
 
 CONTAINS
