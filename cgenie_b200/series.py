@@ -46,3 +46,75 @@ def write_series(outdir, sig=None, t_yr=0.0, outfile_name="biogem", with_sur=Tru
                                   ot, od, len(ATM_TRACERS), an, at, ad, sp, 1 if with_sur else 0)
     if rc:
         raise SeriesError(L.cg_series_last_error().decode())
+
+
+YR_S = 3600.0 * (24.0 * 365.25)          # conv_yr_s, gem_cmn.f90:511-513
+S_YR = 1.0 / YR_S                        # conv_s_yr, gem_cmn.f90:532
+NULLSMALL = 0.999999e-19                 # const_real_nullsmall, gem_cmn.f90:719
+N_DATA_MAX = 32767                       # biogem_lib.f90:504
+
+
+class SeriesSaver:
+    """The save-window logic of BIOGEM's time series for ctrl_misc_t_BP = .FALSE.: sub_init_data_save (biogem_data.f90:2449-2527,
+    the list of save times either from biogem_save_sig.dat through sub_load_data_t1, biogem_lib.f90:1487-1543, or generated
+    from par_data_save_sig_dt) and the window tests of diag_biogem_timeseries (biogem.f90:2757-2769, 3079-3156).  Scalar
+    bookkeeping only: the sums are the device's (Ensemble.biogem_sig_update), the files cg_biogem_series_write's.
+
+    Call step(dts, genie_clock_ms) where genie.f90:395-405 calls diag_biogem_timeseries_wrapper (after step_biogem)."""
+
+    def __init__(self, e, outdir, t_runtime, t_start=0.0, sig_dt=1.0, save_times=None, ben_Dmin=0.0, member=0, with_sur=True,
+                 autoend=False, outfile_name="biogem"):
+        self.e, self.outdir, self.member, self.with_sur, self.outfile_name = e, str(outdir), member, with_sur, outfile_name
+        self.t_runtime, self.t_end = float(t_runtime), float(t_start) + float(t_runtime)
+        self.sig_dt, self.ben_Dmin = float(sig_dt), float(ben_Dmin)
+        t_err = 3600.0 * 1.0 / YR_S      # par_misc_t_err, biogem_data.f90:393
+        data = [float(x) for x in (save_times or [])]
+        if data:                         # sub_load_data_t1, .NOT. ctrl_misc_t_BP: times become "years to go", ascending
+            n = len(data)
+            if data[-1] <= data[0]:
+                sig = [self.t_end - x for x in data]
+            else:
+                sig = [self.t_end - data[n - q] for q in range(1, n + 1)]
+        else:
+            if not self.sig_dt > NULLSMALL:
+                raise SeriesError("time-series save interval must be non-zero and positive")
+            n = int(self.t_runtime / self.sig_dt + NULLSMALL)
+            while n > N_DATA_MAX:
+                self.sig_dt = 10.0 * self.sig_dt
+                n = int(self.t_runtime / self.sig_dt + NULLSMALL)
+            sig = [float(q - 0.5) * self.sig_dt + (self.t_runtime - float(n) * self.sig_dt) for q in range(1, n + 1)]
+        i = len(sig)
+        while i > 0:                     # the first save point that lies inside the run
+            if sig[i - 1] < (self.t_runtime - self.sig_dt / 2.0 + t_err):
+                break
+            i -= 1
+        if autoend:                      # ctrl_data_save_sig_autoend
+            for q in range(i, 0, -1):
+                if sig[q - 1] < (1.0 - self.sig_dt / 2.0 + t_err):
+                    if not sig[q - 1] > (self.sig_dt / 2.0 - t_err):
+                        sig[q - 1] = self.sig_dt / 2.0
+                    break
+        self.sig, self.sig_i = sig, i
+        self.int_t_sig = 0.0
+        self.saved = []
+        write_series(self.outdir, None, outfile_name=outfile_name, with_sur=with_sur)     # sub_init_data_save_runtime
+        e.biogem_sig_reset()
+
+    def step(self, dts, genie_clock_ms):
+        loc_t = self.t_runtime - float(genie_clock_ms) / (1000.0 * YR_S)
+        dtyr = float(dts) / YR_S
+        if not self.sig_i > 0:
+            return
+        if (loc_t - (self.sig[self.sig_i - 1] + self.sig_dt / 2.0)) < -S_YR:      # inside the window
+            self.e.biogem_sig_update(dts, self.ben_Dmin)
+            self.int_t_sig = self.int_t_sig + dtyr          # the device adds the same dtyr to its int_t_sig
+        if (self.sig_dt - self.int_t_sig) < S_YR:           # the window is full: save and move to the next save point
+            yr = self.t_end - loc_t - self.int_t_sig / 2.0
+            yr = float(int(yr)) + float(int(1000.0 * (yr - float(int(yr)) + 0.0005))) / 1000.00
+            if self.int_t_sig > NULLSMALL:
+                write_series(self.outdir, self.e.get("bg_sig", self.member), t_yr=yr, outfile_name=self.outfile_name,
+                             with_sur=self.with_sur)
+                self.saved.append(yr)
+            self.sig_i -= 1
+            self.e.biogem_sig_reset()                       # sub_init_int_timeseries
+            self.int_t_sig = 0.0

@@ -90,3 +90,64 @@ def test_oracle_sig_integrals():
     assert top[:, 0].min() - 1.0 < sur[0] < top[:, 0].max() + 1.0 and sur[0] > ben[0]          # warm surface, cold abyss
     assert ocn[..., 5][wet].min() <= ben[5] <= ocn[..., 5][wet].max() * 1.01 and ben[5] > sur[5]   # PO4 depleted at the surface
     assert abs(atm[2] - 278.0e-6) < 3e-6 and abs(atm[0] - o.f("sfcatm1").reshape(J, I, LA)[..., 0].mean()) < 5.0
+
+
+class _FakeEngine:
+    """Records the diagnostic calls; the integrals it hands back are those of a constant ocean."""
+
+    def __init__(self):
+        self.t, self.updates, self.resets = 0.0, 0, 0
+
+    def biogem_sig_update(self, dts, ben_Dmin):
+        self.t = self.t + dts / (3600.0 * 24.0 * 365.25)
+        self.updates += 1
+
+    def biogem_sig_reset(self):
+        self.t = 0.0
+        self.resets += 1
+
+    def get(self, name, member):
+        assert name == "bg_sig"
+        sig = np.zeros(3 + 3 * L + LA)
+        sig[0], sig[1] = self.t, self.t * 1.35e21
+        sig[3:3 + L] = self.t * 2.0e-3
+        sig[3] = self.t * 277.15
+        return sig
+
+
+def test_series_windows(built, tmp_path):
+    """sub_init_data_save + the window tests of diag_biogem_timeseries: a 3-year run from year 100 with yearly windows gives
+    three lines centred on x.5, each integrating the 48 BIOGEM steps of its year; an explicit list of save times (as in
+    biogem_save_sig.dat) with 0.5-year windows integrates 24 steps around each listed time that fits into the run."""
+    from cgenie_b200.series import SeriesSaver
+    nyear, kb = 96, 10
+    genie_timestep = 3600.0 * 24.0 * 365.25 / 5.0 / nyear
+    tick = int(round(1000.0 * genie_timestep))
+    dts = float(kb) * genie_timestep
+    e = _FakeEngine()
+    s = SeriesSaver(e, tmp_path / "a", t_runtime=3.0, t_start=100.0, sig_dt=1.0)
+    assert [round(x, 9) for x in s.sig] == [0.5, 1.5, 2.5] and s.sig_i == 3
+    per_window, last = [], 0
+    for k in range(kb, 3 * 5 * nyear + 1, kb):
+        s.step(dts, k * tick)
+        if len(s.saved) > len(per_window):
+            per_window.append(e.updates - last)
+            last = e.updates
+    assert s.saved == [100.5, 101.5, 102.5] and per_window == [48, 48, 48] and s.sig_i == 0
+    lines = open(tmp_path / "a" / "biogem_series_ocn_temp.res").read().split("\n")
+    assert len(lines) == 5
+    assert [l[:12] for l in lines[1:4]] == ["     100.500", "     101.500", "     102.500"]
+    assert lines[1][12:24] == "    4.000000"
+    assert open(tmp_path / "a" / "biogem_series_ocn_DIC.res").read().split("\n")[3][12:42] == "  0.2700000E+19  0.2000000E-02"
+    # explicit save times in model years; 99.0 lies before the run
+    e = _FakeEngine()
+    s = SeriesSaver(e, tmp_path / "b", t_runtime=3.0, t_start=100.0, sig_dt=0.5, save_times=[99.0, 100.5, 101.75, 102.9])
+    counts, last = [], 0
+    for k in range(kb, 3 * 5 * nyear + 1, kb):
+        s.step(dts, k * tick)
+        if len(s.saved) > len(counts):
+            counts.append(e.updates - last)
+            last = e.updates
+    assert s.saved == [100.5, 101.75] and counts == [24, 24]
+    # the window around 102.9 opens at 102.65 and is still filling when the run ends: without a forced save it is dropped
+    assert s.sig_i == 1 and 0.0 < s.int_t_sig < 0.5 and e.updates == 48 + round(0.35 * 48)
