@@ -102,6 +102,7 @@ struct cgo_bg {
   double *sfcocn1, *sfxsed1, *focnatm;                 /* interface / diagnostics [l|ls|la][i][j] */
   double *sfxsumsed, *sfcsumocn, *sfxsumrok1;          /* SEDGEM / ROKGEM interface sums (sediment grid = ocean grid) */
   double *sig;                                         /* time-series integrals: t, tot_M, tot_M_sur, ocn(L), sur(L), ben(L), atm(LA) */
+  int sig_auto; double sig_ben_Dmin;                   /* cgo_run takes the diagnostic where genie.f90 does (after step_biogem) */
   double Dbot[64], dD[64], Dmid_surf;
   int go;
 };
@@ -1233,6 +1234,8 @@ void cgo_biogem_sig_update(cgo_t *o, double ben_Dmin) {
   free(mask);
 }
 
+void cgo_biogem_sig_auto(cgo_t *o, int on, double ben_Dmin) { BG->sig_auto = on; BG->sig_ben_Dmin = ben_Dmin; }
+
 /* cpl_flux_ocnsed, sedgem.f90:1029-1068 (loc_scalei = loc_scalej = 1: i1 = i, j1 = j) */
 void cgo_cpl_flux_ocnsed(cgo_t *o, double dts) {
   struct cgo_bg *b = BG;
@@ -1306,6 +1309,7 @@ int cgo_biogem_koverall(cgo_t *o, long k) {
     if (k == b->kbiogem * o->kocn_loop) cgo_biogem_climate_sol(o);
     cgo_biogem_forcing(o);
     err = cgo_biogem_step(o);
+    if (b->sig_auto) cgo_biogem_sig_update(o, b->sig_ben_Dmin);   /* diag_biogem_timeseries_wrapper, genie.f90:395-405 */
     cgo_biogem_tracercoupling(o);
     cgo_biogem_climate(o);
     cgo_cpl_flux_ocnatm(o);

@@ -1,0 +1,69 @@
+"""One model year driven module by module with BIOGEM's time series switched on (series.SeriesSaver where genie.f90 calls
+diag_biogem_timeseries_wrapper, i.e. between step_biogem and the tracer coupling): the .res files of the control member against
+the oracle's integrals over the same 48 BIOGEM steps, taken at the same point of the loop (cgo_biogem_sig_auto) -- run with
+-m gpu on a B200.  Air temperature and humidity are the documented deviation (EMBM's current tq on the device, the copy of the
+last ATCHEM step in the reference and the oracle: one coupling interval apart at this call point), so they get a loose bar."""
+import numpy as np
+import pytest
+
+from cgenie_b200 import Ensemble, materialise
+from cgenie_b200.series import SeriesSaver, write_series
+from oracle_lib import Oracle
+from test_gpu_biogem import CFG, OKW
+
+pytestmark = pytest.mark.gpu
+
+
+def read_res(path):
+    lines = open(path).read().split("\n")
+    assert lines[0].startswith(" % time (yr)") and lines[-1] == ""
+    return [np.array(l.split(), dtype=float) for l in lines[1:-1]]
+
+
+def test_one_year_of_series(built, tmp_path):
+    materialise(str(tmp_path / "job"), CFG)
+    o = Oracle(**OKW)
+    o.biogem_setup()
+    with Ensemble(str(tmp_path / "job"), n_members=2, perturb={"par_bio_k0_PO4": np.array([1.9e-6, 2.3e-6])}) as e:
+        e.set_tracer_variant("col")
+        nk = 5 * e.nyear
+        genie_timestep = 3600.0 * 24.0 * 365.25 / 5.0 / e.nyear
+        tick = int(round(1000.0 * genie_timestep))
+        dts = float(2 * 5) * genie_timestep
+        s = SeriesSaver(e, tmp_path / "dev", t_runtime=1.0, t_start=0.0, sig_dt=1.0, ben_Dmin=1000.0)
+        for k in range(1, nk + 1):
+            if k % 5 == 1:
+                e.surflux()
+            e.step_embm()
+            if k % 5 == 0:
+                e.step_seaice()
+                e.step_goldstein()
+            if k % 10 == 0:
+                e.biogem_forcing(k * tick)
+                e.biogem_step(dts, k * tick)
+                s.step(dts, k * tick)
+                e.biogem_tracercoupling()
+                e.biogem_climate()
+                e.atchem_step(dts)
+        assert s.saved == [0.5] and s.sig_i == 0
+        assert np.all(e.get("bg_sig", 0) == 0.0)                     # reset after the save
+        assert int(e.health().sum()) == 0
+    o.L.cgo_biogem_sig_auto(o.h, 1, 1000.0)
+    o.run(nk)
+    assert abs(o.f("bg_sig")[0] - 1.0) < 1e-12
+    write_series(str(tmp_path / "ora"), None)
+    write_series(str(tmp_path / "ora"), o.f("bg_sig"), t_yr=0.5)
+    for n in ("ocn_temp", "ocn_sal", "ocn_DIC", "ocn_DIC_13C", "ocn_PO4", "ocn_O2", "ocn_ALK", "ocn_DOM_C", "atm_pCO2", "atm_pCO2_13C",
+              "atm_pO2", "atm_temp", "atm_humidity"):
+        a = read_res(tmp_path / "dev" / ("biogem_series_%s.res" % n))
+        b = read_res(tmp_path / "ora" / ("biogem_series_%s.res" % n))
+        assert len(a) == len(b) == 1 and a[0][0] == 0.5, n
+        if n in ("atm_temp", "atm_humidity"):
+            assert np.allclose(a[0], b[0], rtol=0.1, atol=0.5), (n, a[0], b[0])
+        else:     # 1e-6 of the printed value, or the last printed digit of an F12.3 / F12.6 column
+            atol = 2e-3 if "_1" in n else (2e-6 if n in ("ocn_temp", "ocn_sal") else 0.0)
+            assert np.allclose(a[0], b[0], rtol=1e-6, atol=atol), (n, a[0], b[0])
+    dic = read_res(tmp_path / "dev" / "biogem_series_ocn_DIC.res")[0]
+    assert abs(dic[2] - 2.244e-3) < 2e-5 and dic[3] < dic[2] < dic[4] * 1.01      # surface DIC drawn down by export production
+    d13 = read_res(tmp_path / "dev" / "biogem_series_ocn_DIC_13C.res")[0]
+    assert -2.0 < d13[2] < 3.0 and d13[3] > d13[2]                                 # the surface is enriched in 13C
