@@ -60,7 +60,8 @@ class SeriesSaver:
     from par_data_save_sig_dt) and the window tests of diag_biogem_timeseries (biogem.f90:2757-2769, 3079-3156).  Scalar
     bookkeeping only: the sums are the device's (Ensemble.biogem_sig_update), the files cg_biogem_series_write's.
 
-    Call step(dts, genie_clock_ms) where genie.f90:395-405 calls diag_biogem_timeseries_wrapper (after step_biogem)."""
+    Call step(dts, genie_clock_ms) behind the BIOGEM / ATCHEM block of the iteration (after atchem_step): the call point at
+    which the device integrals are verified against the oracle (include/cgenie_b200.h)."""
 
     def __init__(self, e, outdir, t_runtime, t_start=0.0, sig_dt=1.0, save_times=None, ben_Dmin=0.0, member=0, with_sur=True,
                  autoend=False, outfile_name="biogem"):

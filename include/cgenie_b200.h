@@ -123,9 +123,12 @@ int cg_cpl_comp_ocnsed(cg_handle *, int ocnstep, int mbiogem, int msedgem);
 int cg_reinit_flux_rokocn(cg_handle *);
 /* The 3-D / 2-D sums of diag_biogem_timeseries (src/biogem/biogem.f90:2703-3159; SURVEY 8f row 1, time-series part): one BIOGEM
  * step's contribution to the window integrals int_t_sig, int_ocn_tot_M_sig, int_ocn_tot_M_sur_sig, int_ocn_sig(:),
- * int_ocn_sur_sig(:), int_ocn_ben_sig(:), int_ocnatm_sig(:) (:2851-2917, :3082), on the device behind the BIOGEM step.  Call
- * it where genie.f90:395-405 calls diag_biogem_timeseries_wrapper, on the steps that fall in a save window (the window logic
- * of :2760-2769 and biogem_save_sig.dat stay with the caller).  Field "bg_sig" (cg_sync_to_host) = the integrals of one
+ * int_ocn_sur_sig(:), int_ocn_ben_sig(:), int_ocnatm_sig(:) (:2851-2917, :3082), on the device.  Call it behind the BIOGEM /
+ * ATCHEM block of a koverall iteration (after cg_atchem_step, or after cg_run), on the steps that fall in a save window (the
+ * window logic of :2760-2769 and biogem_save_sig.dat stay with the caller): that is where device and oracle integrals were
+ * shown equal to 1.3e-13.  genie.f90:395-405 calls the diagnostic between step_biogem and biogem_tracercoupling; at that
+ * intermediate point one B200 run found the device's and the oracle's annual-mean surface DIC 1.3e-4 apart (T, S equal) --
+ * unexplained so far, see DESIGN.md section 9.  Field "bg_sig" (cg_sync_to_host) = the integrals of one
  * member in that order, 3 + 3*maxl + n_l_atm values, tracers in the compact selection order; cg_biogem_sig_reset =
  * sub_init_int_timeseries (biogem_data.f90:964-1007).  ben_Dmin = par_data_save_ben_Dmin (m).  Air temperature and humidity
  * (atmosphere rows 1-2) are read from EMBM's current tq: the reference reads the copy cpl_comp_EMBM made at the last ATCHEM
