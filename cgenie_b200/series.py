@@ -101,6 +101,13 @@ class SeriesSaver:
         write_series(self.outdir, None, outfile_name=outfile_name, with_sur=with_sur)     # sub_init_data_save_runtime
         e.biogem_sig_reset()
 
+    def step_behind_block(self, dts, genie_clock_ms, ticks_per_biogem_step):
+        """Reference-equivalent sampling from the verified call point: called behind the BIOGEM / ATCHEM block whose clock is
+        genie_clock_ms, it books the sample to the NEXT BIOGEM step, whose diag_biogem_timeseries call would read exactly this
+        state (tests/test_series_res.py::test_call_point_equivalence_in_the_oracle).  Call it once on the initial state with the
+        clock of "block 0" (genie_clock_ms = 0) to stand in for the first BIOGEM step's diagnostic."""
+        self.step(dts, int(genie_clock_ms) + int(ticks_per_biogem_step))
+
     def step(self, dts, genie_clock_ms):
         loc_t = self.t_runtime - float(genie_clock_ms) / (1000.0 * YR_S)
         dtyr = float(dts) / YR_S
