@@ -168,3 +168,23 @@ def test_call_point_equivalence_in_the_oracle():
     o.L.cgo_biogem_sig_auto(o.h, 1, 1000.0)          # inside block 110, at the reference's call point
     o.run(10)
     assert np.array_equal(o.f("bg_sig"), behind) and behind[0] > 0.0
+
+
+def test_res_files_without_surface_columns(built, tmp_path):
+    """ctrl_data_save_sig_ocn_sur = .FALSE.: two-column T / S files, (mol, mol kg-1) for bulk tracers, (mol, o/oo) for isotopes
+    (biogem_data_ascii.f90:59-71, 737-747, 765-776, 797-802)."""
+    out = tmp_path / "nosur"
+    write_series(str(out), with_sur=False)
+    assert open(out / "biogem_series_ocn_temp.res").read() == " % time (yr) / temperature (degrees C)\n"
+    assert open(out / "biogem_series_ocn_ALK.res").read() == " % time (yr) / global ALK (mol) / global ALK (mol kg-1)\n"
+    assert open(out / "biogem_series_ocn_DIC_14C.res").read() == " % time (yr) / global DIC_14C (mol) / global DIC_14C (o/oo)\n"
+    sig = np.zeros(3 + 3 * L + LA)
+    sig[0], sig[1] = 0.25, 0.25 * 1.0e21
+    sig[3], sig[4], sig[5] = 0.25 * 273.15, 0.25 * 35.0, 0.25 * 2.0e-3
+    sig[3 + 4] = 0.25 * 2.0e-3 * 1.176e-12 / (1.0 + 1.176e-12)          # 14C at the standard ratio: delta = 0
+    write_series(str(out), sig, t_yr=7.125, with_sur=False)
+    assert open(out / "biogem_series_ocn_temp.res").read().split("\n")[1] == "       7.125    0.000000"
+    assert open(out / "biogem_series_ocn_sal.res").read().split("\n")[1] == "       7.125   35.000000"
+    assert open(out / "biogem_series_ocn_DIC.res").read().split("\n")[1] == "       7.125  0.2000000E+19  0.2000000E-02"
+    l14 = open(out / "biogem_series_ocn_DIC_14C.res").read().split("\n")[1]
+    assert l14[:27] == "       7.125  0.2352000E+07" and l14[27:] in ("       0.000", "      -0.000")
