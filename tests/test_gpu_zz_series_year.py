@@ -13,7 +13,7 @@ import pytest
 from cgenie_b200 import Ensemble, materialise
 from cgenie_b200.series import SeriesSaver, write_series
 from oracle_lib import Oracle
-from test_gpu_biogem import CFG, OKW
+from test_gpu_biogem import CFG, OKW, I, J, K, L
 
 pytestmark = pytest.mark.gpu
 
@@ -54,10 +54,19 @@ def test_one_year_of_series(built, tmp_path):
         assert s.saved == [0.5] and s.sig_i == 0
         assert np.all(e.get("bg_sig", 0) == 0.0)                     # reset after the save
         assert int(e.health().sum()) == 0
+        end_ocn = e.get("ocn", 0).reshape(-1, L)
     for k in range(10, nk + 1, 10):
         o.run(10)
         o.L.cgo_biogem_sig_update(o.h, 1000.0)
     assert abs(o.f("bg_sig")[0] - 1.0) < 1e-12
+    # the diagnostic calls must not change the trajectory: the year's final state against the oracle's (wet cells, per-tracer scale)
+    k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    wet = (np.arange(1, K + 1)[:, None, None] >= k1[None]).ravel()
+    ref_ocn = o.f("ocn").reshape(-1, L)
+    scale = np.abs(ref_ocn[wet]).max(axis=0) + 1e-300
+    worst = (np.abs(end_ocn - ref_ocn)[wet] / scale).max(axis=0)
+    print("final ocn, worst difference per tracer relative to its scale:", ["%.1e" % x for x in worst])
+    assert worst.max() < 1e-7, worst
     write_series(str(tmp_path / "ora"), None)
     write_series(str(tmp_path / "ora"), o.f("bg_sig"), t_yr=0.5)
     for n in ("ocn_temp", "ocn_sal", "ocn_DIC", "ocn_DIC_13C", "ocn_PO4", "ocn_O2", "ocn_ALK", "ocn_DOM_C", "atm_pCO2", "atm_pCO2_13C",
