@@ -60,6 +60,7 @@ SYMBOLS = {
     "cg_biogem_series_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_int, STRS, I32, I32, C.c_int, STRS, I32, I32,
                                           D, C.c_int]),
     "cg_set_koverall": (C.c_int, [P, C.c_int64]),
+    "cg_refresh_rho": (C.c_int, [P, C.c_int]),
     "cg_atchem_step": (C.c_int, [P, C.c_double]),
     "cg_run": (C.c_int, [P, C.c_int64]),
     "cg_field_size": (C.c_int64, [P, C.c_char_p]),

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <vector>
@@ -138,6 +139,8 @@ struct cg_handle {
   bool bg_overlap = true, bg_pending = false, bg_staged = false;
   bool eager = true;                              // per-module entry points: momentum at surflux time, BIOGEM calls on stream4
   bool mom_pending = false, mom_ready = false;    // eager momentum: still running on stream2 / result valid and unconsumed
+  bool usnap_valid = false;                       // the surface-velocity snapshot for this cycle's sea-ice step was taken before an early momentum step
+  double *u1_snap = nullptr;                      // u1 as it was before an eager momentum step (the one state it reads AND rewrites)
   cudaStream_t stream3 = nullptr;                 // baroclinic shear next to the barotropic solve
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork3 = nullptr, evJoin3 = nullptr;
   bool bg_fuse = false;                           // cg_run: tracer coupling fused into the BIOGEM step kernel (slower on B200)
@@ -181,7 +184,7 @@ struct cg_handle {
   bool bg_go = true;
   SigDev sig{};                       // BIOGEM time-series integrals
   double sig_ben_Dmin = -1.0;
-  double *sig_w_ben = nullptr, *sig_tq = nullptr;
+  double *sig_w_ben = nullptr;
   double *sfxsumsed = nullptr, *sfcsumocn = nullptr, *sfxsumrok1 = nullptr;   // SEDGEM / ROKGEM interface sums, [ls|l][j][i][m]
   ~cg_handle() {
     cudaSetDevice(device);
@@ -279,14 +282,28 @@ static void upload_grid(cg_handle *h) {
   upload_grid_tracer_fast(h->gc, h->stream);
   upload_grid_tracer_col(h->gc, h->stream);
 }
-// constant memory is per process: re-upload when another handle ran last
+// Constant memory (the 1-D grid metrics, GridC) is per process and device, shared by every handle.  Handles of the same job
+// -- the groups of cgenie_b200.EnsembleGroups, driven concurrently from host threads -- hold identical tables (M / MS are not
+// read from constant memory), so nothing is re-uploaded when one of them follows another.  A handle with different tables
+// (another job on the same device) waits for the device to drain before it replaces them: handles of different jobs may
+// share a device but must not be driven concurrently.
+static std::mutex g_active_mu;
+static std::map<int, GridC> g_uploaded;   // device -> tables last uploaded
 static cg_handle *g_active = nullptr;
 static void activate(cg_handle *h) {
   cudaSetDevice(h->device);
-  if (g_active != h) {
+  std::lock_guard<std::mutex> lock(g_active_mu);
+  if (g_active == h) return;
+  GridC want = h->gc;
+  want.M = want.MS = 0;
+  auto it = g_uploaded.find(h->device);
+  if (it == g_uploaded.end() || memcmp(&it->second, &want, sizeof(GridC)) != 0) {
+    if (it != g_uploaded.end()) cudaDeviceSynchronize();
     upload_grid(h);
-    g_active = h;
+    cudaStreamSynchronize(h->stream);
+    g_uploaded[h->device] = want;
   }
+  g_active = h;
 }
 
 // Order the main stream after everything the per-module entry points or cg_run left running on the side streams.
@@ -311,6 +328,25 @@ static int join_side(cg_handle *h) {
     CUDA_OK(cudaStreamWaitEvent(h->stream, h->evTcOld, 0));
     h->tc_old_pending = false;
   }
+  return CG_OK;
+}
+
+// The momentum step of a cycle may have been computed ahead of step_goldstein (eager_momentum).  It reads rho, u1 and constants
+// and rewrites u, u1, ub, psi, gb, bp, sbp; of these only u1 carries over from cycle to cycle (velc: u = rel*u1 + (1-rel)*u_new,
+// u1 = u, goldstein.f90:3648-3654).  A host write to one of its inputs makes the early result stale: u1 is rolled back to the
+// snapshot taken before the early step, which step_goldstein then repeats with the new state -- the relaxation is applied
+// once, as in the reference.  Writes to anything else (ts, cost, the atmosphere, BIOGEM's arrays ...) leave it valid.
+static bool momentum_input(const char *name) {
+  for (const char *n : {"rho", "u", "u1", "ub", "psi", "gb", "bp", "sbp"})
+    if (strcmp(name, n) == 0) return true;
+  return false;
+}
+static int drop_momentum(cg_handle *h) {
+  if (!h->mom_ready) return CG_OK;
+  if (h->mom_pending) { CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin, 0)); h->mom_pending = false; }
+  if (h->u1_snap)
+    CUDA_OK(cudaMemcpyAsync(h->dv.u1, h->u1_snap, (size_t)2 * h->g.I * h->g.J * h->g.K * h->MS * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->mom_ready = false;
   return CG_OK;
 }
 
@@ -381,6 +417,12 @@ extern "C" int cg_create(const char *jobdir, int n_members, int device, cg_handl
 extern "C" int cg_set_member_param(cg_handle *h, const char *name, const double *values) {
   if (!h || !name || !values) return fail(CG_ERR_ARG, "cg_set_member_param: bad argument");
   if (h->initialised) return fail(CG_ERR_STATE, "cg_set_member_param after cg_initialise");
+  // the slope limits ssmax(k) live in constant memory next to the grid metrics: one table for the whole ensemble
+  if (strcmp(name, "ssmaxsurf") == 0 || strcmp(name, "ssmaxdeep") == 0) {
+    for (int m = 1; m < h->M; m++)
+      if (values[m] != values[0]) return fail(CG_ERR_ARG, std::string(name) + " is shared by all members of a handle (per-member values are not supported)");
+    h->base.set(name, values[0]);
+  }
   for (int m = 0; m < h->M; m++)
     if (!h->mp[m].set(name, values[m])) return fail(CG_ERR_ARG, std::string("unknown member parameter ") + name);
   return CG_OK;
@@ -388,7 +430,7 @@ extern "C" int cg_set_member_param(cg_handle *h, const char *name, const double 
 
 extern "C" int cg_destroy(cg_handle *h) {
   if (!h) return CG_OK;
-  if (g_active == h) g_active = nullptr;
+  { std::lock_guard<std::mutex> lock(g_active_mu); if (g_active == h) g_active = nullptr; }
   delete h;
   return CG_OK;
 }
@@ -647,6 +689,7 @@ static int build_device(cg_handle *h) {
     TRY(dalloc(h, &b.surf, (size_t)kBgSurfSlots * ij * MS));
     TRY(dalloc(h, &b.seaice, ij * MS));
     TRY(dalloc(h, &b.seaice_stage, ij * MS));
+    TRY(dalloc(h, &b.tq_stage, 2 * ij * MS));
     TRY(dalloc(h, &b.sfxsumatm, ij * LA * MS));
     TRY(dalloc(h, &b.sfcocn1, ij * L * MS));
     TRY(dalloc(h, &b.sfxsed1, ij * LS * MS));
@@ -706,6 +749,14 @@ static int build_device(cg_handle *h) {
           if (la >= 3) sfc[(size_t)(la - 1) * ij * MS + c] = val;
         }
       }
+      // the initial cpl_comp_EMBM (genie.f90:90): tstar_atm, surf_qstar_atm as initialise_embm left them
+      for (int m = 0; m < MS; m++) {
+        const MemberConsts &c = h->mc[std::min(m, M - 1)];
+        for (size_t q = 0; q < ij; q++) {
+          sfc[q * MS + m] = c.tq0[0 + 2 * q];
+          sfc[(ij + q) * MS + m] = c.tq0[1 + 2 * q];
+        }
+      }
       TRY(dupload(h, &b.atm, atm));
       TRY(dupload(h, &b.sfcatm1, sfc));
     }
@@ -747,7 +798,6 @@ static int build_device(cg_handle *h) {
       TRY(dupload(h, &qi, kb)); h->sig.kbot = qi;
       TRY(dupload(h, &qd, Aall)); h->sig.A = qd;
       TRY(dalloc(h, &h->sig_w_ben, ij)); h->sig.w_ben = h->sig_w_ben;
-      TRY(dalloc(h, &h->sig_tq, 2 * ij * MS)); h->sig.tq = h->sig_tq;
       TRY(dalloc(h, &h->sig.raw, (size_t)nq * MS));
       TRY(dalloc(h, &h->sig.acc, (size_t)nq * MS));
       h->sig.rtot_A_atm = totA > kBgNullSmall ? 1.0 / totA : 0.0;
@@ -1072,7 +1122,7 @@ static int sync_from_host_lane(cg_handle *h, const char *name, int member, const
   IO0(join_side(h));
   h->spec_valid = false;
   h->tc_spec_valid = false;
-  h->mom_ready = false;   // a momentum step computed ahead of time is stale once the host has written state
+  if (momentum_input(name)) IO0(drop_momentum(h));   // a momentum step computed ahead of time is stale: roll u1 back, redo it later
   const bool both = strcmp(name, "ts") == 0 || strcmp(name, "ts1") == 0;
   FieldDesc *f = find_field(h, both ? "ts" : name);
   if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
@@ -1104,7 +1154,7 @@ extern "C" int cg_sync_all_to_host(cg_handle *h, const char *name, double *dst, 
 extern "C" int cg_sync_all_from_host(cg_handle *h, const char *name, const double *src, int64_t n) {
   if (!h || !name || !src || !h->initialised) return fail(CG_ERR_ARG, "cg_sync_all_from_host: bad argument");
   IO0(join_side(h));
-  h->mom_ready = false;
+  if (momentum_input(name)) IO0(drop_momentum(h));
   h->spec_valid = false;
   h->tc_spec_valid = false;
   FieldDesc *f = find_field(h, name);
@@ -1188,7 +1238,7 @@ static int do_seaice(cg_handle *h) {
   // the sea-ice step advects with the surface velocities exported by the last step_goldstein: a snapshot, taken here
   // unless the forked cycle already took it before the momentum branch started
   int n = 0;
-  if (!h->forked && !h->mom_ready) { launch_usnap(h->dv, h->stream); n++; }
+  if (!h->forked && !h->usnap_valid) { launch_usnap(h->dv, h->stream); n++; }
   ps.done(n + launch_seaice(h->dv, h->stream));
   h->istep_sic++;
   return CG_OK;
@@ -1233,6 +1283,7 @@ static int do_momentum(cg_handle *h, cudaStream_t s, cudaStream_t s3 = nullptr) 
 }
 static int bg_join(cg_handle *h);
 static int do_goldstein(cg_handle *h) {
+  h->usnap_valid = false;
   do_gold_pre(h);
   if (h->mom_ready) {   // computed on stream2 since the surflux call of this cycle
     if (h->mom_pending) { CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin, 0)); h->mom_pending = false; }
@@ -1248,6 +1299,11 @@ static int do_goldstein(cg_handle *h) {
 // per-module path: start the momentum step of this cycle now (it needs rho of the previous tracer step only)
 static int eager_momentum(cg_handle *h) {
   if (!h->eager || h->profile || h->mom_ready || getenv("CG_NOEAGER")) return CG_OK;
+  {
+    const size_t n = (size_t)2 * h->g.I * h->g.J * h->g.K * h->MS;
+    if (!h->u1_snap) IO0(dalloc(h, &h->u1_snap, n, false));
+    CUDA_OK(cudaMemcpyAsync(h->u1_snap, h->dv.u1, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
   launch_usnap(h->dv, h->stream);
   h->launches++;
   CUDA_OK(cudaEventRecord(h->evFork, h->stream));
@@ -1257,6 +1313,7 @@ static int eager_momentum(cg_handle *h) {
   CUDA_OK(cudaEventRecord(h->evJoin, h->stream2));
   h->mom_pending = true;
   h->mom_ready = true;
+  h->usnap_valid = true;
   return CG_OK;
 }
 // per-module path: run one BIOGEM / ATCHEM entry point on stream4, ordered after everything issued so far on the main
@@ -1506,9 +1563,8 @@ extern "C" int cg_biogem_sig_update(cg_handle *h, double dts, double ben_Dmin) {
     h->sig.rtot_A_ben = tot > kBgNullSmall ? 1.0 / tot : 0.0;
     h->sig_ben_Dmin = ben_Dmin;
   }
-  // the atmosphere's T, q as they are now, on the caller's stream (as k_bg_stage_seaice does for the sea-ice cover): the
-  // sums themselves run on the BIOGEM stream while the caller's stream goes on with the next cycle's surflux / EMBM steps
-  CUDA_OK(cudaMemcpyAsync(h->sig_tq, h->dv.tq, (size_t)2 * I * J * h->dv.MS * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  // everything the sums read is BIOGEM's own state (ocn, cell masses, the sea-ice snapshot, sfcatm1 incl. the air temperature
+  // and humidity rows cpl_comp_EMBM filled at the last block): they run on the BIOGEM stream
   BgAsyncScope as(h, true);
   IO(side_wait(h));
   ProfScope ps(h, "biogem");
@@ -1918,7 +1974,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
   IO0(join_side(h));
   h->spec_valid = false;
   h->tc_spec_valid = false;
-  h->mom_ready = false;   // cg_run computes the momentum step inside its own schedule
+  IO0(drop_momentum(h));  // cg_run computes the momentum step inside its own schedule
   const Params &p = h->base;
   const bool regular = p.katm_loop == 1 && p.ksic_loop == p.kocn_loop && p.kocn_loop > 1;
   const int trace_n = getenv("CG_TRACE") ? atoi(getenv("CG_TRACE")) : 0;
@@ -2022,7 +2078,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
 extern "C" int cg_set_koverall(cg_handle *h, int64_t koverall) {
   READY(h);
   IO0(join_side(h));
-  h->mom_ready = false;
+  IO0(drop_momentum(h));
   h->spec_valid = false;
   h->tc_spec_valid = false;
   const Params &p = h->base;
@@ -2039,6 +2095,38 @@ extern "C" int cg_set_koverall(cg_handle *h, int64_t koverall) {
     h->bg_go = !((h->bg.t_runtime - (double)clock / (1000.0 * kBgYrS)) < kBgNullSmall) || koverall == 0;
     for (int la = 3; la <= h->bg.LA; la++)
       if (h->bg.rst_sel[la]) { h->bg.rst_sig_i1[la] = (int)h->bg.rst_sig_t[la].size(); h->bg.rst_sig_i2[la] = h->bg.rst_sig_i1[la]; }
+  }
+  return CG_OK;
+}
+
+extern "C" int cg_refresh_rho(cg_handle *h, int member) {
+  READY(h);
+  if (member >= h->M) return fail(CG_ERR_ARG, "cg_refresh_rho: no such member");
+  const int I = h->g.I, J = h->g.J, K = h->g.K, L = h->g.L;
+  std::vector<double> ts((size_t)L * I * J * K), rho((size_t)I * J * K);
+  for (int m = (member < 0 ? 0 : member); m < (member < 0 ? h->M : member + 1); m++) {
+    IO(cg_sync_to_host(h, "ts", m, ts.data(), (int64_t)ts.size()));
+    IO(cg_sync_to_host(h, "rho", m, rho.data(), (int64_t)rho.size()));
+    for (int k = 1; k <= K; k++)
+      for (int j = 1; j <= J; j++)
+        for (int i = 1; i <= I; i++) {
+          if (k < h->g.k1at(i, j)) continue;
+          const size_t c = cell3(I, J, i, j, k);
+          rho[c] = eos(h->mc[m].ec, ts[c * L], ts[c * L + 1]);
+        }
+    IO(cg_sync_from_host(h, "rho", m, rho.data(), (int64_t)rho.size()));
+    if (h->dv.sst) {   // SST / SSS as step_goldstein last exported them (tsval, ssval of initialise_goldstein after a restart)
+      std::vector<double> sst((size_t)2 * I * J);
+      IO(cg_sync_to_host(h, "sst", m, sst.data(), (int64_t)sst.size()));
+      for (int j = 1; j <= J; j++)
+        for (int i = 1; i <= I; i++) {
+          if (h->g.k1at(i, j) > K) continue;
+          const size_t c = cell3(I, J, i, j, K);
+          sst[0 + 2 * cell2(I, i, j)] = ts[c * L];
+          sst[1 + 2 * cell2(I, i, j)] = ts[c * L + 1];
+        }
+      IO(cg_sync_from_host(h, "sst", m, sst.data(), (int64_t)sst.size()));
+    }
   }
   return CG_OK;
 }

@@ -155,6 +155,7 @@ struct BgDev {
   double *carbH;                          // [j][i][m]       surface [H+], seed of the next pH solve
   double *seaice;                         // [j][i][m]       snapshot taken by biogem_climate
   double *seaice_stage;                   // [j][i][m]       sea-ice cover at biogem_climate's call time (k_bg_stage_seaice)
+  double *tq_stage;                       // [2][j][i][m]    EMBM's T, q at the same time: what cpl_comp_EMBM copies (atchem.f90:270-282)
   const double *wspeed, *A, *rA;          // [j][i] member independent
   double *atm, *sfcatm1, *sfxsumatm;      // [la][j][i][m]
   const double *atm_A, *atm_V;            // [j][i]
@@ -167,7 +168,6 @@ constexpr int kSigHead = 3;
 struct SigDev {
   const int *kbot;                        // [j][i] 0-based level of the bottom cell, K on land
   const double *A, *w_ben;                // [j][i] cell area (all cells); benthic mask * area
-  const double *tq;                       // [2][j][i][m] EMBM's tq as it was when the diagnostic was called
   double *raw, *acc;                      // [q][m] sums of this step; integrals of the window
   double rtot_A_ben, rtot_A_atm;          // 1 / SUM(mask_ben * A), 1 / SUM(phys_ocnatm(ipoa_A))
   int LA;

@@ -998,7 +998,11 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
 __global__ void k_bg_stage_seaice(const Dev v, const BgDev b) {
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n = (size_t)v.I * v.J * v.MS;
-  if (q < n) b.seaice_stage[q] = v.varice[n + q];   // varice(2,:,:) = fractional cover
+  if (q < n) {
+    b.seaice_stage[q] = v.varice[n + q];   // varice(2,:,:) = fractional cover
+    b.tq_stage[q] = v.tq[q];               // tstar_atm, surf_qstar_atm of this koverall iteration (embm.f90:177-193)
+    b.tq_stage[n + q] = v.tq[n + q];
+  }
 }
 __global__ void k_bg_climate(const Dev v, const BgDev b) {
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1006,6 +1010,10 @@ __global__ void k_bg_climate(const Dev v, const BgDev b) {
   if (q >= n) return;
   b.seaice[q] = b.seaice_stage[q];
   v.cost[q] = 0.0;
+  // cpl_comp_EMBM (atchem.f90:270-282, genie.f90:454): rows 1-2 of sfcatm1 = air temperature and humidity.  The reference
+  // makes the copy behind the ATCHEM step of the same koverall iteration; nothing in between reads the two rows.
+  b.sfcatm1[q] = b.tq_stage[q];
+  b.sfcatm1[n + q] = b.tq_stage[n + q];
 }
 
 // step_atchem (atchem.f90:63-158) + cpl_comp_atmocn (:252-264).  k_bg_atchem1: thread = (member, cell, tracer), the
@@ -1234,12 +1242,9 @@ __global__ void __launch_bounds__(256) k_bg_sig_sums(const Dev v, const BgDev b,
     }
   } else {
     const int la = q - kSigHead - 3 * L;
-    // rows 1-2 of sfcatm1 (air temperature, humidity: cpl_comp_EMBM, atchem.f90:270-282) are not kept on the device; EMBM's
-    // tq stands in for them (same values when the diagnostic follows the ATCHEM step, one coupling interval newer when it
-    // is taken before it as genie.f90 does).  g.tq is the copy made on the caller's stream at call time: this kernel runs
-    // on the BIOGEM stream, next to the physics of the following cycle, whose surflux already rewrites the humidity.
-    const double *src = la < 2 ? g.tq : b.sfcatm1;
-    for (int c2 = warp; c2 < ij; c2 += 8) s = s + g.A[c2] * src[((size_t)la * ij + c2) * MS + m];
+    // rows 1-2 of sfcatm1 are the air temperature and humidity cpl_comp_EMBM copied at the last BIOGEM / ATCHEM block
+    // (k_bg_climate), whichever side of the tracer coupling the diagnostic is taken on
+    for (int c2 = warp; c2 < ij; c2 += 8) s = s + g.A[c2] * b.sfcatm1[((size_t)la * ij + c2) * MS + m];
   }
   part[warp][lane] = s;
   __syncthreads();

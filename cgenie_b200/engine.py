@@ -256,6 +256,11 @@ class Ensemble(_Base):
         self.istep_atm = int(koverall)
         self.koverall = int(koverall)
 
+    def refresh_rho(self, member=-1):
+        """rho = eos(T, S) at the wet cells of one member (all members: -1) after T, S were rewritten from the host, as
+        initialise_goldstein does behind inm_netcdf (goldstein.f90:1724-1760)."""
+        self._ck(self.L.cg_refresh_rho(self.h, int(member)))
+
     def run_years(self, years):
         self.run(int(round(years * self.nyear * self.ndta)))
 

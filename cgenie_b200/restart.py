@@ -84,6 +84,10 @@ def read_restart(e, paths, member=0):
     _ck(L.cg_restart_goldstein_read(paths["goldstein"].encode(), I, J, K, Lt, _dp(ts), _dp(u), None, None, None, _ip(date)))
     e.put("ts", ts, member)
     e.put("u", u, member)
+    # inm_netcdf: u1(1:2) = the file's velocities, u = u1 (goldstein_data.f90:91-93); velc relaxes the new velocities
+    # against u1 (goldstein.f90:3648-3654), and initialise_goldstein recomputes rho from the restored T, S
+    e.put("u1", np.ascontiguousarray(u.reshape(K, J, I, 3)[..., :2]).ravel(), member)
+    e.refresh_rho(member)
     tq = np.empty(2 * I * J)
     _ck(L.cg_restart_embm_read(paths["embm"].encode(), I, J, _dp(tq), _ip(date)))
     e.put("tq", tq, member)
@@ -189,6 +193,8 @@ def _apply_biogem_restart(e, member, ocn, part, k1, force_goldstein_ts, saln0):
         ts[..., 0] = np.where(wet, o4[..., 0] - 273.15, ts[..., 0])
         ts[..., 1] = np.where(wet, o4[..., 1] - saln0, ts[..., 1])
     e.put("ts", ts.ravel(), member)
+    if force_goldstein_ts:   # T, S changed under GOLDSTEIN: its density follows (the momentum step reads rho first)
+        e.refresh_rho(member)
 
 
 def read_biogem_restart(e, path, member=0, force_goldstein_ts=True, saln0=34.9):

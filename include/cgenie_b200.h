@@ -160,6 +160,10 @@ int cg_run(cg_handle *, int64_t n_koverall);
 /* Restart: continue the coupling loop from iteration `koverall` (multiple of kocn_loop) after the prognostic fields were
  * restored with cg_sync_from_host; sets koverall, istep_ocn/atm/sic, the GENIE clock and BIOGEM's derived counters.   */
 int cg_set_koverall(cg_handle *, int64_t koverall);
+/* After T, S of `member` were rewritten from the host (restart): rho = eos(T, S) at the wet cells, as initialise_goldstein
+ * does behind inm_netcdf (goldstein.f90:1724-1760: ts1 = ts, rho from eos); the momentum step reads rho before the first
+ * tracer step recomputes it.  member < 0 = all members.                                                                  */
+int cg_refresh_rho(cg_handle *, int member);
 
 /* ---- state movement (restart / output / coupling intervals) ----------- */
 /* Named field of ONE member, in the reference's Fortran shape:

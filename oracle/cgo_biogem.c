@@ -613,6 +613,9 @@ void cgo_biogem_setup(cgo_t *o, const char *params) {
           else ATM(la, i, j) = iso_fraction(b->atm_init[la], b->atype[la] == 11 ? BG_STD_13C : BG_STD_14C) * b->atm_init[b->adep[la]];
         }
         for (la = 3; la <= b->LA; la++) SFCATM1(la, i, j) = ATM(la, i, j);
+        /* the initial cpl_comp_EMBM_wrapper (genie.f90:90; atchem.f90:270-282): tstar_atm, surf_qstar_atm of initialise_embm */
+        SFCATM1(1, i, j) = A2(o->tstar_atm, i, j);
+        SFCATM1(2, i, j) = A2(o->qstar_atm, i, j);
       }
   }
   (void)ls;

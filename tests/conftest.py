@@ -22,7 +22,7 @@ def has_gpu():
 
 @pytest.fixture(scope="session")
 def built():
-    """Compile the product library and the oracle if they are missing."""
+    """Compile the product library and the oracle unless they exist and match their sources (content hash)."""
     import __graft_entry__ as g
     g.build(only_missing=True)
     return True

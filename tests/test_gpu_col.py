@@ -211,11 +211,22 @@ def test_module_by_module_matches_run(built, tmp_path):
                     e.step_embm()
                     if k == 153:      # a host read in the middle of a cycle: the calls noted so far are replayed one by one
                         e.get("tq", 0)
+                    if k == 163:      # a host write to an input of the momentum step after it was started early (the read replays
+                        e.put("rho", e.get("rho", 2), 2)   # the noted calls): u1 is rolled back, step_goldstein repeats the step
                     if k % 5 == 0:
                         e.step_seaice()
                         if k == 175:  # ... and between the sea-ice and the ocean step
                             e.get("varice", 0)
-                        e.step_goldstein()
+                        if k == 185:  # go_ts / go_cost INOUT through step_goldstein (goldstein.f90:36, 99, 176): uploaded before the
+                            import ctypes as C            # step, downloaded after; the early momentum step stays valid
+                            from cgenie_b200._lib import D, GoldsteinIO
+                            ts_io, cost_io = e.get("ts", 0).copy(), e.get("cost", 0).copy()     # the Fortran host drives member 0
+                            io = GoldsteinIO()
+                            io.go_ts, io.go_cost = ts_io.ctypes.data_as(D), cost_io.ctypes.data_as(D)
+                            e.step_goldstein(C.byref(io))
+                            assert np.array_equal(ts_io, e.get("ts", 0)) and np.array_equal(cost_io, e.get("cost", 0))
+                        else:
+                            e.step_goldstein()
                     if k % 10 == 0:
                         e.biogem_forcing(k * tick)
                         e.biogem_step(dts, k * tick)

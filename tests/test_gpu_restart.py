@@ -86,3 +86,34 @@ def test_biogem_restart_through_device(built, tmp_path):
             assert np.allclose(ts0[..., l][wet], got_ocn[..., l][wet] * mean_S / got_ocn[..., 1][wet], rtol=1e-12, atol=0)
         e.run(5 * 4)
         assert int(e.health().sum()) == 0
+
+
+def test_run_continued_from_restart_matches_uninterrupted(built, tmp_path):
+    """A fresh handle started from the restart files of a running member (inm_netcdf: T, S, u with u1 = u, rho from eos,
+    tq1 = tq, varice1 = varice) continues bit for bit like the member it was written from: GOLDSTEIN's restart holds
+    doubles, and every other prognostic quantity is rebuilt from the restored ones within the first cycle."""
+    job = tmp_path / "job"
+    materialise(str(job), "eb_go_gs_36x36x8")
+    diff1 = np.array([2000.0, 1700.0])
+    names = ("ts", "u", "u1", "rho", "tq", "varice", "tice")
+    with Ensemble(str(job), n_members=2, perturb={"diff1": diff1}) as e:
+        e.set_tracer_variant("strict")
+        e.run(5 * 40)
+        paths = write_restart(e, str(tmp_path / "rst"), member=1, date=[2003, 4, 12, 0])
+        e.run(5 * 20)
+        want = {n: e.get(n, 1).copy() for n in names}
+        K, J, I, L = e.maxk, e.maxj, e.maxi, e.maxl
+        k1 = e.iconst("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    with Ensemble(str(job), n_members=1, perturb={"diff1": diff1[1:]}) as f:
+        f.set_tracer_variant("strict")
+        read_restart(f, paths, member=0)
+        f.set_koverall(5 * 40)
+        f.run(5 * 20)
+        wet = np.arange(1, K + 1)[:, None, None] >= k1[None]
+        for n in names:
+            got, ref = f.get(n, 0), want[n]
+            if n in ("ts", "rho", "u", "u1"):
+                c = got.size // (K * J * I)
+                got, ref = got.reshape(K, J, I, c)[wet], ref.reshape(K, J, I, c)[wet]
+            assert np.array_equal(got, ref), (n, float(np.abs(got - ref).max()))
+        assert int(f.health().sum()) == 0

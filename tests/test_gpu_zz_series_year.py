@@ -2,11 +2,10 @@
 block): the .res files of the control member against the oracle's integrals over the same 48 BIOGEM steps, taken at the same
 point of the loop -- run with -m gpu on a B200.
 
-Call point: behind the block, where tests/test_gpu_z_sig.py showed device and oracle integrals equal to 1.3e-13.  At genie.f90's
-own call point (between step_biogem and biogem_tracercoupling) the one B200 run of this test's first version found device and
-oracle 1.3e-4 apart on the annual-mean surface DIC with T and S equal (profiles/pytest_gpu_r1_series_year_FAILED_test_bug.log
-holds that run, which also had a wrong oracle parameter); which of the two holds the step's tracer changes differently at that
-intermediate point is open."""
+Both call points: "reference" = genie.f90's own (diag_biogem_timeseries_wrapper between step_biogem and biogem_tracercoupling,
+genie.f90:395-405; the oracle takes it there too, cgo_biogem_sig_auto) and "behind" = after the block's ATCHEM step (the point
+tests/test_gpu_z_sig.py verifies step by step).  Round 1 left this test as a non-strict xfail after one B200 run of its first
+version (profiles/pytest_gpu_r1_series_year_FAILED_test_bug.log); tools/dbg_callpoint.py is the block-by-block diagnostic."""
 import numpy as np
 import pytest
 
@@ -24,9 +23,8 @@ def read_res(path):
     return [np.array(l.split(), dtype=float) for l in lines[1:-1]]
 
 
-@pytest.mark.xfail(strict=False, reason="not re-run on a B200 since its call point moved behind the BIOGEM block (DESIGN.md section 9, "
-                   "item 6b: the round's GPU minutes were spent); XPASS = the open item does not reach this call point")
-def test_one_year_of_series(built, tmp_path):
+@pytest.mark.parametrize("point", ["reference", "behind"])
+def test_one_year_of_series(built, tmp_path, point):
     materialise(str(tmp_path / "job"), CFG)
     o = Oracle(**OKW)
     o.biogem_setup(par_bio_k0_PO4=1.9e-6)       # the control member's uptake rate (the default is 2.0e-6)
@@ -47,17 +45,24 @@ def test_one_year_of_series(built, tmp_path):
             if k % 10 == 0:
                 e.biogem_forcing(k * tick)
                 e.biogem_step(dts, k * tick)
+                if point == "reference":
+                    s.step(dts, k * tick)
                 e.biogem_tracercoupling()
                 e.biogem_climate()
                 e.atchem_step(dts)
-                s.step(dts, k * tick)
+                if point == "behind":
+                    s.step(dts, k * tick)
         assert s.saved == [0.5] and s.sig_i == 0
         assert np.all(e.get("bg_sig", 0) == 0.0)                     # reset after the save
         assert int(e.health().sum()) == 0
         end_ocn = e.get("ocn", 0).reshape(-1, L)
-    for k in range(10, nk + 1, 10):
-        o.run(10)
-        o.L.cgo_biogem_sig_update(o.h, 1000.0)
+    if point == "reference":
+        o.L.cgo_biogem_sig_auto(o.h, 1, 1000.0)
+        o.run(nk)
+    else:
+        for k in range(10, nk + 1, 10):
+            o.run(10)
+            o.L.cgo_biogem_sig_update(o.h, 1000.0)
     assert abs(o.f("bg_sig")[0] - 1.0) < 1e-12
     # the diagnostic calls must not change the trajectory: the year's final state against the oracle's (wet cells, per-tracer scale)
     k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
