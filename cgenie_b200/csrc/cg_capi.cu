@@ -123,6 +123,8 @@ struct cg_handle {
   cudaStream_t stream2 = nullptr;                 // momentum branch of the graph-captured ocean cycle
   cudaStream_t stream4 = nullptr;                 // BIOGEM / ATCHEM block next to the head of the following cycle (low priority)
   cudaEvent_t evT = nullptr, evBG = nullptr, evBGtail = nullptr;   // evBG: ts is ready for tstepo; evBGtail: the whole block (ATCHEM) is done
+  cudaEvent_t evAtchem = nullptr;                 // the ATCHEM step has consumed the staged air temperature / humidity (tq_stage)
+  bool atchem_ev_pending = false;
   bool bg_tail_pending = false;
   bool bg_ahead = false;                          // the step kernel of the next BIOGEM block is already in stream4
   bool tc_old_ready = false;                      // ... and the "old" half of its tracer-coupling sums in stream5 (same validity as bg_ahead)
@@ -200,6 +202,7 @@ struct cg_handle {
     if (evTcOld) cudaEventDestroy(evTcOld);
     if (stream5) cudaStreamDestroy(stream5);
     if (evBGtail) cudaEventDestroy(evBGtail);
+    if (evAtchem) cudaEventDestroy(evAtchem);
     if (evT) cudaEventDestroy(evT);
     if (evBG) cudaEventDestroy(evBG);
     if (stream4) cudaStreamDestroy(stream4);
@@ -461,6 +464,7 @@ extern "C" int cg_initialise(cg_handle *h) {
   CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBGtail, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evAtchem, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));
@@ -1282,6 +1286,15 @@ static int do_momentum(cg_handle *h, cudaStream_t s, cudaStream_t s3 = nullptr) 
   return CG_OK;
 }
 static int bg_join(cg_handle *h);
+// Snapshot, on the caller's stream, of what the BIOGEM / ATCHEM block reads from the physics at the reference's call time: the
+// sea-ice cover (biogem_climate) and the air temperature / humidity (cpl_comp_EMBM).  The block itself may run on its own
+// stream while the caller's stream is already in the next cycle's surflux / EMBM / sea-ice steps.  The previous ATCHEM step
+// must have consumed the previous snapshot first (it finished a cycle ago; the wait is for ordering, not time).
+static int bg_stage_inputs(cg_handle *h, cudaStream_t s) {
+  if (h->atchem_ev_pending) { CUDA_OK(cudaStreamWaitEvent(s, h->evAtchem, 0)); h->atchem_ev_pending = false; }
+  h->launches += launch_bg_stage_seaice(h->dv, h->bgd, s);
+  return CG_OK;
+}
 static int do_goldstein(cg_handle *h) {
   h->usnap_valid = false;
   do_gold_pre(h);
@@ -1641,7 +1654,7 @@ extern "C" int cg_biogem_climate(cg_handle *h) {
     // go_solfor of the last surflux call (embm.f90:3727-3729): row MOD(istot-1,nyear)+1 of solfor
     h->bgd.nsol = h->istep_ocn > 0 ? (h->istep_ocn - 1) % h->g.nyear + 1 : 0;
     int n = 0;
-    if (!h->bg_staged) n += launch_bg_stage_seaice(h->dv, h->bgd, h->stream);   // on the caller's stream: at call time
+    if (!h->bg_staged) IO(bg_stage_inputs(h, h->stream));   // on the caller's stream: at call time
     BgAsyncScope as(h, true);
     h->bg_stage = (h->bg_stage == 2) ? 3 : 0;
     ProfScope ps(h, "biogem");
@@ -1678,8 +1691,13 @@ extern "C" int cg_biogem_init_ocn(cg_handle *h) {
 extern "C" int cg_atchem_step(cg_handle *h, double dts) {
   BGREADY(h);
   if (dts != h->bgd.dts_atchem) return fail(CG_ERR_ARG, "cg_atchem_step: dts differs from conv_kocn_katchem*kocn_loop*genie_timestep");
+  // an ATCHEM step that does not follow this iteration's biogem_climate call (conv_kocn_katchem /= conv_kocn_kbiogem, or
+  // a host that calls it out of the canonical order): the air temperature / humidity cpl_comp_EMBM copies are staged here
+  if (h->stream != h->stream4 && !h->bg_staged && h->bg_stage != 3) IO(bg_stage_inputs(h, h->stream));
   BgAsyncScope as(h, true, true);
   { ProfScope ps(h, "biogem"); ps.done(launch_bg_atchem(h->dv, h->bgd, h->atm_totV, h->stream)); }
+  CUDA_OK(cudaEventRecord(h->evAtchem, h->stream));
+  h->atchem_ev_pending = true;
   // the block came in the canonical order (step, coupling, climate, ATCHEM) on the asynchronous stream: issue the surface
   // part of the next step behind it, for the clock one BIOGEM period later
   const Params &p = h->base;
@@ -1801,7 +1819,9 @@ static int do_biogem_block_async(cg_handle *h, long long k) {
   const bool due = k % ((long long)p.conv_kocn_kbiogem * p.kocn_loop) == 0 || k % ((long long)p.conv_kocn_katchem * p.kocn_loop) == 0;
   if (!due) return CG_OK;
   const bool climate_due = k % ((long long)p.conv_kocn_kbiogem * p.kocn_loop) == 0;
-  if (climate_due) { h->launches += launch_bg_stage_seaice(h->dv, h->bgd, h->stream); h->bg_staged = true; }
+  IO(bg_stage_inputs(h, h->stream));
+  h->bg_staged = true;
+  (void)climate_due;
   CUDA_OK(cudaEventRecord(h->evT, h->stream));
   CUDA_OK(cudaStreamWaitEvent(h->stream4, h->evT, 0));
   cudaStream_t save = h->stream;
@@ -1848,7 +1868,7 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
   if (!h->bg.on || k % period != 0) return CG_OK;
   const long long tick = nint_ll(1000.0 * p.genie_timestep);
   if (k == period) IO(cg_biogem_climate_sol(h));
-  h->launches += launch_bg_stage_seaice(h->dv, h->bgd, h->stream);
+  IO(bg_stage_inputs(h, h->stream));
   CUDA_OK(cudaEventRecord(h->evT, h->stream));
   CUDA_OK(cudaStreamWaitEvent(h->stream5, h->evT, 0));
   cudaStream_t save = h->stream;
@@ -2259,6 +2279,7 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
   CUDA_OK(cudaEventCreateWithFlags(&h->evT, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBG, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evBGtail, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evAtchem, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evFork3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->evJoin3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->ev0));

@@ -1010,10 +1010,13 @@ __global__ void k_bg_climate(const Dev v, const BgDev b) {
   if (q >= n) return;
   b.seaice[q] = b.seaice_stage[q];
   v.cost[q] = 0.0;
-  // cpl_comp_EMBM (atchem.f90:270-282, genie.f90:454): rows 1-2 of sfcatm1 = air temperature and humidity.  The reference
-  // makes the copy behind the ATCHEM step of the same koverall iteration; nothing in between reads the two rows.
-  b.sfcatm1[q] = b.tq_stage[q];
-  b.sfcatm1[n + q] = b.tq_stage[n + q];
+}
+// cpl_comp_EMBM (atchem.f90:270-282; genie.f90:454, behind the ATCHEM step): rows 1-2 of sfcatm1 = air temperature and
+// humidity of this koverall iteration (staged by k_bg_stage_seaice on the caller's stream)
+__global__ void k_bg_cpl_comp_embm(const Dev v, const BgDev b) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)2 * v.I * v.J * v.MS;
+  if (q < n) b.sfcatm1[q] = b.tq_stage[q];
 }
 
 // step_atchem (atchem.f90:63-158) + cpl_comp_atmocn (:252-264).  k_bg_atchem1: thread = (member, cell, tracer), the
@@ -1155,7 +1158,9 @@ int launch_bg_atchem(const Dev &v, const BgDev &b, double atm_totV, cudaStream_t
   const int ij = v.I * v.J;
   k_bg_atchem1<<<dim3(v.MS / 32, (ij + 7) / 8, b.LA - 2), dim3(32, 8), 0, s>>>(v, b, v.bg_part);
   k_bg_atchem2<<<dim3(v.MS / 32, b.LA - 2), 32 * kSumWarps, 0, s>>>(v, b, atm_totV, v.bg_part);
-  return 2;
+  const size_t n = (size_t)2 * ij * v.MS;
+  k_bg_cpl_comp_embm<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v, b);
+  return 3;
 }
 
 int launch_tracercoupling(const Dev &v, cudaStream_t s) {
@@ -1242,8 +1247,8 @@ __global__ void __launch_bounds__(256) k_bg_sig_sums(const Dev v, const BgDev b,
     }
   } else {
     const int la = q - kSigHead - 3 * L;
-    // rows 1-2 of sfcatm1 are the air temperature and humidity cpl_comp_EMBM copied at the last BIOGEM / ATCHEM block
-    // (k_bg_climate), whichever side of the tracer coupling the diagnostic is taken on
+    // rows 1-2 of sfcatm1 are the air temperature and humidity cpl_comp_EMBM copied behind the last ATCHEM step
+    // (k_bg_cpl_comp_embm): at genie.f90's call point (before this block's ATCHEM step) those of the previous block
     for (int c2 = warp; c2 < ij; c2 += 8) s = s + g.A[c2] * b.sfcatm1[((size_t)la * ij + c2) * MS + m];
   }
   part[warp][lane] = s;

@@ -202,6 +202,11 @@ class Ensemble(_Base):
         """biogem_climate_wrapper (genie_loop_wrappers.f90:324-345); resets the convection counter."""
         self._ck(self.L.cg_biogem_climate(self.h))
 
+    def biogem_climate_sol(self):
+        """biogem_climate_sol_wrapper (genie_loop_wrappers.f90:338-342): the insolation of the last surflux call; genie.f90
+        calls it once, ahead of the very first BIOGEM step (genie.f90:369-370)."""
+        self._ck(self.L.cg_biogem_climate_sol(self.h))
+
     def biogem_forcing(self, genie_clock_ms):
         """biogem_forcing_wrapper (genie_loop_wrappers.f90:324-328)."""
         self._ck(self.L.cg_biogem_forcing(self.h, int(genie_clock_ms)))

@@ -60,8 +60,9 @@ class SeriesSaver:
     from par_data_save_sig_dt) and the window tests of diag_biogem_timeseries (biogem.f90:2757-2769, 3079-3156).  Scalar
     bookkeeping only: the sums are the device's (Ensemble.biogem_sig_update), the files cg_biogem_series_write's.
 
-    Call step(dts, genie_clock_ms) behind the BIOGEM / ATCHEM block of the iteration (after atchem_step): the call point at
-    which the device integrals are verified against the oracle (include/cgenie_b200.h)."""
+    Call step(dts, genie_clock_ms) where genie.f90 calls diag_biogem_timeseries_wrapper (genie.f90:401-405): behind
+    biogem_climate, ahead of atchem_step.  (Behind atchem_step the ocean rows are the same and the atmosphere rows one coupling
+    interval newer; device and oracle agree at either point.)"""
 
     def __init__(self, e, outdir, t_runtime, t_start=0.0, sig_dt=1.0, save_times=None, ben_Dmin=0.0, member=0, with_sur=True,
                  autoend=False, outfile_name="biogem"):
@@ -100,13 +101,6 @@ class SeriesSaver:
         self.saved = []
         write_series(self.outdir, None, outfile_name=outfile_name, with_sur=with_sur)     # sub_init_data_save_runtime
         e.biogem_sig_reset()
-
-    def step_behind_block(self, dts, genie_clock_ms, ticks_per_biogem_step):
-        """Reference-equivalent sampling from the verified call point: called behind the BIOGEM / ATCHEM block whose clock is
-        genie_clock_ms, it books the sample to the NEXT BIOGEM step, whose diag_biogem_timeseries call would read exactly this
-        state (tests/test_series_res.py::test_call_point_equivalence_in_the_oracle).  Call it once on the initial state with the
-        clock of "block 0" (genie_clock_ms = 0) to stand in for the first BIOGEM step's diagnostic."""
-        self.step(dts, int(genie_clock_ms) + int(ticks_per_biogem_step))
 
     def step(self, dts, genie_clock_ms):
         loc_t = self.t_runtime - float(genie_clock_ms) / (1000.0 * YR_S)

@@ -123,16 +123,15 @@ int cg_cpl_comp_ocnsed(cg_handle *, int ocnstep, int mbiogem, int msedgem);
 int cg_reinit_flux_rokocn(cg_handle *);
 /* The 3-D / 2-D sums of diag_biogem_timeseries (src/biogem/biogem.f90:2703-3159; SURVEY 8f row 1, time-series part): one BIOGEM
  * step's contribution to the window integrals int_t_sig, int_ocn_tot_M_sig, int_ocn_tot_M_sur_sig, int_ocn_sig(:),
- * int_ocn_sur_sig(:), int_ocn_ben_sig(:), int_ocnatm_sig(:) (:2851-2917, :3082), on the device.  Call it behind the BIOGEM /
- * ATCHEM block of a koverall iteration (after cg_atchem_step, or after cg_run), on the steps that fall in a save window (the
- * window logic of :2760-2769 and biogem_save_sig.dat stay with the caller): that is where device and oracle integrals were
- * shown equal to 1.3e-13.  genie.f90:395-405 calls the diagnostic between step_biogem and biogem_tracercoupling; at that
- * intermediate point one B200 run found the device's and the oracle's annual-mean surface DIC 1.3e-4 apart (T, S equal) --
- * unexplained so far, see DESIGN.md section 9.  Field "bg_sig" (cg_sync_to_host) = the integrals of one
- * member in that order, 3 + 3*maxl + n_l_atm values, tracers in the compact selection order; cg_biogem_sig_reset =
- * sub_init_int_timeseries (biogem_data.f90:964-1007).  ben_Dmin = par_data_save_ben_Dmin (m).  Air temperature and humidity
- * (atmosphere rows 1-2) are read from EMBM's current tq: the reference reads the copy cpl_comp_EMBM made at the last ATCHEM
- * step, which is one coupling interval older at the point genie.f90 calls the diagnostic. */
+ * int_ocn_sur_sig(:), int_ocn_ben_sig(:), int_ocnatm_sig(:) (:2851-2917, :3082), on the device.  Call it where genie.f90 calls
+ * diag_biogem_timeseries_wrapper (src/genie.f90:401-405): behind cg_biogem_climate, ahead of cg_atchem_step, on the steps that
+ * fall in a save window (the window logic of :2760-2769 and biogem_save_sig.dat stay with the caller).  There the ocean sums see
+ * this block's tracer coupling and sfcatm1 still holds what the PREVIOUS block's ATCHEM step / cpl_comp_atmocn / cpl_comp_EMBM
+ * left (air temperature and humidity included: rows 1-2 of sfcatm1 are kept on the device).  Behind cg_atchem_step (or cg_run) the
+ * ocean rows are the same and the atmosphere rows are one coupling interval newer.  Device and oracle integrals agree to 1e-13
+ * at either point (tests/test_gpu_z_sig.py, tests/test_gpu_zz_series_year.py).  Field "bg_sig" (cg_sync_to_host) = the integrals
+ * of one member in that order, 3 + 3*maxl + n_l_atm values, tracers in the compact selection order; cg_biogem_sig_reset =
+ * sub_init_int_timeseries (biogem_data.f90:964-1007).  ben_Dmin = par_data_save_ben_Dmin (m). */
 int cg_biogem_sig_update(cg_handle *, double dts, double ben_Dmin);
 int cg_biogem_sig_reset(cg_handle *);
 /* sub_init_data_save_runtime / sub_data_save_runtime (src/biogem/biogem_data_ascii.f90:23-110, 669-935), the ocn_* and atm_*

@@ -332,6 +332,17 @@ static double calc_solconst(const struct cgo_bg *b, int la, double T_in, double 
   return e / (rho * BG_V);
 }
 
+/* ------------------------------------------------------------------------------------------ check-value hooks
+ * (tests/test_oracle_checkvalues.py: the chemistry above against values printed in the papers it is taken from)
+ * cc: N_CC = 17 constants in the order of the enum above; carb: N_IC = 10 values, carb[0] = [H+] seed in, solution out. */
+void cgo_test_carbconst(double D, double T, double S, double *cc) { calc_carbconst(D, T, S, cc); }
+int cgo_test_calc_carb(double DIC, double ALK, double Ca, double PO4tot, double SiO2tot, double S, const double *cc, double *carb) {
+  return calc_carb(DIC, ALK, Ca, PO4tot, SiO2tot, f_Btot(S), f_SO4tot(S), f_Ftot(S), cc, carb);
+}
+double cgo_test_rho(double T, double S) { return calc_rho(T, S); }
+double cgo_test_iso_delta(double tot, double iso, double standard) { return iso_delta(tot, iso, standard, 0, BG_NULL); }
+double cgo_test_iso_fraction(double delta, double standard) { return iso_fraction(delta, standard); }
+
 void cgo_biogem_climate(cgo_t *o);
 /* ------------------------------------------------------------------------------------------ set-up */
 static double bg_par(const char *params, const char *key, double dflt) {
@@ -1312,9 +1323,11 @@ int cgo_biogem_koverall(cgo_t *o, long k) {
     if (k == b->kbiogem * o->kocn_loop) cgo_biogem_climate_sol(o);
     cgo_biogem_forcing(o);
     err = cgo_biogem_step(o);
-    if (b->sig_auto) cgo_biogem_sig_update(o, b->sig_ben_Dmin);   /* diag_biogem_timeseries_wrapper, genie.f90:395-405 */
     cgo_biogem_tracercoupling(o);
     cgo_biogem_climate(o);
+    /* diag_biogem_timeseries_wrapper, genie.f90:401-405: behind biogem_climate_wrapper (:387), ahead of cpl_flux_ocnatm_wrapper
+     * (:411) and of the ATCHEM step (:446-455) -- the ocean is this block's, sfcatm1 still the previous block's */
+    if (b->sig_auto) cgo_biogem_sig_update(o, b->sig_ben_Dmin);
     cgo_cpl_flux_ocnatm(o);
   }
   if (k % (b->katchem * o->kocn_loop) == 0) cgo_atchem_step(o);

@@ -2,10 +2,16 @@
 block): the .res files of the control member against the oracle's integrals over the same 48 BIOGEM steps, taken at the same
 point of the loop -- run with -m gpu on a B200.
 
-Both call points: "reference" = genie.f90's own (diag_biogem_timeseries_wrapper between step_biogem and biogem_tracercoupling,
-genie.f90:395-405; the oracle takes it there too, cgo_biogem_sig_auto) and "behind" = after the block's ATCHEM step (the point
-tests/test_gpu_z_sig.py verifies step by step).  Round 1 left this test as a non-strict xfail after one B200 run of its first
-version (profiles/pytest_gpu_r1_series_year_FAILED_test_bug.log); tools/dbg_callpoint.py is the block-by-block diagnostic."""
+Both call points: "reference" = genie.f90's own (diag_biogem_timeseries_wrapper, genie.f90:401-405: behind
+biogem_climate_wrapper, ahead of cpl_flux_ocnatm_wrapper and the ATCHEM step; the oracle takes it there too,
+cgo_biogem_sig_auto) and "behind" = after the block's ATCHEM step (the point tests/test_gpu_z_sig.py verifies step by step).
+
+History: round 1 read genie.f90 as calling the diagnostic between step_biogem and biogem_tracercoupling, found device and
+oracle 1.3e-4 apart on the annual-mean surface DIC there and left this test as a non-strict xfail.  Both the reading and the
+test were wrong: the diagnostic follows biogem_climate (see the line numbers above), and the test's module-by-module loop
+never made the biogem_climate_sol call genie.f90 makes ahead of the very first BIOGEM step (genie.f90:369-370), so the
+device's first step saw no insolation and produced no export (tools/dbg_callpoint.py, profiles/dbg_callpoint_r2a.log: the
+device's ocn at the intermediate point IS bit for bit what the previous block left; DOM differed by 100 % after block 1)."""
 import numpy as np
 import pytest
 
@@ -43,12 +49,14 @@ def test_one_year_of_series(built, tmp_path, point):
                 e.step_seaice()
                 e.step_goldstein()
             if k % 10 == 0:
+                if k == 10:
+                    e.biogem_climate_sol()          # genie.f90:369-370
                 e.biogem_forcing(k * tick)
                 e.biogem_step(dts, k * tick)
-                if point == "reference":
-                    s.step(dts, k * tick)
                 e.biogem_tracercoupling()
                 e.biogem_climate()
+                if point == "reference":
+                    s.step(dts, k * tick)
                 e.atchem_step(dts)
                 if point == "behind":
                     s.step(dts, k * tick)

@@ -153,21 +153,27 @@ def test_series_windows(built, tmp_path):
     assert s.sig_i == 1 and 0.0 < s.int_t_sig < 0.5 and e.updates == 48 + round(0.35 * 48)
 
 
-def test_call_point_equivalence_in_the_oracle():
-    """genie.f90:395-405 takes the diagnostic between step_biogem and biogem_tracercoupling, where ocn, the cell masses, the
-    sea-ice snapshot and sfcatm1 are still those the previous BIOGEM / ATCHEM block left (the step's tracer changes wait in
-    vdocn, biogem.f90:1811-1844).  So the sample the reference takes in block k + kbiogem is exactly the sample taken behind
-    block k: a host that samples behind the block and books the sample to the next BIOGEM step reproduces the reference's
-    series."""
+def test_call_point_in_the_oracle():
+    """genie.f90:401-405 takes the diagnostic behind biogem_climate_wrapper (:387) and ahead of cpl_flux_ocnatm_wrapper / the
+    ATCHEM step (:411, :446-455): the ocean rows of that sample are those of a sample taken behind the whole block, the
+    atmosphere rows (sfcatm1: cpl_comp_atmocn / cpl_comp_EMBM run behind ATCHEM) those of a sample behind the PREVIOUS block."""
     o = Oracle("worjh2", maxk=K, maxl=L, nyear=96)
     o.biogem_setup()
     o.run(100)
     o.L.cgo_biogem_sig_update(o.h, 1000.0)           # behind block 100
-    behind = o.f("bg_sig").copy()
+    prev = o.f("bg_sig").copy()
     o.f("bg_sig")[:] = 0.0
     o.L.cgo_biogem_sig_auto(o.h, 1, 1000.0)          # inside block 110, at the reference's call point
     o.run(10)
-    assert np.array_equal(o.f("bg_sig"), behind) and behind[0] > 0.0
+    at = o.f("bg_sig").copy()
+    o.L.cgo_biogem_sig_auto(o.h, 0, 1000.0)
+    o.f("bg_sig")[:] = 0.0
+    o.L.cgo_biogem_sig_update(o.h, 1000.0)           # behind block 110
+    behind = o.f("bg_sig").copy()
+    n_ocn = 3 + 3 * L
+    assert np.array_equal(at[:n_ocn], behind[:n_ocn]) and not np.array_equal(at[:n_ocn], prev[:n_ocn])
+    assert np.array_equal(at[n_ocn:], prev[n_ocn:]) and not np.array_equal(at[n_ocn:], behind[n_ocn:])
+    assert at[0] > 0.0
 
 
 def test_res_files_without_surface_columns(built, tmp_path):

@@ -1,9 +1,11 @@
-"""Diagnostic for DESIGN.md section 9 item 6b (round 1): the BIOGEM time-series integrals sampled at genie.f90's own call
-point (between step_biogem and biogem_tracercoupling, genie.f90:395-405), device against oracle, block by block.
+"""Diagnostic behind round 1's open item: the BIOGEM time-series integrals sampled inside the
+BIOGEM block, device against oracle, block by block.  Usage: dbg_callpoint.py [blocks] [variant] [nosol]
 
-For every BIOGEM block it prints (a) whether the device's ocn / bg_M / seaice at the reference call point are bit for bit
-what the previous block left, (b) the relative difference of every row of bg_sig against the oracle's sample taken at the
-same call point (cgo_biogem_sig_auto), (c) the largest per-cell difference of ocn at that point.  Run on a B200."""
+It established (profiles/dbg_callpoint_r2a.log, with "nosol" = without the biogem_climate_sol call genie.f90 makes ahead of
+the first BIOGEM step, as round 1's test loop was written) that the device's ocn / cell masses between step_biogem and
+biogem_tracercoupling are bit for bit what the previous block left -- the device holds the step's changes in vdocn exactly as
+the Fortran does -- and that device and oracle differed after the very first block (DOM by 100 %): a test-loop bug, not a
+device / oracle difference.  The call point is genie.f90's (:401-405: behind biogem_climate, ahead of ATCHEM)."""
 import os
 import sys
 import tempfile
@@ -20,6 +22,7 @@ K = L = 16
 LA = 8
 NBLK = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 VARIANT = sys.argv[2] if len(sys.argv) > 2 else "col"
+NOSOL = len(sys.argv) > 3 and sys.argv[3] == "nosol"
 d = tempfile.mkdtemp()
 materialise(d, "eb_go_gs_ac_bg_36x36x16")
 o = Oracle(world="worjh2", maxk=16, maxl=16, nyear=96)
@@ -41,15 +44,17 @@ with Ensemble(d, n_members=2, perturb={"par_bio_k0_PO4": np.array([1.9e-6, 2.3e-
                 e.step_seaice()
                 e.step_goldstein()
             if k % 10 == 0:
+                if k == 10 and not NOSOL:
+                    e.biogem_climate_sol()                                # genie.f90:369-370
                 e.biogem_forcing(k * tick)
                 e.biogem_step(dts, k * tick)
-                probe = blk % 2 == 0      # every second block: read the state at the call point (a host read joins the streams)
+                probe = blk % 2 == 0      # every second block: read the state between step and coupling (a host read joins the streams)
                 if probe:
                     now = {n: e.get(n, 0) for n in ("ocn", "bg_M")}
                     same = {n: bool(np.array_equal(now[n], prev[n])) for n in now}
-                e.biogem_sig_update(dts, 1000.0)
                 e.biogem_tracercoupling()
                 e.biogem_climate()
+                e.biogem_sig_update(dts, 1000.0)                          # genie.f90:401-405
                 e.atchem_step(dts)
         o.f("bg_sig")[:] = 0.0
         o.run(10)
@@ -59,7 +64,7 @@ with Ensemble(d, n_members=2, perturb={"par_bio_k0_PO4": np.array([1.9e-6, 2.3e-
         msg = "blk %d: bg_sig worst rel %.2e (row %d); DIC glob %.2e sur %.2e ben %.2e" % (
             blk, rel.max(), int(rel.argmax()), rel[3 + 2], rel[3 + L + 2], rel[3 + 2 * L + 2])
         if probe:
-            msg += "; state at the call point == state behind the previous block: %s" % same
+            msg += "; state between step_biogem and tracercoupling == state behind the previous block: %s" % same
         print(msg)
         prev = {n: e.get(n, 0) for n in ("ocn", "bg_M")}
         oc = o.f("ocn").reshape(-1, L)
