@@ -21,6 +21,9 @@ PERT = {"par_bio_k0_PO4": 2.3e-6, "par_bio_remin_POC_eL1": 430.0, "par_bio_red_P
         "scf": 1.9}
 
 
+FLOOR = 1e-3
+
+
 def rel(a, b, floor):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
 
@@ -61,13 +64,14 @@ def compare(e, oracles, tol, what):
         ocn_d = e.get("ocn", m)
         ts_o = o.f("ts").reshape(K + 2, J + 2, I + 2, L)[1:K + 1, 1:J + 1, 1:I + 1, :].ravel()
         ts_d = e.get("ts", m)
-        # per-tracer floors: a tracer's own typical magnitude (relative error of the field, not of near-zero cells)
+        # per CELL: relative to the cell's own value, floored at 1e-3 of the tracer's largest value (temperature in degC and the
+        # salinity anomaly pass through zero; particles and DOM fall by orders of magnitude with depth)
         scale = np.abs(ocn_o.reshape(-1, L)[wet3.ravel()]).max(axis=0)
-        floor = np.tile(np.maximum(scale, 1e-300), wet3.size)
+        floor = np.tile(np.maximum(FLOOR * scale, 1e-300), wet3.size)
         worst["ocn"] = max(worst.get("ocn", 0), rel(ocn_d[wl], ocn_o[wl], floor[wl]))
         worst["ts"] = max(worst.get("ts", 0), rel(ts_d[wl], ts_o[wl], floor[wl]))
         po, pd = o.f("bio_part"), e.get("bio_part", m)
-        pscale = np.tile(np.maximum(np.abs(po.reshape(-1, LS)).max(axis=0), 1e-300), wet3.size)
+        pscale = np.tile(np.maximum(FLOOR * np.abs(po.reshape(-1, LS)).max(axis=0), 1e-300), wet3.size)
         worst["bio_part"] = max(worst.get("bio_part", 0), rel(pd[ws], po[ws], pscale[ws]))
         wet2 = (k1 <= K).ravel()
         Ho = o.f("carb").reshape(J * I, -1)[:, 0]

@@ -280,7 +280,7 @@ def test_col_century_drift(built, tmp_path):
     years = 100
     tab = perturbation_table(4, biogem=True)
     members = (0, 3)
-    ref = {}
+    ref, keep = {}, {}
 
     def oracle_run(m):
         kw = {k: float(v[m]) for k, v in tab.items()}
@@ -288,7 +288,7 @@ def test_col_century_drift(built, tmp_path):
         o.biogem_setup(**{k: v for k, v in kw.items() if k.startswith("par_bio")})
         o.run(480 * years)
         ref[m] = (o.f("ocn").reshape(-1, L).copy(), o.f("bg_M").copy(), o.f("atm").reshape(-1, LA).copy())
-        o.close()
+        keep[m] = o
     th = [threading.Thread(target=oracle_run, args=(m,)) for m in members]
     for t in th:
         t.start()
@@ -309,3 +309,19 @@ def test_col_century_drift(built, tmp_path):
             print("member %d global mean %s: oracle %.12e device %.12e rel %.2e" % (m, name, mo, md, abs(md - mo) / abs(mo)))
             assert abs(md - mo) <= 1e-6 * abs(mo), (m, name, mo, md)
         assert abs(atm_d[0, 2] - atm_o[0, 2]) <= 1e-6 * atm_o[0, 2]
+    # the per-step bar AT the state the bench times (100 model years old): both members restarted from their oracle's century
+    # state inside a 128-lane ensemble, then 2 BIOGEM steps = 4 ocean steps of the production kernels against the oracle
+    tab128 = perturbation_table(128, biogem=True)
+    with Ensemble(str(tmp_path), n_members=128, perturb=tab128) as e:
+        e.set_tracer_variant("col")
+        for m in members:
+            inject_all(e, keep[m], m)
+        e.set_koverall(480 * years)
+        for step in (1, 2):
+            e.run(10)
+            for m in members:
+                keep[m].run(10)
+                compare(_Member(e, m), [keep[m]], 1e-10, "col, century state, member %d, BIOGEM step %d" % (m, step))
+        assert int(e.health()[list(members)].sum()) == 0
+    for o in keep.values():
+        o.close()
