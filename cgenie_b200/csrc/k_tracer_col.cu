@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(MS, MINB) k_tstep_col(const Dev v) {
   st.sm = reinterpret_cast<double *>(smem_raw);
   st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows<L>::rows * MS * 8);
   st.tid = threadIdx.x;
-  const int c2 = v.rowcols[blockIdx.x];
+  const int c2 = v.col_deep_first ? v.wetcols[blockIdx.x] : v.rowcols[blockIdx.x];
   tstep_column<I, J, K, L, MS, MS, PV, AR>(v, c_g, c2, threadIdx.x, st);
 }
 
@@ -85,6 +85,11 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   // split form (CG_COL_SPLIT=1): two threads per member-column, <= 128 registers, 16 warps per SM
   static int split = -1;
   if (split < 0) { const char *e = getenv("CG_COL_SPLIT"); split = e ? atoi(e) : 0; }
+  static int order = -1, coskip = -1;
+  if (order < 0) { const char *e = getenv("CG_COL_ORDER"); order = e ? atoi(e) : 0; }
+  if (coskip < 0) { const char *e = getenv("CG_CO_SKIP"); coskip = e ? atoi(e) : 1; }
+  Dev v1 = v;
+  v1.col_deep_first = order;
   if (split && MS == 128) {
     constexpr size_t smem2 = (size_t)SplitRows<L>::rows * MS * 8 + 64;
     static bool attr2 = false;
@@ -96,13 +101,14 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
     if (split == 2) k_tstep_split<I, J, K, L, MS, 1><<<v.nwet, 2 * MS, smem2, s>>>(v);
     else k_tstep_split<I, J, K, L, MS, 2><<<v.nwet, 2 * MS, smem2, s>>>(v);
   } else
-  if (cfg == 1) k_tstep_col<I, J, K, L, MS, 1, false><<<v.nwet, MS, smem, s>>>(v);
-  else if (cfg == 2) k_tstep_col<I, J, K, L, MS, 2, false, true><<<v.nwet, MS, smem, s>>>(v);   // mbarrier buffer release
-  else k_tstep_col<I, J, K, L, MS, 2, false><<<v.nwet, MS, smem, s>>>(v);
+  if (cfg == 1) k_tstep_col<I, J, K, L, MS, 1, false><<<v.nwet, MS, smem, s>>>(v1);
+  else if (cfg == 2) k_tstep_col<I, J, K, L, MS, 2, false, true><<<v.nwet, MS, smem, s>>>(v1);   // mbarrier buffer release
+  else k_tstep_col<I, J, K, L, MS, 2, false><<<v.nwet, MS, smem, s>>>(v1);
   static int copf = -1;
   if (copf < 0) { const char *e = getenv("CG_CO_PF"); copf = e ? atoi(e) : 0; }   // measured: the L2 prefetch costs more than it hides (profiles/README_r1.md)
   Dev v2 = v;
   v2.co_prefetch = copf;
+  v2.co_skip_stable = (coskip && !(split && MS == 128)) ? 1 : 0;   // the split form does not write the stability flag
   k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
   return 2;
 }

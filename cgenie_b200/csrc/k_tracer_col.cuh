@@ -379,6 +379,10 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 #pragma unroll
   for (int l = 0; l < L; l++) { P[l] = 0.0; Q[l] = 0.0; }
   unsigned par = 0;
+  // !PV: is any level of the new column statically unstable against the one below (rho(k) >= rho(k-1), the test of
+  // goldstein.f90:2700)?  If none is, the convective adjustment is the identity on this (member, column): k_co_col skips it.
+  bool unstable = false;
+  double rbelow = 0.0;
   // PV: region map of this (member, column); thickness and depth (levels) of the region the march is inside
   const unsigned cmask = PV ? v.comask[(long)c2 * MS + m] : 0u;
   double dzt = 0.0;
@@ -493,6 +497,8 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     if (!PV && stv) {
       const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);   // :2638
       rP[0] = r;
+      if (kk - 1 > k1c) unstable = unstable || !(r < rbelow);
+      rbelow = r;
     }
     // ---- shift one level up
     a = b;
@@ -512,6 +518,13 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     }
     const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
     rP[0] = r;
+    if (K > k1c) unstable = unstable || !(r < rbelow);
+    if (v.comask) v.comask[(long)c2 * MS + m] = unstable ? 1u : 0u;
+    // SST / SSS as step_goldstein exports them (:428-431); k_co_col rewrites them where it mixes
+    if (v.sst) {
+      v.sst[(long)c2 * MS + m] = tnew;
+      v.sst[((long)(I * J) + c2) * MS + m] = snew;
+    }
   } else {
     // passive tracers have no surface flux; level K is either outside any region or the top of one
     double scale = 1.0;
@@ -1014,6 +1027,8 @@ CG_HD void co_passive_pair(const Dev &v, const GridC &g, const int c2, const uns
 // both parts by one thread (host test harness; single-kernel fallback)
 template <int I, int J, int K, int L, int MS>
 CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m) {
+  // the flux kernel found every level of this (member, column) stable: nothing to adjust, SST / SSS are exported already
+  if (v.co_skip_stable && v.comask && v.comask[(long)c2 * MS + m] == 0u) return;
   unsigned in, topb, botb;
   double rdzt[K];
   co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt);

@@ -30,7 +30,7 @@ def one_step_both(e):
     return out["strict"][0], out["col"][0], out["strict"][1], out["col"][1], snap["cost"]
 
 
-def check_step(e, tol=1e-10, floor_frac=1e-3, what=""):
+def check_step(e, tol=1e-10, floor_frac=1e-3, what="", strict_assert=True):
     """Asserts the per-cell bar outside flipped columns and conservation inside them; returns a dict of statistics.
 
     per-cell error of tracer l = |col - strict| / max(|strict|, floor_frac * max|tracer l|): relative to the CELL's own value,
@@ -41,18 +41,32 @@ def check_step(e, tol=1e-10, floor_frac=1e-3, what=""):
     wet3 = np.arange(1, K + 1)[:, None, None] >= k1[None]                       # [K][J][I]
     a = ts_s.reshape(K, J, I, L, MS)[..., :M]
     b = ts_c.reshape(K, J, I, L, MS)[..., :M]
-    flipped = (cost_s.reshape(J, I, MS)[..., :M] != cost_c.reshape(J, I, MS)[..., :M])          # [J][I][M]
+    # A column's convection decisions differ ("flipped") if the two results have different mixed regions.  The adjustment
+    # leaves bit-identical T and S on all levels of a region (goldstein.f90:2732-2764 copies the merged box's values), so the
+    # region map of a result is: level k continues the region of k-1 iff both T and S are bit-equal.  Equal maps = the same
+    # final regions (the convection counter cost is compared too); inside equal regions the values agree to rounding.
+    def region_map(x):
+        same = (x[1:, :, :, 0, :] == x[:-1, :, :, 0, :]) & (x[1:, :, :, 1, :] == x[:-1, :, :, 1, :])      # [K-1][J][I][M]
+        return same & wet3[1:, :, :, None] & wet3[:-1, :, :, None]
+    flipped = (region_map(a) != region_map(b)).any(axis=0)                                       # [J][I][M]
+    flipped |= (cost_s.reshape(J, I, MS)[..., :M] != cost_c.reshape(J, I, MS)[..., :M])
     events = (cost_s.reshape(J, I, MS)[..., :M] - cost0.reshape(J, I, MS)[..., :M])
     wetcol = (k1 <= K)
     scale = np.abs(np.where(wet3[..., None, None], a, 0.0)).reshape(-1, L, M).max(axis=0)       # [L][M]
     denom = np.maximum(np.abs(a), floor_frac * np.maximum(scale, 1e-300)[None, None, None])
     err = np.abs(b - a) / denom
     ok_cells = wet3[..., None, None] & ~flipped[None, :, :, None, :]
-    worst = float(np.where(ok_cells, err, 0.0).max())
+    errok = np.where(ok_cells, err, 0.0)
+    worst = float(errok.max())
+    wk, wj, wi, wl, wm = np.unravel_index(int(errok.argmax()), errok.shape)
     n_cols = int(wetcol.sum()) * M
     n_flip = int((flipped & wetcol[..., None]).sum())
     stats = {"worst_unflipped": worst, "flip_rate": n_flip / max(n_cols, 1), "flipped_columns": n_flip, "columns": n_cols,
-             "convecting_columns": int(((events > 0) & wetcol[..., None]).sum())}
+             "convecting_columns": int(((events > 0) & wetcol[..., None]).sum()),
+             "worst_at": {"k": int(wk) + 1, "j": int(wj) + 1, "i": int(wi) + 1, "tracer": int(wl), "member": int(wm),
+                          "strict": float(a[wk, wj, wi, wl, wm]), "col": float(b[wk, wj, wi, wl, wm]),
+                          "tracer_scale": float(scale[wl, wm])},
+             "worst_by_tracer": [float(x) for x in errok.max(axis=(0, 1, 2, 4))]}
     # a flipped decision moves tracer between the levels of its column, thickness weighted: column inventories are unchanged
     if n_flip:
         dz = np.asarray(e.const("dz"), dtype=np.float64)[1:K + 1]
@@ -66,7 +80,10 @@ def check_step(e, tol=1e-10, floor_frac=1e-3, what=""):
           "flipped %d (rate %.2e)%s" % (what, M, worst, stats["convecting_columns"], n_cols, n_flip, stats["flip_rate"],
                                         "; in flipped columns: worst cell %.1e, worst column inventory %.1e" %
                                         (stats["worst_flipped_cell"], stats["worst_flipped_inventory"]) if n_flip else ""))
-    assert worst <= tol, (what, stats)
-    if n_flip:
-        assert stats["worst_flipped_inventory"] <= 1e-12, (what, stats)
+    if worst > tol:
+        print("   worst cell:", stats["worst_at"], "per tracer:", ["%.1e" % x for x in stats["worst_by_tracer"]])
+    if strict_assert:
+        assert worst <= tol, (what, stats)
+        if n_flip:
+            assert stats["worst_flipped_inventory"] <= 1e-12, (what, stats)
     return stats

@@ -30,9 +30,12 @@ def test_col_per_cell_all_lanes_along_the_spin_up(built, tmp_path):
             e.set_tracer_variant("col")
             e.run(5 * (at - done))
             done = at
-            st = check_step(e, tol=1e-10, what="ocean step %d:" % at)
+            st = check_step(e, tol=1e-10, what="ocean step %d:" % at, strict_assert=False)
             report.append((at, st))
         assert int(e.health().sum()) == 0
+    for at, st in report:      # every checkpoint is held to the bar; the loop above only collects, so that a failure shows all of them
+        assert st["worst_unflipped"] <= 1e-10, (at, st)
+        assert st.get("worst_flipped_inventory", 0.0) <= 1e-12, (at, st)
     rates = [st["flip_rate"] for _, st in report]
     print("flip rate per ocean step along the spin-up:", ["%d: %.1e" % (at, r) for (at, _), r in zip(report, rates)])
     # the flips are a property of the first, neutrally stable months; a stratified ocean has (next to) none

@@ -35,8 +35,8 @@ def test_one_year_of_series(built, tmp_path, point):
     o = Oracle(**OKW)
     o.biogem_setup(par_bio_k0_PO4=1.9e-6)       # the control member's uptake rate (the default is 2.0e-6)
     with Ensemble(str(tmp_path / "job"), n_members=2, perturb={"par_bio_k0_PO4": np.array([1.9e-6, 2.3e-6])}) as e:
-        e.set_tracer_variant("col")
-        nk = 5 * e.nyear
+        e.set_tracer_variant("strict")      # this test is about the series, and a year from the uniform initial state is the regime
+        nk = 5 * e.nyear                    # where 'col' trajectories part at flipped convection decisions (tests/test_gpu_col_proof.py)
         genie_timestep = 3600.0 * 24.0 * 365.25 / 5.0 / e.nyear
         tick = int(round(1000.0 * genie_timestep))
         dts = float(2 * 5) * genie_timestep
