@@ -1,17 +1,23 @@
-! biogem_b200.f90 -- drop-in replacement for the loop entry points of MODULE biogem and MODULE atchem
-! (reference: src/biogem/biogem.f90:528-547, 1885-1890, 2083-2087, 2132-2150, 2243-2247;
-!  src/atchem/atchem.f90:63-67, 252-264, 306-320).  Same module and procedure names and argument lists, so
-! src/wrappers/genie_loop_wrappers.f90:178-183, 310-345, 452-462 compile unchanged.  The biogeochemistry runs
-! on the GPU; the padded interface arrays (dum_sfcatm1, dum_sfxatm1, dum_sfcocn1, dum_sfxsed1 ...) are only
-! filled from the device fields "sfcatm1", "sfcocn1", "sfxsed1" on BIOGEM save intervals
-! (par_data_save_sig / timeslice), through cg_sync_to_host.
-! Syntax-reviewed only: no Fortran compiler exists in the build image (DESIGN.md 1).
-MODULE biogem
+! biogem_b200.f90 -- MODULE biogem_b200 / atchem_b200 / sedgem_b200 / rokgem_b200: the loop entry points of BIOGEM, ATCHEM and
+! the SEDGEM / ROKGEM coupler calls with the reference's procedure names and argument lists (src/biogem/biogem.f90:528-547,
+! 1885-1890, 2083-2087, 2132-2150, 2243-2247; src/atchem/atchem.f90:63-67, 252-282, 306-320; src/sedgem/sedgem.f90:894-937,
+! 1029-1068; src/rokgem/rokgem.f90:472-480), forwarding to the C-ABI.  The reference's own modules stay in the build
+! unchanged (MODULE biogem exports 15 names -- initialise_biogem, diag_biogem_timeslice, biogem_save_restart, end_biogem ...,
+! biogem.f90:6-21 -- that the ini / end / diagnostic wrappers keep calling); fortran/use_b200.py switches the USE lines of the
+! wrappers listed there (genie_loop_wrappers.f90:178-183, 197-203, 219-226, 289-293, 310-342, 439-468).
+! The biogeochemistry runs on the GPU.  The padded interface arrays the coupler owns are filled from the device's compact
+! fields after every BIOGEM step (dum_sfcocn1 <- "sfcocn1", dum_sfxsed1 <- "sfxsed1": one member, 36 x 36 x (16 + 9) doubles)
+! so that unchanged Fortran consumers (diag_biogem_timeslice / _timeseries, SEDGEM) read what the reference would give them;
+! b200_fill_interface = .FALSE. restricts this to the caller's save steps (the copies join the device streams).
+! Not compiled here: no Fortran compiler exists in the build image (DESIGN.md 1).
+MODULE biogem_b200
   USE, INTRINSIC :: ISO_C_BINDING
   USE cgenie_b200_c
+  USE gem_cmn, ONLY: n_l_ocn, n_l_sed, conv_iselected_io, conv_iselected_is
   IMPLICIT NONE
   PRIVATE
   PUBLIC :: step_biogem, biogem_tracercoupling, biogem_forcing, biogem_climate, biogem_climate_sol
+  LOGICAL, PUBLIC, SAVE :: b200_fill_interface = .TRUE.
 
 CONTAINS
 
@@ -32,11 +38,28 @@ CONTAINS
     REAL, INTENT(IN),    DIMENSION(:,:,:) :: dum_sfcsed1
     REAL, INTENT(INOUT), DIMENSION(:,:,:) :: dum_sfxsed1
     REAL, INTENT(INOUT), DIMENSION(:,:,:) :: dum_sfxsumrok1
+    REAL(C_DOUBLE), ALLOCATABLE, TARGET :: buf(:,:,:)
+    INTEGER :: l
     CALL cg_ensure_handle()
-    ! the air-sea flux is accumulated on the device (cpl_flux_ocnatm is fused into the kernel), so the
-    ! host copy handed to the unchanged cpl_flux_ocnatm_wrapper stays zero
-    dum_sfxatm1 = 0.0
     CALL cg_check(cg_biogem_step(cg_h, REAL(dum_dts, C_DOUBLE), INT(dum_genie_clock, C_INT64_T)), 'cg_biogem_step')
+    ! the air-sea flux is accumulated into sfxsumatm on the device (cpl_flux_ocnatm, atchem.f90:306-320, is fused into the
+    ! kernel): the host copy handed on to cpl_flux_ocnatm_wrapper carries no flux
+    dum_sfxatm1 = 0.0
+    IF (b200_fill_interface) THEN
+       ! bottom-water composition and sediment rain of this step (biogem.f90:1724-1761), compact device order -> padded arrays
+       ALLOCATE(buf(n_l_ocn, SIZE(dum_sfcocn1, 2), SIZE(dum_sfcocn1, 3)))     ! field "sfcocn1": Fortran shape (n_l_ocn, maxi, maxj)
+       CALL cg_check(cg_sync_to_host(cg_h, 'sfcocn1' // C_NULL_CHAR, 0_C_INT, C_LOC(buf), INT(SIZE(buf), C_INT64_T)), 'cg_sync_to_host(sfcocn1)')
+       DO l = 1, n_l_ocn
+          dum_sfcocn1(conv_iselected_io(l),:,:) = buf(l,:,:)
+       END DO
+       DEALLOCATE(buf)
+       ALLOCATE(buf(n_l_sed, SIZE(dum_sfxsed1, 2), SIZE(dum_sfxsed1, 3)))
+       CALL cg_check(cg_sync_to_host(cg_h, 'sfxsed1' // C_NULL_CHAR, 0_C_INT, C_LOC(buf), INT(SIZE(buf), C_INT64_T)), 'cg_sync_to_host(sfxsed1)')
+       DO l = 1, n_l_sed
+          dum_sfxsed1(conv_iselected_is(l),:,:) = buf(l,:,:)
+       END DO
+       DEALLOCATE(buf)
+    END IF
   END SUBROUTINE step_biogem
 
   SUBROUTINE biogem_tracercoupling(dum_ts, dum_ts1)
@@ -70,14 +93,13 @@ CONTAINS
     CALL cg_check(cg_biogem_climate_sol(cg_h), 'cg_biogem_climate_sol')
   END SUBROUTINE biogem_climate_sol
 
-END MODULE biogem
-
-MODULE atchem
+END MODULE biogem_b200
+MODULE atchem_b200
   USE, INTRINSIC :: ISO_C_BINDING
   USE cgenie_b200_c
   IMPLICIT NONE
   PRIVATE
-  PUBLIC :: step_atchem, cpl_flux_ocnatm, cpl_comp_atmocn
+  PUBLIC :: step_atchem, cpl_flux_ocnatm, cpl_comp_atmocn, cpl_comp_EMBM
 
 CONTAINS
 
@@ -104,13 +126,21 @@ CONTAINS
     ! fused into cg_atchem_step: the ocean-grid copy "sfcatm1" is device resident
   END SUBROUTINE cpl_comp_atmocn
 
-END MODULE atchem
+  SUBROUTINE cpl_comp_EMBM(dum_t, dum_q, dum_sfcatm1)
+    REAL, DIMENSION(:,:), INTENT(IN) :: dum_t, dum_q
+    REAL, DIMENSION(:,:,:), INTENT(INOUT) :: dum_sfcatm1
+    ! rows 1-2 of the device's "sfcatm1" are filled behind the ATCHEM step (k_bg_cpl_comp_embm); the host copy follows the
+    ! reference (atchem.f90:270-282) so that host-side readers see the same values
+    dum_sfcatm1(1,:,:) = dum_t
+    dum_sfcatm1(2,:,:) = dum_q
+  END SUBROUTINE cpl_comp_EMBM
 
+END MODULE atchem_b200
 ! SEDGEM / ROKGEM coupler routines genie.f90 calls after every BIOGEM step whether or not the modules run
 ! (genie.f90:413-427 through genie_loop_wrappers.f90:197-226, 289-293).  The interface arrays are device resident
 ! (fields "sfxsumsed", "sfcsumocn", "sfxsumrok1"); the host arrays are left alone.  Jobs that really run SEDGEM or ROKGEM
 ! keep the reference's modules and exchange the arrays through cg_sync_to_host / cg_sync_from_host.
-MODULE sedgem
+MODULE sedgem_b200
   USE, INTRINSIC :: ISO_C_BINDING
   USE cgenie_b200_c
   IMPLICIT NONE
@@ -137,9 +167,8 @@ CONTAINS
     CALL cg_check(cg_cpl_comp_ocnsed(cg_h, INT(dum_ocnstep, C_INT), INT(dum_mbiogem, C_INT), INT(dum_msedgem, C_INT)), 'cg_cpl_comp_ocnsed')
   END SUBROUTINE cpl_comp_ocnsed
 
-END MODULE sedgem
-
-MODULE rokgem
+END MODULE sedgem_b200
+MODULE rokgem_b200
   USE, INTRINSIC :: ISO_C_BINDING
   USE cgenie_b200_c
   IMPLICIT NONE
@@ -154,4 +183,4 @@ CONTAINS
     CALL cg_check(cg_reinit_flux_rokocn(cg_h), 'cg_reinit_flux_rokocn')
   END SUBROUTINE reinit_flux_rokocn
 
-END MODULE rokgem
+END MODULE rokgem_b200

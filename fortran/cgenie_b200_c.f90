@@ -1,8 +1,9 @@
 ! cgenie_b200_c.f90 -- ISO_C_BINDING interface to libcgenie_b200.so (include/cgenie_b200.h).
 ! In-tree precedent for BIND(C) interop in the reference: src/utils/itt_fortran.f90:7-41.
 ! Not compilable in the build container (no Fortran compiler there); built by users with gfortran:
-!   gfortran -fdefault-real-8 -c cgenie_b200_c.f90 goldstein_b200.f90 embm_b200.f90 gold_seaice_b200.f90
-!   ... link genie.exe with -L<repo>/cgenie_b200 -lcgenie_b200
+!   python fortran/use_b200.py <cgenie>/src/wrappers/genie_loop_wrappers.f90        (switches the wrappers' USE lines)
+!   gfortran -fdefault-real-8 -c cgenie_b200_c.f90 goldstein_b200.f90 embm_b200.f90 gold_seaice_b200.f90 biogem_b200.f90
+!   ... link genie.exe with these objects next to the unchanged module objects and -L<repo>/cgenie_b200 -lcgenie_b200
 MODULE cgenie_b200_c
   USE, INTRINSIC :: ISO_C_BINDING
   IMPLICIT NONE
@@ -41,16 +42,10 @@ MODULE cgenie_b200_c
        TYPE(C_PTR), VALUE :: h
      END FUNCTION cg_destroy
      INTEGER(C_INT) FUNCTION cg_surflux_step(h, istep, io) BIND(C, NAME='cg_surflux_step')
-       IMPORT :: C_INT, C_PTR, cg_surflux_io
-       TYPE(C_PTR), VALUE :: h
-       INTEGER(C_INT), VALUE :: istep
-       TYPE(cg_surflux_io), INTENT(IN) :: io
-     END FUNCTION cg_surflux_step
-     INTEGER(C_INT) FUNCTION cg_surflux_step_resident(h, istep, io) BIND(C, NAME='cg_surflux_step')
        IMPORT :: C_INT, C_PTR
-       TYPE(C_PTR), VALUE :: h, io            ! io = C_NULL_PTR: everything stays on the GPU
+       TYPE(C_PTR), VALUE :: h, io            ! io = C_LOC(a cg_surflux_io) or C_NULL_PTR: everything stays on the GPU
        INTEGER(C_INT), VALUE :: istep
-     END FUNCTION cg_surflux_step_resident
+     END FUNCTION cg_surflux_step
      INTEGER(C_INT) FUNCTION cg_embm_step(h, istep, io) BIND(C, NAME='cg_embm_step')
        IMPORT :: C_INT, C_PTR
        TYPE(C_PTR), VALUE :: h, io

@@ -1,7 +1,8 @@
-! embm_b200.f90 -- drop-in for MODULE embm's step_embm and surflux (reference: src/embm/embm.f90:13-38,
-! 2548-2588; wrappers src/wrappers/genie_loop_wrappers.f90:7-86).  Argument lists are the reference's;
-! only the arrays the coupler reads on the host are filled, and only on output steps.
-MODULE embm
+! embm_b200.f90 -- MODULE embm_b200: step_embm and surflux with the reference's names and argument lists
+! (src/embm/embm.f90:22-38, 2548-2588).  MODULE embm itself stays in the build (initialise_embm, end_embm, radfor ...,
+! embm.f90:13-19); fortran/use_b200.py switches the USE lines of surflux_wrapper and embm_wrapper
+! (genie_loop_wrappers.f90:7-8, 61-62).  Only the arrays the coupler reads on the host are filled, and only on output steps.
+MODULE embm_b200
   USE, INTRINSIC :: ISO_C_BINDING
   USE cgenie_b200_c
   USE embm_lib, ONLY: maxi, maxj, npstp, iwstp, itstp, ianav, ndta
@@ -74,8 +75,8 @@ CONTAINS
     CALL cg_ensure_handle()
     ! all ~40 flux fields stay on the GPU: their consumers (step_embm, step_seaice, step_goldstein) are
     ! device resident too.  Diagnostics that want them call cg_sync_to_host(name) at output intervals.
-    rc = cg_surflux_step_resident(cg_h, INT(istep, C_INT), C_NULL_PTR)
+    rc = cg_surflux_step(cg_h, INT(istep, C_INT), C_NULL_PTR)
     CALL cg_check(rc, 'cg_surflux_step')
   END SUBROUTINE surflux
 
-END MODULE embm
+END MODULE embm_b200

@@ -1,6 +1,7 @@
-! gold_seaice_b200.f90 -- drop-in for MODULE gold_seaice's step_seaice (reference:
-! src/goldsteinseaice/gold_seaice.f90:511-520; wrapper genie_loop_wrappers.f90:94-113).
-MODULE gold_seaice
+! gold_seaice_b200.f90 -- MODULE gold_seaice_b200: step_seaice with the reference's name and argument list
+! (src/goldsteinseaice/gold_seaice.f90:511-520).  MODULE gold_seaice stays in the build; fortran/use_b200.py switches
+! gold_seaice_wrapper's USE line (genie_loop_wrappers.f90:94-95).
+MODULE gold_seaice_b200
   USE, INTRINSIC :: ISO_C_BINDING
   USE cgenie_b200_c
   USE gold_seaice_lib, ONLY: maxi, maxj, iwstp, itstp, npstp
@@ -31,4 +32,4 @@ CONTAINS
     CALL cg_check(rc, 'cg_seaice_step')
   END SUBROUTINE step_seaice
 
-END MODULE gold_seaice
+END MODULE gold_seaice_b200

@@ -1,8 +1,10 @@
-! goldstein_b200.f90 -- drop-in replacement for MODULE goldstein's step entry point
-! (reference: src/goldstein/goldstein.f90:10-38).  Same module and procedure names, same argument
-! list, so src/wrappers/genie_loop_wrappers.f90:122-151 compiles unchanged.  The step runs on the GPU;
-! host arrays are touched only on output / restart steps (MOD(istep, iwstp|itstp|ianav|npstp) == 0).
-MODULE goldstein
+! goldstein_b200.f90 -- MODULE goldstein_b200: step_goldstein with the reference's procedure name and argument list
+! (src/goldstein/goldstein.f90:17-38), forwarding to the C-ABI.  The reference's MODULE goldstein stays in the build
+! unchanged -- initialise_goldstein, end_goldstein, the restart and diagnostic routines are host code the coupler still
+! calls (goldstein.f90:10-13) -- and only goldstein_wrapper's USE line changes (fortran/use_b200.py:
+! `USE goldstein` -> `USE goldstein_b200, ONLY: step_goldstein`, genie_loop_wrappers.f90:122-123).  The step runs on the
+! GPU; host arrays are touched only on output / restart steps (MOD(istep, iwstp|itstp|ianav|npstp) == 0).
+MODULE goldstein_b200
   USE, INTRINSIC :: ISO_C_BINDING
   USE cgenie_b200_c
   USE goldstein_lib, ONLY: maxi, maxj, maxk, maxl, npstp, iwstp, itstp, ianav
@@ -60,4 +62,4 @@ CONTAINS
     END IF
   END SUBROUTINE step_goldstein
 
-END MODULE goldstein
+END MODULE goldstein_b200

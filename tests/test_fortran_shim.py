@@ -80,15 +80,52 @@ def test_shim_modules_call_declared_functions():
     missing = sorted(n for n in used - declared - helpers - types if not re.search(r"SUBROUTINE\s+%s|FUNCTION\s+%s" % (n, n),
                      open(os.path.join(ROOT, "fortran", "cgenie_b200_c.f90")).read(), flags=re.I))
     assert not missing, "shim modules call undeclared C functions: %s" % missing
-    # the module / procedure names the unchanged genie_loop_wrappers.f90 USEs for the coupler calls of the BIOGEM block
+    # the shim modules and the procedures the coupler's wrappers call through them
     bio = open(os.path.join(ROOT, "fortran", "biogem_b200.f90")).read()
-    for mod, procs in (("biogem", ["step_biogem", "biogem_tracercoupling", "biogem_climate"]),
-                       ("atchem", ["step_atchem", "cpl_flux_ocnatm", "cpl_comp_atmocn"]),
-                       ("sedgem", ["cpl_flux_ocnsed", "cpl_comp_ocnsed"]), ("rokgem", ["reinit_flux_rokocn"])):
+    for mod, procs in (("biogem_b200", ["step_biogem", "biogem_tracercoupling", "biogem_climate", "biogem_climate_sol", "biogem_forcing"]),
+                       ("atchem_b200", ["step_atchem", "cpl_flux_ocnatm", "cpl_comp_atmocn", "cpl_comp_EMBM"]),
+                       ("sedgem_b200", ["cpl_flux_ocnsed", "cpl_comp_ocnsed"]), ("rokgem_b200", ["reinit_flux_rokocn"])):
         m = re.search(r"^MODULE %s\b(.*?)^END MODULE %s\b" % (mod, mod), bio, flags=re.S | re.M)
         assert m, mod
         for p in procs:
             assert re.search(r"SUBROUTINE %s\b" % p, m.group(1)), (mod, p)
+
+
+def test_shims_can_link_next_to_the_reference_modules():
+    """shim modules named like the reference's (MODULE goldstein ...) could neither replace nor coexist with them.
+    Now every shim module has its own name (*_b200), every C binding label is declared exactly once, and
+    fortran/use_b200.py rewrites only the USE line of the hot-path wrappers."""
+    names, labels = [], []
+    for path in glob.glob(os.path.join(ROOT, "fortran", "*.f90")):
+        src = "\n".join(line.split("!")[0] for line in open(path).read().split("\n"))
+        names += re.findall(r"^\s*MODULE\s+(\w+)\s*$", src, flags=re.M | re.I)
+        labels += re.findall(r"BIND\(C,\s*NAME='(\w+)'\)", src, flags=re.I)
+    assert len(names) == 8 and all(n.lower().endswith("_b200") or n == "cgenie_b200_c" for n in names), names
+    assert len(set(n.lower() for n in names)) == len(names)
+    assert len(labels) == len(set(labels)), sorted(x for x in labels if labels.count(x) > 1)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("use_b200", os.path.join(ROOT, "fortran", "use_b200.py"))
+    ub = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ub)
+    # a file shaped like src/wrappers/genie_loop_wrappers.f90: one USE line per wrapper, other wrappers left alone
+    text = "MODULE genie_loop_wrappers\n  USE genie_global\nCONTAINS\n"
+    for w, (ref, shim, procs) in ub.WRAPPERS.items():
+        text += "  SUBROUTINE %s\n    USE %s\n    IMPLICIT NONE\n    CALL %s(x)\n  END SUBROUTINE %s\n" % (w, ref.upper() if w == "embm_wrapper" else ref, procs[0], w)
+    text += "  SUBROUTINE goldstein_save_restart_wrapper\n    USE goldstein_data\n  END SUBROUTINE goldstein_save_restart_wrapper\n"
+    text += "  SUBROUTINE diag_biogem_timeslice_wrapper\n    USE biogem\n  END SUBROUTINE diag_biogem_timeslice_wrapper\nEND MODULE\n"
+    new, changes, missing = ub.rewrite(text)
+    assert not missing and len(changes) == len(ub.WRAPPERS)
+    assert "USE goldstein_b200, ONLY: step_goldstein" in new and "USE goldstein_data" in new
+    assert new.count("USE biogem\n") == 1                       # the diagnostic wrapper keeps the reference module
+    assert ub.rewrite(new)[1] == []                              # idempotent
+    # every procedure the script routes to a shim module is defined there with that name
+    allsrc = "".join(open(pth).read() for pth in glob.glob(os.path.join(ROOT, "fortran", "*.f90")))
+    for w, (ref, shim, procs) in ub.WRAPPERS.items():
+        m = re.search(r"^MODULE %s\b(.*?)^END MODULE %s\b" % (shim, shim), allsrc, flags=re.S | re.M)
+        assert m, shim
+        for p in procs:
+            assert re.search(r"SUBROUTINE %s\b" % p, m.group(1), flags=re.I), (shim, p)
+            assert re.search(r"PUBLIC\s*::.*\b%s\b" % p, m.group(1), flags=re.I), (shim, p)
 
 
 def test_ctypes_table_has_header_arity():
