@@ -24,6 +24,18 @@ __global__ void __launch_bounds__(MS, MINB) k_tstep_col(const Dev v) {
   tstep_column<I, J, K, L, MS, MS, PV, AR>(v, c_g, c2, threadIdx.x, st);
 }
 
+// pipelined form (production): coefficients one level ahead, T and S staged like every other tracer (see tstep_column2)
+template <int I, int J, int K, int L, int MS, int MINB>
+__global__ void __launch_bounds__(MS, MINB) k_tstep_col2(const Dev v) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ColStage st;
+  st.sm = reinterpret_cast<double *>(smem_raw);
+  st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows2<L>::rows * MS * 8);
+  st.tid = threadIdx.x;
+  const int c2 = v.col_deep_first ? v.wetcols[blockIdx.x] : v.rowcols[blockIdx.x];
+  tstep_column2<I, J, K, L, MS, MS>(v, c_g, c2, threadIdx.x, st);
+}
+
 // split form: two threads per (member, column), 2 * MS threads per block (see tstep_column_split)
 template <int I, int J, int K, int L, int MS, int MINB>
 __global__ void __launch_bounds__(2 * MS, MINB) k_tstep_split(const Dev v) {
@@ -53,6 +65,40 @@ __global__ void __launch_bounds__(128) k_co_col(const Dev v) {
   const int ci = blockIdx.y * 4 + (threadIdx.x >> 5);
   if (ci >= v.nwet) return;
   co_column<I, J, K, L, MS>(v, c_g, v.rowcols[ci], m);
+}
+
+// Block-cooperative form of the convective adjustment: one block = 32 members (lanes) of ONE wet column.  Warp 0 takes the
+// decisions for its flagged lanes (T, S, rho of the column, serial per lane: latency bound) and leaves the region maps in shared
+// memory; then every warp averages one pair of passive tracers over the mixed regions, so that the loads of all seven pairs are
+// in flight together instead of one pair after the other in the same thread.  A block none of whose 32 member-columns was flagged
+// unstable by the flux kernel returns at once (the flags are read by all warps alike, so the exit is block-uniform).
+template <int I, int J, int K, int L, int MS, int NW>
+__global__ void __launch_bounds__(32 * NW, 2) k_co_blk(const Dev v) {
+  __shared__ unsigned s_in[32], s_top[32], s_bot[32];
+  __shared__ double s_rdzt[K][32];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = blockIdx.x * 32 + lane;
+  const int c2 = v.rowcols[blockIdx.y];
+  const unsigned flag = v.comask[(long)c2 * MS + m];
+  if (!__any_sync(0xffffffffu, flag != 0u)) return;
+  if (warp == 0) {
+    unsigned in = 0, topb = 0, botb = 0;
+    double rdzt[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) rdzt[k] = 0.0;
+    if (flag) co_decide<I, J, K, L, MS>(v, c_g, c2, m, in, topb, botb, rdzt);
+    s_in[lane] = in; s_top[lane] = topb; s_bot[lane] = botb;
+#pragma unroll
+    for (int k = 0; k < K; k++) s_rdzt[k][lane] = rdzt[k];
+  }
+  __syncthreads();
+  const unsigned in = s_in[lane];
+  if (in == 0u) return;
+  const unsigned topb = s_top[lane], botb = s_bot[lane];
+  double rdzt[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) rdzt[k] = s_rdzt[k][lane];
+  for (int l = 2 + 2 * (int)warp; l < L; l += 2 * NW) co_passive_pair<I, J, K, L, MS>(v, c_g, c2, m, in, topb, botb, rdzt, l);
 }
 
 template <int I, int J, int K, int L, int MS>
@@ -85,6 +131,8 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   // split form (CG_COL_SPLIT=1): two threads per member-column, <= 128 registers, 16 warps per SM
   static int split = -1;
   if (split < 0) { const char *e = getenv("CG_COL_SPLIT"); split = e ? atoi(e) : 0; }
+  static int colv = -1;   // 2 (default): pipelined column kernel, coefficients one level ahead; 1: the round-1 form
+  if (colv < 0) { const char *e = getenv("CG_COL_V"); colv = e ? atoi(e) : 2; }
   static int order = -1, coskip = -1;
   if (order < 0) { const char *e = getenv("CG_COL_ORDER"); order = e ? atoi(e) : 0; }
   if (coskip < 0) { const char *e = getenv("CG_CO_SKIP"); coskip = e ? atoi(e) : 1; }
@@ -101,6 +149,17 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
     if (split == 2) k_tstep_split<I, J, K, L, MS, 1><<<v.nwet, 2 * MS, smem2, s>>>(v);
     else k_tstep_split<I, J, K, L, MS, 2><<<v.nwet, 2 * MS, smem2, s>>>(v);
   } else
+  if (colv == 2) {
+    constexpr size_t smem3 = (size_t)ColRows2<L>::rows * MS * 8 + 64;
+    static bool attr3 = false;
+    if (!attr3) {
+      cudaFuncSetAttribute(k_tstep_col2<I, J, K, L, MS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+      cudaFuncSetAttribute(k_tstep_col2<I, J, K, L, MS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+      attr3 = true;
+    }
+    if (cfg == 1) k_tstep_col2<I, J, K, L, MS, 1><<<v.nwet, MS, smem3, s>>>(v1);
+    else k_tstep_col2<I, J, K, L, MS, 2><<<v.nwet, MS, smem3, s>>>(v1);
+  } else
   if (cfg == 1) k_tstep_col<I, J, K, L, MS, 1, false><<<v.nwet, MS, smem, s>>>(v1);
   else if (cfg == 2) k_tstep_col<I, J, K, L, MS, 2, false, true><<<v.nwet, MS, smem, s>>>(v1);   // mbarrier buffer release
   else k_tstep_col<I, J, K, L, MS, 2, false><<<v.nwet, MS, smem, s>>>(v1);
@@ -109,7 +168,11 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   Dev v2 = v;
   v2.co_prefetch = copf;
   v2.co_skip_stable = (coskip && !(split && MS == 128)) ? 1 : 0;   // the split form does not write the stability flag
-  k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
+  static int cov = -1;
+  if (cov < 0) { const char *e = getenv("CG_CO_V"); cov = e ? atoi(e) : 2; }
+  constexpr int NW = (L - 2 + 1) / 2 > 0 ? ((L - 2 + 1) / 2 < 8 ? (L - 2 + 1) / 2 : 8) : 1;   // one warp per passive tracer pair
+  if (cov == 2 && v2.co_skip_stable && v.comask) k_co_blk<I, J, K, L, MS, NW><<<dim3(MS / 32, v.nwet), 32 * NW, 0, s>>>(v2);
+  else k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
   return 2;
 }
 

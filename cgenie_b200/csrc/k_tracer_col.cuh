@@ -541,6 +541,276 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Pipelined form of the column kernel (production): the per-cell coefficients are computed ONE LEVEL AHEAD.
+//
+// In tstep_column the 16 coefficients of a cell -- upstream weights (four divisions), density slopes on the four isoneutral
+// stencils, slope limiter (two more divisions in sequence) -- are a dependent chain of ~60 fp64 operations at the head of
+// every level, and the tracers' 320 independent FMAs can only start when it has finished: at 8 warps per SM the chain's
+// latency is exposed (ncu: 36 % of the stall cycles "wait", IPC 1.2).  Here the thread computes the coefficients of level
+// kk+1 WHILE it applies those of level kk: the two instruction streams share basic blocks (horizontal coefficients next to
+// tracers 0..L/2-1, vertical / isoneutral coefficients next to tracers L/2..L-1), so the scheduler fills the chain's latency
+// with tracer FMAs.  Consequences for the staging: the T,S / velocity unit C is consumed one level earlier (issued two levels
+// ahead), and T and S of level kk come from shared memory like every other tracer (unit A = tracers 0..L/2-1) because the
+// registers now hold T,S of levels kk+1 and kk+2 for the coefficients.  The slope limiter is taken from 1/tv1 instead of
+// 1/sl^2 (slim = (4 ssmax dzrho^2 / tv1)^2), which makes its division independent of 1/dzrho.
+// Arithmetic per tracer-cell, face formulation, stability flag and SST export are those of tstep_column.
+template <int L>
+struct ColRows2 {
+  static constexpr int nA = L / 2, nB = L - nA;
+  static constexpr int rowsC = 15, rTS = 0, rU = 10;
+  static constexpr int rA = 2 * rowsC, rowsA = 5 * nA;      // + cell * nA + l
+  static constexpr int rB = rA + rowsA, rowsB = 5 * nB;     // + cell * nB + (l - nA)
+  static constexpr int rows = rB + rowsB;
+};
+
+// vertical face kk+1/2 as col_coefs_v, with the two divisions of the slope limiter made independent of each other
+template <int K>
+CG_HD void col_coefs_v2(const ColK &q, const GridC &g, const int kk, const TS5 &a, const TS5 &b, const double vww, double &lc_,
+                        double &lE, double &lW, double &lN, double &lS, double &nuc_, double &nuE, double &nuW, double &nuN,
+                        double &nuS) {
+  const bool top = (kk == K);
+  const double mT = top ? 0.0 : 1.0;
+  const double ec1 = q.ec1, ec2 = q.ec2, ec3 = q.ec3, ec4 = q.ec4, gxx = q.gxx, gyS = q.gyS, gyN = q.gyN;
+  const double rdza = top ? 0.0 : g.rdza[kk];
+  const double pA = vww * g.dza[kk] * q.rdiffv, uA_ = pA * col_rcp(2.0 + fabs(pA)), gA = vww * 0.5 * mT, dA = rdza * q.diffv;
+  double nuc = gA * (1.0 - uA_) - dA;
+  double lc = gA * (1.0 + uA_) + dA;
+  const double tatw = 0.5 * (a.tC + b.tC);
+  const double tec = -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3;
+  const double dzrho = (ec2 * (b.sC - a.sC) - tec * (b.tC - a.tC)) * rdza;
+  const bool iso = dzrho < -1.0e-12;                     // false at the top level (rdza = 0)
+  const double dzs = iso ? dzrho : -1.0, mI = iso ? 1.0 : 0.0;
+  const double x0 = ec2 * ((a.sC - a.sW) * gxx) - tec * ((a.tC - a.tW) * gxx);
+  const double x1 = ec2 * ((a.sE - a.sC) * gxx) - tec * ((a.tE - a.tC) * gxx);
+  const double x2 = ec2 * ((b.sC - b.sW) * gxx) - tec * ((b.tC - b.tW) * gxx);
+  const double x3 = ec2 * ((b.sE - b.sC) * gxx) - tec * ((b.tE - b.tC) * gxx);
+  const double y0 = ec2 * ((a.sC - a.sS) * gyS) - tec * ((a.tC - a.tS) * gyS);
+  const double y1 = ec2 * ((a.sN - a.sC) * gyN) - tec * ((a.tN - a.tC) * gyN);
+  const double y2 = ec2 * ((b.sC - b.sS) * gyS) - tec * ((b.tC - b.tS) * gyS);
+  const double y3 = ec2 * ((b.sN - b.sC) * gyN) - tec * ((b.tN - b.tC) * gyN);
+  const double tv1 = (((x0 * x0 + y0 * y0) + (x1 * x1 + y1 * y1)) + (x2 * x2 + y2 * y2)) + (x3 * x3 + y3 * y3);
+  const double rdz = col_rcp(dzs), rdz2 = rdz * rdz;
+  const double sl = 0.25 * tv1 * rdz2, ssm = g.ssmax[kk];
+  // slim = ssmax^2 / sl^2 = (4 ssmax dzrho^2 / tv1)^2: 1 / tv1 does not wait for 1 / dzrho.  sl > ssmax implies tv1 > 0; where
+  // the limiter is not active the value is discarded by the select (tv1 == 0 gives a NaN there, never used)
+  const double rt = col_rcp(tv1 > 0.0 ? tv1 : 1.0);
+  const double sq = 4.0 * ssm * (dzs * dzs) * rt;
+  const double slim = (sl > ssm) ? sq * sq : 1.0;
+  const double cf = 0.25 * slim * q.diff1 * rdz2 * mI;
+  const double g2 = 2.0 * dzs * cf, gX = g2 * gxx, gS = g2 * gyS, gN = g2 * gyN;
+  const double s2 = tv1 * cf * rdza;
+  const double wx0 = x0 * gX, wx1 = x1 * gX, wx2 = x2 * gX, wx3 = x3 * gX;
+  const double wy0 = y0 * gS, wy1 = y1 * gN, wy2 = y2 * gS, wy3 = y3 * gN;
+  lc += (wx0 - wx1) + (wy0 - wy1) + s2;
+  nuc += (wx2 - wx3) + (wy2 - wy3) - s2;
+  lc_ = lc; nuc_ = nuc;
+  lW = -wx0; lE = wx1; lS = -wy0; lN = wy1;
+  nuW = -wx2; nuE = wx3; nuS = -wy2; nuN = wy3;
+}
+
+template <int I, int J, int K, int L, int MS, int NT>
+CG_HD void tstep_column2(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st) {
+  static_assert(NT == MS, "a block covers all members of one column");
+  using R = ColRows2<L>;
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
+  constexpr long uC3 = 3L * MS, uK = (long)I * J * uC3, rK = (long)I * J * MS;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+#define CGC_K1(ii, jj) ((int)v.k1[(ii) + (I + 2) * (jj)])
+  const int k1c = CGC_K1(i, j);
+  const int ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
+  const int k1e = CGC_K1(ip, j), k1w = CGC_K1(im, j), k1n = CGC_K1(i, j + 1), k1s = CGC_K1(i, j - 1);
+#undef CGC_K1
+  const ColK q = col_consts<I, J>(v, g, m, j);
+  const double ec1 = q.ec1, ec2 = q.ec2, ec3 = q.ec3, ec4 = q.ec4;
+  const long dE = (i < I) ? sC : -(long)(I - 1) * sC, dW = (i > 1) ? -sC : (long)(I - 1) * sC;
+  constexpr long dN = (long)I * sC, dS = -(long)I * sC;
+  const long dUW = (i > 1) ? -uC3 : (long)(I - 1) * uC3, dUS = (j > 1) ? -(long)I * uC3 : 0;
+  const double *const ts0 = v.ts_cur + (long)c2 * sC;
+  const double *const u0 = v.u + (long)c2 * uC3;
+  const double *const sm = st.sm + st.tid;
+
+  // unit C of level `lev`: T,S one level up (the level itself at the top) of the five columns + the five velocities of `lev`
+  auto issueC = [&](const int lev) {
+    const int b = (lev - k1c) & 1;
+    stage_expect(st, b, (unsigned)(R::rowsC * NT * 8));
+    const int lu = (lev < K) ? lev + 1 : K;
+    const double *c1 = ts0 + (long)(lu - 1) * sK;
+    const int r0 = b * R::rowsC;
+    stage_copy<NT>(st, b, r0 + R::rTS + 0, c1, 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 2, c1 + ((lu >= k1e) ? dE : 0), 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 4, c1 + ((lu >= k1w) ? dW : 0), 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 6, c1 + ((lu >= k1n) ? dN : 0), 2);
+    stage_copy<NT>(st, b, r0 + R::rTS + 8, c1 + ((lu >= k1s) ? dS : 0), 2);
+    const double *pu = u0 + (long)(lev - 1) * uK;
+    stage_copy<NT>(st, b, r0 + R::rU + 0, pu, 3);
+    stage_copy<NT>(st, b, r0 + R::rU + 3, pu + dUW, 1);
+    stage_copy<NT>(st, b, r0 + R::rU + 4, pu + dUS + sL, 1);
+  };
+  auto issueA = [&](const int lev) {
+    stage_expect(st, 2, (unsigned)(R::rowsA * NT * 8));
+    const double *c0 = ts0 + (long)(lev - 1) * sK;
+    stage_copy<NT>(st, 2, R::rA + 0 * R::nA, c0, R::nA);
+    stage_copy<NT>(st, 2, R::rA + 1 * R::nA, c0 + ((lev >= k1e) ? dE : 0), R::nA);
+    stage_copy<NT>(st, 2, R::rA + 2 * R::nA, c0 + ((lev >= k1w) ? dW : 0), R::nA);
+    stage_copy<NT>(st, 2, R::rA + 3 * R::nA, c0 + ((lev >= k1n) ? dN : 0), R::nA);
+    stage_copy<NT>(st, 2, R::rA + 4 * R::nA, c0 + ((lev >= k1s) ? dS : 0), R::nA);
+  };
+  auto issueB = [&](const int lev) {
+    stage_expect(st, 3, (unsigned)(R::rowsB * NT * 8));
+    const double *c0 = ts0 + (long)(lev - 1) * sK + R::nA * sL;
+    stage_copy<NT>(st, 3, R::rB + 0 * R::nB, c0, R::nB);
+    stage_copy<NT>(st, 3, R::rB + 1 * R::nB, c0 + ((lev >= k1e) ? dE : 0), R::nB);
+    stage_copy<NT>(st, 3, R::rB + 2 * R::nB, c0 + ((lev >= k1w) ? dW : 0), R::nB);
+    stage_copy<NT>(st, 3, R::rB + 3 * R::nB, c0 + ((lev >= k1n) ? dN : 0), R::nB);
+    stage_copy<NT>(st, 3, R::rB + 4 * R::nB, c0 + ((lev >= k1s) ? dS : 0), R::nB);
+  };
+  auto loadTS = [&](const int cb, TS5 &o) {
+    const double *const smc = sm + cb * R::rowsC * NT;
+    o.tC = smc[(R::rTS + 0) * NT]; o.sC = smc[(R::rTS + 1) * NT]; o.tE = smc[(R::rTS + 2) * NT]; o.sE = smc[(R::rTS + 3) * NT];
+    o.tW = smc[(R::rTS + 4) * NT]; o.sW = smc[(R::rTS + 5) * NT]; o.tN = smc[(R::rTS + 6) * NT]; o.sN = smc[(R::rTS + 7) * NT];
+    o.tS = smc[(R::rTS + 8) * NT]; o.sS = smc[(R::rTS + 9) * NT];
+  };
+
+  stage_init(st);
+  if (stage_leader(st)) {
+    issueC(k1c);
+    if (k1c < K) issueC(k1c + 1);
+    issueA(k1c);
+    issueB(k1c);
+  }
+  // T,S of the five columns at the bottom level (direct loads, once per column)
+  TS5 a;
+  {
+    const double *qC = ts0 + (long)(k1c - 1) * sK + m;
+    const double *qE = qC + ((k1c >= k1e) ? dE : 0), *qW = qC + ((k1c >= k1w) ? dW : 0);
+    const double *qN = qC + ((k1c >= k1n) ? dN : 0), *qS = qC + ((k1c >= k1s) ? dS : 0);
+    a.tC = qC[0]; a.sC = qC[sL]; a.tE = qE[0]; a.sE = qE[sL]; a.tW = qW[0]; a.sW = qW[sL];
+    a.tN = qN[0]; a.sN = qN[sL]; a.tS = qS[0]; a.sS = qS[sL];
+  }
+  // prologue: the coefficients of the bottom level from unit C(k1c) (buffer 0, first fill)
+  double hE, hW, hN, hS, hC, lc, lE, lW, lN, lS, cZ;          // level kk: horizontal faces, lower half of face kk+1/2, dt/dz
+  double nuc, nuE, nuW, nuN, nuS;                            // level kk: upper half of face kk+1/2 (used at level kk+1)
+  {
+    stage_wait(st, 0, 0u);
+    TS5 b;
+    loadTS(0, b);
+    const double *const smc = sm;
+    const double vuE = smc[(R::rU + 0) * NT], vvN = smc[(R::rU + 1) * NT], vww = smc[(R::rU + 2) * NT], vuW = smc[(R::rU + 3) * NT],
+                 vvS = smc[(R::rU + 4) * NT];
+    col_coefs_h(q, k1c >= k1e, k1c >= k1w, k1c >= k1n, k1c >= k1s, vuE, vvN, vuW, vvS, hE, hW, hN, hS, hC);
+    col_coefs_v2<K>(q, g, k1c, a, b, vww, lc, lE, lW, lN, lS, nuc, nuE, nuW, nuN, nuS);
+    cZ = q.dt * g.rdz[k1c];
+    a = b;                                                   // T,S of level k1c+1
+    stage_sync();
+    if (stage_leader(st) && k1c + 2 <= K) issueC(k1c + 2);
+  }
+  double *wP = v.ts_new + ((long)(k1c - 2) * (I * J) + c2) * sC + m;   // level kk-1 of the new array
+  double *rP = v.rho + ((long)(k1c - 2) * (I * J) + c2) * MS + m;
+  double uc = 0.0, uE = 0.0, uW = 0.0, uN = 0.0, uS = 0.0, cZp = 0.0;   // upper half of the face below, cZ of the level below
+  double P[L], Q[L];
+#pragma unroll
+  for (int l = 0; l < L; l++) { P[l] = 0.0; Q[l] = 0.0; }
+  unsigned par = 0;
+  bool unstable = false;
+  double rbelow = 0.0;
+
+  for (int kk = k1c; kk <= K; kk++) {
+    const bool top = (kk == K);
+    const bool stv = kk > k1c;
+    // inputs of the NEXT level's coefficients: T,S of level kk+2 and the velocities of level kk+1 (unit C(kk+1))
+    const int kn = top ? K : kk + 1;
+    const int cb = (kn - k1c) & 1;
+    TS5 b = a;
+    double vuE = 0.0, vvN = 0.0, vww = 0.0, vuW = 0.0, vvS = 0.0;
+    if (!top) {
+      stage_wait(st, cb, ((unsigned)(kn - k1c) >> 1) & 1u);
+      loadTS(cb, b);
+      const double *const smc = sm + cb * R::rowsC * NT;
+      vuE = smc[(R::rU + 0) * NT]; vvN = smc[(R::rU + 1) * NT]; vww = smc[(R::rU + 2) * NT]; vuW = smc[(R::rU + 3) * NT];
+      vvS = smc[(R::rU + 4) * NT];
+    }
+    stage_wait(st, 2, par);
+    // ---- segment 1: horizontal coefficients of level kk+1 next to tracers 0 .. nA-1 of level kk
+    double hE1 = 0.0, hW1 = 0.0, hN1 = 0.0, hS1 = 0.0, hC1 = 0.0;
+    if (!top) col_coefs_h(q, kn >= k1e, kn >= k1w, kn >= k1n, kn >= k1s, vuE, vvN, vuW, vvS, hE1, hW1, hN1, hS1, hC1);
+    double tnew = 0.0, snew = 0.0;
+#define CG_TRACER2(l, cc, EE, WW, NN, SS)                                                     \
+  {                                                                                           \
+    const double c = (cc), E = (EE), W = (WW), N = (NN), S = (SS);                            \
+    const double fab = P[l] + (uc * c + uE * E + uW * W + uN * N + uS * S);                   \
+    if (stv) {                                                                                \
+      const double tn = Q[l] - fab * cZp;                                                     \
+      wP[(l) * sL] = tn;                                                                      \
+      if ((l) == 0) tnew = tn;                                                                \
+      if ((l) == 1) snew = tn;                                                                \
+    }                                                                                         \
+    const double Hh = hC * c + hE * E + hW * W + hN * N + hS * S;                             \
+    Q[l] = (c - Hh) + fab * cZ;                                                               \
+    P[l] = lc * c + lE * E + lW * W + lN * N + lS * S;                                        \
+  }
+#pragma unroll
+    for (int l = 0; l < R::nA; l++) {
+      const int r = R::rA + l;
+      CG_TRACER2(l, sm[(r + 0 * R::nA) * NT], sm[(r + 1 * R::nA) * NT], sm[(r + 2 * R::nA) * NT], sm[(r + 3 * R::nA) * NT],
+                 sm[(r + 4 * R::nA) * NT])
+    }
+    stage_sync();                                            // unit A and unit C(kk+1) are consumed
+    if (stage_leader(st)) {
+      if (kk + 3 <= K) issueC(kk + 3);
+      if (!top) issueA(kk + 1);
+    }
+    stage_wait(st, 3, par);
+    // ---- segment 2: vertical / isoneutral coefficients of level kk+1 next to tracers nA .. L-1 of level kk
+    double lc1 = 0.0, lE1 = 0.0, lW1 = 0.0, lN1 = 0.0, lS1 = 0.0, nuc1 = 0.0, nuE1 = 0.0, nuW1 = 0.0, nuN1 = 0.0, nuS1 = 0.0;
+    if (!top) col_coefs_v2<K>(q, g, kn, a, b, vww, lc1, lE1, lW1, lN1, lS1, nuc1, nuE1, nuW1, nuN1, nuS1);
+#pragma unroll
+    for (int l = R::nA; l < L; l++) {
+      const int r = R::rB + (l - R::nA);
+      CG_TRACER2(l, sm[(r + 0 * R::nB) * NT], sm[(r + 1 * R::nB) * NT], sm[(r + 2 * R::nB) * NT], sm[(r + 3 * R::nB) * NT],
+                 sm[(r + 4 * R::nB) * NT])
+    }
+#undef CG_TRACER2
+    stage_sync();
+    if (!top && stage_leader(st)) issueB(kk + 1);
+    par ^= 1u;
+    if (stv) {
+      const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);   // :2638
+      rP[0] = r;
+      if (kk - 1 > k1c) unstable = unstable || !(r < rbelow);
+      rbelow = r;
+    }
+    // ---- shift one level up
+    uc = nuc; uE = nuE; uW = nuW; uN = nuN; uS = nuS; cZp = cZ;
+    hE = hE1; hW = hW1; hN = hN1; hS = hS1; hC = hC1;
+    lc = lc1; lE = lE1; lW = lW1; lN = lN1; lS = lS1;
+    nuc = nuc1; nuE = nuE1; nuW = nuW1; nuN = nuN1; nuS = nuS1;
+    cZ = q.dt * g.rdz[kn];
+    a = b;
+    wP += sK; rP += rK;
+  }
+  // ---- top level: the flux through the surface is the boundary condition ts(1:2,:,:,maxk+1)   (:2550-2552)
+  {
+    double tnew = 0.0, snew = 0.0;
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      double tn = Q[l];
+      if (l < 2) tn -= v.tsflux[((long)l * (I * J) + c2) * MS + m] * cZp;
+      wP[l * sL] = tn;
+      if (l == 0) tnew = tn;
+      if (l == 1) snew = tn;
+    }
+    const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
+    rP[0] = r;
+    if (K > k1c) unstable = unstable || !(r < rbelow);
+    if (v.comask) v.comask[(long)c2 * MS + m] = unstable ? 1u : 0u;
+    if (v.sst) {
+      v.sst[(long)c2 * MS + m] = tnew;
+      v.sst[((long)(I * J) + c2) * MS + m] = snew;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Split form of the column kernel: TWO threads per (member, column), 2 * NT threads per block.  Half 0 computes the
 // horizontal coefficients of the cell and carries tracers 0 .. L/2-1 (T and S among them), half 1 computes the vertical /
 // isoneutral coefficients and carries tracers L/2 .. L-1.  The halves exchange their coefficients through the rows of

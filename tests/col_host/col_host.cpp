@@ -40,6 +40,20 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
   // the whole "block" (32 members of one column) shares one staging area; bulk copies are emulated element-wise
   std::vector<double> sm((size_t)(ColRows<L>::rows > SplitRows<L>::rows ? ColRows<L>::rows : SplitRows<L>::rows) * 32);
   unsigned long long bar[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (mix == 3) {   // pipelined form (coefficients one level ahead) + stability flag, then co on the flagged member-columns
+    std::vector<double> sm2((size_t)ColRows2<L>::rows * 32);
+    std::vector<unsigned> comask((size_t)I * J * MS, 7u);
+    v.comask = comask.data();
+    v.co_skip_stable = 1;
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) {
+        ColStage st{sm2.data(), bar, m};
+        tstep_column2<I, J, K, L, 32, 32>(v, g, cols[n], (unsigned)m, st);
+      }
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m);
+    return 0;
+  }
   if (mix == 2) {   // split form (two threads per member-column; here one caller plays both halves), then co
     for (int n = 0; n < ncol; n++)
       for (int m = 0; m < MS; m++) {
