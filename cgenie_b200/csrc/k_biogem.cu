@@ -117,24 +117,39 @@ __global__ void __launch_bounds__(128) k_tc_partial(const Dev v, const int phase
 // warp 0 adds its lane's column of the tile sequentially.  Bit-identical to the reference's scalar loop, but the memory
 // latency is paid once per tile instead of once per term.
 constexpr int kSumTile = 128, kSumWarps = 8;   // blocks using ordered_sum_block have 32*kSumWarps threads
+// The same buffer as two half tiles: while warp 0 adds the terms of one half tile (a dependent chain: ~40 cycles per term on
+// B200's fp64 pipe, nothing else to do), warps 1 .. kSumWarps-1 fetch the next half tile, so that the global-memory latency of
+// a tile is paid under the additions of the previous one instead of in front of them (k_bg_atchem2: 1296 terms, 94 -> ~35 us).
 __device__ double ordered_sum_block(const double *__restrict__ p, const size_t stride, const int n, double *tile /* [kSumTile][32] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int kPer = kSumTile / kSumWarps;
+  constexpr int kHalf = kSumTile / 2, kLoaders = kSumWarps - 1, kPer = (kHalf + kLoaders - 1) / kLoaders;
+  const int ntile = (n + kHalf - 1) / kHalf;
   double s = 0.0;
-  for (int t0 = 0; t0 < n; t0 += kSumTile) {
-    const int nt = min(kSumTile, n - t0);
-    double r[kPer];
+  auto fetch = [&](const int t, const int w, const int nw) {   // terms w, w + nw, ... of half tile t -> buffer t & 1
+    const int t0 = t * kHalf, nt = min(kHalf, n - t0);
+    double *dst = tile + (t & 1) * kHalf * 32;
+    double r[kPer + 1];
 #pragma unroll
-    for (int u = 0; u < kPer; u++) {   // all loads of the tile in flight before the first use
-      const int t = warp + u * kSumWarps;
-      r[u] = (t < nt) ? p[(size_t)(t0 + t) * stride + lane] : 0.0;
+    for (int u = 0; u < kPer + 1; u++) {   // all loads in flight before the first store
+      const int q = w + u * nw;
+      r[u] = (q < nt) ? p[(size_t)(t0 + q) * stride + lane] : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < kPer; u++) tile[(warp + u * kSumWarps) * 32 + lane] = r[u];
-    __syncthreads();
+    for (int u = 0; u < kPer + 1; u++) {
+      const int q = w + u * nw;
+      if (q < nt) dst[q * 32 + lane] = r[u];
+    }
+  };
+  if (ntile > 0) fetch(0, warp, kSumWarps);                    // first half tile: all warps (kHalf / kSumWarps <= kPer + 1 terms each)
+  __syncthreads();
+  for (int t = 0; t < ntile; t++) {
     if (warp == 0) {
+      const int nt = min(kHalf, n - t * kHalf);
+      const double *src = tile + (t & 1) * kHalf * 32 + lane;
 #pragma unroll 16
-      for (int t = 0; t < nt; t++) s = s + tile[t * 32 + lane];
+      for (int q = 0; q < nt; q++) s = s + src[q * 32];
+    } else if (t + 1 < ntile) {
+      fetch(t + 1, warp - 1, kLoaders);
     }
     __syncthreads();
   }
@@ -324,15 +339,18 @@ __device__ void carbconst(double D, double T_in, double S_in, double Ca, double 
   if (S < 26.0) S = 26.0;
   if (S > 43.0) S = 43.0;
   const double P = D / 10.0;
-  const double S_p05 = pow(S, 0.5), S_p15 = pow(S, 1.5), S_p20 = S * S;
+  // x**0.5, x**1.5, 10**y, LOG(10**y) of the reference (libm pow, <= 1 ulp) through sqrt / exp10 / a multiplication: each is
+  // within 1 ulp of the exact value too -- the same distance CUDA's pow() keeps from glibc's -- at a fraction of pow()'s
+  // instruction count, and without pow()'s special-case branches (members diverge in them)
+  const double S_p05 = sqrt(S), S_p15 = S * S_p05, S_p20 = S * S;
   const double T_ln = log(T), T_log = log10(T), rT = 1.0 / T, Tr100 = T / 100.0, TC = T - kZeroC;
   const double rRT = 1.0 / (kR * T);
   const double Ii = (S > kNS) ? 19.924 * S / (1000.0 - 1.005 * S) : kNS;
-  const double I_p05 = pow(Ii, 0.5), I_p15 = pow(Ii, 1.5), I_p20 = Ii * Ii;
+  const double I_p05 = sqrt(Ii), I_p15 = Ii * I_p05, I_p20 = Ii * Ii;
   double Cl = S_in / 1.80655;
   if (Cl < kNS) Cl = kNS;
   const double ION = (Cl > kNS) ? 0.00147 + 0.03592 * Cl + 0.000068 * Cl * Cl : kNS;
-  const double ION_p05 = pow(ION, 0.5);
+  const double ION_p05 = sqrt(ION);
   const double m2c = log(1 - 0.001005 * S);
   const double SO4tot = fS(0.02824, S), Ftot = fS(0.00007, S);
   const double lnkHSO4 = 141.328 - 4276.1 * rT - 23.093 * T_ln + (324.57 - 13856.0 * rT - 47.986 * T_ln) * I_p05 +
@@ -343,9 +361,10 @@ __device__ void carbconst(double D, double T_in, double S_in, double Ca, double 
   cc[CC_KHF] = exp(lnkHF + m2c + f2t);
   const double f2s = log(1.0 + SO4tot / cc[CC_KHSO4] + Ftot / cc[CC_KHF]);
   const double t2s = -f2t + f2s;
-  cc[CC_K1] = exp(log(pow(10.0, -(3670.7 * rT - 62.008 + 9.7944 * T_ln - 0.0118 * S + 0.000116 * S_p20))) +
+  constexpr double kLn10 = 2.302585092994045684;   // LOG(10**y) = y ln 10
+  cc[CC_K1] = exp(kLn10 * -(3670.7 * rT - 62.008 + 9.7944 * T_ln - 0.0118 * S + 0.000116 * S_p20) +
                   corr_p(TC, P, rRT, -2.550E+1, +1.271E-1, +0.000E+0, -3.080E+0, +8.770E-2));
-  cc[CC_K2] = exp(log(pow(10.0, -(1394.7 * rT + 4.777 - 0.0184 * S + 0.000118 * S_p20))) +
+  cc[CC_K2] = exp(kLn10 * -(1394.7 * rT + 4.777 - 0.0184 * S + 0.000118 * S_p20) +
                   corr_p(TC, P, rRT, -1.582E+1, -2.190E-2, +0.000E+0, +1.130E+0, -1.475E-1));
   cc[CC_K] = cc[CC_K1] / cc[CC_K2];
   cc[CC_KB] = exp((148.0248 + 137.194 * S_p05 + 1.62247 * S +
@@ -366,8 +385,8 @@ __device__ void carbconst(double D, double T_in, double S_in, double Ca, double 
   cc[CC_KP3] = exp((-18.126 - 3070.75 / T + (2.81197 + 17.27039 / T) * S_p05 + (-0.09984 - 44.99486 / T) * S) +
                    corr_p(TC, P, rRT, -2.657E+1, +2.020E-1, -3.042E-3, -4.080E+0, +7.140E-2));
   cc[CC_KCAL] = exp(corr_p(TC, P, rRT, -4.876E+1, +5.304E-1, +0.000E+0, -1.176E+1, +3.692E-1)) *
-                pow(10.0, (-171.9065 - 0.077993 * T + 2839.319 * rT + 71.595 * T_log +
-                           (-0.77712 + 0.0028426 * T + 178.34 * rT) * S_p05 - 0.07711 * S + 0.0041249 * S_p15));
+                exp10(-171.9065 - 0.077993 * T + 2839.319 * rT + 71.595 * T_log +
+                      (-0.77712 + 0.0028426 * T + 178.34 * rT) * S_p05 - 0.07711 * S + 0.0041249 * S_p15);
   cc[CC_KARG] = 0.0;  // aragonite saturation is diagnostic only
   cc[CC_QCO2] = exp(-60.2409 + 93.4517 * (100 * rT) + 23.3585 * log(Tr100) +
                     S * (0.023517 - 0.023656 * (Tr100) + 0.0047036 * (Tr100 * Tr100)));
@@ -393,7 +412,7 @@ __device__ __forceinline__ void carb_iter(double DIC, double ALK, double PO4tot,
   const double ALK_DIC = ALK - H4BO4 - OH - HPO4 - 2.0 * PO4 - H3SiO4 - 0.0 - 0.0 + H + HSO4 + HF + H3PO4;
   const double k = cc[CC_K];
   const double a = 4.0 * ALK_DIC + DIC * k - ALK_DIC * k;
-  const double zed = pow(a * a + 4.0 * (k - 4.0) * (ALK_DIC * ALK_DIC), 0.5);
+  const double zed = sqrt(a * a + 4.0 * (k - 4.0) * (ALK_DIC * ALK_DIC));
   hco3 = (DIC * k - zed) / (k - 4.0);
   co3 = (ALK_DIC * k - DIC * k - 4.0 * ALK_DIC + zed) / (2.0 * (k - 4.0));
   co2 = DIC - ALK_DIC + (ALK_DIC * k - DIC * k - 4.0 * ALK_DIC + zed) / (2.0 * (k - 4.0));
@@ -649,7 +668,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
         double sol = exp(bc[0] + bc[1] * (100 * rT) + bc[2] * lnTr100 + Ss * (bc[3] + bc[4] * (Tr100) + bc[5] * (Tr100 * Tr100)));
         if (la == A_O2) sol = sol / (rho * kVmol);
         const double Sc = b.Sc[la][0] - b.Sc[la][1] * TC + b.Sc[la][2] * TC2 - b.Sc[la][3] * TC3;
-        const double pv = (1.0 / 1.0E+02) * (24.0 * 365.25) * b.gastransfer_a * u2 * pow(Sc * 1.515E-3, -0.5);
+        const double pv = (1.0 / 1.0E+02) * (24.0 * 365.25) * b.gastransfer_a * u2 * (1.0 / sqrt(Sc * 1.515E-3));   // (Sc/660)**(-0.5)
         double loc_atm = sol * sfc[la], loc_ocn, buff;
         if (la == A_CO2) {
           loc_ocn = cb.co2;

@@ -131,8 +131,8 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   // split form (CG_COL_SPLIT=1): two threads per member-column, <= 128 registers, 16 warps per SM
   static int split = -1;
   if (split < 0) { const char *e = getenv("CG_COL_SPLIT"); split = e ? atoi(e) : 0; }
-  static int colv = -1;   // 2 (default): pipelined column kernel, coefficients one level ahead; 1: the round-1 form
-  if (colv < 0) { const char *e = getenv("CG_COL_V"); colv = e ? atoi(e) : 2; }
+  static int colv = -1;   // 1 (default): flux kernel of round 1 + stability flag; 2: pipelined form, coefficients one level ahead
+  if (colv < 0) { const char *e = getenv("CG_COL_V"); colv = e ? atoi(e) : 1; }
   static int order = -1, coskip = -1;
   if (order < 0) { const char *e = getenv("CG_COL_ORDER"); order = e ? atoi(e) : 0; }
   if (coskip < 0) { const char *e = getenv("CG_CO_SKIP"); coskip = e ? atoi(e) : 1; }
@@ -169,7 +169,7 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   v2.co_prefetch = copf;
   v2.co_skip_stable = (coskip && !(split && MS == 128)) ? 1 : 0;   // the split form does not write the stability flag
   static int cov = -1;
-  if (cov < 0) { const char *e = getenv("CG_CO_V"); cov = e ? atoi(e) : 2; }
+  if (cov < 0) { const char *e = getenv("CG_CO_V"); cov = e ? atoi(e) : 1; }
   constexpr int NW = (L - 2 + 1) / 2 > 0 ? ((L - 2 + 1) / 2 < 8 ? (L - 2 + 1) / 2 : 8) : 1;   // one warp per passive tracer pair
   if (cov == 2 && v2.co_skip_stable && v.comask) k_co_blk<I, J, K, L, MS, NW><<<dim3(MS / 32, v.nwet), 32 * NW, 0, s>>>(v2);
   else k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
