@@ -34,7 +34,32 @@ CONFIG = "eb_go_gs_ac_bg_36x36x16"
 WORKLOAD = ("eb_go_gs_ac_bg 36x36x16 worjh2: EMBM + GOLDSTEIN + sea ice + BIOGEM (16 ocean tracers, 1N1T_PO4MM, "
             "13C/14C, CFCs) + ATCHEM, parameter-perturbed ensemble sharded by member "
             "(BASELINE config #4 shape: 128 members/GPU = 1024 at 8 GPUs)")
+# --config N: the other BASELINE.json configurations (the default line, N = 4, is the one the metric is quoted on)
+#   job configuration, members per GPU, BIOGEM, default untimed spin-up years, workload text
+CONFIGS = {
+    1: ("eb_go_gs_36x36x8", 1, False, 10, "eb_go_gs physics only (EMBM + GOLDSTEIN + sea ice) 36x36x8 worbe2, 100 ocean steps / year, "
+        "SINGLE member (BASELINE config #1, the reference's own CPU test job)"),
+    2: (CONFIG, 1, True, 100, "eb_go_gs_ac_bg 36x36x16 worjh2 with BIOGEM (16 ocean tracers) + ATCHEM, SINGLE member "
+        "(BASELINE config #2: 100-year spin-up on one B200)"),
+    3: (CONFIG, 64, True, 100, "eb_go_gs_ac_bg 36x36x16 worjh2 with BIOGEM + ATCHEM, 64-member parameter-perturbation ensemble on one "
+        "B200 (BASELINE config #3)"),
+    4: (CONFIG, 128, True, 100, WORKLOAD),
+}
 from cgenie_b200.sharding import PERTURBED, PERTURBED_BIOGEM, SEED, perturbation_table, shard  # noqa: E402  (pure numpy)
+
+
+def config_dict(workload, M, I, J, K, L, nyear, variant, biogem, spinup_years, member_stride=None):
+    """The `config` object of the JSON line; the reference arm prints the same object for the same workload."""
+    ms = member_stride or ((M + 31) // 32) * 32
+    working_set = (2 * L + 6) * I * J * K * 8 * ms
+    in_l2 = working_set < 100e6
+    return {"workload": workload, "members_per_gpu": M, "grid": [I, J, K], "tracers": L, "nyear": nyear,
+            "tracer_variant": variant, "perturbed": PERTURBED + (PERTURBED_BIOGEM if biogem else []), "seed": SEED,
+            "adrag_groups": "adrag is perturbed per group of 16 members (members of a group share one barotropic factorisation)",
+            "l2": ("working set %.0f MB per GPU (two ts buffers + u + rho) exceeds the 126 MB L2" if not in_l2 else
+                   "working set %.1f MB per GPU (two ts buffers + u + rho) fits the 126 MB L2: L2-resident run") % (working_set / 1e6),
+            "step": "one model year of every member: %d koverall iterations" % (5 * nyear),
+            "state": "%d model years of untimed spin-up from the uniform initial state, then the warm-up years" % spinup_years}
 
 
 def peaks():
@@ -133,10 +158,133 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "ensemble model-years/wall-hour", "value": value, "unit": "model-years/hour",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "C restatement of the reference (oracle/), not a gfortran build"},
+        "config": config_dict(WORKLOAD, 128, 36, 36, 16, 16, 96, "col", True, 100),
+        "note": "reference arm = the C restatement of the reference (oracle/, -O3 -funroll-loops, no FMA) on the host cores, not a "
+                "gfortran build; it starts from the initial state (no spin-up: the CPU cost of a model year does not depend on it)",
         "cpu_baseline": {"value": value, "unit": "model-years/hour", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "model-years/hour", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+# ----------------------------------------------------------------------------- BASELINE config #5
+def config5_fields(t, k1, I, J, K, L):
+    """tracers c_l = 1 + 0.1 sin(2 pi i / I) cos(pi j / J) (k / K) (1 + l / L), T and S from an analytic
+    stratified profile, horizontal velocities from a prescribed stream function (non-divergent) with w from continuity as velc
+    computes it (goldstein.f90:3668-3678).  One member, Fortran-shaped: ts (K+2, J+2, I+2, L), u (K, J+1, I+1, 3)."""
+    c, cv, ds, dz = t.const("c"), t.const("cv"), t.const("ds"), t.const("dz")
+    rdphi = t.const("scalars")[1]
+    kk, jj, ii = np.meshgrid(np.arange(K + 2), np.arange(J + 2), np.arange(I + 2), indexing="ij")
+    ts = np.zeros((K + 2, J + 2, I + 2, L))
+    ts[..., 0] = 2.0 + 18.0 * (kk / (K + 1.0)) ** 2 + 1.5 * np.cos(2 * np.pi * ii / I) * np.sin(np.pi * jj / J)
+    ts[..., 1] = 0.3 * np.sin(2 * np.pi * ii / I) * (kk / (K + 1.0)) - 0.1 * np.cos(np.pi * jj / J)
+    base = 0.1 * np.sin(2 * np.pi * ii / I) * np.cos(np.pi * jj / J) * (kk / K)
+    for l in range(2, L):
+        ts[..., l] = 1.0 + base * (1 + l / L)
+    ts[K + 1] = 0.0
+    ts[:, :, 0, :] = ts[:, :, I, :]
+    ts[:, :, I + 1, :] = ts[:, :, 1, :]
+    jv, iv = np.arange(J + 1), np.arange(I + 1)
+    psi2 = np.sin(np.pi * np.minimum(jv, J - 2) / (J - 2))[:, None] ** 2 * (1 + 0.5 * np.sin(2 * np.pi * iv / I))[None, :]
+    psi = 0.02 * (np.arange(K + 1) / K)[:, None, None] * psi2[None]                                  # (K+1, J+1, I+1)
+    u = np.zeros((K, J + 1, I + 1, 3))
+    k1e = np.maximum(k1[1:J + 1, 1:I + 1], k1[1:J + 1, 2:I + 2])                                       # east face open from this level
+    k1n = np.maximum(k1[1:J + 1, 1:I + 1], k1[2:J + 2, 1:I + 1])
+    lev = np.arange(1, K + 1)[:, None, None]
+    ue = -c[1:J + 1][None, :, None] * (psi[1:, 1:, 1:] - psi[1:, :-1, 1:]) / ds[1:J + 1][None, :, None]
+    vn = (psi[1:, 1:, 1:] - psi[1:, 1:, :-1]) * rdphi / np.where(cv[1:J + 1] != 0, cv[1:J + 1], 1.0)[None, :, None]
+    u[:, 1:, 1:, 0] = np.where(lev >= k1e[None], ue, 0.0)
+    u[:, 1:, 1:, 1] = np.where((lev >= k1n[None]) & (np.arange(1, J + 1) < J)[None, :, None], vn, 0.0)
+    u[:, :, 0, 0] = u[:, :, I, 0]
+    tv1 = (u[:, 1:, 1:, 0] - u[:, 1:, :-1, 0]) * rdphi / c[1:J + 1][None, :, None]
+    tv2 = (u[:, 1:, 1:, 1] * cv[1:J + 1][None, :, None] - u[:, :-1, 1:, 1] * cv[0:J][None, :, None]) / ds[1:J + 1][None, :, None]
+    wet = lev >= k1[1:J + 1, 1:I + 1][None]
+    w = -np.cumsum(np.where(wet, dz[1:K + 1][:, None, None] * (tv1 + tv2), 0.0), axis=0)
+    w[K - 1] = 0.0
+    u[:, 1:, 1:, 2] = np.where(wet, w, 0.0)
+    return ts, u
+
+
+def run_config5(args, rank, world, local):
+    """Stand-alone tracer step (tstepo_flux + co) on the synthetic 128 x 128 x 32 grid with 40 tracers, M members per GPU, through
+    cg_tracer_create / set / step (the generic-shape kernels: the column kernel is compiled for 36 x 36 x 16, L = 16 only)."""
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from cgenie_b200 import TracerStep
+    I, J, K, L = 128, 128, 32, 40
+    M = args.members or 16
+    k1 = np.ones((J + 2, I + 2), dtype=np.int32)
+    k1[0, :] = 94
+    k1[J - 1:J + 2, :] = 92                                    # 2-cell polar land cap
+    t = TracerStep(I, J, K, L, k1, n_members=M, device=local, diff1=2000.0, diff2=1e-5, nyear=96)
+    t.set_tracer_variant(args.variant if args.variant != "col" else "fast")
+    ts1, u1 = config5_fields(t, k1, I, J, K, L)
+    fac = (1.0 + 0.01 * np.arange(M))[:, None, None, None, None]          # members differ by a scale of the passive tracers
+    ts = np.repeat(ts1[None], M, axis=0)
+    ts[..., 2:] *= fac
+    u = np.repeat(u1[None], M, axis=0)
+    flux = np.zeros((M, J, I, 2))
+    t.set(ts=ts, u=u, tsflux=flux)
+    for _ in range(max(args.warmup, 3)):
+        t.step(1)
+    t.synchronize()
+    if world > 1:
+        dist.barrier()
+    t.launch_count(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    t.timer_start()
+    t.step(args.steps)
+    ms = t.timer_stop_ms()
+    launches = t.launch_count()
+    clocks = sampler.summary()
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    n_wet = int(np.sum(np.clip(K - k1[1:J + 1, 1:I + 1] + 1, 0, None)[k1[1:J + 1, 1:I + 1] <= K]))
+    bytes_per_launch = n_wet * (16 * L + 32) * M
+    avg_ms = ms / args.steps
+    peak, peak_src = peaks()
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    # end to end through the same entry points with host arrays: upload the state, one step, download ts / rho / cost
+    t0 = time.perf_counter()
+    t.set(ts=ts, u=u, tsflux=flux)
+    t.step(1)
+    got = t.fetch()
+    e2e_s = time.perf_counter() - t0
+    assert np.isfinite(got[0]).all()
+    out = {"metric": "tracer-step HBM GB/s vs peak", "value": world * achieved, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": avg_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "synthetic 128x128x32 grid, 40 tracers, stand-alone tracer step (tstepo_flux + co), all-wet flat bottom "
+                                  "with a 2-cell polar land cap (BASELINE config #5)", "members_per_gpu": M, "grid": [I, J, K], "tracers": L,
+                      "tracer_variant": t.tracer_variant_active(),
+                      "l2": "working set %.1f GB per GPU (two ts buffers + u + rho) exceeds the 126 MB L2" % ((2 * L + 6) * I * J * K * 8 * t.member_stride / 1e9),
+                      "step": "one tstepo of every member"},
+           "clocks": clocks, "gpu_launches": launches,
+           "roofline": {"bound": "hbm", "kernel": "tstepo = k_tstepo_flux_coop + k_co_fast2 (generic-shape kernels)", "achieved": achieved,
+                        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms},
+           "e2e": {"value": world * bytes_per_launch / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(ts.nbytes + u.nbytes + flux.nbytes),
+                   "d2h_bytes_per_step": int(sum(a.nbytes for a in got)),
+                   "path": "cg_tracer_set / cg_tracer_step / cg_tracer_get with pageable host arrays (one step)"}}
+    t.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
+    os.close(json_fd)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -145,11 +293,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--members", type=int, default=128, help="ensemble members per GPU")
+    ap.add_argument("--members", type=int, default=None, help="ensemble members per GPU (default: the configuration's)")
+    ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json configuration (4 = default line; 1, 2 = single member: L2-resident; 5 = synthetic "
+                         "128x128x32 x 40 tracers, stand-alone tracer step)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--variant", default="col", choices=["col", "fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--spinup-years", type=int, default=100,
+    ap.add_argument("--spinup-years", type=int, default=None,
                     help="untimed model years from the uniform initial state before the warm-up (config #2's 100-year spin-up: "
                          "the convective adjustment is data dependent, 70 %% of all cells mix in a 4-year-old ocean; ~7 s)")
     args = ap.parse_args()
@@ -158,6 +309,13 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank)
+    if args.config == 5:
+        return run_config5(args, rank, world, local)
+    cfgname, cfg_members, biogem, cfg_spin, workload = CONFIGS[args.config]
+    if args.members is None:
+        args.members = cfg_members
+    if args.spinup_years is None:
+        args.spinup_years = cfg_spin
 
     # stdout carries exactly one JSON line: NCCL prints its version banner with printf on some boxes, so file descriptor 1
     # points at stderr while the job runs and the line is written to the saved descriptor at the end
@@ -188,9 +346,9 @@ def main():
 
     from cgenie_b200 import Ensemble, materialise
     M = args.members
-    pert = shard(perturbation_table(M * world, biogem=True), rank, world, M)
+    pert = shard(perturbation_table(M * world, biogem=biogem), rank, world, M)
     tmp = tempfile.mkdtemp(prefix="cgenie_job_")
-    materialise(tmp, CONFIG)
+    materialise(tmp, cfgname)
     e = Ensemble(tmp, n_members=M, device=local, perturb=pert)
     e.set_tracer_variant(args.variant)
     kyear = e.nyear * e.ndta
@@ -232,14 +390,19 @@ def main():
     avg_ms = (t_ms + c_ms) / max(nstep, 1)                  # tstepo = flux + convection kernels of one step (B_tr covers both)
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    working_set = (2 * L + 6) * I * J * K * 8 * e.member_stride
+    in_l2 = working_set < 100e6
     kern = {"col": "tstepo = k_tstep_col + k_co_col", "fast": "tstepo = k_tstepo_flux_coop + k_co_fast2 (+ k_sst)",
             "strict": "tstepo = k_tstepo_flux_strict + k_co_strict (+ k_sst)"}[e.tracer_variant_active()]
     roofline = {"bound": "hbm", "kernel": kern + " (%s variant), SURVEY 8d B_tr" % e.tracer_variant_active(),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(M, e.tracer_variant_active()), "peak_source": peak_src,
+                "traffic": ncu_traffic(M, e.tracer_variant_active()) if args.config == 4 else None, "peak_source": peak_src,
                 "launches_per_step": (t_n + c_n) / max(nstep, 1),
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "family_ms_per_year": {k: v[0] for k, v in fam.items()}}
+    if in_l2:   # single-member runs: the whole state (%.1f MB) lives in the 126 MB L2, so `achieved` is L2, not HBM, bandwidth
+        roofline["note"] = ("working set %.1f MB is L2 resident: achieved = L2 GB/s of the tracer step (north_star: 'L2 GB/s for "
+                            "single-member runs'); the step is launch / latency bound at this size, not bandwidth bound" % (working_set / 1e6))
 
     # ---- end to end through the per-module C-ABI entry points with host buffers
     try:
@@ -269,7 +432,7 @@ def main():
             if k % 5 == 0:
                 e.step_seaice()
                 e.step_goldstein()
-            if k % 10 == 0:   # conv_kocn_kbiogem = conv_kocn_katchem = 2 (genie.f90:352-447)
+            if biogem and k % 10 == 0:   # conv_kocn_kbiogem = conv_kocn_katchem = 2 (genie.f90:352-447)
                 clock = (e2e_k0[0] + k) * clock_tick
                 e.biogem_forcing(clock)
                 e.biogem_step(dts_bg, clock)
@@ -294,17 +457,12 @@ def main():
         "metric": "ensemble model-years/wall-hour", "value": value, "unit": "model-years/hour", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "members_per_gpu": M, "grid": [I, J, K], "tracers": L, "nyear": e.nyear,
-                   "tracer_variant": args.variant, "perturbed": PERTURBED + PERTURBED_BIOGEM, "seed": SEED,
-                   "l2": "working set %.0f MB per GPU (two ts buffers + u + rho) exceeds the 126 MB L2" %
-                         ((2 * L + 6) * I * J * K * 8 * e.member_stride / 1e6),
-                   "step": "one model year of every member: %d koverall iterations" % kyear,
-                   "state": "%d model years of untimed spin-up from the uniform initial state, then the warm-up years" % args.spinup_years},
+        "config": config_dict(workload, M, I, J, K, L, e.nyear, e.tracer_variant_active(), biogem, args.spinup_years, e.member_stride),
         "clocks": clocks, "gpu_launches": launches, "blown_up_members": bad, "roofline": roofline,
         "e2e": {"value": e2e_val, "unit": "model-years/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "path": "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein/biogem_*/atchem), state in/out of pinned host per year"},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # the CPU arm is timed next to the N=1 line only
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 4:   # the CPU arm is timed next to the N=1 line only
         cores = os.cpu_count() or 1
         rate, wall = cpu_oracle_rate(10.0, cores)
         out["cpu_baseline"] = {"value": rate, "unit": "model-years/hour", "cores": cores, "kind": "port",

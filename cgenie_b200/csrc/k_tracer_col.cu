@@ -168,6 +168,9 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   Dev v2 = v;
   v2.co_prefetch = copf;
   v2.co_skip_stable = (coskip && !(split && MS == 128)) ? 1 : 0;   // the split form does not write the stability flag
+  static int copair = -1;
+  if (copair < 0) { const char *e = getenv("CG_CO_PAIR"); copair = e ? atoi(e) : 0; }
+  v2.co_pairwise = copair;
   static int cov = -1;
   if (cov < 0) { const char *e = getenv("CG_CO_V"); cov = e ? atoi(e) : 1; }
   constexpr int NW = (L - 2 + 1) / 2 > 0 ? ((L - 2 + 1) / 2 < 8 ? (L - 2 + 1) / 2 : 8) : 1;   // one warp per passive tracer pair

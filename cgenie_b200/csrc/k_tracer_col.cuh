@@ -166,6 +166,19 @@ CG_HD bool stage_leader(const ColStage &s) {
   return true;   // host emulation: every "thread" copies its own elements
 #endif
 }
+// The thread that issues staging unit `unit` (0 = C, 1 = A, 2 = B): lane 0 of warp `unit` where the block has that many warps.
+// One leader issuing all 18 copies of a level executes ~270 instructions more per level than the other warps, which then wait
+// for it at the next block barrier (ncu: 18 % of the stall cycles "barrier"); spread over three warps the extra work is even.
+template <int NT>
+CG_HD bool stage_issuer(const ColStage &s, const int unit) {
+#ifdef __CUDA_ARCH__
+  constexpr int NW = NT / 32;
+  return s.tid == 32 * (unit < NW ? unit : NW - 1);
+#else
+  (void)s; (void)unit;
+  return true;
+#endif
+}
 
 // rows of the staging buffers.  Unit C (double buffered, issued 1.5 levels ahead): T,S of the five columns one level
 // up + the five velocities; unit A: tracers 2..LH-1 of the five columns; unit B: tracers LH..L-1.
@@ -355,11 +368,20 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 
   stage_init(st);
   if (ASYNC_REL) stage_init_empty(st, 4, 2, NT / 32);
-  if (stage_leader(st)) {
-    issueC(k1c);
-    if (k1c < K) issueC(k1c + 1);
-    issueA(k1c);
-    issueB(k1c);
+  if (ASYNC_REL) {
+    if (stage_leader(st)) {
+      issueC(k1c);
+      if (k1c < K) issueC(k1c + 1);
+      issueA(k1c);
+      issueB(k1c);
+    }
+  } else {
+    if (stage_issuer<NT>(st, 0)) {
+      issueC(k1c);
+      if (k1c < K) issueC(k1c + 1);
+    }
+    if (stage_issuer<NT>(st, 1)) issueA(k1c);
+    if (stage_issuer<NT>(st, 2)) issueB(k1c);
   }
 
   // T,S of the five columns at the bottom level (direct loads, once per column)
@@ -470,10 +492,8 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
       }
     } else {
       stage_sync();
-      if (stage_leader(st)) {
-        if (kk + 2 <= K) issueC(kk + 2);
-        if (!top) issueA(kk + 1);
-      }
+      if (kk + 2 <= K && stage_issuer<NT>(st, 0)) issueC(kk + 2);
+      if (!top && stage_issuer<NT>(st, 1)) issueA(kk + 1);
     }
     stage_wait(st, 3, par);
 #pragma unroll
@@ -491,7 +511,7 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
       }
     } else {
       stage_sync();
-      if (!top && stage_leader(st)) issueB(kk + 1);
+      if (!top && stage_issuer<NT>(st, 2)) issueB(kk + 1);
     }
     par ^= 1u;
     if (!PV && stv) {
@@ -672,12 +692,12 @@ CG_HD void tstep_column2(const Dev &v, const GridC &g, const int c2, const unsig
   };
 
   stage_init(st);
-  if (stage_leader(st)) {
+  if (stage_issuer<NT>(st, 0)) {
     issueC(k1c);
     if (k1c < K) issueC(k1c + 1);
-    issueA(k1c);
-    issueB(k1c);
   }
+  if (stage_issuer<NT>(st, 1)) issueA(k1c);
+  if (stage_issuer<NT>(st, 2)) issueB(k1c);
   // T,S of the five columns at the bottom level (direct loads, once per column)
   TS5 a;
   {
@@ -702,7 +722,7 @@ CG_HD void tstep_column2(const Dev &v, const GridC &g, const int c2, const unsig
     cZ = q.dt * g.rdz[k1c];
     a = b;                                                   // T,S of level k1c+1
     stage_sync();
-    if (stage_leader(st) && k1c + 2 <= K) issueC(k1c + 2);
+    if (k1c + 2 <= K && stage_issuer<NT>(st, 0)) issueC(k1c + 2);
   }
   double *wP = v.ts_new + ((long)(k1c - 2) * (I * J) + c2) * sC + m;   // level kk-1 of the new array
   double *rP = v.rho + ((long)(k1c - 2) * (I * J) + c2) * MS + m;
@@ -755,10 +775,8 @@ CG_HD void tstep_column2(const Dev &v, const GridC &g, const int c2, const unsig
                  sm[(r + 4 * R::nA) * NT])
     }
     stage_sync();                                            // unit A and unit C(kk+1) are consumed
-    if (stage_leader(st)) {
-      if (kk + 3 <= K) issueC(kk + 3);
-      if (!top) issueA(kk + 1);
-    }
+    if (kk + 3 <= K && stage_issuer<NT>(st, 0)) issueC(kk + 3);
+    if (!top && stage_issuer<NT>(st, 1)) issueA(kk + 1);
     stage_wait(st, 3, par);
     // ---- segment 2: vertical / isoneutral coefficients of level kk+1 next to tracers nA .. L-1 of level kk
     double lc1 = 0.0, lE1 = 0.0, lW1 = 0.0, lN1 = 0.0, lS1 = 0.0, nuc1 = 0.0, nuE1 = 0.0, nuW1 = 0.0, nuN1 = 0.0, nuS1 = 0.0;
@@ -771,7 +789,7 @@ CG_HD void tstep_column2(const Dev &v, const GridC &g, const int c2, const unsig
     }
 #undef CG_TRACER2
     stage_sync();
-    if (!top && stage_leader(st)) issueB(kk + 1);
+    if (!top && stage_issuer<NT>(st, 2)) issueB(kk + 1);
     par ^= 1u;
     if (stv) {
       const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);   // :2638
@@ -1294,7 +1312,44 @@ CG_HD void co_passive_pair(const Dev &v, const GridC &g, const int c2, const uns
   }
 }
 
-// both parts by one thread (host test harness; single-kernel fallback)
+// Part 2, region by region: ALL passive tracers of one mixed region at a time.  co_passive_pair walks the column once per
+// tracer pair, and each walk's loads wait behind the previous walk's stores (same array): seven dependent trips to memory
+// per thread (ncu: 4.5 of 10 stall cycles per instruction "long scoreboard").  Here the loads of a region -- (L - 2) tracers x
+// its levels, all independent -- are issued together, then the means are stored: one trip per region, and a column rarely
+// has more than one or two.  Same sums in the same order (top-down, thickness weighted) as co_passive_pair.
+template <int I, int J, int K, int L, int MS>
+CG_HD void co_passive_regions(const Dev &v, const GridC &g, const int c2, const unsigned m, const unsigned topb, const unsigned botb,
+                              const double *rdzt) {
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
+  constexpr int NP = L - 2;
+  double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m) + 2 * sL;
+  unsigned rem = topb;
+  while (rem) {
+    const int kt = 31 - CG_CLZ(rem);                                  // topmost region not yet done (0-based level)
+    rem &= ~(1u << kt);
+    const int kb = 31 - CG_CLZ(botb & ((2u << kt) - 1u));              // its bottom: the nearest bottom mark below the top
+    double acc[NP];
+#pragma unroll
+    for (int l = 0; l < NP; l++) acc[l] = 0.0;
+#pragma unroll 4
+    for (int k = kt; k >= kb; k--) {
+      const double dz = g.dz[k + 1];
+      const double *__restrict__ p = ts + (long)k * sK;
+#pragma unroll
+      for (int l = 0; l < NP; l++) acc[l] += p[l * sL] * dz;
+    }
+    const double r = rdzt[kb];
+#pragma unroll
+    for (int l = 0; l < NP; l++) acc[l] = acc[l] * r;
+    for (int k = kb; k <= kt; k++) {
+      double *__restrict__ p = ts + (long)k * sK;
+#pragma unroll
+      for (int l = 0; l < NP; l++) p[l * sL] = acc[l];
+    }
+  }
+}
+
+// both parts by one thread (production convection kernel k_co_col; host test harness)
 template <int I, int J, int K, int L, int MS>
 CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m) {
   // the flux kernel found every level of this (member, column) stable: nothing to adjust, SST / SSS are exported already
@@ -1303,7 +1358,11 @@ CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned 
   double rdzt[K];
   co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt);
   if (in == 0) return;
-  for (int l = 2; l < L; l += 2) co_passive_pair<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, l);
+  if (v.co_pairwise) {
+    for (int l = 2; l < L; l += 2) co_passive_pair<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, l);
+  } else if (L > 2) {
+    co_passive_regions<I, J, K, L, MS>(v, g, c2, m, topb, botb, rdzt);
+  }
 }
 
 }  // namespace cg
