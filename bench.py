@@ -53,7 +53,7 @@ def config_dict(workload, M, I, J, K, L, nyear, variant, biogem, spinup_years, m
     ms = member_stride or ((M + 31) // 32) * 32
     working_set = (2 * L + 6) * I * J * K * 8 * ms
     in_l2 = working_set < 100e6
-    return {"workload": workload, "members_per_gpu": M, "grid": [I, J, K], "tracers": L, "nyear": nyear,
+    return {"workload": workload, "members_per_gpu": M, "member_stride": ms, "grid": [I, J, K], "tracers": L, "nyear": nyear,
             "tracer_variant": variant, "perturbed": PERTURBED + (PERTURBED_BIOGEM if biogem else []), "seed": SEED,
             "adrag_groups": "adrag is perturbed per group of 16 members (members of a group share one barotropic factorisation)",
             "l2": ("working set %.0f MB per GPU (two ts buffers + u + rho) exceeds the 126 MB L2" if not in_l2 else
@@ -400,6 +400,24 @@ def main():
                 "launches_per_step": (t_n + c_n) / max(nstep, 1),
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "family_ms_per_year": {k: v[0] for k, v in fam.items()}}
+    # the other kernel families of the step against the same roofline (SURVEY 8d algorithmic bytes per unit; serialised,
+    # instrumented pass: CUDA events around each family's launches)
+    LS = 9
+    nbg = e.nyear // 2
+    others = {}
+    fam_bytes = {"biogem": (n_wet * 8 * (5 * L + 4 * LS) * M, nbg, "BIOGEM / ATCHEM block: k_bg_step (+ k_tc_partial / k_tc_sum / k_tc_factors / "
+                            "k_tc_apply, k_bg_climate, k_bg_atchem1/2), N_wet x 8 x (5 L + 4 Ls) B per member-block"),
+                 "momentum": ((n_wet * (8 + 24 + 24) + 8 * (I * (J + 1)) * (I + 1 + I + 2)) * M, e.nyear,
+                              "velc + jbar + wind + barotropic solve + island: N_wet x 56 B + 8 x 1332 x 75 B of factors per member-step"),
+                 "embm": (I * J * 8 * 8 * M, 5 * e.nyear, "k_embm (tstipa + step_embm): 1296 x 8 x 8 B per member and atmosphere step")}
+    for f, (nbytes, ncall, what) in fam_bytes.items():
+        if not biogem and f == "biogem":
+            continue
+        t = fam[f][0] / max(ncall, 1)
+        if t > 0:
+            others[f] = {"bound": "hbm", "kernel": what, "algorithmic_bytes_per_call": nbytes, "avg_call_ms": t,
+                         "achieved": nbytes / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": nbytes / (t * 1e-3) / 1e9 / peak}
+    roofline["other_families"] = others
     if in_l2:   # single-member runs: the whole state (%.1f MB) lives in the 126 MB L2, so `achieved` is L2, not HBM, bandwidth
         roofline["note"] = ("working set %.1f MB is L2 resident: achieved = L2 GB/s of the tracer step (north_star: 'L2 GB/s for "
                             "single-member runs'); the step is launch / latency bound at this size, not bandwidth bound" % (working_set / 1e6))

@@ -101,6 +101,13 @@ __global__ void __launch_bounds__(32 * NW, 2) k_co_blk(const Dev v) {
   for (int l = 2 + 2 * (int)warp; l < L; l += 2 * NW) co_passive_pair<I, J, K, L, MS>(v, c_g, c2, m, in, topb, botb, rdzt, l);
 }
 
+// passive tracers of the mixed regions, one thread per (member, column, tracer): block = 32 members x (L - 2) tracers of one column
+template <int I, int J, int K, int L, int MS>
+__global__ void __launch_bounds__(32 * (L - 2)) k_co_passive(const Dev v) {
+  const unsigned m = blockIdx.x * 32 + threadIdx.x;
+  co_passive_one<I, J, K, L, MS>(v, c_g, v.rowcols[blockIdx.y], m, 2 + (int)threadIdx.y);
+}
+
 template <int I, int J, int K, int L, int MS>
 static int go(const Dev &v, cudaStream_t s, int cfg) {
   constexpr size_t smem = (size_t)ColRows<L>::rows * MS * 8 + 64;
@@ -175,7 +182,13 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   if (cov < 0) { const char *e = getenv("CG_CO_V"); cov = e ? atoi(e) : 1; }
   constexpr int NW = (L - 2 + 1) / 2 > 0 ? ((L - 2 + 1) / 2 < 8 ? (L - 2 + 1) / 2 : 8) : 1;   // one warp per passive tracer pair
   if (cov == 2 && v2.co_skip_stable && v.comask) k_co_blk<I, J, K, L, MS, NW><<<dim3(MS / 32, v.nwet), 32 * NW, 0, s>>>(v2);
-  else k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
+  else if (cov == 3 && v2.co_skip_stable && v.comask && L > 2) {
+    // decisions (thread = member x column), then the passive tracers with one thread per (member, column, tracer)
+    v2.co_pairwise = 2;
+    k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
+    k_co_passive<I, J, K, L, MS><<<dim3(MS / 32, v.nwet), dim3(32, L - 2), 0, s>>>(v2);
+    return 3;
+  } else k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
   return 2;
 }
 

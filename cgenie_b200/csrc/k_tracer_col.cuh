@@ -369,12 +369,12 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   stage_init(st);
   if (ASYNC_REL) stage_init_empty(st, 4, 2, NT / 32);
   if (ASYNC_REL) {
-    if (stage_leader(st)) {
+    if (stage_issuer<NT>(st, 1)) {
       issueC(k1c);
       if (k1c < K) issueC(k1c + 1);
       issueA(k1c);
-      issueB(k1c);
     }
+    if (stage_issuer<NT>(st, 2)) issueB(k1c);
   } else {
     if (stage_issuer<NT>(st, 0)) {
       issueC(k1c);
@@ -485,7 +485,7 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     // every warp announces that it is done with buffers C[cb] and A; the leader alone waits for all of them
     if (ASYNC_REL) {
       stage_release(st, 4);
-      if (stage_leader(st)) {
+      if (stage_issuer<NT>(st, 1)) {     // only the issuing warp waits for the others; they run on to unit B
         stage_wait(st, 4, par);
         if (kk + 2 <= K) issueC(kk + 2);
         if (!top) issueA(kk + 1);
@@ -505,7 +505,7 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 #undef CG_TRACER
     if (ASYNC_REL) {                                        // ... and with buffer B
       stage_release(st, 5);
-      if (stage_leader(st)) {
+      if (stage_issuer<NT>(st, 2)) {
         stage_wait(st, 5, par);
         if (!top) issueB(kk + 1);
       }
@@ -1349,6 +1349,48 @@ CG_HD void co_passive_regions(const Dev &v, const GridC &g, const int c2, const 
   }
 }
 
+// Part 2 as its own kernel body: ONE passive tracer of one (member, column); the region map comes from comask (bit k-1 = level
+// k lies in a mixed region, bit 16+k-1 = it is the region's top; a region's bottom is the level whose lower neighbour is outside
+// any region or the top of the next one).  All loads of the thread are independent (one trip to memory), the warps of a block
+// are the tracers of 32 members of one column, and a warp none of whose lanes has a region returns at once.  Same sums in the
+// same order as co_passive_pair; the region thickness is accumulated top-down exactly as co_decide_core does.
+template <int I, int J, int K, int L, int MS>
+CG_HD void co_passive_one(const Dev &v, const GridC &g, const int c2, const unsigned m, const int l) {
+  static_assert(K <= 16, "region map is 16 + 16 bits");
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
+  const unsigned cm = v.comask[(long)c2 * MS + m];
+  const unsigned in = cm & 0xffffu, topb = cm >> 16;
+  if (in == 0u) return;
+  double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m) + l * sL;
+  double a[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    a[k] = 0.0;
+    if ((in >> k) & 1u) a[k] = ts[(long)k * sK];
+  }
+  double acc = 0.0, dzt = 0.0;
+#pragma unroll
+  for (int k = K - 1; k >= 0; k--) {
+    if ((in >> k) & 1u) {
+      const double dz = g.dz[k + 1];
+      const bool istop = (topb >> k) & 1u;
+      const bool isbot = (k == 0) || !((in >> (k - 1)) & 1u) || ((topb >> (k - 1)) & 1u);
+      if (istop) { acc = 0.0; dzt = dz; } else dzt = dzt + dz;
+      acc += a[k] * dz;
+      if (isbot) a[k] = acc * (1.0 / dzt);
+    }
+  }
+  double cur = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if ((in >> k) & 1u) {
+      const bool isbot = (k == 0) || !((in >> (k - 1)) & 1u) || ((topb >> (k - 1)) & 1u);
+      if (isbot) cur = a[k];
+      ts[(long)k * sK] = cur;
+    }
+  }
+}
+
 // both parts by one thread (production convection kernel k_co_col; host test harness)
 template <int I, int J, int K, int L, int MS>
 CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m) {
@@ -1357,6 +1399,10 @@ CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned 
   unsigned in, topb, botb;
   double rdzt[K];
   co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt);
+  if (v.co_pairwise == 2) {   // decisions only: the region map goes to comask for k_co_passive (one thread per tracer)
+    v.comask[(long)c2 * MS + m] = in | (topb << 16);
+    return;
+  }
   if (in == 0) return;
   if (v.co_pairwise) {
     for (int l = 2; l < L; l += 2) co_passive_pair<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, l);
