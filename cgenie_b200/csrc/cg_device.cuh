@@ -99,6 +99,7 @@ struct Dev {
   unsigned *comask;          // [j][i][m] region map of the convective adjustment (k_ts_pre -> k_tstep_col passive pass):
                              // bit k-1 = level k lies in a mixed region, bit 16+k-1 = it is the region's top
   int co_prefetch;           // k_co_col: prefetch the column's passive tracers during the decisions (tuning knob)
+  int co_local;              // k_co_col: column arrays of the decision loop in local instead of shared memory (CG_CO_LOCAL=1)
   int co_pairwise;           // k_co_col: average the passive tracers pair by pair (round-1 form, CG_CO_PAIR=1) instead of region by region
   int co_skip_stable;        // k_co_col: skip (member, column)s the flux kernel flagged stable in comask (CG_CO_SKIP=0: off)
   int col_deep_first;        // k_tstep_col: blocks in wetcols order (deepest columns first) instead of row-major (CG_COL_ORDER=1)

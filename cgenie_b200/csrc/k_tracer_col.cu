@@ -61,10 +61,13 @@ __global__ void __launch_bounds__(128, MINB) k_ts_pre(const Dev v) {
 // (member, column, tracer pair)-parallel averaging kernel was measured slower: +3.8 ms per model year at 128 members.)
 template <int I, int J, int K, int L, int MS>
 __global__ void __launch_bounds__(128) k_co_col(const Dev v) {
+  // the column arrays of the decision loop (T, S, rho, box thickness) in shared memory, [level][thread]: see co_decide_core
+  extern __shared__ __align__(16) unsigned char co_smem[];
   const unsigned m = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ci = blockIdx.y * 4 + (threadIdx.x >> 5);
   if (ci >= v.nwet) return;
-  co_column<I, J, K, L, MS>(v, c_g, v.rowcols[ci], m);
+  double *scratch = v.co_local ? nullptr : reinterpret_cast<double *>(co_smem) + threadIdx.x;
+  co_column<I, J, K, L, MS>(v, c_g, v.rowcols[ci], m, scratch, 128);
 }
 
 // Block-cooperative form of the convective adjustment: one block = 32 members (lanes) of ONE wet column.  Warp 0 takes the
@@ -178,6 +181,15 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   static int copair = -1;
   if (copair < 0) { const char *e = getenv("CG_CO_PAIR"); copair = e ? atoi(e) : 0; }
   v2.co_pairwise = copair;
+  constexpr size_t co_smem_full = (size_t)4 * (K + 2) * 128 * sizeof(double);
+  static int colocal = -1;
+  if (colocal < 0) {
+    const char *e = getenv("CG_CO_LOCAL");
+    colocal = e ? atoi(e) : 0;
+    cudaFuncSetAttribute(k_co_col<I, J, K, L, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)co_smem_full);
+  }
+  v2.co_local = colocal;
+  const size_t co_smem_bytes = colocal ? 0 : co_smem_full;
   static int cov = -1;
   if (cov < 0) { const char *e = getenv("CG_CO_V"); cov = e ? atoi(e) : 1; }
   constexpr int NW = (L - 2 + 1) / 2 > 0 ? ((L - 2 + 1) / 2 < 8 ? (L - 2 + 1) / 2 : 8) : 1;   // one warp per passive tracer pair
@@ -185,10 +197,10 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   else if (cov == 3 && v2.co_skip_stable && v.comask && L > 2) {
     // decisions (thread = member x column), then the passive tracers with one thread per (member, column, tracer)
     v2.co_pairwise = 2;
-    k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
+    k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, co_smem_bytes, s>>>(v2);
     k_co_passive<I, J, K, L, MS><<<dim3(MS / 32, v.nwet), dim3(32, L - 2), 0, s>>>(v2);
     return 3;
-  } else k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
+  } else k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, co_smem_bytes, s>>>(v2);
   return 2;
 }
 

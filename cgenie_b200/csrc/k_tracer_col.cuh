@@ -1040,7 +1040,8 @@ CG_HD void tstep_column_split(const Dev &v, const GridC &g, const int c2, const 
 // passive pass (tstep_column<PV = true>) applies on write.
 template <int I, int J, int K, int L, int MS, bool ALL>
 CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsigned m, const int k1c, double *tt, double *ss,
-                          double *rl, unsigned &in, unsigned &topb, unsigned &botb, double *rdzt);
+                          double *rl, unsigned &in, unsigned &topb, unsigned &botb, double *rdzt, const int st = 1,
+                          double *dzm_ext = nullptr);
 
 template <int I, int J, int K, int L, int MS>
 CG_HD void ts_pre_column(const Dev &v, const GridC &g, const int c2, const unsigned m) {
@@ -1124,24 +1125,31 @@ CG_HD void ts_pre_column(const Dev &v, const GridC &g, const int c2, const unsig
 // (at its bottom level).  in == 0: nothing mixed.
 template <int I, int J, int K, int L, int MS, bool ALL>
 CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsigned m, const int k1c, double *tt, double *ss,
-                          double *rl, unsigned &in, unsigned &topb, unsigned &botb, double *rdzt);
+                          double *rl, unsigned &in, unsigned &topb, unsigned &botb, double *rdzt, const int st,
+                          double *dzm_ext);
 
+// scratch (device): four arrays of (K + 2) x st doubles, [level][thread], this thread's column at offset tid; nullptr: local arrays
 template <int I, int J, int K, int L, int MS>
 CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned m, unsigned &in, unsigned &topb, unsigned &botb,
-                     double *rdzt) {
+                     double *rdzt, double *scratch = nullptr, const int st_ = 1) {
   constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC, rK = (long)I * J * MS;
   const int k1c = (int)v.k1[(c2 % I + 1) + (I + 2) * (c2 / I + 1)];
   const double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);         // level-1 cell of this column
   const double *__restrict__ rho = v.rho + ((long)c2 * MS + m);
-  double tt[K + 2], ss[K + 2], rl[K + 2];
+  double tt_loc[K + 2], ss_loc[K + 2], rl_loc[K + 2];
+  const int st = scratch ? st_ : 1;
+  double *const tt = scratch ? scratch : tt_loc, *const ss = scratch ? scratch + (K + 2) * st : ss_loc,
+               *const rl = scratch ? scratch + 2 * (K + 2) * st : rl_loc;
+  double *const dzm = scratch ? scratch + 3 * (K + 2) * st : nullptr;
 #pragma unroll
   for (int q = 1; q <= K; q++) {
-    tt[q] = 0.0; ss[q] = 0.0; rl[q] = 0.0;
+    double t_ = 0.0, s_ = 0.0, r_ = 0.0;
     if (q >= k1c) {
-      tt[q] = ts[(long)(q - 1) * sK];
-      ss[q] = ts[(long)(q - 1) * sK + sL];
-      rl[q] = rho[(long)(q - 1) * rK];
+      t_ = ts[(long)(q - 1) * sK];
+      s_ = ts[(long)(q - 1) * sK + sL];
+      r_ = rho[(long)(q - 1) * rK];
     }
+    tt[q * st] = t_; ss[q * st] = s_; rl[q * st] = r_;
   }
 #ifdef __CUDA_ARCH__
   // the decisions below are a serial, memory-idle stretch: start pulling the column's passive tracers (written by the
@@ -1153,14 +1161,21 @@ CG_HD void co_decide(const Dev &v, const GridC &g, const int c2, const unsigned 
     }
   }
 #endif
-  co_decide_core<I, J, K, L, MS, false>(v, g, c2, m, k1c, tt, ss, rl, in, topb, botb, rdzt);
+  co_decide_core<I, J, K, L, MS, false>(v, g, c2, m, k1c, tt, ss, rl, in, topb, botb, rdzt, st, dzm);
 }
 
 // The decisions proper, on the column's new T, S, rho held in tt, ss, rl[1..K] (thread-private).  ALL = false: T, S, rho
 // of the mixed levels are rewritten in place (they are in memory already); ALL = true: every wet level is written.
 template <int I, int J, int K, int L, int MS, bool ALL>
-CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsigned m, const int k1c, double *tt, double *ss,
-                          double *rl, unsigned &in, unsigned &topb, unsigned &botb, double *rdzt) {
+CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsigned m, const int k1c, double *tt_, double *ss_,
+                          double *rl_, unsigned &in, unsigned &topb, unsigned &botb, double *rdzt, const int st, double *dzm_ext) {
+  // Element k of the column arrays lives at base[k * st]: st = 1 for thread-private arrays (host harness, ts_pre_column);
+  // k_co_col passes shared-memory arrays laid out [level][thread] (st = block size).  The decision loop indexes them with
+  // per-lane values (cur, bl, lo ...): in local memory such an access touches up to 32 cache lines per warp once the members
+  // of a warp take different paths, in shared memory it is one conflict-free LDS (bank = thread whatever the level).
+#define tt(k) tt_[(k) * st]
+#define ss(k) ss_[(k) * st]
+#define rl(k) rl_[(k) * st]
   constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC, rK = (long)I * J * MS;
   in = 0; topb = 0; botb = 0;
   const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
@@ -1170,10 +1185,13 @@ CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsi
   // it down after every merge; here the same set is a bit mask (bit l-1 = level l is a separate box), the neighbours of
   // a level come from clz / ffs, and a merge clears bits -- the sequence of comparisons and merges is the reference's.
   int head[K + 2];
-  double dzm[K + 2];
+  double dzm_loc[K + 2];
+  double *const dzm_ = dzm_ext ? dzm_ext : dzm_loc;
+  const int sd = dzm_ext ? st : 1;
+#define dzm(k) dzm_[(k) * sd]
 #pragma unroll
-  for (int q = 1; q <= K; q++) { head[q] = q; dzm[q] = g.dz[q]; }
-  rl[0] = 0.0;
+  for (int q = 1; q <= K; q++) { head[q] = q; dzm(q) = g.dz[q]; }
+  rl(0) = 0.0;
   unsigned act = (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)) & ~((1u << (k1c - 1)) - 1u);   // levels k1c..K
 #define CG_BELOW(x) ({ const unsigned mb_ = act & ((1u << ((x) - 1)) - 1u); mb_ ? 32 - CG_CLZ(mb_) : 0; })
 #define CG_ABOVE(x) ({ const unsigned ma_ = act >> (x); (x) + CG_FFS(ma_); })
@@ -1182,7 +1200,7 @@ CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsi
   for (;;) {
     const int bl = CG_BELOW(cur);
     if (!(bl > 0 || (lastmix != 0 && cur != K))) break;
-    if (bl == 0 || rl[cur] < rl[bl]) {
+    if (bl == 0 || rl(cur) < rl(bl)) {
       if (lastmix == 0 || cur == K) cur = bl; else cur = CG_ABOVE(cur);
       lastmix = 0;
     } else {
@@ -1192,37 +1210,37 @@ CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsi
       int lo = bl;
       for (;;) {
         const int b2 = CG_BELOW(lo);
-        if (!(b2 > 0 && rl[lo] >= rl[b2])) break;
+        if (!(b2 > 0 && rl(lo) >= rl(b2))) break;
         lo = b2;
       }
       const int h = cur;
-      double sumT = tt[h] * dzm[h], sumS = ss[h] * dzm[h], dznew = dzm[h];
+      double sumT = tt(h) * dzm(h), sumS = ss(h) * dzm(h), dznew = dzm(h);
       for (int q = bl;; q = CG_BELOW(q)) {
-        sumT = sumT + tt[q] * dzm[q];
-        sumS = sumS + ss[q] * dzm[q];
-        dznew = dznew + dzm[q];
+        sumT = sumT + tt(q) * dzm(q);
+        sumS = sumS + ss(q) * dzm(q);
+        dznew = dznew + dzm(q);
         if (q == lo) break;
       }
-      dzm[h] = dznew;
-      tt[h] = sumT / dznew;
-      ss[h] = sumS / dznew;
-      rl[h] = ec1 * tt[h] + ec2 * ss[h] + ec3 * (tt[h] * tt[h]) + ec4 * (tt[h] * tt[h] * tt[h]);
+      dzm(h) = dznew;
+      tt(h) = sumT / dznew;
+      ss(h) = sumS / dznew;
+      rl(h) = ec1 * tt(h) + ec2 * ss(h) + ec3 * (tt(h) * tt(h)) + ec4 * (tt(h) * tt(h) * tt(h));
       act &= ~(((1u << bl) - 1u) & ~((1u << (lo - 1)) - 1u));   // levels lo..bl are now part of box h
     }
   }
   // SST / SSS as exported by step_goldstein (:428-431)
   if (v.sst) {
-    v.sst[(long)c2 * MS + m] = tt[K];
-    v.sst[((long)(I * J) + c2) * MS + m] = ss[K];
+    v.sst[(long)c2 * MS + m] = tt(K);
+    v.sst[((long)(I * J) + c2) * MS + m] = ss(K);
   }
   if (!any) {
     if (ALL) {
 #pragma unroll
       for (int k = 1; k <= K; k++)
         if (k >= k1c) {
-          ts[(long)(k - 1) * sK] = tt[k];
-          ts[(long)(k - 1) * sK + sL] = ss[k];
-          rho[(long)(k - 1) * rK] = rl[k];
+          ts[(long)(k - 1) * sK] = tt(k);
+          ts[(long)(k - 1) * sK + sL] = ss(k);
+          rho[(long)(k - 1) * rK] = rl(k);
         }
     }
     return;
@@ -1261,17 +1279,21 @@ CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsi
         if (istop) topb |= 1u << (k - 1);
         if (isbot) { botb |= 1u << (k - 1); rdzt[k - 1] = 1.0 / dzt; }
         // T, S, rho of the region (the reference's own values, kept at the region top)
-        ts[(long)(k - 1) * sK] = tt[hd];
-        ts[(long)(k - 1) * sK + sL] = ss[hd];
-        rho[(long)(k - 1) * rK] = rl[hd];
+        ts[(long)(k - 1) * sK] = tt(hd);
+        ts[(long)(k - 1) * sK + sL] = ss(hd);
+        rho[(long)(k - 1) * rK] = rl(hd);
       } else if (ALL && k >= k1c) {
-        ts[(long)(k - 1) * sK] = tt[k];
-        ts[(long)(k - 1) * sK + sL] = ss[k];
-        rho[(long)(k - 1) * rK] = rl[k];
+        ts[(long)(k - 1) * sK] = tt(k);
+        ts[(long)(k - 1) * sK + sL] = ss(k);
+        rho[(long)(k - 1) * rK] = rl(k);
       }
     }
   }
 }
+#undef tt
+#undef ss
+#undef rl
+#undef dzm
 
 // Part 2: one pair (l, l+1) of passive tracers of one (member, column): thickness-weighted mean over every mixed region,
 // summed top-down; all loads of the pair are independent.
@@ -1393,12 +1415,12 @@ CG_HD void co_passive_one(const Dev &v, const GridC &g, const int c2, const unsi
 
 // both parts by one thread (production convection kernel k_co_col; host test harness)
 template <int I, int J, int K, int L, int MS>
-CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m) {
+CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m, double *scratch = nullptr, const int st = 1) {
   // the flux kernel found every level of this (member, column) stable: nothing to adjust, SST / SSS are exported already
   if (v.co_skip_stable && v.comask && v.comask[(long)c2 * MS + m] == 0u) return;
   unsigned in, topb, botb;
   double rdzt[K];
-  co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt);
+  co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, scratch, st);
   if (v.co_pairwise == 2) {   // decisions only: the region map goes to comask for k_co_passive (one thread per tracer)
     v.comask[(long)c2 * MS + m] = in | (topb << 16);
     return;

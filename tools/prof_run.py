@@ -19,10 +19,15 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--variant", default="fast")
 ap.add_argument("--config", default="eb_go_gs_ac_bg_36x36x16")
 ap.add_argument("--profile", action="store_true", help="print CUDA-event time per kernel family")
+ap.add_argument("--perturb", action="store_true", help="the bench's parameter-perturbed ensemble instead of identical members")
 a = ap.parse_args()
 d = tempfile.mkdtemp()
 materialise(d, a.config)
-e = Ensemble(d, n_members=a.members)
+pert = None
+if a.perturb:
+    from cgenie_b200.sharding import perturbation_table
+    pert = perturbation_table(a.members, biogem="ac_bg" in a.config)
+e = Ensemble(d, n_members=a.members, perturb=pert)
 e.set_tracer_variant(a.variant)
 e.set_graphs(False)
 L, I, J, K = e.maxl, e.maxi, e.maxj, e.maxk
