@@ -694,6 +694,7 @@ static int build_device(cg_handle *h) {
     TRY(dalloc(h, &b.seaice, ij * MS));
     TRY(dalloc(h, &b.seaice_stage, ij * MS));
     TRY(dalloc(h, &b.tq_stage, 2 * ij * MS));
+    if (!getenv("CG_ATCHEM_FUSED")) TRY(dalloc(h, &b.atm_tot, (size_t)LA * MS));
     TRY(dalloc(h, &b.sfxsumatm, ij * LA * MS));
     TRY(dalloc(h, &b.sfcocn1, ij * L * MS));
     TRY(dalloc(h, &b.sfxsed1, ij * LS * MS));

@@ -1073,6 +1073,10 @@ __global__ void __launch_bounds__(32 * kSumWarps) k_bg_atchem2(const Dev v, cons
   const double tot = ordered_sum_block(scratch + (size_t)(la - 3) * ij * MS + m0, (size_t)MS, ij, tile);
   if (warp == 0) tot_s[lane] = tot;
   __syncthreads();
+  if (b.atm_tot) {   // the homogenised field is written by k_bg_atchem3 (one thread per element instead of 162 cells per warp)
+    if (warp == 0) b.atm_tot[(size_t)(la - 1) * MS + m0 + lane] = tot;
+    return;
+  }
   const double t = tot_s[lane];
   double *__restrict__ atm = b.atm + (size_t)(la - 1) * ij * MS + m0 + lane;
   const double *__restrict__ atmT = b.atm + m0 + lane;
@@ -1085,6 +1089,21 @@ __global__ void __launch_bounds__(32 * kSumWarps) k_bg_atchem2(const Dev v, cons
     sfc[(size_t)c * MS] = a;
     sfx[(size_t)c * MS] = 0.0;
   }
+}
+// atchem.f90:146-150 + cpl_comp_atmocn (:252-264): the homogenised partial pressure of every cell from the member's total
+__global__ void __launch_bounds__(256) k_bg_atchem3(const Dev v, const BgDev b, const double atm_totV) {
+  using namespace bgk;
+  const int MS = v.MS, ij = v.I * v.J;
+  const int m = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.y * blockDim.y + threadIdx.y;
+  const int la = 3 + blockIdx.z;
+  if (c >= ij) return;
+  const double t = b.atm_tot[(size_t)(la - 1) * MS + m];
+  const size_t q = ((size_t)(la - 1) * ij + c) * MS + m;
+  const double a = (t / atm_totV) * kPaAtm * kRSI * b.atm[(size_t)c * MS + m];
+  b.atm[q] = a;
+  b.sfcatm1[q] = a;
+  b.sfxsumatm[q] = 0.0;
 }
 
 static bool bg_fix_shape(const Dev &v) { return v.I == 36 && v.J == 36 && v.K == 16 && v.MS == 128 && !getenv("CG_BG_NOFIX"); }
@@ -1177,9 +1196,10 @@ int launch_bg_atchem(const Dev &v, const BgDev &b, double atm_totV, cudaStream_t
   const int ij = v.I * v.J;
   k_bg_atchem1<<<dim3(v.MS / 32, (ij + 7) / 8, b.LA - 2), dim3(32, 8), 0, s>>>(v, b, v.bg_part);
   k_bg_atchem2<<<dim3(v.MS / 32, b.LA - 2), 32 * kSumWarps, 0, s>>>(v, b, atm_totV, v.bg_part);
+  if (b.atm_tot) k_bg_atchem3<<<dim3(v.MS / 32, (ij + 7) / 8, b.LA - 2), dim3(32, 8), 0, s>>>(v, b, atm_totV);
   const size_t n = (size_t)2 * ij * v.MS;
   k_bg_cpl_comp_embm<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v, b);
-  return 3;
+  return b.atm_tot ? 4 : 3;
 }
 
 int launch_tracercoupling(const Dev &v, cudaStream_t s) {
