@@ -11,6 +11,9 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges per entry point (the reference brackets the same calls with ITT tasks,
+                               // src/genie.f90:13-15, 118-121 under INTEL_PROFILE; src/utils/itt_profile.f90)
+
 #include "../../include/cgenie_b200.h"
 #include "cg_device.cuh"
 #include "cg_host.hpp"
@@ -1355,6 +1358,12 @@ static int check_async(cg_handle *h) {
   (void)h;
   return CG_OK;
 }
+// one NVTX range per C-ABI entry point (visible in Nsight Systems / Compute timelines; a no-op without a tool attached)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define CG_RANGE() NvtxRange nvtx_range_(__func__)
 #define READY(h) do { if (!(h) || !(h)->initialised) return fail(CG_ERR_STATE, "handle not initialised"); if ((h)->tracer_only) return fail(CG_ERR_STATE, "tracer-only handle"); activate(h); } while (0)
 
 static int put(cg_handle *h, const char *name, const double *src) {
@@ -1368,6 +1377,7 @@ static int get(cg_handle *h, const char *name, double *dst) {
 static bool lazy_ok(const cg_handle *h);
 static int lazy_cycle(cg_handle *h);
 extern "C" int cg_surflux_step(cg_handle *h, int istep, const cg_surflux_io *io) {
+  CG_RANGE();
   READY(h);
   if (h->lazy_stage) IO(flush_lazy(h));   // out of pattern: replay what was noted
   if (istep != h->istep_ocn + 1) {  // the host owns the step counter; keep the device copy in line
@@ -1405,6 +1415,7 @@ extern "C" int cg_surflux_step(cg_handle *h, int istep, const cg_surflux_io *io)
 }
 
 extern "C" int cg_embm_step(cg_handle *h, int istep, const cg_embm_io *io) {
+  CG_RANGE();
   READY(h);
   (void)istep;
   if (!io && h->lazy_stage >= 1 && h->lazy_stage <= h->base.kocn_loop) { h->lazy_stage++; return CG_OK; }
@@ -1423,6 +1434,7 @@ extern "C" int cg_embm_step(cg_handle *h, int istep, const cg_embm_io *io) {
 }
 
 extern "C" int cg_seaice_step(cg_handle *h, int istep, const cg_seaice_io *io) {
+  CG_RANGE();
   READY(h);
   (void)istep;
   if (!io && h->lazy_stage == h->base.kocn_loop + 1) { h->lazy_stage++; return CG_OK; }
@@ -1445,6 +1457,7 @@ extern "C" int cg_seaice_step(cg_handle *h, int istep, const cg_seaice_io *io) {
 }
 
 extern "C" int cg_goldstein_step(cg_handle *h, int istep, const cg_goldstein_io *io) {
+  CG_RANGE();
   READY(h);
   (void)istep;
   if (!io && h->lazy_stage == h->base.kocn_loop + 2 && lazy_ok(h)) return lazy_cycle(h);
@@ -1513,6 +1526,7 @@ static long long nint_ll(double x) { return (long long)(x >= 0 ? std::floor(x + 
 
 // biogem_forcing(genie_clock), biogem.f90:2083-2127: time-interpolated restoring targets (host scalars, bit-exact)
 extern "C" int cg_biogem_forcing(cg_handle *h, int64_t genie_clock_ms) {
+  CG_RANGE();
   BGREADY(h);
   bg_forcing(&h->bg, (long long)genie_clock_ms, &h->bgd);
   return CG_OK;
@@ -1520,6 +1534,7 @@ extern "C" int cg_biogem_forcing(cg_handle *h, int64_t genie_clock_ms) {
 // step_biogem(dts, genie_clock, ...), biogem.f90:528-547.  The interface arrays stay on the device
 // ("sfcocn1", "sfxsed1", "sfxsumatm", "focnatm" fields); cpl_flux_ocnatm (atchem.f90:306-320) is fused into the kernel.
 extern "C" int cg_biogem_step(cg_handle *h, double dts, int64_t genie_clock_ms) {
+  CG_RANGE();
   BGREADY(h);
   if (dts != h->bgd.dts) return fail(CG_ERR_ARG, "cg_biogem_step: dts differs from conv_kocn_kbiogem*kocn_loop*genie_timestep");
   const double t = h->bg.t_runtime - (double)genie_clock_ms / (1000.0 * kBgYrS);
@@ -1557,6 +1572,7 @@ static int side_wait(cg_handle *h) {
 // ocn_ben(L), ocnatm(LA)] when a window closes; cg_biogem_sig_reset = sub_init_int_timeseries (biogem_data.f90:964-1007).
 // ben_Dmin = par_data_save_ben_Dmin (benthic mask: bottom cells whose floor lies deeper).
 extern "C" int cg_biogem_sig_update(cg_handle *h, double dts, double ben_Dmin) {
+  CG_RANGE();
   BGREADY(h);
   const Grid &g = h->g;
   const int I = g.I, J = g.J, K = g.K;
@@ -1594,6 +1610,7 @@ extern "C" int cg_biogem_sig_reset(cg_handle *h) {
 }
 // cpl_flux_ocnsed(dts, ...), sedgem.f90:1029-1068: sfxsumsed = sfxsumsed + dts * sfxsed1 (sediment grid = ocean grid)
 extern "C" int cg_cpl_flux_ocnsed(cg_handle *h, double dts) {
+  CG_RANGE();
   BGREADY(h);
   BgAsyncScope as(h, true);
   IO(side_wait(h));
@@ -1604,6 +1621,7 @@ extern "C" int cg_cpl_flux_ocnsed(cg_handle *h, double dts) {
 // cpl_comp_ocnsed(ocnstep, mbiogem, msedgem, ...), sedgem.f90:894-937: running mean of the bottom-water composition over
 // the BIOGEM steps of one SEDGEM step; ocnstep = koverall / kocn_loop (genie_loop_wrappers.f90:219-226)
 extern "C" int cg_cpl_comp_ocnsed(cg_handle *h, int ocnstep, int mbiogem, int msedgem) {
+  CG_RANGE();
   BGREADY(h);
   if (mbiogem <= 0 || msedgem <= 0) return fail(CG_ERR_ARG, "cg_cpl_comp_ocnsed: conv_kocn_kbiogem and conv_kocn_ksedgem must be positive");
   const int w = ((ocnstep - mbiogem) % msedgem) / mbiogem;     // Fortran MOD and C % both truncate towards zero
@@ -1623,6 +1641,7 @@ extern "C" int cg_reinit_flux_rokocn(cg_handle *h) {
 }
 // biogem_tracercoupling(go_ts, go_ts1), biogem.f90:1885-1890.  Host arrays are optional (NULL = resident).
 extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_ts1) {
+  CG_RANGE();
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
   if (h->g.L <= 2 || !h->dv.bg_ocn) return fail(CG_ERR_CONFIG, "tracer coupling needs biogeochemical tracers (maxl > 2)");
   activate(h);
@@ -1648,6 +1667,7 @@ extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_
 // biogem_climate, biogem.f90:2132-2239: the physics it copies (u, rho, sea ice, winds, cost, MLD) is aliased
 // in place on the device; the only state change on this path is the reset of the convection counter (:2238).
 extern "C" int cg_biogem_climate(cg_handle *h) {
+  CG_RANGE();
   if (!h || !h->initialised) return fail(CG_ERR_STATE, "handle not initialised");
   activate(h);
   if (h->lazy_stage) IO(flush_lazy(h));
@@ -1690,6 +1710,7 @@ extern "C" int cg_biogem_init_ocn(cg_handle *h) {
 }
 // step_atchem(dts, sfxsumatm, sfcatm), atchem.f90:63-67, with cpl_comp_atmocn (:252-264) fused
 extern "C" int cg_atchem_step(cg_handle *h, double dts) {
+  CG_RANGE();
   BGREADY(h);
   if (dts != h->bgd.dts_atchem) return fail(CG_ERR_ARG, "cg_atchem_step: dts differs from conv_kocn_katchem*kocn_loop*genie_timestep");
   // an ATCHEM step that does not follow this iteration's biogem_climate call (conv_kocn_katchem /= conv_kocn_kbiogem, or
@@ -1991,6 +2012,7 @@ static int lazy_cycle(cg_handle *h) {   // step_goldstein closing a fully noted 
 }
 
 extern "C" int cg_run(cg_handle *h, int64_t n) {
+  CG_RANGE();
   READY(h);
   IO0(join_side(h));
   h->spec_valid = false;
