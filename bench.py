@@ -300,7 +300,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--variant", default="col", choices=["col", "fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=0, help="end-to-end leg: member groups per GPU (0 = 2 for >= 64 members, else 1)")
+    ap.add_argument("--e2e-groups", type=int, default=0, help="end-to-end leg: member groups per GPU (default 1)")
+    ap.add_argument("--e2e-dense", action="store_true", help="end-to-end leg: ship ts dense (all cells) instead of the wet cells only")
     ap.add_argument("--spinup-years", type=int, default=None,
                     help="untimed model years from the uniform initial state before the warm-up (config #2's 100-year spin-up: "
                          "the convective adjustment is data dependent, 70 %% of all cells mix in a 4-year-old ocean; ~7 s)")
@@ -429,7 +430,9 @@ def main():
     # of module calls the Fortran host makes, and downloads the state again.  With G = 2 one group's copies cross PCIe (both
     # directions) while the other group computes; with G = 1 (--e2e-groups 1, the round-1 form) copies and compute alternate.
     nyear_, variant_active, member_stride = e.nyear, e.tracer_variant_active(), e.member_stride
-    G = args.e2e_groups if args.e2e_groups else (2 if (M >= 64 and M % 64 == 0) else 1)
+    # measured (profiles/README_r2.md): two groups are no faster at N = 1 (5.72 vs 5.81 M) nor at N = 8 (35.2 vs 36.0 M), so one
+    # group is the default and the exchange moves fewer bytes instead (wet cells only)
+    G = args.e2e_groups if args.e2e_groups else 1
     genie_timestep = 3600.0 * 24.0 * 365.25 / 5.0 / nyear_
     clock_tick = int(round(1000.0 * genie_timestep))
     dts_bg = float(2 * 5) * genie_timestep
@@ -463,12 +466,13 @@ def main():
         in_threads(lambda q: (parts[q].run(kyear * (args.spinup_years + 1)), parts[q].synchronize()))
     pins, k0 = [], []
     for p_ in parts:
+        size = {n: ((p_.wet_size(n) if (n == "ts" and not args.e2e_dense) else p_.field_size(n)) * p_.member_stride) for n in ("ts", "tq", "varice")}
         try:
-            pin = {n: torch.empty(p_.field_size(n) * p_.member_stride, dtype=torch.float64).pin_memory().numpy() for n in ("ts", "tq", "varice")}
+            pin = {n: torch.empty(size[n], dtype=torch.float64).pin_memory().numpy() for n in size}
         except Exception:
-            pin = {n: np.empty(p_.field_size(n) * p_.member_stride) for n in ("ts", "tq", "varice")}
+            pin = {n: np.empty(size[n]) for n in size}
         for n in pin:
-            p_.get_all(n, out=pin[n])
+            (p_.get_all_wet if (n == "ts" and not args.e2e_dense) else p_.get_all)(n, out=pin[n])
         pins.append(pin)
         k0.append(((args.spinup_years + args.warmup + args.steps + 1) if G == 1 else (args.spinup_years + 1)) * kyear)
     h2d = sum(a.nbytes for pin in pins for a in pin.values())
@@ -477,7 +481,7 @@ def main():
     def e2e_year(q):
         p_, pin = parts[q], pins[q]
         for n in pin:
-            p_.put_all(n, pin[n])
+            (p_.put_all_wet if (n == "ts" and not args.e2e_dense) else p_.put_all)(n, pin[n])
         p_.put_all("varice1", pin["varice"])
         p_.put_all("tq1", pin["tq"])
         for k in range(1, kyear + 1):
@@ -496,7 +500,7 @@ def main():
                 p_.atchem_step(dts_bg)
         k0[q] += kyear
         for n in pin:
-            p_.get_all(n, out=pin[n])
+            (p_.get_all_wet if (n == "ts" and not args.e2e_dense) else p_.get_all)(n, out=pin[n])
 
     in_threads(e2e_year)
     barrier()
@@ -519,7 +523,8 @@ def main():
                 "path": "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein/biogem_*/atchem), state in/out of pinned host "
                         "per year; the GPU's members run as %d group(s) of %d (one library handle + host thread each), so one group's copies "
                         "overlap the other's compute" % (G, M // G) if G > 1 else
-                        "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein/biogem_*/atchem), state in/out of pinned host per year"},
+                        "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein/biogem_*/atchem), state in/out of pinned host per "
+                        "year (ts: %s)" % ("all cells" if args.e2e_dense else "wet cells only, packed on the device")},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 4:   # the CPU arm is timed next to the N=1 line only
         cores = os.cpu_count() or 1

@@ -68,6 +68,9 @@ SYMBOLS = {
     "cg_sync_from_host": (C.c_int, [P, C.c_char_p, C.c_int, D, C.c_int64]),
     "cg_sync_all_to_host": (C.c_int, [P, C.c_char_p, D, C.c_int64]),
     "cg_sync_all_from_host": (C.c_int, [P, C.c_char_p, D, C.c_int64]),
+    "cg_wet_size": (C.c_int64, [P, C.c_char_p]),
+    "cg_sync_all_wet_to_host": (C.c_int, [P, C.c_char_p, D, C.c_int64]),
+    "cg_sync_all_wet_from_host": (C.c_int, [P, C.c_char_p, D, C.c_int64]),
     "cg_const_size": (C.c_int64, [P, C.c_char_p]),
     "cg_get_const": (C.c_int, [P, C.c_char_p, C.c_int, D, C.c_int64]),
     "cg_get_iconst": (C.c_int, [P, C.c_char_p, C.POINTER(C.c_int32), C.c_int64]),

@@ -157,6 +157,10 @@ struct cg_handle {
   std::map<std::string, std::vector<int>> hiconst;
   double *stage = nullptr;
   size_t stage_n = 0;
+  int *d_wet3 = nullptr;                          // wet cells in ascending cell order (cg_sync_all_wet_*)
+  int n_wet3 = 0;
+  double *wet_stage = nullptr;
+  size_t wet_stage_n = 0;
   double *d_meantemp = nullptr, *d_means = nullptr;
   double *d_bf = nullptr, *d_bb = nullptr, *d_rd = nullptr;  // pivot-major barotropic factors (fast solve)
   double *d_bk = nullptr;                                    // block slabs of the blocked solve (k_baro_blk)
@@ -196,6 +200,7 @@ struct cg_handle {
     for (auto &gv : graph) for (auto &ge : gv) if (ge) cudaGraphExecDestroy(ge);
     for (auto &gv : graph2) for (auto &ge : gv) if (ge) cudaGraphExecDestroy(ge);
     for (void *p : allocs) cudaFree(p);
+    if (wet_stage) cudaFree(wet_stage);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (evFork) cudaEventDestroy(evFork);
@@ -1171,6 +1176,95 @@ extern "C" int cg_sync_all_from_host(cg_handle *h, const char *name, const doubl
   CUDA_OK(cudaMemcpyAsync(f->d, src, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
   if (strcmp(name, "ts") == 0)   // the ping-pong partner's dry cells stay in line: device copy, the host data crosses PCIe once
     CUDA_OK(cudaMemcpyAsync(h->dv.ts_new, f->d, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+
+// ---- wet-cell packed exchange of 3-D ocean fields
+namespace cg {
+// one block per (wet cell, inner index): MS contiguous doubles each way
+__global__ void k_wet_pack(const double *__restrict__ field, double *__restrict__ packed, const int *__restrict__ wet, const int inner,
+                           const int MS, const int to_packed, double *__restrict__ field2) {
+  const size_t w = blockIdx.x;
+  const int q = blockIdx.y;
+  const size_t a = ((size_t)wet[w] * inner + q) * MS, b = (w * inner + q) * MS;
+  for (int m = threadIdx.x; m < MS; m += blockDim.x) {
+    if (to_packed) packed[b + m] = field[a + m];
+    else {
+      const double x = packed[b + m];
+      const_cast<double *>(field)[a + m] = x;
+      if (field2) field2[a + m] = x;
+    }
+  }
+}
+}  // namespace cg
+static int wet_setup(cg_handle *h, const char *name, FieldDesc **fo, int *inner) {
+  if (!h || !name || !h->initialised) return fail(CG_ERR_ARG, "wet exchange: bad argument");
+  FieldDesc *f = find_field(h, name);
+  if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name);
+  const int I = h->g.I, J = h->g.J, K = h->g.K;
+  const int o = f->nd - 3;
+  if (o < 0 || o > 1 || f->dims[o] != I || f->dims[o + 1] != J || f->dims[o + 2] != K)
+    return fail(CG_ERR_ARG, std::string(name) + " is not a 3-D ocean field");
+  const int in = o ? f->dims[0] : 1;
+  if ((o && f->strides[0] != 1) || f->strides[o] != in || f->strides[o + 1] != (long long)in * I || f->strides[o + 2] != (long long)in * I * J)
+    return fail(CG_ERR_ARG, std::string(name) + " is not stored cell-major");
+  if (!h->d_wet3) {
+    std::vector<int> wet;
+    for (int k = 1; k <= K; k++)
+      for (int j = 1; j <= J; j++)
+        for (int i = 1; i <= I; i++)
+          if (k >= h->g.k1at(i, j)) wet.push_back((int)cell3(I, J, i, j, k));
+    h->n_wet3 = (int)wet.size();
+    if (wet.empty()) wet.push_back(0);
+    int rc = dupload(h, &h->d_wet3, wet);
+    if (rc) return rc;
+  }
+  *fo = f;
+  *inner = in;
+  return CG_OK;
+}
+extern "C" int64_t cg_wet_size(cg_handle *h, const char *name) {
+  FieldDesc *f; int in;
+  if (wet_setup(h, name, &f, &in)) return -1;
+  return (int64_t)h->n_wet3 * in;
+}
+static int wet_stage(cg_handle *h, size_t n) {
+  if (h->wet_stage_n >= n) return CG_OK;
+  if (h->wet_stage) cudaFree(h->wet_stage);
+  h->wet_stage = nullptr; h->wet_stage_n = 0;
+  CUDA_OK(cudaMalloc(&h->wet_stage, n * sizeof(double)));
+  h->wet_stage_n = n;
+  return CG_OK;
+}
+extern "C" int cg_sync_all_wet_to_host(cg_handle *h, const char *name, double *dst, int64_t n) {
+  FieldDesc *f; int in;
+  if (!dst) return fail(CG_ERR_ARG, "cg_sync_all_wet_to_host: bad argument");
+  IO0(wet_setup(h, name, &f, &in));
+  if (n != (int64_t)h->n_wet3 * in * h->MS) return fail(CG_ERR_ARG, "cg_sync_all_wet_to_host: size must be cg_wet_size * member_stride");
+  IO0(join_side(h));
+  activate(h);
+  IO0(wet_stage(h, (size_t)n));
+  if (h->n_wet3 > 0) k_wet_pack<<<dim3(h->n_wet3, in), 128, 0, h->stream>>>(f->d, h->wet_stage, h->d_wet3, in, h->MS, 1, nullptr);
+  CUDA_OK(cudaMemcpyAsync(dst, h->wet_stage, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+extern "C" int cg_sync_all_wet_from_host(cg_handle *h, const char *name, const double *src, int64_t n) {
+  FieldDesc *f; int in;
+  if (!src) return fail(CG_ERR_ARG, "cg_sync_all_wet_from_host: bad argument");
+  IO0(wet_setup(h, name, &f, &in));
+  if (n != (int64_t)h->n_wet3 * in * h->MS) return fail(CG_ERR_ARG, "cg_sync_all_wet_from_host: size must be cg_wet_size * member_stride");
+  IO0(join_side(h));
+  if (momentum_input(name)) IO0(drop_momentum(h));
+  h->spec_valid = false;
+  h->tc_spec_valid = false;
+  activate(h);
+  IO0(wet_stage(h, (size_t)n));
+  CUDA_OK(cudaMemcpyAsync(h->wet_stage, src, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  // ts and ts1 are one field on the device: both ping-pong buffers take the wet cells
+  double *second = strcmp(name, "ts") == 0 ? h->dv.ts_new : nullptr;
+  if (h->n_wet3 > 0) k_wet_pack<<<dim3(h->n_wet3, in), 128, 0, h->stream>>>(f->d, h->wet_stage, h->d_wet3, in, h->MS, 0, second);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return CG_OK;
 }

@@ -76,6 +76,25 @@ class _Base:
         a = np.ascontiguousarray(values, dtype=np.float64).ravel()
         self._ck(self.L.cg_sync_all_from_host(self.h, name.encode(), _dp(a), a.size))
 
+    def wet_size(self, name):
+        """doubles per member of a 3-D ocean field in the wet-cell packed exchange layout"""
+        n = self.L.cg_wet_size(self.h, name.encode())
+        if n < 0:
+            raise CgenieError(1, self.L.cg_last_error().decode())
+        return n
+
+    def get_all_wet(self, name, out=None):
+        """All members of a 3-D ocean field, wet cells only: [wet cell][inner][member_stride] (cg_sync_all_wet_to_host)."""
+        n = self.wet_size(name) * self.member_stride
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        self._ck(self.L.cg_sync_all_wet_to_host(self.h, name.encode(), _dp(out), n))
+        return out
+
+    def put_all_wet(self, name, values):
+        a = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        self._ck(self.L.cg_sync_all_wet_from_host(self.h, name.encode(), _dp(a), a.size))
+
     def const(self, name):
         n = self.L.cg_const_size(self.h, name.encode())
         if n < 0:

@@ -176,6 +176,14 @@ int cg_sync_from_host(cg_handle *, const char *name, int member, const double *s
 /* All members at once, device-native layout [..][member]; pinned-host friendly. */
 int cg_sync_all_to_host(cg_handle *, const char *name, double *dst, int64_t n);
 int cg_sync_all_from_host(cg_handle *, const char *name, const double *src, int64_t n);
+/* The same for 3-D ocean fields ("ts", "u", "rho", "ocn", "bio_part" ...) with the WET cells only, packed on the device:
+ * layout [wet cell][inner][member], wet cells in ascending cell order (k, j, i), inner = the field's leading dimension
+ * (tracers of ts, components of u; 1 for rho).  worjh2: 12 511 of 20 736 cells are wet, so a state exchange moves 60 % of the
+ * bytes.  cg_wet_size = doubles per member (n_wet * inner); n = cg_wet_size * member_stride.  Dry cells are left untouched
+ * by the upload.                                                                                                        */
+int64_t cg_wet_size(cg_handle *, const char *name);
+int cg_sync_all_wet_to_host(cg_handle *, const char *name, double *dst, int64_t n);
+int cg_sync_all_wet_from_host(cg_handle *, const char *name, const double *src, int64_t n);
 
 /* Host-side constants as built by cg_initialise (bit-exactness checks):
  * "dz","dza","s","c","sv","cv","ds","dsv","rc","rc2","cv2","rds","rdsv","zro","zw","ssmax",
