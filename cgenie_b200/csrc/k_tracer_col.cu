@@ -36,6 +36,20 @@ __global__ void __launch_bounds__(MS, MINB) k_tstep_col2(const Dev v) {
   tstep_column2<I, J, K, L, MS, MS>(v, c_g, c2, threadIdx.x, st);
 }
 
+// warp-tile form: one block = one warp = 32 members of one column; consecutive blocks are the MS / 32 tiles of a column
+template <int I, int J, int K, int L, int MS>
+__global__ void __launch_bounds__(32, 8) k_tstep_colw(const Dev v) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NTILE = MS / 32;
+  ColStage st;
+  st.sm = reinterpret_cast<double *>(smem_raw);
+  st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows<L>::rows * 32 * 8);
+  st.tid = threadIdx.x;
+  const int c2 = v.rowcols[blockIdx.x / NTILE];
+  const unsigned m = (blockIdx.x % NTILE) * 32 + threadIdx.x;
+  tstep_column_w<I, J, K, L, MS>(v, c_g, c2, m, st);
+}
+
 // split form: two threads per (member, column), 2 * MS threads per block (see tstep_column_split)
 template <int I, int J, int K, int L, int MS, int MINB>
 __global__ void __launch_bounds__(2 * MS, MINB) k_tstep_split(const Dev v) {
@@ -158,6 +172,10 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
     }
     if (split == 2) k_tstep_split<I, J, K, L, MS, 1><<<v.nwet, 2 * MS, smem2, s>>>(v);
     else k_tstep_split<I, J, K, L, MS, 2><<<v.nwet, 2 * MS, smem2, s>>>(v);
+  } else
+  if (colv == 3) {
+    constexpr size_t smemw = (size_t)ColRows<L>::rows * 32 * 8 + 64;
+    k_tstep_colw<I, J, K, L, MS><<<v.nwet * (MS / 32), 32, smemw, s>>>(v1);
   } else
   if (colv == 2) {
     constexpr size_t smem3 = (size_t)ColRows2<L>::rows * MS * 8 + 64;

@@ -561,6 +561,251 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Warp-tile form of the column kernel: one block = ONE WARP = 32 members (a 256-byte slice of every row) of one wet column.
+// The arithmetic is tstep_column's.  What changes is the staging: the block's four warps no longer meet at two block
+// barriers per level (ncu: 19 % of the stall samples sit behind them and 9 % in the waits for rows that the slowest warp
+// requested late), every warp owns its staging rows and mbarriers, re-requests a unit as soon as IT has consumed it, and
+// runs up to eight such one-warp blocks per SM drift freely against each other.  A row slice is a 256-byte bulk copy; the
+// copies of a unit are issued by ONE warp-wide instruction (lane r copies row r: cp.async.bulk is a per-thread operation), so
+// the per-level issue cost is a few instructions, not one instruction sequence per copy.
+CG_HD void stage_expect_w(const ColStage &s, const int which, const unsigned bytes) {
+#ifdef __CUDA_ARCH__
+  if (s.tid == 0) stage_expect(s, which, bytes);
+  __syncwarp();
+#else
+  (void)s; (void)which; (void)bytes;
+#endif
+}
+CG_HD void stage_syncw() {
+#ifdef __CUDA_ARCH__
+  __syncwarp();
+#endif
+}
+
+template <int I, int J, int K, int L, int MS>
+CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st) {
+  constexpr int NT = 32;
+  using R = ColRows<L>;
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
+  constexpr long uC3 = 3L * MS, uK = (long)I * J * uC3, rK = (long)I * J * MS;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+#define CGC_K1(ii, jj) ((int)v.k1[(ii) + (I + 2) * (jj)])
+  const int k1c = CGC_K1(i, j);
+  const int ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
+  const int k1e = CGC_K1(ip, j), k1w = CGC_K1(im, j), k1n = CGC_K1(i, j + 1), k1s = CGC_K1(i, j - 1);
+#undef CGC_K1
+  const ColK q = col_consts<I, J>(v, g, m, j);
+  const double ec1 = q.ec1, ec2 = q.ec2, ec3 = q.ec3, ec4 = q.ec4;
+  const long dE = (i < I) ? sC : -(long)(I - 1) * sC, dW = (i > 1) ? -sC : (long)(I - 1) * sC;
+  constexpr long dN = (long)I * sC, dS = -(long)I * sC;
+  const long dUW = (i > 1) ? -uC3 : (long)(I - 1) * uC3, dUS = (j > 1) ? -(long)I * uC3 : 0;
+  const unsigned m0 = m - (unsigned)st.tid;                       // first member of this warp's tile
+  const double *const ts0 = v.ts_cur + (long)c2 * sC + m0;       // level-1 cell, tracer 0, first member of the tile
+  const double *const u0 = v.u + (long)c2 * uC3 + m0;
+  const double *const sm = st.sm + st.tid;
+
+  // Unit C of level lev: rows 0..9 = T,S one level up of the five columns, rows 10..14 = uE, vN, ww, uW, vS.  Lane r picks
+  // the source of row r; one warp-wide copy instruction for the ten T,S rows, one for the five velocity rows.
+  auto issueC = [&](const int lev) {
+    const int b = (lev - k1c) & 1;
+    stage_expect_w(st, b, (unsigned)(R::rowsC * NT * 8));
+    const int lu = (lev < K) ? lev + 1 : K;
+    const int r = st.tid, cell = r >> 1;
+    const long dcol = (cell == 0) ? 0 : (cell == 1) ? ((lu >= k1e) ? dE : 0) : (cell == 2) ? ((lu >= k1w) ? dW : 0)
+                      : (cell == 3) ? ((lu >= k1n) ? dN : 0) : ((lu >= k1s) ? dS : 0);
+    const double *srcTS = ts0 + (long)(lu - 1) * sK + dcol + (long)(r & 1) * sL;
+    {
+#ifdef __CUDA_ARCH__
+      if (r < 10) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(st.sm + (b * R::rowsC + R::rTS + r) * 32);
+        const unsigned a = (unsigned)__cvta_generic_to_shared(st.bar) + 8u * b;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(srcTS), "r"(256u),
+                     "r"(a)
+                     : "memory");
+      }
+#else
+      for (int rr = 0; rr < 10; rr++) {
+        const int cc = rr >> 1;
+        const long dc = (cc == 0) ? 0 : (cc == 1) ? ((lu >= k1e) ? dE : 0) : (cc == 2) ? ((lu >= k1w) ? dW : 0)
+                        : (cc == 3) ? ((lu >= k1n) ? dN : 0) : ((lu >= k1s) ? dS : 0);
+        st.sm[(b * R::rowsC + R::rTS + rr) * 32 + st.tid] = ts0[(long)(lu - 1) * sK + dc + (long)(rr & 1) * sL + st.tid];
+      }
+      (void)srcTS;
+#endif
+    }
+    const double *pu = u0 + (long)(lev - 1) * uK;
+    {
+      const long du = (r < 3) ? (long)r * sL : (r == 3) ? dUW : (dUS + sL);
+#ifdef __CUDA_ARCH__
+      if (r < 5) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(st.sm + (b * R::rowsC + R::rU + r) * 32);
+        const unsigned a = (unsigned)__cvta_generic_to_shared(st.bar) + 8u * b;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(pu + du), "r"(256u),
+                     "r"(a)
+                     : "memory");
+      }
+#else
+      (void)du;
+      for (int rr = 0; rr < 5; rr++) {
+        const long d2 = (rr < 3) ? (long)rr * sL : (rr == 3) ? dUW : (dUS + sL);
+        st.sm[(b * R::rowsC + R::rU + rr) * 32 + st.tid] = pu[d2 + st.tid];
+      }
+#endif
+    }
+  };
+  // units A (tracers 2 .. lB0-1) and B (lB0 .. L-1): staged row = base + cell * n + (l - l0); lanes cover 32 rows per instruction
+  auto issueT = [&](const int which, const int base, const int l0, const int n, const int lev) {
+    stage_expect_w(st, which, (unsigned)(5 * n * NT * 8));
+    const double *c0 = ts0 + (long)(lev - 1) * sK + (long)l0 * sL;
+    for (int r0 = 0; r0 < 5 * n; r0 += 32) {
+      const int r = r0 + st.tid, cell = r / n, ll = r - cell * n;
+      const long dcol = (cell == 0) ? 0 : (cell == 1) ? ((lev >= k1e) ? dE : 0) : (cell == 2) ? ((lev >= k1w) ? dW : 0)
+                        : (cell == 3) ? ((lev >= k1n) ? dN : 0) : ((lev >= k1s) ? dS : 0);
+#ifdef __CUDA_ARCH__
+      if (r < 5 * n) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(st.sm + (base + r) * 32);
+        const unsigned a = (unsigned)__cvta_generic_to_shared(st.bar) + 8u * which;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                     "l"(c0 + dcol + (long)ll * sL), "r"(256u), "r"(a)
+                     : "memory");
+      }
+#else
+      (void)dcol; (void)ll;
+      {
+        for (int rr = r0; rr < r0 + 32 && rr < 5 * n; rr++) {
+          const int cc = rr / n, l2 = rr - cc * n;
+          const long dc = (cc == 0) ? 0 : (cc == 1) ? ((lev >= k1e) ? dE : 0) : (cc == 2) ? ((lev >= k1w) ? dW : 0)
+                          : (cc == 3) ? ((lev >= k1n) ? dN : 0) : ((lev >= k1s) ? dS : 0);
+          st.sm[(base + rr) * 32 + st.tid] = c0[dc + (long)l2 * sL + st.tid];
+        }
+      }
+#endif
+    }
+  };
+  auto issueA = [&](const int lev) { if (R::nA > 0) issueT(2, R::rA, 2, R::nA, lev); };
+  auto issueB = [&](const int lev) { issueT(3, R::rB, R::lB0, R::nB, lev); };
+
+#ifdef __CUDA_ARCH__
+  if (st.tid == 0) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(st.bar);
+    for (unsigned qb = 0; qb < 4; qb++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a + 8 * qb), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+#endif
+  issueC(k1c);
+  if (k1c < K) issueC(k1c + 1);
+  issueA(k1c);
+  issueB(k1c);
+
+  // T,S of the five columns at the bottom level (direct loads, once per column)
+  TS5 a;
+  {
+    const double *qC = ts0 + (long)(k1c - 1) * sK + st.tid;
+    const double *qE = qC + ((k1c >= k1e) ? dE : 0), *qW = qC + ((k1c >= k1w) ? dW : 0);
+    const double *qN = qC + ((k1c >= k1n) ? dN : 0), *qS = qC + ((k1c >= k1s) ? dS : 0);
+    a.tC = qC[0]; a.sC = qC[sL]; a.tE = qE[0]; a.sE = qE[sL]; a.tW = qW[0]; a.sW = qW[sL];
+    a.tN = qN[0]; a.sN = qN[sL]; a.tS = qS[0]; a.sS = qS[sL];
+  }
+  double *wP = v.ts_new + ((long)(k1c - 2) * (I * J) + c2) * sC + m;   // level kk-1 of the new array
+  double *rP = v.rho + ((long)(k1c - 2) * (I * J) + c2) * MS + m;
+  double uc = 0.0, uE = 0.0, uW = 0.0, uN = 0.0, uS = 0.0, cZp = 0.0;
+  double P[L], Q[L];
+#pragma unroll
+  for (int l = 0; l < L; l++) { P[l] = 0.0; Q[l] = 0.0; }
+  unsigned par = 0;
+  bool unstable = false;
+  double rbelow = 0.0;
+
+  for (int kk = k1c; kk <= K; kk++) {
+    const bool top = (kk == K);
+    const bool opE = kk >= k1e, opW = kk >= k1w, opN = kk >= k1n, opS = kk >= k1s;
+    const int cb = (kk - k1c) & 1;
+    stage_wait(st, cb, ((unsigned)(kk - k1c) >> 1) & 1u);
+    const double *const smc = sm + cb * R::rowsC * NT;
+    TS5 b;
+    b.tC = smc[(R::rTS + 0) * NT]; b.sC = smc[(R::rTS + 1) * NT]; b.tE = smc[(R::rTS + 2) * NT]; b.sE = smc[(R::rTS + 3) * NT];
+    b.tW = smc[(R::rTS + 4) * NT]; b.sW = smc[(R::rTS + 5) * NT]; b.tN = smc[(R::rTS + 6) * NT]; b.sN = smc[(R::rTS + 7) * NT];
+    b.tS = smc[(R::rTS + 8) * NT]; b.sS = smc[(R::rTS + 9) * NT];
+    const double vuE = smc[(R::rU + 0) * NT], vvN = smc[(R::rU + 1) * NT], vww = smc[(R::rU + 2) * NT], vuW = smc[(R::rU + 3) * NT],
+                 vvS = smc[(R::rU + 4) * NT];
+    // unit C[cb] is in registers now: request the one two levels up at once (this warp is its only reader)
+    stage_syncw();
+    if (kk + 2 <= K) issueC(kk + 2);
+    ColCoef cf;
+    col_coefs<K>(q, g, kk, opE, opW, opN, opS, a, b, vuE, vvN, vww, vuW, vvS, cf);
+    const double hE = cf.hE, hW = cf.hW, hN = cf.hN, hS = cf.hS, hC = cf.hC;
+    const double lc = cf.lc, lE = cf.lE, lW = cf.lW, lN = cf.lN, lS = cf.lS, cZ = cf.cZ;
+    const bool stv = kk > k1c;
+    double tnew = 0.0, snew = 0.0;
+#define CG_TRACERW(l, cc, EE, WW, NN, SS)                                                     \
+  {                                                                                           \
+    const double c = (cc), E = (EE), W = (WW), N = (NN), S = (SS);                            \
+    const double fab = P[l] + (uc * c + uE * E + uW * W + uN * N + uS * S);                   \
+    if (stv) {                                                                                \
+      const double tn = Q[l] - fab * cZp;                                                     \
+      wP[(l) * sL] = tn;                                                                      \
+      if ((l) == 0) tnew = tn;                                                                \
+      if ((l) == 1) snew = tn;                                                                \
+    }                                                                                         \
+    const double Hh = hC * c + hE * E + hW * W + hN * N + hS * S;                             \
+    Q[l] = (c - Hh) + fab * cZ;                                                               \
+    P[l] = lc * c + lE * E + lW * W + lN * N + lS * S;                                        \
+  }
+    CG_TRACERW(0, a.tC, a.tE, a.tW, a.tN, a.tS)
+    CG_TRACERW(1, a.sC, a.sE, a.sW, a.sN, a.sS)
+    if (R::nA > 0) stage_wait(st, 2, par);
+#pragma unroll
+    for (int l = 2; l < R::lB0; l++) {
+      const int r = R::rA + (l - 2);
+      CG_TRACERW(l, sm[(r + 0 * R::nA) * NT], sm[(r + 1 * R::nA) * NT], sm[(r + 2 * R::nA) * NT], sm[(r + 3 * R::nA) * NT],
+                 sm[(r + 4 * R::nA) * NT])
+    }
+    stage_syncw();                                           // every lane has read unit A: re-request it for the next level
+    if (!top) issueA(kk + 1);
+    stage_wait(st, 3, par);
+#pragma unroll
+    for (int l = R::lB0; l < L; l++) {
+      const int r = R::rB + (l - R::lB0);
+      CG_TRACERW(l, sm[(r + 0 * R::nB) * NT], sm[(r + 1 * R::nB) * NT], sm[(r + 2 * R::nB) * NT], sm[(r + 3 * R::nB) * NT],
+                 sm[(r + 4 * R::nB) * NT])
+    }
+#undef CG_TRACERW
+    stage_syncw();
+    if (!top) issueB(kk + 1);
+    par ^= 1u;
+    if (stv) {
+      const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);   // :2638
+      rP[0] = r;
+      if (kk - 1 > k1c) unstable = unstable || !(r < rbelow);
+      rbelow = r;
+    }
+    a = b;
+    uc = cf.nuc; uE = cf.nuE; uW = cf.nuW; uN = cf.nuN; uS = cf.nuS; cZp = cZ;
+    wP += sK; rP += rK;
+  }
+  {
+    double tnew = 0.0, snew = 0.0;
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      double tn = Q[l];
+      if (l < 2) tn -= v.tsflux[((long)l * (I * J) + c2) * MS + m] * cZp;
+      wP[l * sL] = tn;
+      if (l == 0) tnew = tn;
+      if (l == 1) snew = tn;
+    }
+    const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
+    rP[0] = r;
+    if (K > k1c) unstable = unstable || !(r < rbelow);
+    if (v.comask) v.comask[(long)c2 * MS + m] = unstable ? 1u : 0u;
+    if (v.sst) {
+      v.sst[(long)c2 * MS + m] = tnew;
+      v.sst[((long)(I * J) + c2) * MS + m] = snew;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Pipelined form of the column kernel (production): the per-cell coefficients are computed ONE LEVEL AHEAD.
 //
 // In tstep_column the 16 coefficients of a cell -- upstream weights (four divisions), density slopes on the four isoneutral

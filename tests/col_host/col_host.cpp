@@ -40,6 +40,20 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
   // the whole "block" (32 members of one column) shares one staging area; bulk copies are emulated element-wise
   std::vector<double> sm((size_t)(ColRows<L>::rows > SplitRows<L>::rows ? ColRows<L>::rows : SplitRows<L>::rows) * 32);
   unsigned long long bar[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (mix == 5) {   // warp-tile form (one warp = 32 members of a column, lane-parallel row copies) + flag + co
+    std::vector<unsigned> comask((size_t)I * J * MS, 7u);
+    v.comask = comask.data();
+    v.co_skip_stable = 1;
+    v.co_pairwise = 1;
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) {
+        ColStage st{sm.data(), bar, m};
+        tstep_column_w<I, J, K, L, 32>(v, g, cols[n], (unsigned)m, st);
+      }
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m);
+    return 0;
+  }
   if (mix == 4) {   // round-1 flux kernel + stability flag, decisions only, then one "thread" per passive tracer (k_co_passive)
     std::vector<unsigned> comask((size_t)I * J * MS, 7u);
     v.comask = comask.data();

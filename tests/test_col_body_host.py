@@ -39,10 +39,11 @@ def _after(o):
     return ts[1:K + 1, 1:J + 1, 1:I + 1, :].copy(), rho[1:, 1:J + 1, 1:I + 1].copy(), o.f("cost").reshape(J, I).copy()
 
 
+# 5: warp-tile column kernel (one warp per block, lane-parallel row copies) + co;
 # 4: round-1 flux kernel + stability flag, decisions-only convection kernel + one thread per passive tracer;
 # 3: pipelined column kernel (coefficients one level ahead; production) + stability flag + co on flagged member-columns;
 # 2: split column kernel (two threads per member-column) + co; 1: T,S pre-pass + mix-on-write passive pass; 0: round-1 flux kernel + co
-@pytest.mark.parametrize("mix", [4, 3, 2, 1, 0])
+@pytest.mark.parametrize("mix", [5, 4, 3, 2, 1, 0])
 @pytest.mark.parametrize("nsteps", [5 * 40, 5 * 150])   # not the first steps: a uniform start is neutrally stable and
 # the convection decisions there flip on the last bit (true of every non-strict variant)
 def test_col_body_matches_oracle(nsteps, mix):
