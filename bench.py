@@ -48,14 +48,15 @@ CONFIGS = {
 from cgenie_b200.sharding import PERTURBED, PERTURBED_BIOGEM, SEED, perturbation_table, shard  # noqa: E402  (pure numpy)
 
 
-def config_dict(workload, M, I, J, K, L, nyear, variant, biogem, spinup_years, member_stride=None):
+def config_dict(workload, M, I, J, K, L, nyear, variant, biogem, spinup_years, member_stride=None, adrag_group=16):
     """The `config` object of the JSON line; the reference arm prints the same object for the same workload."""
     ms = member_stride or ((M + 31) // 32) * 32
     working_set = (2 * L + 6) * I * J * K * 8 * ms
     in_l2 = working_set < 100e6
     return {"workload": workload, "members_per_gpu": M, "member_stride": ms, "grid": [I, J, K], "tracers": L, "nyear": nyear,
             "tracer_variant": variant, "perturbed": PERTURBED + (PERTURBED_BIOGEM if biogem else []), "seed": SEED,
-            "adrag_groups": "adrag is perturbed per group of 16 members (members of a group share one barotropic factorisation)",
+            "adrag_groups": ("adrag is perturbed per group of %d members (members of a group share one barotropic factorisation)" % adrag_group)
+                            if adrag_group > 1 else "adrag is perturbed per member (one barotropic factorisation each)",
             "l2": ("working set %.0f MB per GPU (two ts buffers + u + rho) exceeds the 126 MB L2" if not in_l2 else
                    "working set %.1f MB per GPU (two ts buffers + u + rho) fits the 126 MB L2: L2-resident run") % (working_set / 1e6),
             "step": "one model year of every member: %d koverall iterations" % (5 * nyear),
@@ -301,6 +302,7 @@ def main():
     ap.add_argument("--variant", default="col", choices=["col", "fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-groups", type=int, default=0, help="end-to-end leg: member groups per GPU (default 1)")
+    ap.add_argument("--adrag-group", type=int, default=16, help="members per distinct adrag value (1: every member its own barotropic factors)")
     ap.add_argument("--e2e-dense", action="store_true", help="end-to-end leg: ship ts dense (all cells) instead of the wet cells only")
     ap.add_argument("--spinup-years", type=int, default=None,
                     help="untimed model years from the uniform initial state before the warm-up (config #2's 100-year spin-up: "
@@ -348,7 +350,7 @@ def main():
 
     from cgenie_b200 import Ensemble, materialise
     M = args.members
-    pert = shard(perturbation_table(M * world, biogem=biogem), rank, world, M)
+    pert = shard(perturbation_table(M * world, biogem=biogem, adrag_group=args.adrag_group), rank, world, M)
     tmp = tempfile.mkdtemp(prefix="cgenie_job_")
     materialise(tmp, cfgname)
     e = Ensemble(tmp, n_members=M, device=local, perturb=pert)
@@ -516,7 +518,7 @@ def main():
         "metric": "ensemble model-years/wall-hour", "value": value, "unit": "model-years/hour", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(workload, M, I, J, K, L, nyear_, variant_active, biogem, args.spinup_years, member_stride),
+        "config": config_dict(workload, M, I, J, K, L, nyear_, variant_active, biogem, args.spinup_years, member_stride, args.adrag_group),
         "clocks": clocks, "gpu_launches": launches, "blown_up_members": bad, "roofline": roofline,
         "e2e": {"value": e2e_val, "unit": "model-years/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "groups": G, "years_timed": nrep,

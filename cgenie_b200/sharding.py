@@ -12,17 +12,20 @@ PERTURBED_BIOGEM = list(BASE_BIOGEM)
 ADRAG_GROUP = 16  # members per barotropic factorisation (adrag is perturbed per group)
 
 
-def perturbation_table(n_total, seed=SEED, biogem=False):
+def perturbation_table(n_total, seed=SEED, biogem=False, adrag_group=None):
     """Member m scales each whitelisted parameter by U(0.8, 1.25); member 0 is the unperturbed control
-    (SURVEY.md 8d).  Deterministic in (n_total, seed); the first n rows do not depend on n_total."""
+    (SURVEY.md 8d).  Deterministic in (n_total, seed); the first n rows do not depend on n_total.
+    adrag_group: members per distinct drag value (default ADRAG_GROUP = 16: members with equal adrag share one barotropic
+    factorisation on the device; 1 = every member its own, as SURVEY 8d words it)."""
+    ag = ADRAG_GROUP if adrag_group is None else int(adrag_group)
     tab = {}
     base = dict(BASE, **BASE_BIOGEM) if biogem else BASE
     for q, k in enumerate(PERTURBED + (PERTURBED_BIOGEM if biogem else [])):
         rng = np.random.default_rng([seed, q])
         f = rng.uniform(0.8, 1.25, size=n_total)
         if k == "adrag":
-            f = np.repeat(f[::ADRAG_GROUP], ADRAG_GROUP)[:n_total]
-            f[:ADRAG_GROUP] = 1.0
+            f = np.repeat(f[::ag], ag)[:n_total]
+            f[:ag] = 1.0
         f[0] = 1.0
         tab[k] = base[k] * f
     return tab
