@@ -1,7 +1,15 @@
 // k_tracer_col.cu -- tracer step as two kernels: tstepo_flux with cp.async.bulk staging (one block per wet column), then
 // the convective adjustment + SST export (one thread per member-column).  See k_tracer_col.cuh for the formulation.  Compiled with FMA
 // contraction (fast variant family, <= 1e-10 per step against the strict kernels / the oracle).
+#include <cuda.h>   // CUtensorMap, cuTensorMapEncodeTiled (resolved through cudaGetDriverEntryPoint: no link against libcuda)
+
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "k_tracer_col.cuh"
 
 namespace cg {
@@ -38,7 +46,7 @@ __global__ void __launch_bounds__(MS, MINB) k_tstep_col2(const Dev v) {
 
 // warp-tile form: one block = one warp = 32 members of one column; consecutive blocks are the MS / 32 tiles of a column
 template <int I, int J, int K, int L, int MS>
-__global__ void __launch_bounds__(32, 8) k_tstep_colw(const Dev v) {
+__global__ void __launch_bounds__(32, 8) k_tstep_colw(const Dev v, const __grid_constant__ ColMaps maps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NTILE = MS / 32;
   ColStage st;
@@ -47,7 +55,47 @@ __global__ void __launch_bounds__(32, 8) k_tstep_colw(const Dev v) {
   st.tid = threadIdx.x;
   const int c2 = v.rowcols[blockIdx.x / NTILE];
   const unsigned m = (blockIdx.x % NTILE) * 32 + threadIdx.x;
-  tstep_column_w<I, J, K, L, MS>(v, c_g, c2, m, st);
+  tstep_column_w<I, J, K, L, MS>(v, c_g, c2, m, st, &maps);
+}
+
+// 2-D tensor maps of a field seen as [row][member] (fp64, row pitch MS doubles), box = 32 members x `rows` rows, no swizzle
+static bool make_map(void *out128, const void *base, unsigned long long nrows, int MS, int rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                               CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || !p) return false;
+    fn = (EncodeFn)p;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)MS, (cuuint64_t)nrows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)MS * sizeof(double)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMap tmap;
+  const CUresult r = fn(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  memcpy(out128, &tmap, 128);
+  return true;
+}
+template <int I, int J, int K, int L, int MS>
+static const ColMaps *col_maps(const Dev &v) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, const void *>, ColMaps> cache;   // (ts buffer read this step, u) -> maps
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_pair((const void *)v.ts_cur, (const void *)v.u);
+  auto it = cache.find(key);
+  if (it != cache.end()) return &it->second;
+  ColMaps mp;
+  using R = ColRows<L>;
+  const unsigned long long nts = (unsigned long long)I * J * K * L, nu = (unsigned long long)I * J * K * 3;
+  if (!make_map(mp.ts2, v.ts_cur, nts, MS, 2) || !make_map(mp.tsA, v.ts_cur, nts, MS, R::nA > 0 ? R::nA : 1) ||
+      !make_map(mp.tsB, v.ts_cur, nts, MS, R::nB) || !make_map(mp.u3, v.u, nu, MS, 3) || !make_map(mp.u1, v.u, nu, MS, 1))
+    return nullptr;
+  return &(cache[key] = mp);
 }
 
 // split form: two threads per (member, column), 2 * MS threads per block (see tstep_column_split)
@@ -162,6 +210,7 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   if (coskip < 0) { const char *e = getenv("CG_CO_SKIP"); coskip = e ? atoi(e) : 1; }
   Dev v1 = v;
   v1.col_deep_first = order;
+  const ColMaps *maps = (colv == 3) ? col_maps<I, J, K, L, MS>(v) : nullptr;
   if (split && MS == 128) {
     constexpr size_t smem2 = (size_t)SplitRows<L>::rows * MS * 8 + 64;
     static bool attr2 = false;
@@ -173,9 +222,9 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
     if (split == 2) k_tstep_split<I, J, K, L, MS, 1><<<v.nwet, 2 * MS, smem2, s>>>(v);
     else k_tstep_split<I, J, K, L, MS, 2><<<v.nwet, 2 * MS, smem2, s>>>(v);
   } else
-  if (colv == 3) {
+  if (colv == 3 && maps) {
     constexpr size_t smemw = (size_t)ColRows<L>::rows * 32 * 8 + 64;
-    k_tstep_colw<I, J, K, L, MS><<<v.nwet * (MS / 32), 32, smemw, s>>>(v1);
+    k_tstep_colw<I, J, K, L, MS><<<v.nwet * (MS / 32), 32, smemw, s>>>(v1, *maps);
   } else
   if (colv == 2) {
     constexpr size_t smem3 = (size_t)ColRows2<L>::rows * MS * 8 + 64;

@@ -564,16 +564,31 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 // Warp-tile form of the column kernel: one block = ONE WARP = 32 members (a 256-byte slice of every row) of one wet column.
 // The arithmetic is tstep_column's.  What changes is the staging: the block's four warps no longer meet at two block
 // barriers per level (ncu: 19 % of the stall samples sit behind them and 9 % in the waits for rows that the slowest warp
-// requested late), every warp owns its staging rows and mbarriers, re-requests a unit as soon as IT has consumed it, and
-// runs up to eight such one-warp blocks per SM drift freely against each other.  A row slice is a 256-byte bulk copy; the
-// copies of a unit are issued by ONE warp-wide instruction (lane r copies row r: cp.async.bulk is a per-thread operation), so
-// the per-level issue cost is a few instructions, not one instruction sequence per copy.
-CG_HD void stage_expect_w(const ColStage &s, const int which, const unsigned bytes) {
+// requested late); every warp owns its staging rows and mbarriers, re-requests a unit as soon as IT has consumed it, and the
+// up to eight one-warp blocks of an SM drift freely against each other.  A warp's slice of a staging unit is a 2-D box of
+// the field seen as [row = (cell, tracer)][member]: 32 members x the unit's consecutive tracer rows of one stencil column,
+// fetched by one tensor-map copy (cp.async.bulk.tensor.2d, SASS UTMALDG) -- 18 copies per level, as the 128-member block
+// issues, but per warp.  (A first version copied the 256-byte row slices with "one warp-wide cp.async.bulk, lane r = row r":
+// the instruction takes its operands from the uniform datapath, so the compiler turns per-lane addresses into a serial loop
+// over the lanes, 95 copies per warp and level, twice the kernel's instructions: profiles/README_r2.md.)
+// Tensor maps of the two fields the kernel stages, by box height (rows per copy); built on the host (k_tracer_col.cu).
+struct ColMaps {
+  alignas(64) unsigned long long ts2[16], tsA[16], tsB[16], u3[16], u1[16];   // CUtensorMap is 128 opaque bytes, 64-byte aligned
+};
+// box (32 members starting at member c0) x (rows starting at row c1) -> staging rows dstrow ...; host emulation: element-wise
+template <int MS>
+CG_HD void stage_box(const ColStage &s, const int which, const int dstrow, const void *tmap, const double *field, const int c0,
+                     const long c1, const int rows) {
 #ifdef __CUDA_ARCH__
-  if (s.tid == 0) stage_expect(s, which, bytes);
-  __syncwarp();
+  (void)field; (void)rows;
+  const unsigned d = (unsigned)__cvta_generic_to_shared(s.sm + dstrow * 32);
+  const unsigned a = (unsigned)__cvta_generic_to_shared(s.bar) + 8u * which;
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(d), "l"(tmap),
+               "r"(a), "r"(c0), "r"((int)c1)
+               : "memory");
 #else
-  (void)s; (void)which; (void)bytes;
+  (void)which; (void)tmap;
+  for (int r = 0; r < rows; r++) s.sm[(dstrow + r) * 32 + s.tid] = field[(c1 + r) * MS + c0 + s.tid];
 #endif
 }
 CG_HD void stage_syncw() {
@@ -583,11 +598,12 @@ CG_HD void stage_syncw() {
 }
 
 template <int I, int J, int K, int L, int MS>
-CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st) {
+CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st, const ColMaps *tm) {
   constexpr int NT = 32;
   using R = ColRows<L>;
   constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
-  constexpr long uC3 = 3L * MS, uK = (long)I * J * uC3, rK = (long)I * J * MS;
+  constexpr long rK = (long)I * J * MS;
+  constexpr int IJ = I * J;
   const int i = c2 % I + 1, j = c2 / I + 1;
 #define CGC_K1(ii, jj) ((int)v.k1[(ii) + (I + 2) * (jj)])
   const int k1c = CGC_K1(i, j);
@@ -596,94 +612,56 @@ CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsi
 #undef CGC_K1
   const ColK q = col_consts<I, J>(v, g, m, j);
   const double ec1 = q.ec1, ec2 = q.ec2, ec3 = q.ec3, ec4 = q.ec4;
-  const long dE = (i < I) ? sC : -(long)(I - 1) * sC, dW = (i > 1) ? -sC : (long)(I - 1) * sC;
-  constexpr long dN = (long)I * sC, dS = -(long)I * sC;
-  const long dUW = (i > 1) ? -uC3 : (long)(I - 1) * uC3, dUS = (j > 1) ? -(long)I * uC3 : 0;
-  const unsigned m0 = m - (unsigned)st.tid;                       // first member of this warp's tile
-  const double *const ts0 = v.ts_cur + (long)c2 * sC + m0;       // level-1 cell, tracer 0, first member of the tile
-  const double *const u0 = v.u + (long)c2 * uC3 + m0;
+  // neighbour columns as CELL offsets (periodic in i); a closed face points at the centre column (differences vanish exactly)
+  const int cE = (i < I) ? 1 : -(I - 1), cW = (i > 1) ? -1 : (I - 1);
+  constexpr int cN = I, cS = -I;
+  const int cUS = (j > 1) ? -I : 0;
+  const int m0 = (int)(m - (unsigned)st.tid);                     // first member of this warp's tile
   const double *const sm = st.sm + st.tid;
-
-  // Unit C of level lev: rows 0..9 = T,S one level up of the five columns, rows 10..14 = uE, vN, ww, uW, vS.  Lane r picks
-  // the source of row r; one warp-wide copy instruction for the ten T,S rows, one for the five velocity rows.
+#ifdef __CUDA_ARCH__
+  const bool leader = (st.tid == 0);
+#else
+  const bool leader = true;                                       // host emulation: every "thread" copies its own elements
+#endif
+  const void *const mTS2 = tm ? (const void *)tm->ts2 : nullptr, *const mTSA = tm ? (const void *)tm->tsA : nullptr,
+                   *const mTSB = tm ? (const void *)tm->tsB : nullptr, *const mU3 = tm ? (const void *)tm->u3 : nullptr,
+                   *const mU1 = tm ? (const void *)tm->u1 : nullptr;
+  auto colcell = [&](const int lev, const int cell) {             // cell offset of stencil column `cell` at level lev
+    return (cell == 0) ? 0 : (cell == 1) ? ((lev >= k1e) ? cE : 0) : (cell == 2) ? ((lev >= k1w) ? cW : 0)
+           : (cell == 3) ? ((lev >= k1n) ? cN : 0) : ((lev >= k1s) ? cS : 0);
+  };
+  // Unit C of level lev: rows 0..9 = T,S one level up of the five columns, rows 10..14 = uE, vN, ww, uW, vS
   auto issueC = [&](const int lev) {
+    if (!leader) return;
     const int b = (lev - k1c) & 1;
-    stage_expect_w(st, b, (unsigned)(R::rowsC * NT * 8));
+    stage_expect(st, b, (unsigned)(R::rowsC * NT * 8));
     const int lu = (lev < K) ? lev + 1 : K;
-    const int r = st.tid, cell = r >> 1;
-    const long dcol = (cell == 0) ? 0 : (cell == 1) ? ((lu >= k1e) ? dE : 0) : (cell == 2) ? ((lu >= k1w) ? dW : 0)
-                      : (cell == 3) ? ((lu >= k1n) ? dN : 0) : ((lu >= k1s) ? dS : 0);
-    const double *srcTS = ts0 + (long)(lu - 1) * sK + dcol + (long)(r & 1) * sL;
-    {
-#ifdef __CUDA_ARCH__
-      if (r < 10) {
-        const unsigned d = (unsigned)__cvta_generic_to_shared(st.sm + (b * R::rowsC + R::rTS + r) * 32);
-        const unsigned a = (unsigned)__cvta_generic_to_shared(st.bar) + 8u * b;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(srcTS), "r"(256u),
-                     "r"(a)
-                     : "memory");
-      }
-#else
-      for (int rr = 0; rr < 10; rr++) {
-        const int cc = rr >> 1;
-        const long dc = (cc == 0) ? 0 : (cc == 1) ? ((lu >= k1e) ? dE : 0) : (cc == 2) ? ((lu >= k1w) ? dW : 0)
-                        : (cc == 3) ? ((lu >= k1n) ? dN : 0) : ((lu >= k1s) ? dS : 0);
-        st.sm[(b * R::rowsC + R::rTS + rr) * 32 + st.tid] = ts0[(long)(lu - 1) * sK + dc + (long)(rr & 1) * sL + st.tid];
-      }
-      (void)srcTS;
-#endif
-    }
-    const double *pu = u0 + (long)(lev - 1) * uK;
-    {
-      const long du = (r < 3) ? (long)r * sL : (r == 3) ? dUW : (dUS + sL);
-#ifdef __CUDA_ARCH__
-      if (r < 5) {
-        const unsigned d = (unsigned)__cvta_generic_to_shared(st.sm + (b * R::rowsC + R::rU + r) * 32);
-        const unsigned a = (unsigned)__cvta_generic_to_shared(st.bar) + 8u * b;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(pu + du), "r"(256u),
-                     "r"(a)
-                     : "memory");
-      }
-#else
-      (void)du;
-      for (int rr = 0; rr < 5; rr++) {
-        const long d2 = (rr < 3) ? (long)rr * sL : (rr == 3) ? dUW : (dUS + sL);
-        st.sm[(b * R::rowsC + R::rU + rr) * 32 + st.tid] = pu[d2 + st.tid];
-      }
-#endif
-    }
+    const long cellu = (long)(lu - 1) * IJ + c2;
+    const int r0 = b * R::rowsC;
+#pragma unroll
+    for (int cell = 0; cell < 5; cell++)
+      stage_box<MS>(st, b, r0 + R::rTS + 2 * cell, mTS2, v.ts_cur, m0, (cellu + colcell(lu, cell)) * L, 2);
+    const long cellv = (long)(lev - 1) * IJ + c2;
+    stage_box<MS>(st, b, r0 + R::rU + 0, mU3, v.u, m0, cellv * 3, 3);
+    stage_box<MS>(st, b, r0 + R::rU + 3, mU1, v.u, m0, (cellv + cW) * 3, 1);
+    stage_box<MS>(st, b, r0 + R::rU + 4, mU1, v.u, m0, (cellv + cUS) * 3 + 1, 1);
   };
-  // units A (tracers 2 .. lB0-1) and B (lB0 .. L-1): staged row = base + cell * n + (l - l0); lanes cover 32 rows per instruction
-  auto issueT = [&](const int which, const int base, const int l0, const int n, const int lev) {
-    stage_expect_w(st, which, (unsigned)(5 * n * NT * 8));
-    const double *c0 = ts0 + (long)(lev - 1) * sK + (long)l0 * sL;
-    for (int r0 = 0; r0 < 5 * n; r0 += 32) {
-      const int r = r0 + st.tid, cell = r / n, ll = r - cell * n;
-      const long dcol = (cell == 0) ? 0 : (cell == 1) ? ((lev >= k1e) ? dE : 0) : (cell == 2) ? ((lev >= k1w) ? dW : 0)
-                        : (cell == 3) ? ((lev >= k1n) ? dN : 0) : ((lev >= k1s) ? dS : 0);
-#ifdef __CUDA_ARCH__
-      if (r < 5 * n) {
-        const unsigned d = (unsigned)__cvta_generic_to_shared(st.sm + (base + r) * 32);
-        const unsigned a = (unsigned)__cvta_generic_to_shared(st.bar) + 8u * which;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
-                     "l"(c0 + dcol + (long)ll * sL), "r"(256u), "r"(a)
-                     : "memory");
-      }
-#else
-      (void)dcol; (void)ll;
-      {
-        for (int rr = r0; rr < r0 + 32 && rr < 5 * n; rr++) {
-          const int cc = rr / n, l2 = rr - cc * n;
-          const long dc = (cc == 0) ? 0 : (cc == 1) ? ((lev >= k1e) ? dE : 0) : (cc == 2) ? ((lev >= k1w) ? dW : 0)
-                          : (cc == 3) ? ((lev >= k1n) ? dN : 0) : ((lev >= k1s) ? dS : 0);
-          st.sm[(base + rr) * 32 + st.tid] = c0[dc + (long)l2 * sL + st.tid];
-        }
-      }
-#endif
-    }
+  auto issueA = [&](const int lev) {
+    if (R::nA == 0 || !leader) return;
+    stage_expect(st, 2, (unsigned)(R::rowsA * NT * 8));
+    const long cell0 = (long)(lev - 1) * IJ + c2;
+#pragma unroll
+    for (int cell = 0; cell < 5; cell++)
+      stage_box<MS>(st, 2, R::rA + cell * R::nA, mTSA, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * L + 2, R::nA);
   };
-  auto issueA = [&](const int lev) { if (R::nA > 0) issueT(2, R::rA, 2, R::nA, lev); };
-  auto issueB = [&](const int lev) { issueT(3, R::rB, R::lB0, R::nB, lev); };
+  auto issueB = [&](const int lev) {
+    if (!leader) return;
+    stage_expect(st, 3, (unsigned)(R::rowsB * NT * 8));
+    const long cell0 = (long)(lev - 1) * IJ + c2;
+#pragma unroll
+    for (int cell = 0; cell < 5; cell++)
+      stage_box<MS>(st, 3, R::rB + cell * R::nB, mTSB, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * L + R::lB0, R::nB);
+  };
 
 #ifdef __CUDA_ARCH__
   if (st.tid == 0) {
@@ -701,14 +679,14 @@ CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsi
   // T,S of the five columns at the bottom level (direct loads, once per column)
   TS5 a;
   {
-    const double *qC = ts0 + (long)(k1c - 1) * sK + st.tid;
-    const double *qE = qC + ((k1c >= k1e) ? dE : 0), *qW = qC + ((k1c >= k1w) ? dW : 0);
-    const double *qN = qC + ((k1c >= k1n) ? dN : 0), *qS = qC + ((k1c >= k1s) ? dS : 0);
+    const double *qC = v.ts_cur + ((long)(k1c - 1) * IJ + c2) * sC + m;
+    const double *qE = qC + (long)colcell(k1c, 1) * sC, *qW = qC + (long)colcell(k1c, 2) * sC;
+    const double *qN = qC + (long)colcell(k1c, 3) * sC, *qS = qC + (long)colcell(k1c, 4) * sC;
     a.tC = qC[0]; a.sC = qC[sL]; a.tE = qE[0]; a.sE = qE[sL]; a.tW = qW[0]; a.sW = qW[sL];
     a.tN = qN[0]; a.sN = qN[sL]; a.tS = qS[0]; a.sS = qS[sL];
   }
-  double *wP = v.ts_new + ((long)(k1c - 2) * (I * J) + c2) * sC + m;   // level kk-1 of the new array
-  double *rP = v.rho + ((long)(k1c - 2) * (I * J) + c2) * MS + m;
+  double *wP = v.ts_new + ((long)(k1c - 2) * IJ + c2) * sC + m;   // level kk-1 of the new array
+  double *rP = v.rho + ((long)(k1c - 2) * IJ + c2) * MS + m;
   double uc = 0.0, uE = 0.0, uW = 0.0, uN = 0.0, uS = 0.0, cZp = 0.0;
   double P[L], Q[L];
 #pragma unroll
@@ -729,13 +707,14 @@ CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsi
     b.tS = smc[(R::rTS + 8) * NT]; b.sS = smc[(R::rTS + 9) * NT];
     const double vuE = smc[(R::rU + 0) * NT], vvN = smc[(R::rU + 1) * NT], vww = smc[(R::rU + 2) * NT], vuW = smc[(R::rU + 3) * NT],
                  vvS = smc[(R::rU + 4) * NT];
-    // unit C[cb] is in registers now: request the one two levels up at once (this warp is its only reader)
-    stage_syncw();
-    if (kk + 2 <= K) issueC(kk + 2);
     ColCoef cf;
     col_coefs<K>(q, g, kk, opE, opW, opN, opS, a, b, vuE, vvN, vww, vuW, vvS, cf);
     const double hE = cf.hE, hW = cf.hW, hN = cf.hN, hS = cf.hS, hC = cf.hC;
     const double lc = cf.lc, lE = cf.lE, lW = cf.lW, lN = cf.lN, lS = cf.lS, cZ = cf.cZ;
+    // unit C[cb] has been consumed (its values went through the coefficient arithmetic above): this warp, its only reader,
+    // requests the unit two levels up
+    stage_syncw();
+    if (kk + 2 <= K) issueC(kk + 2);
     const bool stv = kk > k1c;
     double tnew = 0.0, snew = 0.0;
 #define CG_TRACERW(l, cc, EE, WW, NN, SS)                                                     \
@@ -789,7 +768,7 @@ CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsi
 #pragma unroll
     for (int l = 0; l < L; l++) {
       double tn = Q[l];
-      if (l < 2) tn -= v.tsflux[((long)l * (I * J) + c2) * MS + m] * cZp;
+      if (l < 2) tn -= v.tsflux[((long)l * IJ + c2) * MS + m] * cZp;
       wP[l * sL] = tn;
       if (l == 0) tnew = tn;
       if (l == 1) snew = tn;
@@ -800,7 +779,7 @@ CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsi
     if (v.comask) v.comask[(long)c2 * MS + m] = unstable ? 1u : 0u;
     if (v.sst) {
       v.sst[(long)c2 * MS + m] = tnew;
-      v.sst[((long)(I * J) + c2) * MS + m] = snew;
+      v.sst[((long)IJ + c2) * MS + m] = snew;
     }
   }
 }

@@ -48,7 +48,7 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
     for (int n = 0; n < ncol; n++)
       for (int m = 0; m < MS; m++) {
         ColStage st{sm.data(), bar, m};
-        tstep_column_w<I, J, K, L, 32>(v, g, cols[n], (unsigned)m, st);
+        tstep_column_w<I, J, K, L, 32>(v, g, cols[n], (unsigned)m, st, nullptr);
       }
     for (int n = 0; n < ncol; n++)
       for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m);
