@@ -55,6 +55,8 @@ SYMBOLS = {
     "cg_cpl_comp_ocnsed": (C.c_int, [P, C.c_int, C.c_int, C.c_int]),
     "cg_reinit_flux_rokocn": (C.c_int, [P]),
     "cg_biogem_sig_update": (C.c_int, [P, C.c_double, C.c_double]),
+    "cg_biogem_slice_update": (C.c_int, [P, C.c_double]),
+    "cg_biogem_slice_reset": (C.c_int, [P]),
     "cg_biogem_sig_reset": (C.c_int, [P]),
     "cg_series_last_error": (C.c_char_p, []),
     "cg_biogem_series_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_int, STRS, I32, I32, C.c_int, STRS, I32, I32,

@@ -312,6 +312,11 @@ void bg_fill_tables(const BgConfig &c, const Params &p, const Grid &g, BgDev *b)
       b->POC_f2[k] = (1.0 - std::exp(-b->dD[k] / c.POC_eL2));
     }
     b->Dmid_surf = kDsc * dzal[K];
+    for (int k = 1; k <= K; k++) {   // phys_ocn(ipo_Dmid,i,j,k) = SUM(goldstein_dsc*loc_grid_dza(k:n_k)), biogem_data.f90:1120
+      double s = 0.0;
+      for (int kk = k; kk <= K; kk++) s = s + kDsc * dzal[kk];
+      b->Dmid[k] = s;
+    }
   }
 }
 

@@ -46,6 +46,7 @@ void launch_global_means(const Dev &, double *out, cudaStream_t);
 int launch_tracercoupling(const Dev &, cudaStream_t);
 int launch_bg_reset_cost(const Dev &, cudaStream_t);
 int launch_bg_sig(const Dev &, const BgDev &, const SigDev &, double dtyr, cudaStream_t);
+int launch_bg_slice(const Dev &, const BgDev &, const SliceDev &, double dtyr, int init, cudaStream_t);
 int launch_cpl_ocnsed(double *sum, const double *src, size_t n, double a, double b, int mode, cudaStream_t);
 int launch_bg_step(const Dev &, const BgDev &, int init_only, int fuse, cudaStream_t);
 int launch_tc_sums_first(const Dev &, cudaStream_t);
@@ -192,6 +193,7 @@ struct cg_handle {
   double atm_totV = 0.0;
   bool bg_go = true;
   SigDev sig{};                       // BIOGEM time-series integrals
+  SliceDev slice{};                   // BIOGEM time-slice diagnostics (integrals allocated on first use)
   double sig_ben_Dmin = -1.0;
   double *sig_w_ben = nullptr;
   double *sfxsumsed = nullptr, *sfcsumocn = nullptr, *sfxsumrok1 = nullptr;   // SEDGEM / ROKGEM interface sums, [ls|l][j][i][m]
@@ -505,6 +507,7 @@ extern "C" int cg_initialise(cg_handle *h) {
   if (h->bg.on) {
     // sub_init_carb (biogem_data.f90:2336-2430) and the biogem_climate call before the main loop (genie.f90:109-112)
     h->launches += launch_bg_step(h->dv, h->bgd, 1, 0, h->stream);
+    h->launches += launch_bg_slice(h->dv, h->bgd, h->slice, 0.0, 1, h->stream);   // ... and the cells below the surface
     h->bgd.nsol = 0;
     h->launches += launch_bg_climate(h->dv, h->bgd, h->stream);
   }
@@ -816,6 +819,20 @@ static int build_device(cg_handle *h) {
       h->sig.rtot_A_atm = totA > kBgNullSmall ? 1.0 / totA : 0.0;
       h->sig.LA = LA;
       reg_field(h, "bg_sig", h->sig.acc, {nq}, {1});
+    }
+    {
+      // time-slice diagnostics: [H+] and RF0 of every cell from sub_init_carb on, the wet-cell list
+      std::vector<int> wet;
+      for (int k = 1; k <= K; k++)
+        for (int j = 1; j <= J; j++)
+          for (int i = 1; i <= I; i++)
+            if (k >= g.k1at(i, j)) wet.push_back((int)cell3(I, J, i, j, k));
+      h->slice.nwet3 = (int)wet.size();
+      if (wet.empty()) wet.push_back(0);
+      int *qi; TRY(dupload(h, &qi, wet)); h->slice.wet = qi;
+      TRY(dalloc(h, &h->slice.carbH3, ijk * MS));
+      TRY(dalloc(h, &h->slice.rf03, ijk * MS));
+      reg_field(h, "carbH3", h->slice.carbH3, {I, J, K}, {1, I, (long long)I * J});
     }
     // genie_sfxsumsed, genie_sfcsumocn, genie_sfxsumrok1 (genie_global.f90) of a job whose sediment grid is the ocean grid
     TRY(dalloc(h, &h->sfxsumsed, ij * LS * MS));
@@ -1694,6 +1711,58 @@ extern "C" int cg_biogem_sig_update(cg_handle *h, double dts, double ben_Dmin) {
   ProfScope ps(h, "biogem");
   ps.done(launch_bg_sig(h->dv, h->bgd, h->sig, dts / kBgYrS, h->stream));
   return check_async(h);
+}
+// diag_biogem_timeslice (biogem.f90:2421-2699), its arithmetic: the 3-D carbonate re-solve (:2478-2567) and the growth of the
+// window integrals int_ocn / int_bio_part / int_carb / int_carbconst / int_carbisor / int_t _timeslice (:2572-2579) on the
+// device.  Call it where genie.f90 calls diag_biogem_timeslice_wrapper (:391-395: behind cg_biogem_climate, ahead of the
+// time-series diagnostic and ATCHEM) on the BIOGEM steps inside a save window; the window bookkeeping (:2460-2470, 2627-2696)
+// and the netCDF writer stay with the host, which reads the integrals as fields "sl_ocn" (maxl,i,j,k), "sl_part", "sl_carb"
+// (10,...), "sl_carbconst" (17,...), "sl_carbisor" (8,...), "sl_t" (1) and divides by sl_t as sub_save_netcdf_3d does.
+static int slice_alloc(cg_handle *h) {
+  if (h->slice.ocn) return CG_OK;
+  const size_t ijk = (size_t)h->g.I * h->g.J * h->g.K, MS = h->MS;
+  const int I = h->g.I, J = h->g.J, K = h->g.K, L = h->g.L, LS = h->bg.LS;
+  IO0(dalloc(h, &h->slice.ocn, ijk * L * MS));
+  IO0(dalloc(h, &h->slice.part, ijk * LS * MS));
+  IO0(dalloc(h, &h->slice.carb, ijk * kSlCarb * MS));
+  IO0(dalloc(h, &h->slice.cc, ijk * kSlCC * MS));
+  IO0(dalloc(h, &h->slice.iso, ijk * kSlIso * MS));
+  IO0(dalloc(h, &h->slice.t, MS));
+  CUDA_OK(cudaStreamSynchronize(h->stream));   // the zero fills
+  const long long ij = (long long)I * J;
+  reg_field(h, "sl_ocn", h->slice.ocn, {L, I, J, K}, {1, L, (long long)L * I, (long long)L * ij});
+  reg_field(h, "sl_part", h->slice.part, {LS, I, J, K}, {1, LS, (long long)LS * I, (long long)LS * ij});
+  reg_field(h, "sl_carb", h->slice.carb, {kSlCarb, I, J, K}, {1, kSlCarb, (long long)kSlCarb * I, (long long)kSlCarb * ij});
+  reg_field(h, "sl_carbconst", h->slice.cc, {kSlCC, I, J, K}, {1, kSlCC, (long long)kSlCC * I, (long long)kSlCC * ij});
+  reg_field(h, "sl_carbisor", h->slice.iso, {kSlIso, I, J, K}, {1, kSlIso, (long long)kSlIso * I, (long long)kSlIso * ij});
+  reg_field(h, "sl_t", h->slice.t, {1}, {1});
+  return CG_OK;
+}
+extern "C" int cg_biogem_slice_update(cg_handle *h, double dts) {
+  CG_RANGE();
+  BGREADY(h);
+  IO(join_side(h));            // allocation + field registration happen on the main stream
+  IO(slice_alloc(h));
+  h->spec_valid = false;       // the surface [H+] seed changes under a surface part issued ahead
+  BgAsyncScope as(h, true);
+  IO(side_wait(h));
+  ProfScope ps(h, "biogem");
+  ps.done(launch_bg_slice(h->dv, h->bgd, h->slice, dts / kBgYrS, 0, h->stream));
+  return check_async(h);
+}
+extern "C" int cg_biogem_slice_reset(cg_handle *h) {   // sub_init_int_timeslice, biogem_data.f90:1012-1060
+  BGREADY(h);
+  IO(join_side(h));
+  IO(slice_alloc(h));
+  const size_t ijk = (size_t)h->g.I * h->g.J * h->g.K, MS = h->MS;
+  CUDA_OK(cudaMemsetAsync(h->slice.ocn, 0, ijk * h->g.L * MS * 8, h->stream));
+  CUDA_OK(cudaMemsetAsync(h->slice.part, 0, ijk * h->bg.LS * MS * 8, h->stream));
+  CUDA_OK(cudaMemsetAsync(h->slice.carb, 0, ijk * kSlCarb * MS * 8, h->stream));
+  CUDA_OK(cudaMemsetAsync(h->slice.cc, 0, ijk * kSlCC * MS * 8, h->stream));
+  CUDA_OK(cudaMemsetAsync(h->slice.iso, 0, ijk * kSlIso * MS * 8, h->stream));
+  CUDA_OK(cudaMemsetAsync(h->slice.t, 0, MS * 8, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
 }
 extern "C" int cg_biogem_sig_reset(cg_handle *h) {
   BGREADY(h);

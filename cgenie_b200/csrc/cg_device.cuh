@@ -148,7 +148,7 @@ struct BgDev {
   double c0_PO4, red_POP_POC, red_DOMfrac, red_RDOMfrac, red_POC_CaCO3_pP, DOMlifetime, POC_frac2, POC_dfrac2, POC_c0frac2,
       CaCO3_frac2, sinkingrate, remin_k_O2, remin_c0_O2, gastransfer_a, d13C_DIC_Corg_ef, Fgeothermal, solar_constant, dsc;
   double dts, dtyr, dts_atchem, dtyr_atchem;
-  double Dbot[kBgMaxK + 1], dD[kBgMaxK + 2], Dmid_surf;
+  double Dbot[kBgMaxK + 1], dD[kBgMaxK + 2], Dmid_surf, Dmid[kBgMaxK + 1];
   double CaCO3_f1[kBgMaxK + 1], CaCO3_f2[kBgMaxK + 1], POC_f2[kBgMaxK + 1];   // 1-exp(-dD(k)/eL), host computed
   const double *POC_f1;                   // [k][m] (par_bio_remin_POC_eL1 is a perturbed parameter)
   const double *k0_PO4, *red_POC_CaCO3;   // [m]
@@ -167,6 +167,16 @@ struct BgDev {
   double *sfcocn1, *sfxsed1, *focnatm;    // interface / diagnostics: [l|ls|la][j][i][m]
   int *err;                               // [m] carbonate chemistry failure flag (error_stop)
   double *surf;                           // [kBgSurfSlots][wet column][m] surface-cell results (k_bg_step PART 1 -> PART 2)
+};
+// time-slice diagnostics (diag_biogem_timeslice, biogem.f90:2421-2699): the carbonate system of every wet cell and the window
+// integrals.  carbH3 / rf03 exist from cg_initialise on (sub_init_carb solves every cell); the integrals on first use.
+constexpr int kSlCarb = 10, kSlCC = 17, kSlIso = 8;   // carb(ic_*), carbconst(icc_*), carbisor(ici_*) entries the path fills
+struct SliceDev {
+  const int *wet;                         // wet cells in ascending cell order
+  int nwet3;
+  double *carbH3, *rf03;                  // [k][j][i][m] [H+] of the cell's last solve (k < K; the surface cell's is BgDev::carbH), RF0
+  double *ocn, *part, *carb, *cc, *iso;   // int_*_timeslice, [cell][q][m]
+  double *t;                              // [m] int_t_timeslice
 };
 // window integrals of BIOGEM's time series (k_bg_sig_*): per-quantity rows of MS members
 constexpr int kSigHead = 3;

@@ -1321,6 +1321,121 @@ __global__ void k_bg_sig_acc(const Dev v, const SigDev g, const double dtyr) {
     a[q] = a[q] + dtyr * r[q] * g.rtot_A_atm;
   }
 }
+// diag_biogem_timeslice (biogem.f90:2478-2579): thread = (member, wet cell).  The cell's carbonate system is solved from the
+// cell's last [H+] (for the surface cell that is BgDev::carbH, the seed of step_biogem's own solve: the diagnostic feeds back
+// into the next step as it does in the reference), then the window integrals grow by dtyr * field.  init != 0: sub_init_carb
+// (biogem_data.f90:2336-2430) for the cells below the surface -- seed 10**(-7.8), RF0 of the cell -- no integrals.
+__global__ void __launch_bounds__(128) k_bg_slice(const Dev v, const BgDev b, const SliceDev sl, const double dtyr, const int init) {
+  using namespace bgk;
+  using namespace lay;
+  const int I = v.I, J = v.J, K = v.K, MS = v.MS;
+  constexpr int L = NL, LS = NLS;
+  const int m = blockIdx.x * 32 + threadIdx.x;
+  const int w = blockIdx.y * blockDim.y + threadIdx.y;
+  if (w >= sl.nwet3) return;
+  const int c = sl.wet[w];
+  const int k = c / (I * J) + 1;
+  const bool surface = (k == K);
+  if (init && surface) return;                    // the surface cell's initial solve is k_bg_step's (init_only)
+  const size_t oc = (size_t)c * L * MS + m;
+  double x[L + 1];
+#pragma unroll
+  for (int l = 1; l <= L; l++) x[l] = v.bg_ocn[oc + (size_t)(l - 1) * MS];
+  double cc[N_CC];
+  carbconst(b.Dmid[k], x[T], x[S], x[CA], x[MG], cc);
+  // the constants the surface solve never reads (sub_calc_carbconst :205-262), for int_carbconst_timeslice
+  double Tc = x[T], Sc = x[S];
+  if (Tc < (kZeroC + 2.0)) Tc = kZeroC + 2.0;
+  if (Tc > (kZeroC + 35.0)) Tc = kZeroC + 35.0;
+  if (Sc < 26.0) Sc = 26.0;
+  if (Sc > 43.0) Sc = 43.0;
+  const double rT = 1.0 / Tc, T_ln = log(Tc), T_log = log10(Tc), Tr100 = Tc / 100.0, TC = Tc - kZeroC, rRT = 1.0 / (kR * Tc), P = b.Dmid[k] / 10.0;
+  const double S_p05 = sqrt(Sc), S_p15 = Sc * S_p05;
+  double t2s;
+  {
+    const double Ii = (Sc > kNS) ? 19.924 * Sc / (1000.0 - 1.005 * Sc) : kNS;
+    const double I_p05 = sqrt(Ii), I_p15 = Ii * I_p05, I_p20 = Ii * Ii;
+    double Cl = x[S] / 1.80655;
+    if (Cl < kNS) Cl = kNS;
+    const double ION = (Cl > kNS) ? 0.00147 + 0.03592 * Cl + 0.000068 * Cl * Cl : kNS;
+    const double m2c = log(1 - 0.001005 * Sc);
+    const double SO4tot = fS(0.02824, Sc), Ftot = fS(0.00007, Sc);
+    const double lnkHSO4 = 141.328 - 4276.1 * rT - 23.093 * T_ln + (324.57 - 13856.0 * rT - 47.986 * T_ln) * I_p05 +
+                           (-771.54 + 35474.0 * rT + 114.723 * T_ln) * Ii - 2698.0 * rT * I_p15 + 1776.0 * rT * I_p20;
+    const double kHSO4f = exp(lnkHSO4 + m2c);
+    const double f2t = log(1.0 + SO4tot / kHSO4f);
+    const double kHFt = exp(1590.2 / Tc - 12.641 + 1.525 * sqrt(ION) + m2c + f2t);
+    t2s = -f2t + log(1.0 + SO4tot / kHSO4f + Ftot / kHFt);
+  }
+  const double kH2S = exp((225.838 - 13275.3 * rT - 34.6435 * T_ln + 0.3449 * S_p05 - 0.0274 * Sc) + t2s +
+                          corr_p(TC, P, rRT, -1.107E+1, +9.000E-3, -9.420E-4, +2.890E+0, +5.400E-2));
+  const double kNH4 = exp((-6285.33 * rT + 0.0001635 * Tc - 0.25444 + (0.46532 - 123.7184 * rT) * S_p05 + (-0.01992 + 3.17556 * rT) * Sc) +
+                          corr_p(TC, P, rRT, -2.643E+0, +8.890E-1, -9.050E-3, -5.030E+0, +8.140E-2));
+  const double kArg = exp(corr_p(TC, P, rRT, -4.596E+1, +5.304E-1, +0.000E+0, -1.176E+1, +3.692E-1)) *
+                      exp10(-171.945 - 0.077993 * Tc + 2903.293 * rT + 71.595 * T_log + (-0.068393 + 0.0017276 * Tc + 88.135 * rT) * S_p05 -
+                            0.10018 * Sc + 0.0059415 * S_p15);
+  const double qO2 = exp(-173.9894 + 255.5907 * (100.0 * rT) + 146.4813 * log(Tr100) - 22.2040 * (Tr100) +
+                         Sc * (-0.037362 + 0.016504 * (Tr100) - 0.0020564 * (Tr100 * Tr100)) - log(1.0E6) - log(0.20946));
+  double *Hp = surface ? &b.carbH[((size_t)(c - (size_t)(K - 1) * I * J)) * MS + m] : &sl.carbH3[(size_t)c * MS + m];
+  double *RFp = &sl.rf03[(size_t)c * MS + m];
+  Carb cb;
+  cb.H = init ? pow(10.0, -7.8) : *Hp;
+  cb.RF0 = init ? 0.0 : *RFp;
+  const bool rf = init || surface;
+  double keepRF = cb.RF0;
+  if (!solve_carb(x[DIC], x[ALK], x[CA], x[PO4], x[S], cc, cb, rf)) b.err[m] = 1;
+  if (!rf) cb.RF0 = keepRF;
+  *Hp = cb.H;
+  if (rf) *RFp = cb.RF0;
+  if (init) return;
+  // sub_calc_carb_r13C / r14C in full (gem_carbchem.f90:677-780): ratios of DIC, CO2(aq), HCO3-, CO3--
+  double iso[kSlIso];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const double mult = q ? 2.0 : 1.0, standard = q ? kStd14C : kStd13C, DICi = q ? x[DIC14] : x[DIC13];
+    const double d = iso_delta(x[DIC], DICi, standard);
+    const double e_bg = mult * (-0.1141 * (x[T] - kZeroC) + 10.78), e_dg = mult * (+0.0049 * (x[T] - kZeroC) - 1.31),
+                 e_cg = mult * (-0.052 * (x[T] - kZeroC) + 7.22);
+    const double e_cb = e_cg - e_bg / (1.0 + e_bg * 1.0E-3), e_db = e_dg - e_bg / (1.0 + e_bg * 1.0E-3);
+    const double dHCO3 = (d * x[DIC] - (e_db * cb.co2 + e_cb * cb.co3)) /
+                         ((1.0 + e_db * 1.0E-3) * cb.co2 + cb.hco3 + (1.0 + e_cb * 1.0E-3) * cb.co3);
+    const double dCO2 = e_db + dHCO3 * (1.0 + e_db * 1.0E-3), dCO3 = e_cb + dHCO3 * (1.0 + e_cb * 1.0E-3);
+    const double rCO2 = iso_fraction(dCO2, standard), rHCO3 = iso_fraction(dHCO3, standard), rCO3 = iso_fraction(dCO3, standard);
+    iso[4 * q + 0] = (rCO2 * cb.co2 + rHCO3 * cb.hco3 + rCO3 * cb.co3) / x[DIC];
+    iso[4 * q + 1] = rCO2; iso[4 * q + 2] = rHCO3; iso[4 * q + 3] = rCO3;
+  }
+  // ---- window integrals
+  {
+    double *a = sl.ocn + oc;
+#pragma unroll
+    for (int l = 1; l <= L; l++) a[(size_t)(l - 1) * MS] = a[(size_t)(l - 1) * MS] + dtyr * x[l];
+    const size_t pc = (size_t)c * LS * MS + m;
+#pragma unroll
+    for (int ls = 0; ls < LS; ls++) sl.part[pc + (size_t)ls * MS] = sl.part[pc + (size_t)ls * MS] + dtyr * b.bio_part[pc + (size_t)ls * MS];
+    // carb(ic_*): H, CO2, CO3, HCO3, fug_CO2, ohm_cal, ohm_arg, dCO3_cal, dCO3_arg, RF0   (gem_carbchem.f90:497-512)
+    const double carb[kSlCarb] = {cb.H, cb.co2, cb.co3, cb.hco3, cb.co2 / cc[CC_QCO2], cb.ohm_cal, x[CA] * cb.co3 / kArg,
+                                  cb.co3 - cc[CC_KCAL] * 1.0 / x[CA], cb.co3 - kArg * 1.0 / x[CA], cb.RF0};
+    double *ac = sl.carb + (size_t)c * kSlCarb * MS + m;
+#pragma unroll
+    for (int q = 0; q < kSlCarb; q++) ac[(size_t)q * MS] = ac[(size_t)q * MS] + dtyr * carb[q];
+    // carbconst(icc_*) in the oracle's order: k1 k2 k kB kW kSi kHF kHSO4 kP1 kP2 kP3 kH2S kNH4 kcal karg QCO2 QO2
+    const double ccv[kSlCC] = {cc[CC_K1], cc[CC_K2], cc[CC_K], cc[CC_KB], cc[CC_KW], cc[CC_KSI], cc[CC_KHF], cc[CC_KHSO4], cc[CC_KP1],
+                               cc[CC_KP2], cc[CC_KP3], kH2S, kNH4, cc[CC_KCAL], kArg, cc[CC_QCO2], qO2};
+    double *acc = sl.cc + (size_t)c * kSlCC * MS + m;
+#pragma unroll
+    for (int q = 0; q < kSlCC; q++) acc[(size_t)q * MS] = acc[(size_t)q * MS] + dtyr * ccv[q];
+    double *ai = sl.iso + (size_t)c * kSlIso * MS + m;
+#pragma unroll
+    for (int q = 0; q < kSlIso; q++) ai[(size_t)q * MS] = ai[(size_t)q * MS] + dtyr * iso[q];
+    if (w == 0) sl.t[m] = sl.t[m] + dtyr;
+  }
+}
+int launch_bg_slice(const Dev &v, const BgDev &b, const SliceDev &sl, double dtyr, int init, cudaStream_t s) {
+  if (sl.nwet3 <= 0) return 0;
+  k_bg_slice<<<dim3(v.MS / 32, (sl.nwet3 + 3) / 4), dim3(32, 4), 0, s>>>(v, b, sl, dtyr, init);
+  return 1;
+}
+
 int launch_bg_sig(const Dev &v, const BgDev &b, const SigDev &g, double dtyr, cudaStream_t s) {
   const int nq = kSigHead + 3 * v.L + g.LA;
   k_bg_sig_sums<<<dim3(v.MS / 32, nq), dim3(32, 8), 0, s>>>(v, b, g);

@@ -578,17 +578,17 @@ struct ColMaps {
 // box (32 members starting at member c0) x (rows starting at row c1) -> staging rows dstrow ...; host emulation: element-wise
 template <int MS>
 CG_HD void stage_box(const ColStage &s, const int which, const int dstrow, const void *tmap, const double *field, const int c0,
-                     const long c1, const int rows) {
+                     const int c1, const int rows) {
 #ifdef __CUDA_ARCH__
   (void)field; (void)rows;
   const unsigned d = (unsigned)__cvta_generic_to_shared(s.sm + dstrow * 32);
   const unsigned a = (unsigned)__cvta_generic_to_shared(s.bar) + 8u * which;
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(d), "l"(tmap),
-               "r"(a), "r"(c0), "r"((int)c1)
+               "r"(a), "r"(c0), "r"(c1)
                : "memory");
 #else
   (void)which; (void)tmap;
-  for (int r = 0; r < rows; r++) s.sm[(dstrow + r) * 32 + s.tid] = field[(c1 + r) * MS + c0 + s.tid];
+  for (int r = 0; r < rows; r++) s.sm[(dstrow + r) * 32 + s.tid] = field[(long)(c1 + r) * MS + c0 + s.tid];
 #endif
 }
 CG_HD void stage_syncw() {
@@ -636,12 +636,12 @@ CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsi
     const int b = (lev - k1c) & 1;
     stage_expect(st, b, (unsigned)(R::rowsC * NT * 8));
     const int lu = (lev < K) ? lev + 1 : K;
-    const long cellu = (long)(lu - 1) * IJ + c2;
+    const int cellu = (lu - 1) * IJ + c2;
     const int r0 = b * R::rowsC;
 #pragma unroll
     for (int cell = 0; cell < 5; cell++)
       stage_box<MS>(st, b, r0 + R::rTS + 2 * cell, mTS2, v.ts_cur, m0, (cellu + colcell(lu, cell)) * L, 2);
-    const long cellv = (long)(lev - 1) * IJ + c2;
+    const int cellv = (lev - 1) * IJ + c2;
     stage_box<MS>(st, b, r0 + R::rU + 0, mU3, v.u, m0, cellv * 3, 3);
     stage_box<MS>(st, b, r0 + R::rU + 3, mU1, v.u, m0, (cellv + cW) * 3, 1);
     stage_box<MS>(st, b, r0 + R::rU + 4, mU1, v.u, m0, (cellv + cUS) * 3 + 1, 1);
@@ -649,7 +649,7 @@ CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsi
   auto issueA = [&](const int lev) {
     if (R::nA == 0 || !leader) return;
     stage_expect(st, 2, (unsigned)(R::rowsA * NT * 8));
-    const long cell0 = (long)(lev - 1) * IJ + c2;
+    const int cell0 = (lev - 1) * IJ + c2;
 #pragma unroll
     for (int cell = 0; cell < 5; cell++)
       stage_box<MS>(st, 2, R::rA + cell * R::nA, mTSA, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * L + 2, R::nA);
@@ -657,7 +657,7 @@ CG_HD void tstep_column_w(const Dev &v, const GridC &g, const int c2, const unsi
   auto issueB = [&](const int lev) {
     if (!leader) return;
     stage_expect(st, 3, (unsigned)(R::rowsB * NT * 8));
-    const long cell0 = (long)(lev - 1) * IJ + c2;
+    const int cell0 = (lev - 1) * IJ + c2;
 #pragma unroll
     for (int cell = 0; cell < 5; cell++)
       stage_box<MS>(st, 3, R::rB + cell * R::nB, mTSB, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * L + R::lB0, R::nB);

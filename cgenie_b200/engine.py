@@ -243,6 +243,15 @@ class Ensemble(_Base):
         call it on the steps of a save window, read the window with get("bg_sig", member)."""
         self._ck(self.L.cg_biogem_sig_update(self.h, float(dts), float(ben_Dmin)))
 
+    def biogem_slice_update(self, dts):
+        """diag_biogem_timeslice's arithmetic for one BIOGEM step of a save window: 3-D carbonate re-solve + window integrals
+        (fields sl_ocn, sl_part, sl_carb, sl_carbconst, sl_carbisor, sl_t); call it behind biogem_climate (genie.f90:391-395)."""
+        self._ck(self.L.cg_biogem_slice_update(self.h, float(dts)))
+
+    def biogem_slice_reset(self):
+        """sub_init_int_timeslice (biogem_data.f90:1012-1060)."""
+        self._ck(self.L.cg_biogem_slice_reset(self.h))
+
     def biogem_sig_reset(self):
         """sub_init_int_timeseries (biogem_data.f90:964-1007)."""
         self._ck(self.L.cg_biogem_sig_reset(self.h))

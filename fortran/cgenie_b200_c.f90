@@ -131,6 +131,16 @@ MODULE cgenie_b200_c
        IMPORT :: C_INT, C_PTR
        TYPE(C_PTR), VALUE :: h
      END FUNCTION cg_biogem_sig_reset
+     ! diag_biogem_timeslice's arithmetic (biogem.f90:2421-2699): 3-D carbonate re-solve + window integrals on the device
+     INTEGER(C_INT) FUNCTION cg_biogem_slice_update(h, dts) BIND(C, NAME='cg_biogem_slice_update')
+       IMPORT :: C_INT, C_PTR, C_DOUBLE
+       TYPE(C_PTR), VALUE :: h
+       REAL(C_DOUBLE), VALUE :: dts
+     END FUNCTION cg_biogem_slice_update
+     INTEGER(C_INT) FUNCTION cg_biogem_slice_reset(h) BIND(C, NAME='cg_biogem_slice_reset')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h
+     END FUNCTION cg_biogem_slice_reset
   END INTERFACE
 
 CONTAINS

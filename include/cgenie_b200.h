@@ -133,6 +133,18 @@ int cg_reinit_flux_rokocn(cg_handle *);
  * of one member in that order, 3 + 3*maxl + n_l_atm values, tracers in the compact selection order; cg_biogem_sig_reset =
  * sub_init_int_timeseries (biogem_data.f90:964-1007).  ben_Dmin = par_data_save_ben_Dmin (m). */
 int cg_biogem_sig_update(cg_handle *, double dts, double ben_Dmin);
+/* diag_biogem_timeslice (src/biogem/biogem.f90:2421-2699; SURVEY 8f row 1, time-slice part), its arithmetic: inside a save
+ * window the carbonate system of EVERY wet cell is solved again from the cell's last [H+] (:2478-2567; the surface cell's feeds
+ * back into step_biogem's next solve, as in the reference) and the window integrals int_ocn, int_bio_part, int_carb,
+ * int_carbconst, int_carbisor, int_t _timeslice grow by dtyr * field (:2572-2579).  Call it where genie.f90 calls
+ * diag_biogem_timeslice_wrapper (:391-395: behind cg_biogem_climate, ahead of cg_biogem_sig_update and cg_atchem_step) on the
+ * steps of a save window; the window bookkeeping and the netCDF writer stay with the host, which reads the fields "sl_ocn"
+ * (maxl,i,j,k), "sl_part" (n_l_sed,...), "sl_carb" (10,...: H, CO2, CO3, HCO3, fug_CO2, ohm_cal, ohm_arg, dCO3_cal, dCO3_arg,
+ * RF0), "sl_carbconst" (17,...: k1 k2 k kB kW kSi kHF kHSO4 kP1 kP2 kP3 kH2S kNH4 kcal karg QCO2 QO2), "sl_carbisor" (8,...)
+ * and "sl_t".  cg_biogem_slice_reset = sub_init_int_timeslice.  Not on the device: the 2-D interface integrals (focnatm,
+ * focnsed ...), the overturning stream functions and the diag_* arrays of :2580-2606. */
+int cg_biogem_slice_update(cg_handle *, double dts);
+int cg_biogem_slice_reset(cg_handle *);
 int cg_biogem_sig_reset(cg_handle *);
 /* sub_init_data_save_runtime / sub_data_save_runtime (src/biogem/biogem_data_ascii.f90:23-110, 669-935), the ocn_* and atm_*
  * series: <outdir>/<outfile_name>_series_ocn_<name>.res and ..._atm_<name>.res in the reference's formats

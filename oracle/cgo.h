@@ -81,6 +81,8 @@ void cgo_cpl_comp_ocnsed(cgo_t *, int ocnstep, int mbiogem, int msedgem);
 void cgo_reinit_flux_rokocn(cgo_t *);
 void cgo_biogem_sig_update(cgo_t *, double ben_Dmin);
 void cgo_biogem_sig_auto(cgo_t *, int on, double ben_Dmin);
+void cgo_biogem_slice_update(cgo_t *);
+void cgo_biogem_slice_auto(cgo_t *, int on);
 void cgo_atchem_step(cgo_t *);
 
 /* run n iterations of the genie.f90 koverall loop (one EMBM step each) */

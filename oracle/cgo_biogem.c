@@ -103,6 +103,12 @@ struct cgo_bg {
   double *sfxsumsed, *sfcsumocn, *sfxsumrok1;          /* SEDGEM / ROKGEM interface sums (sediment grid = ocean grid) */
   double *sig;                                         /* time-series integrals: t, tot_M, tot_M_sur, ocn(L), sur(L), ben(L), atm(LA) */
   int sig_auto; double sig_ben_Dmin;                   /* cgo_run takes the diagnostic where genie.f90 does (after step_biogem) */
+  /* time-slice diagnostics (diag_biogem_timeslice): 3-D carbonate system of every wet cell below the surface (the surface
+   * cell's is carb / carbisor above, shared with step_biogem as in the reference) and the window integrals */
+  double *carb3, *ciso3, *cc3;                         /* [N_IC|N_ICI|N_CC][i][j][k] (level K unused: see carb) */
+  double *sl_ocn, *sl_part, *sl_carb, *sl_cc, *sl_ciso, *sl_t;   /* int_ocn / bio_part / carb / carbconst / carbisor _timeslice, int_t_timeslice */
+  int slice_auto;
+  double Dmid[64];
   double Dbot[64], dD[64], Dmid_surf;
   int go;
 };
@@ -506,6 +512,9 @@ void cgo_biogem_setup(cgo_t *o, const char *params) {
   b->atm_A = bg_alloc(o, "atm_A", ij); b->atm_V = bg_alloc(o, "atm_V", ij);
   b->sfcocn1 = bg_alloc(o, "sfcocn1", ij * NL); b->sfxsed1 = bg_alloc(o, "sfxsed1", ij * b->LS); b->focnatm = bg_alloc(o, "focnatm", ij * b->LA);
   b->sig = bg_alloc(o, "bg_sig", 3 + 3 * NL + b->LA);
+  b->carb3 = bg_alloc(o, "carb3", n3 * N_IC); b->ciso3 = bg_alloc(o, "carbisor3", n3 * N_ICI); b->cc3 = bg_alloc(o, "carbconst3", n3 * N_CC);
+  b->sl_ocn = bg_alloc(o, "sl_ocn", n3 * NL); b->sl_part = bg_alloc(o, "sl_part", n3 * b->LS); b->sl_carb = bg_alloc(o, "sl_carb", n3 * N_IC);
+  b->sl_cc = bg_alloc(o, "sl_carbconst", n3 * N_CC); b->sl_ciso = bg_alloc(o, "sl_carbisor", n3 * N_ICI); b->sl_t = bg_alloc(o, "sl_t", 1);
   b->sfxsumsed = bg_alloc(o, "sfxsumsed", ij * b->LS); b->sfcsumocn = bg_alloc(o, "sfcsumocn", ij * NL); b->sfxsumrok1 = bg_alloc(o, "sfxsumrok1", ij * NL);
   b->rst_I = bg_alloc(o, "rst_atm_I", ij * b->LA); b->rst_II = bg_alloc(o, "rst_atm_II", ij * b->LA);
   b->rst_atm = bg_alloc(o, "force_restore_atm", ij * b->LA);
@@ -524,6 +533,12 @@ void cgo_biogem_setup(cgo_t *o, const char *params) {
       b->Dbot[k] = s;
     }
     b->Dmid_surf = CG_DSC * dzal[K];
+    for (k = 1; k <= K; k++) {   /* phys_ocn(ipo_Dmid,i,j,k) = SUM(goldstein_dsc*loc_grid_dza(k:n_k)), biogem_data.f90:1120 */
+      double s = 0.0;
+      int kk;
+      for (kk = k; kk <= K; kk++) s = s + CG_DSC * dzal[kk];
+      b->Dmid[k] = s;
+    }
   }
   for (i = 1; i <= I; i++)
     for (j = 1; j <= J; j++) {
@@ -575,6 +590,23 @@ void cgo_biogem_setup(cgo_t *o, const char *params) {
                       f_Ftot(S), cc, cb);
         calc_carb_riso(OCN(1, i, j, K), OCN(b->l_DIC, i, j, K), OCN(b->l_DIC13, i, j, K), cb, 1.0, BG_STD_13C, &CISO(ICI_DIC_R13C, i, j));
         calc_carb_riso(OCN(1, i, j, K), OCN(b->l_DIC, i, j, K), OCN(b->l_DIC14, i, j, K), cb, 2.0, BG_STD_14C, &CISO(ICI_DIC_R14C, i, j));
+      }
+  /* sub_init_carb, the cells below the surface (k < n_k): same seed, same calls; read by the time-slice diagnostics only */
+  for (i = 1; i <= I; i++)
+    for (j = 1; j <= J; j++)
+      for (k = K1(i, j); k < K; k++) {
+        const long c = (i - 1) + (long)I * ((j - 1) + (long)J * (k - 1));
+        double *cc = &b->cc3[N_CC * c], *cb = &b->carb3[N_IC * c];
+        const double S = OCN(2, i, j, k);
+        calc_carbconst(b->Dmid[k], OCN(1, i, j, k), S, cc);
+        adj_carbconst(OCN(b->l_Ca, i, j, k), OCN(b->l_Mg, i, j, k), cc);
+        cb[IC_H] = pow(10.0, -7.8);
+        calc_carb(OCN(b->l_DIC, i, j, k), OCN(b->l_ALK, i, j, k), OCN(b->l_Ca, i, j, k), OCN(b->l_PO4, i, j, k), 0.0, f_Btot(S),
+                  f_SO4tot(S), f_Ftot(S), cc, cb);
+        calc_carb_RF0(OCN(b->l_DIC, i, j, k), OCN(b->l_ALK, i, j, k), OCN(b->l_PO4, i, j, k), 0.0, f_Btot(S), f_SO4tot(S),
+                      f_Ftot(S), cc, cb);
+        calc_carb_riso(OCN(1, i, j, k), OCN(b->l_DIC, i, j, k), OCN(b->l_DIC13, i, j, k), cb, 1.0, BG_STD_13C, &b->ciso3[N_ICI * c + ICI_DIC_R13C]);
+        calc_carb_riso(OCN(1, i, j, k), OCN(b->l_DIC, i, j, k), OCN(b->l_DIC14, i, j, k), cb, 2.0, BG_STD_14C, &b->ciso3[N_ICI * c + ICI_DIC_R14C]);
       }
   /* sub_init_force_restore_atm :2706-2791 with data/biogem/worjh2_preindustrial (I = 0, II = 1 at wet points, 2-point signal) */
   {
@@ -1248,6 +1280,49 @@ void cgo_biogem_sig_update(cgo_t *o, double ben_Dmin) {
   free(mask);
 }
 
+/* diag_biogem_timeslice (biogem.f90:2421-2699), the part that is arithmetic: inside a save window with dum_save, the carbonate
+ * system of EVERY wet cell is solved again from the cell's last [H+] (:2478-2567; the surface cell's carb is the array
+ * step_biogem seeds its own solve from, so the diagnostic feeds back into the next step exactly as in the reference), then the
+ * window integrals grow (:2572-2579): int_ocn, int_bio_part, int_carb, int_carbconst, int_carbisor += dtyr * field, int_t += dtyr.
+ * The window bookkeeping (par_data_save_timeslice, :2460-2470, 2627-2696) and the netCDF writer stay with the host. */
+void cgo_biogem_slice_update(cgo_t *o) {
+  struct cgo_bg *b = BG;
+  const int I = NI, J = NJ, K = NK;
+  int i, j, k, l, ls, q;
+  const double dts = (double)(b->kbiogem * o->kocn_loop) * b->genie_timestep;
+  const double dtyr = dts / BG_YR_S;
+  for (i = 1; i <= I; i++)
+    for (j = 1; j <= J; j++)
+      for (k = K1(i, j); k <= K; k++) {
+        const long c = (i - 1) + (long)I * ((j - 1) + (long)J * (k - 1));
+        double ccs[N_CC];
+        double *cc = (k < K) ? &b->cc3[N_CC * c] : ccs;
+        double *cb = (k < K) ? &b->carb3[N_IC * c] : &CARB(0, i, j);
+        double *ci = (k < K) ? &b->ciso3[N_ICI * c] : &CISO(0, i, j);
+        const double S = OCN(2, i, j, k);
+        calc_carbconst(b->Dmid[k], OCN(1, i, j, k), S, cc);
+        adj_carbconst(OCN(b->l_Ca, i, j, k), OCN(b->l_Mg, i, j, k), cc);
+        calc_carb(OCN(b->l_DIC, i, j, k), OCN(b->l_ALK, i, j, k), OCN(b->l_Ca, i, j, k), OCN(b->l_PO4, i, j, k), 0.0, f_Btot(S),
+                  f_SO4tot(S), f_Ftot(S), cc, cb);
+        if (k == K) {
+          /* sub_calc_carb_RF0 is called at every k with the SURFACE cell's arguments (:2533-2545); only the call behind the
+           * surface solve leaves a value that survives (it writes carb(ic_RF0,i,j,n_k) alone) */
+          const double Ss = OCN(2, i, j, K);
+          calc_carb_RF0(OCN(b->l_DIC, i, j, K), OCN(b->l_ALK, i, j, K), OCN(b->l_PO4, i, j, K), 0.0, f_Btot(Ss), f_SO4tot(Ss),
+                        f_Ftot(Ss), cc, cb);
+        }
+        calc_carb_riso(OCN(1, i, j, k), OCN(b->l_DIC, i, j, k), OCN(b->l_DIC13, i, j, k), cb, 1.0, BG_STD_13C, &ci[ICI_DIC_R13C]);
+        calc_carb_riso(OCN(1, i, j, k), OCN(b->l_DIC, i, j, k), OCN(b->l_DIC14, i, j, k), cb, 2.0, BG_STD_14C, &ci[ICI_DIC_R14C]);
+        for (l = 1; l <= NL; l++) b->sl_ocn[(l - 1) + NL * c] = b->sl_ocn[(l - 1) + NL * c] + dtyr * OCN(l, i, j, k);
+        for (ls = 1; ls <= b->LS; ls++) b->sl_part[(ls - 1) + b->LS * c] = b->sl_part[(ls - 1) + b->LS * c] + dtyr * PART(ls, i, j, k);
+        for (q = 0; q < N_IC; q++) b->sl_carb[q + N_IC * c] = b->sl_carb[q + N_IC * c] + dtyr * cb[q];
+        for (q = 0; q < N_CC; q++) b->sl_cc[q + N_CC * c] = b->sl_cc[q + N_CC * c] + dtyr * cc[q];
+        for (q = 0; q < N_ICI; q++) b->sl_ciso[q + N_ICI * c] = b->sl_ciso[q + N_ICI * c] + dtyr * ci[q];
+      }
+  b->sl_t[0] = b->sl_t[0] + dtyr;
+}
+void cgo_biogem_slice_auto(cgo_t *o, int on) { BG->slice_auto = on; }
+
 void cgo_biogem_sig_auto(cgo_t *o, int on, double ben_Dmin) { BG->sig_auto = on; BG->sig_ben_Dmin = ben_Dmin; }
 
 /* cpl_flux_ocnsed, sedgem.f90:1029-1068 (loc_scalei = loc_scalej = 1: i1 = i, j1 = j) */
@@ -1327,6 +1402,7 @@ int cgo_biogem_koverall(cgo_t *o, long k) {
     cgo_biogem_climate(o);
     /* diag_biogem_timeseries_wrapper, genie.f90:401-405: behind biogem_climate_wrapper (:387), ahead of cpl_flux_ocnatm_wrapper
      * (:411) and of the ATCHEM step (:446-455) -- the ocean is this block's, sfcatm1 still the previous block's */
+    if (b->slice_auto) cgo_biogem_slice_update(o);             /* diag_biogem_timeslice_wrapper, genie.f90:391-395 */
     if (b->sig_auto) cgo_biogem_sig_update(o, b->sig_ben_Dmin);
     cgo_cpl_flux_ocnatm(o);
   }

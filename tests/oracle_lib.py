@@ -44,6 +44,8 @@ def lib():
         L.cgo_reinit_flux_rokocn.argtypes, L.cgo_reinit_flux_rokocn.restype = [P], None
         L.cgo_biogem_sig_update.argtypes, L.cgo_biogem_sig_update.restype = [P, C.c_double], None
         L.cgo_biogem_sig_auto.argtypes, L.cgo_biogem_sig_auto.restype = [P, C.c_int, C.c_double], None
+        L.cgo_biogem_slice_update.argtypes, L.cgo_biogem_slice_update.restype = [P], None
+        L.cgo_biogem_slice_auto.argtypes, L.cgo_biogem_slice_auto.restype = [P, C.c_int], None
         L.cgo_biogem_step.argtypes = [P]
         L.cgo_biogem_step.restype = C.c_int
         L.cgo_biogem_setup.argtypes = [P, C.c_char_p]

@@ -135,3 +135,48 @@ def test_sedgem_coupler_sums():
     o.f("sfxsumrok1")[:] = 3.0
     o.L.cgo_reinit_flux_rokocn(o.h)
     assert np.all(o.f("sfxsumrok1") == 0.0)
+
+
+def test_timeslice_diagnostics():
+    """diag_biogem_timeslice (biogem.f90:2421-2699) restated: the window integrals are dtyr-weighted sums of the fields at the
+    call point, the 3-D carbonate re-solve lands on the published deep-ocean ranges (pH 7.5 - 8.3, calcite under-saturated at
+    depth, over-saturated at the surface), and the only thing the diagnostic changes in the model is the surface [H+] seed of the
+    next step's solve (same fixed point: the trajectory moves by no more than the solver's 0.1 % tolerance allows)."""
+    N_IC, N_CC = 10, 17
+    o = Oracle("worjh2", maxk=K, maxl=L, nyear=96)
+    o.biogem_setup()
+    ref = Oracle("worjh2", maxk=K, maxl=L, nyear=96)
+    ref.biogem_setup()
+    dtyr = float(2 * 5) / 5.0 / 96
+    k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    wet3 = (np.arange(1, K + 1)[:, None, None] >= k1[None]).ravel()
+    o.run(480)
+    ref.run(480)
+    acc, accp = np.zeros(K * J * I * L), np.zeros(K * J * I * LS)
+    for blk in range(3):
+        o.run(10)
+        ref.run(10)
+        o.L.cgo_biogem_slice_update(o.h)
+        acc = acc + dtyr * o.f("ocn")
+        accp = accp + dtyr * o.f("bio_part")
+    w = np.repeat(wet3, L)
+    assert np.array_equal(o.f("sl_ocn")[w], acc[w]) and np.all(o.f("sl_ocn")[~w] == 0.0)
+    assert np.array_equal(o.f("sl_part")[np.repeat(wet3, LS)], accp[np.repeat(wet3, LS)])
+    assert abs(o.f("sl_t")[0] - 3 * dtyr) < 1e-15
+    carb = (o.f("sl_carb") / o.f("sl_t")[0]).reshape(K, J * I, N_IC)
+    w3 = wet3.reshape(K, J * I)
+    pH = -np.log10(carb[..., 0][w3])
+    assert 7.4 < pH.min() and pH.max() < 8.4, (pH.min(), pH.max())
+    assert carb[K - 1, :, 5][w3[K - 1]].min() > 1.0          # calcite saturation at the surface
+    deep = carb[0, :, 5][w3[0]]                              # the deepest level: 5000 m
+    assert deep.size > 0 and deep.max() < 1.2 and deep.min() > 0.3
+    # CO2 + HCO3 + CO3 = DIC in every cell
+    dic = (o.f("sl_ocn") / o.f("sl_t")[0]).reshape(K, J * I, L)[..., DIC]
+    s = carb[..., 1] + carb[..., 2] + carb[..., 3]
+    assert np.max(np.abs(s[w3] / dic[w3] - 1.0)) < 1e-12
+    cc = (o.f("sl_carbconst") / o.f("sl_t")[0]).reshape(K, J * I, N_CC)
+    pK1 = -np.log10(cc[K - 1, :, 0][w3[K - 1]])
+    assert 5.7 < pK1.min() and pK1.max() < 6.2                # Mehrbach refit: pK1 = 5.84 at 25 degC, 6.1 at 0 degC
+    # the model went on unchanged but for the surface seed
+    rel = np.abs(o.f("ocn")[w] - ref.f("ocn")[w]) / np.maximum(np.abs(ref.f("ocn")[w]), 1e-3 * np.abs(ref.f("ocn")[w]).max())
+    assert rel.max() < 1e-6
