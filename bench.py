@@ -33,7 +33,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CONFIG = "eb_go_gs_ac_bg_36x36x16"
 WORKLOAD = ("eb_go_gs_ac_bg 36x36x16 worjh2: EMBM + GOLDSTEIN + sea ice + BIOGEM (16 ocean tracers, 1N1T_PO4MM, "
             "13C/14C, CFCs) + ATCHEM, parameter-perturbed ensemble sharded by member "
-            "(BASELINE config #4 shape: 128 members/GPU = 1024 at 8 GPUs)")
+            "(BASELINE config #4: the 1024-member ensemble's shard at 2 GPUs, 512 members/GPU, held per GPU at every N -- one "
+            "library handle, the kernels run over 128-member tiles; --members 128 is round 1's shard)")
+MEMBERS_PER_GPU = 512
 # --config N: the other BASELINE.json configurations (the default line, N = 4, is the one the metric is quoted on)
 #   job configuration, members per GPU, BIOGEM, default untimed spin-up years, workload text
 CONFIGS = {
@@ -43,7 +45,7 @@ CONFIGS = {
         "(BASELINE config #2: 100-year spin-up on one B200)"),
     3: (CONFIG, 64, True, 100, "eb_go_gs_ac_bg 36x36x16 worjh2 with BIOGEM + ATCHEM, 64-member parameter-perturbation ensemble on one "
         "B200 (BASELINE config #3)"),
-    4: (CONFIG, 128, True, 100, WORKLOAD),
+    4: (CONFIG, MEMBERS_PER_GPU, True, 100, WORKLOAD),
 }
 from cgenie_b200.sharding import PERTURBED, PERTURBED_BIOGEM, SEED, perturbation_table, shard  # noqa: E402  (pure numpy)
 
@@ -159,7 +161,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "ensemble model-years/wall-hour", "value": value, "unit": "model-years/hour",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(WORKLOAD, 128, 36, 36, 16, 16, 96, "col", True, 100),
+        "config": config_dict(WORKLOAD, MEMBERS_PER_GPU, 36, 36, 16, 16, 96, "col", True, 100),
         "note": "reference arm = the C restatement of the reference (oracle/, -O3 -funroll-loops, no FMA) on the host cores, not a "
                 "gfortran build; it starts from the initial state (no spin-up: the CPU cost of a model year does not depend on it)",
         "cpu_baseline": {"value": value, "unit": "model-years/hour", "cores": cores, "kind": "port", "sample": sample},

@@ -391,12 +391,20 @@ static void register_hconst(cg_handle *h, const MemberConsts &c) {
 // ------------------------------------------------------------------ life cycle
 extern "C" const char *cg_last_error(void) { return g_err.c_str(); }
 
+// Member stride: members rounded up to whole warps; above 128 to the strides the fixed-shape kernels are compiled for (256, 512:
+// 128-member tiles of one handle), padding lanes carry copies of the last member.  More than 512 members: generic kernels.
+static int member_stride_for(int n_members) {
+  const int ms = ((n_members + 31) / 32) * 32;
+  if (ms > 128 && ms <= 256) return 256;
+  if (ms > 256 && ms <= 512) return 512;
+  return ms;
+}
 extern "C" int cg_create(const char *jobdir, int n_members, int device, cg_handle **out) {
   if (!jobdir || !out || n_members < 1) return fail(CG_ERR_ARG, "cg_create: bad argument");
   std::unique_ptr<cg_handle> h(new cg_handle);
   h->device = device;
   h->M = n_members;
-  h->MS = ((n_members + 31) / 32) * 32;
+  h->MS = member_stride_for(n_members);
   std::string err;
   if (!load_job(jobdir, &h->base, &h->g, &h->isl, &h->w, &err)) {
     const bool io = err.find("could not open") != std::string::npos || err.find("too short") != std::string::npos;
@@ -2434,7 +2442,7 @@ extern "C" int cg_tracer_create(int maxi, int maxj, int maxk, int maxl, int n_me
   std::unique_ptr<cg_handle> h(new cg_handle);
   h->device = device;
   h->M = n_members;
-  h->MS = ((n_members + 31) / 32) * 32;
+  h->MS = ((n_members + 31) / 32) * 32;   // stand-alone tracer step: generic-shape kernels, any stride
   h->tracer_only = true;
   Params p;
   p.maxi = maxi; p.maxj = maxj; p.maxk = maxk; p.maxl = maxl; p.nyear = nyear; p.diff1 = diff1; p.diff2 = diff2;

@@ -8,11 +8,22 @@
 // the ordered sum over columns -- so every total is bit-identical to the sequential code.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include "cg_device.cuh"
 #include "cg_host.hpp"
 
 namespace cg {
-static inline bool tc_fix_shape(const Dev &v) { return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && v.MS == 128 && !getenv("CG_BG_NOFIX"); }
+// Compiled member strides of the fixed-shape (36 x 36 x 16) kernel instances: 128 (one tile), 256, 512 (larger shards of one handle)
+static inline bool fix_ms(int MS) { return MS == 128 || MS == 256 || MS == 512; }
+static inline bool tc_fix_shape(const Dev &v) { return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && fix_ms(v.MS) && !getenv("CG_BG_NOFIX"); }
+// f(integral_constant<int, FMS>): FMS = the handle's member stride where an instance with that stride exists, else 0 (generic kernel)
+template <class F>
+static inline void fix_dispatch(const bool ok, const int MS, F f) {
+  if (ok && MS == 128) f(std::integral_constant<int, 128>());
+  else if (ok && MS == 256) f(std::integral_constant<int, 256>());
+  else if (ok && MS == 512) f(std::integral_constant<int, 512>());
+  else f(std::integral_constant<int, 0>());
+}
 
 constexpr double kBgZeroC = 273.15;          // gem_cmn.f90:690
 constexpr double kBgNullSmall = 0.999999e-19; // gem_cmn.f90:719
@@ -23,9 +34,10 @@ constexpr double kBgNullSmall = 0.999999e-19; // gem_cmn.f90:719
 //   2 .. L-1     : sum_k ocn(l)*M, l = 3..L             (old inventories)          [phase A]
 //   L .. 2L-3    : sum_k loc_vocn(l)*M, l = 3..L        (salinity-adjusted new)    [phase B]
 // FIX: grid shape, tracer count and member stride of the bench configuration as compile-time constants (see k_bg_step)
-template <bool FIX>
+template <int FMS>
 __global__ void __launch_bounds__(128) k_tc_partial(const Dev v, const int phase) {
-  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, L = FIX ? 16 : v.L, MS = FIX ? 128 : v.MS;
+  constexpr bool FIX = FMS > 0;
+  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, L = FIX ? 16 : v.L, MS = FIX ? FMS : v.MS;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y * blockDim.y + threadIdx.y;
   if (m >= MS || n >= v.nwet) return;
@@ -192,10 +204,11 @@ __global__ void k_tc_factors(const Dev v) {
   }
 }
 constexpr int kApplyCellsPerWarp = 1, kApplyWarps = 4;
-template <bool FIX>
+template <int FMS>
 __global__ void __launch_bounds__(32 * kApplyWarps, 4) k_tc_apply(const Dev v) {
   __shared__ double s_f[kBgMaxL][32], s_rmean[32], s_sr[32], s_rsr[32], s_mnew[32];
-  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, L = FIX ? 16 : v.L, MS = FIX ? 128 : v.MS;
+  constexpr bool FIX = FMS > 0;
+  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, L = FIX ? 16 : v.L, MS = FIX ? FMS : v.MS;
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int m = blockIdx.x * 32 + lane;
   {
@@ -545,12 +558,13 @@ __device__ __forceinline__ void rem_add(Rem7 &r, const double f, const double *p
 // FIX: the grid shape and the member stride of the bench configuration (36 x 36 x 16, 128 members) as compile-time
 // constants -- every address becomes base + immediate (40 % of the generic kernel's instructions are 64-bit address
 // arithmetic).
-template <int MINB, int PART, bool FIX>
+template <int MINB, int PART, int FMS>
 __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev b, const int init_only, const int mode) {
   const bool fuse = (mode & 1) != 0, pf = (mode & 2) == 0;
   using namespace bgk;
   using namespace lay;
-  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, MS = FIX ? 128 : v.MS;
+  constexpr bool FIX = FMS > 0;
+  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, MS = FIX ? FMS : v.MS;
   constexpr int L = NL, LS = NLS, LA = NLA;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y * blockDim.y + threadIdx.y;
@@ -1106,7 +1120,7 @@ __global__ void __launch_bounds__(256) k_bg_atchem3(const Dev v, const BgDev b, 
   b.sfxsumatm[q] = 0.0;
 }
 
-static bool bg_fix_shape(const Dev &v) { return v.I == 36 && v.J == 36 && v.K == 16 && v.MS == 128 && !getenv("CG_BG_NOFIX"); }
+static bool bg_fix_shape(const Dev &v) { return v.I == 36 && v.J == 36 && v.K == 16 && fix_ms(v.MS) && !getenv("CG_BG_NOFIX"); }
 int launch_bg_step(const Dev &v, const BgDev &b, int init_only, int fuse, cudaStream_t s) {
   // registers per thread 255 / 168 / 128 for MINB = 2 / 3 / 4 (CG_BG_MINB overrides; tuning knob)
   static int minb = -1;
@@ -1115,10 +1129,9 @@ int launch_bg_step(const Dev &v, const BgDev &b, int init_only, int fuse, cudaSt
   if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
   fuse |= nopf;
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
-  if (minb == 4) k_bg_step<4, 0, false><<<g, bl, 0, s>>>(v, b, init_only, fuse);
-  else if (minb == 3) k_bg_step<3, 0, false><<<g, bl, 0, s>>>(v, b, init_only, fuse);
-  else if (bg_fix_shape(v)) k_bg_step<2, 0, true><<<g, bl, 0, s>>>(v, b, init_only, fuse);
-  else k_bg_step<2, 0, false><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  if (minb == 4) k_bg_step<4, 0, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  else if (minb == 3) k_bg_step<3, 0, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
+  else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<2, 0, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, init_only, fuse); });
   return 1;
 }
 // the two parts of the step (see k_bg_step): surface cell, then sediment return + water-column sweep
@@ -1126,9 +1139,8 @@ int launch_bg_surf(const Dev &v, const BgDev &b, cudaStream_t s) {
   static int minb = -1;   // registers per thread 134 / 128 for 3 / 4 (CG_BG_SURF_MINB; tuning knob)
   if (minb < 0) { const char *e = getenv("CG_BG_SURF_MINB"); minb = e ? atoi(e) : 4; }
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
-  if (minb == 3) k_bg_step<3, 1, false><<<g, bl, 0, s>>>(v, b, 0, 0);
-  else if (bg_fix_shape(v)) k_bg_step<4, 1, true><<<g, bl, 0, s>>>(v, b, 0, 0);
-  else k_bg_step<4, 1, false><<<g, bl, 0, s>>>(v, b, 0, 0);
+  if (minb == 3) k_bg_step<3, 1, 0><<<g, bl, 0, s>>>(v, b, 0, 0);
+  else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<4, 1, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, 0); });
   return 1;
 }
 int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s) {
@@ -1137,11 +1149,8 @@ int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s) {
   static int nopf = -1;
   if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
-  if (minb == 3) {
-    if (bg_fix_shape(v)) k_bg_step<3, 2, true><<<g, bl, 0, s>>>(v, b, 0, nopf);
-    else k_bg_step<3, 2, false><<<g, bl, 0, s>>>(v, b, 0, nopf);
-  } else if (bg_fix_shape(v)) k_bg_step<2, 2, true><<<g, bl, 0, s>>>(v, b, 0, nopf);
-  else k_bg_step<2, 2, false><<<g, bl, 0, s>>>(v, b, 0, nopf);
+  if (minb == 3) k_bg_step<3, 2, 0><<<g, bl, 0, s>>>(v, b, 0, nopf);
+  else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<2, 2, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, nopf); });
   return 1;
 }
 // step (1) of biogem_tracercoupling taken BEFORE step_biogem (fused coupling, see k_bg_step)
@@ -1149,9 +1158,9 @@ int launch_tc_sums_first(const Dev &v, cudaStream_t s) {
   const dim3 b(32, 4);
   const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
   const int L = v.L;
-  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 2); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 2);
+  fix_dispatch(tc_fix_shape(v), v.MS, [&](auto ms) { k_tc_partial<decltype(ms)::value><<<gc, b, 0, s>>>(v, 2); });
   k_tc_sum<<<dim3(v.MS / 32, L), 32 * kSumWarps, 0, s>>>(v, 0, L);
-  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 1); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 1);
+  fix_dispatch(tc_fix_shape(v), v.MS, [&](auto ms) { k_tc_partial<decltype(ms)::value><<<gc, b, 0, s>>>(v, 1); });
   k_tc_sum<<<dim3(v.MS / 32, L - 2), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2);
   k_tc_factors<<<(v.MS + 127) / 128, 128, 0, s>>>(v);
   return 5;
@@ -1160,7 +1169,7 @@ int launch_tc_sums_first(const Dev &v, cudaStream_t s) {
 int launch_tc_sums_old(const Dev &v, cudaStream_t s) {
   const dim3 b(32, 4);
   const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
-  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 3); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 3);
+  fix_dispatch(tc_fix_shape(v), v.MS, [&](auto ms) { k_tc_partial<decltype(ms)::value><<<gc, b, 0, s>>>(v, 3); });
   k_tc_sum<<<dim3(v.MS / 32, v.L), 32 * kSumWarps, 0, s>>>(v, 0, v.L, -2);
   return 2;
 }
@@ -1169,7 +1178,7 @@ int launch_tc_sums_new(const Dev &v, cudaStream_t s) {
   const dim3 b(32, 4);
   const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
   const int L = v.L;
-  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 4); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 4);
+  fix_dispatch(tc_fix_shape(v), v.MS, [&](auto ms) { k_tc_partial<decltype(ms)::value><<<gc, b, 0, s>>>(v, 4); });
   k_tc_sum<<<dim3(v.MS / 32, L - 1), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2, 1);
   k_tc_factors<<<(v.MS + 127) / 128, 128, 0, s>>>(v);
   return 3;
@@ -1177,8 +1186,7 @@ int launch_tc_sums_new(const Dev &v, cudaStream_t s) {
 // steps (2)+(3) alone, after launch_tc_sums_first
 int launch_tc_apply_only(const Dev &v, cudaStream_t s) {
   const int ncell = v.I * v.J * v.K, per_block = kApplyWarps * kApplyCellsPerWarp;
-  if (tc_fix_shape(v)) k_tc_apply<true><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
-  else k_tc_apply<false><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
+  fix_dispatch(tc_fix_shape(v), v.MS, [&](auto ms) { k_tc_apply<decltype(ms)::value><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v); });
   return 1;
 }
 int launch_bg_stage_seaice(const Dev &v, const BgDev &b, cudaStream_t s) {
@@ -1206,17 +1214,16 @@ int launch_tracercoupling(const Dev &v, cudaStream_t s) {
   const dim3 b(32, 4);
   const dim3 gc(v.MS / 32, (v.nwet + 3) / 4);
   const int L = v.L;
-  if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 0); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 0);
+  fix_dispatch(tc_fix_shape(v), v.MS, [&](auto ms) { k_tc_partial<decltype(ms)::value><<<gc, b, 0, s>>>(v, 0); });
   k_tc_sum<<<dim3(v.MS / 32, L), 32 * kSumWarps, 0, s>>>(v, 0, L);
   if (L > 2) {
-    if (tc_fix_shape(v)) k_tc_partial<true><<<gc, b, 0, s>>>(v, 1); else k_tc_partial<false><<<gc, b, 0, s>>>(v, 1);
+    fix_dispatch(tc_fix_shape(v), v.MS, [&](auto ms) { k_tc_partial<decltype(ms)::value><<<gc, b, 0, s>>>(v, 1); });
     k_tc_sum<<<dim3(v.MS / 32, L - 2), 32 * kSumWarps, 0, s>>>(v, L, 2 * L - 2);
   }
   {
     const int ncell = v.I * v.J * v.K, per_block = kApplyWarps * kApplyCellsPerWarp;
     k_tc_factors<<<(v.MS + 127) / 128, 128, 0, s>>>(v);
-    if (tc_fix_shape(v)) k_tc_apply<true><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
-  else k_tc_apply<false><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v);
+    fix_dispatch(tc_fix_shape(v), v.MS, [&](auto ms) { k_tc_apply<decltype(ms)::value><<<dim3(v.MS / 32, (ncell + per_block - 1) / per_block), dim3(32, kApplyWarps), 0, s>>>(v); });
   }
   return L > 2 ? 6 : 4;
 }

@@ -58,8 +58,23 @@ __global__ void __launch_bounds__(32, 8) k_tstep_colw(const Dev v, const __grid_
   tstep_column_w<I, J, K, L, MS>(v, c_g, c2, m, st, &maps);
 }
 
-// 2-D tensor maps of a field seen as [row][member] (fp64, row pitch MS doubles), box = 32 members x `rows` rows, no swizzle
-static bool make_map(void *out128, const void *base, unsigned long long nrows, int MS, int rows) {
+// tile form of the block kernel: one block = NT = 128 members (tile blockIdx.x / nwet) of one wet column of a handle whose member
+// stride is MS = 256 or 512; tile-major block order, so that the stencil rows a tile's neighbouring columns share stay in L2 as
+// they do at MS = 128.  Staging through 2-D tensor maps (see tstep_column, TM).
+template <int I, int J, int K, int L, int MS, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_tstep_colt(const Dev v, const __grid_constant__ ColMaps maps) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ColStage st;
+  st.sm = reinterpret_cast<double *>(smem_raw);
+  st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows<L>::rows * NT * 8);
+  st.tid = threadIdx.x;
+  const int tile = blockIdx.x / v.nwet, ci = blockIdx.x - tile * v.nwet;
+  const int c2 = v.col_deep_first ? v.wetcols[ci] : v.rowcols[ci];
+  tstep_column<I, J, K, L, MS, NT, false, false, true>(v, c_g, c2, (unsigned)(tile * NT) + threadIdx.x, st, &maps);
+}
+
+// 2-D tensor maps of a field seen as [row][member] (fp64, row pitch MS doubles), box = `boxw` members x `rows` rows, no swizzle
+static bool make_map(void *out128, const void *base, unsigned long long nrows, int MS, int rows, unsigned boxw = 32u) {
   typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                CUtensorMapFloatOOBfill);
@@ -72,7 +87,7 @@ static bool make_map(void *out128, const void *base, unsigned long long nrows, i
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)MS, (cuuint64_t)nrows};
   const cuuint64_t gstr[1] = {(cuuint64_t)MS * sizeof(double)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)rows};
+  const cuuint32_t box[2] = {boxw, (cuuint32_t)rows};
   const cuuint32_t estr[2] = {1u, 1u};
   CUtensorMap tmap;
   const CUresult r = fn(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -81,7 +96,7 @@ static bool make_map(void *out128, const void *base, unsigned long long nrows, i
   memcpy(out128, &tmap, 128);
   return true;
 }
-template <int I, int J, int K, int L, int MS>
+template <int I, int J, int K, int L, int MS, unsigned BOXW = 32u>
 static const ColMaps *col_maps(const Dev &v) {
   static std::mutex mu;
   static std::map<std::pair<const void *, const void *>, ColMaps> cache;   // (ts buffer read this step, u) -> maps
@@ -92,8 +107,8 @@ static const ColMaps *col_maps(const Dev &v) {
   ColMaps mp;
   using R = ColRows<L>;
   const unsigned long long nts = (unsigned long long)I * J * K * L, nu = (unsigned long long)I * J * K * 3;
-  if (!make_map(mp.ts2, v.ts_cur, nts, MS, 2) || !make_map(mp.tsA, v.ts_cur, nts, MS, R::nA > 0 ? R::nA : 1) ||
-      !make_map(mp.tsB, v.ts_cur, nts, MS, R::nB) || !make_map(mp.u3, v.u, nu, MS, 3) || !make_map(mp.u1, v.u, nu, MS, 1))
+  if (!make_map(mp.ts2, v.ts_cur, nts, MS, 2, BOXW) || !make_map(mp.tsA, v.ts_cur, nts, MS, R::nA > 0 ? R::nA : 1, BOXW) ||
+      !make_map(mp.tsB, v.ts_cur, nts, MS, R::nB, BOXW) || !make_map(mp.u3, v.u, nu, MS, 3, BOXW) || !make_map(mp.u1, v.u, nu, MS, 1, BOXW))
     return nullptr;
   return &(cache[key] = mp);
 }
@@ -271,8 +286,37 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   return 2;
 }
 
+// member strides above 128: the flux kernel in its tile form (128-member tiles through tensor maps), the convection kernel as it is
+// (its grid already runs over 32-member tiles)
+template <int I, int J, int K, int L, int MS>
+static int go_tiled(const Dev &v, cudaStream_t s) {
+  constexpr int NT = 128;
+  constexpr size_t smem = (size_t)ColRows<L>::rows * NT * 8 + 64;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_tstep_colt<I, J, K, L, MS, NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_co_col<I, J, K, L, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * (K + 2) * 128 * sizeof(double)));
+    attr = true;
+  }
+  const ColMaps *maps = col_maps<I, J, K, L, MS, 128u>(v);
+  if (!maps) return 0;
+  static int order = -1, coskip = -1;
+  if (order < 0) { const char *e = getenv("CG_COL_ORDER"); order = e ? atoi(e) : 0; }
+  if (coskip < 0) { const char *e = getenv("CG_CO_SKIP"); coskip = e ? atoi(e) : 1; }
+  Dev v1 = v;
+  v1.col_deep_first = order;
+  k_tstep_colt<I, J, K, L, MS, NT, 2><<<v.nwet * (MS / NT), NT, smem, s>>>(v1, *maps);
+  Dev v2 = v;
+  v2.co_prefetch = 0;
+  v2.co_skip_stable = coskip ? 1 : 0;
+  v2.co_pairwise = 1;
+  v2.co_local = 1;
+  k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
+  return 2;
+}
+
 bool tstep_col_supported(const Dev &v) {
-  return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && (v.MS == 32 || v.MS == 64 || v.MS == 128);
+  return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && (v.MS == 32 || v.MS == 64 || v.MS == 128 || v.MS == 256 || v.MS == 512);
 }
 
 // 0 = this grid shape / member stride has no compiled instance (the caller falls back to the generic kernels)
@@ -283,6 +327,8 @@ int launch_tstep_col(const Dev &v, cudaStream_t s) {
     cfg = e ? atoi(e) : 0;
   }
   if (!tstep_col_supported(v)) return 0;
+  if (v.MS == 256) return go_tiled<36, 36, 16, 16, 256>(v, s);
+  if (v.MS == 512) return go_tiled<36, 36, 16, 16, 512>(v, s);
   if (v.MS == 32) return go<36, 36, 16, 16, 32>(v, s, cfg);
   if (v.MS == 64) return go<36, 36, 16, 16, 64>(v, s, cfg);
   return go<36, 36, 16, 16, 128>(v, s, cfg);

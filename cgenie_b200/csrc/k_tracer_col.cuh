@@ -180,6 +180,28 @@ CG_HD bool stage_issuer(const ColStage &s, const int unit) {
 #endif
 }
 
+// Tensor maps of the two fields the kernels stage, by box height (rows per copy); built on the host (k_tracer_col.cu).  Box width =
+// the member tile of the kernel that uses them (32: warp-tile form; 128: block form on a member stride > 128).
+struct ColMaps {
+  alignas(64) unsigned long long ts2[16], tsA[16], tsB[16], u3[16], u1[16];   // CUtensorMap is 128 opaque bytes, 64-byte aligned
+};
+// box (NT members starting at member c0) x (rows starting at row c1) -> staging rows dstrow ...; host emulation: element-wise
+template <int MS, int NT = 32>
+CG_HD void stage_box(const ColStage &s, const int which, const int dstrow, const void *tmap, const double *field, const int c0,
+                     const int c1, const int rows) {
+#ifdef __CUDA_ARCH__
+  (void)field; (void)rows;
+  const unsigned d = (unsigned)__cvta_generic_to_shared(s.sm + dstrow * NT);
+  const unsigned a = (unsigned)__cvta_generic_to_shared(s.bar) + 8u * which;
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(d), "l"(tmap),
+               "r"(a), "r"(c0), "r"(c1)
+               : "memory");
+#else
+  (void)which; (void)tmap;
+  for (int r = 0; r < rows; r++) s.sm[(dstrow + r) * NT + s.tid] = field[(long)(c1 + r) * MS + c0 + s.tid];
+#endif
+}
+
 // rows of the staging buffers.  Unit C (double buffered, issued 1.5 levels ahead): T,S of the five columns one level
 // up + the five velocities; unit A: tracers 2..LH-1 of the five columns; unit B: tracers LH..L-1.
 template <int L>
@@ -302,9 +324,12 @@ CG_HD void col_coefs(const ColK &q, const GridC &g, const int kk, const bool opE
 //   ts_pre_column.  While the march is inside a region the running thickness-weighted sum rides in Q (Q = sum + dz * the
 //   level's partial update), so no extra accumulator is needed; at the region's top the mean is stored to all of its
 //   levels.  A level outside any region has weight 1 and carry 0: its value is exactly the unmixed one.
-template <int I, int J, int K, int L, int MS, int NT, bool PV, bool ASYNC_REL = false>
-CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st) {
-  static_assert(NT == MS, "a block covers all members of one column");
+// TM = true: the block is an NT-member TILE of a member stride MS > NT (one handle holding more than 128 members): the rows of
+//   a staging unit are then NT * 8 bytes out of every MS * 8, fetched as 2-D tensor-map boxes (NT members x the unit's rows,
+//   cp.async.bulk.tensor.2d / UTMALDG) instead of contiguous bulk copies; m = tile * NT + thread.  Everything else is unchanged.
+template <int I, int J, int K, int L, int MS, int NT, bool PV, bool ASYNC_REL = false, bool TM = false>
+CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st, const ColMaps *tm = nullptr) {
+  static_assert(TM || NT == MS, "a block covers all members of one column, or a tile of them through tensor maps");
   static_assert(!PV || K <= 16, "region map is 16 + 16 bits");
   using R = ColRows<L>;
   constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
@@ -328,14 +353,35 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   const double *const u0 = v.u + (long)c2 * uC3;
   const double *const sm = st.sm + st.tid;
 
+  // TM: first member of the tile, neighbour columns as CELL offsets, the maps
+  constexpr int IJ = I * J;
+  const int m0 = (int)(m - (unsigned)st.tid);
+  const int cE = (i < I) ? 1 : -(I - 1), cW = (i > 1) ? -1 : (I - 1), cUS = (j > 1) ? -I : 0;
+  const void *const mTS2 = (TM && tm) ? (const void *)tm->ts2 : nullptr, *const mTSA = (TM && tm) ? (const void *)tm->tsA : nullptr,
+                   *const mTSB = (TM && tm) ? (const void *)tm->tsB : nullptr, *const mU3 = (TM && tm) ? (const void *)tm->u3 : nullptr,
+                   *const mU1 = (TM && tm) ? (const void *)tm->u1 : nullptr;
+  auto colcell = [&](const int lev, const int cell) {             // cell offset of stencil column `cell` at level lev
+    return (cell == 0) ? 0 : (cell == 1) ? ((lev >= k1e) ? cE : 0) : (cell == 2) ? ((lev >= k1w) ? cW : 0)
+           : (cell == 3) ? ((lev >= k1n) ? I : 0) : ((lev >= k1s) ? -I : 0);
+  };
   // issue the staging units of level `lev` (lev <= K).  Unit C: T,S one level up (or the level itself at the top,
   // where every upper coefficient is zero) and the five velocities; units A / B: the passive tracers.
   auto issueC = [&](const int lev) {
     const int b = (lev - k1c) & 1;
     stage_expect(st, b, (unsigned)(R::rowsC * NT * 8));
     const int lu = (lev < K) ? lev + 1 : K;
-    const double *c1 = ts0 + (long)(lu - 1) * sK;
     const int r0 = b * R::rowsC;
+    if (TM) {
+      const int cellu = (lu - 1) * IJ + c2, cellv = (lev - 1) * IJ + c2;
+#pragma unroll
+      for (int cell = 0; cell < 5; cell++)
+        stage_box<MS, NT>(st, b, r0 + R::rTS + 2 * cell, mTS2, v.ts_cur, m0, (cellu + colcell(lu, cell)) * L, 2);
+      stage_box<MS, NT>(st, b, r0 + R::rU + 0, mU3, v.u, m0, cellv * 3, 3);
+      stage_box<MS, NT>(st, b, r0 + R::rU + 3, mU1, v.u, m0, (cellv + cW) * 3, 1);
+      stage_box<MS, NT>(st, b, r0 + R::rU + 4, mU1, v.u, m0, (cellv + cUS) * 3 + 1, 1);
+      return;
+    }
+    const double *c1 = ts0 + (long)(lu - 1) * sK;
     stage_copy<NT>(st, b, r0 + R::rTS + 0, c1, 2);
     stage_copy<NT>(st, b, r0 + R::rTS + 2, c1 + ((lu >= k1e) ? dE : 0), 2);
     stage_copy<NT>(st, b, r0 + R::rTS + 4, c1 + ((lu >= k1w) ? dW : 0), 2);
@@ -349,6 +395,13 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   auto issueA = [&](const int lev) {
     if (R::nA == 0) return;
     stage_expect(st, 2, (unsigned)(R::rowsA * NT * 8));
+    if (TM) {
+      const int cell0 = (lev - 1) * IJ + c2;
+#pragma unroll
+      for (int cell = 0; cell < 5; cell++)
+        stage_box<MS, NT>(st, 2, R::rA + cell * R::nA, mTSA, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * L + 2, R::nA);
+      return;
+    }
     const double *c0 = ts0 + (long)(lev - 1) * sK + 2 * sL;
     stage_copy<NT>(st, 2, R::rA + 0 * R::nA, c0, R::nA);
     stage_copy<NT>(st, 2, R::rA + 1 * R::nA, c0 + ((lev >= k1e) ? dE : 0), R::nA);
@@ -358,6 +411,13 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
   };
   auto issueB = [&](const int lev) {
     stage_expect(st, 3, (unsigned)(R::rowsB * NT * 8));
+    if (TM) {
+      const int cell0 = (lev - 1) * IJ + c2;
+#pragma unroll
+      for (int cell = 0; cell < 5; cell++)
+        stage_box<MS, NT>(st, 3, R::rB + cell * R::nB, mTSB, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * L + R::lB0, R::nB);
+      return;
+    }
     const double *c0 = ts0 + (long)(lev - 1) * sK + R::lB0 * sL;
     stage_copy<NT>(st, 3, R::rB + 0 * R::nB, c0, R::nB);
     stage_copy<NT>(st, 3, R::rB + 1 * R::nB, c0 + ((lev >= k1e) ? dE : 0), R::nB);
@@ -571,26 +631,6 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 // issues, but per warp.  (A first version copied the 256-byte row slices with "one warp-wide cp.async.bulk, lane r = row r":
 // the instruction takes its operands from the uniform datapath, so the compiler turns per-lane addresses into a serial loop
 // over the lanes, 95 copies per warp and level, twice the kernel's instructions: profiles/README_r2.md.)
-// Tensor maps of the two fields the kernel stages, by box height (rows per copy); built on the host (k_tracer_col.cu).
-struct ColMaps {
-  alignas(64) unsigned long long ts2[16], tsA[16], tsB[16], u3[16], u1[16];   // CUtensorMap is 128 opaque bytes, 64-byte aligned
-};
-// box (32 members starting at member c0) x (rows starting at row c1) -> staging rows dstrow ...; host emulation: element-wise
-template <int MS>
-CG_HD void stage_box(const ColStage &s, const int which, const int dstrow, const void *tmap, const double *field, const int c0,
-                     const int c1, const int rows) {
-#ifdef __CUDA_ARCH__
-  (void)field; (void)rows;
-  const unsigned d = (unsigned)__cvta_generic_to_shared(s.sm + dstrow * 32);
-  const unsigned a = (unsigned)__cvta_generic_to_shared(s.bar) + 8u * which;
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(d), "l"(tmap),
-               "r"(a), "r"(c0), "r"(c1)
-               : "memory");
-#else
-  (void)which; (void)tmap;
-  for (int r = 0; r < rows; r++) s.sm[(dstrow + r) * 32 + s.tid] = field[(long)(c1 + r) * MS + c0 + s.tid];
-#endif
-}
 CG_HD void stage_syncw() {
 #ifdef __CUDA_ARCH__
   __syncwarp();
