@@ -342,6 +342,14 @@ __device__ __forceinline__ double calc_rho(double T, double S) {  // gem_util.f9
 __device__ __forceinline__ double corr_p(double TC, double P, double rRT, double d1, double d2, double d3, double d4, double d5) {
   return (-(d1 + d2 * TC + d3 * TC * TC) + (5.0E-4 * (d4 + d5 * TC)) * P) * P * rRT;  // gem_carbchem.f90:1175-1186
 }
+// a / b with y = 1.0 / b already known (correctly rounded): q = a y is within an ulp or two of the quotient, r = a - b q is exact in
+// one FMA, q + r y rounds to RN(a / b) (Markstein 1990; holds for normal operands unless b's significand is all ones) -- three
+// instructions for the ~28 of the IEEE division sequence, same result.  Used where one denominator serves several divisions.
+__device__ __forceinline__ double div_by(const double a, const double b, const double y) {
+  const double q = a * y;
+  const double r = fma(-b, q, a);
+  return fma(r, y, q);
+}
 __device__ __forceinline__ double fS(double c, double S) { double x = c * S / 35.0; if (x < kNS) x = kNS; return x; }
 
 // sub_calc_carbconst (Mehrbach) + sub_adj_carbconst, gem_carbchem.f90:59-297; only the constants the surface solve reads
@@ -368,7 +376,7 @@ __device__ void carbconst(double D, double T_in, double S_in, double Ca, double 
   const double SO4tot = fS(0.02824, S), Ftot = fS(0.00007, S);
   const double lnkHSO4 = 141.328 - 4276.1 * rT - 23.093 * T_ln + (324.57 - 13856.0 * rT - 47.986 * T_ln) * I_p05 +
                          (-771.54 + 35474.0 * rT + 114.723 * T_ln) * Ii - 2698.0 * rT * I_p15 + 1776.0 * rT * I_p20;
-  const double lnkHF = 1590.2 / T - 12.641 + 1.525 * ION_p05;
+  const double lnkHF = div_by(1590.2, T, rT) - 12.641 + 1.525 * ION_p05;
   cc[CC_KHSO4] = exp(lnkHSO4 + m2c);
   const double f2t = log(1.0 + SO4tot / cc[CC_KHSO4]);
   cc[CC_KHF] = exp(lnkHF + m2c + f2t);
@@ -391,11 +399,11 @@ __device__ void carbconst(double D, double T_in, double S_in, double Ca, double 
                    m2c + corr_p(TC, P, rRT, -2.948E+1, +1.622E-1, +2.608E-3, -2.840E+0, +0.000E+0));
   cc[CC_KHF] = exp(lnkHF + m2c + f2s + corr_p(TC, P, rRT, -9.780E+0, -9.000E-3, -9.420E-4, -3.910E+0, +5.400E-2));
   cc[CC_KHSO4] = exp(lnkHSO4 + m2c + f2s + corr_p(TC, P, rRT, -1.803E+1, +4.660E-2, +3.160E-4, -4.530E+0, +9.000E-2));
-  cc[CC_KP1] = exp((115.54 - 4576.752 / T - 18.453 * T_ln + (0.69171 - 106.736 / T) * S_p05 + (-0.01844 - 0.65643 / T) * S) +
+  cc[CC_KP1] = exp((115.54 - div_by(4576.752, T, rT) - 18.453 * T_ln + (0.69171 - div_by(106.736, T, rT)) * S_p05 + (-0.01844 - div_by(0.65643, T, rT)) * S) +
                    corr_p(TC, P, rRT, -1.451E+1, +1.211E-1, -3.210E-4, -2.670E+0, +4.270E-2));
-  cc[CC_KP2] = exp((172.1033 - 8814.715 / T - 27.927 * T_ln + (1.3566 - 160.340 / T) * S_p05 + (-0.05778 + 0.37335 / T) * S) +
+  cc[CC_KP2] = exp((172.1033 - div_by(8814.715, T, rT) - 27.927 * T_ln + (1.3566 - div_by(160.340, T, rT)) * S_p05 + (-0.05778 + div_by(0.37335, T, rT)) * S) +
                    corr_p(TC, P, rRT, -2.312E+1, +1.758E-1, -2.647E-3, -5.150E+0, +9.000E-2));
-  cc[CC_KP3] = exp((-18.126 - 3070.75 / T + (2.81197 + 17.27039 / T) * S_p05 + (-0.09984 - 44.99486 / T) * S) +
+  cc[CC_KP3] = exp((-18.126 - div_by(3070.75, T, rT) + (2.81197 + div_by(17.27039, T, rT)) * S_p05 + (-0.09984 - div_by(44.99486, T, rT)) * S) +
                    corr_p(TC, P, rRT, -2.657E+1, +2.020E-1, -3.042E-3, -4.080E+0, +7.140E-2));
   cc[CC_KCAL] = exp(corr_p(TC, P, rRT, -4.876E+1, +5.304E-1, +0.000E+0, -1.176E+1, +3.692E-1)) *
                 exp10(-171.9065 - 0.077993 * T + 2839.319 * rT + 71.595 * T_log +
@@ -410,25 +418,38 @@ __device__ void carbconst(double D, double T_in, double S_in, double Ca, double 
   cc[CC_K1] = (1.0 + 0.155 * (Mg - kConcMg) / kConcMg) * cc[CC_K1];
   cc[CC_K2] = (1.0 + 0.422 * (Mg - kConcMg) / kConcMg) * cc[CC_K2];
 }
-// one pass of the implicit [H] loop (gem_carbchem.f90:352-424 / 578-640); H2S, NH4, SiO2 totals are zero here
+// reciprocals of the constants of one solve that carb_iter divides by (taken once per solve)
+struct CarbR { double rKB, rKP2, rKP3, rK12, rK23, rK123, K12, K23, K123, km4, rkm4, km4x2, rkm4x2; };
+__device__ __forceinline__ void carb_recips(const double *cc, CarbR &r) {
+  r.K12 = cc[CC_KP1] * cc[CC_KP2]; r.K23 = cc[CC_KP2] * cc[CC_KP3]; r.K123 = cc[CC_KP1] * cc[CC_KP2] * cc[CC_KP3];
+  r.rKB = 1.0 / cc[CC_KB]; r.rKP2 = 1.0 / cc[CC_KP2]; r.rKP3 = 1.0 / cc[CC_KP3];
+  r.rK12 = 1.0 / r.K12; r.rK23 = 1.0 / r.K23; r.rK123 = 1.0 / r.K123;
+  r.km4 = cc[CC_K] - 4.0; r.rkm4 = 1.0 / r.km4; r.km4x2 = 2.0 * r.km4; r.rkm4x2 = 1.0 / r.km4x2;
+}
+// one pass of the implicit [H] loop (gem_carbchem.f90:352-424 / 578-640); H2S, NH4, SiO2 totals are zero here.  Every quotient
+// is the reference's (same operands, correctly rounded); the 16 whose denominator is a constant of the solve or a power of H go
+// through div_by with one reciprocal each instead of the full division sequence.  H3SiO4 = 0 / (1 + H / kSi) is +0.0 as written.
 __device__ __forceinline__ void carb_iter(double DIC, double ALK, double PO4tot, double Btot, double SO4tot, double Ftot,
-                                          const double *cc, double H, double &co2, double &co3, double &hco3, double &H1, double &H2) {
+                                          const double *cc, const CarbR &rk, double H, double &co2, double &co3, double &hco3, double &H1,
+                                          double &H2) {
   const double H_p2 = H * H, H_p3 = H * H_p2;
-  const double OH = cc[CC_KW] / H;
-  const double H4BO4 = Btot / (1.0 + H / cc[CC_KB]);
-  const double H3SiO4 = 0.0 / (1.0 + H / cc[CC_KSI]);
-  const double HSO4 = SO4tot / (1.0 + cc[CC_KHSO4] / H);
-  const double HF = Ftot / (1.0 + cc[CC_KHF] / H);
-  const double H3PO4 = PO4tot / (1.0 + cc[CC_KP1] / H + (cc[CC_KP1] * cc[CC_KP2]) / H_p2 + (cc[CC_KP1] * cc[CC_KP2] * cc[CC_KP3]) / H_p3);
-  const double HPO4 = PO4tot / (1.0 + H / cc[CC_KP2] + H_p2 / (cc[CC_KP1] * cc[CC_KP2]) + cc[CC_KP3] / H);
-  const double PO4 = PO4tot / (1.0 + H / cc[CC_KP3] + H_p2 / (cc[CC_KP2] * cc[CC_KP3]) + H_p3 / (cc[CC_KP1] * cc[CC_KP2] * cc[CC_KP3]));
+  const double rH = 1.0 / H, rH2 = 1.0 / H_p2, rH3 = 1.0 / H_p3;
+  const double OH = div_by(cc[CC_KW], H, rH);
+  const double H4BO4 = Btot / (1.0 + div_by(H, cc[CC_KB], rk.rKB));
+  const double H3SiO4 = 0.0;
+  const double HSO4 = SO4tot / (1.0 + div_by(cc[CC_KHSO4], H, rH));
+  const double HF = Ftot / (1.0 + div_by(cc[CC_KHF], H, rH));
+  const double H3PO4 = PO4tot / (1.0 + div_by(cc[CC_KP1], H, rH) + div_by(rk.K12, H_p2, rH2) + div_by(rk.K123, H_p3, rH3));
+  const double HPO4 = PO4tot / (1.0 + div_by(H, cc[CC_KP2], rk.rKP2) + div_by(H_p2, rk.K12, rk.rK12) + div_by(cc[CC_KP3], H, rH));
+  const double PO4 = PO4tot / (1.0 + div_by(H, cc[CC_KP3], rk.rKP3) + div_by(H_p2, rk.K23, rk.rK23) + div_by(H_p3, rk.K123, rk.rK123));
   const double ALK_DIC = ALK - H4BO4 - OH - HPO4 - 2.0 * PO4 - H3SiO4 - 0.0 - 0.0 + H + HSO4 + HF + H3PO4;
   const double k = cc[CC_K];
   const double a = 4.0 * ALK_DIC + DIC * k - ALK_DIC * k;
   const double zed = sqrt(a * a + 4.0 * (k - 4.0) * (ALK_DIC * ALK_DIC));
-  hco3 = (DIC * k - zed) / (k - 4.0);
-  co3 = (ALK_DIC * k - DIC * k - 4.0 * ALK_DIC + zed) / (2.0 * (k - 4.0));
-  co2 = DIC - ALK_DIC + (ALK_DIC * k - DIC * k - 4.0 * ALK_DIC + zed) / (2.0 * (k - 4.0));
+  hco3 = div_by(DIC * k - zed, rk.km4, rk.rkm4);
+  const double t = ALK_DIC * k - DIC * k - 4.0 * ALK_DIC + zed;
+  co3 = div_by(t, rk.km4x2, rk.rkm4x2);
+  co2 = DIC - ALK_DIC + co3;
   H1 = cc[CC_K1] * co2 / hco3;
   H2 = cc[CC_K2] * hco3 / co3;
 }
@@ -436,10 +457,12 @@ __device__ __forceinline__ void carb_iter(double DIC, double ALK, double PO4tot,
 __device__ bool solve_carb(double DIC, double ALK, double Ca, double PO4tot, double S, const double *cc, Carb &c, bool with_RF0) {
   const double Btot = fS(0.000416, S), SO4tot = fS(0.02824, S), Ftot = fS(0.00007, S);
   double H = c.H, H_old, co2, co3, hco3, H1, H2;
+  CarbR rk;
+  carb_recips(cc, rk);
   int n = 1;
   for (;;) {
     H_old = H;
-    carb_iter(DIC, ALK, PO4tot, Btot, SO4tot, Ftot, cc, H, co2, co3, hco3, H1, H2);
+    carb_iter(DIC, ALK, PO4tot, Btot, SO4tot, Ftot, cc, rk, H, co2, co3, hco3, H1, H2);
     if ((H1 < kNS) || (H2 < kNS)) return false;
     H = sqrt(H1 * H2);
     if (fabs(1.0 - H / H_old) < (1.0E-8 / H) * 0.001) {
@@ -455,7 +478,7 @@ __device__ bool solve_carb(double DIC, double ALK, double Ca, double PO4tot, dou
     n = 1;
     for (;;) {
       H_old = H;
-      carb_iter(DIC_RF0, ALK, PO4tot, Btot, SO4tot, Ftot, cc, H, co2, co3, hco3, H1, H2);
+      carb_iter(DIC_RF0, ALK, PO4tot, Btot, SO4tot, Ftot, cc, rk, H, co2, co3, hco3, H1, H2);
       H = sqrt(H1 * H2);
       if (fabs(1.0 - H / H_old) < 0.001) { c.RF0 = (co2 / c.co2 - 1.0) / (DIC_RF0 / DIC - 1.0); break; }
       n = n + 1;
@@ -1371,7 +1394,7 @@ __global__ void __launch_bounds__(128) k_bg_slice(const Dev v, const BgDev b, co
                            (-771.54 + 35474.0 * rT + 114.723 * T_ln) * Ii - 2698.0 * rT * I_p15 + 1776.0 * rT * I_p20;
     const double kHSO4f = exp(lnkHSO4 + m2c);
     const double f2t = log(1.0 + SO4tot / kHSO4f);
-    const double kHFt = exp(1590.2 / Tc - 12.641 + 1.525 * sqrt(ION) + m2c + f2t);
+    const double kHFt = exp(div_by(1590.2, Tc, rT) - 12.641 + 1.525 * sqrt(ION) + m2c + f2t);
     t2s = -f2t + log(1.0 + SO4tot / kHSO4f + Ftot / kHFt);
   }
   const double kH2S = exp((225.838 - 13275.3 * rT - 34.6435 * T_ln + 0.3449 * S_p05 - 0.0274 * Sc) + t2s +

@@ -322,6 +322,14 @@ __global__ void __launch_bounds__(704) k_embm(const Dev v, const int nsteps) {
       }
     }
   }
+  // the implicit iterations divide by 1 + cimp * dt * cdiv, the same number for a cell in all 4 iterations of all nsteps steps:
+  // one reciprocal, then q = a y, r = a - b q (exact in one FMA), q + r y = RN(a / b) -- the correctly rounded quotient the
+  // division sequence returns (Markstein 1990), bit for bit the reference's result at 3 instructions instead of ~28
+  double rden[2][CPT];
+#pragma unroll
+  for (int l = 0; l < 2; l++)
+#pragma unroll
+    for (int n = 0; n < CPT; n++) rden[l][n] = 1.0 / (1 + cimp * (dtloc * cdiv[l][n]));
   for (int step = 0; step < nsteps; step++) {
 #pragma unroll
     for (int l = 0; l < 2; l++) {
@@ -348,7 +356,9 @@ __global__ void __launch_bounds__(704) k_embm(const Dev v, const int nsteps) {
                                (cin[l][n] * T2(i, j + 1) - cism[l][n] * T2(i, j - 1)) * c_g.rds[j];
             if (iits < 4) {
               const double centre = dtloc * cdiv[l][n];
-              tq[l][n] = (tq1[l][n] * (1.0 - (1.0 - cimp) * centre) - dtloc * flx) / (1 + cimp * centre);
+              const double num = tq1[l][n] * (1.0 - (1.0 - cimp) * centre) - dtloc * flx, den = 1 + cimp * centre;
+              const double qq = num * rden[l][n];
+              tq[l][n] = fma(fma(-den, qq, num), rden[l][n], qq);
             } else {
               tq[l][n] = tq1[l][n] - dtloc * flx - dtloc * T2(i, j) * cdiv[l][n];
             }
