@@ -357,6 +357,8 @@ def main():
     materialise(tmp, cfgname)
     e = Ensemble(tmp, n_members=M, device=local, perturb=pert)
     e.set_tracer_variant(args.variant)
+    if os.environ.get("CG_BENCH_FUSE"):      # A/B knob: tracer coupling fused into the BIOGEM step kernel (cg_set_biogem_fusion)
+        e.set_biogem_fusion(True)
     kyear = e.nyear * e.ndta
     L, I, J, K = e.maxl, e.maxi, e.maxj, e.maxk
 

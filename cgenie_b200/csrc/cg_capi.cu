@@ -287,6 +287,7 @@ static void fill_gridc(cg_handle *h) {
   for (int k = 0; k <= g.K + 1 && k < kMaxK; k++) {
     c.dz[k] = g.dz[k]; c.dza[k] = g.dza[k]; c.rdz[k] = g.rdz[k]; c.rdza[k] = g.rdza[k]; c.zw[k] = g.zw[k];
     c.ssmax[k] = h->mc.empty() ? 0.0 : h->mc[0].ssmax[k];
+    c.diffmax[k] = (h->mc.empty() || k >= (int)h->mc[0].diffmax.size()) ? 0.0 : h->mc[0].diffmax[k];
   }
 }
 static void upload_grid(cg_handle *h) {
@@ -578,6 +579,13 @@ static int build_device(cg_handle *h) {
   TRY(dparam(h, &p.rsictscsf, col([](const MemberConsts &c) { return c.rsictscsf; })));
   TRY(dparam(h, &p.albocn, col([](const MemberConsts &c) { return c.p.albocn; })));
   TRY(dparam(h, &p.hosing_trend, col([](const MemberConsts &c) { return c.hosing_trend; })));
+  v.iediff = h->base.iediff; v.ediffpow2i = h->mc[0].ediffpow2i; v.ediffpow2 = h->base.ediffpow2;
+  if (v.iediff) {   // per member: ediff1p scales with diff(2) - ediff0, both perturbable
+    TRY(dparam(h, &p.ediff0, col([](const MemberConsts &c) { return c.ediff0; })));
+    std::vector<const std::vector<double> *> src;
+    for (int m = 0; m < M; m++) src.push_back(&h->mc[m].ediff1p);
+    double *q; TRY(dmember_array(h, &q, (size_t)K + 2, src)); p.ediff1p = q;
+  }
   {
     std::vector<int> t(MS, 0);
     for (int m = 0; m < M; m++) t[m] = h->mc[m].nsteps_hosing;

@@ -25,6 +25,7 @@ struct GridC {
   double ds[kMaxJ], dsv[kMaxJ], rds2[kMaxJ], s[kMaxJ], c[kMaxJ], sv[kMaxJ], cv[kMaxJ], rc[kMaxJ], rc2[kMaxJ],
       rcv[kMaxJ], rdsv[kMaxJ], cv2[kMaxJ], rds[kMaxJ];
   double dz[kMaxK], dza[kMaxK], rdz[kMaxK], rdza[kMaxK], zw[kMaxK], ssmax[kMaxK];
+  double diffmax[kMaxK];   // iediff > 0: 0.5 * 0.125 * dz^2 / dt (goldstein.f90:3042)
 };
 
 // Per-member scalar parameters ([MS] each) and per-member 2-D constants ([j][i][m]).
@@ -32,6 +33,7 @@ struct MemberP {
   const double *diff1, *diff2, *ec1, *ec2, *ec3, *ec4, *rel, *scf, *saln0, *rpmesco, *rsictscsf, *albocn;
   const double *hosing_trend;
   const int *nsteps_hosing;
+  const double *ediff0, *ediff1p;   // iediff > 0: [m], [k][m] (ediff1(i,j,k) = ediff1p(k): ediffvar = 0)
   // EMBM / surflux
   const double *dtatm, *rdtdim, *rfluxsca, *rpmesca, *rmax, *betaz1, *betaz2, *betam1, *betam2, *ppmin, *ppmax,
       *delf2x, *olr_adj0, *olr_adj, *t_eqm, *par_sich_max, *par_albsic_min, *par_albsic_max, *rate_co2, *rate_ch4,
@@ -103,6 +105,8 @@ struct Dev {
   int co_pairwise;           // k_co_col: average the passive tracers pair by pair (round-1 form, CG_CO_PAIR=1) instead of region by region
   int co_skip_stable;        // k_co_col: skip (member, column)s the flux kernel flagged stable in comask (CG_CO_SKIP=0: off)
   int col_deep_first;        // k_tstep_col: blocks in wetcols order (deepest columns first) instead of row-major (CG_COL_ORDER=1)
+  int iediff, ediffpow2i;    // stratification-dependent vertical diffusivity (goldstein.f90:2501-2515); 0 = constant diff(2)
+  double ediffpow2;
   int *istep_ocn;            // device-resident ocean step counter (read by graph-replayed kernels)
   MemberP p;
 };

@@ -109,7 +109,7 @@ bool Params::set(const std::string &n, double v) {
   S(tatm) S(relh0_ocean) S(relh0_land) S(extra1a) S(extra1b) S(extra1c) S(scl_fwf) S(diffa_scl) S(delf2x)
   S(olr_adj0) S(olr_adj) S(t_eqm) S(albedop_offs) S(albedop_amp) S(par_sich_max) S(par_albsic_min)
   S(par_albsic_max) S(radfor_scl_co2) S(radfor_pc_co2_rise) S(diffsic) S(par_sica_thresh) S(par_sich_thresh)
-  S(solconst) S(par_bio_k0_PO4) S(par_bio_remin_POC_eL1) S(par_bio_red_POC_CaCO3)
+  S(solconst) S(ediff0) S(ediffpow1) S(ediffpow2) S(par_bio_k0_PO4) S(par_bio_remin_POC_eL1) S(par_bio_red_POC_CaCO3)
 #undef S
   return false;
 }
@@ -532,6 +532,30 @@ void build_member(const Grid &g, const Islands &isl, const WindFiles &w, const P
     const double efold = 200 / kDsc, dep0 = -300 / kDsc;
     for (int k = 1; k <= K - 1; k++) mc.ssmax[k] = std::exp(mid + dif * std::tanh((g.zw[k] - dep0) / efold));
   }
+  // IF (iediff > 0) CALL ediff (goldstein.f90:2053-2055, 2936-3044); ediffvar = 0: ediff1(i,j,k) = ediff1p(k)
+  mc.ediff1p.assign(K + 2, 0.0);
+  mc.diffmax.assign(K + 2, 0.0);
+  if (p.iediff > 0 && p.iediff < 3) {
+    mc.ediff0 = p.ediff0 * kRsc / (kUsc * kDsc * kDsc);
+    const double ediff10 = mc.diff2 - mc.ediff0;
+    for (int k = 1; k <= K - 1; k++) {
+      const double dzrho_lev = (-5.5e-3 / kRhosc * kDsc) * std::exp(g.zw[k] * (kDsc / 650.0));
+      double ediffk0;
+      if (p.iediff == 1) {
+        ediffk0 = std::exp(-(g.zw[k] + 2500.0 / kDsc) * (kDsc / 700.0));
+        const double ediffklim = 1 / 3.0e0;
+        ediffk0 = 1 / ((1 - ediffklim) / ediffk0 + ediffklim);
+      } else {
+        ediffk0 = 1 + (2 / (4 * std::atan(1.0))) * std::atan(-(g.zw[k] + 2500.0 / kDsc) * (4.5e-3 * kDsc));
+      }
+      mc.ediff1p[k] = ediff10 * std::pow(ediffk0, p.ediffpow1) * std::pow(-dzrho_lev, p.ediffpow2);
+    }
+    if (p.ediffpow2 > -1.0e-7 && p.ediffpow2 < 1.0e-7) mc.ediffpow2i = 0;
+    else if (p.ediffpow2 > (1.0 - 1.0e-7) && p.ediffpow2 < (1.0 + 1.0e-7)) mc.ediffpow2i = 1;
+    else if (p.ediffpow2 > (0.5 - 1.0e-7) && p.ediffpow2 < (0.5 + 1.0e-7)) mc.ediffpow2i = 2;
+    else mc.ediffpow2i = -999;
+    for (int k = 1; k <= K; k++) mc.diffmax[k] = 0.5 * 0.125 * g.dz[k] * g.dz[k] / g.dt;
+  }
   if (w.taux_u.empty()) return;  // tracer-only handle: no atmosphere / sea ice
 
   // ---- EMBM (embm.f90:739-1475)
@@ -795,11 +819,16 @@ bool load_job(const std::string &jobdir, Params *p, Grid *g, Islands *isl, WindF
   p->diff2 = go.num("diff(2)", d.diff2);
   GN(go, adrag); GN(go, hosing); GN(go, hosing_trend); GI(go, nyears_hosing); GN(go, albocn); GI(go, iconv);
   GI(go, imld); GI(go, iediff); GI(go, ieos); GN(go, ssmaxsurf); GN(go, ssmaxdeep); GN(go, saln0);
+  GN(go, ediff0); GN(go, ediffpow1); GN(go, ediffpow2); GN(go, ediffvar);
   p->diso = go.flag("diso", true);
   p->world = go.str("world", d.world);
   p->go_indir = go.str("indir_name", d.go_indir);
-  if (p->iconv != 0 || p->imld != 0 || p->iediff != 0 || p->ieos != 0) {
-    if (err) *err = "iconv/imld/iediff/ieos /= 0 are outside the B200 hot path (SURVEY 8f.4)";
+  if (p->iconv != 0 || p->imld != 0 || p->ieos != 0) {
+    if (err) *err = "iconv/imld/ieos /= 0 are outside the B200 hot path (SURVEY 8f.4)";
+    return false;
+  }
+  if (p->iediff < 0 || p->iediff > 2 || (p->iediff != 0 && (p->ediffvar < -1.0e-7 || p->ediffvar > 1.0e-7))) {
+    if (err) *err = "iediff must be 0, 1 or 2 and ediffvar 0 (no ediffvargrid.dat) on the B200 hot path (SURVEY 8f.4)";
     return false;
   }
   if (lower(go.str("fwanomin", "n")) == "y") {

@@ -51,7 +51,7 @@ struct Params {
   int igrid = 0, nyear = 100;
   double yearlen = 365.25, temp0 = 5.0, temp1 = 5.0, rel = 0.9, scf = 2.0, diff1 = 2000.0, diff2 = 1.0e-5,
          adrag = 2.5, hosing = 0.0, hosing_trend = 0.0, albocn = 0.05, ssmaxsurf = 10.0, ssmaxdeep = 10.0,
-         saln0 = 34.9;
+         saln0 = 34.9, ediff0 = 0.0, ediffpow1 = 1.0, ediffpow2 = 1.0, ediffvar = 0.0;
   int nyears_hosing = 0, iconv = 0, imld = 0, iediff = 0, ieos = 0;
   bool diso = true;
   std::string world = "worbe2", go_indir = "input/goldstein";
@@ -109,6 +109,10 @@ struct MemberConsts {
   double hosing = 0, hosing_trend = 0;
   int nsteps_hosing = 0;
   std::vector<double> ssmax;                  // (K-1)
+  // stratification-dependent vertical diffusivity, iediff = 1 | 2 (SUBROUTINE ediff, goldstein.f90:2936-3044, ediffvar = 0)
+  double ediff0 = 0.0;                        // non-dimensional
+  int ediffpow2i = 0;
+  std::vector<double> ediff1p, diffmax;       // (K-1), (K)
   std::vector<double> drag, rtv, rtv3;        // (2,I+1,J), (I,J), (I,J)
   std::vector<double> gap, ratm;              // (nm, 2I+3), (nm, I+1)
   std::vector<double> ubisl, psisl, erisl;    // island unit solves

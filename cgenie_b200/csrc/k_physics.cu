@@ -257,17 +257,17 @@ __global__ void __launch_bounds__(128) k_surflux2(const Dev v) {
 // One block = one member; thread owns CPT cells; tq2 lives in shared memory (halo rows 0 and J+1
 // are zero, the i-halo is index arithmetic).  embm.f90:2039-2138 + step_embm :48-70.
 template <int CPT>
-__global__ void __launch_bounds__(704) k_embm(const Dev v, const int nsteps) {
+__global__ void __launch_bounds__(CPT == 3 ? 448 : 704) k_embm(const Dev v, const int nsteps) {
   DIMS
-  extern __shared__ double tq2[];  // (I, 0:J+1)
+  extern __shared__ double tq2[];  // (I, 0:J+1) x 2 fields
   const int m = blockIdx.x;
   const int nc = I * J, tc = blockDim.x;
   const double cimp = 0.5;
   const double dtloc = v.p.dtatm[m], rfluxsca = v.p.rfluxsca[m], rpmesca = v.p.rpmesca[m];
   double tq[2][CPT], tq1[2][CPT], tqa[2][CPT];
   double cie[2][CPT], ciwm[2][CPT], cin[2][CPT], cism[2][CPT], cdiv[2][CPT];
-#define T2(i, j) tq2[((i)-1) + I * (j)]
-  for (int q = threadIdx.x; q < I; q += tc) { T2(q + 1, 0) = 0.0; T2(q + 1, J + 1) = 0.0; }
+#define T2(l, i, j) tq2[(l) * (I * (J + 2)) + ((i)-1) + I * (j)]
+  for (int q = threadIdx.x; q < I; q += tc) { T2(0, q + 1, 0) = 0.0; T2(0, q + 1, J + 1) = 0.0; T2(1, q + 1, 0) = 0.0; T2(1, q + 1, J + 1) = 0.0; }
 #pragma unroll
   for (int n = 0; n < CPT; n++) {
     const int c2 = threadIdx.x + n * tc;
@@ -330,37 +330,55 @@ __global__ void __launch_bounds__(704) k_embm(const Dev v, const int nsteps) {
   for (int l = 0; l < 2; l++)
 #pragma unroll
     for (int n = 0; n < CPT; n++) rden[l][n] = 1.0 / (1 + cimp * (dtloc * cdiv[l][n]));
-  for (int step = 0; step < nsteps; step++) {
+  // The two fields (l = 0: temperature, l = 1: humidity) do not see each other inside tstipa, so their five iterations run side
+  // by side on two planes of shared memory: half the block barriers of the field-after-field loop and two independent chains
+  // per cell and thread.  Per field the operations and their order are the reference's.  The cell's five shared-memory offsets
+  // are taken once (the index arithmetic was most of the loop's instructions).
+  int oc[CPT], oe[CPT], ow[CPT], on[CPT], os[CPT];
+  double rdsj[CPT];
+  bool ok[CPT];
+  const int plane = I * (J + 2);
 #pragma unroll
-    for (int l = 0; l < 2; l++) {
-      for (int iits = 0; iits < 5; iits++) {
-        __syncthreads();
+  for (int n = 0; n < CPT; n++) {
+    const int c2 = threadIdx.x + n * tc;
+    ok[n] = c2 < nc;
+    const int cc = ok[n] ? c2 : 0;
+    const int i = cc % I + 1, j = cc / I + 1, ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
+    oc[n] = (i - 1) + I * j; oe[n] = (ip - 1) + I * j; ow[n] = (im - 1) + I * j; on[n] = (i - 1) + I * (j + 1); os[n] = (i - 1) + I * (j - 1);
+    rdsj[n] = c_g.rds[j];
+  }
+  for (int step = 0; step < nsteps; step++) {
+    for (int iits = 0; iits < 5; iits++) {
+      __syncthreads();
+#pragma unroll
+      for (int l = 0; l < 2; l++) {
 #pragma unroll
         for (int n = 0; n < CPT; n++) {
-          const int c2 = threadIdx.x + n * tc;
-          if (c2 < nc) {
-            const int i = c2 % I + 1, j = c2 / I + 1;
+          if (ok[n]) {
+            double *t2 = tq2 + l * plane + oc[n];
             if (iits < 4)
-              T2(i, j) = cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n];
+              *t2 = cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n];
             else
-              T2(i, j) = 0.5 * (T2(i, j) + cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n]);
+              *t2 = 0.5 * (*t2 + cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n]);
           }
         }
-        __syncthreads();
+      }
+      __syncthreads();
+#pragma unroll
+      for (int l = 0; l < 2; l++) {
 #pragma unroll
         for (int n = 0; n < CPT; n++) {
-          const int c2 = threadIdx.x + n * tc;
-          if (c2 < nc) {
-            const int i = c2 % I + 1, j = c2 / I + 1, ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
-            const double flx = -tqa[l][n] + cie[l][n] * T2(ip, j) - ciwm[l][n] * T2(im, j) +
-                               (cin[l][n] * T2(i, j + 1) - cism[l][n] * T2(i, j - 1)) * c_g.rds[j];
+          if (ok[n]) {
+            const double *t2 = tq2 + l * plane;
+            const double flx = -tqa[l][n] + cie[l][n] * t2[oe[n]] - ciwm[l][n] * t2[ow[n]] +
+                               (cin[l][n] * t2[on[n]] - cism[l][n] * t2[os[n]]) * rdsj[n];
             if (iits < 4) {
               const double centre = dtloc * cdiv[l][n];
               const double num = tq1[l][n] * (1.0 - (1.0 - cimp) * centre) - dtloc * flx, den = 1 + cimp * centre;
               const double qq = num * rden[l][n];
               tq[l][n] = fma(fma(-den, qq, num), rden[l][n], qq);
             } else {
-              tq[l][n] = tq1[l][n] - dtloc * flx - dtloc * T2(i, j) * cdiv[l][n];
+              tq[l][n] = tq1[l][n] - dtloc * flx - dtloc * t2[oc[n]] * cdiv[l][n];
             }
           }
         }
@@ -1186,9 +1204,10 @@ int launch_surflux(const Dev &v, double *meantemp, bool need_mean, cudaStream_t 
 }
 int launch_embm(const Dev &v, int nsteps, cudaStream_t s) {
   const int nc = v.I * v.J;
-  const size_t sm = sizeof(double) * v.I * (v.J + 2);
+  const size_t sm = sizeof(double) * 2 * v.I * (v.J + 2);
   auto thr = [&](int cpt) { return (((nc + cpt - 1) / cpt + 31) / 32) * 32; };
   if (nc <= 704) k_embm<1><<<v.M, thr(1), sm, s>>>(v, nsteps);
+  else if (nc <= 1344 && !getenv("CG_EMBM_CPT2")) k_embm<3><<<v.M, thr(3), sm, s>>>(v, nsteps);   // 36 x 36: 448 threads x 3 cells, no spills (2 cells x 672 threads: 80 registers, spills)
   else if (nc <= 1408) k_embm<2><<<v.M, thr(2), sm, s>>>(v, nsteps);
   else if (nc <= 2816) k_embm<4><<<v.M, thr(4), sm, s>>>(v, nsteps);
   else return -1;

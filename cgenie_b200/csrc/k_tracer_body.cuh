@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(TPB, MINB) CG_KNAME(k_tstepo_flux)(const Dev v
   const int ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
   const int k1e = CG_K1(v, ip, j), k1w = CG_K1(v, im, j), k1n = CG_K1(v, i, j + 1), k1s = CG_K1(v, i, j - 1);
 
-  const double diff1 = v.p.diff1[m], diffv = v.p.diff2[m];
+  const double diff1 = v.p.diff1[m];
+  double diffv = v.p.diff2[m];
   const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
   const double scc = ec2;
   const double dt = c_g.dt, dphi = c_g.dphi, rdphi = c_g.rdphi;
@@ -92,8 +93,6 @@ __global__ void __launch_bounds__(TPB, MINB) CG_KNAME(k_tstepo_flux)(const Dev v
     const double upsN = pec / (2.0 + fabs(pec));
     pec = vS * dsvS / diff1;
     const double upsS = pec / (2.0 + fabs(pec));
-    pec = ww * c_g.dza[k] / diffv;
-    const double upsA = pec / (2.0 + fabs(pec));
     const double rdza = topl ? 0.0 : c_g.rdza[k], rdzk = c_g.rdz[k];
 
     // ---- density slopes from T,S (goldstein.f90:2490-2500, 2561-2603)
@@ -140,7 +139,20 @@ __global__ void __launch_bounds__(TPB, MINB) CG_KNAME(k_tstepo_flux)(const Dev v
         const double ssm = c_g.ssmax[k];
         if (tv1 > ssm) slim = ssm * ssm / (tv1 * tv1);
       }
+      if (v.iediff) {   // local vertical diffusivity, goldstein.f90:2496-2515 (ediff1(i,j,k) = ediff1p(k))
+        const double rdzrho = iso ? 1.0 / dzrho : -1.0e12;
+        const double e0 = v.p.ediff0[m], e1 = v.p.ediff1p[(size_t)k * MS + m];
+        if (v.ediffpow2i == 0) diffv = e0 + e1;
+        else if (v.ediffpow2i == 1) diffv = e0 + e1 * (-rdzrho);
+        else if (v.ediffpow2i == 2) diffv = e0 + e1 * sqrt(-rdzrho);
+        else diffv = e0 + e1 * pow(-rdzrho, v.ediffpow2);
+        if (diffv > c_g.diffmax[k + 1]) diffv = c_g.diffmax[k + 1];
+      }
     }
+    // (the reference keeps the last diffv where it computes none -- at k = maxk, where w = 0 and dza = 0 make pec = 0 for any
+    // diffusivity and the flux through the top face is the boundary condition)
+    pec = ww * c_g.dza[k] / diffv;
+    const double upsA = pec / (2.0 + fabs(pec));
 
 #if CG_TRACER_FAST
     // ---- per-cell stencil coefficients (hoisted out of the tracer loop)

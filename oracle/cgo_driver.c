@@ -89,6 +89,7 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
   PD(hosing, 0.0); PD(hosing_trend, 0.0); PI_(nyears_hosing, 0); PD(albocn, 0.05);
   PI_(iconv, 0); PI_(imld, 0); PI_(iediff, 0); PI_(ieos, 0); PI_(diso, 1);
   PD(ssmaxsurf, 10.0); PD(ssmaxdeep, 10.0); PD(saln0, 34.9);
+  PD(ediff0, 0.0); PD(ediffpow1, 1.0); PD(ediffpow2, 1.0); PD(ediffvar, 0.0);
   /* embm-defaults.nml */
   PI_(ndta, 5); PD(rmax, 0.85);
   v = 5.0e6; parse_kv(params, "diffamp1", &v); o->diffamp[1] = v;
@@ -112,8 +113,9 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
   /* genie main */
   PD(solconst, 1368.0); PD(gn_daysperyear, 365.25);
   PI_(kocn_loop, 5); PI_(katm_loop, 1); PI_(ksic_loop, 5);
-  if (o->iconv != 0 || o->imld != 0 || o->iediff != 0 || o->ieos != 0) {
-    fprintf(stderr, "cgo: iconv/imld/iediff/ieos != 0 are outside the restated path\n");
+  if (o->iconv != 0 || o->imld != 0 || o->iediff < 0 || o->iediff > 2 || o->ieos != 0 ||
+      (o->iediff != 0 && (o->ediffvar < -1.0e-7 || o->ediffvar > 1.0e-7))) {
+    fprintf(stderr, "cgo: iconv/imld/ieos != 0, iediff outside 0..2 and ediffvar != 0 are outside the restated path\n");
     free(o);
     return NULL;
   }
@@ -133,7 +135,7 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
     AL1(dt, K + 2); AL1(ds, J + 2); AL1(dsv, J + 2); AL1(rds2, J + 2); AL1(dz, K + 2); AL1(s, J + 2); AL1(c, J + 2);
     AL1(sv, J + 2); AL1(cv, J + 2); AL1(dza, K + 2); AL1(zro, K + 2); AL1(zw, K + 2); AL1(rc, J + 2); AL1(rc2, J + 2);
     AL1(rcv, J + 2); AL1(rdsv, J + 2); AL1(cv2, J + 2); AL1(rds, J + 2); AL1(rdz, K + 2); AL1(rdza, K + 2);
-    AL1(asurf, J + 2); AL1(ssmax, K + 2);
+    AL1(asurf, J + 2); AL1(ssmax, K + 2); AL1(ediff1p, K + 2); AL1(diffmax, K + 2);
     AL1(rtv, ij); AL1(rtv3, ij);
     AL1(u, 3L * (I + 1) * (J + 1) * K); AL1(u1, 3L * (I + 1) * (J + 1) * K);
     AL1(ts, (long)L * (I + 2) * (J + 2) * (K + 2)); AL1(ts1, (long)L * (I + 2) * (J + 2) * (K + 2));
@@ -229,6 +231,7 @@ void cgo_destroy(cgo_t *o) {
   for (int i = 0; i < o->nfields; i++) free(o->fields[i].p - 64);
   for (int i = 0; i < o->nifields; i++) free(o->ifields[i].p - 64);
   free(o->params);
+  free(o->tf_scratch);
   free(o->bg);
   free(o);
 }

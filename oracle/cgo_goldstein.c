@@ -361,12 +361,13 @@ static void velc(cgo_t *o) {
 void cgo_tstepo_flux(cgo_t *o) {
   const int L = NL;
   double tv, ups[4], pec[4];
-  double *fe = (double *)calloc(L + 1, 8), *fw = (double *)calloc(L + 1, 8), *fn = (double *)calloc(L + 1, 8),
-         *fa = (double *)calloc(L + 1, 8), *fwsave = (double *)calloc(L + 1, 8);
-  double *fs = (double *)calloc((size_t)(L + 1) * (NI + 1), 8);
-  double *fb = (double *)calloc((size_t)(L + 1) * (NI + 1) * (NJ + 1), 8);
-  double *dxts = (double *)calloc((size_t)(L + 1) * 5, 8), *dyts = (double *)calloc((size_t)(L + 1) * 5, 8),
-         *dzts = (double *)calloc(L + 1, 8);
+  /* work arrays: allocated once per model (fe, fw, fn, fa, fwsave, dzts: L+1 each; fs; fb; dxts, dyts), zeroed per call as the
+   * reference's locals are where it matters (fb = 0, fs = 0 per level) */
+  const size_t n1 = (size_t)(L + 1), nfs = n1 * (NI + 1), nfb = n1 * (NI + 1) * (NJ + 1), nd = n1 * 5;
+  if (!o->tf_scratch) o->tf_scratch = (double *)calloc(6 * n1 + nfs + nfb + 2 * nd, 8);
+  double *fe = o->tf_scratch, *fw = fe + n1, *fn = fw + n1, *fa = fn + n1, *fwsave = fa + n1, *dzts = fwsave + n1;
+  double *fs = dzts + n1, *fb = fs + nfs, *dxts = fb + nfb, *dyts = dxts + nd;
+  memset(o->tf_scratch, 0, (6 * n1 + nfs + nfb + 2 * nd) * 8);
 #define FS(l, i) fs[(l) + (L + 1) * (i)]
 #define FB(l, i, j) fb[(l) + (L + 1) * ((i) + (NI + 1) * (j))]
 #define DXTS(l, a) dxts[(l) + (L + 1) * (a)]
@@ -404,7 +405,13 @@ void cgo_tstepo_flux(cgo_t *o) {
             rdzrho = 1.0 / dzrho;
           else
             rdzrho = -1.0e12;
-          /* iediff>0 branch (goldstein.f90:2501-2515) flag-gated out of scope */
+          if (o->iediff > 0 && o->iediff < 3) {   /* :2501-2515 (ediff1(i,j,k) = ediff1p(k): ediffvar = 0) */
+            if (o->ediffpow2i == 0) diffv = o->ediff0 + o->ediff1p[k];
+            else if (o->ediffpow2i == 1) diffv = o->ediff0 + o->ediff1p[k] * (-rdzrho);
+            else if (o->ediffpow2i == 2) diffv = o->ediff0 + o->ediff1p[k] * sqrt(-rdzrho);
+            else diffv = o->ediff0 + o->ediff1p[k] * pow(-rdzrho, o->ediffpow2);
+            if (diffv > o->diffmax[k + 1]) diffv = o->diffmax[k + 1];
+          }
         }
         pec[1] = U(1, i, j, k) * o->dphi / diff[1];
         ups[1] = pec[1] / (2.0 + fabs(pec[1]));
@@ -493,7 +500,6 @@ void cgo_tstepo_flux(cgo_t *o) {
       }
     }
   }
-  free(fe); free(fw); free(fn); free(fa); free(fwsave); free(fs); free(fb); free(dxts); free(dyts); free(dzts);
 #undef FS
 #undef FB
 #undef DXTS
@@ -987,6 +993,28 @@ void cgo_goldstein_init(cgo_t *o) {
       zssmax = (o->zw[k] - ssmaxtanh0dep) / ssmaxtanhefold;
       o->ssmax[k] = exp(ssmaxmid + ssmaxdiff * tanh(zssmax));
     }
+  }
+  /* IF (iediff > 0) CALL ediff, :2053-2055; SUBROUTINE ediff :2936-3044 with ediffvar = 0 (no ediffvargrid.dat) */
+  if (o->iediff > 0 && o->iediff < 3) {
+    double ediff10, dzrho_lev, ediffk0 = 0.0, ediffklim;
+    o->ediff0 = o->ediff0 * CG_RSC / (CG_USC * CG_DSC * CG_DSC);
+    ediff10 = o->diff[2] - o->ediff0;
+    for (k = 1; k <= NK - 1; k++) {
+      dzrho_lev = (-5.5e-3 / CG_RHOSC * CG_DSC) * exp(o->zw[k] * (CG_DSC / 650.0));
+      if (o->iediff == 1) {
+        ediffk0 = exp(-(o->zw[k] + 2500.0 / CG_DSC) * (CG_DSC / 700.0));
+        ediffklim = 1 / 3.0e0;
+        ediffk0 = 1 / ((1 - ediffklim) / ediffk0 + ediffklim);
+      } else {
+        ediffk0 = 1 + (2 / CG_PI) * atan(-(o->zw[k] + 2500.0 / CG_DSC) * (4.5e-3 * CG_DSC));
+      }
+      o->ediff1p[k] = ediff10 * pow(ediffk0, o->ediffpow1) * pow(-dzrho_lev, o->ediffpow2);
+    }
+    if (o->ediffpow2 > -1.0e-7 && o->ediffpow2 < 1.0e-7) o->ediffpow2i = 0;
+    else if (o->ediffpow2 > (1.0 - 1.0e-7) && o->ediffpow2 < (1.0 + 1.0e-7)) o->ediffpow2i = 1;
+    else if (o->ediffpow2 > (0.5 - 1.0e-7) && o->ediffpow2 < (0.5 + 1.0e-7)) o->ediffpow2i = 2;
+    else o->ediffpow2i = -999;
+    for (k = 1; k <= NK; k++) o->diffmax[k] = 0.5 * 0.125 * o->dz[k] * o->dz[k] / o->dt[k];
   }
   /* output arguments :2015-2023 */
   for (j = 1; j <= NJ; j++)

@@ -70,6 +70,7 @@ struct cgo {
   double hosing, hosing_trend; int nyears_hosing, nsteps_hosing;
   double albocn; int iconv, imld, iediff, ieos, diso;
   double ssmaxsurf, ssmaxdeep, saln0;
+  double ediff0, ediffpow1, ediffpow2, ediffvar; int ediffpow2i;   /* iediff = 1 | 2 (goldstein.f90:2936-3044) */
   double rmax, diffamp[3], diffwid, difflin, betaz[3], betam[3];
   double tatm, relh0_ocean, relh0_land, extra1a, extra1b, extra1c, scl_fwf;
   double z1_embm, diffa_scl; int diffa_len;
@@ -91,6 +92,8 @@ struct cgo {
   double dmax; int limps;
   double *dt, *ds, *dsv, *rds2, *dz, *s, *c, *sv, *cv, *dza, *zro, *zw;
   double *rc, *rc2, *rcv, *rdsv, *cv2, *rds, *rdz, *rdza, *asurf, *ssmax;
+  double *ediff1p, *diffmax;            /* ediff1(i,j,k) = ediff1p(k) (ediffvar = 0), diffmax(k) */
+  double *tf_scratch;                   /* work arrays of cgo_tstepo_flux, allocated once */
   double *rtv, *rtv3, *u, *u1, *ts, *ts1, *rho, *tau, *drag, *dztau, *dztav;
   double *ratm, *gap, *gb, *gbold, *ub, *psi, *rh, *cost, *bp, *sbp;
   double *fw_hosing, *rhosing, *fw_anom, *fw_anom_rate;

@@ -124,3 +124,23 @@ def test_self_generated_golden_vector():
                cost=float(o.f("cost").sum()))
     for k, v in g["values"].items():
         assert np.isclose(got[k], v, rtol=1e-12, atol=1e-300), (k, got[k], v)
+
+
+def test_ediff_option():
+    """iediff (SUBROUTINE ediff, goldstein.f90:2936-3044; tstepo_flux :2496-2515): with ediff0 = diff(2) the stratification-
+    dependent part vanishes and the run is the constant-diffusivity one "except for rounding differences" (the reference's own
+    words, :2890-2893); with ediff0 < diff(2) and ediffpow2 = 1 the diffusivity is ediff0 + ediff1(k) / N^2-like and capped by
+    diffmax = dz^2 / (16 dt); the exponent cases 0, 1, 1/2 take the reference's pow-free branches."""
+    base = dict(world="worbe2", maxk=8, maxl=2, nyear=100)
+    o0 = Oracle(**base)
+    o1 = Oracle(iediff=1, ediff0=1.0e-5, **base)
+    o2 = Oracle(iediff=1, ediff0=0.3e-5, ediffpow2=1.0, **base)
+    o3 = Oracle(iediff=1, ediff0=0.3e-5, ediffpow2=0.5, **base)
+    o4 = Oracle(iediff=1, ediff0=0.3e-5, ediffpow2=0.5 + 1e-5, **base)     # the general pow() branch next to the sqrt branch
+    for o in (o0, o1, o2, o3, o4):
+        o.run(5 * 100)
+    t = [o.f("ts").copy() for o in (o0, o1, o2, o3, o4)]
+    assert np.abs(t[1] - t[0]).max() <= 1e-12 and not np.array_equal(t[2], t[0])
+    assert 1e-7 < np.abs(t[2] - t[0]).max() < 1.0
+    assert 0.0 < np.abs(t[4] - t[3]).max() < 1e-5
+    assert np.isfinite(t[2]).all() and np.isfinite(t[3]).all()
