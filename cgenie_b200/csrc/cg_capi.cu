@@ -53,7 +53,7 @@ int launch_tc_sums_first(const Dev &, cudaStream_t);
 int launch_tc_sums_old(const Dev &, cudaStream_t);
 int launch_tc_sums_new(const Dev &, cudaStream_t);
 int launch_bg_surf(const Dev &, const BgDev &, cudaStream_t);
-int launch_bg_sweep(const Dev &, const BgDev &, cudaStream_t);
+int launch_bg_sweep(const Dev &, const BgDev &, cudaStream_t, int fuse = 0);
 int launch_tc_apply_only(const Dev &, cudaStream_t);
 bool bg_layout_ok(const BgDev &, int L);
 int launch_bg_climate(const Dev &, const BgDev &, cudaStream_t);
@@ -2081,7 +2081,11 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
       if (cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
       if ((rc = h->bg_split ? bg_issue_surf(h, k * tick) : bg_issue_step(h, k * tick))) break;
     }
-    if (h->bg_split && h->bg_surf_issued) {   // sediment return + water-column sweep, after this cycle's tracer step
+    // CG_BG_FUSE2=1 (experiment): the sweep is not issued ahead but here, behind the coupling's sums, with the per-cell update of
+    // biogem_tracercoupling applied as each cell's anomaly is known (k_bg_step's `fuse`): no vdocn round trip, no k_tc_apply
+    static const bool fuse2 = getenv("CG_BG_FUSE2") && atoi(getenv("CG_BG_FUSE2")) != 0;
+    const bool fuse_now = fuse2 && h->bg_split && h->bg_surf_issued && h->bg_go;
+    if (!fuse_now && h->bg_split && h->bg_surf_issued) {   // sediment return + water-column sweep, after this cycle's tracer step
       if (cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
       h->launches += launch_bg_sweep(h->dv, h->bgd, h->stream4);
       h->bg_surf_issued = false;
@@ -2089,6 +2093,13 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
     const bool old_ready = h->bg_ahead && h->tc_old_ready;
     h->bg_ahead = false;
     h->tc_old_ready = false;
+    if (fuse_now) {
+      h->launches += old_ready ? launch_tc_sums_new(h->dv, h->stream5) : launch_tc_sums_first(h->dv, h->stream5);
+      if (cudaEventRecord(h->evJoin5, h->stream5) != cudaSuccess || cudaStreamWaitEvent(h->stream4, h->evJoin5, 0) != cudaSuccess ||
+          cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
+      h->launches += launch_bg_sweep(h->dv, h->bgd, h->stream4, 1);
+      h->bg_surf_issued = false;
+    } else
     if (h->bg_go) {       // biogem_tracercoupling: sums on stream5 (they need ts of this cycle, not the step's anomaly)
       // the sums over BIOGEM's own state (old mean salinity, old inventories) were taken one block ahead if old_ready
       h->launches += old_ready ? launch_tc_sums_new(h->dv, h->stream5) : launch_tc_sums_first(h->dv, h->stream5);
@@ -2115,7 +2126,7 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
       if ((rc = h->bg_split ? bg_issue_surf(h, (k + period) * tick) : bg_issue_step(h, (k + period) * tick))) break;
       // ... and the sweep right behind it (default; CG_BG_SWEEP_EARLY=1: behind the tracer step of the cycle before the
       // block's, 0: at the block's nominal place.  Measured 79.5 / 81.2 / 82.4 ms per model year.)
-      if (h->bg_split && h->bg_surf_issued && !(getenv("CG_BG_SWEEP_EARLY") && atoi(getenv("CG_BG_SWEEP_EARLY")) != 2)) {
+      if (!fuse2 && h->bg_split && h->bg_surf_issued && !(getenv("CG_BG_SWEEP_EARLY") && atoi(getenv("CG_BG_SWEEP_EARLY")) != 2)) {
         h->launches += launch_bg_sweep(h->dv, h->bgd, h->stream);
         h->bg_surf_issued = false;
       }
@@ -2252,7 +2263,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
         // split form, cycle before the block's cycle: the sweep kernel of the coming block is issued behind this tracer
         // step, i.e. it runs next to the head of the next cycle (momentum: latency bound, SMs mostly idle) and not at the
         // block's nominal place on the critical path.  It reads and writes BIOGEM's own arrays only.
-        if (h->bg_ahead && h->bg_split && h->bg_surf_issued && h->bg.on) {
+        if (h->bg_ahead && h->bg_split && h->bg_surf_issued && h->bg.on && !(getenv("CG_BG_FUSE2") && atoi(getenv("CG_BG_FUSE2")) != 0)) {
           const long long period = (long long)p.conv_kocn_kbiogem * p.kocn_loop;
           const bool early = !(getenv("CG_BG_SWEEP_EARLY") && atoi(getenv("CG_BG_SWEEP_EARLY")) == 0);
           if (early && h->koverall % period != 0 && (h->koverall + p.kocn_loop) % period == 0) {

@@ -1166,14 +1166,14 @@ int launch_bg_surf(const Dev &v, const BgDev &b, cudaStream_t s) {
   else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<4, 1, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, 0); });
   return 1;
 }
-int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s) {
+int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s, int fuse) {
   static int minb = -1;
   if (minb < 0) { const char *e = getenv("CG_BG_SWEEP_MINB"); minb = e ? atoi(e) : 2; }
   static int nopf = -1;
   if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
-  if (minb == 3) k_bg_step<3, 2, 0><<<g, bl, 0, s>>>(v, b, 0, nopf);
-  else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<2, 2, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, nopf); });
+  if (minb == 3) k_bg_step<3, 2, 0><<<g, bl, 0, s>>>(v, b, 0, nopf | (fuse ? 1 : 0));
+  else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<2, 2, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, nopf | (fuse ? 1 : 0)); });
   return 1;
 }
 // step (1) of biogem_tracercoupling taken BEFORE step_biogem (fused coupling, see k_bg_step)

@@ -1207,7 +1207,7 @@ int launch_embm(const Dev &v, int nsteps, cudaStream_t s) {
   const size_t sm = sizeof(double) * 2 * v.I * (v.J + 2);
   auto thr = [&](int cpt) { return (((nc + cpt - 1) / cpt + 31) / 32) * 32; };
   if (nc <= 704) k_embm<1><<<v.M, thr(1), sm, s>>>(v, nsteps);
-  else if (nc <= 1344 && !getenv("CG_EMBM_CPT2")) k_embm<3><<<v.M, thr(3), sm, s>>>(v, nsteps);   // 36 x 36: 448 threads x 3 cells, no spills (2 cells x 672 threads: 80 registers, spills)
+  else if (nc <= 1344 && getenv("CG_EMBM_CPT3")) k_embm<3><<<v.M, thr(3), sm, s>>>(v, nsteps);   // 36 x 36: 448 threads x 3 cells, no spills (2 cells x 672 threads: 80 registers, spills)
   else if (nc <= 1408) k_embm<2><<<v.M, thr(2), sm, s>>>(v, nsteps);
   else if (nc <= 2816) k_embm<4><<<v.M, thr(4), sm, s>>>(v, nsteps);
   else return -1;

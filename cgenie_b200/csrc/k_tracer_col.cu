@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128) k_co_col(const Dev v) {
   // the column arrays of the decision loop (T, S, rho, box thickness) in shared memory, [level][thread]: see co_decide_core
   extern __shared__ __align__(16) unsigned char co_smem[];
   const unsigned m = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int ci = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const int ci = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);   // blockDim.x / 32 columns per block (1 .. 4)
   if (ci >= v.nwet) return;
   double *scratch = v.co_local ? nullptr : reinterpret_cast<double *>(co_smem) + threadIdx.x;
   co_column<I, J, K, L, MS>(v, c_g, v.rowcols[ci], m, scratch, 128);
@@ -282,7 +282,11 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
     k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, co_smem_bytes, s>>>(v2);
     k_co_passive<I, J, K, L, MS><<<dim3(MS / 32, v.nwet), dim3(32, L - 2), 0, s>>>(v2);
     return 3;
-  } else k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, co_smem_bytes, s>>>(v2);
+  } else {
+    static int wpb = -1;   // see go_tiled
+    if (wpb < 0) { const char *e = getenv("CG_CO_WPB"); wpb = e ? atoi(e) : 1; if (wpb < 1 || wpb > 4 || !colocal) wpb = 4; }
+    k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + wpb - 1) / wpb), 32 * wpb, co_smem_bytes, s>>>(v2);
+  }
   return 2;
 }
 
@@ -311,7 +315,12 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
   v2.co_skip_stable = coskip ? 1 : 0;
   v2.co_pairwise = 1;
   v2.co_local = 1;
-  k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + 3) / 4), 128, 0, s>>>(v2);
+  // One warp = 32 members of one column.  In a stratified ocean most warps find all their member-columns flagged stable and leave
+  // at once; with several warps per block the few that work keep the registers of their idle neighbours allocated until the block
+  // retires, so the default is one warp per block (CG_CO_WPB = 1 .. 4)
+  static int wpb = -1;
+  if (wpb < 0) { const char *e = getenv("CG_CO_WPB"); wpb = e ? atoi(e) : 1; if (wpb < 1 || wpb > 4) wpb = 1; }
+  k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + wpb - 1) / wpb), 32 * wpb, 0, s>>>(v2);
   return 2;
 }
 
