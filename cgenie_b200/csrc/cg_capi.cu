@@ -54,6 +54,9 @@ int launch_tc_sums_old(const Dev &, cudaStream_t);
 int launch_tc_sums_new(const Dev &, cudaStream_t);
 int launch_bg_surf(const Dev &, const BgDev &, cudaStream_t);
 int launch_bg_sweep(const Dev &, const BgDev &, cudaStream_t, int fuse = 0);
+int launch_bg_packets(const Dev &, const BgDev &, int pend, cudaStream_t);
+int launch_bg_cell(const Dev &, const BgDev &, cudaStream_t);
+int launch_bg_part_scale(const Dev &, const BgDev &, cudaStream_t);
 int launch_tc_apply_only(const Dev &, cudaStream_t);
 bool bg_layout_ok(const BgDev &, int L);
 int launch_bg_climate(const Dev &, const BgDev &, cudaStream_t);
@@ -171,6 +174,10 @@ struct cg_handle {
   long long koverall = 0;
   int istep_ocn = 0, istep_atm = 0, istep_sic = 0;
   bool bg_split = false, bg_surf_issued = false;   // pipelined BIOGEM block, split form (see bg_issue_surf)
+  // packets / cells form of the sweep (k_bg_step PART 3 + k_bg_cell, CG_BG_PD=0: off): pd_pending = the packets half of a step has
+  // run and its cell half (with the coupling update) is owed; part_pending = bio_part lacks the last coupling's rescaling
+  bool bg_pd = true, pd_pending = false, part_pending = false;
+  std::vector<int> bg_colidx;                      // (i,j) -> index in the BIOGEM column order, -1 on land
   // per-module entry points: the surface part of the NEXT step_biogem is issued speculatively at the end of cg_atchem_step
   // (it has no side effect outside bgd.surf); cg_biogem_step uses it if it is called with the predicted clock and nothing
   // touched the state in between, and drops it otherwise
@@ -286,6 +293,7 @@ static void fill_gridc(cg_handle *h) {
   }
   for (int k = 0; k <= g.K + 1 && k < kMaxK; k++) {
     c.dz[k] = g.dz[k]; c.dza[k] = g.dza[k]; c.rdz[k] = g.rdz[k]; c.rdza[k] = g.rdza[k]; c.zw[k] = g.zw[k];
+    c.zro[k] = k < (int)g.zro.size() ? g.zro[k] : 0.0;
     c.ssmax[k] = h->mc.empty() ? 0.0 : h->mc[0].ssmax[k];
     c.diffmax[k] = (h->mc.empty() || k >= (int)h->mc[0].diffmax.size()) ? 0.0 : h->mc[0].diffmax[k];
   }
@@ -572,6 +580,8 @@ static int build_device(cg_handle *h) {
   TRY(dparam(h, &p.ec2, col([](const MemberConsts &c) { return c.ec[2]; })));
   TRY(dparam(h, &p.ec3, col([](const MemberConsts &c) { return c.ec[3]; })));
   TRY(dparam(h, &p.ec4, col([](const MemberConsts &c) { return c.ec[4]; })));
+  TRY(dparam(h, &p.ec5, col([](const MemberConsts &c) { return c.ec[5]; })));
+  v.ieos = h->base.ieos;
   TRY(dparam(h, &p.rel, col([](const MemberConsts &c) { return c.p.rel; })));
   TRY(dparam(h, &p.scf, col([](const MemberConsts &c) { return c.p.scf; })));
   TRY(dparam(h, &p.saln0, col([](const MemberConsts &c) { return c.p.saln0; })));
@@ -696,6 +706,8 @@ static int build_device(cg_handle *h) {
     TRY(dupload(h, &v.bg_M, Mm));
     TRY(dupload(h, &v.bg_rM, rMm));
     { int *q; TRY(dupload(h, &q, cols)); v.bgcols = q; }
+    h->bg_colidx.assign((size_t)I * J, -1);
+    for (int n = 0; n < v.nwet; n++) h->bg_colidx[cols[n]] = n;
     TRY(dalloc(h, &v.bg_ocn, ijk * L * MS));
     TRY(dalloc(h, &v.bg_vdocn, ijk * L * MS));
     TRY(dalloc(h, &v.bg_part, (size_t)2 * L * std::max(v.nwet, 1) * MS));
@@ -718,6 +730,14 @@ static int build_device(cg_handle *h) {
     TRY(dalloc(h, &b.settle_k1, ij * LS * MS));
     TRY(dalloc(h, &b.carbH, ij * MS));
     TRY(dalloc(h, &b.surf, (size_t)kBgSurfSlots * ij * MS));
+    {
+      const char *e = getenv("CG_BG_PD");
+      h->bg_pd = !(e && atoi(e) == 0);
+      TRY(dalloc(h, &b.lrem, ijk * 7 * MS));
+      TRY(dalloc(h, &b.fsedv, (size_t)7 * std::max(v.nwet, 1) * MS));
+      TRY(dalloc(h, &b.pscale, (size_t)MS));
+      int *q; TRY(dupload(h, &q, h->bg_colidx)); b.colidx = q;
+    }
     TRY(dalloc(h, &b.seaice, ij * MS));
     TRY(dalloc(h, &b.seaice_stage, ij * MS));
     TRY(dalloc(h, &b.tq_stage, 2 * ij * MS));
@@ -1126,9 +1146,37 @@ static int ensure_stage(cg_handle *h, size_t n) {
   h->stage_n = n;
   return CG_OK;
 }
+
+// ---- the water-column sweep and the coupling update in their two forms (see k_bg_cell) ----
+static int bg_part_materialise(cg_handle *h, cudaStream_t s) {   // bio_part as the reference holds it (biogem.f90:2042-2043 applied)
+  if (!h->part_pending) return 0;
+  h->part_pending = false;
+  return launch_bg_part_scale(h->dv, h->bgd, s);
+}
+static int bg_launch_sweep(cg_handle *h, cudaStream_t s, int fuse = 0) {
+  if (h->bg_pd && !fuse && !h->pd_pending) {
+    const int pend = h->part_pending ? 1 : 0;
+    h->part_pending = false;
+    h->pd_pending = true;
+    return launch_bg_packets(h->dv, h->bgd, pend, s);
+  }
+  int n = bg_part_materialise(h, s);
+  return n + launch_bg_sweep(h->dv, h->bgd, s, fuse);
+}
+static int bg_launch_apply(cg_handle *h, cudaStream_t s) {
+  if (h->pd_pending) {
+    h->pd_pending = false;
+    h->part_pending = true;
+    return launch_bg_cell(h->dv, h->bgd, s);
+  }
+  return launch_tc_apply_only(h->dv, s);
+}
 static FieldDesc *find_field(cg_handle *h, const char *name) {
   auto it = h->fields.find(name);
   if (it == h->fields.end()) return nullptr;
+  // bio_part is read or written as the reference holds it: apply a rescaling the last coupling left pending (callers have joined
+  // the side streams)
+  if (h->part_pending && h->initialised && it->first == "bio_part") { activate(h); bg_part_materialise(h, h->stream); }
   // ts / ts1 alias the current ping-pong buffer
   if (it->first == "ts") it->second.d = h->dv.ts_cur;
   return &it->second;
@@ -1669,8 +1717,8 @@ extern "C" int cg_biogem_step(cg_handle *h, double dts, int64_t genie_clock_ms) 
   BgAsyncScope as(h, true);
   {
     ProfScope ps(h, "biogem");
-    if (as.on && h->spec_valid && h->spec_clock == (long long)genie_clock_ms) ps.done(launch_bg_sweep(h->dv, h->bgd, h->stream));
-    else ps.done(launch_bg_step(h->dv, h->bgd, 0, 0, h->stream));
+    if (as.on && h->spec_valid && h->spec_clock == (long long)genie_clock_ms) ps.done(bg_launch_sweep(h, h->stream));
+    else { const int n = bg_part_materialise(h, h->stream); ps.done(n + launch_bg_step(h->dv, h->bgd, 0, 0, h->stream)); }
   }
   h->spec_valid = false;
   h->bg_last_clock = (long long)genie_clock_ms;
@@ -1763,7 +1811,8 @@ extern "C" int cg_biogem_slice_update(cg_handle *h, double dts) {
   BgAsyncScope as(h, true);
   IO(side_wait(h));
   ProfScope ps(h, "biogem");
-  ps.done(launch_bg_slice(h->dv, h->bgd, h->slice, dts / kBgYrS, 0, h->stream));
+  const int nmat = bg_part_materialise(h, h->stream);   // int_bio_part_timeslice integrates bio_part as the reference holds it
+  ps.done(nmat + launch_bg_slice(h->dv, h->bgd, h->slice, dts / kBgYrS, 0, h->stream));
   return check_async(h);
 }
 extern "C" int cg_biogem_slice_reset(cg_handle *h) {   // sub_init_int_timeslice, biogem_data.f90:1012-1060
@@ -1835,7 +1884,8 @@ extern "C" int cg_biogem_tracercoupling(cg_handle *h, double *go_ts, double *go_
   h->tc_spec_valid = false;
   {
     ProfScope ps(h, "biogem");
-    if (ahead) { const int n = launch_tc_sums_new(h->dv, h->stream); ps.done(n + launch_tc_apply_only(h->dv, h->stream)); }
+    if (ahead) { const int n = launch_tc_sums_new(h->dv, h->stream); ps.done(n + bg_launch_apply(h, h->stream)); }
+    else if (h->pd_pending) { const int n = launch_tc_sums_first(h->dv, h->stream); ps.done(n + bg_launch_apply(h, h->stream)); }
     else ps.done(launch_tracercoupling(h->dv, h->stream));
   }
   IO(check_async(h));
@@ -1939,9 +1989,10 @@ static int do_biogem_block(cg_handle *h, long long k) {
       CUDA_OK(cudaStreamWaitEvent(h->stream5, h->evFork5, 0));
       h->launches += launch_tc_sums_first(h->dv, h->stream5);
       CUDA_OK(cudaEventRecord(h->evJoin5, h->stream5));
+      h->launches += bg_part_materialise(h, h->stream);
       h->launches += launch_bg_step(h->dv, h->bgd, 0, 0, h->stream);
       CUDA_OK(cudaStreamWaitEvent(h->stream, h->evJoin5, 0));
-      h->launches += launch_tc_apply_only(h->dv, h->stream);
+      h->launches += bg_launch_apply(h, h->stream);
       if (t < kBgNullSmall) h->bg_go = false;
       IO(check_async(h));
     } else if (nofuse || !h->bg_fuse) {
@@ -1953,6 +2004,7 @@ static int do_biogem_block(cg_handle *h, long long k) {
       const double t = h->bg.t_runtime - (double)clock / (1000.0 * kBgYrS);
       ProfScope ps(h, "biogem");
       int n = launch_tc_sums_first(h->dv, h->stream);
+      n += bg_part_materialise(h, h->stream);
       n += launch_bg_step(h->dv, h->bgd, 0, 1, h->stream);
       ps.done(n);
       if (t < kBgNullSmall) h->bg_go = false;
@@ -2046,6 +2098,7 @@ static int bg_issue_step(cg_handle *h, long long clock) {
   IO(cg_biogem_forcing(h, clock));
   const double t = h->bg.t_runtime - (double)clock / (1000.0 * kBgYrS);
   if (!h->bg_go) return CG_OK;   // par_misc_t_go (biogem.f90:1851-1853)
+  h->launches += bg_part_materialise(h, h->stream);
   h->launches += launch_bg_step(h->dv, h->bgd, 0, 0, h->stream);
   if (t < kBgNullSmall) h->bg_go = false;
   return CG_OK;
@@ -2087,7 +2140,7 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
     const bool fuse_now = fuse2 && h->bg_split && h->bg_surf_issued && h->bg_go;
     if (!fuse_now && h->bg_split && h->bg_surf_issued) {   // sediment return + water-column sweep, after this cycle's tracer step
       if (cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
-      h->launches += launch_bg_sweep(h->dv, h->bgd, h->stream4);
+      h->launches += bg_launch_sweep(h, h->stream4);
       h->bg_surf_issued = false;
     }
     const bool old_ready = h->bg_ahead && h->tc_old_ready;
@@ -2097,7 +2150,7 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
       h->launches += old_ready ? launch_tc_sums_new(h->dv, h->stream5) : launch_tc_sums_first(h->dv, h->stream5);
       if (cudaEventRecord(h->evJoin5, h->stream5) != cudaSuccess || cudaStreamWaitEvent(h->stream4, h->evJoin5, 0) != cudaSuccess ||
           cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
-      h->launches += launch_bg_sweep(h->dv, h->bgd, h->stream4, 1);
+      h->launches += bg_launch_sweep(h, h->stream4, 1);
       h->bg_surf_issued = false;
     } else
     if (h->bg_go) {       // biogem_tracercoupling: sums on stream5 (they need ts of this cycle, not the step's anomaly)
@@ -2105,7 +2158,7 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
       h->launches += old_ready ? launch_tc_sums_new(h->dv, h->stream5) : launch_tc_sums_first(h->dv, h->stream5);
       if (cudaEventRecord(h->evJoin5, h->stream5) != cudaSuccess || cudaStreamWaitEvent(h->stream4, h->evJoin5, 0) != cudaSuccess ||
           cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
-      h->launches += launch_tc_apply_only(h->dv, h->stream4);
+      h->launches += bg_launch_apply(h, h->stream4);
     } else if (cudaStreamWaitEvent(h->stream4, h->evT, 0) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "stream wait"); break; }
     if ((rc = cg_biogem_climate(h))) break;
     if (cudaEventRecord(h->evBG, h->stream4) != cudaSuccess) { rc = fail(CG_ERR_CUDA, "event record"); break; }
@@ -2127,7 +2180,7 @@ static int do_biogem_block_pipelined(cg_handle *h, long long k, long long remain
       // ... and the sweep right behind it (default; CG_BG_SWEEP_EARLY=1: behind the tracer step of the cycle before the
       // block's, 0: at the block's nominal place.  Measured 79.5 / 81.2 / 82.4 ms per model year.)
       if (!fuse2 && h->bg_split && h->bg_surf_issued && !(getenv("CG_BG_SWEEP_EARLY") && atoi(getenv("CG_BG_SWEEP_EARLY")) != 2)) {
-        h->launches += launch_bg_sweep(h->dv, h->bgd, h->stream);
+        h->launches += bg_launch_sweep(h, h->stream);
         h->bg_surf_issued = false;
       }
       h->bg_ahead = true;
@@ -2269,7 +2322,7 @@ extern "C" int cg_run(cg_handle *h, int64_t n) {
           if (early && h->koverall % period != 0 && (h->koverall + p.kocn_loop) % period == 0) {
             CUDA_OK(cudaEventRecord(h->evT, h->stream));
             CUDA_OK(cudaStreamWaitEvent(h->stream4, h->evT, 0));
-            h->launches += launch_bg_sweep(h->dv, h->bgd, h->stream4);
+            h->launches += bg_launch_sweep(h, h->stream4);
             h->bg_surf_issued = false;
           }
         }
@@ -2345,7 +2398,7 @@ extern "C" int cg_refresh_rho(cg_handle *h, int member) {
         for (int i = 1; i <= I; i++) {
           if (k < h->g.k1at(i, j)) continue;
           const size_t c = cell3(I, J, i, j, k);
-          rho[c] = eos(h->mc[m].ec, ts[c * L], ts[c * L + 1]);
+          rho[c] = eos_z(h->mc[m].ec, h->base.ieos, ts[c * L], ts[c * L + 1], h->g.zro[k]);
         }
     IO(cg_sync_from_host(h, "rho", m, rho.data(), (int64_t)rho.size()));
     if (h->dv.sst) {   // SST / SSS as step_goldstein last exported them (tsval, ssval of initialise_goldstein after a restart)

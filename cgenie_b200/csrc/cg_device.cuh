@@ -25,12 +25,13 @@ struct GridC {
   double ds[kMaxJ], dsv[kMaxJ], rds2[kMaxJ], s[kMaxJ], c[kMaxJ], sv[kMaxJ], cv[kMaxJ], rc[kMaxJ], rc2[kMaxJ],
       rcv[kMaxJ], rdsv[kMaxJ], cv2[kMaxJ], rds[kMaxJ];
   double dz[kMaxK], dza[kMaxK], rdz[kMaxK], rdza[kMaxK], zw[kMaxK], ssmax[kMaxK];
+  double zro[kMaxK];       // depth of the density levels (ieos = 1: rho at zro(k))
   double diffmax[kMaxK];   // iediff > 0: 0.5 * 0.125 * dz^2 / dt (goldstein.f90:3042)
 };
 
 // Per-member scalar parameters ([MS] each) and per-member 2-D constants ([j][i][m]).
 struct MemberP {
-  const double *diff1, *diff2, *ec1, *ec2, *ec3, *ec4, *rel, *scf, *saln0, *rpmesco, *rsictscsf, *albocn;
+  const double *diff1, *diff2, *ec1, *ec2, *ec3, *ec4, *ec5, *rel, *scf, *saln0, *rpmesco, *rsictscsf, *albocn;
   const double *hosing_trend;
   const int *nsteps_hosing;
   const double *ediff0, *ediff1p;   // iediff > 0: [m], [k][m] (ediff1(i,j,k) = ediff1p(k): ediffvar = 0)
@@ -105,6 +106,7 @@ struct Dev {
   int co_pairwise;           // k_co_col: average the passive tracers pair by pair (round-1 form, CG_CO_PAIR=1) instead of region by region
   int co_skip_stable;        // k_co_col: skip (member, column)s the flux kernel flagged stable in comask (CG_CO_SKIP=0: off)
   int col_deep_first;        // k_tstep_col: blocks in wetcols order (deepest columns first) instead of row-major (CG_COL_ORDER=1)
+  int ieos;                  // 1: thermobaricity term in the equation of state (goldstein.f90:3048-3082), strict kernels only
   int iediff, ediffpow2i;    // stratification-dependent vertical diffusivity (goldstein.f90:2501-2515); 0 = constant diff(2)
   double ediffpow2;
   int *istep_ocn;            // device-resident ocean step counter (read by graph-replayed kernels)
@@ -170,6 +172,12 @@ struct BgDev {
   const double *atm_A, *atm_V;            // [j][i]
   double *sfcocn1, *sfxsed1, *focnatm;    // interface / diagnostics: [l|ls|la][j][i][m]
   int *err;                               // [m] carbonate chemistry failure flag (error_stop)
+  // packets / cells split of the sweep (k_bg_step PART 3 -> k_bg_cell): remineralisation products of the sinking particles per
+  // cell, sediment return per column, wet-column index of a column, pending rescaling of bio_part (see k_bg_cell)
+  double *lrem;                           // [k][j][i][7][m]
+  double *fsedv;                          // [7][wet column][m]
+  const int *colidx;                      // [j][i] -> index in Dev::bgcols, -1 on land
+  double *pscale;                         // [m] Sratio of the last coupling, not yet applied to bio_part
   double *surf;                           // [kBgSurfSlots][wet column][m] surface-cell results (k_bg_step PART 1 -> PART 2)
 };
 // time-slice diagnostics (diag_biogem_timeslice, biogem.f90:2421-2699): the carbonate system of every wet cell and the window

@@ -415,7 +415,7 @@ void build_member(const Grid &g, const Islands &isl, const WindFiles &w, const P
   mc.ec[2] = 0.7968 / kRhosc;
   mc.ec[3] = -0.0063 / kRhosc;
   mc.ec[4] = 3.7315e-5 / kRhosc;
-  mc.ec[5] = 0.0;
+  mc.ec[5] = (p.ieos == 1) ? 2.5e-5 * kDsc / kRhosc : 0.0;   // goldstein.f90:1066-1075
   mc.hosing = p.hosing;
   mc.hosing_trend = p.hosing_trend / (1.0e3 * syr);
   mc.nsteps_hosing = p.nyears_hosing * p.nyear;
@@ -489,7 +489,7 @@ void build_member(const Grid &g, const Islands &isl, const WindFiles &w, const P
         const size_t c = (size_t)(i - 1) + (size_t)I * ((j - 1) + (size_t)J * (k - 1));
         mc.ts0[0 + (size_t)L * c] = t;
         if (L > 1) mc.ts0[1 + (size_t)L * c] = 0.0;
-        mc.rho0[c] = eos(mc.ec, t, 0.0);
+        mc.rho0[c] = eos_z(mc.ec, p.ieos, t, 0.0, g.zro[k]);   // goldstein.f90:1450
       }
   // barotropic factorisation + unit island solves (goldstein.f90:1788-1814)
   if (isl.isles > 0) {
@@ -823,8 +823,8 @@ bool load_job(const std::string &jobdir, Params *p, Grid *g, Islands *isl, WindF
   p->diso = go.flag("diso", true);
   p->world = go.str("world", d.world);
   p->go_indir = go.str("indir_name", d.go_indir);
-  if (p->iconv != 0 || p->imld != 0 || p->ieos != 0) {
-    if (err) *err = "iconv/imld/ieos /= 0 are outside the B200 hot path (SURVEY 8f.4)";
+  if (p->iconv != 0 || p->imld != 0 || p->ieos < 0 || p->ieos > 1) {
+    if (err) *err = "iconv/imld /= 0 and ieos outside 0..1 are outside the B200 hot path (SURVEY 8f.4)";
     return false;
   }
   if (p->iediff < 0 || p->iediff > 2 || (p->iediff != 0 && (p->ediffvar < -1.0e-7 || p->ediffvar > 1.0e-7))) {

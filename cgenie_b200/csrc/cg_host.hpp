@@ -134,8 +134,12 @@ struct MemberConsts {
 
 struct WindFiles { std::vector<double> taux_u, tauy_u, taux_v, tauy_v, uncep, vncep; };
 
-// equation of state, goldstein.f90:3048-3061 (ieos==0)
+// equation of state, goldstein.f90:3048-3061: ieos == 0 (ec[5] == 0), and ieos == 1 with the thermobaricity term ec(5) * t * z
 inline double eos(const double *ec, double t, double s) { return ec[1] * t + ec[2] * s + ec[3] * (t * t) + ec[4] * (t * t * t); }
+inline double eos_z(const double *ec, int ieos, double t, double s, double z) {
+  if (ieos == 0) return eos(ec, t, s);
+  return ec[1] * t + ec[2] * s + ec[3] * (t * t) + ec[4] * (t * t * t) + ec[5] * t * z;
+}
 
 // builds the per-member constants; `shared_baro`, when non-null and the drag parameters match,
 // lets members reuse one barotropic factorisation.

@@ -583,7 +583,12 @@ __device__ __forceinline__ void rem_add(Rem7 &r, const double f, const double *p
 // arithmetic).
 template <int MINB, int PART, int FMS>
 __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev b, const int init_only, const int mode) {
-  const bool fuse = (mode & 1) != 0, pf = (mode & 2) == 0;
+  const bool fuse = (mode & 1) != 0, pf = (mode & 2) == 0, pend = (mode & 4) != 0;
+  // PART = 3: PART 2 without its per-cell half -- sediment return, the packets of sinking particles, the new particulate field,
+  // the settling flux; the remineralisation products of every cell (lrem, 7 numbers) and the column's sediment return go to
+  // b.lrem / b.fsedv, and the per-cell half (DOM, decay, anomaly, tracer coupling) runs cell-parallel in k_bg_cell.
+  // pend: bio_part still lacks the last coupling's rescaling (Sratio, b.pscale): applied to the values as they are read
+  constexpr bool PK = (PART == 3);
   using namespace bgk;
   using namespace lay;
   constexpr bool FIX = FMS > 0;
@@ -624,7 +629,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
 #define RM_(k) v.bg_rM[p0 + (size_t)((k)-1) * pK]
 #define SET1_(ls) b.settle_k1[(c2d * LS + ((ls)-1)) * MS + m]
   const double dtyr = b.dtyr;
-  const double Tsf = OCN_(T, K), Ssf = OCN_(S, K);
+  const double Tsf = PK ? 0.0 : OCN_(T, K), Ssf = PK ? 0.0 : OCN_(S, K);
   double cc[N_CC];
   Carb cb;
   if (init_only) {  // sub_init_carb, biogem_data.f90:2336-2430 (surface cell)
@@ -652,7 +657,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
   double focn_surf[LA + 1];   // -conv_atm_ocn*focnatm of each gas, applied to its ocean tracer at the surface (:1612-1616)
   double psurf[LS + 1], dom_add[LS + 1];
   Rem7 uptake;
-  if (PART != 2) {
+  if (PART != 2 && PART != 3) {
   // ---- surface cell: carbonate chemistry, solubility, piston velocity (:1026-1104)
   carbconst(b.Dmid_surf, Tsf, Ssf, OCN_(CA, K), OCN_(MG, K), cc);
   cb.H = b.carbH[c2d * MS + m];
@@ -818,7 +823,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
     SC_(kBgSurfSlots - 1) = 0.0;
     return;
   }
-  if (PART == 2) {
+  if (PART == 2 || PART == 3) {
     if (SC_(kBgSurfSlots - 1) != 0.0) { b.err[m] = 1; return; }   // the carbonate solve of this column failed (error_stop)
     b.carbH[c2d * MS + m] = SC_(kBgSurfH);
 #pragma unroll
@@ -838,6 +843,13 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
     uptake.po4 = SC_(LA - 2 + LS + 7); uptake.o2 = SC_(LA - 2 + LS + 8); uptake.alk = SC_(LA - 2 + LS + 9);
     uptake.ca = SC_(LA - 2 + LS + 10);
   }
+  if (PK) {
+    double *fo = b.fsedv + (size_t)n * MS + m;
+    const size_t fq = (size_t)v.nwet * MS;
+    fo[0] = fsed.dic; fo[fq] = fsed.d13; fo[2 * fq] = fsed.d14; fo[3 * fq] = fsed.po4; fo[4 * fq] = fsed.o2; fo[5 * fq] = fsed.alk;
+    fo[6 * fq] = fsed.ca;
+  }
+  const double pscale = (PK && pend) ? b.pscale[m] : 1.0;
   // ---- water column, one downward sweep (K -> k1).  sub_box_remin_part (:2412-2875) follows each source layer's
   // particles down to the deepest layer they reach in dt; here all packets in flight are advanced level by level, kept in
   // source order (shallowest source first = the reference's k loop), so every sum over sources at a given layer
@@ -859,14 +871,19 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
   for (int kk = K; kk >= k1; kk--) {
     // pull the next level's rows towards the SM while this level is being worked on (no registers tied up)
     if (pf && kk > k1) {
+      if (PK) asm volatile("prefetch.global.L1 [%0];" ::"l"(&OCN_(O2, kk - 1)));
+      else {
 #pragma unroll
       for (int l = 1; l <= L; l++) asm volatile("prefetch.global.L1 [%0];" ::"l"(&OCN_(l, kk - 1)));
+      }
       if (fuse) {
 #pragma unroll
         for (int l = 1; l <= L; l++) asm volatile("prefetch.global.L1 [%0];" ::"l"(v.ts_cur + (o0 + (size_t)(kk - 2) * sK + (size_t)(l - 1) * MS)));
       }
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(&M_(kk - 1)));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(&RM_(kk - 1)));
+      if (!PK) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(&M_(kk - 1)));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(&RM_(kk - 1)));
+      }
       if (kk - 1 >= klim) {
 #pragma unroll
         for (int ls = 1; ls <= LS; ls++) asm volatile("prefetch.global.L1 [%0];" ::"l"(&PART_(ls, kk - 1)));
@@ -877,10 +894,13 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
     rem_zero(lrem);
 #pragma unroll
     for (int ls = 1; ls <= LS; ls++) pnew[ls] = 0.0;
-    const double Mk = M_(kk), rM = RM_(kk);
+    const double Mk = (PK && kk != k1) ? 0.0 : M_(kk), rM = PK ? 0.0 : RM_(kk);   // PART 3 needs the bottom cell's mass only
     double x[L + 1];
+    if (PK) x[O2] = OCN_(O2, kk);
+    else {
 #pragma unroll
-    for (int l = 1; l <= L; l++) x[l] = OCN_(l, kk);
+      for (int l = 1; l <= L; l++) x[l] = OCN_(l, kk);
+    }
     const double f = redfield_factor(b, x[O2]);
     const double fO2POC = f * cO2POC, fO2POP = f * cO2POP, fALKPOP = f * cALKPOP, fALKCa = f * cALKCa;
     // (1) packets from the layers above pass through / stop in layer kk
@@ -928,6 +948,10 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
       double old[LS + 1];
 #pragma unroll
       for (int ls = 1; ls <= LS; ls++) old[ls] = PART_(ls, kk);
+      if (PK && pend) {   // biogem.f90:2042-2043 of the last coupling, not applied yet (k_bg_cell leaves it to the next reader)
+#pragma unroll
+        for (int ls = 1; ls <= LS; ls++) old[ls] = pscale * (old[ls] + 0.0);
+      }
       if (sed_decays) { old[POC14] = fd13 * old[POC14]; old[CACO314] = fd13 * old[CACO314]; }
       double part_tot = 0.0;
       part_tot = part_tot + old[POC];
@@ -953,6 +977,12 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
     for (int ls = 1; ls <= LS; ls++) {
       const double pv = (kk == K) ? psurf[ls] : pnew[ls];
       PART_(ls, kk) = fuse ? s_sr[threadIdx.x] * (pv + 0.0) : pv;   // biogem.f90:2042-2043 (vdbio_part = 0)
+    }
+    if (PK) {   // the cell's half of the work is k_bg_cell's: hand over the remineralisation products of the particles
+      double *lo = b.lrem + (cell3(I, J, i, j, kk) * 7) * MS + m;
+      lo[0] = lrem.dic; lo[MS] = lrem.d13; lo[2 * (size_t)MS] = lrem.d14; lo[3 * (size_t)MS] = lrem.po4; lo[4 * (size_t)MS] = lrem.o2;
+      lo[5 * (size_t)MS] = lrem.alk; lo[6 * (size_t)MS] = lrem.ca;
+      continue;
     }
     // (4) sub_box_remin_DOM for this layer: DOM -> POM -> inorganic products
     const bool has_dom = x[DOMC] > kNS;
@@ -1046,6 +1076,176 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
 #undef RM_
 #undef SET1_
 #undef SC_
+}
+
+// =============================================================================================================
+// The per-cell half of step_biogem's water-column work + biogem_tracercoupling's steps (2)+(3), cell-parallel: one warp = 32
+// members of ONE wet cell (as k_tc_apply).  Behind k_bg_step PART 3 (which left the particles' remineralisation products of
+// every cell in b.lrem and the column's sediment return in b.fsedv) and the coupling's sums / factors, the thread does what the
+// sweep did per level -- sub_box_remin_DOM (biogem_box.f90:2287-2406), the decay terms (biogem.f90:838-871), the tracer anomaly
+// (:1811-1844), the bottom-water interface (:1736-1744) -- and applies the coupling to the cell at once (:2033-2061): the
+// anomaly never goes to memory (no vdocn round trip), ocn and ts are read once and written once.  Same expressions in the same
+// order as k_bg_step (`fuse`) / k_tc_apply: bit-identical results.  bio_part is NOT rescaled here (a pass over 9 tracers for
+// one multiplication): the factor stays pending in b.pscale and the next reader applies it (k_bg_step PART 3, k_bg_part_scale).
+template <int FMS, int MINB>
+__global__ void __launch_bounds__(32 * kApplyWarps, MINB) k_bg_cell(const Dev v, const BgDev b) {
+  using namespace bgk;
+  using namespace lay;
+  constexpr bool FIX = FMS > 0;
+  constexpr int L = NL, LS = NLS, LA = NLA;
+  __shared__ double s_f[L][32], s_rmean[32], s_sr[32], s_rsr[32], s_mnew[32];
+  const int I = FIX ? 36 : v.I, J = FIX ? 36 : v.J, K = FIX ? 16 : v.K, MS = FIX ? FMS : v.MS;
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int m = blockIdx.x * 32 + lane;
+  {
+    const double *fac = v.bg_tot + (size_t)2 * L * MS + m;
+    if (warp == 0) {
+      s_rmean[lane] = fac[0];
+      s_sr[lane] = fac[(size_t)MS];
+      s_rsr[lane] = fac[(size_t)2 * MS];
+      s_mnew[lane] = fac[(size_t)3 * MS];
+    }
+    for (int l = 2 + warp; l < L; l += kApplyWarps) s_f[l][lane] = fac[(size_t)(4 + l) * MS];
+  }
+  __syncthreads();
+  const int c = blockIdx.y * kApplyWarps + warp;
+  if (c >= I * J * K) return;
+  const int kk = c / (I * J) + 1, r2 = c % (I * J), j = r2 / I + 1, i = r2 % I + 1;
+  const int k1 = (int)v.k1[i + (I + 2) * j];
+  if (kk < k1) return;
+  const size_t c2d = cell2(I, i, j);
+  const int n = b.colidx[c2d];
+  if (kk == K && c2d == (size_t)v.bgcols[0]) b.pscale[m] = s_sr[lane];   // the rescaling of bio_part this coupling owes
+#define SC_(slot) b.surf[((size_t)(slot) * (I * J) + n) * MS + m]
+  if (SC_(kBgSurfSlots - 1) != 0.0) return;   // the carbonate solve of this column failed (error_stop): flagged by PART 3
+  const bool bot = (kk == k1), top = (kk == K);
+  const size_t o = (size_t)c * L * MS + m;
+  const double dtyr = b.dtyr;
+  double x[L + 1], tv[L + 1];
+#pragma unroll
+  for (int l = 1; l <= L; l++) { x[l] = v.bg_ocn[o + (size_t)(l - 1) * MS]; tv[l] = v.ts_cur[o + (size_t)(l - 1) * MS]; }
+  const double Mk = v.bg_M[(size_t)c * MS + m], rM = v.bg_rM[(size_t)c * MS + m];
+  Rem7 lrem, fsed, uptake;
+  {
+    const double *lo = b.lrem + ((size_t)c * 7) * MS + m;
+    lrem.dic = lo[0]; lrem.d13 = lo[MS]; lrem.d14 = lo[2 * (size_t)MS]; lrem.po4 = lo[3 * (size_t)MS]; lrem.o2 = lo[4 * (size_t)MS];
+    lrem.alk = lo[5 * (size_t)MS]; lrem.ca = lo[6 * (size_t)MS];
+  }
+  rem_zero(fsed);
+  rem_zero(uptake);
+  if (bot) {
+    const double *fo = b.fsedv + (size_t)n * MS + m;
+    const size_t fq = (size_t)v.nwet * MS;
+    fsed.dic = fo[0]; fsed.d13 = fo[fq]; fsed.d14 = fo[2 * fq]; fsed.po4 = fo[3 * fq]; fsed.o2 = fo[4 * fq]; fsed.alk = fo[5 * fq];
+    fsed.ca = fo[6 * fq];
+  }
+  double focn_surf[LA + 1], dom_add[LS + 1];
+#pragma unroll
+  for (int la = 1; la <= LA; la++) focn_surf[la] = 0.0;
+#pragma unroll
+  for (int ls = 1; ls <= LS; ls++) dom_add[ls] = 0.0;
+  if (top) {
+#pragma unroll
+    for (int la = 3; la <= LA; la++) focn_surf[la] = SC_(la - 3);
+    dom_add[POC] = SC_(LA - 2 + LS + 0); dom_add[POC13] = SC_(LA - 2 + LS + 1); dom_add[POC14] = SC_(LA - 2 + LS + 2);
+    dom_add[POP] = SC_(LA - 2 + LS + 3);
+    uptake.dic = SC_(LA - 2 + LS + 4); uptake.d13 = SC_(LA - 2 + LS + 5); uptake.d14 = SC_(LA - 2 + LS + 6);
+    uptake.po4 = SC_(LA - 2 + LS + 7); uptake.o2 = SC_(LA - 2 + LS + 8); uptake.alk = SC_(LA - 2 + LS + 9);
+    uptake.ca = SC_(LA - 2 + LS + 10);
+  }
+#undef SC_
+  const double cO2POC = b.conv_ls_lo[POC][1], cO2POP = b.conv_ls_lo[POP][1], cALKPOP = b.conv_ls_lo[POP][2],
+               cALKCa = b.conv_ls_lo[CACO3][1];
+  const bool ocn_decays = fabs(b.lam_ocn[DIC14]) > kNS;
+  const double decay14 = 1.0 - b.fd_ocn[DIC14];
+  double ratio;
+  if (b.DOMlifetime > dtyr) ratio = dtyr / b.DOMlifetime; else ratio = 1.0;
+  const double A = b.A[c2d];
+  const double f = redfield_factor(b, x[O2]);
+  const double fO2POC = f * cO2POC, fO2POP = f * cO2POP, fALKPOP = f * cALKPOP, fALKCa = f * cALKCa;
+  // (4) sub_box_remin_DOM for this layer: DOM -> POM -> inorganic products
+  const bool has_dom = x[DOMC] > kNS;
+  double dom[LS + 1];
+#pragma unroll
+  for (int ls = 1; ls <= LS; ls++) dom[ls] = 0.0;
+  if (has_dom) {
+    dom[POC] = dom[POC] + 1.0 * ratio * x[DOMC];
+    dom[POC13] = dom[POC13] + 1.0 * ratio * x[DOMC13];
+    dom[POC14] = dom[POC14] + 1.0 * ratio * x[DOMC14];
+    dom[POP] = dom[POP] + 1.0 * ratio * x[DOMP];
+  }
+  Rem7 domrem;
+  rem_zero(domrem);
+  rem_add(domrem, f, dom, fO2POC, fO2POP, fALKPOP, fALKCa);
+  // (5) tracer anomaly vdocn(l, kk) = bio_remin + dtyr*rM*focn, the bottom-water interface (:1736-1744), and the coupling
+  const double saln0 = v.p.saln0[m];
+  double rn_cpl = 0.0;   // mean_S_NEW / Snew of this cell
+#pragma unroll
+  for (int l = 1; l <= L; l++) {
+    double vrem = 0.0, lr = 0.0, fs = 0.0, up = 0.0, da = 0.0, gas = 0.0;
+    bool slot = false;
+    switch (l) {
+      case DIC: vrem = vrem + domrem.dic; lr = lrem.dic; fs = fsed.dic; up = uptake.dic; slot = true; gas = focn_surf[A_CO2]; break;
+      case DIC13: vrem = vrem + domrem.d13; lr = lrem.d13; fs = fsed.d13; up = uptake.d13; slot = true; gas = focn_surf[A_CO213]; break;
+      case DIC14: vrem = vrem + domrem.d14; lr = lrem.d14; fs = fsed.d14; up = uptake.d14; slot = true; gas = focn_surf[A_CO214]; break;
+      case PO4: vrem = vrem + domrem.po4; lr = lrem.po4; fs = fsed.po4; up = uptake.po4; slot = true; break;
+      case O2: vrem = vrem + domrem.o2; lr = lrem.o2; fs = fsed.o2; up = uptake.o2; slot = true; gas = focn_surf[A_O2]; break;
+      case ALK: vrem = vrem + domrem.alk; lr = lrem.alk; fs = fsed.alk; up = uptake.alk; slot = true; break;
+      case CA: vrem = vrem + domrem.ca; lr = lrem.ca; fs = fsed.ca; up = uptake.ca; slot = true; break;
+      case DOMC: if (has_dom) vrem = vrem - ratio * x[l]; da = dom_add[POC]; break;
+      case DOMC13: if (has_dom) vrem = vrem - ratio * x[l]; da = dom_add[POC13]; break;
+      case DOMC14: if (has_dom) vrem = vrem - ratio * x[l]; da = dom_add[POC14]; break;
+      case DOMP: if (has_dom) vrem = vrem - ratio * x[l]; da = dom_add[POP]; break;
+      case CFC11: gas = focn_surf[A_CFC11]; break;
+      case CFC12: gas = focn_surf[A_CFC12]; break;
+      default: break;
+    }
+    double rem = 0.0;
+    if (bot && l >= 3) rem = rem + rM * fs;
+    rem = rem + (vrem + lr);
+    double focn = 0.0;
+    if ((l == DIC14 || l == DOMC14) && ocn_decays) focn = focn - Mk * decay14 * x[l] / dtyr;
+    if (l == 1 && bot) focn = focn + kYrS * b.Fgeothermal * A / (1.0E+03 * kCp);
+    if (top) {
+      focn = focn + gas;
+      if (l >= 3) {
+        if (l == DOMC || l == DOMC13 || l == DOMC14 || l == DOMP) rem = rem + da;
+        rem = rem - (slot ? up : 0.0);
+      }
+    }
+    const double dval = rem + dtyr * rM * focn;
+    if (bot) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = x[l] + rem + dtyr * rM * focn;
+    double *tsp = v.ts_cur + (o + (size_t)(l - 1) * MS);
+    double *ocp = v.bg_ocn + (o + (size_t)(l - 1) * MS);
+    if (l == 1) {
+      const double Tn = tv[l] + kBgZeroC + dval;
+      *ocp = Tn;
+      *tsp = Tn - kBgZeroC;
+    } else if (l == 2) {
+      const double Sn = tv[l] + saln0 + dval;
+      rn_cpl = s_mnew[lane] / Sn;
+      *ocp = Sn;
+      *tsp = Sn - saln0;
+    } else {
+      const double lv = tv[l] * x[S] * s_rmean[lane];
+      double xx = s_f[l - 1][lane] * lv + dval;
+      xx = s_sr[lane] * xx;
+      *ocp = xx;
+      *tsp = rn_cpl * xx;
+    }
+  }
+  v.bg_M[(size_t)c * MS + m] = s_rsr[lane] * Mk;
+  v.bg_rM[(size_t)c * MS + m] = s_sr[lane] * rM;
+}
+// the rescaling of bio_part a coupling through k_bg_cell left pending (biogem.f90:2042-2043), for readers other than k_bg_step
+__global__ void __launch_bounds__(256) k_bg_part_scale(const Dev v, const BgDev b) {
+  const int MS = v.MS;
+  const int m = blockIdx.x * 32 + threadIdx.x;
+  const size_t row = (size_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const size_t nrow = (size_t)v.I * v.J * v.K * b.LS;
+  if (row >= nrow) return;
+  double *p = b.bio_part + row * MS + m;
+  *p = b.pscale[m] * (*p + 0.0);
 }
 
 // biogem_climate (:2132-2239): snapshot the sea-ice fraction, reset the convection counter
@@ -1164,6 +1364,33 @@ int launch_bg_surf(const Dev &v, const BgDev &b, cudaStream_t s) {
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
   if (minb == 3) k_bg_step<3, 1, 0><<<g, bl, 0, s>>>(v, b, 0, 0);
   else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<4, 1, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, 0); });
+  return 1;
+}
+// packets half of the sweep (PART 3) + its cell half fused with the coupling update (k_bg_cell); pend: see k_bg_step
+int launch_bg_packets(const Dev &v, const BgDev &b, int pend, cudaStream_t s) {
+  static int nopf = -1;
+  if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
+  static int minb = -1;
+  if (minb < 0) { const char *e = getenv("CG_BG_PK_MINB"); minb = e ? atoi(e) : 3; }
+  const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
+  const int mode = nopf | (pend ? 4 : 0);
+  if (minb == 2) fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<2, 3, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, mode); });
+  else if (minb == 4) fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<4, 3, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, mode); });
+  else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<3, 3, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, mode); });
+  return 1;
+}
+int launch_bg_cell(const Dev &v, const BgDev &b, cudaStream_t s) {
+  const int ncell = v.I * v.J * v.K;
+  static int minb = -1;   // 4: 128 registers (200 bytes of spills), 3: 168 registers
+  if (minb < 0) { const char *e = getenv("CG_BG_CELL_MINB"); minb = e ? atoi(e) : 4; }   // measured: 8.49 vs 8.36 M model-years/hour
+  const dim3 g(v.MS / 32, (ncell + kApplyWarps - 1) / kApplyWarps), bl(32, kApplyWarps);
+  if (minb == 4) fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_cell<decltype(ms)::value, 4><<<g, bl, 0, s>>>(v, b); });
+  else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_cell<decltype(ms)::value, 3><<<g, bl, 0, s>>>(v, b); });
+  return 1;
+}
+int launch_bg_part_scale(const Dev &v, const BgDev &b, cudaStream_t s) {
+  const size_t nrow = (size_t)v.I * v.J * v.K * b.LS;
+  k_bg_part_scale<<<dim3(v.MS / 32, (unsigned)((nrow + 7) / 8)), dim3(32, 8), 0, s>>>(v, b);
   return 1;
 }
 int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s, int fuse) {

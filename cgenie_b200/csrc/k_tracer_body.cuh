@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(TPB, MINB) CG_KNAME(k_tstepo_flux)(const Dev v
     if (!topl) {
       const double t0 = ts1[oC + ko], t1 = ts1[oC + ko + sK], s0 = ts1[oC + ko + sL], s1 = ts1[oC + ko + sK + sL];
       const double tatw = 0.5 * (t0 + t1);
-      const double tec = -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3;
+      const double tec = v.ieos ? -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3 - v.p.ec5[m] * c_g.zw[k]   // eosd, ieos = 1
+                                : -ec1 - ec3 * tatw * 2 - ec4 * tatw * tatw * 3;
       dzrho = (ec2 * (s1 - s0) - tec * (t1 - t0)) * rdza;
       if (dzrho < -1.0e-12) {
         iso = true;
@@ -287,7 +288,10 @@ __global__ void __launch_bounds__(TPB, MINB) CG_KNAME(k_tstepo_flux)(const Dev v
       }
     }
     // density of the new state (goldstein.f90:2638)
-    if (l0 == 0) v.rho[cell3(I, J, i, j, k) * MS + m] = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
+    if (l0 == 0)
+      v.rho[cell3(I, J, i, j, k) * MS + m] =
+          v.ieos ? ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew) + v.p.ec5[m] * tnew * c_g.zro[k]
+                 : ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
   }
 }
 
@@ -535,7 +539,19 @@ __global__ void __launch_bounds__(128) CG_KNAME(k_co)(const Dev v) {
   }
   int mm = K, lastmix = 0;
   bool any = false;
+  // ieos = 1 (:2692-2698, 2714-2730): the two boxes of a comparison are brought to one depth -- the interface above box k(m-1) --
+  // before every test; the stored column is made vertically local again at the end (tstepo :2396-2408)
+  const double ec5 = v.ieos ? v.p.ec5[m] : 0.0;
+  auto eosz = [&](const int lev, const double z) {
+    const double t = TSK(0, lev), s_ = TSK(1, lev);
+    return ec1 * t + ec2 * s_ + ec3 * (t * t) + ec4 * (t * t * t) + ec5 * t * z;
+  };
   while (kk[mm - 1] > 0 || (lastmix != 0 && kk[mm] != K)) {
+    if (v.ieos && kk[mm - 1] > 0) {
+      const double z = c_g.zw[kk[mm - 1]];
+      rl[kk[mm]] = eosz(kk[mm], z);
+      rl[kk[mm - 1]] = eosz(kk[mm - 1], z);
+    }
     if (kk[mm - 1] == 0 || rl[kk[mm]] < rl[kk[mm - 1]]) {
       if (lastmix == 0 || kk[mm] == K) mm = mm - 1; else mm = mm + 1;
       lastmix = 0;
@@ -543,6 +559,13 @@ __global__ void __launch_bounds__(128) CG_KNAME(k_co)(const Dev v) {
       lastmix = 1;
       any = true;
       int n = mm - 1;
+      if (v.ieos) {
+        if (kk[n - 1] > 0) { const double z = c_g.zw[kk[n - 1]]; rl[kk[n]] = eosz(kk[n], z); rl[kk[n - 1]] = eosz(kk[n - 1], z); }
+        while (kk[n - 1] > 0 && rl[kk[n]] >= rl[kk[n - 1]]) {
+          n = n - 1;
+          if (kk[n - 1] > 0) { const double z = c_g.zw[kk[n - 1]]; rl[kk[n]] = eosz(kk[n], z); rl[kk[n - 1]] = eosz(kk[n - 1], z); }
+        }
+      } else
       while (kk[n - 1] > 0 && rl[kk[n]] >= rl[kk[n - 1]]) n = n - 1;
       // thickness-weighted mix of all tracers over index entries n..mm (:2732-2737)
       double dznew = dzm[kk[mm]];
@@ -587,6 +610,9 @@ __global__ void __launch_bounds__(128) CG_KNAME(k_co)(const Dev v) {
     }
     // cost(i,j) is incremented by 1.0 per filled level; a sum of small integers is exact
     v.cost[cell2(I, i, j) * MS + m] += cnt;
+  }
+  if (v.ieos) {   // "make sure rho calculation is vertically local", tstepo :2396-2408 (wet levels; the dry ones hold eos(0, 0) = 0)
+    for (int k = k1c; k <= K; k++) RHOK(k) = eosz(k, c_g.zro[k]);
   }
 #undef RHOK
 #undef TSK

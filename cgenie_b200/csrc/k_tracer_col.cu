@@ -325,7 +325,7 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
 }
 
 bool tstep_col_supported(const Dev &v) {
-  if (v.iediff) return false;   // the column kernel takes diff(2) as a per-member constant
+  if (v.iediff || v.ieos) return false;   // the column kernel takes diff(2) as a per-member constant and has no thermobaric term
   return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && (v.MS == 32 || v.MS == 64 || v.MS == 128 || v.MS == 256 || v.MS == 512);
 }
 

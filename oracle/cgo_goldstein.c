@@ -10,17 +10,18 @@
 #define IPISL(p, n) o->ipisl[((p)-1) + o->mpi * ((n)-1)]
 #define JPISL(p, n) o->jpisl[((p)-1) + o->mpi * ((n)-1)]
 
-/* goldstein.f90:3048-3061 (ieos==0 only; ieos=1 is flag-gated out of scope) */
+/* goldstein.f90:3048-3061: ieos = 0, and ieos = 1 with the thermobaricity term ec(5) * t * z */
 void cgo_eos(const cgo_t *o, double t, double s, double z, double *rho) {
-  (void)z;
-  *rho = o->ec[1] * t + o->ec[2] * s + o->ec[3] * (t * t) + o->ec[4] * (t * t * t);
+  if (o->ieos == 0) *rho = o->ec[1] * t + o->ec[2] * s + o->ec[3] * (t * t) + o->ec[4] * (t * t * t);
+  else *rho = o->ec[1] * t + o->ec[2] * s + o->ec[3] * (t * t) + o->ec[4] * (t * t * t) + o->ec[5] * t * z;
 }
 
 /* goldstein.f90:3064-3082 */
-static void eosd(const cgo_t *o, double t1, double t2, double s1, double s2,
+static void eosd(const cgo_t *o, double t1, double t2, double s1, double s2, double z,
                  double rdz, double *dzrho, double *tec) {
   double tatw = 0.5 * (t1 + t2);
-  *tec = -o->ec[1] - o->ec[3] * tatw * 2 - o->ec[4] * tatw * tatw * 3;
+  if (o->ieos == 0) *tec = -o->ec[1] - o->ec[3] * tatw * 2 - o->ec[4] * tatw * tatw * 3;
+  else *tec = -o->ec[1] - o->ec[3] * tatw * 2 - o->ec[4] * tatw * tatw * 3 - o->ec[5] * z;
   *dzrho = (o->ec[2] * (s2 - s1) - *tec * (t2 - t1)) * rdz;
 }
 
@@ -400,7 +401,7 @@ void cgo_tstepo_flux(cgo_t *o) {
       }
       for (i = 1; i <= NI; i++) {
         if (k >= K1(i, j) && k < NK) {
-          eosd(o, TS1(1, i, j, k), TS1(1, i, j, k + 1), TS1(2, i, j, k), TS1(2, i, j, k + 1), o->rdza[k], &dzrho, &tec);
+          eosd(o, TS1(1, i, j, k), TS1(1, i, j, k + 1), TS1(2, i, j, k), TS1(2, i, j, k + 1), o->zw[k], o->rdza[k], &dzrho, &tec);
           if (dzrho < -1.0e-12)
             rdzrho = 1.0 / dzrho;
           else
@@ -523,6 +524,12 @@ void cgo_co(cgo_t *o) {
         m = NK;
         lastmix = 0;
         while (kk[m - 1] > 0 || (lastmix != 0 && kk[m] != NK)) {
+          /* added code for thermobaricity (:2692-2698): both boxes at the depth of the interface below box k(m-1)'s top.  With
+           * k(m-1) = 0 the reference evaluates level 0 of the halo into rho(i,j,0), which nothing reads: skipped */
+          if (o->ieos != 0 && kk[m - 1] > 0) {
+            cgo_eos(o, TS(1, i, j, kk[m]), TS(2, i, j, kk[m]), o->zw[kk[m - 1]], &RHO(i, j, kk[m]));
+            cgo_eos(o, TS(1, i, j, kk[m - 1]), TS(2, i, j, kk[m - 1]), o->zw[kk[m - 1]], &RHO(i, j, kk[m - 1]));
+          }
           if (kk[m - 1] == 0 || RHO(i, j, kk[m]) < RHO(i, j, kk[m - 1])) {
             if (lastmix == 0 || kk[m] == NK)
               m = m - 1;
@@ -532,14 +539,24 @@ void cgo_co(cgo_t *o) {
           } else {
             lastmix = 1;
             n = m - 1;
-            while (kk[n - 1] > 0 && RHO(i, j, kk[n]) >= RHO(i, j, kk[n - 1])) n = n - 1;
+            if (o->ieos != 0 && kk[n - 1] > 0) {   /* :2714-2720 */
+              cgo_eos(o, TS(1, i, j, kk[n]), TS(2, i, j, kk[n]), o->zw[kk[n - 1]], &RHO(i, j, kk[n]));
+              cgo_eos(o, TS(1, i, j, kk[n - 1]), TS(2, i, j, kk[n - 1]), o->zw[kk[n - 1]], &RHO(i, j, kk[n - 1]));
+            }
+            while (kk[n - 1] > 0 && RHO(i, j, kk[n]) >= RHO(i, j, kk[n - 1])) {
+              n = n - 1;
+              if (o->ieos != 0 && kk[n - 1] > 0) {   /* :2724-2730 */
+                cgo_eos(o, TS(1, i, j, kk[n]), TS(2, i, j, kk[n]), o->zw[kk[n - 1]], &RHO(i, j, kk[n]));
+                cgo_eos(o, TS(1, i, j, kk[n - 1]), TS(2, i, j, kk[n - 1]), o->zw[kk[n - 1]], &RHO(i, j, kk[n - 1]));
+              }
+            }
             for (l = 1; l <= L; l++) sum[l] = TS(l, i, j, kk[m]) * dzm[kk[m]];
             for (ni = 1; ni <= m - n; ni++) {
               for (l = 1; l <= L; l++) sum[l] = sum[l] + TS(l, i, j, kk[m - ni]) * dzm[kk[m - ni]];
               dzm[kk[m]] = dzm[kk[m]] + dzm[kk[m - ni]];
             }
             for (l = 1; l <= L; l++) TS(l, i, j, kk[m]) = sum[l] / dzm[kk[m]];
-            cgo_eos(o, TS(1, i, j, kk[m]), TS(2, i, j, kk[m]), 0.0, &RHO(i, j, kk[m]));
+            cgo_eos(o, TS(1, i, j, kk[m]), TS(2, i, j, kk[m]), o->zw[kk[m - 1]], &RHO(i, j, kk[m]));
             ni = m - 1;
             while (kk[ni + 1] > 0) {
               kk[ni] = kk[ni - m + n];
@@ -551,7 +568,7 @@ void cgo_co(cgo_t *o) {
         for (n = NK - 1; n >= K1(i, j); n--) {
           if (n > kk[m]) {
             for (l = 1; l <= L; l++) TS(l, i, j, n) = TS(l, i, j, kk[m + 1]);
-            cgo_eos(o, TS(1, i, j, n), TS(2, i, j, n), 0.0, &RHO(i, j, n));
+            cgo_eos(o, TS(1, i, j, n), TS(2, i, j, n), o->zw[kk[n - 1]], &RHO(i, j, n));
             A2(o->cost, i, j) = A2(o->cost, i, j) + 1.0;
           } else {
             m = m - 1;
@@ -567,6 +584,12 @@ void cgo_tstepo(cgo_t *o) {
   int i, j, k, l;
   cgo_tstepo_flux(o);
   cgo_co(o);
+  if (o->ieos != 0) {   /* if thermobaricity is on, make sure rho calculation is vertically local (:2396-2408) */
+    for (i = 1; i <= NI; i++)
+      for (j = 1; j <= NJ; j++)
+        if (K1(i, j) <= NK)
+          for (k = 1; k <= NK; k++) cgo_eos(o, TS(1, i, j, k), TS(2, i, j, k), o->zro[k], &RHO(i, j, k));
+  }
   for (j = 1; j <= NJ; j++) {
     for (k = K1(0, j); k <= NK; k++) {
       RHO(0, j, k) = RHO(NI, j, k);
@@ -799,7 +822,7 @@ void cgo_goldstein_init(cgo_t *o) {
   o->ec[2] = 0.7968 / CG_RHOSC;
   o->ec[3] = -0.0063 / CG_RHOSC;
   o->ec[4] = 3.7315e-5 / CG_RHOSC;
-  o->ec[5] = 0.0;
+  if (o->ieos == 1) o->ec[5] = 2.5e-5 * CG_DSC / CG_RHOSC; else o->ec[5] = 0.0;   /* :1066-1075 */
   o->hosing_trend = o->hosing_trend / (1.0e3 * syr);
   o->nsteps_hosing = o->nyears_hosing * o->nyear;
   /* k1 already loaded (periodic wrap applied) by cgo_create */
