@@ -581,7 +581,7 @@ static int build_device(cg_handle *h) {
   TRY(dparam(h, &p.ec3, col([](const MemberConsts &c) { return c.ec[3]; })));
   TRY(dparam(h, &p.ec4, col([](const MemberConsts &c) { return c.ec[4]; })));
   TRY(dparam(h, &p.ec5, col([](const MemberConsts &c) { return c.ec[5]; })));
-  v.ieos = h->base.ieos;
+  v.ieos = h->base.ieos; v.iconv = h->base.iconv;
   TRY(dparam(h, &p.rel, col([](const MemberConsts &c) { return c.p.rel; })));
   TRY(dparam(h, &p.scf, col([](const MemberConsts &c) { return c.p.scf; })));
   TRY(dparam(h, &p.saln0, col([](const MemberConsts &c) { return c.p.saln0; })));

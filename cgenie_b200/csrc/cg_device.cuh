@@ -106,6 +106,7 @@ struct Dev {
   int co_pairwise;           // k_co_col: average the passive tracers pair by pair (round-1 form, CG_CO_PAIR=1) instead of region by region
   int co_skip_stable;        // k_co_col: skip (member, column)s the flux kernel flagged stable in comask (CG_CO_SKIP=0: off)
   int col_deep_first;        // k_tstep_col: blocks in wetcols order (deepest columns first) instead of row-major (CG_COL_ORDER=1)
+  int iconv;                 // 1: Mueller convection scheme (coshuffle + depth diagnostic, goldstein.f90:2667-2672, 2781-2841), strict kernels only
   int ieos;                  // 1: thermobaricity term in the equation of state (goldstein.f90:3048-3082), strict kernels only
   int iediff, ediffpow2i;    // stratification-dependent vertical diffusivity (goldstein.f90:2501-2515); 0 = constant diff(2)
   double ediffpow2;

@@ -823,8 +823,8 @@ bool load_job(const std::string &jobdir, Params *p, Grid *g, Islands *isl, WindF
   p->diso = go.flag("diso", true);
   p->world = go.str("world", d.world);
   p->go_indir = go.str("indir_name", d.go_indir);
-  if (p->iconv != 0 || p->imld != 0 || p->ieos < 0 || p->ieos > 1) {
-    if (err) *err = "iconv/imld /= 0 and ieos outside 0..1 are outside the B200 hot path (SURVEY 8f.4)";
+  if (p->iconv < 0 || p->iconv > 1 || p->imld != 0 || p->ieos < 0 || p->ieos > 1) {
+    if (err) *err = "imld /= 0 (krausturner) and iconv / ieos outside 0..1 are outside the B200 hot path (SURVEY 8f.4)";
     return false;
   }
   if (p->iediff < 0 || p->iediff > 2 || (p->iediff != 0 && (p->ediffvar < -1.0e-7 || p->ediffvar > 1.0e-7))) {

@@ -256,8 +256,17 @@ __global__ void __launch_bounds__(128) k_surflux2(const Dev v) {
 // ---------------------------------------------------------------- EMBM: tstipa, nsteps fused
 // One block = one member; thread owns CPT cells; tq2 lives in shared memory (halo rows 0 and J+1
 // are zero, the i-halo is index arithmetic).  embm.f90:2039-2138 + step_embm :48-70.
+// EXACT: blockDim.x * CPT == I * J, every thread owns CPT cells: no guards in the iteration loops (36 x 36: 648 threads x 2)
+template <int CPT, bool EXACT>
+__device__ __forceinline__ void embm_body(const Dev &v, const int nsteps);
 template <int CPT>
-__global__ void __launch_bounds__(CPT == 3 ? 448 : 704) k_embm(const Dev v, const int nsteps) {
+__global__ void __launch_bounds__(CPT == 3 ? 448 : 704) k_embm(const Dev v, const int nsteps) { embm_body<CPT, false>(v, nsteps); }
+// exact forms for 36 x 36: 648 threads x 2 cells (21 warps: a sub-partition holds 6 of them, 16384 / (6 x 32) = 85 -> 80 registers,
+// which is why __launch_bounds__ stops there and a larger __maxnreg__ cannot launch) and 432 threads x 3 cells (14 warps, 128 registers)
+__global__ void __launch_bounds__(648) k_embm_x2(const Dev v, const int nsteps) { embm_body<2, true>(v, nsteps); }
+__global__ void __launch_bounds__(432) k_embm_x3(const Dev v, const int nsteps) { embm_body<3, true>(v, nsteps); }
+template <int CPT, bool EXACT>
+__device__ __forceinline__ void embm_body(const Dev &v, const int nsteps) {
   DIMS
   extern __shared__ double tq2[];  // (I, 0:J+1) x 2 fields
   const int m = blockIdx.x;
@@ -341,46 +350,60 @@ __global__ void __launch_bounds__(CPT == 3 ? 448 : 704) k_embm(const Dev v, cons
 #pragma unroll
   for (int n = 0; n < CPT; n++) {
     const int c2 = threadIdx.x + n * tc;
-    ok[n] = c2 < nc;
+    ok[n] = EXACT || c2 < nc;
     const int cc = ok[n] ? c2 : 0;
     const int i = cc % I + 1, j = cc / I + 1, ip = (i < I) ? i + 1 : 1, im = (i > 1) ? i - 1 : I;
     oc[n] = (i - 1) + I * j; oe[n] = (ip - 1) + I * j; ow[n] = (im - 1) + I * j; on[n] = (i - 1) + I * (j + 1); os[n] = (i - 1) + I * (j - 1);
     rdsj[n] = c_g.rds[j];
   }
   for (int step = 0; step < nsteps; step++) {
-    for (int iits = 0; iits < 5; iits++) {
+    // four implicit iterations ...
+    for (int iits = 0; iits < 4; iits++) {
       __syncthreads();
 #pragma unroll
       for (int l = 0; l < 2; l++) {
 #pragma unroll
-        for (int n = 0; n < CPT; n++) {
-          if (ok[n]) {
-            double *t2 = tq2 + l * plane + oc[n];
-            if (iits < 4)
-              *t2 = cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n];
-            else
-              *t2 = 0.5 * (*t2 + cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n]);
-          }
-        }
+        for (int n = 0; n < CPT; n++)
+          if (EXACT || ok[n]) tq2[l * plane + oc[n]] = cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n];
       }
       __syncthreads();
 #pragma unroll
       for (int l = 0; l < 2; l++) {
 #pragma unroll
         for (int n = 0; n < CPT; n++) {
-          if (ok[n]) {
+          if (EXACT || ok[n]) {
             const double *t2 = tq2 + l * plane;
             const double flx = -tqa[l][n] + cie[l][n] * t2[oe[n]] - ciwm[l][n] * t2[ow[n]] +
                                (cin[l][n] * t2[on[n]] - cism[l][n] * t2[os[n]]) * rdsj[n];
-            if (iits < 4) {
-              const double centre = dtloc * cdiv[l][n];
-              const double num = tq1[l][n] * (1.0 - (1.0 - cimp) * centre) - dtloc * flx, den = 1 + cimp * centre;
-              const double qq = num * rden[l][n];
-              tq[l][n] = fma(fma(-den, qq, num), rden[l][n], qq);
-            } else {
-              tq[l][n] = tq1[l][n] - dtloc * flx - dtloc * t2[oc[n]] * cdiv[l][n];
-            }
+            const double centre = dtloc * cdiv[l][n];
+            const double num = tq1[l][n] * (1.0 - (1.0 - cimp) * centre) - dtloc * flx, den = 1 + cimp * centre;
+            const double qq = num * rden[l][n];
+            tq[l][n] = fma(fma(-den, qq, num), rden[l][n], qq);
           }
+        }
+      }
+    }
+    // ... and the explicit corrector on the average of the last two iterates (iits = 5 of the reference's loop)
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+#pragma unroll
+      for (int n = 0; n < CPT; n++)
+        if (EXACT || ok[n]) {
+          double *t2 = tq2 + l * plane + oc[n];
+          *t2 = 0.5 * (*t2 + cimp * tq[l][n] + (1.0 - cimp) * tq1[l][n]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+#pragma unroll
+      for (int n = 0; n < CPT; n++) {
+        if (EXACT || ok[n]) {
+          const double *t2 = tq2 + l * plane;
+          const double flx = -tqa[l][n] + cie[l][n] * t2[oe[n]] - ciwm[l][n] * t2[ow[n]] +
+                             (cin[l][n] * t2[on[n]] - cism[l][n] * t2[os[n]]) * rdsj[n];
+          tq[l][n] = tq1[l][n] - dtloc * flx - dtloc * t2[oc[n]] * cdiv[l][n];
         }
       }
     }
@@ -913,6 +936,94 @@ __global__ void __launch_bounds__(32) k_baro_blk(const Dev v, const double *__re
   __syncwarp();
   for (int r = lane; r < nm; r += 32) v.gb[(size_t)r * MS + m] = x[r];
 }
+// k_baro_blk with FOUR warps per member.  The one-warp form issues ~280 dependent-ish instructions per block of 32 unknowns from
+// a single warp (ncu: IPC 0.43 per SM at 3.5 warps per SM, 144 us per launch at 512 members: pure issue latency).  Here warp w
+// owns accumulator w of both sums -- the terms d with (d & 3) == w of the substitution and the terms c with (c & 3) == w of
+// z = Tbb^-1 b -- so each warp issues a quarter of the instructions, and the four partial sums meet in the SAME order
+// ((a0 + a1) + (a2 + a3)) as in the one-warp form: bit-identical results.  The values the one-warp form passes by shuffle
+// (the two previous blocks' unknowns, the block's right-hand side) are read from the vector in shared memory (one broadcast
+// LDS instead of two SHFL).  Two block barriers per block of unknowns.
+template <int BW>
+__global__ void __launch_bounds__(128) k_baro_blk4(const Dev v, const double *__restrict__ bk_all, const int nb) {
+  extern __shared__ __align__(128) double bsm[];
+  constexpr int T = BW + 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, m = blockIdx.x;
+  const int nm = v.nm, MS = v.MS, npad = nb * 32, ntot = 2 * nb;
+  double *ring = bsm;                                   // kBlkRing slabs of T x 32
+  double *x = ring + (size_t)kBlkRing * T * 32;         // the vector, padded to npad
+  double *pa = x + npad;                                // [4][32] partial sums of the substitution
+  double *pz = pa + 128;                                // [4][32] partial sums of z of the next block
+  double *zs = pz + 128;                                // [32] z of the current block
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(zs + 32);
+  const double *__restrict__ bk = bk_all + (size_t)v.baro_group[m] * ntot * T * 32;
+  auto issue = [&](const int g) {
+    const unsigned b = baro_sa(bar + (g & (kBlkRing - 1)));
+    constexpr unsigned bytes = T * 32 * 8;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     baro_sa(ring + (size_t)(g & (kBlkRing - 1)) * T * 32)),
+                 "l"(bk + (size_t)g * T * 32), "r"(bytes), "r"(b)
+                 : "memory");
+  };
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < kBlkRing; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(baro_sa(bar + q)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int g = 0; g < kBlkRing && g < ntot; g++) issue(g);
+  }
+  for (int r = threadIdx.x; r < npad; r += 128) x[r] = (r < nm) ? v.gb[(size_t)r * MS + m] : 0.0;
+  __syncthreads();
+  // this warp's quarter of z = Tbb^-1 b_blk of block g (terms c = w, w + 4, ...: accumulator w of the one-warp form)
+  auto zpart = [&](const int g) -> double {
+    const int sw = (g >= nb) ? 1 : 0, B = g - sw * nb;
+    const double *cf = ring + (size_t)(g & (kBlkRing - 1)) * T * 32 + lane;
+    double b = 0.0;
+#pragma unroll
+    for (int c = w; c < 32; c += 4) {
+      const int ep = 32 * B + c;
+      const double rc = x[sw ? npad - 1 - ep : ep];
+      b = __fma_rn(cf[(BW + c) * 32], rc, b);
+    }
+    return b;
+  };
+  baro_wait(0, bar);
+  pz[w * 32 + lane] = zpart(0);
+  __syncthreads();
+  if (w == 0) zs[lane] = (pz[lane] + pz[32 + lane]) + (pz[64 + lane] + pz[96 + lane]);
+  __syncthreads();
+  for (int g = 0; g < ntot; g++) {
+    const int sw = (g >= nb) ? 1 : 0, B = g - sw * nb;
+    const double *cf = ring + (size_t)(g & (kBlkRing - 1)) * T * 32 + lane;
+    const int ep = 32 * B + lane, phys = sw ? npad - 1 - ep : ep;
+    const bool ahead = (g + 1 < ntot) && (g + 1 != nb);
+    if (g + 1 < ntot) baro_wait(g + 1, bar);
+    if (ahead) pz[w * 32 + lane] = zpart(g + 1);
+    // accumulator w: the terms d with (d & 3) == w, d ascending (d = 4, 8, ... for w = 0)
+    double a = 0.0;
+#pragma unroll
+    for (int d = (w == 0 ? 4 : w); d <= BW; d += 4) {
+      // the value d rows before this block's first row (zero ahead of the sweep's first block)
+      const int e = 32 * B - d;
+      const double val = (e >= 0) ? x[sw ? npad - 1 - e : e] : 0.0;
+      a = __fma_rn(cf[(d - 1) * 32], val, a);
+    }
+    pa[w * 32 + lane] = a;
+    __syncthreads();                                      // partial sums complete; every warp has read slab g and the vector
+    if (w == 0) {
+      const double a0 = pa[lane], a1 = pa[32 + lane], a2 = pa[64 + lane], a3 = pa[96 + lane];
+      x[phys] = zs[lane] - ((a0 + a1) + (a2 + a3));
+      if (ahead) zs[lane] = (pz[lane] + pz[32 + lane]) + (pz[64 + lane] + pz[96 + lane]);
+      if (lane == 0 && g + kBlkRing < ntot) issue(g + kBlkRing);
+    }
+    __syncthreads();                                      // x holds this block's unknowns
+    if (!ahead && g + 1 < ntot) {                         // the turn of the sweeps: z of the first backward block needs them
+      pz[w * 32 + lane] = zpart(g + 1);
+      __syncthreads();
+      if (w == 0) zs[lane] = (pz[lane] + pz[32 + lane]) + (pz[64 + lane] + pz[96 + lane]);
+      __syncthreads();
+    }
+  }
+  for (int r = threadIdx.x; r < nm; r += 128) v.gb[(size_t)r * MS + m] = x[r];
+}
 static_assert(kBlkRing == kBaroRing, "k_baro_blk reuses baro_wait");
 
 bool baro_reg_ok(const Dev &v) { return v.I + 1 > 32 && v.I + 1 <= 64 && (v.nm % 2) == 0 && v.nm >= 64; }
@@ -1208,6 +1319,11 @@ int launch_embm(const Dev &v, int nsteps, cudaStream_t s) {
   auto thr = [&](int cpt) { return (((nc + cpt - 1) / cpt + 31) / 32) * 32; };
   if (nc <= 704) k_embm<1><<<v.M, thr(1), sm, s>>>(v, nsteps);
   else if (nc <= 1344 && getenv("CG_EMBM_CPT3")) k_embm<3><<<v.M, thr(3), sm, s>>>(v, nsteps);   // 36 x 36: 448 threads x 3 cells, no spills (2 cells x 672 threads: 80 registers, spills)
+  else if (nc == 1296 && getenv("CG_EMBM_EXACT")) {   // 36 x 36, every thread owns its cells, no guards, corrector peeled: measured SLOWER
+    // (52.8 / 48.2 against 46.2 us per member-year: the peeled loop spills more), kept as a knob
+    if (getenv("CG_EMBM_X3")) k_embm_x3<<<v.M, 432, sm, s>>>(v, nsteps);
+    else k_embm_x2<<<v.M, 648, sm, s>>>(v, nsteps);
+  }
   else if (nc <= 1408) k_embm<2><<<v.M, thr(2), sm, s>>>(v, nsteps);
   else if (nc <= 2816) k_embm<4><<<v.M, thr(4), sm, s>>>(v, nsteps);
   else return -1;
@@ -1253,8 +1369,15 @@ int launch_momentum(const Dev &v, int fast, const double *bf, const double *bb, 
     const int nb = (v.nm + 31) / 32;
     const size_t smem = sizeof(double) * ((size_t)kBlkRing * (BW + 32) * 32 + (size_t)nb * 32) + 8 * kBlkRing;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_baro_blk<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-    k_baro_blk<BW><<<v.M, 32, smem, s>>>(v, bk, nb);
+    if (!attr) {
+      cudaFuncSetAttribute(k_baro_blk<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k_baro_blk4<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    const char *e4 = getenv("CG_BARO_W4");   // CG_BARO_W4=0: the one-warp form (read per launch: the captured graphs keep their choice)
+    const int w4 = e4 ? atoi(e4) : 1;
+    if (w4) k_baro_blk4<BW><<<v.M, 128, smem + (128 + 128 + 32) * sizeof(double), s>>>(v, bk, nb);
+    else k_baro_blk<BW><<<v.M, 32, smem, s>>>(v, bk, nb);
   } else if (fast == 2 && baro_reg_ok(v)) {
     const size_t smem = sizeof(double) * ((size_t)kBaroRing * 32 * (v.I + 1) + 2 * 32 * kBaroRow + 128 + ((v.nm + 1) & ~1)) + 8 * kBaroRing;
     static bool attr = false;

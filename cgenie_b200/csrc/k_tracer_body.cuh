@@ -546,6 +546,32 @@ __global__ void __launch_bounds__(128) CG_KNAME(k_co)(const Dev v) {
     const double t = TSK(0, lev), s_ = TSK(1, lev);
     return ec1 * t + ec2 * s_ + ec3 * (t * t) + ec4 * (t * t * t) + ec5 * t * z;
   };
+  // iconv = 1, Mueller convection scheme: coshuffle first (:2667-2672, SUBROUTINE coshuffle :2781-2841) -- the surface box sinks to
+  // the level of its own density, the boxes it passes move up by its thickness -- on this column, then the adjustment below
+  int icosd = 0, icond = 0;
+  if (v.iconv == 1) {
+    int k0 = 0, ipass = 0;
+    while (k0 < K && ipass < K) {
+      ipass = ipass + 1;
+      int k = K - 1;
+      if (v.ieos && k >= k1c) { rl[K] = eosz(K, c_g.zw[k]); rl[k] = eosz(k, c_g.zw[k]); }
+      while (k >= k1c && rl[K] > rl[k]) {
+        k = k - 1;
+        if (v.ieos && k >= k1c) { rl[K] = eosz(K, c_g.zw[k]); rl[k] = eosz(k, c_g.zw[k]); }
+      }
+      k0 = k + 1;
+      if (k0 < K) {
+        const double dzK = c_g.dz[K];
+        for (int l = 0; l < L; l++) {
+          const double tv_temp = TSK(l, K);
+          for (int q = K; q >= k0 + 1; q--) TSK(l, q) = ((c_g.dz[q] - dzK) * TSK(l, q) + dzK * TSK(l, q - 1)) * c_g.rdz[q];
+          TSK(l, k0) = ((c_g.dz[k0] - dzK) * TSK(l, k0) + dzK * tv_temp) * c_g.rdz[k0];
+        }
+        for (int q = k0; q <= K; q++) { rl[q] = eosz(q, c_g.zw[K - 1]); RHOK(q) = rl[q]; }
+        if (K - k0 > icosd) icosd = K - k0;
+      }
+    }
+  }
   while (kk[mm - 1] > 0 || (lastmix != 0 && kk[mm] != K)) {
     if (v.ieos && kk[mm - 1] > 0) {
       const double z = c_g.zw[kk[mm - 1]];
@@ -603,13 +629,17 @@ __global__ void __launch_bounds__(128) CG_KNAME(k_co)(const Dev v) {
           if (l == 1) smix = val;
         }
         RHOK(n) = ec1 * tmix + ec2 * smix + ec3 * (tmix * tmix) + ec4 * (tmix * tmix * tmix);
-        cnt = cnt + 1.0;
+        if (v.iconv == 1) icond = icond + 1; else cnt = cnt + 1.0;
       } else {
         mq = mq - 1;
       }
     }
     // cost(i,j) is incremented by 1.0 per filled level; a sum of small integers is exact
-    v.cost[cell2(I, i, j) * MS + m] += cnt;
+    if (v.iconv != 1) v.cost[cell2(I, i, j) * MS + m] += cnt;
+  }
+  if (v.iconv == 1) {   // the convection diagnostic BIOGEM reads (:2766-2770): depth of the deepest convection of this call
+    if (icond > icosd) icosd = icond;
+    v.cost[cell2(I, i, j) * MS + m] = 5.0e3 * c_g.zw[K - 1 - icosd];   // dsc * zw(maxk-1-icosd)
   }
   if (v.ieos) {   // "make sure rho calculation is vertically local", tstepo :2396-2408 (wet levels; the dry ones hold eos(0, 0) = 0)
     for (int k = k1c; k <= K; k++) RHOK(k) = eosz(k, c_g.zro[k]);

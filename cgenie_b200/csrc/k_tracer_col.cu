@@ -318,14 +318,24 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
   // One warp = 32 members of one column.  In a stratified ocean most warps find all their member-columns flagged stable and leave
   // at once; with several warps per block the few that work keep the registers of their idle neighbours allocated until the block
   // retires, so the default is one warp per block (CG_CO_WPB = 1 .. 4)
-  static int wpb = -1;
+  static int wpb = -1, cov = -1, copair = -1;
   if (wpb < 0) { const char *e = getenv("CG_CO_WPB"); wpb = e ? atoi(e) : 1; if (wpb < 1 || wpb > 4) wpb = 1; }
+  if (cov < 0) { const char *e = getenv("CG_CO_V"); cov = e ? atoi(e) : 1; }
+  if (copair < 0) { const char *e = getenv("CG_CO_PAIR"); copair = e ? atoi(e) : 1; }
+  v2.co_pairwise = copair;
+  if (cov == 3 && v2.co_skip_stable && v.comask && L > 2) {
+    // decisions (thread = member x column), then the passive tracers with one thread per (member, column, tracer)
+    v2.co_pairwise = 2;
+    k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + wpb - 1) / wpb), 32 * wpb, 0, s>>>(v2);
+    k_co_passive<I, J, K, L, MS><<<dim3(MS / 32, v.nwet), dim3(32, L - 2), 0, s>>>(v2);
+    return 3;
+  }
   k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + wpb - 1) / wpb), 32 * wpb, 0, s>>>(v2);
   return 2;
 }
 
 bool tstep_col_supported(const Dev &v) {
-  if (v.iediff || v.ieos) return false;   // the column kernel takes diff(2) as a per-member constant and has no thermobaric term
+  if (v.iediff || v.ieos || v.iconv) return false;   // the column kernel takes diff(2) as a per-member constant and has no thermobaric term
   return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && (v.MS == 32 || v.MS == 64 || v.MS == 128 || v.MS == 256 || v.MS == 512);
 }
 

@@ -48,7 +48,14 @@ enum {
  * name (<world>.k1/.psiles/.paths, wind stress *.interp, wind speed *.silo),
  * exactly as initialise_goldstein/initialise_embm/initialise_seaice do
  * (goldstein.f90:514-2084, embm.f90:198-2018, gold_seaice.f90:17-508).
- * Nothing is uploaded yet.                                                  */
+ * Nothing is uploaded yet.
+ * Physics options of data_GOLD: iediff = 0 | 1 | 2 with ediffvar = 0 (SUBROUTINE ediff, goldstein.f90:2936-3044),
+ * ieos = 0 | 1 (thermobaric equation of state, :3048-3082), iconv = 0 | 1 (Mueller convection scheme, coshuffle :2781-2841) are
+ * on the device path -- with one of them on, the tracer step runs the generic kernels (reference operation order), not the
+ * shape-specialised column kernels; imld = 1 (krausturner), ediffvar /= 0, fwanomin = 'y', topographies with more than one
+ * island, and BIOGEM selections other than the frozen 16-tracer one are refused with CG_ERR_CONFIG.
+ * n_members: up to 128 members share one 128-wide member stride; 129 .. 256 and 257 .. 512 run on strides 256 / 512 (128-member
+ * tiles of the same kernels, bit-identical per member); more than 512 fall back to the generic-shape kernels.          */
 int cg_create(const char *jobdir, int n_members, int device, cg_handle **out);
 
 /* Per-member override of a whitelisted scalar parameter BEFORE cg_initialise:

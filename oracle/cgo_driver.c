@@ -113,9 +113,9 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
   /* genie main */
   PD(solconst, 1368.0); PD(gn_daysperyear, 365.25);
   PI_(kocn_loop, 5); PI_(katm_loop, 1); PI_(ksic_loop, 5);
-  if (o->iconv != 0 || o->imld != 0 || o->iediff < 0 || o->iediff > 2 || o->ieos < 0 || o->ieos > 1 ||
+  if (o->iconv < 0 || o->iconv > 1 || o->imld != 0 || o->iediff < 0 || o->iediff > 2 || o->ieos < 0 || o->ieos > 1 ||
       (o->iediff != 0 && (o->ediffvar < -1.0e-7 || o->ediffvar > 1.0e-7))) {
-    fprintf(stderr, "cgo: iconv/imld != 0, ieos outside 0..1, iediff outside 0..2 and ediffvar != 0 are outside the restated path\n");
+    fprintf(stderr, "cgo: imld != 0, iconv / ieos outside 0..1, iediff outside 0..2 and ediffvar != 0 are outside the restated path\n");
     free(o);
     return NULL;
   }

@@ -508,14 +508,59 @@ void cgo_tstepo_flux(cgo_t *o) {
 }
 
 /* goldstein.f90:2657-2777, iconv==0, ieos==0 path */
-void cgo_co(cgo_t *o) {
+/* coshuffle (Mueller convection scheme, iconv = 1), goldstein.f90:2781-2841: the surface box is moved down to the level of its own
+ * density, the boxes in between move up by its thickness; icosd(i,j) = the deepest such displacement of this call (levels) */
+static void coshuffle(cgo_t *o, int *icosd) {
   const int L = NL;
-  int i, j, m, n, ni, lastmix, l;
-  int *kk = (int *)calloc(NK + 2, sizeof(int));
-  double *dzm = (double *)calloc(NK + 2, 8), *sum = (double *)calloc(L + 1, 8);
+  int i, j, k, k0, l, ipass, maxpass = NK;
+  double tv_temp;
   for (j = 1; j <= NJ; j++)
     for (i = 1; i <= NI; i++) {
       if (K1(i, j) <= NK) {
+        icosd[i + (NI + 1) * j] = 0;
+        k0 = 0;
+        ipass = 0;
+        while (k0 < NK && ipass < maxpass) {
+          ipass = ipass + 1;
+          k = NK - 1;
+          if (o->ieos != 0) {
+            cgo_eos(o, TS(1, i, j, NK), TS(2, i, j, NK), o->zw[k], &RHO(i, j, NK));
+            cgo_eos(o, TS(1, i, j, k), TS(2, i, j, k), o->zw[k], &RHO(i, j, k));
+          }
+          while (k >= K1(i, j) && (RHO(i, j, NK) > RHO(i, j, k))) {   /* (the reference tests rho first; with k < k1 it reads a dry level) */
+            k = k - 1;
+            if (o->ieos != 0) {
+              cgo_eos(o, TS(1, i, j, NK), TS(2, i, j, NK), o->zw[k], &RHO(i, j, NK));
+              cgo_eos(o, TS(1, i, j, k), TS(2, i, j, k), o->zw[k], &RHO(i, j, k));
+            }
+          }
+          k0 = k + 1;
+          if (k0 < NK) {
+            for (l = 1; l <= L; l++) {
+              tv_temp = TS(l, i, j, NK);
+              for (k = NK; k >= k0 + 1; k--)
+                TS(l, i, j, k) = ((o->dz[k] - o->dz[NK]) * TS(l, i, j, k) + o->dz[NK] * TS(l, i, j, k - 1)) * o->rdz[k];
+              TS(l, i, j, k0) = ((o->dz[k0] - o->dz[NK]) * TS(l, i, j, k0) + o->dz[NK] * tv_temp) * o->rdz[k0];
+            }
+            for (k = k0; k <= NK; k++) cgo_eos(o, TS(1, i, j, k), TS(2, i, j, k), o->zw[NK - 1], &RHO(i, j, k));
+            if (NK - k0 > icosd[i + (NI + 1) * j]) icosd[i + (NI + 1) * j] = NK - k0;
+          }
+        }
+      }
+    }
+}
+
+void cgo_co(cgo_t *o) {
+  const int L = NL;
+  int i, j, m, n, ni, lastmix, l, icond = 0;
+  int *kk = (int *)calloc(NK + 2, sizeof(int));
+  int *icosd = (int *)calloc((size_t)(NI + 1) * (NJ + 1), sizeof(int));
+  double *dzm = (double *)calloc(NK + 2, 8), *sum = (double *)calloc(L + 1, 8);
+  if (o->iconv == 1) coshuffle(o, icosd);   /* :2667-2672 */
+  for (j = 1; j <= NJ; j++)
+    for (i = 1; i <= NI; i++) {
+      if (K1(i, j) <= NK) {
+        if (o->iconv == 1) icond = 0;
         kk[K1(i, j) - 1] = 0;
         for (m = K1(i, j); m <= NK; m++) {
           kk[m] = m;
@@ -569,14 +614,19 @@ void cgo_co(cgo_t *o) {
           if (n > kk[m]) {
             for (l = 1; l <= L; l++) TS(l, i, j, n) = TS(l, i, j, kk[m + 1]);
             cgo_eos(o, TS(1, i, j, n), TS(2, i, j, n), o->zw[kk[n - 1]], &RHO(i, j, n));
-            A2(o->cost, i, j) = A2(o->cost, i, j) + 1.0;
+            if (o->iconv == 1) icond = icond + 1;
+            else A2(o->cost, i, j) = A2(o->cost, i, j) + 1.0;
           } else {
             m = m - 1;
           }
         }
+        if (o->iconv == 1) {   /* :2766-2770: convection diagnostic needed by biogem = depth of the deepest convection of this call */
+          if (icond > icosd[i + (NI + 1) * j]) icosd[i + (NI + 1) * j] = icond;
+          A2(o->cost, i, j) = CG_DSC * o->zw[NK - 1 - icosd[i + (NI + 1) * j]];
+        }
       }
     }
-  free(kk); free(dzm); free(sum);
+  free(kk); free(dzm); free(sum); free(icosd);
 }
 
 /* goldstein.f90:2280-2432 with imld==0, ieos==0 (dead copies :2311-2316 skipped) */

@@ -118,6 +118,29 @@ def test_baro_solves_agree(built, tmp_path):
     assert np.abs(out[("col", "1")]["psi"]).max() > 0.0
 
 
+def test_baro_four_warp_form_bit_identical(built, tmp_path):
+    """k_baro_blk4 (four warps per member, warp w = accumulator w of the one-warp form's two sums, partial sums combined in the
+    same order) against k_baro_blk: gb, psi, ub, u bit for bit after ocean steps of perturbed members."""
+    import os
+    materialise(str(tmp_path), CFG)
+    M = 40
+    pert = {"adrag": np.repeat(np.linspace(2.0, 3.0, 5), 8), "scf": np.linspace(1.5, 2.5, M), "diff1": np.linspace(1500.0, 2500.0, M)}
+    out = {}
+    for w4 in ("1", "0"):
+        os.environ["CG_BARO_W4"] = w4
+        try:
+            with Ensemble(str(tmp_path), n_members=M, perturb=pert) as e:
+                e.set_tracer_variant("col")
+                e.run(5 * 6)
+                out[w4] = {n: np.stack([e.get(n, m) for m in (0, 17, M - 1)]) for n in ("gb", "psi", "ub", "u", "ts")}
+                assert int(e.health().sum()) == 0
+        finally:
+            os.environ.pop("CG_BARO_W4", None)
+    for n in out["1"]:
+        assert np.array_equal(out["1"][n], out["0"][n]), n
+    assert np.abs(out["1"]["psi"]).max() > 0.0
+
+
 def test_biogem_fused_coupling_bit_identical(built, tmp_path):
     """cg_run applies biogem_tracercoupling's per-cell update inside the step_biogem kernel (the global sums are taken
     first: they do not depend on the step's anomaly).  Same expressions in the same order: every field is bit-identical

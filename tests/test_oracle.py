@@ -144,3 +144,49 @@ def test_ediff_option():
     assert 1e-7 < np.abs(t[2] - t[0]).max() < 1.0
     assert 0.0 < np.abs(t[4] - t[3]).max() < 1e-5
     assert np.isfinite(t[2]).all() and np.isfinite(t[3]).all()
+
+
+def test_thermobaric_eos_option():
+    """ieos = 1 (goldstein.f90:1066-1075, 3048-3082, 2692-2730, 2396-2408): rho carries ec(5) * T * z with ec(5) = 2.5e-5 dsc / rhosc,
+    evaluated at the level's own depth zro(k) after every tstepo; cold water is relatively denser at depth, so the convective
+    adjustment compares the two boxes at their interface and mixes a different set of columns than the depth-independent one."""
+    base = dict(world="worbe2", maxk=8, maxl=2, nyear=100)
+    o0, o1 = Oracle(**base), Oracle(ieos=1, **base)
+    for o in (o0, o1):
+        o.run(5 * 200)
+    K, J, I = 8, 36, 36
+    ts = o1.f("ts").reshape(K + 2, J + 2, I + 2, 2)[1:K + 1, 1:J + 1, 1:I + 1]
+    rho = o1.f("rho").reshape(K + 1, J + 2, I + 2)[1:, 1:J + 1, 1:I + 1]
+    k1 = o1.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    wet = np.arange(1, K + 1)[:, None, None] >= k1[None]
+    rhosc = 1.0e3 * (2 * 7.2921e-5) * 0.05 * 6.37e6 / 9.81 / 5.0e3
+    e1, e2, e3, e4, e5 = -0.0559 / rhosc, 0.7968 / rhosc, -0.0063 / rhosc, 3.7315e-5 / rhosc, 2.5e-5 * 5.0e3 / rhosc
+    zro = o1.f("zro")[1:K + 1]
+    t, s_ = ts[..., 0], ts[..., 1]
+    want = e1 * t + e2 * s_ + e3 * (t * t) + e4 * (t * t * t) + e5 * t * zro[:, None, None]
+    assert np.array_equal(rho[wet], want[wet])
+    assert np.abs(o1.f("ts") - o0.f("ts")).max() > 1e-3 and np.isfinite(o1.f("ts")).all()
+    assert o1.f("cost").sum() != o0.f("cost").sum()
+
+
+def test_mueller_convection_option():
+    """iconv = 1 (coshuffle + co, goldstein.f90:2667-2672, 2781-2841): moving the surface box down and the boxes it passes up by its
+    thickness conserves every tracer's column inventory; afterwards no level is denser than the one below it (co has removed what
+    the shuffle left); the convection diagnostic is a depth in metres (dsc * zw), 0 where nothing convected."""
+    K, J, I = 8, 36, 36
+    o = Oracle("worbe2", maxk=K, maxl=2, nyear=100, iconv=1)
+    o.run(5 * 150)
+    o.call("tstepo_flux")
+    dz = o.f("dz")[1:K + 1]
+    k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    wet = (np.arange(1, K + 1)[:, None, None] >= k1[None])[..., None]
+    inv = lambda: (np.where(wet, o.f("ts").reshape(K + 2, J + 2, I + 2, 2)[1:K + 1, 1:J + 1, 1:I + 1], 0.0) * dz[:, None, None, None]).sum(axis=0)
+    before = inv()
+    o.call("co")
+    after = inv()
+    assert np.abs(after - before).max() <= 1e-13 * np.abs(before).max()
+    rho = o.f("rho").reshape(K + 1, J + 2, I + 2)[1:, 1:J + 1, 1:I + 1]
+    both = wet[1:, ..., 0] & wet[:-1, ..., 0]
+    assert np.all((rho[1:] <= rho[:-1])[both])
+    cost = o.f("cost").reshape(J, I)
+    assert cost.min() < -100.0 and cost.max() <= 0.0 and np.all(cost[k1 > K] == 0.0)
