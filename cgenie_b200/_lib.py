@@ -54,6 +54,10 @@ SYMBOLS = {
     "cg_cpl_flux_ocnsed": (C.c_int, [P, C.c_double]),
     "cg_cpl_comp_ocnsed": (C.c_int, [P, C.c_int, C.c_int, C.c_int]),
     "cg_reinit_flux_rokocn": (C.c_int, [P]),
+    "cg_exchange_begin_upload": (C.c_int, [P, C.c_char_p, C.c_int, C.c_void_p, C.c_int64]),
+    "cg_exchange_commit_upload": (C.c_int, [P, C.c_char_p, C.c_char_p]),
+    "cg_exchange_begin_download": (C.c_int, [P, C.c_char_p, C.c_int, C.c_void_p, C.c_int64]),
+    "cg_exchange_wait": (C.c_int, [P]),
     "cg_biogem_sig_update": (C.c_int, [P, C.c_double, C.c_double]),
     "cg_biogem_slice_update": (C.c_int, [P, C.c_double]),
     "cg_biogem_slice_reset": (C.c_int, [P]),

@@ -165,6 +165,11 @@ struct cg_handle {
   int n_wet3 = 0;
   double *wet_stage = nullptr;
   size_t wet_stage_n = 0;
+  // double-buffered state exchange (cg_exchange_*): per field one device staging buffer per direction, a copy stream and the
+  // events that order it against the compute stream
+  struct Xchg { double *up = nullptr, *down = nullptr; size_t n = 0; bool wet = false; int inner = 1; cudaEvent_t up_done = nullptr, down_ready = nullptr; bool up_pending = false; };
+  std::map<std::string, Xchg> xchg;
+  cudaStream_t xstream = nullptr;
   double *d_meantemp = nullptr, *d_means = nullptr;
   double *d_bf = nullptr, *d_bb = nullptr, *d_rd = nullptr;  // pivot-major barotropic factors (fast solve)
   double *d_bk = nullptr;                                    // block slabs of the blocked solve (k_baro_blk)
@@ -210,6 +215,13 @@ struct cg_handle {
     for (auto &gv : graph2) for (auto &ge : gv) if (ge) cudaGraphExecDestroy(ge);
     for (void *p : allocs) cudaFree(p);
     if (wet_stage) cudaFree(wet_stage);
+    for (auto &kv : xchg) {
+      if (kv.second.up) cudaFree(kv.second.up);
+      if (kv.second.down) cudaFree(kv.second.down);
+      if (kv.second.up_done) cudaEventDestroy(kv.second.up_done);
+      if (kv.second.down_ready) cudaEventDestroy(kv.second.down_ready);
+    }
+    if (xstream) cudaStreamDestroy(xstream);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (evFork) cudaEventDestroy(evFork);
@@ -1347,6 +1359,109 @@ extern "C" int cg_sync_all_wet_from_host(cg_handle *h, const char *name, const d
   double *second = strcmp(name, "ts") == 0 ? h->dv.ts_new : nullptr;
   if (h->n_wet3 > 0) k_wet_pack<<<dim3(h->n_wet3, in), 128, 0, h->stream>>>(f->d, h->wet_stage, h->d_wet3, in, h->MS, 0, second);
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CG_OK;
+}
+
+// ---- double-buffered state exchange -------------------------------------------------------------------------------------
+// The coupling-interval exchange of a resident ensemble (all members of one field, device layout; 3-D ocean fields as wet cells)
+// without stalling the compute stream on PCIe: an upload crosses into a device staging buffer on a copy stream while the model
+// runs and is committed (unpacked into the field: a device-to-device pass) where the host program wants the new state; a
+// download is packed into a staging buffer on the compute stream and crosses to the host on the copy stream while the next
+// interval computes.  Host buffers must be page-locked for the copies to be asynchronous and must stay untouched until
+// cg_exchange_wait.  wet != 0: the cg_sync_all_wet_* layout (cg_wet_size doubles per member), else cg_field_size.
+static int check_async(cg_handle *h);
+static int xchg_setup(cg_handle *h, const char *name, int wet, int64_t n, cg_handle::Xchg **out) {
+  if (!h || !name || !h->initialised) return fail(CG_ERR_ARG, "cg_exchange: bad argument");
+  FieldDesc *f = nullptr; int in = 1;
+  if (wet) { IO0(wet_setup(h, name, &f, &in)); if (n != (int64_t)h->n_wet3 * in * h->MS) return fail(CG_ERR_ARG, "cg_exchange: size must be cg_wet_size * member_stride"); }
+  else { f = find_field(h, name); if (!f) return fail(CG_ERR_ARG, std::string("unknown field ") + name); if (n != f->count() * h->MS) return fail(CG_ERR_ARG, "cg_exchange: size must be field_size * member_stride"); }
+  cg_handle::Xchg &x = h->xchg[name];
+  if (!x.up) {
+    activate(h);
+    if (!h->xstream) CUDA_OK(cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking));
+    CUDA_OK(cudaMalloc(&x.up, (size_t)n * 8));
+    CUDA_OK(cudaMalloc(&x.down, (size_t)n * 8));
+    CUDA_OK(cudaEventCreateWithFlags(&x.up_done, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&x.down_ready, cudaEventDisableTiming));
+    x.n = (size_t)n; x.wet = wet != 0; x.inner = in;
+  }
+  if (x.n != (size_t)n || x.wet != (wet != 0)) return fail(CG_ERR_ARG, "cg_exchange: a field keeps the layout of its first exchange");
+  *out = &x;
+  return CG_OK;
+}
+extern "C" int cg_exchange_begin_upload(cg_handle *h, const char *name, int wet, const double *src, int64_t n) {
+  cg_handle::Xchg *x;
+  if (!src) return fail(CG_ERR_ARG, "cg_exchange_begin_upload: bad argument");
+  IO0(xchg_setup(h, name, wet, n, &x));
+  // the staging buffer may still feed the commit of the previous upload on the compute stream
+  if (x->up_pending) return fail(CG_ERR_STATE, "cg_exchange_begin_upload: the previous upload of this field was not committed");
+  CUDA_OK(cudaMemcpyAsync(x->up, src, (size_t)n * 8, cudaMemcpyHostToDevice, h->xstream));
+  CUDA_OK(cudaEventRecord(x->up_done, h->xstream));
+  x->up_pending = true;
+  return CG_OK;
+}
+// commit the staged upload of `name` into field `target` (NULL: `name` itself; e.g. the state staged as "tq" also into "tq1")
+static int xchg_commit(cg_handle *h, const char *name, const char *target, bool last) {
+  auto it = h->xchg.find(name);
+  if (it == h->xchg.end() || !it->second.up_pending) return fail(CG_ERR_STATE, "cg_exchange_commit_upload: nothing staged for this field");
+  cg_handle::Xchg &x = it->second;
+  const char *tn = target ? target : name;
+  IO0(join_side(h));
+  if (momentum_input(tn)) IO0(drop_momentum(h));
+  h->spec_valid = false;
+  h->tc_spec_valid = false;
+  activate(h);
+  CUDA_OK(cudaStreamWaitEvent(h->stream, x.up_done, 0));
+  if (x.wet) {
+    FieldDesc *f; int in;
+    IO0(wet_setup(h, tn, &f, &in));
+    if ((size_t)h->n_wet3 * in * h->MS != x.n) return fail(CG_ERR_ARG, "cg_exchange_commit_upload: target has another layout");
+    double *second = strcmp(tn, "ts") == 0 ? h->dv.ts_new : nullptr;
+    if (h->n_wet3 > 0) k_wet_pack<<<dim3(h->n_wet3, in), 128, 0, h->stream>>>(f->d, x.up, h->d_wet3, in, h->MS, 0, second);
+  } else {
+    FieldDesc *f = find_field(h, tn);
+    if (!f || (size_t)f->count() * h->MS != x.n) return fail(CG_ERR_ARG, "cg_exchange_commit_upload: target has another layout");
+    CUDA_OK(cudaMemcpyAsync(f->d, x.up, x.n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if (strcmp(tn, "ts") == 0) CUDA_OK(cudaMemcpyAsync(h->dv.ts_new, x.up, x.n * 8, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (last) {
+    // the next upload into this staging buffer must not start before the compute stream has read it
+    CUDA_OK(cudaEventRecord(x.down_ready, h->stream));
+    CUDA_OK(cudaStreamWaitEvent(h->xstream, x.down_ready, 0));
+    x.up_pending = false;
+  }
+  return check_async(h);
+}
+extern "C" int cg_exchange_commit_upload(cg_handle *h, const char *name, const char *also) {
+  if (!h || !name || !h->initialised) return fail(CG_ERR_ARG, "cg_exchange_commit_upload: bad argument");
+  if (also && *also) IO0(xchg_commit(h, name, also, false));
+  return xchg_commit(h, name, nullptr, true);
+}
+extern "C" int cg_exchange_begin_download(cg_handle *h, const char *name, int wet, double *dst, int64_t n) {
+  cg_handle::Xchg *x;
+  if (!dst) return fail(CG_ERR_ARG, "cg_exchange_begin_download: bad argument");
+  IO0(xchg_setup(h, name, wet, n, &x));
+  IO0(join_side(h));
+  activate(h);
+  // the previous download out of this staging buffer is on the copy stream: in order behind it
+  CUDA_OK(cudaEventRecord(x->down_ready, h->xstream));
+  CUDA_OK(cudaStreamWaitEvent(h->stream, x->down_ready, 0));
+  if (x->wet) {
+    FieldDesc *f; int in;
+    IO0(wet_setup(h, name, &f, &in));
+    if (h->n_wet3 > 0) k_wet_pack<<<dim3(h->n_wet3, in), 128, 0, h->stream>>>(f->d, x->down, h->d_wet3, in, h->MS, 1, nullptr);
+  } else {
+    FieldDesc *f = find_field(h, name);
+    CUDA_OK(cudaMemcpyAsync(x->down, f->d, x->n * 8, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  CUDA_OK(cudaEventRecord(x->down_ready, h->stream));
+  CUDA_OK(cudaStreamWaitEvent(h->xstream, x->down_ready, 0));
+  CUDA_OK(cudaMemcpyAsync(dst, x->down, (size_t)n * 8, cudaMemcpyDeviceToHost, h->xstream));
+  return check_async(h);
+}
+extern "C" int cg_exchange_wait(cg_handle *h) {   // every staged copy has crossed PCIe
+  if (!h || !h->initialised) return fail(CG_ERR_ARG, "cg_exchange_wait: bad argument");
+  if (h->xstream) CUDA_OK(cudaStreamSynchronize(h->xstream));
   return CG_OK;
 }
 

@@ -894,9 +894,12 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
     rem_zero(lrem);
 #pragma unroll
     for (int ls = 1; ls <= LS; ls++) pnew[ls] = 0.0;
-    const double Mk = (PK && kk != k1) ? 0.0 : M_(kk), rM = PK ? 0.0 : RM_(kk);   // PART 3 needs the bottom cell's mass only
+    // PART 3 does the per-cell half for the BOTTOM cell only (the bottom-water interface sfcocn1 is an output of step_biogem,
+    // biogem.f90:1736-1744: it must stand when the step returns, not when the coupling has run); elsewhere it reads O2 alone
+    const bool pk_skip = PK && kk != k1;
+    const double Mk = pk_skip ? 0.0 : M_(kk), rM = pk_skip ? 0.0 : RM_(kk);
     double x[L + 1];
-    if (PK) x[O2] = OCN_(O2, kk);
+    if (pk_skip) x[O2] = OCN_(O2, kk);
     else {
 #pragma unroll
       for (int l = 1; l <= L; l++) x[l] = OCN_(l, kk);
@@ -982,7 +985,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
       double *lo = b.lrem + (cell3(I, J, i, j, kk) * 7) * MS + m;
       lo[0] = lrem.dic; lo[MS] = lrem.d13; lo[2 * (size_t)MS] = lrem.d14; lo[3 * (size_t)MS] = lrem.po4; lo[4 * (size_t)MS] = lrem.o2;
       lo[5 * (size_t)MS] = lrem.alk; lo[6 * (size_t)MS] = lrem.ca;
-      continue;
+      if (pk_skip) continue;
     }
     // (4) sub_box_remin_DOM for this layer: DOM -> POM -> inorganic products
     const bool has_dom = x[DOMC] > kNS;
@@ -1036,7 +1039,9 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
       }
       const double dval = rem + dtyr * rM * focn;
       if (bot) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = x[l] + rem + dtyr * rM * focn;
-      if (!fuse) {
+      if (PK) {
+        // the anomaly itself is k_bg_cell's business
+      } else if (!fuse) {
         DOCN_(l, kk) = dval;
       } else {
         double *tsp = v.ts_cur + (o0 + (size_t)(kk - 1) * sK + (size_t)(l - 1) * MS);
@@ -1213,8 +1218,7 @@ __global__ void __launch_bounds__(32 * kApplyWarps, MINB) k_bg_cell(const Dev v,
         rem = rem - (slot ? up : 0.0);
       }
     }
-    const double dval = rem + dtyr * rM * focn;
-    if (bot) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = x[l] + rem + dtyr * rM * focn;
+    const double dval = rem + dtyr * rM * focn;   // (the bottom-water interface sfcocn1 = x + dval was written by PART 3)
     double *tsp = v.ts_cur + (o + (size_t)(l - 1) * MS);
     double *ocp = v.bg_ocn + (o + (size_t)(l - 1) * MS);
     if (l == 1) {

@@ -95,6 +95,24 @@ class _Base:
         a = np.ascontiguousarray(values, dtype=np.float64).ravel()
         self._ck(self.L.cg_sync_all_wet_from_host(self.h, name.encode(), _dp(a), a.size))
 
+    # ---- double-buffered exchange (cg_exchange_*): copies cross PCIe on a copy stream while the model computes
+    def exchange_begin_upload(self, name, values, wet=False):
+        """Start the asynchronous upload of all members of `name` (device layout; wet: wet cells only) from a page-locked array
+        that stays untouched until exchange_wait()."""
+        a = values if (isinstance(values, np.ndarray) and values.dtype == np.float64 and values.flags.c_contiguous) else np.ascontiguousarray(values, dtype=np.float64)
+        self._ck(self.L.cg_exchange_begin_upload(self.h, name.encode(), 1 if wet else 0, a.ctypes.data, a.size))
+
+    def exchange_commit_upload(self, name, also=None):
+        """The staged upload of `name` becomes the field (and, with also=, a second field that takes the same data)."""
+        self._ck(self.L.cg_exchange_commit_upload(self.h, name.encode(), also.encode() if also else None))
+
+    def exchange_begin_download(self, name, out, wet=False):
+        """Start the asynchronous download of all members of `name` into the page-locked array `out` (valid after exchange_wait())."""
+        self._ck(self.L.cg_exchange_begin_download(self.h, name.encode(), 1 if wet else 0, out.ctypes.data, out.size))
+
+    def exchange_wait(self):
+        self._ck(self.L.cg_exchange_wait(self.h))
+
     def const(self, name):
         n = self.L.cg_const_size(self.h, name.encode())
         if n < 0:

@@ -203,6 +203,22 @@ int cg_sync_all_from_host(cg_handle *, const char *name, const double *src, int6
 int64_t cg_wet_size(cg_handle *, const char *name);
 int cg_sync_all_wet_to_host(cg_handle *, const char *name, double *dst, int64_t n);
 int cg_sync_all_wet_from_host(cg_handle *, const char *name, const double *src, int64_t n);
+/* Double-buffered exchange of a resident ensemble's state at coupling / output intervals (genie.f90's model of "host copies only
+ * at coupling and output intervals", without stalling the device on PCIe).  All members of one field in the device layout
+ * (wet != 0: 3-D ocean fields as wet cells, cg_wet_size doubles per member; else cg_field_size).
+ *   cg_exchange_begin_upload   async copy of the host buffer into a device staging buffer on a copy stream; returns at once.
+ *   cg_exchange_commit_upload  the compute stream waits for that copy and unpacks it into the field (`also`: a second field that
+ *                              takes the same data, e.g. "tq1" next to "tq"; NULL / "": none).
+ *   cg_exchange_begin_download packs the field into a staging buffer behind the work issued so far, then the copy stream moves it
+ *                              to the host buffer while the compute stream goes on.
+ *   cg_exchange_wait           blocks until the copy stream is idle (host buffers of begun downloads are valid, those of begun
+ *                              uploads reusable).
+ * Host buffers must be page-locked (cudaHostAlloc / torch pin_memory) for the copies to overlap. */
+int cg_exchange_begin_upload(cg_handle *, const char *name, int wet, const double *src, int64_t n);
+int cg_exchange_commit_upload(cg_handle *, const char *name, const char *also);
+int cg_exchange_begin_download(cg_handle *, const char *name, int wet, double *dst, int64_t n);
+int cg_exchange_wait(cg_handle *);
+
 
 /* Host-side constants as built by cg_initialise (bit-exactness checks):
  * "dz","dza","s","c","sv","cv","ds","dsv","rc","rc2","cv2","rds","rdsv","zro","zw","ssmax",
