@@ -305,6 +305,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-groups", type=int, default=0, help="end-to-end leg: member groups per GPU (default 1)")
     ap.add_argument("--adrag-group", type=int, default=16, help="members per distinct adrag value (1: every member its own barotropic factors)")
+    ap.add_argument("--e2e-serial", action="store_true", help="end-to-end leg: only the serial exchange (upload, compute, download one after the other)")
     ap.add_argument("--e2e-dense", action="store_true", help="end-to-end leg: ship ts dense (all cells) instead of the wet cells only")
     ap.add_argument("--spinup-years", type=int, default=None,
                     help="untimed model years from the uniform initial state before the warm-up (config #2's 100-year spin-up: "
@@ -516,6 +517,72 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_val = world * M * nrep / (e2e_s / 3600.0)
+    e2e_serial = None
+    e2e_path_note = ""
+    if G == 1 and not args.e2e_serial:
+        # Double-buffered exchange (cg_exchange_*): every model year the GPU takes a NEW batch of members' state from pinned host
+        # memory and returns the finished batch's -- an ensemble larger than the GPU's shard, run batch after batch.  The inputs of
+        # batch n+1 cross PCIe into a device staging buffer on a copy stream while batch n computes, the results of batch n cross
+        # back while batch n+1 computes; committing / packing are device-to-device passes on the compute stream.  Same bytes per
+        # year in both directions as the serial form above (kept as e2e.serial_value), same 480 iterations of module calls.
+        e2e_serial = e2e_val
+        p_ = parts[0]
+        wetf = lambda n: (n == "ts" and not args.e2e_dense)
+        def pinned_like(a):
+            try:
+                return torch.empty(a.size, dtype=torch.float64).pin_memory().numpy()
+            except Exception:
+                return np.empty(a.size)
+        bufs_in = [{n: pinned_like(a) for n, a in pins[0].items()} for _ in range(2)]
+        bufs_out = [{n: pinned_like(a) for n, a in pins[0].items()} for _ in range(2)]
+        for b_ in bufs_in:
+            for n in b_:
+                b_[n][:] = pins[0][n]
+
+        def stage_in(year):
+            for n, a in bufs_in[year % 2].items():
+                p_.exchange_begin_upload(n, a, wet=wetf(n))
+
+        def e2e_year_db(year, last):
+            for n in bufs_in[0]:
+                p_.exchange_commit_upload(n, also={"varice": "varice1", "tq": "tq1"}.get(n))
+            if not last:
+                stage_in(year + 1)                 # the next batch starts crossing PCIe now
+            for k in range(1, kyear + 1):
+                if k % 5 == 1:
+                    p_.surflux()
+                p_.step_embm()
+                if k % 5 == 0:
+                    p_.step_seaice()
+                    p_.step_goldstein()
+                if biogem and k % 10 == 0:
+                    clock = (k0[0] + k) * clock_tick
+                    p_.biogem_forcing(clock)
+                    p_.biogem_step(dts_bg, clock)
+                    p_.biogem_tracercoupling()
+                    p_.biogem_climate()
+                    p_.atchem_step(dts_bg)
+            k0[0] += kyear
+            for n, a in bufs_out[year % 2].items():
+                p_.exchange_begin_download(n, a, wet=wetf(n))
+
+        stage_in(0)
+        e2e_year_db(0, False)                      # untimed: fills the pipeline
+        p_.exchange_wait()
+        p_.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for y in range(1, nrep + 1):
+            e2e_year_db(y, y == nrep)
+        p_.exchange_wait()                         # the last batch's results are on the host
+        p_.synchronize()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_val = world * M * nrep / (e2e_s / 3600.0)
+        assert all(np.isfinite(a).all() for a in bufs_out[nrep % 2].values())
+        e2e_path_note = ("; double buffered (cg_exchange_*): a new batch of members' state every model year, batch n+1 crosses PCIe on a "
+                         "copy stream while batch n computes, results of batch n while n+1 computes; serial_value = the same exchange "
+                         "without overlap")
     bad += sum(int(p_.health().sum()) for p_ in parts) if G > 1 else 0
 
     out = {
@@ -525,12 +592,12 @@ def main():
         "config": config_dict(workload, M, I, J, K, L, nyear_, variant_active, biogem, args.spinup_years, member_stride, args.adrag_group),
         "clocks": clocks, "gpu_launches": launches, "blown_up_members": bad, "roofline": roofline,
         "e2e": {"value": e2e_val, "unit": "model-years/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "groups": G, "years_timed": nrep,
+                "groups": G, "years_timed": nrep, "serial_value": e2e_serial,
                 "path": "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein/biogem_*/atchem), state in/out of pinned host "
                         "per year; the GPU's members run as %d group(s) of %d (one library handle + host thread each), so one group's copies "
                         "overlap the other's compute" % (G, M // G) if G > 1 else
                         "per-module C-ABI calls (surflux/step_embm/step_seaice/step_goldstein/biogem_*/atchem), state in/out of pinned host per "
-                        "year (ts: %s)" % ("all cells" if args.e2e_dense else "wet cells only, packed on the device")},
+                        "year (ts: %s)%s" % ("all cells" if args.e2e_dense else "wet cells only, packed on the device", e2e_path_note)},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 4:   # the CPU arm is timed next to the N=1 line only
         cores = os.cpu_count() or 1

@@ -40,3 +40,42 @@ def test_wet_exchange_round_trip(built, tmp_path):
             assert np.array_equal(e.get_all(name), f.get_all(name)), name
         with pytest.raises(Exception):
             e.get_all_wet("tq")                    # not a 3-D ocean field
+
+
+def test_double_buffered_exchange(built, tmp_path):
+    """cg_exchange_*: what the staged copies deliver is what the blocking calls deliver, a commit into two fields, uploads and
+    downloads in flight next to running work, and an ensemble whose state left and re-entered through the staging buffers every
+    block goes on bit for bit like one that stayed resident."""
+    import torch
+    materialise(str(tmp_path), "eb_go_gs_ac_bg_36x36x16")
+    M = 6
+    pert = {"diff1": np.linspace(1800.0, 2400.0, M)}
+    pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    with Ensemble(str(tmp_path), n_members=M, perturb=pert) as e, Ensemble(str(tmp_path), n_members=M, perturb=pert) as f:
+        for x in (e, f):
+            x.set_tracer_variant("col")
+            x.run(100)
+        MS = e.member_stride
+        names = (("ts", True), ("tq", False), ("varice", False))
+        out = {n: pin((e.wet_size(n) if w else e.field_size(n)) * MS) for n, w in names}
+        for n, w in names:
+            e.exchange_begin_download(n, out[n], wet=w)
+        e.run(10)                                   # the copies cross while this runs; they hold the state BEFORE it
+        e.exchange_wait()
+        ref = {n: (f.get_all_wet(n) if w else f.get_all(n)) for n, w in names}       # f stayed at iteration 100
+        for n, w in names:
+            assert np.array_equal(out[n], ref[n]), n
+        # staged uploads: e (now at 110) takes f's state through the staging buffers, tq also into tq1, varice into varice1
+        cur = {n: pin(out[n].size) for n, _ in names}
+        for n, w in names:
+            cur[n][:] = ref[n]
+            e.exchange_begin_upload(n, cur[n], wet=w)
+        for n, _ in names:
+            e.exchange_commit_upload(n, also={"tq": "tq1", "varice": "varice1"}.get(n))
+        e.exchange_wait()
+        for n, w in names:
+            assert np.array_equal(e.get_all_wet(n) if w else e.get_all(n), ref[n]), n
+        assert np.array_equal(e.get_all("tq1"), f.get_all("tq")) and np.array_equal(e.get_all("varice1"), f.get_all("varice"))
+        with pytest.raises(Exception):
+            e.exchange_commit_upload("ts")          # nothing staged
+        assert int(e.health().sum()) == 0

@@ -37,10 +37,21 @@ def test_create_fails_loudly_on_missing_job(built, tmp_path):
 
 def test_out_of_scope_option_rejected(built, tmp_path):
     lib = _lib.load()
-    materialise(str(tmp_path), "eb_go_gs_36x36x8", {"go_ieos": 1})
-    h = _lib.P()
-    rc = lib.cg_create(str(tmp_path).encode(), 1, 0, C.byref(h))
-    assert rc == 3 and b"outside the B200 hot path" in lib.cg_last_error()
+    # krausturner (imld = 1), a second equation-of-state option and a spatially varying ediff grid are not on the device path
+    for q, ov in enumerate(({"go_imld": 1}, {"go_ieos": 2}, {"go_iediff": 1, "go_ediffvar": 0.5}, {"go_iediff": 3})):
+        d = tmp_path / ("job%d" % q)
+        materialise(str(d), "eb_go_gs_36x36x8", ov)
+        h = _lib.P()
+        rc = lib.cg_create(str(d).encode(), 1, 0, C.byref(h))
+        assert rc == 3 and b"outside the B200 hot path" in lib.cg_last_error() or b"on the B200 hot path" in lib.cg_last_error(), ov
+        assert rc == 3, ov
+    # ... the ones that are: accepted
+    for q, ov in enumerate(({"go_ieos": 1}, {"go_iconv": 1}, {"go_iediff": 2, "go_ediff0": 0.275e-4})):
+        d = tmp_path / ("ok%d" % q)
+        materialise(str(d), "eb_go_gs_36x36x8", ov)
+        h = _lib.P()
+        assert lib.cg_create(str(d).encode(), 1, 0, C.byref(h)) == 0, (ov, lib.cg_last_error())
+        lib.cg_destroy(h)
 
 
 class HostOnly:
