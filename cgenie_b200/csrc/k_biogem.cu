@@ -1092,7 +1092,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
 // anomaly never goes to memory (no vdocn round trip), ocn and ts are read once and written once.  Same expressions in the same
 // order as k_bg_step (`fuse`) / k_tc_apply: bit-identical results.  bio_part is NOT rescaled here (a pass over 9 tracers for
 // one multiplication): the factor stays pending in b.pscale and the next reader applies it (k_bg_step PART 3, k_bg_part_scale).
-template <int FMS, int MINB>
+template <int FMS, int MINB, bool CS = false>
 __global__ void __launch_bounds__(32 * kApplyWarps, MINB) k_bg_cell(const Dev v, const BgDev b) {
   using namespace bgk;
   using namespace lay;
@@ -1128,13 +1128,21 @@ __global__ void __launch_bounds__(32 * kApplyWarps, MINB) k_bg_cell(const Dev v,
   const double dtyr = b.dtyr;
   double x[L + 1], tv[L + 1];
 #pragma unroll
-  for (int l = 1; l <= L; l++) { x[l] = v.bg_ocn[o + (size_t)(l - 1) * MS]; tv[l] = v.ts_cur[o + (size_t)(l - 1) * MS]; }
+  for (int l = 1; l <= L; l++) {   // read once, written once: streaming (evict-first) accesses keep the pass out of L2's way
+    x[l] = CS ? __ldcs(v.bg_ocn + o + (size_t)(l - 1) * MS) : v.bg_ocn[o + (size_t)(l - 1) * MS];
+    tv[l] = CS ? __ldcs(v.ts_cur + o + (size_t)(l - 1) * MS) : v.ts_cur[o + (size_t)(l - 1) * MS];
+  }
   const double Mk = v.bg_M[(size_t)c * MS + m], rM = v.bg_rM[(size_t)c * MS + m];
   Rem7 lrem, fsed, uptake;
   {
     const double *lo = b.lrem + ((size_t)c * 7) * MS + m;
-    lrem.dic = lo[0]; lrem.d13 = lo[MS]; lrem.d14 = lo[2 * (size_t)MS]; lrem.po4 = lo[3 * (size_t)MS]; lrem.o2 = lo[4 * (size_t)MS];
-    lrem.alk = lo[5 * (size_t)MS]; lrem.ca = lo[6 * (size_t)MS];
+    if (CS) {
+      lrem.dic = __ldcs(lo); lrem.d13 = __ldcs(lo + MS); lrem.d14 = __ldcs(lo + 2 * (size_t)MS); lrem.po4 = __ldcs(lo + 3 * (size_t)MS);
+      lrem.o2 = __ldcs(lo + 4 * (size_t)MS); lrem.alk = __ldcs(lo + 5 * (size_t)MS); lrem.ca = __ldcs(lo + 6 * (size_t)MS);
+    } else {
+      lrem.dic = lo[0]; lrem.d13 = lo[MS]; lrem.d14 = lo[2 * (size_t)MS]; lrem.po4 = lo[3 * (size_t)MS]; lrem.o2 = lo[4 * (size_t)MS];
+      lrem.alk = lo[5 * (size_t)MS]; lrem.ca = lo[6 * (size_t)MS];
+    }
   }
   rem_zero(fsed);
   rem_zero(uptake);
@@ -1223,19 +1231,16 @@ __global__ void __launch_bounds__(32 * kApplyWarps, MINB) k_bg_cell(const Dev v,
     double *ocp = v.bg_ocn + (o + (size_t)(l - 1) * MS);
     if (l == 1) {
       const double Tn = tv[l] + kBgZeroC + dval;
-      *ocp = Tn;
-      *tsp = Tn - kBgZeroC;
+      if (CS) { __stcs(ocp, Tn); __stcs(tsp, Tn - kBgZeroC); } else { *ocp = Tn; *tsp = Tn - kBgZeroC; }
     } else if (l == 2) {
       const double Sn = tv[l] + saln0 + dval;
       rn_cpl = s_mnew[lane] / Sn;
-      *ocp = Sn;
-      *tsp = Sn - saln0;
+      if (CS) { __stcs(ocp, Sn); __stcs(tsp, Sn - saln0); } else { *ocp = Sn; *tsp = Sn - saln0; }
     } else {
       const double lv = tv[l] * x[S] * s_rmean[lane];
       double xx = s_f[l - 1][lane] * lv + dval;
       xx = s_sr[lane] * xx;
-      *ocp = xx;
-      *tsp = rn_cpl * xx;
+      if (CS) { __stcs(ocp, xx); __stcs(tsp, rn_cpl * xx); } else { *ocp = xx; *tsp = rn_cpl * xx; }
     }
   }
   v.bg_M[(size_t)c * MS + m] = s_rsr[lane] * Mk;
@@ -1388,7 +1393,10 @@ int launch_bg_cell(const Dev &v, const BgDev &b, cudaStream_t s) {
   static int minb = -1;   // 4: 128 registers (200 bytes of spills), 3: 168 registers
   if (minb < 0) { const char *e = getenv("CG_BG_CELL_MINB"); minb = e ? atoi(e) : 4; }   // measured: 8.49 vs 8.36 M model-years/hour
   const dim3 g(v.MS / 32, (ncell + kApplyWarps - 1) / kApplyWarps), bl(32, kApplyWarps);
-  if (minb == 4) fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_cell<decltype(ms)::value, 4><<<g, bl, 0, s>>>(v, b); });
+  static int cs = -1;     // CG_BG_CELL_CS=1: streaming loads / stores (ld.global.cs / st.global.cs)
+  if (cs < 0) { const char *e = getenv("CG_BG_CELL_CS"); cs = e ? atoi(e) : 0; }
+  if (minb == 4 && cs) fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_cell<decltype(ms)::value, 4, true><<<g, bl, 0, s>>>(v, b); });
+  else if (minb == 4) fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_cell<decltype(ms)::value, 4><<<g, bl, 0, s>>>(v, b); });
   else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_cell<decltype(ms)::value, 3><<<g, bl, 0, s>>>(v, b); });
   return 1;
 }

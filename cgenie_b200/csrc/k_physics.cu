@@ -257,24 +257,30 @@ __global__ void __launch_bounds__(128) k_surflux2(const Dev v) {
 // One block = one member; thread owns CPT cells; tq2 lives in shared memory (halo rows 0 and J+1
 // are zero, the i-halo is index arithmetic).  embm.f90:2039-2138 + step_embm :48-70.
 // EXACT: blockDim.x * CPT == I * J, every thread owns CPT cells: no guards in the iteration loops (36 x 36: 648 threads x 2)
-template <int CPT, bool EXACT>
+template <int CPT, bool EXACT, bool SMC = false>
 __device__ __forceinline__ void embm_body(const Dev &v, const int nsteps);
 template <int CPT>
 __global__ void __launch_bounds__(CPT == 3 ? 448 : 704) k_embm(const Dev v, const int nsteps) { embm_body<CPT, false>(v, nsteps); }
+// SMC: the four face coefficients of a cell (constant over the launch) live in shared memory, [field][coefficient][cell], instead
+// of registers: at 672 threads a thread has 80 registers and the 36 doubles of per-cell state spilled to local memory (111 of the
+// loop's 371 instructions were LDL / STL)
+__global__ void __launch_bounds__(704) k_embm_s2(const Dev v, const int nsteps) { embm_body<2, false, true>(v, nsteps); }
 // exact forms for 36 x 36: 648 threads x 2 cells (21 warps: a sub-partition holds 6 of them, 16384 / (6 x 32) = 85 -> 80 registers,
 // which is why __launch_bounds__ stops there and a larger __maxnreg__ cannot launch) and 432 threads x 3 cells (14 warps, 128 registers)
 __global__ void __launch_bounds__(648) k_embm_x2(const Dev v, const int nsteps) { embm_body<2, true>(v, nsteps); }
 __global__ void __launch_bounds__(432) k_embm_x3(const Dev v, const int nsteps) { embm_body<3, true>(v, nsteps); }
-template <int CPT, bool EXACT>
+template <int CPT, bool EXACT, bool SMC>
 __device__ __forceinline__ void embm_body(const Dev &v, const int nsteps) {
   DIMS
-  extern __shared__ double tq2[];  // (I, 0:J+1) x 2 fields
+  extern __shared__ double tq2[];  // (I, 0:J+1) x 2 fields [+ SMC: 8 x I*J coefficients]
   const int m = blockIdx.x;
   const int nc = I * J, tc = blockDim.x;
   const double cimp = 0.5;
   const double dtloc = v.p.dtatm[m], rfluxsca = v.p.rfluxsca[m], rpmesca = v.p.rpmesca[m];
   double tq[2][CPT], tq1[2][CPT], tqa[2][CPT];
   double cie[2][CPT], ciwm[2][CPT], cin[2][CPT], cism[2][CPT], cdiv[2][CPT];
+  double *const cs = tq2 + 2 * (I * (J + 2));
+#define CSM(q, l, n) cs[((l) * 4 + (q)) * nc + threadIdx.x + (n) * tc]
 #define T2(l, i, j) tq2[(l) * (I * (J + 2)) + ((i)-1) + I * (j)]
   for (int q = threadIdx.x; q < I; q += tc) { T2(0, q + 1, 0) = 0.0; T2(0, q + 1, J + 1) = 0.0; T2(1, q + 1, 0) = 0.0; T2(1, q + 1, J + 1) = 0.0; }
 #pragma unroll
@@ -326,7 +332,8 @@ __device__ __forceinline__ void embm_body(const Dev &v, const int nsteps) {
           cis_s = nn * (1 + ups) + tv;
           cin_s = nn * (1 - ups) - tv;
         }
-        cie[l][n] = cie_c; ciwm[l][n] = ciw_w; cin[l][n] = cin_c; cism[l][n] = cis_s;
+        if (SMC) { CSM(0, l, n) = cie_c; CSM(1, l, n) = ciw_w; CSM(2, l, n) = cin_c; CSM(3, l, n) = cis_s; }
+        else { cie[l][n] = cie_c; ciwm[l][n] = ciw_w; cin[l][n] = cin_c; cism[l][n] = cis_s; }
         cdiv[l][n] = ciw_c - cie_w + (cis_c - cin_s) * c_g.rds[j];
       }
     }
@@ -373,8 +380,9 @@ __device__ __forceinline__ void embm_body(const Dev &v, const int nsteps) {
         for (int n = 0; n < CPT; n++) {
           if (EXACT || ok[n]) {
             const double *t2 = tq2 + l * plane;
-            const double flx = -tqa[l][n] + cie[l][n] * t2[oe[n]] - ciwm[l][n] * t2[ow[n]] +
-                               (cin[l][n] * t2[on[n]] - cism[l][n] * t2[os[n]]) * rdsj[n];
+            const double kE = SMC ? CSM(0, l, n) : cie[l][n], kW = SMC ? CSM(1, l, n) : ciwm[l][n], kN = SMC ? CSM(2, l, n) : cin[l][n],
+                         kS = SMC ? CSM(3, l, n) : cism[l][n];
+            const double flx = -tqa[l][n] + kE * t2[oe[n]] - kW * t2[ow[n]] + (kN * t2[on[n]] - kS * t2[os[n]]) * rdsj[n];
             const double centre = dtloc * cdiv[l][n];
             const double num = tq1[l][n] * (1.0 - (1.0 - cimp) * centre) - dtloc * flx, den = 1 + cimp * centre;
             const double qq = num * rden[l][n];
@@ -401,8 +409,9 @@ __device__ __forceinline__ void embm_body(const Dev &v, const int nsteps) {
       for (int n = 0; n < CPT; n++) {
         if (EXACT || ok[n]) {
           const double *t2 = tq2 + l * plane;
-          const double flx = -tqa[l][n] + cie[l][n] * t2[oe[n]] - ciwm[l][n] * t2[ow[n]] +
-                             (cin[l][n] * t2[on[n]] - cism[l][n] * t2[os[n]]) * rdsj[n];
+          const double kE = SMC ? CSM(0, l, n) : cie[l][n], kW = SMC ? CSM(1, l, n) : ciwm[l][n], kN = SMC ? CSM(2, l, n) : cin[l][n],
+                       kS = SMC ? CSM(3, l, n) : cism[l][n];
+          const double flx = -tqa[l][n] + kE * t2[oe[n]] - kW * t2[ow[n]] + (kN * t2[on[n]] - kS * t2[os[n]]) * rdsj[n];
           tq[l][n] = tq1[l][n] - dtloc * flx - dtloc * t2[oc[n]] * cdiv[l][n];
         }
       }
@@ -1323,6 +1332,12 @@ int launch_embm(const Dev &v, int nsteps, cudaStream_t s) {
     // (52.8 / 48.2 against 46.2 us per member-year: the peeled loop spills more), kept as a knob
     if (getenv("CG_EMBM_X3")) k_embm_x3<<<v.M, 432, sm, s>>>(v, nsteps);
     else k_embm_x2<<<v.M, 648, sm, s>>>(v, nsteps);
+  }
+  else if (nc <= 1408 && getenv("CG_EMBM_SMC")) {   // measured: 47.0 against 46.1 us per member-year -- the loop loses 40 % of its instructions and no time
+    const size_t sm2 = sm + sizeof(double) * 8 * nc;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_embm_s2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+    k_embm_s2<<<v.M, thr(2), sm2, s>>>(v, nsteps);
   }
   else if (nc <= 1408) k_embm<2><<<v.M, thr(2), sm, s>>>(v, nsteps);
   else if (nc <= 2816) k_embm<4><<<v.M, thr(4), sm, s>>>(v, nsteps);
