@@ -432,7 +432,7 @@ extern "C" int cg_create(const char *jobdir, int n_members, int device, cg_handl
     return fail(io ? CG_ERR_IO : CG_ERR_CONFIG, err);
   }
   if (h->g.J + 2 > kMaxJ || h->g.K + 2 > kMaxK) return fail(CG_ERR_CONFIG, "grid larger than the compiled metric tables");
-  if (h->isl.isles != 1) return fail(CG_ERR_CONFIG, "only single-island topographies (isles == 1) are on the B200 path");
+  if (h->isl.isles < 1 || h->isl.isles > kMaxIsles) return fail(CG_ERR_CONFIG, "topographies with 1 .. 8 islands are on the B200 path");
   if (!load_biogem(jobdir, h->base, h->g, &h->bg, &err)) {
     const bool io = err.find("could not open") != std::string::npos;
     return fail(io ? CG_ERR_IO : CG_ERR_CONFIG, err);
@@ -901,8 +901,8 @@ static int build_device(cg_handle *h) {
   TRY(dalloc(h, &v.gb, (size_t)v.nm * MS));
   TRY(dalloc(h, &v.ub, (size_t)2 * (I + 2) * (J + 1) * MS));
   TRY(dalloc(h, &v.psi, (size_t)(I + 1) * (J + 1) * MS));
-  TRY(dalloc(h, &v.erisl_rhs, MS));
-  TRY(dalloc(h, &v.psibc, MS));
+  TRY(dalloc(h, &v.erisl_rhs, (size_t)std::max(h->isl.isles, 1) * MS));   // [island][m]
+  TRY(dalloc(h, &v.psibc, (size_t)std::max(h->isl.isles, 1) * MS));
   { double *q; TRY(dupload(h, &q, g.rh)); v.rh = q; }
   auto members = [&](auto getter) {
     std::vector<const std::vector<double> *> s(M);
@@ -933,9 +933,11 @@ static int build_device(cg_handle *h) {
     const int nm = v.nm, bw = I + 1, gw = 2 * I + 3;
     std::vector<double> R((size_t)h->nbaro * nm * bw), G((size_t)h->nbaro * nm * gw), UBI, PSI, ER;
     std::vector<int> seen(h->nbaro, 0);
-    UBI.resize((size_t)h->nbaro * 2 * (I + 2) * (J + 1));
-    PSI.resize((size_t)h->nbaro * (I + 1) * (J + 1));
-    ER.resize((size_t)h->nbaro * 2);
+    const int nis = h->isl.isles;
+    const size_t nub = (size_t)2 * (I + 2) * (J + 1), nps = (size_t)(I + 1) * (J + 1), ner = (size_t)nis * (nis + 1);
+    UBI.resize((size_t)h->nbaro * nis * nub);      // [group][island][...]
+    PSI.resize((size_t)h->nbaro * nis * nps);
+    ER.resize((size_t)h->nbaro * ner);             // erisl(isl, 1:isles) after matinv_gold, Fortran order (isl fastest)
     for (int m = 0; m < M; m++) {
       const int grp = h->baro_group[m];
       if (seen[grp]) continue;
@@ -945,10 +947,9 @@ static int build_device(cg_handle *h) {
         for (int t = 0; t < bw; t++) R[((size_t)grp * nm + r) * bw + t] = c.ratm[(size_t)r + (size_t)nm * t];
         for (int q = 0; q < gw; q++) G[((size_t)grp * nm + r) * gw + q] = c.gap[(size_t)r + (size_t)nm * q];
       }
-      std::copy(c.ubisl.begin(), c.ubisl.begin() + (size_t)2 * (I + 2) * (J + 1), UBI.begin() + (size_t)grp * 2 * (I + 2) * (J + 1));
-      std::copy(c.psisl.begin(), c.psisl.begin() + (size_t)(I + 1) * (J + 1), PSI.begin() + (size_t)grp * (I + 1) * (J + 1));
-      ER[2 * grp] = c.erisl[0];
-      ER[2 * grp + 1] = c.erisl.size() > 1 ? c.erisl[1] : 0.0;
+      std::copy(c.ubisl.begin(), c.ubisl.begin() + nis * nub, UBI.begin() + (size_t)grp * nis * nub);
+      std::copy(c.psisl.begin(), c.psisl.begin() + nis * nps, PSI.begin() + (size_t)grp * nis * nps);
+      for (size_t q = 0; q < ner; q++) ER[(size_t)grp * ner + q] = q < c.erisl.size() ? c.erisl[q] : 0.0;
     }
     {
       // pivot-major copies for the warp-cooperative solve
@@ -1023,14 +1024,22 @@ static int build_device(cg_handle *h) {
   }
   { double *q; TRY(dupload(h, &q, h->mc[0].rhosing)); v.rhosing = q; }
   {
-    // island 1 path
-    const int n = h->isl.npi[1];
-    std::vector<int> a(n), b(n), c(n);
-    for (int q = 0; q < n; q++) { a[q] = h->isl.lpisl[q]; b[q] = h->isl.ipisl[q]; c[q] = h->isl.jpisl[q]; }
+    // island paths, [island][mpi] as the host holds them
+    const int nis = h->isl.isles, mpi = h->isl.mpi;
+    std::vector<int> a((size_t)nis * mpi, 0), b((size_t)nis * mpi, 1), c((size_t)nis * mpi, 1), np(nis, 0);
+    for (int is = 1; is <= nis; is++) {
+      np[is - 1] = h->isl.npi[is];
+      for (int q = 0; q < h->isl.npi[is]; q++) {
+        const size_t src = (size_t)q + (size_t)mpi * (is - 1);
+        a[src] = h->isl.lpisl[src]; b[src] = h->isl.ipisl[src]; c[src] = h->isl.jpisl[src];
+      }
+    }
     int *q;
     TRY(dupload(h, &q, a)); v.lpisl = q;
     TRY(dupload(h, &q, b)); v.ipisl = q;
     TRY(dupload(h, &q, c)); v.jpisl = q;
+    TRY(dupload(h, &q, np)); v.npi = q;
+    v.isles = nis; v.mpi = mpi;
   }
   reg_field(h, "ub", v.ub, {2, I + 2, J + 1}, {1, 2, 2LL * (I + 2)});
   reg_field(h, "psi", v.psi, {I + 1, J + 1}, {1, I + 1});

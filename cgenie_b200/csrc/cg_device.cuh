@@ -17,6 +17,7 @@ namespace cg {
 
 constexpr int kMaxJ = 132;  // metric arrays in constant memory (config #5: 128 x 128 x 32)
 constexpr int kMaxK = 36;
+constexpr int kMaxIsles = 8;  // islands of one topography (the reference's worlds have up to 5)
 
 // Member-independent grid metrics, uploaded to __constant__ memory of every kernel TU.
 struct GridC {
@@ -56,7 +57,9 @@ struct Dev {
   const unsigned char *getj; // (I, J)
   const int *iroff_src;      // runoff gather lists: CSR over wet cells, sources in reference order
   const int *iroff_ptr;
-  const int *lpisl, *ipisl, *jpisl;  // island 1 path (npi1 points)
+  const int *lpisl, *ipisl, *jpisl;  // island paths, [island][mpi]
+  const int *npi;                    // [island] points on each path
+  int isles, mpi;                    // islands (1 .. kMaxIsles), path stride
   const int *wetcols;        // 0-based (i-1)+I*(j-1) of the wet columns, deepest first
   const int *rowcols;        // the same columns in row-major (j, then i) order: neighbours in the list are neighbours in i
   int nwet;

@@ -1063,65 +1063,109 @@ __global__ void __launch_bounds__(128) k_psi2ub(const Dev v) {
 // reference's order (t1(1), t2(1), t1(2), ...), so the sum is the sequential one bit for bit.
 __global__ void __launch_bounds__(128) k_island(const Dev v) {
   DIMS
-  __shared__ double terms[4][2 * 160];
+  extern __shared__ double isl_terms[];            // [warps per block][2 * mpi]
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + wib;
   if (m >= v.M) return;
+  double *terms = isl_terms + (size_t)wib * 2 * v.mpi;
   const size_t nf = (size_t)I * J * MS;
-  const int np = c_g.npi1;
-  for (int p = lane; p < np; p += 32) {
-    const int lpi = v.lpisl[p], ipi = v.ipisl[p], jpi = v.jpisl[p];
-    const int al = abs(lpi), sg = (lpi >= 0) ? 1 : -1;
-    double cor;
-    if (al == 1)
-      cor = -c_g.s[jpi] * 0.25 * (UBX(2, ipi, jpi) + UBX(2, ipi + 1, jpi) + UBX(2, ipi, jpi - 1) + UBX(2, ipi + 1, jpi - 1));
-    else
-      cor = c_g.sv[jpi] * 0.25 * (UBX(1, ipi - 1, jpi) + UBX(1, ipi, jpi) + UBX(1, ipi - 1, jpi + 1) + UBX(1, ipi, jpi + 1));
-    const double tau = v.tau[A2I(ipi, jpi) + (al - 1) * nf];
-    const double t1 = sg * (DRAGX(al, ipi, jpi) * UBX(al, ipi, jpi) + cor - 1 * tau * RHX(al, ipi, jpi)) *
-                      (c_g.c[jpi] * c_g.dphi * (2.0 - al) + c_g.rcv[jpi] * c_g.dsv[jpi] * (al - 1.0));
-    double t2;
-    const int ipw = (ipi < I) ? ipi + 1 : 1;
-    if (al == 1) {
-      double tv1 = 0.0;
-      for (int k = KUX(1, ipi, jpi); k <= MKX(ipi + 1, jpi); k++) tv1 = tv1 + BPX(ipw, jpi, k) * c_g.dz[k];
-      for (int k = KUX(1, ipi, jpi); k <= MKX(ipi, jpi); k++) tv1 = tv1 - BPX(ipi, jpi, k) * c_g.dz[k];
-      t2 = (SBPX(ipw, jpi) - SBPX(ipi, jpi) + tv1) * sg * RHX(1, ipi, jpi);
-    } else {
-      double tv2 = 0.0;
-      for (int k = KUX(2, ipi, jpi); k <= MKX(ipi, jpi + 1); k++) tv2 = tv2 + BPX(ipi, jpi + 1, k) * c_g.dz[k];
-      for (int k = KUX(2, ipi, jpi); k <= MKX(ipi, jpi); k++) tv2 = tv2 - BPX(ipi, jpi, k) * c_g.dz[k];
-      t2 = (SBPX(ipi, jpi + 1) - SBPX(ipi, jpi) + tv2) * sg * RHX(2, ipi, jpi);
+  const int nis = v.isles;
+  double rhs[kMaxIsles];
+  for (int is = 0; is < nis; is++) {
+    const int np = v.npi[is];
+    const int *lp = v.lpisl + (size_t)is * v.mpi, *ip_ = v.ipisl + (size_t)is * v.mpi, *jp = v.jpisl + (size_t)is * v.mpi;
+    for (int p = lane; p < np; p += 32) {
+      const int lpi = lp[p], ipi = ip_[p], jpi = jp[p];
+      const int al = abs(lpi), sg = (lpi >= 0) ? 1 : -1;
+      double cor;
+      if (al == 1)
+        cor = -c_g.s[jpi] * 0.25 * (UBX(2, ipi, jpi) + UBX(2, ipi + 1, jpi) + UBX(2, ipi, jpi - 1) + UBX(2, ipi + 1, jpi - 1));
+      else
+        cor = c_g.sv[jpi] * 0.25 * (UBX(1, ipi - 1, jpi) + UBX(1, ipi, jpi) + UBX(1, ipi - 1, jpi + 1) + UBX(1, ipi, jpi + 1));
+      const double tau = v.tau[A2I(ipi, jpi) + (al - 1) * nf];
+      const double t1 = sg * (DRAGX(al, ipi, jpi) * UBX(al, ipi, jpi) + cor - 1 * tau * RHX(al, ipi, jpi)) *
+                        (c_g.c[jpi] * c_g.dphi * (2.0 - al) + c_g.rcv[jpi] * c_g.dsv[jpi] * (al - 1.0));
+      double t2;
+      const int ipw = (ipi < I) ? ipi + 1 : 1;
+      if (al == 1) {
+        double tv1 = 0.0;
+        for (int k = KUX(1, ipi, jpi); k <= MKX(ipi + 1, jpi); k++) tv1 = tv1 + BPX(ipw, jpi, k) * c_g.dz[k];
+        for (int k = KUX(1, ipi, jpi); k <= MKX(ipi, jpi); k++) tv1 = tv1 - BPX(ipi, jpi, k) * c_g.dz[k];
+        t2 = (SBPX(ipw, jpi) - SBPX(ipi, jpi) + tv1) * sg * RHX(1, ipi, jpi);
+      } else {
+        double tv2 = 0.0;
+        for (int k = KUX(2, ipi, jpi); k <= MKX(ipi, jpi + 1); k++) tv2 = tv2 + BPX(ipi, jpi + 1, k) * c_g.dz[k];
+        for (int k = KUX(2, ipi, jpi); k <= MKX(ipi, jpi); k++) tv2 = tv2 - BPX(ipi, jpi, k) * c_g.dz[k];
+        t2 = (SBPX(ipi, jpi + 1) - SBPX(ipi, jpi) + tv2) * sg * RHX(2, ipi, jpi);
+      }
+      terms[2 * p] = t1;
+      terms[2 * p + 1] = t2;
     }
-    terms[wib][2 * p] = t1;
-    terms[wib][2 * p + 1] = t2;
-  }
-  __syncwarp();
-  if (lane == 0) {
+    __syncwarp();
     double e = 0.0;
-    for (int p = 0; p < 2 * np; p++) e = e + terms[wib][p];
-    v.erisl_rhs[m] = e;
-    v.psibc[m] = -e / v.erisl[2 * v.baro_group[m]];  // isles == 1: psibc(1) = -erisl(1,2)/erisl(1,1)
+    for (int p = 0; p < 2 * np; p++) e = e + terms[p];   // every lane adds the same terms in the reference's order
+    rhs[is] = e;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    const double *A = v.erisl + (size_t)v.baro_group[m] * nis * (nis + 1);   // erisl(isl, col), isl fastest, after matinv_gold
+#define EA(r, c) A[((r)-1) + nis * ((c)-1)]
+    for (int is = 0; is < nis; is++) v.erisl_rhs[(size_t)is * MS + m] = rhs[is];
+    if (nis > 1) {
+      // matmult (goldstein.f90:3470-3492) on the right-hand side, then psibc(isl) = -erisl(isl, isles+1)
+      for (int i = 1; i <= nis - 1; i++)
+        for (int j = i + 1; j <= nis; j++) rhs[j - 1] = EA(i, i) * rhs[j - 1] - EA(j, i) * rhs[i - 1];
+      rhs[nis - 1] = rhs[nis - 1] / EA(nis, nis);
+      for (int i = nis - 1; i >= 1; i--) {
+        for (int j = i + 1; j <= nis; j++) rhs[i - 1] = rhs[i - 1] - EA(i, j) * rhs[j - 1];
+        rhs[i - 1] = rhs[i - 1] / EA(i, i);
+      }
+      for (int is = 0; is < nis; is++) v.psibc[(size_t)is * MS + m] = -rhs[is];
+    } else {
+      v.psibc[m] = -rhs[0] / EA(1, 1);  // isles == 1: psibc(1) = -erisl(1,2)/erisl(1,1)
+    }
+#undef EA
   }
 }
 
-// add the island contribution to ub and psi (goldstein.f90:218-230)
+// add the island contribution to ub and psi (goldstein.f90:218-230): ub + SUM(ubisl(:, 1:isles) * psibc(1:isles))
 __global__ void __launch_bounds__(128) k_ubadd(const Dev v) {
   DIMS
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int p = blockIdx.y * blockDim.y + threadIdx.y;
   if (m >= v.M || p >= (I + 2) * (J + 1)) return;
   const int i = p % (I + 2), j = p / (I + 2);
-  const double psibc = v.psibc[m];
+  const int nis = v.isles;
   const size_t g = v.baro_group[m];
+  const size_t nub = (size_t)2 * (I + 2) * (J + 1), nps = (size_t)(I + 1) * (J + 1);
+  if (nis == 1) {
+    const double psibc = v.psibc[m];
+    if (j >= 1) {
+      const double *ubisl = v.ubisl + g * nub;
+      UBX(1, i, j) = UBX(1, i, j) + ubisl[0 + 2 * (i + (I + 2) * j)] * psibc;
+      UBX(2, i, j) = UBX(2, i, j) + ubisl[1 + 2 * (i + (I + 2) * j)] * psibc;
+    }
+    if (i <= I) {
+      const double *psisl = v.psisl + g * nps;
+      PSIX(i, j) = PSIX(i, j) + psisl[i + (I + 1) * j] * psibc;
+    }
+    return;
+  }
   if (j >= 1) {
-    const double *ubisl = v.ubisl + g * 2 * (I + 2) * (J + 1);
-    UBX(1, i, j) = UBX(1, i, j) + ubisl[0 + 2 * (i + (I + 2) * j)] * psibc;
-    UBX(2, i, j) = UBX(2, i, j) + ubisl[1 + 2 * (i + (I + 2) * j)] * psibc;
+    double s1 = 0.0, s2 = 0.0;
+    for (int is = 0; is < nis; is++) {
+      const double *ubisl = v.ubisl + (g * nis + is) * nub;
+      const double pb = v.psibc[(size_t)is * MS + m];
+      s1 = s1 + ubisl[0 + 2 * (i + (I + 2) * j)] * pb;
+      s2 = s2 + ubisl[1 + 2 * (i + (I + 2) * j)] * pb;
+    }
+    UBX(1, i, j) = UBX(1, i, j) + s1;
+    UBX(2, i, j) = UBX(2, i, j) + s2;
   }
   if (i <= I) {
-    const double *psisl = v.psisl + g * (I + 1) * (J + 1);
-    PSIX(i, j) = PSIX(i, j) + psisl[i + (I + 1) * j] * psibc;
+    double s = 0.0;
+    for (int is = 0; is < nis; is++) s = s + v.psisl[(g * nis + is) * nps + i + (I + 1) * j] * v.psibc[(size_t)is * MS + m];
+    PSIX(i, j) = PSIX(i, j) + s;
   }
 }
 
@@ -1405,7 +1449,7 @@ int launch_momentum(const Dev &v, int fast, const double *bf, const double *bb, 
     k_baro_strict<<<(v.M + 31) / 32, 32, 0, s>>>(v);
   }
   k_psi2ub<<<grid2(v, (v.I + 2) * (v.J + 1), b), b, 0, s>>>(v);
-  k_island<<<(v.M + 3) / 4, 128, 0, s>>>(v);
+  k_island<<<(v.M + 3) / 4, 128, (size_t)4 * 2 * v.mpi * sizeof(double), s>>>(v);
   k_ubadd<<<grid2(v, (v.I + 2) * (v.J + 1), b), b, 0, s>>>(v);
   return 6;
 }

@@ -19,6 +19,9 @@ CONFIGS = {
     "eb_go_gs_36x36x8": dict(world="worbe2", maxk=8, maxl=2, nyear=100),     # config #1 (t100, the CPU test job)
     "eb_go_gs_36x36x16": dict(world="worjh2", maxk=16, maxl=2, nyear=96),     # physics of configs #2-4
     "eb_go_gs_36x36x16_L16": dict(world="worjh2", maxk=16, maxl=16, nyear=96),  # + 14 passive tracers on ts
+    # multi-island topographies of the reference's data/goldstein (2 and 3 islands): the barotropic closure with matmult
+    "eb_go_gs_p0055c_36x36x16": dict(world="p0055c", maxk=16, maxl=2, nyear=96),
+    "eb_go_gs_p0251a_36x36x16": dict(world="p0251a", maxk=16, maxl=2, nyear=96),
     # configs #2-4: BIOGEM + ATCHEM with the frozen 16-tracer selection (DESIGN.md "BIOGEM configuration")
     "eb_go_gs_ac_bg_36x36x16": dict(world="worjh2", maxk=16, maxl=16, nyear=96, biogem=True),
 }

@@ -15,7 +15,10 @@ from oracle_lib import Oracle
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CASES = [("eb_go_gs_36x36x8", dict(world="worbe2", maxk=8, maxl=2, nyear=100)),
-         ("eb_go_gs_36x36x16_L16", dict(world="worjh2", maxk=16, maxl=16, nyear=96))]
+         ("eb_go_gs_36x36x16_L16", dict(world="worjh2", maxk=16, maxl=16, nyear=96)),
+         # topographies with two and three islands (unit island solves, erisl after matinv_gold)
+         ("eb_go_gs_p0055c_36x36x16", dict(world="p0055c", maxk=16, maxl=2, nyear=96)),
+         ("eb_go_gs_p0251a_36x36x16", dict(world="p0251a", maxk=16, maxl=2, nyear=96))]
 
 
 def test_header_symbols_exported(built):

@@ -41,7 +41,9 @@ def read_paths(path):
 
 def main():
     out = {}
-    for world in ("worbe2", "worjh2"):
+    # worbe2 / worjh2: the target configurations (one island each); p0055c (2 islands), p0251a (3 islands): 36 x 36 x 16 worlds for
+    # the multi-island barotropic closure (matmult, goldstein.f90:203-216, 3470-3492)
+    for world in ("worbe2", "worjh2", "p0055c", "p0251a"):
         g = os.path.join(REF, "data", "goldstein", world)
         k1 = np.array([int(t) for t in open(g + ".k1").read().split()], dtype=np.int32)
         out[world + "/k1"] = k1.reshape(38, 38)          # file order: first row j=maxj+1
