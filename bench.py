@@ -533,11 +533,10 @@ def main():
                 return torch.empty(a.size, dtype=torch.float64).pin_memory().numpy()
             except Exception:
                 return np.empty(a.size)
-        bufs_in = [{n: pinned_like(a) for n, a in pins[0].items()} for _ in range(2)]
+        bufs_in = [pins[0], {n: pinned_like(a) for n, a in pins[0].items()}]       # two batches' inputs, two batches' results
         bufs_out = [{n: pinned_like(a) for n, a in pins[0].items()} for _ in range(2)]
-        for b_ in bufs_in:
-            for n in b_:
-                b_[n][:] = pins[0][n]
+        for n in bufs_in[1]:
+            bufs_in[1][n][:] = pins[0][n]
 
         def stage_in(year):
             for n, a in bufs_in[year % 2].items():
