@@ -223,12 +223,12 @@ def run_config5(args, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from cgenie_b200 import TracerStep
     I, J, K, L = 128, 128, 32, 40
-    M = args.members or 16
+    M = args.members or 64
     k1 = np.ones((J + 2, I + 2), dtype=np.int32)
     k1[0, :] = 94
     k1[J - 1:J + 2, :] = 92                                    # 2-cell polar land cap
     t = TracerStep(I, J, K, L, k1, n_members=M, device=local, diff1=2000.0, diff2=1e-5, nyear=96)
-    t.set_tracer_variant(args.variant if args.variant != "col" else "fast")
+    t.set_tracer_variant(args.variant)      # col: the tracer-window column kernels (member strides 32 / 64 / 128), else the generic kernels
     ts1, u1 = config5_fields(t, k1, I, J, K, L)
     fac = (1.0 + 0.01 * np.arange(M))[:, None, None, None, None]          # members differ by a scale of the passive tracers
     ts = np.repeat(ts1[None], M, axis=0)
@@ -274,7 +274,8 @@ def run_config5(args, rank, world, local):
                       "l2": "working set %.1f GB per GPU (two ts buffers + u + rho) exceeds the 126 MB L2" % ((2 * L + 6) * I * J * K * 8 * t.member_stride / 1e9),
                       "step": "one tstepo of every member"},
            "clocks": clocks, "gpu_launches": launches,
-           "roofline": {"bound": "hbm", "kernel": "tstepo = k_tstepo_flux_coop + k_co_fast2 (generic-shape kernels)", "achieved": achieved,
+           "roofline": {"bound": "hbm", "kernel": ("tstepo = 3 x k_tstep_colx (tracer windows 16 + 12 + 12) + k_co_col" if t.tracer_variant_active() == "col"
+                                                    else "tstepo = k_tstepo_flux_coop + k_co_fast2 (generic-shape kernels)"), "achieved": achieved,
                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms},
            "e2e": {"value": world * bytes_per_launch / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(ts.nbytes + u.nbytes + flux.nbytes),

@@ -290,6 +290,42 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   return 2;
 }
 
+// Tracer windows: one block = one wet column x MS members x a WINDOW of LW tracers starting at tracer L0 of a state that carries
+// LT tracers per cell (BASELINE config #5: 128 x 128 x 32 with 40 tracers = windows of 16 + 12 + 12; one thread cannot carry the P / Q
+// pairs of 40 tracers).  Every window computes the cell coefficients from T, S; the window with L0 = 0 advances T, S, rho and the
+// stability flag.
+template <int I, int J, int K, int LT, int MS, int LW, int L0, int MINB>
+__global__ void __launch_bounds__(MS, MINB) k_tstep_colx(const Dev v) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ColStage st;
+  st.sm = reinterpret_cast<double *>(smem_raw);
+  st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows<LW, L0 == 0>::rows * MS * 8);
+  st.tid = threadIdx.x;
+  const int c2 = v.rowcols[blockIdx.x];
+  tstep_column<I, J, K, LW, MS, MS, false, false, false, LT, L0>(v, c_g, c2, threadIdx.x, st);
+}
+template <int I, int J, int K, int LT, int MS, int LW, int L0>
+static void launch_window(const Dev &v, cudaStream_t s) {
+  constexpr size_t smem = (size_t)ColRows<LW, L0 == 0>::rows * MS * 8 + 64;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_tstep_colx<I, J, K, LT, MS, LW, L0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  k_tstep_colx<I, J, K, LT, MS, LW, L0, 2><<<v.nwet, MS, smem, s>>>(v);
+}
+// 128 x 128 x 32, 40 tracers: three windows + the convection kernel
+template <int MS>
+static int go_config5(const Dev &v, cudaStream_t s) {
+  constexpr int I = 128, J = 128, K = 32, LT = 40;
+  Dev v1 = v;
+  v1.col_deep_first = 0;
+  launch_window<I, J, K, LT, MS, 16, 0>(v1, s);
+  launch_window<I, J, K, LT, MS, 12, 16>(v1, s);
+  launch_window<I, J, K, LT, MS, 12, 28>(v1, s);
+  Dev v2 = v;
+  v2.co_prefetch = 0; v2.co_skip_stable = 1; v2.co_pairwise = 1; v2.co_local = 1;
+  k_co_col<I, J, K, LT, MS><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
+  return 4;
+}
+
 // member strides above 128: the flux kernel in its tile form (128-member tiles through tensor maps), the convection kernel as it is
 // (its grid already runs over 32-member tiles)
 template <int I, int J, int K, int L, int MS>
@@ -336,6 +372,7 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
 
 bool tstep_col_supported(const Dev &v) {
   if (v.iediff || v.ieos || v.iconv) return false;   // the column kernel takes diff(2) as a per-member constant and has no thermobaric term
+  if (v.I == 128 && v.J == 128 && v.K == 32 && v.L == 40 && (v.MS == 32 || v.MS == 64 || v.MS == 128)) return true;   // BASELINE config #5
   return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && (v.MS == 32 || v.MS == 64 || v.MS == 128 || v.MS == 256 || v.MS == 512);
 }
 
@@ -347,6 +384,7 @@ int launch_tstep_col(const Dev &v, cudaStream_t s) {
     cfg = e ? atoi(e) : 0;
   }
   if (!tstep_col_supported(v)) return 0;
+  if (v.I == 128) return v.MS == 32 ? go_config5<32>(v, s) : v.MS == 64 ? go_config5<64>(v, s) : go_config5<128>(v, s);
   if (v.MS == 256) return go_tiled<36, 36, 16, 16, 256>(v, s);
   if (v.MS == 512) return go_tiled<36, 36, 16, 16, 512>(v, s);
   if (v.MS == 32) return go<36, 36, 16, 16, 32>(v, s, cfg);

@@ -204,14 +204,15 @@ CG_HD void stage_box(const ColStage &s, const int which, const int dstrow, const
 
 // rows of the staging buffers.  Unit C (double buffered, issued 1.5 levels ahead): T,S of the five columns one level
 // up + the five velocities; unit A: tracers 2..LH-1 of the five columns; unit B: tracers LH..L-1.
-template <int L>
+template <int L, bool TSW = true>
 struct ColRows {
+  static constexpr int lA0 = TSW ? 2 : 0;          // first tracer (window-local) that comes through the staging units
   static constexpr int LH = L / 2;
-  static constexpr int lB0 = (LH > 2) ? LH : 2;
-  static constexpr int nA = lB0 - 2, nB = L - lB0;
+  static constexpr int lB0 = (LH > lA0) ? LH : lA0;
+  static constexpr int nA = lB0 - lA0, nB = L - lB0;
   static constexpr int rowsC = 15;                 // rTS: 5 cells x (T,S); rU: uE, vN, ww (centre), uW (west), vS (south)
   static constexpr int rTS = 0, rU = 10;
-  static constexpr int rA = 2 * rowsC;             // + cell * nA + (l - 2)
+  static constexpr int rA = 2 * rowsC;             // + cell * nA + (l - lA0)
   static constexpr int rowsA = 5 * nA;
   static constexpr int rB = rA + rowsA;            // + cell * nB + (l - lB0)
   static constexpr int rowsB = 5 * nB;
@@ -327,12 +328,18 @@ CG_HD void col_coefs(const ColK &q, const GridC &g, const int kk, const bool opE
 // TM = true: the block is an NT-member TILE of a member stride MS > NT (one handle holding more than 128 members): the rows of
 //   a staging unit are then NT * 8 bytes out of every MS * 8, fetched as 2-D tensor-map boxes (NT members x the unit's rows,
 //   cp.async.bulk.tensor.2d / UTMALDG) instead of contiguous bulk copies; m = tile * NT + thread.  Everything else is unchanged.
-template <int I, int J, int K, int L, int MS, int NT, bool PV, bool ASYNC_REL = false, bool TM = false>
+// LT, L0: the block advances the WINDOW of L tracers starting at tracer L0 of a state that carries LT tracers per cell (grids
+//   whose tracer count does not fit one thread's registers: 40 tracers = windows of 16 + 12 + 12).  Every window computes the
+//   cell coefficients from T, S (unit C); only the window with L0 = 0 advances T and S themselves, writes rho, the stability flag
+//   and SST.  LT = L, L0 = 0: the whole tracer set in one block, as for the 16-tracer BIOGEM configuration.
+template <int I, int J, int K, int L, int MS, int NT, bool PV, bool ASYNC_REL = false, bool TM = false, int LT = L, int L0 = 0>
 CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st, const ColMaps *tm = nullptr) {
   static_assert(TM || NT == MS, "a block covers all members of one column, or a tile of them through tensor maps");
+  static_assert(L0 == 0 || (!PV && !TM), "tracer windows: plain form only");
+  constexpr bool TSW = (L0 == 0);            // this window holds T and S
   static_assert(!PV || K <= 16, "region map is 16 + 16 bits");
-  using R = ColRows<L>;
-  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC;
+  using R = ColRows<L, TSW>;
+  constexpr long sL = MS, sC = (long)LT * MS, sK = (long)I * J * sC;
   constexpr long uC3 = 3L * MS, uK = (long)I * J * uC3, rK = (long)I * J * MS;
   const int i = c2 % I + 1, j = c2 / I + 1;
 #define CGC_K1(ii, jj) ((int)v.k1[(ii) + (I + 2) * (jj)])
@@ -375,7 +382,7 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
       const int cellu = (lu - 1) * IJ + c2, cellv = (lev - 1) * IJ + c2;
 #pragma unroll
       for (int cell = 0; cell < 5; cell++)
-        stage_box<MS, NT>(st, b, r0 + R::rTS + 2 * cell, mTS2, v.ts_cur, m0, (cellu + colcell(lu, cell)) * L, 2);
+        stage_box<MS, NT>(st, b, r0 + R::rTS + 2 * cell, mTS2, v.ts_cur, m0, (cellu + colcell(lu, cell)) * LT, 2);
       stage_box<MS, NT>(st, b, r0 + R::rU + 0, mU3, v.u, m0, cellv * 3, 3);
       stage_box<MS, NT>(st, b, r0 + R::rU + 3, mU1, v.u, m0, (cellv + cW) * 3, 1);
       stage_box<MS, NT>(st, b, r0 + R::rU + 4, mU1, v.u, m0, (cellv + cUS) * 3 + 1, 1);
@@ -399,10 +406,10 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
       const int cell0 = (lev - 1) * IJ + c2;
 #pragma unroll
       for (int cell = 0; cell < 5; cell++)
-        stage_box<MS, NT>(st, 2, R::rA + cell * R::nA, mTSA, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * L + 2, R::nA);
+        stage_box<MS, NT>(st, 2, R::rA + cell * R::nA, mTSA, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * LT + L0 + R::lA0, R::nA);
       return;
     }
-    const double *c0 = ts0 + (long)(lev - 1) * sK + 2 * sL;
+    const double *c0 = ts0 + (long)(lev - 1) * sK + (L0 + R::lA0) * sL;
     stage_copy<NT>(st, 2, R::rA + 0 * R::nA, c0, R::nA);
     stage_copy<NT>(st, 2, R::rA + 1 * R::nA, c0 + ((lev >= k1e) ? dE : 0), R::nA);
     stage_copy<NT>(st, 2, R::rA + 2 * R::nA, c0 + ((lev >= k1w) ? dW : 0), R::nA);
@@ -415,10 +422,10 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
       const int cell0 = (lev - 1) * IJ + c2;
 #pragma unroll
       for (int cell = 0; cell < 5; cell++)
-        stage_box<MS, NT>(st, 3, R::rB + cell * R::nB, mTSB, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * L + R::lB0, R::nB);
+        stage_box<MS, NT>(st, 3, R::rB + cell * R::nB, mTSB, v.ts_cur, m0, (cell0 + colcell(lev, cell)) * LT + L0 + R::lB0, R::nB);
       return;
     }
-    const double *c0 = ts0 + (long)(lev - 1) * sK + R::lB0 * sL;
+    const double *c0 = ts0 + (long)(lev - 1) * sK + (L0 + R::lB0) * sL;
     stage_copy<NT>(st, 3, R::rB + 0 * R::nB, c0, R::nB);
     stage_copy<NT>(st, 3, R::rB + 1 * R::nB, c0 + ((lev >= k1e) ? dE : 0), R::nB);
     stage_copy<NT>(st, 3, R::rB + 2 * R::nB, c0 + ((lev >= k1w) ? dW : 0), R::nB);
@@ -453,7 +460,7 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     a.tC = qC[0]; a.sC = qC[sL]; a.tE = qE[0]; a.sE = qE[sL]; a.tW = qW[0]; a.sW = qW[sL];
     a.tN = qN[0]; a.sN = qN[sL]; a.tS = qS[0]; a.sS = qS[sL];
   }
-  double *wP = v.ts_new + ((long)(k1c - 2) * (I * J) + c2) * sC + m;   // level kk-1 of the new array
+  double *wP = v.ts_new + ((long)(k1c - 2) * (I * J) + c2) * sC + L0 * sL + m;   // level kk-1 of the new array, first tracer of the window
   double *rP = v.rho + ((long)(k1c - 2) * (I * J) + c2) * MS + m;
   // upper-half coefficients of the face below the current level, cZ of the level below
   double uc = 0.0, uE = 0.0, uW = 0.0, uN = 0.0, uS = 0.0, cZp = 0.0;
@@ -531,14 +538,14 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
     else Q[l] = wcur * ((c - Hh) + fab * cZ) + cr;                                            \
     P[l] = lc * c + lE * E + lW * W + lN * N + lS * S;                                        \
   }
-    if (!PV) {
+    if (!PV && TSW) {
       CG_TRACER(0, a.tC, a.tE, a.tW, a.tN, a.tS)
       CG_TRACER(1, a.sC, a.sE, a.sW, a.sN, a.sS)
     }
     if (R::nA > 0) stage_wait(st, 2, par);
 #pragma unroll
-    for (int l = 2; l < R::lB0; l++) {
-      const int r = R::rA + (l - 2);
+    for (int l = R::lA0; l < R::lB0; l++) {
+      const int r = R::rA + (l - R::lA0);
       CG_TRACER(l, sm[(r + 0 * R::nA) * NT], sm[(r + 1 * R::nA) * NT], sm[(r + 2 * R::nA) * NT], sm[(r + 3 * R::nA) * NT],
                 sm[(r + 4 * R::nA) * NT])
     }
@@ -574,7 +581,7 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
       if (!top && stage_issuer<NT>(st, 2)) issueB(kk + 1);
     }
     par ^= 1u;
-    if (!PV && stv) {
+    if (!PV && TSW && stv) {
       const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);   // :2638
       rP[0] = r;
       if (kk - 1 > k1c) unstable = unstable || !(r < rbelow);
@@ -591,19 +598,21 @@ CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsign
 #pragma unroll
     for (int l = 0; l < L; l++) {
       double tn = Q[l];
-      if (l < 2) tn -= v.tsflux[((long)l * (I * J) + c2) * MS + m] * cZp;
+      if (TSW && l < 2) tn -= v.tsflux[((long)l * (I * J) + c2) * MS + m] * cZp;
       wP[l * sL] = tn;
       if (l == 0) tnew = tn;
       if (l == 1) snew = tn;
     }
-    const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
-    rP[0] = r;
-    if (K > k1c) unstable = unstable || !(r < rbelow);
-    if (v.comask) v.comask[(long)c2 * MS + m] = unstable ? 1u : 0u;
-    // SST / SSS as step_goldstein exports them (:428-431); k_co_col rewrites them where it mixes
-    if (v.sst) {
-      v.sst[(long)c2 * MS + m] = tnew;
-      v.sst[((long)(I * J) + c2) * MS + m] = snew;
+    if (TSW) {
+      const double r = ec1 * tnew + ec2 * snew + ec3 * (tnew * tnew) + ec4 * (tnew * tnew * tnew);
+      rP[0] = r;
+      if (K > k1c) unstable = unstable || !(r < rbelow);
+      if (v.comask) v.comask[(long)c2 * MS + m] = unstable ? 1u : 0u;
+      // SST / SSS as step_goldstein exports them (:428-431); k_co_col rewrites them where it mixes
+      if (v.sst) {
+        v.sst[(long)c2 * MS + m] = tnew;
+        v.sst[((long)(I * J) + c2) * MS + m] = snew;
+      }
     }
   } else {
     // passive tracers have no surface flux; level K is either outside any region or the top of one

@@ -134,3 +134,41 @@ def test_config5_full_size_properties(built):
     assert np.array_equal(got[0], got[1])
     assert np.isfinite(got).all()
     t.close()
+
+
+def test_config5_window_kernels_match_strict(built):
+    """128 x 128 x 32, 40 tracers through the shape-specialised column kernels (three tracer windows of 16 + 12 + 12, the
+    convection kernel) against the strict kernels (reference operation order) from one common state: per cell <= 1e-10 outside
+    columns whose convection decisions differ, the counter cost equal elsewhere, inventories conserved."""
+    I, J, K, L, M = 128, 128, 32, 40, 2
+    k1 = make_k1(I, J, K, rough=False)
+    k1[40:44, 30:36] = 20                      # a ridge: columns of different depth, closed faces inside the stencil
+    k1[:, 0] = k1[:, I]
+    k1[:, I + 1] = k1[:, 1]
+    t = TracerStep(I, J, K, L, k1, n_members=M, diff1=2000.0, diff2=1e-5, nyear=96)
+    ts, u = make_fields(t, k1, I, J, K, L, 1)
+    ts = np.repeat(ts, M, axis=0)
+    u = np.repeat(u, M, axis=0)
+    ts[1, ..., 2:] *= 1.01                     # the members differ in their passive tracers
+    flux = ts[:, K + 1, 1:J + 1, 1:I + 1, :2].copy()
+    out = {}
+    for variant in ("strict", "col"):
+        t.set(ts=ts, u=u, tsflux=flux)
+        t.set_tracer_variant(variant)
+        assert t.tracer_variant_active() == variant
+        t.step(2)
+        out[variant] = t.fetch()
+    wet = (k1[None, 1:J + 1, 1:I + 1] <= np.arange(1, K + 1)[:, None, None])
+    for m in range(M):
+        a, b = out["strict"][0][m], out["col"][0][m]
+        same_cols = (out["strict"][2][m] == out["col"][2][m])                       # cost equal: same number of mixed levels
+        ok = wet & same_cols[None]
+        scale = np.abs(a[wet]).reshape(-1, L).max(axis=0)
+        err = np.abs(b - a) / np.maximum(np.abs(a), 1e-3 * scale)
+        worst = float(err[ok].max())
+        flipped = int((~same_cols & (k1[1:J + 1, 1:I + 1] <= K)).sum())
+        print("config #5 windows vs strict, member %d: worst per-cell error %.2e, %d of %d columns with other decisions"
+              % (m, worst, flipped, int((k1[1:J + 1, 1:I + 1] <= K).sum())))
+        assert worst <= 1e-10 and flipped <= 0.01 * I * J
+    assert out["col"][2].sum() > 0             # convection ran
+    t.close()
