@@ -104,6 +104,8 @@ SYMBOLS = {
     "cg_restart_embm_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, D, I32]),
     "cg_restart_seaice_write": (C.c_int, [C.c_char_p, C.c_int, C.c_int, I32, D, D, D, D, D, I32]),
     "cg_restart_seaice_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, D, D, D, I32]),
+    "cg_restart_date_write": (C.c_int, [C.c_char_p, I32]),
+    "cg_restart_date_read": (C.c_int, [C.c_char_p, I32]),
     "cg_restart_biogem_write": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [I32] + [D] * 6 + [C.c_int, STRS, STRS, D] * 2 +
                                 [C.c_double, C.c_char_p]),
     "cg_restart_biogem_read": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [I32] + [C.c_int, STRS, D, I32] * 2),

@@ -426,6 +426,25 @@ extern "C" int cg_restart_seaice_read(const char *path, int maxi, int maxj, doub
   for (long long c = 0; c < n2; c++) { varice[2 * c] = v[0]->data[c]; varice[2 * c + 1] = v[1]->data[c]; tice[c] = v[2]->data[c]; albice[c] = v[3]->data[c]; }
   return CG_OK;
 }
+// the date block alone (genie-main's main_restart_N.nc: data/main/main_restart_0.nc is one, written by the netCDF library)
+extern "C" int cg_restart_date_write(const char *path, const int32_t date[4]) {
+  if (!path || !date) return rfail("cg_restart_date_write: bad argument");
+  cg::Nc3File f;
+  Common c;
+  c.nrecs = f.add_dim("nrecs", 1);
+  define_date(f, c, date);
+  std::string err;
+  if (!f.write(path, &err)) return rfail(err);
+  return CG_OK;
+}
+extern "C" int cg_restart_date_read(const char *path, int32_t date[4]) {
+  if (!path || !date) return rfail("cg_restart_date_read: bad argument");
+  cg::Nc3File f;
+  std::string err;
+  if (!f.read(path, &err)) return rfail(err);
+  if (f.dim_len("nrecs") != 1 || !get_date(f, date)) return rfail(std::string(path) + ": date variables missing");
+  return CG_OK;
+}
 
 // ------------------------------------------------------------------ BIOGEM restart (ctrl_ncrst = .TRUE., the default)
 // sub_data_netCDF_ncrstsave, src/biogem/biogem_data_netCDF.f90:24-142, through the helpers of src/common/gem_netcdf.f90

@@ -96,7 +96,7 @@ static bool make_map(void *out128, const void *base, unsigned long long nrows, i
   memcpy(out128, &tmap, 128);
   return true;
 }
-template <int I, int J, int K, int L, int MS, unsigned BOXW = 32u>
+template <int I, int J, int K, int L, int MS, unsigned BOXW = 32u, int LW = L, int L0 = 0>
 static const ColMaps *col_maps(const Dev &v) {
   static std::mutex mu;
   static std::map<std::pair<const void *, const void *>, ColMaps> cache;   // (ts buffer read this step, u) -> maps
@@ -105,7 +105,7 @@ static const ColMaps *col_maps(const Dev &v) {
   auto it = cache.find(key);
   if (it != cache.end()) return &it->second;
   ColMaps mp;
-  using R = ColRows<L>;
+  using R = ColRows<LW, L0 == 0>;
   const unsigned long long nts = (unsigned long long)I * J * K * L, nu = (unsigned long long)I * J * K * 3;
   if (!make_map(mp.ts2, v.ts_cur, nts, MS, 2, BOXW) || !make_map(mp.tsA, v.ts_cur, nts, MS, R::nA > 0 ? R::nA : 1, BOXW) ||
       !make_map(mp.tsB, v.ts_cur, nts, MS, R::nB, BOXW) || !make_map(mp.u3, v.u, nu, MS, 3, BOXW) || !make_map(mp.u1, v.u, nu, MS, 1, BOXW))
@@ -326,6 +326,31 @@ static int go_config5(const Dev &v, cudaStream_t s) {
   return 4;
 }
 
+// ... and the tile form advancing a window of LW tracers starting at L0 (see k_tstep_colx): two windows of 8 tracers need 60 KB of
+// staging and ~170 registers per block instead of 100 KB and 238, at the price of computing the cell coefficients twice
+template <int I, int J, int K, int LT, int MS, int NT, int LW, int L0, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_tstep_coltw(const Dev v, const __grid_constant__ ColMaps maps) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ColStage st;
+  st.sm = reinterpret_cast<double *>(smem_raw);
+  st.bar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)ColRows<LW, L0 == 0>::rows * NT * 8);
+  st.tid = threadIdx.x;
+  const int tile = blockIdx.x / v.nwet, ci = blockIdx.x - tile * v.nwet;
+  const int c2 = v.rowcols[ci];
+  tstep_column<I, J, K, LW, MS, NT, false, false, true, LT, L0>(v, c_g, c2, (unsigned)(tile * NT) + threadIdx.x, st, &maps);
+}
+template <int I, int J, int K, int LT, int MS, int LW, int L0, int MINB>
+static bool launch_window_tiled(const Dev &v, cudaStream_t s) {
+  constexpr int NT = 128;
+  constexpr size_t smem = (size_t)ColRows<LW, L0 == 0>::rows * NT * 8 + 64;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_tstep_coltw<I, J, K, LT, MS, NT, LW, L0, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  const ColMaps *maps = col_maps<I, J, K, LT, MS, 128u, LW, L0>(v);
+  if (!maps) return false;
+  k_tstep_coltw<I, J, K, LT, MS, NT, LW, L0, MINB><<<v.nwet * (MS / NT), NT, smem, s>>>(v, *maps);
+  return true;
+}
+
 // member strides above 128: the flux kernel in its tile form (128-member tiles through tensor maps), the convection kernel as it is
 // (its grid already runs over 32-member tiles)
 template <int I, int J, int K, int L, int MS>
@@ -345,6 +370,13 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
   if (coskip < 0) { const char *e = getenv("CG_CO_SKIP"); coskip = e ? atoi(e) : 1; }
   Dev v1 = v;
   v1.col_deep_first = order;
+  static int win = -1;   // CG_COL_WIN=1: two tracer windows of 8 (3 blocks per SM), 2: the same at 2 blocks per SM
+  if (win < 0) { const char *e = getenv("CG_COL_WIN"); win = e ? atoi(e) : 0; }
+  if (win == 1 && L == 16) {
+    if (!launch_window_tiled<I, J, K, L, MS, 8, 0, 3>(v1, s) || !launch_window_tiled<I, J, K, L, MS, 8, 8, 3>(v1, s)) return 0;
+  } else if (win == 2 && L == 16) {
+    if (!launch_window_tiled<I, J, K, L, MS, 8, 0, 2>(v1, s) || !launch_window_tiled<I, J, K, L, MS, 8, 8, 2>(v1, s)) return 0;
+  } else
   k_tstep_colt<I, J, K, L, MS, NT, 2><<<v.nwet * (MS / NT), NT, smem, s>>>(v1, *maps);
   Dev v2 = v;
   v2.co_prefetch = 0;

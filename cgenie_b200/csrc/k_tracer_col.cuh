@@ -335,7 +335,7 @@ CG_HD void col_coefs(const ColK &q, const GridC &g, const int kk, const bool opE
 template <int I, int J, int K, int L, int MS, int NT, bool PV, bool ASYNC_REL = false, bool TM = false, int LT = L, int L0 = 0>
 CG_HD void tstep_column(const Dev &v, const GridC &g, const int c2, const unsigned m, const ColStage &st, const ColMaps *tm = nullptr) {
   static_assert(TM || NT == MS, "a block covers all members of one column, or a tile of them through tensor maps");
-  static_assert(L0 == 0 || (!PV && !TM), "tracer windows: plain form only");
+  static_assert(L0 == 0 || !PV, "tracer windows: not with mix-on-write");
   constexpr bool TSW = (L0 == 0);            // this window holds T and S
   static_assert(!PV || K <= 16, "region map is 16 + 16 bits");
   using R = ColRows<L, TSW>;

@@ -291,6 +291,12 @@ int cg_restart_embm_read(const char *path, int maxi, int maxj, double *tq, int32
 int cg_restart_seaice_write(const char *path, int maxi, int maxj, const int32_t *k1, const double *lon, const double *lat,
                             const double *varice, const double *tice, const double *albice, const int32_t date[4]);
 int cg_restart_seaice_read(const char *path, int maxi, int maxj, double *varice, double *tice, double *albice, int32_t date[4]);
+/* The date block on its own: dimension nrecs = 1 and the INT variables ioffset, iyear, imonth, iday over it -- what every module's
+ * restart starts with (goldstein_data.f90:247-251) and ALL that genie-main's own restart holds (fname_restart_main,
+ * src/main-defaults.nml:38; the reference ships one, data/main/main_restart_0.nc, written by the netCDF library: the writer
+ * reproduces that file byte for byte, tests/test_restart_nc.py).  date = {iyear, imonth, iday, ioffset}. */
+int cg_restart_date_write(const char *path, const int32_t date[4]);
+int cg_restart_date_read(const char *path, int32_t date[4]);
 /* BIOGEM's restart (ctrl_ncrst = .TRUE.): sub_data_netCDF_ncrstsave (src/biogem/biogem_data_netCDF.f90:24-142) and the netCDF
  * branch of sub_data_load_rst (src/biogem/biogem_data.f90:438-568).  ocn (n_ocn,n_i,n_j,n_k), bio_part (n_sed,n_i,n_j,n_k);
  * names = string_ocn / string_sed of the selected tracers (tracer_define.ocn / .sed column 1), long names column 5.  The

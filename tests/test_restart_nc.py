@@ -306,3 +306,26 @@ def test_binary_restarts_are_fortran_records(built, tmp_path):
     assert L.cg_restart_atchem_read_bin(pb.encode(), I, J, na, ip(ia), dp(atm2), ip(fa)) != 0
     open(str(tmp_path / "trunc"), "wb").write(open(pa, "rb").read()[:-9])
     assert L.cg_restart_atchem_read_bin(str(tmp_path / "trunc").encode(), I, J, na, ip(ia), dp(atm2), ip(fa)) != 0
+
+
+@pytest.mark.parametrize("name, date", [("main_restart_0.nc", (2000, 1, 2, 0)), ("main_fluxes_0_date.nc", (1999, 12, 30, 0))])
+def test_codec_against_the_netcdf_files_the_reference_ships(built, tmp_path, name, date):
+    """data/main/main_restart_0.nc and main_fluxes_0_date.nc are the two files in the reference tree that the netCDF library itself
+    wrote (hex copies under tests/golden/, tools/make_golden.py ref_date_files): the date block every module's restart starts
+    with.  The reader must take the date out of them and the writer must reproduce them BYTE FOR BYTE -- header layout, name
+    padding, begin offsets, big-endian INT data of the codec are the library's."""
+    import binascii
+    import os
+    L = _lib.load()
+    ref = binascii.unhexlify(open(os.path.join(os.path.dirname(__file__), "golden", "ref_" + name + ".hex")).read().strip())
+    p = str(tmp_path / name)
+    open(p, "wb").write(ref)
+    got = np.zeros(4, dtype=np.int32)
+    assert L.cg_restart_date_read(p.encode(), ip(got)) == 0, L.cg_restart_last_error()
+    assert tuple(int(x) for x in got) == date                       # {iyear, imonth, iday, ioffset}
+    q = str(tmp_path / ("mine_" + name))
+    assert L.cg_restart_date_write(q.encode(), ip(np.array(date, dtype=np.int32))) == 0, L.cg_restart_last_error()
+    assert open(q, "rb").read() == ref
+    # and the module restarts' readers accept the date block of such a file's layout (same variable names and types)
+    with netcdf_file(q, "r", mmap=False) as f:
+        assert list(f.variables) == ["ioffset", "iyear", "imonth", "iday"] and list(f.dimensions.items()) == [("nrecs", 1)]
