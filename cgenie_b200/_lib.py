@@ -44,6 +44,7 @@ SYMBOLS = {
     "cg_embm_step": (C.c_int, [P, C.c_int, C.POINTER(EmbmIO)]),
     "cg_seaice_step": (C.c_int, [P, C.c_int, C.POINTER(SeaiceIO)]),
     "cg_goldstein_step": (C.c_int, [P, C.c_int, C.POINTER(GoldsteinIO)]),
+    "cg_goldstein_mldta": (C.c_int, [P, C.c_int, D]),
     "cg_biogem_forcing": (C.c_int, [P, C.c_int64]),
     "cg_biogem_step": (C.c_int, [P, C.c_double, C.c_int64]),
     "cg_biogem_tracercoupling": (C.c_int, [P, D, D]),

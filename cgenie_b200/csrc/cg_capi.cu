@@ -38,6 +38,9 @@ int launch_surflux(const Dev &, double *meantemp, bool need_mean, cudaStream_t);
 int launch_embm(const Dev &, int nsteps, cudaStream_t);
 int launch_seaice(const Dev &, cudaStream_t);
 int launch_gold_pre(const Dev &, cudaStream_t);
+int launch_mld_pre(const Dev &, cudaStream_t);
+int launch_mld_save(const Dev &, cudaStream_t);
+int launch_mld_kt(const Dev &, cudaStream_t);
 int launch_sst(const Dev &, cudaStream_t);
 int launch_momentum(const Dev &, int fast, const double *bf, const double *bb, const double *rd, const double *bk, cudaStream_t);
 int launch_velc1(const Dev &, cudaStream_t);
@@ -308,6 +311,8 @@ static void fill_gridc(cg_handle *h) {
     c.zro[k] = k < (int)g.zro.size() ? g.zro[k] : 0.0;
     c.ssmax[k] = h->mc.empty() ? 0.0 : h->mc[0].ssmax[k];
     c.diffmax[k] = (h->mc.empty() || k >= (int)h->mc[0].diffmax.size()) ? 0.0 : h->mc[0].diffmax[k];
+    c.mlddec[k] = (h->mc.empty() || k >= (int)h->mc[0].mlddec.size()) ? 0.0 : h->mc[0].mlddec[k];
+    c.mlddecd[k] = (h->mc.empty() || k >= (int)h->mc[0].mlddecd.size()) ? 0.0 : h->mc[0].mlddecd[k];
   }
 }
 static void upload_grid(cg_handle *h) {
@@ -396,6 +401,7 @@ static void register_hconst(cg_handle *h, const MemberConsts &c) {
   hc("cv", g.cv); hc("dza", g.dza); hc("zro", g.zro); hc("zw", g.zw); hc("rc", g.rc); hc("rc2", g.rc2); hc("rcv", g.rcv);
   hc("rdsv", g.rdsv); hc("cv2", g.cv2); hc("rds", g.rds); hc("rdz", g.rdz); hc("rdza", g.rdza); hc("asurf", g.asurf);
   hc("rh", g.rh);
+  hc("mldketau", c.mldketau); hc("mlddec", c.mlddec); hc("mlddecd", c.mlddecd);
   hc("scalars", {g.dphi, g.rdphi, g.dzz, g.dt, c.diff1, c.diff2, c.adrag, c.ec[1], c.ec[2], c.ec[3], c.ec[4], c.rpmesco,
                  c.rsictscsf, c.dtatm, c.rdtdim, c.rfluxsca, c.rpmesca, c.dtsic, c.sic_rdtdim, c.diffsic});
   hc("ssmax", c.ssmax); hc("drag", c.drag); hc("rtv", c.rtv); hc("rtv3", c.rtv3); hc("rhosing", c.rhosing);
@@ -685,6 +691,20 @@ static int build_device(cg_handle *h) {
   reg_field(h, "u", v.u, {3, I, J, K}, {1, 3, 3LL * I, 3LL * I * J});
   reg_field(h, "u1", v.u1, {2, I, J, K}, {1, 2, 2LL * I, 2LL * I * J});
   reg_field(h, "cost", v.cost, {I, J}, {1, I});
+  v.imld = h->base.imld;
+  if (v.imld) {   // Kraus-Turner mixed-layer scheme (goldstein.f90:2294-2390, 3337-3442)
+    v.mldpebuoycoeff = h->base.mldpebuoycoeff;
+    std::vector<const std::vector<double> *> src;
+    for (int m = 0; m < M; m++) src.push_back(&h->mc[m].mldketau);
+    double *q; TRY(dmember_array(h, &q, ij, src)); v.mldketau = q;
+    TRY(dalloc(h, &v.mld_pel1, ij * MS));
+    TRY(dalloc(h, &v.mld_rhoold, ijk * MS));
+    TRY(dalloc(h, &v.mld, ij * MS));
+    TRY(dalloc(h, &v.mldk, ij * MS));
+    reg_field(h, "mld", v.mld, {I, J}, {1, I});
+    reg_field(h, "mldketau", const_cast<double *>(v.mldketau), {I, J}, {1, I});
+    reg_field(h, "mldpelayer1", v.mld_pel1, {I, J}, {1, I});
+  }
   reg_field(h, "tsflux", v.tsflux, {2, I, J}, {(long long)ij, 1, I});
   if (L > 2) {
     // BIOGEM tracer coupling state (sub_init_phys_ocn, biogem_data.f90:1098-1137; ts->ocn offsets biogem.f90:283-285)
@@ -736,6 +756,10 @@ static int build_device(cg_handle *h) {
     const int LS = bc.LS, LA = bc.LA;
     bg_fill_tables(bc, h->base, g, &b);
     if (!bg_layout_ok(b, L)) return fail(CG_ERR_CONFIG, "BIOGEM: tracer tables differ from the layout k_bg_step is compiled for");
+    // imld = 1 hands BIOGEM a mixed-layer depth (go_mldta) and sub_calc_bio_uptake then spreads the export production over the levels
+    // k_mld .. n_k (biogem_box.f90:423-430); the surface kernel produces it in the top level only (k_mld = n_k, mld = 0)
+    if (h->base.imld) return fail(CG_ERR_CONFIG, "imld = 1 with BIOGEM: export production over a mixed layer deeper than the top level is outside the B200 hot path");
+    if (L > 64) return fail(CG_ERR_CONFIG, "more than 64 tracers");
     CUDA_OK(cudaMemcpy(v.bg_ocn, h->bg_ocn0.data(), h->bg_ocn0.size() * 8, cudaMemcpyHostToDevice));
     h->bg_ocn0.clear(); h->bg_ocn0.shrink_to_fit();
     TRY(dalloc(h, &b.bio_part, ijk * LS * MS));
@@ -1551,6 +1575,18 @@ static int do_seaice(cg_handle *h) {
   return CG_OK;
 }
 static void do_tstepo(cg_handle *h) {
+  if (h->dv.imld) {   // Kraus-Turner mixed-layer scheme (tstepo, goldstein.f90:2294-2390) around the generic flux / convection kernels
+    { ProfScope ps(h, "co"); ps.done(launch_mld_pre(h->dv, h->stream)); }
+    { ProfScope ps(h, "tstepo_flux"); ps.done(h->variant ? launch_tstepo_flux_fast(h->dv, h->stream) : launch_tstepo_flux_strict(h->dv, h->stream)); }
+    ProfScope ps(h, "co");
+    int n = launch_mld_save(h->dv, h->stream);
+    n += h->variant ? launch_co_fast(h->dv, h->stream) : launch_co_strict(h->dv, h->stream);
+    n += launch_mld_kt(h->dv, h->stream);
+    std::swap(h->dv.ts_cur, h->dv.ts_new);
+    if (h->dv.sst) n += launch_sst(h->dv, h->stream);
+    ps.done(n);
+    return;
+  }
   if (h->variant == 2) {  // fused column kernel: flux + convection + SST export in one pass (compiled shapes only)
     ProfScope ps(h, "tstepo_flux");
     const int n = launch_tstep_col(h->dv, h->stream);
@@ -1752,6 +1788,21 @@ extern "C" int cg_seaice_step(cg_handle *h, int istep, const cg_seaice_io *io) {
     IO(get(h, "waterflux_ocn", io->waterflux_ocn));
     IO(get(h, "conductflux_ocn", io->conductflux_ocn));
   }
+  return CG_OK;
+}
+
+// go_mldta = REAL(-5000.0 * mld) (goldstein.f90:449): mixed-layer depth in metres below the surface as handed to BIOGEM
+extern "C" int cg_goldstein_mldta(cg_handle *h, int member, double *go_mldta) {
+  CG_RANGE();
+  READY(h);
+  if (!go_mldta || member < 0 || member >= h->M) return fail(CG_ERR_ARG, "cg_goldstein_mldta: bad argument");
+  const size_t ij = (size_t)h->g.I * h->g.J;
+  if (!h->dv.imld) {   // mld stays 0 without the scheme
+    for (size_t q = 0; q < ij; q++) go_mldta[q] = -5000.0 * 0.0;
+    return CG_OK;
+  }
+  IO(cg_sync_to_host(h, "mld", member, go_mldta, (int64_t)ij));
+  for (size_t q = 0; q < ij; q++) go_mldta[q] = -5000.0 * go_mldta[q];
   return CG_OK;
 }
 

@@ -28,6 +28,7 @@ struct GridC {
   double dz[kMaxK], dza[kMaxK], rdz[kMaxK], rdza[kMaxK], zw[kMaxK], ssmax[kMaxK];
   double zro[kMaxK];       // depth of the density levels (ieos = 1: rho at zro(k))
   double diffmax[kMaxK];   // iediff > 0: 0.5 * 0.125 * dz^2 / dt (goldstein.f90:3042)
+  double mlddec[kMaxK], mlddecd[kMaxK];   // imld = 1: wind-energy decay with depth (goldstein.f90:1675-1686)
 };
 
 // Per-member scalar parameters ([MS] each) and per-member 2-D constants ([j][i][m]).
@@ -113,6 +114,13 @@ struct Dev {
   int ieos;                  // 1: thermobaricity term in the equation of state (goldstein.f90:3048-3082), strict kernels only
   int iediff, ediffpow2i;    // stratification-dependent vertical diffusivity (goldstein.f90:2501-2515); 0 = constant diff(2)
   double ediffpow2;
+  int imld;                  // 1: Kraus-Turner mixed-layer scheme behind the convective adjustment (tstepo, goldstein.f90:2294-2390)
+  double mldpebuoycoeff;
+  const double *mldketau;    // [j][i][m] wind energy input (per member: tau scales with scf)
+  double *mld_pel1;          // [j][i][m] mldpelayer1: energy of mixing the surface forcing over the top layer
+  double *mld_rhoold;        // [k][j][i][m] density of the column before the convective adjustment (mldrhoold)
+  double *mld;               // [j][i][m] mixed-layer depth (<= 0, units of dsc); go_mldta = -5000 * mld
+  int *mldk;                 // [j][i][m] level holding the mixed-layer base
   int *istep_ocn;            // device-resident ocean step counter (read by graph-replayed kernels)
   MemberP p;
 };

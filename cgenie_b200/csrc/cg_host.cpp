@@ -762,6 +762,30 @@ void build_member(const Grid &g, const Islands &isl, const WindFiles &w, const P
     if (p.par_wind_polar_avg != 2 && (j <= 2 || j >= J - 1))
       for (int i = 1; i <= I; i++) at2(mc.usurf, i, j) = tv3 / I;
   }
+  // wind energy input of the mixed-layer scheme (imld = 1, goldstein.f90:112-141: "taken from surflux, but min(j, maxj-1)") and its
+  // decay with depth (:1675-1686; mldwindkedec in units of dsc)
+  mc.mldketau.assign(ij, 0.0);
+  mc.mlddec.assign(K + 2, 0.0);
+  mc.mlddecd.assign(K + 2, 0.0);
+  if (p.imld == 1) {
+    for (int j = 1; j <= J; j++) {
+      double tv3 = 0.0;
+      for (int i = 1; i <= I; i++) {
+        const double tv4 = (i == 1) ? (at3(mc.tau, 1, i, j) + at3(mc.tau, 1, I, j)) * 0.5 : (at3(mc.tau, 1, i, j) + at3(mc.tau, 1, i - 1, j)) * 0.5;
+        const double tv2 = (j == 1) ? at3(mc.tau, 2, i, j) * 0.5 : (at3(mc.tau, 2, i, std::min(j, J - 1)) + at3(mc.tau, 2, i, j - 1)) * 0.5;
+        const double r = std::sqrt(std::sqrt(tv4 * tv4 + tv2 * tv2));
+        at2(mc.mldketau, i, j) = p.mldketaucoeff * (r * r * r);
+        tv3 = tv3 + at2(mc.mldketau, i, j);
+      }
+      if (j <= 2 || j >= J - 1)
+        for (int i = 1; i <= I; i++) at2(mc.mldketau, i, j) = tv3 / I;
+    }
+    const double dec = p.mldwindkedec / kDsc;
+    for (int k = K; k >= 1; k--) {
+      mc.mlddec[k] = std::exp(g.zro[k] / dec);
+      mc.mlddecd[k] = (k < K) ? mc.mlddec[k] / mc.mlddec[k + 1] : mc.mlddec[K];
+    }
+  }
   // wind speeds as exported to the coupler and read back by step_embm (embm.f90:1680-1681, 49-50)
   mc.lowestlu2.assign(ij, 0.0);
   mc.lowestlv3.assign(ij, 0.0);
@@ -820,11 +844,12 @@ bool load_job(const std::string &jobdir, Params *p, Grid *g, Islands *isl, WindF
   GN(go, adrag); GN(go, hosing); GN(go, hosing_trend); GI(go, nyears_hosing); GN(go, albocn); GI(go, iconv);
   GI(go, imld); GI(go, iediff); GI(go, ieos); GN(go, ssmaxsurf); GN(go, ssmaxdeep); GN(go, saln0);
   GN(go, ediff0); GN(go, ediffpow1); GN(go, ediffpow2); GN(go, ediffvar);
+  GN(go, mldpebuoycoeff); GN(go, mldketaucoeff); GN(go, mldwindkedec);
   p->diso = go.flag("diso", true);
   p->world = go.str("world", d.world);
   p->go_indir = go.str("indir_name", d.go_indir);
-  if (p->iconv < 0 || p->iconv > 1 || p->imld != 0 || p->ieos < 0 || p->ieos > 1) {
-    if (err) *err = "imld /= 0 (krausturner) and iconv / ieos outside 0..1 are outside the B200 hot path (SURVEY 8f.4)";
+  if (p->iconv < 0 || p->iconv > 1 || p->imld < 0 || p->imld > 1 || p->ieos < 0 || p->ieos > 1) {
+    if (err) *err = "imld / iconv / ieos outside 0..1 are outside the B200 hot path (SURVEY 8f.4)";
     return false;
   }
   if (p->iediff < 0 || p->iediff > 2 || (p->iediff != 0 && (p->ediffvar < -1.0e-7 || p->ediffvar > 1.0e-7))) {

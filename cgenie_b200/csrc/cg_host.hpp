@@ -51,7 +51,8 @@ struct Params {
   int igrid = 0, nyear = 100;
   double yearlen = 365.25, temp0 = 5.0, temp1 = 5.0, rel = 0.9, scf = 2.0, diff1 = 2000.0, diff2 = 1.0e-5,
          adrag = 2.5, hosing = 0.0, hosing_trend = 0.0, albocn = 0.05, ssmaxsurf = 10.0, ssmaxdeep = 10.0,
-         saln0 = 34.9, ediff0 = 0.0, ediffpow1 = 1.0, ediffpow2 = 1.0, ediffvar = 0.0;
+         saln0 = 34.9, ediff0 = 0.0, ediffpow1 = 1.0, ediffpow2 = 1.0, ediffvar = 0.0,
+         mldpebuoycoeff = 0.15, mldketaucoeff = 2.5, mldwindkedec = 25.0;   // imld = 1 (goldstein-defaults.nml:31-34)
   int nyears_hosing = 0, iconv = 0, imld = 0, iediff = 0, ieos = 0;
   bool diso = true;
   std::string world = "worbe2", go_indir = "input/goldstein";
@@ -123,6 +124,8 @@ struct MemberConsts {
   std::vector<double> diffa;   // (2,2,J)
   std::vector<double> albcl, ca, pmeadj, uatm, us_dztau, us_dztav, solfor, lowestlu2, lowestlv3;
   std::vector<double> tau, dztau, dztav, usurf;  // from stresses * scf (goldstein.f90:102-107, embm.f90:2762-2816)
+  std::vector<double> mldketau;                  // (I,J) wind energy input of the mixed-layer scheme, imld = 1 (goldstein.f90:112-141)
+  std::vector<double> mlddec, mlddecd;           // (K) its decay with depth (goldstein.f90:1675-1686)
   std::vector<int> iroff, jroff;
   // sea ice
   double dtsic = 0, sic_rdtdim = 0, diffsic = 0;

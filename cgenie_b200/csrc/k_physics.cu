@@ -1412,6 +1412,160 @@ int launch_sst(const Dev &v, cudaStream_t s) {
   k_sst<<<dim3(v.MS / 32, (v.I * v.J + 3) / 4), b, 0, s>>>(v);
   return 1;
 }
+// ---------------------------------------------------------------- Kraus-Turner mixed-layer scheme (imld = 1)
+// tstepo, goldstein.f90:2294-2390, and SUBROUTINE krausturner, :3337-3442.  Thread = (member, wet column); the column's cells lie
+// MS doubles apart per tracer, so a warp reads 256-byte rows.  Reference operation order throughout (-fmad=false): bit-exact
+// against the oracle's restatement.  The 2-D "depth" grids dzg / z2dzg / rdzg (:1013-1027) are formed from zw on the fly: the
+// same IEEE subtraction, products and division the reference stores.
+#define TSN(l, k) v.ts_new[((cell3(I, J, i, j, (k)) * L) + ((l)-1)) * MS + m]
+__device__ inline double mld_eos(const Dev &v, const int m, const double t, const double s, const double z) {
+  const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
+  if (!v.ieos) return ec1 * t + ec2 * s + ec3 * (t * t) + ec4 * (t * t * t);
+  return ec1 * t + ec2 * s + ec3 * (t * t) + ec4 * (t * t * t) + v.p.ec5[m] * t * z;
+}
+__device__ inline double mld_dzg(const int k, const int kk) { return c_g.zw[k] - c_g.zw[kk - 1]; }
+__device__ inline double mld_z2dzg(const int k, const int kk) { return -c_g.zw[k] * c_g.zw[k] + c_g.zw[kk - 1] * c_g.zw[kk - 1]; }
+__device__ inline double mld_rdzg(const int k, const int kk) { return (k != kk - 1) ? 1.0 / mld_dzg(k, kk) : 1.0e10; }
+
+// before tstepo_flux (:2294-2309): energy consumed or released in mixing the surface forcing over the top layer
+__global__ void __launch_bounds__(128) k_mld_pre(const Dev v) {
+  DIMS
+  const int L = v.L;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= MS || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  if (CG_K1(v, i, j) > K) return;
+  const size_t q = (size_t)c2 * MS + m;
+  const double *tsc = v.ts_cur + ((cell3(I, J, i, j, K) * L) * MS + m);
+  const double t = tsc[0] - v.tsflux[q], sa = tsc[MS] - v.tsflux[(size_t)I * J * MS + q];
+  const double r = mld_eos(v, m, t, sa, c_g.zro[K]);
+  v.mld_pel1[q] = (r - RHOX(i, j, K)) * mld_z2dzg(K, K);
+}
+// behind tstepo_flux, ahead of co (:2320-2331): the reference remembers T and S of every level "only so we can calculate PE
+// change"; what it takes from them is eos(T, S, zro(k)) (:2346), kept here instead
+__global__ void __launch_bounds__(128) k_mld_save(const Dev v) {
+  DIMS
+  const int L = v.L;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= MS || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  if (CG_K1(v, i, j) > K) return;
+  for (int k = K; k > 0; k--) v.mld_rhoold[cell3(I, J, i, j, k) * MS + m] = mld_eos(v, m, TSN(1, k), TSN(2, k), c_g.zro[k]);
+}
+// behind co (:2336-2390): PE released by the convective adjustment, wind energy, then krausturner on the column
+constexpr int kMldMaxL = 64;
+__global__ void __launch_bounds__(128) k_mld_kt(const Dev v) {
+  DIMS
+  const int L = v.L;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= MS || c2 >= I * J) return;
+  const int i = c2 % I + 1, j = c2 / I + 1;
+  const int tvkl = CG_K1(v, i, j);
+  if (tvkl > K) return;
+  const size_t q = (size_t)c2 * MS + m;
+  double peconv = 0;
+  for (int k = K; k > 0; k--) {
+    const double rnew = mld_eos(v, m, TSN(1, k), TSN(2, k), c_g.zro[k]);
+    peconv = peconv + (rnew - v.mld_rhoold[cell3(I, J, i, j, k) * MS + m]) * mld_z2dzg(k, k);
+  }
+  const double pel1 = v.mld_pel1[q];
+  double pebuoy = peconv + pel1;
+  if (pebuoy > 0.0) pebuoy = pebuoy * v.mldpebuoycoeff;
+  const double ketau = v.mldketau[q];
+  const double emix = pebuoy + ketau * c_g.mlddec[K];
+  if (emix > 0.0) {
+    // ---- krausturner(ts(:, i, j, :), pebuoy, ketau, mldpk, mld, mldk, k1)
+    double qmix[kMldMaxL + 1];
+    double em, empe, emke, eneed, emr, smix, tmix, rhou = 0.0, rhol = 0.0, rhomix;
+    int k = K, partmix = 1;
+    const int mldpk = K;
+    empe = pebuoy;
+    emke = ketau * c_g.mlddec[k];
+    em = empe + emke;
+    eneed = 0.0;
+    tmix = TSN(1, k);
+    smix = TSN(2, k);
+    for (int l = 1; l <= L; l++) qmix[l] = TSN(l, k);
+    rhomix = mld_eos(v, m, tmix, smix, c_g.zw[k]);
+    while (eneed < em && em > 0) {
+      if (k < mldpk) {
+        qmix[1] = tmix;
+        qmix[2] = smix;
+        for (int l = 3; l <= L; l++) qmix[l] = mld_rdzg(K, k) * (qmix[l] * mld_dzg(K, k + 1) + TSN(l, k) * c_g.dz[k]);
+      }
+      if (k == tvkl) {
+        v.mldk[q] = k;
+        v.mld[q] = c_g.zw[k - 1];
+        partmix = 0;
+        em = -1.0e-8;
+        if (k < K)
+          for (int l = 1; l <= L; l++)
+            for (int n = k; n <= K; n++) TSN(l, n) = qmix[l];
+      } else {
+        k = k - 1;
+        emr = (em - eneed) / em;
+        empe = empe * emr;
+        emke = emke * emr * c_g.mlddecd[k];
+        em = empe + emke;
+        if (v.ieos) rhou = mld_eos(v, m, tmix, smix, c_g.zw[k]); else rhou = rhomix;
+        tmix = mld_rdzg(K, k) * (tmix * mld_dzg(K, k + 1) + TSN(1, k) * c_g.dz[k]);
+        smix = mld_rdzg(K, k) * (smix * mld_dzg(K, k + 1) + TSN(2, k) * c_g.dz[k]);
+        rhol = mld_eos(v, m, TSN(1, k), TSN(2, k), c_g.zw[k]);
+        rhomix = mld_eos(v, m, tmix, smix, c_g.zw[k]);
+        eneed = mld_z2dzg(K, k + 1) * rhou + mld_z2dzg(k, k) * rhol - mld_z2dzg(K, k) * rhomix;
+      }
+    }
+    if (partmix == 1 && em > 0) {
+      v.mldk[q] = k;
+      const double mlda = mld_dzg(K, k + 1) * mld_rdzg(K, k) * em / eneed;
+      const double mldb = (mld_dzg(K, k) * mld_rdzg(K, k + 1) - 1) * mlda;
+      for (int l = 1; l <= L; l++) {
+        const double top = (1 - mldb) * qmix[l] + mldb * TSN(l, k);
+        TSN(l, K) = top;
+        for (int n = k + 1; n <= K - 1; n++) TSN(l, n) = top;
+        TSN(l, k) = mlda * qmix[l] + (1 - mlda) * TSN(l, k);
+      }
+      if (k < K) {
+        const double mldtadd = em / (c_g.zw[k] * (rhol - rhou));
+        v.mld[q] = c_g.zw[k] + mldtadd;
+      } else {
+        v.mld[q] = 0.0;
+      }
+    } else if (partmix == 1 && k < K) {
+      v.mldk[q] = k + 1;
+      v.mld[q] = c_g.zw[k];
+    }
+  } else {
+    // not enough energy even to homogenise the first layer (:2376-2387)
+    v.mldk[q] = K;
+    if (pel1 < 0) v.mld[q] = c_g.zw[K - 1] * (1 - emix / pel1);
+    else v.mld[q] = c_g.zw[K - 1];
+  }
+  // "if thermobaricity is on, make sure rho calculation is vertically local" (:2396-2408) follows krausturner in the reference:
+  // the convection kernel's pass saw the column before the mixed-layer scheme changed it
+  if (v.ieos)
+    for (int k = tvkl; k <= K; k++) RHOX(i, j, k) = mld_eos(v, m, TSN(1, k), TSN(2, k), c_g.zro[k]);
+}
+#undef TSN
+int launch_mld_pre(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_mld_pre<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  return 1;
+}
+int launch_mld_save(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_mld_save<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  return 1;
+}
+int launch_mld_kt(const Dev &v, cudaStream_t s) {
+  const dim3 b(32, 4);
+  k_mld_kt<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);
+  return 1;
+}
+
 int launch_gold_pre(const Dev &v, cudaStream_t s) {
   const dim3 b(32, 4);
   k_gold_pre<<<grid2(v, v.I * v.J, b), b, 0, s>>>(v);

@@ -147,6 +147,12 @@ __global__ void __launch_bounds__(128) k_co_col(const Dev v) {
   co_column<I, J, K, L, MS>(v, c_g, v.rowcols[ci], m, scratch, 128);
 }
 
+// the same, one warp per block, compiled for MINB resident blocks per SM (column arrays thread-private)
+template <int I, int J, int K, int L, int MS, int MINB>
+__global__ void __launch_bounds__(32, MINB) k_co_col1(const Dev v) {
+  co_column<I, J, K, L, MS>(v, c_g, v.rowcols[blockIdx.y], blockIdx.x * 32 + threadIdx.x, nullptr, 1);
+}
+
 // Block-cooperative form of the convective adjustment: one block = 32 members (lanes) of ONE wet column.  Warp 0 takes the
 // decisions for its flagged lanes (T, S, rho of the column, serial per lane: latency bound) and leaves the region maps in shared
 // memory; then every warp averages one pair of passive tracers over the mixed regions, so that the loads of all seven pairs are
@@ -398,12 +404,24 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
     k_co_passive<I, J, K, L, MS><<<dim3(MS / 32, v.nwet), dim3(32, L - 2), 0, s>>>(v2);
     return 3;
   }
+  // The one-warp-per-block form compiled for 16 | 20 | 24 resident blocks per SM (128 / 96 / 80 registers instead of 164; the kernel
+  // is bound by issue latency at 12 warps per SM).  Measured on the bench state (ab_r4a.log, us per tracer step, results
+  // bit-identical): 164 registers 556.2, 128 registers 522.8 (default), 96 registers 532.7, 80 registers 532.1.  CG_CO_MINB=0: the old form.
+  static int minb = -1;
+  if (minb < 0) { const char *e = getenv("CG_CO_MINB"); minb = e ? atoi(e) : 16; }
+  if (minb && wpb == 1) {
+    const dim3 g(MS / 32, v.nwet);
+    if (minb == 16) k_co_col1<I, J, K, L, MS, 16><<<g, 32, 0, s>>>(v2);
+    else if (minb == 20) k_co_col1<I, J, K, L, MS, 20><<<g, 32, 0, s>>>(v2);
+    else k_co_col1<I, J, K, L, MS, 24><<<g, 32, 0, s>>>(v2);
+    return 2;
+  }
   k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + wpb - 1) / wpb), 32 * wpb, 0, s>>>(v2);
   return 2;
 }
 
 bool tstep_col_supported(const Dev &v) {
-  if (v.iediff || v.ieos || v.iconv) return false;   // the column kernel takes diff(2) as a per-member constant and has no thermobaric term
+  if (v.iediff || v.ieos || v.iconv || v.imld) return false;   // the column kernel takes diff(2) as a per-member constant and has no thermobaric term
   if (v.I == 128 && v.J == 128 && v.K == 32 && v.L == 40 && (v.MS == 32 || v.MS == 64 || v.MS == 128)) return true;   // BASELINE config #5
   return v.I == 36 && v.J == 36 && v.K == 16 && v.L == 16 && (v.MS == 32 || v.MS == 64 || v.MS == 128 || v.MS == 256 || v.MS == 512);
 }

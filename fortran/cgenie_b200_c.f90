@@ -61,6 +61,11 @@ MODULE cgenie_b200_c
        TYPE(C_PTR), VALUE :: h, io
        INTEGER(C_INT), VALUE :: istep
      END FUNCTION cg_goldstein_step
+     INTEGER(C_INT) FUNCTION cg_goldstein_mldta(h, member, go_mldta) BIND(C, NAME='cg_goldstein_mldta')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h, go_mldta
+       INTEGER(C_INT), VALUE :: member
+     END FUNCTION cg_goldstein_mldta
      INTEGER(C_INT) FUNCTION cg_sync_to_host(h, name, member, dst, n) BIND(C, NAME='cg_sync_to_host')
        IMPORT :: C_INT, C_INT64_T, C_CHAR, C_PTR
        TYPE(C_PTR), VALUE :: h, dst

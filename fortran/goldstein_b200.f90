@@ -56,6 +56,8 @@ CONTAINS
        rc = cg_sync_to_host(cg_h, 'ts' // C_NULL_CHAR, 0_C_INT, C_LOC(go_ts), INT(SIZE(go_ts), C_INT64_T))
        CALL cg_check(rc, 'cg_sync_to_host(ts)')
        go_ts1 = go_ts
+       rc = cg_goldstein_mldta(cg_h, 0_C_INT, C_LOC(go_mldta))     ! -5000 * mld; zero unless imld = 1
+       CALL cg_check(rc, 'cg_goldstein_mldta')
     ELSE
        rc = cg_goldstein_step(cg_h, INT(istep, C_INT), C_NULL_PTR)
        CALL cg_check(rc, 'cg_goldstein_step')

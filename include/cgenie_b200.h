@@ -105,6 +105,9 @@ typedef struct {
   double *test_energy_ocean, *test_water_ocean; /* OUT scalars (goldstein.f90:458-478)          */
 } cg_goldstein_io;
 int cg_goldstein_step(cg_handle *, int istep, const cg_goldstein_io *io);
+/* step_goldstein's go_mldta (goldstein.f90:449: -5000 * mld, metres; zero unless imld = 1, the Kraus-Turner mixed-layer scheme
+ * of tstepo :2294-2390 and SUBROUTINE krausturner :3337-3442) of one member, (maxi,maxj). */
+int cg_goldstein_mldta(cg_handle *, int member, double *go_mldta);
 /* io == NULL ("stay resident") calls of the four steps above are deferred: they are executed, in order, at the latest when
  * the next call passes arrays or touches state from the host (cg_sync_*, cg_get_*, cg_synchronize, cg_run, BIOGEM / ATCHEM);
  * a complete cycle surflux, kocn_loop x step_embm, step_seaice, step_goldstein is executed at the step_goldstein call as

@@ -1208,7 +1208,7 @@ void cgo_biogem_climate(cgo_t *o) {
   for (i = 1; i <= NI; i++)
     for (j = 1; j <= NJ; j++) {
       if (NK >= K1(i, j)) {
-        A2(b->mld, i, j) = -5000.0 * 0.0;   /* go_mldta = -5000*mld, mld = 0 for imld = 0 (goldstein.f90:449) */
+        A2(b->mld, i, j) = -5000.0 * A2(o->mld, i, j);   /* go_mldta = -5000*mld (goldstein.f90:449); mld = 0 for imld = 0 */
         A2(b->rho_surf, i, j) = calc_rho(OCN(1, i, j, NK), OCN(2, i, j, NK));
       }
       A2(b->solfor, i, j) = o->go_solfor[j];

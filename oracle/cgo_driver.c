@@ -90,6 +90,7 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
   PI_(iconv, 0); PI_(imld, 0); PI_(iediff, 0); PI_(ieos, 0); PI_(diso, 1);
   PD(ssmaxsurf, 10.0); PD(ssmaxdeep, 10.0); PD(saln0, 34.9);
   PD(ediff0, 0.0); PD(ediffpow1, 1.0); PD(ediffpow2, 1.0); PD(ediffvar, 0.0);
+  PD(mldpebuoycoeff, 0.15); PD(mldketaucoeff, 2.5); PD(mldwindkedec, 25.0);
   /* embm-defaults.nml */
   PI_(ndta, 5); PD(rmax, 0.85);
   v = 5.0e6; parse_kv(params, "diffamp1", &v); o->diffamp[1] = v;
@@ -113,9 +114,9 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
   /* genie main */
   PD(solconst, 1368.0); PD(gn_daysperyear, 365.25);
   PI_(kocn_loop, 5); PI_(katm_loop, 1); PI_(ksic_loop, 5);
-  if (o->iconv < 0 || o->iconv > 1 || o->imld != 0 || o->iediff < 0 || o->iediff > 2 || o->ieos < 0 || o->ieos > 1 ||
+  if (o->iconv < 0 || o->iconv > 1 || o->imld < 0 || o->imld > 1 || o->iediff < 0 || o->iediff > 2 || o->ieos < 0 || o->ieos > 1 ||
       (o->iediff != 0 && (o->ediffvar < -1.0e-7 || o->ediffvar > 1.0e-7))) {
-    fprintf(stderr, "cgo: imld != 0, iconv / ieos outside 0..1, iediff outside 0..2 and ediffvar != 0 are outside the restated path\n");
+    fprintf(stderr, "cgo: imld / iconv / ieos outside 0..1, iediff outside 0..2 and ediffvar != 0 are outside the restated path\n");
     free(o);
     return NULL;
   }
@@ -147,6 +148,10 @@ cgo_t *cgo_create(const char *params, const int *k1file, const double *psiles, i
     AL1(cost, ij); AL1(bp, (long)(I + 1) * J * K); AL1(sbp, (long)(I + 1) * J);
     AL1(fw_hosing, ij); AL1(rhosing, ij); AL1(fw_anom, ij); AL1(fw_anom_rate, ij); AL1(albcl_go, ij);
     AL1(dzu, 2L * K);
+    AL1(dzg, (long)(K + 1) * (K + 1)); AL1(z2dzg, (long)(K + 1) * (K + 1)); AL1(rdzg, (long)(K + 1) * (K + 1));
+    AL1(mlddec, K + 2); AL1(mlddecd, K + 2);
+    AL1(mldketau, ij); AL1(mldpelayer1, ij); AL1(mldpeconv, ij); AL1(mldpebuoy, ij); AL1(mldemix, ij); AL1(mld, ij);
+    o->mldk = cgo_ialloc(o, "mldk", ij);
     /* EMBM */
     AL1(tq, 2 * ij); AL1(tq1, 2 * ij); AL1(tqa, 2 * ij); AL1(uatm, 2 * ij); AL1(diffa, 4L * J); AL1(albcl, ij);
     AL1(ca, ij); AL1(co2, ij); AL1(ch4, ij); AL1(n2o, ij); AL1(usurf, ij); AL1(pmeadj, ij); AL1(pptn, ij);

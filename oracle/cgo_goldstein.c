@@ -10,6 +10,10 @@
 #define IPISL(p, n) o->ipisl[((p)-1) + o->mpi * ((n)-1)]
 #define JPISL(p, n) o->jpisl[((p)-1) + o->mpi * ((n)-1)]
 
+#define DZG(k, kk) o->dzg[(k) + (NK + 1) * (kk)]
+#define Z2DZG(k, kk) o->z2dzg[(k) + (NK + 1) * (kk)]
+#define RDZG(k, kk) o->rdzg[(k) + (NK + 1) * (kk)]
+
 /* goldstein.f90:3048-3061: ieos = 0, and ieos = 1 with the thermobaricity term ec(5) * t * z */
 void cgo_eos(const cgo_t *o, double t, double s, double z, double *rho) {
   if (o->ieos == 0) *rho = o->ec[1] * t + o->ec[2] * s + o->ec[3] * (t * t) + o->ec[4] * (t * t * t);
@@ -629,11 +633,124 @@ void cgo_co(cgo_t *o) {
   free(kk); free(dzm); free(sum); free(icosd);
 }
 
-/* goldstein.f90:2280-2432 with imld==0, ieos==0 (dead copies :2311-2316 skipped) */
+/* SUBROUTINE krausturner, goldstein.f90:3337-3442: the PE released in co and the KE from the wind deepen the mixed layer of
+ * column (i, j); tv = ts(:, i, j, 1:maxk) in place.  mldt / mldkt keep their old values on the path that assigns neither. */
+static void krausturner(cgo_t *o, int i, int j, double pebuoy, double ketau, double *mldt, int *mldkt, int tvkl) {
+  const int L = NL;
+  double em, empe, emke, eneed, emr, smix, tmix, qmix[CGO_MAXL + 1];
+  double rhou = 0.0, rhol = 0.0, rhomix, mlda, mldb, mldtadd;
+  int k, l, n, partmix;
+  const int mldpk = NK;
+  k = mldpk;
+  empe = pebuoy;
+  emke = ketau * o->mlddec[k];
+  em = empe + emke;
+  eneed = 0.0;
+  tmix = TS(1, i, j, k);
+  smix = TS(2, i, j, k);
+  for (l = 1; l <= L; l++) qmix[l] = TS(l, i, j, k);
+  cgo_eos(o, tmix, smix, o->zw[k], &rhomix);
+  partmix = 1;
+  while (eneed < em && em > 0) {
+    if (k < mldpk) {
+      qmix[1] = tmix;
+      qmix[2] = smix;
+      for (l = 3; l <= L; l++) qmix[l] = RDZG(NK, k) * (qmix[l] * DZG(NK, k + 1) + TS(l, i, j, k) * o->dz[k]);
+    }
+    if (k == tvkl) {
+      *mldkt = k;
+      *mldt = o->zw[k - 1];
+      partmix = 0;
+      em = -1.0e-8;
+      if (k < NK)
+        for (l = 1; l <= L; l++)
+          for (n = k; n <= NK; n++) TS(l, i, j, n) = qmix[l];
+    } else {
+      k = k - 1;
+      emr = (em - eneed) / em;
+      empe = empe * emr;
+      emke = emke * emr * o->mlddecd[k];
+      em = empe + emke;
+      if (o->ieos != 0) cgo_eos(o, tmix, smix, o->zw[k], &rhou); else rhou = rhomix;
+      tmix = RDZG(NK, k) * (tmix * DZG(NK, k + 1) + TS(1, i, j, k) * o->dz[k]);
+      smix = RDZG(NK, k) * (smix * DZG(NK, k + 1) + TS(2, i, j, k) * o->dz[k]);
+      cgo_eos(o, TS(1, i, j, k), TS(2, i, j, k), o->zw[k], &rhol);
+      cgo_eos(o, tmix, smix, o->zw[k], &rhomix);
+      eneed = Z2DZG(NK, k + 1) * rhou + Z2DZG(k, k) * rhol - Z2DZG(NK, k) * rhomix;
+    }
+  }
+  if (partmix == 1 && em > 0) {
+    *mldkt = k;
+    mlda = DZG(NK, k + 1) * RDZG(NK, k) * em / eneed;
+    mldb = (DZG(NK, k) * RDZG(NK, k + 1) - 1) * mlda;
+    for (l = 1; l <= L; l++) {
+      TS(l, i, j, NK) = (1 - mldb) * qmix[l] + mldb * TS(l, i, j, k);
+      for (n = k + 1; n <= NK - 1; n++) TS(l, i, j, n) = TS(l, i, j, NK);
+      TS(l, i, j, k) = mlda * qmix[l] + (1 - mlda) * TS(l, i, j, k);
+    }
+    if (k < NK) {
+      mldtadd = em / (o->zw[k] * (rhol - rhou));
+      *mldt = o->zw[k] + mldtadd;
+    } else {
+      *mldt = 0.0;
+    }
+  } else if (partmix == 1 && k < NK) {
+    *mldkt = k + 1;
+    *mldt = o->zw[k];
+  }
+}
+
+/* goldstein.f90:2280-2432 (dead copies :2311-2316 skipped) */
 void cgo_tstepo(cgo_t *o) {
   int i, j, k, l;
+  if (o->imld == 1) {   /* energy consumed or released in mixing the surface forcing over the top layer, :2294-2309 */
+    for (j = 1; j <= NJ; j++)
+      for (i = 1; i <= NI; i++) {
+        const double t = TS(1, i, j, NK) - TS(1, i, j, NK + 1), sa = TS(2, i, j, NK) - TS(2, i, j, NK + 1);
+        double r;
+        cgo_eos(o, t, sa, o->zro[NK], &r);
+        A2(o->mldpelayer1, i, j) = (r - RHO(i, j, NK)) * Z2DZG(NK, NK);
+      }
+  }
   cgo_tstepo_flux(o);
-  cgo_co(o);
+  if (o->imld == 1) {   /* :2320-2390 */
+    double *tsold = (double *)malloc(sizeof(double) * 2 * (size_t)NI * NJ * (NK + 1));
+#define TSOLD(l, i, j, k) tsold[((l)-1) + 2 * (((i)-1) + (size_t)NI * (((j)-1) + (size_t)NJ * (k)))]
+    for (i = 1; i <= NI; i++)
+      for (j = 1; j <= NJ; j++)
+        if (K1(i, j) <= NK)
+          for (k = 1; k <= NK; k++) { TSOLD(1, i, j, k) = TS(1, i, j, k); TSOLD(2, i, j, k) = TS(2, i, j, k); }
+    cgo_co(o);
+    for (i = 1; i <= NI; i++)
+      for (j = 1; j <= NJ; j++)
+        if (K1(i, j) <= NK) {
+          double rold, rnew;
+          A2(o->mldpeconv, i, j) = 0;
+          for (k = NK; k > 0; k--) {
+            cgo_eos(o, TSOLD(1, i, j, k), TSOLD(2, i, j, k), o->zro[k], &rold);
+            cgo_eos(o, TS(1, i, j, k), TS(2, i, j, k), o->zro[k], &rnew);
+            A2(o->mldpeconv, i, j) = A2(o->mldpeconv, i, j) + (rnew - rold) * Z2DZG(k, k);
+          }
+          A2(o->mldpebuoy, i, j) = A2(o->mldpeconv, i, j) + A2(o->mldpelayer1, i, j);
+          if (A2(o->mldpebuoy, i, j) > 0.0) A2(o->mldpebuoy, i, j) = A2(o->mldpebuoy, i, j) * o->mldpebuoycoeff;
+          A2(o->mldemix, i, j) = A2(o->mldpebuoy, i, j) + A2(o->mldketau, i, j) * o->mlddec[NK];
+        }
+    free(tsold);
+#undef TSOLD
+    for (i = 1; i <= NI; i++)
+      for (j = 1; j <= NJ; j++)
+        if (K1(i, j) <= NK) {
+          if (A2(o->mldemix, i, j) > 0.0) {
+            krausturner(o, i, j, A2(o->mldpebuoy, i, j), A2(o->mldketau, i, j), &A2(o->mld, i, j), &A2(o->mldk, i, j), K1(i, j));
+          } else {
+            A2(o->mldk, i, j) = NK;
+            if (A2(o->mldpelayer1, i, j) < 0) A2(o->mld, i, j) = o->zw[NK - 1] * (1 - A2(o->mldemix, i, j) / A2(o->mldpelayer1, i, j));
+            else A2(o->mld, i, j) = o->zw[NK - 1];
+          }
+        }
+  } else {
+    cgo_co(o);
+  }
   if (o->ieos != 0) {   /* if thermobaricity is on, make sure rho calculation is vertically local (:2396-2408) */
     for (i = 1; i <= NI; i++)
       for (j = 1; j <= NJ; j++)
@@ -731,6 +848,20 @@ void cgo_goldstein_step(cgo_t *o) {
       TAU(1, i, j) = DZTAU(1, i, j) * o->dzz;
       TAU(2, i, j) = DZTAV(2, i, j) * o->dzz;
     }
+  if (o->imld == 1) {   /* wind energy input of the mixed-layer scheme, :112-141 */
+    double tv2, tv3, tv4;
+    for (j = 1; j <= NJ; j++) {
+      tv3 = 0.0;
+      for (i = 1; i <= NI; i++) {
+        if (i == 1) tv4 = (TAU(1, i, j) + TAU(1, NI, j)) * 0.5; else tv4 = (TAU(1, i, j) + TAU(1, i - 1, j)) * 0.5;
+        if (j == 1) tv2 = TAU(2, i, j) * 0.5; else tv2 = (TAU(2, i, (j < NJ - 1 ? j : NJ - 1)) + TAU(2, i, j - 1)) * 0.5;
+        { const double r = sqrt(sqrt(tv4 * tv4 + tv2 * tv2)); A2(o->mldketau, i, j) = o->mldketaucoeff * (r * r * r); }
+        tv3 = tv3 + A2(o->mldketau, i, j);
+      }
+      for (i = 1; i <= NI; i++)
+        if (j <= 2 || j >= NJ - 1) A2(o->mldketau, i, j) = tv3 / NI;
+    }
+  }
   get_hosing(o, istep);
   for (j = 1; j <= NJ; j++)
     for (i = 1; i <= NI; i++) {
@@ -861,6 +992,13 @@ void cgo_goldstein_init(cgo_t *o) {
     if (k > 1) o->zro[k - 1] = o->zro[k] - o->dza[k - 1];
     o->zw[k - 1] = o->zw[k] - o->dz[k];
   }
+  /* 2-D "depth" grids of the difference between each pair of levels, and of the squares (PE), :1013-1027 */
+  for (k = NK; k >= 1; k--)
+    for (kk = NK; kk >= 1; kk--) {
+      DZG(k, kk) = o->zw[k] - o->zw[kk - 1];
+      Z2DZG(k, kk) = -o->zw[k] * o->zw[k] + o->zw[kk - 1] * o->zw[kk - 1];
+      if (k != kk - 1) RDZG(k, kk) = 1.0 / DZG(k, kk); else RDZG(k, kk) = 1.0e10;
+    }
   o->dzz = o->dz[NK] * o->dza[NK - 1] / 2;
   for (k = 1; k <= NK - 1; k++) {
     o->rdz[k] = 1.0 / o->dz[k];
@@ -1055,6 +1193,12 @@ void cgo_goldstein_init(cgo_t *o) {
     for (isl = 1; isl <= o->isles; isl++) island(o, &UBISL(1, 0, 0, isol), &ERISL(isl, isol), isl, 0);
   }
   matinv_gold(o);
+  /* mixed-layer scheme: wind decay efficiency :1675-1686 (mldwindkedec in units of dsc) */
+  o->mldwindkedec = o->mldwindkedec / CG_DSC;
+  for (k = NK; k >= 1; k--) {
+    o->mlddec[k] = exp(o->zro[k] / o->mldwindkedec);
+    if (k < NK) o->mlddecd[k] = o->mlddec[k] / o->mlddec[k + 1]; else o->mlddecd[NK] = o->mlddec[NK];
+  }
   /* ssmax :2058-2070 */
   if (o->ssmaxsurf - o->ssmaxdeep < 1.0e-7 && o->ssmaxsurf - o->ssmaxdeep > -1.0e-7) {
     for (k = 1; k <= NK - 1; k++) o->ssmax[k] = o->ssmaxdeep;

@@ -57,6 +57,8 @@
 #define CG_TSIC (-1.8)
 #define CG_CD 0.0013
 
+#define CGO_MAXL 127   /* tracers a column routine keeps on its stack */
+
 struct cgo_field_ent { const char *name; double *p; long n; };
 struct cgo_ifield_ent { const char *name; int *p; long n; };
 struct cgo_scalar_ent { const char *name; double *p; };
@@ -71,6 +73,9 @@ struct cgo {
   double albocn; int iconv, imld, iediff, ieos, diso;
   double ssmaxsurf, ssmaxdeep, saln0;
   double ediff0, ediffpow1, ediffpow2, ediffvar; int ediffpow2i;   /* iediff = 1 | 2 (goldstein.f90:2936-3044) */
+  double mldpebuoycoeff, mldketaucoeff, mldwindkedec;                /* imld = 1 (goldstein.f90:1667-1686) */
+  double *dzg, *z2dzg, *rdzg, *mlddec, *mlddecd;                      /* (maxk,maxk) x 3, (maxk) x 2 */
+  double *mldketau, *mldpelayer1, *mldpeconv, *mldpebuoy, *mldemix, *mld; int *mldk;   /* (maxi,maxj) */
   double rmax, diffamp[3], diffwid, difflin, betaz[3], betam[3];
   double tatm, relh0_ocean, relh0_land, extra1a, extra1b, extra1c, scl_fwf;
   double z1_embm, diffa_scl; int diffa_len;

@@ -40,8 +40,8 @@ def test_create_fails_loudly_on_missing_job(built, tmp_path):
 
 def test_out_of_scope_option_rejected(built, tmp_path):
     lib = _lib.load()
-    # krausturner (imld = 1), a second equation-of-state option and a spatially varying ediff grid are not on the device path
-    for q, ov in enumerate(({"go_imld": 1}, {"go_ieos": 2}, {"go_iediff": 1, "go_ediffvar": 0.5}, {"go_iediff": 3})):
+    # an unknown mixed-layer option, a second equation-of-state option and a spatially varying ediff grid are not on the device path
+    for q, ov in enumerate(({"go_imld": 2}, {"go_ieos": 2}, {"go_iediff": 1, "go_ediffvar": 0.5}, {"go_iediff": 3})):
         d = tmp_path / ("job%d" % q)
         materialise(str(d), "eb_go_gs_36x36x8", ov)
         h = _lib.P()
@@ -49,7 +49,7 @@ def test_out_of_scope_option_rejected(built, tmp_path):
         assert rc == 3 and b"outside the B200 hot path" in lib.cg_last_error() or b"on the B200 hot path" in lib.cg_last_error(), ov
         assert rc == 3, ov
     # ... the ones that are: accepted
-    for q, ov in enumerate(({"go_ieos": 1}, {"go_iconv": 1}, {"go_iediff": 2, "go_ediff0": 0.275e-4})):
+    for q, ov in enumerate(({"go_ieos": 1}, {"go_iconv": 1}, {"go_iediff": 2, "go_ediff0": 0.275e-4}, {"go_imld": 1})):
         d = tmp_path / ("ok%d" % q)
         materialise(str(d), "eb_go_gs_36x36x8", ov)
         h = _lib.P()
@@ -129,6 +129,22 @@ def test_host_init_bit_exact_vs_oracle(built, tmp_path, config, okw):
     same(p.const("tq0"), o.f("tq"), "tq0")
     # winds: the oracle holds uatm after initialise_embm; the product keeps the same array
     same(p.const("uatm"), o.f("uatm"), "uatm")
+    p.close()
+    o.close()
+
+
+def test_mixed_layer_tables_bit_exact_vs_oracle(built, tmp_path):
+    """imld = 1: the wind energy input (goldstein.f90:112-141, from tau = scf * stress) and its decay with depth (:1675-1686) as the
+    product's host initialisation builds them against the oracle's, for a non-default scf and decay scale."""
+    kw = dict(imld=1, scf=1.7, mldketaucoeff=3.0, mldwindkedec=40.0)
+    materialise(str(tmp_path), "eb_go_gs_36x36x8", {"go_" + k: v for k, v in kw.items()})
+    p = HostOnly(str(tmp_path))
+    o = Oracle("worbe2", maxk=8, maxl=2, nyear=100, **kw)
+    o.run(5)                                   # mldketau is formed in step_goldstein
+    same(p.const("mldketau"), o.f("mldketau"), "mldketau")
+    same(p.const("mlddec")[1:9], o.f("mlddec")[1:9], "mlddec")
+    same(p.const("mlddecd")[1:9], o.f("mlddecd")[1:9], "mlddecd")
+    assert p.const("mldketau").max() > 0
     p.close()
     o.close()
 

@@ -1,0 +1,66 @@
+"""Oracle restatement of the Kraus-Turner mixed-layer scheme (imld = 1: tstepo goldstein.f90:2294-2390, SUBROUTINE krausturner
+:3337-3442, wind energy input :112-141, tables :1013-1027, 1675-1686) -- CPU checks of the restatement itself:
+the scheme only redistributes tracer within a column, so what it adds to the convective adjustment conserves every column
+inventory; the diagnosed depth lies between the surface and the column's bottom; imld = 0 is untouched."""
+import numpy as np
+
+from oracle_lib import Oracle
+
+I = J = 36
+K, L = 8, 2
+
+
+def _cols(o):
+    ts = o.f("ts").reshape(K + 2, J + 2, I + 2, L)[1:K + 1, 1:J + 1, 1:I + 1, :]
+    dz = o.f("dz")[1:K + 1]
+    return (ts * dz[:, None, None, None]).sum(axis=0)
+
+
+def test_krausturner_conserves_column_inventories_and_bounds_the_depth():
+    a = Oracle("worbe2", maxk=K, maxl=L, nyear=100, imld=1)
+    b = Oracle("worbe2", maxk=K, maxl=L, nyear=100, imld=0)
+    a.run(5 * 60)
+    # twin without the scheme, from the same state: flux + convective adjustment are common to both
+    for n in ("ts", "ts1", "rho", "u", "u1", "cost"):
+        b.f(n)[:] = a.f(n)
+    before = a.f("ts").copy()
+    a.call("tstepo")
+    b.call("tstepo")
+    assert not np.array_equal(a.f("ts"), b.f("ts"))                       # the scheme acted
+    inv_a, inv_b = _cols(a), _cols(b)
+    assert np.abs(inv_a - inv_b).max() <= 1e-13 * np.abs(inv_b).max()     # ... and moved tracer only within columns
+    k1 = a.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    zw = a.f("zw")
+    mld = a.f("mld").reshape(J, I)
+    wet = k1 <= K
+    assert (mld[wet] <= 0.0).all() and (mld[wet] >= zw[k1[wet] - 1] - 1e-12).all()
+    assert (mld[~wet] == 0.0).all()
+    mldk = a.i("mldk").reshape(J, I)
+    assert ((mldk[wet] >= k1[wet]) & (mldk[wet] <= K)).all()
+    # the mixed layer is homogeneous above the level holding its base, for both tracers
+    ts = a.f("ts").reshape(K + 2, J + 2, I + 2, L)[1:K + 1, 1:J + 1, 1:I + 1, :]
+    emix = a.f("mldemix").reshape(J, I)
+    n_checked = 0
+    for j in range(J):
+        for i in range(I):
+            if wet[j, i] and emix[j, i] > 0 and mldk[j, i] < K - 1:
+                col = ts[mldk[j, i]:K, j, i, :]                           # levels mldk+1 .. K (0-based slice)
+                assert np.abs(col - col[-1]).max() == 0.0
+                n_checked += 1
+    assert n_checked > 20
+    assert before.shape == a.f("ts").shape
+
+
+def test_wind_energy_input_follows_the_stress():
+    o = Oracle("worbe2", maxk=K, maxl=L, nyear=100, imld=1)
+    o.run(5)
+    ke = o.f("mldketau").reshape(J, I)
+    tau = o.f("tau").reshape(J, I, 2)
+    assert (ke >= 0).all() and ke.max() > 0
+    for j in (0, 1, J - 2, J - 1):                                        # polar rows carry their zonal mean
+        assert np.ptp(ke[j]) == 0.0
+    j, i = 17, 9
+    tv4 = (tau[j, i, 0] + tau[j, i - 1, 0]) * 0.5
+    tv2 = (tau[j, i, 1] + tau[j - 1, i, 1]) * 0.5
+    r = np.sqrt(np.sqrt(tv4 * tv4 + tv2 * tv2))
+    assert ke[j, i] == 2.5 * (r * r * r)

@@ -19,6 +19,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--variant", default="fast")
 ap.add_argument("--config", default="eb_go_gs_ac_bg_36x36x16")
 ap.add_argument("--profile", action="store_true", help="print CUDA-event time per kernel family")
+ap.add_argument("--hash", action="store_true", help="print a sha256 of the final ts (knob variants that claim bit-identity must agree)")
 ap.add_argument("--perturb", action="store_true", help="the bench's parameter-perturbed ensemble instead of identical members")
 a = ap.parse_args()
 d = tempfile.mkdtemp()
@@ -47,4 +48,7 @@ if a.profile:
     fam = {f: e.profile_get(f) for f in ("tstepo_flux", "co", "momentum", "embm", "surflux", "seaice", "biogem")}
     print("cfg=%s variant=%s M=%d us/step: " % (os.environ.get("CG_TRACER_CFG", "0"), a.variant, a.members) +
           " ".join("%s=%.1f" % (k, 1e3 * v[0] / a.steps) for k, v in fam.items()))
+if a.hash:
+    import hashlib
+    print("ts sha256", hashlib.sha256(np.ascontiguousarray(e.get_all("ts")).tobytes()).hexdigest()[:16])
 print("done", e.launch_count())
