@@ -60,12 +60,15 @@ SYMBOLS = {
     "cg_exchange_begin_download": (C.c_int, [P, C.c_char_p, C.c_int, C.c_void_p, C.c_int64]),
     "cg_exchange_wait": (C.c_int, [P]),
     "cg_biogem_sig_update": (C.c_int, [P, C.c_double, C.c_double]),
+    "cg_biogem_sig_extended": (C.c_int, [P]),
     "cg_biogem_slice_update": (C.c_int, [P, C.c_double]),
     "cg_biogem_slice_reset": (C.c_int, [P]),
     "cg_biogem_sig_reset": (C.c_int, [P]),
     "cg_series_last_error": (C.c_char_p, []),
     "cg_biogem_series_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_int, STRS, I32, I32, C.c_int, STRS, I32, I32,
                                           D, C.c_int]),
+    "cg_biogem_series_write_ext": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, STRS, I32, I32, C.c_int,
+                                             STRS, I32, I32, D, D, C.c_double, C.c_double, C.c_int]),
     "cg_set_koverall": (C.c_int, [P, C.c_int64]),
     "cg_refresh_rho": (C.c_int, [P, C.c_int]),
     "cg_atchem_step": (C.c_int, [P, C.c_double]),

@@ -63,6 +63,8 @@ int launch_bg_part_scale(const Dev &, const BgDev &, cudaStream_t);
 int launch_tc_apply_only(const Dev &, cudaStream_t);
 bool bg_layout_ok(const BgDev &, int L);
 int launch_bg_climate(const Dev &, const BgDev &, cudaStream_t);
+int launch_bg_sig2_stage(const Dev &, const SigDev &, const double *dz, const double *cv, double dphi, cudaStream_t);
+int launch_bg_sig2(const Dev &, const BgDev &, const SigDev &, double dtyr, cudaStream_t);
 int launch_bg_stage_seaice(const Dev &, const BgDev &, cudaStream_t);
 int launch_bg_atchem(const Dev &, const BgDev &, double atm_totV, cudaStream_t);
 void launch_health(const Dev &, int *flags, cudaStream_t);
@@ -210,6 +212,7 @@ struct cg_handle {
   SigDev sig{};                       // BIOGEM time-series integrals
   SliceDev slice{};                   // BIOGEM time-slice diagnostics (integrals allocated on first use)
   double sig_ben_Dmin = -1.0;
+  double *sig2_dz = nullptr, *sig2_cv = nullptr;   // device copies of dz(0:maxk), cv(0:maxj) for the overturning stream function
   double *sig_w_ben = nullptr;
   double *sfxsumsed = nullptr, *sfcsumocn = nullptr, *sfxsumrok1 = nullptr;   // SEDGEM / ROKGEM interface sums, [ls|l][j][i][m]
   ~cg_handle() {
@@ -881,6 +884,12 @@ static int build_device(cg_handle *h) {
         }
       for (int j = 1; j <= J; j++)          // SUM(phys_ocnatm(ipoa_A,:,:)) in array element order
         for (int i = 1; i <= I; i++) totA = totA + Aall[cell2(I, i, j)];
+      {
+        double totAo = 0.0;                 // SUM(phys_ocn(ipo_A,:,:,n_k)): the ocean cells (loc_ocn_tot_A, biogem_data_ascii.f90:695)
+        for (int j = 1; j <= J; j++)
+          for (int i = 1; i <= I; i++) if (g.k1at(i, j) <= K) totAo = totAo + Aall[cell2(I, i, j)]; else totAo = totAo + 0.0;
+        h->hconst["bg_ocn_tot_A"] = std::vector<double>(1, totAo);
+      }
       const int nq = kSigHead + 3 * L + LA;
       int *qi; double *qd;
       TRY(dupload(h, &qi, kb)); h->sig.kbot = qi;
@@ -1943,13 +1952,61 @@ extern "C" int cg_biogem_sig_update(cg_handle *h, double dts, double ben_Dmin) {
     h->sig.rtot_A_ben = tot > kBgNullSmall ? 1.0 / tot : 0.0;
     h->sig_ben_Dmin = ben_Dmin;
   }
+  // extended integrals: what they take from the physics (velocities, sea-ice thickness) is read NOW, on the caller's stream -- the
+  // next cycle's momentum and sea-ice steps may run before the BIOGEM stream gets to the sums.  (The previous call's sums have
+  // finished: the caller's stream has joined the BIOGEM stream at least once per ocean step since.)
+  if (h->sig.acc2) h->launches += launch_bg_sig2_stage(h->dv, h->sig, h->sig2_dz, h->sig2_cv, h->g.dphi, h->stream);
   // everything the sums read is BIOGEM's own state (ocn, cell masses, the sea-ice snapshot, sfcatm1 incl. the air temperature
   // and humidity rows cpl_comp_EMBM filled at the last block): they run on the BIOGEM stream
   BgAsyncScope as(h, true);
   IO(side_wait(h));
   ProfScope ps(h, "biogem");
-  ps.done(launch_bg_sig(h->dv, h->bgd, h->sig, dts / kBgYrS, h->stream));
+  int n = launch_bg_sig(h->dv, h->bgd, h->sig, dts / kBgYrS, h->stream);
+  if (h->sig.acc2) n += launch_bg_sig2(h->dv, h->bgd, h->sig, dts / kBgYrS, h->stream);
+  ps.done(n);
   return check_async(h);
+}
+// The flux, export and "misc" integrals of diag_biogem_timeseries on the device as well (field "bg_sig2", layout in
+// include/cgenie_b200.h): from this call on step_biogem keeps sfxatm1 and the export through the base of the surface layer, and
+// cg_biogem_sig_update also accumulates int_misc_seaice_sig / _th / _vol (biogem.f90:2926-2937), the extrema of the overturning
+// stream functions (:2938-2945), int_misc_SLT_sig (:2946-2964), int_fexport_sig (:2870-2876), int_focnatm_sig (:2877-2883) and
+// int_diag_airsea_sig (:3058-3062).  Call it before the first BIOGEM step whose window integrals are wanted.
+extern "C" int cg_biogem_sig_extended(cg_handle *h) {
+  CG_RANGE();
+  BGREADY(h);
+  if (h->sig.acc2) return CG_OK;
+  const Grid &g = h->g;
+  const int I = g.I, J = g.J, K = g.K, LS = h->bg.LS, LA = h->bg.LA, MS = h->MS;
+  const size_t ij = (size_t)I * J;
+  IO(join_side(h));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->spec_valid = false;          // a surface part issued ahead would not have kept its sfxatm1
+  const int nq = kSig2Head + LS + 2 * LA;
+  IO0(dalloc(h, &h->bgd.sfxatm1, (size_t)LA * ij * MS));
+  IO0(dalloc(h, &h->bgd.settle_sur, ij * LS * MS));
+  IO0(dalloc(h, &h->sig.raw2, (size_t)(4 + LS + 2 * LA) * MS));
+  IO0(dalloc(h, &h->sig.opsi_stage, (size_t)4 * MS));
+  IO0(dalloc(h, &h->sig.th_stage, ij * MS));
+  std::vector<int> ias(g.ias.begin(), g.ias.end()), iaf(g.iaf.begin(), g.iaf.end());
+  ias.resize(J + 2, 1); iaf.resize(J + 2, 0);
+  int *qi;
+  IO0(dupload(h, &qi, ias)); h->sig.ias = qi;
+  IO0(dupload(h, &qi, iaf)); h->sig.iaf = qi;
+  std::vector<double> dz(g.dz.begin(), g.dz.begin() + K + 1), cv(g.cv.begin(), g.cv.begin() + J + 1);
+  IO0(dupload(h, &h->sig2_dz, dz));
+  IO0(dupload(h, &h->sig2_cv, cv));
+  h->sig.jsf = g.jsf; h->sig.LS = LS;
+  double land = 0.0;   // loc_tot_A of :2950-2958: i outer, j inner
+  for (int i = 1; i <= I; i++)
+    for (int j = 1; j <= J; j++)
+      if (K < g.k1at(i, j)) land = land + 2.0 * kBgPi * (kBgREarth * kBgREarth) * (1.0 / I) * (g.sv[j] - g.sv[j - 1]);
+  h->sig.land_A = land;
+  double *acc2;
+  IO0(dalloc(h, &acc2, (size_t)nq * MS));
+  reg_field(h, "bg_sig2", acc2, {nq}, {1});
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->sig.acc2 = acc2;
+  return CG_OK;
 }
 // diag_biogem_timeslice (biogem.f90:2421-2699), its arithmetic: the 3-D carbonate re-solve (:2478-2567) and the growth of the
 // window integrals int_ocn / int_bio_part / int_carb / int_carbconst / int_carbisor / int_t _timeslice (:2572-2579) on the
@@ -2009,6 +2066,7 @@ extern "C" int cg_biogem_sig_reset(cg_handle *h) {
   BgAsyncScope as(h, true);
   IO(side_wait(h));
   CUDA_OK(cudaMemsetAsync(h->sig.acc, 0, (size_t)(kSigHead + 3 * h->g.L + h->bg.LA) * h->dv.MS * sizeof(double), h->stream));
+  if (h->sig.acc2) CUDA_OK(cudaMemsetAsync(h->sig.acc2, 0, (size_t)(kSig2Head + h->bg.LS + 2 * h->bg.LA) * h->dv.MS * sizeof(double), h->stream));
   return CG_OK;
 }
 // cpl_flux_ocnsed(dts, ...), sedgem.f90:1029-1068: sfxsumsed = sfxsumsed + dts * sfxsed1 (sediment grid = ocean grid)

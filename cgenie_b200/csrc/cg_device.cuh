@@ -183,6 +183,9 @@ struct BgDev {
   double *atm, *sfcatm1, *sfxsumatm;      // [la][j][i][m]
   const double *atm_A, *atm_V;            // [j][i]
   double *sfcocn1, *sfxsed1, *focnatm;    // interface / diagnostics: [l|ls|la][j][i][m]
+  double *sfxatm1;                        // [la][j][i][m] sfxatm1 as step_biogem leaves it (biogem.f90:1731-1734); NULL unless the extended
+                                          // time-series integrals are on (cg_biogem_sig_extended)
+  double *settle_sur;                     // [j][i][ls][m] bio_settle(:,i,j,n_k) of this step (k_bg_settle_sur); NULL likewise
   int *err;                               // [m] carbonate chemistry failure flag (error_stop)
   // packets / cells split of the sweep (k_bg_step PART 3 -> k_bg_cell): remineralisation products of the sinking particles per
   // cell, sediment return per column, wet-column index of a column, pending rescaling of bio_part (see k_bg_cell)
@@ -210,5 +213,15 @@ struct SigDev {
   double *raw, *acc;                      // [q][m] sums of this step; integrals of the window
   double rtot_A_ben, rtot_A_atm;          // 1 / SUM(mask_ben * A), 1 / SUM(phys_ocnatm(ipoa_A))
   int LA;
+  // extended integrals ("bg_sig2": sea ice, overturning, land temperature, export, air-sea fluxes), on when acc2 != NULL
+  double *raw2, *acc2;                    // [q][m]
+  double *opsi_stage;                     // [4][m] min / max of the global and the Atlantic overturning stream function at call time
+  double *th_stage;                       // [j][i][m] sea-ice thickness at call time
+  const int *ias, *iaf;                   // [J + 2] Atlantic columns per row
+  int jsf, LS;
+  double land_A;                          // SUM(phys_ocnatm(ipoa_A)) over the land cells
 };
+// layout of "bg_sig2": 0 seaice area, 1 mean thickness, 2 volume, 3 / 4 opsi min / max, 5 / 6 opsia min / max, 7 land air temperature,
+// 8 + ls fexport, 8 + LS + la focnatm, 8 + LS + LA + la air-sea gas exchange (la >= 2, 0-based: the gases)
+constexpr int kSig2Head = 8;
 }  // namespace cg

@@ -157,3 +157,133 @@ extern "C" int cg_biogem_series_write(const char *outdir, const char *outfile_na
   }
   return CG_OK;
 }
+
+namespace {
+// fun_calc_isotope_delta with dum_allow_negative = .TRUE. (fluxes: a negative total is a flux out), gem_util.f90:568-598
+double iso_delta_signed(double tot, double iso, double standard) {
+  if (std::fabs(tot) > kNullSmall) {
+    const double f = iso / tot;
+    if ((1.0 - f) > kNullSmall) {
+      const double R = f / (1.0 - f);
+      return 1000.0 * (R / standard - 1.0);
+    }
+  }
+  return kNullIso;
+}
+// fun_convert_delta14CtoD14C, gem_util.f90:623-637 (Stuiver and Polach 1977)
+double delta14C_to_D14C(double d13C, double d14C) {
+  return 1000.0 * ((1.0 + d14C / 1000.0) * (0.975 * 0.975) / ((1.0 + d13C / 1000.0) * (1.0 + d13C / 1000.0)) - 1.0);
+}
+}  // namespace
+
+// The fexport_*, fseaair_*, focnatm_* and misc_seaice / misc_opsi / misc_atm_D14C / misc_SLT series of sub_init_data_save_runtime
+// (biogem_data_ascii.f90:107-197, 320-400) and sub_data_save_runtime (:955-1096, 1245-1340), from the integrals "bg_sig" (int_t_sig,
+// the atmosphere rows) and "bg_sig2" (cg_biogem_sig_extended).  sed_type: 1 bio ... 7 scavenged (flux + density), 8 age,
+// 11 / 12 isotopes, 9 (frac2) writes nothing; ocn_tot_A = SUM(phys_ocn(ipo_A,:,:,n_k)); opsi_scale = goldstein_dsc * goldstein_usc *
+// const_rEarth * 1.0E-6; atlantic != 0 for the topographies whose file carries the Atlantic columns (worbe2, worjh2 ...: :1282-1293).
+extern "C" int cg_biogem_series_write_ext(const char *outdir, const char *outfile_name, int create, double t_yr, int n_ocn, int n_sed,
+                                          const char *const *sed_names, const int32_t *sed_type, const int32_t *sed_dep, int n_atm,
+                                          const char *const *atm_names, const int32_t *atm_type, const int32_t *atm_dep,
+                                          const double *sig, const double *sig2, double ocn_tot_A, double opsi_scale, int atlantic) {
+  if (!outdir || !outfile_name || n_sed < 0 || n_atm < 0 || n_ocn < 0 || (n_sed && (!sed_names || !sed_type || !sed_dep)) ||
+      (n_atm && (!atm_names || !atm_type || !atm_dep)) || (!create && (!sig || !sig2)))
+    return sfail("cg_biogem_series_write_ext: bad argument");
+  std::string base = outdir;
+  if (!base.empty() && base.back() != '/') base += '/';
+  base += std::string(outfile_name) + "_series_";
+  const double t_sig = (sig && !create) ? sig[0] : 1.0;
+  if (!create && !(t_sig > kNullSmall)) return CG_OK;
+  const double *S_atm = sig ? sig + 3 + 3 * n_ocn : nullptr;
+  const double *X = sig2, *F_exp = sig2 ? sig2 + 8 : nullptr, *F_oa = sig2 ? sig2 + 8 + n_sed : nullptr,
+               *F_as = sig2 ? sig2 + 8 + n_sed + n_atm : nullptr;
+  // ---- fexport
+  for (int l = 0; l < n_sed; l++) {
+    const std::string n = sed_names[l], path = base + "fexport_" + n + ".res";
+    const int ty = sed_type[l];
+    const bool bulk = ty >= 1 && ty <= 7, age = ty == 8, iso = ty >= 11 && ty <= 20;
+    if (!(bulk || age || iso)) continue;
+    if (create) {
+      std::string h;
+      if (bulk) h = "% time (yr) / global " + n + " flux (mol yr-1) / global " + n + " density (mol m-2 yr-1)";
+      else if (age) h = "% time (yr) / CaCO3 age (yr)";
+      else h = "% time (yr) / global " + n + " flux (mol yr-1) / global " + n + " delta (o/oo)";
+      if (int rc = put_line(path, "w", " " + h)) return rc;
+      continue;
+    }
+    std::string line = fmt_f(t_yr, 12, 3);
+    if (bulk) {
+      const double v = F_exp[l] / t_sig;
+      line += fmt_e(v, 15, 7) + fmt_e(v / ocn_tot_A, 15, 7);
+    } else if (age) {
+      const int d = sed_dep[l];
+      line += fmt_e((d >= 0 && d < n_sed && F_exp[d] > kNullSmall) ? F_exp[l] / t_sig : 0.0, 15, 7);
+    } else {
+      const int d = sed_dep[l];
+      if (d < 0 || d >= n_sed) return sfail("cg_biogem_series_write_ext: isotope without its bulk tracer");
+      const double frac = F_exp[l] / t_sig;
+      line += fmt_e(frac, 15, 7) + fmt_f(iso_delta(F_exp[d] / t_sig, frac, ty == 11 ? kStd13C : kStd14C), 14, 3);
+    }
+    if (int rc = put_line(path, "a", line)) return rc;
+  }
+  // ---- fseaair (int_diag_airsea_sig) and focnatm, the gases only (l = 3 .. n_l_atm)
+  for (int pass = 0; pass < 2; pass++) {
+    const double *F = pass == 0 ? F_as : F_oa;
+    for (int l = 2; l < n_atm; l++) {
+      const std::string n = atm_names[l], path = base + (pass == 0 ? "fseaair_" : "focnatm_") + n + ".res";
+      const int ty = atm_type[l];
+      const bool bulk = ty == 1, iso = ty >= 11 && ty <= 20;
+      if (!(bulk || iso)) continue;
+      if (create) {
+        std::string h;
+        if (pass == 0) {
+          if (bulk) h = "% time (yr) / global " + n + " sea->air transfer flux (mol yr-1) / global " + n + " density (mol m-2 yr-1)";
+          else h = "% time (yr) / global " + n + " sea->air transfer flux (mol yr-1) / global " + n + " (o/oo)";
+        } else {
+          if (bulk) h = "% time (yr) / global " + n + " flux (mol yr-1) / global " + n + " density (mol m-2 yr-1) ";
+          else h = "% time (yr) / global " + n + " flux (mol yr-1) / global " + n + " (o/oo)";
+          h += " NOTE: is the atmospheric forcing flux *net* of the sea-air gas exchange flux.";
+        }
+        if (int rc = put_line(path, "w", " " + h)) return rc;
+        continue;
+      }
+      std::string line = fmt_f(t_yr, 12, 3);
+      if (bulk) {
+        const double v = F[l] / t_sig;
+        line += fmt_e(v, 15, 7) + fmt_f(v / ocn_tot_A, 12, 3);
+      } else {
+        const int d = atm_dep[l];
+        if (d < 0 || d >= n_atm) return sfail("cg_biogem_series_write_ext: isotope without its bulk tracer");
+        const double frac = F[l] / t_sig;
+        line += fmt_e(frac, 15, 7) + fmt_f(iso_delta_signed(F[d] / t_sig, frac, ty == 11 ? kStd13C : kStd14C), 14, 3);
+      }
+      if (int rc = put_line(path, "a", line)) return rc;
+    }
+  }
+  // ---- misc
+  int l13 = -1, l14 = -1;
+  for (int l = 0; l < n_atm; l++) { if (atm_type[l] == 11 && l13 < 0) l13 = l; if (atm_type[l] == 12 && l14 < 0) l14 = l; }
+  if (create) {
+    if (int rc = put_line(base + "misc_seaice.res", "w", " % time (yr) / global sea-ice area (m2) / mean sea-ice cover (%) / global sea-ice volume (m3) / mean sea-ice thickness (m)")) return rc;
+    if (int rc = put_line(base + "misc_opsi.res", "w", atlantic ? " % time (yr) / global min overturning (Sv) / global max overturning (Sv) / Atlantic min overturning (Sv) / Atlantic max overturning (Sv)"
+                                                                 : " % time (yr) / global min overturning (Sv) / global max overturning (Sv)")) return rc;
+    if (l14 >= 0) if (int rc = put_line(base + "misc_atm_D14C.res", "w", " % time (yr) / mean isotopic composition (o/oo)")) return rc;
+    if (int rc = put_line(base + "misc_SLT.res", "w", " % time (yr) / mean (land) surface air temperature (degrees C)")) return rc;
+    return CG_OK;
+  }
+  {
+    std::string line = fmt_f(t_yr, 12, 3) + fmt_e(X[0] / t_sig, 12, 4) + fmt_f(100.0 * (1.0 / ocn_tot_A) * X[0] / t_sig, 9, 3) +
+                       fmt_e(X[2] / t_sig, 12, 4) + fmt_f(X[1] / t_sig, 9, 3);
+    if (int rc = put_line(base + "misc_seaice.res", "a", line)) return rc;
+    line = fmt_f(t_yr, 12, 3) + fmt_f(opsi_scale * X[3] / t_sig, 9, 3) + fmt_f(opsi_scale * X[4] / t_sig, 9, 3);
+    if (atlantic) line += fmt_f(opsi_scale * X[5] / t_sig, 9, 3) + fmt_f(opsi_scale * X[6] / t_sig, 9, 3);
+    if (int rc = put_line(base + "misc_opsi.res", "a", line)) return rc;
+    if (l14 >= 0 && l13 >= 0) {
+      const int d = atm_dep[l14];
+      const double tot = S_atm[d] / t_sig;
+      const double d13 = iso_delta(tot, S_atm[l13] / t_sig, kStd13C), d14 = iso_delta(tot, S_atm[l14] / t_sig, kStd14C);
+      if (int rc = put_line(base + "misc_atm_D14C.res", "a", fmt_f(t_yr, 12, 3) + fmt_f(delta14C_to_D14C(d13, d14), 12, 3))) return rc;
+    }
+    if (int rc = put_line(base + "misc_SLT.res", "a", fmt_f(t_yr, 12, 3) + fmt_f(X[7] / t_sig, 12, 6))) return rc;
+  }
+  return CG_OK;
+}

@@ -758,6 +758,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
       } else {
         b.focnatm[qa] = focnatm[la];
         b.sfxsumatm[qa] = b.sfxsumatm[qa] + b.dts * sfx;
+        if (b.sfxatm1) b.sfxatm1[qa] = sfx;
       }
     }
   }
@@ -832,6 +833,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
       b.focnatm[qa] = SC_(kBgSurfH + 1 + (la - 3));
       const double sfx = SC_(kBgSurfH + 1 + (LA - 2) + (la - 3));
       b.sfxsumatm[qa] = b.sfxsumatm[qa] + b.dts * sfx;
+      if (b.sfxatm1) b.sfxatm1[qa] = sfx;
     }
 #pragma unroll
     for (int la = 1; la <= LA; la++) focn_surf[la] = (la >= 3) ? SC_(la - 3) : 0.0;
@@ -1353,7 +1355,9 @@ __global__ void __launch_bounds__(256) k_bg_atchem3(const Dev v, const BgDev b, 
 }
 
 static bool bg_fix_shape(const Dev &v) { return v.I == 36 && v.J == 36 && v.K == 16 && fix_ms(v.MS) && !getenv("CG_BG_NOFIX"); }
+int launch_bg_settle_sur(const Dev &, const BgDev &, int pend, cudaStream_t);   // extended time-series integrals: export through the surface layer's base
 int launch_bg_step(const Dev &v, const BgDev &b, int init_only, int fuse, cudaStream_t s) {
+  const int nx = init_only ? 0 : launch_bg_settle_sur(v, b, 0, s);
   // registers per thread 255 / 168 / 128 for MINB = 2 / 3 / 4 (CG_BG_MINB overrides; tuning knob)
   static int minb = -1;
   if (minb < 0) { const char *e = getenv("CG_BG_MINB"); minb = e ? atoi(e) : 2; }
@@ -1364,7 +1368,7 @@ int launch_bg_step(const Dev &v, const BgDev &b, int init_only, int fuse, cudaSt
   if (minb == 4) k_bg_step<4, 0, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
   else if (minb == 3) k_bg_step<3, 0, 0><<<g, bl, 0, s>>>(v, b, init_only, fuse);
   else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<2, 0, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, init_only, fuse); });
-  return 1;
+  return 1 + nx;
 }
 // the two parts of the step (see k_bg_step): surface cell, then sediment return + water-column sweep
 int launch_bg_surf(const Dev &v, const BgDev &b, cudaStream_t s) {
@@ -1383,10 +1387,11 @@ int launch_bg_packets(const Dev &v, const BgDev &b, int pend, cudaStream_t s) {
   if (minb < 0) { const char *e = getenv("CG_BG_PK_MINB"); minb = e ? atoi(e) : 3; }
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
   const int mode = nopf | (pend ? 4 : 0);
+  const int nx = launch_bg_settle_sur(v, b, pend, s);
   if (minb == 2) fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<2, 3, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, mode); });
   else if (minb == 4) fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<4, 3, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, mode); });
   else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<3, 3, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, mode); });
-  return 1;
+  return 1 + nx;
 }
 int launch_bg_cell(const Dev &v, const BgDev &b, cudaStream_t s) {
   const int ncell = v.I * v.J * v.K;
@@ -1411,9 +1416,10 @@ int launch_bg_sweep(const Dev &v, const BgDev &b, cudaStream_t s, int fuse) {
   static int nopf = -1;
   if (nopf < 0) nopf = getenv("CG_BG_NOPF") ? 2 : 0;
   const dim3 g(v.MS / 32, (v.nwet + 3) / 4), bl(32, 4);
+  const int nx = launch_bg_settle_sur(v, b, 0, s);
   if (minb == 3) k_bg_step<3, 2, 0><<<g, bl, 0, s>>>(v, b, 0, nopf | (fuse ? 1 : 0));
   else fix_dispatch(bg_fix_shape(v), v.MS, [&](auto ms) { k_bg_step<2, 2, decltype(ms)::value><<<g, bl, 0, s>>>(v, b, 0, nopf | (fuse ? 1 : 0)); });
-  return 1;
+  return 1 + nx;
 }
 // step (1) of biogem_tracercoupling taken BEFORE step_biogem (fused coupling, see k_bg_step)
 int launch_tc_sums_first(const Dev &v, cudaStream_t s) {
@@ -1703,6 +1709,140 @@ int launch_bg_slice(const Dev &v, const BgDev &b, const SliceDev &sl, double dty
   if (sl.nwet3 <= 0) return 0;
   k_bg_slice<<<dim3(v.MS / 32, (sl.nwet3 + 3) / 4), dim3(32, 4), 0, s>>>(v, b, sl, dtyr, init);
   return 1;
+}
+
+// ---- extended time-series integrals ("bg_sig2"; diag_biogem_timeseries, biogem.f90:2870-2883, 2926-2964, 3058-3062) -------------
+// bio_settle(:,i,j,n_k) of the sweep that follows on the same stream: the surface layer is a source only, so what settles through
+// its base is the layer's particulate field as the sweep reads it (rescaling of the last coupling applied if still pending, 14C
+// decayed: sub_box_remin_part, biogem_box.f90:2412-2875, k = n_k; the frac2 arrays pass unweighted, the rest times the cell mass)
+__global__ void __launch_bounds__(128) k_bg_settle_sur(const Dev v, const BgDev b, const int pend) {
+  using namespace lay;
+  const int I = v.I, J = v.J, K = v.K, MS = v.MS;
+  constexpr int LS = NLS;
+  const int m = blockIdx.x * 32 + threadIdx.x;
+  const int n = blockIdx.y * blockDim.y + threadIdx.y;
+  if (n >= v.nwet) return;
+  const int c2d = v.bgcols[n];
+  const size_t c = (size_t)(K - 1) * I * J + c2d;
+  double old[LS + 1];
+#pragma unroll
+  for (int ls = 1; ls <= LS; ls++) old[ls] = b.bio_part[(c * LS + (ls - 1)) * MS + m];
+  if (pend) {
+    const double pscale = b.pscale[m];
+#pragma unroll
+    for (int ls = 1; ls <= LS; ls++) old[ls] = pscale * (old[ls] + 0.0);
+  }
+  if (fabs(b.lam_sed[POC14]) > bgk::kNS) { old[POC14] = b.fd_sed[POC14] * old[POC14]; old[CACO314] = b.fd_sed[POC14] * old[CACO314]; }
+  double part_tot = 0.0;
+  part_tot = part_tot + old[POC];
+  part_tot = part_tot + old[CACO3];
+  const double Mk = v.bg_M[c * MS + m];
+#pragma unroll
+  for (int ls = 1; ls <= LS; ls++)
+    b.settle_sur[((size_t)c2d * LS + (ls - 1)) * MS + m] = (part_tot > bgk::kNS) ? ((ls >= POCF2) ? old[ls] : Mk * old[ls]) : 0.0;
+}
+int launch_bg_settle_sur(const Dev &v, const BgDev &b, int pend, cudaStream_t s) {
+  if (!b.settle_sur) return 0;
+  k_bg_settle_sur<<<dim3(v.MS / 32, (v.nwet + 3) / 4), dim3(32, 4), 0, s>>>(v, b, pend);
+  return 1;
+}
+// On the CALLER's stream, at the time diag_biogem_timeseries is called: sea-ice thickness (phys_ocnatm(ipoa_seaice_th) =
+// hght_sic of this koverall iteration) and the extrema of the overturning stream functions (sub_calc_psi, biogem_box.f90:3796-3852,
+// from the velocities biogem_climate copied) -- the next cycle's sea-ice and momentum steps may overwrite both before the BIOGEM
+// stream gets to the sums.  Block = 32 members x 32 rows j; each thread integrates its rows upward in the reference's order.
+__global__ void __launch_bounds__(1024) k_bg_sig2_stage(const Dev v, const SigDev g, const double *__restrict__ dz, const double *__restrict__ cv,
+                                                        const double dphi) {
+  __shared__ double red[4][32][33];
+  const int I = v.I, J = v.J, K = v.K, MS = v.MS;
+  const int lane = threadIdx.x, row = threadIdx.y;
+  const int m = blockIdx.x * 32 + lane;
+  double omin = 0.0, omax = 0.0, omina = 0.0, omaxa = 0.0;
+  for (int j = 1 + row; j <= J - 1; j += 32) {
+    double opsi = 0.0, opsia = 0.0;
+    const bool atl = j >= g.jsf + 1;
+    const int ia0 = g.ias[j], ia1 = g.iaf[j];
+    for (int k = 1; k <= K - 1; k++) {
+      double ou = 0.0, oua = 0.0;
+      const double *u2 = v.u + ((cell3(I, J, 1, j, k) * 3 + 1) * (size_t)MS + m);
+      for (int i = 1; i <= I; i++) {
+        const double t = cv[j] * u2[(size_t)(i - 1) * 3 * MS] * dphi;
+        ou = ou + t;
+        if (atl && i >= ia0 && i <= ia1) oua = oua + t;
+      }
+      opsi = opsi - dz[k] * ou;
+      omin = fmin(omin, opsi); omax = fmax(omax, opsi);
+      if (atl) {
+        opsia = opsia - dz[k] * oua;
+        if (k <= K / 2) { omina = fmin(omina, opsia); omaxa = fmax(omaxa, opsia); }
+      }
+    }
+  }
+  red[0][row][lane] = omin; red[1][row][lane] = omax; red[2][row][lane] = omina; red[3][row][lane] = omaxa;
+  __syncthreads();
+  if (row < 4) {
+    double r = red[row][0][lane];
+    for (int q = 1; q < 32; q++) r = (row & 1) ? fmax(r, red[row][q][lane]) : fmin(r, red[row][q][lane]);
+    g.opsi_stage[(size_t)row * MS + m] = r;
+  }
+  // sea-ice thickness: varice(1,:,:)
+  const size_t n = (size_t)I * J * MS;
+  for (size_t q = (size_t)blockIdx.x * 1024 + row * 32 + lane; q < n; q += (size_t)gridDim.x * 1024) g.th_stage[q] = v.varice[q];
+}
+// sums of one step: block = (32-member tile, quantity), 8 warps stride over the cells (partial sums added in warp order)
+//   0 SUM(A*seaice)  1 SUM(seaice)  2 SUM(th*A*seaice)  3 SUM over land of A*sfcatm1(T)
+//   4 + ls  SUM(bio_settle(ls,:,:,n_k))   4 + LS + la  SUM(conv_yr_s*A*sfxatm1(la)) over the ocean   4 + LS + LA + la  SUM(focnatm(la))
+__global__ void __launch_bounds__(256) k_bg_sig2_sums(const Dev v, const BgDev b, const SigDev g) {
+  __shared__ double part[8][32];
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int I = v.I, J = v.J, K = v.K, MS = v.MS, ij = I * J, LS = g.LS, LA = g.LA;
+  const int m = blockIdx.x * 32 + lane, q = blockIdx.y;
+  double s = 0.0;
+  for (int c2 = warp; c2 < ij; c2 += 8) {
+    const bool wet = g.kbot[c2] < K;
+    const size_t c = (size_t)c2 * MS + m;
+    if (q == 0) { if (wet) s = s + g.A[c2] * b.seaice[c]; }
+    else if (q == 1) s = s + b.seaice[c];
+    else if (q == 2) { if (wet) s = s + g.th_stage[c] * g.A[c2] * b.seaice[c]; }
+    else if (q == 3) { if (!wet) s = s + g.A[c2] * b.sfcatm1[c]; }
+    else if (q < 4 + LS) { if (wet) s = s + b.settle_sur[((size_t)c2 * LS + (q - 4)) * MS + m]; }
+    else if (q < 4 + LS + LA) { if (wet) s = s + bgk::kYrS * g.A[c2] * b.sfxatm1[((size_t)(q - 4 - LS) * ij + c2) * MS + m]; }
+    else { if (wet) s = s + b.focnatm[((size_t)(q - 4 - LS - LA) * ij + c2) * MS + m]; }
+  }
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double t = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; w++) t = t + part[w][lane];
+    g.raw2[(size_t)q * MS + m] = t;
+  }
+}
+__global__ void k_bg_sig2_acc(const Dev v, const SigDev g, const double dtyr) {
+  const int MS = v.MS, LS = g.LS, LA = g.LA;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= MS) return;
+  const double *r = g.raw2 + m;
+  double *a = g.acc2 + m;
+  a[0] = a[0] + dtyr * r[0];                                                          // int_misc_seaice_sig
+  if (r[(size_t)MS] > kBgNullSmall) a[(size_t)MS] = a[(size_t)MS] + dtyr * r[(size_t)2 * MS] / r[0];   // ..._th
+  a[(size_t)2 * MS] = a[(size_t)2 * MS] + dtyr * r[(size_t)2 * MS];                  // ..._vol
+  for (int q = 0; q < 4; q++) a[(size_t)(3 + q) * MS] = a[(size_t)(3 + q) * MS] + dtyr * g.opsi_stage[(size_t)q * MS + m];
+  if (g.land_A > kBgNullSmall) a[(size_t)7 * MS] = a[(size_t)7 * MS] + dtyr * r[(size_t)3 * MS] / g.land_A; else a[(size_t)7 * MS] = 0.0;
+  for (int ls = 0; ls < LS; ls++) a[(size_t)(kSig2Head + ls) * MS] = a[(size_t)(kSig2Head + ls) * MS] + r[(size_t)(4 + ls) * MS];
+  for (int la = 2; la < LA; la++) {
+    const size_t qa = (size_t)(kSig2Head + LS + la) * MS, qd = (size_t)(kSig2Head + LS + LA + la) * MS;
+    a[qa] = a[qa] + dtyr * r[(size_t)(4 + LS + la) * MS];
+    a[qd] = a[qd] + dtyr * r[(size_t)(4 + LS + LA + la) * MS];
+  }
+}
+int launch_bg_sig2_stage(const Dev &v, const SigDev &g, const double *dz, const double *cv, double dphi, cudaStream_t s) {
+  k_bg_sig2_stage<<<v.MS / 32, dim3(32, 32), 0, s>>>(v, g, dz, cv, dphi);
+  return 1;
+}
+int launch_bg_sig2(const Dev &v, const BgDev &b, const SigDev &g, double dtyr, cudaStream_t s) {
+  k_bg_sig2_sums<<<dim3(v.MS / 32, 4 + g.LS + 2 * g.LA), dim3(32, 8), 0, s>>>(v, b, g);
+  k_bg_sig2_acc<<<(v.MS + 127) / 128, 128, 0, s>>>(v, g, dtyr);
+  return 2;
 }
 
 int launch_bg_sig(const Dev &v, const BgDev &b, const SigDev &g, double dtyr, cudaStream_t s) {

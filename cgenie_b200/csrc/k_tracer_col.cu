@@ -153,6 +153,13 @@ __global__ void __launch_bounds__(32, MINB) k_co_col1(const Dev v) {
   co_column<I, J, K, L, MS>(v, c_g, v.rowcols[blockIdx.y], blockIdx.x * 32 + threadIdx.x, nullptr, 1);
 }
 
+// ... and its decisions alone (the region maps go to comask for k_co_passive): without the averaging code the kernel needs fewer
+// registers and its warps retire sooner
+template <int I, int J, int K, int L, int MS, int MINB>
+__global__ void __launch_bounds__(32, MINB) k_co_dec1(const Dev v) {
+  co_column<I, J, K, L, MS, true>(v, c_g, v.rowcols[blockIdx.y], blockIdx.x * 32 + threadIdx.x, nullptr, 1);
+}
+
 // Block-cooperative form of the convective adjustment: one block = 32 members (lanes) of ONE wet column.  Warp 0 takes the
 // decisions for its flagged lanes (T, S, rho of the column, serial per lane: latency bound) and leaves the region maps in shared
 // memory; then every warp averages one pair of passive tracers over the mixed regions, so that the loads of all seven pairs are
@@ -397,6 +404,13 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
   if (cov < 0) { const char *e = getenv("CG_CO_V"); cov = e ? atoi(e) : 1; }
   if (copair < 0) { const char *e = getenv("CG_CO_PAIR"); copair = e ? atoi(e) : 1; }
   v2.co_pairwise = copair;
+  if ((cov == 4 || cov == 5) && v2.co_skip_stable && v.comask && L > 2) {
+    // the same split with the decisions kernel compiled on its own (CG_CO_V=4: 20 blocks per SM, 5: 24)
+    if (cov == 4) k_co_dec1<I, J, K, L, MS, 20><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
+    else k_co_dec1<I, J, K, L, MS, 24><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
+    k_co_passive<I, J, K, L, MS><<<dim3(MS / 32, v.nwet), dim3(32, L - 2), 0, s>>>(v2);
+    return 3;
+  }
   if (cov == 3 && v2.co_skip_stable && v.comask && L > 2) {
     // decisions (thread = member x column), then the passive tracers with one thread per (member, column, tracer)
     v2.co_pairwise = 2;

@@ -1687,14 +1687,14 @@ CG_HD void co_passive_one(const Dev &v, const GridC &g, const int c2, const unsi
 }
 
 // both parts by one thread (production convection kernel k_co_col; host test harness)
-template <int I, int J, int K, int L, int MS>
+template <int I, int J, int K, int L, int MS, bool DEC_ONLY = false>
 CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m, double *scratch = nullptr, const int st = 1) {
   // the flux kernel found every level of this (member, column) stable: nothing to adjust, SST / SSS are exported already
   if (v.co_skip_stable && v.comask && v.comask[(long)c2 * MS + m] == 0u) return;
   unsigned in, topb, botb;
   double rdzt[K];
   co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, scratch, st);
-  if (v.co_pairwise == 2) {   // decisions only: the region map goes to comask for k_co_passive (one thread per tracer)
+  if (DEC_ONLY || v.co_pairwise == 2) {   // decisions only: the region map goes to comask for k_co_passive (one thread per tracer)
     v.comask[(long)c2 * MS + m] = in | (topb << 16);
     return;
   }

@@ -261,6 +261,12 @@ class Ensemble(_Base):
         call it on the steps of a save window, read the window with get("bg_sig", member)."""
         self._ck(self.L.cg_biogem_sig_update(self.h, float(dts), float(ben_Dmin)))
 
+    def biogem_sig_extended(self):
+        """From now on step_biogem keeps sfxatm1 and the export through the surface layer's base, and biogem_sig_update also
+        accumulates the sea-ice, overturning, land-temperature, export and air-sea flux integrals (field "bg_sig2";
+        biogem.f90:2870-2883, 2926-2964, 3058-3062).  Call before the first BIOGEM step of interest."""
+        self._ck(self.L.cg_biogem_sig_extended(self.h))
+
     def biogem_slice_update(self, dts):
         """diag_biogem_timeslice's arithmetic for one BIOGEM step of a save window: 3-D carbonate re-solve + window integrals
         (fields sl_ocn, sl_part, sl_carb, sl_carbconst, sl_carbisor, sl_t); call it behind biogem_climate (genie.f90:391-395)."""

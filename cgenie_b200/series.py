@@ -48,6 +48,35 @@ def write_series(outdir, sig=None, t_yr=0.0, outfile_name="biogem", with_sur=Tru
         raise SeriesError(L.cg_series_last_error().decode())
 
 
+# sed_type / sed_dep of the frozen particulate selection (tracer_define.sed columns 4 and 3; dep as 0-based compact index)
+SED_TYPE = [1, 11, 12, 3, 1, 11, 12, 9, 9]
+SED_DEP = [0, 0, 0, 3, 4, 4, 4, 7, 8]
+ATLANTIC_TOPOS = ("worbe2", "worjh2", "worjh4", "worlg2", "worlg4", "wv2jh2", "wv3jh2", "worri4")     # biogem_data_ascii.f90:1282
+
+
+def write_series_ext(outdir, sig=None, sig2=None, t_yr=0.0, outfile_name="biogem", ocn_tot_A=1.0, opsi_scale=1592.5, atlantic=True):
+    """The fexport_*, fseaair_*, focnatm_*, misc_seaice, misc_opsi, misc_atm_D14C, misc_SLT files (cg_biogem_series_write_ext):
+    sig = sig2 = None creates them with their header lines, otherwise one line per file from "bg_sig" and "bg_sig2"."""
+    from .restart import SED_TRACERS
+    L = _lib.load()
+    os.makedirs(outdir, exist_ok=True)
+    sn, k1 = _strs([n for n, _ in SED_TRACERS])
+    an, k2 = _strs([n for _, n, _ in ATM_TRACERS])
+    st, k3 = _i32(SED_TYPE); sd, k4 = _i32(SED_DEP); at, k5 = _i32(ATM_TYPE); ad, k6 = _i32(ATM_DEP)
+    sp = sp2 = None
+    if sig is not None:
+        sig = np.ascontiguousarray(sig, dtype=np.float64)
+        sig2 = np.ascontiguousarray(sig2, dtype=np.float64)
+        if sig.size != 3 + 3 * len(OCN_TRACERS) + len(ATM_TRACERS) or sig2.size != 8 + len(SED_TRACERS) + 2 * len(ATM_TRACERS):
+            raise SeriesError("series: the integrals are not those of the frozen tracer selection")
+        sp, sp2 = sig.ctypes.data_as(_lib.D), sig2.ctypes.data_as(_lib.D)
+    rc = L.cg_biogem_series_write_ext(str(outdir).encode(), outfile_name.encode(), 1 if sig is None else 0, float(t_yr), len(OCN_TRACERS),
+                                      len(SED_TRACERS), sn, st, sd, len(ATM_TRACERS), an, at, ad, sp, sp2, float(ocn_tot_A),
+                                      float(opsi_scale), 1 if atlantic else 0)
+    if rc:
+        raise SeriesError(L.cg_series_last_error().decode())
+
+
 YR_S = 3600.0 * (24.0 * 365.25)          # conv_yr_s, gem_cmn.f90:511-513
 S_YR = 1.0 / YR_S                        # conv_s_yr, gem_cmn.f90:532
 NULLSMALL = 0.999999e-19                 # const_real_nullsmall, gem_cmn.f90:719
@@ -65,7 +94,7 @@ class SeriesSaver:
     interval newer; device and oracle agree at either point.)"""
 
     def __init__(self, e, outdir, t_runtime, t_start=0.0, sig_dt=1.0, save_times=None, ben_Dmin=0.0, member=0, with_sur=True,
-                 autoend=False, outfile_name="biogem"):
+                 autoend=False, outfile_name="biogem", extended=False, world="worjh2"):
         self.e, self.outdir, self.member, self.with_sur, self.outfile_name = e, str(outdir), member, with_sur, outfile_name
         self.t_runtime, self.t_end = float(t_runtime), float(t_start) + float(t_runtime)
         self.sig_dt, self.ben_Dmin = float(sig_dt), float(ben_Dmin)
@@ -100,6 +129,11 @@ class SeriesSaver:
         self.int_t_sig = 0.0
         self.saved = []
         write_series(self.outdir, None, outfile_name=outfile_name, with_sur=with_sur)     # sub_init_data_save_runtime
+        self.extended = bool(extended)
+        if self.extended:                # the export, air-sea flux and "misc" series as well
+            e.biogem_sig_extended()
+            self.ext_kw = dict(outfile_name=outfile_name, ocn_tot_A=float(e.const("bg_ocn_tot_A")[0]), atlantic=world in ATLANTIC_TOPOS)
+            write_series_ext(self.outdir, **self.ext_kw)
         e.biogem_sig_reset()
 
     def step(self, dts, genie_clock_ms):
@@ -116,6 +150,9 @@ class SeriesSaver:
             if self.int_t_sig > NULLSMALL:
                 write_series(self.outdir, self.e.get("bg_sig", self.member), t_yr=yr, outfile_name=self.outfile_name,
                              with_sur=self.with_sur)
+                if self.extended:
+                    write_series_ext(self.outdir, self.e.get("bg_sig", self.member), self.e.get("bg_sig2", self.member), t_yr=yr,
+                                     **self.ext_kw)
                 self.saved.append(yr)
             self.sig_i -= 1
             self.e.biogem_sig_reset()                       # sub_init_int_timeseries

@@ -143,6 +143,15 @@ int cg_reinit_flux_rokocn(cg_handle *);
  * of one member in that order, 3 + 3*maxl + n_l_atm values, tracers in the compact selection order; cg_biogem_sig_reset =
  * sub_init_int_timeseries (biogem_data.f90:964-1007).  ben_Dmin = par_data_save_ben_Dmin (m). */
 int cg_biogem_sig_update(cg_handle *, double dts, double ben_Dmin);
+/* The flux, export and "misc" integrals of the same routine: after cg_biogem_sig_extended (call it before the first BIOGEM step
+ * whose integrals are wanted) step_biogem keeps sfxatm1 and the export through the base of the surface layer, and
+ * cg_biogem_sig_update also accumulates, as field "bg_sig2" of one member,
+ *   [0] int_misc_seaice_sig  [1] ..._th  [2] ..._vol (biogem.f90:2926-2937)   [3] [4] int_misc_opsi_min / max_sig
+ *   [5] [6] int_misc_opsia_min / max_sig (:2938-2945; sub_calc_psi, biogem_box.f90:3796-3852)   [7] int_misc_SLT_sig (:2946-2964)
+ *   [8 + ls] int_fexport_sig (:2870-2876)   [8 + n_l_sed + la] int_focnatm_sig (:2877-2883)
+ *   [8 + n_l_sed + n_l_atm + la] int_diag_airsea_sig (:3058-3062)     (0-based compact indices; la >= 2: the gases).
+ * Not on the device: int_carb_sur_sig, the insolation / short-wave means, the sediment-interface and diag_bio / diag_geochem sums. */
+int cg_biogem_sig_extended(cg_handle *);
 /* diag_biogem_timeslice (src/biogem/biogem.f90:2421-2699; SURVEY 8f row 1, time-slice part), its arithmetic: inside a save
  * window the carbonate system of EVERY wet cell is solved again from the cell's last [H+] (:2478-2567; the surface cell's feeds
  * back into step_biogem's next solve, as in the reference) and the window integrals int_ocn, int_bio_part, int_carb,
@@ -168,6 +177,15 @@ int cg_biogem_series_write(const char *outdir, const char *outfile_name, int cre
                            const char *const *ocn_names, const int32_t *ocn_type, const int32_t *ocn_dep, int n_atm,
                            const char *const *atm_names, const int32_t *atm_type, const int32_t *atm_dep, const double *sig,
                            int with_sur);
+/* ... and the fexport_<sed>, fseaair_<atm>, focnatm_<atm>, misc_seaice, misc_opsi, misc_atm_D14C and misc_SLT series of the same two
+ * routines (biogem_data_ascii.f90:107-197, 320-400; 955-1096, 1245-1340) from "bg_sig" (int_t_sig, the atmosphere rows) and
+ * "bg_sig2".  sed_type: tracer_define.sed column 4 (1 ... 7 bulk, 8 age, 9 frac2: no file, 11 / 12 isotopes); ocn_tot_A =
+ * SUM(phys_ocn(ipo_A,:,:,n_k)) (m2); opsi_scale = goldstein_dsc * goldstein_usc * const_rEarth * 1.0E-6; atlantic != 0 for the
+ * topographies of :1282-1283 (worbe2, worjh2 ...).  Host only. */
+int cg_biogem_series_write_ext(const char *outdir, const char *outfile_name, int create, double t_yr, int n_ocn, int n_sed,
+                               const char *const *sed_names, const int32_t *sed_type, const int32_t *sed_dep, int n_atm,
+                               const char *const *atm_names, const int32_t *atm_type, const int32_t *atm_dep, const double *sig,
+                               const double *sig2, double ocn_tot_A, double opsi_scale, int atlantic);
 /* (re)build BIOGEM's ocn array from the current ts (initialise_biogem, biogem.f90:283-285: T in K, S absolute) */
 int cg_biogem_init_ocn(cg_handle *);
 int cg_atchem_step(cg_handle *, double dts);

@@ -102,6 +102,7 @@ struct cgo_bg {
   double *sfcocn1, *sfxsed1, *focnatm;                 /* interface / diagnostics [l|ls|la][i][j] */
   double *sfxsumsed, *sfcsumocn, *sfxsumrok1;          /* SEDGEM / ROKGEM interface sums (sediment grid = ocean grid) */
   double *sig;                                         /* time-series integrals: t, tot_M, tot_M_sur, ocn(L), sur(L), ben(L), atm(LA) */
+  double *sig2;                                        /* ... seaice, seaice_th, seaice_vol, opsi min / max, opsia min / max, SLT, fexport(LS), focnatm(LA), airsea(LA) */
   int sig_auto; double sig_ben_Dmin;                   /* cgo_run takes the diagnostic where genie.f90 does (after step_biogem) */
   /* time-slice diagnostics (diag_biogem_timeslice): 3-D carbonate system of every wet cell below the surface (the surface
    * cell's is carb / carbisor above, shared with step_biogem as in the reference) and the window integrals */
@@ -512,6 +513,7 @@ void cgo_biogem_setup(cgo_t *o, const char *params) {
   b->atm_A = bg_alloc(o, "atm_A", ij); b->atm_V = bg_alloc(o, "atm_V", ij);
   b->sfcocn1 = bg_alloc(o, "sfcocn1", ij * NL); b->sfxsed1 = bg_alloc(o, "sfxsed1", ij * b->LS); b->focnatm = bg_alloc(o, "focnatm", ij * b->LA);
   b->sig = bg_alloc(o, "bg_sig", 3 + 3 * NL + b->LA);
+  b->sig2 = bg_alloc(o, "bg_sig2", 8 + b->LS + 2 * b->LA);
   b->carb3 = bg_alloc(o, "carb3", n3 * N_IC); b->ciso3 = bg_alloc(o, "carbisor3", n3 * N_ICI); b->cc3 = bg_alloc(o, "carbconst3", n3 * N_CC);
   b->sl_ocn = bg_alloc(o, "sl_ocn", n3 * NL); b->sl_part = bg_alloc(o, "sl_part", n3 * b->LS); b->sl_carb = bg_alloc(o, "sl_carb", n3 * N_IC);
   b->sl_cc = bg_alloc(o, "sl_carbconst", n3 * N_CC); b->sl_ciso = bg_alloc(o, "sl_carbisor", n3 * N_ICI); b->sl_t = bg_alloc(o, "sl_t", 1);
@@ -1275,6 +1277,77 @@ void cgo_biogem_sig_update(cgo_t *o, double ben_Dmin) {
     for (j = 1; j <= J; j++) for (i = 1; i <= I; i++)
       sa = sa + 2.0 * BG_PI * (BG_REARTH * BG_REARTH) * (1.0 / I) * (o->sv[j] - o->sv[j - 1]) * b->sfcatm1[(la - 1) + b->LA * ((i - 1) + I * (j - 1))];
     S[3 + 3 * NL + (la - 1)] = S[3 + 3 * NL + (la - 1)] + dtyr * sa * rtot_A_atm;
+  }
+  /* the flux, export and "misc" integrals of the same routine: int_fexport_sig (:2870-2876), int_focnatm_sig (:2877-2883, with
+   * locij_focnatm :2807-2811), int_diag_airsea_sig (:3058-3062), int_misc_seaice_sig / _th / _vol (:2926-2937), the overturning
+   * stream function (:2938-2945, sub_calc_psi biogem_box.f90:3796-3869) and the mean land air temperature (:2946-2964) */
+  {
+    double *S2 = b->sig2;
+    const int LS = b->LS, LA = b->LA;
+    int ls;
+    double s_ice = 0.0, s_icesum = 0.0, s_vol = 0.0;
+    for (j = 1; j <= J; j++) for (i = 1; i <= I; i++) {
+      const double A = (K1(i, j) <= K) ? 2.0 * BG_PI * (BG_REARTH * BG_REARTH) * (1.0 / I) * (o->sv[j] - o->sv[j - 1]) : 0.0;   /* phys_ocn(ipo_A,:,:,n_k) */
+      s_ice = s_ice + A * A2(b->seaice, i, j);
+      s_icesum = s_icesum + A2(b->seaice, i, j);
+      s_vol = s_vol + A2(b->seaice_th, i, j) * A * A2(b->seaice, i, j);
+    }
+    S2[0] = S2[0] + dtyr * s_ice;
+    if (s_icesum > BG_NULLSMALL) S2[1] = S2[1] + dtyr * s_vol / s_ice;
+    S2[2] = S2[2] + dtyr * s_vol;
+    {
+      /* sub_calc_psi: the caller's loc_opsi(0:n_j,0:n_k) takes rows / columns 1.. from the routine, 0 stays 0 */
+      double *opsi = (double *)calloc((size_t)(J + 1) * (K + 1), 8), *opsia = (double *)calloc((size_t)(J + 1) * (K + 1), 8);
+      double omin = 0.0, omax = 0.0, omina = 0.0, omaxa = 0.0, ou;
+#define OP(a, j, k) a[(j) + (J + 1) * (k)]
+      for (j = 1; j <= J - 1; j++)
+        for (k = 1; k <= K - 1; k++) {
+          ou = 0.0;
+          for (i = 1; i <= I; i++) ou = ou + o->cv[j] * U(2, i, j, k) * o->dphi;
+          OP(opsi, j, k) = OP(opsi, j, k - 1) - o->dz[k] * ou;
+        }
+      for (j = o->jsf + 1; j <= J - 1; j++)
+        for (k = 1; k <= K - 1; k++) {
+          ou = 0.0;
+          for (i = o->ias[j]; i <= o->iaf[j]; i++) ou = ou + o->cv[j] * U(2, i, j, k) * o->dphi;
+          OP(opsia, j, k) = OP(opsia, j, k - 1) - o->dz[k] * ou;
+          if (OP(opsia, j, k) < omina && k <= K / 2) omina = OP(opsia, j, k);
+          if (OP(opsia, j, k) > omaxa && k <= K / 2) omaxa = OP(opsia, j, k);
+        }
+      for (j = 0; j <= J; j++) for (k = 0; k <= K; k++) {      /* minval / maxval(loc_opsi(:,:)) */
+        if (OP(opsi, j, k) < omin) omin = OP(opsi, j, k);
+        if (OP(opsi, j, k) > omax) omax = OP(opsi, j, k);
+      }
+#undef OP
+      S2[3] = S2[3] + dtyr * omin; S2[4] = S2[4] + dtyr * omax;
+      S2[5] = S2[5] + dtyr * omina; S2[6] = S2[6] + dtyr * omaxa;
+      free(opsi); free(opsia);
+    }
+    {
+      double sg = 0.0, ta = 0.0;
+      for (i = 1; i <= I; i++) for (j = 1; j <= J; j++)
+        if (K < K1(i, j)) {
+          const double A = 2.0 * BG_PI * (BG_REARTH * BG_REARTH) * (1.0 / I) * (o->sv[j] - o->sv[j - 1]);
+          sg = sg + A * SFCATM1(1, i, j);
+          ta = ta + A;
+        }
+      if (ta > BG_NULLSMALL) S2[7] = S2[7] + dtyr * sg / ta; else S2[7] = 0.0;
+    }
+    for (ls = 1; ls <= LS; ls++) {
+      double s = 0.0;
+      for (j = 1; j <= J; j++) for (i = 1; i <= I; i++) s = s + SETTLE(ls, i, j, K);
+      S2[8 + (ls - 1)] = S2[8 + (ls - 1)] + s;
+    }
+    for (la = 3; la <= LA; la++) {
+      double s = 0.0, sd = 0.0;
+      for (j = 1; j <= J; j++) for (i = 1; i <= I; i++) {
+        if (K >= K1(i, j))
+          s = s + BG_YR_S * (2.0 * BG_PI * (BG_REARTH * BG_REARTH) * (1.0 / I) * (o->sv[j] - o->sv[j - 1])) * SFXATM1(la, i, j);
+        sd = sd + b->focnatm[(la - 1) + LA * ((i - 1) + I * (j - 1))];
+      }
+      S2[8 + LS + (la - 1)] = S2[8 + LS + (la - 1)] + dtyr * s;
+      S2[8 + LS + LA + (la - 1)] = S2[8 + LS + LA + (la - 1)] + dtyr * sd;
+    }
   }
   S[0] = S[0] + dtyr;
   free(mask);

@@ -180,3 +180,33 @@ def test_timeslice_diagnostics():
     # the model went on unchanged but for the surface seed
     rel = np.abs(o.f("ocn")[w] - ref.f("ocn")[w]) / np.maximum(np.abs(ref.f("ocn")[w]), 1e-3 * np.abs(ref.f("ocn")[w]).max())
     assert rel.max() < 1e-6
+
+
+def test_extended_timeseries_integrals_are_consistent():
+    """The oracle's restatement of the flux / export / misc integrals of diag_biogem_timeseries (cgo_biogem_sig_update, "bg_sig2";
+    biogem.f90:2870-2883, 2926-2964, 3058-3062): six BIOGEM steps of the third model year -- the integrals must tie in with state the
+    model keeps elsewhere (particulate export against the POC the surface layer produced, isotope ratios of the fluxes against
+    those of their bulk tracers, sea ice against the cover, the overturning extrema around zero)."""
+    import numpy as np
+    from oracle_lib import Oracle
+    o = Oracle(world="worjh2", maxk=16, maxl=16, nyear=96)
+    o.biogem_setup()
+    o.run(1400)                                       # the first sea ice forms at the end of the third model year
+    o.L.cgo_biogem_sig_auto(o.h, 1, 1000.0)
+    o.run(60)
+    S, X = o.f("bg_sig"), o.f("bg_sig2")
+    LS, LA = 9, 8
+    assert abs(S[0] - 6.0 / 48.0) < 1e-12 and X.size == 8 + LS + 2 * LA
+    fe, oa, sa = X[8:8 + LS], X[8 + LS:8 + LS + LA], X[8 + LS + LA:]
+    assert X[0] > 1e9 and X[2] > 0 and 0 < X[1] / S[0] < 10.0             # m2 yr, m3 yr, m yr
+    assert X[3] < 0 < X[4] and X[5] <= 0 <= X[6] and abs(X[3]) < 1 and abs(X[4]) < 1
+    assert -40.0 < X[7] / S[0] < 40.0                                            # degrees C over land
+    assert fe[0] > 0 and fe[4] > 0 and fe[3] > 0
+    assert abs(fe[0] / fe[3] - 106.0) < 1e-6 * 106.0                      # POC : POP leave the surface in the Redfield ratio
+    assert 0.0105 < fe[1] / fe[0] < 0.0112 and 0.0108 < fe[5] / fe[4] < 0.0113   # 13C fractions of POC and CaCO3
+    assert oa[0] == 0 and oa[1] == 0 and sa[0] == 0 and sa[1] == 0         # temperature and humidity carry no flux
+    assert sa[2] != 0 and sa[5] != 0 and 0.010 < sa[3] / sa[2] < 0.012     # CO2, O2 exchange; 13C fraction of the CO2 flux
+    # focnatm is the restoring forcing net of the gas exchange: with pCO2 restored it differs from the pure exchange
+    assert oa[2] != sa[2]
+    # ... and O2 is not restored: the interface flux (conv_yr_s * A * sfxatm1) IS the gas exchange (mol yr-1), two routes to one number
+    assert abs(oa[5] - sa[5]) <= 1e-12 * abs(sa[5])

@@ -194,3 +194,53 @@ def test_res_files_without_surface_columns(built, tmp_path):
     assert open(out / "biogem_series_ocn_DIC.res").read().split("\n")[1] == "       7.125  0.2000000E+19  0.2000000E-02"
     l14 = open(out / "biogem_series_ocn_DIC_14C.res").read().split("\n")[1]
     assert l14[:27] == "       7.125  0.2352000E+07" and l14[27:] in ("       0.000", "      -0.000")
+
+
+def test_extended_series_files(built, tmp_path):
+    """fexport_*, fseaair_*, focnatm_*, misc_* (cg_biogem_series_write_ext) in the reference's headers and edit descriptors
+    (biogem_data_ascii.f90:107-197, 320-400; 955-1096, 1245-1340) from hand-set integrals."""
+    from cgenie_b200.series import write_series_ext
+    nL, nS, nA = 16, 9, 8
+    sig = np.zeros(3 + 3 * nL + nA)
+    sig2 = np.zeros(8 + nS + 2 * nA)
+    t = 0.5
+    sig[0] = t
+    atm = sig[3 + 3 * nL:]
+    atm[2] = t * 278.0e-6
+    atm[3] = t * 278.0e-6 * 0.011057        # r13C
+    atm[4] = t * 278.0e-6 * 1.2e-12
+    sig2[0:8] = t * np.array([1.5e13, 1.25, 2.0e13, -0.0123, 0.0234, -0.002, 0.0101, 3.25])
+    fe = sig2[8:8 + nS]
+    fe[0] = t * 8.0e14; fe[1] = t * 8.0e14 * 0.0109; fe[3] = t * 7.5e12; fe[4] = t * 1.0e14
+    oa = sig2[8 + nS:8 + nS + nA]
+    oa[2] = t * -2.5e13; oa[3] = t * -2.5e13 * 0.0111; oa[5] = t * 4.0e12
+    sa = sig2[8 + nS + nA:]
+    sa[2] = t * 1.0e12; sa[5] = t * -3.0e12
+    out = tmp_path / "o"
+    write_series_ext(str(out), ocn_tot_A=3.6e14)
+    files = sorted(p.name for p in out.iterdir())
+    assert "biogem_series_fexport_POC_frac2.res" not in files and "biogem_series_fseaair_pCO2.res" in files
+    assert len(files) == 7 + 6 + 6 + 4
+    assert open(out / "biogem_series_fexport_POC.res").read() == " % time (yr) / global POC flux (mol yr-1) / global POC density (mol m-2 yr-1)\n"
+    assert open(out / "biogem_series_misc_opsi.res").read().startswith(" % time (yr) / global min overturning (Sv) / global max overturning (Sv) / Atlantic min")
+    write_series_ext(str(out), sig, sig2, t_yr=12.5, ocn_tot_A=3.6e14)
+    line = lambda n: open(out / ("biogem_series_%s.res" % n)).read().split("\n")[1]
+    assert line("fexport_POC") == "      12.500  0.8000000E+15  0.2222222E+01"
+    assert line("fexport_POP") == "      12.500  0.7500000E+13  0.2083333E-01"
+    got = line("fexport_POC_13C")
+    r = 0.0109 / (1 - 0.0109)
+    assert got[:27] == "      12.500  0.8720000E+13" and abs(float(got[27:]) - 1000.0 * (r / 0.011202 - 1.0)) < 1e-3 and len(got) == 12 + 15 + 14
+    assert line("focnatm_pCO2") == "      12.500 -0.2500000E+14      -0.069"
+    assert line("focnatm_pO2") == "      12.500  0.4000000E+13       0.011"
+    assert line("fseaair_pO2") == "      12.500 -0.3000000E+13      -0.008"
+    assert line("misc_seaice") == "      12.500  0.1500E+14    4.167  0.2000E+14    1.250"
+    assert line("misc_opsi") == "      12.500  -19.588   37.264   -3.185   16.084"     # 1592.5 * 0.0234 = 37.26449999999999...
+    assert line("misc_SLT") == "      12.500    3.250000"
+    d13 = 1000.0 * (0.011057 / (1 - 0.011057) / 0.011202 - 1.0)
+    d14 = 1000.0 * (1.2e-12 / (1 - 1.2e-12) / 1.176e-12 - 1.0)
+    D14 = 1000.0 * ((1.0 + d14 / 1000.0) * 0.975 ** 2 / (1.0 + d13 / 1000.0) ** 2 - 1.0)
+    assert abs(float(line("misc_atm_D14C").split()[1]) - D14) < 1e-3
+    # a topography without the Atlantic columns prints two overturning values
+    write_series_ext(str(tmp_path / "p"), atlantic=False)
+    write_series_ext(str(tmp_path / "p"), sig, sig2, t_yr=12.5, atlantic=False)
+    assert open(tmp_path / "p" / "biogem_series_misc_opsi.res").read().split("\n")[1] == "      12.500  -19.588   37.264"
