@@ -148,9 +148,9 @@ __global__ void __launch_bounds__(128) k_co_col(const Dev v) {
 }
 
 // the same, one warp per block, compiled for MINB resident blocks per SM (column arrays thread-private)
-template <int I, int J, int K, int L, int MS, int MINB>
+template <int I, int J, int K, int L, int MS, int MINB, int PMODE = -1>
 __global__ void __launch_bounds__(32, MINB) k_co_col1(const Dev v) {
-  co_column<I, J, K, L, MS>(v, c_g, v.rowcols[blockIdx.y], blockIdx.x * 32 + threadIdx.x, nullptr, 1);
+  co_column<I, J, K, L, MS, false, PMODE>(v, c_g, v.rowcols[blockIdx.y], blockIdx.x * 32 + threadIdx.x, nullptr, 1);
 }
 
 // ... and its decisions alone (the region maps go to comask for k_co_passive): without the averaging code the kernel needs fewer
@@ -418,13 +418,24 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
     k_co_passive<I, J, K, L, MS><<<dim3(MS / 32, v.nwet), dim3(32, L - 2), 0, s>>>(v2);
     return 3;
   }
-  // The one-warp-per-block form compiled for 16 | 20 | 24 resident blocks per SM (128 / 96 / 80 registers instead of 164; the kernel
-  // is bound by issue latency at 12 warps per SM).  Measured on the bench state (ab_r4a.log, us per tracer step, results
-  // bit-identical): 164 registers 556.2, 128 registers 522.8 (default), 96 registers 532.7, 80 registers 532.1.  CG_CO_MINB=0: the old form.
+  // The one-warp-per-block form compiled for more resident blocks per SM (the kernel is bound by latency at 12 warps per SM).
+  // Measured on the bench state (profiles/ab_r4a_*.log, ab_r4d.log; us per tracer step, results bit-identical throughout):
+  //   averaging form chosen at run time (both compiled in): 164 registers 556.2 | 128 registers 522.8 | 96 (spills) 532.7 | 80 532.1
+  //   pairs form alone, 128 registers 519.8;  regions form alone (no spills at any cap): 126 registers 519.3 | 96 515.7 | 80 511.7 |
+  //   72 510.8 | 64 registers = 32 warps per SM 510.3 (default, CG_CO_MINB=232).  CG_CO_MINB=0: the old form.
   static int minb = -1;
-  if (minb < 0) { const char *e = getenv("CG_CO_MINB"); minb = e ? atoi(e) : 16; }
+  if (minb < 0) { const char *e = getenv("CG_CO_MINB"); minb = e ? atoi(e) : 232; }
   if (minb && wpb == 1) {
     const dim3 g(MS / 32, v.nwet);
+    // CG_CO_MINB = 116 | 120 | 124 | 216 | 220: the averaging form fixed at compile time (1xx pairs, 2xx regions) at 16 / 20 / 24 blocks
+    if (minb == 116) { k_co_col1<I, J, K, L, MS, 16, 1><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 120) { k_co_col1<I, J, K, L, MS, 20, 1><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 124) { k_co_col1<I, J, K, L, MS, 24, 1><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 216) { k_co_col1<I, J, K, L, MS, 16, 0><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 220) { k_co_col1<I, J, K, L, MS, 20, 0><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 224) { k_co_col1<I, J, K, L, MS, 24, 0><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 228) { k_co_col1<I, J, K, L, MS, 28, 0><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 232) { k_co_col1<I, J, K, L, MS, 32, 0><<<g, 32, 0, s>>>(v2); return 2; }
     if (minb == 16) k_co_col1<I, J, K, L, MS, 16><<<g, 32, 0, s>>>(v2);
     else if (minb == 20) k_co_col1<I, J, K, L, MS, 20><<<g, 32, 0, s>>>(v2);
     else k_co_col1<I, J, K, L, MS, 24><<<g, 32, 0, s>>>(v2);

@@ -1687,7 +1687,7 @@ CG_HD void co_passive_one(const Dev &v, const GridC &g, const int c2, const unsi
 }
 
 // both parts by one thread (production convection kernel k_co_col; host test harness)
-template <int I, int J, int K, int L, int MS, bool DEC_ONLY = false>
+template <int I, int J, int K, int L, int MS, bool DEC_ONLY = false, int PMODE = -1>   // PMODE: -1 = v.co_pairwise decides, 0 = regions, 1 = pairs
 CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m, double *scratch = nullptr, const int st = 1) {
   // the flux kernel found every level of this (member, column) stable: nothing to adjust, SST / SSS are exported already
   if (v.co_skip_stable && v.comask && v.comask[(long)c2 * MS + m] == 0u) return;
@@ -1699,7 +1699,7 @@ CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned 
     return;
   }
   if (in == 0) return;
-  if (v.co_pairwise) {
+  if (PMODE == 1 || (PMODE < 0 && v.co_pairwise)) {
     for (int l = 2; l < L; l += 2) co_passive_pair<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, l);
   } else if (L > 2) {
     co_passive_regions<I, J, K, L, MS>(v, g, c2, m, topb, botb, rdzt);
