@@ -592,6 +592,14 @@ static int build_device(cg_handle *h) {
     std::sort(wc.begin(), wc.end());
     TRY(dupload(h, &q, wc));
     v.rowcols = q;
+    // ... and poleward rows first: the convective adjustment has work at high latitudes only, so its long-running blocks should be
+    // the first to be scheduled (the stable columns of the tropics fill the tail of the grid at no cost)
+    std::stable_sort(wc.begin(), wc.end(), [&](int a, int b) {
+      const int ja = a / I + 1, jb = b / I + 1;
+      return std::min(ja - 1, J - ja) < std::min(jb - 1, J - jb);
+    });
+    TRY(dupload(h, &q, wc));
+    v.polcols = q;
   }
   auto col = [&](auto getter) { std::vector<double> t(M); for (int m = 0; m < M; m++) t[m] = getter(h->mc[m]); return t; };
   MemberP &p = v.p;

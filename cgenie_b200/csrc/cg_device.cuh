@@ -63,6 +63,7 @@ struct Dev {
   int isles, mpi;                    // islands (1 .. kMaxIsles), path stride
   const int *wetcols;        // 0-based (i-1)+I*(j-1) of the wet columns, deepest first
   const int *rowcols;        // the same columns in row-major (j, then i) order: neighbours in the list are neighbours in i
+  const int *polcols;        // the same columns, poleward rows first (rows J, 1, J-1, 2 ...): where the ocean convects
   int nwet;
   // tracer state, ping-pong
   double *ts_cur, *ts_new;

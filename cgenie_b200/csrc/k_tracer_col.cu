@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(128) k_co_col(const Dev v) {
 // the same, one warp per block, compiled for MINB resident blocks per SM (column arrays thread-private)
 template <int I, int J, int K, int L, int MS, int MINB, int PMODE = -1>
 __global__ void __launch_bounds__(32, MINB) k_co_col1(const Dev v) {
-  co_column<I, J, K, L, MS, false, PMODE>(v, c_g, v.rowcols[blockIdx.y], blockIdx.x * 32 + threadIdx.x, nullptr, 1);
+  const int c2 = v.col_deep_first ? v.polcols[blockIdx.y] : v.rowcols[blockIdx.y];   // (col_deep_first doubles as "poleward rows first" here)
+  co_column<I, J, K, L, MS, false, PMODE>(v, c_g, c2, blockIdx.x * 32 + threadIdx.x, nullptr, 1);
 }
 
 // ... and its decisions alone (the region maps go to comask for k_co_passive): without the averaging code the kernel needs fewer
@@ -427,6 +428,9 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
   if (minb < 0) { const char *e = getenv("CG_CO_MINB"); minb = e ? atoi(e) : 232; }
   if (minb && wpb == 1) {
     const dim3 g(MS / 32, v.nwet);
+    static int copol = -1;   // CG_CO_POLAR=1: blocks of the poleward rows first
+    if (copol < 0) { const char *e = getenv("CG_CO_POLAR"); copol = e ? atoi(e) : 0; }
+    v2.col_deep_first = copol;
     // CG_CO_MINB = 116 | 120 | 124 | 216 | 220: the averaging form fixed at compile time (1xx pairs, 2xx regions) at 16 / 20 / 24 blocks
     if (minb == 116) { k_co_col1<I, J, K, L, MS, 16, 1><<<g, 32, 0, s>>>(v2); return 2; }
     if (minb == 120) { k_co_col1<I, J, K, L, MS, 20, 1><<<g, 32, 0, s>>>(v2); return 2; }
