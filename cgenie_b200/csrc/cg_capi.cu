@@ -768,8 +768,12 @@ static int build_device(cg_handle *h) {
     bg_fill_tables(bc, h->base, g, &b);
     if (!bg_layout_ok(b, L)) return fail(CG_ERR_CONFIG, "BIOGEM: tracer tables differ from the layout k_bg_step is compiled for");
     // imld = 1 hands BIOGEM a mixed-layer depth (go_mldta) and sub_calc_bio_uptake then spreads the export production over the levels
-    // k_mld .. n_k (biogem_box.f90:423-430); the surface kernel produces it in the top level only (k_mld = n_k, mld = 0)
-    if (h->base.imld) return fail(CG_ERR_CONFIG, "imld = 1 with BIOGEM: export production over a mixed layer deeper than the top level is outside the B200 hot path");
+    // k_mld .. n_k (biogem_box.f90:423-430): bg_k_mld in the sweep and cells kernels
+    if (h->base.imld) {
+      TRY(dalloc(h, &b.mld, ij * MS));
+      TRY(dalloc(h, &b.mld_stage, ij * MS));
+      reg_field(h, "bg_mld", b.mld, {I, J}, {1, I});
+    }
     if (L > 64) return fail(CG_ERR_CONFIG, "more than 64 tracers");
     CUDA_OK(cudaMemcpy(v.bg_ocn, h->bg_ocn0.data(), h->bg_ocn0.size() * 8, cudaMemcpyHostToDevice));
     h->bg_ocn0.clear(); h->bg_ocn0.shrink_to_fit();

@@ -178,6 +178,8 @@ struct BgDev {
   double *carbH;                          // [j][i][m]       surface [H+], seed of the next pH solve
   double *seaice;                         // [j][i][m]       snapshot taken by biogem_climate
   double *seaice_stage;                   // [j][i][m]       sea-ice cover at biogem_climate's call time (k_bg_stage_seaice)
+  double *mld, *mld_stage;                // [j][i][m]       imld = 1: mixed-layer depth biogem_climate takes over (m below the surface,
+                                          //                 go_mldta = -5000 * mld) and GOLDSTEIN's mld at that call's time; else NULL
   double *atm_tot;                        // [la][m]         mole-weighted totals of the ATCHEM step (k_bg_atchem2 -> k_bg_atchem3)
   double *tq_stage;                       // [2][j][i][m]    EMBM's T, q at the same time: what cpl_comp_EMBM copies (atchem.f90:270-282)
   const double *wspeed, *A, *rA;          // [j][i] member independent

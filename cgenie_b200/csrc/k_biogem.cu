@@ -521,6 +521,17 @@ enum { T = 1, S, DIC, DIC13, DIC14, PO4, O2, ALK, DOMC, DOMC13, DOMC14, DOMP, CA
 enum { POC = 1, POC13, POC14, POP, CACO3, CACO313, CACO314, POCF2, CACO3F2, NLS = 9 };
 enum { A_T = 1, A_Q, A_CO2, A_CO213, A_CO214, A_O2, A_CFC11, A_CFC12, NLA = 8 };
 }  // namespace lay
+// loc_k_mld of sub_calc_bio_uptake (biogem_box.f90:423-430): the shallowest level whose floor lies at or below the mixed-layer depth;
+// export production, its DOM fraction and the nutrient uptake are applied to every level k_mld .. n_k (:1186-1378).  Without the
+// mixed-layer scheme (imld = 0: mld = 0) that is the top level alone.
+__device__ __forceinline__ int bg_k_mld(const BgDev &b, const int K, const int k1, const size_t q) {
+  if (!b.mld) return K;
+  const double mld = b.mld[q];
+  int km = k1;
+  for (int k = K; k >= 1; k--)
+    if (b.Dbot[k] >= mld) { km = k; break; }
+  return km;
+}
 bool bg_layout_ok(const BgDev &b, int L) {
   using namespace lay;
   if (L != NL || b.LS != NLS || b.LA != NLA) return false;
@@ -619,6 +630,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
   const int i = c2 % I + 1, j = c2 / I + 1;
   const int k1 = (int)v.k1[i + (I + 2) * j];
   const size_t c2d = cell2(I, i, j);
+  const int k_mld = bg_k_mld(b, K, k1, c2d * MS + m);
   const size_t sK = (size_t)I * J * L * MS, o0 = cell3(I, J, i, j, 1) * L * MS + m;
   const size_t qK = (size_t)I * J * LS * MS, q0 = cell3(I, J, i, j, 1) * LS * MS + m;
   const size_t pK = (size_t)I * J * MS, p0 = cell3(I, J, i, j, 1) * MS + m;
@@ -980,7 +992,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
     // (3) new particulate field of this layer
 #pragma unroll
     for (int ls = 1; ls <= LS; ls++) {
-      const double pv = (kk == K) ? psurf[ls] : pnew[ls];
+      const double pv = (kk >= k_mld) ? psurf[ls] : pnew[ls];
       PART_(ls, kk) = fuse ? s_sr[threadIdx.x] * (pv + 0.0) : pv;   // biogem.f90:2042-2043 (vdbio_part = 0)
     }
     if (PK) {   // the cell's half of the work is k_bg_cell's: hand over the remineralisation products of the particles
@@ -1004,7 +1016,7 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
     rem_zero(domrem);
     rem_add(domrem, f, dom, fO2POC, fO2POP, fALKPOP, fALKCa);
     // (5) tracer anomaly vdocn(l, kk) = bio_remin + dtyr*rM*focn and the bottom-water interface (:1736-1744)
-    const bool bot = (kk == k1), top = (kk == K);
+    const bool bot = (kk == k1), top = (kk == K), prod = (kk >= k_mld);
     double rn_cpl = 0.0;   // mean_S_NEW / Snew of this cell (fused coupling)
 #pragma unroll
     for (int l = 1; l <= L; l++) {
@@ -1032,12 +1044,10 @@ __global__ void __launch_bounds__(128, MINB) k_bg_step(const Dev v, const BgDev 
       double focn = 0.0;
       if ((l == DIC14 || l == DOMC14) && ocn_decays) focn = focn - Mk * decay14 * x[l] / dtyr;
       if (l == 1 && bot) focn = focn + kYrS * b.Fgeothermal * A / (1.0E+03 * kCp);
-      if (top) {
-        focn = focn + gas;
-        if (l >= 3) {
-          if (l == DOMC || l == DOMC13 || l == DOMC14 || l == DOMP) rem = rem + da;
-          rem = rem - (slot ? up : 0.0);
-        }
+      if (top) focn = focn + gas;
+      if (prod && l >= 3) {
+        if (l == DOMC || l == DOMC13 || l == DOMC14 || l == DOMP) rem = rem + da;
+        rem = rem - (slot ? up : 0.0);
       }
       const double dval = rem + dtyr * rM * focn;
       if (bot) b.sfcocn1[((size_t)(l - 1) * I * J + c2d) * MS + m] = x[l] + rem + dtyr * rM * focn;
@@ -1125,7 +1135,7 @@ __global__ void __launch_bounds__(32 * kApplyWarps, MINB) k_bg_cell(const Dev v,
   if (kk == K && c2d == (size_t)v.bgcols[0]) b.pscale[m] = s_sr[lane];   // the rescaling of bio_part this coupling owes
 #define SC_(slot) b.surf[((size_t)(slot) * (I * J) + n) * MS + m]
   if (SC_(kBgSurfSlots - 1) != 0.0) return;   // the carbonate solve of this column failed (error_stop): flagged by PART 3
-  const bool bot = (kk == k1), top = (kk == K);
+  const bool bot = (kk == k1), top = (kk == K), prod = (kk >= bg_k_mld(b, K, k1, c2d * MS + m));
   const size_t o = (size_t)c * L * MS + m;
   const double dtyr = b.dtyr;
   double x[L + 1], tv[L + 1];
@@ -1162,6 +1172,8 @@ __global__ void __launch_bounds__(32 * kApplyWarps, MINB) k_bg_cell(const Dev v,
   if (top) {
 #pragma unroll
     for (int la = 3; la <= LA; la++) focn_surf[la] = SC_(la - 3);
+  }
+  if (prod) {
     dom_add[POC] = SC_(LA - 2 + LS + 0); dom_add[POC13] = SC_(LA - 2 + LS + 1); dom_add[POC14] = SC_(LA - 2 + LS + 2);
     dom_add[POP] = SC_(LA - 2 + LS + 3);
     uptake.dic = SC_(LA - 2 + LS + 4); uptake.d13 = SC_(LA - 2 + LS + 5); uptake.d14 = SC_(LA - 2 + LS + 6);
@@ -1221,12 +1233,10 @@ __global__ void __launch_bounds__(32 * kApplyWarps, MINB) k_bg_cell(const Dev v,
     double focn = 0.0;
     if ((l == DIC14 || l == DOMC14) && ocn_decays) focn = focn - Mk * decay14 * x[l] / dtyr;
     if (l == 1 && bot) focn = focn + kYrS * b.Fgeothermal * A / (1.0E+03 * kCp);
-    if (top) {
-      focn = focn + gas;
-      if (l >= 3) {
-        if (l == DOMC || l == DOMC13 || l == DOMC14 || l == DOMP) rem = rem + da;
-        rem = rem - (slot ? up : 0.0);
-      }
+    if (top) focn = focn + gas;
+    if (prod && l >= 3) {
+      if (l == DOMC || l == DOMC13 || l == DOMC14 || l == DOMP) rem = rem + da;
+      rem = rem - (slot ? up : 0.0);
     }
     const double dval = rem + dtyr * rM * focn;   // (the bottom-water interface sfcocn1 = x + dval was written by PART 3)
     double *tsp = v.ts_cur + (o + (size_t)(l - 1) * MS);
@@ -1267,6 +1277,7 @@ __global__ void k_bg_stage_seaice(const Dev v, const BgDev b) {
   const size_t n = (size_t)v.I * v.J * v.MS;
   if (q < n) {
     b.seaice_stage[q] = v.varice[n + q];   // varice(2,:,:) = fractional cover
+    if (b.mld_stage) b.mld_stage[q] = v.mld[q];   // GOLDSTEIN's mixed-layer depth behind this cycle's tstepo (imld = 1)
     b.tq_stage[q] = v.tq[q];               // tstar_atm, surf_qstar_atm of this koverall iteration (embm.f90:177-193)
     b.tq_stage[n + q] = v.tq[n + q];
   }
@@ -1276,6 +1287,7 @@ __global__ void k_bg_climate(const Dev v, const BgDev b) {
   const size_t n = (size_t)v.I * v.J * v.MS;
   if (q >= n) return;
   b.seaice[q] = b.seaice_stage[q];
+  if (b.mld) b.mld[q] = -5000.0 * b.mld_stage[q];   // go_mldta (goldstein.f90:449) -> phys_ocnatm(ipoa_mld) (biogem.f90:2183)
   v.cost[q] = 0.0;
 }
 // cpl_comp_EMBM (atchem.f90:270-282; genie.f90:454, behind the ATCHEM step): rows 1-2 of sfcatm1 = air temperature and

@@ -81,7 +81,38 @@ def test_mld_run_matches_oracle(built, tmp_path):
     assert np.abs(interior(o0, "ts") - got[0]["ts"]).max() > 1e-6     # the option is acting
 
 
-def test_mld_refused_with_biogem(built, tmp_path):
-    materialise(str(tmp_path), "eb_go_gs_ac_bg_36x36x16", overrides={"go_imld": 1})
-    with pytest.raises(Exception, match="imld"):
-        Ensemble(str(tmp_path), n_members=1)
+def test_mld_with_biogem_matches_oracle(built, tmp_path):
+    """imld = 1 under BIOGEM: biogem_climate takes the mixed-layer depth over (go_mldta, biogem.f90:2183) and sub_calc_bio_uptake
+    spreads export production, its DOM fraction and the nutrient uptake over the levels k_mld .. n_k (biogem_box.f90:423-430,
+    1186-1378) -- bg_k_mld in the sweep / packets and cells kernels.  Ten BIOGEM blocks from the initial state against the oracle,
+    per cell; the mixed layer reaches below the top level in most columns from the first block on."""
+    from test_gpu_biogem import CFG, OKW, compare, I, J, K, LS
+    materialise(str(tmp_path), CFG, overrides={"go_imld": 1})
+    scf = np.array([2.0, 1.8])
+    oracles = []
+    for m in range(2):
+        o = Oracle(**OKW, imld=1, scf=float(scf[m]))
+        o.biogem_setup()
+        oracles.append(o)
+    with Ensemble(str(tmp_path), n_members=2, perturb={"scf": scf}) as e:
+        e.set_tracer_variant("strict")
+        e.run(10)
+        for o in oracles:
+            o.run(10)
+        compare(e, oracles, 1e-12, "imld + BIOGEM, 1 block")
+        e.run(90)
+        for o in oracles:
+            o.run(90)
+        compare(e, oracles, 2e-9, "imld + BIOGEM, 10 blocks")
+        for m, o in enumerate(oracles):
+            assert np.abs(e.get("bg_mld", m) - o.f("bg_mld")).max() <= 1e-6           # metres
+        assert int(e.health().sum()) == 0
+    o = oracles[0]
+    k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+    deep = (o.f("bg_mld").reshape(J, I) > 100.0) & (k1 < K)                           # deeper than the top level (80.8 m)
+    part = o.f("bio_part").reshape(K, J, I, LS)
+    assert deep.sum() > 200 and (part[K - 2, :, :, 0][deep] > 0).sum() > 200         # POC produced in the second level there
+    o0 = Oracle(**OKW)
+    o0.biogem_setup()
+    o0.run(100)
+    assert np.abs(o0.f("ocn") - o.f("ocn")).max() > 1e-9                             # and the run differs from imld = 0
