@@ -154,6 +154,13 @@ __global__ void __launch_bounds__(32, MINB) k_co_col1(const Dev v) {
   co_column<I, J, K, L, MS, false, PMODE>(v, c_g, c2, blockIdx.x * 32 + threadIdx.x, nullptr, 1);
 }
 
+// two member tiles of one column per block (64 threads): at <= 48 registers 21 blocks = 42 warps are resident per SM, more than the
+// hardware's 32 one-warp blocks
+template <int I, int J, int K, int L, int MS, int MINB>
+__global__ void __launch_bounds__(64, MINB) k_co_col2w(const Dev v) {
+  co_column<I, J, K, L, MS, false, 0>(v, c_g, v.rowcols[blockIdx.y], blockIdx.x * 64 + threadIdx.x, nullptr, 1);
+}
+
 // ... and its decisions alone (the region maps go to comask for k_co_passive): without the averaging code the kernel needs fewer
 // registers and its warps retire sooner
 template <int I, int J, int K, int L, int MS, int MINB>
@@ -440,6 +447,10 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
     if (minb == 224) { k_co_col1<I, J, K, L, MS, 24, 0><<<g, 32, 0, s>>>(v2); return 2; }
     if (minb == 228) { k_co_col1<I, J, K, L, MS, 28, 0><<<g, 32, 0, s>>>(v2); return 2; }
     if (minb == 232) { k_co_col1<I, J, K, L, MS, 32, 0><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 321) { k_co_col2w<I, J, K, L, MS, 21><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 48 registers, 42 warps per SM
+    if (minb == 320) { k_co_col2w<I, J, K, L, MS, 20><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 48 registers, 40 warps per SM
+    if (minb == 318) { k_co_col2w<I, J, K, L, MS, 18><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 56 registers, 36 warps per SM
+    if (minb == 316) { k_co_col2w<I, J, K, L, MS, 16><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 64 registers, 32 warps per SM
     if (minb == 16) k_co_col1<I, J, K, L, MS, 16><<<g, 32, 0, s>>>(v2);
     else if (minb == 20) k_co_col1<I, J, K, L, MS, 20><<<g, 32, 0, s>>>(v2);
     else k_co_col1<I, J, K, L, MS, 24><<<g, 32, 0, s>>>(v2);
