@@ -148,10 +148,10 @@ __global__ void __launch_bounds__(128) k_co_col(const Dev v) {
 }
 
 // the same, one warp per block, compiled for MINB resident blocks per SM (column arrays thread-private)
-template <int I, int J, int K, int L, int MS, int MINB, int PMODE = -1>
+template <int I, int J, int K, int L, int MS, int MINB, int PMODE = -1, bool LOCKSTEP = false>
 __global__ void __launch_bounds__(32, MINB) k_co_col1(const Dev v) {
   const int c2 = v.col_deep_first ? v.polcols[blockIdx.y] : v.rowcols[blockIdx.y];   // (col_deep_first doubles as "poleward rows first" here)
-  co_column<I, J, K, L, MS, false, PMODE>(v, c_g, c2, blockIdx.x * 32 + threadIdx.x, nullptr, 1);
+  co_column<I, J, K, L, MS, false, PMODE, LOCKSTEP>(v, c_g, c2, blockIdx.x * 32 + threadIdx.x, nullptr, 1);
 }
 
 // two member tiles of one column per block (64 threads): at <= 48 registers 21 blocks = 42 warps are resident per SM, more than the
@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(32 * (L - 2)) k_co_passive(const Dev v) {
   const unsigned m = blockIdx.x * 32 + threadIdx.x;
   co_passive_one<I, J, K, L, MS>(v, c_g, v.rowcols[blockIdx.y], m, 2 + (int)threadIdx.y);
 }
+
+constexpr int kCoMinbDefault = 232;   // form of the convection kernel (table in go_tiled); CG_CO_MINB overrides
 
 template <int I, int J, int K, int L, int MS>
 static int go(const Dev &v, cudaStream_t s, int cfg) {
@@ -306,6 +308,14 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
   } else {
     static int wpb = -1;   // see go_tiled
     if (wpb < 0) { const char *e = getenv("CG_CO_WPB"); wpb = e ? atoi(e) : 1; if (wpb < 1 || wpb > 4 || !colocal) wpb = 4; }
+    static int lock = -1;  // CG_CO_MINB >= 400: the lockstep form of the decisions, as in go_tiled (one code path for every member stride)
+    if (lock < 0) { const char *e = getenv("CG_CO_MINB"); lock = e ? atoi(e) : kCoMinbDefault; }
+    if (lock >= 400 && v2.co_skip_stable && v.comask && L > 2) {
+      v2.col_deep_first = 0;
+      if (lock == 412) k_co_col1<I, J, K, L, MS, 12, 0, true><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
+      else k_co_col1<I, J, K, L, MS, 16, 0, true><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
+      return 2;
+    }
     k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + wpb - 1) / wpb), 32 * wpb, co_smem_bytes, s>>>(v2);
   }
   return 2;
@@ -432,7 +442,7 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
   //   pairs form alone, 128 registers 519.8;  regions form alone (no spills at any cap): 126 registers 519.3 | 96 515.7 | 80 511.7 |
   //   72 510.8 | 64 registers = 32 warps per SM 510.3 (default, CG_CO_MINB=232).  CG_CO_MINB=0: the old form.
   static int minb = -1;
-  if (minb < 0) { const char *e = getenv("CG_CO_MINB"); minb = e ? atoi(e) : 232; }
+  if (minb < 0) { const char *e = getenv("CG_CO_MINB"); minb = e ? atoi(e) : kCoMinbDefault; }
   if (minb && wpb == 1) {
     const dim3 g(MS / 32, v.nwet);
     static int copol = -1;   // CG_CO_POLAR=1: blocks of the poleward rows first
@@ -447,6 +457,11 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
     if (minb == 224) { k_co_col1<I, J, K, L, MS, 24, 0><<<g, 32, 0, s>>>(v2); return 2; }
     if (minb == 228) { k_co_col1<I, J, K, L, MS, 28, 0><<<g, 32, 0, s>>>(v2); return 2; }
     if (minb == 232) { k_co_col1<I, J, K, L, MS, 32, 0><<<g, 32, 0, s>>>(v2); return 2; }
+    // 4xx: the decisions in lockstep form (column in registers, passes every lane executes alike: co_decide_static) + regions averaging
+    if (minb == 412) { k_co_col1<I, J, K, L, MS, 12, 0, true><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 416) { k_co_col1<I, J, K, L, MS, 16, 0, true><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 420) { k_co_col1<I, J, K, L, MS, 20, 0, true><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 424) { k_co_col1<I, J, K, L, MS, 24, 0, true><<<g, 32, 0, s>>>(v2); return 2; }
     if (minb == 321) { k_co_col2w<I, J, K, L, MS, 21><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 48 registers, 42 warps per SM
     if (minb == 320) { k_co_col2w<I, J, K, L, MS, 20><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 48 registers, 40 warps per SM
     if (minb == 318) { k_co_col2w<I, J, K, L, MS, 18><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 56 registers, 36 warps per SM

@@ -35,9 +35,11 @@
 #ifdef __CUDA_ARCH__
 #define CG_CLZ(x) __clz((int)(x))
 #define CG_FFS(x) __ffs((int)(x))
+#define CG_POPC(x) __popc(x)
 #else
 #define CG_CLZ(x) __builtin_clz(x)
 #define CG_FFS(x) __builtin_ffs((int)(x))
+#define CG_POPC(x) __builtin_popcount(x)
 #endif
 
 namespace cg {
@@ -1568,6 +1570,85 @@ CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsi
 #undef rl
 #undef dzm
 
+// The decisions in LOCKSTEP form: the column's T, S, rho live in registers (static indices only) and the adjustment is a sequence of
+// passes every lane executes alike -- (1) mark every boundary between two boxes whose upper box is not lighter than the lower one
+// (the reference's test, goldstein.f90:2712 / 2724: mix unless rho(upper) < rho(lower)), (2) remove the marked boundaries, re-form
+// the thickness-weighted means of the boxes that grew (summed top-down over the levels, as the passive tracers' means are) and their
+// density, (3) repeat until a pass marks nothing.  A chain of unstable pairs is merged in one pass, as the reference merges a run;
+// boxes that did not grow keep their values bit for bit (an unmixed level keeps the rho the flux kernel stored, so ties are decided
+// on the reference's operands).  The walk of co_decide_core (one box at a time, down and back up, thread-private arrays indexed per
+// lane) visits the same comparisons in another order: same final partition, box means equal to rounding (the means of means of the
+// sequential merges against sums over levels); cost counts the same levels.  ieos = 0, iconv = 0 only (as every `col` kernel).
+template <int I, int J, int K, int L, int MS>
+CG_HD void co_decide_static(const Dev &v, const GridC &g, const int c2, const unsigned m, unsigned &in, unsigned &topb, unsigned &botb,
+                            double *rdzt) {
+  static_assert(K <= 31, "level masks are 32 bits");
+  constexpr long sL = MS, sC = (long)L * MS, sK = (long)I * J * sC, rK = (long)I * J * MS;
+  const int k1c = (int)v.k1[(c2 % I + 1) + (I + 2) * (c2 / I + 1)];
+  double *__restrict__ ts = v.ts_new + ((long)c2 * sC + m);
+  double *__restrict__ rho = v.rho + ((long)c2 * MS + m);
+  const double ec1 = v.p.ec1[m], ec2 = v.p.ec2[m], ec3 = v.p.ec3[m], ec4 = v.p.ec4[m];
+  const unsigned wet = ((1u << K) - 1u) & ~((1u << (k1c - 1)) - 1u);          // bit q = level q + 1 is wet
+  double T[K], S[K], R[K];
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    T[q] = 0.0; S[q] = 0.0; R[q] = 0.0;
+    if ((wet >> q) & 1u) { T[q] = ts[(long)q * sK]; S[q] = ts[(long)q * sK + sL]; R[q] = rho[(long)q * rK]; }
+  }
+  unsigned sep = wet & ~(1u << (k1c - 1));      // bit q: a box boundary lies between level q + 1 and level q (q >= k1c)
+  for (;;) {
+    unsigned merge = 0u;
+#pragma unroll
+    for (int q = K - 1; q >= 1; q--)
+      if (((sep >> q) & 1u) && !(R[q] < R[q - 1])) merge |= 1u << q;
+    if (merge == 0u) break;
+    sep &= ~merge;
+    double sT = 0.0, sS = 0.0, sD = 0.0;
+    bool grew = false;
+#pragma unroll
+    for (int q = K - 1; q >= 0; q--) {
+      if ((wet >> q) & 1u) {
+        const bool top = (q == K - 1) || ((sep >> (q + 1)) & 1u);
+        const bool bot = ((sep >> q) & 1u) || (q + 1 == k1c);
+        const double dz = g.dz[q + 1];
+        if (top) { sT = T[q] * dz; sS = S[q] * dz; sD = dz; grew = false; }
+        else { sT = sT + T[q] * dz; sS = sS + S[q] * dz; sD = sD + dz; grew = grew || ((merge >> (q + 1)) & 1u); }
+        if (bot && grew) {
+          const double tm = sT / sD, sm = sS / sD;
+          T[q] = tm; S[q] = sm;
+          R[q] = ec1 * tm + ec2 * sm + ec3 * (tm * tm) + ec4 * (tm * tm * tm);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 1; q < K; q++)     // a box's values are those of its bottom level: hand them up
+      if (((wet >> q) & 1u) && q + 1 > k1c && !((sep >> q) & 1u)) { T[q] = T[q - 1]; S[q] = S[q - 1]; R[q] = R[q - 1]; }
+  }
+  if (v.sst) {   // SST / SSS as exported by step_goldstein (:428-431)
+    v.sst[(long)c2 * MS + m] = T[K - 1];
+    v.sst[((long)(I * J) + c2) * MS + m] = S[K - 1];
+  }
+  const unsigned bot_all = sep | (1u << (k1c - 1));
+  const unsigned top_all = ((bot_all >> 1) | (1u << (K - 1))) & wet;
+  in = wet & ~(top_all & bot_all);              // levels of boxes of more than one level
+  topb = top_all & in;
+  botb = bot_all & in;
+  if (in == 0u) return;
+  v.cost[(long)c2 * MS + m] += (double)CG_POPC(wet & ~top_all);   // levels that are no longer a box of their own (:2749-2764)
+  double dzt = 0.0;
+#pragma unroll
+  for (int q = K - 1; q >= 0; q--) {
+    rdzt[q] = 0.0;
+    if ((in >> q) & 1u) {
+      dzt = ((topb >> q) & 1u) ? g.dz[q + 1] : dzt + g.dz[q + 1];
+      if ((botb >> q) & 1u) rdzt[q] = 1.0 / dzt;
+      ts[(long)q * sK] = T[q];
+      ts[(long)q * sK + sL] = S[q];
+      rho[(long)q * rK] = R[q];
+    }
+  }
+}
+
 // Part 2: one pair (l, l+1) of passive tracers of one (member, column): thickness-weighted mean over every mixed region,
 // summed top-down; all loads of the pair are independent.
 template <int I, int J, int K, int L, int MS>
@@ -1687,13 +1768,14 @@ CG_HD void co_passive_one(const Dev &v, const GridC &g, const int c2, const unsi
 }
 
 // both parts by one thread (production convection kernel k_co_col; host test harness)
-template <int I, int J, int K, int L, int MS, bool DEC_ONLY = false, int PMODE = -1>   // PMODE: -1 = v.co_pairwise decides, 0 = regions, 1 = pairs
+template <int I, int J, int K, int L, int MS, bool DEC_ONLY = false, int PMODE = -1, bool LOCKSTEP = false>   // PMODE: -1 = v.co_pairwise decides, 0 = regions, 1 = pairs
 CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m, double *scratch = nullptr, const int st = 1) {
   // the flux kernel found every level of this (member, column) stable: nothing to adjust, SST / SSS are exported already
   if (v.co_skip_stable && v.comask && v.comask[(long)c2 * MS + m] == 0u) return;
   unsigned in, topb, botb;
   double rdzt[K];
-  co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, scratch, st);
+  if constexpr (LOCKSTEP) co_decide_static<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt);
+  else co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, scratch, st);
   if (DEC_ONLY || v.co_pairwise == 2) {   // decisions only: the region map goes to comask for k_co_passive (one thread per tracer)
     v.comask[(long)c2 * MS + m] = in | (topb << 16);
     return;

@@ -54,6 +54,19 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
       for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m);
     return 0;
   }
+  if (mix == 6) {   // round-1 flux kernel + stability flag, then co with the decisions in lockstep form + region-wise averaging
+    std::vector<unsigned> comask((size_t)I * J * MS, 7u);
+    v.comask = comask.data();
+    v.co_skip_stable = 1;
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) {
+        ColStage st{sm.data(), bar, m};
+        tstep_column<I, J, K, L, 32, 32, false>(v, g, cols[n], (unsigned)m, st);
+      }
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32, false, 0, true>(v, g, cols[n], (unsigned)m);
+    return 0;
+  }
   if (mix == 4) {   // round-1 flux kernel + stability flag, decisions only, then one "thread" per passive tracer (k_co_passive)
     std::vector<unsigned> comask((size_t)I * J * MS, 7u);
     v.comask = comask.data();

@@ -43,10 +43,22 @@ def _after(o):
 # 4: round-1 flux kernel + stability flag, decisions-only convection kernel + one thread per passive tracer;
 # 3: pipelined column kernel (coefficients one level ahead; production) + stability flag + co on flagged member-columns;
 # 2: split column kernel (two threads per member-column) + co; 1: T,S pre-pass + mix-on-write passive pass; 0: round-1 flux kernel + co
-@pytest.mark.parametrize("mix", [5, 4, 3, 2, 1, 0])
+# 6: round-1 flux kernel + stability flag, convection decisions in lockstep form (co_decide_static) + region-wise averaging;
+@pytest.mark.parametrize("mix", [6, 5, 4, 3, 2, 1, 0])
 @pytest.mark.parametrize("nsteps", [5 * 40, 5 * 150])   # not the first steps: a uniform start is neutrally stable and
 # the convection decisions there flip on the last bit (true of every non-strict variant)
 def test_col_body_matches_oracle(nsteps, mix):
+    _check_against_oracle(nsteps, mix)
+
+
+# the lockstep form of the convection decisions (mix 6) visits the comparisons in another order than the reference's walk: more states,
+# from the young ocean (most columns convect over many levels) to a two-year-old one
+@pytest.mark.parametrize("nsteps", [5 * 80, 5 * 300, 5 * 480, 5 * 960])   # (from the uniform start every non-strict form flips decisions for ~20 ocean steps)
+def test_lockstep_convection_decisions_match_oracle(nsteps):
+    _check_against_oracle(nsteps, 6)
+
+
+def _check_against_oracle(nsteps, mix):
     lib = _lib()
     oras = [Oracle("worjh2", maxk=K, maxl=L, nyear=96), Oracle("worjh2", maxk=K, maxl=L, nyear=96, diff1=2600.0, diff2=1.3e-5)]
     for o in oras:
