@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128) k_co_col(const Dev v) {
 }
 
 // the same, one warp per block, compiled for MINB resident blocks per SM (column arrays thread-private)
-template <int I, int J, int K, int L, int MS, int MINB, int PMODE = -1, bool LOCKSTEP = false>
+template <int I, int J, int K, int L, int MS, int MINB, int PMODE = -1, int LOCKSTEP = 0>
 __global__ void __launch_bounds__(32, MINB) k_co_col1(const Dev v) {
   const int c2 = v.col_deep_first ? v.polcols[blockIdx.y] : v.rowcols[blockIdx.y];   // (col_deep_first doubles as "poleward rows first" here)
   co_column<I, J, K, L, MS, false, PMODE, LOCKSTEP>(v, c_g, c2, blockIdx.x * 32 + threadIdx.x, nullptr, 1);
@@ -312,8 +312,9 @@ static int go(const Dev &v, cudaStream_t s, int cfg) {
     if (lock < 0) { const char *e = getenv("CG_CO_MINB"); lock = e ? atoi(e) : kCoMinbDefault; }
     if (lock >= 400 && v2.co_skip_stable && v.comask && L > 2) {
       v2.col_deep_first = 0;
-      if (lock == 412) k_co_col1<I, J, K, L, MS, 12, 0, true><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
-      else k_co_col1<I, J, K, L, MS, 16, 0, true><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
+      if (lock == 412) k_co_col1<I, J, K, L, MS, 12, 0, 1><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
+      else if (lock >= 500) k_co_col1<I, J, K, L, MS, 16, 0, 2><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
+      else k_co_col1<I, J, K, L, MS, 16, 0, 1><<<dim3(MS / 32, v.nwet), 32, 0, s>>>(v2);
       return 2;
     }
     k_co_col<I, J, K, L, MS><<<dim3(MS / 32, (v.nwet + wpb - 1) / wpb), 32 * wpb, co_smem_bytes, s>>>(v2);
@@ -463,10 +464,14 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
     if (minb == 228) { k_co_col1<I, J, K, L, MS, 28, 0><<<g, 32, 0, s>>>(v2); return 2; }
     if (minb == 232) { k_co_col1<I, J, K, L, MS, 32, 0><<<g, 32, 0, s>>>(v2); return 2; }
     // 4xx: the decisions in lockstep form (column in registers, passes every lane executes alike: co_decide_static) + regions averaging
-    if (minb == 412) { k_co_col1<I, J, K, L, MS, 12, 0, true><<<g, 32, 0, s>>>(v2); return 2; }
-    if (minb == 416) { k_co_col1<I, J, K, L, MS, 16, 0, true><<<g, 32, 0, s>>>(v2); return 2; }
-    if (minb == 420) { k_co_col1<I, J, K, L, MS, 20, 0, true><<<g, 32, 0, s>>>(v2); return 2; }
-    if (minb == 424) { k_co_col1<I, J, K, L, MS, 24, 0, true><<<g, 32, 0, s>>>(v2); return 2; }
+    // 5xx: the lockstep passes in the reference's own order of merges (co_decide_static<WALK>): identical partition by construction
+    if (minb == 512) { k_co_col1<I, J, K, L, MS, 12, 0, 2><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 516) { k_co_col1<I, J, K, L, MS, 16, 0, 2><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 520) { k_co_col1<I, J, K, L, MS, 20, 0, 2><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 412) { k_co_col1<I, J, K, L, MS, 12, 0, 1><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 416) { k_co_col1<I, J, K, L, MS, 16, 0, 1><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 420) { k_co_col1<I, J, K, L, MS, 20, 0, 1><<<g, 32, 0, s>>>(v2); return 2; }
+    if (minb == 424) { k_co_col1<I, J, K, L, MS, 24, 0, 1><<<g, 32, 0, s>>>(v2); return 2; }
     if (minb == 321) { k_co_col2w<I, J, K, L, MS, 21><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 48 registers, 42 warps per SM
     if (minb == 320) { k_co_col2w<I, J, K, L, MS, 20><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 48 registers, 40 warps per SM
     if (minb == 318) { k_co_col2w<I, J, K, L, MS, 18><<<dim3(MS / 64, v.nwet), 64, 0, s>>>(v2); return 2; }   // 56 registers, 36 warps per SM

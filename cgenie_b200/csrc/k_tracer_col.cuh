@@ -1579,7 +1579,12 @@ CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsi
 // on the reference's operands).  The walk of co_decide_core (one box at a time, down and back up, thread-private arrays indexed per
 // lane) visits the same comparisons in another order: same final partition, box means equal to rounding (the means of means of the
 // sequential merges against sums over levels); cost counts the same levels.  ieos = 0, iconv = 0 only (as every `col` kernel).
-template <int I, int J, int K, int L, int MS>
+// WALK = true: the passes follow the reference's own ORDER of merges -- its walk (one box at a time from the top, after a merge first
+// against the box below, then back up one box at a time) is replayed on the mask of unstable boundaries (integer work only: the
+// comparisons of a pass are all taken beforehand, in static loops), and a pass merges exactly the run the walk would merge next.  With a
+// nonlinear equation of state the final partition can depend on that order (two unstable runs close to each other in one column:
+// 0.5 % of random columns with 2 K of noise per level, none in model states); WALK = false merges every unstable run of a pass at once.
+template <int I, int J, int K, int L, int MS, bool WALK = false>
 CG_HD void co_decide_static(const Dev &v, const GridC &g, const int c2, const unsigned m, unsigned &in, unsigned &topb, unsigned &botb,
                             double *rdzt) {
   static_assert(K <= 31, "level masks are 32 bits");
@@ -1596,11 +1601,40 @@ CG_HD void co_decide_static(const Dev &v, const GridC &g, const int c2, const un
     if ((wet >> q) & 1u) { T[q] = ts[(long)q * sK]; S[q] = ts[(long)q * sK + sL]; R[q] = rho[(long)q * rK]; }
   }
   unsigned sep = wet & ~(1u << (k1c - 1));      // bit q: a box boundary lies between level q + 1 and level q (q >= k1c)
+  int cur = K, lastmix = 0;                     // WALK: the reference's position (top level of the box under test) and flag
   for (;;) {
     unsigned merge = 0u;
 #pragma unroll
     for (int q = K - 1; q >= 1; q--)
       if (((sep >> q) & 1u) && !(R[q] < R[q - 1])) merge |= 1u << q;
+    if (WALK) {
+      // every unstable boundary of the column is in `merge`; pick the run the reference's walk merges next (goldstein.f90:2700-2746).
+      // Box tops: level K and every level above a boundary; the boundary between a box and the box whose top is level b is bit b.
+      const unsigned unst = merge;
+      const unsigned tops = ((sep >> 1) | (1u << (K - 1))) & wet;
+      merge = 0u;
+      for (;;) {
+        const unsigned mb = tops & ((1u << (cur - 1)) - 1u);
+        const int bl = mb ? 32 - CG_CLZ(mb) : 0;                              // top level of the box below, 0: none
+        if (!(bl > 0 || (lastmix != 0 && cur != K))) break;
+        if (bl == 0 || !((unst >> bl) & 1u)) {                                // stable (or nothing below)
+          if (lastmix == 0 || cur == K) cur = bl;
+          else cur = cur + CG_FFS(tops >> cur);                               // back up one box
+          lastmix = 0;
+        } else {                                                              // unstable: cur's box takes the run below it
+          lastmix = 1;
+          int lo = bl;
+          for (;;) {
+            const unsigned m2 = tops & ((1u << (lo - 1)) - 1u);
+            const int b2 = m2 ? 32 - CG_CLZ(m2) : 0;
+            if (!(b2 > 0 && ((unst >> b2) & 1u))) break;
+            lo = b2;
+          }
+          merge = sep & ((2u << bl) - 1u) & ~((1u << lo) - 1u);               // boundaries bit lo .. bit bl
+          break;
+        }
+      }
+    }
     if (merge == 0u) break;
     sep &= ~merge;
     double sT = 0.0, sS = 0.0, sD = 0.0;
@@ -1768,13 +1802,13 @@ CG_HD void co_passive_one(const Dev &v, const GridC &g, const int c2, const unsi
 }
 
 // both parts by one thread (production convection kernel k_co_col; host test harness)
-template <int I, int J, int K, int L, int MS, bool DEC_ONLY = false, int PMODE = -1, bool LOCKSTEP = false>   // PMODE: -1 = v.co_pairwise decides, 0 = regions, 1 = pairs
+template <int I, int J, int K, int L, int MS, bool DEC_ONLY = false, int PMODE = -1, int LOCKSTEP = 0>   // PMODE: -1 = v.co_pairwise decides, 0 = regions, 1 = pairs; LOCKSTEP: 1 = every unstable run of a pass, 2 = the reference's order
 CG_HD void co_column(const Dev &v, const GridC &g, const int c2, const unsigned m, double *scratch = nullptr, const int st = 1) {
   // the flux kernel found every level of this (member, column) stable: nothing to adjust, SST / SSS are exported already
   if (v.co_skip_stable && v.comask && v.comask[(long)c2 * MS + m] == 0u) return;
   unsigned in, topb, botb;
   double rdzt[K];
-  if constexpr (LOCKSTEP) co_decide_static<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt);
+  if constexpr (LOCKSTEP != 0) co_decide_static<I, J, K, L, MS, LOCKSTEP == 2>(v, g, c2, m, in, topb, botb, rdzt);
   else co_decide<I, J, K, L, MS>(v, g, c2, m, in, topb, botb, rdzt, scratch, st);
   if (DEC_ONLY || v.co_pairwise == 2) {   // decisions only: the region map goes to comask for k_co_passive (one thread per tracer)
     v.comask[(long)c2 * MS + m] = in | (topb << 16);

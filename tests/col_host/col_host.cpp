@@ -54,6 +54,17 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
       for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32>(v, g, cols[n], (unsigned)m);
     return 0;
   }
+  if (mix >= 7 && mix <= 9) {   // the convective adjustment alone on the caller's ts_new / rho (7: the reference's walk on thread-private
+    v.co_skip_stable = 0;       // arrays, 8: lockstep passes merging every unstable run at once, 9: lockstep passes in the walk's order)
+    v.co_pairwise = 0;
+    for (int n = 0; n < ncol; n++)
+      for (int m = 0; m < MS; m++) {
+        if (mix == 9) co_column<I, J, K, L, 32, false, 0, 2>(v, g, cols[n], (unsigned)m);
+        else if (mix == 8) co_column<I, J, K, L, 32, false, 0, 1>(v, g, cols[n], (unsigned)m);
+        else co_column<I, J, K, L, 32, false, 0, 0>(v, g, cols[n], (unsigned)m);
+      }
+    return 0;
+  }
   if (mix == 6) {   // round-1 flux kernel + stability flag, then co with the decisions in lockstep form + region-wise averaging
     std::vector<unsigned> comask((size_t)I * J * MS, 7u);
     v.comask = comask.data();
@@ -64,7 +75,7 @@ extern "C" int col_host_step(int MS, const unsigned char *k1, const int *cols, i
         tstep_column<I, J, K, L, 32, 32, false>(v, g, cols[n], (unsigned)m, st);
       }
     for (int n = 0; n < ncol; n++)
-      for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32, false, 0, true>(v, g, cols[n], (unsigned)m);
+      for (int m = 0; m < MS; m++) co_column<I, J, K, L, 32, false, 0, 2>(v, g, cols[n], (unsigned)m);
     return 0;
   }
   if (mix == 4) {   // round-1 flux kernel + stability flag, decisions only, then one "thread" per passive tracer (k_co_passive)

@@ -109,3 +109,72 @@ def _check_against_oracle(nsteps, mix):
                 np.max(np.abs(sst[0, :, :, m][wet[K - 1]] - ts_ref[K - 1, :, :, 0][wet[K - 1]])) < 1e-12
         nmixed += int((cost_ref - st[w]["cost"]).sum())
     assert nmixed > 0          # the state exercises the convective adjustment
+
+
+def test_lockstep_decisions_equal_the_walk_on_random_columns():
+    """co_decide_static<WALK> (passes over a register-held column, in the reference's order of merges) against co_decide_core (the
+    reference's walk on thread-private arrays) on 41 472 random columns per case: stable profiles with inversions of every length and
+    size, exact ties between neighbouring levels (equal T and S: the reference mixes on `>=`), columns of every depth, passive tracers.
+    Same partition in EVERY column (the convection counter `cost` equal), T / S / rho / passive tracers of the mixed boxes equal to
+    rounding, every column inventory conserved, the result stable.  The form that merges every unstable run of a pass at once (mix 8)
+    is held to the same on the moderate cases and may part from the walk where two unstable runs interact through the cubic equation
+    of state (2 K of noise per level: reported)."""
+    lib = _lib()
+    o = Oracle("worjh2", maxk=K, maxl=L, nyear=96)
+    dz = o.f("dz")[:K + 2].copy()
+    km = np.ascontiguousarray(np.stack([o.f(n)[:K + 2] for n in ("dz", "dza", "rdz", "rdza", "ssmax")]))
+    jm = np.ascontiguousarray(np.stack([o.f(n)[:J + 2] for n in ("rc", "rc2", "cv", "cv2", "dsv", "rdsv", "rds")]))
+    ecv = np.array([o.s("ec%d" % q) for q in (1, 2, 3, 4)])
+    ec = np.ascontiguousarray(np.repeat(ecv[:, None], MS, axis=1))
+    dp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for case, (noise, tie_rate) in enumerate([(0.3, 0.0), (2.0, 0.0), (0.8, 0.3), (0.02, 0.6)]):
+        rng = np.random.default_rng(100 + case)
+        k1g = rng.integers(1, K + 1, size=(J + 2, I + 2)).astype(np.uint8)          # every cell wet, bottom level 1 .. K
+        cols = np.arange(I * J, dtype=np.int32)
+        lev = np.arange(K)[:, None, None, None]
+        base_T = 2.0 + 18.0 * (lev / (K - 1.0)) ** 2                                  # warm on top: stable
+        T = base_T + noise * rng.normal(size=(K, J, I, MS)) * (1.0 + 4.0 * (rng.random((1, J, I, MS)) < 0.3))
+        S = 0.2 * rng.normal(size=(K, J, I, MS)) * noise
+        tie = rng.random((K, J, I, MS)) < tie_rate                                     # level k takes the values of level k - 1
+        for k in range(1, K):
+            T[k] = np.where(tie[k], T[k - 1], T[k])
+            S[k] = np.where(tie[k], S[k - 1], S[k])
+        ts0 = np.zeros((K, J, I, L, MS))
+        ts0[:, :, :, 0, :], ts0[:, :, :, 1, :] = T, S
+        ts0[:, :, :, 2:, :] = rng.random((K, J, I, L - 2, MS)) + 0.5
+        rho0 = ecv[0] * T + ecv[1] * S + ecv[2] * (T * T) + ecv[3] * (T * T * T)       # as eos() forms it (goldstein.f90:3048-3061)
+        out = {}
+        for mix in (7, 8, 9):
+            ts, rho = ts0.copy(), np.ascontiguousarray(rho0.copy())
+            cost, sst = np.zeros((J, I, MS)), np.zeros((2, J, I, MS))
+            dummy3, dummyu = np.zeros((2, J, I, MS)), np.zeros((K, J, I, 3, MS))
+            d1 = np.ones(MS)
+            rc = lib.col_host_step(MS, dp(k1g), dp(cols), len(cols), dp(ts0), dp(ts), dp(dummy3), dp(sst), dp(rho), dp(dummyu), dp(cost),
+                                   dp(d1), dp(d1), dp(ec), dp(jm), dp(km), C.c_double(o.s("dphi")), C.c_double(o.s("rdphi")),
+                                   C.c_double(float(o.f("dt")[K])), mix)
+            assert rc == 0
+            out[mix] = (ts, rho, cost, sst)
+        (tw, rw, cw, sw), (tl, rl, cl, sl) = out[7], out[9]
+        k1 = k1g[1:J + 1, 1:I + 1].astype(int)
+        wet = (np.arange(1, K + 1)[:, None, None] >= k1[None])[..., None, None]
+        assert np.array_equal(cw, cl), "case %d: partitions differ in %d columns" % (case, int((cw != cl).sum()))
+        nd = int((out[8][2] != cw).sum())
+        print("case %d (noise %.2f K, ties %.0f %%): all-runs-at-once form differs from the walk in %d of %d columns" %
+              (case, noise, 100 * tie_rate, nd, cw.size))
+        assert nd <= 0.01 * cw.size
+        assert cw.sum() > 0.2 * cw.size                                                # the adjustment is exercised
+        scale = np.abs(ts0).reshape(-1, L, MS).max(axis=(0, 2))[None, None, None, :, None]
+        err = np.abs(tw - tl) / scale
+        assert err.max() <= 1e-14, (case, float(err.max()))
+        assert np.abs(rw - rl).max() <= 1e-14 * np.abs(rw).max()
+        assert np.abs(sw - sl).max() <= 1e-13
+        w = dz[1:K + 1][:, None, None, None, None] * wet                               # thickness of the wet levels
+        inv0 = (ts0 * w).sum(axis=0)
+        for t in (tw, tl):
+            assert np.abs((t * w).sum(axis=0) - inv0).max() <= 1e-12 * np.abs(inv0).max()
+        # and the result is stable: no box is denser than (or as dense as) the box below it unless they are one box
+        for t, r in ((tw, rw), (tl, rl)):
+            for k in range(1, K):
+                both = (k + 0 >= k1)[..., None]                                        # level k (index k - 1) and k + 1 wet
+                same = (t[k, :, :, 0, :] == t[k - 1, :, :, 0, :]) & (t[k, :, :, 1, :] == t[k - 1, :, :, 1, :])
+                assert (~both | same | (r[k] < r[k - 1])).all(), (case, k)
