@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(32 * (L - 2)) k_co_passive(const Dev v) {
   co_passive_one<I, J, K, L, MS>(v, c_g, v.rowcols[blockIdx.y], m, 2 + (int)threadIdx.y);
 }
 
-constexpr int kCoMinbDefault = 416;   // form of the convection kernel (table in go_tiled); CG_CO_MINB overrides
+constexpr int kCoMinbDefault = 516;   // form of the convection kernel (table in go_tiled); CG_CO_MINB overrides
 
 template <int I, int J, int K, int L, int MS>
 static int go(const Dev &v, cudaStream_t s, int cfg) {
@@ -443,10 +443,14 @@ static int go_tiled(const Dev &v, cudaStream_t s) {
   //   pairs form alone, 128 registers 519.8;  regions form alone (no spills at any cap): 126 registers 519.3 | 96 515.7 | 80 511.7 |
   //   72 510.8 | 64 registers = 32 warps per SM 510.3 (CG_CO_MINB=232).  CG_CO_MINB=0: the old form.
   // Decisions in lockstep form (co_decide_static: the column in registers, passes every lane executes alike) + regions averaging
-  // (profiles/ab_r4j_co_lockstep.log): 166 registers / 12 blocks per SM 490.3 | 128 registers / 16 blocks 486.1 (default, CG_CO_MINB=416) |
-  // 96 registers (spills) / 20 blocks 497.7 -- against 512.5 for the 64-register walk on that box.  Same decisions as the walk (cost equal,
-  // no flipped column from the first model year on against the strict kernels), box means equal to rounding, so not bit-identical
-  // to the 2xx / 1xx forms; every member stride uses the same form (go and go_tiled).
+  // (profiles/ab_r4j_co_lockstep.log): 166 registers / 12 blocks per SM 490.3 | 128 registers / 16 blocks 486.1 (CG_CO_MINB=416) |
+  // 96 registers (spills) / 20 blocks 497.7 -- against 512.5 for the 64-register walk on that box.  That form merges every unstable run
+  // of a pass at once: same decisions as the walk in every model state tried (cost equal, no flipped column from the first model year
+  // on against the strict kernels), but not by construction (0.5 % of random columns with 2 K of noise per level end in another
+  // partition: two unstable runs interacting through the cubic equation of state).  The DEFAULT (CG_CO_MINB=516) is the lockstep form
+  // that replays the reference's own order of merges on the mask of unstable boundaries: identical partition on 166k random columns
+  // incl. those (tests/test_col_body_host.py), 504.9 us (profiles/ab_r4l_co_lockstep_walk_order.log).  Box means equal to rounding in
+  // both, so neither is bit-identical to the 2xx / 1xx forms; every member stride uses the same form (go and go_tiled).
   static int minb = -1;
   if (minb < 0) { const char *e = getenv("CG_CO_MINB"); minb = e ? atoi(e) : kCoMinbDefault; }
   if (minb && wpb == 1) {
