@@ -244,3 +244,54 @@ def test_extended_series_files(built, tmp_path):
     write_series_ext(str(tmp_path / "p"), atlantic=False)
     write_series_ext(str(tmp_path / "p"), sig, sig2, t_yr=12.5, atlantic=False)
     assert open(tmp_path / "p" / "biogem_series_misc_opsi.res").read().split("\n")[1] == "      12.500  -19.588   37.264"
+
+
+def test_series_saver_extended(built, tmp_path):
+    """SeriesSaver(extended=True): switches the extended integrals on before the first window, and at every save writes the export /
+    air-sea flux / misc files next to the ocn_* / atm_* ones from "bg_sig" and "bg_sig2" (recording engine, constant integrands)."""
+    from cgenie_b200.series import SeriesSaver
+
+    class Eng(_FakeEngine):
+        def __init__(self):
+            super().__init__()
+            self.extended_calls = 0
+
+        def biogem_sig_extended(self):
+            assert self.updates == 0            # before the first BIOGEM step of interest
+            self.extended_calls += 1
+
+        def const(self, name):
+            assert name == "bg_ocn_tot_A"
+            return np.array([3.6e14])
+
+        def get(self, name, member):
+            if name == "bg_sig":
+                return super().get(name, member)
+            assert name == "bg_sig2"
+            x = np.zeros(8 + 9 + 2 * LA)
+            x[0], x[3], x[4] = self.t * 1.0e13, self.t * -0.01, self.t * 0.02
+            x[8] = 48 * self.t * 1.0e13             # export: summed per step, not time weighted
+            x[8 + 9 + 2] = self.t * -2.0e13
+            return x
+
+    nyear, kb = 96, 10
+    genie_timestep = 3600.0 * 24.0 * 365.25 / 5.0 / nyear
+    tick = int(round(1000.0 * genie_timestep))
+    dts = float(kb) * genie_timestep
+    e = Eng()
+    s = SeriesSaver(e, tmp_path / "x", t_runtime=2.0, t_start=0.0, sig_dt=1.0, extended=True, world="worjh2")
+    assert e.extended_calls == 1
+    for k in range(kb, 2 * 5 * nyear + 1, kb):
+        s.step(dts, k * tick)
+    assert s.saved == [0.5, 1.5]
+    opsi = open(tmp_path / "x" / "biogem_series_misc_opsi.res").read().split("\n")
+    assert len(opsi) == 4 and opsi[1] == "       0.500  -15.925   31.850    0.000    0.000" and opsi[2][:12] == "       1.500"
+    assert open(tmp_path / "x" / "biogem_series_fexport_POC.res").read().split("\n")[2] == "       1.500  0.4800000E+15  0.1333333E+01"
+    assert open(tmp_path / "x" / "biogem_series_focnatm_pCO2.res").read().split("\n")[1] == "       0.500 -0.2000000E+14      -0.056"
+    assert len(open(tmp_path / "x" / "biogem_series_ocn_temp.res").read().split("\n")) == 4
+    # a topography without the Atlantic columns
+    e2 = Eng()
+    s2 = SeriesSaver(e2, tmp_path / "y", t_runtime=1.0, sig_dt=1.0, extended=True, world="p0055c")
+    for k in range(kb, 5 * nyear + 1, kb):
+        s2.step(dts, k * tick)
+    assert open(tmp_path / "y" / "biogem_series_misc_opsi.res").read().split("\n")[1] == "       0.500  -15.925   31.850"
