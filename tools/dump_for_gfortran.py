@@ -13,6 +13,10 @@ biogem_data_netCDF.f90:24-142, atchem_data_netCDF.f90:22-109) and biogem_series_
   python tools/dump_for_gfortran.py --config 1 --years 10 --out dumps/      # eb_go_gs 36x36x8 (BASELINE config #1)
   python tools/dump_for_gfortran.py --config 2 --years 2 --out dumps/       # eb_go_gs_ac_bg 36x36x16 (config #2, shortened)
   ... --device                                                             # also run the CUDA path (strict variant) and dump it
+  ... --set go_imld=1 --set go_iconv=1                                     # GOLDSTEIN options on top: in the oracle,
+                                                                           # the device job and the user_config alike
+Config 2 also writes the export / air-sea flux / misc series (fexport_*, fseaair_*, focnatm_*, misc_seaice, misc_opsi, misc_atm_D14C,
+misc_SLT: biogem_data_ascii.f90:955-1096, 1245-1340) the reference writes at its default save level.
 
 Output: <out>/config<N>/{oracle,device}/..., <out>/config<N>/user_config (the job's namelist keys in new-job's prefix form),
 <out>/config<N>/RECIPE.md."""
@@ -62,6 +66,13 @@ class OracleAsEnsemble:
         return self.get(name).size
 
 
+OPTS = {}      # --set go_imld=1 ...: GOLDSTEIN options on top of the configuration (oracle, device job and user_config alike)
+
+
+def _oracle_opts():
+    return {k[3:]: v for k, v in OPTS.items() if k.startswith("go_")}
+
+
 def user_config(cfgname):
     """The job's namelists as new-job user-config lines (`<prefix>_<key>=<value>`, tools/config_utils.py:253-281)."""
     from cgenie_b200 import materialise
@@ -69,7 +80,7 @@ def user_config(cfgname):
             "data_BIOGEM": "bg", "data_ATCHEM": "ac"}
     lines = []
     with tempfile.TemporaryDirectory() as d:
-        materialise(d, cfgname)
+        materialise(d, cfgname, overrides=dict(OPTS) or None)
         for f, p in pref.items():
             path = os.path.join(d, f)
             if not os.path.exists(path):
@@ -93,21 +104,28 @@ def dump_biogem(e, outdir, year):
 
 
 def run_oracle(n, years, outdir):
-    from cgenie_b200.series import write_series
+    from cgenie_b200.series import write_series, write_series_ext
     from oracle_lib import Oracle
     cfgname, okw = CFG[n]
-    o = Oracle(**okw)
+    o = Oracle(**okw, **_oracle_opts())
     kyear = 5 * okw["nyear"]
     e = OracleAsEnsemble(o, okw)
     if n == 2:
         o.biogem_setup(par_misc_t_runtime=float(years))
         write_series(outdir, None)                           # headers (sub_init_data_save_runtime)
+        k1 = o.i("k1").reshape(J + 2, I + 2)[1:J + 1, 1:I + 1]
+        sv = o.f("sv")
+        A = 2.0 * np.pi * 6.37e6 ** 2 * (1.0 / I) * (sv[1:J + 1] - sv[0:J])              # phys_ocn(ipo_A,:,:,n_k), biogem_data.f90:1156
+        ext = dict(ocn_tot_A=float((A[:, None] * (k1 <= okw["maxk"])).sum()), atlantic=True)
+        write_series_ext(outdir, **ext)                      # fexport_*, fseaair_*, focnatm_*, misc_* headers
         o.L.cgo_biogem_sig_auto(o.h, 1, 0.0)                 # par_data_save_ben_Dmin = 0.0 (biogem-defaults.nml)
     for y in range(1, years + 1):
         o.run(kyear)
         if n == 2:
             write_series(outdir, o.f("bg_sig"), t_yr=float(y) - 0.5)      # one save window per model year (par_data_save_sig_dt = 1.0)
+            write_series_ext(outdir, o.f("bg_sig"), o.f("bg_sig2"), t_yr=float(y) - 0.5, **ext)
             o.f("bg_sig")[:] = 0.0
+            o.f("bg_sig2")[:] = 0.0
     dump_physics(e, outdir, years)
     if n == 2:
         dump_biogem(e, outdir, years)
@@ -119,7 +137,7 @@ def run_device(n, years, outdir):
     from cgenie_b200.series import SeriesSaver
     cfgname, okw = CFG[n]
     with tempfile.TemporaryDirectory() as d:
-        materialise(d, cfgname, overrides={"bg_par_misc_t_runtime": float(years)} if n == 2 else None)
+        materialise(d, cfgname, overrides=dict(OPTS, **({"bg_par_misc_t_runtime": float(years)} if n == 2 else {})) or None)
         with Ensemble(d, n_members=1) as e:
             e.set_tracer_variant("strict")
             kyear = 5 * e.nyear
@@ -128,7 +146,7 @@ def run_device(n, years, outdir):
             else:
                 gts = 3600.0 * 24.0 * 365.25 / 5.0 / e.nyear
                 tick, dts = int(round(1000.0 * gts)), 10.0 * gts
-                s = SeriesSaver(e, outdir, t_runtime=float(years), sig_dt=1.0, ben_Dmin=0.0)
+                s = SeriesSaver(e, outdir, t_runtime=float(years), sig_dt=1.0, ben_Dmin=0.0, extended=True, world=okw["world"])
                 for k in range(1, kyear * years + 1):            # genie.f90's loop, module by module
                     if k % 5 == 1:
                         e.surflux()
@@ -187,7 +205,14 @@ def main():
     ap.add_argument("--years", type=int, default=None)
     ap.add_argument("--out", default="dumps")
     ap.add_argument("--device", action="store_true", help="also run the CUDA path (needs a GPU)")
+    ap.add_argument("--set", action="append", default=[], metavar="go_KEY=VALUE",
+                    help="a GOLDSTEIN option on top of the configuration, e.g. go_imld=1, go_iconv=1, go_ieos=1, go_iediff=1 (repeatable)")
     a = ap.parse_args()
+    for kv in a.set:
+        k, v = kv.split("=", 1)
+        if not k.startswith("go_"):
+            ap.error("--set takes GOLDSTEIN keys (go_...)")
+        OPTS[k] = float(v) if "." in v or "e" in v.lower() else int(v)
     n = a.config
     years = a.years if a.years is not None else (10 if n == 1 else 2)
     cfgname, okw = CFG[n]
