@@ -132,6 +132,12 @@ MODULE cgenie_b200_c
        TYPE(C_PTR), VALUE :: h
        REAL(C_DOUBLE), VALUE :: dts, ben_dmin
      END FUNCTION cg_biogem_sig_update
+     ! the export / air-sea flux / "misc" integrals of diag_biogem_timeseries as well (field "bg_sig2"; biogem.f90:2870-2883, 2926-2964,
+     ! 3058-3062): call once, before the first BIOGEM step whose window integrals are wanted (initialise_biogem's place)
+     INTEGER(C_INT) FUNCTION cg_biogem_sig_extended(h) BIND(C, NAME='cg_biogem_sig_extended')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: h
+     END FUNCTION cg_biogem_sig_extended
      INTEGER(C_INT) FUNCTION cg_biogem_sig_reset(h) BIND(C, NAME='cg_biogem_sig_reset')
        IMPORT :: C_INT, C_PTR
        TYPE(C_PTR), VALUE :: h
