@@ -75,13 +75,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(members, variant):
+def ncu_traffic(members, variant, note=False):
     """dram__bytes_read.sum + dram__bytes_write.sum per tstepo launch (flux + convection kernels) from the committed
-    `ncu --set full` capture of this configuration (profiles/ncu_traffic.json), or None when none was taken."""
+    `ncu --set full` capture of this configuration (profiles/ncu_traffic.json), or None when none was taken.  note=True: which
+    capture that is (round, kernels, the entry's own remark)."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         for row in reversed(json.load(open(p))["captures"]):   # latest capture of this configuration
             if row["members"] == members and row["variant"] == variant and row["config"] == CONFIG:
+                if note:
+                    return "capture %s (%s)%s" % (row.get("round"), ", ".join(sorted(row.get("kernels", {}))),
+                                                  "; " + row["note"] if row.get("note") else "")
                 return row["dram_bytes_per_tstepo_launch"]
     except Exception:
         pass
@@ -406,7 +410,8 @@ def main():
             "strict": "tstepo = k_tstepo_flux_strict + k_co_strict (+ k_sst)"}[e.tracer_variant_active()]
     roofline = {"bound": "hbm", "kernel": kern + " (%s variant), SURVEY 8d B_tr" % e.tracer_variant_active(),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(M, e.tracer_variant_active()) if args.config == 4 else None, "peak_source": peak_src,
+                "traffic": ncu_traffic(M, e.tracer_variant_active()) if args.config == 4 else None,
+                "traffic_source": ncu_traffic(M, e.tracer_variant_active(), note=True) if args.config == 4 else None, "peak_source": peak_src,
                 "launches_per_step": (t_n + c_n) / max(nstep, 1),
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "family_ms_per_year": {k: v[0] for k, v in fam.items()}}
