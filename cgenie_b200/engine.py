@@ -261,6 +261,13 @@ class Ensemble(_Base):
         call it on the steps of a save window, read the window with get("bg_sig", member)."""
         self._ck(self.L.cg_biogem_sig_update(self.h, float(dts), float(ben_Dmin)))
 
+    def goldstein_mldta(self, member=0):
+        """step_goldstein's go_mldta (goldstein.f90:449): mixed-layer depth in metres below the surface, (maxi,maxj); zero unless
+        imld = 1."""
+        out = np.zeros(self.maxi * self.maxj, dtype=np.float64)
+        self._ck(self.L.cg_goldstein_mldta(self.h, int(member), _dp(out)))
+        return out
+
     def biogem_sig_extended(self):
         """From now on step_biogem keeps sfxatm1 and the export through the surface layer's base, and biogem_sig_update also
         accumulates the sea-ice, overturning, land-temperature, export and air-sea flux integrals (field "bg_sig2";

@@ -165,7 +165,8 @@ def materialise(jobdir, config="eb_go_gs_36x36x8", overrides=None):
         ("indir_name", "input/goldstein"), ("igrid", 0), ("world", world), ("ans", "n"), ("yearlen", 365.25),
         ("nyear", nyear), ("temp0", 5.0), ("temp1", 5.0), ("rel", 0.9), ("scf", 2.0), ("diff(1)", 2000.0),
         ("diff(2)", 1.0e-5), ("adrag", 2.5), ("hosing", 0.0), ("hosing_trend", 0.0), ("nyears_hosing", 0),
-        ("fwanomin", "n"), ("albocn", 0.05), ("iconv", 0), ("imld", 0), ("iediff", 0), ("ieos", 0), ("dosc", True),
+        ("fwanomin", "n"), ("albocn", 0.05), ("iconv", 0), ("imld", 0), ("mldpebuoycoeff", 0.15), ("mldketaucoeff", 2.5),
+        ("mldwindkedec", 25.0), ("iediff", 0), ("ieos", 0), ("dosc", True),
         ("diso", True), ("ssmaxsurf", 10.0), ("ssmaxdeep", 10.0), ("saln0", 34.9)]))
     _write_nml(os.path.join(jobdir, "data_EMBM"), "INI_EMBM_NML", sect("ea", [
         ("indir_name", "input/embm"), ("igrid", 0), ("world", world), ("xu_wstress", "taux_u.interp"),
