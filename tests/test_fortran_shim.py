@@ -133,3 +133,44 @@ def test_ctypes_table_has_header_arity():
     for name, (_, argtypes) in _lib.SYMBOLS.items():
         assert name in protos, name
         assert len(argtypes) == len(protos[name]), (name, len(argtypes), protos[name])
+
+
+def test_shim_procedures_take_the_reference_argument_lists():
+    """The drop-in must take exactly what genie_loop_wrappers.f90 passes.  tests/golden/ref_signatures.json holds the dummy-argument
+    lists of the reference's hot-path procedures (name, type, rank, INTENT; parsed from the reference's own Fortran with
+    numpy.f2py.crackfortran by tools/make_golden.py); the shim modules, parsed the same way, must agree argument for argument:
+    same names in the same order, same type and rank, and no INTENT that contradicts the reference's."""
+    import contextlib
+    import io
+    import json
+    from numpy.f2py import crackfortran
+    crackfortran.verbose = 0
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_signatures.json")))["procedures"]
+
+    def walk(b, out):
+        if b.get("block") in ("subroutine", "function"):
+            out[b["name"].lower()] = b
+        for c in b.get("body", []):
+            walk(c, out)
+
+    procs = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "fortran", "*_b200.f90"))):
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            blocks = crackfortran.crackfortran([path])
+        for b in blocks:
+            assert b["block"] == "module" and b["name"].endswith("_b200"), (path, b["name"])
+            walk(b, procs)
+    assert len(ref) == 16
+    for name, sig in ref.items():
+        assert name in procs, "no shim for %s (%s)" % (name, sig["file"])
+        p = procs[name]
+        assert [a.lower() for a in p["args"]] == [a["name"] for a in sig["args"]], name
+        for a in sig["args"]:
+            v = p["vars"][[x for x in p["args"] if x.lower() == a["name"]][0]]
+            assert v.get("typespec") == a["type"], (name, a["name"], v.get("typespec"), a["type"])
+            assert len(v.get("dimension", [])) == a["rank"], (name, a["name"], v.get("dimension"), a["rank"])
+            mine = sorted(v.get("intent") or [])
+            mine = [x for x in mine if x in ("in", "out", "inout")]
+            if a["intent"] and mine:
+                # the shim may be stricter about what it leaves alone, never write what the reference only reads
+                assert not (a["intent"] == ["in"] and mine != ["in"]), (name, a["name"], mine, a["intent"])

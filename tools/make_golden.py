@@ -35,3 +35,44 @@ def ref_date_files():
 
 if os.path.isdir("/root/reference/data/main"):
     ref_date_files()
+
+
+def ref_signatures():
+    """Dummy-argument lists of the reference's hot-path module procedures (name, type, rank, INTENT per argument), parsed from the
+    reference's Fortran with numpy.f2py.crackfortran: tests/golden/ref_signatures.json.  tests/test_fortran_shim.py holds the shim
+    modules (fortran/*_b200.f90) to them -- the drop-in must take exactly what genie_loop_wrappers.f90 passes."""
+    import contextlib
+    import io
+    from numpy.f2py import crackfortran
+    crackfortran.verbose = 0
+    want = {"goldstein/goldstein.f90": ["step_goldstein"], "embm/embm.f90": ["step_embm", "surflux"],
+            "goldsteinseaice/gold_seaice.f90": ["step_seaice"],
+            "biogem/biogem.f90": ["biogem_forcing", "step_biogem", "biogem_tracercoupling", "biogem_climate", "biogem_climate_sol"],
+            "atchem/atchem.f90": ["step_atchem", "cpl_flux_ocnatm", "cpl_comp_atmocn", "cpl_comp_embm"],
+            "sedgem/sedgem.f90": ["cpl_flux_ocnsed", "cpl_comp_ocnsed"], "rokgem/rokgem.f90": ["reinit_flux_rokocn"]}
+
+    def walk(b, out):
+        if b.get("block") in ("subroutine", "function"):
+            out[b["name"].lower()] = b
+        for c in b.get("body", []):
+            walk(c, out)
+
+    sigs = {}
+    for f, names in want.items():
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            blocks = crackfortran.crackfortran(["/root/reference/src/" + f])
+        procs = {}
+        for b in blocks:
+            walk(b, procs)
+        for n in names:
+            p = procs[n]
+            sigs[n] = {"file": "src/" + f, "args": [{"name": a.lower(), "type": p["vars"][a].get("typespec"),
+                                                     "rank": len(p["vars"][a].get("dimension", [])),
+                                                     "intent": sorted(p["vars"][a].get("intent") or [])} for a in p["args"]]}
+    out = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ref_signatures.json")
+    json.dump({"source": "numpy.f2py.crackfortran over /root/reference/src (tools/make_golden.py ref_signatures)", "procedures": sigs},
+              open(out, "w"), indent=1)
+
+
+if os.path.isdir("/root/reference/src"):
+    ref_signatures()
