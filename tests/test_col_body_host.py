@@ -58,7 +58,12 @@ def test_lockstep_convection_decisions_match_oracle(nsteps):
     _check_against_oracle(nsteps, 6)
 
 
-def _check_against_oracle(nsteps, mix):
+@pytest.mark.parametrize("nsteps,nrepeat", [(5 * 80, 12), (5 * 960, 8)])
+def test_lockstep_convection_decisions_along_a_trajectory(nsteps, nrepeat):
+    _check_against_oracle(nsteps, 6, nrepeat)
+
+
+def _check_against_oracle(nsteps, mix, nrepeat=1):
     lib = _lib()
     oras = [Oracle("worjh2", maxk=K, maxl=L, nyear=96), Oracle("worjh2", maxk=K, maxl=L, nyear=96, diff1=2600.0, diff2=1.3e-5)]
     for o in oras:
@@ -88,26 +93,31 @@ def _check_against_oracle(nsteps, mix):
     jm = np.ascontiguousarray(np.stack([o0.f(n)[:J + 2] for n in ("rc", "rc2", "cv", "cv2", "dsv", "rdsv", "rds")]))
     km = np.ascontiguousarray(np.stack([o0.f(n)[:K + 2] for n in ("dz", "dza", "rdz", "rdza", "ssmax")]))
     dp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.col_host_step(MS, dp(k1), dp(cols), len(cols), dp(ts_cur), dp(ts_new), dp(tsflux), dp(sst), dp(rho), dp(u),
-                           dp(cost), dp(diff1), dp(diff2), dp(ec), dp(jm), dp(km), C.c_double(o0.s("dphi")),
-                           C.c_double(o0.s("rdphi")), C.c_double(float(o0.f("dt")[K])), mix)
-    assert rc == 0
     wet = (k1i[1:J + 1, 1:I + 1][None, :, :] <= np.arange(1, K + 1)[:, None, None])
     nmixed = 0
-    for w, o in enumerate(oras):
-        o.call("tstepo")
-        ts_ref, rho_ref, cost_ref = _after(o)
-        for m in (w, w + 30):
-            got = ts_new[..., m]
-            scale = np.maximum(np.abs(ts_ref[wet]).max(axis=0), 1e-30)
-            err = np.max(np.abs(got[wet] - ts_ref[wet]) / scale)
-            erho = np.max(np.abs(rho[..., m][wet] - rho_ref[wet]) / np.abs(rho_ref[wet]).max())
-            assert err < 1e-12, (w, m, err)
-            assert erho < 1e-12, (w, m, erho)
-            assert np.array_equal(cost[..., m], cost_ref)       # same mixing decisions, level for level
-            assert np.array_equal(sst[0, :, :, m][wet[K - 1]], ts_ref[K - 1, :, :, 0][wet[K - 1]]) or \
-                np.max(np.abs(sst[0, :, :, m][wet[K - 1]] - ts_ref[K - 1, :, :, 0][wet[K - 1]])) < 1e-12
-        nmixed += int((cost_ref - st[w]["cost"]).sum())
+    # nrepeat > 1: the tracer step repeated under the frozen flow and surface fluxes of the state (the oracle's tstepo leaves ts1 = ts
+    # and the halo refreshed, :2410-2432): the decisions must stay the oracle's along a trajectory, not just for one step
+    for rep in range(nrepeat):
+        rc = lib.col_host_step(MS, dp(k1), dp(cols), len(cols), dp(ts_cur), dp(ts_new), dp(tsflux), dp(sst), dp(rho), dp(u),
+                               dp(cost), dp(diff1), dp(diff2), dp(ec), dp(jm), dp(km), C.c_double(o0.s("dphi")),
+                               C.c_double(o0.s("rdphi")), C.c_double(float(o0.f("dt")[K])), mix)
+        assert rc == 0
+        for w, o in enumerate(oras):
+            before = o.f("cost").sum()
+            o.call("tstepo")
+            ts_ref, rho_ref, cost_ref = _after(o)
+            for m in (w, w + 30):
+                got = ts_new[..., m]
+                scale = np.maximum(np.abs(ts_ref[wet]).max(axis=0), 1e-30)
+                err = np.max(np.abs(got[wet] - ts_ref[wet]) / scale)
+                erho = np.max(np.abs(rho[..., m][wet] - rho_ref[wet]) / np.abs(rho_ref[wet]).max())
+                assert err < 1e-12 * (rep + 1), (rep, w, m, err)
+                assert erho < 1e-12 * (rep + 1), (rep, w, m, erho)
+                assert np.array_equal(cost[..., m], cost_ref), (rep, w, m)      # same mixing decisions, level for level
+                assert np.array_equal(sst[0, :, :, m][wet[K - 1]], ts_ref[K - 1, :, :, 0][wet[K - 1]]) or \
+                    np.max(np.abs(sst[0, :, :, m][wet[K - 1]] - ts_ref[K - 1, :, :, 0][wet[K - 1]])) < 1e-12 * (rep + 1)
+            nmixed += int(cost_ref.sum() - before)
+        ts_cur, ts_new = ts_new, ts_cur
     assert nmixed > 0          # the state exercises the convective adjustment
 
 
