@@ -1576,9 +1576,10 @@ CG_HD void co_decide_core(const Dev &v, const GridC &g, const int c2, const unsi
 // the thickness-weighted means of the boxes that grew (summed top-down over the levels, as the passive tracers' means are) and their
 // density, (3) repeat until a pass marks nothing.  A chain of unstable pairs is merged in one pass, as the reference merges a run;
 // boxes that did not grow keep their values bit for bit (an unmixed level keeps the rho the flux kernel stored, so ties are decided
-// on the reference's operands).  The walk of co_decide_core (one box at a time, down and back up, thread-private arrays indexed per
-// lane) visits the same comparisons in another order: same final partition, box means equal to rounding (the means of means of the
-// sequential merges against sums over levels); cost counts the same levels.  ieos = 0, iconv = 0 only (as every `col` kernel).
+// on the reference's operands).  Box means equal those of co_decide_core's walk (one box at a time, down and back up, thread-private
+// arrays indexed per lane) to rounding -- sums over levels against the means of means of the sequential merges -- and cost counts the
+// same levels whenever the partition is the same, which is a matter of the ORDER of the merges (next paragraph).  ieos = 0, iconv = 0
+// only (as every `col` kernel).
 // WALK = true: the passes follow the reference's own ORDER of merges -- its walk (one box at a time from the top, after a merge first
 // against the box below, then back up one box at a time) is replayed on the mask of unstable boundaries (integer work only: the
 // comparisons of a pass are all taken beforehand, in static loops), and a pass merges exactly the run the walk would merge next.  With a
