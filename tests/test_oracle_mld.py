@@ -64,3 +64,19 @@ def test_wind_energy_input_follows_the_stress():
     tv2 = (tau[j, i, 1] + tau[j - 1, i, 1]) * 0.5
     r = np.sqrt(np.sqrt(tv4 * tv4 + tv2 * tv2))
     assert ke[j, i] == 2.5 * (r * r * r)
+
+
+def test_self_generated_regression_vector():
+    """One model year with imld = 1 against numbers this oracle produced when the restatement was written (tests/golden/, self-generated:
+    it pins the oracle against accidental change, not against gfortran)."""
+    import json
+    import os
+    from test_oracle import inventory
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_eb_go_gs_36x36x8_imld_1yr.json")))
+    o = Oracle("worbe2", maxk=K, maxl=L, nyear=100, imld=1)
+    o.run(500)
+    inv = inventory(o, K, L)
+    got = dict(T=float(inv[0]), S=float(inv[1]), mld_sum=float(o.f("mld").sum()), mld_min=float(o.f("mld").min()),
+               mldk_sum=int(o.i("mldk").sum()), cost=float(o.f("cost").sum()), psi_max=float(o.f("psi").max()))
+    for k, v in g["values"].items():
+        assert np.isclose(got[k], v, rtol=1e-10, atol=1e-300), (k, got[k], v)
