@@ -80,3 +80,21 @@ def test_self_generated_regression_vector():
                mldk_sum=int(o.i("mldk").sum()), cost=float(o.f("cost").sum()), psi_max=float(o.f("psi").max()))
     for k, v in g["values"].items():
         assert np.isclose(got[k], v, rtol=1e-10, atol=1e-300), (k, got[k], v)
+
+
+def test_self_generated_regression_vector_with_biogem():
+    """... and one model year of the BIOGEM configuration with imld = 1: export production spread over the mixed layer
+    (sub_calc_bio_uptake, biogem_box.f90:423-430, 1194-1378; cgo_biogem.c surface_column)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_eb_go_gs_ac_bg_36x36x16_imld_1yr.json")))
+    o = Oracle(world="worjh2", maxk=16, maxl=16, nyear=96, imld=1)
+    o.biogem_setup()
+    o.run(480)
+    ocn, part = o.f("ocn").reshape(16, J, I, 16), o.f("bio_part").reshape(16, J, I, 9)
+    got = dict(DIC_sum=float(ocn[..., 2].sum()), PO4_surf=float(ocn[15, :, :, 5].sum()), O2_sum=float(ocn[..., 6].sum()),
+               POC_lev15=float(part[14, :, :, 0].sum()), mld_sum=float(o.f("bg_mld").sum()),
+               atm_pCO2=float(o.f("atm").reshape(J * I, 8)[:, 2].mean()))
+    assert got["POC_lev15"] > 0                      # production below the top level: the mixed layer reaches there
+    for k, v in g["values"].items():
+        assert np.isclose(got[k], v, rtol=1e-9, atol=1e-300), (k, got[k], v)
