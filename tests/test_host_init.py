@@ -155,3 +155,36 @@ def test_jobdir_roundtrip_bit_exact(tmp_path):
     z = np.load(os.path.join(ROOT, "configs", "inputs.npz"))
     back = np.array([float(t) for t in open(tmp_path / "input" / "embm" / "taux_u.interp").read().split()])
     assert np.array_equal(back.view(np.uint64), z["winds/taux_u"].view(np.uint64))
+
+
+def test_product_constants_are_the_references():
+    """The product's own constants (csrc/cg_host.hpp, cg_biogem.hpp: written separately from the oracle's macros) against the values of
+    the reference's PARAMETER declarations (tests/golden/ref_constants.json, evaluated from the reference's text), bit for bit."""
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_constants.json")))["constants"]
+    defs = {}
+    for f in ("cg_host.hpp", "cg_biogem.hpp"):
+        text = open(os.path.join(ROOT, "cgenie_b200", "csrc", f)).read()
+        for stmt in re.findall(r"constexpr double ([^;]+);", text):
+            for part in re.split(r",\s*(?=k[A-Z])", stmt):
+                name, expr = part.split("=", 1)
+                defs[name.strip()] = expr.strip()
+
+    def value(name, depth=0):
+        assert depth < 20
+        expr = re.sub(r"\bk[A-Z][A-Za-z0-9]*\b", lambda q: repr(value(q.group(0), depth + 1)), defs[name])
+        return float(eval(expr, {"__builtins__": {}}, {}))
+
+    names = {"CG_USC": "kUsc", "CG_RSC": "kRsc", "CG_DSC": "kDsc", "CG_FSC": "kFsc", "CG_GSC": "kGsc", "CG_RH0SC": "kRh0sc",
+             "CG_RHOSC": "kRhosc", "CG_TSC": "kTsc", "CG_CPSC": "kCpsc", "CG_RHOAIR": "kRhoair", "CG_RHO0": "kRho0", "CG_RHOAO": "kRhoao",
+             "CG_M2MM": "kM2mm", "CG_MM2M": "kMm2m", "CG_RFLUXSC": "kRfluxsc", "CG_CPA": "kCpa", "CG_CONST1": "kConst1",
+             "CG_CONST2": "kConst2", "CG_CONST3": "kConst3", "CG_CONST4": "kConst4", "CG_CONST5": "kConst5", "CG_SIGMA": "kSigma",
+             "CG_EMO": "kEmo", "CG_EMA": "kEma", "CG_TFREEZ": "kTfreez", "CG_HLV": "kHlv", "CG_HLF": "kHlf", "CG_HLS": "kHls",
+             "CG_CONSIC": "kConsic", "CG_ZEROC": "kZeroc", "CG_CPO_ICE": "kCpoIce", "CG_RHOICE": "kRhoice", "CG_HMIN": "kHmin",
+             "CG_RHMIN": "kRhmin", "CG_RHOOI": "kRhooi", "CG_RHOIO": "kRhoio", "CG_RRHOLF": "kRrholf", "CG_CO20": "kCo20",
+             "CG_CH40": "kCh40", "CG_N2O0": "kN2o0", "CG_ALPHACH4": "kAlphaCh4", "CG_ALPHAN2O": "kAlphaN2o", "CG_TSIC": "kTsic",
+             "CG_CD": "kCd", "BG_ZEROC": "kBgZeroC", "BG_NULL": "kBgNull", "BG_NULLSMALL": "kBgNullSmall", "BG_YR_S": "kBgYrS",
+             "BG_LAMBDA_14C": "kBgLambda14C", "BG_M3_KG": "kBgM3Kg", "BG_PI": "kBgPi", "BG_REARTH": "kBgREarth"}
+    for macro, k in names.items():
+        assert k in defs, k
+        assert value(k).hex() == ref[macro]["hex"], (k, value(k), ref[macro])

@@ -140,3 +140,32 @@ def test_insolation_annual_global_mean():
     lat_mean = sol.reshape(100, 36).mean(axis=0)       # solfor(maxj, nyear), Fortran order
     assert lat_mean[0] < 200.0 and lat_mean[-1] < 200.0 and 390.0 < lat_mean[17] < 430.0      # ~175 W m-2 at the poles, ~417 at the equator
     assert np.all(sol >= 0.0)
+
+
+def test_oracle_constants_are_the_references():
+    """Every physical constant the oracle carries as a macro (oracle/cgo_impl.h, cgo_biogem.c) against the value of the reference's own
+    PARAMETER declaration, evaluated from the reference's text (goldstein_lib.f90, embm_lib.f90, gem_cmn.f90: tests/golden/
+    ref_constants.json, tools/make_golden.py) -- bit for bit, derived constants (rhosc, rfluxsc, conv_yr_s ...) included."""
+    import json
+    import math
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(root, "tests", "golden", "ref_constants.json")))["constants"]
+    assert len(ref) >= 59
+    defs = {}
+    for f in ("cgo_impl.h", "cgo_biogem.c"):
+        for line in open(os.path.join(root, "oracle", f)):
+            m = re.match(r"#define\s+((?:CG|BG)_[A-Z0-9_]+)\s+(.+?)\s*(?:/\*.*)?$", line)
+            if m:
+                defs.setdefault(m.group(1), m.group(2))
+
+    def value(name, depth=0):
+        assert depth < 20
+        expr = re.sub(r"\b((?:CG|BG)_[A-Z0-9_]+)\b", lambda q: repr(value(q.group(1), depth + 1)), defs[name])
+        return float(eval(expr, {"__builtins__": {}}, {"atan": math.atan}))
+
+    for macro, r in ref.items():
+        assert macro in defs, macro
+        got = value(macro)
+        assert got.hex() == r["hex"], "%s = %r, the reference's %s (%s) = %r" % (macro, got, r["name"], r["file"], r["value"])

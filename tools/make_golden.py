@@ -76,3 +76,83 @@ def ref_signatures():
 
 if os.path.isdir("/root/reference/src"):
     ref_signatures()
+
+
+# oracle macro -> (reference file under src/, PARAMETER name); the values themselves come from the reference's text
+REF_CONSTANTS = {
+    "goldstein/goldstein_lib.f90": dict(CG_USC="usc", CG_RSC="rsc", CG_DSC="dsc", CG_FSC="fsc", CG_GSC="gsc", CG_RH0SC="rh0sc", CG_RHOSC="rhosc",
+                                        CG_TSC="tsc", CG_CPSC="cpsc", CG_RHOAIR="rhoair", CG_RHO0="rho0", CG_RHOAO="rhoao", CG_M2MM="m2mm",
+                                        CG_MM2M="mm2m", CG_RFLUXSC="rfluxsc", CG_CPA="cpa", CG_PI="pi", CG_ZEROC="zeroc", CG_CPO_ICE="cpo_ice"),
+    "embm/embm_lib.f90": dict(CG_CONST1="const1", CG_CONST2="const2", CG_CONST3="const3", CG_CONST4="const4", CG_CONST5="const5",
+                              CG_SIGMA="sigma", CG_EMO="emo", CG_EMA="ema", CG_TFREEZ="tfreez", CG_HLV="hlv", CG_HLF="hlf", CG_HLS="hls",
+                              CG_CONSIC="consic", CG_RHOICE="rhoice", CG_HMIN="hmin", CG_RHMIN="rhmin", CG_RHOOI="rhooi", CG_RHOIO="rhoio",
+                              CG_RRHOLF="rrholf", CG_CO20="co20", CG_CH40="ch40", CG_N2O0="n2o0", CG_ALPHACH4="alphach4",
+                              CG_ALPHAN2O="alphan2o", CG_TSIC="tsic", CG_CD="cd"),
+    "common/gem_cmn.f90": dict(BG_PI="const_pi", BG_REARTH="const_rearth", BG_M3_KG="conv_m3_kg", BG_ZEROC="const_zeroc", BG_NULL="const_real_null",
+                               BG_NULLSMALL="const_real_nullsmall", BG_YR_S="conv_yr_s", BG_ATM_MOL="conv_atm_mol", BG_R="const_r",
+                               BG_R_SI="const_r_si", BG_V="const_v", BG_CP="const_cp", BG_CONC_MG="const_conc_mg",
+                               BG_CONC_MGTOCA="const_conc_mgtoca", BG_LAMBDA_14C="const_lambda_14c", BG_PA_ATM="conv_pa_atm"),
+}
+
+
+def fortran_parameters(path):
+    """REAL / INTEGER PARAMETER constants of a Fortran source as {lower-case name: value}: the declarations are evaluated in order, with
+    the names defined so far in scope (E / D exponents, ATAN, ** as written); what cannot be evaluated (arrays, kind expressions) is
+    skipped.  -fdefault-real-8 (platforms/LINUX:7-17) makes every REAL literal a double, as a Python float is."""
+    import math
+    import re
+    text = open(path, errors="replace").read()
+    text = re.sub(r"&\s*\n\s*&?", " ", text)
+    ns = {"atan": math.atan, "sqrt": math.sqrt, "exp": math.exp, "log": math.log, "real": float}
+    out = {}
+    for line in text.split("\n"):
+        line = line.split("!")[0]
+        m = re.match(r"\s*(REAL|INTEGER)\b[^:]*\bPARAMETER\b[^:]*::(.*)", line, flags=re.I)
+        if not m:
+            continue
+        depth, cur, parts = 0, "", []
+        for ch in m.group(2):
+            if ch == "(":
+                depth += 1
+            if ch == ")":
+                depth -= 1
+            if ch == "," and depth == 0:
+                parts.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        parts.append(cur)
+        for p in parts:
+            if "=" not in p:
+                continue
+            name, expr = p.split("=", 1)
+            name, expr = name.strip().lower(), expr.strip().lower()
+            if "(" in name:
+                continue
+            expr = re.sub(r"(\d\.?\d*|\.\d+)d([-+]?\d+)", r"\1e\2", expr)
+            expr = re.sub(r"_\w+\b", "", expr) if re.search(r"\d_\w+", expr) else expr
+            try:
+                out[name] = float(eval(expr, {"__builtins__": {}}, dict(ns, **out)))
+            except Exception:
+                pass
+    return out
+
+
+def ref_constants():
+    """tests/golden/ref_constants.json: the reference's own values of every physical constant the oracle carries as a macro."""
+    vals = {}
+    for f, table in REF_CONSTANTS.items():
+        pars = fortran_parameters("/root/reference/src/" + f)
+        for macro, name in table.items():
+            if name in pars:
+                vals[macro] = {"file": "src/" + f, "name": name, "value": pars[name], "hex": float(pars[name]).hex()}
+            else:
+                print("ref_constants: %s not found in %s" % (name, f))
+    out = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ref_constants.json")
+    json.dump({"source": "PARAMETER declarations of /root/reference/src (tools/make_golden.py ref_constants)", "constants": vals},
+              open(out, "w"), indent=1)
+    return vals
+
+
+if os.path.isdir("/root/reference/src"):
+    ref_constants()
