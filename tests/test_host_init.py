@@ -188,3 +188,105 @@ def test_product_constants_are_the_references():
     for macro, k in names.items():
         assert k in defs, k
         assert value(k).hex() == ref[macro]["hex"], (k, value(k), ref[macro])
+
+
+@pytest.mark.parametrize("config", ["eb_go_gs_36x36x8", "eb_go_gs_ac_bg_36x36x16"])
+def test_job_namelists_are_the_reference_defaults_but_for_the_configuration(tmp_path, config):
+    """The base configs of the BASELINE jobs live in the un-vendored cgenie-data repository, so the job directories of this repo are
+    reconstructions.  What can be held to the reference is held: every key a job namelist carries exists in the reference's
+    own *-defaults.nml (tests/golden/ref_namelist_defaults.json, parsed from src/), and every value IS the reference's default except
+    the ones that make the configuration -- module flags, time stepping, topography / dimensions, tracer selections, initial
+    inventories, the forcing directory."""
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_namelist_defaults.json")))["defaults"]
+    materialise(str(tmp_path), config)
+    allowed = {"data_genie": r"flag_\w+|k\w+_loop|conv_kocn_k\w+|genie_timestep|fname_topo|dim_goldsteinn\w+",
+               "data_GOLD": r"world|nyear", "data_EMBM": r"world|nyear", "data_goldSIC": r"world|nyear",
+               "data_GEM": r"(ocn|sed|atm)_select\(\d+\)", "data_BIOGEM": r"ocn_init\(\d+\)|par_fordir_name", "data_ATCHEM": r"atm_init\(\d+\)"}
+
+    def parse(path):
+        out = {}
+        for ln in open(path):
+            ln = ln.strip()
+            if not ln or ln[0] in "&/!" or "=" not in ln:
+                continue
+            k, v = ln.rstrip(",").split("=", 1)
+            out[k.strip().lower()] = v.strip()
+        return out
+
+    def norm(v):
+        v = v.strip().strip('"').strip("'")
+        if v.upper() in (".TRUE.", "T", ".T."):
+            return True
+        if v.upper() in (".FALSE.", "F", ".F."):
+            return False
+        try:
+            return float(v.lower().replace("d", "e"))
+        except ValueError:
+            return v
+
+    nkeys = ndev = 0
+    for f, pat in allowed.items():
+        p = tmp_path / f
+        if not p.exists():
+            assert f in ("data_GEM", "data_BIOGEM", "data_ATCHEM") and "ac_bg" not in config
+            continue
+        for k, v in parse(p).items():
+            nkeys += 1
+            assert k in ref[f], "%s: key %s is not in the reference's defaults file" % (f, k)
+            if norm(v) != norm(ref[f][k]):
+                ndev += 1
+                assert re.fullmatch(pat, k), "%s: %s = %s differs from the reference's default %s" % (f, k, v, ref[f][k])
+    print("%s: %d keys, %d set by the configuration" % (config, nkeys, ndev))
+    assert nkeys > 100 and ndev < 70
+
+
+def test_builtin_parameter_defaults_are_the_references():
+    """The defaults the product (struct Params, csrc/cg_host.hpp) and the oracle (PD / PI_ in oracle/cgo_driver.c) fall back to when a
+    namelist does not carry a key, against the reference's *-defaults.nml (tests/golden/ref_namelist_defaults.json)."""
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_namelist_defaults.json")))["defaults"]
+    pool = {}
+    for f in ("data_GOLD", "data_EMBM", "data_goldSIC", "data_genie", "data_BIOGEM"):
+        for k, v in ref[f].items():
+            pool.setdefault(k, []).append(v)
+    alias = {"diff1": "diff(1)", "diff2": "diff(2)", "diffamp1": "diffamp(1)", "diffamp2": "diffamp(2)", "betaz1": "betaz(1)",
+             "betaz2": "betaz(2)", "betam1": "betam(1)", "betam2": "betam(2)", "solconst": "genie_solar_constant",
+             "z1_embm": "z1_embm", "maxi": "dim_goldsteinnlons", "maxj": "dim_goldsteinnlats", "maxk": "dim_goldsteinnlevs",
+             "maxl": "dim_goldsteinntracs"}
+
+    def num(v):
+        v = v.strip().strip('"').strip("'")
+        if v.upper() in (".TRUE.", "T"):
+            return 1.0
+        if v.upper() in (".FALSE.", "F"):
+            return 0.0
+        if v.lower() in ("y", "n"):               # the reference's CHARACTER switches (atchem_radfor, fwanomin ...)
+            return 1.0 if v.lower() == "y" else 0.0
+        try:
+            return float(v.lower().replace("d", "e"))
+        except ValueError:
+            return v
+
+    mine = {}
+    hpp = open(os.path.join(ROOT, "cgenie_b200", "csrc", "cg_host.hpp")).read()
+    body = hpp[hpp.index("struct Params {"):hpp.index("bool set(const std::string &name, double v);")]
+    body = re.sub(r"//[^\n]*", "", body)
+    for name, val in re.findall(r"\b([a-z_][a-z0-9_]*)\s*=\s*(-?[0-9][0-9.eE+-]*|true|false)\b", body):
+        mine.setdefault(name, []).append(("product", 1.0 if val == "true" else 0.0 if val == "false" else float(val)))
+    drv = open(os.path.join(ROOT, "oracle", "cgo_driver.c")).read()
+    for name, val in re.findall(r"\bP(?:D|I_)\(\s*([a-z_0-9]+)\s*,\s*(-?[0-9][0-9.eE+-]*)\s*\)", drv):
+        mine.setdefault(name, []).append(("oracle", float(val)))
+    # what makes a configuration, not a default: set by every job directory (timestepping() of jobdir.py, config_utils.py:103-162)
+    config_keys = {"kocn_loop", "ksic_loop", "katm_loop", "conv_kocn_kbiogem", "conv_kocn_katchem", "genie_timestep", "maxk", "maxl",
+                   "flag_biogem", "flag_atchem"}
+    checked = 0
+    for name, lst in mine.items():
+        key = alias.get(name, name)
+        if key not in pool or name in config_keys:
+            continue
+        want = {num(v) for v in pool[key]}
+        for who, val in lst:
+            assert val in want, "%s default of %s = %r, the reference's %s" % (who, name, val, sorted(map(str, want)))
+            checked += 1
+    assert checked >= 120, checked

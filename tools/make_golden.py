@@ -156,3 +156,32 @@ def ref_constants():
 
 if os.path.isdir("/root/reference/src"):
     ref_constants()
+
+
+REF_NAMELISTS = {"data_genie": "main-defaults.nml", "data_GOLD": "goldstein/goldstein-defaults.nml", "data_EMBM": "embm/embm-defaults.nml",
+                 "data_goldSIC": "goldsteinseaice/goldsteinseaice-defaults.nml", "data_GEM": "gem-defaults.nml",
+                 "data_BIOGEM": "biogem/biogem-defaults.nml", "data_ATCHEM": "atchem/atchem-defaults.nml"}
+
+
+def parse_namelist(path):
+    out = {}
+    for ln in open(path, errors="replace"):
+        ln = ln.strip()
+        if not ln or ln[0] in "&/!" or "=" not in ln:
+            continue
+        k, v = ln.rstrip(",").split("=", 1)
+        out[k.strip().lower()] = v.strip()
+    return out
+
+
+def ref_namelist_defaults():
+    """tests/golden/ref_namelist_defaults.json: the reference's *-defaults.nml files (src/), key by key, for the namelists a job directory
+    of this repo carries (cgenie_b200/jobdir.py).  tests/test_host_init.py holds the reconstructed BASELINE configurations to them."""
+    d = {f: parse_namelist("/root/reference/src/" + r) for f, r in REF_NAMELISTS.items()}
+    out = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ref_namelist_defaults.json")
+    json.dump({"source": "src/*-defaults.nml of /root/reference (tools/make_golden.py ref_namelist_defaults)", "files": REF_NAMELISTS,
+               "defaults": d}, open(out, "w"), indent=0)
+
+
+if os.path.isdir("/root/reference/src"):
+    ref_namelist_defaults()
