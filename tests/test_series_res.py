@@ -295,3 +295,25 @@ def test_series_saver_extended(built, tmp_path):
     for k in range(kb, 5 * nyear + 1, kb):
         s2.step(dts, k * tick)
     assert open(tmp_path / "y" / "biogem_series_misc_opsi.res").read().split("\n")[1] == "       0.500  -15.925   31.850"
+
+
+def test_frozen_tracer_tables_are_the_references():
+    """The frozen 16 / 8 / 9 tracer selection as the Python host carries it (restart.OCN_TRACERS / ATM_TRACERS / SED_TRACERS with their
+    global indices, series.*_TYPE / *_DEP) against data/main/tracer_define.{ocn,atm,sed} of the reference (tests/golden/
+    ref_tracer_define.json): names, long names, types, and the dependencies mapped to compact indices."""
+    import json
+    import os
+    from cgenie_b200 import restart, series
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_tracer_define.json")))["tracers"]
+    by = {k: {r["index"]: r for r in rows} for k, rows in ref.items()}
+    sel = {"ocn": (restart.OCN_IDS, [n for n, _ in restart.OCN_TRACERS], [l for _, l in restart.OCN_TRACERS], series.OCN_TYPE, series.OCN_DEP),
+           "atm": ([i for i, _, _ in restart.ATM_TRACERS], [n for _, n, _ in restart.ATM_TRACERS], [l for _, _, l in restart.ATM_TRACERS],
+                   series.ATM_TYPE, series.ATM_DEP),
+           "sed": (restart.SED_IDS, [n for n, _ in restart.SED_TRACERS], [l for _, l in restart.SED_TRACERS], series.SED_TYPE, series.SED_DEP)}
+    for kind, (ids, names, longs, types, deps) in sel.items():
+        assert len(ids) == len(names) == len(types) == len(deps)
+        for q, gi in enumerate(ids):
+            r = by[kind][gi]
+            assert r["name"] == names[q] and r["long_name"] == longs[q], (kind, gi, r, names[q], longs[q])
+            assert r["type"] == types[q], (kind, r["name"], r["type"], types[q])
+            assert ids.index(r["dep"]) == deps[q], (kind, r["name"], r["dep"], deps[q])

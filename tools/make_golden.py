@@ -185,3 +185,33 @@ def ref_namelist_defaults():
 
 if os.path.isdir("/root/reference/src"):
     ref_namelist_defaults()
+
+
+def ref_tracer_definitions():
+    """tests/golden/ref_tracer_define.json: data/main/tracer_define.{ocn,atm,sed} of the reference (name, index, dependency, type, long
+    name, units per tracer) -- what the frozen 16 / 8 / 9 tracer selection of the product is held to."""
+    import re
+    out = {}
+    for kind in ("ocn", "atm", "sed"):
+        rows, on = [], False
+        for ln in open("/root/reference/data/main/tracer_define." + kind, errors="replace"):
+            if "-START-OF-DATA-" in ln:
+                on = True
+                continue
+            if "-END-OF-DATA-" in ln:
+                break
+            if not on or not ln.strip():
+                continue
+            m = re.match(r"\s*(\S+)\s+(\d+)\s+(\d+)\s+(\d+)\s+'([^']*)'\s+'([^']*)'", ln)
+            if m:
+                rows.append({"name": m.group(1), "index": int(m.group(2)), "dep": int(m.group(3)), "type": int(m.group(4)),
+                             "long_name": m.group(5), "units": m.group(6)})
+        out[kind] = rows
+    p = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ref_tracer_define.json")
+    json.dump({"source": "data/main/tracer_define.{ocn,atm,sed} of /root/reference (tools/make_golden.py ref_tracer_definitions)",
+               "tracers": out}, open(p, "w"), indent=0)
+    return out
+
+
+if os.path.isdir("/root/reference/data/main"):
+    ref_tracer_definitions()
