@@ -169,3 +169,24 @@ def test_oracle_constants_are_the_references():
         assert macro in defs, macro
         got = value(macro)
         assert got.hex() == r["hex"], "%s = %r, the reference's %s (%s) = %r" % (macro, got, r["name"], r["file"], r["value"])
+
+
+def test_gas_exchange_tables_are_the_references():
+    """Schmidt-number and Bunsen-coefficient rows of the four gases of the frozen selection, as the oracle (cgo_biogem.c) and the product
+    (csrc/cg_biogem.cu) carry them, against src/common/gem_data.f90:69-136 (tests/golden/ref_gas_tables.json)."""
+    import json
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(root, "tests", "golden", "ref_gas_tables.json")))["tables"]
+    label = {"IA_PCO2": "pCO2", "IA_PO2": "pO2", "IA_PCFC11": "pCFC11", "IA_PCFC12": "pCFC12"}
+    for path in (os.path.join(root, "oracle", "cgo_biogem.c"), os.path.join(root, "cgenie_b200", "csrc", "cg_biogem.cu")):
+        text = open(path).read()
+        for arr, key, n in (("Sc", "schmidt", 4), ("Bu", "bunsen", 6)):
+            body = text[text.index("double %s[][%d] = {" % (arr, n + 1)):]
+            body = body[:body.index("};")]
+            rows = re.findall(r"\{(IA_\w+),([^}]*)\}", body)
+            assert len(rows) == 4, (path, arr)
+            for ia, nums in rows:
+                got = [float(x) for x in nums.split(",")]
+                assert got == ref[key][label[ia]], (path, arr, ia, got, ref[key][label[ia]])

@@ -215,3 +215,28 @@ def ref_tracer_definitions():
 
 if os.path.isdir("/root/reference/data/main"):
     ref_tracer_definitions()
+
+
+def ref_gas_tables():
+    """tests/golden/ref_gas_tables.json: the Schmidt-number and Bunsen-coefficient tables of src/common/gem_data.f90:69-136, row by row
+    (keyed by the row's comment label)."""
+    import re
+    text = open("/root/reference/src/common/gem_data.f90", errors="replace").read()
+    out = {}
+    for key, start in (("schmidt", "par_Sc_coef(:,:) = reshape"), ("bunsen", "par_bunsen_coef(:,:) = reshape")):
+        body = text[text.index(start):]
+        body = body[:body.index("/), &")]
+        rows = {}
+        for ln in body.split("\n"):
+            m = re.match(r"\s*&\s*((?:\s*-?\d+\.\d+\s*,?)+)\s*&\s*!\s*(\S+)", ln)
+            if m:
+                rows[m.group(2)] = [float(x) for x in m.group(1).replace(" ", "").rstrip(",").split(",")]
+        out[key] = rows
+    p = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ref_gas_tables.json")
+    json.dump({"source": "src/common/gem_data.f90:69-136 of /root/reference (tools/make_golden.py ref_gas_tables)", "tables": out},
+              open(p, "w"), indent=0)
+    return out
+
+
+if os.path.isfile("/root/reference/src/common/gem_data.f90"):
+    ref_gas_tables()
