@@ -290,3 +290,20 @@ def test_builtin_parameter_defaults_are_the_references():
             assert val in want, "%s default of %s = %r, the reference's %s" % (who, name, val, sorted(map(str, want)))
             checked += 1
     assert checked >= 120, checked
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data/goldstein"), reason="the reference tree is not mounted here")
+def test_packed_inputs_are_the_reference_data_files():
+    """configs/inputs.npz (what tests, smoke() and bench.py read where /root/reference does not exist) against the reference's data
+    files themselves -- topographies, island paths, wind stresses and speeds, BIOGEM's wind-speed field -- value for value.  Runs in
+    the build container only (the GPU box has no reference tree)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pack_inputs", os.path.join(ROOT, "tools", "pack_inputs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fresh = mod.collect()
+    z = np.load(os.path.join(ROOT, "configs", "inputs.npz"))
+    assert set(z.files) == set(fresh), sorted(set(z.files) ^ set(fresh))
+    for k, v in fresh.items():
+        assert z[k].dtype == v.dtype and z[k].shape == v.shape, k
+        assert np.array_equal(z[k].view(np.uint8), np.ascontiguousarray(v).view(np.uint8)), k

@@ -39,7 +39,8 @@ def read_paths(path):
     return np.array(npi, dtype=np.int32), np.array(trip, dtype=np.int32).reshape(-1, 3)
 
 
-def main():
+def collect():
+    """The packed arrays, read from the reference's data files."""
     out = {}
     # worbe2 / worjh2: the target configurations (one island each); p0055c (2 islands), p0251a (3 islands): 36 x 36 x 16 worlds for
     # the multi-island barotropic closure (matmult, goldstein.f90:203-216, 3470-3492)
@@ -59,6 +60,11 @@ def main():
     # BIOGEM prescribed wind speed, file rows j = maxj..1, i = 1..maxi per row (gem_util.f90:511-536)
     b = os.path.join(REF, "data", "biogem", "worjh2_preindustrial", "windspeed.dat")
     out["biogem/worjh2_windspeed"] = np.array(read_numbers(b)).reshape(36, 36)   # [row = maxj - j][i - 1]
+    return out
+
+
+def main():
+    out = collect()
     for k, v in out.items():
         print(k, v.shape, v.dtype)
     np.savez_compressed(OUT, **out)
