@@ -190,3 +190,31 @@ def test_gas_exchange_tables_are_the_references():
             for ia, nums in rows:
                 got = [float(x) for x in nums.split(",")]
                 assert got == ref[key][label[ia]], (path, arr, ia, got, ref[key][label[ia]])
+
+
+def test_restoring_forcing_is_the_references():
+    """The atmospheric restoring forcing of the frozen configuration -- which tracers, time constant, two-point signal, end members 0 / 1
+    -- as the job directory (cgenie_b200/jobdir.py BG_RESTORE) and the oracle (cgo_biogem.c, sub_init_force_restore_atm block) carry it,
+    against data/biogem/worjh2_preindustrial of the reference (tests/golden/ref_forcing_worjh2_preindustrial.json)."""
+    import json
+    import os
+    import re
+    from cgenie_b200 import jobdir
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(root, "tests", "golden", "ref_forcing_worjh2_preindustrial.json")))
+    assert ref["n_atm_rows"] == 19
+    assert sorted(jobdir.BG_RESTORE) == ref["restored"]
+    for ia, (tc, val) in jobdir.BG_RESTORE.items():
+        r = ref["restore_atm"][str(ia)]
+        assert jobdir.BG_ATM_NAMES[ia] == r["name"]
+        assert tc == r["tconst"] and not r["flux"]
+        assert r["sig"] == [[0.0, val], [999999.0, val]]
+        assert r["I"] == [0.0, 0.0, 1296] and r["II"] == [0.0, 1.0, 1296]
+    text = open(os.path.join(root, "oracle", "cgo_biogem.c")).read()
+    body = text[text.index("static const double sig[][2] = {"):]
+    body = body[:body.index("};")]
+    rows = dict(re.findall(r"\{(IA_\w+),\s*([^}]+)\}", body))
+    assert len(rows) == len(ref["restored"])
+    for r in ref["restore_atm"].values():
+        assert float(rows["IA_" + r["name"].upper()]) == r["sig"][0][1]
+    assert "b->rst_tconst[la] = 0.1;" in text

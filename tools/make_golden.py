@@ -240,3 +240,41 @@ def ref_gas_tables():
 
 if os.path.isfile("/root/reference/src/common/gem_data.f90"):
     ref_gas_tables()
+
+
+def ref_forcing_set():
+    """tests/golden/ref_forcing_worjh2_preindustrial.json: the restoring forcing of data/biogem/worjh2_preindustrial as the frozen
+    configuration uses it -- which atmosphere tracers are restored and with which time constant (configure_forcings_atm.dat), the
+    time signal of each (*_sig.dat) and the range of the two spatial end members (*_I.dat, *_II.dat)."""
+    import re
+    d = "/root/reference/data/biogem/worjh2_preindustrial/"
+    rows, on = [], False
+    for ln in open(d + "configure_forcings_atm.dat", errors="replace"):
+        if "-START-OF-DATA-" in ln:
+            on = True
+            continue
+        if "-END-OF-DATA-" in ln:
+            break
+        if on and ln.strip():
+            t = ln.split()
+            rows.append({"restore": t[0].lower() == "t", "tconst": float(t[1]), "flux": t[2].lower() == "t"})
+    names = {3: "pCO2", 4: "pCO2_13C", 5: "pCO2_14C", 6: "pO2", 18: "pCFC11", 19: "pCFC12"}
+    out = {}
+    for ia, r in enumerate(rows, start=1):
+        if not r["restore"]:
+            continue
+        n = names[ia]
+        sig = [[float(x) for x in ln.split()] for ln in open(d + "biogem_force_restore_atm_%s_sig.dat" % n) if re.match(r"\s*-?\d", ln)]
+        ends = {}
+        for e in ("I", "II"):
+            v = [float(x) for x in open(d + "biogem_force_restore_atm_%s_%s.dat" % (n, e)).read().split()]
+            ends[e] = [min(v), max(v), len(v)]
+        out[str(ia)] = {"name": n, "tconst": r["tconst"], "flux": r["flux"], "sig": sig, "I": ends["I"], "II": ends["II"]}
+    p = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ref_forcing_worjh2_preindustrial.json")
+    json.dump({"source": "data/biogem/worjh2_preindustrial of /root/reference (tools/make_golden.py ref_forcing_set)", "restore_atm": out,
+               "n_atm_rows": len(rows), "restored": sorted(int(k) for k in out)}, open(p, "w"), indent=0)
+    return out
+
+
+if os.path.isdir("/root/reference/data/biogem/worjh2_preindustrial"):
+    ref_forcing_set()
