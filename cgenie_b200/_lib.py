@@ -112,6 +112,8 @@ SYMBOLS = {
     "cg_restart_date_read": (C.c_int, [C.c_char_p, I32]),
     "cg_restart_biogem_write": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [I32] + [D] * 6 + [C.c_int, STRS, STRS, D] * 2 +
                                 [C.c_double, C.c_char_p]),
+    "cg_slice_biogem_write_3d": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [I32] + [D] * 6 + [C.c_int, STRS, STRS, STRS, D, I32, I32, D] +
+                                 [C.c_int, STRS, I32, I32, D] + [C.c_int, STRS, D] * 2 + [D, C.c_double, C.c_double, C.c_char_p]),
     "cg_restart_biogem_read": (C.c_int, [C.c_char_p] + [C.c_int] * 3 + [I32] + [C.c_int, STRS, D, I32] * 2),
     "cg_restart_atchem_write": (C.c_int, [C.c_char_p, C.c_int, C.c_int] + [D] * 4 + [C.c_int, STRS, STRS, D, C.c_double, C.c_char_p]),
     "cg_restart_atchem_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, STRS, D, I32]),

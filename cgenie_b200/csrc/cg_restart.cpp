@@ -90,8 +90,9 @@ int Nc3File::add_dim(const std::string &name, int len) { dims.push_back({name, l
 int Nc3File::add_var(const std::string &name, int type, const std::vector<int> &dimids) {
   Nc3Var v;
   v.name = name; v.type = type; v.dimids = dimids; v.count = 1;
-  for (int d : dimids) v.count *= dims[d].second;
-  v.data.assign((size_t)v.count, 0.0);
+  v.rec = !dimids.empty() && dims[dimids[0]].second == 0;
+  for (size_t q = v.rec ? 1 : 0; q < dimids.size(); q++) v.count *= dims[dimids[q]].second;
+  v.data.assign((size_t)v.count * (size_t)(v.rec ? numrecs : 1), 0.0);
   vars.push_back(v);
   return (int)vars.size() - 1;
 }
@@ -105,6 +106,12 @@ void Nc3File::put_att_num(int varid, const std::string &name, int type, const st
 }
 void Nc3File::put(int varid, const double *v, long long n) { for (long long q = 0; q < n && q < vars[varid].count; q++) vars[varid].data[q] = v[q]; }
 void Nc3File::put(int varid, const int *v, long long n) { for (long long q = 0; q < n && q < vars[varid].count; q++) vars[varid].data[q] = v[q]; }
+void Nc3File::put_rec(int varid, int rec, const double *v, long long n) {
+  if (rec + 1 > numrecs) numrecs = rec + 1;
+  for (auto &w : vars) if (w.rec && w.data.size() < (size_t)w.count * (size_t)numrecs) w.data.resize((size_t)w.count * (size_t)numrecs, 0.0);
+  Nc3Var &w = vars[varid];
+  for (long long q = 0; q < n && q < w.count; q++) w.data[(size_t)rec * (size_t)w.count + (size_t)q] = v[q];
+}
 const Nc3Var *Nc3File::var(const std::string &name) const {
   for (auto &v : vars) if (v.name == name) return &v;
   return nullptr;
@@ -115,10 +122,11 @@ int Nc3File::dim_len(const std::string &name) const {
 }
 
 bool Nc3File::write(const std::string &path, std::string *err) const {
+  auto vsize = [](const Nc3Var &v) { return ((size_t)v.count * type_size(v.type) + 3) / 4 * 4; };   // record variables: of one record
   auto header = [&](const std::vector<uint32_t> &begin) {
     Out o;
     o.b = {'C', 'D', 'F', 1};
-    o.u32(0);   // numrecs: no record variables
+    o.u32((uint32_t)numrecs);
     if (dims.empty()) { o.u32(0); o.u32(0); }
     else { o.u32(kDimTag); o.u32((uint32_t)dims.size()); for (auto &d : dims) { o.name(d.first); o.u32((uint32_t)d.second); } }
     o.atts(gatts);
@@ -132,29 +140,37 @@ bool Nc3File::write(const std::string &path, std::string *err) const {
         for (int d : v.dimids) o.u32((uint32_t)d);
         o.atts(v.atts);
         o.u32((uint32_t)v.type);
-        o.u32((uint32_t)(((size_t)v.count * type_size(v.type) + 3) / 4 * 4));
+        o.u32((uint32_t)vsize(v));
         o.u32(begin[q]);
       }
     }
     return o;
   };
+  // the fixed-size variables in definition order, then the records: per record one slab of every record variable, in definition order
   std::vector<uint32_t> begin(vars.size(), 0);
-  size_t off = header(begin).b.size();
-  for (size_t q = 0; q < vars.size(); q++) {
-    begin[q] = (uint32_t)off;
-    off += ((size_t)vars[q].count * type_size(vars[q].type) + 3) / 4 * 4;
-    if (off > 0x7fffffffULL) { if (err) *err = "file too large for the classic format"; return false; }
-  }
+  size_t off = header(begin).b.size(), recsize = 0;
+  for (int pass = 0; pass < 2; pass++)
+    for (size_t q = 0; q < vars.size(); q++) {
+      if (vars[q].rec != (pass == 1)) continue;
+      begin[q] = (uint32_t)off;
+      off += vsize(vars[q]);
+      if (pass) recsize += vsize(vars[q]);
+    }
+  if (off + recsize * (size_t)(numrecs > 0 ? numrecs - 1 : 0) > 0x7fffffffULL) { if (err) *err = "file too large for the classic format"; return false; }
   Out o = header(begin);
-  for (auto &v : vars) {
-    for (long long q = 0; q < v.count; q++) {
+  auto emit = [&](const Nc3Var &v, size_t q0) {
+    if (v.data.size() < q0 + (size_t)v.count) { o.b.insert(o.b.end(), vsize(v), 0); return; }
+    for (size_t q = q0; q < q0 + (size_t)v.count; q++) {
       if (v.type == NC3_DOUBLE) { uint64_t u; std::memcpy(&u, &v.data[q], 8); o.u64(u); }
       else if (v.type == NC3_FLOAT) { const float f = (float)v.data[q]; uint32_t u; std::memcpy(&u, &f, 4); o.u32(u); }
       else if (v.type == NC3_INT) o.u32((uint32_t)(int32_t)std::llround(v.data[q]));
       else o.b.push_back((unsigned char)v.data[q]);
     }
     o.pad();
-  }
+  };
+  for (auto &v : vars) if (!v.rec) emit(v, 0);
+  for (int r = 0; r < numrecs; r++)
+    for (auto &v : vars) if (v.rec) emit(v, (size_t)r * (size_t)v.count);
   FILE *f = std::fopen(path.c_str(), "wb");
   if (!f) { if (err) *err = "cannot open " + path + " for writing"; return false; }
   const bool ok = std::fwrite(o.b.data(), 1, o.b.size(), f) == o.b.size();
@@ -164,7 +180,7 @@ bool Nc3File::write(const std::string &path, std::string *err) const {
 }
 
 bool Nc3File::read(const std::string &path, std::string *err) {
-  dims.clear(); gatts.clear(); vars.clear();
+  dims.clear(); gatts.clear(); vars.clear(); numrecs = 0;
   FILE *f = std::fopen(path.c_str(), "rb");
   if (!f) { if (err) *err = "Missing file " + path; return false; }
   std::vector<unsigned char> b;
@@ -179,7 +195,8 @@ bool Nc3File::read(const std::string &path, std::string *err) {
   const bool wide = b[3] == 2;
   In in(b);
   in.p = 4;
-  in.u32();   // numrecs
+  numrecs = (int)in.u32();
+  if (numrecs < 0) numrecs = 0;   // NC_STREAMING (0xffffffff) is never written for these files
   int recdim = -1;
   {
     const uint32_t tag = in.u32(), nd = in.u32();
@@ -195,6 +212,7 @@ bool Nc3File::read(const std::string &path, std::string *err) {
   }
   in.atts(&gatts);
   std::vector<uint64_t> begin;
+  std::vector<uint32_t> vsz;
   {
     const uint32_t tag = in.u32(), nv = in.u32();
     if (!(tag == 0 && nv == 0)) {
@@ -207,19 +225,26 @@ bool Nc3File::read(const std::string &path, std::string *err) {
         for (uint32_t d = 0; d < nd && in.ok; d++) {
           const int id = (int)in.u32();
           if (id < 0 || id >= (int)dims.size()) { in.ok = false; break; }
-          if (id == recdim) { if (err) *err = path + ": record variables are not supported (" + v.name + ")"; return false; }
+          if (id == recdim) {
+            if (d != 0) { if (err) *err = path + ": record dimension not the first of variable " + v.name; return false; }
+            v.rec = true;
+          }
           v.dimids.push_back(id);
-          v.count *= dims[id].second;
+          if (id != recdim) v.count *= dims[id].second;
         }
         in.atts(&v.atts);
         v.type = (int)in.u32();
-        in.u32();   // vsize
+        vsz.push_back(in.u32());
         begin.push_back(wide ? in.u64() : in.u32());
         vars.push_back(v);
       }
     }
   }
   if (!in.ok) { if (err) *err = path + ": damaged netCDF header"; return false; }
+  // one record = the slabs of all record variables (vsize each; a lone record variable is not padded, which the 4- and 8-byte
+  // types of these files never need)
+  size_t recsize = 0;
+  for (size_t q = 0; q < vars.size(); q++) if (vars[q].rec) recsize += vsz[q];
   for (size_t q = 0; q < vars.size(); q++) {
     Nc3Var &v = vars[q];
     if (v.type != NC3_DOUBLE && v.type != NC3_FLOAT && v.type != NC3_INT && v.type != NC3_CHAR) {
@@ -227,15 +252,19 @@ bool Nc3File::read(const std::string &path, std::string *err) {
       return false;
     }
     const size_t ts = (size_t)type_size(v.type);
-    if (begin[q] + (uint64_t)v.count * ts > b.size()) { if (err) *err = path + ": truncated data of variable " + v.name; return false; }
-    v.data.resize((size_t)v.count);
-    const unsigned char *p = &b[begin[q]];
-    for (long long e = 0; e < v.count; e++, p += ts) {
-      if (v.type == NC3_DOUBLE) { uint64_t u = 0; for (int s = 0; s < 8; s++) u = (u << 8) | p[s]; double d; std::memcpy(&d, &u, 8); v.data[e] = d; }
-      else if (v.type == NC3_CHAR) v.data[e] = p[0];
-      else {
-        uint32_t u = 0; for (int s = 0; s < 4; s++) u = (u << 8) | p[s];
-        if (v.type == NC3_FLOAT) { float x; std::memcpy(&x, &u, 4); v.data[e] = x; } else v.data[e] = (int32_t)u;
+    const size_t nrec = v.rec ? (size_t)numrecs : 1;
+    if (nrec && begin[q] + (uint64_t)(nrec - 1) * recsize + (uint64_t)v.count * ts > b.size()) { if (err) *err = path + ": truncated data of variable " + v.name; return false; }
+    v.data.resize((size_t)v.count * nrec);
+    for (size_t r = 0; r < nrec; r++) {
+      const unsigned char *p = &b[begin[q] + r * recsize];
+      double *out = &v.data[r * (size_t)v.count];
+      for (long long e = 0; e < v.count; e++, p += ts) {
+        if (v.type == NC3_DOUBLE) { uint64_t u = 0; for (int s = 0; s < 8; s++) u = (u << 8) | p[s]; double d; std::memcpy(&d, &u, 8); out[e] = d; }
+        else if (v.type == NC3_CHAR) out[e] = p[0];
+        else {
+          uint32_t u = 0; for (int s = 0; s < 4; s++) u = (u << 8) | p[s];
+          if (v.type == NC3_FLOAT) { float x; std::memcpy(&x, &u, 4); out[e] = x; } else out[e] = (int32_t)u;
+        }
       }
     }
   }
@@ -563,6 +592,208 @@ extern "C" int cg_restart_biogem_read(const char *path, int n_i, int n_j, int n_
   }
   return CG_OK;
 }
+
+// ------------------------------------------------------------------ BIOGEM time slices: fields_biogem_3d.nc
+// sub_init_netcdf (dd = 3), sub_save_netcdf, sub_save_netcdf_3d: src/biogem/biogem_data_netCDF.f90:148-277, 282-459, 1959-2315
+namespace {
+constexpr double kSliceNullSmall = 0.999999e-19;   // const_real_nullsmall, gem_cmn.f90:719
+constexpr double kSliceNull = -0.999999e+19;       // const_real_null, :717 (the null the time-slice writer passes, not const_nulliso)
+constexpr double kStd13C = 0.011202, kStd14C = 1.176e-12;   // const_standards(11:12), gem_cmn.f90:629-631 (as cg_series.cpp)
+// fun_calc_isotope_delta(tot, iso, standard, .FALSE., const_real_null), gem_util.f90:568-598
+double slice_delta(double tot, double iso, double standard) {
+  if (tot > kSliceNullSmall) {
+    const double f = iso / tot;
+    if ((1.0 - f) > kSliceNullSmall) {
+      const double R = f / (1.0 - f);
+      return 1000.0 * (R / standard - 1.0);
+    }
+  }
+  return kSliceNull;
+}
+double slice_standard(int type) { return type == 11 ? kStd13C : kStd14C; }
+// sub_adddef_netcdf (dino = 4) + sub_defvar ('F'): [valid_range as two floats if min != max,] missing_value, long_name, units
+int def_field(cg::Nc3File &f, const std::string &name, const std::vector<int> &dimids, const std::string &lname,
+              const std::string &units, double rmin, double rmax) {
+  if (f.var(name)) { for (size_t q = 0; q < f.vars.size(); q++) if (f.vars[q].name == name) return (int)q; }
+  const int id = f.add_var(name, cg::NC3_FLOAT, dimids);
+  if (rmin != rmax) f.put_att_num(id, "valid_range", cg::NC3_FLOAT, {rmin, rmax});
+  f.put_att_num(id, "missing_value", cg::NC3_DOUBLE, {kNcFillDouble});
+  if (lname != " " && !lname.empty()) f.put_att(id, "long_name", lname);
+  if (units != " " && !units.empty()) f.put_att(id, "units", units);
+  return id;
+}
+}  // namespace
+
+extern "C" int cg_slice_biogem_write_3d(const char *path, int n_i, int n_j, int n_k, const int32_t *k1, const double *lon,
+                                        const double *lat, const double *lon_e, const double *lat_e, const double *zt,
+                                        const double *zt_e, int n_ocn, const char *const *ocn_names,
+                                        const char *const *ocn_longnames, const char *const *ocn_units, const double *ocn_mima,
+                                        const int32_t *ocn_type, const int32_t *ocn_dep, const double *int_ocn, int n_sed,
+                                        const char *const *sed_names, const int32_t *sed_type, const int32_t *sed_dep,
+                                        const double *int_part, int n_carb, const char *const *carb_names, const double *int_carb,
+                                        int n_carbconst, const char *const *carbconst_names, const double *int_carbconst,
+                                        const double *mass, double int_t, double year_mid, const char *run_id) {
+  if (!path || n_i <= 0 || n_j <= 0 || n_k <= 0 || !k1 || !lon || !lat || !lon_e || !lat_e || !zt || !zt_e || n_ocn < 0 || n_sed < 0 ||
+      n_carb < 0 || n_carbconst < 0 ||
+      (n_ocn && (!ocn_names || !ocn_longnames || !ocn_units || !ocn_mima || !ocn_type || !ocn_dep || !int_ocn)) ||
+      (n_sed && (!sed_names || !sed_type || !sed_dep || !int_part)) || (n_carb && (!carb_names || !int_carb)) ||
+      (n_carbconst && (!carbconst_names || !int_carbconst)))
+    return rfail("cg_slice_biogem_write_3d: bad argument");
+  if (!(int_t > 0.0)) return rfail("cg_slice_biogem_write_3d: int_t_timeslice is not positive (no step of the save window was integrated)");
+  for (int l = 0; l < n_ocn; l++) if (ocn_dep[l] < 0 || ocn_dep[l] >= n_ocn) return rfail("cg_slice_biogem_write_3d: ocn_dep out of range");
+  for (int l = 0; l < n_sed; l++) if (sed_dep[l] < 0 || sed_dep[l] >= n_sed) return rfail("cg_slice_biogem_write_3d: sed_dep out of range");
+  cg::Nc3File f;
+  std::string err;
+  int rec = 0;
+  FILE *probe = std::fopen(path, "rb");
+  if (probe) {   // sub_opennext: the file exists -> the record behind the last one
+    std::fclose(probe);
+    if (!f.read(path, &err)) return rfail(err);
+    if (f.dim_len("time") != 0 || f.dim_len("lon") != n_i || f.dim_len("lat") != n_j || f.dim_len("zt") != n_k || !f.var("time") || !f.var("year"))
+      return rfail(std::string(path) + ": not a time-slice file of this grid");
+    rec = f.numrecs;
+  } else {
+    // sub_init_netcdf: global attributes, dimensions and axis variables in the reference's order (dimension ids follow it too)
+    f.put_att(-1, "Conventions", "CF-1.0");
+    f.put_att(-1, "file_name", path);
+    f.put_att(-1, "title", "Time averaged integrals");
+    if (run_id && *run_id) f.put_att(-1, "experiment_name", run_id);
+    f.put_att(-1, "time_unit", "Year mid-point");
+    const int d_time = f.add_dim("time", 0), d_xu = f.add_dim("xu", n_i), d_lon = f.add_dim("lon", n_i), d_lat = f.add_dim("lat", n_j),
+              d_zt = f.add_dim("zt", n_k), d_yu = f.add_dim("yu", n_j), d_lone = f.add_dim("lon_edges", n_i + 1),
+              d_late = f.add_dim("lat_edges", n_j + 1), d_zte = f.add_dim("zt_edges", n_k + 1), d_xue = f.add_dim("xu_edges", n_i + 1),
+              d_yue = f.add_dim("yu_edges", n_j + 1);
+    f.add_dim("lat_moc", n_j + 1); f.add_dim("zt_moc", n_k + 1); f.add_dim("lat_moc_edges", n_j + 2); f.add_dim("zt_moc_edges", n_k + 2);
+    f.add_dim("para", 1);
+    defvar(f, "time", cg::NC3_DOUBLE, {d_time}, "T", "Year", "time", "Year mid-point");
+    defvar(f, "year", cg::NC3_FLOAT, {d_time}, " ", "year", " ", " ");
+    const int v_lon = defvar(f, "lon", cg::NC3_DOUBLE, {d_lon}, "X", "longitude of the t grid", "longitude", "degrees_east");
+    const int v_lat = defvar(f, "lat", cg::NC3_DOUBLE, {d_lat}, "Y", "latitude of the t grid", "latitude", "degrees_north");
+    const int v_zt = defvar(f, "zt", cg::NC3_DOUBLE, {d_zt}, "Z", "z-level mid depth", "depth", "m");
+    const int v_xu = defvar(f, "xu", cg::NC3_DOUBLE, {d_xu}, "X", "longitude of the u grid", "longitude", "degrees_east");
+    const int v_yu = defvar(f, "yu", cg::NC3_DOUBLE, {d_yu}, "Y", "latitude of the u grid", "latitude", "degrees_north");
+    const int v_lone = defvar(f, "lon_edges", cg::NC3_DOUBLE, {d_lone}, " ", "longitude of t grid edges", " ", "degrees");
+    const int v_late = defvar(f, "lat_edges", cg::NC3_DOUBLE, {d_late}, " ", "latitude of t grid edges", " ", "degrees");
+    const int v_zte = defvar(f, "zt_edges", cg::NC3_DOUBLE, {d_zte}, " ", "depth of t grid edges", " ", "m");
+    const int v_xue = defvar(f, "xu_edges", cg::NC3_DOUBLE, {d_xue}, " ", "longitude of u grid edges", " ", "degrees");
+    const int v_yue = defvar(f, "yu_edges", cg::NC3_DOUBLE, {d_yue}, " ", "latitude of u grid edges", " ", "degrees");
+    // grid_level 'I' with valid_range (0, 100) as two ints; grid_mask 'F' (0, 100), grid_topo 'F' (0, 5000) as two floats
+    const int v_lev = f.add_var("grid_level", cg::NC3_INT, {d_lat, d_lon});
+    f.put_att_num(v_lev, "valid_range", cg::NC3_INT, {0.0, 100.0});
+    f.put_att_num(v_lev, "missing_value", cg::NC3_DOUBLE, {kNcFillDouble});
+    f.put_att(v_lev, "long_name", "grid definition"); f.put_att(v_lev, "standard_name", "model_level_number"); f.put_att(v_lev, "units", "n/a");
+    const int v_mask = f.add_var("grid_mask", cg::NC3_FLOAT, {d_lat, d_lon});
+    f.put_att_num(v_mask, "valid_range", cg::NC3_FLOAT, {0.0, 100.0});
+    f.put_att_num(v_mask, "missing_value", cg::NC3_DOUBLE, {kNcFillDouble});
+    f.put_att(v_mask, "long_name", "land-sea mask"); f.put_att(v_mask, "units", "n/a");
+    const int v_topo = f.add_var("grid_topo", cg::NC3_FLOAT, {d_lat, d_lon});
+    f.put_att_num(v_topo, "valid_range", cg::NC3_FLOAT, {0.0, 5000.0});
+    f.put_att_num(v_topo, "missing_value", cg::NC3_DOUBLE, {kNcFillDouble});
+    f.put_att(v_topo, "long_name", "ocean depth "); f.put_att(v_topo, "units", "m");
+    // sub_save_netcdf, first record only: the axes.  xu = lon_edges(1:n_i), yu = lat_edges(1:n_j); the u-grid edges through
+    // edge_maker(2, ...): the t-grid points, then the last point plus the last cell's width (ipo_dlon, ipo_dlat)
+    f.put(v_lon, lon, n_i); f.put(v_lone, lon_e, n_i + 1); f.put(v_xu, lon_e, n_i);
+    std::vector<double> e(lon, lon + n_i);
+    e.push_back(lon[n_i - 1] + 360.0 / n_i);
+    f.put(v_xue, e.data(), n_i + 1);
+    f.put(v_lat, lat, n_j); f.put(v_late, lat_e, n_j + 1); f.put(v_yu, lat_e, n_j);
+    e.assign(lat, lat + n_j);
+    e.push_back(lat[n_j - 1] + (lat_e[n_j] - lat_e[n_j - 1]));
+    f.put(v_yue, e.data(), n_j + 1);
+    f.put(v_zt, zt, n_k); f.put(v_zte, zt_e, n_k + 1);
+    std::vector<double> lev((size_t)n_i * n_j), mk((size_t)n_i * n_j), topo((size_t)n_i * n_j);
+    for (int j = 0; j < n_j; j++)
+      for (int i = 0; i < n_i; i++) {
+        const int kk = k1[(i + 1) + (size_t)(n_i + 2) * (j + 1)];
+        const bool ocean = kk <= n_k;                       // phys_ocn(ipo_mask_ocn,i,j,n_k) = 1
+        lev[i + (size_t)n_i * j] = kk;
+        mk[i + (size_t)n_i * j] = ocean ? 1.0 : kNcFillDouble;
+        topo[i + (size_t)n_i * j] = ocean ? zt_e[n_k - kk + 1] : kNcFillDouble;   // phys_ocn(ipo_Dbot,i,j,k1(i,j))
+      }
+    f.put(v_lev, lev.data(), (long long)lev.size()); f.put(v_mask, mk.data(), (long long)mk.size()); f.put(v_topo, topo.data(), (long long)topo.size());
+  }
+  int d_time = -1, d_lon = -1, d_lat = -1, d_zt = -1;
+  for (size_t q = 0; q < f.dims.size(); q++) {
+    if (f.dims[q].first == "time") d_time = (int)q;
+    if (f.dims[q].first == "lon") d_lon = (int)q;
+    if (f.dims[q].first == "lat") d_lat = (int)q;
+    if (f.dims[q].first == "zt") d_zt = (int)q;
+  }
+  const std::vector<int> d4 = {d_time, d_zt, d_lat, d_lon};
+  const size_t n3 = (size_t)n_i * n_j * n_k;
+  std::vector<double> a(n3);
+  auto idv = [&](const char *name) { for (size_t q = 0; q < f.vars.size(); q++) if (f.vars[q].name == name) return (int)q; return -1; };
+  const double yr = year_mid, yri = (double)std::llround(year_mid);
+  f.put_rec(idv("time"), rec, &yr, 1);
+  f.put_rec(idv("year"), rec, &yri, 1);
+  // one field: value(l-independent functor) at the wet cells, surface level first, fill value elsewhere (sub_putvar3d_g)
+  auto put_field = [&](const std::string &name, const std::string &lname, const std::string &units, double rmin, double rmax, auto &&value) {
+    for (int k = 0; k < n_k; k++)
+      for (int j = 0; j < n_j; j++)
+        for (int i = 0; i < n_i; i++) {
+          const int km = n_k - k;
+          const bool wet = km >= k1[(i + 1) + (size_t)(n_i + 2) * (j + 1)];
+          const size_t cell = (size_t)i + (size_t)n_i * (j + (size_t)n_j * (km - 1));
+          a[(size_t)i + (size_t)n_i * (j + (size_t)n_j * k)] = wet ? value(cell) : kNcFillDouble;
+        }
+    f.put_rec(def_field(f, name, d4, lname, units, rmin, rmax), rec, a.data(), (long long)n3);
+  };
+  auto ocn = [&](int l, size_t cell) { return int_ocn[l + (size_t)n_ocn * cell]; };
+  // ctrl_data_save_slice_ocn, :1981-2022
+  int l_dic = -1, l_13 = -1, l_14 = -1, l_s = n_ocn > 1 ? 1 : -1;
+  for (int l = 0; l < n_ocn; l++) {
+    const std::string nm = ocn_names[l];
+    if (nm == "DIC") l_dic = l;
+    if (nm == "DIC_13C") l_13 = l;
+    if (nm == "DIC_14C") l_14 = l;
+    const int ty = ocn_type[l];
+    put_field("ocn_" + nm, ocn_longnames[l], ocn_units[l], ocn_mima[2 * l], ocn_mima[2 * l + 1], [&](size_t c) {
+      if (ty == 0) return l == 0 ? ocn(l, c) / int_t - 273.15 : ocn(l, c) / int_t;
+      if (ty == 1) return ocn(l, c) / int_t;
+      const double tot = ocn(ocn_dep[l], c) / int_t, frac = ocn(l, c) / int_t;
+      return slice_delta(tot, frac, slice_standard(ty));
+    });
+  }
+  if (l_dic >= 0 && l_13 >= 0 && l_14 >= 0)   // :2023-2046
+    put_field("ocn_DIC_D14C", " oceanic D14C (big delta)", "o/oo", 0.0, 0.0, [&](size_t c) {
+      const double tot = ocn(l_dic, c) / int_t;
+      const double d13 = slice_delta(tot, ocn(l_13, c) / int_t, kStd13C), d14 = slice_delta(tot, ocn(l_14, c) / int_t, kStd14C);
+      return 1000.0 * ((1.0 + d14 / 1000.0) * (0.975 * 0.975) / ((1.0 + d13 / 1000.0) * (1.0 + d13 / 1000.0)) - 1.0);
+    });
+  if (mass && l_s >= 0) {   // ctrl_data_save_derived, :2053-2107
+    double sm = 0.0, m = 0.0;   // loc_ocn_mean_S = SUM(int_S * M) / SUM(M) over the whole array (dry cells hold zeros)
+    for (size_t c = 0; c < n3; c++) { sm = sm + ocn(l_s, c) * mass[c]; m = m + mass[c]; }
+    const double mean_s = sm / m;
+    for (int l = 2; l < n_ocn; l++)
+      if (ocn_type[l] == 0 || ocn_type[l] == 1)
+        put_field(std::string("ocn_") + ocn_names[l] + "_Snorm", std::string(ocn_names[l]) + " normalized by salinity", "mol kg-1", 0.0, 0.0,
+                  [&](size_t c) { return ocn(l, c) * (mean_s / ocn(l_s, c)) / int_t; });
+    for (int l = 2; l < n_ocn; l++)
+      if (ocn_type[l] == 1 || (ocn_type[l] >= 11 && ocn_type[l] <= 22))
+        put_field(std::string("ocn_") + ocn_names[l] + "_tot", std::string(ocn_names[l]) + " volume integrated inventory", "mol", 0.0, 0.0,
+                  [&](size_t c) { return mass[c] * ocn(l, c) / int_t; });
+  }
+  for (int ic = 0; ic < n_carb; ic++)   // ctrl_data_save_slice_carb, :2146-2155
+    put_field(std::string("carb_") + carb_names[ic], std::string("carbonate chemistry properties - ") + carb_names[ic], " ", 0.0, 0.0,
+              [&](size_t c) { return int_carb[ic + (size_t)n_carb * c] / int_t; });
+  for (int ic = 0; ic < n_carbconst; ic++)   // ctrl_data_save_slice_carbconst, :2156-2165
+    put_field(std::string("carb_const_") + carbconst_names[ic],
+              std::string("carbonate chemistry dissociation constants - ") + carbconst_names[ic], " ", 0.0, 0.0,
+              [&](size_t c) { return int_carbconst[ic + (size_t)n_carbconst * c] / int_t; });
+  if (mass)   // ctrl_data_save_slice_bio .AND. ctrl_data_save_derived, :2167-2199
+    for (int l = 0; l < n_sed; l++) {
+      const int ty = sed_type[l];
+      if (!((ty >= 1 && ty <= 7) || (ty >= 11 && ty <= 22))) continue;   // par_sed_type_age / _frac / _misc have no variable
+      put_field(std::string("bio_part_") + sed_names[l], std::string("particulate density - ") + sed_names[l], ty >= 11 ? "o/oo" : "mol kg-1",
+                0.0, 0.0, [&](size_t c) {
+                  if (ty < 11) return int_part[l + (size_t)n_sed * c] / int_t;
+                  return slice_delta(int_part[sed_dep[l] + (size_t)n_sed * c] / int_t, int_part[l + (size_t)n_sed * c] / int_t, slice_standard(ty));
+                });
+    }
+  if (!f.write(path, &err)) return rfail(err);
+  return CG_OK;
+}
+
 
 // ------------------------------------------------------------------ ATCHEM restart (ctrl_ncrst = .TRUE., the default)
 // sub_data_netCDF_ncrstsave, src/atchem/atchem_data_netCDF.f90:22-109 (title, dimensions lon / lat / lon_edges / lat_edges, one

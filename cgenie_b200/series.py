@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 from . import _lib
-from .restart import ATM_TRACERS, OCN_TRACERS, _strs
+from .restart import ATM_TRACERS, OCN_TRACERS, SED_TRACERS, _strs, biogem_axes
 
 # ocn_type / ocn_dep (0-based compact index of the bulk tracer) and atm_type / atm_dep of the frozen selection
 # (data/main/tracer_define.ocn, tracer_define.atm columns 4 and 3)
@@ -81,6 +81,64 @@ YR_S = 3600.0 * (24.0 * 365.25)          # conv_yr_s, gem_cmn.f90:511-513
 S_YR = 1.0 / YR_S                        # conv_s_yr, gem_cmn.f90:532
 NULLSMALL = 0.999999e-19                 # const_real_nullsmall, gem_cmn.f90:719
 N_DATA_MAX = 32767                       # biogem_lib.f90:504
+
+# ---------------------------------------------------------------------------------------------------------------- time slices
+# units and valid range of the frozen ocean selection (data/main/tracer_define.ocn columns 6 - 8)
+OCN_UNITS = ["degrees C", "PSU", "mol kg-1", "o/oo", "o/oo"] + ["mol kg-1"] * 4 + ["o/oo", "o/oo"] + ["mol kg-1"] * 5
+OCN_MIMA = [(-9.999, 99.999), (0.0, 99.999), (-9.99E+2, 9.99E-1), (-9.99E+2, 9.99E+2), (-9.99E+5, 9.99E+5)] + \
+    [(-9.99E+2, 9.99E-1)] * 4 + [(-9.99E+2, 9.99E+2), (-9.99E+5, 9.99E+5)] + [(-9.99E+2, 9.99E-1)] * 5
+# rows of the device's "sl_carb" / "sl_carbconst" (include/cgenie_b200.h) and the reference's order of variables
+# (string_carb / string_carbconst, gem_cmn.f90:425-455)
+SL_CARB = ["H", "conc_CO2", "conc_CO3", "conc_HCO3", "fug_CO2", "ohm_cal", "ohm_arg", "dCO3_cal", "dCO3_arg", "RF0"]
+SL_CARBCONST = ["k1", "k2", "k", "kB", "kW", "kSi", "kHF", "kHSO4", "kP1", "kP2", "kP3", "kH2S", "kNH4", "kcal", "karg", "QCO2", "QO2"]
+REF_CARB = ["H", "fug_CO2", "conc_CO2", "conc_CO3", "conc_HCO3", "ohm_cal", "ohm_arg", "dCO3_cal", "dCO3_arg", "RF0"]
+REF_CARBCONST = ["k", "k1", "k2", "kB", "kW", "kSi", "kHF", "kHSO4", "kP1", "kP2", "kP3", "kcal", "karg", "QCO2", "QO2", "kH2S", "kNH4"]
+
+
+def ocean_mass(e):
+    """phys_ocn(ipo_M) (biogem_data.f90:1126-1130): conv_m3_kg * dD * A at the wet cells, zero elsewhere; flat (n_i,n_j,n_k)."""
+    I, J, K = e.maxi, e.maxj, e.maxk
+    k1 = np.asarray(e.iconst("k1")).reshape(J + 2, I + 2)
+    sv, dz = e.const("sv"), e.const("dz")
+    m = np.zeros((K, J, I))
+    for j in range(1, J + 1):
+        A = 2.0 * 3.141592653589793 * (6.37e6 * 6.37e6) * (1.0 / I) * (sv[j] - sv[j - 1])
+        for k in range(1, K + 1):
+            m[k - 1, j - 1, :] = np.where(k1[j, 1:I + 1] <= k, 1027.649 * ((5.0e3 * dz[k]) * A), 0.0)
+    return m.ravel()
+
+
+def write_timeslice_3d(e, path, year_mid, member=0, run_id="", derived=True, carbconst=False):
+    """One record of fields_biogem_3d.nc from the device's window integrals of one member (sub_save_netcdf + sub_save_netcdf_3d,
+    biogem_data_netCDF.f90:282-459, 1959-2315; the caller resets the integrals afterwards as sub_init_int_timeslice does).
+    derived = ctrl_data_save_derived (the _Snorm / _tot / bio_part_ blocks), carbconst = ctrl_data_save_slice_carbconst."""
+    L = _lib.load()
+    I, J, K = e.maxi, e.maxj, e.maxk
+    if e.maxl != len(OCN_TRACERS):
+        raise SeriesError("time slices: the job's tracer selection is not the frozen one")
+    k1 = np.ascontiguousarray(e.iconst("k1"), dtype=np.int32)
+    ax = [np.ascontiguousarray(a, dtype=np.float64) for a in biogem_axes(I, J, K, e.const("s"), e.const("sv"), e.const("dz"), e.const("dza"))]
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    n3 = I * J * K
+    ocn = np.ascontiguousarray(e.get("sl_ocn", member))
+    part = np.ascontiguousarray(e.get("sl_part", member))
+    carb = np.ascontiguousarray(e.get("sl_carb", member).reshape(n3, len(SL_CARB))[:, [SL_CARB.index(n) for n in REF_CARB]])
+    cc = np.ascontiguousarray(e.get("sl_carbconst", member).reshape(n3, len(SL_CARBCONST))[:, [SL_CARBCONST.index(n) for n in REF_CARBCONST]])
+    t = float(e.get("sl_t", member)[0])
+    on, k_1 = _strs([n for n, _ in OCN_TRACERS]); ol, k_2 = _strs([l for _, l in OCN_TRACERS]); ou, k_3 = _strs(OCN_UNITS)
+    mima = np.ascontiguousarray(OCN_MIMA, dtype=np.float64)
+    ot, k_4 = _i32(OCN_TYPE); od, k_5 = _i32(OCN_DEP)
+    sn, k_6 = _strs([n for n, _ in SED_TRACERS]); st, k_7 = _i32(SED_TYPE); sd, k_8 = _i32(SED_DEP)
+    cn, k_9 = _strs(REF_CARB); ccn, k_10 = _strs(REF_CARBCONST)
+    mass = np.ascontiguousarray(ocean_mass(e)) if derived else None
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    rc = L.cg_slice_biogem_write_3d(path.encode(), I, J, K, k1.ctypes.data_as(C.POINTER(C.c_int32)), *[dp(a) for a in ax],
+                                    len(OCN_TRACERS), on, ol, ou, dp(mima), ot, od, dp(ocn), len(SED_TRACERS), sn, st, sd, dp(part),
+                                    len(REF_CARB), cn, dp(carb), len(REF_CARBCONST) if carbconst else 0, ccn, dp(cc),
+                                    dp(mass) if derived else None, t, float(year_mid), run_id.encode())
+    if rc != 0:
+        raise SeriesError(L.cg_restart_last_error().decode())
+    return path
 
 
 class SeriesSaver:

@@ -352,6 +352,32 @@ int cg_restart_biogem_write_bin(const char *path, int n_i, int n_j, int n_k, int
 int cg_restart_biogem_read_bin(const char *path, int n_i, int n_j, int n_k, int n_ocn, const int32_t *ocn_ids, double *ocn,
                                int32_t *found_ocn, int n_sed, const int32_t *sed_ids, double *bio_part, int32_t *found_sed);
 
+/* BIOGEM's 3-D time-slice file fields_biogem_3d.nc: sub_init_netcdf (dd = 3) + sub_save_netcdf + sub_save_netcdf_3d
+ * (src/biogem/biogem_data_netCDF.f90:148-277, 282-459, 1959-2315; helpers src/common/gem_netcdf.f90:19-76 sub_opennext, 250-359
+ * sub_defvar, 702-744 sub_putvar3d_g, 790-840 sub_adddef_netcdf).  The first call creates `path` (dimensions time = unlimited, xu,
+ * lon, lat, zt, yu, the *_edges, lat_moc, zt_moc and their edges, para; the axes; grid_level, grid_mask, grid_topo) and writes
+ * record 1; a call on an existing file appends the next record (sub_opennext: ntrec = length of time + 1).  One record = time
+ * (year mid-point), year = nint(time), and as FLOAT (zt, lat, lon) variables with the surface level first and the fill value on
+ * dry cells: ocn_<name> = int_ocn / int_t (ctrl_data_save_slice_ocn; temperature minus 273.15; isotopes as delta values through
+ * fun_calc_isotope_delta, gem_util.f90:568-598; valid_range from tracer_define.ocn), ocn_DIC_D14C when DIC_13C and DIC_14C are
+ * both there (fun_convert_delta14CtoD14C, gem_util.f90:623-637), with `mass` (phys_ocn(ipo_M), (n_i,n_j,n_k); NULL leaves the
+ * derived fields out = ctrl_data_save_derived off) ocn_<name>_Snorm and ocn_<name>_tot, carb_<name> (ctrl_data_save_slice_carb),
+ * carb_const_<name> (ctrl_data_save_slice_carbconst) and, with `mass`, bio_part_<name>.  int_ocn (n_ocn,n_i,n_j,n_k), int_part
+ * (n_sed,...), int_carb (n_carb,...), int_carbconst (n_carbconst,...) are the window integrals of ONE member in Fortran order
+ * (the fields "sl_ocn", "sl_part", "sl_carb", "sl_carbconst" of cg_biogem_slice_update; the carbonate rows in the ORDER OF THE
+ * NAMES passed -- the reference's is string_carb / string_carbconst, gem_cmn.f90:425-455), int_t = int_t_timeslice.  *_type: 0,
+ * 1, 11 (13C), 12 (14C) ...; *_dep: 0-based compact index of an isotope's bulk tracer; ocn_mima (2,n_ocn).  n_sed / n_carb /
+ * n_carbconst = 0 leave a block out.  Axes as for cg_restart_biogem_write.  Not written: the remin / phys_ocn / settling-flux /
+ * diag_geochem / velocity blocks (:2108-2135, 2200-2314).  Host only; errors through cg_restart_last_error(). */
+int cg_slice_biogem_write_3d(const char *path, int n_i, int n_j, int n_k, const int32_t *k1, const double *lon, const double *lat,
+                             const double *lon_e, const double *lat_e, const double *zt, const double *zt_e, int n_ocn,
+                             const char *const *ocn_names, const char *const *ocn_longnames, const char *const *ocn_units,
+                             const double *ocn_mima, const int32_t *ocn_type, const int32_t *ocn_dep, const double *int_ocn,
+                             int n_sed, const char *const *sed_names, const int32_t *sed_type, const int32_t *sed_dep,
+                             const double *int_part, int n_carb, const char *const *carb_names, const double *int_carb,
+                             int n_carbconst, const char *const *carbconst_names, const double *int_carbconst, const double *mass,
+                             double int_t, double year_mid, const char *run_id);
+
 #ifdef __cplusplus
 }
 #endif
