@@ -140,6 +140,75 @@ def write_timeslice_3d(e, path, year_mid, member=0, run_id="", derived=True, car
         raise SeriesError(L.cg_restart_last_error().decode())
     return path
 
+class SliceSaver:
+    """The save-window logic of BIOGEM's time slices for ctrl_misc_t_BP = .FALSE.: the list of slice mid-points of sub_init_data_save
+    (biogem_data.f90:2528-2584: the dates of biogem_save_timeslice.dat through sub_load_data_t1 as "years to go", the first one inside
+    the run, ctrl_data_save_slice_autoend) and the window tests of diag_biogem_timeslice (biogem.f90:2451-2466, 2608-2696).  Scalar
+    bookkeeping only: the integrals are the device's (Ensemble.biogem_slice_update), the file cg_slice_biogem_write_3d's.
+
+    Call step(dts, genie_clock_ms) where genie.f90 calls diag_biogem_timeslice_wrapper (genie.f90:391-395): behind biogem_climate,
+    ahead of the time-series update and atchem_step."""
+
+    def __init__(self, e, path, t_runtime, save_times, t_start=0.0, slice_dt=1.0, slice_n=0, member=0, autoend=False, run_id="",
+                 derived=True, carbconst=False):
+        self.e, self.path, self.member, self.run_id, self.derived, self.carbconst = e, str(path), member, run_id, derived, carbconst
+        self.t_runtime, self.t_end = float(t_runtime), float(t_start) + float(t_runtime)
+        self.slice_dt, self.slice_n = float(slice_dt), int(slice_n)       # par_data_save_slice_dt, par_data_save_slice_n
+        t_err = 3600.0 * 1.0 / YR_S
+        data = [float(x) for x in (save_times or [])]
+        n = len(data)
+        if n and data[-1] <= data[0]:            # sub_load_data_t1, .NOT. ctrl_misc_t_BP (biogem_lib.f90:1487-1543)
+            ts = [self.t_end - x for x in data]
+        else:
+            ts = [self.t_end - data[n - q] for q in range(1, n + 1)]
+        i = n
+        while i > 0:
+            if ts[i - 1] < (self.t_runtime - self.slice_dt / 2.0 + t_err):
+                break
+            i -= 1
+        if i > 0 and ts[i - 1] < (self.slice_dt / 2.0 - t_err):
+            i = 0
+        if autoend:
+            if i == 0:
+                ts, i = [self.slice_dt / 2.0], 1
+            else:
+                for q in range(i, 0, -1):
+                    if ts[q - 1] < (1.0 - self.slice_dt / 2.0 + t_err):
+                        if not ts[q - 1] > (self.slice_dt / 2.0 - t_err):
+                            ts[q - 1] = self.slice_dt / 2.0
+                        break
+        self.ts, self.i = ts, i
+        self.int_t, self.int_t_tot, self.count = 0.0, 0.0, 0
+        self.saved = []
+        e.biogem_slice_reset()
+
+    def step(self, dts, genie_clock_ms):
+        """One BIOGEM step.  Returns the year a record was written for, else None."""
+        if self.i <= 0:
+            return None
+        s_yr = 1.0 / YR_S                                                    # conv_s_yr
+        loc_t = self.t_runtime - float(genie_clock_ms) / (1000.0 * YR_S)
+        if not (loc_t - (self.ts[self.i - 1] + self.slice_dt / 2.0)) < -s_yr:
+            return None
+        dtyr = float(dts) / YR_S
+        self.e.biogem_slice_update(dts)
+        self.int_t += dtyr
+        self.int_t_tot += dtyr
+        self.count += 1
+        full = (self.slice_dt - self.int_t) < s_yr
+        if not (full or self.count == self.slice_n):
+            return None
+        yr = self.t_end - loc_t - self.int_t / 2.0
+        yr = float(int(yr)) + float(int(1000.0 * (yr - float(int(yr)) + 0.0005))) / 1000.0
+        write_timeslice_3d(self.e, self.path, yr, member=self.member, run_id=self.run_id, derived=self.derived, carbconst=self.carbconst)
+        self.saved.append(yr)
+        self.e.biogem_slice_reset()                                          # sub_init_int_timeslice
+        self.int_t, self.count = 0.0, 0
+        if (self.slice_dt - self.int_t_tot) < s_yr:
+            self.int_t_tot = 0.0
+            self.i -= 1
+        return yr
+
 
 class SeriesSaver:
     """The save-window logic of BIOGEM's time series for ctrl_misc_t_BP = .FALSE.: sub_init_data_save (biogem_data.f90:2449-2527,

@@ -162,3 +162,52 @@ def test_time_slice_refuses_another_grid_and_an_empty_window(built, tmp_path):
     e2 = _Engine(3, 1.0, K=K - 1)
     with pytest.raises(series.SeriesError):
         series.write_timeslice_3d(e2, p, 1.5)
+
+
+class _Recorder(_Engine):
+    """The stand-in with the two engine calls SliceSaver makes: the integrals grow by dtyr per update and are zeroed by a reset."""
+
+    def __init__(self):
+        super().__init__(5, 1.0)
+        self.unit = {n: v.copy() for n, v in self.f.items()}
+        self.calls = []
+        self.biogem_slice_reset()
+
+    def biogem_slice_update(self, dts):
+        self.calls.append("u")
+        for n in self.f:
+            self.f[n] = self.f[n] + self.unit[n] * (dts / series.YR_S)
+
+    def biogem_slice_reset(self):
+        self.calls.append("r")
+        for n in self.f:
+            self.f[n] = np.zeros_like(self.unit[n])
+
+
+def test_slice_saver_windows(built, tmp_path):
+    """A 10-year run of 48 BIOGEM steps per year, slices of one year centred on years 0.5, 4.5 and 9.5 (biogem_save_timeslice.dat lists
+    mid-points): three records at those years, each the mean over exactly the 48 steps of its window; steps outside a window never
+    touch the device integrals."""
+    p = str(tmp_path / "fields_biogem_3d.nc")
+    e = _Recorder()
+    sv = series.SliceSaver(e, p, t_runtime=10.0, save_times=[0.5, 4.5, 9.5], slice_dt=1.0, run_id="w")
+    dts = series.YR_S / 48.0
+    got = []
+    for istep in range(1, 10 * 48 + 1):
+        y = sv.step(dts, int(round(istep * dts * 1000.0)))
+        if y is not None:
+            got.append((istep, y))
+    assert [y for _, y in got] == [0.5, 4.5, 9.5] and sv.saved == [0.5, 4.5, 9.5]
+    assert [i for i, _ in got] == [48, 5 * 48, 10 * 48]
+    assert e.calls.count("u") == 3 * 48 and e.calls.count("r") == 5 and sv.i == 0      # the stand-in's own, the saver's, one per record
+    with netcdf_file(p, "r", mmap=False) as f:
+        assert np.array_equal(f.variables["time"][:], [0.5, 4.5, 9.5])
+        want = np.where(e.wet, e.unit["sl_ocn"].reshape(K, J, I, L)[..., 2], FILL)[::-1].astype(np.float32)
+        for rec in range(3):
+            assert np.allclose(f.variables["ocn_DIC"][rec], want, rtol=3e-7, atol=0.0)
+    # no date inside the run: nothing is saved, unless ctrl_data_save_slice_autoend adds the last half window
+    e2 = _Recorder()
+    sv2 = series.SliceSaver(e2, str(tmp_path / "none.nc"), t_runtime=2.0, save_times=[50.5])
+    assert sv2.i == 0 and sv2.step(dts, 1000) is None and e2.calls == ["r", "r"]
+    sv3 = series.SliceSaver(_Recorder(), str(tmp_path / "end.nc"), t_runtime=2.0, save_times=[50.5], autoend=True)
+    assert sv3.i == 1 and sv3.ts == [0.5]
